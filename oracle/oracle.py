@@ -1,0 +1,230 @@
+"""TEST INFRASTRUCTURE ONLY.  ctypes view of the C restatement oracle/oxdna_oracle.c (built with gcc into
+oracle/_build/liboxoracle.so).  Imported only by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "liboxoracle.so")
+_SRC = [os.path.join(_HERE, "oxdna_oracle.c")]
+_HDR = [os.path.join(_HERE, "oxdna_oracle.h")]
+
+NTERMS = 8
+TERM_NAMES = ["FENE", "BEXC", "STCK", "NEXC", "HB", "CRSTCK", "CXSTCK", "DH"]
+
+
+def build(force=False):
+    """gcc -O2 (no -ffast-math: the oracle is plain IEEE double)."""
+    os.makedirs(os.path.dirname(_SO), exist_ok=True)
+    newest = max(os.path.getmtime(p) for p in _SRC + _HDR)
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < newest:
+        cmd = ["gcc", "-O2", "-std=c11", "-fPIC", "-shared", "-o", _SO] + _SRC + ["-lm"]
+        subprocess.check_call(cmd)
+    return _SO
+
+
+class _F1(C.Structure):
+    _fields_ = [(n, C.c_double) for n in "a rc r0 blow bhigh rlow rhigh rclow rchigh".split()] + [
+        ("eps", (C.c_double * 5) * 5), ("shift", (C.c_double * 5) * 5)]
+
+
+class _F2(C.Structure):
+    _fields_ = [(n, C.c_double) for n in "k rc r0 blow rlow rclow bhigh rhigh rchigh".split()]
+
+
+class _F4(C.Structure):
+    _fields_ = [(n, C.c_double) for n in "a b t0 ts tc".split()]
+
+
+class _F5(C.Structure):
+    _fields_ = [(n, C.c_double) for n in "a b xc xs".split()]
+
+
+class _Excl(C.Structure):
+    _fields_ = [(n, C.c_double) for n in "sigma rstar b rc".split()]
+
+
+class DNA2Params(C.Structure):
+    _fields_ = (
+        [(n, C.c_double) for n in "back_a1 back_a2 stack_a1 base_a1 backref_a1 T fene_eps fene_r0 fene_delta fene_delta2".split()]
+        + [("use_mbf", C.c_int)]
+        + [(n, C.c_double) for n in "mbf_xmax mbf_fmax mbf_finf".split()]
+        + [("excl", _Excl * 4), ("excl_eps", C.c_double), ("hb", _F1), ("stck", _F1), ("crst", _F2), ("cxst", _F2)]
+        + [(n, _F4) for n in "stck_t4 stck_t5 hb_t1 hb_t2 hb_t4 hb_t7 crst_t1 crst_t2 crst_t4 crst_t7 cxst_t1 cxst_t4 cxst_t5".split()]
+        + [("cxst_t1_sa", C.c_double), ("cxst_t1_sb", C.c_double), ("stck_phi1", _F5), ("stck_phi2", _F5)]
+        + [(n, C.c_double) for n in "dh_minus_kappa dh_prefactor dh_rhigh dh_rc dh_b".split()]
+        + [("dh_half_charged_ends", C.c_int), ("hb_multiplier", C.c_double), ("rcut", C.c_double)]
+    )
+
+
+class ExtForce(C.Structure):
+    _fields_ = [("type", C.c_int), ("particle", C.c_int), ("ref", C.c_int), ("pbc", C.c_int)] + [
+        (n, C.c_double) for n in "stiff r0 rate stiff_rate F0".split()] + [("dir", C.c_double * 3), ("pos0", C.c_double * 3)]
+
+
+EXT_STRING, EXT_TRAP, EXT_MUTUAL = 0, 1, 2
+
+
+class _MD(C.Structure):
+    _fields_ = [("N", C.c_int)] + [(n, C.c_void_p) for n in "pos axes vel L force torque_body list_pos btype n3 n5".split()] + [
+        ("box", C.c_double * 3), ("dt", C.c_double), ("skin", C.c_double), ("pairs", C.c_void_p), ("npairs", C.c_longlong),
+        ("max_pairs", C.c_longlong), ("step", C.c_longlong), ("nf", C.c_int), ("ef", C.c_void_p), ("U", C.c_double)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        _lib.oxo_verlet_pairs.restype = C.c_longlong
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _d(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def kelvin(T):
+    """src/Utilities/Utils.cpp:316-346"""
+    return T * 0.1 / 300.0
+
+
+def celsius(T):
+    return (T + 273.15) * 0.1 / 300.0
+
+
+def dna2_params(T, salt=0.5, dh_half_charged_ends=True, max_backbone_force=None, max_backbone_force_far=0.04):
+    P = DNA2Params()
+    mbf = max_backbone_force is not None
+    lib().oxo_dna2_params_init(C.byref(P), C.c_double(T), C.c_double(salt), int(dh_half_charged_ends), int(mbf),
+                               C.c_double(max_backbone_force if mbf else 0.0),
+                               C.c_double(float(np.float32(max_backbone_force_far))))
+    return P
+
+
+def dna2_params_seqdep(P, stck16, stck_fact_eps, hb_AT, hb_GC):
+    s = _d(stck16).reshape(16)
+    lib().oxo_dna2_params_seqdep(C.byref(P), _p(s), C.c_double(stck_fact_eps), C.c_double(hb_AT), C.c_double(hb_GC))
+    return P
+
+
+def axes_from_a1a3(a1, a3):
+    a1, a3 = _d(a1), _d(a3)
+    N = a1.shape[0]
+    ax = np.zeros((N, 9))
+    lib().oxo_axes_from_a1a3(N, _p(a1), _p(a3), _p(ax))
+    return ax
+
+
+def verlet_pairs(pos, n3, n5, box, rv):
+    pos, n3, n5, box = _d(pos), _i(n3), _i(n5), _d(box)
+    N = pos.shape[0]
+    cap = max(64 * N, 1024)
+    while True:
+        out = np.zeros((cap, 2), dtype=np.int32)
+        n = lib().oxo_verlet_pairs(N, _p(pos), _p(n3), _p(n5), _p(box), C.c_double(rv), _p(out), C.c_longlong(cap))
+        if n <= cap:
+            return out[:n].copy()
+        cap = n
+
+
+def forces(P, pos, axes, btype, n3, n5, box, pairs):
+    pos, axes, box = _d(pos), _d(axes), _d(box)
+    btype, n3, n5, pairs = _i(btype), _i(n3), _i(n5), _i(pairs)
+    N = pos.shape[0]
+    f, tl, tb = np.zeros((N, 3)), np.zeros((N, 3)), np.zeros((N, 3))
+    et, ep = np.zeros(NTERMS), np.zeros(N)
+    lib().oxo_dna2_forces(C.byref(P), N, _p(pos), _p(axes), _p(btype), _p(n3), _p(n5), _p(box), _p(pairs),
+                          C.c_longlong(pairs.shape[0]), _p(f), _p(tl), _p(tb), _p(et), _p(ep))
+    return dict(force=f, torque_lab=tl, torque_body=tb, eterms=et, epart=ep, U=et.sum())
+
+
+def make_ext(forces_list):
+    arr = (ExtForce * max(len(forces_list), 1))()
+    for k, d in enumerate(forces_list):
+        e = arr[k]
+        e.type = {"string": EXT_STRING, "trap": EXT_TRAP, "mutual_trap": EXT_MUTUAL}[d["type"]]
+        e.particle = d["particle"]
+        e.ref = d.get("ref_particle", -1)
+        e.pbc = int(d.get("PBC", 0))
+        e.stiff, e.r0, e.rate = d.get("stiff", 0.0), d.get("r0", 0.0), d.get("rate", 0.0)
+        e.stiff_rate, e.F0 = d.get("stiff_rate", 0.0), d.get("F0", 0.0)
+        dr = np.array(d.get("dir", (0, 0, 1)), dtype=np.float64)
+        if e.type != EXT_MUTUAL:
+            dr = dr / np.linalg.norm(dr)
+        for c in range(3):
+            e.dir[c] = dr[c]
+            e.pos0[c] = d.get("pos0", (0, 0, 0))[c]
+    return arr
+
+
+def ext_forces(ext, pos, box, step):
+    pos, box = _d(pos), _d(box)
+    f = np.zeros_like(pos)
+    arr = make_ext(ext)
+    lib().oxo_ext_forces(len(ext), arr, pos.shape[0], _p(pos), _p(box), C.c_longlong(step), _p(f))
+    return f
+
+
+class MD:
+    """NVE velocity-Verlet driver around oxo_md_steps (MD_CPUBackend restatement)."""
+
+    def __init__(self, P, pos, axes, vel, L, btype, n3, n5, box, dt, skin, ext=()):
+        self.P = P
+        self.N = N = pos.shape[0]
+        self.pos, self.axes, self.vel, self.L = _d(pos).copy(), _d(axes).copy(), _d(vel).copy(), _d(L).copy()
+        self.force, self.torque_body, self.list_pos = np.zeros((N, 3)), np.zeros((N, 3)), np.zeros((N, 3))
+        self.btype, self.n3, self.n5 = _i(btype).copy(), _i(n3).copy(), _i(n5).copy()
+        self.max_pairs = 80 * N + 1024
+        self.pairs = np.zeros((self.max_pairs, 2), dtype=np.int32)
+        self.ext = make_ext(list(ext))
+        S = self.S = _MD()
+        S.N = N
+        for n in "pos axes vel L force torque_body list_pos btype n3 n5 pairs".split():
+            setattr(S, n, getattr(self, n).ctypes.data)
+        for k in range(3):
+            S.box[k] = float(box[k])
+        S.dt, S.skin, S.max_pairs, S.step = dt, skin, self.max_pairs, 0
+        S.nf = len(ext)
+        S.ef = C.cast(self.ext, C.c_void_p)
+        p = verlet_pairs(self.pos, self.n3, self.n5, box, P.rcut + 2 * skin)
+        self.pairs[: len(p)] = p
+        S.npairs = len(p)
+        self.list_pos[:] = self.pos
+        lib().oxo_md_compute_forces(C.byref(P), C.byref(S))
+
+    def step(self, n=1):
+        return lib().oxo_md_steps(C.byref(self.P), C.byref(self.S), int(n))
+
+    @property
+    def U(self):
+        return self.S.U
+
+    def current_pairs(self):
+        return self.pairs[: self.S.npairs].copy()
+
+
+def brownian_params(T, dt, newtonian_steps, pt=0.0, diff_coeff=0.0):
+    a, b, c = C.c_double(), C.c_double(), C.c_double()
+    lib().oxo_brownian_params(C.c_double(T), C.c_double(dt), int(newtonian_steps), C.c_double(pt), C.c_double(diff_coeff),
+                              C.byref(a), C.byref(b), C.byref(c))
+    return a.value, b.value, c.value
+
+
+def langevin_params(T, dt, gamma_trans=0.0, diff_coeff=0.0):
+    v = [C.c_double() for _ in range(4)]
+    lib().oxo_langevin_params(C.c_double(T), C.c_double(dt), C.c_double(gamma_trans), C.c_double(diff_coeff), *[C.byref(x) for x in v])
+    return tuple(x.value for x in v)

@@ -1,0 +1,700 @@
+/* TEST INFRASTRUCTURE ONLY -- see oxdna_oracle.h.
+ *
+ * CPU restatement of the oxDNA2 force field, Verlet list and velocity-Verlet step, double precision.
+ * It follows the *algorithm* of the reference's CPU classes (cited per function) but is organised
+ * differently: every angular/radial factor is differentiated through one generic chain-rule helper
+ * instead of the reference's hand-expanded expressions, which makes it an independent check.
+ */
+#include "oxdna_oracle.h"
+
+#include <float.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* the reference defines PI as a *float* literal (src/defs.h:14); every t0 derived from it inherits that rounding */
+#define OXO_PI 3.141592653589793238462643f
+#define SQ(x) ((x) * (x))
+
+/* ------------------------------------------------------------------ small vector helpers */
+static inline double dot3(const double *a, const double *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+static inline void cross3(const double *a, const double *b, double *o) {
+	o[0] = a[1] * b[2] - a[2] * b[1];
+	o[1] = a[2] * b[0] - a[0] * b[2];
+	o[2] = a[0] * b[1] - a[1] * b[0];
+}
+static inline void axpy3(double s, const double *x, double *y) { y[0] += s * x[0]; y[1] += s * x[1]; y[2] += s * x[2]; }
+
+/* ------------------------------------------------------------------ parameters */
+static void set_f4(oxo_f4 *f, double a, double b, double t0, double ts, double tc) {
+	f->a = a; f->b = b; f->t0 = t0; f->ts = ts; f->tc = tc;
+}
+
+static void fill_f1(oxo_f1 *f, double eps) {
+	/* shift = eps * (1 - exp(-(rc - r0) a))^2, src/Interactions/DNA2Interaction.cpp:114-121.  (rc - r0)*a is float
+	 * arithmetic in the reference (float macros); exp() there resolves to the double overload. */
+	for(int i = 0; i < 5; i++) for(int j = 0; j < 5; j++) {
+		f->eps[i][j] = eps;
+		f->shift[i][j] = eps * SQ(1 - exp(-(double) ((float) (f->rc - f->r0) * (float) f->a)));
+	}
+}
+
+void oxo_dna2_params_init(oxo_dna2_params *P, double T, double salt, int dh_half, int use_mbf, double mbf_fmax, double mbf_finf) {
+	memset(P, 0, sizeof(*P));
+	P->T = T;
+	/* sites: src/model.h:14-18 (oxDNA2 "major-minor grooving" backbone), DNANucleotide.cpp:76-80 */
+	P->back_a1 = -0.3400f; P->back_a2 = 0.3408f; P->stack_a1 = 0.34f;
+	P->base_a1 = P->stack_a1 * ((double) 0.4f / (double) 0.34f);
+	P->backref_a1 = -0.4f;
+	/* FENE: model.h:46-50; max_backbone_force: DNAInteraction.cpp:258-276 */
+	P->fene_eps = 2.0f; P->fene_r0 = 0.7564f; P->fene_delta = 0.25f; P->fene_delta2 = 0.0625f;
+	P->use_mbf = use_mbf;
+	if(use_mbf) {
+		P->mbf_fmax = mbf_fmax;
+		P->mbf_finf = mbf_finf;
+		P->mbf_xmax = (-P->fene_eps + sqrt(P->fene_eps * P->fene_eps + 4.f * mbf_fmax * mbf_fmax * P->fene_delta2)) / (2.f * mbf_fmax);
+	}
+	/* excluded volume: model.h:55-88 */
+	P->excl_eps = 2.0f;
+	P->excl[0] = (oxo_excl){ 0.70f, 0.675f, 892.016223343f, 0.711879214356f };
+	P->excl[1] = (oxo_excl){ 0.33f, 0.32f, 4119.70450017f, 0.335388426126f };
+	P->excl[2] = (oxo_excl){ 0.515f, 0.50f, 1707.30627298f, 0.52329943261f };
+	P->excl[3] = (oxo_excl){ 0.515f, 0.50f, 1707.30627298f, 0.52329943261f };
+	/* hydrogen bonding radial part: model.h:93-106; oxDNA2 eps: DNA2Interaction.cpp:119 */
+	P->hb.a = 8.f; P->hb.rc = 0.75f; P->hb.r0 = 0.4f; P->hb.blow = -126.243f; P->hb.bhigh = -7.87708f;
+	P->hb.rlow = 0.34f; P->hb.rhigh = 0.7f; P->hb.rclow = 0.276908f; P->hb.rchigh = 0.783775f;
+	fill_f1(&P->hb, 1.0678f);
+	/* stacking radial part: model.h:153-166; eps(T): DNA2Interaction.cpp:115 */
+	P->stck.a = 6.f; P->stck.rc = 0.9f; P->stck.r0 = 0.4f; P->stck.blow = -68.1857f; P->stck.bhigh = -3.12992f;
+	P->stck.rlow = 0.32f; P->stck.rhigh = 0.75f; P->stck.rclow = 0.23239f; P->stck.rchigh = 0.956f;
+	fill_f1(&P->stck, 1.3523f + 2.6717f * T);
+	/* cross stacking / coaxial stacking radial parts: model.h:202-211, 369-381; oxDNA2 K: DNA2Interaction.cpp:10 */
+	P->crst = (oxo_f2){ 47.5f, 0.675f, 0.575f, -0.888889f, 0.495f, 0.45f, -0.888889f, 0.655f, 0.7f };
+	P->cxst = (oxo_f2){ 58.5f, 0.6f, 0.400f, -2.13158f, 0.22f, 0.177778f, -2.13158f, 0.58f, 0.6222222f };
+	/* angular parts */
+	set_f4(&P->stck_t4, 1.3f, 6.4381f, 0.f, 0.8f, 0.961538f);
+	set_f4(&P->stck_t5, 0.9f, 3.89361f, 0.f, 0.95f, 1.16959f);
+	set_f4(&P->hb_t1, 1.5f, 4.16038f, 0.f, 0.7f, 0.952381f);
+	set_f4(&P->hb_t2, 1.5f, 4.16038f, 0.f, 0.7f, 0.952381f);
+	set_f4(&P->hb_t4, 0.46f, 0.133855f, OXO_PI, 0.7f, 3.10559f);
+	set_f4(&P->hb_t7, 4.f, 17.0526f, (OXO_PI * 0.5f), 0.45f, 0.555556f);
+	set_f4(&P->crst_t1, 2.25f, 7.00545f, (OXO_PI - 2.35f), 0.58f, 0.766284f);
+	set_f4(&P->crst_t2, 1.70f, 6.2469f, 1.f, 0.68f, 0.865052f);
+	set_f4(&P->crst_t4, 1.50f, 2.59556f, 0.f, 0.65f, 1.02564f);
+	set_f4(&P->crst_t7, 1.70f, 6.2469f, 0.875f, 0.68f, 0.865052f);
+	set_f4(&P->cxst_t1, 2.f, 10.9032f, (OXO_PI - 0.25f), 0.65f, 0.769231f);
+	set_f4(&P->cxst_t4, 1.3f, 6.4381f, 0.f, 0.8f, 0.961538f);
+	set_f4(&P->cxst_t5, 0.9f, 3.89361f, 0.f, 0.95f, 1.16959f);
+	P->cxst_t1_sa = 20.f;
+	P->cxst_t1_sb = (OXO_PI - 0.1f * (OXO_PI - (OXO_PI - 0.25f)));
+	P->stck_phi1 = (oxo_f5){ 2.0f, 10.9032f, -0.769231f, -0.65f };
+	P->stck_phi2 = P->stck_phi1;
+	/* Debye-Hueckel: DNA2Interaction.cpp:66-84 (get_settings) and :124-149 (init).  The smoothing onset RHIGH is
+	 * computed in get_settings with a *float* 0.1f, lambda in init with a double 0.1 -- reproduced as is. */
+	const double lfac = 0.3616455, q = 0.0543;
+	double lambda_gs = lfac * sqrt(T / 0.1f) / sqrt(salt);
+	double lambda = lfac * sqrt(T / 0.1) / sqrt(salt);
+	P->dh_rhigh = 3.0 * lambda_gs;
+	P->dh_minus_kappa = -1.0 / lambda;
+	P->dh_prefactor = q;
+	double x = P->dh_rhigh, l = lambda;
+	P->dh_b = -(exp(-x / l) * q * q * (x + l) * (x + l)) / (-4. * x * x * x * l * l * q);
+	P->dh_rc = x * (q * x + 3. * q * l) / (q * (x + l));
+	P->dh_half_charged_ends = dh_half;
+	P->hb_multiplier = 1.0;
+	/* cutoff: DNAInteraction.cpp:296-311, DNA2Interaction.cpp:137-149 (float macros => float products) */
+	double rcutback = 2 * sqrt((double) ((-0.3400f) * (-0.3400f) + (0.3408f) * (0.3408f))) + (double) 0.711879214356f;
+	double rcutbase = 2 * fabs((double) 0.4f) + (double) 0.783775f;
+	P->rcut = fmax(rcutback, rcutbase);
+	double debyecut = 2.0 * sqrt((double) (SQ(-0.3400f) + SQ(0.3408f))) + P->dh_rc;
+	if(debyecut > P->rcut) P->rcut = debyecut;
+}
+
+void oxo_dna2_params_seqdep(oxo_dna2_params *P, const double *stck_raw16, double stck_fact_eps, double hb_AT, double hb_GC) {
+	/* DNAInteraction.cpp:329-375; base order A=0 G=1 C=2 T=3 (src/defs.h) */
+	double sh_st = SQ(1 - exp(-(double) ((float) (P->stck.rc - P->stck.r0) * (float) P->stck.a)));
+	double sh_hb = SQ(1 - exp(-(double) ((float) (P->hb.rc - P->hb.r0) * (float) P->hb.a)));
+	for(int i = 0; i < 4; i++) for(int j = 0; j < 4; j++) {
+		P->stck.eps[i][j] = stck_raw16[4 * i + j] * (1.0 - stck_fact_eps + (P->T * 9.0 * stck_fact_eps));
+		P->stck.shift[i][j] = P->stck.eps[i][j] * sh_st;
+	}
+	P->hb.eps[0][3] = P->hb.eps[3][0] = hb_AT;
+	P->hb.eps[1][2] = P->hb.eps[2][1] = hb_GC;
+	P->hb.shift[0][3] = P->hb.shift[3][0] = hb_AT * sh_hb;
+	P->hb.shift[1][2] = P->hb.shift[2][1] = hb_GC * sh_hb;
+}
+
+/* ------------------------------------------------------------------ modulation functions */
+/* value and d/dr of f1 (DNAInteraction.cpp:1249-1283) */
+static void f1_eval(const oxo_f1 *f, double r, int n3t, int n5t, double *v, double *d) {
+	double eps = f->eps[n3t][n5t];
+	*v = 0; *d = 0;
+	if(r < f->rchigh) {
+		if(r > f->rhigh) { *v = eps * f->bhigh * SQ(r - f->rchigh); *d = eps * 2 * f->bhigh * (r - f->rchigh); }
+		else if(r > f->rlow) {
+			double e = exp(-(r - f->r0) * f->a);
+			*v = eps * SQ(1 - e) - f->shift[n3t][n5t];
+			*d = eps * 2 * (1 - e) * e * f->a;
+		}
+		else if(r > f->rclow) { *v = eps * f->blow * SQ(r - f->rclow); *d = eps * 2 * f->blow * (r - f->rclow); }
+	}
+}
+
+/* f2 (DNAInteraction.cpp:1285-1315) */
+static void f2_eval(const oxo_f2 *f, double r, double *v, double *d) {
+	*v = 0; *d = 0;
+	if(r < f->rchigh) {
+		if(r > f->rhigh) { *v = f->k * f->bhigh * SQ(r - f->rchigh); *d = 2. * f->k * f->bhigh * (r - f->rchigh); }
+		else if(r > f->rlow) { *v = (f->k / 2.) * (SQ(r - f->r0) - SQ(f->rc - f->r0)); *d = f->k * (r - f->r0); }
+		else if(r > f->rclow) { *v = f->k * f->blow * SQ(r - f->rclow); *d = 2. * f->k * f->blow * (r - f->rclow); }
+	}
+}
+
+static double clamp_acos(double c) { return acos(fmax(-1.0, fmin(1.0, c))); }
+
+/* f4 as a function of cos(theta): value and derivative with respect to the cosine.
+ * d f4(acos c)/dc = -f4'(theta)/sin(theta), with the reference's small-angle guard (DNAInteraction.cpp:1351-1420). */
+static void f4_eval(const oxo_f4 *f, double c, double *v, double *dc) {
+	double t = clamp_acos(c);
+	double x = t - f->t0, m = 1;
+	if(x < 0) { x = -x; m = -1; }
+	*v = 0; *dc = 0;
+	if(x < f->tc) {
+		double s = sin(t), dsin;
+		if(x > f->ts) { *v = f->b * SQ(f->tc - x); dsin = m * 2 * f->b * (x - f->tc) / s; }
+		else {
+			*v = 1. - f->a * SQ(x);
+			dsin = (SQ(s) > 1e-8) ? -m * 2 * f->a * x / s : -m * 2 * f->a;
+		}
+		*dc = -dsin;
+	}
+}
+
+/* symmetrised version F(c) = f4(c) + f4(-c), used by cross and coaxial stacking */
+static void f4_sym(const oxo_f4 *f, double c, double *v, double *dc) {
+	double v1, d1, v2, d2;
+	f4_eval(f, c, &v1, &d1);
+	f4_eval(f, -c, &v2, &d2);
+	*v = v1 + v2;
+	*dc = d1 - d2;
+}
+
+/* oxDNA2 coaxial theta1: f4 plus a pure harmonic beyond t = sb (DNA2Interaction.cpp:308-363) */
+static void f4_cxst_t1(const oxo_dna2_params *P, double c, double *v, double *dc) {
+	if(c * c > 1) c = copysign(1, c);
+	f4_eval(&P->cxst_t1, c, v, dc);
+	double t = acos(c), x = t - P->cxst_t1_sb;
+	if(x >= 0) {
+		double s = sin(t);
+		*v += P->cxst_t1_sa * SQ(x);
+		double dsin = (SQ(s) > 1e-8) ? 2 * P->cxst_t1_sa * x / s : 2 * P->cxst_t1_sa;
+		*dc += -dsin;
+	}
+}
+
+/* f5 (DNAInteraction.cpp:1422-1454) */
+static void f5_eval(const oxo_f5 *f, double c, double *v, double *d) {
+	*v = 0; *d = 0;
+	if(c > f->xc) {
+		if(c < f->xs) { *v = f->b * SQ(f->xc - c); *d = 2 * f->b * (c - f->xc); }
+		else if(c < 0) { *v = 1. - f->a * SQ(c); *d = -2. * f->a * c; }
+		else { *v = 1; }
+	}
+}
+
+/* ------------------------------------------------------------------ pair accumulator + generic chain rule */
+typedef struct { double Fq[3], Tp[3], Tq[3]; } pacc; /* force on q (p gets -Fq), lab-frame torques */
+
+/* a force F acting on q at lever sq and -F acting on p at lever sp */
+static void site_force(pacc *A, const double *sp, const double *sq, const double *F) {
+	double x[3];
+	axpy3(1, F, A->Fq);
+	cross3(sp, F, x); axpy3(-1, x, A->Tp);
+	cross3(sq, F, x); axpy3(1, x, A->Tq);
+}
+
+/* c = u.v, u rigidly attached to p and v to q, g = dE/dc */
+static void chain_body_body(pacc *A, double g, const double *u, const double *v) {
+	double x[3];
+	cross3(u, v, x);
+	axpy3(-g, x, A->Tp);
+	axpy3(g, x, A->Tq);
+}
+
+/* c = u.rhat with rhat the unit vector from site sp (on p) to site sq (on q), |r| = rmod; u attached to p (onq=0) or q (onq=1) */
+static void chain_body_dir(pacc *A, double g, const double *u, const double *rhat, double rmod, double c, int onq,
+		const double *sp, const double *sq) {
+	double F[3], x[3];
+	for(int k = 0; k < 3; k++) F[k] = -g * (u[k] - c * rhat[k]) / rmod;
+	site_force(A, sp, sq, F);
+	cross3(u, rhat, x);
+	axpy3(-g, x, onq ? A->Tq : A->Tp);
+}
+
+static double excl_eval(const oxo_dna2_params *P, const oxo_excl *e, const double *r, double *F) {
+	/* DNAInteraction.cpp:1182-1205; F = force on q */
+	double r2 = dot3(r, r), en = 0;
+	F[0] = F[1] = F[2] = 0;
+	if(r2 < SQ(e->rc)) {
+		if(r2 > SQ(e->rstar)) {
+			double rm = sqrt(r2), rrc = rm - e->rc;
+			en = P->excl_eps * e->b * SQ(rrc);
+			double s = -(2 * P->excl_eps * e->b * rrc / rm);
+			for(int k = 0; k < 3; k++) F[k] = s * r[k];
+		}
+		else {
+			double t = SQ(e->sigma) / r2, lj = t * t * t;
+			en = 4 * P->excl_eps * (SQ(lj) - lj);
+			double s = -(24 * P->excl_eps * (lj - 2 * SQ(lj)) / r2);
+			for(int k = 0; k < 3; k++) F[k] = s * r[k];
+		}
+	}
+	if(en == 0) F[0] = F[1] = F[2] = 0;
+	return en;
+}
+
+typedef struct { double back[3], stack[3], base[3], backref[3]; const double *a1, *a2, *a3; } sites_t;
+
+static void make_sites(const oxo_dna2_params *P, const double *ax, sites_t *S) {
+	S->a1 = ax; S->a2 = ax + 3; S->a3 = ax + 6;
+	for(int k = 0; k < 3; k++) {
+		S->back[k] = S->a1[k] * P->back_a1 + S->a2[k] * P->back_a2;
+		S->stack[k] = S->a1[k] * P->stack_a1;
+		S->base[k] = S->stack[k] * ((double) 0.4f / (double) 0.34f);
+		S->backref[k] = S->a1[k] * P->backref_a1;
+	}
+}
+
+static void site_sep(const double *r, const double *sp, const double *sq, double *out, double *mod, double *hat) {
+	for(int k = 0; k < 3; k++) out[k] = r[k] + sq[k] - sp[k];
+	*mod = sqrt(dot3(out, out));
+	if(hat) for(int k = 0; k < 3; k++) hat[k] = out[k] / *mod;
+}
+
+static void neg3(const double *a, double *o) { o[0] = -a[0]; o[1] = -a[1]; o[2] = -a[2]; }
+
+/* ------------------------------------------------------------------ bonded pair p -> q = n3(p) */
+static void bonded_pair(const oxo_dna2_params *P, const double *r, const sites_t *sp, const sites_t *sq, int tp, int tq,
+		pacc *A, double *e) {
+	double v[3], m, F[3];
+	/* FENE on the backbone sites: DNAInteraction.cpp:415-466 */
+	site_sep(r, sp->back, sq->back, v, &m, NULL);
+	double x = m - P->fene_r0, en, s;
+	if(P->use_mbf && fabs(x) > P->mbf_xmax) {
+		double fene_xmax = -(P->fene_eps / 2.f) * log(1.f - SQ(P->mbf_xmax) / P->fene_delta2);
+		double long_xmax = (P->mbf_fmax - P->mbf_finf) * P->mbf_xmax * log(P->mbf_xmax) + P->mbf_finf * P->mbf_xmax;
+		en = (P->mbf_fmax - P->mbf_finf) * P->mbf_xmax * log(fabs(x)) + P->mbf_finf * fabs(x) - long_xmax + fene_xmax;
+		s = -copysign(1.f, x) * ((P->mbf_fmax - P->mbf_finf) * P->mbf_xmax / fabs(x) + P->mbf_finf) / m;
+	}
+	else if(fabs(x) > P->fene_delta - DBL_EPSILON) {
+		en = 1.e12; s = 0;
+	}
+	else {
+		en = -(P->fene_eps / 2.f) * log(1.f - SQ(x) / P->fene_delta2);
+		s = -(P->fene_eps * x / (P->fene_delta2 - SQ(x))) / m;
+	}
+	for(int k = 0; k < 3; k++) F[k] = s * v[k];
+	site_force(A, sp->back, sq->back, F);
+	e[OXO_FENE] += en;
+
+	/* bonded excluded volume: DNAInteraction.cpp:468-528 */
+	site_sep(r, sp->base, sq->base, v, &m, NULL);
+	e[OXO_BEXC] += excl_eval(P, &P->excl[1], v, F); site_force(A, sp->base, sq->base, F);
+	site_sep(r, sp->base, sq->back, v, &m, NULL);
+	e[OXO_BEXC] += excl_eval(P, &P->excl[2], v, F); site_force(A, sp->base, sq->back, F);
+	site_sep(r, sp->back, sq->base, v, &m, NULL);
+	e[OXO_BEXC] += excl_eval(P, &P->excl[3], v, F); site_force(A, sp->back, sq->base, F);
+
+	/* stacking: DNAInteraction.cpp:530-705.  Angles: t4 = (a3,b3), t5 = (a3,-rhat), t6 = (b3,-rhat); phi1, phi2 are
+	 * cosines of a2, b2 against the unit vector between the *ungrooved* backbone sites (-0.4 a1). */
+	double rst[3], rstm, rsth[3], w[3], wm, wh[3];
+	site_sep(r, sp->stack, sq->stack, rst, &rstm, rsth);
+	site_sep(r, sp->backref, sq->backref, w, &wm, wh);
+	double ma3[3], mb3[3];
+	neg3(sp->a3, ma3); neg3(sq->a3, mb3);
+	double c4 = dot3(sp->a3, sq->a3), c5 = dot3(ma3, rsth), c6 = dot3(mb3, rsth);
+	double cp1 = dot3(sp->a2, wh), cp2 = dot3(sq->a2, wh);
+	double f1, f1d, g4, g4d, g5, g5d, g6, g6d, h1, h1d, h2, h2d;
+	f1_eval(&P->stck, rstm, tq, tp, &f1, &f1d);
+	f4_eval(&P->stck_t4, c4, &g4, &g4d);
+	f4_eval(&P->stck_t5, c5, &g5, &g5d);
+	f4_eval(&P->stck_t5, c6, &g6, &g6d);
+	f5_eval(&P->stck_phi1, cp1, &h1, &h1d);
+	f5_eval(&P->stck_phi2, cp2, &h2, &h2d);
+	double E = f1 * g4 * g5 * g6 * h1 * h2;
+	e[OXO_STCK] += E;
+	if(E != 0.) {
+		for(int k = 0; k < 3; k++) F[k] = -rsth[k] * (f1d * g4 * g5 * g6 * h1 * h2);
+		site_force(A, sp->stack, sq->stack, F);
+		chain_body_body(A, f1 * g4d * g5 * g6 * h1 * h2, sp->a3, sq->a3);
+		chain_body_dir(A, f1 * g4 * g5d * g6 * h1 * h2, ma3, rsth, rstm, c5, 0, sp->stack, sq->stack);
+		chain_body_dir(A, f1 * g4 * g5 * g6d * h1 * h2, mb3, rsth, rstm, c6, 1, sp->stack, sq->stack);
+		chain_body_dir(A, f1 * g4 * g5 * g6 * h1d * h2, sp->a2, wh, wm, cp1, 0, sp->backref, sq->backref);
+		chain_body_dir(A, f1 * g4 * g5 * g6 * h1 * h2d, sq->a2, wh, wm, cp2, 1, sp->backref, sq->backref);
+	}
+}
+
+/* ------------------------------------------------------------------ non-bonded pair */
+static void nonbonded_pair(const oxo_dna2_params *P, const double *r, const sites_t *sp, const sites_t *sq, int btp, int btq,
+		int tp, int tq, int p_end, int q_end, pacc *A, double *e) {
+	double v[3], m, h[3], F[3];
+	/* excluded volume, four site pairs: DNAInteraction.cpp:707-777 */
+	site_sep(r, sp->base, sq->base, v, &m, NULL);
+	e[OXO_NEXC] += excl_eval(P, &P->excl[1], v, F); site_force(A, sp->base, sq->base, F);
+	site_sep(r, sp->back, sq->base, v, &m, NULL);
+	e[OXO_NEXC] += excl_eval(P, &P->excl[3], v, F); site_force(A, sp->back, sq->base, F);
+	site_sep(r, sp->base, sq->back, v, &m, NULL);
+	e[OXO_NEXC] += excl_eval(P, &P->excl[2], v, F); site_force(A, sp->base, sq->back, F);
+	site_sep(r, sp->back, sq->back, v, &m, NULL);
+	e[OXO_NEXC] += excl_eval(P, &P->excl[0], v, F); site_force(A, sp->back, sq->back, F);
+
+	/* base-base vector shared by HB and cross stacking */
+	site_sep(r, sp->base, sq->base, v, &m, h);
+	double ma1[3], mb1[3], mb3[3];
+	neg3(sp->a1, ma1); neg3(sq->a1, mb1); neg3(sq->a3, mb3);
+	double c1 = dot3(ma1, sq->a1), c2 = dot3(mb1, h), c3 = dot3(sp->a1, h);
+	double c4 = dot3(sp->a3, sq->a3), c7 = dot3(mb3, h), c8 = dot3(sp->a3, h);
+
+	/* hydrogen bonding: DNAInteraction.cpp:779-902 */
+	if(btp + btq == 3 && P->hb.rclow < m && m < P->hb.rchigh) {
+		double mult = (abs(btq) >= 300 && abs(btp) >= 300) ? P->hb_multiplier : 1.;
+		double f1, f1d, g[6], d[6];
+		f1_eval(&P->hb, m, tq, tp, &f1, &f1d);
+		f1 *= mult; f1d *= mult;
+		f4_eval(&P->hb_t1, c1, &g[0], &d[0]);
+		f4_eval(&P->hb_t2, c2, &g[1], &d[1]);
+		f4_eval(&P->hb_t2, c3, &g[2], &d[2]);
+		f4_eval(&P->hb_t4, c4, &g[3], &d[3]);
+		f4_eval(&P->hb_t7, c7, &g[4], &d[4]);
+		f4_eval(&P->hb_t7, c8, &g[5], &d[5]);
+		double E = f1 * g[0] * g[1] * g[2] * g[3] * g[4] * g[5];
+		e[OXO_HB] += E;
+		if(E != 0.) {
+			double rest[6];
+			for(int i = 0; i < 6; i++) { rest[i] = f1 * d[i]; for(int j = 0; j < 6; j++) if(j != i) rest[i] *= g[j]; }
+			for(int k = 0; k < 3; k++) F[k] = -h[k] * (f1d * g[0] * g[1] * g[2] * g[3] * g[4] * g[5]);
+			site_force(A, sp->base, sq->base, F);
+			chain_body_body(A, rest[0], ma1, sq->a1);
+			chain_body_dir(A, rest[1], mb1, h, m, c2, 1, sp->base, sq->base);
+			chain_body_dir(A, rest[2], sp->a1, h, m, c3, 0, sp->base, sq->base);
+			chain_body_body(A, rest[3], sp->a3, sq->a3);
+			chain_body_dir(A, rest[4], mb3, h, m, c7, 1, sp->base, sq->base);
+			chain_body_dir(A, rest[5], sp->a3, h, m, c8, 0, sp->base, sq->base);
+		}
+	}
+
+	/* cross stacking: DNAInteraction.cpp:904-1021 */
+	if(P->crst.rclow < m && m < P->crst.rchigh) {
+		double f2, f2d, g[6], d[6];
+		f2_eval(&P->crst, m, &f2, &f2d);
+		f4_eval(&P->crst_t1, c1, &g[0], &d[0]);
+		f4_eval(&P->crst_t2, c2, &g[1], &d[1]);
+		f4_eval(&P->crst_t2, c3, &g[2], &d[2]);
+		f4_sym(&P->crst_t4, c4, &g[3], &d[3]);
+		f4_sym(&P->crst_t7, c7, &g[4], &d[4]);
+		f4_sym(&P->crst_t7, c8, &g[5], &d[5]);
+		double E = f2 * g[0] * g[1] * g[2] * g[3] * g[4] * g[5];
+		e[OXO_CRST] += E;
+		if(E != 0.) {
+			double rest[6];
+			for(int i = 0; i < 6; i++) { rest[i] = f2 * d[i]; for(int j = 0; j < 6; j++) if(j != i) rest[i] *= g[j]; }
+			for(int k = 0; k < 3; k++) F[k] = -h[k] * (f2d * g[0] * g[1] * g[2] * g[3] * g[4] * g[5]);
+			site_force(A, sp->base, sq->base, F);
+			chain_body_body(A, rest[0], ma1, sq->a1);
+			chain_body_dir(A, rest[1], mb1, h, m, c2, 1, sp->base, sq->base);
+			chain_body_dir(A, rest[2], sp->a1, h, m, c3, 0, sp->base, sq->base);
+			chain_body_body(A, rest[3], sp->a3, sq->a3);
+			chain_body_dir(A, rest[4], mb3, h, m, c7, 1, sp->base, sq->base);
+			chain_body_dir(A, rest[5], sp->a3, h, m, c8, 0, sp->base, sq->base);
+		}
+	}
+
+	/* coaxial stacking, oxDNA2 form: DNA2Interaction.cpp:212-306 */
+	site_sep(r, sp->stack, sq->stack, v, &m, h);
+	if(P->cxst.rclow < m && m < P->cxst.rchigh) {
+		double c5 = dot3(sp->a3, h), c6 = dot3(mb3, h);
+		double f2, f2d, g[4], d[4];
+		f2_eval(&P->cxst, m, &f2, &f2d);
+		f4_cxst_t1(P, c1, &g[0], &d[0]);
+		f4_eval(&P->cxst_t4, c4, &g[1], &d[1]);
+		f4_sym(&P->cxst_t5, c5, &g[2], &d[2]);
+		f4_sym(&P->cxst_t5, c6, &g[3], &d[3]);
+		double E = f2 * g[0] * g[1] * g[2] * g[3];
+		e[OXO_CXST] += E;
+		if(E != 0.) {
+			double rest[4];
+			for(int i = 0; i < 4; i++) { rest[i] = f2 * d[i]; for(int j = 0; j < 4; j++) if(j != i) rest[i] *= g[j]; }
+			for(int k = 0; k < 3; k++) F[k] = -h[k] * (f2d * g[0] * g[1] * g[2] * g[3]);
+			site_force(A, sp->stack, sq->stack, F);
+			chain_body_body(A, rest[0], ma1, sq->a1);
+			chain_body_body(A, rest[1], sp->a3, sq->a3);
+			chain_body_dir(A, rest[2], sp->a3, h, m, c5, 0, sp->stack, sq->stack);
+			chain_body_dir(A, rest[3], mb3, h, m, c6, 1, sp->stack, sq->stack);
+		}
+	}
+
+	/* Debye-Hueckel on the backbone sites: DNA2Interaction.cpp:157-210 */
+	site_sep(r, sp->back, sq->back, v, &m, h);
+	if(m < P->dh_rc) {
+		double cut = 1.0f;
+		if(P->dh_half_charged_ends && p_end) cut *= 0.5f;
+		if(P->dh_half_charged_ends && q_end) cut *= 0.5f;
+		double en, fs;
+		if(m < P->dh_rhigh) {
+			en = exp(m * P->dh_minus_kappa) * (P->dh_prefactor / m);
+			fs = -1.0f * (P->dh_prefactor * exp(P->dh_minus_kappa * m)) * (P->dh_minus_kappa / m - 1.0f / SQ(m));
+		}
+		else {
+			en = P->dh_b * SQ(m - P->dh_rc);
+			fs = -(2.0f * P->dh_b * (m - P->dh_rc));
+		}
+		e[OXO_DH] += en * cut;
+		for(int k = 0; k < 3; k++) F[k] = h[k] * fs * cut;
+		site_force(A, sp->back, sq->back, F);
+	}
+}
+
+static inline int type_of(int btype) { return (btype < 0) ? 3 - ((3 - btype) % 4) : btype % 4; }
+
+static void min_image(const double *box, const double *p, const double *q, double *r) {
+	/* src/Boxes/CubicBox.cpp:51-57 (and OrthogonalBox) */
+	for(int k = 0; k < 3; k++) r[k] = q[k] - p[k] - rint((q[k] - p[k]) / box[k]) * box[k];
+}
+
+static void scatter(const pacc *A, int p, int q, double half_e, double *force, double *tl, double *epart) {
+	for(int k = 0; k < 3; k++) {
+		if(force) { force[3 * p + k] -= A->Fq[k]; force[3 * q + k] += A->Fq[k]; }
+		if(tl) { tl[3 * p + k] += A->Tp[k]; tl[3 * q + k] += A->Tq[k]; }
+	}
+	if(epart) { epart[p] += half_e; epart[q] += half_e; }
+}
+
+void oxo_dna2_forces(const oxo_dna2_params *P, int N, const double *pos, const double *axes, const int *btype,
+		const int *n3, const int *n5, const double *box, const int *pairs, long long npairs,
+		double *force, double *torque_lab, double *torque_body, double *eterms, double *epart) {
+	double *tl = torque_lab ? torque_lab : (torque_body ? (double *) calloc(3 * (size_t) N, sizeof(double)) : NULL);
+	double et[OXO_NTERMS] = { 0 };
+	if(force) memset(force, 0, 3 * (size_t) N * sizeof(double));
+	if(torque_lab) memset(torque_lab, 0, 3 * (size_t) N * sizeof(double));
+	if(epart) memset(epart, 0, (size_t) N * sizeof(double));
+	sites_t *S = (sites_t *) malloc((size_t) N * sizeof(sites_t));
+	for(int i = 0; i < N; i++) make_sites(P, axes + 9 * (size_t) i, &S[i]);
+
+	for(int p = 0; p < N; p++) {
+		int q = n3[p];
+		if(q < 0) continue;
+		double r[3] = { pos[3 * q] - pos[3 * p], pos[3 * q + 1] - pos[3 * p + 1], pos[3 * q + 2] - pos[3 * p + 2] };
+		pacc A; memset(&A, 0, sizeof(A));
+		double e[OXO_NTERMS] = { 0 };
+		bonded_pair(P, r, &S[p], &S[q], type_of(btype[p]), type_of(btype[q]), &A, e);
+		double tot = 0;
+		for(int t = 0; t < OXO_NTERMS; t++) { et[t] += e[t]; tot += e[t]; }
+		scatter(&A, p, q, 0.5 * tot, force, tl, epart);
+	}
+	double rc2 = SQ(P->rcut);
+	for(long long i = 0; i < npairs; i++) {
+		/* the reference evaluates pair (p, q) with p the higher index (Cells.cpp:163) */
+		int a = pairs[2 * i], b = pairs[2 * i + 1];
+		int p = a > b ? a : b, q = a > b ? b : a;
+		if(n3[p] == q || n5[p] == q) continue;
+		double r[3];
+		min_image(box, pos + 3 * (size_t) p, pos + 3 * (size_t) q, r);
+		if(dot3(r, r) >= rc2) continue;
+		pacc A; memset(&A, 0, sizeof(A));
+		double e[OXO_NTERMS] = { 0 };
+		nonbonded_pair(P, r, &S[p], &S[q], btype[p], btype[q], type_of(btype[p]), type_of(btype[q]),
+				n3[p] < 0 || n5[p] < 0, n3[q] < 0 || n5[q] < 0, &A, e);
+		double tot = 0;
+		for(int t = 0; t < OXO_NTERMS; t++) { et[t] += e[t]; tot += e[t]; }
+		scatter(&A, p, q, 0.5 * tot, force, tl, epart);
+	}
+	if(torque_body) {
+		for(int i = 0; i < N; i++) {
+			const double *ax = axes + 9 * (size_t) i;
+			for(int k = 0; k < 3; k++) torque_body[3 * i + k] = dot3(ax + 3 * k, tl + 3 * (size_t) i);
+		}
+	}
+	if(eterms) memcpy(eterms, et, sizeof(et));
+	if(tl && tl != torque_lab) free(tl);
+	free(S);
+}
+
+/* ------------------------------------------------------------------ external forces */
+void oxo_ext_forces(int nf, const oxo_ext_force *ef, int N, const double *pos, const double *box, long long step, double *force) {
+	(void) N;
+	for(int i = 0; i < nf; i++) {
+		const oxo_ext_force *f = &ef[i];
+		const double *pp = pos + 3 * (size_t) f->particle;
+		double *F = force + 3 * (size_t) f->particle;
+		if(f->type == OXO_EXT_STRING) {
+			/* src/Forces/ConstantRateForce.cpp:52-61 */
+			double s = f->F0 + f->rate * step;
+			axpy3(s, f->dir, F);
+		}
+		else if(f->type == OXO_EXT_TRAP) {
+			/* src/Forces/MovingTrap.cpp:50-64 */
+			for(int k = 0; k < 3; k++) F[k] += -f->stiff * (pp[k] - (f->pos0[k] + (f->rate * step) * f->dir[k]));
+		}
+		else if(f->type == OXO_EXT_MUTUAL) {
+			/* src/Forces/MutualTrap.cpp:54-66 */
+			const double *qq = pos + 3 * (size_t) f->ref;
+			double dr[3];
+			if(f->pbc) min_image(box, pp, qq, dr);
+			else for(int k = 0; k < 3; k++) dr[k] = qq[k] - pp[k];
+			double m = sqrt(dot3(dr, dr));
+			double s = (m - (f->r0 + (f->rate * step))) * (f->stiff + (f->stiff_rate * step));
+			for(int k = 0; k < 3; k++) F[k] += (dr[k] / m) * s;
+		}
+	}
+}
+
+/* ------------------------------------------------------------------ Verlet list */
+static int cell_of(const double *box, const int *nc, const double *p) {
+	/* src/Lists/Cells.h:60-65 */
+	int c[3];
+	for(int k = 0; k < 3; k++) c[k] = (int) ((p[k] / box[k] - floor(p[k] / box[k])) * (1. - DBL_EPSILON) * nc[k]);
+	return c[0] + nc[0] * (c[1] + nc[1] * c[2]);
+}
+
+long long oxo_verlet_pairs(int N, const double *pos, const int *n3, const int *n5, const double *box, double rv,
+		int *pairs, long long max_pairs) {
+	int nc[3];
+	for(int k = 0; k < 3; k++) {
+		/* Cells.cpp:47-58 without cells_auto_optimisation: does not change the pair set */
+		nc[k] = (int) (floor(box[k] / rv) + 0.1);
+		if(nc[k] < 3) nc[k] = 3;
+		if(nc[k] > 256) nc[k] = 256; /* memory guard only */
+	}
+	int ncells = nc[0] * nc[1] * nc[2];
+	int *head = (int *) malloc((size_t) ncells * sizeof(int));
+	int *next = (int *) malloc((size_t) N * sizeof(int));
+	int *cell = (int *) malloc((size_t) N * sizeof(int));
+	for(int c = 0; c < ncells; c++) head[c] = -1;
+	for(int i = 0; i < N; i++) {
+		int c = cell_of(box, nc, pos + 3 * (size_t) i);
+		cell[i] = c; next[i] = head[c]; head[c] = i;
+	}
+	double rv2 = rv * rv;
+	long long n = 0;
+	for(int p = 0; p < N; p++) {
+		int c = cell[p];
+		int ind[3] = { c % nc[0], (c / nc[0]) % nc[1], c / (nc[0] * nc[1]) };
+		int seen[27], nseen = 0;
+		for(int dz = -1; dz <= 1; dz++) for(int dy = -1; dy <= 1; dy++) for(int dx = -1; dx <= 1; dx++) {
+			int cc = ((ind[0] + dx + nc[0]) % nc[0]) + nc[0] * (((ind[1] + dy + nc[1]) % nc[1]) + nc[1] * ((ind[2] + dz + nc[2]) % nc[2]));
+			int dup = 0;
+			for(int s = 0; s < nseen; s++) if(seen[s] == cc) dup = 1;
+			if(dup) continue;
+			seen[nseen++] = cc;
+			for(int q = head[cc]; q != -1; q = next[q]) {
+				if(q >= p) continue;
+				if(n3[p] == q || n5[p] == q) continue;
+				double r[3];
+				min_image(box, pos + 3 * (size_t) p, pos + 3 * (size_t) q, r);
+				if(dot3(r, r) < rv2) {
+					if(n < max_pairs) { pairs[2 * n] = q; pairs[2 * n + 1] = p; }
+					n++;
+				}
+			}
+		}
+	}
+	free(head); free(next); free(cell);
+	return n;
+}
+
+void oxo_axes_from_a1a3(int N, const double *a1, const double *a3, double *axes) {
+	/* orthonormalisation of the configuration reader, src/Backends/SimBackend.cpp:623-629 */
+	for(int i = 0; i < N; i++) {
+		double v1[3], v3[3], v2[3];
+		double n1 = sqrt(dot3(a1 + 3 * i, a1 + 3 * i)), n3 = sqrt(dot3(a3 + 3 * i, a3 + 3 * i));
+		for(int k = 0; k < 3; k++) { v1[k] = a1[3 * i + k] / n1; v3[k] = a3[3 * i + k] / n3; }
+		double d = dot3(v1, v3);
+		for(int k = 0; k < 3; k++) v1[k] -= v3[k] * d;
+		n1 = sqrt(dot3(v1, v1));
+		for(int k = 0; k < 3; k++) v1[k] /= n1;
+		cross3(v3, v1, v2);
+		double n2 = sqrt(dot3(v2, v2));
+		for(int k = 0; k < 3; k++) v2[k] /= n2;
+		memcpy(axes + 9 * (size_t) i, v1, sizeof(v1));
+		memcpy(axes + 9 * (size_t) i + 3, v2, sizeof(v2));
+		memcpy(axes + 9 * (size_t) i + 6, v3, sizeof(v3));
+	}
+}
+
+/* ------------------------------------------------------------------ MD step */
+void oxo_md_compute_forces(const oxo_dna2_params *P, oxo_md *S) {
+	double et[OXO_NTERMS];
+	double *tl = (double *) calloc(3 * (size_t) S->N, sizeof(double));
+	oxo_dna2_forces(P, S->N, S->pos, S->axes, S->btype, S->n3, S->n5, S->box, S->pairs, S->npairs, S->force, tl, NULL, et, NULL);
+	/* external forces enter before the interactions in the reference (MD_CPUBackend.cpp:149-153); addition commutes */
+	if(S->nf > 0) oxo_ext_forces(S->nf, S->ef, S->N, S->pos, S->box, S->step, S->force);
+	for(int i = 0; i < S->N; i++) {
+		const double *ax = S->axes + 9 * (size_t) i;
+		for(int k = 0; k < 3; k++) S->torque_body[3 * i + k] = dot3(ax + 3 * k, tl + 3 * (size_t) i);
+	}
+	S->U = 0;
+	for(int t = 0; t < OXO_NTERMS; t++) S->U += et[t];
+	free(tl);
+}
+
+static void rebuild(const oxo_dna2_params *P, oxo_md *S) {
+	S->npairs = oxo_verlet_pairs(S->N, S->pos, S->n3, S->n5, S->box, P->rcut + 2 * S->skin, S->pairs, S->max_pairs);
+	memcpy(S->list_pos, S->pos, 3 * (size_t) S->N * sizeof(double));
+}
+
+int oxo_md_steps(const oxo_dna2_params *P, oxo_md *S, int nsteps) {
+	int rebuilds = 0;
+	const double dt = S->dt;
+	for(int it = 0; it < nsteps; it++) {
+		int stale = 0;
+		/* first half: MD_CPUBackend.cpp:67-144 */
+		for(int i = 0; i < S->N; i++) {
+			double *v = S->vel + 3 * i, *x = S->pos + 3 * i, *L = S->L + 3 * i, *ax = S->axes + 9 * (size_t) i;
+			for(int k = 0; k < 3; k++) { v[k] += S->force[3 * i + k] * (dt * 0.5); x[k] += v[k] * dt; }
+			for(int k = 0; k < 3; k++) L[k] += S->torque_body[3 * i + k] * (dt * 0.5);
+			double norm = sqrt(dot3(L, L));
+			double u[3] = { L[0] / norm, L[1] / norm, L[2] / norm };
+			double s = sin(dt * norm), c = cos(dt * norm), o = 1. - c;
+			double R[3][3] = {
+				{ u[0] * u[0] * o + c, u[0] * u[1] * o - u[2] * s, u[0] * u[2] * o + u[1] * s },
+				{ u[0] * u[1] * o + u[2] * s, u[1] * u[1] * o + c, u[1] * u[2] * o - u[0] * s },
+				{ u[0] * u[2] * o - u[1] * s, u[1] * u[2] * o + u[0] * s, u[2] * u[2] * o + c } };
+			/* orientation (columns = body axes) <- orientation * R, i.e. new axis j = sum_k old axis k * R[k][j] */
+			double na[9];
+			for(int j = 0; j < 3; j++) for(int k = 0; k < 3; k++)
+				na[3 * j + k] = ax[k] * R[0][j] + ax[3 + k] * R[1][j] + ax[6 + k] * R[2][j];
+			memcpy(ax, na, sizeof(na));
+			double d[3] = { x[0] - S->list_pos[3 * i], x[1] - S->list_pos[3 * i + 1], x[2] - S->list_pos[3 * i + 2] };
+			if(dot3(d, d) > SQ(S->skin)) stale = 1;
+		}
+		if(stale) { rebuild(P, S); rebuilds++; }
+		oxo_md_compute_forces(P, S);
+		for(int i = 0; i < S->N; i++) for(int k = 0; k < 3; k++) {
+			S->vel[3 * i + k] += S->force[3 * i + k] * dt * 0.5;
+			S->L[3 * i + k] += S->torque_body[3 * i + k] * dt * 0.5;
+		}
+		S->step++;
+	}
+	return rebuilds;
+}
+
+/* ------------------------------------------------------------------ thermostat parameters */
+void oxo_brownian_params(double T, double dt_in, int ns, double pt_in, double diff_coeff, double *pt, double *pr, double *rescale) {
+	/* BrownianThermostat.cpp:27-54: pt, diff_coeff and dt are read as *floats* */
+	double dt = (float) dt_in, D = (float) diff_coeff, p = (float) pt_in;
+	if(p == 0.) p = (2 * T * ns * dt) / (T * ns * dt + 2 * D);
+	D = T * ns * dt * (1. / p - 1. / 2.);
+	*pt = p;
+	*pr = (2 * T * ns * dt) / (T * ns * dt + 2 * 3 * D);
+	*rescale = sqrt(T);
+}
+
+void oxo_langevin_params(double T, double dt, double gamma_in, double diff_in, double *gt, double *gr, double *rt, double *rr) {
+	/* LangevinThermostat.cpp:27-76: gamma_trans / diff_coeff are read as floats, dt as a number */
+	double g = (float) gamma_in, D = (float) diff_in;
+	if(D == 0.) D = T / g; else g = T / D;
+	double Dr = 3. * D;
+	*gt = g; *gr = T / Dr;
+	*rt = sqrt(2. * g * T / dt);
+	*rr = sqrt(2. * (*gr) * T / dt);
+}

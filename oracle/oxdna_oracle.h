@@ -1,0 +1,103 @@
+/* TEST INFRASTRUCTURE ONLY -- CPU restatement (plain C, double precision) of the reference's algorithm for
+ * the oxDNA2 MD step.  Used only by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg as the
+ * checker; the product (oxdna_b200/) never includes, links or calls anything in this directory.
+ *
+ * Pinning: validated against (i) the reference's golden vector test/DNA/FORCE_FIELD/AVG_SEQ/reference.dat
+ * and (ii) the unmodified reference compiled into oracle/_ref (forces, torques, per-term energies, Verlet
+ * pair sets, NVE trajectories) -- see tests/test_oracle.py.
+ */
+#ifndef OXDNA_ORACLE_H
+#define OXDNA_ORACLE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { OXO_FENE = 0, OXO_BEXC, OXO_STCK, OXO_NEXC, OXO_HB, OXO_CRST, OXO_CXST, OXO_DH, OXO_NTERMS };
+
+/* radial well ("f1", Morse-like) -- src/Interactions/DNAInteraction.cpp:1249-1283 */
+typedef struct { double a, rc, r0, blow, bhigh, rlow, rhigh, rclow, rchigh; double eps[5][5], shift[5][5]; } oxo_f1;
+/* radial well ("f2", harmonic) -- DNAInteraction.cpp:1285-1315 */
+typedef struct { double k, rc, r0, blow, rlow, rclow, bhigh, rhigh, rchigh; } oxo_f2;
+/* angular modulation ("f4") -- DNAInteraction.cpp:1351-1420 */
+typedef struct { double a, b, t0, ts, tc; } oxo_f4;
+/* angular modulation in cos space ("f5") -- DNAInteraction.cpp:1422-1454 */
+typedef struct { double a, b, xc, xs; } oxo_f5;
+/* repulsive LJ with quadratic smoothing -- DNAInteraction.cpp:1182-1205 */
+typedef struct { double sigma, rstar, b, rc; } oxo_excl;
+
+typedef struct {
+	/* site geometry, src/Particles/DNANucleotide.cpp:66-88, src/model.h:14-18 */
+	double back_a1, back_a2, stack_a1, base_a1, backref_a1;
+	double T;
+	/* bonded */
+	double fene_eps, fene_r0, fene_delta, fene_delta2;
+	int use_mbf;
+	double mbf_xmax, mbf_fmax, mbf_finf;
+	oxo_excl excl[4]; /* 0: back-back, 1: base-base, 2: base(p)-back(q), 3: back(p)-base(q) */
+	double excl_eps;
+	oxo_f1 hb, stck;
+	oxo_f2 crst, cxst;
+	oxo_f4 stck_t4, stck_t5, hb_t1, hb_t2, hb_t4, hb_t7, crst_t1, crst_t2, crst_t4, crst_t7, cxst_t1, cxst_t4, cxst_t5;
+	double cxst_t1_sa, cxst_t1_sb; /* pure-harmonic branch of the oxDNA2 coaxial theta1, DNA2Interaction.cpp:324-363 */
+	oxo_f5 stck_phi1, stck_phi2;
+	/* Debye-Hueckel, DNA2Interaction.cpp:104-149 */
+	double dh_minus_kappa, dh_prefactor, dh_rhigh, dh_rc, dh_b;
+	int dh_half_charged_ends;
+	double hb_multiplier;
+	double rcut;
+} oxo_dna2_params;
+
+/* average-sequence oxDNA2 parameters at temperature T (simulation units) and molar salt.
+ * seq_dep: 0 = average sequence; 1 = stck_eps[4][4] (already multiplied by the T factor is NOT assumed: raw file
+ * values STCK_X_Y) + stck_fact_eps + hb_eps_AT, hb_eps_GC are taken from the arguments. */
+void oxo_dna2_params_init(oxo_dna2_params *P, double T, double salt, int dh_half_charged_ends,
+		int use_mbf, double mbf_fmax, double mbf_finf);
+void oxo_dna2_params_seqdep(oxo_dna2_params *P, const double *stck_raw16, double stck_fact_eps, double hb_AT, double hb_GC);
+
+typedef struct { int type; int particle; int ref; int pbc; double stiff, r0, rate, stiff_rate, F0; double dir[3], pos0[3]; } oxo_ext_force;
+enum { OXO_EXT_STRING = 0, OXO_EXT_TRAP = 1, OXO_EXT_MUTUAL = 2 };
+
+/* axes: N x 9 doubles = a1(3) a2(3) a3(3).  pairs: npairs x 2 ints (non-bonded candidates, each unique pair once).
+ * Outputs (any may be NULL): force N x 3 (lab), torque_lab N x 3, torque_body N x 3, eterms[OXO_NTERMS] totals,
+ * epart[N] per-particle energy (half of each pair energy to each partner). */
+void oxo_dna2_forces(const oxo_dna2_params *P, int N, const double *pos, const double *axes, const int *btype,
+		const int *n3, const int *n5, const double *box, const int *pairs, long long npairs,
+		double *force, double *torque_lab, double *torque_body, double *eterms, double *epart);
+
+/* external forces (src/Forces/{ConstantRateForce,MovingTrap,MutualTrap}.cpp), added to force (lab frame) */
+void oxo_ext_forces(int nf, const oxo_ext_force *ef, int N, const double *pos, const double *box, long long step, double *force);
+
+/* Verlet list exactly as src/Lists/Cells.cpp:120-181 + VerletList.cpp:35-66: unique pairs (q<p), not bonded,
+ * |min_image|^2 < rv^2 with rv = rcut + 2 skin.  Returns the number of pairs; writes at most max_pairs. */
+long long oxo_verlet_pairs(int N, const double *pos, const int *n3, const int *n5, const double *box, double rv,
+		int *pairs, long long max_pairs);
+
+/* axes helpers */
+void oxo_axes_from_a1a3(int N, const double *a1, const double *a3, double *axes);
+
+/* One or more NVE/thermostat-free velocity-Verlet steps exactly as src/Backends/MD_CPUBackend.cpp:67-218
+ * (forces must be valid on entry; they are valid on exit).  The Verlet list is kept in `pairs` and rebuilt
+ * when a particle has moved more than skin from list_pos.  Returns number of list rebuilds. */
+typedef struct {
+	int N;
+	double *pos, *axes, *vel, *L, *force, *torque_body, *list_pos;
+	const int *btype, *n3, *n5;
+	double box[3];
+	double dt, skin;
+	int *pairs; long long npairs, max_pairs;
+	long long step;
+	int nf; const oxo_ext_force *ef;
+	double U;
+} oxo_md;
+int oxo_md_steps(const oxo_dna2_params *P, oxo_md *S, int nsteps);
+void oxo_md_compute_forces(const oxo_dna2_params *P, oxo_md *S);
+
+/* thermostat parameter derivation (src/Backends/Thermostats/{Brownian,Langevin,Bussi}Thermostat.cpp) */
+void oxo_brownian_params(double T, double dt, int newtonian_steps, double pt_in, double diff_coeff, double *pt, double *pr, double *rescale);
+void oxo_langevin_params(double T, double dt, double gamma_trans_in, double diff_coeff_in, double *gamma_t, double *gamma_r, double *resc_t, double *resc_r);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
