@@ -1,0 +1,141 @@
+/* oxdna_b200 -- C ABI of the B200-native oxDNA GPU MD step.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types, int status returns
+ * (0 = ok; oxb_last_error() gives the message), one context = one simulated system on one GPU and one
+ * CUDA stream.  Every entry point names the reference interface it replaces (paths relative to the
+ * reference tree, lorenzo-rovigatti/oxDNA).
+ *
+ * All host arrays are in ORIGINAL particle order (the order of the topology file); the device keeps
+ * particles in Hilbert-sorted order internally and remaps on the way in and out.
+ */
+#ifndef OXDNA_B200_H
+#define OXDNA_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct oxb_ctx oxb_ctx;
+
+enum { OXB_PRECISION_FLOAT = 0, OXB_PRECISION_MIXED = 1 };
+enum { OXB_THERMOSTAT_NONE = 0, OXB_THERMOSTAT_BROWNIAN = 1, OXB_THERMOSTAT_LANGEVIN = 2, OXB_THERMOSTAT_BUSSI = 3 };
+enum { OXB_EXT_STRING = 0, OXB_EXT_TRAP = 1, OXB_EXT_MUTUAL_TRAP = 2 };
+enum { OXB_TERM_FENE = 0, OXB_TERM_BEXC, OXB_TERM_STCK, OXB_TERM_NEXC, OXB_TERM_HB, OXB_TERM_CRST, OXB_TERM_CXST, OXB_TERM_DH, OXB_NTERMS };
+
+/* ---- force-field parameters (device constant block).  Replaces the __constant__ upload of
+ * src/CUDA/Interactions/CUDADNAInteraction.cu:61-154 (values derived from the CPU DNA2Interaction). */
+typedef struct { float a, rc, r0, blow, bhigh, rlow, rhigh, rclow, rchigh; } oxb_f1;
+typedef struct { float k, rc, r0, blow, rlow, rclow, bhigh, rhigh, rchigh; } oxb_f2;
+typedef struct { float a, b, t0, ts, tc; } oxb_f4;
+typedef struct { float a, b, xc, xs; } oxb_f5;
+typedef struct { float sigma2, rstar2, b, rc, rc2; } oxb_excl;
+
+enum { OXB_F4_STCK_T4 = 0, OXB_F4_STCK_T5, OXB_F4_HB_T1, OXB_F4_HB_T2, OXB_F4_HB_T4, OXB_F4_HB_T7, OXB_F4_CRST_T1,
+	OXB_F4_CRST_T2, OXB_F4_CRST_T4, OXB_F4_CRST_T7, OXB_F4_CXST_T1, OXB_F4_CXST_T4, OXB_F4_CXST_T5, OXB_NF4 };
+
+typedef struct {
+	float back_a1, back_a2, stack_a1, base_a1, backref_a1; /* interaction-site offsets along a1 / a2 */
+	float fene_eps, fene_r0, fene_delta, fene_delta2;
+	int use_mbf;
+	float mbf_xmax, mbf_fmax, mbf_finf, mbf_e0; /* mbf_e0 = fene(xmax) - long(xmax), the energy offset of the log tail */
+	float excl_eps;
+	oxb_excl excl[4]; /* back-back, base-base, base(p)-back(q), back(p)-base(q) */
+	oxb_f1 hb, stck;
+	float hb_eps[25], hb_shift[25], stck_eps[25], stck_shift[25]; /* [type_n3 * 5 + type_n5] */
+	oxb_f2 crst, cxst;
+	oxb_f4 f4[OXB_NF4];
+	float cxst_t1_sa, cxst_t1_sb;
+	oxb_f5 phi1, phi2;
+	float dh_minus_kappa, dh_prefactor, dh_rhigh, dh_rc, dh_b;
+	int dh_half_charged_ends;
+	float hb_multiplier;
+	float rcut; /* global interaction cutoff on the centre-of-mass distance */
+	float rcut_near; /* centre-of-mass distance beyond which only Debye-Hueckel can act */
+} oxb_dna2_params;
+
+/* Host-side derivation of the oxDNA2 parameter block at temperature T (simulation units, K/3000) and molar
+ * salt -- what DNA2Interaction::get_settings/init (src/Interactions/DNA2Interaction.cpp:61-149) followed by
+ * CUDADNAInteraction::cuda_init computes.  seq-dependent tables may then be overwritten by the caller.
+ * `rcut_out` receives the double-precision cutoff used for the Verlet radius. */
+int oxb_dna2_params_init(oxb_dna2_params *P, double T, double salt_concentration, int dh_half_charged_ends,
+		int use_max_backbone_force, double max_backbone_force, double max_backbone_force_far, double *rcut_out);
+/* sequence-dependent stacking / HB strengths (src/Interactions/DNAInteraction.cpp:329-375):
+ * stck_raw[4][4] are the STCK_X_Y entries of the parameter file (order A, G, C, T). */
+int oxb_dna2_params_seqdep(oxb_dna2_params *P, double T, const double *stck_raw16, double stck_fact_eps, double hb_AT, double hb_GC);
+
+typedef struct {
+	int type;      /* OXB_EXT_* */
+	int particle;  /* original index */
+	int ref;       /* mutual trap partner, original index */
+	int pbc;
+	double stiff, r0, rate, stiff_rate, F0;
+	double dir[3], pos0[3];
+} oxb_ext_force;
+
+/* ---- life cycle.  Replaces MD_CUDABackend / CUDAMixedBackend construction + init_cuda
+ * (src/CUDA/Backends/CUDABaseBackend.cu:143-242, MD_CUDABackend.cu:674-747). */
+int oxb_create(oxb_ctx **out, int device, int N, int precision);
+void oxb_destroy(oxb_ctx *ctx);
+const char *oxb_last_error(const oxb_ctx *ctx);
+/* use an existing CUDA stream (cudaStream_t passed as void*); default: a private non-blocking stream */
+int oxb_set_stream(oxb_ctx *ctx, void *cuda_stream);
+
+int oxb_set_box(oxb_ctx *ctx, const double box[3]);                                           /* CUDABox, src/CUDA/cuda_utils/CUDABox.h */
+int oxb_set_topology(oxb_ctx *ctx, const int *btype, const int *n3, const int *n5, const int *strand);
+int oxb_set_model_dna2(oxb_ctx *ctx, const oxb_dna2_params *P, double rcut);                  /* CUDADNAInteraction::cuda_init */
+/* CUDASimpleVerletList::get_settings/init (src/CUDA/Lists/CUDASimpleVerletList.cu:47-56,165-202) + CUDA_sort_every, use_edge */
+int oxb_set_lists(oxb_ctx *ctx, double verlet_skin, int use_edge, int sort_every, double max_density_multiplier);
+int oxb_set_dt(oxb_ctx *ctx, double dt);
+/* CUDAThermostatFactory + CUDA{Brownian,Langevin,Bussi}Thermostat (src/CUDA/Thermostats/); already-derived parameters:
+ *  brownian: a = pt, b = pr, c = rescale factor sqrt(T), every = newtonian_steps
+ *  langevin: a = gamma_trans, b = gamma_rot, c = rescale_trans, d = rescale_rot, every = 1
+ *  bussi:    a = T, b = exp(-newtonian_steps / tau), every = newtonian_steps */
+int oxb_set_thermostat(oxb_ctx *ctx, int type, int every, double a, double b, double c, double d, unsigned long long seed);
+/* MD_CUDABackend::_apply_external_forces_changes (src/CUDA/Backends/MD_CUDABackend.cu:108-229) */
+int oxb_set_ext_forces(oxb_ctx *ctx, int n, const oxb_ext_force *forces);
+
+/* ---- state marshalling.  Replaces apply_changes_to_simulation_data / apply_simulation_data_changes
+ * (src/CUDA/Backends/MD_CUDABackend.cu:231-394).  pos, a1, a3, vel, L: N x 3 doubles, original order. */
+int oxb_set_state(oxb_ctx *ctx, const double *pos, const double *a1, const double *a3, const double *vel, const double *L);
+int oxb_get_state(oxb_ctx *ctx, double *pos, double *a1, double *a3, double *vel, double *L);
+int oxb_set_step(oxb_ctx *ctx, long long step);
+long long oxb_get_step(const oxb_ctx *ctx);
+
+/* ---- the individual operators of the step (also reachable one by one for parity tests) */
+int oxb_sort(oxb_ctx *ctx);                 /* MD_CUDABackend::_sort_particles, src/CUDA/CUDA_sort.cu */
+int oxb_update_lists(oxb_ctx *ctx);         /* CUDASimpleVerletList::update */
+int oxb_compute_forces(oxb_ctx *ctx);       /* set_external_forces + CUDADNAInteraction::compute_forces */
+int oxb_first_step(oxb_ctx *ctx);           /* first_step[_mixed] */
+int oxb_second_step(oxb_ctx *ctx);          /* second_step[_mixed] */
+int oxb_thermostat(oxb_ctx *ctx);           /* CUDABaseThermostat::apply_cuda at the current step */
+
+/* ---- the hot loop: n calls of MD_CUDABackend::sim_step (src/CUDA/Backends/MD_CUDABackend.cu:567-619), device-resident,
+ * no host synchronisation inside; forces must be valid on entry (oxb_set_state makes them so). */
+int oxb_run(oxb_ctx *ctx, long long n_steps);
+int oxb_synchronize(oxb_ctx *ctx);
+
+/* ---- read-backs (original order; any pointer may be NULL).  force: lab frame; torque: body frame as the reference
+ * stores it; torque_lab: lab frame; energy: per-particle sum of pair energies (system U = sum/2); hb_energy likewise. */
+int oxb_get_forces(oxb_ctx *ctx, double *force, double *torque_body, double *torque_lab, double *energy, double *hb_energy);
+/* potential energy U and kinetic energy K of the whole system (GpuUtils::sum_c_number4_to_double_on_GPU, CUDA_print_energy) */
+int oxb_energy(oxb_ctx *ctx, double *U, double *K);
+/* unique Verlet pairs (i < j, original ids); call with pairs = NULL to get the count */
+int oxb_get_pairs(oxb_ctx *ctx, int *pairs, long long max_pairs, long long *n_pairs);
+/* number of list rebuilds / sorts so far; current neighbour-matrix capacity; overflow flags (0 = ok) */
+int oxb_get_stats(oxb_ctx *ctx, long long *n_list_updates, long long *n_sorts, int *max_neigh, int *error_flags);
+/* device pointers for zero-copy consumers (CUDABaseInteraction plugin seam): float4 positions with packed
+ * (btype<<22 | index) in .w, float4 quaternions, column-major neighbour matrix, neighbour counts, int2 edge list */
+int oxb_device_views(oxb_ctx *ctx, void **poss_f4, void **orientations_f4, void **matrix_neighs, void **number_neighs,
+		void **edge_list, void **n_edges);
+/* number of kernel launches issued by this context so far (bench.py's gpu_launches claim) */
+long long oxb_launch_count(const oxb_ctx *ctx);
+
+/* ---- per-kernel timing hooks for the benchmark: time `reps` back-to-back launches of one operator with CUDA events on
+ * the context's stream; returns milliseconds per launch.  which: 0 = non-bonded+bonded force pass, 1 = integrate (first
+ * step), 2 = list rebuild, 3 = sort */
+int oxb_time_kernel(oxb_ctx *ctx, int which, int reps, float *ms_per_launch);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

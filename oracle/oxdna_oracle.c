@@ -92,6 +92,7 @@ void oxo_dna2_params_init(oxo_dna2_params *P, double T, double salt, int dh_half
 	/* Debye-Hueckel: DNA2Interaction.cpp:66-84 (get_settings) and :124-149 (init).  The smoothing onset RHIGH is
 	 * computed in get_settings with a *float* 0.1f, lambda in init with a double 0.1 -- reproduced as is. */
 	const double lfac = 0.3616455, q = 0.0543;
+	salt = (double) (float) salt; /* DNA2Interaction.h:31: the salt concentration is stored in a float */
 	double lambda_gs = lfac * sqrt(T / 0.1f) / sqrt(salt);
 	double lambda = lfac * sqrt(T / 0.1) / sqrt(salt);
 	P->dh_rhigh = 3.0 * lambda_gs;

@@ -1,0 +1,249 @@
+"""ctypes binding of the C ABI (include/oxdna_b200.h -> liboxdna_b200.so).
+
+Nothing here computes: every call forwards host buffers to the CUDA library.  If the library cannot be loaded, or no
+CUDA device is present, calls raise -- there is deliberately no CPU fallback in the product path.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "liboxdna_b200.so")
+
+PRECISION_FLOAT, PRECISION_MIXED = 0, 1
+THERMOSTAT_NONE, THERMOSTAT_BROWNIAN, THERMOSTAT_LANGEVIN, THERMOSTAT_BUSSI = 0, 1, 2, 3
+EXT_STRING, EXT_TRAP, EXT_MUTUAL_TRAP = 0, 1, 2
+NTERMS = 8
+NF4 = 13
+
+
+class F1(C.Structure):
+    _fields_ = [(n, C.c_float) for n in "a rc r0 blow bhigh rlow rhigh rclow rchigh".split()]
+
+
+class F2(C.Structure):
+    _fields_ = [(n, C.c_float) for n in "k rc r0 blow rlow rclow bhigh rhigh rchigh".split()]
+
+
+class F4(C.Structure):
+    _fields_ = [(n, C.c_float) for n in "a b t0 ts tc".split()]
+
+
+class F5(C.Structure):
+    _fields_ = [(n, C.c_float) for n in "a b xc xs".split()]
+
+
+class Excl(C.Structure):
+    _fields_ = [(n, C.c_float) for n in "sigma2 rstar2 b rc rc2".split()]
+
+
+class DNA2Params(C.Structure):
+    _fields_ = (
+        [(n, C.c_float) for n in "back_a1 back_a2 stack_a1 base_a1 backref_a1 fene_eps fene_r0 fene_delta fene_delta2".split()]
+        + [("use_mbf", C.c_int)]
+        + [(n, C.c_float) for n in "mbf_xmax mbf_fmax mbf_finf mbf_e0 excl_eps".split()]
+        + [("excl", Excl * 4), ("hb", F1), ("stck", F1)]
+        + [(n, C.c_float * 25) for n in "hb_eps hb_shift stck_eps stck_shift".split()]
+        + [("crst", F2), ("cxst", F2), ("f4", F4 * NF4), ("cxst_t1_sa", C.c_float), ("cxst_t1_sb", C.c_float), ("phi1", F5), ("phi2", F5)]
+        + [(n, C.c_float) for n in "dh_minus_kappa dh_prefactor dh_rhigh dh_rc dh_b".split()]
+        + [("dh_half_charged_ends", C.c_int), ("hb_multiplier", C.c_float), ("rcut", C.c_float), ("rcut_near", C.c_float)]
+    )
+
+
+class ExtForce(C.Structure):
+    _fields_ = [("type", C.c_int), ("particle", C.c_int), ("ref", C.c_int), ("pbc", C.c_int)] + [
+        (n, C.c_double) for n in "stiff r0 rate stiff_rate F0".split()] + [("dir", C.c_double * 3), ("pos0", C.c_double * 3)]
+
+
+EXPORTED = """oxb_dna2_params_init oxb_dna2_params_seqdep oxb_create oxb_destroy oxb_last_error oxb_set_stream oxb_set_box
+oxb_set_topology oxb_set_model_dna2 oxb_set_lists oxb_set_dt oxb_set_thermostat oxb_set_ext_forces oxb_set_state oxb_get_state
+oxb_set_step oxb_get_step oxb_sort oxb_update_lists oxb_compute_forces oxb_first_step oxb_second_step oxb_thermostat oxb_run
+oxb_synchronize oxb_get_forces oxb_energy oxb_get_pairs oxb_get_stats oxb_device_views oxb_launch_count oxb_time_kernel""".split()
+
+_lib = None
+
+
+def lib():
+    """Loads the CUDA library; raises if it is missing (build it with oxdna_b200/build.py or __graft_entry__.build())."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise RuntimeError(f"{SO_PATH} not built: oxdna_b200 has no fallback path, run `python oxdna_b200/build.py`")
+        L = C.CDLL(SO_PATH)
+        L.oxb_last_error.restype = C.c_char_p
+        L.oxb_get_step.restype = C.c_longlong
+        L.oxb_launch_count.restype = C.c_longlong
+        L.oxb_last_error.argtypes = [C.c_void_p]
+        L.oxb_destroy.argtypes = [C.c_void_p]
+        L.oxb_destroy.restype = None
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _d(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.int32)
+
+
+class OxbError(RuntimeError):
+    pass
+
+
+def dna2_params(T, salt=0.5, dh_half_charged_ends=True, max_backbone_force=None, max_backbone_force_far=0.04):
+    """oxb_dna2_params_init.  Returns (params, rcut)."""
+    P = DNA2Params()
+    rc = C.c_double()
+    mbf = max_backbone_force is not None
+    r = lib().oxb_dna2_params_init(C.byref(P), C.c_double(T), C.c_double(salt), int(dh_half_charged_ends), int(mbf),
+                                   C.c_double(max_backbone_force if mbf else 0.0), C.c_double(max_backbone_force_far), C.byref(rc))
+    if r != 0:
+        raise OxbError("oxb_dna2_params_init failed")
+    return P, rc.value
+
+
+class Context:
+    """One simulated system on one GPU (opaque oxb_ctx*)."""
+
+    def __init__(self, N, device=0, precision=PRECISION_MIXED):
+        self.N = int(N)
+        self._h = C.c_void_p()
+        self._L = lib()
+        rc = self._L.oxb_create(C.byref(self._h), int(device), self.N, int(precision))
+        if rc != 0:
+            msg = self._L.oxb_last_error(self._h).decode() if self._h else "oxb_create failed"
+            raise OxbError(msg)
+
+    def close(self):
+        if self._h:
+            self._L.oxb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise OxbError(self._L.oxb_last_error(self._h).decode() + f" (code {rc})")
+
+    # ---- configuration
+    def set_box(self, box):
+        b = _d(box)
+        self._ck(self._L.oxb_set_box(self._h, _p(b)))
+
+    def set_topology(self, btype, n3, n5, strand=None):
+        a, b, c, d = _i(btype), _i(n3), _i(n5), _i(strand)
+        self._ck(self._L.oxb_set_topology(self._h, _p(a), _p(b), _p(c), _p(d)))
+
+    def set_model_dna2(self, P, rcut):
+        self._ck(self._L.oxb_set_model_dna2(self._h, C.byref(P), C.c_double(rcut)))
+
+    def set_lists(self, verlet_skin=0.05, use_edge=False, sort_every=0, max_density_multiplier=3.0):
+        self._ck(self._L.oxb_set_lists(self._h, C.c_double(verlet_skin), int(use_edge), int(sort_every), C.c_double(max_density_multiplier)))
+
+    def set_dt(self, dt):
+        self._ck(self._L.oxb_set_dt(self._h, C.c_double(dt)))
+
+    def set_thermostat(self, kind, every=1, a=0.0, b=0.0, c=0.0, d=0.0, seed=0):
+        self._ck(self._L.oxb_set_thermostat(self._h, int(kind), int(every), C.c_double(a), C.c_double(b), C.c_double(c), C.c_double(d),
+                                            C.c_ulonglong(seed)))
+
+    def set_ext_forces(self, forces):
+        n = len(forces)
+        arr = (ExtForce * max(n, 1))()
+        for k, f in enumerate(forces):
+            e = arr[k]
+            e.type = {"string": EXT_STRING, "trap": EXT_TRAP, "mutual_trap": EXT_MUTUAL_TRAP}[f["type"]]
+            e.particle = int(f["particle"])
+            e.ref = int(f.get("ref_particle", -1))
+            e.pbc = int(f.get("PBC", 0))
+            e.stiff, e.r0, e.rate = float(f.get("stiff", 0.0)), float(f.get("r0", 0.0)), float(f.get("rate", 0.0))
+            e.stiff_rate, e.F0 = float(f.get("stiff_rate", 0.0)), float(f.get("F0", 0.0))
+            for x in range(3):
+                e.dir[x] = float(f.get("dir", (0, 0, 1))[x])
+                e.pos0[x] = float(f.get("pos0", (0, 0, 0))[x])
+        self._ck(self._L.oxb_set_ext_forces(self._h, n, arr))
+
+    # ---- state
+    def set_state(self, pos, a1, a3, vel=None, L=None):
+        a, b, c, d, e = _d(pos), _d(a1), _d(a3), _d(vel), _d(L)
+        self._ck(self._L.oxb_set_state(self._h, _p(a), _p(b), _p(c), _p(d), _p(e)))
+
+    def get_state(self):
+        out = [np.zeros((self.N, 3)) for _ in range(5)]
+        self._ck(self._L.oxb_get_state(self._h, *[_p(x) for x in out]))
+        return dict(pos=out[0], a1=out[1], a3=out[2], vel=out[3], L=out[4])
+
+    def set_step(self, s):
+        self._ck(self._L.oxb_set_step(self._h, C.c_longlong(s)))
+
+    @property
+    def step(self):
+        return self._L.oxb_get_step(self._h)
+
+    # ---- operators
+    def sort(self):
+        self._ck(self._L.oxb_sort(self._h))
+
+    def update_lists(self):
+        self._ck(self._L.oxb_update_lists(self._h))
+
+    def compute_forces(self):
+        self._ck(self._L.oxb_compute_forces(self._h))
+
+    def first_step(self):
+        self._ck(self._L.oxb_first_step(self._h))
+
+    def second_step(self):
+        self._ck(self._L.oxb_second_step(self._h))
+
+    def thermostat(self):
+        self._ck(self._L.oxb_thermostat(self._h))
+
+    def run(self, n):
+        self._ck(self._L.oxb_run(self._h, C.c_longlong(n)))
+
+    def synchronize(self):
+        self._ck(self._L.oxb_synchronize(self._h))
+
+    # ---- read-backs
+    def get_forces(self):
+        N = self.N
+        f, tb, tl, e, hb = np.zeros((N, 3)), np.zeros((N, 3)), np.zeros((N, 3)), np.zeros(N), np.zeros(N)
+        self._ck(self._L.oxb_get_forces(self._h, _p(f), _p(tb), _p(tl), _p(e), _p(hb)))
+        return dict(force=f, torque_body=tb, torque_lab=tl, energy=e, hb_energy=hb, U=0.5 * e.sum())
+
+    def energy(self):
+        U, K = C.c_double(), C.c_double()
+        self._ck(self._L.oxb_energy(self._h, C.byref(U), C.byref(K)))
+        return U.value, K.value
+
+    def get_pairs(self):
+        n = C.c_longlong()
+        self._ck(self._L.oxb_get_pairs(self._h, None, C.c_longlong(0), C.byref(n)))
+        out = np.zeros((max(n.value, 1), 2), dtype=np.int32)
+        self._ck(self._L.oxb_get_pairs(self._h, _p(out), C.c_longlong(n.value), C.byref(n)))
+        return out[: n.value]
+
+    def stats(self):
+        a, b, c, d = C.c_longlong(), C.c_longlong(), C.c_int(), C.c_int()
+        self._ck(self._L.oxb_get_stats(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return dict(n_list_updates=a.value, n_sorts=b.value, max_neigh=c.value, error_flags=d.value)
+
+    def launch_count(self):
+        return self._L.oxb_launch_count(self._h)
+
+    def time_kernel(self, which, reps=10):
+        ms = C.c_float()
+        self._ck(self._L.oxb_time_kernel(self._h, int(which), int(reps), C.byref(ms)))
+        return ms.value

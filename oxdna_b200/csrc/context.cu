@@ -1,0 +1,892 @@
+// Context + C ABI of oxdna_b200 (see include/oxdna_b200.h).  Host-side orchestration of the MD step:
+// replaces MD_CUDABackend::sim_step and its helpers (src/CUDA/Backends/MD_CUDABackend.cu:518-619,
+// MD_CUDAMixedBackend.cu:82-148).  There is no CPU fallback: every entry point that computes launches CUDA kernels.
+//
+// Step structure (per step, steady state): [forces (+ext)] -> [one fused integrate kernel: second half-kick(n),
+// thermostat(n), first half-kick + drift + rotation(n+1), staleness check].  Launches are issued in speculative
+// batches: if the staleness check fires, a device-side "halt" word turns the rest of the batch into no-ops, the host
+// synchronises once, rebuilds (sort + cells + Verlet list) and resumes at the pending force evaluation.  The reference
+// synchronises >= 6 times per step (timers) and reads a pinned flag every step.
+#include "kernels.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace oxb {
+void launch_integrate_epoch(cudaStream_t s, const IntegrateArgs &a, int phases, int epoch);
+}
+
+struct oxb_ctx {
+	int device = 0, N = 0, precision = OXB_PRECISION_MIXED, n_sm = 148;
+	cudaStream_t stream = nullptr;
+	bool own_stream = true;
+	std::string err;
+	long long launches = 0;
+
+	// host-side topology (original order)
+	std::vector<int> h_btype, h_n3, h_n5, h_strand;
+	bool have_topology = false, have_box = false, have_model = false, have_state = false;
+	double box[3] = { 0, 0, 0 };
+	BoxF boxf;
+
+	// double-buffered state (slot order)
+	int cur = 0;
+	double4 *posd[2] = { nullptr, nullptr }, *veld[2] = { nullptr, nullptr }, *Ld[2] = { nullptr, nullptr }, *quatd[2] = { nullptr, nullptr };
+	int4 *ipos[2] = { nullptr, nullptr }, *list_ipos[2] = { nullptr, nullptr };
+	float4 *quat[2] = { nullptr, nullptr }, *F[2] = { nullptr, nullptr }, *T[2] = { nullptr, nullptr };
+	int2 *bonds[2] = { nullptr, nullptr };
+	int *slot_of = nullptr;
+	float4 *pos_f4 = nullptr; // optional reference-layout view, filled on demand
+
+	// control
+	int *flags = nullptr;       // device, OXB_FLAG_WORDS
+	int *h_flags = nullptr;     // pinned
+	KinSums *sums = nullptr;
+	double *d_energy = nullptr; // device scalar
+	double *h_scalars = nullptr; // pinned
+
+	// model
+	oxb_dna2_params model;
+	double rcut = 0.;
+
+	// lists
+	double skin = 0.05, max_density_multiplier = 3.;
+	int use_edge = 0, sort_every = 0;
+	int ncell[3] = { 0, 0, 0 };
+	int max_neigh = 0;
+	int *cell_key = nullptr, *cell_key_sorted = nullptr, *cell_val = nullptr, *cell_val_sorted = nullptr, *cell_start = nullptr;
+	int *nbr = nullptr, *nnbr = nullptr;
+	int2 *edges = nullptr;
+	int *edge_offsets = nullptr, *n_edges = nullptr;
+	long long edge_capacity = 0;
+	int edge_hint = 0;
+	void *cub_tmp = nullptr;
+	size_t cub_tmp_bytes = 0;
+	unsigned *hkeys = nullptr, *hkeys_sorted = nullptr;
+	int *hvals = nullptr, *hvals_sorted = nullptr, *hinv = nullptr;
+	bool lists_allocated = false, lists_valid = false, forces_valid = false;
+	long long n_list_updates = 0, n_sorts = 0;
+	int error_flags = 0;
+
+	// dynamics
+	double dt = 0.003;
+	long long step = 0;
+	bool mid_step = false; // positions already advanced for `step`, forces pending
+	ThermostatCfg th;
+	bool bussi_init = false;
+	int n_ext = 0;
+	DevExtForce *ext = nullptr;
+	double avg_interval = 8.;
+};
+
+namespace {
+
+int fail(oxb_ctx *c, int code, const char *fmt, ...) {
+	char buf[512];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof(buf), fmt, ap);
+	va_end(ap);
+	if(c != nullptr) c->err = buf;
+	return code;
+}
+
+#define CU(call)                                                                                             \
+	do {                                                                                                     \
+		cudaError_t e_ = (call);                                                                             \
+		if(e_ != cudaSuccess) return fail(c, 100 + (int) e_, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+	} while(0)
+
+template<typename T>
+cudaError_t dalloc(T **p, size_t n) {
+	return cudaMalloc((void **) p, sizeof(T) * std::max<size_t>(n, 1));
+}
+
+void set_boxf(oxb_ctx *c) {
+	c->boxf.lx = (float) c->box[0]; c->boxf.ly = (float) c->box[1]; c->boxf.lz = (float) c->box[2];
+	c->boxf.sx = (float) (c->box[0] / 4294967296.0); c->boxf.sy = (float) (c->box[1] / 4294967296.0); c->boxf.sz = (float) (c->box[2] / 4294967296.0);
+}
+
+void free_lists(oxb_ctx *c) {
+	cudaFree(c->cell_key); cudaFree(c->cell_key_sorted); cudaFree(c->cell_val); cudaFree(c->cell_val_sorted); cudaFree(c->cell_start);
+	cudaFree(c->nbr); cudaFree(c->nnbr); cudaFree(c->edges); cudaFree(c->edge_offsets); cudaFree(c->n_edges); cudaFree(c->cub_tmp);
+	c->cell_key = c->cell_key_sorted = c->cell_val = c->cell_val_sorted = c->cell_start = c->nbr = c->nnbr = c->edge_offsets = c->n_edges = nullptr;
+	c->edges = nullptr;
+	c->cub_tmp = nullptr;
+	c->lists_allocated = false;
+}
+
+int alloc_lists(oxb_ctx *c, int max_neigh) {
+	free_lists(c);
+	const int N = c->N;
+	double rv = c->rcut + 2. * c->skin;
+	long long ncells = 1;
+	for(int k = 0; k < 3; k++) {
+		// CUDASimpleVerletList::_compute_N_cells_side (CUDASimpleVerletList.cu:96-110): floor(L / r_verlet), at least 3
+		int n = (int) std::floor(c->box[k] / rv + 1e-9);
+		if(n < 3) n = 3;
+		if(n > 1024) n = 1024;
+		c->ncell[k] = n;
+		ncells *= n;
+	}
+	// keep the cell table bounded for huge dilute boxes: coarsen uniformly (cells only need to be >= r_verlet wide)
+	while(ncells > 8ll * N + 4096) {
+		ncells = 1;
+		for(int k = 0; k < 3; k++) {
+			c->ncell[k] = std::max(3, (c->ncell[k] * 4) / 5);
+			ncells *= c->ncell[k];
+		}
+	}
+	c->max_neigh = max_neigh;
+	CU(dalloc(&c->cell_key, N)); CU(dalloc(&c->cell_key_sorted, N)); CU(dalloc(&c->cell_val, N)); CU(dalloc(&c->cell_val_sorted, N));
+	CU(dalloc(&c->cell_start, 2 * (size_t) ncells));
+	CU(dalloc(&c->nbr, (size_t) max_neigh * N)); CU(dalloc(&c->nnbr, N));
+	CU(dalloc(&c->edge_offsets, (size_t) N + 1)); CU(dalloc(&c->n_edges, 1));
+	CU(cudaMemset(c->n_edges, 0, sizeof(int)));
+	c->edge_capacity = c->use_edge ? ((long long) N * max_neigh) / 2 + N : 1;
+	CU(dalloc(&c->edges, (size_t) c->edge_capacity));
+	c->cub_tmp_bytes = std::max(oxb::lists_tmp_bytes(N, (int) ncells), oxb::sort_tmp_bytes(N));
+	CU(cudaMalloc(&c->cub_tmp, c->cub_tmp_bytes));
+	c->lists_allocated = true;
+	return 0;
+}
+
+oxb::ListArgs list_args(oxb_ctx *c) {
+	oxb::ListArgs a;
+	a.N = c->N;
+	for(int k = 0; k < 3; k++) { a.box[k] = c->box[k]; a.ncell[k] = c->ncell[k]; }
+	a.boxf = c->boxf;
+	a.rv = c->rcut + 2. * c->skin;
+	a.posd = c->posd[c->cur]; a.ipos = c->ipos[c->cur]; a.bonds = c->bonds[c->cur];
+	a.cell_key = c->cell_key; a.cell_key_sorted = c->cell_key_sorted; a.cell_val = c->cell_val; a.cell_val_sorted = c->cell_val_sorted;
+	a.cell_start = c->cell_start;
+	a.nbr = c->nbr; a.nnbr = c->nnbr; a.max_neigh = c->max_neigh; a.stride = c->N;
+	a.edges = c->edges; a.edge_offsets = c->edge_offsets; a.n_edges = c->n_edges; a.edge_capacity = c->edge_capacity;
+	a.list_ipos = c->list_ipos[c->cur];
+	a.flags = c->flags;
+	a.cub_tmp = c->cub_tmp; a.cub_tmp_bytes = c->cub_tmp_bytes;
+	a.build_edges = c->use_edge != 0;
+	return a;
+}
+
+int read_flags(oxb_ctx *c) {
+	CU(cudaMemcpyAsync(c->h_flags, c->flags, sizeof(int) * OXB_FLAG_WORDS, cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	c->error_flags |= c->h_flags[OXB_FLAG_ERROR];
+	return 0;
+}
+
+int do_sort(oxb_ctx *c) {
+	if(!c->lists_allocated) { int rc = alloc_lists(c, c->max_neigh > 0 ? c->max_neigh : 64); if(rc) return rc; }
+	const int N = c->N, a = c->cur, b = 1 - c->cur;
+	if(c->hkeys == nullptr) {
+		CU(dalloc(&c->hkeys, N)); CU(dalloc(&c->hkeys_sorted, N)); CU(dalloc(&c->hvals, N)); CU(dalloc(&c->hvals_sorted, N)); CU(dalloc(&c->hinv, N));
+	}
+	oxb::SortArgs s;
+	s.N = N;
+	for(int k = 0; k < 3; k++) s.box[k] = c->box[k];
+	s.posd = c->posd[a];
+	s.keys = c->hkeys; s.keys_sorted = c->hkeys_sorted; s.vals = c->hvals; s.vals_sorted = c->hvals_sorted; s.inv = c->hinv;
+	s.cub_tmp = c->cub_tmp; s.cub_tmp_bytes = c->cub_tmp_bytes;
+	oxb::launch_hilbert_order(c->stream, s);
+	oxb::PermuteArgs p;
+	p.N = N; p.perm = c->hvals_sorted; p.inv = c->hinv;
+	p.posd_in = c->posd[a]; p.veld_in = c->veld[a]; p.Ld_in = c->Ld[a]; p.quatd_in = c->quatd[a];
+	p.posd_out = c->posd[b]; p.veld_out = c->veld[b]; p.Ld_out = c->Ld[b]; p.quatd_out = c->quatd[b];
+	p.ipos_in = c->ipos[a]; p.list_ipos_in = c->list_ipos[a]; p.ipos_out = c->ipos[b]; p.list_ipos_out = c->list_ipos[b];
+	p.quat_in = c->quat[a]; p.F_in = c->F[a]; p.T_in = c->T[a]; p.quat_out = c->quat[b]; p.F_out = c->F[b]; p.T_out = c->T[b];
+	p.bonds_in = c->bonds[a]; p.bonds_out = c->bonds[b];
+	p.slot_of = c->slot_of;
+	oxb::launch_permute(c->stream, p);
+	c->launches += 5;
+	c->cur = b;
+	c->n_sorts++;
+	c->lists_valid = false;
+	CU(cudaGetLastError());
+	return 0;
+}
+
+int do_build(oxb_ctx *c) {
+	if(!c->lists_allocated) { int rc = alloc_lists(c, 64); if(rc) return rc; }
+	for(int attempt = 0; attempt < 6; attempt++) {
+		CU(cudaMemsetAsync(c->flags + OXB_FLAG_ERROR, 0, sizeof(int), c->stream));
+		oxb::launch_build_lists(c->stream, list_args(c));
+		c->launches += c->use_edge ? 7 : 4;
+		CU(cudaGetLastError());
+		int rc = read_flags(c);
+		if(rc) return rc;
+		int seen = c->h_flags[OXB_FLAG_MAX_NEIGH_SEEN];
+		if((c->h_flags[OXB_FLAG_ERROR] & (OXB_ERR_NEIGH_OVERFLOW | OXB_ERR_EDGE_OVERFLOW)) == 0) {
+			c->error_flags &= ~(OXB_ERR_NEIGH_OVERFLOW | OXB_ERR_EDGE_OVERFLOW);
+			if(c->use_edge) {
+				int ne = 0;
+				CU(cudaMemcpyAsync(&ne, c->n_edges, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+				CU(cudaStreamSynchronize(c->stream));
+				c->edge_hint = ne;
+			}
+			c->lists_valid = true;
+			c->n_list_updates++;
+			return 0;
+		}
+		// a row overflowed: grow the matrix (the reference silently corrupts the next column here) and rebuild
+		int want = ((int) (seen * 1.5) + 15) / 8 * 8;
+		c->error_flags &= ~(OXB_ERR_NEIGH_OVERFLOW | OXB_ERR_EDGE_OVERFLOW);
+		rc = alloc_lists(c, std::max(want, c->max_neigh * 2));
+		if(rc) return rc;
+	}
+	return fail(c, 3, "neighbour list does not fit after repeated growth (max_neigh = %d)", c->max_neigh);
+}
+
+int ensure_lists(oxb_ctx *c) {
+	if(c->lists_valid) return 0;
+	if(!c->have_state || !c->have_model || !c->have_box) return fail(c, 2, "box, model and state must be set before building lists");
+	if(c->sort_every > 0 && (c->n_list_updates % c->sort_every) == 0) {
+		int rc = do_sort(c);
+		if(rc) return rc;
+	}
+	return do_build(c);
+}
+
+// hw: index of the halt word the launched kernels must honour
+int launch_forces(oxb_ctx *c, int hw) {
+	const int a = c->cur;
+	if(c->use_edge) {
+		oxb::launch_forces_edge(c->stream, c->model, c->boxf, c->N, c->n_edges, std::max(c->edge_hint, 1), c->ipos[a], c->quat[a], c->bonds[a], c->edges,
+				c->F[a], c->T[a], c->flags, hw, c->n_sm);
+		c->launches += 2;
+	}
+	else {
+		oxb::launch_forces_particle(c->stream, c->model, c->boxf, c->N, c->ipos[a], c->quat[a], c->bonds[a], c->nbr, c->nnbr, c->N, c->F[a], c->T[a],
+				c->flags, hw);
+		c->launches += 1;
+	}
+	if(c->n_ext > 0) {
+		oxb::launch_ext_forces(c->stream, c->n_ext, c->ext, c->slot_of, c->ipos[a], c->posd[a], c->boxf, c->step, c->F[a], c->flags, hw);
+		c->launches += 1;
+	}
+	return 0;
+}
+
+oxb::IntegrateArgs integ_args(oxb_ctx *c, long long step) {
+	oxb::IntegrateArgs a;
+	const int k = c->cur;
+	a.N = c->N; a.dt = c->dt;
+	for(int d = 0; d < 3; d++) a.box_inv[d] = 1. / c->box[d];
+	a.skin2 = (float) (c->skin * c->skin);
+	a.box = c->boxf;
+	a.posd = c->posd[k]; a.veld = c->veld[k]; a.Ld = c->Ld[k]; a.quatd = c->quatd[k];
+	a.ipos = c->ipos[k]; a.quat = c->quat[k]; a.list_ipos = c->list_ipos[k];
+	a.F = c->F[k]; a.T = c->T[k];
+	a.flags = c->flags; a.sums = c->sums; a.th = c->th; a.step = step;
+	return a;
+}
+
+int reset_batch_flags(oxb_ctx *c) {
+	CU(cudaMemsetAsync(c->flags + OXB_FLAG_STEPS_DONE, 0, sizeof(int), c->stream));
+	CU(cudaMemsetAsync(c->flags + OXB_FLAG_COUNT, 0, 2 * sizeof(int), c->stream));
+	return 0;
+}
+
+bool thermostat_active(const oxb_ctx *c, long long s) {
+	if(c->th.type == OXB_THERMOSTAT_NONE) return false;
+	if(c->th.type == OXB_THERMOSTAT_LANGEVIN) return true;
+	return (s % c->th.every) == 0;
+}
+
+int init_bussi(oxb_ctx *c) {
+	KinSums h;
+	std::memset(&h, 0, sizeof(h));
+	double T = c->th.a;
+	h.K_t = 0.5 * (3. * (c->N - 1)) * T; // BussiThermostat.cpp:36-43,152-158
+	h.K_r = 0.5 * (3. * c->N) * T;
+	h.factor_t = h.factor_r = 1.;
+	CU(cudaMemcpyAsync(c->sums, &h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
+	c->bussi_init = true;
+	return 0;
+}
+
+int check_ready(oxb_ctx *c) {
+	if(!c->have_topology) return fail(c, 2, "topology not set");
+	if(!c->have_box) return fail(c, 2, "box not set");
+	if(!c->have_model) return fail(c, 2, "interaction model not set");
+	if(!c->have_state) return fail(c, 2, "state not set");
+	return 0;
+}
+
+int ensure_forces(oxb_ctx *c) {
+	int rc = check_ready(c);
+	if(rc) return rc;
+	rc = ensure_lists(c);
+	if(rc) return rc;
+	if(!c->forces_valid) {
+		rc = reset_batch_flags(c);
+		if(rc) return rc;
+		launch_forces(c, OXB_FLAG_COUNT);
+		CU(cudaGetLastError());
+		c->forces_valid = true;
+	}
+	return 0;
+}
+
+} // namespace
+
+// ------------------------------------------------------------------------------------------------------------ C ABI
+extern "C" {
+
+int oxb_create(oxb_ctx **out, int device, int N, int precision) {
+	if(out == nullptr || N <= 0) return 1;
+	if(N >= (1 << 22)) return 1; // packed index is 22 bits, as in the reference (MD_CUDABackend.cu:243-254)
+	oxb_ctx *c = new oxb_ctx();
+	*out = c;
+	c->device = device; c->N = N; c->precision = precision;
+	std::memset(&c->th, 0, sizeof(c->th));
+	c->th.every = 1;
+	if(precision != OXB_PRECISION_MIXED) return fail(c, 4, "only backend_precision = mixed is implemented in this build");
+	int ndev = 0;
+	cudaError_t e = cudaGetDeviceCount(&ndev);
+	if(e != cudaSuccess || ndev == 0) return fail(c, 5, "no CUDA device available (%s): oxdna_b200 has no CPU fallback", cudaGetErrorString(e));
+	CU(cudaSetDevice(device));
+	CU(cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, device));
+	CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	for(int k = 0; k < 2; k++) {
+		CU(dalloc(&c->posd[k], N)); CU(dalloc(&c->veld[k], N)); CU(dalloc(&c->Ld[k], N)); CU(dalloc(&c->quatd[k], N));
+		CU(dalloc(&c->ipos[k], N)); CU(dalloc(&c->list_ipos[k], N)); CU(dalloc(&c->quat[k], N)); CU(dalloc(&c->F[k], N)); CU(dalloc(&c->T[k], N));
+		CU(dalloc(&c->bonds[k], N));
+		CU(cudaMemset(c->F[k], 0, sizeof(float4) * N)); CU(cudaMemset(c->T[k], 0, sizeof(float4) * N));
+		CU(cudaMemset(c->list_ipos[k], 0, sizeof(int4) * N));
+	}
+	CU(dalloc(&c->slot_of, N));
+	CU(dalloc(&c->flags, OXB_FLAG_WORDS));
+	CU(cudaMemset(c->flags, 0, sizeof(int) * OXB_FLAG_WORDS));
+	CU(cudaMallocHost((void **) &c->h_flags, sizeof(int) * OXB_FLAG_WORDS));
+	CU(dalloc(&c->sums, 1));
+	CU(cudaMemset(c->sums, 0, sizeof(KinSums)));
+	CU(dalloc(&c->d_energy, 2));
+	CU(cudaMallocHost((void **) &c->h_scalars, sizeof(double) * 16));
+	return 0;
+}
+
+void oxb_destroy(oxb_ctx *c) {
+	if(c == nullptr) return;
+	cudaSetDevice(c->device);
+	if(c->stream) cudaStreamSynchronize(c->stream);
+	for(int k = 0; k < 2; k++) {
+		cudaFree(c->posd[k]); cudaFree(c->veld[k]); cudaFree(c->Ld[k]); cudaFree(c->quatd[k]); cudaFree(c->ipos[k]); cudaFree(c->list_ipos[k]);
+		cudaFree(c->quat[k]); cudaFree(c->F[k]); cudaFree(c->T[k]); cudaFree(c->bonds[k]);
+	}
+	cudaFree(c->slot_of); cudaFree(c->flags); cudaFree(c->sums); cudaFree(c->d_energy); cudaFree(c->ext); cudaFree(c->pos_f4);
+	cudaFree(c->hkeys); cudaFree(c->hkeys_sorted); cudaFree(c->hvals); cudaFree(c->hvals_sorted); cudaFree(c->hinv);
+	free_lists(c);
+	if(c->h_flags) cudaFreeHost(c->h_flags);
+	if(c->h_scalars) cudaFreeHost(c->h_scalars);
+	if(c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+	delete c;
+}
+
+const char *oxb_last_error(const oxb_ctx *c) { return c ? c->err.c_str() : "null context"; }
+
+int oxb_set_stream(oxb_ctx *c, void *s) {
+	if(c == nullptr) return 1;
+	if(c->own_stream && c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+	c->stream = (cudaStream_t) s;
+	c->own_stream = false;
+	return 0;
+}
+
+int oxb_set_box(oxb_ctx *c, const double box[3]) {
+	if(c == nullptr || box == nullptr) return 1;
+	for(int k = 0; k < 3; k++) {
+		if(!(box[k] > 0)) return fail(c, 1, "box sides must be positive");
+		c->box[k] = box[k];
+	}
+	set_boxf(c);
+	c->have_box = true;
+	c->lists_valid = false; c->forces_valid = false;
+	if(c->lists_allocated) free_lists(c);
+	return 0;
+}
+
+int oxb_set_topology(oxb_ctx *c, const int *btype, const int *n3, const int *n5, const int *strand) {
+	if(c == nullptr || btype == nullptr || n3 == nullptr || n5 == nullptr) return 1;
+	const int N = c->N;
+	c->h_btype.assign(btype, btype + N); c->h_n3.assign(n3, n3 + N); c->h_n5.assign(n5, n5 + N);
+	if(strand) c->h_strand.assign(strand, strand + N); else c->h_strand.assign(N, 0);
+	for(int i = 0; i < N; i++) {
+		if(n3[i] >= N || n5[i] >= N) return fail(c, 1, "wrong topology for particle %d (neighbour index out of range)", i);
+		if(btype[i] > 511 || btype[i] < -511) return fail(c, 1, "base type of particle %d does not fit the packed word (|btype| <= 511)", i);
+	}
+	c->have_topology = true;
+	c->have_state = false;
+	return 0;
+}
+
+int oxb_set_model_dna2(oxb_ctx *c, const oxb_dna2_params *P, double rcut) {
+	if(c == nullptr || P == nullptr) return 1;
+	c->model = *P;
+	bool rcut_changed = (rcut != c->rcut);
+	c->rcut = rcut;
+	c->have_model = true;
+	c->forces_valid = false;
+	if(rcut_changed) {
+		c->lists_valid = false;
+		if(c->lists_allocated) free_lists(c);
+	}
+	return 0;
+}
+
+int oxb_set_lists(oxb_ctx *c, double verlet_skin, int use_edge, int sort_every, double max_density_multiplier) {
+	if(c == nullptr) return 1;
+	if(!(verlet_skin > 0)) return fail(c, 1, "verlet_skin must be > 0");
+	c->skin = verlet_skin; c->use_edge = use_edge ? 1 : 0; c->sort_every = sort_every < 0 ? 0 : sort_every;
+	c->max_density_multiplier = max_density_multiplier;
+	c->lists_valid = false; c->forces_valid = false;
+	if(c->lists_allocated) free_lists(c);
+	return 0;
+}
+
+int oxb_set_dt(oxb_ctx *c, double dt) {
+	if(c == nullptr) return 1;
+	c->dt = dt;
+	return 0;
+}
+
+int oxb_set_thermostat(oxb_ctx *c, int type, int every, double a, double b, double cc, double d, unsigned long long seed) {
+	if(c == nullptr) return 1;
+	if(type < OXB_THERMOSTAT_NONE || type > OXB_THERMOSTAT_BUSSI) return fail(c, 1, "unknown thermostat %d", type);
+	if(type != OXB_THERMOSTAT_NONE && every < 1) return fail(c, 1, "'newtonian_steps' must be > 0");
+	c->th.type = type; c->th.every = every < 1 ? 1 : every;
+	c->th.a = (float) a; c->th.b = (float) b; c->th.c = (float) cc; c->th.d = (float) d; c->th.seed = seed;
+	c->bussi_init = false;
+	return 0;
+}
+
+int oxb_set_ext_forces(oxb_ctx *c, int n, const oxb_ext_force *f) {
+	if(c == nullptr || n < 0 || (n > 0 && f == nullptr)) return 1;
+	std::vector<DevExtForce> h(std::max(n, 1));
+	for(int k = 0; k < n; k++) {
+		if(f[k].particle < 0 || f[k].particle >= c->N) return fail(c, 1, "external force %d: invalid particle %d", k, f[k].particle);
+		if(f[k].type == OXB_EXT_MUTUAL_TRAP && (f[k].ref < 0 || f[k].ref >= c->N)) return fail(c, 1, "Invalid reference particle %d for Mutual Trap", f[k].ref);
+		if(f[k].type < OXB_EXT_STRING || f[k].type > OXB_EXT_MUTUAL_TRAP) return fail(c, 1, "external force %d: unsupported type %d", k, f[k].type);
+		DevExtForce &d = h[k];
+		d.type = f[k].type; d.particle = f[k].particle; d.ref = f[k].ref < 0 ? 0 : f[k].ref; d.pbc = f[k].pbc;
+		d.stiff = (float) f[k].stiff; d.r0 = (float) f[k].r0; d.rate = (float) f[k].rate; d.stiff_rate = (float) f[k].stiff_rate; d.F0 = (float) f[k].F0;
+		double nrm = std::sqrt(f[k].dir[0] * f[k].dir[0] + f[k].dir[1] * f[k].dir[1] + f[k].dir[2] * f[k].dir[2]);
+		for(int x = 0; x < 3; x++) {
+			d.dir[x] = (float) ((f[k].type != OXB_EXT_MUTUAL_TRAP && nrm > 0) ? f[k].dir[x] / nrm : f[k].dir[x]);
+			d.pos0[x] = f[k].pos0[x];
+		}
+	}
+	cudaFree(c->ext);
+	c->ext = nullptr;
+	CU(dalloc(&c->ext, (size_t) std::max(n, 1)));
+	if(n > 0) CU(cudaMemcpy(c->ext, h.data(), sizeof(DevExtForce) * n, cudaMemcpyHostToDevice));
+	c->n_ext = n;
+	c->forces_valid = false;
+	return 0;
+}
+
+int oxb_set_state(oxb_ctx *c, const double *pos, const double *a1, const double *a3, const double *vel, const double *L) {
+	if(c == nullptr || pos == nullptr || a1 == nullptr || a3 == nullptr) return 1;
+	if(!c->have_topology) return fail(c, 2, "topology must be set before the state");
+	if(!c->have_box) return fail(c, 2, "box must be set before the state");
+	const int N = c->N;
+	std::vector<double4> hp(N), hv(N), hL(N), hq(N);
+	std::vector<int4> hi(N);
+	std::vector<float4> hqf(N);
+	std::vector<int2> hb(N);
+	std::vector<int> hs(N);
+	for(int i = 0; i < N; i++) {
+		hp[i] = make_double4(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], 0.);
+		hv[i] = vel ? make_double4(vel[3 * i], vel[3 * i + 1], vel[3 * i + 2], 0.) : make_double4(0., 0., 0., 0.);
+		hL[i] = L ? make_double4(L[3 * i], L[3 * i + 1], L[3 * i + 2], 0.) : make_double4(0., 0., 0., 0.);
+		// orthonormalise exactly like the reference's configuration reader (src/Backends/SimBackend.cpp:623-629)
+		double v1[3] = { a1[3 * i], a1[3 * i + 1], a1[3 * i + 2] }, v3_[3] = { a3[3 * i], a3[3 * i + 1], a3[3 * i + 2] }, v2[3];
+		double n1 = std::sqrt(v1[0] * v1[0] + v1[1] * v1[1] + v1[2] * v1[2]), n3 = std::sqrt(v3_[0] * v3_[0] + v3_[1] * v3_[1] + v3_[2] * v3_[2]);
+		if(n1 < 0.9 || n3 < 0.9) {
+			// the reader normalises first; a null vector is an error there as well
+			if(n1 == 0. || n3 == 0.) return fail(c, 1, "Invalid orientation for particle %d: at least one of the vectors is a null vector", i);
+		}
+		for(int k = 0; k < 3; k++) { v1[k] /= n1; v3_[k] /= n3; }
+		double d = v1[0] * v3_[0] + v1[1] * v3_[1] + v1[2] * v3_[2];
+		for(int k = 0; k < 3; k++) v1[k] -= v3_[k] * d;
+		n1 = std::sqrt(v1[0] * v1[0] + v1[1] * v1[1] + v1[2] * v1[2]);
+		for(int k = 0; k < 3; k++) v1[k] /= n1;
+		v2[0] = v3_[1] * v1[2] - v3_[2] * v1[1]; v2[1] = v3_[2] * v1[0] - v3_[0] * v1[2]; v2[2] = v3_[0] * v1[1] - v3_[1] * v1[0];
+		double n2 = std::sqrt(v2[0] * v2[0] + v2[1] * v2[1] + v2[2] * v2[2]);
+		for(int k = 0; k < 3; k++) v2[k] /= n2;
+		quatd q = quat_from_axes(v1, v2, v3_);
+		hq[i] = make_double4(q.x, q.y, q.z, q.w);
+		hqf[i] = make_float4((float) q.x, (float) q.y, (float) q.z, (float) q.w);
+		hi[i].x = (int) to_fixed(pos[3 * i], 1. / c->box[0]);
+		hi[i].y = (int) to_fixed(pos[3 * i + 1], 1. / c->box[1]);
+		hi[i].z = (int) to_fixed(pos[3 * i + 2], 1. / c->box[2]);
+		hi[i].w = pack_word(c->h_btype[i], i);
+		hb[i] = make_int2(c->h_n3[i], c->h_n5[i]);
+		hs[i] = i;
+	}
+	const int k = c->cur;
+	CU(cudaMemcpyAsync(c->posd[k], hp.data(), sizeof(double4) * N, cudaMemcpyHostToDevice, c->stream));
+	CU(cudaMemcpyAsync(c->veld[k], hv.data(), sizeof(double4) * N, cudaMemcpyHostToDevice, c->stream));
+	CU(cudaMemcpyAsync(c->Ld[k], hL.data(), sizeof(double4) * N, cudaMemcpyHostToDevice, c->stream));
+	CU(cudaMemcpyAsync(c->quatd[k], hq.data(), sizeof(double4) * N, cudaMemcpyHostToDevice, c->stream));
+	CU(cudaMemcpyAsync(c->ipos[k], hi.data(), sizeof(int4) * N, cudaMemcpyHostToDevice, c->stream));
+	CU(cudaMemcpyAsync(c->quat[k], hqf.data(), sizeof(float4) * N, cudaMemcpyHostToDevice, c->stream));
+	CU(cudaMemcpyAsync(c->bonds[k], hb.data(), sizeof(int2) * N, cudaMemcpyHostToDevice, c->stream));
+	CU(cudaMemcpyAsync(c->slot_of, hs.data(), sizeof(int) * N, cudaMemcpyHostToDevice, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	c->have_state = true;
+	c->lists_valid = false; c->forces_valid = false; c->mid_step = false;
+	return 0;
+}
+
+int oxb_get_state(oxb_ctx *c, double *pos, double *a1, double *a3, double *vel, double *L) {
+	if(c == nullptr) return 1;
+	if(!c->have_state) return fail(c, 2, "state not set");
+	const int N = c->N, k = c->cur;
+	std::vector<double4> hp(N), hv(N), hL(N), hq(N);
+	std::vector<int4> hi(N);
+	CU(cudaMemcpyAsync(hp.data(), c->posd[k], sizeof(double4) * N, cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaMemcpyAsync(hv.data(), c->veld[k], sizeof(double4) * N, cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaMemcpyAsync(hL.data(), c->Ld[k], sizeof(double4) * N, cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaMemcpyAsync(hq.data(), c->quatd[k], sizeof(double4) * N, cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaMemcpyAsync(hi.data(), c->ipos[k], sizeof(int4) * N, cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	for(int s = 0; s < N; s++) {
+		int i = word_index(hi[s].w);
+		if(pos) { pos[3 * i] = hp[s].x; pos[3 * i + 1] = hp[s].y; pos[3 * i + 2] = hp[s].z; }
+		if(vel) { vel[3 * i] = hv[s].x; vel[3 * i + 1] = hv[s].y; vel[3 * i + 2] = hv[s].z; }
+		if(L) { L[3 * i] = hL[s].x; L[3 * i + 1] = hL[s].y; L[3 * i + 2] = hL[s].z; }
+		if(a1 || a3) {
+			quatd q = { hq[s].x, hq[s].y, hq[s].z, hq[s].w };
+			double x1[3], x2[3], x3[3];
+			axes_from_quatd(q, x1, x2, x3);
+			for(int d = 0; d < 3; d++) {
+				if(a1) a1[3 * i + d] = x1[d];
+				if(a3) a3[3 * i + d] = x3[d];
+			}
+		}
+	}
+	return 0;
+}
+
+int oxb_set_step(oxb_ctx *c, long long step) {
+	if(c == nullptr) return 1;
+	c->step = step;
+	c->forces_valid = c->forces_valid && (c->n_ext == 0);
+	return 0;
+}
+
+long long oxb_get_step(const oxb_ctx *c) { return c ? c->step : -1; }
+
+int oxb_sort(oxb_ctx *c) {
+	if(c == nullptr) return 1;
+	int rc = check_ready(c);
+	if(rc) return rc;
+	return do_sort(c);
+}
+
+int oxb_update_lists(oxb_ctx *c) {
+	if(c == nullptr) return 1;
+	int rc = check_ready(c);
+	if(rc) return rc;
+	c->lists_valid = false;
+	return ensure_lists(c);
+}
+
+int oxb_compute_forces(oxb_ctx *c) {
+	if(c == nullptr) return 1;
+	c->forces_valid = false;
+	int rc = ensure_forces(c);
+	if(rc) return rc;
+	CU(cudaStreamSynchronize(c->stream));
+	return 0;
+}
+
+int oxb_first_step(oxb_ctx *c) {
+	if(c == nullptr) return 1;
+	int rc = ensure_forces(c);
+	if(rc) return rc;
+	rc = reset_batch_flags(c);
+	if(rc) return rc;
+	oxb::launch_integrate_epoch(c->stream, integ_args(c, c->step), OXB_PH_FIRST, 0);
+	c->launches++;
+	rc = read_flags(c);
+	if(rc) return rc;
+	if(c->h_flags[OXB_FLAG_COUNT] || c->h_flags[OXB_FLAG_COUNT + 1]) c->lists_valid = false;
+	c->forces_valid = false;
+	c->mid_step = true;
+	return 0;
+}
+
+int oxb_second_step(oxb_ctx *c) {
+	if(c == nullptr) return 1;
+	int rc = ensure_forces(c);
+	if(rc) return rc;
+	rc = reset_batch_flags(c);
+	if(rc) return rc;
+	oxb::launch_integrate_epoch(c->stream, integ_args(c, c->step), OXB_PH_SECOND | OXB_PH_COUNT_STEP, 0);
+	c->launches++;
+	c->mid_step = false;
+	CU(cudaStreamSynchronize(c->stream));
+	return 0;
+}
+
+int oxb_thermostat(oxb_ctx *c) {
+	if(c == nullptr) return 1;
+	int rc = check_ready(c);
+	if(rc) return rc;
+	if(!thermostat_active(c, c->step)) return 0;
+	rc = reset_batch_flags(c);
+	if(rc) return rc;
+	oxb::IntegrateArgs a = integ_args(c, c->step);
+	if(c->th.type == OXB_THERMOSTAT_BUSSI) {
+		if(!c->bussi_init) { rc = init_bussi(c); if(rc) return rc; }
+		oxb::launch_kinetic_sums(c->stream, c->N, c->veld[c->cur], c->Ld[c->cur], c->sums);
+		oxb::launch_bussi_update_epoch(c->stream, c->sums, c->N, c->th, c->step, c->flags, 0);
+		oxb::launch_integrate_epoch(c->stream, a, OXB_PH_BUSSI_APPLY, 0);
+		c->launches += 4;
+	}
+	else {
+		oxb::launch_integrate_epoch(c->stream, a, OXB_PH_THERMO, 0);
+		c->launches++;
+	}
+	CU(cudaStreamSynchronize(c->stream));
+	return 0;
+}
+
+int oxb_run(oxb_ctx *c, long long n_steps) {
+	if(c == nullptr || n_steps < 0) return 1;
+	if(n_steps == 0) return 0;
+	int rc = check_ready(c);
+	if(rc) return rc;
+	if(c->th.type == OXB_THERMOSTAT_BUSSI && !c->bussi_init) { rc = init_bussi(c); if(rc) return rc; }
+	long long remaining = n_steps;
+	long long since_rebuild = 0;
+	while(remaining > 0) {
+		rc = ensure_lists(c);
+		if(rc) return rc;
+		rc = reset_batch_flags(c);
+		if(rc) return rc;
+		int epoch = 0;
+		if(!c->mid_step) {
+			// start of a run: forces for the current positions, then the first half-kick + drift
+			if(!c->forces_valid) { launch_forces(c, OXB_FLAG_COUNT + (epoch & 1)); c->forces_valid = true; }
+			oxb::launch_integrate_epoch(c->stream, integ_args(c, c->step), OXB_PH_FIRST, epoch++);
+			c->launches++;
+		}
+		long long batch = std::min<long long>(remaining, std::max<long long>(1, std::min<long long>(64, (long long) (0.75 * c->avg_interval + 0.5))));
+		for(long long b = 0; b < batch; b++) {
+			const long long s = c->step + b;
+			c->step = s; // external forces read c->step at launch time
+			launch_forces(c, OXB_FLAG_COUNT + (epoch & 1));
+			const bool last = (b == batch - 1) && (batch == remaining);
+			const bool th = thermostat_active(c, s);
+			oxb::IntegrateArgs a = integ_args(c, s);
+			if(th && c->th.type == OXB_THERMOSTAT_BUSSI) {
+				oxb::launch_clear_sums(c->stream, c->sums, c->flags, epoch);
+				oxb::launch_integrate_epoch(c->stream, a, OXB_PH_SECOND | OXB_PH_BUSSI_SUMS | OXB_PH_COUNT_STEP, epoch++);
+				oxb::launch_bussi_update_epoch(c->stream, c->sums, c->N, c->th, s, c->flags, epoch);
+				oxb::launch_integrate_epoch(c->stream, a, last ? OXB_PH_BUSSI_APPLY : (OXB_PH_BUSSI_APPLY | OXB_PH_FIRST), epoch++);
+				c->launches += 4;
+			}
+			else {
+				int ph = OXB_PH_SECOND | OXB_PH_COUNT_STEP | (th ? OXB_PH_THERMO : 0) | (last ? 0 : OXB_PH_FIRST);
+				oxb::launch_integrate_epoch(c->stream, a, ph, epoch++);
+				c->launches++;
+			}
+		}
+		c->step -= (batch - 1);
+		CU(cudaGetLastError());
+		rc = read_flags(c);
+		if(rc) return rc;
+		const int done = c->h_flags[OXB_FLAG_STEPS_DONE];
+		const bool halted = c->h_flags[OXB_FLAG_COUNT] || c->h_flags[OXB_FLAG_COUNT + 1];
+		c->step += done;
+		remaining -= done;
+		since_rebuild += done;
+		if(c->error_flags & OXB_ERR_FENE_BROKEN) {
+			return fail(c, 6, "the distance between bonded neighbors exceeded acceptable values (FENE range) around step %lld", c->step);
+		}
+		if(halted) {
+			c->lists_valid = false;
+			c->mid_step = true;
+			c->forces_valid = false;
+			c->avg_interval = 0.7 * c->avg_interval + 0.3 * (double) std::max<long long>(since_rebuild, 1);
+			since_rebuild = 0;
+		}
+		else {
+			c->mid_step = (remaining > 0);
+			c->forces_valid = false;
+			if(done != batch) return fail(c, 7, "internal error: batch of %lld steps completed %d without a halt", batch, done);
+		}
+	}
+	// at the end of a run the forces in memory belong to the last completed step's positions: still valid
+	c->forces_valid = true;
+	c->mid_step = false;
+	return 0;
+}
+
+int oxb_synchronize(oxb_ctx *c) {
+	if(c == nullptr) return 1;
+	CU(cudaStreamSynchronize(c->stream));
+	return 0;
+}
+
+int oxb_get_forces(oxb_ctx *c, double *force, double *torque_body, double *torque_lab, double *energy, double *hb_energy) {
+	if(c == nullptr) return 1;
+	int rc = ensure_forces(c);
+	if(rc) return rc;
+	const int N = c->N, k = c->cur;
+	std::vector<float4> hF(N), hT(N);
+	std::vector<double4> hq(N);
+	std::vector<int4> hi(N);
+	CU(cudaMemcpyAsync(hF.data(), c->F[k], sizeof(float4) * N, cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaMemcpyAsync(hT.data(), c->T[k], sizeof(float4) * N, cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaMemcpyAsync(hq.data(), c->quatd[k], sizeof(double4) * N, cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaMemcpyAsync(hi.data(), c->ipos[k], sizeof(int4) * N, cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	for(int s = 0; s < N; s++) {
+		int i = word_index(hi[s].w);
+		if(force) { force[3 * i] = hF[s].x; force[3 * i + 1] = hF[s].y; force[3 * i + 2] = hF[s].z; }
+		if(torque_body) { torque_body[3 * i] = hT[s].x; torque_body[3 * i + 1] = hT[s].y; torque_body[3 * i + 2] = hT[s].z; }
+		if(torque_lab) {
+			quatd q = { hq[s].x, hq[s].y, hq[s].z, hq[s].w };
+			double x1[3], x2[3], x3[3];
+			axes_from_quatd(q, x1, x2, x3);
+			for(int d = 0; d < 3; d++) torque_lab[3 * i + d] = x1[d] * hT[s].x + x2[d] * hT[s].y + x3[d] * hT[s].z;
+		}
+		if(energy) energy[i] = hF[s].w;
+		if(hb_energy) hb_energy[i] = hT[s].w;
+	}
+	return 0;
+}
+
+int oxb_energy(oxb_ctx *c, double *U, double *K) {
+	if(c == nullptr) return 1;
+	int rc = ensure_forces(c);
+	if(rc) return rc;
+	const int k = c->cur;
+	oxb::launch_energy_sum(c->stream, c->N, c->F[k], c->d_energy);
+	KinSums hs;
+	// keep the Bussi state words intact: only the five running sums are cleared/refilled
+	oxb::launch_kinetic_sums(c->stream, c->N, c->veld[k], c->Ld[k], c->sums);
+	c->launches += 3;
+	CU(cudaMemcpyAsync(c->h_scalars, c->d_energy, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaMemcpyAsync(&hs, c->sums, sizeof(KinSums), cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	if(U) *U = 0.5 * c->h_scalars[0];
+	if(K) *K = 0.5 * (hs.v2 + hs.L2);
+	return 0;
+}
+
+int oxb_get_pairs(oxb_ctx *c, int *pairs, long long max_pairs, long long *n_pairs) {
+	if(c == nullptr || n_pairs == nullptr) return 1;
+	int rc = check_ready(c);
+	if(rc) return rc;
+	rc = ensure_lists(c);
+	if(rc) return rc;
+	const int N = c->N;
+	std::vector<int> hn(N), hm((size_t) c->max_neigh * N);
+	std::vector<int4> hi(N);
+	CU(cudaMemcpyAsync(hn.data(), c->nnbr, sizeof(int) * N, cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaMemcpyAsync(hm.data(), c->nbr, sizeof(int) * (size_t) c->max_neigh * N, cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaMemcpyAsync(hi.data(), c->ipos[c->cur], sizeof(int4) * N, cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	long long n = 0;
+	for(int s = 0; s < N; s++) {
+		int i = word_index(hi[s].w);
+		for(int k = 0; k < hn[s]; k++) {
+			int j = word_index(hi[hm[(size_t) k * N + s]].w);
+			if(i < j) {
+				if(pairs != nullptr && n < max_pairs) { pairs[2 * n] = i; pairs[2 * n + 1] = j; }
+				n++;
+			}
+		}
+	}
+	*n_pairs = n;
+	return 0;
+}
+
+int oxb_get_stats(oxb_ctx *c, long long *n_list_updates, long long *n_sorts, int *max_neigh, int *error_flags) {
+	if(c == nullptr) return 1;
+	if(n_list_updates) *n_list_updates = c->n_list_updates;
+	if(n_sorts) *n_sorts = c->n_sorts;
+	if(max_neigh) *max_neigh = c->max_neigh;
+	if(error_flags) *error_flags = c->error_flags;
+	return 0;
+}
+
+namespace {
+__global__ void k_pos_view(int N, const double4 *__restrict__ posd, const int4 *__restrict__ ipos, float4 *__restrict__ out) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= N) return;
+	double4 p = posd[i];
+	out[i] = make_float4((float) p.x, (float) p.y, (float) p.z, __int_as_float(ipos[i].w));
+}
+} // namespace
+
+int oxb_device_views(oxb_ctx *c, void **poss_f4, void **orientations_f4, void **matrix_neighs, void **number_neighs, void **edge_list, void **n_edges) {
+	if(c == nullptr) return 1;
+	int rc = check_ready(c);
+	if(rc) return rc;
+	rc = ensure_lists(c);
+	if(rc) return rc;
+	if(poss_f4) {
+		if(c->pos_f4 == nullptr) CU(dalloc(&c->pos_f4, c->N));
+		k_pos_view<<<(c->N + 255) / 256, 256, 0, c->stream>>>(c->N, c->posd[c->cur], c->ipos[c->cur], c->pos_f4);
+		c->launches++;
+		CU(cudaStreamSynchronize(c->stream));
+		*poss_f4 = c->pos_f4;
+	}
+	if(orientations_f4) *orientations_f4 = c->quat[c->cur];
+	if(matrix_neighs) *matrix_neighs = c->nbr;
+	if(number_neighs) *number_neighs = c->nnbr;
+	if(edge_list) *edge_list = c->edges;
+	if(n_edges) *n_edges = c->n_edges;
+	return 0;
+}
+
+long long oxb_launch_count(const oxb_ctx *c) { return c ? c->launches : 0; }
+
+int oxb_time_kernel(oxb_ctx *c, int which, int reps, float *ms) {
+	if(c == nullptr || ms == nullptr || reps < 1) return 1;
+	int rc = ensure_forces(c);
+	if(rc) return rc;
+	cudaEvent_t e0, e1;
+	CU(cudaEventCreate(&e0));
+	CU(cudaEventCreate(&e1));
+	rc = reset_batch_flags(c);
+	if(rc) return rc;
+	CU(cudaStreamSynchronize(c->stream));
+	CU(cudaEventRecord(e0, c->stream));
+	for(int r = 0; r < reps; r++) {
+		if(which == 0) launch_forces(c, OXB_FLAG_COUNT);
+		else if(which == 1) {
+			// dt = 0 leaves the state bit-identical while moving exactly the same bytes
+			oxb::IntegrateArgs a = integ_args(c, c->step);
+			a.dt = 0.;
+			oxb::launch_integrate_epoch(c->stream, a, OXB_PH_SECOND | OXB_PH_FIRST | OXB_PH_COUNT_STEP, 0);
+			c->launches++;
+		}
+		else if(which == 2) { oxb::launch_build_lists(c->stream, list_args(c)); c->launches += c->use_edge ? 7 : 4; }
+		else if(which == 3) { rc = do_sort(c); if(rc) return rc; }
+		else return fail(c, 1, "unknown kernel selector %d", which);
+	}
+	CU(cudaEventRecord(e1, c->stream));
+	CU(cudaEventSynchronize(e1));
+	float t = 0.f;
+	CU(cudaEventElapsedTime(&t, e0, e1));
+	*ms = t / reps;
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	if(which == 3) { c->lists_valid = false; c->forces_valid = false; rc = ensure_forces(c); if(rc) return rc; }
+	CU(cudaStreamSynchronize(c->stream));
+	return 0;
+}
+
+} // extern "C"

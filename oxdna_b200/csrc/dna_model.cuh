@@ -1,0 +1,468 @@
+// oxDNA2 pair potential, FP32 device functions (hand-written for sm_100a; no tensor cores: the work is
+// transcendental/SFU + FP32-pipe bound).
+//
+// What it evaluates is the reference's model (src/CUDA/Interactions/CUDA_DNA.cuh:43-725, CPU mirror
+// src/Interactions/DNAInteraction.cpp:415-1172 + DNA2Interaction.cpp:157-306); how it evaluates it is different:
+//  * every factor f(cos theta) is differentiated with respect to the COSINE and the chain rule is applied through
+//    two generic moves (axis.axis and axis.direction), so hydrogen bonding and cross stacking -- which share their
+//    six angles -- accumulate their derivatives first and touch the vectors once;
+//  * sin(theta) is taken from the cross product that the torque needs anyway, and theta = atan2(sin, cos): unlike
+//    acosf(cos) this keeps FP32 relative accuracy when theta approaches 0 or pi (coaxial stacking lives near pi);
+//  * site forces are accumulated per lever arm (a1-collinear sites share one accumulator), two cross products per
+//    particle per pair instead of one per site interaction.
+#pragma once
+
+#include "common.cuh"
+
+struct AngVal {
+	float v;  // f(theta)
+	float dc; // d f / d cos(theta)
+};
+
+// f4 in cosine space.  c = cos(theta), s = sin(theta) >= 0 (from a cross product).
+OXB_HD AngVal f4_cs(const oxb_f4 &f, float c, float s) {
+	AngVal r;
+	r.v = 0.f;
+	r.dc = 0.f;
+	float t = atan2f(s, c);
+	float x = t - f.t0;
+	float m = 1.f;
+	if(x < 0.f) {
+		x = -x;
+		m = -1.f;
+	}
+	if(x < f.tc) {
+		if(x > f.ts) {
+			float d = f.tc - x;
+			r.v = f.b * d * d;
+			// d/dtheta = m 2 b (x - tc);  d/dcos = -(d/dtheta) / sin
+			r.dc = m * 2.f * f.b * d / fmaxf(s, 1e-12f);
+		}
+		else {
+			r.v = 1.f - f.a * x * x;
+			// same small-angle limit as the CPU code (DNAInteraction.cpp:1411-1414)
+			r.dc = (s * s > 1e-8f) ? m * 2.f * f.a * x / s : m * 2.f * f.a;
+		}
+	}
+	return r;
+}
+
+// F(c) = f4(c) + f4(-c)
+OXB_HD AngVal f4_cs_sym(const oxb_f4 &f, float c, float s) {
+	AngVal p = f4_cs(f, c, s), n = f4_cs(f, -c, s);
+	AngVal r;
+	r.v = p.v + n.v;
+	r.dc = p.dc - n.dc;
+	return r;
+}
+
+// oxDNA2 coaxial-stacking theta1: f4 plus a pure harmonic beyond theta = sb (DNA2Interaction.cpp:308-363)
+OXB_HD AngVal f4_cs_cxst_t1(const oxb_dna2_params &M, float c, float s) {
+	AngVal r = f4_cs(M.f4[OXB_F4_CXST_T1], c, s);
+	float t = atan2f(s, c);
+	float x = t - M.cxst_t1_sb;
+	if(x >= 0.f) {
+		r.v += M.cxst_t1_sa * x * x;
+		r.dc -= (s * s > 1e-8f) ? 2.f * M.cxst_t1_sa * x / s : 2.f * M.cxst_t1_sa;
+	}
+	return r;
+}
+
+OXB_HD AngVal f5_c(const oxb_f5 &f, float c) {
+	AngVal r;
+	r.v = 0.f;
+	r.dc = 0.f;
+	if(c > f.xc) {
+		if(c < f.xs) {
+			float d = f.xc - c;
+			r.v = f.b * d * d;
+			r.dc = -2.f * f.b * d;
+		}
+		else if(c < 0.f) {
+			r.v = 1.f - f.a * c * c;
+			r.dc = -2.f * f.a * c;
+		}
+		else {
+			r.v = 1.f;
+		}
+	}
+	return r;
+}
+
+struct RadVal {
+	float v, d;
+};
+
+OXB_HD RadVal f1_r(const oxb_f1 &f, float eps, float shift, float r) {
+	RadVal o;
+	o.v = 0.f;
+	o.d = 0.f;
+	if(r < f.rchigh) {
+		if(r > f.rhigh) {
+			float x = r - f.rchigh;
+			o.v = eps * f.bhigh * x * x;
+			o.d = 2.f * eps * f.bhigh * x;
+		}
+		else if(r > f.rlow) {
+			float e = expf(-(r - f.r0) * f.a);
+			float t = 1.f - e;
+			o.v = eps * t * t - shift;
+			o.d = 2.f * eps * t * e * f.a;
+		}
+		else if(r > f.rclow) {
+			float x = r - f.rclow;
+			o.v = eps * f.blow * x * x;
+			o.d = 2.f * eps * f.blow * x;
+		}
+	}
+	return o;
+}
+
+OXB_HD RadVal f2_r(const oxb_f2 &f, float r) {
+	RadVal o;
+	o.v = 0.f;
+	o.d = 0.f;
+	if(r < f.rchigh) {
+		if(r > f.rhigh) {
+			float x = r - f.rchigh;
+			o.v = f.k * f.bhigh * x * x;
+			o.d = 2.f * f.k * f.bhigh * x;
+		}
+		else if(r > f.rlow) {
+			float x = r - f.r0, y = f.rc - f.r0;
+			o.v = 0.5f * f.k * (x * x - y * y);
+			o.d = f.k * x;
+		}
+		else if(r > f.rclow) {
+			float x = r - f.rclow;
+			o.v = f.k * f.blow * x * x;
+			o.d = 2.f * f.k * f.blow * x;
+		}
+	}
+	return o;
+}
+
+// repulsive LJ + quadratic smoothing: returns energy, writes the scalar s with force-on-q = s * r
+OXB_HD float excl_s(const oxb_excl &e, float eps, v3 r, float &s) {
+	float r2 = dot(r, r);
+	float en = 0.f;
+	s = 0.f;
+	if(r2 < e.rc2) {
+		if(r2 > e.rstar2) {
+			float rm = sqrtf(r2);
+			float rrc = rm - e.rc;
+			en = eps * e.b * rrc * rrc;
+			s = -2.f * eps * e.b * rrc / rm;
+		}
+		else {
+			float t = e.sigma2 / r2;
+			float lj = t * t * t;
+			en = 4.f * eps * (lj * lj - lj);
+			s = -24.f * eps * (lj - 2.f * lj * lj) / r2;
+		}
+	}
+	return en;
+}
+
+// Accumulator for one pair (p, q).  F is the force on q (p receives -F).  Forces acting at a1-collinear sites
+// (base, stack, ungrooved backbone reference) are summed pre-multiplied by their offset along a1; forces at the
+// (grooved) backbone site are summed separately.  Tp/Tq collect the pure (non lever-arm) torques, lab frame.
+struct PairAcc {
+	v3 F, Pa, Pk, Qa, Qk, Tp, Tq;
+	OXB_HD void clear() {
+		F = Pa = Pk = Qa = Qk = Tp = Tq = mk3(0.f, 0.f, 0.f);
+	}
+	// site codes: coefficient along a1, or "backbone" handled by the *_k variants
+	OXB_HD void site_aa(v3 f, float cp, float cq) { F += f; axpy(Pa, cp, f); axpy(Qa, cq, f); }
+	OXB_HD void site_ak(v3 f, float cp) { F += f; axpy(Pa, cp, f); Qk += f; }
+	OXB_HD void site_ka(v3 f, float cq) { F += f; Pk += f; axpy(Qa, cq, f); }
+	OXB_HD void site_kk(v3 f) { F += f; Pk += f; Qk += f; }
+	// lab-frame torques including lever arms
+	OXB_HD v3 torque_p(const Axes &A, v3 pback) const { return Tp - cross(A.a1, Pa) - cross(pback, Pk); }
+	OXB_HD v3 torque_q(const Axes &B, v3 qback) const { return Tq + cross(B.a1, Qa) + cross(qback, Qk); }
+};
+
+struct Angle {
+	float c, s;
+	v3 x; // u cross v
+};
+
+OXB_HD Angle make_angle(v3 u, v3 v) {
+	Angle a;
+	a.c = dot(u, v);
+	a.x = cross(u, v);
+	a.s = sqrtf(dot(a.x, a.x));
+	return a;
+}
+
+// chain rule, c = u.v with u on p and v on q, g = dE/dc
+OXB_HD void chain_bb(PairAcc &A, float g, const Angle &a) {
+	axpy(A.Tp, -g, a.x);
+	axpy(A.Tq, g, a.x);
+}
+// chain rule, c = u.rhat; returns the site force (on q) -g (u - c rhat) / r; pure torque goes to the owner of u
+template<bool ON_Q>
+OXB_HD v3 chain_bd(PairAcc &A, float g, v3 u, v3 rhat, float inv_r, const Angle &a) {
+	if(ON_Q) axpy(A.Tq, -g, a.x);
+	else axpy(A.Tp, -g, a.x);
+	return (u - rhat * a.c) * (-g * inv_r);
+}
+
+struct PairEnergy {
+	float total, hb;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Non-bonded pair.  r = min-image(q - p) between centres of mass.  Terms: excluded volume (4 site pairs),
+// hydrogen bonding, cross stacking, coaxial stacking (oxDNA2 form), Debye-Hueckel.
+// ---------------------------------------------------------------------------------------------------------------
+OXB_HD PairEnergy dna2_nonbonded(const oxb_dna2_params &M, v3 r, const Axes &A, const Axes &B, int btp, int btq,
+		bool p_end, bool q_end, v3 pback, v3 qback, PairAcc &acc) {
+	PairEnergy E;
+	E.total = 0.f;
+	E.hb = 0.f;
+
+	float r2 = dot(r, r);
+	if(r2 >= M.rcut * M.rcut) return E; // DNA2Interaction.cpp:46-48
+
+	// ---- Debye-Hueckel + back-back excluded volume on the backbone-backbone vector
+	v3 rbb = r + qback - pback;
+	float rbb2 = dot(rbb, rbb);
+	if(rbb2 < M.dh_rc * M.dh_rc) {
+		float m = sqrtf(rbb2);
+		float cut = 1.f;
+		if(M.dh_half_charged_ends) {
+			if(p_end) cut *= 0.5f;
+			if(q_end) cut *= 0.5f;
+		}
+		float en, fs; // force on q = fs * rhat
+		if(m < M.dh_rhigh) {
+			float ex = expf(m * M.dh_minus_kappa) * M.dh_prefactor / m;
+			en = ex;
+			fs = -ex * (M.dh_minus_kappa - 1.f / m);
+		}
+		else {
+			float x = m - M.dh_rc;
+			en = M.dh_b * x * x;
+			fs = -2.f * M.dh_b * x;
+		}
+		E.total += en * cut;
+		acc.site_kk(rbb * (fs * cut / m));
+	}
+
+	if(r2 >= M.rcut_near * M.rcut_near) return E;
+
+	const float cb = M.base_a1, cs = M.stack_a1;
+	float s;
+	float en = excl_s(M.excl[0], M.excl_eps, rbb, s);
+	if(en != 0.f) { E.total += en; acc.site_kk(rbb * s); }
+
+	v3 pbase = A.a1 * cb, qbase = B.a1 * cb;
+	v3 rb = r + qbase - pbase; // base-base, shared by excluded volume, HB and cross stacking
+	en = excl_s(M.excl[1], M.excl_eps, rb, s);
+	if(en != 0.f) { E.total += en; acc.site_aa(rb * s, cb, cb); }
+	{
+		v3 d = r + qbase - pback; // back(p) - base(q)
+		en = excl_s(M.excl[3], M.excl_eps, d, s);
+		if(en != 0.f) { E.total += en; acc.site_ka(d * s, cb); }
+		d = r + qback - pbase; // base(p) - back(q)
+		en = excl_s(M.excl[2], M.excl_eps, d, s);
+		if(en != 0.f) { E.total += en; acc.site_ak(d * s, cb); }
+	}
+
+	// ---- hydrogen bonding + cross stacking (same six angles on the base-base vector)
+	float rbm2 = dot(rb, rb);
+	bool hb_on = (btp + btq == 3) && rbm2 > M.hb.rclow * M.hb.rclow && rbm2 < M.hb.rchigh * M.hb.rchigh;
+	bool cr_on = rbm2 > M.crst.rclow * M.crst.rclow && rbm2 < M.crst.rchigh * M.crst.rchigh;
+	if(hb_on || cr_on) {
+		float m = sqrtf(rbm2);
+		float inv = 1.f / m;
+		v3 h = rb * inv;
+		Angle t1 = make_angle(-A.a1, B.a1);
+		Angle t2 = make_angle(-B.a1, h);
+		Angle t3 = make_angle(A.a1, h);
+		Angle t4 = make_angle(A.a3, B.a3);
+		Angle t7 = make_angle(-B.a3, h);
+		Angle t8 = make_angle(A.a3, h);
+		float g1 = 0.f, g2 = 0.f, g3 = 0.f, g4 = 0.f, g7 = 0.f, g8 = 0.f, grad = 0.f;
+		if(hb_on) {
+			int ti = btype_to_type(btq) * 5 + btype_to_type(btp);
+			float mult = (abs(btq) >= 300 && abs(btp) >= 300) ? M.hb_multiplier : 1.f;
+			RadVal f1 = f1_r(M.hb, M.hb_eps[ti], M.hb_shift[ti], m);
+			f1.v *= mult;
+			f1.d *= mult;
+			AngVal a1 = f4_cs(M.f4[OXB_F4_HB_T1], t1.c, t1.s);
+			AngVal a2 = f4_cs(M.f4[OXB_F4_HB_T2], t2.c, t2.s);
+			AngVal a3 = f4_cs(M.f4[OXB_F4_HB_T2], t3.c, t3.s);
+			AngVal a4 = f4_cs(M.f4[OXB_F4_HB_T4], t4.c, t4.s);
+			AngVal a7 = f4_cs(M.f4[OXB_F4_HB_T7], t7.c, t7.s);
+			AngVal a8 = f4_cs(M.f4[OXB_F4_HB_T7], t8.c, t8.s);
+			float p12 = a1.v * a2.v, p34 = a3.v * a4.v, p78 = a7.v * a8.v;
+			float ang = p12 * p34 * p78;
+			float e = f1.v * ang;
+			if(e != 0.f) {
+				E.total += e;
+				E.hb += e;
+				grad += f1.d * ang;
+				float f34_78 = f1.v * p34 * p78, f12_78 = f1.v * p12 * p78, f12_34 = f1.v * p12 * p34;
+				g1 += f34_78 * a1.dc * a2.v;
+				g2 += f34_78 * a1.v * a2.dc;
+				g3 += f12_78 * a3.dc * a4.v;
+				g4 += f12_78 * a3.v * a4.dc;
+				g7 += f12_34 * a7.dc * a8.v;
+				g8 += f12_34 * a7.v * a8.dc;
+			}
+		}
+		if(cr_on) {
+			RadVal f2 = f2_r(M.crst, m);
+			AngVal a1 = f4_cs(M.f4[OXB_F4_CRST_T1], t1.c, t1.s);
+			AngVal a2 = f4_cs(M.f4[OXB_F4_CRST_T2], t2.c, t2.s);
+			AngVal a3 = f4_cs(M.f4[OXB_F4_CRST_T2], t3.c, t3.s);
+			AngVal a4 = f4_cs_sym(M.f4[OXB_F4_CRST_T4], t4.c, t4.s);
+			AngVal a7 = f4_cs_sym(M.f4[OXB_F4_CRST_T7], t7.c, t7.s);
+			AngVal a8 = f4_cs_sym(M.f4[OXB_F4_CRST_T7], t8.c, t8.s);
+			float p12 = a1.v * a2.v, p34 = a3.v * a4.v, p78 = a7.v * a8.v;
+			float ang = p12 * p34 * p78;
+			float e = f2.v * ang;
+			if(e != 0.f) {
+				E.total += e;
+				grad += f2.d * ang;
+				float f34_78 = f2.v * p34 * p78, f12_78 = f2.v * p12 * p78, f12_34 = f2.v * p12 * p34;
+				g1 += f34_78 * a1.dc * a2.v;
+				g2 += f34_78 * a1.v * a2.dc;
+				g3 += f12_78 * a3.dc * a4.v;
+				g4 += f12_78 * a3.v * a4.dc;
+				g7 += f12_34 * a7.dc * a8.v;
+				g8 += f12_34 * a7.v * a8.dc;
+			}
+		}
+		v3 f = h * (-grad);
+		chain_bb(acc, g1, t1);
+		f += chain_bd<true>(acc, g2, -B.a1, h, inv, t2);
+		f += chain_bd<false>(acc, g3, A.a1, h, inv, t3);
+		chain_bb(acc, g4, t4);
+		f += chain_bd<true>(acc, g7, -B.a3, h, inv, t7);
+		f += chain_bd<false>(acc, g8, A.a3, h, inv, t8);
+		acc.site_aa(f, cb, cb);
+	}
+
+	// ---- coaxial stacking (oxDNA2: no phi3 term, harmonic add-on to theta1)
+	v3 rs = r + B.a1 * cs - A.a1 * cs;
+	float rs2 = dot(rs, rs);
+	if(rs2 > M.cxst.rclow * M.cxst.rclow && rs2 < M.cxst.rchigh * M.cxst.rchigh) {
+		float m = sqrtf(rs2);
+		float inv = 1.f / m;
+		v3 h = rs * inv;
+		Angle t1 = make_angle(-A.a1, B.a1);
+		Angle t4 = make_angle(A.a3, B.a3);
+		Angle t5 = make_angle(A.a3, h);
+		Angle t6 = make_angle(-B.a3, h);
+		RadVal f2 = f2_r(M.cxst, m);
+		AngVal a1 = f4_cs_cxst_t1(M, t1.c, t1.s);
+		AngVal a4 = f4_cs(M.f4[OXB_F4_CXST_T4], t4.c, t4.s);
+		AngVal a5 = f4_cs_sym(M.f4[OXB_F4_CXST_T5], t5.c, t5.s);
+		AngVal a6 = f4_cs_sym(M.f4[OXB_F4_CXST_T5], t6.c, t6.s);
+		float p14 = a1.v * a4.v, p56 = a5.v * a6.v;
+		float e = f2.v * p14 * p56;
+		if(e != 0.f) {
+			E.total += e;
+			v3 f = h * (-(f2.d * p14 * p56));
+			chain_bb(acc, f2.v * p56 * a1.dc * a4.v, t1);
+			chain_bb(acc, f2.v * p56 * a1.v * a4.dc, t4);
+			f += chain_bd<false>(acc, f2.v * p14 * a5.dc * a6.v, A.a3, h, inv, t5);
+			f += chain_bd<true>(acc, f2.v * p14 * a5.v * a6.dc, -B.a3, h, inv, t6);
+			acc.site_aa(f, cs, cs);
+		}
+	}
+	return E;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Bonded pair p -> q = n3(p).  r = q - p.  Terms: FENE backbone, bonded excluded volume (3 site pairs), stacking.
+// Returns energy; sets *broken when the bond is outside the FENE range (reference throws; we flag).
+// ---------------------------------------------------------------------------------------------------------------
+OXB_HD float dna2_bonded(const oxb_dna2_params &M, v3 r, const Axes &A, const Axes &B, int btp, int btq, v3 pback,
+		v3 qback, PairAcc &acc, bool &broken) {
+	float E = 0.f;
+	const float cb = M.base_a1, cs = M.stack_a1, cr = M.backref_a1;
+
+	// FENE
+	{
+		v3 d = r + qback - pback;
+		float m = sqrtf(dot(d, d));
+		float x = m - M.fene_r0;
+		float en, s;
+		if(M.use_mbf && fabsf(x) > M.mbf_xmax) {
+			float ax = fabsf(x);
+			float k = (M.mbf_fmax - M.mbf_finf) * M.mbf_xmax;
+			en = k * logf(ax) + M.mbf_finf * ax + M.mbf_e0;
+			s = -copysignf(1.f, x) * (k / ax + M.mbf_finf) / m;
+		}
+		else {
+			float den = M.fene_delta2 - x * x;
+			if(den <= 0.f) {
+				broken = true;
+				den = 1e-6f;
+			}
+			en = -0.5f * M.fene_eps * logf(den / M.fene_delta2);
+			s = -(M.fene_eps * x / den) / m;
+		}
+		E += en;
+		acc.site_kk(d * s);
+	}
+	// bonded excluded volume
+	{
+		float s;
+		v3 pbase = A.a1 * cb, qbase = B.a1 * cb;
+		v3 d = r + qbase - pbase;
+		float en = excl_s(M.excl[1], M.excl_eps, d, s);
+		if(en != 0.f) { E += en; acc.site_aa(d * s, cb, cb); }
+		d = r + qback - pbase;
+		en = excl_s(M.excl[2], M.excl_eps, d, s);
+		if(en != 0.f) { E += en; acc.site_ak(d * s, cb); }
+		d = r + qbase - pback;
+		en = excl_s(M.excl[3], M.excl_eps, d, s);
+		if(en != 0.f) { E += en; acc.site_ka(d * s, cb); }
+	}
+	// stacking
+	{
+		v3 rs = r + B.a1 * cs - A.a1 * cs;
+		float m = sqrtf(dot(rs, rs));
+		int ti = btype_to_type(btq) * 5 + btype_to_type(btp);
+		RadVal f1 = f1_r(M.stck, M.stck_eps[ti], M.stck_shift[ti], m);
+		if(f1.v != 0.f || f1.d != 0.f) {
+			float inv = 1.f / m;
+			v3 h = rs * inv;
+			v3 w = r + B.a1 * cr - A.a1 * cr;
+			float wm = sqrtf(dot(w, w));
+			float winv = 1.f / wm;
+			v3 wh = w * winv;
+			Angle t4 = make_angle(A.a3, B.a3);
+			Angle t5 = make_angle(-A.a3, h);
+			Angle t6 = make_angle(-B.a3, h);
+			Angle p1 = make_angle(A.a2, wh);
+			Angle p2 = make_angle(B.a2, wh);
+			AngVal a4 = f4_cs(M.f4[OXB_F4_STCK_T4], t4.c, t4.s);
+			AngVal a5 = f4_cs(M.f4[OXB_F4_STCK_T5], t5.c, t5.s);
+			AngVal a6 = f4_cs(M.f4[OXB_F4_STCK_T5], t6.c, t6.s);
+			AngVal b1 = f5_c(M.phi1, p1.c);
+			AngVal b2 = f5_c(M.phi2, p2.c);
+			float p456 = a4.v * a5.v * a6.v, pb = b1.v * b2.v;
+			float e = f1.v * p456 * pb;
+			if(e != 0.f) {
+				E += e;
+				v3 f = h * (-(f1.d * p456 * pb));
+				float fb = f1.v * pb;
+				chain_bb(acc, fb * a4.dc * a5.v * a6.v, t4);
+				f += chain_bd<false>(acc, fb * a4.v * a5.dc * a6.v, -A.a3, h, inv, t5);
+				f += chain_bd<true>(acc, fb * a4.v * a5.v * a6.dc, -B.a3, h, inv, t6);
+				acc.site_aa(f, cs, cs);
+				float fa = f1.v * p456;
+				v3 fw = chain_bd<false>(acc, fa * b1.dc * b2.v, A.a2, wh, winv, p1);
+				fw += chain_bd<true>(acc, fa * b1.v * b2.dc, B.a2, wh, winv, p2);
+				acc.site_aa(fw, cr, cr);
+			}
+		}
+	}
+	return E;
+}

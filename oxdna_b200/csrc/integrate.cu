@@ -1,0 +1,286 @@
+// Velocity-Verlet quaternion integrator + thermostats, one fused streaming kernel (sm_100a, HBM-bound).
+//
+// Reference: first_step_mixed / second_step_mixed (src/CUDA/Backends/CUDA_mixed.cuh:8-93), brownian_thermostat
+// (src/CUDA/Thermostats/CUDABrownianThermostat.cu:15-51), langevin_thermostat (CUDALangevinThermostat.cu:14-40),
+// bussi_thermostat + host-side K update (CUDABussiThermostat.cu:55-122, src/Backends/Thermostats/BussiThermostat.cpp:45-150).
+//
+// Differences by design:
+//  * the second half-kick of step n, the thermostat of step n and the first half-kick + drift + rotation of step n+1
+//    act on the same per-particle data with the same forces, so they are ONE pass over the FP64 state instead of
+//    three (the reference streams velocities/momenta 3x and converts precision around the thermostat);
+//  * RNG is counter-based Philox keyed by (seed, original particle id, step): no 48-byte curandState per particle;
+//  * the Bussi kinetic-energy dynamics runs on the device (one warp), no host round trip;
+//  * list staleness raises a device flag that turns the rest of a speculative batch of launches into no-ops.
+#include "kernels.h"
+
+namespace {
+
+__device__ __forceinline__ void philox_gauss4(unsigned long long seed, unsigned id, unsigned long long step, unsigned draw, float g[4]) {
+	uint4 ctr = make_uint4(id, (unsigned) step, (unsigned) (step >> 32), draw);
+	uint2 key = make_uint2((unsigned) seed, (unsigned) (seed >> 32));
+	uint4 r = Philox::gen(ctr, key);
+	float u0 = u01(r.x), u1 = u01(r.y), u2 = u01(r.z), u3 = u01(r.w);
+	float m0 = sqrtf(-2.f * logf(u0)), m1 = sqrtf(-2.f * logf(u2));
+	float s0, c0, s1, c1;
+	sincospif(2.f * u1, &s0, &c0);
+	sincospif(2.f * u3, &s1, &c1);
+	g[0] = m0 * c0; g[1] = m0 * s0; g[2] = m1 * c1; g[3] = m1 * s1;
+}
+
+__device__ __forceinline__ uint4 philox_u4(unsigned long long seed, unsigned id, unsigned long long step, unsigned draw) {
+	return Philox::gen(make_uint4(id, (unsigned) step, (unsigned) (step >> 32), draw), make_uint2((unsigned) seed, (unsigned) (seed >> 32)));
+}
+
+template<int PH>
+__global__ void __launch_bounds__(256) k_integrate(oxb::IntegrateArgs a, int epoch) {
+	int *flags = a.flags;
+	const int rd = OXB_FLAG_COUNT + (epoch & 1), wr = OXB_FLAG_COUNT + ((epoch + 1) & 1);
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(flags[rd]) { // halted earlier in this batch: stay halted (sticky), do nothing
+		if(i == 0) flags[wr] = 1;
+		return;
+	}
+	if(i == 0 && (PH & OXB_PH_COUNT_STEP)) atomicAdd(flags + OXB_FLAG_STEPS_DONE, 1);
+
+	double sv[5] = { 0., 0., 0., 0., 0. };
+	if(i < a.N) {
+		const double hdt = 0.5 * a.dt;
+		float4 F = a.F[i], T = a.T[i];
+		double4 v = a.veld[i], L = a.Ld[i];
+		if(PH & OXB_PH_SECOND) {
+			v.x += F.x * hdt; v.y += F.y * hdt; v.z += F.z * hdt;
+			L.x += T.x * hdt; L.y += T.y * hdt; L.z += T.z * hdt;
+		}
+		if(PH & OXB_PH_BUSSI_SUMS) {
+			sv[0] = v.x; sv[1] = v.y; sv[2] = v.z;
+			sv[3] = v.x * v.x + v.y * v.y + v.z * v.z;
+			sv[4] = L.x * L.x + L.y * L.y + L.z * L.z;
+		}
+		if(PH & OXB_PH_BUSSI_APPLY) {
+			const KinSums S = *a.sums;
+			double cx = S.vx / a.N, cy = S.vy / a.N, cz = S.vz / a.N;
+			v.x = (v.x - cx) * S.factor_t + cx; v.y = (v.y - cy) * S.factor_t + cy; v.z = (v.z - cz) * S.factor_t + cz;
+			L.x *= S.factor_r; L.y *= S.factor_r; L.z *= S.factor_r;
+		}
+		if(PH & OXB_PH_THERMO) {
+			unsigned id = (unsigned) word_index(a.ipos[i].w);
+			if(a.th.type == OXB_THERMOSTAT_BROWNIAN) {
+				uint4 u = philox_u4(a.th.seed, id, (unsigned long long) a.step, 0u);
+				bool rt = u01(u.x) < a.th.a, rr = u01(u.y) < a.th.b;
+				if(rt || rr) {
+					float g0[4], g1[4];
+					philox_gauss4(a.th.seed, id, (unsigned long long) a.step, 1u, g0);
+					philox_gauss4(a.th.seed, id, (unsigned long long) a.step, 2u, g1);
+					if(rt) { v.x = g0[0] * a.th.c; v.y = g0[1] * a.th.c; v.z = g0[2] * a.th.c; }
+					if(rr) { L.x = g1[0] * a.th.c; L.y = g1[1] * a.th.c; L.z = g1[2] * a.th.c; }
+				}
+			}
+			else if(a.th.type == OXB_THERMOSTAT_LANGEVIN) {
+				float g0[4], g1[4];
+				philox_gauss4(a.th.seed, id, (unsigned long long) a.step, 1u, g0);
+				philox_gauss4(a.th.seed, id, (unsigned long long) a.step, 2u, g1);
+				double dt = a.dt;
+				v.x += dt * (-a.th.a * v.x + g0[0] * a.th.c); v.y += dt * (-a.th.a * v.y + g0[1] * a.th.c); v.z += dt * (-a.th.a * v.z + g0[2] * a.th.c);
+				L.x += dt * (-a.th.b * L.x + g1[0] * a.th.d); L.y += dt * (-a.th.b * L.y + g1[1] * a.th.d); L.z += dt * (-a.th.b * L.z + g1[2] * a.th.d);
+			}
+		}
+		if(PH & OXB_PH_FIRST) {
+			v.x += F.x * hdt; v.y += F.y * hdt; v.z += F.z * hdt;
+			L.x += T.x * hdt; L.y += T.y * hdt; L.z += T.z * hdt;
+			double4 r = a.posd[i];
+			r.x += v.x * a.dt; r.y += v.y * a.dt; r.z += v.z * a.dt;
+			a.posd[i] = r;
+			int4 ip = a.ipos[i];
+			ip.x = (int) to_fixed(r.x, a.box_inv[0]); ip.y = (int) to_fixed(r.y, a.box_inv[1]); ip.z = (int) to_fixed(r.z, a.box_inv[2]);
+			a.ipos[i] = ip;
+			// body-frame rotation by |L| dt about L: q <- q (x) (Lhat sin(th/2), cos(th/2))
+			double n2 = L.x * L.x + L.y * L.y + L.z * L.z;
+			if(n2 > 0.) {
+				double n = sqrt(n2), sh, ch;
+				sincos(0.5 * a.dt * n, &sh, &ch);
+				double k = sh / n;
+				double bx = L.x * k, by = L.y * k, bz = L.z * k, bw = ch;
+				double4 q = a.quatd[i], o;
+				o.w = q.w * bw - q.x * bx - q.y * by - q.z * bz;
+				o.x = q.w * bx + q.x * bw + q.y * bz - q.z * by;
+				o.y = q.w * by - q.x * bz + q.y * bw + q.z * bx;
+				o.z = q.w * bz + q.x * by - q.y * bx + q.z * bw;
+				a.quatd[i] = o;
+				a.quat[i] = make_float4((float) o.x, (float) o.y, (float) o.z, (float) o.w);
+			}
+			v3 d = min_image_fixed(a.box, a.list_ipos[i], ip);
+			if(dot(d, d) > a.skin2) flags[wr] = 1;
+		}
+		a.veld[i] = v;
+		a.Ld[i] = L;
+	}
+	if(PH & OXB_PH_BUSSI_SUMS) {
+		__shared__ double sh[5][8];
+#pragma unroll
+		for(int c = 0; c < 5; c++) {
+			double x = sv[c];
+			for(int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+			if((threadIdx.x & 31) == 0) sh[c][threadIdx.x >> 5] = x;
+		}
+		__syncthreads();
+		if(threadIdx.x < 5) {
+			double x = 0.;
+			for(int w = 0; w < (int) (blockDim.x >> 5); w++) x += sh[threadIdx.x][w];
+			double *dst = &a.sums->vx + threadIdx.x;
+			atomicAdd(dst, x);
+		}
+	}
+}
+
+// ---- Bussi stochastic velocity rescaling, kinetic-energy dynamics (BussiThermostat.cpp:45-52,105-150) on one thread.
+struct SerialRng {
+	unsigned long long seed, step;
+	unsigned draw;
+	__device__ float gauss() {
+		float g[4];
+		philox_gauss4(seed, 0xFFFFFFFFu, step, draw++, g);
+		return g[0];
+	}
+	__device__ float unif() {
+		uint4 u = philox_u4(seed, 0xFFFFFFFEu, step, draw++);
+		return u01(u.x);
+	}
+	// Gamma(k, 1), Marsaglia-Tsang (k >= 1) -- same distribution as the reference's gamdev(ia) for integer ia
+	__device__ double gamma(double k) {
+		double d = k - 1. / 3., c = 1. / sqrt(9. * d);
+		for(int it = 0; it < 64; it++) {
+			double x = gauss(), v = 1. + c * x;
+			if(v <= 0.) continue;
+			v = v * v * v;
+			double u = unif();
+			if(log(u) < 0.5 * x * x + d - d * v + d * log(v)) return d * v;
+		}
+		return d;
+	}
+	// sum of nn squared standard normals
+	__device__ double sum_noises(int nn) {
+		if(nn == 0) return 0.;
+		if(nn == 1) { double r = gauss(); return r * r; }
+		if(nn % 2 == 0) return 2. * gamma(nn / 2);
+		double r = gauss();
+		return 2. * gamma((nn - 1) / 2) + r * r;
+	}
+};
+
+__device__ void bussi_update_K(SerialRng &R, double &K, int dof, double T, double ex) {
+	double Kt = 0.5 * dof * T;
+	double rr = R.gauss();
+	double dK = (1.0 - ex) * (Kt * (R.sum_noises(dof - 1) + rr * rr) / dof - K) + 2.0 * rr * sqrt(K * Kt / dof * (1.0 - ex) * ex);
+	K += dK;
+}
+
+__global__ void k_bussi_update(KinSums *S, int N, ThermostatCfg th, long long step, const int *flags, int epoch) {
+	if(flags[OXB_FLAG_COUNT + (epoch & 1)]) return;
+	if(threadIdx.x != 0 || blockIdx.x != 0) return;
+	SerialRng R;
+	R.seed = th.seed; R.step = (unsigned long long) step; R.draw = 16;
+	double T = th.a, ex = th.b;
+	int dof_t = 3 * (N - 1), dof_r = 3 * N;
+	double cx = S->vx / N, cy = S->vy / N, cz = S->vz / N;
+	double Know_t = 0.5 * (S->v2 - N * (cx * cx + cy * cy + cz * cz));
+	double Know_r = 0.5 * S->L2;
+	double Kt = S->K_t, Kr = S->K_r;
+	bussi_update_K(R, Kt, dof_t, T, ex);
+	bussi_update_K(R, Kr, dof_r, T, ex);
+	S->K_t = Kt; S->K_r = Kr;
+	S->factor_t = sqrt(Kt / Know_t);
+	S->factor_r = sqrt(Kr / Know_r);
+}
+
+__global__ void k_clear_sums(KinSums *S, const int *flags, int epoch) {
+	if(epoch >= 0 && flags[OXB_FLAG_COUNT + (epoch & 1)]) return;
+	S->vx = S->vy = S->vz = S->v2 = S->L2 = 0.;
+}
+
+__global__ void __launch_bounds__(256) k_kinetic_sums(int N, const double4 *__restrict__ veld, const double4 *__restrict__ Ld, KinSums *S) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	double sv[5] = { 0., 0., 0., 0., 0. };
+	if(i < N) {
+		double4 v = veld[i], L = Ld[i];
+		sv[0] = v.x; sv[1] = v.y; sv[2] = v.z;
+		sv[3] = v.x * v.x + v.y * v.y + v.z * v.z;
+		sv[4] = L.x * L.x + L.y * L.y + L.z * L.z;
+	}
+	__shared__ double sh[5][8];
+#pragma unroll
+	for(int c = 0; c < 5; c++) {
+		double x = sv[c];
+		for(int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+		if((threadIdx.x & 31) == 0) sh[c][threadIdx.x >> 5] = x;
+	}
+	__syncthreads();
+	if(threadIdx.x < 5) {
+		double x = 0.;
+		for(int w = 0; w < (int) (blockDim.x >> 5); w++) x += sh[threadIdx.x][w];
+		atomicAdd(&S->vx + threadIdx.x, x);
+	}
+}
+
+__global__ void __launch_bounds__(256) k_energy_sum(int N, const float4 *__restrict__ F, double *out) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	double x = (i < N) ? (double) F[i].w : 0.;
+	for(int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+	__shared__ double sh[8];
+	if((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = x;
+	__syncthreads();
+	if(threadIdx.x == 0) {
+		double s = 0.;
+		for(int w = 0; w < (int) (blockDim.x >> 5); w++) s += sh[w];
+		atomicAdd(out, s);
+	}
+}
+
+template<int PH>
+void launch_ph(cudaStream_t s, const oxb::IntegrateArgs &a, int epoch) {
+	int tpb = 256;
+	k_integrate<PH><<<(a.N + tpb - 1) / tpb, tpb, 0, s>>>(a, epoch);
+}
+
+} // namespace
+
+namespace oxb {
+
+// `phases` selects one of the instantiated variants; `epoch` is the running launch index inside the batch
+void launch_integrate_epoch(cudaStream_t s, const IntegrateArgs &a, int phases, int epoch) {
+	switch(phases) {
+	case OXB_PH_FIRST: launch_ph<OXB_PH_FIRST>(s, a, epoch); break;
+	case OXB_PH_SECOND | OXB_PH_COUNT_STEP: launch_ph<OXB_PH_SECOND | OXB_PH_COUNT_STEP>(s, a, epoch); break;
+	case OXB_PH_SECOND | OXB_PH_THERMO | OXB_PH_COUNT_STEP: launch_ph<OXB_PH_SECOND | OXB_PH_THERMO | OXB_PH_COUNT_STEP>(s, a, epoch); break;
+	case OXB_PH_SECOND | OXB_PH_FIRST | OXB_PH_COUNT_STEP: launch_ph<OXB_PH_SECOND | OXB_PH_FIRST | OXB_PH_COUNT_STEP>(s, a, epoch); break;
+	case OXB_PH_SECOND | OXB_PH_THERMO | OXB_PH_FIRST | OXB_PH_COUNT_STEP:
+		launch_ph<OXB_PH_SECOND | OXB_PH_THERMO | OXB_PH_FIRST | OXB_PH_COUNT_STEP>(s, a, epoch);
+		break;
+	case OXB_PH_SECOND | OXB_PH_BUSSI_SUMS | OXB_PH_COUNT_STEP: launch_ph<OXB_PH_SECOND | OXB_PH_BUSSI_SUMS | OXB_PH_COUNT_STEP>(s, a, epoch); break;
+	case OXB_PH_BUSSI_APPLY: launch_ph<OXB_PH_BUSSI_APPLY>(s, a, epoch); break;
+	case OXB_PH_BUSSI_APPLY | OXB_PH_FIRST: launch_ph<OXB_PH_BUSSI_APPLY | OXB_PH_FIRST>(s, a, epoch); break;
+	case OXB_PH_THERMO: launch_ph<OXB_PH_THERMO>(s, a, epoch); break;
+	default: break;
+	}
+}
+
+void launch_bussi_update_epoch(cudaStream_t s, KinSums *sums, int N, ThermostatCfg th, long long step, const int *flags, int epoch) {
+	k_bussi_update<<<1, 32, 0, s>>>(sums, N, th, step, flags, epoch);
+}
+
+void launch_clear_sums(cudaStream_t s, KinSums *sums, const int *flags, int epoch) {
+	k_clear_sums<<<1, 1, 0, s>>>(sums, flags, epoch);
+}
+
+void launch_kinetic_sums(cudaStream_t s, int N, const double4 *veld, const double4 *Ld, KinSums *sums) {
+	k_clear_sums<<<1, 1, 0, s>>>(sums, nullptr, -1);
+	int tpb = 256;
+	k_kinetic_sums<<<(N + tpb - 1) / tpb, tpb, 0, s>>>(N, veld, Ld, sums);
+}
+
+void launch_energy_sum(cudaStream_t s, int N, const float4 *F, double *out) {
+	cudaMemsetAsync(out, 0, sizeof(double), s);
+	int tpb = 256;
+	k_energy_sum<<<(N + tpb - 1) / tpb, tpb, 0, s>>>(N, F, out);
+}
+
+} // namespace oxb

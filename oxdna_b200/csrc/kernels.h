@@ -1,0 +1,135 @@
+// Internal launch interface between the context (context.cu) and the kernel translation units.
+#pragma once
+
+#include "common.cuh"
+
+// device-side control words (one int array per context)
+enum : int {
+	OXB_FLAG_UNUSED0 = 0,
+	OXB_FLAG_ERROR = 1,      // OXB_ERR_* bits
+	OXB_FLAG_STEPS_DONE = 2, // full steps completed inside the current batch
+	OXB_FLAG_PENDING = 3,    // 1 = positions of step `STEPS_DONE` are already advanced, forces not yet computed
+	OXB_FLAG_MAX_NEIGH_SEEN = 4,
+	// Two "halt" words, [OXB_FLAG_COUNT + 0/1].  The integrator launch with running index e reads word (e & 1) and may set
+	// word ((e + 1) & 1) when a particle has moved further than the skin; every kernel launched after it reads that word
+	// and turns into a no-op, so a speculative batch of launches stops at the step that needs a list rebuild without any
+	// host synchronisation inside the batch.  No kernel ever reads a word that it can write itself.
+	OXB_FLAG_COUNT = 8,
+	OXB_FLAG_WORDS = 16,
+};
+
+struct DevExtForce {
+	int type, particle, ref, pbc;
+	float stiff, r0, rate, stiff_rate, F0;
+	float dir[3];
+	double pos0[3];
+};
+
+struct ThermostatCfg {
+	int type;
+	int every;
+	float a, b, c, d; // see oxb_set_thermostat
+	unsigned long long seed;
+};
+
+// sums for the Bussi thermostat and for kinetic-energy read-back (doubles, atomically accumulated per block)
+struct KinSums {
+	double vx, vy, vz; // sum of velocities
+	double v2;         // sum |v|^2
+	double L2;         // sum |L|^2
+	double factor_t, factor_r; // Bussi rescale factors computed on device
+	double K_t, K_r;           // Bussi target kinetic energies (state)
+};
+
+// phases: bit 0 = second half-kick of step `step`, bit 1 = thermostat of step `step`, bit 2 = first half-kick + drift of step+1
+enum { OXB_PH_SECOND = 1, OXB_PH_THERMO = 2, OXB_PH_FIRST = 4, OXB_PH_BUSSI_SUMS = 8, OXB_PH_BUSSI_APPLY = 16, OXB_PH_COUNT_STEP = 32 };
+
+namespace oxb {
+
+// ---- forces.cu
+void launch_forces_particle(cudaStream_t s, const oxb_dna2_params &M, BoxF box, int N, const int4 *ipos, const float4 *quat, const int2 *bonds,
+		const int *nbr, const int *nnbr, int stride, float4 *F, float4 *T, int *flags, int hw);
+void launch_forces_edge(cudaStream_t s, const oxb_dna2_params &M, BoxF box, int N, const int *n_edges, int edge_capacity_hint, const int4 *ipos,
+		const float4 *quat, const int2 *bonds, const int2 *edges, float4 *F, float4 *T, int *flags, int hw, int n_sm);
+void launch_ext_forces(cudaStream_t s, int n, const DevExtForce *ef, const int *slot_of, const int4 *ipos, const double4 *posd, BoxF box,
+		long long step, float4 *F, const int *flags, int hw);
+
+// ---- integrate.cu
+struct IntegrateArgs {
+	int N;
+	double dt;
+	double box_inv[3];
+	float skin2;
+	BoxF box;
+	double4 *posd, *veld, *Ld, *quatd;
+	int4 *ipos;
+	float4 *quat;
+	const int4 *list_ipos;
+	const float4 *F, *T;
+	int *flags;
+	KinSums *sums;
+	ThermostatCfg th;
+	long long step; // step index of the thermostat application / of the first half-kick
+};
+void launch_integrate_epoch(cudaStream_t s, const IntegrateArgs &a, int phases, int epoch);
+void launch_bussi_update_epoch(cudaStream_t s, KinSums *sums, int N, ThermostatCfg th, long long step, const int *flags, int epoch);
+void launch_clear_sums(cudaStream_t s, KinSums *sums, const int *flags, int epoch);
+void launch_kinetic_sums(cudaStream_t s, int N, const double4 *veld, const double4 *Ld, KinSums *sums);
+void launch_energy_sum(cudaStream_t s, int N, const float4 *F, double *out);
+
+// ---- lists.cu
+struct ListArgs {
+	int N;
+	double box[3];
+	BoxF boxf;
+	int ncell[3];
+	double rv;      // Verlet radius rcut + 2 skin (double: the exact predicate)
+	const double4 *posd;
+	const int4 *ipos;
+	const int2 *bonds;
+	int *cell_key, *cell_key_sorted, *cell_val, *cell_val_sorted, *cell_start; // N, N, N, N, ncells + 1
+	int *nbr, *nnbr;
+	int max_neigh, stride;
+	int2 *edges;
+	int *edge_offsets; // N + 1
+	int *n_edges;
+	long long edge_capacity;
+	int4 *list_ipos;
+	int *flags;
+	void *cub_tmp;
+	size_t cub_tmp_bytes;
+	bool build_edges;
+};
+size_t lists_tmp_bytes(int N, int ncells);
+void launch_build_lists(cudaStream_t s, const ListArgs &a);
+
+// ---- sort.cu
+struct SortArgs {
+	int N;
+	double box[3];
+	const double4 *posd;
+	unsigned *keys, *keys_sorted;
+	int *vals, *vals_sorted; // vals_sorted[new_slot] = old_slot
+	int *inv;                // inv[old_slot] = new_slot
+	void *cub_tmp;
+	size_t cub_tmp_bytes;
+};
+size_t sort_tmp_bytes(int N);
+void launch_hilbert_order(cudaStream_t s, const SortArgs &a);
+struct PermuteArgs {
+	int N;
+	const int *perm; // perm[new] = old
+	const int *inv;  // inv[old] = new
+	const double4 *posd_in, *veld_in, *Ld_in, *quatd_in;
+	double4 *posd_out, *veld_out, *Ld_out, *quatd_out;
+	const int4 *ipos_in, *list_ipos_in;
+	int4 *ipos_out, *list_ipos_out;
+	const float4 *quat_in, *F_in, *T_in;
+	float4 *quat_out, *F_out, *T_out;
+	const int2 *bonds_in;
+	int2 *bonds_out;
+	int *slot_of; // slot_of[original id] = new slot
+};
+void launch_permute(cudaStream_t s, const PermuteArgs &a);
+
+} // namespace oxb

@@ -1,0 +1,158 @@
+// Cell-binned Verlet list construction (sm_100a, HBM/L2-bound integer work).
+//
+// Replaces CUDASimpleVerletList::update and its kernels simple_fill_cells, simple_update_neigh_list,
+// edge_update_neigh_list, compress_matrix_neighs (src/CUDA/Lists/CUDASimpleVerletList.cu:231-289,
+// src/CUDA/Lists/CUDA_simple_verlet.cuh:23-175).  Differences by design:
+//  * binning is a stable radix sort of (cell, slot) -> contiguous cell ranges, no fixed-capacity cells, no atomics,
+//    no overflow, deterministic neighbour order;
+//  * the distance predicate is decided in FP32 on fixed-point coordinates and re-decided in FP64 with the CPU's exact
+//    expression (src/Boxes/CubicBox.cpp:51-61, src/Lists/Cells.cpp:170) whenever it falls within a guard band of the
+//    cutoff, so the pair SET is bit-identical to the reference's CPU Verlet list built from the same FP64 positions;
+//  * neighbour rows are bounds-checked (the reference is not) and overflow raises a flag;
+//  * the unique-pair (edge) list is produced by an exclusive scan on the device, its length stays on the device.
+#include "kernels.h"
+
+#include <cub/cub.cuh>
+
+namespace {
+
+__device__ __forceinline__ int cell_coord(double x, double L, int n) {
+	// src/Lists/Cells.h:60-65
+	double f = x / L - floor(x / L);
+	int c = (int) (f * (1. - 2.220446049250313e-16) * n);
+	return min(c, n - 1);
+}
+
+__global__ void __launch_bounds__(256) k_cell_keys(int N, const double4 *__restrict__ posd, double Lx, double Ly, double Lz, int nx, int ny, int nz,
+		int *__restrict__ key, int *__restrict__ val) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= N) return;
+	double4 p = posd[i];
+	int cx = cell_coord(p.x, Lx, nx), cy = cell_coord(p.y, Ly, ny), cz = cell_coord(p.z, Lz, nz);
+	key[i] = cx + nx * (cy + ny * cz);
+	val[i] = i;
+}
+
+__global__ void __launch_bounds__(256) k_cell_ranges(int N, const int *__restrict__ key_sorted, int *__restrict__ cell_start, int *__restrict__ cell_end) {
+	int j = blockIdx.x * blockDim.x + threadIdx.x;
+	if(j >= N) return;
+	int k = key_sorted[j];
+	if(j == 0 || key_sorted[j - 1] != k) cell_start[k] = j;
+	if(j == N - 1 || key_sorted[j + 1] != k) cell_end[k] = j + 1;
+}
+
+__device__ __forceinline__ bool within_exact(double4 p, double4 q, double Lx, double Ly, double Lz, double rv2) {
+	double dx = q.x - p.x - rint((q.x - p.x) / Lx) * Lx;
+	double dy = q.y - p.y - rint((q.y - p.y) / Ly) * Ly;
+	double dz = q.z - p.z - rint((q.z - p.z) / Lz) * Lz;
+	// same association as LR_vector::norm(): x*x + y*y + z*z, no FMA contraction
+	double n = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+	return n < rv2;
+}
+
+// one thread per particle: visit the 27 surrounding cells, keep non-bonded particles closer than rv
+__global__ void __launch_bounds__(128) k_build_neigh(oxb::ListArgs a, const int *__restrict__ cell_start, const int *__restrict__ cell_end) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= a.N) return;
+	const int4 ip = a.ipos[i];
+	const int2 b = a.bonds[i];
+	const int nx = a.ncell[0], ny = a.ncell[1], nz = a.ncell[2];
+	const double4 pd = a.posd[i];
+	const int cx = cell_coord(pd.x, a.box[0], nx), cy = cell_coord(pd.y, a.box[1], ny), cz = cell_coord(pd.z, a.box[2], nz);
+	const float rv2f = (float) (a.rv * a.rv);
+	const float band = 1e-4f * rv2f;
+	const double rv2 = a.rv * a.rv;
+	int count = 0, higher = 0;
+	for(int dz = -1; dz <= 1; dz++) {
+		int zc = cz + dz; zc += (zc < 0) ? nz : 0; zc -= (zc >= nz) ? nz : 0;
+		for(int dy = -1; dy <= 1; dy++) {
+			int yc = cy + dy; yc += (yc < 0) ? ny : 0; yc -= (yc >= ny) ? ny : 0;
+			for(int dx = -1; dx <= 1; dx++) {
+				int xc = cx + dx; xc += (xc < 0) ? nx : 0; xc -= (xc >= nx) ? nx : 0;
+				int c = xc + nx * (yc + ny * zc);
+				int s = __ldg(cell_start + c), e = __ldg(cell_end + c);
+				for(int j = s; j < e; j++) {
+					int m = __ldg(a.cell_val_sorted + j);
+					if(m == i || m == b.x || m == b.y) continue;
+					v3 d = min_image_fixed(a.boxf, ip, __ldg(a.ipos + m));
+					float d2 = dot(d, d);
+					bool in = d2 < rv2f;
+					if(fabsf(d2 - rv2f) < band) in = within_exact(pd, a.posd[m], a.box[0], a.box[1], a.box[2], rv2);
+					if(in) {
+						if(count < a.max_neigh) a.nbr[(size_t) count * a.stride + i] = m;
+						count++;
+						higher += (m > i);
+					}
+				}
+			}
+		}
+	}
+	if(count > a.max_neigh) {
+		atomicOr(a.flags + OXB_FLAG_ERROR, OXB_ERR_NEIGH_OVERFLOW);
+		atomicMax(a.flags + OXB_FLAG_MAX_NEIGH_SEEN, count);
+		count = a.max_neigh;
+	}
+	else atomicMax(a.flags + OXB_FLAG_MAX_NEIGH_SEEN, count);
+	a.nnbr[i] = count;
+	a.list_ipos[i] = ip;
+	if(a.build_edges) a.edge_offsets[i] = higher;
+}
+
+// edge (i, m) for every listed neighbour m > i; rows are contiguous in the output (grouped by `from`)
+__global__ void __launch_bounds__(128) k_fill_edges(oxb::ListArgs a) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= a.N) return;
+	int off = a.edge_offsets[i];
+	int nn = a.nnbr[i];
+	for(int k = 0; k < nn; k++) {
+		int m = a.nbr[(size_t) k * a.stride + i];
+		if(m > i) {
+			if(off < a.edge_capacity) a.edges[off] = make_int2(i, m);
+			off++;
+		}
+	}
+	if(i == a.N - 1) {
+		*a.n_edges = (off <= a.edge_capacity) ? off : (int) a.edge_capacity;
+		if(off > a.edge_capacity) atomicOr(a.flags + OXB_FLAG_ERROR, OXB_ERR_EDGE_OVERFLOW);
+	}
+}
+
+int bits_for(int n) {
+	int b = 1;
+	while((1ll << b) < n) b++;
+	return b;
+}
+
+} // namespace
+
+namespace oxb {
+
+size_t lists_tmp_bytes(int N, int ncells) {
+	size_t a = 0, b = 0;
+	cub::DeviceRadixSort::SortPairs(nullptr, a, (int *) nullptr, (int *) nullptr, (int *) nullptr, (int *) nullptr, N, 0, bits_for(ncells));
+	cub::DeviceScan::ExclusiveSum(nullptr, b, (int *) nullptr, (int *) nullptr, N + 1);
+	return (a > b ? a : b) + 256;
+}
+
+// cell_start has room for 2 * ncells ints: starts then ends
+void launch_build_lists(cudaStream_t s, const ListArgs &a) {
+	const int N = a.N;
+	const int ncells = a.ncell[0] * a.ncell[1] * a.ncell[2];
+	int *cell_start = a.cell_start, *cell_end = a.cell_start + ncells;
+	int tpb = 256;
+	k_cell_keys<<<(N + tpb - 1) / tpb, tpb, 0, s>>>(N, a.posd, a.box[0], a.box[1], a.box[2], a.ncell[0], a.ncell[1], a.ncell[2], a.cell_key, a.cell_val);
+	size_t tmp = a.cub_tmp_bytes;
+	cub::DeviceRadixSort::SortPairs(a.cub_tmp, tmp, a.cell_key, a.cell_key_sorted, a.cell_val, a.cell_val_sorted, N, 0, bits_for(ncells), s);
+	cudaMemsetAsync(cell_start, 0, sizeof(int) * 2 * (size_t) ncells, s);
+	k_cell_ranges<<<(N + tpb - 1) / tpb, tpb, 0, s>>>(N, a.cell_key_sorted, cell_start, cell_end);
+	cudaMemsetAsync(a.flags + OXB_FLAG_MAX_NEIGH_SEEN, 0, sizeof(int), s);
+	k_build_neigh<<<(N + 127) / 128, 128, 0, s>>>(a, cell_start, cell_end);
+	if(a.build_edges) {
+		tmp = a.cub_tmp_bytes;
+		// in-place exclusive scan over N + 1 entries (the last input entry is ignored: its output is the total)
+		cub::DeviceScan::ExclusiveSum(a.cub_tmp, tmp, a.edge_offsets, a.edge_offsets, N + 1, s);
+		k_fill_edges<<<(N + 127) / 128, 128, 0, s>>>(a);
+	}
+}
+
+} // namespace oxb

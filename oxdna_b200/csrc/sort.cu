@@ -1,0 +1,104 @@
+// Hilbert-curve re-sorting of the particle arrays (sm_100a, HBM-bound).
+//
+// Replaces hilbert_curve / get_inverted_sorted_hindex / permute_particles and the six device-to-device copy-backs of
+// the reference (src/CUDA/CUDA_sort.cu:37-193, src/CUDA/Backends/MD_CUDABackend.cu:535-550, CUDABaseBackend.cu:263-281).
+// Differences by design: 30-bit keys (10 levels instead of 8) from the FP64 positions; the state is double-buffered so
+// the gather writes straight into the arrays that become current (pointer swap, no copy-back and no precision
+// round trip); everything indexed by particle is remapped -- bonds, the original-id -> slot table used by external
+// forces and by host read-backs -- so sorting is legal with external forces and strand-end detection stays correct
+// (SURVEY appendix B.6, B.7).
+#include "kernels.h"
+
+#include <cub/cub.cuh>
+
+namespace {
+
+// Skilling's transform (AIP Conf. Proc. 707, 381 (2004)): axes -> transposed Hilbert index, then bit interleave
+__device__ __forceinline__ unsigned hilbert_key(unsigned x, unsigned y, unsigned z, int bits) {
+	unsigned X[3] = { x, y, z };
+	unsigned M = 1u << (bits - 1);
+	for(unsigned Q = M; Q > 1; Q >>= 1) {
+		unsigned P = Q - 1;
+#pragma unroll
+		for(int i = 0; i < 3; i++) {
+			if(X[i] & Q) X[0] ^= P;
+			else {
+				unsigned t = (X[0] ^ X[i]) & P;
+				X[0] ^= t;
+				X[i] ^= t;
+			}
+		}
+	}
+	X[1] ^= X[0];
+	X[2] ^= X[1];
+	unsigned t = 0;
+	for(unsigned Q = M; Q > 1; Q >>= 1) if(X[2] & Q) t ^= Q - 1;
+	X[0] ^= t; X[1] ^= t; X[2] ^= t;
+	unsigned key = 0;
+	for(int b = bits - 1; b >= 0; b--) {
+		key = (key << 3) | (((X[0] >> b) & 1u) << 2) | (((X[1] >> b) & 1u) << 1) | ((X[2] >> b) & 1u);
+	}
+	return key;
+}
+
+__global__ void __launch_bounds__(256) k_hilbert_keys(int N, const double4 *__restrict__ posd, double Lx, double Ly, double Lz, unsigned *__restrict__ keys,
+		int *__restrict__ vals) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= N) return;
+	double4 p = posd[i];
+	const int bits = 10;
+	unsigned x = to_fixed(p.x, 1. / Lx) >> (32 - bits), y = to_fixed(p.y, 1. / Ly) >> (32 - bits), z = to_fixed(p.z, 1. / Lz) >> (32 - bits);
+	keys[i] = hilbert_key(x, y, z, bits);
+	vals[i] = i;
+}
+
+__global__ void __launch_bounds__(256) k_invert(int N, const int *__restrict__ perm, int *__restrict__ inv) {
+	int n = blockIdx.x * blockDim.x + threadIdx.x;
+	if(n < N) inv[perm[n]] = n;
+}
+
+__global__ void __launch_bounds__(256) k_permute(oxb::PermuteArgs a) {
+	int n = blockIdx.x * blockDim.x + threadIdx.x;
+	if(n >= a.N) return;
+	int o = a.perm[n];
+	a.posd_out[n] = a.posd_in[o];
+	a.veld_out[n] = a.veld_in[o];
+	a.Ld_out[n] = a.Ld_in[o];
+	a.quatd_out[n] = a.quatd_in[o];
+	int4 ip = a.ipos_in[o];
+	a.ipos_out[n] = ip;
+	a.list_ipos_out[n] = a.list_ipos_in[o];
+	a.quat_out[n] = a.quat_in[o];
+	a.F_out[n] = a.F_in[o];
+	a.T_out[n] = a.T_in[o];
+	int2 b = a.bonds_in[o];
+	b.x = (b.x >= 0) ? a.inv[b.x] : b.x;
+	b.y = (b.y >= 0) ? a.inv[b.y] : b.y;
+	a.bonds_out[n] = b;
+	a.slot_of[word_index(ip.w)] = n;
+}
+
+} // namespace
+
+namespace oxb {
+
+size_t sort_tmp_bytes(int N) {
+	size_t a = 0;
+	cub::DeviceRadixSort::SortPairs(nullptr, a, (unsigned *) nullptr, (unsigned *) nullptr, (int *) nullptr, (int *) nullptr, N, 0, 30);
+	return a + 256;
+}
+
+void launch_hilbert_order(cudaStream_t s, const SortArgs &a) {
+	int tpb = 256, nb = (a.N + tpb - 1) / tpb;
+	k_hilbert_keys<<<nb, tpb, 0, s>>>(a.N, a.posd, a.box[0], a.box[1], a.box[2], a.keys, a.vals);
+	size_t tmp = a.cub_tmp_bytes;
+	cub::DeviceRadixSort::SortPairs(a.cub_tmp, tmp, a.keys, a.keys_sorted, a.vals, a.vals_sorted, a.N, 0, 30, s);
+	k_invert<<<nb, tpb, 0, s>>>(a.N, a.vals_sorted, a.inv);
+}
+
+void launch_permute(cudaStream_t s, const PermuteArgs &a) {
+	int tpb = 256;
+	k_permute<<<(a.N + tpb - 1) / tpb, tpb, 0, s>>>(a);
+}
+
+} // namespace oxb

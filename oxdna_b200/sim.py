@@ -1,0 +1,132 @@
+"""Python mirror of the reference's input-file driven set-up for the GPU MD path (`backend = CUDA`).
+
+`Simulation(inp, topology, conf)` accepts the reference's input keys (docs/source/input.md; the CUDA ones are read in
+src/CUDA/Backends/CUDABaseBackend.cu:110-141, MD_CUDABackend.cu:621-672, CUDAThermostatFactory.cu:18-45) and drives
+the C ABI.  It is the host-side convenience used by tests, bench.py and the REMD driver; the C++ host classes in
+oxdna_b200/host mirror the same interface for linking against the reference's SimManager.
+"""
+import numpy as np
+
+from . import capi
+
+
+def parse_temperature(raw):
+    """src/Utilities/Utils.cpp:316-346: '300K', '27C' or a number in simulation units."""
+    if isinstance(raw, (int, float)):
+        return float(raw)
+    s = str(raw).strip()
+    if s[-1] in "kK":
+        return float(s[:-1]) * 0.1 / 300.0
+    if s[-1] in "cC":
+        return (float(s[:-1]) + 273.15) * 0.1 / 300.0
+    return float(s)
+
+
+def _bool(v):
+    if isinstance(v, str):
+        return v.strip().lower() in ("1", "true", "yes", "on")
+    return bool(v)
+
+
+def brownian_params(T, dt, newtonian_steps, pt=0.0, diff_coeff=0.0):
+    """BrownianThermostat::init (src/Backends/Thermostats/BrownianThermostat.cpp:43-54); pt/diff_coeff/dt are floats there."""
+    dt, D, p = float(np.float32(dt)), float(np.float32(diff_coeff)), float(np.float32(pt))
+    if p == 0.0:
+        p = (2 * T * newtonian_steps * dt) / (T * newtonian_steps * dt + 2 * D)
+    if p > 1.0:
+        raise ValueError(f"pt ({p}) must be smaller than 1")
+    D = T * newtonian_steps * dt * (1.0 / p - 0.5)
+    pr = (2 * T * newtonian_steps * dt) / (T * newtonian_steps * dt + 2 * 3 * D)
+    return p, pr, np.sqrt(T)
+
+
+def langevin_params(T, dt, gamma_trans=0.0, diff_coeff=0.0):
+    """LangevinThermostat::init (src/Backends/Thermostats/LangevinThermostat.cpp:57-76)."""
+    g, D = float(np.float32(gamma_trans)), float(np.float32(diff_coeff))
+    if g != 0.0 and D != 0.0:
+        raise ValueError("Cannot specify both gamma_trans and diff_coeff. Remove one of them from the input file")
+    if g == 0.0 and D == 0.0:
+        raise ValueError("Must specify one of gamma_trans and diff_coeff for the Langevin thermostat to work")
+    if D == 0.0:
+        D = T / g
+    else:
+        g = T / D
+    gr = T / (3.0 * D)
+    return g, gr, np.sqrt(2.0 * g * T / dt), np.sqrt(2.0 * gr * T / dt)
+
+
+class Simulation:
+    def __init__(self, inp, topology, conf, device=0):
+        """topology: dict(btype, n3, n5, strand); conf: dict(box, pos, a1, a3[, vel, L])."""
+        self.inp = dict(inp)
+        g = self.inp.get
+        if str(g("backend", "CUDA")).upper() != "CUDA":
+            raise ValueError("oxdna_b200 only implements backend = CUDA")
+        itype = str(g("interaction_type", "DNA2"))
+        if itype not in ("DNA2", "DNA2_nomesh"):
+            raise ValueError(f"interaction_type = {itype} is not available in this build (DNA2 only)")
+        prec = str(g("backend_precision", "mixed"))
+        if prec not in ("mixed",):
+            raise ValueError(f"backend_precision = {prec} is not available in this build")
+        if "reload_from" in self.inp:
+            # CUDABaseBackend.cu:137-140
+            raise ValueError("The CUDA backend does not support checkpoints (reload_from)")
+        self.use_edge = _bool(g("use_edge", 0))
+        if str(g("CUDA_list", "verlet")) == "no" and self.use_edge:
+            raise ValueError("'CUDA_list = no' and 'use_edge = true' are incompatible")  # CUDANoList.cu:20-26
+        self.T = parse_temperature(g("T"))
+        self.dt = float(g("dt", 0.003))
+        self.N = N = len(topology["btype"])
+        self.ctx = capi.Context(N, device=device)
+        c = self.ctx
+        c.set_box(conf["box"])
+        c.set_topology(topology["btype"], topology["n3"], topology["n5"], topology.get("strand"))
+        self._set_model()
+        c.set_lists(float(g("verlet_skin", 0.05)), self.use_edge, int(g("CUDA_sort_every", 0)), float(g("max_density_multiplier", 3.0)))
+        c.set_dt(self.dt)
+        self.seed = int(g("seed", 42))
+        self._set_thermostat()
+        ext = g("external_forces_list", None)
+        if ext:
+            c.set_ext_forces(ext)
+        c.set_state(conf["pos"], conf["a1"], conf["a3"], conf.get("vel"), conf.get("L"))
+
+    def _set_model(self):
+        g = self.inp.get
+        mbf = g("max_backbone_force", None)
+        self.params, self.rcut = capi.dna2_params(self.T, float(g("salt_concentration", 0.5)), _bool(g("dh_half_charged_ends", 1)),
+                                                  None if mbf is None else float(mbf), float(g("max_backbone_force_far", 0.04)))
+        self.ctx.set_model_dna2(self.params, self.rcut)
+
+    def _set_thermostat(self):
+        g = self.inp.get
+        kind = str(g("thermostat", "no")).lower()
+        if kind == "no":
+            self.ctx.set_thermostat(capi.THERMOSTAT_NONE)
+        elif kind in ("john", "brownian"):  # synonyms, CUDAThermostatFactory.cu:23-28
+            ns = int(g("newtonian_steps"))
+            pt, pr, resc = brownian_params(self.T, self.dt, ns, float(g("pt", 0.0)), float(g("diff_coeff", 0.0)))
+            self.ctx.set_thermostat(capi.THERMOSTAT_BROWNIAN, ns, pt, pr, resc, 0.0, self.seed)
+        elif kind == "langevin":
+            gt, gr, rt, rr = langevin_params(self.T, self.dt, float(g("gamma_trans", 0.0)), float(g("diff_coeff", 0.0)))
+            self.ctx.set_thermostat(capi.THERMOSTAT_LANGEVIN, 1, gt, gr, rt, rr, self.seed)
+        elif kind == "bussi":
+            ns, tau = int(g("newtonian_steps")), int(g("bussi_tau"))
+            self.ctx.set_thermostat(capi.THERMOSTAT_BUSSI, ns, self.T, np.exp(-ns / float(tau)), 0.0, 0.0, self.seed)
+        else:
+            raise ValueError(f"Invalid thermostat '{kind}'")
+
+    def update_temperature(self, T):
+        """ConfigInfo::update_temperature -> interaction re-init + thermostat re-init."""
+        self.T = parse_temperature(T)
+        self._set_model()
+        self._set_thermostat()
+
+    def run(self, steps):
+        self.ctx.run(steps)
+
+    def system_energy(self):
+        return self.ctx.energy()[0]
+
+    def close(self):
+        self.ctx.close()

@@ -1,0 +1,54 @@
+// TEST SUPPORT: runs the product's FP32 pair-potential functions (oxdna_b200/csrc/dna_model.cuh, compiled for the
+// host by nvcc) over a pair list, so their formulation can be checked against the oracle on a machine without a GPU.
+// This is a unit test of device code's arithmetic, not a product code path.
+#include "../../oxdna_b200/csrc/dna_model.cuh"
+
+#include <cmath>
+#include <vector>
+
+extern "C" void host_dna2_forces(const oxb_dna2_params *Mp, int N, const double *pos, const double *axes, const int *btype, const int *n3,
+		const int *n5, const double *box, const int *pairs, long long npairs, double *F, double *Tlab, double *epart) {
+	const oxb_dna2_params &M = *Mp;
+	BoxF b;
+	b.lx = (float) box[0]; b.ly = (float) box[1]; b.lz = (float) box[2];
+	b.sx = (float) (box[0] / 4294967296.0); b.sy = (float) (box[1] / 4294967296.0); b.sz = (float) (box[2] / 4294967296.0);
+	std::vector<int4> ip(N);
+	std::vector<Axes> ax(N);
+	std::vector<v3> back(N);
+	for(int i = 0; i < N; i++) {
+		ip[i].x = (int) to_fixed(pos[3 * i], 1. / box[0]);
+		ip[i].y = (int) to_fixed(pos[3 * i + 1], 1. / box[1]);
+		ip[i].z = (int) to_fixed(pos[3 * i + 2], 1. / box[2]);
+		ip[i].w = pack_word(btype[i], i);
+		quatd q = quat_from_axes(axes + 9 * i, axes + 9 * i + 3, axes + 9 * i + 6);
+		float4 qf = make_float4((float) q.x, (float) q.y, (float) q.z, (float) q.w);
+		ax[i] = axes_from_quat(qf);
+		back[i] = ax[i].a1 * M.back_a1 + ax[i].a2 * M.back_a2;
+	}
+	for(int i = 0; i < 3 * N; i++) F[i] = Tlab[i] = 0.;
+	for(int i = 0; i < N; i++) epart[i] = 0.;
+	auto scatter = [&](int p, int q, const PairAcc &acc, float e) {
+		v3 tp = acc.torque_p(ax[p], back[p]), tq = acc.torque_q(ax[q], back[q]);
+		F[3 * p] -= acc.F.x; F[3 * p + 1] -= acc.F.y; F[3 * p + 2] -= acc.F.z;
+		F[3 * q] += acc.F.x; F[3 * q + 1] += acc.F.y; F[3 * q + 2] += acc.F.z;
+		Tlab[3 * p] += tp.x; Tlab[3 * p + 1] += tp.y; Tlab[3 * p + 2] += tp.z;
+		Tlab[3 * q] += tq.x; Tlab[3 * q + 1] += tq.y; Tlab[3 * q + 2] += tq.z;
+		epart[p] += 0.5 * e; epart[q] += 0.5 * e;
+	};
+	for(int p = 0; p < N; p++) {
+		int q = n3[p];
+		if(q < 0) continue;
+		v3 r = min_image_fixed(b, ip[p], ip[q]);
+		PairAcc acc; acc.clear();
+		bool broken = false;
+		float e = dna2_bonded(M, r, ax[p], ax[q], btype[p], btype[q], back[p], back[q], acc, broken);
+		scatter(p, q, acc, e);
+	}
+	for(long long k = 0; k < npairs; k++) {
+		int p = pairs[2 * k + 1], q = pairs[2 * k];
+		v3 r = min_image_fixed(b, ip[p], ip[q]);
+		PairAcc acc; acc.clear();
+		PairEnergy e = dna2_nonbonded(M, r, ax[p], ax[q], btype[p], btype[q], n3[p] < 0 || n5[p] < 0, n3[q] < 0 || n5[q] < 0, back[p], back[q], acc);
+		scatter(p, q, acc, e.total);
+	}
+}

@@ -1,0 +1,213 @@
+"""GPU parity tests (through the C ABI) against the oracle and the committed reference fixtures.
+
+Tolerances (north star): Verlet pair sets bit-exact; forces/torques |d| <= 1e-5 * max|.| (mixed precision, FP32 pair
+arithmetic), energies relative 1e-6; NVE trajectories against the double-precision CPU step over 200 steps: 2e-4 absolute
+(FP32 force round-off amplified by chaotic dynamics; measured ~1e-5)."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, pair_set
+from oracle import oracle as O
+from oxdna_b200 import capi, lattice
+from oxdna_b200.sim import Simulation, parse_temperature
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["force_field_dna/ref_dna2_nomesh", "lattice8", "lattice27_dense"]
+EXT = [dict(type="mutual_trap", particle=0, ref_particle=39, stiff=0.1, r0=1.2, PBC=1),
+       dict(type="mutual_trap", particle=39, ref_particle=0, stiff=0.1, r0=1.2, PBC=1),
+       dict(type="trap", particle=45, pos0=(5.0, 5.0, 5.0), stiff=0.5, rate=0.001, dir=(1.0, 0.0, 0.0)),
+       dict(type="string", particle=80, F0=0.2, rate=0.0001, dir=(0.0, 1.0, 1.0))]
+
+
+def make_sim(g, **over):
+    inp = dict(backend="CUDA", interaction_type="DNA2", T=str(g["T"]), salt_concentration=float(g["salt"]), dt=0.003,
+               verlet_skin=0.05, thermostat="no", CUDA_sort_every=0, use_edge=0, seed=11)
+    inp.update(over)
+    topo = dict(btype=g["btype"], n3=g["n3"], n5=g["n5"], strand=g["strand"])
+    conf = dict(box=g["box"], pos=g["pos"], a1=g["a1"], a3=g["a3"], vel=g["vel"], L=g["L"])
+    return Simulation(inp, topo, conf)
+
+
+def check_forces(out, g, tol=1e-5):
+    fmax = np.linalg.norm(g["force"], axis=1).max()
+    tmax = np.linalg.norm(g["torque_lab"], axis=1).max()
+    dF = np.linalg.norm(out["force"] - g["force"], axis=1).max()
+    dT = np.linalg.norm(out["torque_lab"] - g["torque_lab"], axis=1).max()
+    dTb = np.linalg.norm(out["torque_body"] - g["torque_body"], axis=1).max()
+    assert dF <= tol * fmax, (dF, fmax)
+    assert dT <= tol * tmax, (dT, tmax)
+    assert dTb <= tol * tmax, (dTb, tmax)
+    assert abs(out["U"] - float(g["U"])) <= 1e-6 * abs(float(g["U"]))
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("use_edge", [0, 1])
+@pytest.mark.parametrize("sort_every", [0, 1])
+def test_forces_torques_energy_vs_reference(case, use_edge, sort_every):
+    g = load_golden(case)
+    sim = make_sim(g, use_edge=use_edge, CUDA_sort_every=sort_every)
+    try:
+        check_forces(sim.ctx.get_forces(), g)
+        U, K = sim.ctx.energy()
+        assert abs(U - float(g["U"])) <= 1e-6 * abs(float(g["U"]))
+        Kref = 0.5 * (np.sum(g["vel"] ** 2) + np.sum(g["L"] ** 2))
+        assert abs(K - Kref) <= 1e-12 * max(Kref, 1.0)
+        hb = sim.ctx.get_forces()["hb_energy"].sum() * 0.5
+        assert abs(hb - float(g["energy_split"][4])) <= 1e-5 * abs(float(g["energy_split"][4])) + 1e-6
+    finally:
+        sim.close()
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("sort_every", [0, 1])
+def test_verlet_pair_set_bit_exact(case, sort_every):
+    g = load_golden(case)
+    sim = make_sim(g, CUDA_sort_every=sort_every, use_edge=1)
+    try:
+        assert pair_set(sim.ctx.get_pairs()) == pair_set(g["pairs"])
+        # again after an explicit Hilbert sort + rebuild: the pair set is a property of the configuration
+        sim.ctx.sort()
+        sim.ctx.update_lists()
+        assert pair_set(sim.ctx.get_pairs()) == pair_set(g["pairs"])
+        st = sim.ctx.get_state()
+        assert np.array_equal(st["pos"], g["pos"]) and np.array_equal(st["vel"], g["vel"])
+    finally:
+        sim.close()
+
+
+def test_pair_set_near_cutoff_boundary():
+    """Pairs placed within a few ulp of the Verlet radius: the FP64 re-check must agree with the CPU predicate."""
+    rng = np.random.default_rng(5)
+    T = parse_temperature("300K")
+    P, rcut = capi.dna2_params(T, 0.5)
+    rv = rcut + 0.1
+    n = 64
+    box = np.array([40.0, 40.0, 40.0])
+    base = rng.uniform(0, 40, size=(n, 3))
+    dirs = rng.normal(size=(n, 3))
+    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    eps = rng.integers(-3, 4, size=n) * 4.4e-16
+    pos = np.concatenate([base, base + dirs * (rv * (1.0 + eps))[:, None]])
+    N = 2 * n
+    a1 = np.tile([1.0, 0, 0], (N, 1))
+    a3 = np.tile([0, 0, 1.0], (N, 1))
+    none = np.full(N, -1, dtype=np.int32)
+    c = capi.Context(N)
+    try:
+        c.set_box(box)
+        c.set_topology(np.zeros(N, dtype=np.int32), none, none, np.arange(N, dtype=np.int32))
+        c.set_model_dna2(P, rcut)
+        c.set_lists(0.05, False, 0, 3.0)
+        c.set_state(pos, a1, a3)
+        want = O.verlet_pairs(pos, none, none, box, rv)
+        assert pair_set(c.get_pairs()) == pair_set(want)
+    finally:
+        c.close()
+
+
+@pytest.mark.parametrize("use_edge,sort_every", [(0, 0), (1, 1)])
+def test_nve_trajectory_vs_reference(use_edge, sort_every):
+    g = load_golden("lattice8")
+    sim = make_sim(g, use_edge=use_edge, CUDA_sort_every=sort_every)
+    try:
+        n = int(g["nve_steps"])
+        sim.run(n)
+        st = sim.ctx.get_state()
+        assert np.abs(st["pos"] - g["pos1"]).max() < 2e-4
+        assert np.abs(st["vel"] - g["vel1"]).max() < 2e-3
+        assert np.abs(st["a1"] - g["a11"]).max() < 2e-3
+        assert sim.ctx.step == n
+        # energy conservation over the segment (velocity Verlet, dt = 0.003)
+        U, K = sim.ctx.energy()
+        E0 = float(g["U"]) + 0.5 * (np.sum(g["vel"] ** 2) + np.sum(g["L"] ** 2))
+        assert abs((U + K) - E0) < 2e-3 * abs(E0)
+        assert sim.ctx.stats()["n_list_updates"] >= int(g["n_updates"])
+    finally:
+        sim.close()
+
+
+def test_operator_by_operator_step_matches_run():
+    g = load_golden("lattice8")
+    a, b = make_sim(g), make_sim(g)
+    try:
+        for s in range(5):
+            a.ctx.set_step(s)
+            a.ctx.first_step()
+            a.ctx.compute_forces()
+            a.ctx.second_step()
+            a.ctx.thermostat()
+        b.run(5)
+        sa, sb = a.ctx.get_state(), b.ctx.get_state()
+        for k in ("pos", "vel", "L", "a1"):
+            assert np.abs(sa[k] - sb[k]).max() < 1e-12, k
+    finally:
+        a.close()
+        b.close()
+
+
+def test_external_forces_vs_reference():
+    g = load_golden("lattice8_ext")
+    for use_edge, sort_every in [(0, 0), (1, 1)]:
+        sim = make_sim(g, use_edge=use_edge, CUDA_sort_every=sort_every, external_forces_list=EXT)
+        try:
+            check_forces(sim.ctx.get_forces(), g)
+            sim.run(int(g["nve_steps"]))
+            st = sim.ctx.get_state()
+            assert np.abs(st["pos"] - g["pos1"]).max() < 2e-4
+        finally:
+            sim.close()
+
+
+def test_run_is_deterministic_particle_centric():
+    g = load_golden("lattice8")
+    outs = []
+    for _ in range(2):
+        sim = make_sim(g, thermostat="brownian", newtonian_steps=7, diff_coeff=2.5, CUDA_sort_every=1)
+        sim.run(60)
+        outs.append(sim.ctx.get_state())
+        sim.close()
+    assert np.array_equal(outs[0]["pos"], outs[1]["pos"]) and np.array_equal(outs[0]["vel"], outs[1]["vel"])
+
+
+@pytest.mark.parametrize("thermostat", ["brownian", "langevin", "bussi"])
+def test_thermostats_equipartition(thermostat):
+    """<K/N> = 3T (1.5 T translational + 1.5 T rotational), as the reference's THERMOSTATS quick tests check."""
+    sysm = lattice.duplex_lattice(64, bp=20, spacing=10.0, seed=9)
+    T = parse_temperature("300K")
+    v, L = lattice.maxwell_velocities(len(sysm["pos"]), 0.5 * T, 3)  # start cold: the thermostat has to do work
+    conf = dict(box=sysm["box"], pos=sysm["pos"], a1=sysm["a1"], a3=sysm["a3"], vel=v, L=L)
+    inp = dict(backend="CUDA", interaction_type="DNA2", T="300K", salt_concentration=0.5, dt=0.003, verlet_skin=0.05,
+               thermostat=thermostat, newtonian_steps=53, diff_coeff=2.5, bussi_tau=500, CUDA_sort_every=1, use_edge=1, seed=5)
+    if thermostat == "bussi":
+        inp.pop("diff_coeff")
+    sim = Simulation(inp, sysm, conf)
+    try:
+        sim.run(6000)
+        ks = []
+        for _ in range(40):
+            sim.run(250)
+            ks.append(sim.ctx.energy()[1] / sim.N)
+        k = np.mean(ks)
+        assert abs(k - 3 * T) < 0.03 * 3 * T, (k, 3 * T)
+        U = sim.ctx.energy()[0] / sim.N
+        assert -1.8 < U < -1.2
+    finally:
+        sim.close()
+
+
+def test_temperature_update_changes_model():
+    g = load_golden("lattice8")
+    sim = make_sim(g)
+    try:
+        U0 = sim.system_energy()
+        sim.update_temperature("330K")
+        U1 = sim.system_energy()
+        P = O.dna2_params(parse_temperature("330K"), float(g["salt"]))
+        ax = O.axes_from_a1a3(g["a1"], g["a3"])
+        pairs = O.verlet_pairs(g["pos"], g["n3"], g["n5"], g["box"], P.rcut + 0.1)
+        ref = O.forces(P, g["pos"], ax, g["btype"], g["n3"], g["n5"], g["box"], pairs)
+        assert abs(U1 - ref["U"]) < 1e-6 * abs(ref["U"])
+        assert abs(U1 - U0) > 1e-3
+    finally:
+        sim.close()
