@@ -680,8 +680,9 @@ int oxb_run(oxb_ctx *c, long long n_steps) {
 			c->launches++;
 		}
 		long long batch = std::min<long long>(remaining, std::max<long long>(1, std::min<long long>(64, (long long) (0.75 * c->avg_interval + 0.5))));
+		const long long step0 = c->step;
 		for(long long b = 0; b < batch; b++) {
-			const long long s = c->step + b;
+			const long long s = step0 + b;
 			c->step = s; // external forces read c->step at launch time
 			launch_forces(c, OXB_FLAG_COUNT + (epoch & 1));
 			const bool last = (b == batch - 1) && (batch == remaining);
@@ -700,7 +701,7 @@ int oxb_run(oxb_ctx *c, long long n_steps) {
 				c->launches++;
 			}
 		}
-		c->step -= (batch - 1);
+		c->step = step0;
 		CU(cudaGetLastError());
 		rc = read_flags(c);
 		if(rc) return rc;

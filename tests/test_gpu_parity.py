@@ -178,12 +178,13 @@ def test_thermostats_equipartition(thermostat):
     v, L = lattice.maxwell_velocities(len(sysm["pos"]), 0.5 * T, 3)  # start cold: the thermostat has to do work
     conf = dict(box=sysm["box"], pos=sysm["pos"], a1=sysm["a1"], a3=sysm["a3"], vel=v, L=L)
     inp = dict(backend="CUDA", interaction_type="DNA2", T="300K", salt_concentration=0.5, dt=0.003, verlet_skin=0.05,
-               thermostat=thermostat, newtonian_steps=53, diff_coeff=2.5, bussi_tau=500, CUDA_sort_every=1, use_edge=1, seed=5)
-    if thermostat == "bussi":
-        inp.pop("diff_coeff")
+               thermostat=thermostat, CUDA_sort_every=1, use_edge=1, seed=5)
+    # strong coupling so that the test equilibrates in a few thousand steps
+    inp.update(dict(brownian=dict(newtonian_steps=20, pt=0.2), langevin=dict(gamma_trans=1.0),
+                    bussi=dict(newtonian_steps=20, bussi_tau=200))[thermostat])
     sim = Simulation(inp, sysm, conf)
     try:
-        sim.run(6000)
+        sim.run(8000)
         ks = []
         for _ in range(40):
             sim.run(250)
