@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""Benchmark of the oxDNA GPU MD step (BASELINE.json metric: particle-steps/s).
+
+  python bench.py --gpus 1 --steps K --warmup W              our CUDA path, N = 1: config C2 (81,920 nt duplex lattice)
+  torchrun ... bench.py --gpus N ...                          N > 1: one C2 replica per GPU, replica exchange over NCCL
+  python bench.py --impl reference ...                        the reference's own CPU implementation on the host cores
+
+One bench "step" = one block of `md_steps_per_step` MD steps (the unit the reference's OxpyManager.run(steps) /
+REMD pt_move_every works in); value = N_particles * md_steps / device time.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+T_STR, SALT, DT = "300K", 0.5, 0.003
+FLOP_FAR, FLOP_DH, FLOP_CONTACT, FLOP_BONDED = 170.0, 60.0, 1500.0, 900.0  # SURVEY 8(d) per-pair figures
+
+
+def workload(name):
+    from oxdna_b200 import lattice
+    if name == "c2":
+        sysm = lattice.duplex_lattice(2048, bp=20, spacing=10.0, seed=12345)  # 13^3 sites, L = 130
+        desc = "C2: oxDNA2 synthetic lattice of 2,048 x 20-bp duplexes (81,920 nt), L=130, salt 0.5, T=300K"
+    elif name == "c4":
+        sysm = lattice.duplex_lattice(25000, bp=20, spacing=10.0, seed=12345, sites_per_side=30)
+        desc = "C4: oxDNA2 1M-nt lattice (25,000 x 20-bp), L=300, salt 0.5, 50,000 mutual traps"
+    elif name == "small":
+        sysm = lattice.duplex_lattice(64, bp=20, spacing=10.0, seed=12345)
+        desc = "small: 64 x 20-bp duplexes (2,560 nt)"
+    else:
+        raise ValueError(name)
+    return sysm, desc
+
+
+def base_input(args, T=T_STR):
+    return dict(backend="CUDA", backend_precision="mixed", interaction_type="DNA2", T=T, salt_concentration=SALT, dt=DT,
+                verlet_skin=0.05, thermostat="brownian", newtonian_steps=103, diff_coeff=2.5, CUDA_list="verlet",
+                CUDA_sort_every=args.sort_every, use_edge=args.use_edge, seed=42)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                    if r[col].lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=sorted(reasons), samples=len(sm))
+
+
+def pair_statistics(sim, sysm):
+    """Unique listed pairs / DH-range pairs / near pairs per particle of the current configuration (for the FLOP model)."""
+    st = sim.ctx.get_state()
+    pairs = sim.ctx.get_pairs()
+    N = sim.N
+    from oxdna_b200 import io as oio
+    ax = oio.orthonormal_axes(st["a1"], st["a3"])
+    back = st["pos"] + ax[:, 0:3] * (-0.34) + ax[:, 3:6] * 0.3408
+    box = sysm["box"]
+    d = back[pairs[:, 1]] - back[pairs[:, 0]]
+    d -= np.rint(d / box) * box
+    rb = np.linalg.norm(d, axis=1)
+    dc = st["pos"][pairs[:, 1]] - st["pos"][pairs[:, 0]]
+    dc -= np.rint(dc / box) * box
+    rc = np.linalg.norm(dc, axis=1)
+    return dict(listed=len(pairs) / N, dh=float(np.sum(rb < float(sim.params.dh_rc))) / N, near=float(np.sum(rc < float(sim.params.rcut_near))) / N,
+                contact=float(np.sum(rc < 1.0)) / N)
+
+
+# ----------------------------------------------------------------------------------------------------------- CPU baseline
+def write_case(sysm, T, d):
+    from oxdna_b200 import io as oio, lattice
+    from oxdna_b200.sim import parse_temperature
+    top, conf = os.path.join(d, "bench.top"), os.path.join(d, "bench.dat")
+    oio.write_topology(top, sysm["btype"], sysm["n3"], sysm["n5"], sysm["strand"])
+    v, L = lattice.maxwell_velocities(len(sysm["pos"]), parse_temperature(T), 5)
+    oio.write_conf(conf, sysm["box"], sysm["pos"], sysm["a1"], sysm["a3"], v, L)
+    return top, conf
+
+
+def _ref_worker(kind, top, conf, md_steps, warm, steps, barrier, q):
+    """One single-threaded CPU MD process (the reference is single-threaded by design)."""
+    try:
+        if kind == "reference":
+            from oracle.refharness import Reference
+            r = Reference(top, conf, interaction_type="DNA2", salt_concentration=SALT, T=T_STR, thermostat="brownian", newtonian_steps=103,
+                          diff_coeff=2.5, dt=DT, seed=42)
+            stepper = r.step
+        else:
+            from oracle import oracle as O
+            from oxdna_b200 import io as oio
+            from oxdna_b200.sim import parse_temperature
+            t, c = oio.read_topology(top), oio.read_conf(conf)
+            P = O.dna2_params(parse_temperature(T_STR), SALT)
+            md = O.MD(P, c["pos"], O.axes_from_a1a3(c["a1"], c["a3"]), c["vel"], c["L"], t["btype"], t["n3"], t["n5"], c["box"], DT, 0.05)
+            stepper = md.step
+        barrier.wait()
+        for _ in range(warm):
+            stepper(md_steps)
+        barrier.wait()
+        for _ in range(steps):
+            stepper(md_steps)
+        barrier.wait()
+        q.put("ok")
+    except Exception as e:  # pragma: no cover
+        q.put("error: " + repr(e))
+        try:
+            barrier.abort()
+        except Exception:
+            pass
+
+
+def run_cpu(sysm, md_steps, warm, steps, procs):
+    """Times `procs` independent single-threaded CPU simulations of the workload.  Returns (particle-steps/s, kind, seconds)."""
+    import multiprocessing as mp
+    from oracle import refharness
+    from oracle import oracle as O
+    kind = "reference" if refharness.available() else "port"
+    if kind == "port":
+        O.build()
+    ctx = mp.get_context("spawn")
+    d = tempfile.mkdtemp()
+    top, conf = write_case(sysm, T_STR, d)
+    barrier = ctx.Barrier(procs + 1)
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_ref_worker, args=(kind, top, conf, md_steps, warm, steps, barrier, q)) for _ in range(procs)]
+    for p in ps:
+        p.start()
+    barrier.wait()
+    barrier.wait()
+    t0 = time.perf_counter()
+    barrier.wait()
+    t1 = time.perf_counter()
+    res = [q.get() for _ in ps]
+    for p in ps:
+        p.join()
+    if any(r != "ok" for r in res):
+        raise RuntimeError(str(res))
+    N = len(sysm["pos"])
+    return procs * N * md_steps * steps / (t1 - t0), kind, t1 - t0
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sysm, desc = workload(args.workload)
+    procs = args.ref_procs or min(host_cores(), 32)
+    md = args.ref_md_steps
+    val, kind, secs = run_cpu(sysm, md, args.warmup, args.steps, procs)
+    N = len(sysm["pos"])
+    line = {"impl": "reference", "metric": "particle-steps/s", "value": val, "unit": "particle-steps/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "md_steps_per_step": md, "sample": f"{procs} independent single-threaded CPU processes x {md} MD steps per step",
+                       "thermostat": "brownian", "dt": DT},
+            "cpu_baseline": {"value": val, "unit": "particle-steps/s", "cores": procs, "kind": kind,
+                             "sample": f"{args.steps} x {md} MD steps of {N} nt on each of {procs} cores (aggregate)"},
+            "e2e": {"value": val, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------- our arm
+def ours(args):
+    import torch
+    import torch.distributed as dist
+    from oxdna_b200 import capi, lattice
+    from oxdna_b200.remd import ReplicaExchange, TorchComm, geometric_ladder
+    from oxdna_b200.sim import Simulation, parse_temperature
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: oxdna_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    sysm, desc = workload(args.workload)
+    N = len(sysm["pos"])
+    md = args.md_steps
+    n_rep = world  # one replica per GPU: weak scaling
+    ladder_K = geometric_ladder(290.0, 350.0, n_rep) if n_rep > 1 else np.array([300.0])
+    T_sim = ladder_K * 0.1 / 300.0
+    myT = f"{ladder_K[rank]:.6f}K"
+    v, L = lattice.maxwell_velocities(N, parse_temperature(myT), 5 + rank)
+    conf = dict(box=sysm["box"], pos=sysm["pos"], a1=sysm["a1"], a3=sysm["a3"], vel=v, L=L)
+    inp = base_input(args, myT)
+    if args.workload == "c4":
+        inp["external_forces_list"] = lattice.mutual_traps(sysm)
+    sim = Simulation(inp, sysm, conf, device=local_rank)
+    stream = torch.cuda.Stream()
+    # the context launches on torch's stream so that torch.cuda.Event brackets exactly our kernels
+    sim.ctx._ck(capi.lib().oxb_set_stream(sim.ctx._h, __import__("ctypes").c_void_p(stream.cuda_stream)))
+    remd = ReplicaExchange([sim], T_sim, TorchComm(torch.device("cuda", local_rank)) if world > 1 else None, seed=42) if world > 1 else None
+
+    with torch.cuda.stream(stream):
+        sim.run(args.equil)
+        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+
+        def one_step():
+            sim.run(md)
+            if remd is not None:
+                remd.exchange()
+
+        for _ in range(args.warmup):
+            one_step()
+        stats0 = sim.ctx.stats()
+        launches0 = sim.ctx.launch_count()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        total_ms = 0.0
+        for _ in range(args.steps):
+            flush.zero_()  # L2 flush between timed iterations (state of C2 is smaller than the 126 MB L2)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            one_step()
+            e1.record(stream)
+            e1.synchronize()
+            total_ms += e0.elapsed_time(e1)
+        torch.cuda.synchronize()
+        clocks = sampler.stop() if rank == 0 else None
+        if world > 1:
+            dist.barrier()
+            t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total_ms = float(t.item())
+        launches = sim.ctx.launch_count() - launches0
+        stats1 = sim.ctx.stats()
+        value = n_rep * N * md * args.steps / (total_ms * 1e-3)
+
+        if rank != 0:
+            if world > 1:
+                dist.barrier()
+                dist.destroy_process_group()
+            return
+
+        # ---- per-kernel roofline figures, measured live with CUDA events on the launching stream
+        t_force = sim.ctx.time_kernel(0, 20)
+        t_integ = sim.ctx.time_kernel(1, 20)
+        t_list = sim.ctx.time_kernel(2, 5)
+        t_sort = sim.ctx.time_kernel(3, 5)
+        ps = pair_statistics(sim, sysm)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+        # algorithmic bytes per particle of the force pass: 40 B state read + 32 B F,T write + 8 B per listed unique pair
+        force_bytes = N * (40.0 + 32.0 + 8.0 * ps["listed"])
+        force_gbs = force_bytes / (t_force * 1e-3) / 1e9
+        flops = N * (FLOP_FAR * ps["listed"] + FLOP_DH * ps["dh"] + FLOP_CONTACT * ps["contact"] + FLOP_BONDED * 1.0)
+        if not args.use_edge:
+            flops = N * (2 * (FLOP_FAR * ps["listed"] + FLOP_DH * ps["dh"] + FLOP_CONTACT * ps["contact"]) + 2 * FLOP_BONDED)
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+        integ_bytes = N * 336.0  # first_step_mixed: 176 B read + 160 B written per particle; second half-kick fused
+        integ_gbs = integ_bytes / (t_integ * 1e-3) / 1e9
+        step_ms = total_ms / (args.steps * md)
+        rebuild_every = md * args.steps / max(stats1["n_list_updates"] - stats0["n_list_updates"], 1)
+
+        # ---- end to end through the public API with host buffers (OxpyManager.run semantics: H2D, steps, D2H)
+        st = sim.ctx.get_state()
+        pin = {k: torch.from_numpy(st[k]).pin_memory().numpy() for k in ("pos", "a1", "a3", "vel", "L")}
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e2e_steps = max(1, min(args.steps, 3))
+        for _ in range(e2e_steps):
+            sim.ctx.set_state(pin["pos"], pin["a1"], pin["a3"], pin["vel"], pin["L"])
+            sim.run(md)
+            out = sim.ctx.get_state()
+            U, K = sim.ctx.energy()
+            for k in pin:
+                pin[k][...] = out[k]
+        torch.cuda.synchronize()
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+        e2e = {"value": N * md / e2e_s, "unit": "particle-steps/s", "h2d_bytes_per_step": N * 172, "d2h_bytes_per_step": N * 144 + 16,
+               "api": "set_state (H2D) + run(md_steps) + get_state + energy (D2H), wall clock, n_gpus=1 leg", "U_per_particle": U / N, "K_per_particle": K / N}
+
+        # ---- CPU baseline on a bounded sample of the same workload (rank 0, N = 1 only)
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                cval, kind, secs = run_cpu(sysm, args.cpu_md_steps, 0, 1, 1)
+                cpu = {"value": cval, "unit": "particle-steps/s", "cores": 1, "kind": kind,
+                       "sample": f"{args.cpu_md_steps} MD steps of the same {N}-nt system on one host core ({secs:.1f} s), host has {host_cores()} cores"}
+            except Exception as e:  # pragma: no cover
+                cpu = {"value": None, "unit": "particle-steps/s", "cores": 1, "kind": "port", "sample": "failed: " + repr(e)}
+
+        line = {"metric": "particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 forces / f64 integration (mixed)",
+                "data": "synthetic",
+                "config": {"workload": desc, "md_steps_per_step": md, "replicas": n_rep, "parallelism": "1 replica per GPU, replica exchange every step" if world > 1 else "single system",
+                           "use_edge": int(args.use_edge), "CUDA_sort_every": args.sort_every, "thermostat": "brownian (newtonian_steps 103)", "dt": DT, "verlet_skin": 0.05,
+                           "equilibration_md_steps": args.equil, "l2": "256 MiB buffer written between timed iterations (L2 flush)",
+                           "ns_per_day": 86400.0 / (step_ms * 1e-3) * DT * 3.03e-3, "md_steps_per_s": 1e3 / step_ms, "list_rebuild_every_md_steps": rebuild_every,
+                           "pairs_per_particle": ps},
+                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                "roofline": {"kernel": "forces (edge non-bonded + bonded)" if args.use_edge else "forces (particle-centric)", "bound": "hbm", "achieved": force_gbs, "peak": hbm_peak,
+                             "unit": "GB/s", "frac": force_gbs / hbm_peak, "traffic": None, "peak_source": peak_src, "ms": t_force,
+                             "share_of_step": t_force / step_ms,
+                             "note": "the force kernel is FP32/SFU-bound, not HBM-bound (see roofline_fp32); HBM figure given as the contract asks"},
+                "roofline_fp32": {"achieved_tflops": flops / (t_force * 1e-3) / 1e12, "peak_tflops": fp32_peak, "frac": flops / (t_force * 1e-3) / 1e12 / fp32_peak,
+                                  "model": "SURVEY 8(d) algorithmic FLOP per pair class", "sm_mhz": sm_mhz},
+                "roofline_integrate": {"kernel": "fused second half-kick + thermostat + first half-kick/drift/rotate", "bound": "hbm", "achieved": integ_gbs, "peak": hbm_peak,
+                                       "unit": "GB/s", "frac": integ_gbs / hbm_peak, "ms": t_integ, "share_of_step": t_integ / step_ms},
+                "kernels_ms": {"forces": t_force, "integrate": t_integ, "list_rebuild": t_list, "sort": t_sort, "md_step_mean": step_ms},
+                "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4", "small"])
+    ap.add_argument("--md-steps", type=int, default=1000, help="MD steps per bench step")
+    ap.add_argument("--equil", type=int, default=10000, help="untimed equilibration MD steps")
+    ap.add_argument("--use-edge", type=int, default=1)
+    ap.add_argument("--sort-every", type=int, default=1)
+    ap.add_argument("--ref-md-steps", type=int, default=4, help="MD steps per bench step of the CPU reference arm")
+    ap.add_argument("--ref-procs", type=int, default=0)
+    ap.add_argument("--cpu-md-steps", type=int, default=40)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        ours(args)
+
+
+if __name__ == "__main__":
+    main()
