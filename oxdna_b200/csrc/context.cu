@@ -37,7 +37,8 @@ struct oxb_ctx {
 	// double-buffered state (slot order)
 	int cur = 0;
 	double4 *posd[2] = { nullptr, nullptr }, *veld[2] = { nullptr, nullptr }, *Ld[2] = { nullptr, nullptr }, *quatd[2] = { nullptr, nullptr };
-	int4 *ipos[2] = { nullptr, nullptr }, *list_ipos[2] = { nullptr, nullptr };
+	int4 *ipos[2] = { nullptr, nullptr }, *list_ipos[2] = { nullptr, nullptr }, *iback[2] = { nullptr, nullptr };
+	float4 *Fb = nullptr;
 	float4 *quat[2] = { nullptr, nullptr }, *F[2] = { nullptr, nullptr }, *T[2] = { nullptr, nullptr };
 	int2 *bonds[2] = { nullptr, nullptr };
 	int *slot_of = nullptr;
@@ -62,9 +63,12 @@ struct oxb_ctx {
 	int *cell_key = nullptr, *cell_key_sorted = nullptr, *cell_val = nullptr, *cell_val_sorted = nullptr, *cell_start = nullptr;
 	int *nbr = nullptr, *nnbr = nullptr;
 	int2 *edges = nullptr;
-	int *edge_offsets = nullptr, *n_edges = nullptr;
+	int *edge_offsets = nullptr, *far_offsets = nullptr, *n_edges = nullptr;
 	long long edge_capacity = 0;
-	int edge_hint = 0;
+	int edge_hint = 0, near_hint = 0;
+	int2 *hb_list = nullptr, *cx_list = nullptr;
+	int *counters = nullptr;
+	int hb_cap = 0, cx_cap = 0;
 	void *cub_tmp = nullptr;
 	size_t cub_tmp_bytes = 0;
 	unsigned *hkeys = nullptr, *hkeys_sorted = nullptr;
@@ -114,9 +118,11 @@ void set_boxf(oxb_ctx *c) {
 
 void free_lists(oxb_ctx *c) {
 	cudaFree(c->cell_key); cudaFree(c->cell_key_sorted); cudaFree(c->cell_val); cudaFree(c->cell_val_sorted); cudaFree(c->cell_start);
-	cudaFree(c->nbr); cudaFree(c->nnbr); cudaFree(c->edges); cudaFree(c->edge_offsets); cudaFree(c->n_edges); cudaFree(c->cub_tmp);
+	cudaFree(c->nbr); cudaFree(c->nnbr); cudaFree(c->edges); cudaFree(c->edge_offsets); cudaFree(c->far_offsets); cudaFree(c->n_edges); cudaFree(c->cub_tmp);
+	cudaFree(c->hb_list); cudaFree(c->cx_list); cudaFree(c->counters);
 	c->cell_key = c->cell_key_sorted = c->cell_val = c->cell_val_sorted = c->cell_start = c->nbr = c->nnbr = c->edge_offsets = c->n_edges = nullptr;
-	c->edges = nullptr;
+	c->far_offsets = c->counters = nullptr;
+	c->edges = c->hb_list = c->cx_list = nullptr;
 	c->cub_tmp = nullptr;
 	c->lists_allocated = false;
 }
@@ -146,8 +152,12 @@ int alloc_lists(oxb_ctx *c, int max_neigh) {
 	CU(dalloc(&c->cell_key, N)); CU(dalloc(&c->cell_key_sorted, N)); CU(dalloc(&c->cell_val, N)); CU(dalloc(&c->cell_val_sorted, N));
 	CU(dalloc(&c->cell_start, 2 * (size_t) ncells));
 	CU(dalloc(&c->nbr, (size_t) max_neigh * N)); CU(dalloc(&c->nnbr, N));
-	CU(dalloc(&c->edge_offsets, (size_t) N + 1)); CU(dalloc(&c->n_edges, 1));
-	CU(cudaMemset(c->n_edges, 0, sizeof(int)));
+	CU(dalloc(&c->edge_offsets, (size_t) N + 1)); CU(dalloc(&c->far_offsets, (size_t) N + 1)); CU(dalloc(&c->n_edges, 2));
+	CU(cudaMemset(c->n_edges, 0, 2 * sizeof(int)));
+	c->hb_cap = c->use_edge ? 6 * N + 1024 : 1;
+	c->cx_cap = c->use_edge ? 3 * N + 1024 : 1;
+	CU(dalloc(&c->hb_list, (size_t) c->hb_cap)); CU(dalloc(&c->cx_list, (size_t) c->cx_cap)); CU(dalloc(&c->counters, 2));
+	CU(cudaMemset(c->counters, 0, 2 * sizeof(int)));
 	c->edge_capacity = c->use_edge ? ((long long) N * max_neigh) / 2 + N : 1;
 	CU(dalloc(&c->edges, (size_t) c->edge_capacity));
 	c->cub_tmp_bytes = std::max(oxb::lists_tmp_bytes(N, (int) ncells), oxb::sort_tmp_bytes(N));
@@ -166,7 +176,13 @@ oxb::ListArgs list_args(oxb_ctx *c) {
 	a.cell_key = c->cell_key; a.cell_key_sorted = c->cell_key_sorted; a.cell_val = c->cell_val; a.cell_val_sorted = c->cell_val_sorted;
 	a.cell_start = c->cell_start;
 	a.nbr = c->nbr; a.nnbr = c->nnbr; a.max_neigh = c->max_neigh; a.stride = c->N;
-	a.edges = c->edges; a.edge_offsets = c->edge_offsets; a.n_edges = c->n_edges; a.edge_capacity = c->edge_capacity;
+	a.edges = c->edges; a.edge_offsets = c->edge_offsets; a.far_offsets = c->far_offsets; a.n_edges = c->n_edges; a.edge_capacity = c->edge_capacity;
+	{
+		// pairs further apart than this at build time cannot come within rcut_near before the next rebuild (each particle
+		// moves at most `skin` plus one step): they only ever feel Debye-Hueckel
+		double rn = (double) c->model.rcut_near + 2. * c->skin + 0.02;
+		a.rnear2 = (float) (rn * rn);
+	}
 	a.list_ipos = c->list_ipos[c->cur];
 	a.flags = c->flags;
 	a.cub_tmp = c->cub_tmp; a.cub_tmp_bytes = c->cub_tmp_bytes;
@@ -199,6 +215,7 @@ int do_sort(oxb_ctx *c) {
 	p.posd_in = c->posd[a]; p.veld_in = c->veld[a]; p.Ld_in = c->Ld[a]; p.quatd_in = c->quatd[a];
 	p.posd_out = c->posd[b]; p.veld_out = c->veld[b]; p.Ld_out = c->Ld[b]; p.quatd_out = c->quatd[b];
 	p.ipos_in = c->ipos[a]; p.list_ipos_in = c->list_ipos[a]; p.ipos_out = c->ipos[b]; p.list_ipos_out = c->list_ipos[b];
+	p.iback_in = c->iback[a]; p.iback_out = c->iback[b];
 	p.quat_in = c->quat[a]; p.F_in = c->F[a]; p.T_in = c->T[a]; p.quat_out = c->quat[b]; p.F_out = c->F[b]; p.T_out = c->T[b];
 	p.bonds_in = c->bonds[a]; p.bonds_out = c->bonds[b];
 	p.slot_of = c->slot_of;
@@ -224,10 +241,11 @@ int do_build(oxb_ctx *c) {
 		if((c->h_flags[OXB_FLAG_ERROR] & (OXB_ERR_NEIGH_OVERFLOW | OXB_ERR_EDGE_OVERFLOW)) == 0) {
 			c->error_flags &= ~(OXB_ERR_NEIGH_OVERFLOW | OXB_ERR_EDGE_OVERFLOW);
 			if(c->use_edge) {
-				int ne = 0;
-				CU(cudaMemcpyAsync(&ne, c->n_edges, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+				int ne[2] = { 0, 0 };
+				CU(cudaMemcpyAsync(ne, c->n_edges, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
 				CU(cudaStreamSynchronize(c->stream));
-				c->edge_hint = ne;
+				c->edge_hint = ne[0];
+				c->near_hint = ne[1];
 			}
 			c->lists_valid = true;
 			c->n_list_updates++;
@@ -252,13 +270,17 @@ int ensure_lists(oxb_ctx *c) {
 	return do_build(c);
 }
 
-// hw: index of the halt word the launched kernels must honour
-int launch_forces(oxb_ctx *c, int hw) {
+// hw: index of the halt word the launched kernels must honour; clear: F/T/Fb are not known to be zero
+int launch_forces(oxb_ctx *c, int hw, bool clear) {
 	const int a = c->cur;
 	if(c->use_edge) {
-		oxb::launch_forces_edge(c->stream, c->model, c->boxf, c->N, c->n_edges, std::max(c->edge_hint, 1), c->ipos[a], c->quat[a], c->bonds[a], c->edges,
-				c->F[a], c->T[a], c->flags, hw, c->n_sm);
-		c->launches += 2;
+		oxb::EdgeArgs e;
+		e.N = c->N; e.ipos = c->ipos[a]; e.iback = c->iback[a]; e.quat = c->quat[a]; e.bonds = c->bonds[a]; e.edges = c->edges;
+		e.n_near = c->n_edges + 1; e.n_edges = c->n_edges; e.near_hint = std::max(c->near_hint, 1); e.edge_hint = std::max(c->edge_hint, 1);
+		e.F = c->F[a]; e.T = c->T[a]; e.Fb = c->Fb; e.hb_list = c->hb_list; e.cx_list = c->cx_list; e.counters = c->counters;
+		e.hb_cap = c->hb_cap; e.cx_cap = c->cx_cap; e.clear_first = clear;
+		oxb::launch_forces_edge(c->stream, c->model, c->boxf, e, c->flags, hw, c->n_sm);
+		c->launches += 5;
 	}
 	else {
 		oxb::launch_forces_particle(c->stream, c->model, c->boxf, c->N, c->ipos[a], c->quat[a], c->bonds[a], c->nbr, c->nnbr, c->N, c->F[a], c->T[a],
@@ -281,7 +303,8 @@ oxb::IntegrateArgs integ_args(oxb_ctx *c, long long step) {
 	a.box = c->boxf;
 	a.posd = c->posd[k]; a.veld = c->veld[k]; a.Ld = c->Ld[k]; a.quatd = c->quatd[k];
 	a.ipos = c->ipos[k]; a.quat = c->quat[k]; a.list_ipos = c->list_ipos[k];
-	a.F = c->F[k]; a.T = c->T[k];
+	a.F = c->F[k]; a.T = c->T[k]; a.Fb = c->Fb; a.iback = c->iback[k];
+	a.back_a1 = c->model.back_a1; a.back_a2 = c->model.back_a2;
 	a.flags = c->flags; a.sums = c->sums; a.th = c->th; a.step = step;
 	return a;
 }
@@ -326,7 +349,7 @@ int ensure_forces(oxb_ctx *c) {
 	if(!c->forces_valid) {
 		rc = reset_batch_flags(c);
 		if(rc) return rc;
-		launch_forces(c, OXB_FLAG_COUNT);
+		launch_forces(c, OXB_FLAG_COUNT, true);
 		CU(cudaGetLastError());
 		c->forces_valid = true;
 	}
@@ -355,12 +378,14 @@ int oxb_create(oxb_ctx **out, int device, int N, int precision) {
 	CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	for(int k = 0; k < 2; k++) {
 		CU(dalloc(&c->posd[k], N)); CU(dalloc(&c->veld[k], N)); CU(dalloc(&c->Ld[k], N)); CU(dalloc(&c->quatd[k], N));
-		CU(dalloc(&c->ipos[k], N)); CU(dalloc(&c->list_ipos[k], N)); CU(dalloc(&c->quat[k], N)); CU(dalloc(&c->F[k], N)); CU(dalloc(&c->T[k], N));
+		CU(dalloc(&c->ipos[k], N)); CU(dalloc(&c->list_ipos[k], N)); CU(dalloc(&c->iback[k], N)); CU(dalloc(&c->quat[k], N)); CU(dalloc(&c->F[k], N)); CU(dalloc(&c->T[k], N));
 		CU(dalloc(&c->bonds[k], N));
 		CU(cudaMemset(c->F[k], 0, sizeof(float4) * N)); CU(cudaMemset(c->T[k], 0, sizeof(float4) * N));
 		CU(cudaMemset(c->list_ipos[k], 0, sizeof(int4) * N));
 	}
 	CU(dalloc(&c->slot_of, N));
+	CU(dalloc(&c->Fb, N));
+	CU(cudaMemset(c->Fb, 0, sizeof(float4) * N));
 	CU(dalloc(&c->flags, OXB_FLAG_WORDS));
 	CU(cudaMemset(c->flags, 0, sizeof(int) * OXB_FLAG_WORDS));
 	CU(cudaMallocHost((void **) &c->h_flags, sizeof(int) * OXB_FLAG_WORDS));
@@ -377,8 +402,9 @@ void oxb_destroy(oxb_ctx *c) {
 	if(c->stream) cudaStreamSynchronize(c->stream);
 	for(int k = 0; k < 2; k++) {
 		cudaFree(c->posd[k]); cudaFree(c->veld[k]); cudaFree(c->Ld[k]); cudaFree(c->quatd[k]); cudaFree(c->ipos[k]); cudaFree(c->list_ipos[k]);
-		cudaFree(c->quat[k]); cudaFree(c->F[k]); cudaFree(c->T[k]); cudaFree(c->bonds[k]);
+		cudaFree(c->quat[k]); cudaFree(c->F[k]); cudaFree(c->T[k]); cudaFree(c->bonds[k]); cudaFree(c->iback[k]);
 	}
+	cudaFree(c->Fb);
 	cudaFree(c->slot_of); cudaFree(c->flags); cudaFree(c->sums); cudaFree(c->d_energy); cudaFree(c->ext); cudaFree(c->pos_f4);
 	cudaFree(c->hkeys); cudaFree(c->hkeys_sorted); cudaFree(c->hvals); cudaFree(c->hvals_sorted); cudaFree(c->hinv);
 	free_lists(c);
@@ -494,9 +520,10 @@ int oxb_set_state(oxb_ctx *c, const double *pos, const double *a1, const double 
 	if(c == nullptr || pos == nullptr || a1 == nullptr || a3 == nullptr) return 1;
 	if(!c->have_topology) return fail(c, 2, "topology must be set before the state");
 	if(!c->have_box) return fail(c, 2, "box must be set before the state");
+	if(!c->have_model) return fail(c, 2, "interaction model must be set before the state (it fixes the backbone-site geometry)");
 	const int N = c->N;
 	std::vector<double4> hp(N), hv(N), hL(N), hq(N);
-	std::vector<int4> hi(N);
+	std::vector<int4> hi(N), hk(N);
 	std::vector<float4> hqf(N);
 	std::vector<int2> hb(N);
 	std::vector<int> hs(N);
@@ -526,6 +553,14 @@ int oxb_set_state(oxb_ctx *c, const double *pos, const double *a1, const double 
 		hi[i].y = (int) to_fixed(pos[3 * i + 1], 1. / c->box[1]);
 		hi[i].z = (int) to_fixed(pos[3 * i + 2], 1. / c->box[2]);
 		hi[i].w = pack_word(c->h_btype[i], i);
+		{
+			// backbone site (grooved): r + back_a1 a1 + back_a2 a2, from the same float-rounded constants the kernels use
+			double b1 = c->model.back_a1, b2 = c->model.back_a2;
+			hk[i].x = (int) to_fixed(pos[3 * i] + b1 * v1[0] + b2 * v2[0], 1. / c->box[0]);
+			hk[i].y = (int) to_fixed(pos[3 * i + 1] + b1 * v1[1] + b2 * v2[1], 1. / c->box[1]);
+			hk[i].z = (int) to_fixed(pos[3 * i + 2] + b1 * v1[2] + b2 * v2[2], 1. / c->box[2]);
+			hk[i].w = (c->h_n3[i] < 0 || c->h_n5[i] < 0) ? 1 : 0;
+		}
 		hb[i] = make_int2(c->h_n3[i], c->h_n5[i]);
 		hs[i] = i;
 	}
@@ -535,6 +570,7 @@ int oxb_set_state(oxb_ctx *c, const double *pos, const double *a1, const double 
 	CU(cudaMemcpyAsync(c->Ld[k], hL.data(), sizeof(double4) * N, cudaMemcpyHostToDevice, c->stream));
 	CU(cudaMemcpyAsync(c->quatd[k], hq.data(), sizeof(double4) * N, cudaMemcpyHostToDevice, c->stream));
 	CU(cudaMemcpyAsync(c->ipos[k], hi.data(), sizeof(int4) * N, cudaMemcpyHostToDevice, c->stream));
+	CU(cudaMemcpyAsync(c->iback[k], hk.data(), sizeof(int4) * N, cudaMemcpyHostToDevice, c->stream));
 	CU(cudaMemcpyAsync(c->quat[k], hqf.data(), sizeof(float4) * N, cudaMemcpyHostToDevice, c->stream));
 	CU(cudaMemcpyAsync(c->bonds[k], hb.data(), sizeof(int2) * N, cudaMemcpyHostToDevice, c->stream));
 	CU(cudaMemcpyAsync(c->slot_of, hs.data(), sizeof(int) * N, cudaMemcpyHostToDevice, c->stream));
@@ -675,7 +711,7 @@ int oxb_run(oxb_ctx *c, long long n_steps) {
 		int epoch = 0;
 		if(!c->mid_step) {
 			// start of a run: forces for the current positions, then the first half-kick + drift
-			if(!c->forces_valid) { launch_forces(c, OXB_FLAG_COUNT + (epoch & 1)); c->forces_valid = true; }
+			if(!c->forces_valid) { launch_forces(c, OXB_FLAG_COUNT + (epoch & 1), true); c->forces_valid = true; }
 			oxb::launch_integrate_epoch(c->stream, integ_args(c, c->step), OXB_PH_FIRST, epoch++);
 			c->launches++;
 		}
@@ -684,7 +720,7 @@ int oxb_run(oxb_ctx *c, long long n_steps) {
 		for(long long b = 0; b < batch; b++) {
 			const long long s = step0 + b;
 			c->step = s; // external forces read c->step at launch time
-			launch_forces(c, OXB_FLAG_COUNT + (epoch & 1));
+			launch_forces(c, OXB_FLAG_COUNT + (epoch & 1), false);
 			const bool last = (b == batch - 1) && (batch == remaining);
 			const bool th = thermostat_active(c, s);
 			oxb::IntegrateArgs a = integ_args(c, s);
@@ -754,12 +790,15 @@ int oxb_get_forces(oxb_ctx *c, double *force, double *torque_body, double *torqu
 	for(int s = 0; s < N; s++) {
 		int i = word_index(hi[s].w);
 		if(force) { force[3 * i] = hF[s].x; force[3 * i + 1] = hF[s].y; force[3 * i + 2] = hF[s].z; }
-		if(torque_body) { torque_body[3 * i] = hT[s].x; torque_body[3 * i + 1] = hT[s].y; torque_body[3 * i + 2] = hT[s].z; }
-		if(torque_lab) {
+		// the device keeps the torque in the lab frame; the reference stores it in the body frame (R^T tau)
+		if(torque_lab) { torque_lab[3 * i] = hT[s].x; torque_lab[3 * i + 1] = hT[s].y; torque_lab[3 * i + 2] = hT[s].z; }
+		if(torque_body) {
 			quatd q = { hq[s].x, hq[s].y, hq[s].z, hq[s].w };
 			double x1[3], x2[3], x3[3];
 			axes_from_quatd(q, x1, x2, x3);
-			for(int d = 0; d < 3; d++) torque_lab[3 * i + d] = x1[d] * hT[s].x + x2[d] * hT[s].y + x3[d] * hT[s].z;
+			torque_body[3 * i] = x1[0] * hT[s].x + x1[1] * hT[s].y + x1[2] * hT[s].z;
+			torque_body[3 * i + 1] = x2[0] * hT[s].x + x2[1] * hT[s].y + x2[2] * hT[s].z;
+			torque_body[3 * i + 2] = x3[0] * hT[s].x + x3[1] * hT[s].y + x3[2] * hT[s].z;
 		}
 		if(energy) energy[i] = hF[s].w;
 		if(hb_energy) hb_energy[i] = hT[s].w;
@@ -866,7 +905,7 @@ int oxb_time_kernel(oxb_ctx *c, int which, int reps, float *ms) {
 	CU(cudaStreamSynchronize(c->stream));
 	CU(cudaEventRecord(e0, c->stream));
 	for(int r = 0; r < reps; r++) {
-		if(which == 0) launch_forces(c, OXB_FLAG_COUNT);
+		if(which == 0) launch_forces(c, OXB_FLAG_COUNT, true);
 		else if(which == 1) {
 			// dt = 0 leaves the state bit-identical while moving exactly the same bytes
 			oxb::IntegrateArgs a = integ_args(c, c->step);
@@ -885,7 +924,7 @@ int oxb_time_kernel(oxb_ctx *c, int which, int reps, float *ms) {
 	*ms = t / reps;
 	cudaEventDestroy(e0);
 	cudaEventDestroy(e1);
-	if(which == 3) { c->lists_valid = false; c->forces_valid = false; rc = ensure_forces(c); if(rc) return rc; }
+	if(which == 3 || which == 1) { if(which == 3) c->lists_valid = false; c->forces_valid = false; rc = ensure_forces(c); if(rc) return rc; }
 	CU(cudaStreamSynchronize(c->stream));
 	return 0;
 }

@@ -213,129 +213,133 @@ struct PairEnergy {
 };
 
 // ---------------------------------------------------------------------------------------------------------------
-// Non-bonded pair.  r = min-image(q - p) between centres of mass.  Terms: excluded volume (4 site pairs),
-// hydrogen bonding, cross stacking, coaxial stacking (oxDNA2 form), Debye-Hueckel.
+// Non-bonded pair, split into the pieces the staged edge pipeline launches separately (forces.cu):
+//   dna2_dh        Debye-Hueckel on the backbone-backbone vector (the only term beyond rcut_near)
+//   dna2_excl      the four excluded-volume site pairs
+//   dna2_hbcr      hydrogen bonding + cross stacking (same six angles on the base-base vector)
+//   dna2_cxst      coaxial stacking (oxDNA2 form: no phi3 term, harmonic add-on to theta1)
+// r = min-image(q - p) between centres of mass; forces are "on q".
 // ---------------------------------------------------------------------------------------------------------------
-OXB_HD PairEnergy dna2_nonbonded(const oxb_dna2_params &M, v3 r, const Axes &A, const Axes &B, int btp, int btq,
-		bool p_end, bool q_end, v3 pback, v3 qback, PairAcc &acc) {
-	PairEnergy E;
-	E.total = 0.f;
-	E.hb = 0.f;
 
-	float r2 = dot(r, r);
-	if(r2 >= M.rcut * M.rcut) return E; // DNA2Interaction.cpp:46-48
-
-	// ---- Debye-Hueckel + back-back excluded volume on the backbone-backbone vector
-	v3 rbb = r + qback - pback;
-	float rbb2 = dot(rbb, rbb);
-	if(rbb2 < M.dh_rc * M.dh_rc) {
-		float m = sqrtf(rbb2);
-		float cut = 1.f;
-		if(M.dh_half_charged_ends) {
-			if(p_end) cut *= 0.5f;
-			if(q_end) cut *= 0.5f;
-		}
-		float en, fs; // force on q = fs * rhat
-		if(m < M.dh_rhigh) {
-			float ex = expf(m * M.dh_minus_kappa) * M.dh_prefactor / m;
-			en = ex;
-			fs = -ex * (M.dh_minus_kappa - 1.f / m);
-		}
-		else {
-			float x = m - M.dh_rc;
-			en = M.dh_b * x * x;
-			fs = -2.f * M.dh_b * x;
-		}
-		E.total += en * cut;
-		acc.site_kk(rbb * (fs * cut / m));
+// returns the DH energy; fs such that force-on-q = fs * rbb (zero outside the range)
+OXB_HD float dna2_dh(const oxb_dna2_params &M, float rbb2, bool p_end, bool q_end, float &fs) {
+	fs = 0.f;
+	if(rbb2 >= M.dh_rc * M.dh_rc) return 0.f;
+	float m = sqrtf(rbb2);
+	float cut = 1.f;
+	if(M.dh_half_charged_ends) {
+		if(p_end) cut *= 0.5f;
+		if(q_end) cut *= 0.5f;
 	}
+	float en, f; // force on q = f * rhat
+	if(m < M.dh_rhigh) {
+		float ex = expf(m * M.dh_minus_kappa) * M.dh_prefactor / m;
+		en = ex;
+		f = -ex * (M.dh_minus_kappa - 1.f / m);
+	}
+	else {
+		float x = m - M.dh_rc;
+		en = M.dh_b * x * x;
+		f = -2.f * M.dh_b * x;
+	}
+	fs = f * cut / m;
+	return en * cut;
+}
 
-	if(r2 >= M.rcut_near * M.rcut_near) return E;
-
-	const float cb = M.base_a1, cs = M.stack_a1;
-	float s;
+OXB_HD float dna2_excl(const oxb_dna2_params &M, v3 r, v3 rbb, v3 rb, const Axes &A, const Axes &B, v3 pback, v3 qback, PairAcc &acc) {
+	const float cb = M.base_a1;
+	float s, E = 0.f;
 	float en = excl_s(M.excl[0], M.excl_eps, rbb, s);
-	if(en != 0.f) { E.total += en; acc.site_kk(rbb * s); }
-
-	v3 pbase = A.a1 * cb, qbase = B.a1 * cb;
-	v3 rb = r + qbase - pbase; // base-base, shared by excluded volume, HB and cross stacking
+	if(en != 0.f) { E += en; acc.site_kk(rbb * s); }
 	en = excl_s(M.excl[1], M.excl_eps, rb, s);
-	if(en != 0.f) { E.total += en; acc.site_aa(rb * s, cb, cb); }
-	{
-		v3 d = r + qbase - pback; // back(p) - base(q)
-		en = excl_s(M.excl[3], M.excl_eps, d, s);
-		if(en != 0.f) { E.total += en; acc.site_ka(d * s, cb); }
-		d = r + qback - pbase; // base(p) - back(q)
-		en = excl_s(M.excl[2], M.excl_eps, d, s);
-		if(en != 0.f) { E.total += en; acc.site_ak(d * s, cb); }
-	}
+	if(en != 0.f) { E += en; acc.site_aa(rb * s, cb, cb); }
+	v3 d = r + B.a1 * cb - pback; // back(p) - base(q)
+	en = excl_s(M.excl[3], M.excl_eps, d, s);
+	if(en != 0.f) { E += en; acc.site_ka(d * s, cb); }
+	d = r + qback - A.a1 * cb; // base(p) - back(q)
+	en = excl_s(M.excl[2], M.excl_eps, d, s);
+	if(en != 0.f) { E += en; acc.site_ak(d * s, cb); }
+	return E;
+}
 
-	// ---- hydrogen bonding + cross stacking (same six angles on the base-base vector)
-	float rbm2 = dot(rb, rb);
-	bool hb_on = (btp + btq == 3) && rbm2 > M.hb.rclow * M.hb.rclow && rbm2 < M.hb.rchigh * M.hb.rchigh;
-	bool cr_on = rbm2 > M.crst.rclow * M.crst.rclow && rbm2 < M.crst.rchigh * M.crst.rchigh;
-	if(hb_on || cr_on) {
-		float m = sqrtf(rbm2);
-		float inv = 1.f / m;
-		v3 h = rb * inv;
-		Angle t1 = make_angle(-A.a1, B.a1);
-		Angle t2 = make_angle(-B.a1, h);
-		Angle t3 = make_angle(A.a1, h);
-		Angle t4 = make_angle(A.a3, B.a3);
-		Angle t7 = make_angle(-B.a3, h);
-		Angle t8 = make_angle(A.a3, h);
-		float g1 = 0.f, g2 = 0.f, g3 = 0.f, g4 = 0.f, g7 = 0.f, g8 = 0.f, grad = 0.f;
-		if(hb_on) {
-			int ti = btype_to_type(btq) * 5 + btype_to_type(btp);
-			float mult = (abs(btq) >= 300 && abs(btp) >= 300) ? M.hb_multiplier : 1.f;
-			RadVal f1 = f1_r(M.hb, M.hb_eps[ti], M.hb_shift[ti], m);
-			f1.v *= mult;
-			f1.d *= mult;
-			AngVal a1 = f4_cs(M.f4[OXB_F4_HB_T1], t1.c, t1.s);
-			AngVal a2 = f4_cs(M.f4[OXB_F4_HB_T2], t2.c, t2.s);
-			AngVal a3 = f4_cs(M.f4[OXB_F4_HB_T2], t3.c, t3.s);
-			AngVal a4 = f4_cs(M.f4[OXB_F4_HB_T4], t4.c, t4.s);
-			AngVal a7 = f4_cs(M.f4[OXB_F4_HB_T7], t7.c, t7.s);
-			AngVal a8 = f4_cs(M.f4[OXB_F4_HB_T7], t8.c, t8.s);
-			float p12 = a1.v * a2.v, p34 = a3.v * a4.v, p78 = a7.v * a8.v;
-			float ang = p12 * p34 * p78;
-			float e = f1.v * ang;
-			if(e != 0.f) {
-				E.total += e;
-				E.hb += e;
-				grad += f1.d * ang;
-				float f34_78 = f1.v * p34 * p78, f12_78 = f1.v * p12 * p78, f12_34 = f1.v * p12 * p34;
-				g1 += f34_78 * a1.dc * a2.v;
-				g2 += f34_78 * a1.v * a2.dc;
-				g3 += f12_78 * a3.dc * a4.v;
-				g4 += f12_78 * a3.v * a4.dc;
-				g7 += f12_34 * a7.dc * a8.v;
-				g8 += f12_34 * a7.v * a8.dc;
-			}
+OXB_HD bool dna2_hb_in_range(const oxb_dna2_params &M, float rbm2, int btp, int btq) {
+	return (btp + btq == 3) && rbm2 > M.hb.rclow * M.hb.rclow && rbm2 < M.hb.rchigh * M.hb.rchigh;
+}
+OXB_HD bool dna2_crst_in_range(const oxb_dna2_params &M, float rbm2) {
+	return rbm2 > M.crst.rclow * M.crst.rclow && rbm2 < M.crst.rchigh * M.crst.rchigh;
+}
+OXB_HD bool dna2_cxst_in_range(const oxb_dna2_params &M, float rs2) {
+	return rs2 > M.cxst.rclow * M.cxst.rclow && rs2 < M.cxst.rchigh * M.cxst.rchigh;
+}
+
+// rb = base-base vector.  Returns total energy (HB + cross stacking), ehb = the HB part.
+OXB_HD float dna2_hbcr(const oxb_dna2_params &M, v3 rb, float rbm2, const Axes &A, const Axes &B, int btp, int btq, bool hb_on, bool cr_on,
+		PairAcc &acc, float &ehb) {
+	const float cb = M.base_a1;
+	float E = 0.f;
+	ehb = 0.f;
+	float m = sqrtf(rbm2);
+	float inv = 1.f / m;
+	v3 h = rb * inv;
+	Angle t1 = make_angle(-A.a1, B.a1);
+	Angle t2 = make_angle(-B.a1, h);
+	Angle t3 = make_angle(A.a1, h);
+	Angle t4 = make_angle(A.a3, B.a3);
+	Angle t7 = make_angle(-B.a3, h);
+	Angle t8 = make_angle(A.a3, h);
+	float g1 = 0.f, g2 = 0.f, g3 = 0.f, g4 = 0.f, g7 = 0.f, g8 = 0.f, grad = 0.f;
+	if(hb_on) {
+		int ti = btype_to_type(btq) * 5 + btype_to_type(btp);
+		float mult = (abs(btq) >= 300 && abs(btp) >= 300) ? M.hb_multiplier : 1.f;
+		RadVal f1 = f1_r(M.hb, M.hb_eps[ti], M.hb_shift[ti], m);
+		f1.v *= mult;
+		f1.d *= mult;
+		AngVal a1 = f4_cs(M.f4[OXB_F4_HB_T1], t1.c, t1.s);
+		AngVal a2 = f4_cs(M.f4[OXB_F4_HB_T2], t2.c, t2.s);
+		AngVal a3 = f4_cs(M.f4[OXB_F4_HB_T2], t3.c, t3.s);
+		AngVal a4 = f4_cs(M.f4[OXB_F4_HB_T4], t4.c, t4.s);
+		AngVal a7 = f4_cs(M.f4[OXB_F4_HB_T7], t7.c, t7.s);
+		AngVal a8 = f4_cs(M.f4[OXB_F4_HB_T7], t8.c, t8.s);
+		float p12 = a1.v * a2.v, p34 = a3.v * a4.v, p78 = a7.v * a8.v;
+		float ang = p12 * p34 * p78;
+		float e = f1.v * ang;
+		if(e != 0.f) {
+			E += e;
+			ehb += e;
+			grad += f1.d * ang;
+			float f34_78 = f1.v * p34 * p78, f12_78 = f1.v * p12 * p78, f12_34 = f1.v * p12 * p34;
+			g1 += f34_78 * a1.dc * a2.v;
+			g2 += f34_78 * a1.v * a2.dc;
+			g3 += f12_78 * a3.dc * a4.v;
+			g4 += f12_78 * a3.v * a4.dc;
+			g7 += f12_34 * a7.dc * a8.v;
+			g8 += f12_34 * a7.v * a8.dc;
 		}
-		if(cr_on) {
-			RadVal f2 = f2_r(M.crst, m);
-			AngVal a1 = f4_cs(M.f4[OXB_F4_CRST_T1], t1.c, t1.s);
-			AngVal a2 = f4_cs(M.f4[OXB_F4_CRST_T2], t2.c, t2.s);
-			AngVal a3 = f4_cs(M.f4[OXB_F4_CRST_T2], t3.c, t3.s);
-			AngVal a4 = f4_cs_sym(M.f4[OXB_F4_CRST_T4], t4.c, t4.s);
-			AngVal a7 = f4_cs_sym(M.f4[OXB_F4_CRST_T7], t7.c, t7.s);
-			AngVal a8 = f4_cs_sym(M.f4[OXB_F4_CRST_T7], t8.c, t8.s);
-			float p12 = a1.v * a2.v, p34 = a3.v * a4.v, p78 = a7.v * a8.v;
-			float ang = p12 * p34 * p78;
-			float e = f2.v * ang;
-			if(e != 0.f) {
-				E.total += e;
-				grad += f2.d * ang;
-				float f34_78 = f2.v * p34 * p78, f12_78 = f2.v * p12 * p78, f12_34 = f2.v * p12 * p34;
-				g1 += f34_78 * a1.dc * a2.v;
-				g2 += f34_78 * a1.v * a2.dc;
-				g3 += f12_78 * a3.dc * a4.v;
-				g4 += f12_78 * a3.v * a4.dc;
-				g7 += f12_34 * a7.dc * a8.v;
-				g8 += f12_34 * a7.v * a8.dc;
-			}
+	}
+	if(cr_on) {
+		RadVal f2 = f2_r(M.crst, m);
+		AngVal a1 = f4_cs(M.f4[OXB_F4_CRST_T1], t1.c, t1.s);
+		AngVal a2 = f4_cs(M.f4[OXB_F4_CRST_T2], t2.c, t2.s);
+		AngVal a3 = f4_cs(M.f4[OXB_F4_CRST_T2], t3.c, t3.s);
+		AngVal a4 = f4_cs_sym(M.f4[OXB_F4_CRST_T4], t4.c, t4.s);
+		AngVal a7 = f4_cs_sym(M.f4[OXB_F4_CRST_T7], t7.c, t7.s);
+		AngVal a8 = f4_cs_sym(M.f4[OXB_F4_CRST_T7], t8.c, t8.s);
+		float p12 = a1.v * a2.v, p34 = a3.v * a4.v, p78 = a7.v * a8.v;
+		float ang = p12 * p34 * p78;
+		float e = f2.v * ang;
+		if(e != 0.f) {
+			E += e;
+			grad += f2.d * ang;
+			float f34_78 = f2.v * p34 * p78, f12_78 = f2.v * p12 * p78, f12_34 = f2.v * p12 * p34;
+			g1 += f34_78 * a1.dc * a2.v;
+			g2 += f34_78 * a1.v * a2.dc;
+			g3 += f12_78 * a3.dc * a4.v;
+			g4 += f12_78 * a3.v * a4.dc;
+			g7 += f12_34 * a7.dc * a8.v;
+			g8 += f12_34 * a7.v * a8.dc;
 		}
+	}
+	if(E != 0.f) {
 		v3 f = h * (-grad);
 		chain_bb(acc, g1, t1);
 		f += chain_bd<true>(acc, g2, -B.a1, h, inv, t2);
@@ -345,35 +349,62 @@ OXB_HD PairEnergy dna2_nonbonded(const oxb_dna2_params &M, v3 r, const Axes &A, 
 		f += chain_bd<false>(acc, g8, A.a3, h, inv, t8);
 		acc.site_aa(f, cb, cb);
 	}
+	return E;
+}
 
-	// ---- coaxial stacking (oxDNA2: no phi3 term, harmonic add-on to theta1)
-	v3 rs = r + B.a1 * cs - A.a1 * cs;
-	float rs2 = dot(rs, rs);
-	if(rs2 > M.cxst.rclow * M.cxst.rclow && rs2 < M.cxst.rchigh * M.cxst.rchigh) {
-		float m = sqrtf(rs2);
-		float inv = 1.f / m;
-		v3 h = rs * inv;
-		Angle t1 = make_angle(-A.a1, B.a1);
-		Angle t4 = make_angle(A.a3, B.a3);
-		Angle t5 = make_angle(A.a3, h);
-		Angle t6 = make_angle(-B.a3, h);
-		RadVal f2 = f2_r(M.cxst, m);
-		AngVal a1 = f4_cs_cxst_t1(M, t1.c, t1.s);
-		AngVal a4 = f4_cs(M.f4[OXB_F4_CXST_T4], t4.c, t4.s);
-		AngVal a5 = f4_cs_sym(M.f4[OXB_F4_CXST_T5], t5.c, t5.s);
-		AngVal a6 = f4_cs_sym(M.f4[OXB_F4_CXST_T5], t6.c, t6.s);
-		float p14 = a1.v * a4.v, p56 = a5.v * a6.v;
-		float e = f2.v * p14 * p56;
-		if(e != 0.f) {
-			E.total += e;
-			v3 f = h * (-(f2.d * p14 * p56));
-			chain_bb(acc, f2.v * p56 * a1.dc * a4.v, t1);
-			chain_bb(acc, f2.v * p56 * a1.v * a4.dc, t4);
-			f += chain_bd<false>(acc, f2.v * p14 * a5.dc * a6.v, A.a3, h, inv, t5);
-			f += chain_bd<true>(acc, f2.v * p14 * a5.v * a6.dc, -B.a3, h, inv, t6);
-			acc.site_aa(f, cs, cs);
-		}
+// rs = stack-stack vector
+OXB_HD float dna2_cxst(const oxb_dna2_params &M, v3 rs, float rs2, const Axes &A, const Axes &B, PairAcc &acc) {
+	const float cs = M.stack_a1;
+	float m = sqrtf(rs2);
+	float inv = 1.f / m;
+	v3 h = rs * inv;
+	Angle t1 = make_angle(-A.a1, B.a1);
+	Angle t4 = make_angle(A.a3, B.a3);
+	Angle t5 = make_angle(A.a3, h);
+	Angle t6 = make_angle(-B.a3, h);
+	RadVal f2 = f2_r(M.cxst, m);
+	AngVal a1 = f4_cs_cxst_t1(M, t1.c, t1.s);
+	AngVal a4 = f4_cs(M.f4[OXB_F4_CXST_T4], t4.c, t4.s);
+	AngVal a5 = f4_cs_sym(M.f4[OXB_F4_CXST_T5], t5.c, t5.s);
+	AngVal a6 = f4_cs_sym(M.f4[OXB_F4_CXST_T5], t6.c, t6.s);
+	float p14 = a1.v * a4.v, p56 = a5.v * a6.v;
+	float e = f2.v * p14 * p56;
+	if(e != 0.f) {
+		v3 f = h * (-(f2.d * p14 * p56));
+		chain_bb(acc, f2.v * p56 * a1.dc * a4.v, t1);
+		chain_bb(acc, f2.v * p56 * a1.v * a4.dc, t4);
+		f += chain_bd<false>(acc, f2.v * p14 * a5.dc * a6.v, A.a3, h, inv, t5);
+		f += chain_bd<true>(acc, f2.v * p14 * a5.v * a6.dc, -B.a3, h, inv, t6);
+		acc.site_aa(f, cs, cs);
 	}
+	return e;
+}
+
+// the whole non-bonded interaction of one pair (particle-centric kernel, host-side unit test)
+OXB_HD PairEnergy dna2_nonbonded(const oxb_dna2_params &M, v3 r, const Axes &A, const Axes &B, int btp, int btq,
+		bool p_end, bool q_end, v3 pback, v3 qback, PairAcc &acc) {
+	PairEnergy E;
+	E.total = 0.f;
+	E.hb = 0.f;
+	float r2 = dot(r, r);
+	if(r2 >= M.rcut * M.rcut) return E; // DNA2Interaction.cpp:46-48
+	v3 rbb = r + qback - pback;
+	float fs;
+	float en = dna2_dh(M, dot(rbb, rbb), p_end, q_end, fs);
+	if(en != 0.f) { E.total += en; acc.site_kk(rbb * fs); }
+	if(r2 >= M.rcut_near * M.rcut_near) return E;
+	v3 rb = r + (B.a1 - A.a1) * M.base_a1;
+	E.total += dna2_excl(M, r, rbb, rb, A, B, pback, qback, acc);
+	float rbm2 = dot(rb, rb);
+	bool hb_on = dna2_hb_in_range(M, rbm2, btp, btq), cr_on = dna2_crst_in_range(M, rbm2);
+	if(hb_on || cr_on) {
+		float ehb;
+		E.total += dna2_hbcr(M, rb, rbm2, A, B, btp, btq, hb_on, cr_on, acc, ehb);
+		E.hb += ehb;
+	}
+	v3 rs = r + (B.a1 - A.a1) * M.stack_a1;
+	float rs2 = dot(rs, rs);
+	if(dna2_cxst_in_range(M, rs2)) E.total += dna2_cxst(M, rs, rs2, A, B, acc);
 	return E;
 }
 

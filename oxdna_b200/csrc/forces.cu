@@ -7,6 +7,8 @@
 #include "dna_model.cuh"
 #include "kernels.h"
 
+#include <algorithm>
+
 namespace {
 
 struct Particle {
@@ -24,8 +26,6 @@ __device__ __forceinline__ Particle load_particle(const oxb_dna2_params &M, cons
 	P.btype = word_btype(P.ip.w);
 	return P;
 }
-
-__device__ __forceinline__ v3 to_body(const Axes &A, v3 t) { return mk3(dot(A.a1, t), dot(A.a2, t), dot(A.a3, t)); }
 
 // ------------------------------------------------------------------------------------------------------------
 // Particle-centric: one thread per particle, every listed pair evaluated from both ends, no atomics, deterministic.
@@ -77,26 +77,49 @@ __global__ void __launch_bounds__(128) k_forces_particle(const __grid_constant__
 		t += acc.torque_p(P.ax, P.back);
 	}
 
-	v3 tb = to_body(P.ax, t);
+	// torque stays in the lab frame; the integrator rotates it into the body frame
 	F[i] = make_float4(f.x, f.y, f.z, e);
-	T[i] = make_float4(tb.x, tb.y, tb.z, ehb);
+	T[i] = make_float4(t.x, t.y, t.z, ehb);
 	if(broken) atomicOr(flags + OXB_FLAG_ERROR, OXB_ERR_FENE_BROKEN);
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Edge-centric: one thread per unique pair.  Edges are grouped by `from` (list order), so lanes of a warp that share the
-// same `from` particle first reduce among themselves with shuffles (segmented suffix sum); only segment heads issue
-// the vector atomic for the `from` side.  The `to` side is scattered with one float4 atomic per array.
-// F/T hold lab-frame sums here; k_forces_edge_bonded finishes the job.
+// Edge-centric, staged.  One thread per unique pair, but the pair population is split by COST so that every kernel is
+// (nearly) uniform across a warp -- the single-kernel version ran with 8 of 32 lanes active (ncu r01):
+//   k_edge_dh     all edges, Debye-Hueckel only, needs just the two fixed-point backbone-site positions (2 x 16 B)
+//   k_edge_near   edges that can come within rcut_near before the next rebuild: 4 excluded-volume site pairs +
+//                 detection of pairs inside the hydrogen-bonding / cross-stacking / coaxial-stacking radial ranges,
+//                 which are appended (warp-aggregated) to two compact work lists
+//   k_edge_hbcr   dense list of base-base contacts: hydrogen bonding + cross stacking
+//   k_edge_cxst   dense list of stack-stack contacts: coaxial stacking
+//   k_bonded_finalize  per particle: FENE + bonded excluded volume + stacking with its n3 neighbour (each bond once),
+//                 and folding of the backbone-site force sum Fb into force and torque
+// Edges are grouped by `from`, so lanes sharing `from` first reduce with shuffles (segmented suffix sum) and only the
+// segment head issues the 128-bit vector atomic (red.global.add.v4.f32).  F/T/Fb hold lab-frame sums; the integrator
+// rotates the torque into the body frame.
 // ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void atomic_add4(float4 *dst, float x, float y, float z, float w) {
-	// sm_90+ 128-bit vector reduction (red.global.add.v4.f32)
 	atomicAdd(dst, make_float4(x, y, z, w));
 }
 
-__global__ void __launch_bounds__(128) k_forces_edge_nonbonded(const __grid_constant__ oxb_dna2_params M, BoxF box, const int *__restrict__ n_edges,
-		const int4 *__restrict__ ipos, const float4 *__restrict__ quat, const int2 *__restrict__ bonds, const int2 *__restrict__ edges,
-		float4 *__restrict__ F, float4 *__restrict__ T, const int *__restrict__ flags, int hw) {
+template<int NV>
+__device__ __forceinline__ bool segmented_reduce(int key, unsigned lane, float (&v)[NV]) {
+#pragma unroll
+	for(int d = 1; d < 32; d <<= 1) {
+		int okey = __shfl_down_sync(0xffffffffu, key, d);
+		bool take = (lane + d < 32) && (okey == key);
+#pragma unroll
+		for(int k = 0; k < NV; k++) {
+			float o = __shfl_down_sync(0xffffffffu, v[k], d);
+			if(take) v[k] += o;
+		}
+	}
+	int pkey = __shfl_up_sync(0xffffffffu, key, 1);
+	return (lane == 0) || (pkey != key);
+}
+
+__global__ void __launch_bounds__(256) k_edge_dh(const __grid_constant__ oxb_dna2_params M, BoxF box, const int *__restrict__ n_edges,
+		const int2 *__restrict__ edges, const int4 *__restrict__ iback, float4 *__restrict__ Fb, const int *__restrict__ flags, int hw) {
 	if(flags[hw]) return;
 	const int ne = *n_edges;
 	const unsigned lane = threadIdx.x & 31;
@@ -104,79 +127,160 @@ __global__ void __launch_bounds__(128) k_forces_edge_nonbonded(const __grid_cons
 		int eidx = base + lane;
 		bool valid = eidx < ne;
 		int2 ed = valid ? __ldg(edges + eidx) : make_int2(-1 - (int) lane, -1);
-		float fx = 0.f, fy = 0.f, fz = 0.f, fe = 0.f, tx = 0.f, ty = 0.f, tz = 0.f, th = 0.f;
+		float v[4] = { 0.f, 0.f, 0.f, 0.f };
+		if(valid) {
+			int4 bp = __ldg(iback + ed.x), bq = __ldg(iback + ed.y);
+			v3 rbb = min_image_fixed(box, bp, bq);
+			float fs;
+			float en = dna2_dh(M, dot(rbb, rbb), bp.w & 1, bq.w & 1, fs);
+			if(en != 0.f) {
+				v3 f = rbb * fs;
+				atomic_add4(Fb + ed.y, f.x, f.y, f.z, en);
+				v[0] = -f.x; v[1] = -f.y; v[2] = -f.z; v[3] = en;
+			}
+		}
+		bool head = segmented_reduce<4>(ed.x, lane, v);
+		if(valid && head && v[3] != 0.f) atomic_add4(Fb + ed.x, v[0], v[1], v[2], v[3]);
+	}
+}
+
+__device__ __forceinline__ void warp_append(bool flag, int2 item, int2 *__restrict__ list, int *__restrict__ counter, int cap, int *flags) {
+	unsigned mask = __ballot_sync(0xffffffffu, flag);
+	if(mask == 0u) return;
+	unsigned lane = threadIdx.x & 31;
+	int leader = __ffs(mask) - 1;
+	int base = 0;
+	if((int) lane == leader) base = atomicAdd(counter, __popc(mask));
+	base = __shfl_sync(0xffffffffu, base, leader);
+	if(flag) {
+		int pos = base + __popc(mask & ((1u << lane) - 1u));
+		if(pos < cap) list[pos] = item;
+		else atomicOr(flags + OXB_FLAG_ERROR, OXB_ERR_EDGE_OVERFLOW);
+	}
+}
+
+__global__ void __launch_bounds__(128) k_edge_near(const __grid_constant__ oxb_dna2_params M, BoxF box, const int *__restrict__ n_near,
+		const int2 *__restrict__ edges, const int4 *__restrict__ ipos, const float4 *__restrict__ quat, float4 *__restrict__ F, float4 *__restrict__ T,
+		int2 *__restrict__ hb_list, int2 *__restrict__ cx_list, int *__restrict__ counters, int hb_cap, int cx_cap, int *__restrict__ flags, int hw) {
+	if(flags[hw]) return;
+	const int ne = *n_near;
+	const unsigned lane = threadIdx.x & 31;
+	for(int base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < ne; base += gridDim.x * blockDim.x) {
+		int eidx = base + lane;
+		bool valid = eidx < ne;
+		int2 ed = valid ? __ldg(edges + eidx) : make_int2(-1 - (int) lane, -1);
+		float v[6] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
+		float ve = 0.f;
+		bool want_hb = false, want_cx = false;
 		if(valid) {
 			Particle P = load_particle(M, ipos, quat, ed.x);
 			Particle Q = load_particle(M, ipos, quat, ed.y);
-			int2 bp = __ldg(bonds + ed.x), bq = __ldg(bonds + ed.y);
-			PairAcc acc;
-			acc.clear();
-			PairEnergy pe = dna2_nonbonded(M, min_image_fixed(box, P.ip, Q.ip), P.ax, Q.ax, P.btype, Q.btype, (bp.x < 0 || bp.y < 0),
-					(bq.x < 0 || bq.y < 0), P.back, Q.back, acc);
-			if(pe.total != 0.f || acc.F.x != 0.f || acc.F.y != 0.f || acc.F.z != 0.f) {
-				v3 tq = acc.torque_q(Q.ax, Q.back);
-				atomic_add4(F + ed.y, acc.F.x, acc.F.y, acc.F.z, pe.total);
-				atomic_add4(T + ed.y, tq.x, tq.y, tq.z, pe.hb);
-				v3 tp = acc.torque_p(P.ax, P.back);
-				fx = -acc.F.x; fy = -acc.F.y; fz = -acc.F.z; fe = pe.total;
-				tx = tp.x; ty = tp.y; tz = tp.z; th = pe.hb;
+			v3 r = min_image_fixed(box, P.ip, Q.ip);
+			if(dot(r, r) < M.rcut_near * M.rcut_near) {
+				v3 rbb = r + Q.back - P.back;
+				v3 rb = r + (Q.ax.a1 - P.ax.a1) * M.base_a1;
+				PairAcc acc;
+				acc.clear();
+				float en = dna2_excl(M, r, rbb, rb, P.ax, Q.ax, P.back, Q.back, acc);
+				if(en != 0.f) {
+					v3 tq = acc.torque_q(Q.ax, Q.back), tp = acc.torque_p(P.ax, P.back);
+					atomic_add4(F + ed.y, acc.F.x, acc.F.y, acc.F.z, en);
+					atomic_add4(T + ed.y, tq.x, tq.y, tq.z, 0.f);
+					v[0] = -acc.F.x; v[1] = -acc.F.y; v[2] = -acc.F.z;
+					v[3] = tp.x; v[4] = tp.y; v[5] = tp.z;
+					ve = en;
+				}
+				float rbm2 = dot(rb, rb);
+				want_hb = dna2_hb_in_range(M, rbm2, P.btype, Q.btype) || dna2_crst_in_range(M, rbm2);
+				v3 rs = r + (Q.ax.a1 - P.ax.a1) * M.stack_a1;
+				want_cx = dna2_cxst_in_range(M, dot(rs, rs));
 			}
 		}
-		// segmented suffix reduction over lanes with equal `from`
-		int key = ed.x;
-#pragma unroll
-		for(int d = 1; d < 32; d <<= 1) {
-			int okey = __shfl_down_sync(0xffffffffu, key, d);
-			float ofx = __shfl_down_sync(0xffffffffu, fx, d), ofy = __shfl_down_sync(0xffffffffu, fy, d);
-			float ofz = __shfl_down_sync(0xffffffffu, fz, d), ofe = __shfl_down_sync(0xffffffffu, fe, d);
-			float otx = __shfl_down_sync(0xffffffffu, tx, d), oty = __shfl_down_sync(0xffffffffu, ty, d);
-			float otz = __shfl_down_sync(0xffffffffu, tz, d), oth = __shfl_down_sync(0xffffffffu, th, d);
-			if(lane + d < 32 && okey == key) {
-				fx += ofx; fy += ofy; fz += ofz; fe += ofe;
-				tx += otx; ty += oty; tz += otz; th += oth;
+		warp_append(want_hb, ed, hb_list, counters + 0, hb_cap, flags);
+		warp_append(want_cx, ed, cx_list, counters + 1, cx_cap, flags);
+		// excluded volume between non-bonded nucleotides is rare: skip the shuffle reduction when the warp has none
+		if(__any_sync(0xffffffffu, ve != 0.f)) {
+			float w[7] = { v[0], v[1], v[2], v[3], v[4], v[5], ve };
+			bool head = segmented_reduce<7>(ed.x, lane, w);
+			if(valid && head && w[6] != 0.f) {
+				atomic_add4(F + ed.x, w[0], w[1], w[2], w[6]);
+				atomic_add4(T + ed.x, w[3], w[4], w[5], 0.f);
 			}
-		}
-		int pkey = __shfl_up_sync(0xffffffffu, key, 1);
-		bool head = (lane == 0) || (pkey != key);
-		if(valid && head && (fx != 0.f || fy != 0.f || fz != 0.f || fe != 0.f || tx != 0.f || ty != 0.f || tz != 0.f)) {
-			atomic_add4(F + key, fx, fy, fz, fe);
-			atomic_add4(T + key, tx, ty, tz, th);
 		}
 	}
 }
 
-// bonded terms per particle + lab->body rotation of the accumulated torque (must run after the edge kernel)
-__global__ void __launch_bounds__(128) k_forces_edge_bonded(const __grid_constant__ oxb_dna2_params M, BoxF box, int N, const int4 *__restrict__ ipos,
-		const float4 *__restrict__ quat, const int2 *__restrict__ bonds, float4 *__restrict__ F, float4 *__restrict__ T, int *__restrict__ flags, int hw) {
+template<bool CXST>
+__global__ void __launch_bounds__(128) k_edge_heavy(const __grid_constant__ oxb_dna2_params M, BoxF box, const int *__restrict__ count,
+		const int2 *__restrict__ list, int cap, const int4 *__restrict__ ipos, const float4 *__restrict__ quat, float4 *__restrict__ F,
+		float4 *__restrict__ T, const int *__restrict__ flags, int hw) {
+	if(flags[hw]) return;
+	int n = *count;
+	if(n > cap) n = cap;
+	for(int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+		int2 ed = __ldg(list + k);
+		Particle P = load_particle(M, ipos, quat, ed.x);
+		Particle Q = load_particle(M, ipos, quat, ed.y);
+		v3 r = min_image_fixed(box, P.ip, Q.ip);
+		PairAcc acc;
+		acc.clear();
+		float en, ehb = 0.f;
+		if(CXST) {
+			v3 rs = r + (Q.ax.a1 - P.ax.a1) * M.stack_a1;
+			en = dna2_cxst(M, rs, dot(rs, rs), P.ax, Q.ax, acc);
+		}
+		else {
+			v3 rb = r + (Q.ax.a1 - P.ax.a1) * M.base_a1;
+			float rbm2 = dot(rb, rb);
+			en = dna2_hbcr(M, rb, rbm2, P.ax, Q.ax, P.btype, Q.btype, dna2_hb_in_range(M, rbm2, P.btype, Q.btype), dna2_crst_in_range(M, rbm2), acc,
+					ehb);
+		}
+		if(en != 0.f) {
+			v3 tp = acc.torque_p(P.ax, P.back), tq = acc.torque_q(Q.ax, Q.back);
+			atomic_add4(F + ed.x, -acc.F.x, -acc.F.y, -acc.F.z, en);
+			atomic_add4(T + ed.x, tp.x, tp.y, tp.z, ehb);
+			atomic_add4(F + ed.y, acc.F.x, acc.F.y, acc.F.z, en);
+			atomic_add4(T + ed.y, tq.x, tq.y, tq.z, ehb);
+		}
+	}
+}
+
+// per particle: bonded interaction with the n3 neighbour (each bond evaluated once), folding of the backbone-site
+// force accumulator, reset of the work-list counters for the next step (this is the last kernel of the force pass)
+__global__ void __launch_bounds__(128) k_bonded_finalize(const __grid_constant__ oxb_dna2_params M, BoxF box, int N, const int4 *__restrict__ ipos,
+		const float4 *__restrict__ quat, const int2 *__restrict__ bonds, const float4 *__restrict__ Fb, float4 *__restrict__ F, float4 *__restrict__ T,
+		int *__restrict__ counters, int *__restrict__ flags, int hw) {
 	if(flags[hw]) return;
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i == 0 && counters != nullptr) { counters[0] = 0; counters[1] = 0; }
 	if(i >= N) return;
 	Particle P = load_particle(M, ipos, quat, i);
 	int2 b = __ldg(bonds + i);
-	float4 f4 = F[i], t4 = T[i];
-	v3 f = mk3(f4.x, f4.y, f4.z), t = mk3(t4.x, t4.y, t4.z);
-	float e = f4.w;
-	bool broken = false;
+	v3 f = mk3(0.f, 0.f, 0.f), t = mk3(0.f, 0.f, 0.f);
+	float e = 0.f;
+	if(Fb != nullptr) {
+		float4 fb = Fb[i];
+		v3 g = mk3(fb.x, fb.y, fb.z);
+		f += g;
+		t += cross(P.back, g);
+		e += fb.w;
+	}
 	if(b.x >= 0) {
 		Particle Q = load_particle(M, ipos, quat, b.x);
 		PairAcc acc;
 		acc.clear();
-		e += dna2_bonded(M, min_image_fixed(box, P.ip, Q.ip), P.ax, Q.ax, P.btype, Q.btype, P.back, Q.back, acc, broken);
+		bool broken = false;
+		float en = dna2_bonded(M, min_image_fixed(box, P.ip, Q.ip), P.ax, Q.ax, P.btype, Q.btype, P.back, Q.back, acc, broken);
 		f -= acc.F;
 		t += acc.torque_p(P.ax, P.back);
+		e += en;
+		v3 tq = acc.torque_q(Q.ax, Q.back);
+		atomic_add4(F + b.x, acc.F.x, acc.F.y, acc.F.z, en);
+		atomic_add4(T + b.x, tq.x, tq.y, tq.z, 0.f);
+		if(broken) atomicOr(flags + OXB_FLAG_ERROR, OXB_ERR_FENE_BROKEN);
 	}
-	if(b.y >= 0) {
-		Particle Q = load_particle(M, ipos, quat, b.y);
-		PairAcc acc;
-		acc.clear();
-		e += dna2_bonded(M, min_image_fixed(box, Q.ip, P.ip), Q.ax, P.ax, Q.btype, P.btype, Q.back, P.back, acc, broken);
-		f += acc.F;
-		t += acc.torque_q(P.ax, P.back);
-	}
-	v3 tb = to_body(P.ax, t);
-	F[i] = make_float4(f.x, f.y, f.z, e);
-	T[i] = make_float4(tb.x, tb.y, tb.z, t4.w);
-	if(broken) atomicOr(flags + OXB_FLAG_ERROR, OXB_ERR_FENE_BROKEN);
+	atomic_add4(F + i, f.x, f.y, f.z, e);
+	atomic_add4(T + i, t.x, t.y, t.z, 0.f);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -233,18 +337,25 @@ void launch_forces_particle(cudaStream_t s, const oxb_dna2_params &M, BoxF box, 
 	k_forces_particle<<<(N + tpb - 1) / tpb, tpb, 0, s>>>(M, box, N, ipos, quat, bonds, nbr, nnbr, stride, F, T, flags, hw);
 }
 
-void launch_forces_edge(cudaStream_t s, const oxb_dna2_params &M, BoxF box, int N, const int *n_edges, int edge_capacity_hint, const int4 *ipos,
-		const float4 *quat, const int2 *bonds, const int2 *edges, float4 *F, float4 *T, int *flags, int hw, int n_sm) {
-	cudaMemsetAsync(F, 0, sizeof(float4) * (size_t) N, s);
-	cudaMemsetAsync(T, 0, sizeof(float4) * (size_t) N, s);
-	int tpb = 128;
-	// grid-stride over the device-side edge count: enough CTAs to cover the expected edge count, a multiple of the SM count
-	long long want = ((long long) edge_capacity_hint + tpb - 1) / tpb;
-	int per_sm = (int) ((want + n_sm - 1) / n_sm);
-	if(per_sm < 1) per_sm = 1;
-	int blocks = per_sm * n_sm;
-	k_forces_edge_nonbonded<<<blocks, tpb, 0, s>>>(M, box, n_edges, ipos, quat, bonds, edges, F, T, flags, hw);
-	k_forces_edge_bonded<<<(N + tpb - 1) / tpb, tpb, 0, s>>>(M, box, N, ipos, quat, bonds, F, T, flags, hw);
+void launch_forces_edge(cudaStream_t s, const oxb_dna2_params &M, BoxF box, const EdgeArgs &a, int *flags, int hw, int n_sm) {
+	if(a.clear_first) {
+		cudaMemsetAsync(a.F, 0, sizeof(float4) * (size_t) a.N, s);
+		cudaMemsetAsync(a.T, 0, sizeof(float4) * (size_t) a.N, s);
+		cudaMemsetAsync(a.Fb, 0, sizeof(float4) * (size_t) a.N, s);
+	}
+	auto grid_for = [&](long long items, int tpb) {
+		long long want = (items + tpb - 1) / tpb;
+		if(want < 1) want = 1;
+		return (int) want;
+	};
+	k_edge_dh<<<grid_for(a.edge_hint, 256), 256, 0, s>>>(M, box, a.n_edges, a.edges, a.iback, a.Fb, flags, hw);
+	k_edge_near<<<grid_for(a.near_hint, 128), 128, 0, s>>>(M, box, a.n_near, a.edges, a.ipos, a.quat, a.F, a.T, a.hb_list, a.cx_list, a.counters,
+			a.hb_cap, a.cx_cap, flags, hw);
+	// the work-list lengths live on the device: fixed grids sized for the typical contact density, grid-stride inside
+	int hb_blocks = std::max(n_sm, grid_for((long long) (1.5 * a.N), 128)), cx_blocks = std::max(n_sm, grid_for((long long) (0.25 * a.N), 128));
+	k_edge_heavy<false><<<hb_blocks, 128, 0, s>>>(M, box, a.counters + 0, a.hb_list, a.hb_cap, a.ipos, a.quat, a.F, a.T, flags, hw);
+	k_edge_heavy<true><<<cx_blocks, 128, 0, s>>>(M, box, a.counters + 1, a.cx_list, a.cx_cap, a.ipos, a.quat, a.F, a.T, flags, hw);
+	k_bonded_finalize<<<(a.N + 127) / 128, 128, 0, s>>>(M, box, a.N, a.ipos, a.quat, a.bonds, a.Fb, a.F, a.T, a.counters, flags, hw);
 }
 
 void launch_ext_forces(cudaStream_t s, int n, const DevExtForce *ef, const int *slot_of, const int4 *ipos, const double4 *posd, BoxF box,

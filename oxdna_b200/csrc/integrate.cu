@@ -46,6 +46,13 @@ __global__ void __launch_bounds__(256) k_integrate(oxb::IntegrateArgs a, int epo
 	if(i < a.N) {
 		const double hdt = 0.5 * a.dt;
 		float4 F = a.F[i], T = a.T[i];
+		if(PH & (OXB_PH_SECOND | OXB_PH_FIRST)) {
+			// the force kernels accumulate the torque in the lab frame: rotate it into the body frame (L is a body-frame
+			// angular momentum with unit inertia, src/CUDA/Interactions/CUDA_DNA.cuh:896)
+			Axes A = axes_from_quat(a.quat[i]);
+			v3 tl = mk3(T.x, T.y, T.z);
+			T.x = dot(A.a1, tl); T.y = dot(A.a2, tl); T.z = dot(A.a3, tl);
+		}
 		double4 v = a.veld[i], L = a.Ld[i];
 		if(PH & OXB_PH_SECOND) {
 			v.x += F.x * hdt; v.y += F.y * hdt; v.z += F.z * hdt;
@@ -95,19 +102,37 @@ __global__ void __launch_bounds__(256) k_integrate(oxb::IntegrateArgs a, int epo
 			a.ipos[i] = ip;
 			// body-frame rotation by |L| dt about L: q <- q (x) (Lhat sin(th/2), cos(th/2))
 			double n2 = L.x * L.x + L.y * L.y + L.z * L.z;
+			double4 qn = a.quatd[i];
 			if(n2 > 0.) {
 				double n = sqrt(n2), sh, ch;
 				sincos(0.5 * a.dt * n, &sh, &ch);
 				double k = sh / n;
 				double bx = L.x * k, by = L.y * k, bz = L.z * k, bw = ch;
-				double4 q = a.quatd[i], o;
+				double4 q = qn, o;
 				o.w = q.w * bw - q.x * bx - q.y * by - q.z * bz;
 				o.x = q.w * bx + q.x * bw + q.y * bz - q.z * by;
 				o.y = q.w * by - q.x * bz + q.y * bw + q.z * bx;
 				o.z = q.w * bz + q.x * by - q.y * bx + q.z * bw;
 				a.quatd[i] = o;
 				a.quat[i] = make_float4((float) o.x, (float) o.y, (float) o.z, (float) o.w);
+				qn = o;
 			}
+			{
+				// fixed-point backbone-site position for the Debye-Hueckel kernel: r + back_a1 a1 + back_a2 a2
+				double sqx = qn.x * qn.x, sqy = qn.y * qn.y, sqz = qn.z * qn.z, sqw = qn.w * qn.w;
+				double xy = qn.x * qn.y, xz = qn.x * qn.z, xw = qn.x * qn.w, yz = qn.y * qn.z, yw = qn.y * qn.w, zw = qn.z * qn.w;
+				double b1 = a.back_a1, b2 = a.back_a2;
+				double bx = r.x + b1 * (sqx - sqy - sqz + sqw) + b2 * (2. * (xy - zw));
+				double by = r.y + b1 * (2. * (xy + zw)) + b2 * (-sqx + sqy - sqz + sqw);
+				double bz = r.z + b1 * (2. * (xz - yw)) + b2 * (2. * (yz + xw));
+				int4 ib = a.iback[i];
+				ib.x = (int) to_fixed(bx, a.box_inv[0]); ib.y = (int) to_fixed(by, a.box_inv[1]); ib.z = (int) to_fixed(bz, a.box_inv[2]);
+				a.iback[i] = ib;
+			}
+			// forces are consumed: leave zeroed accumulators for the next force pass
+			a.F[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+			a.T[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+			a.Fb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 			v3 d = min_image_fixed(a.box, a.list_ipos[i], ip);
 			if(dot(d, d) > a.skin2) flags[wr] = 1;
 		}

@@ -49,8 +49,20 @@ namespace oxb {
 // ---- forces.cu
 void launch_forces_particle(cudaStream_t s, const oxb_dna2_params &M, BoxF box, int N, const int4 *ipos, const float4 *quat, const int2 *bonds,
 		const int *nbr, const int *nnbr, int stride, float4 *F, float4 *T, int *flags, int hw);
-void launch_forces_edge(cudaStream_t s, const oxb_dna2_params &M, BoxF box, int N, const int *n_edges, int edge_capacity_hint, const int4 *ipos,
-		const float4 *quat, const int2 *bonds, const int2 *edges, float4 *F, float4 *T, int *flags, int hw, int n_sm);
+struct EdgeArgs {
+	int N;
+	const int4 *ipos, *iback;
+	const float4 *quat;
+	const int2 *bonds, *edges; // edges: [0, n_near) can reach rcut_near before the next rebuild, [n_near, n_edges) are Debye-Hueckel only
+	const int *n_near, *n_edges;
+	long long near_hint, edge_hint; // host copies of the counts at the last rebuild (grid sizing)
+	float4 *F, *T, *Fb;
+	int2 *hb_list, *cx_list;
+	int *counters; // [0] hb/cross-stacking work items, [1] coaxial work items
+	int hb_cap, cx_cap;
+	bool clear_first;
+};
+void launch_forces_edge(cudaStream_t s, const oxb_dna2_params &M, BoxF box, const EdgeArgs &a, int *flags, int hw, int n_sm);
 void launch_ext_forces(cudaStream_t s, int n, const DevExtForce *ef, const int *slot_of, const int4 *ipos, const double4 *posd, BoxF box,
 		long long step, float4 *F, const int *flags, int hw);
 
@@ -65,7 +77,9 @@ struct IntegrateArgs {
 	int4 *ipos;
 	float4 *quat;
 	const int4 *list_ipos;
-	const float4 *F, *T;
+	float4 *F, *T, *Fb; // lab-frame force / torque accumulators (zeroed by the first-half phase once consumed)
+	int4 *iback;        // fixed-point backbone-site position, .w bit 0 = strand end
+	float back_a1, back_a2;
 	int *flags;
 	KinSums *sums;
 	ThermostatCfg th;
@@ -90,9 +104,11 @@ struct ListArgs {
 	int *cell_key, *cell_key_sorted, *cell_val, *cell_val_sorted, *cell_start; // N, N, N, N, ncells + 1
 	int *nbr, *nnbr;
 	int max_neigh, stride;
-	int2 *edges;
-	int *edge_offsets; // N + 1
-	int *n_edges;
+	int2 *edges;       // near edges first, then far (Debye-Hueckel only) edges
+	int *edge_offsets; // N + 1: near-edge offsets
+	int *far_offsets;  // N + 1
+	int *n_edges;      // [0] total, [1] near
+	float rnear2;      // (rcut_near + 2 skin + margin)^2: pairs beyond it at build time stay Debye-Hueckel-only until the next rebuild
 	long long edge_capacity;
 	int4 *list_ipos;
 	int *flags;
@@ -122,8 +138,8 @@ struct PermuteArgs {
 	const int *inv;  // inv[old] = new
 	const double4 *posd_in, *veld_in, *Ld_in, *quatd_in;
 	double4 *posd_out, *veld_out, *Ld_out, *quatd_out;
-	const int4 *ipos_in, *list_ipos_in;
-	int4 *ipos_out, *list_ipos_out;
+	const int4 *ipos_in, *list_ipos_in, *iback_in;
+	int4 *ipos_out, *list_ipos_out, *iback_out;
 	const float4 *quat_in, *F_in, *T_in;
 	float4 *quat_out, *F_out, *T_out;
 	const int2 *bonds_in;

@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(128) k_build_neigh(oxb::ListArgs a, const int 
 	const float rv2f = (float) (a.rv * a.rv);
 	const float band = 1e-4f * rv2f;
 	const double rv2 = a.rv * a.rv;
-	int count = 0, higher = 0;
+	int count = 0, higher_near = 0, higher_far = 0;
 	for(int dz = -1; dz <= 1; dz++) {
 		int zc = cz + dz; zc += (zc < 0) ? nz : 0; zc -= (zc >= nz) ? nz : 0;
 		for(int dy = -1; dy <= 1; dy++) {
@@ -81,7 +81,10 @@ __global__ void __launch_bounds__(128) k_build_neigh(oxb::ListArgs a, const int 
 					if(in) {
 						if(count < a.max_neigh) a.nbr[(size_t) count * a.stride + i] = m;
 						count++;
-						higher += (m > i);
+						if(m > i) {
+							if(d2 < a.rnear2) higher_near++;
+							else higher_far++;
+						}
 					}
 				}
 			}
@@ -95,25 +98,40 @@ __global__ void __launch_bounds__(128) k_build_neigh(oxb::ListArgs a, const int 
 	else atomicMax(a.flags + OXB_FLAG_MAX_NEIGH_SEEN, count);
 	a.nnbr[i] = count;
 	a.list_ipos[i] = ip;
-	if(a.build_edges) a.edge_offsets[i] = higher;
+	if(a.build_edges) {
+		a.edge_offsets[i] = higher_near;
+		a.far_offsets[i] = higher_far;
+	}
 }
 
-// edge (i, m) for every listed neighbour m > i; rows are contiguous in the output (grouped by `from`)
+// edge (i, m) for every listed neighbour m > i; rows are contiguous in the output (grouped by `from`).  Near edges
+// (those that may come within rcut_near before the next rebuild) fill [0, n_near), Debye-Hueckel-only edges follow.
 __global__ void __launch_bounds__(128) k_fill_edges(oxb::ListArgs a) {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= a.N) return;
-	int off = a.edge_offsets[i];
+	const int n_near = a.edge_offsets[a.N], n_far = a.far_offsets[a.N];
+	int off_near = a.edge_offsets[i], off_far = n_near + a.far_offsets[i];
+	const int4 ip = a.ipos[i];
 	int nn = a.nnbr[i];
 	for(int k = 0; k < nn; k++) {
 		int m = a.nbr[(size_t) k * a.stride + i];
 		if(m > i) {
-			if(off < a.edge_capacity) a.edges[off] = make_int2(i, m);
-			off++;
+			v3 d = min_image_fixed(a.boxf, ip, __ldg(a.ipos + m));
+			if(dot(d, d) < a.rnear2) {
+				if(off_near < a.edge_capacity) a.edges[off_near] = make_int2(i, m);
+				off_near++;
+			}
+			else {
+				if(off_far < a.edge_capacity) a.edges[off_far] = make_int2(i, m);
+				off_far++;
+			}
 		}
 	}
 	if(i == a.N - 1) {
-		*a.n_edges = (off <= a.edge_capacity) ? off : (int) a.edge_capacity;
-		if(off > a.edge_capacity) atomicOr(a.flags + OXB_FLAG_ERROR, OXB_ERR_EDGE_OVERFLOW);
+		long long tot = (long long) n_near + n_far;
+		a.n_edges[0] = (tot <= a.edge_capacity) ? (int) tot : (int) a.edge_capacity;
+		a.n_edges[1] = (n_near <= a.edge_capacity) ? n_near : (int) a.edge_capacity;
+		if(tot > a.edge_capacity) atomicOr(a.flags + OXB_FLAG_ERROR, OXB_ERR_EDGE_OVERFLOW);
 	}
 }
 
@@ -151,6 +169,8 @@ void launch_build_lists(cudaStream_t s, const ListArgs &a) {
 		tmp = a.cub_tmp_bytes;
 		// in-place exclusive scan over N + 1 entries (the last input entry is ignored: its output is the total)
 		cub::DeviceScan::ExclusiveSum(a.cub_tmp, tmp, a.edge_offsets, a.edge_offsets, N + 1, s);
+		tmp = a.cub_tmp_bytes;
+		cub::DeviceScan::ExclusiveSum(a.cub_tmp, tmp, a.far_offsets, a.far_offsets, N + 1, s);
 		k_fill_edges<<<(N + 127) / 128, 128, 0, s>>>(a);
 	}
 }
