@@ -44,6 +44,7 @@ typedef struct {
 	float hb_eps[25], hb_shift[25], stck_eps[25], stck_shift[25]; /* [type_n3 * 5 + type_n5] */
 	oxb_f2 crst, cxst;
 	oxb_f4 f4[OXB_NF4];
+	float f4_cmin[OXB_NF4], f4_cmax[OXB_NF4]; /* f4[k](theta) != 0 only if cos(theta) lies in (cmin, cmax): cheap pre-filter */
 	float cxst_t1_sa, cxst_t1_sb;
 	oxb_f5 phi1, phi2;
 	float dh_minus_kappa, dh_prefactor, dh_rhigh, dh_rc, dh_b;
@@ -124,7 +125,8 @@ int oxb_get_pairs(oxb_ctx *ctx, int *pairs, long long max_pairs, long long *n_pa
 /* number of list rebuilds / sorts so far; current neighbour-matrix capacity; overflow flags (0 = ok) */
 int oxb_get_stats(oxb_ctx *ctx, long long *n_list_updates, long long *n_sorts, int *max_neigh, int *error_flags);
 /* device pointers for zero-copy consumers (CUDABaseInteraction plugin seam): float4 positions with packed
- * (btype<<22 | index) in .w, float4 quaternions, column-major neighbour matrix, neighbour counts, int2 edge list */
+ * (btype<<22 | index) in .w, float4 quaternions, column-major neighbour matrix, neighbour counts, and the int2 list of
+ * unique pairs closer than rcut_near + 2 skin at the last rebuild (the pairs that can feel more than Debye-Hueckel) */
 int oxb_device_views(oxb_ctx *ctx, void **poss_f4, void **orientations_f4, void **matrix_neighs, void **number_neighs,
 		void **edge_list, void **n_edges);
 /* number of kernel launches issued by this context so far (bench.py's gpu_launches claim) */

@@ -45,7 +45,7 @@ class DNA2Params(C.Structure):
         + [(n, C.c_float) for n in "mbf_xmax mbf_fmax mbf_finf mbf_e0 excl_eps".split()]
         + [("excl", Excl * 4), ("hb", F1), ("stck", F1)]
         + [(n, C.c_float * 25) for n in "hb_eps hb_shift stck_eps stck_shift".split()]
-        + [("crst", F2), ("cxst", F2), ("f4", F4 * NF4), ("cxst_t1_sa", C.c_float), ("cxst_t1_sb", C.c_float), ("phi1", F5), ("phi2", F5)]
+        + [("crst", F2), ("cxst", F2), ("f4", F4 * NF4), ("f4_cmin", C.c_float * NF4), ("f4_cmax", C.c_float * NF4), ("cxst_t1_sa", C.c_float), ("cxst_t1_sb", C.c_float), ("phi1", F5), ("phi2", F5)]
         + [(n, C.c_float) for n in "dh_minus_kappa dh_prefactor dh_rhigh dh_rc dh_b".split()]
         + [("dh_half_charged_ends", C.c_int), ("hb_multiplier", C.c_float), ("rcut", C.c_float), ("rcut_near", C.c_float)]
     )

@@ -37,7 +37,7 @@ struct oxb_ctx {
 	// double-buffered state (slot order)
 	int cur = 0;
 	double4 *posd[2] = { nullptr, nullptr }, *veld[2] = { nullptr, nullptr }, *Ld[2] = { nullptr, nullptr }, *quatd[2] = { nullptr, nullptr };
-	int4 *ipos[2] = { nullptr, nullptr }, *list_ipos[2] = { nullptr, nullptr }, *iback[2] = { nullptr, nullptr };
+	int4 *ipos[2] = { nullptr, nullptr }, *list_ipos[2] = { nullptr, nullptr }, *iback[2] = { nullptr, nullptr }, *list_iback[2] = { nullptr, nullptr };
 	float4 *Fb = nullptr;
 	float4 *quat[2] = { nullptr, nullptr }, *F[2] = { nullptr, nullptr }, *T[2] = { nullptr, nullptr };
 	int2 *bonds[2] = { nullptr, nullptr };
@@ -63,9 +63,11 @@ struct oxb_ctx {
 	int *cell_key = nullptr, *cell_key_sorted = nullptr, *cell_val = nullptr, *cell_val_sorted = nullptr, *cell_start = nullptr;
 	int *nbr = nullptr, *nnbr = nullptr;
 	int2 *edges = nullptr;
-	int *edge_offsets = nullptr, *far_offsets = nullptr, *n_edges = nullptr;
+	int *edge_offsets = nullptr, *n_edges = nullptr;
 	long long edge_capacity = 0;
-	int edge_hint = 0, near_hint = 0;
+	int edge_hint = 0;
+	int *dh_nbr = nullptr, *dh_nnbr = nullptr;
+	int max_dh = 0;
 	int2 *hb_list = nullptr, *cx_list = nullptr;
 	int *counters = nullptr;
 	int hb_cap = 0, cx_cap = 0;
@@ -118,10 +120,11 @@ void set_boxf(oxb_ctx *c) {
 
 void free_lists(oxb_ctx *c) {
 	cudaFree(c->cell_key); cudaFree(c->cell_key_sorted); cudaFree(c->cell_val); cudaFree(c->cell_val_sorted); cudaFree(c->cell_start);
-	cudaFree(c->nbr); cudaFree(c->nnbr); cudaFree(c->edges); cudaFree(c->edge_offsets); cudaFree(c->far_offsets); cudaFree(c->n_edges); cudaFree(c->cub_tmp);
+	cudaFree(c->nbr); cudaFree(c->nnbr); cudaFree(c->edges); cudaFree(c->edge_offsets); cudaFree(c->n_edges); cudaFree(c->cub_tmp);
+	cudaFree(c->dh_nbr); cudaFree(c->dh_nnbr);
 	cudaFree(c->hb_list); cudaFree(c->cx_list); cudaFree(c->counters);
 	c->cell_key = c->cell_key_sorted = c->cell_val = c->cell_val_sorted = c->cell_start = c->nbr = c->nnbr = c->edge_offsets = c->n_edges = nullptr;
-	c->far_offsets = c->counters = nullptr;
+	c->counters = c->dh_nbr = c->dh_nnbr = nullptr;
 	c->edges = c->hb_list = c->cx_list = nullptr;
 	c->cub_tmp = nullptr;
 	c->lists_allocated = false;
@@ -152,13 +155,15 @@ int alloc_lists(oxb_ctx *c, int max_neigh) {
 	CU(dalloc(&c->cell_key, N)); CU(dalloc(&c->cell_key_sorted, N)); CU(dalloc(&c->cell_val, N)); CU(dalloc(&c->cell_val_sorted, N));
 	CU(dalloc(&c->cell_start, 2 * (size_t) ncells));
 	CU(dalloc(&c->nbr, (size_t) max_neigh * N)); CU(dalloc(&c->nnbr, N));
-	CU(dalloc(&c->edge_offsets, (size_t) N + 1)); CU(dalloc(&c->far_offsets, (size_t) N + 1)); CU(dalloc(&c->n_edges, 2));
+	CU(dalloc(&c->edge_offsets, (size_t) N + 1)); CU(dalloc(&c->n_edges, 2));
 	CU(cudaMemset(c->n_edges, 0, 2 * sizeof(int)));
+	c->max_dh = max_neigh;
+	CU(dalloc(&c->dh_nbr, (size_t) c->max_dh * N)); CU(dalloc(&c->dh_nnbr, N));
 	c->hb_cap = c->use_edge ? 6 * N + 1024 : 1;
 	c->cx_cap = c->use_edge ? 3 * N + 1024 : 1;
 	CU(dalloc(&c->hb_list, (size_t) c->hb_cap)); CU(dalloc(&c->cx_list, (size_t) c->cx_cap)); CU(dalloc(&c->counters, 2));
 	CU(cudaMemset(c->counters, 0, 2 * sizeof(int)));
-	c->edge_capacity = c->use_edge ? ((long long) N * max_neigh) / 2 + N : 1;
+	c->edge_capacity = c->use_edge ? ((long long) N * max_neigh) / 4 + N : 1;
 	CU(dalloc(&c->edges, (size_t) c->edge_capacity));
 	c->cub_tmp_bytes = std::max(oxb::lists_tmp_bytes(N, (int) ncells), oxb::sort_tmp_bytes(N));
 	CU(cudaMalloc(&c->cub_tmp, c->cub_tmp_bytes));
@@ -176,7 +181,12 @@ oxb::ListArgs list_args(oxb_ctx *c) {
 	a.cell_key = c->cell_key; a.cell_key_sorted = c->cell_key_sorted; a.cell_val = c->cell_val; a.cell_val_sorted = c->cell_val_sorted;
 	a.cell_start = c->cell_start;
 	a.nbr = c->nbr; a.nnbr = c->nnbr; a.max_neigh = c->max_neigh; a.stride = c->N;
-	a.edges = c->edges; a.edge_offsets = c->edge_offsets; a.far_offsets = c->far_offsets; a.n_edges = c->n_edges; a.edge_capacity = c->edge_capacity;
+	a.edges = c->edges; a.edge_offsets = c->edge_offsets; a.n_edges = c->n_edges; a.edge_capacity = c->edge_capacity;
+	a.iback = c->iback[c->cur]; a.list_iback = c->list_iback[c->cur]; a.dh_nbr = c->dh_nbr; a.dh_nnbr = c->dh_nnbr; a.max_dh = c->max_dh;
+	{
+		double rd = (double) c->model.dh_rc + 2. * c->skin + 0.02;
+		a.rdh2 = (float) (rd * rd);
+	}
 	{
 		// pairs further apart than this at build time cannot come within rcut_near before the next rebuild (each particle
 		// moves at most `skin` plus one step): they only ever feel Debye-Hueckel
@@ -215,7 +225,7 @@ int do_sort(oxb_ctx *c) {
 	p.posd_in = c->posd[a]; p.veld_in = c->veld[a]; p.Ld_in = c->Ld[a]; p.quatd_in = c->quatd[a];
 	p.posd_out = c->posd[b]; p.veld_out = c->veld[b]; p.Ld_out = c->Ld[b]; p.quatd_out = c->quatd[b];
 	p.ipos_in = c->ipos[a]; p.list_ipos_in = c->list_ipos[a]; p.ipos_out = c->ipos[b]; p.list_ipos_out = c->list_ipos[b];
-	p.iback_in = c->iback[a]; p.iback_out = c->iback[b];
+	p.iback_in = c->iback[a]; p.iback_out = c->iback[b]; p.list_iback_in = c->list_iback[a]; p.list_iback_out = c->list_iback[b];
 	p.quat_in = c->quat[a]; p.F_in = c->F[a]; p.T_in = c->T[a]; p.quat_out = c->quat[b]; p.F_out = c->F[b]; p.T_out = c->T[b];
 	p.bonds_in = c->bonds[a]; p.bonds_out = c->bonds[b];
 	p.slot_of = c->slot_of;
@@ -241,11 +251,10 @@ int do_build(oxb_ctx *c) {
 		if((c->h_flags[OXB_FLAG_ERROR] & (OXB_ERR_NEIGH_OVERFLOW | OXB_ERR_EDGE_OVERFLOW)) == 0) {
 			c->error_flags &= ~(OXB_ERR_NEIGH_OVERFLOW | OXB_ERR_EDGE_OVERFLOW);
 			if(c->use_edge) {
-				int ne[2] = { 0, 0 };
-				CU(cudaMemcpyAsync(ne, c->n_edges, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+				int ne = 0;
+				CU(cudaMemcpyAsync(&ne, c->n_edges, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
 				CU(cudaStreamSynchronize(c->stream));
-				c->edge_hint = ne[0];
-				c->near_hint = ne[1];
+				c->edge_hint = ne;
 			}
 			c->lists_valid = true;
 			c->n_list_updates++;
@@ -276,7 +285,7 @@ int launch_forces(oxb_ctx *c, int hw, bool clear) {
 	if(c->use_edge) {
 		oxb::EdgeArgs e;
 		e.N = c->N; e.ipos = c->ipos[a]; e.iback = c->iback[a]; e.quat = c->quat[a]; e.bonds = c->bonds[a]; e.edges = c->edges;
-		e.n_near = c->n_edges + 1; e.n_edges = c->n_edges; e.near_hint = std::max(c->near_hint, 1); e.edge_hint = std::max(c->edge_hint, 1);
+		e.n_edges = c->n_edges; e.edge_hint = std::max(c->edge_hint, 1); e.dh_nbr = c->dh_nbr; e.dh_nnbr = c->dh_nnbr;
 		e.F = c->F[a]; e.T = c->T[a]; e.Fb = c->Fb; e.hb_list = c->hb_list; e.cx_list = c->cx_list; e.counters = c->counters;
 		e.hb_cap = c->hb_cap; e.cx_cap = c->cx_cap; e.clear_first = clear;
 		oxb::launch_forces_edge(c->stream, c->model, c->boxf, e, c->flags, hw, c->n_sm);
@@ -303,7 +312,7 @@ oxb::IntegrateArgs integ_args(oxb_ctx *c, long long step) {
 	a.box = c->boxf;
 	a.posd = c->posd[k]; a.veld = c->veld[k]; a.Ld = c->Ld[k]; a.quatd = c->quatd[k];
 	a.ipos = c->ipos[k]; a.quat = c->quat[k]; a.list_ipos = c->list_ipos[k];
-	a.F = c->F[k]; a.T = c->T[k]; a.Fb = c->Fb; a.iback = c->iback[k];
+	a.F = c->F[k]; a.T = c->T[k]; a.Fb = c->Fb; a.iback = c->iback[k]; a.list_iback = c->list_iback[k];
 	a.back_a1 = c->model.back_a1; a.back_a2 = c->model.back_a2;
 	a.flags = c->flags; a.sums = c->sums; a.th = c->th; a.step = step;
 	return a;
@@ -378,7 +387,8 @@ int oxb_create(oxb_ctx **out, int device, int N, int precision) {
 	CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	for(int k = 0; k < 2; k++) {
 		CU(dalloc(&c->posd[k], N)); CU(dalloc(&c->veld[k], N)); CU(dalloc(&c->Ld[k], N)); CU(dalloc(&c->quatd[k], N));
-		CU(dalloc(&c->ipos[k], N)); CU(dalloc(&c->list_ipos[k], N)); CU(dalloc(&c->iback[k], N)); CU(dalloc(&c->quat[k], N)); CU(dalloc(&c->F[k], N)); CU(dalloc(&c->T[k], N));
+		CU(dalloc(&c->ipos[k], N)); CU(dalloc(&c->list_ipos[k], N)); CU(dalloc(&c->iback[k], N)); CU(dalloc(&c->list_iback[k], N));
+		CU(cudaMemset(c->list_iback[k], 0, sizeof(int4) * N)); CU(dalloc(&c->quat[k], N)); CU(dalloc(&c->F[k], N)); CU(dalloc(&c->T[k], N));
 		CU(dalloc(&c->bonds[k], N));
 		CU(cudaMemset(c->F[k], 0, sizeof(float4) * N)); CU(cudaMemset(c->T[k], 0, sizeof(float4) * N));
 		CU(cudaMemset(c->list_ipos[k], 0, sizeof(int4) * N));
@@ -402,7 +412,7 @@ void oxb_destroy(oxb_ctx *c) {
 	if(c->stream) cudaStreamSynchronize(c->stream);
 	for(int k = 0; k < 2; k++) {
 		cudaFree(c->posd[k]); cudaFree(c->veld[k]); cudaFree(c->Ld[k]); cudaFree(c->quatd[k]); cudaFree(c->ipos[k]); cudaFree(c->list_ipos[k]);
-		cudaFree(c->quat[k]); cudaFree(c->F[k]); cudaFree(c->T[k]); cudaFree(c->bonds[k]); cudaFree(c->iback[k]);
+		cudaFree(c->quat[k]); cudaFree(c->F[k]); cudaFree(c->T[k]); cudaFree(c->bonds[k]); cudaFree(c->iback[k]); cudaFree(c->list_iback[k]);
 	}
 	cudaFree(c->Fb);
 	cudaFree(c->slot_of); cudaFree(c->flags); cudaFree(c->sums); cudaFree(c->d_energy); cudaFree(c->ext); cudaFree(c->pos_f4);

@@ -19,12 +19,12 @@ struct AngVal {
 	float dc; // d f / d cos(theta)
 };
 
-// f4 in cosine space.  c = cos(theta), s = sin(theta) >= 0 (from a cross product).
-OXB_HD AngVal f4_cs(const oxb_f4 &f, float c, float s) {
+// f4 as a function of theta with the derivative taken with respect to cos(theta); s = sin(theta) >= 0 comes from the
+// cross product the torque needs anyway.
+OXB_HD AngVal f4_ts(const oxb_f4 &f, float t, float s) {
 	AngVal r;
 	r.v = 0.f;
 	r.dc = 0.f;
-	float t = atan2f(s, c);
 	float x = t - f.t0;
 	float m = 1.f;
 	if(x < 0.f) {
@@ -47,9 +47,10 @@ OXB_HD AngVal f4_cs(const oxb_f4 &f, float c, float s) {
 	return r;
 }
 
-// F(c) = f4(c) + f4(-c)
-OXB_HD AngVal f4_cs_sym(const oxb_f4 &f, float c, float s) {
-	AngVal p = f4_cs(f, c, s), n = f4_cs(f, -c, s);
+#define OXB_PI_F 3.14159265358979f
+// F(theta) = f4(theta) + f4(pi - theta)
+OXB_HD AngVal f4_ts_sym(const oxb_f4 &f, float t, float s) {
+	AngVal p = f4_ts(f, t, s), n = f4_ts(f, OXB_PI_F - t, s);
 	AngVal r;
 	r.v = p.v + n.v;
 	r.dc = p.dc - n.dc;
@@ -57,9 +58,8 @@ OXB_HD AngVal f4_cs_sym(const oxb_f4 &f, float c, float s) {
 }
 
 // oxDNA2 coaxial-stacking theta1: f4 plus a pure harmonic beyond theta = sb (DNA2Interaction.cpp:308-363)
-OXB_HD AngVal f4_cs_cxst_t1(const oxb_dna2_params &M, float c, float s) {
-	AngVal r = f4_cs(M.f4[OXB_F4_CXST_T1], c, s);
-	float t = atan2f(s, c);
+OXB_HD AngVal f4_ts_cxst_t1(const oxb_dna2_params &M, float t, float s) {
+	AngVal r = f4_ts(M.f4[OXB_F4_CXST_T1], t, s);
 	float x = t - M.cxst_t1_sb;
 	if(x >= 0.f) {
 		r.v += M.cxst_t1_sa * x * x;
@@ -183,8 +183,8 @@ struct PairAcc {
 };
 
 struct Angle {
-	float c, s;
-	v3 x; // u cross v
+	float c, s, t; // cos, sin (>= 0), theta = atan2(sin, cos)
+	v3 x;          // u cross v
 };
 
 OXB_HD Angle make_angle(v3 u, v3 v) {
@@ -192,8 +192,12 @@ OXB_HD Angle make_angle(v3 u, v3 v) {
 	a.c = dot(u, v);
 	a.x = cross(u, v);
 	a.s = sqrtf(dot(a.x, a.x));
+	a.t = atan2f(a.s, a.c);
 	return a;
 }
+
+OXB_HD bool in_window(const oxb_dna2_params &M, int k, float c) { return c > M.f4_cmin[k] && c < M.f4_cmax[k]; }
+OXB_HD bool in_window_sym(const oxb_dna2_params &M, int k, float c) { return in_window(M, k, c) || in_window(M, k, -c); }
 
 // chain rule, c = u.v with u on p and v on q, g = dE/dc
 OXB_HD void chain_bb(PairAcc &A, float g, const Angle &a) {
@@ -272,6 +276,23 @@ OXB_HD bool dna2_cxst_in_range(const oxb_dna2_params &M, float rs2) {
 	return rs2 > M.cxst.rclow * M.cxst.rclow && rs2 < M.cxst.rchigh * M.cxst.rchigh;
 }
 
+// Can the hydrogen-bonding / cross-stacking product be non-zero?  Only dot products: every factor f4 vanishes outside a
+// cosine window.  h = rb / |rb|.
+OXB_HD bool dna2_hbcr_may_act(const oxb_dna2_params &M, v3 h, const Axes &A, const Axes &B, bool hb_on, bool cr_on) {
+	float c1 = -dot(A.a1, B.a1), c2 = -dot(B.a1, h), c3 = dot(A.a1, h), c4 = dot(A.a3, B.a3), c7 = -dot(B.a3, h), c8 = dot(A.a3, h);
+	bool hb = hb_on && in_window(M, OXB_F4_HB_T1, c1) && in_window(M, OXB_F4_HB_T2, c2) && in_window(M, OXB_F4_HB_T2, c3) &&
+			in_window(M, OXB_F4_HB_T4, c4) && in_window(M, OXB_F4_HB_T7, c7) && in_window(M, OXB_F4_HB_T7, c8);
+	bool cr = cr_on && in_window(M, OXB_F4_CRST_T1, c1) && in_window(M, OXB_F4_CRST_T2, c2) && in_window(M, OXB_F4_CRST_T2, c3) &&
+			in_window_sym(M, OXB_F4_CRST_T4, c4) && in_window_sym(M, OXB_F4_CRST_T7, c7) && in_window_sym(M, OXB_F4_CRST_T7, c8);
+	return hb || cr;
+}
+
+OXB_HD bool dna2_cxst_may_act(const oxb_dna2_params &M, v3 h, const Axes &A, const Axes &B) {
+	float c1 = -dot(A.a1, B.a1), c4 = dot(A.a3, B.a3), c5 = dot(A.a3, h), c6 = -dot(B.a3, h);
+	return in_window(M, OXB_F4_CXST_T1, c1) && in_window(M, OXB_F4_CXST_T4, c4) && in_window_sym(M, OXB_F4_CXST_T5, c5) &&
+			in_window_sym(M, OXB_F4_CXST_T5, c6);
+}
+
 // rb = base-base vector.  Returns total energy (HB + cross stacking), ehb = the HB part.
 OXB_HD float dna2_hbcr(const oxb_dna2_params &M, v3 rb, float rbm2, const Axes &A, const Axes &B, int btp, int btq, bool hb_on, bool cr_on,
 		PairAcc &acc, float &ehb) {
@@ -294,12 +315,12 @@ OXB_HD float dna2_hbcr(const oxb_dna2_params &M, v3 rb, float rbm2, const Axes &
 		RadVal f1 = f1_r(M.hb, M.hb_eps[ti], M.hb_shift[ti], m);
 		f1.v *= mult;
 		f1.d *= mult;
-		AngVal a1 = f4_cs(M.f4[OXB_F4_HB_T1], t1.c, t1.s);
-		AngVal a2 = f4_cs(M.f4[OXB_F4_HB_T2], t2.c, t2.s);
-		AngVal a3 = f4_cs(M.f4[OXB_F4_HB_T2], t3.c, t3.s);
-		AngVal a4 = f4_cs(M.f4[OXB_F4_HB_T4], t4.c, t4.s);
-		AngVal a7 = f4_cs(M.f4[OXB_F4_HB_T7], t7.c, t7.s);
-		AngVal a8 = f4_cs(M.f4[OXB_F4_HB_T7], t8.c, t8.s);
+		AngVal a1 = f4_ts(M.f4[OXB_F4_HB_T1], t1.t, t1.s);
+		AngVal a2 = f4_ts(M.f4[OXB_F4_HB_T2], t2.t, t2.s);
+		AngVal a3 = f4_ts(M.f4[OXB_F4_HB_T2], t3.t, t3.s);
+		AngVal a4 = f4_ts(M.f4[OXB_F4_HB_T4], t4.t, t4.s);
+		AngVal a7 = f4_ts(M.f4[OXB_F4_HB_T7], t7.t, t7.s);
+		AngVal a8 = f4_ts(M.f4[OXB_F4_HB_T7], t8.t, t8.s);
 		float p12 = a1.v * a2.v, p34 = a3.v * a4.v, p78 = a7.v * a8.v;
 		float ang = p12 * p34 * p78;
 		float e = f1.v * ang;
@@ -318,12 +339,12 @@ OXB_HD float dna2_hbcr(const oxb_dna2_params &M, v3 rb, float rbm2, const Axes &
 	}
 	if(cr_on) {
 		RadVal f2 = f2_r(M.crst, m);
-		AngVal a1 = f4_cs(M.f4[OXB_F4_CRST_T1], t1.c, t1.s);
-		AngVal a2 = f4_cs(M.f4[OXB_F4_CRST_T2], t2.c, t2.s);
-		AngVal a3 = f4_cs(M.f4[OXB_F4_CRST_T2], t3.c, t3.s);
-		AngVal a4 = f4_cs_sym(M.f4[OXB_F4_CRST_T4], t4.c, t4.s);
-		AngVal a7 = f4_cs_sym(M.f4[OXB_F4_CRST_T7], t7.c, t7.s);
-		AngVal a8 = f4_cs_sym(M.f4[OXB_F4_CRST_T7], t8.c, t8.s);
+		AngVal a1 = f4_ts(M.f4[OXB_F4_CRST_T1], t1.t, t1.s);
+		AngVal a2 = f4_ts(M.f4[OXB_F4_CRST_T2], t2.t, t2.s);
+		AngVal a3 = f4_ts(M.f4[OXB_F4_CRST_T2], t3.t, t3.s);
+		AngVal a4 = f4_ts_sym(M.f4[OXB_F4_CRST_T4], t4.t, t4.s);
+		AngVal a7 = f4_ts_sym(M.f4[OXB_F4_CRST_T7], t7.t, t7.s);
+		AngVal a8 = f4_ts_sym(M.f4[OXB_F4_CRST_T7], t8.t, t8.s);
 		float p12 = a1.v * a2.v, p34 = a3.v * a4.v, p78 = a7.v * a8.v;
 		float ang = p12 * p34 * p78;
 		float e = f2.v * ang;
@@ -363,10 +384,10 @@ OXB_HD float dna2_cxst(const oxb_dna2_params &M, v3 rs, float rs2, const Axes &A
 	Angle t5 = make_angle(A.a3, h);
 	Angle t6 = make_angle(-B.a3, h);
 	RadVal f2 = f2_r(M.cxst, m);
-	AngVal a1 = f4_cs_cxst_t1(M, t1.c, t1.s);
-	AngVal a4 = f4_cs(M.f4[OXB_F4_CXST_T4], t4.c, t4.s);
-	AngVal a5 = f4_cs_sym(M.f4[OXB_F4_CXST_T5], t5.c, t5.s);
-	AngVal a6 = f4_cs_sym(M.f4[OXB_F4_CXST_T5], t6.c, t6.s);
+	AngVal a1 = f4_ts_cxst_t1(M, t1.t, t1.s);
+	AngVal a4 = f4_ts(M.f4[OXB_F4_CXST_T4], t4.t, t4.s);
+	AngVal a5 = f4_ts_sym(M.f4[OXB_F4_CXST_T5], t5.t, t5.s);
+	AngVal a6 = f4_ts_sym(M.f4[OXB_F4_CXST_T5], t6.t, t6.s);
 	float p14 = a1.v * a4.v, p56 = a5.v * a6.v;
 	float e = f2.v * p14 * p56;
 	if(e != 0.f) {
@@ -473,9 +494,9 @@ OXB_HD float dna2_bonded(const oxb_dna2_params &M, v3 r, const Axes &A, const Ax
 			Angle t6 = make_angle(-B.a3, h);
 			Angle p1 = make_angle(A.a2, wh);
 			Angle p2 = make_angle(B.a2, wh);
-			AngVal a4 = f4_cs(M.f4[OXB_F4_STCK_T4], t4.c, t4.s);
-			AngVal a5 = f4_cs(M.f4[OXB_F4_STCK_T5], t5.c, t5.s);
-			AngVal a6 = f4_cs(M.f4[OXB_F4_STCK_T5], t6.c, t6.s);
+			AngVal a4 = f4_ts(M.f4[OXB_F4_STCK_T4], t4.t, t4.s);
+			AngVal a5 = f4_ts(M.f4[OXB_F4_STCK_T5], t5.t, t5.s);
+			AngVal a6 = f4_ts(M.f4[OXB_F4_STCK_T5], t6.t, t6.s);
 			AngVal b1 = f5_c(M.phi1, p1.c);
 			AngVal b2 = f5_c(M.phi2, p2.c);
 			float p456 = a4.v * a5.v * a6.v, pb = b1.v * b2.v;

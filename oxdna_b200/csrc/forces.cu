@@ -86,10 +86,11 @@ __global__ void __launch_bounds__(128) k_forces_particle(const __grid_constant__
 // ------------------------------------------------------------------------------------------------------------
 // Edge-centric, staged.  One thread per unique pair, but the pair population is split by COST so that every kernel is
 // (nearly) uniform across a warp -- the single-kernel version ran with 8 of 32 lanes active (ncu r01):
-//   k_edge_dh     all edges, Debye-Hueckel only, needs just the two fixed-point backbone-site positions (2 x 16 B)
+//   k_dh_particle Debye-Hueckel, one thread per particle over a backbone-site neighbour matrix (2 x 16 B per pair, no atomics)
 //   k_edge_near   edges that can come within rcut_near before the next rebuild: 4 excluded-volume site pairs +
-//                 detection of pairs inside the hydrogen-bonding / cross-stacking / coaxial-stacking radial ranges,
-//                 which are appended (warp-aggregated) to two compact work lists
+//                 detection of pairs inside the hydrogen-bonding / cross-stacking / coaxial-stacking radial ranges AND
+//                 inside the cosine window of every angular factor; those are appended (warp-aggregated) to two
+//                 compact work lists
 //   k_edge_hbcr   dense list of base-base contacts: hydrogen bonding + cross stacking
 //   k_edge_cxst   dense list of stack-stack contacts: coaxial stacking
 //   k_bonded_finalize  per particle: FENE + bonded excluded volume + stacking with its n3 neighbour (each bond once),
@@ -118,30 +119,29 @@ __device__ __forceinline__ bool segmented_reduce(int key, unsigned lane, float (
 	return (lane == 0) || (pkey != key);
 }
 
-__global__ void __launch_bounds__(256) k_edge_dh(const __grid_constant__ oxb_dna2_params M, BoxF box, const int *__restrict__ n_edges,
-		const int2 *__restrict__ edges, const int4 *__restrict__ iback, float4 *__restrict__ Fb, const int *__restrict__ flags, int hw) {
+// Debye-Hueckel, particle-centric over its own neighbour matrix (selected on the backbone-site distance): per neighbour one
+// coalesced index load + one 16-byte gather of a fixed-point backbone site; no atomics, deterministic.  Writes the
+// backbone-site force sum Fb (.w = energy); k_bonded_finalize folds it into force and torque.
+__global__ void __launch_bounds__(128) k_dh_particle(const __grid_constant__ oxb_dna2_params M, BoxF box, int N, const int4 *__restrict__ iback,
+		const int *__restrict__ dh_nbr, const int *__restrict__ dh_nnbr, float4 *__restrict__ Fb, const int *__restrict__ flags, int hw) {
 	if(flags[hw]) return;
-	const int ne = *n_edges;
-	const unsigned lane = threadIdx.x & 31;
-	for(int base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < ne; base += gridDim.x * blockDim.x) {
-		int eidx = base + lane;
-		bool valid = eidx < ne;
-		int2 ed = valid ? __ldg(edges + eidx) : make_int2(-1 - (int) lane, -1);
-		float v[4] = { 0.f, 0.f, 0.f, 0.f };
-		if(valid) {
-			int4 bp = __ldg(iback + ed.x), bq = __ldg(iback + ed.y);
-			v3 rbb = min_image_fixed(box, bp, bq);
-			float fs;
-			float en = dna2_dh(M, dot(rbb, rbb), bp.w & 1, bq.w & 1, fs);
-			if(en != 0.f) {
-				v3 f = rbb * fs;
-				atomic_add4(Fb + ed.y, f.x, f.y, f.z, en);
-				v[0] = -f.x; v[1] = -f.y; v[2] = -f.z; v[3] = en;
-			}
-		}
-		bool head = segmented_reduce<4>(ed.x, lane, v);
-		if(valid && head && v[3] != 0.f) atomic_add4(Fb + ed.x, v[0], v[1], v[2], v[3]);
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= N) return;
+	const int4 bp = __ldg(iback + i);
+	const int nn = __ldg(dh_nnbr + i);
+	const bool p_end = bp.w & 1;
+	v3 f = mk3(0.f, 0.f, 0.f);
+	float e = 0.f;
+	for(int k = 0; k < nn; k++) {
+		int j = __ldg(dh_nbr + (size_t) k * N + i);
+		int4 bq = __ldg(iback + j);
+		v3 rbb = min_image_fixed(box, bp, bq);
+		float fs;
+		float en = dna2_dh(M, dot(rbb, rbb), p_end, bq.w & 1, fs);
+		e += en;
+		axpy(f, -fs, rbb);
 	}
+	Fb[i] = make_float4(f.x, f.y, f.z, e);
 }
 
 __device__ __forceinline__ void warp_append(bool flag, int2 item, int2 *__restrict__ list, int *__restrict__ counter, int cap, int *flags) {
@@ -159,11 +159,11 @@ __device__ __forceinline__ void warp_append(bool flag, int2 item, int2 *__restri
 	}
 }
 
-__global__ void __launch_bounds__(128) k_edge_near(const __grid_constant__ oxb_dna2_params M, BoxF box, const int *__restrict__ n_near,
+__global__ void __launch_bounds__(128) k_edge_near(const __grid_constant__ oxb_dna2_params M, BoxF box, const int *__restrict__ n_edges,
 		const int2 *__restrict__ edges, const int4 *__restrict__ ipos, const float4 *__restrict__ quat, float4 *__restrict__ F, float4 *__restrict__ T,
 		int2 *__restrict__ hb_list, int2 *__restrict__ cx_list, int *__restrict__ counters, int hb_cap, int cx_cap, int *__restrict__ flags, int hw) {
 	if(flags[hw]) return;
-	const int ne = *n_near;
+	const int ne = *n_edges;
 	const unsigned lane = threadIdx.x & 31;
 	for(int base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < ne; base += gridDim.x * blockDim.x) {
 		int eidx = base + lane;
@@ -190,10 +190,14 @@ __global__ void __launch_bounds__(128) k_edge_near(const __grid_constant__ oxb_d
 					v[3] = tp.x; v[4] = tp.y; v[5] = tp.z;
 					ve = en;
 				}
+				// radial range first, then the cosine windows of every angular factor: only pairs whose product can be
+				// non-zero reach the heavy kernels
 				float rbm2 = dot(rb, rb);
-				want_hb = dna2_hb_in_range(M, rbm2, P.btype, Q.btype) || dna2_crst_in_range(M, rbm2);
+				bool hb_on = dna2_hb_in_range(M, rbm2, P.btype, Q.btype), cr_on = dna2_crst_in_range(M, rbm2);
+				if(hb_on || cr_on) want_hb = dna2_hbcr_may_act(M, rb * rsqrtf(rbm2), P.ax, Q.ax, hb_on, cr_on);
 				v3 rs = r + (Q.ax.a1 - P.ax.a1) * M.stack_a1;
-				want_cx = dna2_cxst_in_range(M, dot(rs, rs));
+				float rs2 = dot(rs, rs);
+				if(dna2_cxst_in_range(M, rs2)) want_cx = dna2_cxst_may_act(M, rs * rsqrtf(rs2), P.ax, Q.ax);
 			}
 		}
 		warp_append(want_hb, ed, hb_list, counters + 0, hb_cap, flags);
@@ -341,18 +345,17 @@ void launch_forces_edge(cudaStream_t s, const oxb_dna2_params &M, BoxF box, cons
 	if(a.clear_first) {
 		cudaMemsetAsync(a.F, 0, sizeof(float4) * (size_t) a.N, s);
 		cudaMemsetAsync(a.T, 0, sizeof(float4) * (size_t) a.N, s);
-		cudaMemsetAsync(a.Fb, 0, sizeof(float4) * (size_t) a.N, s);
 	}
 	auto grid_for = [&](long long items, int tpb) {
 		long long want = (items + tpb - 1) / tpb;
 		if(want < 1) want = 1;
 		return (int) want;
 	};
-	k_edge_dh<<<grid_for(a.edge_hint, 256), 256, 0, s>>>(M, box, a.n_edges, a.edges, a.iback, a.Fb, flags, hw);
-	k_edge_near<<<grid_for(a.near_hint, 128), 128, 0, s>>>(M, box, a.n_near, a.edges, a.ipos, a.quat, a.F, a.T, a.hb_list, a.cx_list, a.counters,
+	k_dh_particle<<<(a.N + 127) / 128, 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, flags, hw);
+	k_edge_near<<<grid_for(a.edge_hint, 128), 128, 0, s>>>(M, box, a.n_edges, a.edges, a.ipos, a.quat, a.F, a.T, a.hb_list, a.cx_list, a.counters,
 			a.hb_cap, a.cx_cap, flags, hw);
 	// the work-list lengths live on the device: fixed grids sized for the typical contact density, grid-stride inside
-	int hb_blocks = std::max(n_sm, grid_for((long long) (1.5 * a.N), 128)), cx_blocks = std::max(n_sm, grid_for((long long) (0.25 * a.N), 128));
+	int hb_blocks = std::max(n_sm, grid_for((long long) (1.0 * a.N), 128)), cx_blocks = std::max(n_sm, grid_for((long long) (0.125 * a.N), 128));
 	k_edge_heavy<false><<<hb_blocks, 128, 0, s>>>(M, box, a.counters + 0, a.hb_list, a.hb_cap, a.ipos, a.quat, a.F, a.T, flags, hw);
 	k_edge_heavy<true><<<cx_blocks, 128, 0, s>>>(M, box, a.counters + 1, a.cx_list, a.cx_cap, a.ipos, a.quat, a.F, a.T, flags, hw);
 	k_bonded_finalize<<<(a.N + 127) / 128, 128, 0, s>>>(M, box, a.N, a.ipos, a.quat, a.bonds, a.Fb, a.F, a.T, a.counters, flags, hw);

@@ -128,6 +128,9 @@ __global__ void __launch_bounds__(256) k_integrate(oxb::IntegrateArgs a, int epo
 				int4 ib = a.iback[i];
 				ib.x = (int) to_fixed(bx, a.box_inv[0]); ib.y = (int) to_fixed(by, a.box_inv[1]); ib.z = (int) to_fixed(bz, a.box_inv[2]);
 				a.iback[i] = ib;
+				// rotational staleness: the backbone site must not have moved further than the skin either
+				v3 db = min_image_fixed(a.box, a.list_iback[i], ib);
+				if(dot(db, db) > a.skin2) flags[wr] = 1;
 			}
 			// forces are consumed: leave zeroed accumulators for the next force pass
 			a.F[i] = make_float4(0.f, 0.f, 0.f, 0.f);

@@ -53,9 +53,10 @@ struct EdgeArgs {
 	int N;
 	const int4 *ipos, *iback;
 	const float4 *quat;
-	const int2 *bonds, *edges; // edges: [0, n_near) can reach rcut_near before the next rebuild, [n_near, n_edges) are Debye-Hueckel only
-	const int *n_near, *n_edges;
-	long long near_hint, edge_hint; // host copies of the counts at the last rebuild (grid sizing)
+	const int2 *bonds, *edges; // near edges
+	const int *n_edges;
+	long long edge_hint;       // host copy of the count at the last rebuild (grid sizing)
+	const int *dh_nbr, *dh_nnbr; // Debye-Hueckel neighbour matrix, column-major, stride N
 	float4 *F, *T, *Fb;
 	int2 *hb_list, *cx_list;
 	int *counters; // [0] hb/cross-stacking work items, [1] coaxial work items
@@ -76,7 +77,7 @@ struct IntegrateArgs {
 	double4 *posd, *veld, *Ld, *quatd;
 	int4 *ipos;
 	float4 *quat;
-	const int4 *list_ipos;
+	const int4 *list_ipos, *list_iback;
 	float4 *F, *T, *Fb; // lab-frame force / torque accumulators (zeroed by the first-half phase once consumed)
 	int4 *iback;        // fixed-point backbone-site position, .w bit 0 = strand end
 	float back_a1, back_a2;
@@ -104,11 +105,16 @@ struct ListArgs {
 	int *cell_key, *cell_key_sorted, *cell_val, *cell_val_sorted, *cell_start; // N, N, N, N, ncells + 1
 	int *nbr, *nnbr;
 	int max_neigh, stride;
-	int2 *edges;       // near edges first, then far (Debye-Hueckel only) edges
-	int *edge_offsets; // N + 1: near-edge offsets
-	int *far_offsets;  // N + 1
-	int *n_edges;      // [0] total, [1] near
-	float rnear2;      // (rcut_near + 2 skin + margin)^2: pairs beyond it at build time stay Debye-Hueckel-only until the next rebuild
+	int2 *edges;       // unique pairs that can come within rcut_near before the next rebuild ("near" edges), grouped by `from`
+	int *edge_offsets; // N + 1
+	int *n_edges;      // device-side length of `edges`
+	float rnear2;      // (rcut_near + 2 skin + margin)^2
+	// Debye-Hueckel neighbour matrix (full, both directions), selected on the backbone-site distance
+	const int4 *iback;
+	int4 *list_iback;
+	int *dh_nbr, *dh_nnbr;
+	int max_dh;
+	float rdh2;        // (dh_rc + 2 skin + margin)^2
 	long long edge_capacity;
 	int4 *list_ipos;
 	int *flags;
@@ -138,8 +144,8 @@ struct PermuteArgs {
 	const int *inv;  // inv[old] = new
 	const double4 *posd_in, *veld_in, *Ld_in, *quatd_in;
 	double4 *posd_out, *veld_out, *Ld_out, *quatd_out;
-	const int4 *ipos_in, *list_ipos_in, *iback_in;
-	int4 *ipos_out, *list_ipos_out, *iback_out;
+	const int4 *ipos_in, *list_ipos_in, *iback_in, *list_iback_in;
+	int4 *ipos_out, *list_ipos_out, *iback_out, *list_iback_out;
 	const float4 *quat_in, *F_in, *T_in;
 	float4 *quat_out, *F_out, *T_out;
 	const int2 *bonds_in;

@@ -62,7 +62,8 @@ __global__ void __launch_bounds__(128) k_build_neigh(oxb::ListArgs a, const int 
 	const float rv2f = (float) (a.rv * a.rv);
 	const float band = 1e-4f * rv2f;
 	const double rv2 = a.rv * a.rv;
-	int count = 0, higher_near = 0, higher_far = 0;
+	const int4 ib = a.iback[i];
+	int count = 0, higher_near = 0, ndh = 0;
 	for(int dz = -1; dz <= 1; dz++) {
 		int zc = cz + dz; zc += (zc < 0) ? nz : 0; zc -= (zc >= nz) ? nz : 0;
 		for(int dy = -1; dy <= 1; dy++) {
@@ -81,9 +82,13 @@ __global__ void __launch_bounds__(128) k_build_neigh(oxb::ListArgs a, const int 
 					if(in) {
 						if(count < a.max_neigh) a.nbr[(size_t) count * a.stride + i] = m;
 						count++;
-						if(m > i) {
-							if(d2 < a.rnear2) higher_near++;
-							else higher_far++;
+						if(m > i && d2 < a.rnear2) higher_near++;
+						// Debye-Hueckel acts between backbone sites: keep m if the sites can come within dh_rc before the
+						// next rebuild (both the centre and the backbone site of every particle move less than `skin`)
+						v3 db = min_image_fixed(a.boxf, ib, __ldg(a.iback + m));
+						if(dot(db, db) < a.rdh2) {
+							if(ndh < a.max_dh) a.dh_nbr[(size_t) ndh * a.stride + i] = m;
+							ndh++;
 						}
 					}
 				}
@@ -96,21 +101,22 @@ __global__ void __launch_bounds__(128) k_build_neigh(oxb::ListArgs a, const int 
 		count = a.max_neigh;
 	}
 	else atomicMax(a.flags + OXB_FLAG_MAX_NEIGH_SEEN, count);
-	a.nnbr[i] = count;
-	a.list_ipos[i] = ip;
-	if(a.build_edges) {
-		a.edge_offsets[i] = higher_near;
-		a.far_offsets[i] = higher_far;
+	if(ndh > a.max_dh) {
+		atomicOr(a.flags + OXB_FLAG_ERROR, OXB_ERR_NEIGH_OVERFLOW);
+		ndh = a.max_dh;
 	}
+	a.nnbr[i] = count;
+	a.dh_nnbr[i] = ndh;
+	a.list_ipos[i] = ip;
+	a.list_iback[i] = ib;
+	if(a.build_edges) a.edge_offsets[i] = higher_near;
 }
 
-// edge (i, m) for every listed neighbour m > i; rows are contiguous in the output (grouped by `from`).  Near edges
-// (those that may come within rcut_near before the next rebuild) fill [0, n_near), Debye-Hueckel-only edges follow.
+// near edge (i, m) for every listed neighbour m > i within rnear; rows are contiguous in the output (grouped by `from`)
 __global__ void __launch_bounds__(128) k_fill_edges(oxb::ListArgs a) {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= a.N) return;
-	const int n_near = a.edge_offsets[a.N], n_far = a.far_offsets[a.N];
-	int off_near = a.edge_offsets[i], off_far = n_near + a.far_offsets[i];
+	int off = a.edge_offsets[i];
 	const int4 ip = a.ipos[i];
 	int nn = a.nnbr[i];
 	for(int k = 0; k < nn; k++) {
@@ -118,20 +124,14 @@ __global__ void __launch_bounds__(128) k_fill_edges(oxb::ListArgs a) {
 		if(m > i) {
 			v3 d = min_image_fixed(a.boxf, ip, __ldg(a.ipos + m));
 			if(dot(d, d) < a.rnear2) {
-				if(off_near < a.edge_capacity) a.edges[off_near] = make_int2(i, m);
-				off_near++;
-			}
-			else {
-				if(off_far < a.edge_capacity) a.edges[off_far] = make_int2(i, m);
-				off_far++;
+				if(off < a.edge_capacity) a.edges[off] = make_int2(i, m);
+				off++;
 			}
 		}
 	}
 	if(i == a.N - 1) {
-		long long tot = (long long) n_near + n_far;
-		a.n_edges[0] = (tot <= a.edge_capacity) ? (int) tot : (int) a.edge_capacity;
-		a.n_edges[1] = (n_near <= a.edge_capacity) ? n_near : (int) a.edge_capacity;
-		if(tot > a.edge_capacity) atomicOr(a.flags + OXB_FLAG_ERROR, OXB_ERR_EDGE_OVERFLOW);
+		a.n_edges[0] = (off <= a.edge_capacity) ? off : (int) a.edge_capacity;
+		if(off > a.edge_capacity) atomicOr(a.flags + OXB_FLAG_ERROR, OXB_ERR_EDGE_OVERFLOW);
 	}
 }
 
@@ -169,8 +169,6 @@ void launch_build_lists(cudaStream_t s, const ListArgs &a) {
 		tmp = a.cub_tmp_bytes;
 		// in-place exclusive scan over N + 1 entries (the last input entry is ignored: its output is the total)
 		cub::DeviceScan::ExclusiveSum(a.cub_tmp, tmp, a.edge_offsets, a.edge_offsets, N + 1, s);
-		tmp = a.cub_tmp_bytes;
-		cub::DeviceScan::ExclusiveSum(a.cub_tmp, tmp, a.far_offsets, a.far_offsets, N + 1, s);
 		k_fill_edges<<<(N + 127) / 128, 128, 0, s>>>(a);
 	}
 }

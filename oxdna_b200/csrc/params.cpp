@@ -100,7 +100,13 @@ extern "C" int oxb_dna2_params_init(oxb_dna2_params *P, double T, double salt, i
 		{ 1.3f, 6.4381f, 0.f, 0.8f, 0.961538f },              // CXST theta4
 		{ 0.9f, 3.89361f, 0.f, 0.95f, 1.16959f },             // CXST theta5 / theta6
 	};
-	for(int i = 0; i < OXB_NF4; i++) P->f4[i] = oxb_f4{ f4tab[i].a, f4tab[i].b, f4tab[i].t0, f4tab[i].ts, f4tab[i].tc };
+	for(int i = 0; i < OXB_NF4; i++) {
+		P->f4[i] = oxb_f4{ f4tab[i].a, f4tab[i].b, f4tab[i].t0, f4tab[i].ts, f4tab[i].tc };
+		// support of f4 in cosine space, slightly widened: theta in (t0 - tc, t0 + tc) intersected with [0, pi]
+		double lo = std::fmax(0., (double) f4tab[i].t0 - f4tab[i].tc), hi = std::fmin(3.14159265358979323846, (double) f4tab[i].t0 + f4tab[i].tc);
+		P->f4_cmin[i] = (float) (std::cos(hi) - 1e-4);
+		P->f4_cmax[i] = (float) (std::cos(lo) + 1e-4);
+	}
 	P->cxst_t1_sa = 20.f;
 	P->cxst_t1_sb = kPi - 0.1f * (kPi - (kPi - 0.25f));
 	P->phi1 = oxb_f5{ 2.0f, 10.9032f, -0.769231f, -0.65f };

@@ -13,6 +13,9 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # keep the in-tree CUDA library in step with its sources (no-op when fresh; nvcc cross-compiles without a GPU)
+    from oxdna_b200 import build as _b
+    _b.build()
 
 
 def load_golden(name):
