@@ -37,7 +37,7 @@ struct oxb_ctx {
 	// double-buffered state (slot order)
 	int cur = 0;
 	double4 *posd[2] = { nullptr, nullptr }, *veld[2] = { nullptr, nullptr }, *Ld[2] = { nullptr, nullptr }, *quatd[2] = { nullptr, nullptr };
-	int4 *ipos[2] = { nullptr, nullptr }, *list_ipos[2] = { nullptr, nullptr }, *iback[2] = { nullptr, nullptr }, *list_iback[2] = { nullptr, nullptr };
+	int4 *ipos[2] = { nullptr, nullptr }, *list_ipos[2] = { nullptr, nullptr }, *iback[2] = { nullptr, nullptr }, *list_iback[2] = { nullptr, nullptr }, *list_ibase[2] = { nullptr, nullptr };
 	float4 *Fb = nullptr;
 	float4 *quat[2] = { nullptr, nullptr }, *F[2] = { nullptr, nullptr }, *T[2] = { nullptr, nullptr };
 	int2 *bonds[2] = { nullptr, nullptr };
@@ -182,7 +182,17 @@ oxb::ListArgs list_args(oxb_ctx *c) {
 	a.cell_start = c->cell_start;
 	a.nbr = c->nbr; a.nnbr = c->nnbr; a.max_neigh = c->max_neigh; a.stride = c->N;
 	a.edges = c->edges; a.edge_offsets = c->edge_offsets; a.n_edges = c->n_edges; a.edge_capacity = c->edge_capacity;
-	a.iback = c->iback[c->cur]; a.list_iback = c->list_iback[c->cur]; a.dh_nbr = c->dh_nbr; a.dh_nnbr = c->dh_nnbr; a.max_dh = c->max_dh;
+	a.iback = c->iback[c->cur]; a.list_iback = c->list_iback[c->cur]; a.list_ibase = c->list_ibase[c->cur]; a.quat = c->quat[c->cur];
+	a.base_a1 = c->model.base_a1; a.stack_a1 = c->model.stack_a1;
+	{
+		const oxb_dna2_params &M = c->model;
+		double pad = 2. * c->skin + 0.02;
+		auto sq = [](double x) { return (float) (x * x); };
+		a.r2_bb = sq(M.excl[0].rc + pad);
+		a.r2_base = sq(std::max(std::max((double) M.hb.rchigh, (double) M.crst.rchigh), (double) M.excl[1].rc) + pad);
+		a.r2_bk = sq(std::max((double) M.excl[2].rc, (double) M.excl[3].rc) + pad);
+		a.r2_stack = sq((double) M.cxst.rchigh + pad);
+	} a.dh_nbr = c->dh_nbr; a.dh_nnbr = c->dh_nnbr; a.max_dh = c->max_dh;
 	{
 		double rd = (double) c->model.dh_rc + 2. * c->skin + 0.02;
 		a.rdh2 = (float) (rd * rd);
@@ -226,6 +236,7 @@ int do_sort(oxb_ctx *c) {
 	p.posd_out = c->posd[b]; p.veld_out = c->veld[b]; p.Ld_out = c->Ld[b]; p.quatd_out = c->quatd[b];
 	p.ipos_in = c->ipos[a]; p.list_ipos_in = c->list_ipos[a]; p.ipos_out = c->ipos[b]; p.list_ipos_out = c->list_ipos[b];
 	p.iback_in = c->iback[a]; p.iback_out = c->iback[b]; p.list_iback_in = c->list_iback[a]; p.list_iback_out = c->list_iback[b];
+	p.list_ibase_in = c->list_ibase[a]; p.list_ibase_out = c->list_ibase[b];
 	p.quat_in = c->quat[a]; p.F_in = c->F[a]; p.T_in = c->T[a]; p.quat_out = c->quat[b]; p.F_out = c->F[b]; p.T_out = c->T[b];
 	p.bonds_in = c->bonds[a]; p.bonds_out = c->bonds[b];
 	p.slot_of = c->slot_of;
@@ -312,8 +323,8 @@ oxb::IntegrateArgs integ_args(oxb_ctx *c, long long step) {
 	a.box = c->boxf;
 	a.posd = c->posd[k]; a.veld = c->veld[k]; a.Ld = c->Ld[k]; a.quatd = c->quatd[k];
 	a.ipos = c->ipos[k]; a.quat = c->quat[k]; a.list_ipos = c->list_ipos[k];
-	a.F = c->F[k]; a.T = c->T[k]; a.Fb = c->Fb; a.iback = c->iback[k]; a.list_iback = c->list_iback[k];
-	a.back_a1 = c->model.back_a1; a.back_a2 = c->model.back_a2;
+	a.F = c->F[k]; a.T = c->T[k]; a.Fb = c->Fb; a.iback = c->iback[k]; a.list_iback = c->list_iback[k]; a.list_ibase = c->list_ibase[k];
+	a.back_a1 = c->model.back_a1; a.back_a2 = c->model.back_a2; a.base_a1 = c->model.base_a1;
 	a.flags = c->flags; a.sums = c->sums; a.th = c->th; a.step = step;
 	return a;
 }
@@ -387,8 +398,8 @@ int oxb_create(oxb_ctx **out, int device, int N, int precision) {
 	CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	for(int k = 0; k < 2; k++) {
 		CU(dalloc(&c->posd[k], N)); CU(dalloc(&c->veld[k], N)); CU(dalloc(&c->Ld[k], N)); CU(dalloc(&c->quatd[k], N));
-		CU(dalloc(&c->ipos[k], N)); CU(dalloc(&c->list_ipos[k], N)); CU(dalloc(&c->iback[k], N)); CU(dalloc(&c->list_iback[k], N));
-		CU(cudaMemset(c->list_iback[k], 0, sizeof(int4) * N)); CU(dalloc(&c->quat[k], N)); CU(dalloc(&c->F[k], N)); CU(dalloc(&c->T[k], N));
+		CU(dalloc(&c->ipos[k], N)); CU(dalloc(&c->list_ipos[k], N)); CU(dalloc(&c->iback[k], N)); CU(dalloc(&c->list_iback[k], N)); CU(dalloc(&c->list_ibase[k], N));
+		CU(cudaMemset(c->list_iback[k], 0, sizeof(int4) * N)); CU(cudaMemset(c->list_ibase[k], 0, sizeof(int4) * N)); CU(dalloc(&c->quat[k], N)); CU(dalloc(&c->F[k], N)); CU(dalloc(&c->T[k], N));
 		CU(dalloc(&c->bonds[k], N));
 		CU(cudaMemset(c->F[k], 0, sizeof(float4) * N)); CU(cudaMemset(c->T[k], 0, sizeof(float4) * N));
 		CU(cudaMemset(c->list_ipos[k], 0, sizeof(int4) * N));
@@ -412,7 +423,7 @@ void oxb_destroy(oxb_ctx *c) {
 	if(c->stream) cudaStreamSynchronize(c->stream);
 	for(int k = 0; k < 2; k++) {
 		cudaFree(c->posd[k]); cudaFree(c->veld[k]); cudaFree(c->Ld[k]); cudaFree(c->quatd[k]); cudaFree(c->ipos[k]); cudaFree(c->list_ipos[k]);
-		cudaFree(c->quat[k]); cudaFree(c->F[k]); cudaFree(c->T[k]); cudaFree(c->bonds[k]); cudaFree(c->iback[k]); cudaFree(c->list_iback[k]);
+		cudaFree(c->quat[k]); cudaFree(c->F[k]); cudaFree(c->T[k]); cudaFree(c->bonds[k]); cudaFree(c->iback[k]); cudaFree(c->list_iback[k]); cudaFree(c->list_ibase[k]);
 	}
 	cudaFree(c->Fb);
 	cudaFree(c->slot_of); cudaFree(c->flags); cudaFree(c->sums); cudaFree(c->d_energy); cudaFree(c->ext); cudaFree(c->pos_f4);

@@ -196,6 +196,16 @@ OXB_HD Angle make_angle(v3 u, v3 v) {
 	return a;
 }
 
+// cosine + cross product only (for the f5 factors, which are functions of the cosine itself)
+OXB_HD Angle make_angle_cos(v3 u, v3 v) {
+	Angle a;
+	a.c = dot(u, v);
+	a.x = cross(u, v);
+	a.s = 0.f;
+	a.t = 0.f;
+	return a;
+}
+
 OXB_HD bool in_window(const oxb_dna2_params &M, int k, float c) { return c > M.f4_cmin[k] && c < M.f4_cmax[k]; }
 OXB_HD bool in_window_sym(const oxb_dna2_params &M, int k, float c) { return in_window(M, k, c) || in_window(M, k, -c); }
 
@@ -249,6 +259,35 @@ OXB_HD float dna2_dh(const oxb_dna2_params &M, float rbb2, bool p_end, bool q_en
 	fs = f * cut / m;
 	return en * cut;
 }
+
+#ifdef __CUDACC__
+// device-only variant with SFU intrinsics (rsqrt, ex2): no IEEE division / square root on the most frequent path.
+// Relative error ~2e-7, far inside the 1e-5 force tolerance.
+__device__ __forceinline__ float dna2_dh_fast(const oxb_dna2_params &M, float rbb2, bool p_end, bool q_end, float &fs) {
+	fs = 0.f;
+	if(rbb2 >= M.dh_rc * M.dh_rc) return 0.f;
+	float inv = rsqrtf(rbb2);
+	float m = rbb2 * inv;
+	float cut = 1.f;
+	if(M.dh_half_charged_ends) {
+		if(p_end) cut *= 0.5f;
+		if(q_end) cut *= 0.5f;
+	}
+	float en, f;
+	if(m < M.dh_rhigh) {
+		float ex = __expf(m * M.dh_minus_kappa) * M.dh_prefactor * inv;
+		en = ex;
+		f = -ex * (M.dh_minus_kappa - inv);
+	}
+	else {
+		float x = m - M.dh_rc;
+		en = M.dh_b * x * x;
+		f = -2.f * M.dh_b * x;
+	}
+	fs = f * cut * inv;
+	return en * cut;
+}
+#endif
 
 OXB_HD float dna2_excl(const oxb_dna2_params &M, v3 r, v3 rbb, v3 rb, const Axes &A, const Axes &B, v3 pback, v3 qback, PairAcc &acc) {
 	const float cb = M.base_a1;
@@ -492,8 +531,8 @@ OXB_HD float dna2_bonded(const oxb_dna2_params &M, v3 r, const Axes &A, const Ax
 			Angle t4 = make_angle(A.a3, B.a3);
 			Angle t5 = make_angle(-A.a3, h);
 			Angle t6 = make_angle(-B.a3, h);
-			Angle p1 = make_angle(A.a2, wh);
-			Angle p2 = make_angle(B.a2, wh);
+			Angle p1 = make_angle_cos(A.a2, wh);
+			Angle p2 = make_angle_cos(B.a2, wh);
 			AngVal a4 = f4_ts(M.f4[OXB_F4_STCK_T4], t4.t, t4.s);
 			AngVal a5 = f4_ts(M.f4[OXB_F4_STCK_T5], t5.t, t5.s);
 			AngVal a6 = f4_ts(M.f4[OXB_F4_STCK_T5], t6.t, t6.s);

@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(128) k_dh_particle(const __grid_constant__ oxb
 		int4 bq = __ldg(iback + j);
 		v3 rbb = min_image_fixed(box, bp, bq);
 		float fs;
-		float en = dna2_dh(M, dot(rbb, rbb), p_end, bq.w & 1, fs);
+		float en = dna2_dh_fast(M, dot(rbb, rbb), p_end, bq.w & 1, fs);
 		e += en;
 		axpy(f, -fs, rbb);
 	}

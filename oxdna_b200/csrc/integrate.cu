@@ -128,14 +128,20 @@ __global__ void __launch_bounds__(256) k_integrate(oxb::IntegrateArgs a, int epo
 				int4 ib = a.iback[i];
 				ib.x = (int) to_fixed(bx, a.box_inv[0]); ib.y = (int) to_fixed(by, a.box_inv[1]); ib.z = (int) to_fixed(bz, a.box_inv[2]);
 				a.iback[i] = ib;
-				// rotational staleness: the backbone site must not have moved further than the skin either
+				// rotational staleness: neither the backbone site nor the base site may have moved further than the skin
 				v3 db = min_image_fixed(a.box, a.list_iback[i], ib);
 				if(dot(db, db) > a.skin2) flags[wr] = 1;
+				double c1 = a.base_a1;
+				int4 is = ib;
+				is.x = (int) to_fixed(r.x + c1 * (sqx - sqy - sqz + sqw), a.box_inv[0]);
+				is.y = (int) to_fixed(r.y + c1 * (2. * (xy + zw)), a.box_inv[1]);
+				is.z = (int) to_fixed(r.z + c1 * (2. * (xz - yw)), a.box_inv[2]);
+				v3 ds = min_image_fixed(a.box, a.list_ibase[i], is);
+				if(dot(ds, ds) > a.skin2) flags[wr] = 1;
 			}
 			// forces are consumed: leave zeroed accumulators for the next force pass
 			a.F[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 			a.T[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-			a.Fb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 			v3 d = min_image_fixed(a.box, a.list_ipos[i], ip);
 			if(dot(d, d) > a.skin2) flags[wr] = 1;
 		}

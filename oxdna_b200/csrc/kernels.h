@@ -77,10 +77,10 @@ struct IntegrateArgs {
 	double4 *posd, *veld, *Ld, *quatd;
 	int4 *ipos;
 	float4 *quat;
-	const int4 *list_ipos, *list_iback;
+	const int4 *list_ipos, *list_iback, *list_ibase;
 	float4 *F, *T, *Fb; // lab-frame force / torque accumulators (zeroed by the first-half phase once consumed)
 	int4 *iback;        // fixed-point backbone-site position, .w bit 0 = strand end
-	float back_a1, back_a2;
+	float back_a1, back_a2, base_a1;
 	int *flags;
 	KinSums *sums;
 	ThermostatCfg th;
@@ -111,7 +111,10 @@ struct ListArgs {
 	float rnear2;      // (rcut_near + 2 skin + margin)^2
 	// Debye-Hueckel neighbour matrix (full, both directions), selected on the backbone-site distance
 	const int4 *iback;
-	int4 *list_iback;
+	int4 *list_iback, *list_ibase;
+	const float4 *quat;
+	float base_a1, stack_a1;
+	float r2_bb, r2_base, r2_bk, r2_stack; // squared site-site selection radii of the near-edge list (range + 2 skin + margin)
 	int *dh_nbr, *dh_nnbr;
 	int max_dh;
 	float rdh2;        // (dh_rc + 2 skin + margin)^2
@@ -144,8 +147,8 @@ struct PermuteArgs {
 	const int *inv;  // inv[old] = new
 	const double4 *posd_in, *veld_in, *Ld_in, *quatd_in;
 	double4 *posd_out, *veld_out, *Ld_out, *quatd_out;
-	const int4 *ipos_in, *list_ipos_in, *iback_in, *list_iback_in;
-	int4 *ipos_out, *list_ipos_out, *iback_out, *list_iback_out;
+	const int4 *ipos_in, *list_ipos_in, *iback_in, *list_iback_in, *list_ibase_in;
+	int4 *ipos_out, *list_ipos_out, *iback_out, *list_iback_out, *list_ibase_out;
 	const float4 *quat_in, *F_in, *T_in;
 	float4 *quat_out, *F_out, *T_out;
 	const int2 *bonds_in;

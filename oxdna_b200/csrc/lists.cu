@@ -50,6 +50,27 @@ __device__ __forceinline__ bool within_exact(double4 p, double4 q, double Lx, do
 	return n < rv2;
 }
 
+// Site-based selection of the "near" edges: a pair can feel something other than Debye-Hueckel before the next rebuild
+// only if one of its site-site distances is within the range of the corresponding term plus twice the skin (every site
+// -- centre, backbone, base and, being between centre and base, stack -- moves less than `skin` between rebuilds).
+__device__ __forceinline__ bool near_pair(const oxb::ListArgs &a, v3 r, v3 a1p, v3 a1q, v3 bkp, v3 bkq) {
+	v3 rbb = r + bkq - bkp;
+	if(dot(rbb, rbb) < a.r2_bb) return true;
+	v3 da = a1q - a1p;
+	v3 rb = r + da * a.base_a1;
+	if(dot(rb, rb) < a.r2_base) return true;
+	v3 rs = r + da * a.stack_a1;
+	if(dot(rs, rs) < a.r2_stack) return true;
+	v3 d1 = r + bkq - a1p * a.base_a1; // base(p) - back(q)
+	if(dot(d1, d1) < a.r2_bk) return true;
+	v3 d2 = r + a1q * a.base_a1 - bkp; // back(p) - base(q)
+	return dot(d2, d2) < a.r2_bk;
+}
+
+__device__ __forceinline__ v3 a1_of(float4 q) {
+	return mk3(q.x * q.x - q.y * q.y - q.z * q.z + q.w * q.w, 2.f * (q.x * q.y + q.z * q.w), 2.f * (q.x * q.z - q.y * q.w));
+}
+
 // one thread per particle: visit the 27 surrounding cells, keep non-bonded particles closer than rv
 __global__ void __launch_bounds__(128) k_build_neigh(oxb::ListArgs a, const int *__restrict__ cell_start, const int *__restrict__ cell_end) {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -63,6 +84,8 @@ __global__ void __launch_bounds__(128) k_build_neigh(oxb::ListArgs a, const int 
 	const float band = 1e-4f * rv2f;
 	const double rv2 = a.rv * a.rv;
 	const int4 ib = a.iback[i];
+	const v3 a1p = a1_of(a.quat[i]);
+	const v3 bkp = min_image_fixed(a.boxf, ip, ib);
 	int count = 0, higher_near = 0, ndh = 0;
 	for(int dz = -1; dz <= 1; dz++) {
 		int zc = cz + dz; zc += (zc < 0) ? nz : 0; zc -= (zc >= nz) ? nz : 0;
@@ -75,17 +98,19 @@ __global__ void __launch_bounds__(128) k_build_neigh(oxb::ListArgs a, const int 
 				for(int j = s; j < e; j++) {
 					int m = __ldg(a.cell_val_sorted + j);
 					if(m == i || m == b.x || m == b.y) continue;
-					v3 d = min_image_fixed(a.boxf, ip, __ldg(a.ipos + m));
+					const int4 ipm = __ldg(a.ipos + m);
+					v3 d = min_image_fixed(a.boxf, ip, ipm);
 					float d2 = dot(d, d);
 					bool in = d2 < rv2f;
 					if(fabsf(d2 - rv2f) < band) in = within_exact(pd, a.posd[m], a.box[0], a.box[1], a.box[2], rv2);
 					if(in) {
 						if(count < a.max_neigh) a.nbr[(size_t) count * a.stride + i] = m;
 						count++;
-						if(m > i && d2 < a.rnear2) higher_near++;
 						// Debye-Hueckel acts between backbone sites: keep m if the sites can come within dh_rc before the
 						// next rebuild (both the centre and the backbone site of every particle move less than `skin`)
-						v3 db = min_image_fixed(a.boxf, ib, __ldg(a.iback + m));
+						const int4 ibm = __ldg(a.iback + m);
+						v3 db = min_image_fixed(a.boxf, ib, ibm);
+						if(m > i && d2 < a.rnear2 && near_pair(a, d, a1p, a1_of(__ldg(a.quat + m)), bkp, min_image_fixed(a.boxf, ipm, ibm))) higher_near++;
 						if(dot(db, db) < a.rdh2) {
 							if(ndh < a.max_dh) a.dh_nbr[(size_t) ndh * a.stride + i] = m;
 							ndh++;
@@ -109,6 +134,13 @@ __global__ void __launch_bounds__(128) k_build_neigh(oxb::ListArgs a, const int 
 	a.dh_nnbr[i] = ndh;
 	a.list_ipos[i] = ip;
 	a.list_iback[i] = ib;
+	{
+		int4 bs = ip;
+		bs.x = (int) ((unsigned) ip.x + (unsigned) (int) rintf(a1p.x * a.base_a1 / a.boxf.sx));
+		bs.y = (int) ((unsigned) ip.y + (unsigned) (int) rintf(a1p.y * a.base_a1 / a.boxf.sy));
+		bs.z = (int) ((unsigned) ip.z + (unsigned) (int) rintf(a1p.z * a.base_a1 / a.boxf.sz));
+		a.list_ibase[i] = bs;
+	}
 	if(a.build_edges) a.edge_offsets[i] = higher_near;
 }
 
@@ -118,12 +150,16 @@ __global__ void __launch_bounds__(128) k_fill_edges(oxb::ListArgs a) {
 	if(i >= a.N) return;
 	int off = a.edge_offsets[i];
 	const int4 ip = a.ipos[i];
+	const int4 ib = a.iback[i];
+	const v3 a1p = a1_of(a.quat[i]);
+	const v3 bkp = min_image_fixed(a.boxf, ip, ib);
 	int nn = a.nnbr[i];
 	for(int k = 0; k < nn; k++) {
 		int m = a.nbr[(size_t) k * a.stride + i];
 		if(m > i) {
-			v3 d = min_image_fixed(a.boxf, ip, __ldg(a.ipos + m));
-			if(dot(d, d) < a.rnear2) {
+			const int4 ipm = __ldg(a.ipos + m);
+			v3 d = min_image_fixed(a.boxf, ip, ipm);
+			if(dot(d, d) < a.rnear2 && near_pair(a, d, a1p, a1_of(__ldg(a.quat + m)), bkp, min_image_fixed(a.boxf, ipm, __ldg(a.iback + m)))) {
 				if(off < a.edge_capacity) a.edges[off] = make_int2(i, m);
 				off++;
 			}
