@@ -14,6 +14,38 @@
 
 #include "common.cuh"
 
+// ---- fast elementary functions.  On the device: SFU reciprocal / rsqrt / ex2 (1-2 ulp); on the host (unit test build):
+// the plain libm equivalents.  The arctangent is our own (both sides): Cephes-style range reduction + degree-9 odd
+// polynomial, |error| < 1.5e-7 rad on [0, pi].
+#ifdef __CUDA_ARCH__
+#define OXB_DIV(a, b) __fdividef((a), (b))
+#define OXB_RSQRT(x) rsqrtf(x)
+#define OXB_EXP(x) __expf(x)
+#else
+#define OXB_DIV(a, b) ((a) / (b))
+#define OXB_RSQRT(x) (1.0f / sqrtf(x))
+#define OXB_EXP(x) expf(x)
+#endif
+
+// theta = atan2(s, c) for s >= 0
+OXB_HD float atan2_pos(float s, float c) {
+	float ax = fabsf(c);
+	float mx = fmaxf(ax, s), mn = fminf(ax, s);
+	if(mx == 0.f) return 0.f;
+	float a = OXB_DIV(mn, mx);
+	float base = 0.f;
+	if(a > 0.41421356f) {
+		a = OXB_DIV(a - 1.f, a + 1.f);
+		base = 0.78539816339744831f;
+	}
+	float z = a * a;
+	float p = ((8.05374449538e-2f * z - 1.38776856032e-1f) * z + 1.99777106478e-1f) * z - 3.33329491539e-1f;
+	float r = base + (a + a * z * p);
+	if(s > ax) r = 1.57079632679489662f - r;
+	if(c < 0.f) r = 3.14159265358979324f - r;
+	return r;
+}
+
 struct AngVal {
 	float v;  // f(theta)
 	float dc; // d f / d cos(theta)
@@ -36,12 +68,12 @@ OXB_HD AngVal f4_ts(const oxb_f4 &f, float t, float s) {
 			float d = f.tc - x;
 			r.v = f.b * d * d;
 			// d/dtheta = m 2 b (x - tc);  d/dcos = -(d/dtheta) / sin
-			r.dc = m * 2.f * f.b * d / fmaxf(s, 1e-12f);
+			r.dc = OXB_DIV(m * 2.f * f.b * d, fmaxf(s, 1e-12f));
 		}
 		else {
 			r.v = 1.f - f.a * x * x;
 			// same small-angle limit as the CPU code (DNAInteraction.cpp:1411-1414)
-			r.dc = (s * s > 1e-8f) ? m * 2.f * f.a * x / s : m * 2.f * f.a;
+			r.dc = (s * s > 1e-8f) ? OXB_DIV(m * 2.f * f.a * x, s) : m * 2.f * f.a;
 		}
 	}
 	return r;
@@ -63,7 +95,7 @@ OXB_HD AngVal f4_ts_cxst_t1(const oxb_dna2_params &M, float t, float s) {
 	float x = t - M.cxst_t1_sb;
 	if(x >= 0.f) {
 		r.v += M.cxst_t1_sa * x * x;
-		r.dc -= (s * s > 1e-8f) ? 2.f * M.cxst_t1_sa * x / s : 2.f * M.cxst_t1_sa;
+		r.dc -= (s * s > 1e-8f) ? OXB_DIV(2.f * M.cxst_t1_sa * x, s) : 2.f * M.cxst_t1_sa;
 	}
 	return r;
 }
@@ -104,7 +136,7 @@ OXB_HD RadVal f1_r(const oxb_f1 &f, float eps, float shift, float r) {
 			o.d = 2.f * eps * f.bhigh * x;
 		}
 		else if(r > f.rlow) {
-			float e = expf(-(r - f.r0) * f.a);
+			float e = OXB_EXP(-(r - f.r0) * f.a);
 			float t = 1.f - e;
 			o.v = eps * t * t - shift;
 			o.d = 2.f * eps * t * e * f.a;
@@ -149,16 +181,17 @@ OXB_HD float excl_s(const oxb_excl &e, float eps, v3 r, float &s) {
 	s = 0.f;
 	if(r2 < e.rc2) {
 		if(r2 > e.rstar2) {
-			float rm = sqrtf(r2);
-			float rrc = rm - e.rc;
+			float inv = OXB_RSQRT(r2);
+			float rrc = r2 * inv - e.rc;
 			en = eps * e.b * rrc * rrc;
-			s = -2.f * eps * e.b * rrc / rm;
+			s = -2.f * eps * e.b * rrc * inv;
 		}
 		else {
-			float t = e.sigma2 / r2;
+			float ir2 = OXB_DIV(1.f, r2);
+			float t = e.sigma2 * ir2;
 			float lj = t * t * t;
 			en = 4.f * eps * (lj * lj - lj);
-			s = -24.f * eps * (lj - 2.f * lj * lj) / r2;
+			s = -24.f * eps * (lj - 2.f * lj * lj) * ir2;
 		}
 	}
 	return en;
@@ -191,8 +224,9 @@ OXB_HD Angle make_angle(v3 u, v3 v) {
 	Angle a;
 	a.c = dot(u, v);
 	a.x = cross(u, v);
-	a.s = sqrtf(dot(a.x, a.x));
-	a.t = atan2f(a.s, a.c);
+	float s2 = dot(a.x, a.x);
+	a.s = (s2 > 0.f) ? s2 * OXB_RSQRT(s2) : 0.f;
+	a.t = atan2_pos(a.s, a.c);
 	return a;
 }
 
@@ -338,8 +372,8 @@ OXB_HD float dna2_hbcr(const oxb_dna2_params &M, v3 rb, float rbm2, const Axes &
 	const float cb = M.base_a1;
 	float E = 0.f;
 	ehb = 0.f;
-	float m = sqrtf(rbm2);
-	float inv = 1.f / m;
+	float inv = OXB_RSQRT(rbm2);
+	float m = rbm2 * inv;
 	v3 h = rb * inv;
 	Angle t1 = make_angle(-A.a1, B.a1);
 	Angle t2 = make_angle(-B.a1, h);
@@ -415,8 +449,8 @@ OXB_HD float dna2_hbcr(const oxb_dna2_params &M, v3 rb, float rbm2, const Axes &
 // rs = stack-stack vector
 OXB_HD float dna2_cxst(const oxb_dna2_params &M, v3 rs, float rs2, const Axes &A, const Axes &B, PairAcc &acc) {
 	const float cs = M.stack_a1;
-	float m = sqrtf(rs2);
-	float inv = 1.f / m;
+	float inv = OXB_RSQRT(rs2);
+	float m = rs2 * inv;
 	v3 h = rs * inv;
 	Angle t1 = make_angle(-A.a1, B.a1);
 	Angle t4 = make_angle(A.a3, B.a3);
@@ -480,14 +514,16 @@ OXB_HD float dna2_bonded(const oxb_dna2_params &M, v3 r, const Axes &A, const Ax
 	// FENE
 	{
 		v3 d = r + qback - pback;
-		float m = sqrtf(dot(d, d));
+		float d2 = dot(d, d);
+		float invm = OXB_RSQRT(d2);
+		float m = d2 * invm;
 		float x = m - M.fene_r0;
 		float en, s;
 		if(M.use_mbf && fabsf(x) > M.mbf_xmax) {
 			float ax = fabsf(x);
 			float k = (M.mbf_fmax - M.mbf_finf) * M.mbf_xmax;
 			en = k * logf(ax) + M.mbf_finf * ax + M.mbf_e0;
-			s = -copysignf(1.f, x) * (k / ax + M.mbf_finf) / m;
+			s = -copysignf(1.f, x) * (OXB_DIV(k, ax) + M.mbf_finf) * invm;
 		}
 		else {
 			float den = M.fene_delta2 - x * x;
@@ -496,7 +532,7 @@ OXB_HD float dna2_bonded(const oxb_dna2_params &M, v3 r, const Axes &A, const Ax
 				den = 1e-6f;
 			}
 			en = -0.5f * M.fene_eps * logf(den / M.fene_delta2);
-			s = -(M.fene_eps * x / den) / m;
+			s = -OXB_DIV(M.fene_eps * x, den) * invm;
 		}
 		E += en;
 		acc.site_kk(d * s);
@@ -518,15 +554,15 @@ OXB_HD float dna2_bonded(const oxb_dna2_params &M, v3 r, const Axes &A, const Ax
 	// stacking
 	{
 		v3 rs = r + B.a1 * cs - A.a1 * cs;
-		float m = sqrtf(dot(rs, rs));
+		float rs2 = dot(rs, rs);
+		float inv = OXB_RSQRT(rs2);
+		float m = rs2 * inv;
 		int ti = btype_to_type(btq) * 5 + btype_to_type(btp);
 		RadVal f1 = f1_r(M.stck, M.stck_eps[ti], M.stck_shift[ti], m);
 		if(f1.v != 0.f || f1.d != 0.f) {
-			float inv = 1.f / m;
 			v3 h = rs * inv;
 			v3 w = r + B.a1 * cr - A.a1 * cr;
-			float wm = sqrtf(dot(w, w));
-			float winv = 1.f / wm;
+			float winv = OXB_RSQRT(dot(w, w));
 			v3 wh = w * winv;
 			Angle t4 = make_angle(A.a3, B.a3);
 			Angle t5 = make_angle(-A.a3, h);
