@@ -179,6 +179,25 @@ def run_cpu(sysm, md_steps, warm, steps, procs):
     return procs * N * md_steps * steps / (t1 - t0), kind, t1 - t0
 
 
+def run_ref_cuda(sysm, workload_name, steps_a, steps_b):
+    """The reference's own CUDA backend on this GPU, same workload, via its stock CLI (oracle/ref_cuda_bench.py)."""
+    from oracle import ref_cuda_bench as R
+    from oxdna_b200 import lattice
+    if not R.available():
+        return {"value": None, "unavailable": "oracle/_ref/oxDNA_cuda not built (make -f oracle/Makefile.refcuda)"}
+    d = tempfile.mkdtemp()
+    top, conf = write_case(sysm, T_STR, d)
+    N = len(sysm["pos"])
+    if workload_name == "c4":
+        # the reference refuses external forces together with CUDA_sort_every > 0 (MD_CUDABackend.cu:110-112)
+        res = R.time_reference_cuda(top, conf, N, steps_a, steps_b, [(1, 0), (0, 0)], T=T_STR, salt=SALT, dt=DT, ext_forces=lattice.mutual_traps(sysm))
+    else:
+        res = R.time_reference_cuda(top, conf, N, steps_a, steps_b, [(1, 1), (0, 1), (1, 0), (0, 0)], T=T_STR, salt=SALT, dt=DT)
+    best = res["best"]
+    return {"value": best["value"] if best else None, "unit": "particle-steps/s", "best": best, "runs": res["runs"], "method": res["method"],
+            "build": "unmodified /root/reference/src/CUDA, nvcc -arch=sm_100 -O3 -use_fast_math (oracle/Makefile.refcuda), backend_precision = mixed"}
+
+
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -341,6 +360,14 @@ def ours(args):
             except Exception as e:  # pragma: no cover
                 cpu = {"value": None, "unit": "particle-steps/s", "cores": 1, "kind": "port", "sample": "failed: " + repr(e)}
 
+        ref_cuda = None
+        if world == 1 and not args.no_ref_cuda:
+            try:
+                a, b = args.ref_cuda_steps
+                ref_cuda = run_ref_cuda(sysm, args.workload, a, b)
+            except Exception as e:  # pragma: no cover
+                ref_cuda = {"value": None, "unavailable": repr(e)[-300:]}
+
         line = {"metric": "particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 forces / f64 integration (mixed)",
                 "data": "synthetic",
@@ -359,7 +386,7 @@ def ours(args):
                 "roofline_integrate": {"kernel": "fused second half-kick + thermostat + first half-kick/drift/rotate", "bound": "hbm", "achieved": integ_gbs, "peak": hbm_peak,
                                        "unit": "GB/s", "frac": integ_gbs / hbm_peak, "ms": t_integ, "share_of_step": t_integ / step_ms},
                 "kernels_ms": {"forces": t_force, "integrate": t_integ, "list_rebuild": t_list, "sort": t_sort, "md_step_mean": step_ms},
-                "cpu_baseline": cpu}
+                "cpu_baseline": cpu, "reference_cuda": ref_cuda}
         print(json.dumps(line), flush=True)
         if world > 1:
             dist.barrier()
@@ -371,7 +398,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cuda"])
     ap.add_argument("--workload", default="c2", choices=["c2", "c4", "small"])
     ap.add_argument("--md-steps", type=int, default=1000, help="MD steps per bench step")
     ap.add_argument("--equil", type=int, default=10000, help="untimed equilibration MD steps")
@@ -381,9 +408,18 @@ def main():
     ap.add_argument("--ref-procs", type=int, default=0)
     ap.add_argument("--cpu-md-steps", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-cuda", action="store_true", help="skip the reference-CUDA-backend comparator leg")
+    ap.add_argument("--ref-cuda-steps", type=int, nargs=2, default=[10000, 20000], help="steps=A and steps=B runs of the reference CLI")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
+    elif args.impl == "reference-cuda":
+        if int(os.environ.get("RANK", "0")) == 0:
+            sysm, desc = workload(args.workload)
+            a, b = args.ref_cuda_steps
+            r = run_ref_cuda(sysm, args.workload, a, b)
+            print(json.dumps({"impl": "reference-cuda", "metric": "particle-steps/s", "value": r.get("value"), "unit": "particle-steps/s", "n_gpus": 1,
+                              "higher_is_better": True, "config": {"workload": desc}, "reference_cuda": r}), flush=True)
     else:
         ours(args)
 
