@@ -107,13 +107,17 @@ def pair_statistics(sim, sysm):
 
 
 # ----------------------------------------------------------------------------------------------------------- CPU baseline
-def write_case(sysm, T, d):
+def write_case(sysm, T, d, state=None):
+    """Topology + configuration files of the workload; `state` (a get_state() dict) replaces the ideal lattice."""
     from oxdna_b200 import io as oio, lattice
     from oxdna_b200.sim import parse_temperature
     top, conf = os.path.join(d, "bench.top"), os.path.join(d, "bench.dat")
     oio.write_topology(top, sysm["btype"], sysm["n3"], sysm["n5"], sysm["strand"])
-    v, L = lattice.maxwell_velocities(len(sysm["pos"]), parse_temperature(T), 5)
-    oio.write_conf(conf, sysm["box"], sysm["pos"], sysm["a1"], sysm["a3"], v, L)
+    if state is None:
+        v, L = lattice.maxwell_velocities(len(sysm["pos"]), parse_temperature(T), 5)
+        oio.write_conf(conf, sysm["box"], sysm["pos"], sysm["a1"], sysm["a3"], v, L)
+    else:
+        oio.write_conf(conf, sysm["box"], state["pos"], state["a1"], state["a3"], state["vel"], state["L"])
     return top, conf
 
 
@@ -179,14 +183,17 @@ def run_cpu(sysm, md_steps, warm, steps, procs):
     return procs * N * md_steps * steps / (t1 - t0), kind, t1 - t0
 
 
-def run_ref_cuda(sysm, workload_name, steps_a, steps_b):
-    """The reference's own CUDA backend on this GPU, same workload, via its stock CLI (oracle/ref_cuda_bench.py)."""
+def run_ref_cuda(sysm, workload_name, steps_a, steps_b, state):
+    """The reference's own CUDA backend on this GPU, same workload, via its stock CLI (oracle/ref_cuda_bench.py).
+    It starts from `state`, a thermalised configuration produced by our engine: on the IDEAL lattice (exactly parallel
+    base normals) the reference's GPU kernels normalise a zero cross product and fill the system with NaNs at step 0
+    (profiles/micro/reflog.py), after which it never rebuilds its lists and its timing is void."""
     from oracle import ref_cuda_bench as R
     from oxdna_b200 import lattice
     if not R.available():
         return {"value": None, "unavailable": "oracle/_ref/oxDNA_cuda not built (make -f oracle/Makefile.refcuda)"}
     d = tempfile.mkdtemp()
-    top, conf = write_case(sysm, T_STR, d)
+    top, conf = write_case(sysm, T_STR, d, state)
     N = len(sysm["pos"])
     if workload_name == "c4":
         # the reference refuses external forces together with CUDA_sort_every > 0 (MD_CUDABackend.cu:110-112)
@@ -364,7 +371,7 @@ def ours(args):
         if world == 1 and not args.no_ref_cuda:
             try:
                 a, b = args.ref_cuda_steps
-                ref_cuda = run_ref_cuda(sysm, args.workload, a, b)
+                ref_cuda = run_ref_cuda(sysm, args.workload, a, b, sim.ctx.get_state())
             except Exception as e:  # pragma: no cover
                 ref_cuda = {"value": None, "unavailable": repr(e)[-300:]}
 
@@ -415,9 +422,16 @@ def main():
         reference_arm(args)
     elif args.impl == "reference-cuda":
         if int(os.environ.get("RANK", "0")) == 0:
+            from oxdna_b200 import lattice
+            from oxdna_b200.sim import Simulation, parse_temperature
             sysm, desc = workload(args.workload)
             a, b = args.ref_cuda_steps
-            r = run_ref_cuda(sysm, args.workload, a, b)
+            v, L = lattice.maxwell_velocities(len(sysm["pos"]), parse_temperature(T_STR), 5)
+            sim = Simulation(base_input(args), sysm, dict(box=sysm["box"], pos=sysm["pos"], a1=sysm["a1"], a3=sysm["a3"], vel=v, L=L))
+            sim.run(args.equil)
+            state = sim.ctx.get_state()
+            sim.close()
+            r = run_ref_cuda(sysm, args.workload, a, b, state)
             print(json.dumps({"impl": "reference-cuda", "metric": "particle-steps/s", "value": r.get("value"), "unit": "particle-steps/s", "n_gpus": 1,
                               "higher_is_better": True, "config": {"workload": desc}, "reference_cuda": r}), flush=True)
     else:

@@ -2,12 +2,14 @@
 oracle/Makefile.refcuda from /root/reference/src/CUDA) on the same synthetic workload bench.py uses, through the
 reference's own CLI and input file -- the comparator BASELINE.json names ("the reference's own CUDA backend on one B200").
 
-Method: the stock binary is run twice from the same files with `steps = A` and `steps = B` (A < B); the wall-clock
-difference covers MD steps A..B only (initialisation, file IO and the first A equilibration steps cancel), which is the
-same region bench.py times for our path.  Input follows SURVEY.md appendix C (timers left on, as users run it).
+Method: the stock binary is run twice from the same files with `steps = A` and `steps = B` (A < B); the difference of
+the reference's own "Total Running Time" (its SimBackend timer, simulation loop only) covers MD steps A..B, i.e. the
+same post-equilibration region bench.py times for our path.  Input follows SURVEY.md appendix C (timers left on, as users run it).
+The start configuration must be thermalised (velocities included, `refresh_vel = 0`): see bench.run_ref_cuda.
 Never imported by the product package.
 """
 import os
+import re
 import subprocess
 import tempfile
 import time
@@ -39,7 +41,7 @@ edge_n_forces = 1
 max_density_multiplier = 3
 CUDA_avoid_cpu_calculations = 1
 seed = 42
-refresh_vel = 1
+refresh_vel = 0
 topology = {top}
 conf_file = {conf}
 trajectory_file = {d}/trajectory.dat
@@ -75,7 +77,15 @@ def _run(d, top, conf, steps, use_edge, sort_every, T, salt, dt, ext_path):
     t1 = time.perf_counter()
     if p.returncode != 0:
         raise RuntimeError("reference CUDA backend failed:\n" + p.stdout[-2000:])
-    return t1 - t0
+    text = p.stdout
+    try:
+        text += open(os.path.join(d, "log.dat")).read()
+    except OSError:
+        pass
+    # "INFO: Total Running Time: X s, per step: Y ms" = the reference's own SimBackend timer (simulation loop only)
+    m = re.search(r"Total Running Time:\s*([0-9.eE+-]+)\s*s", text)
+    u = re.search(r"Lists updated\s*(\d+)\s*times", text)
+    return (float(m.group(1)) if m else t1 - t0), ("SimBackend timer" if m else "wall clock"), (int(u.group(1)) if u else None)
 
 
 def time_reference_cuda(top, conf, N, steps_a, steps_b, variants, T="300K", salt=0.5, dt=0.003, ext_forces=None):
@@ -88,14 +98,16 @@ def time_reference_cuda(top, conf, N, steps_a, steps_b, variants, T="300K", salt
     runs = []
     for (use_edge, sort_every) in variants:
         try:
-            ta = _run(d, top, conf, steps_a, use_edge, sort_every, T, salt, dt, ext_path)
-            tb = _run(d, top, conf, steps_b, use_edge, sort_every, T, salt, dt, ext_path)
+            ta, how, ua = _run(d, top, conf, steps_a, use_edge, sort_every, T, salt, dt, ext_path)
+            tb, how, ub = _run(d, top, conf, steps_b, use_edge, sort_every, T, salt, dt, ext_path)
             val = N * (steps_b - steps_a) / max(tb - ta, 1e-9)
             runs.append(dict(use_edge=use_edge, CUDA_sort_every=sort_every, value=val, ms_per_md_step=1e3 * (tb - ta) / (steps_b - steps_a),
-                             wall_s=[ta, tb]))
+                             loop_s=[ta, tb], clock=how,
+                             list_rebuild_every_md_steps=(steps_b - steps_a) / max(ub - ua, 1) if (ua is not None and ub is not None) else None))
         except Exception as e:  # pragma: no cover
             runs.append(dict(use_edge=use_edge, CUDA_sort_every=sort_every, value=None, error=str(e)[-400:]))
     ok = [r for r in runs if r.get("value")]
     best = max(ok, key=lambda r: r["value"]) if ok else None
     return dict(best=best, runs=runs, unit="particle-steps/s",
-                method=f"stock CLI, wall-clock difference between steps={steps_b} and steps={steps_a} runs (timers on, default threads_per_block)")
+                method=f"stock CLI; difference of the reference's own 'Total Running Time' (SimBackend timer: simulation loop only) between a steps={steps_b} and a "
+                       f"steps={steps_a} run, i.e. MD steps {steps_a}..{steps_b} after equilibration; timers on, default threads_per_block")

@@ -1,4 +1,6 @@
-// Micro-test: CUDA graph with fork/join + (nested) conditional IF nodes set from device code; launch throughput.
+// Micro-test: launch overhead of the step structures considered for the MD loop (sm_100a):
+//  A serial stream launches; B graph of serial kernels; C graph with fork/join; D = C + device-set IF node;
+//  E = C unrolled 8x per graph; F = WHILE node looping C on the device (one launch for all steps).
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o graph_cond graph_cond.cu
 #include <cstdio>
 #include <cuda_runtime.h>
@@ -12,94 +14,174 @@ __global__ void k_work(float *p, int n, int iters) {
 	for(int k = 0; k < iters; k++) x = x * 1.0001f + 0.5f;
 	p[i] = x;
 }
-__global__ void k_decide(int *ctr, cudaGraphConditionalHandle h, cudaGraphConditionalHandle h2) {
+__global__ void k_decide(int *ctr, cudaGraphConditionalHandle h, int every) {
 	int c = atomicAdd(ctr, 1);
-	cudaGraphSetConditional(h, (c % 10) == 0);
-	cudaGraphSetConditional(h2, (c % 20) == 0);
+	cudaGraphSetConditional(h, (c % every) == 0);
+}
+__global__ void k_loop(int *ctr, cudaGraphConditionalHandle h, int total) {
+	int c = atomicAdd(ctr, 1);
+	cudaGraphSetConditional(h, (c + 1) < total);
 }
 __global__ void k_count(int *ctr) { atomicAdd(ctr, 1); }
 
-int main() {
-	const int n = 81920;
-	float *a, *b, *c, *d;
-	int *ctr;
-	CK(cudaMalloc(&a, n * 4)); CK(cudaMalloc(&b, n * 4)); CK(cudaMalloc(&c, n * 4)); CK(cudaMalloc(&d, n * 4));
-	CK(cudaMalloc(&ctr, 16)); CK(cudaMemset(ctr, 0, 16));
-	cudaStream_t s, s2, s3;
-	CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&s3, cudaStreamNonBlocking));
-	cudaEvent_t ef, e2, e3;
-	CK(cudaEventCreateWithFlags(&ef, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&e3, cudaEventDisableTiming));
+const int n = 81920, IT = 200;
+float *a, *b, *c, *d;
+int *ctr;
+cudaStream_t s, s2, s3;
+cudaEvent_t ef, e2, e3;
 
-	cudaGraph_t g;
-	CK(cudaGraphCreate(&g, 0));
-	cudaGraphConditionalHandle h, h2;
-	CK(cudaGraphConditionalHandleCreate(&h, g, 0, cudaGraphCondAssignDefault));
-	CK(cudaGraphConditionalHandleCreate(&h2, g, 0, cudaGraphCondAssignDefault));
-	// capture the fork/join part into g
-	CK(cudaStreamBeginCaptureToGraph(s, g, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+int step_forkjoin() {
 	CK(cudaEventRecord(ef, s));
 	CK(cudaStreamWaitEvent(s2, ef, 0)); CK(cudaStreamWaitEvent(s3, ef, 0));
-	k_work<<<(n + 127) / 128, 128, 0, s>>>(a, n, 200);
-	k_work<<<(n + 127) / 128, 128, 0, s2>>>(b, n, 200);
-	k_work<<<(n + 127) / 128, 128, 0, s3>>>(c, n, 200);
+	k_work<<<(n + 127) / 128, 128, 0, s>>>(a, n, IT);
+	k_work<<<(n + 127) / 128, 128, 0, s2>>>(b, n, IT);
+	k_work<<<(n + 127) / 128, 128, 0, s3>>>(c, n, IT);
 	CK(cudaEventRecord(e2, s2)); CK(cudaEventRecord(e3, s3));
 	CK(cudaStreamWaitEvent(s, e2, 0)); CK(cudaStreamWaitEvent(s, e3, 0));
-	k_work<<<(n + 127) / 128, 128, 0, s>>>(d, n, 200);
-	k_decide<<<1, 1, 0, s>>>(ctr, h, h2);
-	// conditional node appended behind the capture's current dependencies
-	cudaStreamCaptureStatus st; const cudaGraphNode_t *deps; size_t ndeps; cudaGraph_t cg;
-	CK(cudaStreamGetCaptureInfo(s, &st, nullptr, &cg, &deps, &ndeps));
-	cudaGraphNodeParams cp = {};
-	cp.type = cudaGraphNodeTypeConditional;
-	cp.conditional.handle = h; cp.conditional.type = cudaGraphCondTypeIf; cp.conditional.size = 1;
-	cudaGraphNode_t cond;
-	CK(cudaGraphAddNode(&cond, cg, deps, ndeps, &cp));
-	cudaGraph_t body = cp.conditional.phGraph_out[0];
-	CK(cudaStreamUpdateCaptureDependencies(s, &cond, 1, cudaStreamSetCaptureDependencies));
-	CK(cudaStreamEndCapture(s, &cg));
-	// body: count + nested IF
-	CK(cudaStreamBeginCaptureToGraph(s, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
-	k_count<<<1, 1, 0, s>>>(ctr + 1);
-	CK(cudaStreamGetCaptureInfo(s, &st, nullptr, &cg, &deps, &ndeps));
-	cudaGraphNodeParams cp2 = {};
-	cp2.type = cudaGraphNodeTypeConditional;
-	cp2.conditional.handle = h2; cp2.conditional.type = cudaGraphCondTypeIf; cp2.conditional.size = 1;
-	cudaGraphNode_t cond2;
-	CK(cudaGraphAddNode(&cond2, cg, deps, ndeps, &cp2));
-	cudaGraph_t body2 = cp2.conditional.phGraph_out[0];
-	CK(cudaStreamUpdateCaptureDependencies(s, &cond2, 1, cudaStreamSetCaptureDependencies));
-	k_work<<<(n + 127) / 128, 128, 0, s>>>(d, n, 10);
-	CK(cudaStreamEndCapture(s, &cg));
-	CK(cudaStreamBeginCaptureToGraph(s, body2, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
-	k_count<<<1, 1, 0, s>>>(ctr + 2);
-	CK(cudaStreamEndCapture(s, &cg));
+	k_work<<<(n + 127) / 128, 128, 0, s>>>(d, n, IT);
+	k_work<<<(n + 127) / 128, 128, 0, s>>>(d, n, IT);
+	return 0;
+}
+int step_serial() {
+	k_work<<<(n + 127) / 128, 128, 0, s>>>(a, n, IT); k_work<<<(n + 127) / 128, 128, 0, s>>>(b, n, IT);
+	k_work<<<(n + 127) / 128, 128, 0, s>>>(c, n, IT); k_work<<<(n + 127) / 128, 128, 0, s>>>(d, n, IT);
+	k_work<<<(n + 127) / 128, 128, 0, s>>>(d, n, IT);
+	return 0;
+}
 
-	cudaGraphExec_t ge;
-	CK(cudaGraphInstantiate(&ge, g, 0));
+int time_exec(const char *name, cudaGraphExec_t ge, int launches, int steps_per_launch) {
 	cudaEvent_t t0, t1;
 	CK(cudaEventCreate(&t0)); CK(cudaEventCreate(&t1));
 	for(int rep = 0; rep < 3; rep++) {
 		CK(cudaMemsetAsync(ctr, 0, 16, s));
 		CK(cudaEventRecord(t0, s));
-		for(int i = 0; i < 1000; i++) CK(cudaGraphLaunch(ge, s));
+		for(int i = 0; i < launches; i++) CK(cudaGraphLaunch(ge, s));
 		CK(cudaEventRecord(t1, s));
 		CK(cudaEventSynchronize(t1));
 		float ms; CK(cudaEventElapsedTime(&ms, t0, t1));
-		int h_ctr[4]; CK(cudaMemcpy(h_ctr, ctr, 16, cudaMemcpyDeviceToHost));
-		printf("graph: 1000 launches %.3f ms (%.2f us/launch)  decide=%d if=%d nested=%d\n", ms, ms, h_ctr[0], h_ctr[1], h_ctr[2]);
+		int h[4]; CK(cudaMemcpy(h, ctr, 16, cudaMemcpyDeviceToHost));
+		if(rep == 2) printf("%-44s %8.2f us/step   (ctr %d %d)\n", name, 1e3 * ms / (launches * steps_per_launch), h[0], h[1]);
 	}
-	// the same kernels as plain serial launches
-	for(int rep = 0; rep < 2; rep++) {
+	return 0;
+}
+
+int add_if(cudaStream_t st, cudaGraphConditionalHandle h, enum cudaGraphConditionalNodeType type, cudaGraph_t *body) {
+	cudaStreamCaptureStatus cs; const cudaGraphNode_t *deps; size_t ndeps; cudaGraph_t cg;
+	CK(cudaStreamGetCaptureInfo(st, &cs, nullptr, &cg, &deps, &ndeps));
+	cudaGraphNodeParams cp = {};
+	cp.type = cudaGraphNodeTypeConditional;
+	cp.conditional.handle = h; cp.conditional.type = type; cp.conditional.size = 1;
+	cudaGraphNode_t cond;
+	CK(cudaGraphAddNode(&cond, cg, deps, ndeps, &cp));
+	*body = cp.conditional.phGraph_out[0];
+	CK(cudaStreamUpdateCaptureDependencies(st, &cond, 1, cudaStreamSetCaptureDependencies));
+	return 0;
+}
+
+int main() {
+	CK(cudaMalloc(&a, n * 4)); CK(cudaMalloc(&b, n * 4)); CK(cudaMalloc(&c, n * 4)); CK(cudaMalloc(&d, n * 4));
+	CK(cudaMalloc(&ctr, 16)); CK(cudaMemset(ctr, 0, 16));
+	CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&s3, cudaStreamNonBlocking));
+	CK(cudaEventCreateWithFlags(&ef, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&e3, cudaEventDisableTiming));
+	cudaEvent_t t0, t1;
+	CK(cudaEventCreate(&t0)); CK(cudaEventCreate(&t1));
+	cudaGraph_t g; cudaGraphExec_t ge;
+
+	// A: plain stream launches
+	for(int rep = 0; rep < 3; rep++) {
 		CK(cudaEventRecord(t0, s));
-		for(int i = 0; i < 1000; i++) {
-			k_work<<<(n + 127) / 128, 128, 0, s>>>(a, n, 200); k_work<<<(n + 127) / 128, 128, 0, s>>>(b, n, 200);
-			k_work<<<(n + 127) / 128, 128, 0, s>>>(c, n, 200); k_work<<<(n + 127) / 128, 128, 0, s>>>(d, n, 200);
-			k_count<<<1, 1, 0, s>>>(ctr + 3);
-		}
-		CK(cudaEventRecord(t1, s));
-		CK(cudaEventSynchronize(t1));
+		for(int i = 0; i < 1000; i++) step_serial();
+		CK(cudaEventRecord(t1, s)); CK(cudaEventSynchronize(t1));
 		float ms; CK(cudaEventElapsedTime(&ms, t0, t1));
-		printf("serial launches: %.2f us per 5-kernel step\n", ms);
+		if(rep == 2) printf("%-44s %8.2f us/step\n", "A  5 serial stream launches", ms);
+	}
+	// A2: fork/join with streams+events, no graph
+	for(int rep = 0; rep < 3; rep++) {
+		CK(cudaEventRecord(t0, s));
+		for(int i = 0; i < 1000; i++) step_forkjoin();
+		CK(cudaEventRecord(t1, s)); CK(cudaEventSynchronize(t1));
+		float ms; CK(cudaEventElapsedTime(&ms, t0, t1));
+		if(rep == 2) printf("%-44s %8.2f us/step\n", "A2 fork/join on 3 streams, no graph", ms);
+	}
+	// B: graph of 5 serial kernels
+	CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal)); step_serial(); CK(cudaStreamEndCapture(s, &g));
+	CK(cudaGraphInstantiate(&ge, g, 0)); time_exec("B  graph, 5 serial kernels", ge, 1000, 1);
+	// C: graph fork/join
+	CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal)); step_forkjoin(); CK(cudaStreamEndCapture(s, &g));
+	CK(cudaGraphInstantiate(&ge, g, 0)); time_exec("C  graph, fork/join (3 wide) + 2", ge, 1000, 1);
+	// D: C + decide kernel + IF node (body = 1 kernel, taken every 10th)
+	{
+		CK(cudaGraphCreate(&g, 0));
+		cudaGraphConditionalHandle h;
+		CK(cudaGraphConditionalHandleCreate(&h, g, 0, cudaGraphCondAssignDefault));
+		CK(cudaStreamBeginCaptureToGraph(s, g, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+		step_forkjoin();
+		k_decide<<<1, 1, 0, s>>>(ctr, h, 10);
+		cudaGraph_t body, cg;
+		if(add_if(s, h, cudaGraphCondTypeIf, &body)) return 1;
+		CK(cudaStreamEndCapture(s, &cg));
+		CK(cudaStreamBeginCaptureToGraph(s, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+		k_count<<<1, 1, 0, s>>>(ctr + 1);
+		CK(cudaStreamEndCapture(s, &cg));
+		CK(cudaGraphInstantiate(&ge, g, 0)); time_exec("D  C + decide + IF node", ge, 1000, 1);
+	}
+	// D2: C + decide kernel only (no IF)
+	{
+		CK(cudaGraphCreate(&g, 0));
+		cudaGraphConditionalHandle h;
+		CK(cudaGraphConditionalHandleCreate(&h, g, 0, cudaGraphCondAssignDefault));
+		CK(cudaStreamBeginCaptureToGraph(s, g, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+		step_forkjoin();
+		k_count<<<1, 1, 0, s>>>(ctr);
+		cudaGraph_t cg;
+		CK(cudaStreamEndCapture(s, &cg));
+		CK(cudaGraphInstantiate(&ge, g, 0)); time_exec("D2 C + 1 tiny kernel (no IF)", ge, 1000, 1);
+	}
+	// E: 8 steps of C per graph
+	CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+	for(int k = 0; k < 8; k++) step_forkjoin();
+	CK(cudaStreamEndCapture(s, &g));
+	CK(cudaGraphInstantiate(&ge, g, 0)); time_exec("E  graph, 8 x fork/join step per launch", ge, 125, 8);
+	// E2: 8 serial steps per graph
+	CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+	for(int k = 0; k < 8; k++) step_serial();
+	CK(cudaStreamEndCapture(s, &g));
+	CK(cudaGraphInstantiate(&ge, g, 0)); time_exec("E2 graph, 8 x serial step per launch", ge, 125, 8);
+	// F: WHILE node, body = serial step + loop kernel; one launch = 1000 steps
+	{
+		CK(cudaGraphCreate(&g, 0));
+		cudaGraphConditionalHandle h;
+		CK(cudaGraphConditionalHandleCreate(&h, g, 1, cudaGraphCondAssignDefault));
+		CK(cudaStreamBeginCaptureToGraph(s, g, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+		cudaGraph_t body, cg;
+		if(add_if(s, h, cudaGraphCondTypeWhile, &body)) return 1;
+		CK(cudaStreamEndCapture(s, &cg));
+		CK(cudaStreamBeginCaptureToGraph(s, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+		step_serial();
+		k_loop<<<1, 1, 0, s>>>(ctr, h, 1000);
+		CK(cudaStreamEndCapture(s, &cg));
+		CK(cudaGraphInstantiate(&ge, g, 0)); time_exec("F  WHILE node, serial step body, 1 launch", ge, 1, 1000);
+	}
+	// G: WHILE node with fork/join body and nested IF
+	{
+		CK(cudaGraphCreate(&g, 0));
+		cudaGraphConditionalHandle h, h2;
+		CK(cudaGraphConditionalHandleCreate(&h, g, 1, cudaGraphCondAssignDefault));
+		CK(cudaGraphConditionalHandleCreate(&h2, g, 0, cudaGraphCondAssignDefault));
+		CK(cudaStreamBeginCaptureToGraph(s, g, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+		cudaGraph_t body, body2, cg;
+		if(add_if(s, h, cudaGraphCondTypeWhile, &body)) return 1;
+		CK(cudaStreamEndCapture(s, &cg));
+		CK(cudaStreamBeginCaptureToGraph(s, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+		step_forkjoin();
+		k_decide<<<1, 1, 0, s>>>(ctr + 1, h2, 10);
+		if(add_if(s, h2, cudaGraphCondTypeIf, &body2)) return 1;
+		k_loop<<<1, 1, 0, s>>>(ctr, h, 1000);
+		CK(cudaStreamEndCapture(s, &cg));
+		CK(cudaStreamBeginCaptureToGraph(s, body2, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+		k_count<<<1, 1, 0, s>>>(ctr + 2);
+		CK(cudaStreamEndCapture(s, &cg));
+		CK(cudaGraphInstantiate(&ge, g, 0)); time_exec("G  WHILE{fork/join + decide + IF{..}}", ge, 1, 1000);
 	}
 	printf("OK\n");
 	return 0;
