@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -88,6 +89,15 @@ struct oxb_ctx {
 	int n_ext = 0;
 	DevExtForce *ext = nullptr;
 	double avg_interval = 8.;
+
+	// concurrency inside one force pass (independent kernels on forked streams) and graph-captured batches of steps
+	cudaStream_t aux[2] = { nullptr, nullptr };
+	cudaEvent_t ev_fork = nullptr, ev_near = nullptr, ev_join[2] = { nullptr, nullptr };
+	long long *cur_step = nullptr; // device, 2 words (see k_integrate)
+	struct BatchGraph { int units, cur; cudaGraphExec_t exec; };
+	std::vector<BatchGraph> graphs;
+	bool use_graphs = true;
+	long long graph_launches = 0;
 };
 
 namespace {
@@ -113,12 +123,19 @@ cudaError_t dalloc(T **p, size_t n) {
 	return cudaMalloc((void **) p, sizeof(T) * std::max<size_t>(n, 1));
 }
 
+// everything a captured batch freezes (pointers, model constants, dt, thermostat, grids) invalidates the cache
+void drop_graphs(oxb_ctx *c) {
+	for(auto &g : c->graphs) cudaGraphExecDestroy(g.exec);
+	c->graphs.clear();
+}
+
 void set_boxf(oxb_ctx *c) {
 	c->boxf.lx = (float) c->box[0]; c->boxf.ly = (float) c->box[1]; c->boxf.lz = (float) c->box[2];
 	c->boxf.sx = (float) (c->box[0] / 4294967296.0); c->boxf.sy = (float) (c->box[1] / 4294967296.0); c->boxf.sz = (float) (c->box[2] / 4294967296.0);
 }
 
 void free_lists(oxb_ctx *c) {
+	drop_graphs(c);
 	cudaFree(c->cell_key); cudaFree(c->cell_key_sorted); cudaFree(c->cell_val); cudaFree(c->cell_val_sorted); cudaFree(c->cell_start);
 	cudaFree(c->nbr); cudaFree(c->nnbr); cudaFree(c->edges); cudaFree(c->edge_offsets); cudaFree(c->n_edges); cudaFree(c->cub_tmp);
 	cudaFree(c->dh_nbr); cudaFree(c->dh_nnbr);
@@ -245,6 +262,7 @@ int do_sort(oxb_ctx *c) {
 	c->cur = b;
 	c->n_sorts++;
 	c->lists_valid = false;
+	c->forces_valid = false; // Fb (backbone-site force sums) is not permuted
 	CU(cudaGetLastError());
 	return 0;
 }
@@ -290,26 +308,52 @@ int ensure_lists(oxb_ctx *c) {
 	return do_build(c);
 }
 
-// hw: index of the halt word the launched kernels must honour; clear: F/T/Fb are not known to be zero
-int launch_forces(oxb_ctx *c, int hw, bool clear) {
+// hw: index of the halt word the launched kernels must honour; clear: F/T are not known to be zero; step < 0: kernels read
+// the step index from the device counter.  Edge pipeline = 5 kernels on 3 streams:
+//   main: near edges -> hydrogen bonding / cross stacking      aux0: Debye-Hueckel      aux1: bonds, external forces, coaxial stacking
+// joined back into main before the integrator.  Under stream capture the same calls become the fork/join edges of a graph.
+int launch_forces(oxb_ctx *c, int hw, bool clear, long long step) {
 	const int a = c->cur;
+	cudaStream_t m = c->stream;
 	if(c->use_edge) {
+		if(clear) {
+			CU(cudaMemsetAsync(c->F[a], 0, sizeof(float4) * (size_t) c->N, m));
+			CU(cudaMemsetAsync(c->T[a], 0, sizeof(float4) * (size_t) c->N, m));
+			CU(cudaMemsetAsync(c->counters, 0, 2 * sizeof(int), m));
+		}
 		oxb::EdgeArgs e;
 		e.N = c->N; e.ipos = c->ipos[a]; e.iback = c->iback[a]; e.quat = c->quat[a]; e.bonds = c->bonds[a]; e.edges = c->edges;
-		e.n_edges = c->n_edges; e.edge_hint = std::max(c->edge_hint, 1); e.dh_nbr = c->dh_nbr; e.dh_nnbr = c->dh_nnbr;
+		e.n_edges = c->n_edges; e.dh_nbr = c->dh_nbr; e.dh_nnbr = c->dh_nnbr;
 		e.F = c->F[a]; e.T = c->T[a]; e.Fb = c->Fb; e.hb_list = c->hb_list; e.cx_list = c->cx_list; e.counters = c->counters;
-		e.hb_cap = c->hb_cap; e.cx_cap = c->cx_cap; e.clear_first = clear;
-		oxb::launch_forces_edge(c->stream, c->model, c->boxf, e, c->flags, hw, c->n_sm);
+		e.hb_cap = c->hb_cap; e.cx_cap = c->cx_cap;
+		CU(cudaEventRecord(c->ev_fork, m));
+		CU(cudaStreamWaitEvent(c->aux[0], c->ev_fork, 0));
+		CU(cudaStreamWaitEvent(c->aux[1], c->ev_fork, 0));
+		oxb::launch_edge_stage(c->aux[0], 0, c->model, c->boxf, e, c->flags, hw, c->n_sm);
+		oxb::launch_edge_stage(c->aux[1], 4, c->model, c->boxf, e, c->flags, hw, c->n_sm);
+		oxb::launch_edge_stage(m, 1, c->model, c->boxf, e, c->flags, hw, c->n_sm);
+		CU(cudaEventRecord(c->ev_near, m));
+		oxb::launch_edge_stage(m, 2, c->model, c->boxf, e, c->flags, hw, c->n_sm);
+		if(c->n_ext > 0) {
+			oxb::launch_ext_forces(c->aux[1], c->n_ext, c->ext, c->slot_of, c->ipos[a], c->posd[a], c->boxf, step, c->cur_step, c->F[a], c->flags, hw);
+			c->launches += 1;
+		}
+		CU(cudaStreamWaitEvent(c->aux[1], c->ev_near, 0));
+		oxb::launch_edge_stage(c->aux[1], 3, c->model, c->boxf, e, c->flags, hw, c->n_sm);
+		CU(cudaEventRecord(c->ev_join[0], c->aux[0]));
+		CU(cudaEventRecord(c->ev_join[1], c->aux[1]));
+		CU(cudaStreamWaitEvent(m, c->ev_join[0], 0));
+		CU(cudaStreamWaitEvent(m, c->ev_join[1], 0));
 		c->launches += 5;
 	}
 	else {
-		oxb::launch_forces_particle(c->stream, c->model, c->boxf, c->N, c->ipos[a], c->quat[a], c->bonds[a], c->nbr, c->nnbr, c->N, c->F[a], c->T[a],
+		oxb::launch_forces_particle(m, c->model, c->boxf, c->N, c->ipos[a], c->quat[a], c->bonds[a], c->nbr, c->nnbr, c->N, c->F[a], c->T[a],
 				c->flags, hw);
 		c->launches += 1;
-	}
-	if(c->n_ext > 0) {
-		oxb::launch_ext_forces(c->stream, c->n_ext, c->ext, c->slot_of, c->ipos[a], c->posd[a], c->boxf, c->step, c->F[a], c->flags, hw);
-		c->launches += 1;
+		if(c->n_ext > 0) {
+			oxb::launch_ext_forces(m, c->n_ext, c->ext, c->slot_of, c->ipos[a], c->posd[a], c->boxf, step, c->cur_step, c->F[a], c->flags, hw);
+			c->launches += 1;
+		}
 	}
 	return 0;
 }
@@ -323,15 +367,26 @@ oxb::IntegrateArgs integ_args(oxb_ctx *c, long long step) {
 	a.box = c->boxf;
 	a.posd = c->posd[k]; a.veld = c->veld[k]; a.Ld = c->Ld[k]; a.quatd = c->quatd[k];
 	a.ipos = c->ipos[k]; a.quat = c->quat[k]; a.list_ipos = c->list_ipos[k];
-	a.F = c->F[k]; a.T = c->T[k]; a.Fb = c->Fb; a.iback = c->iback[k]; a.list_iback = c->list_iback[k]; a.list_ibase = c->list_ibase[k];
+	a.F = c->F[k]; a.T = c->T[k]; a.Fb = c->use_edge ? c->Fb : nullptr; a.iback = c->iback[k]; a.list_iback = c->list_iback[k]; a.list_ibase = c->list_ibase[k];
 	a.back_a1 = c->model.back_a1; a.back_a2 = c->model.back_a2; a.base_a1 = c->model.base_a1;
 	a.flags = c->flags; a.sums = c->sums; a.th = c->th; a.step = step;
+	a.cur_step = c->cur_step; a.counters = c->use_edge ? c->counters : nullptr;
 	return a;
 }
 
+__global__ void k_batch_begin(int *flags, long long *cur_step, long long step) {
+	flags[OXB_FLAG_STEPS_DONE] = 0;
+	flags[OXB_FLAG_COUNT] = 0;
+	flags[OXB_FLAG_COUNT + 1] = 0;
+	cur_step[0] = step;
+	cur_step[1] = step;
+}
+
+// start of a batch of launches: clears the halt words and the completed-step counter, seeds the device-side step index
 int reset_batch_flags(oxb_ctx *c) {
-	CU(cudaMemsetAsync(c->flags + OXB_FLAG_STEPS_DONE, 0, sizeof(int), c->stream));
-	CU(cudaMemsetAsync(c->flags + OXB_FLAG_COUNT, 0, 2 * sizeof(int), c->stream));
+	k_batch_begin<<<1, 1, 0, c->stream>>>(c->flags, c->cur_step, c->step);
+	c->launches++;
+	CU(cudaGetLastError());
 	return 0;
 }
 
@@ -369,9 +424,90 @@ int ensure_forces(oxb_ctx *c) {
 	if(!c->forces_valid) {
 		rc = reset_batch_flags(c);
 		if(rc) return rc;
-		launch_forces(c, OXB_FLAG_COUNT, true);
+		rc = launch_forces(c, OXB_FLAG_COUNT, true, c->step);
+		if(rc) return rc;
 		CU(cudaGetLastError());
 		c->forces_valid = true;
+	}
+	return 0;
+}
+
+// One unit of the hot loop with launch index `epoch`: force pass for the pending positions, then ONE integrate launch doing
+// the second half-kick + thermostat of step s and (with_first) the first half-kick + drift + rotation of step s + 1.
+// step < 0: graph capture, the kernels take the step index from the device counter.
+int launch_unit(oxb_ctx *c, int epoch, long long step, bool with_first) {
+	int rc = launch_forces(c, OXB_FLAG_COUNT + (epoch & 1), false, step);
+	if(rc) return rc;
+	oxb::IntegrateArgs a = integ_args(c, step);
+	const bool th_cfg = (c->th.type == OXB_THERMOSTAT_BROWNIAN || c->th.type == OXB_THERMOSTAT_LANGEVIN);
+	if(c->th.type == OXB_THERMOSTAT_BUSSI && step >= 0 && thermostat_active(c, step)) {
+		oxb::launch_clear_sums(c->stream, c->sums, c->flags, epoch);
+		oxb::launch_integrate_epoch(c->stream, a, OXB_PH_SECOND | OXB_PH_BUSSI_SUMS | OXB_PH_COUNT_STEP, epoch);
+		// the two extra launches of a Bussi step keep the halt-word parity: update reads the word integrate wrote, apply
+		// reads it too and writes the one the next unit reads
+		oxb::launch_bussi_update_epoch(c->stream, c->sums, c->N, c->th, step, c->flags, epoch + 1);
+		a.step = step + 1; // the apply launch carries the step counter forward without counting a step
+		oxb::launch_integrate_epoch(c->stream, a, with_first ? (OXB_PH_BUSSI_APPLY | OXB_PH_FIRST) : OXB_PH_BUSSI_APPLY, epoch + 1);
+		c->launches += 4;
+		return 2; // consumed two launch indices
+	}
+	int ph = OXB_PH_SECOND | OXB_PH_COUNT_STEP | (th_cfg ? OXB_PH_THERMO : 0) | (with_first ? OXB_PH_FIRST : 0);
+	oxb::launch_integrate_epoch(c->stream, a, ph, epoch);
+	c->launches++;
+	return 0;
+}
+
+// cached graph of `units` consecutive full units starting at an even launch index, for the current state buffers
+int batch_graph(oxb_ctx *c, int units, cudaGraphExec_t *out) {
+	for(auto &g : c->graphs) if(g.units == units && g.cur == c->cur) { *out = g.exec; return 0; }
+	cudaGraph_t graph = nullptr;
+	const long long launches0 = c->launches;
+	CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+	int rc = 0;
+	for(int k = 0; k < units && rc == 0; k++) rc = launch_unit(c, k, -1, true);
+	cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+	c->launches = launches0; // capturing launches nothing
+	if(rc) { if(graph) cudaGraphDestroy(graph); return rc; }
+	if(e != cudaSuccess) return fail(c, 100 + (int) e, "graph capture failed: %s", cudaGetErrorString(e));
+	cudaGraphExec_t exec = nullptr;
+	e = cudaGraphInstantiate(&exec, graph, 0);
+	cudaGraphDestroy(graph);
+	if(e != cudaSuccess) return fail(c, 100 + (int) e, "graph instantiation failed: %s", cudaGetErrorString(e));
+	c->graphs.push_back({ units, c->cur, exec });
+	*out = exec;
+	return 0;
+}
+
+// `n` full units for steps step0, step0 + 1, ...; `epoch` is advanced by the number of launch indices used.  Graph-launched
+// in chunks of 8/4/2 units (even sizes keep the frozen parity valid) while the index is even; the rest goes out as plain
+// stream launches.
+int launch_full_units(oxb_ctx *c, long long n, long long step0, int &epoch) {
+	const bool graphable = c->use_graphs && c->th.type != OXB_THERMOSTAT_BUSSI;
+	const int per_unit = (c->use_edge ? 5 : 1) + (c->n_ext > 0 ? 1 : 0) + 1;
+	long long k = 0;
+	while(k < n) {
+		int chunk = 0;
+		if(graphable && (epoch & 1) == 0) {
+			if(n - k >= 8) chunk = 8;
+			else if(n - k >= 4) chunk = 4;
+			else if(n - k >= 2) chunk = 2;
+		}
+		if(chunk > 0) {
+			cudaGraphExec_t g = nullptr;
+			int rc = batch_graph(c, chunk, &g);
+			if(rc) return rc;
+			CU(cudaGraphLaunch(g, c->stream));
+			c->launches += (long long) per_unit * chunk;
+			c->graph_launches++;
+			epoch += chunk;
+			k += chunk;
+		}
+		else {
+			int rc = launch_unit(c, epoch, step0 + k, true);
+			if(rc != 0 && rc != 2) return rc;
+			epoch += (rc == 2) ? 2 : 1;
+			k += 1;
+		}
 	}
 	return 0;
 }
@@ -397,6 +533,18 @@ int oxb_create(oxb_ctx **out, int device, int N, int precision) {
 	CU(cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, device));
 	CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	for(int k = 0; k < 2; k++) {
+		CU(cudaStreamCreateWithFlags(&c->aux[k], cudaStreamNonBlocking));
+		CU(cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming));
+	}
+	CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+	CU(cudaEventCreateWithFlags(&c->ev_near, cudaEventDisableTiming));
+	CU(dalloc(&c->cur_step, 2));
+	CU(cudaMemset(c->cur_step, 0, 2 * sizeof(long long)));
+	{
+		const char *g = getenv("OXB_NO_GRAPHS");
+		c->use_graphs = !(g != nullptr && g[0] == '1');
+	}
+	for(int k = 0; k < 2; k++) {
 		CU(dalloc(&c->posd[k], N)); CU(dalloc(&c->veld[k], N)); CU(dalloc(&c->Ld[k], N)); CU(dalloc(&c->quatd[k], N));
 		CU(dalloc(&c->ipos[k], N)); CU(dalloc(&c->list_ipos[k], N)); CU(dalloc(&c->iback[k], N)); CU(dalloc(&c->list_iback[k], N)); CU(dalloc(&c->list_ibase[k], N));
 		CU(cudaMemset(c->list_iback[k], 0, sizeof(int4) * N)); CU(cudaMemset(c->list_ibase[k], 0, sizeof(int4) * N)); CU(dalloc(&c->quat[k], N)); CU(dalloc(&c->F[k], N)); CU(dalloc(&c->T[k], N));
@@ -421,6 +569,14 @@ void oxb_destroy(oxb_ctx *c) {
 	if(c == nullptr) return;
 	cudaSetDevice(c->device);
 	if(c->stream) cudaStreamSynchronize(c->stream);
+	drop_graphs(c);
+	for(int k = 0; k < 2; k++) {
+		if(c->aux[k]) { cudaStreamSynchronize(c->aux[k]); cudaStreamDestroy(c->aux[k]); }
+		if(c->ev_join[k]) cudaEventDestroy(c->ev_join[k]);
+	}
+	if(c->ev_fork) cudaEventDestroy(c->ev_fork);
+	if(c->ev_near) cudaEventDestroy(c->ev_near);
+	cudaFree(c->cur_step);
 	for(int k = 0; k < 2; k++) {
 		cudaFree(c->posd[k]); cudaFree(c->veld[k]); cudaFree(c->Ld[k]); cudaFree(c->quatd[k]); cudaFree(c->ipos[k]); cudaFree(c->list_ipos[k]);
 		cudaFree(c->quat[k]); cudaFree(c->F[k]); cudaFree(c->T[k]); cudaFree(c->bonds[k]); cudaFree(c->iback[k]); cudaFree(c->list_iback[k]); cudaFree(c->list_ibase[k]);
@@ -442,6 +598,7 @@ int oxb_set_stream(oxb_ctx *c, void *s) {
 	if(c->own_stream && c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
 	c->stream = (cudaStream_t) s;
 	c->own_stream = false;
+	drop_graphs(c);
 	return 0;
 }
 
@@ -452,6 +609,7 @@ int oxb_set_box(oxb_ctx *c, const double box[3]) {
 		c->box[k] = box[k];
 	}
 	set_boxf(c);
+	drop_graphs(c);
 	c->have_box = true;
 	c->lists_valid = false; c->forces_valid = false;
 	if(c->lists_allocated) free_lists(c);
@@ -475,6 +633,7 @@ int oxb_set_topology(oxb_ctx *c, const int *btype, const int *n3, const int *n5,
 int oxb_set_model_dna2(oxb_ctx *c, const oxb_dna2_params *P, double rcut) {
 	if(c == nullptr || P == nullptr) return 1;
 	c->model = *P;
+	drop_graphs(c);
 	bool rcut_changed = (rcut != c->rcut);
 	c->rcut = rcut;
 	c->have_model = true;
@@ -499,6 +658,7 @@ int oxb_set_lists(oxb_ctx *c, double verlet_skin, int use_edge, int sort_every, 
 int oxb_set_dt(oxb_ctx *c, double dt) {
 	if(c == nullptr) return 1;
 	c->dt = dt;
+	drop_graphs(c);
 	return 0;
 }
 
@@ -509,6 +669,7 @@ int oxb_set_thermostat(oxb_ctx *c, int type, int every, double a, double b, doub
 	c->th.type = type; c->th.every = every < 1 ? 1 : every;
 	c->th.a = (float) a; c->th.b = (float) b; c->th.c = (float) cc; c->th.d = (float) d; c->th.seed = seed;
 	c->bussi_init = false;
+	drop_graphs(c);
 	return 0;
 }
 
@@ -534,6 +695,7 @@ int oxb_set_ext_forces(oxb_ctx *c, int n, const oxb_ext_force *f) {
 	if(n > 0) CU(cudaMemcpy(c->ext, h.data(), sizeof(DevExtForce) * n, cudaMemcpyHostToDevice));
 	c->n_ext = n;
 	c->forces_valid = false;
+	drop_graphs(c);
 	return 0;
 }
 
@@ -729,36 +891,30 @@ int oxb_run(oxb_ctx *c, long long n_steps) {
 		if(rc) return rc;
 		rc = reset_batch_flags(c);
 		if(rc) return rc;
-		int epoch = 0;
+		const long long step0 = c->step;
 		if(!c->mid_step) {
-			// start of a run: forces for the current positions, then the first half-kick + drift
-			if(!c->forces_valid) { launch_forces(c, OXB_FLAG_COUNT + (epoch & 1), true); c->forces_valid = true; }
-			oxb::launch_integrate_epoch(c->stream, integ_args(c, c->step), OXB_PH_FIRST, epoch++);
+			// start of a run: forces for the current positions, then the first half-kick + drift.  Launch index -1: reads halt
+			// word 1, writes word 0, so that the first full unit below always has index 0 (captured graphs freeze the parity)
+			if(!c->forces_valid) { rc = launch_forces(c, OXB_FLAG_COUNT + 1, true, step0); if(rc) return rc; c->forces_valid = true; }
+			oxb::launch_integrate_epoch(c->stream, integ_args(c, step0), OXB_PH_FIRST, -1);
 			c->launches++;
 		}
-		long long batch = std::min<long long>(remaining, std::max<long long>(1, std::min<long long>(64, (long long) (0.75 * c->avg_interval + 0.5))));
-		const long long step0 = c->step;
-		for(long long b = 0; b < batch; b++) {
-			const long long s = step0 + b;
-			c->step = s; // external forces read c->step at launch time
-			launch_forces(c, OXB_FLAG_COUNT + (epoch & 1), false);
-			const bool last = (b == batch - 1) && (batch == remaining);
-			const bool th = thermostat_active(c, s);
-			oxb::IntegrateArgs a = integ_args(c, s);
-			if(th && c->th.type == OXB_THERMOSTAT_BUSSI) {
-				oxb::launch_clear_sums(c->stream, c->sums, c->flags, epoch);
-				oxb::launch_integrate_epoch(c->stream, a, OXB_PH_SECOND | OXB_PH_BUSSI_SUMS | OXB_PH_COUNT_STEP, epoch++);
-				oxb::launch_bussi_update_epoch(c->stream, c->sums, c->N, c->th, s, c->flags, epoch);
-				oxb::launch_integrate_epoch(c->stream, a, last ? OXB_PH_BUSSI_APPLY : (OXB_PH_BUSSI_APPLY | OXB_PH_FIRST), epoch++);
-				c->launches += 4;
-			}
-			else {
-				int ph = OXB_PH_SECOND | OXB_PH_COUNT_STEP | (th ? OXB_PH_THERMO : 0) | (last ? 0 : OXB_PH_FIRST);
-				oxb::launch_integrate_epoch(c->stream, a, ph, epoch++);
-				c->launches++;
-			}
+		// the batch: `full` units that end with the first half of the following step, then (only at the very end of the run)
+		// one closing unit without it
+		// speculate up to ~0.8 x the running mean rebuild interval past the last rebuild, then in pairs (launches behind a halt are
+		// no-ops but still cost their launch latency); even sizes keep the graph path usable
+		long long budget = (long long) (0.8 * c->avg_interval + 0.5) - since_rebuild;
+		budget = std::max<long long>(2, std::min<long long>(64, budget)) & ~1ll;
+		const bool closes = (remaining <= budget);
+		long long full = closes ? remaining - 1 : budget;
+		int epoch = 0;
+		rc = launch_full_units(c, full, step0, epoch);
+		if(rc) return rc;
+		if(closes) {
+			rc = launch_unit(c, epoch++, step0 + full, false);
+			if(rc != 0 && rc != 2) return rc;
 		}
-		c->step = step0;
+		const long long batch = full + (closes ? 1 : 0);
 		CU(cudaGetLastError());
 		rc = read_flags(c);
 		if(rc) return rc;
@@ -800,9 +956,10 @@ int oxb_get_forces(oxb_ctx *c, double *force, double *torque_body, double *torqu
 	int rc = ensure_forces(c);
 	if(rc) return rc;
 	const int N = c->N, k = c->cur;
-	std::vector<float4> hF(N), hT(N);
+	std::vector<float4> hF(N), hT(N), hB(N, make_float4(0.f, 0.f, 0.f, 0.f));
 	std::vector<double4> hq(N);
 	std::vector<int4> hi(N);
+	if(c->use_edge) CU(cudaMemcpyAsync(hB.data(), c->Fb, sizeof(float4) * N, cudaMemcpyDeviceToHost, c->stream));
 	CU(cudaMemcpyAsync(hF.data(), c->F[k], sizeof(float4) * N, cudaMemcpyDeviceToHost, c->stream));
 	CU(cudaMemcpyAsync(hT.data(), c->T[k], sizeof(float4) * N, cudaMemcpyDeviceToHost, c->stream));
 	CU(cudaMemcpyAsync(hq.data(), c->quatd[k], sizeof(double4) * N, cudaMemcpyDeviceToHost, c->stream));
@@ -810,6 +967,17 @@ int oxb_get_forces(oxb_ctx *c, double *force, double *torque_body, double *torqu
 	CU(cudaStreamSynchronize(c->stream));
 	for(int s = 0; s < N; s++) {
 		int i = word_index(hi[s].w);
+		if(c->use_edge) {
+			// edge pipeline: the Debye-Hueckel force sum acts at the backbone site and is kept apart on the device (the integrator
+			// folds it in); fold it here the same way: F += Fb, tau += back x Fb, energy += Fb.w
+			quatd q = { hq[s].x, hq[s].y, hq[s].z, hq[s].w };
+			double x1[3], x2[3], x3[3];
+			axes_from_quatd(q, x1, x2, x3);
+			double bk[3], g[3] = { hB[s].x, hB[s].y, hB[s].z };
+			for(int d = 0; d < 3; d++) bk[d] = (double) c->model.back_a1 * x1[d] + (double) c->model.back_a2 * x2[d];
+			hF[s].x += hB[s].x; hF[s].y += hB[s].y; hF[s].z += hB[s].z; hF[s].w += hB[s].w;
+			hT[s].x += (float) (bk[1] * g[2] - bk[2] * g[1]); hT[s].y += (float) (bk[2] * g[0] - bk[0] * g[2]); hT[s].z += (float) (bk[0] * g[1] - bk[1] * g[0]);
+		}
 		if(force) { force[3 * i] = hF[s].x; force[3 * i + 1] = hF[s].y; force[3 * i + 2] = hF[s].z; }
 		// the device keeps the torque in the lab frame; the reference stores it in the body frame (R^T tau)
 		if(torque_lab) { torque_lab[3 * i] = hT[s].x; torque_lab[3 * i + 1] = hT[s].y; torque_lab[3 * i + 2] = hT[s].z; }
@@ -832,7 +1000,7 @@ int oxb_energy(oxb_ctx *c, double *U, double *K) {
 	int rc = ensure_forces(c);
 	if(rc) return rc;
 	const int k = c->cur;
-	oxb::launch_energy_sum(c->stream, c->N, c->F[k], c->d_energy);
+	oxb::launch_energy_sum(c->stream, c->N, c->F[k], c->use_edge ? c->Fb : nullptr, c->d_energy);
 	KinSums hs;
 	// keep the Bussi state words intact: only the five running sums are cleared/refilled
 	oxb::launch_kinetic_sums(c->stream, c->N, c->veld[k], c->Ld[k], c->sums);
@@ -926,7 +1094,7 @@ int oxb_time_kernel(oxb_ctx *c, int which, int reps, float *ms) {
 	CU(cudaStreamSynchronize(c->stream));
 	CU(cudaEventRecord(e0, c->stream));
 	for(int r = 0; r < reps; r++) {
-		if(which == 0) launch_forces(c, OXB_FLAG_COUNT, true);
+		if(which == 0) { rc = launch_forces(c, OXB_FLAG_COUNT, true, c->step); if(rc) return rc; }
 		else if(which == 1) {
 			// dt = 0 leaves the state bit-identical while moving exactly the same bytes
 			oxb::IntegrateArgs a = integ_args(c, c->step);

@@ -249,42 +249,27 @@ __global__ void __launch_bounds__(128) k_edge_heavy(const __grid_constant__ oxb_
 	}
 }
 
-// per particle: bonded interaction with the n3 neighbour (each bond evaluated once), folding of the backbone-site
-// force accumulator, reset of the work-list counters for the next step (this is the last kernel of the force pass)
-__global__ void __launch_bounds__(128) k_bonded_finalize(const __grid_constant__ oxb_dna2_params M, BoxF box, int N, const int4 *__restrict__ ipos,
-		const float4 *__restrict__ quat, const int2 *__restrict__ bonds, const float4 *__restrict__ Fb, float4 *__restrict__ F, float4 *__restrict__ T,
-		int *__restrict__ counters, int *__restrict__ flags, int hw) {
+// per particle: bonded interaction with its n3 neighbour (each bond evaluated once).  Independent of the other kernels of
+// the force pass (it only adds into F/T), so it runs concurrently with them on its own stream.
+__global__ void __launch_bounds__(128) k_bonded(const __grid_constant__ oxb_dna2_params M, BoxF box, int N, const int4 *__restrict__ ipos,
+		const float4 *__restrict__ quat, const int2 *__restrict__ bonds, float4 *__restrict__ F, float4 *__restrict__ T, int *__restrict__ flags, int hw) {
 	if(flags[hw]) return;
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if(i == 0 && counters != nullptr) { counters[0] = 0; counters[1] = 0; }
 	if(i >= N) return;
-	Particle P = load_particle(M, ipos, quat, i);
 	int2 b = __ldg(bonds + i);
-	v3 f = mk3(0.f, 0.f, 0.f), t = mk3(0.f, 0.f, 0.f);
-	float e = 0.f;
-	if(Fb != nullptr) {
-		float4 fb = Fb[i];
-		v3 g = mk3(fb.x, fb.y, fb.z);
-		f += g;
-		t += cross(P.back, g);
-		e += fb.w;
-	}
-	if(b.x >= 0) {
-		Particle Q = load_particle(M, ipos, quat, b.x);
-		PairAcc acc;
-		acc.clear();
-		bool broken = false;
-		float en = dna2_bonded(M, min_image_fixed(box, P.ip, Q.ip), P.ax, Q.ax, P.btype, Q.btype, P.back, Q.back, acc, broken);
-		f -= acc.F;
-		t += acc.torque_p(P.ax, P.back);
-		e += en;
-		v3 tq = acc.torque_q(Q.ax, Q.back);
-		atomic_add4(F + b.x, acc.F.x, acc.F.y, acc.F.z, en);
-		atomic_add4(T + b.x, tq.x, tq.y, tq.z, 0.f);
-		if(broken) atomicOr(flags + OXB_FLAG_ERROR, OXB_ERR_FENE_BROKEN);
-	}
-	atomic_add4(F + i, f.x, f.y, f.z, e);
-	atomic_add4(T + i, t.x, t.y, t.z, 0.f);
+	if(b.x < 0) return;
+	Particle P = load_particle(M, ipos, quat, i);
+	Particle Q = load_particle(M, ipos, quat, b.x);
+	PairAcc acc;
+	acc.clear();
+	bool broken = false;
+	float en = dna2_bonded(M, min_image_fixed(box, P.ip, Q.ip), P.ax, Q.ax, P.btype, Q.btype, P.back, Q.back, acc, broken);
+	v3 tp = acc.torque_p(P.ax, P.back), tq = acc.torque_q(Q.ax, Q.back);
+	atomic_add4(F + i, -acc.F.x, -acc.F.y, -acc.F.z, en);
+	atomic_add4(T + i, tp.x, tp.y, tp.z, 0.f);
+	atomic_add4(F + b.x, acc.F.x, acc.F.y, acc.F.z, en);
+	atomic_add4(T + b.x, tq.x, tq.y, tq.z, 0.f);
+	if(broken) atomicOr(flags + OXB_FLAG_ERROR, OXB_ERR_FENE_BROKEN);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -293,8 +278,11 @@ __global__ void __launch_bounds__(128) k_bonded_finalize(const __grid_constant__
 // Hilbert re-sort needs no table rewrite (the reference forbids sort + external forces, MD_CUDABackend.cu:110-112).
 // ------------------------------------------------------------------------------------------------------------
 __global__ void k_ext_forces(int n, const DevExtForce *__restrict__ ef, const int *__restrict__ slot_of, const int4 *__restrict__ ipos,
-		const double4 *__restrict__ posd, BoxF box, long long step, float4 *__restrict__ F, const int *__restrict__ flags, int hw) {
+		const double4 *__restrict__ posd, BoxF box, long long step, const long long *__restrict__ cur_step, float4 *__restrict__ F,
+		const int *__restrict__ flags, int hw) {
 	if(flags[hw]) return;
+	// graph-launched batches: the step index lives on the device (the word the integrator of the previous launch wrote)
+	if(step < 0) step = cur_step[hw & 1];
 	int k = blockIdx.x * blockDim.x + threadIdx.x;
 	if(k >= n) return;
 	DevExtForce e = ef[k];
@@ -341,31 +329,35 @@ void launch_forces_particle(cudaStream_t s, const oxb_dna2_params &M, BoxF box, 
 	k_forces_particle<<<(N + tpb - 1) / tpb, tpb, 0, s>>>(M, box, N, ipos, quat, bonds, nbr, nnbr, stride, F, T, flags, hw);
 }
 
-void launch_forces_edge(cudaStream_t s, const oxb_dna2_params &M, BoxF box, const EdgeArgs &a, int *flags, int hw, int n_sm) {
-	if(a.clear_first) {
-		cudaMemsetAsync(a.F, 0, sizeof(float4) * (size_t) a.N, s);
-		cudaMemsetAsync(a.T, 0, sizeof(float4) * (size_t) a.N, s);
+// the kernels of the edge pipeline, launched one by one so that the context can place them on concurrent streams:
+//   which = 0 Debye-Hueckel (writes Fb) | 1 near edges (F, T, work lists) | 2 HB + cross stacking | 3 coaxial stacking | 4 bonds
+void launch_edge_stage(cudaStream_t s, int which, const oxb_dna2_params &M, BoxF box, const EdgeArgs &a, int *flags, int hw, int n_sm) {
+	auto blocks_for = [&](long long items) { return (int) std::max<long long>(1, (items + 127) / 128); };
+	// the list lengths live on the device: fixed grids (so that a captured graph stays valid across rebuilds), grid-stride inside
+	const int cap_blocks = n_sm * 16;
+	switch(which) {
+	case 0: k_dh_particle<<<blocks_for(a.N), 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, flags, hw); break;
+	case 1:
+		k_edge_near<<<std::min(cap_blocks, blocks_for(8ll * a.N)), 128, 0, s>>>(M, box, a.n_edges, a.edges, a.ipos, a.quat, a.F, a.T, a.hb_list, a.cx_list,
+				a.counters, a.hb_cap, a.cx_cap, flags, hw);
+		break;
+	case 2:
+		k_edge_heavy<false><<<std::min(cap_blocks, blocks_for(2ll * a.N)), 128, 0, s>>>(M, box, a.counters + 0, a.hb_list, a.hb_cap, a.ipos, a.quat, a.F, a.T,
+				flags, hw);
+		break;
+	case 3:
+		k_edge_heavy<true><<<std::min(cap_blocks, blocks_for(a.N / 4)), 128, 0, s>>>(M, box, a.counters + 1, a.cx_list, a.cx_cap, a.ipos, a.quat, a.F, a.T, flags,
+				hw);
+		break;
+	default: k_bonded<<<blocks_for(a.N), 128, 0, s>>>(M, box, a.N, a.ipos, a.quat, a.bonds, a.F, a.T, flags, hw); break;
 	}
-	auto grid_for = [&](long long items, int tpb) {
-		long long want = (items + tpb - 1) / tpb;
-		if(want < 1) want = 1;
-		return (int) want;
-	};
-	k_dh_particle<<<(a.N + 127) / 128, 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, flags, hw);
-	k_edge_near<<<grid_for(a.edge_hint, 128), 128, 0, s>>>(M, box, a.n_edges, a.edges, a.ipos, a.quat, a.F, a.T, a.hb_list, a.cx_list, a.counters,
-			a.hb_cap, a.cx_cap, flags, hw);
-	// the work-list lengths live on the device: fixed grids sized for the typical contact density, grid-stride inside
-	int hb_blocks = std::max(n_sm, grid_for((long long) (1.0 * a.N), 128)), cx_blocks = std::max(n_sm, grid_for((long long) (0.125 * a.N), 128));
-	k_edge_heavy<false><<<hb_blocks, 128, 0, s>>>(M, box, a.counters + 0, a.hb_list, a.hb_cap, a.ipos, a.quat, a.F, a.T, flags, hw);
-	k_edge_heavy<true><<<cx_blocks, 128, 0, s>>>(M, box, a.counters + 1, a.cx_list, a.cx_cap, a.ipos, a.quat, a.F, a.T, flags, hw);
-	k_bonded_finalize<<<(a.N + 127) / 128, 128, 0, s>>>(M, box, a.N, a.ipos, a.quat, a.bonds, a.Fb, a.F, a.T, a.counters, flags, hw);
 }
 
 void launch_ext_forces(cudaStream_t s, int n, const DevExtForce *ef, const int *slot_of, const int4 *ipos, const double4 *posd, BoxF box,
-		long long step, float4 *F, const int *flags, int hw) {
+		long long step, const long long *cur_step, float4 *F, const int *flags, int hw) {
 	if(n <= 0) return;
 	int tpb = 128;
-	k_ext_forces<<<(n + tpb - 1) / tpb, tpb, 0, s>>>(n, ef, slot_of, ipos, posd, box, step, F, flags, hw);
+	k_ext_forces<<<(n + tpb - 1) / tpb, tpb, 0, s>>>(n, ef, slot_of, ipos, posd, box, step, cur_step, F, flags, hw);
 }
 
 } // namespace oxb

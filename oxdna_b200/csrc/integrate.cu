@@ -40,7 +40,15 @@ __global__ void __launch_bounds__(256) k_integrate(oxb::IntegrateArgs a, int epo
 		if(i == 0) flags[wr] = 1;
 		return;
 	}
-	if(i == 0 && (PH & OXB_PH_COUNT_STEP)) atomicAdd(flags + OXB_FLAG_STEPS_DONE, 1);
+	// step index: explicit (stream-launched paths) or the device-side counter (graph-launched batches, where kernel
+	// arguments are frozen): word (epoch & 1) is read, word ((epoch + 1) & 1) is written -- never the same word
+	const long long step = (a.step >= 0) ? a.step : a.cur_step[epoch & 1];
+	if(i == 0) {
+		if(PH & OXB_PH_COUNT_STEP) atomicAdd(flags + OXB_FLAG_STEPS_DONE, 1);
+		a.cur_step[(epoch + 1) & 1] = step + ((PH & OXB_PH_COUNT_STEP) ? 1 : 0);
+		// this launch runs after every consumer of the heavy work lists of the current force pass: reset their lengths
+		if((PH & OXB_PH_FIRST) && a.counters != nullptr) { a.counters[0] = 0; a.counters[1] = 0; }
+	}
 
 	double sv[5] = { 0., 0., 0., 0., 0. };
 	if(i < a.N) {
@@ -51,6 +59,13 @@ __global__ void __launch_bounds__(256) k_integrate(oxb::IntegrateArgs a, int epo
 			// angular momentum with unit inertia, src/CUDA/Interactions/CUDA_DNA.cuh:896)
 			Axes A = axes_from_quat(a.quat[i]);
 			v3 tl = mk3(T.x, T.y, T.z);
+			if(a.Fb != nullptr) {
+				// edge pipeline: the Debye-Hueckel kernel leaves its force sum, acting at the backbone site, in Fb
+				float4 fb = a.Fb[i];
+				v3 g = mk3(fb.x, fb.y, fb.z);
+				F.x += g.x; F.y += g.y; F.z += g.z;
+				tl += cross(A.a1 * a.back_a1 + A.a2 * a.back_a2, g);
+			}
 			T.x = dot(A.a1, tl); T.y = dot(A.a2, tl); T.z = dot(A.a3, tl);
 		}
 		double4 v = a.veld[i], L = a.Ld[i];
@@ -69,23 +84,23 @@ __global__ void __launch_bounds__(256) k_integrate(oxb::IntegrateArgs a, int epo
 			v.x = (v.x - cx) * S.factor_t + cx; v.y = (v.y - cy) * S.factor_t + cy; v.z = (v.z - cz) * S.factor_t + cz;
 			L.x *= S.factor_r; L.y *= S.factor_r; L.z *= S.factor_r;
 		}
-		if(PH & OXB_PH_THERMO) {
+		if((PH & OXB_PH_THERMO) && (a.th.type == OXB_THERMOSTAT_LANGEVIN || (step % a.th.every) == 0)) {
 			unsigned id = (unsigned) word_index(a.ipos[i].w);
 			if(a.th.type == OXB_THERMOSTAT_BROWNIAN) {
-				uint4 u = philox_u4(a.th.seed, id, (unsigned long long) a.step, 0u);
+				uint4 u = philox_u4(a.th.seed, id, (unsigned long long) step, 0u);
 				bool rt = u01(u.x) < a.th.a, rr = u01(u.y) < a.th.b;
 				if(rt || rr) {
 					float g0[4], g1[4];
-					philox_gauss4(a.th.seed, id, (unsigned long long) a.step, 1u, g0);
-					philox_gauss4(a.th.seed, id, (unsigned long long) a.step, 2u, g1);
+					philox_gauss4(a.th.seed, id, (unsigned long long) step, 1u, g0);
+					philox_gauss4(a.th.seed, id, (unsigned long long) step, 2u, g1);
 					if(rt) { v.x = g0[0] * a.th.c; v.y = g0[1] * a.th.c; v.z = g0[2] * a.th.c; }
 					if(rr) { L.x = g1[0] * a.th.c; L.y = g1[1] * a.th.c; L.z = g1[2] * a.th.c; }
 				}
 			}
 			else if(a.th.type == OXB_THERMOSTAT_LANGEVIN) {
 				float g0[4], g1[4];
-				philox_gauss4(a.th.seed, id, (unsigned long long) a.step, 1u, g0);
-				philox_gauss4(a.th.seed, id, (unsigned long long) a.step, 2u, g1);
+				philox_gauss4(a.th.seed, id, (unsigned long long) step, 1u, g0);
+				philox_gauss4(a.th.seed, id, (unsigned long long) step, 2u, g1);
 				double dt = a.dt;
 				v.x += dt * (-a.th.a * v.x + g0[0] * a.th.c); v.y += dt * (-a.th.a * v.y + g0[1] * a.th.c); v.z += dt * (-a.th.a * v.z + g0[2] * a.th.c);
 				L.x += dt * (-a.th.b * L.x + g1[0] * a.th.d); L.y += dt * (-a.th.b * L.y + g1[1] * a.th.d); L.z += dt * (-a.th.b * L.z + g1[2] * a.th.d);
@@ -255,9 +270,10 @@ __global__ void __launch_bounds__(256) k_kinetic_sums(int N, const double4 *__re
 	}
 }
 
-__global__ void __launch_bounds__(256) k_energy_sum(int N, const float4 *__restrict__ F, double *out) {
+__global__ void __launch_bounds__(256) k_energy_sum(int N, const float4 *__restrict__ F, const float4 *__restrict__ Fb, double *out) {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	double x = (i < N) ? (double) F[i].w : 0.;
+	if(Fb != nullptr && i < N) x += (double) Fb[i].w;
 	for(int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
 	__shared__ double sh[8];
 	if((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = x;
@@ -311,10 +327,10 @@ void launch_kinetic_sums(cudaStream_t s, int N, const double4 *veld, const doubl
 	k_kinetic_sums<<<(N + tpb - 1) / tpb, tpb, 0, s>>>(N, veld, Ld, sums);
 }
 
-void launch_energy_sum(cudaStream_t s, int N, const float4 *F, double *out) {
+void launch_energy_sum(cudaStream_t s, int N, const float4 *F, const float4 *Fb, double *out) {
 	cudaMemsetAsync(out, 0, sizeof(double), s);
 	int tpb = 256;
-	k_energy_sum<<<(N + tpb - 1) / tpb, tpb, 0, s>>>(N, F, out);
+	k_energy_sum<<<(N + tpb - 1) / tpb, tpb, 0, s>>>(N, F, Fb, out);
 }
 
 } // namespace oxb

@@ -55,17 +55,15 @@ struct EdgeArgs {
 	const float4 *quat;
 	const int2 *bonds, *edges; // near edges
 	const int *n_edges;
-	long long edge_hint;       // host copy of the count at the last rebuild (grid sizing)
 	const int *dh_nbr, *dh_nnbr; // Debye-Hueckel neighbour matrix, column-major, stride N
 	float4 *F, *T, *Fb;
 	int2 *hb_list, *cx_list;
 	int *counters; // [0] hb/cross-stacking work items, [1] coaxial work items
 	int hb_cap, cx_cap;
-	bool clear_first;
 };
-void launch_forces_edge(cudaStream_t s, const oxb_dna2_params &M, BoxF box, const EdgeArgs &a, int *flags, int hw, int n_sm);
+void launch_edge_stage(cudaStream_t s, int which, const oxb_dna2_params &M, BoxF box, const EdgeArgs &a, int *flags, int hw, int n_sm);
 void launch_ext_forces(cudaStream_t s, int n, const DevExtForce *ef, const int *slot_of, const int4 *ipos, const double4 *posd, BoxF box,
-		long long step, float4 *F, const int *flags, int hw);
+		long long step, const long long *cur_step, float4 *F, const int *flags, int hw);
 
 // ---- integrate.cu
 struct IntegrateArgs {
@@ -84,13 +82,15 @@ struct IntegrateArgs {
 	int *flags;
 	KinSums *sums;
 	ThermostatCfg th;
-	long long step; // step index of the thermostat application / of the first half-kick
+	long long step;      // step index of the thermostat application, or < 0: read it from cur_step (graph-launched batches)
+	long long *cur_step; // two device words, see k_integrate
+	int *counters;       // work-list lengths of the edge pipeline (reset here), or nullptr
 };
 void launch_integrate_epoch(cudaStream_t s, const IntegrateArgs &a, int phases, int epoch);
 void launch_bussi_update_epoch(cudaStream_t s, KinSums *sums, int N, ThermostatCfg th, long long step, const int *flags, int epoch);
 void launch_clear_sums(cudaStream_t s, KinSums *sums, const int *flags, int epoch);
 void launch_kinetic_sums(cudaStream_t s, int N, const double4 *veld, const double4 *Ld, KinSums *sums);
-void launch_energy_sum(cudaStream_t s, int N, const float4 *F, double *out);
+void launch_energy_sum(cudaStream_t s, int N, const float4 *F, const float4 *Fb, double *out);
 
 // ---- lists.cu
 struct ListArgs {

@@ -125,18 +125,6 @@ int main() {
 		CK(cudaStreamEndCapture(s, &cg));
 		CK(cudaGraphInstantiate(&ge, g, 0)); time_exec("D  C + decide + IF node", ge, 1000, 1);
 	}
-	// D2: C + decide kernel only (no IF)
-	{
-		CK(cudaGraphCreate(&g, 0));
-		cudaGraphConditionalHandle h;
-		CK(cudaGraphConditionalHandleCreate(&h, g, 0, cudaGraphCondAssignDefault));
-		CK(cudaStreamBeginCaptureToGraph(s, g, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
-		step_forkjoin();
-		k_count<<<1, 1, 0, s>>>(ctr);
-		cudaGraph_t cg;
-		CK(cudaStreamEndCapture(s, &cg));
-		CK(cudaGraphInstantiate(&ge, g, 0)); time_exec("D2 C + 1 tiny kernel (no IF)", ge, 1000, 1);
-	}
 	// E: 8 steps of C per graph
 	CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
 	for(int k = 0; k < 8; k++) step_forkjoin();

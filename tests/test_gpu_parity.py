@@ -139,8 +139,11 @@ def test_operator_by_operator_step_matches_run():
             a.ctx.thermostat()
         b.run(5)
         sa, sb = a.ctx.get_state(), b.ctx.get_state()
+        # same arithmetic, but the fused kernel variant and the single-phase variants are separate template instantiations
+        # whose FP32 torque rotation may be FMA-contracted differently: agreement is at FP32 round-off of one kick
+        # (1e-7 * |tau| * dt/2 ~ 1e-9), measured 1.4e-9 on L after 5 steps
         for k in ("pos", "vel", "L", "a1"):
-            assert np.abs(sa[k] - sb[k]).max() < 1e-12, k
+            assert np.abs(sa[k] - sb[k]).max() < 2e-8, k
     finally:
         a.close()
         b.close()
