@@ -65,6 +65,8 @@ struct oxb_ctx {
 	int *nbr = nullptr, *nnbr = nullptr;
 	int2 *edges = nullptr;
 	int *edge_offsets = nullptr, *n_edges = nullptr;
+	ulonglong2 *near_mask = nullptr;
+	bool slots_cell_ordered = false; // the last re-sort ordered the slots by cell and left the cell ids in cell_key_sorted
 	long long edge_capacity = 0;
 	int edge_hint = 0;
 	int *dh_nbr = nullptr, *dh_nnbr = nullptr;
@@ -138,7 +140,9 @@ void free_lists(oxb_ctx *c) {
 	drop_graphs(c);
 	cudaFree(c->cell_key); cudaFree(c->cell_key_sorted); cudaFree(c->cell_val); cudaFree(c->cell_val_sorted); cudaFree(c->cell_start);
 	cudaFree(c->nbr); cudaFree(c->nnbr); cudaFree(c->edges); cudaFree(c->edge_offsets); cudaFree(c->n_edges); cudaFree(c->cub_tmp);
-	cudaFree(c->dh_nbr); cudaFree(c->dh_nnbr);
+	cudaFree(c->dh_nbr); cudaFree(c->dh_nnbr); cudaFree(c->near_mask);
+	c->near_mask = nullptr;
+	c->slots_cell_ordered = false;
 	cudaFree(c->hb_list); cudaFree(c->cx_list); cudaFree(c->counters);
 	c->cell_key = c->cell_key_sorted = c->cell_val = c->cell_val_sorted = c->cell_start = c->nbr = c->nnbr = c->edge_offsets = c->n_edges = nullptr;
 	c->counters = c->dh_nbr = c->dh_nnbr = nullptr;
@@ -172,7 +176,7 @@ int alloc_lists(oxb_ctx *c, int max_neigh) {
 	CU(dalloc(&c->cell_key, N)); CU(dalloc(&c->cell_key_sorted, N)); CU(dalloc(&c->cell_val, N)); CU(dalloc(&c->cell_val_sorted, N));
 	CU(dalloc(&c->cell_start, 2 * (size_t) ncells));
 	CU(dalloc(&c->nbr, (size_t) max_neigh * N)); CU(dalloc(&c->nnbr, N));
-	CU(dalloc(&c->edge_offsets, (size_t) N + 1)); CU(dalloc(&c->n_edges, 2));
+	CU(dalloc(&c->edge_offsets, (size_t) N + 1)); CU(dalloc(&c->n_edges, 2)); CU(dalloc(&c->near_mask, (size_t) N));
 	CU(cudaMemset(c->n_edges, 0, 2 * sizeof(int)));
 	c->max_dh = max_neigh;
 	CU(dalloc(&c->dh_nbr, (size_t) c->max_dh * N)); CU(dalloc(&c->dh_nnbr, N));
@@ -224,6 +228,8 @@ oxb::ListArgs list_args(oxb_ctx *c) {
 	a.flags = c->flags;
 	a.cub_tmp = c->cub_tmp; a.cub_tmp_bytes = c->cub_tmp_bytes;
 	a.build_edges = c->use_edge != 0;
+	a.near_mask = c->near_mask;
+	a.direct = c->slots_cell_ordered;
 	return a;
 }
 
@@ -244,6 +250,7 @@ int do_sort(oxb_ctx *c) {
 	s.N = N;
 	for(int k = 0; k < 3; k++) s.box[k] = c->box[k];
 	s.posd = c->posd[a];
+	for(int k = 0; k < 3; k++) s.ncell[k] = c->ncell[k];
 	s.keys = c->hkeys; s.keys_sorted = c->hkeys_sorted; s.vals = c->hvals; s.vals_sorted = c->hvals_sorted; s.inv = c->hinv;
 	s.cub_tmp = c->cub_tmp; s.cub_tmp_bytes = c->cub_tmp_bytes;
 	oxb::launch_hilbert_order(c->stream, s);
@@ -257,7 +264,10 @@ int do_sort(oxb_ctx *c) {
 	p.quat_in = c->quat[a]; p.F_in = c->F[a]; p.T_in = c->T[a]; p.quat_out = c->quat[b]; p.F_out = c->F[b]; p.T_out = c->T[b];
 	p.bonds_in = c->bonds[a]; p.bonds_out = c->bonds[b];
 	p.slot_of = c->slot_of;
+	p.cell_lin = c->cell_key_sorted;
+	for(int k = 0; k < 3; k++) { p.box[k] = c->box[k]; p.ncell[k] = c->ncell[k]; }
 	oxb::launch_permute(c->stream, p);
+	c->slots_cell_ordered = true; // consumed (and cleared) by the list build that follows
 	c->launches += 5;
 	c->cur = b;
 	c->n_sorts++;
@@ -279,13 +289,8 @@ int do_build(oxb_ctx *c) {
 		int seen = c->h_flags[OXB_FLAG_MAX_NEIGH_SEEN];
 		if((c->h_flags[OXB_FLAG_ERROR] & (OXB_ERR_NEIGH_OVERFLOW | OXB_ERR_EDGE_OVERFLOW)) == 0) {
 			c->error_flags &= ~(OXB_ERR_NEIGH_OVERFLOW | OXB_ERR_EDGE_OVERFLOW);
-			if(c->use_edge) {
-				int ne = 0;
-				CU(cudaMemcpyAsync(&ne, c->n_edges, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-				CU(cudaStreamSynchronize(c->stream));
-				c->edge_hint = ne;
-			}
 			c->lists_valid = true;
+			c->slots_cell_ordered = false; // particles move on: the next build bins them itself unless a re-sort precedes it
 			c->n_list_updates++;
 			return 0;
 		}
@@ -1102,7 +1107,13 @@ int oxb_time_kernel(oxb_ctx *c, int which, int reps, float *ms) {
 			oxb::launch_integrate_epoch(c->stream, a, OXB_PH_SECOND | OXB_PH_FIRST | OXB_PH_COUNT_STEP, 0);
 			c->launches++;
 		}
-		else if(which == 2) { oxb::launch_build_lists(c->stream, list_args(c)); c->launches += c->use_edge ? 7 : 4; }
+		else if(which == 2) {
+			// a rebuild as the hot loop does it: re-sort (if enabled) + list build
+			if(c->sort_every > 0) { rc = do_sort(c); if(rc) return rc; }
+			oxb::launch_build_lists(c->stream, list_args(c));
+			c->slots_cell_ordered = false;
+			c->launches += c->use_edge ? 7 : 4;
+		}
 		else if(which == 3) { rc = do_sort(c); if(rc) return rc; }
 		else return fail(c, 1, "unknown kernel selector %d", which);
 	}
@@ -1113,7 +1124,7 @@ int oxb_time_kernel(oxb_ctx *c, int which, int reps, float *ms) {
 	*ms = t / reps;
 	cudaEventDestroy(e0);
 	cudaEventDestroy(e1);
-	if(which == 3 || which == 1) { if(which == 3) c->lists_valid = false; c->forces_valid = false; rc = ensure_forces(c); if(rc) return rc; }
+	if(which != 0) { if(which != 1) c->lists_valid = false; c->forces_valid = false; rc = ensure_forces(c); if(rc) return rc; }
 	CU(cudaStreamSynchronize(c->stream));
 	return 0;
 }

@@ -107,6 +107,8 @@ struct ListArgs {
 	int max_neigh, stride;
 	int2 *edges;       // unique pairs that can come within rcut_near before the next rebuild ("near" edges), grouped by `from`
 	int *edge_offsets; // N + 1
+	ulonglong2 *near_mask; // per row: which entries are near edges to a higher slot
+	bool direct;       // particle arrays are ordered by cell: cell members are the slots [start, end) themselves
 	int *n_edges;      // device-side length of `edges`
 	float rnear2;      // (rcut_near + 2 skin + margin)^2
 	// Debye-Hueckel neighbour matrix (full, both directions), selected on the backbone-site distance
@@ -133,6 +135,7 @@ struct SortArgs {
 	int N;
 	double box[3];
 	const double4 *posd;
+	int ncell[3];            // > 0: sort by the Hilbert index of the list builder's cell coordinates (binning for free)
 	unsigned *keys, *keys_sorted;
 	int *vals, *vals_sorted; // vals_sorted[new_slot] = old_slot
 	int *inv;                // inv[old_slot] = new_slot
@@ -154,6 +157,9 @@ struct PermuteArgs {
 	const int2 *bonds_in;
 	int2 *bonds_out;
 	int *slot_of; // slot_of[original id] = new slot
+	int *cell_lin; // optional: linear cell id of every new slot (what the list builder's binning would have produced)
+	double box[3];
+	int ncell[3];
 };
 void launch_permute(cudaStream_t s, const PermuteArgs &a);
 

@@ -71,15 +71,44 @@ __device__ __forceinline__ v3 a1_of(float4 q) {
 	return mk3(q.x * q.x - q.y * q.y - q.z * q.z + q.w * q.w, 2.f * (q.x * q.y + q.z * q.w), 2.f * (q.x * q.z - q.y * q.w));
 }
 
-// one thread per particle: visit the 27 surrounding cells, keep non-bonded particles closer than rv
+// One thread per particle: visit the 27 surrounding cells, keep non-bonded particles closer than rv.
+//  * the 27 (start, end) cell ranges are fetched up front as independent loads and parked in shared memory, so the scan
+//    pays one memory latency for them instead of 27 dependent ones;
+//  * DIRECT = the particle arrays are already ordered by cell (this rebuild re-sorted them): a cell's members are the
+//    slots [start, end) themselves, no index indirection and the candidate loads are contiguous;
+//  * the candidate's position is prefetched one iteration ahead;
+//  * neighbours m > i that can feel more than Debye-Hueckel before the next rebuild are flagged in a 128-bit row mask
+//    (bit k = row entry k), from which k_fill_edges emits the edge list without touching any geometry again.
+template<bool DIRECT>
 __global__ void __launch_bounds__(128) k_build_neigh(oxb::ListArgs a, const int *__restrict__ cell_start, const int *__restrict__ cell_end) {
+	__shared__ int2 s_range[27][128];
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if(i >= a.N) return;
+	const bool active = i < a.N;
+	if(!active) i = a.N - 1;
 	const int4 ip = a.ipos[i];
 	const int2 b = a.bonds[i];
 	const int nx = a.ncell[0], ny = a.ncell[1], nz = a.ncell[2];
 	const double4 pd = a.posd[i];
 	const int cx = cell_coord(pd.x, a.box[0], nx), cy = cell_coord(pd.y, a.box[1], ny), cz = cell_coord(pd.z, a.box[2], nz);
+	{
+		int q = 0;
+#pragma unroll
+		for(int dz = -1; dz <= 1; dz++) {
+			int zc = cz + dz; zc += (zc < 0) ? nz : 0; zc -= (zc >= nz) ? nz : 0;
+#pragma unroll
+			for(int dy = -1; dy <= 1; dy++) {
+				int yc = cy + dy; yc += (yc < 0) ? ny : 0; yc -= (yc >= ny) ? ny : 0;
+#pragma unroll
+				for(int dx = -1; dx <= 1; dx++) {
+					int xc = cx + dx; xc += (xc < 0) ? nx : 0; xc -= (xc >= nx) ? nx : 0;
+					int c = xc + nx * (yc + ny * zc);
+					s_range[q][threadIdx.x] = make_int2(__ldg(cell_start + c), __ldg(cell_end + c));
+					q++;
+				}
+			}
+		}
+	}
+	if(!active) return;
 	const float rv2f = (float) (a.rv * a.rv);
 	const float band = 1e-4f * rv2f;
 	const double rv2 = a.rv * a.rv;
@@ -87,36 +116,42 @@ __global__ void __launch_bounds__(128) k_build_neigh(oxb::ListArgs a, const int 
 	const v3 a1p = a1_of(a.quat[i]);
 	const v3 bkp = min_image_fixed(a.boxf, ip, ib);
 	int count = 0, higher_near = 0, ndh = 0;
-	for(int dz = -1; dz <= 1; dz++) {
-		int zc = cz + dz; zc += (zc < 0) ? nz : 0; zc -= (zc >= nz) ? nz : 0;
-		for(int dy = -1; dy <= 1; dy++) {
-			int yc = cy + dy; yc += (yc < 0) ? ny : 0; yc -= (yc >= ny) ? ny : 0;
-			for(int dx = -1; dx <= 1; dx++) {
-				int xc = cx + dx; xc += (xc < 0) ? nx : 0; xc -= (xc >= nx) ? nx : 0;
-				int c = xc + nx * (yc + ny * zc);
-				int s = __ldg(cell_start + c), e = __ldg(cell_end + c);
-				for(int j = s; j < e; j++) {
-					int m = __ldg(a.cell_val_sorted + j);
-					if(m == i || m == b.x || m == b.y) continue;
-					const int4 ipm = __ldg(a.ipos + m);
-					v3 d = min_image_fixed(a.boxf, ip, ipm);
-					float d2 = dot(d, d);
-					bool in = d2 < rv2f;
-					if(fabsf(d2 - rv2f) < band) in = within_exact(pd, a.posd[m], a.box[0], a.box[1], a.box[2], rv2);
-					if(in) {
-						if(count < a.max_neigh) a.nbr[(size_t) count * a.stride + i] = m;
-						count++;
-						// Debye-Hueckel acts between backbone sites: keep m if the sites can come within dh_rc before the
-						// next rebuild (both the centre and the backbone site of every particle move less than `skin`)
-						const int4 ibm = __ldg(a.iback + m);
-						v3 db = min_image_fixed(a.boxf, ib, ibm);
-						if(m > i && d2 < a.rnear2 && near_pair(a, d, a1p, a1_of(__ldg(a.quat + m)), bkp, min_image_fixed(a.boxf, ipm, ibm))) higher_near++;
-						if(dot(db, db) < a.rdh2) {
-							if(ndh < a.max_dh) a.dh_nbr[(size_t) ndh * a.stride + i] = m;
-							ndh++;
-						}
-					}
+	unsigned long long mask0 = 0ull, mask1 = 0ull;
+	bool mask_overflow = false;
+	for(int q = 0; q < 27; q++) {
+		const int2 rg = s_range[q][threadIdx.x];
+		if(rg.x >= rg.y) continue;
+		int m_next = DIRECT ? rg.x : __ldg(a.cell_val_sorted + rg.x);
+		int4 ip_next = __ldg(a.ipos + m_next);
+		for(int j = rg.x; j < rg.y; j++) {
+			const int m = m_next;
+			const int4 ipm = ip_next;
+			if(j + 1 < rg.y) {
+				m_next = DIRECT ? j + 1 : __ldg(a.cell_val_sorted + j + 1);
+				ip_next = __ldg(a.ipos + m_next);
+			}
+			if(m == i || m == b.x || m == b.y) continue;
+			v3 d = min_image_fixed(a.boxf, ip, ipm);
+			float d2 = dot(d, d);
+			bool in = d2 < rv2f;
+			if(fabsf(d2 - rv2f) < band) in = within_exact(pd, a.posd[m], a.box[0], a.box[1], a.box[2], rv2);
+			if(in) {
+				if(count < a.max_neigh) a.nbr[(size_t) count * a.stride + i] = m;
+				// Debye-Hueckel acts between backbone sites: keep m if the sites can come within dh_rc before the
+				// next rebuild (both the centre and the backbone site of every particle move less than `skin`)
+				const int4 ibm = __ldg(a.iback + m);
+				v3 db = min_image_fixed(a.boxf, ib, ibm);
+				if(m > i && d2 < a.rnear2 && near_pair(a, d, a1p, a1_of(__ldg(a.quat + m)), bkp, min_image_fixed(a.boxf, ipm, ibm))) {
+					higher_near++;
+					if(count < 64) mask0 |= 1ull << count;
+					else if(count < 128) mask1 |= 1ull << (count - 64);
+					else mask_overflow = true;
 				}
+				if(dot(db, db) < a.rdh2) {
+					if(ndh < a.max_dh) a.dh_nbr[(size_t) ndh * a.stride + i] = m;
+					ndh++;
+				}
+				count++;
 			}
 		}
 	}
@@ -141,27 +176,53 @@ __global__ void __launch_bounds__(128) k_build_neigh(oxb::ListArgs a, const int 
 		bs.z = (int) ((unsigned) ip.z + (unsigned) (int) rintf(a1p.z * a.base_a1 / a.boxf.sz));
 		a.list_ibase[i] = bs;
 	}
-	if(a.build_edges) a.edge_offsets[i] = higher_near;
+	if(a.build_edges) {
+		a.edge_offsets[i] = higher_near;
+		// rows longer than the mask fall back to the geometric test in k_fill_edges (top bit of word 1 doubles as the marker:
+		// entry 127 can only be flagged together with an overflow, which takes the fallback anyway)
+		if(mask_overflow) mask1 |= 1ull << 63;
+		a.near_mask[i] = make_ulonglong2(mask0, mask1);
+	}
 }
 
-// near edge (i, m) for every listed neighbour m > i within rnear; rows are contiguous in the output (grouped by `from`)
+// near edge (i, m) for every flagged row entry; rows are contiguous in the output (grouped by `from`)
 __global__ void __launch_bounds__(128) k_fill_edges(oxb::ListArgs a) {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= a.N) return;
 	int off = a.edge_offsets[i];
-	const int4 ip = a.ipos[i];
-	const int4 ib = a.iback[i];
-	const v3 a1p = a1_of(a.quat[i]);
-	const v3 bkp = min_image_fixed(a.boxf, ip, ib);
-	int nn = a.nnbr[i];
-	for(int k = 0; k < nn; k++) {
-		int m = a.nbr[(size_t) k * a.stride + i];
-		if(m > i) {
-			const int4 ipm = __ldg(a.ipos + m);
-			v3 d = min_image_fixed(a.boxf, ip, ipm);
-			if(dot(d, d) < a.rnear2 && near_pair(a, d, a1p, a1_of(__ldg(a.quat + m)), bkp, min_image_fixed(a.boxf, ipm, __ldg(a.iback + m)))) {
-				if(off < a.edge_capacity) a.edges[off] = make_int2(i, m);
-				off++;
+	const int nn = a.nnbr[i];
+	ulonglong2 mk = a.near_mask[i];
+	if(nn <= 127 || !(mk.y >> 63)) {
+		unsigned long long w = mk.x;
+		while(w) {
+			int k = __ffsll((long long) w) - 1;
+			w &= w - 1;
+			if(off < a.edge_capacity) a.edges[off] = make_int2(i, a.nbr[(size_t) k * a.stride + i]);
+			off++;
+		}
+		w = mk.y;
+		while(w) {
+			int k = 64 + __ffsll((long long) w) - 1;
+			w &= w - 1;
+			if(off < a.edge_capacity) a.edges[off] = make_int2(i, a.nbr[(size_t) k * a.stride + i]);
+			off++;
+		}
+	}
+	else {
+		// very long row: redo the geometric selection (same predicate as in k_build_neigh)
+		const int4 ip = a.ipos[i];
+		const int4 ib = a.iback[i];
+		const v3 a1p = a1_of(a.quat[i]);
+		const v3 bkp = min_image_fixed(a.boxf, ip, ib);
+		for(int k = 0; k < nn; k++) {
+			int m = a.nbr[(size_t) k * a.stride + i];
+			if(m > i) {
+				const int4 ipm = __ldg(a.ipos + m);
+				v3 d = min_image_fixed(a.boxf, ip, ipm);
+				if(dot(d, d) < a.rnear2 && near_pair(a, d, a1p, a1_of(__ldg(a.quat + m)), bkp, min_image_fixed(a.boxf, ipm, __ldg(a.iback + m)))) {
+					if(off < a.edge_capacity) a.edges[off] = make_int2(i, m);
+					off++;
+				}
 			}
 		}
 	}
@@ -194,13 +255,18 @@ void launch_build_lists(cudaStream_t s, const ListArgs &a) {
 	const int ncells = a.ncell[0] * a.ncell[1] * a.ncell[2];
 	int *cell_start = a.cell_start, *cell_end = a.cell_start + ncells;
 	int tpb = 256;
-	k_cell_keys<<<(N + tpb - 1) / tpb, tpb, 0, s>>>(N, a.posd, a.box[0], a.box[1], a.box[2], a.ncell[0], a.ncell[1], a.ncell[2], a.cell_key, a.cell_val);
 	size_t tmp = a.cub_tmp_bytes;
-	cub::DeviceRadixSort::SortPairs(a.cub_tmp, tmp, a.cell_key, a.cell_key_sorted, a.cell_val, a.cell_val_sorted, N, 0, bits_for(ncells), s);
+	if(!a.direct) {
+		// binning = stable sort of (cell, slot); with a.direct the re-sort that has just run left the particles ordered by
+		// cell and wrote each slot's cell id into cell_key_sorted (sort.cu: k_permute)
+		k_cell_keys<<<(N + tpb - 1) / tpb, tpb, 0, s>>>(N, a.posd, a.box[0], a.box[1], a.box[2], a.ncell[0], a.ncell[1], a.ncell[2], a.cell_key, a.cell_val);
+		cub::DeviceRadixSort::SortPairs(a.cub_tmp, tmp, a.cell_key, a.cell_key_sorted, a.cell_val, a.cell_val_sorted, N, 0, bits_for(ncells), s);
+	}
 	cudaMemsetAsync(cell_start, 0, sizeof(int) * 2 * (size_t) ncells, s);
 	k_cell_ranges<<<(N + tpb - 1) / tpb, tpb, 0, s>>>(N, a.cell_key_sorted, cell_start, cell_end);
 	cudaMemsetAsync(a.flags + OXB_FLAG_MAX_NEIGH_SEEN, 0, sizeof(int), s);
-	k_build_neigh<<<(N + 127) / 128, 128, 0, s>>>(a, cell_start, cell_end);
+	if(a.direct) k_build_neigh<true><<<(N + 127) / 128, 128, 0, s>>>(a, cell_start, cell_end);
+	else k_build_neigh<false><<<(N + 127) / 128, 128, 0, s>>>(a, cell_start, cell_end);
 	if(a.build_edges) {
 		tmp = a.cub_tmp_bytes;
 		// in-place exclusive scan over N + 1 entries (the last input entry is ignored: its output is the total)

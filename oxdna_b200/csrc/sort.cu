@@ -11,6 +11,8 @@
 
 #include <cub/cub.cuh>
 
+#include <algorithm>
+
 namespace {
 
 // Skilling's transform (AIP Conf. Proc. 707, 381 (2004)): axes -> transposed Hilbert index, then bit interleave
@@ -52,6 +54,24 @@ __global__ void __launch_bounds__(256) k_hilbert_keys(int N, const double4 *__re
 	vals[i] = i;
 }
 
+// Same cell rule as the list builder (lists.cu cell_coord, src/Lists/Cells.h:60-65).  Sorting by the Hilbert index of the
+// CELL coordinates makes one radix sort do both jobs: spatial locality for the gathers of the force kernels, and binning
+// (a cell's members end up in consecutive slots, so the list builder needs no second sort and no index indirection).
+__device__ __forceinline__ int cell_coord_s(double x, double L, int n) {
+	double f = x / L - floor(x / L);
+	int c = (int) (f * (1. - 2.220446049250313e-16) * n);
+	return min(c, n - 1);
+}
+
+__global__ void __launch_bounds__(256) k_cell_hilbert_keys(int N, const double4 *__restrict__ posd, double Lx, double Ly, double Lz, int nx, int ny, int nz,
+		int bits, unsigned *__restrict__ keys, int *__restrict__ vals) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= N) return;
+	double4 p = posd[i];
+	keys[i] = hilbert_key((unsigned) cell_coord_s(p.x, Lx, nx), (unsigned) cell_coord_s(p.y, Ly, ny), (unsigned) cell_coord_s(p.z, Lz, nz), bits);
+	vals[i] = i;
+}
+
 __global__ void __launch_bounds__(256) k_invert(int N, const int *__restrict__ perm, int *__restrict__ inv) {
 	int n = blockIdx.x * blockDim.x + threadIdx.x;
 	if(n < N) inv[perm[n]] = n;
@@ -79,6 +99,10 @@ __global__ void __launch_bounds__(256) k_permute(oxb::PermuteArgs a) {
 	b.y = (b.y >= 0) ? a.inv[b.y] : b.y;
 	a.bonds_out[n] = b;
 	a.slot_of[word_index(ip.w)] = n;
+	if(a.cell_lin != nullptr) {
+		double4 p = a.posd_in[o];
+		a.cell_lin[n] = cell_coord_s(p.x, a.box[0], a.ncell[0]) + a.ncell[0] * (cell_coord_s(p.y, a.box[1], a.ncell[1]) + a.ncell[1] * cell_coord_s(p.z, a.box[2], a.ncell[2]));
+	}
 }
 
 } // namespace
@@ -93,9 +117,17 @@ size_t sort_tmp_bytes(int N) {
 
 void launch_hilbert_order(cudaStream_t s, const SortArgs &a) {
 	int tpb = 256, nb = (a.N + tpb - 1) / tpb;
-	k_hilbert_keys<<<nb, tpb, 0, s>>>(a.N, a.posd, a.box[0], a.box[1], a.box[2], a.keys, a.vals);
 	size_t tmp = a.cub_tmp_bytes;
-	cub::DeviceRadixSort::SortPairs(a.cub_tmp, tmp, a.keys, a.keys_sorted, a.vals, a.vals_sorted, a.N, 0, 30, s);
+	if(a.ncell[0] > 0) {
+		int bits = 1;
+		while((1 << bits) < std::max(a.ncell[0], std::max(a.ncell[1], a.ncell[2]))) bits++;
+		k_cell_hilbert_keys<<<nb, tpb, 0, s>>>(a.N, a.posd, a.box[0], a.box[1], a.box[2], a.ncell[0], a.ncell[1], a.ncell[2], bits, a.keys, a.vals);
+		cub::DeviceRadixSort::SortPairs(a.cub_tmp, tmp, a.keys, a.keys_sorted, a.vals, a.vals_sorted, a.N, 0, 3 * bits, s);
+	}
+	else {
+		k_hilbert_keys<<<nb, tpb, 0, s>>>(a.N, a.posd, a.box[0], a.box[1], a.box[2], a.keys, a.vals);
+		cub::DeviceRadixSort::SortPairs(a.cub_tmp, tmp, a.keys, a.keys_sorted, a.vals, a.vals_sorted, a.N, 0, 30, s);
+	}
 	k_invert<<<nb, tpb, 0, s>>>(a.N, a.vals_sorted, a.inv);
 }
 
