@@ -90,7 +90,11 @@ __global__ void __launch_bounds__(128) k_build_neigh(oxb::ListArgs a, const int 
 	const int nx = a.ncell[0], ny = a.ncell[1], nz = a.ncell[2];
 	const double4 pd = a.posd[i];
 	const int cx = cell_coord(pd.x, a.box[0], nx), cy = cell_coord(pd.y, a.box[1], ny), cz = cell_coord(pd.z, a.box[2], nz);
+	// phase 1: the 27 ranges as independent loads; only the non-empty ones are kept (in scan order, which keeps the neighbour
+	// order deterministic), so that all lanes of a warp walk through candidates instead of through mostly empty cells
+	int n_rg = 0;
 	{
+		int2 rg[27];
 		int q = 0;
 #pragma unroll
 		for(int dz = -1; dz <= 1; dz++) {
@@ -102,13 +106,20 @@ __global__ void __launch_bounds__(128) k_build_neigh(oxb::ListArgs a, const int 
 				for(int dx = -1; dx <= 1; dx++) {
 					int xc = cx + dx; xc += (xc < 0) ? nx : 0; xc -= (xc >= nx) ? nx : 0;
 					int c = xc + nx * (yc + ny * zc);
-					s_range[q][threadIdx.x] = make_int2(__ldg(cell_start + c), __ldg(cell_end + c));
+					rg[q] = make_int2(__ldg(cell_start + c), __ldg(cell_end + c));
 					q++;
 				}
 			}
 		}
+#pragma unroll
+		for(q = 0; q < 27; q++) {
+			if(rg[q].x < rg[q].y) {
+				s_range[n_rg][threadIdx.x] = rg[q];
+				n_rg++;
+			}
+		}
 	}
-	if(!active) return;
+	if(!active || n_rg == 0) n_rg = 0;
 	const float rv2f = (float) (a.rv * a.rv);
 	const float band = 1e-4f * rv2f;
 	const double rv2 = a.rv * a.rv;
@@ -118,43 +129,57 @@ __global__ void __launch_bounds__(128) k_build_neigh(oxb::ListArgs a, const int 
 	int count = 0, higher_near = 0, ndh = 0;
 	unsigned long long mask0 = 0ull, mask1 = 0ull;
 	bool mask_overflow = false;
-	for(int q = 0; q < 27; q++) {
-		const int2 rg = s_range[q][threadIdx.x];
-		if(rg.x >= rg.y) continue;
-		int m_next = DIRECT ? rg.x : __ldg(a.cell_val_sorted + rg.x);
-		int4 ip_next = __ldg(a.ipos + m_next);
-		for(int j = rg.x; j < rg.y; j++) {
-			const int m = m_next;
-			const int4 ipm = ip_next;
-			if(j + 1 < rg.y) {
-				m_next = DIRECT ? j + 1 : __ldg(a.cell_val_sorted + j + 1);
-				ip_next = __ldg(a.ipos + m_next);
-			}
-			if(m == i || m == b.x || m == b.y) continue;
-			v3 d = min_image_fixed(a.boxf, ip, ipm);
-			float d2 = dot(d, d);
-			bool in = d2 < rv2f;
-			if(fabsf(d2 - rv2f) < band) in = within_exact(pd, a.posd[m], a.box[0], a.box[1], a.box[2], rv2);
-			if(in) {
-				if(count < a.max_neigh) a.nbr[(size_t) count * a.stride + i] = m;
-				// Debye-Hueckel acts between backbone sites: keep m if the sites can come within dh_rc before the
-				// next rebuild (both the centre and the backbone site of every particle move less than `skin`)
-				const int4 ibm = __ldg(a.iback + m);
-				v3 db = min_image_fixed(a.boxf, ib, ibm);
-				if(m > i && d2 < a.rnear2 && near_pair(a, d, a1p, a1_of(__ldg(a.quat + m)), bkp, min_image_fixed(a.boxf, ipm, ibm))) {
-					higher_near++;
-					if(count < 64) mask0 |= 1ull << count;
-					else if(count < 128) mask1 |= 1ull << (count - 64);
-					else mask_overflow = true;
-				}
-				if(dot(db, db) < a.rdh2) {
-					if(ndh < a.max_dh) a.dh_nbr[(size_t) ndh * a.stride + i] = m;
-					ndh++;
-				}
-				count++;
+	// phase 2: one flat loop over this particle's candidates (cursor = range r, slot j), next candidate prefetched
+	int r = 0, j = 0, jend = 0;
+	int m_next = 0;
+	int4 ip_next = ip;
+	if(n_rg > 0) {
+		int2 g = s_range[0][threadIdx.x];
+		j = g.x; jend = g.y;
+		m_next = DIRECT ? j : __ldg(a.cell_val_sorted + j);
+		ip_next = __ldg(a.ipos + m_next);
+	}
+	while(r < n_rg) {
+		const int m = m_next;
+		const int4 ipm = ip_next;
+		// advance the cursor and prefetch
+		j++;
+		if(j >= jend) {
+			r++;
+			if(r < n_rg) {
+				int2 g = s_range[r][threadIdx.x];
+				j = g.x; jend = g.y;
 			}
 		}
+		if(r < n_rg) {
+			m_next = DIRECT ? j : __ldg(a.cell_val_sorted + j);
+			ip_next = __ldg(a.ipos + m_next);
+		}
+		if(m == i || m == b.x || m == b.y) continue;
+		v3 d = min_image_fixed(a.boxf, ip, ipm);
+		float d2 = dot(d, d);
+		bool in = d2 < rv2f;
+		if(fabsf(d2 - rv2f) < band) in = within_exact(pd, a.posd[m], a.box[0], a.box[1], a.box[2], rv2);
+		if(in) {
+			if(count < a.max_neigh) a.nbr[(size_t) count * a.stride + i] = m;
+			// Debye-Hueckel acts between backbone sites: keep m if the sites can come within dh_rc before the
+			// next rebuild (both the centre and the backbone site of every particle move less than `skin`)
+			const int4 ibm = __ldg(a.iback + m);
+			v3 db = min_image_fixed(a.boxf, ib, ibm);
+			if(m > i && d2 < a.rnear2 && near_pair(a, d, a1p, a1_of(__ldg(a.quat + m)), bkp, min_image_fixed(a.boxf, ipm, ibm))) {
+				higher_near++;
+				if(count < 64) mask0 |= 1ull << count;
+				else if(count < 128) mask1 |= 1ull << (count - 64);
+				else mask_overflow = true;
+			}
+			if(dot(db, db) < a.rdh2) {
+				if(ndh < a.max_dh) a.dh_nbr[(size_t) ndh * a.stride + i] = m;
+				ndh++;
+			}
+			count++;
+		}
 	}
+	if(!active) return;
 	if(count > a.max_neigh) {
 		atomicOr(a.flags + OXB_FLAG_ERROR, OXB_ERR_NEIGH_OVERFLOW);
 		atomicMax(a.flags + OXB_FLAG_MAX_NEIGH_SEEN, count);
