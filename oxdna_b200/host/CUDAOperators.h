@@ -1,0 +1,182 @@
+// Host-side operator classes of the B200 MD path, written against the reference's own headers (compiled with
+// -I<reference>/src, linked against its unmodified CPU objects).  They keep the names, input keys, error messages and
+// call order of the reference's CUDA-side classes, but own no device memory and launch no kernels themselves: every
+// method forwards to the C ABI of liboxdna_b200.so (include/oxdna_b200.h).
+//
+//   class here                      replaces (reference file)
+//   CUDABaseInteraction             src/CUDA/Interactions/CUDABaseInteraction.h:20-64
+//   CUDADNAInteraction              src/CUDA/Interactions/CUDADNAInteraction.{h,cu}
+//   CUDAInteractionFactory          src/CUDA/Interactions/CUDAInteractionFactory.cu:28-53
+//   CUDABaseList / CUDASimpleVerletList / CUDAListFactory   src/CUDA/Lists/*.{h,cu}
+//   CUDABaseThermostat, CUDA{No,Brownian,Langevin,Bussi}Thermostat, CUDAThermostatFactory   src/CUDA/Thermostats/*.{h,cu}
+//
+// Difference in the signatures: the reference passes raw device pointers (poss, orientations, forces ...) between its
+// classes; here the opaque oxb_ctx owns the device arrays, so the operators take the context instead.  Third-party
+// kernels that need the raw arrays get them from oxb_device_views() in the reference's layouts.
+#pragma once
+
+#include "../../include/oxdna_b200.h"
+
+#include "Backends/Thermostats/BaseThermostat.h"
+#include "Backends/Thermostats/BrownianThermostat.h"
+#include "Backends/Thermostats/BussiThermostat.h"
+#include "Backends/Thermostats/LangevinThermostat.h"
+#include "Backends/Thermostats/NoThermostat.h"
+#include "Boxes/BaseBox.h"
+#include "Interactions/DNA2Interaction.h"
+#include "Utilities/oxDNAException.h"
+
+#include <memory>
+#include <string>
+
+/// throws oxDNAException with the context's message if a C-ABI call failed (the reference's CUDA_SAFE_CALL exits instead)
+void oxb_check(oxb_ctx *ctx, int rc, const char *what);
+
+// ---------------------------------------------------------------------------------------------------- interactions
+class CUDABaseInteraction {
+protected:
+	bool _use_edge = false;
+	/// force slots per particle (edge_n_forces): accepted for compatibility, the kernels need no slots
+	int _n_forces = 1;
+	int _N = -1;
+	oxb_ctx *_ctx = nullptr;
+
+public:
+	CUDABaseInteraction() {}
+	virtual ~CUDABaseInteraction() {}
+
+	virtual void get_settings(input_file &inp) = 0;
+	virtual void get_cuda_settings(input_file &inp);
+	/// uploads the model constants to the device context (the reference copies them to __constant__ memory here)
+	virtual void cuda_init(oxb_ctx *ctx, int N);
+	virtual number get_cuda_rcut() = 0;
+
+	virtual void sync_host() {}
+	virtual void sync_GPU() {}
+
+	bool use_edge() const { return _use_edge; }
+	/// forces, torques and per-particle energies for the context's current positions and lists
+	virtual void compute_forces(oxb_ctx *ctx);
+};
+
+/// interaction_type = DNA2: the CPU DNA2Interaction supplies every constant (sequence dependence, salt, dh_* keys,
+/// hb_multiplier, max_backbone_force), exactly as the reference's CUDADNAInteraction inherits them from DNAInteraction
+class CUDADNAInteraction: public CUDABaseInteraction, public DNA2Interaction {
+protected:
+	void _upload();
+	void _on_T_update() override;
+
+public:
+	CUDADNAInteraction();
+	virtual ~CUDADNAInteraction();
+
+	void get_settings(input_file &inp) override;
+	void cuda_init(oxb_ctx *ctx, int N) override;
+	number get_cuda_rcut() override {
+		return this->get_rcut();
+	}
+};
+
+class CUDAInteractionFactory {
+public:
+	static std::shared_ptr<CUDABaseInteraction> make_interaction(input_file &inp);
+};
+
+// ---------------------------------------------------------------------------------------------------------- lists
+class CUDABaseList {
+protected:
+	bool _use_edge = false;
+	int _N = -1;
+	oxb_ctx *_ctx = nullptr;
+
+public:
+	CUDABaseList() {}
+	virtual ~CUDABaseList() {}
+
+	virtual void get_settings(input_file &inp) = 0;
+	virtual void init(oxb_ctx *ctx, int N, number rcut, int sort_every);
+	/// rebuilds cells + Verlet (and edge) lists for the current positions; throws on overflow like the reference
+	virtual void update() = 0;
+	virtual void clean() = 0;
+	bool use_edge() { return _use_edge; }
+};
+
+class CUDASimpleVerletList: public CUDABaseList {
+protected:
+	number _verlet_skin = 0.;
+	number _max_density_multiplier = 3.;
+	bool _auto_optimisation = true;
+	bool _print_problematic_ids = false;
+
+public:
+	void get_settings(input_file &inp) override;
+	void init(oxb_ctx *ctx, int N, number rcut, int sort_every) override;
+	void update() override;
+	void clean() override {}
+};
+
+class CUDAListFactory {
+public:
+	static std::shared_ptr<CUDABaseList> make_list(input_file &inp);
+};
+
+// ----------------------------------------------------------------------------------------------------- thermostats
+class CUDABaseThermostat: public virtual IBaseThermostat {
+protected:
+	llint _seed = 0;
+	oxb_ctx *_ctx = nullptr;
+	/// sends the derived parameters to the device context (no RNG state: Philox is keyed by seed, particle id and step)
+	virtual void _upload() = 0;
+
+public:
+	CUDABaseThermostat() {}
+	virtual ~CUDABaseThermostat() {}
+
+	virtual void set_seed(llint seed) { _seed = seed; }
+	virtual void get_cuda_settings(input_file &inp) {}
+	virtual void attach(oxb_ctx *ctx) { _ctx = ctx; _upload(); }
+	/// applies the thermostat at curr_step on its own (inside oxb_run it is fused into the integrator launch)
+	virtual void apply_cuda(llint curr_step);
+	virtual bool would_activate(llint curr_step) = 0;
+};
+
+class CUDANoThermostat: public CUDABaseThermostat, public NoThermostat {
+protected:
+	void _upload() override;
+public:
+	void get_settings(input_file &inp) override { NoThermostat::get_settings(inp); }
+	void init() override { NoThermostat::init(); }
+	bool would_activate(llint) override { return false; }
+};
+
+class CUDABrownianThermostat: public CUDABaseThermostat, public BrownianThermostat {
+protected:
+	void _upload() override;
+public:
+	void get_settings(input_file &inp) override;
+	void init() override;
+	bool would_activate(llint curr_step) override;
+};
+
+class CUDALangevinThermostat: public CUDABaseThermostat, public LangevinThermostat {
+protected:
+	void _upload() override;
+public:
+	void get_settings(input_file &inp) override;
+	void init() override;
+	bool would_activate(llint) override { return true; }
+};
+
+class CUDABussiThermostat: public CUDABaseThermostat, public BussiThermostat {
+protected:
+	void _upload() override;
+public:
+	void get_settings(input_file &inp) override;
+	void init() override;
+	bool would_activate(llint curr_step) override;
+};
+
+class CUDAThermostatFactory {
+public:
+	static std::shared_ptr<CUDABaseThermostat> make_thermostat(input_file &inp, BaseBox *box);
+};

@@ -1,0 +1,257 @@
+// See MD_CUDABackend.h.  Call order and input keys follow src/CUDA/Backends/CUDABaseBackend.cu:110-242 and
+// src/CUDA/Backends/MD_CUDABackend.cu:231-394,567-747; the device work goes through the C ABI (include/oxdna_b200.h).
+#include "MD_CUDABackend.h"
+
+#include "Forces/ConstantRateForce.h"
+#include "Forces/MovingTrap.h"
+#include "Forces/MutualTrap.h"
+#include "Lists/BaseList.h"
+#include "Observables/ObservableOutput.h"
+#include "Particles/BaseParticle.h"
+#include "Utilities/ConfigInfo.h"
+#include "Utilities/Logger.h"
+#include "Utilities/Utils.h"
+
+#include <typeinfo>
+#include <vector>
+
+MD_CUDABackend::MD_CUDABackend() :
+				MDBackend() {
+}
+
+MD_CUDABackend::~MD_CUDABackend() {
+	if(_ctx != nullptr) oxb_destroy(_ctx);
+}
+
+void MD_CUDABackend::get_settings(input_file &inp) {
+	MDBackend::get_settings(inp);
+
+	if(getInputInt(&inp, "CUDA_device", &_device_number, 0) == KEY_NOT_FOUND) {
+		OX_LOG(Logger::LOG_INFO, "CUDA device not specified");
+		_device_number = -1;
+	}
+	else {
+		OX_LOG(Logger::LOG_INFO, "Using CUDA device %d", _device_number);
+	}
+	if(getInputInt(&inp, "CUDA_sort_every", &_sort_every, 0) == KEY_NOT_FOUND) {
+		OX_LOG(Logger::LOG_INFO, "CUDA sort_every not specified, using 0");
+	}
+	getInputInt(&inp, "threads_per_block", &_threads_per_block, 0);
+
+	_cuda_interaction = CUDAInteractionFactory::make_interaction(inp);
+	_cuda_interaction->get_settings(inp);
+	_cuda_interaction->get_cuda_settings(inp);
+
+	_cuda_lists = CUDAListFactory::make_list(inp);
+	_cuda_lists->get_settings(inp);
+
+	std::string reload_from;
+	if(getInputString(&inp, "reload_from", reload_from, 0) == KEY_FOUND) {
+		throw oxDNAException("The CUDA backend does not support reloading checkpoints, owing to its intrinsically stochastic nature");
+	}
+
+	if(getInputBool(&inp, "use_edge", &_use_edge, 0) == KEY_FOUND) {
+		if(_use_edge && _use_barostat) {
+			throw oxDNAException("use_edge and use_barostat are not compatible");
+		}
+	}
+	if(_use_barostat) {
+		throw oxDNAException("use_barostat is not available in the oxdna_b200 CUDA backend");
+	}
+
+	getInputBool(&inp, "CUDA_avoid_cpu_calculations", &_avoid_cpu_calculations, 0);
+	getInputBool(&inp, "CUDA_print_energy", &_print_energy, 0);
+	getInputLLInt(&inp, "CUDA_max_queued_steps", &_max_pending, 0);
+
+	_cuda_thermostat = CUDAThermostatFactory::make_thermostat(inp, _box.get());
+	_cuda_thermostat->get_settings(inp);
+
+	// same trimming of the default outputs as the reference (MD_CUDABackend.cu:652-671)
+	if(_avoid_cpu_calculations) {
+		_obs_output_file->clear();
+		_obs_output_file->add_observable("type = step\nunits = MD");
+		bool no_stdout_energy = false;
+		getInputBool(&inp, "no_stdout_energy", &no_stdout_energy, 0);
+		if(!no_stdout_energy) {
+			_obs_output_stdout->clear();
+			_obs_output_stdout->add_observable("type = step");
+			_obs_output_stdout->add_observable("type = step\nunits = MD");
+		}
+	}
+}
+
+void MD_CUDABackend::init() {
+	MDBackend::init();
+
+	const int n = N();
+	int dev = _device_number < 0 ? 0 : _device_number;
+	int rc = oxb_create(&_ctx, dev, n, _precision);
+	if(rc != 0) {
+		std::string msg = _ctx ? oxb_last_error(_ctx) : "out of memory";
+		throw oxDNAException("Cannot initialise the oxdna_b200 device context: %s", msg.c_str());
+	}
+	OX_LOG(Logger::LOG_INFO, "oxdna_b200 backend running on device %d", dev);
+
+	LR_vector sides = _box->box_sides();
+	double box[3] = { (double) sides.x, (double) sides.y, (double) sides.z };
+	oxb_check(_ctx, oxb_set_box(_ctx, box), "set_box");
+
+	std::vector<int> btype(n), n3(n), n5(n), strand(n);
+	for(int i = 0; i < n; i++) {
+		BaseParticle *p = _particles[i];
+		btype[i] = p->btype;
+		n3[i] = (p->n3 == P_VIRTUAL) ? -1 : p->n3->index;
+		n5[i] = (p->n5 == P_VIRTUAL) ? -1 : p->n5->index;
+		strand[i] = p->strand_id;
+		if(p->btype > 511 || p->btype < -511) {
+			throw oxDNAException("Could not treat the type (A, C, G, T or something specific) of particle %d; On CUDA, integer base types cannot be larger than 511 or smaller than -511", i);
+		}
+	}
+	oxb_check(_ctx, oxb_set_topology(_ctx, btype.data(), n3.data(), n5.data(), strand.data()), "set_topology");
+
+	_cuda_interaction->cuda_init(_ctx, n);
+	_cuda_lists->init(_ctx, n, _cuda_interaction->get_cuda_rcut(), _sort_every);
+	oxb_check(_ctx, oxb_set_dt(_ctx, (double) _dt), "set_dt");
+
+	_cuda_thermostat->set_seed(lrand48());
+	_cuda_thermostat->init();
+	_cuda_thermostat->attach(_ctx);
+
+	// copy all the particle related stuff to device memory, then lists and forces for the first step
+	apply_changes_to_simulation_data();
+	oxb_check(_ctx, oxb_set_step(_ctx, current_step()), "set_step");
+	_cuda_lists->update();
+	_cuda_interaction->compute_forces(_ctx);
+}
+
+void MD_CUDABackend::_host_to_gpu() {
+	const int n = N();
+	std::vector<double> pos(3 * n), a1(3 * n), a3(3 * n), vel(3 * n), L(3 * n);
+	for(int i = 0; i < n; i++) {
+		BaseParticle *p = _particles[i];
+		const LR_vector &v1 = p->orientationT.v1, &v3 = p->orientationT.v3;
+		pos[3 * i] = p->pos.x; pos[3 * i + 1] = p->pos.y; pos[3 * i + 2] = p->pos.z;
+		a1[3 * i] = v1.x; a1[3 * i + 1] = v1.y; a1[3 * i + 2] = v1.z;
+		a3[3 * i] = v3.x; a3[3 * i + 1] = v3.y; a3[3 * i + 2] = v3.z;
+		vel[3 * i] = p->vel.x; vel[3 * i + 1] = p->vel.y; vel[3 * i + 2] = p->vel.z;
+		L[3 * i] = p->L.x; L[3 * i + 1] = p->L.y; L[3 * i + 2] = p->L.z;
+	}
+	oxb_check(_ctx, oxb_set_state(_ctx, pos.data(), a1.data(), a3.data(), vel.data(), L.data()), "set_state");
+}
+
+void MD_CUDABackend::_gpu_to_host() {
+	const int n = N();
+	std::vector<double> pos(3 * n), a1(3 * n), a3(3 * n), vel(3 * n), L(3 * n);
+	oxb_check(_ctx, oxb_get_state(_ctx, pos.data(), a1.data(), a3.data(), vel.data(), L.data()), "get_state");
+	std::vector<double> F, T;
+	if(!_avoid_cpu_calculations) {
+		// superset of the reference, which never writes the GPU forces back
+		F.resize(3 * n);
+		T.resize(3 * n);
+		oxb_check(_ctx, oxb_get_forces(_ctx, F.data(), T.data(), nullptr, nullptr, nullptr), "get_forces");
+	}
+	for(int i = 0; i < n; i++) {
+		BaseParticle *p = _particles[i];
+		p->pos = LR_vector(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
+		p->vel = LR_vector(vel[3 * i], vel[3 * i + 1], vel[3 * i + 2]);
+		p->L = LR_vector(L[3 * i], L[3 * i + 1], L[3 * i + 2]);
+		LR_vector v1(a1[3 * i], a1[3 * i + 1], a1[3 * i + 2]), v3(a3[3 * i], a3[3 * i + 1], a3[3 * i + 2]);
+		LR_vector v2 = v3.cross(v1);
+		// orientationT has the axes as rows, orientation as columns
+		p->orientationT = LR_matrix(v1, v2, v3);
+		p->orientation = p->orientationT.get_transpose();
+		p->set_positions();
+		if(!F.empty()) {
+			p->force = LR_vector(F[3 * i], F[3 * i + 1], F[3 * i + 2]);
+			p->torque = LR_vector(T[3 * i], T[3 * i + 1], T[3 * i + 2]);
+		}
+	}
+}
+
+void MD_CUDABackend::_apply_external_forces_changes() {
+	if(!_external_forces) return;
+	std::vector<oxb_ext_force> table;
+	for(int i = 0; i < N(); i++) {
+		BaseParticle *p = _particles[i];
+		for(auto f : p->ext_forces) {
+			oxb_ext_force e;
+			memset(&e, 0, sizeof(e));
+			e.particle = i;
+			auto &ft = typeid(*f);
+			if(ft == typeid(ConstantRateForce)) {
+				ConstantRateForce *cf = static_cast<ConstantRateForce *>(f);
+				if(cf->dir_as_centre) throw oxDNAException("ConstantRateForce with dir_as_centre = true is not supported by the oxdna_b200 CUDA backend");
+				e.type = OXB_EXT_STRING;
+				e.F0 = cf->_F0; e.rate = cf->_rate;
+				e.dir[0] = cf->_direction.x; e.dir[1] = cf->_direction.y; e.dir[2] = cf->_direction.z;
+			}
+			else if(ft == typeid(MutualTrap)) {
+				MutualTrap *mf = static_cast<MutualTrap *>(f);
+				e.type = OXB_EXT_MUTUAL_TRAP;
+				e.ref = mf->_p_ptr->index;
+				e.pbc = mf->PBC ? 1 : 0;
+				e.stiff = mf->_stiff; e.r0 = mf->_r0; e.rate = mf->_rate; e.stiff_rate = mf->_stiff_rate;
+			}
+			else if(ft == typeid(MovingTrap)) {
+				MovingTrap *tf = static_cast<MovingTrap *>(f);
+				e.type = OXB_EXT_TRAP;
+				e.stiff = tf->_stiff; e.rate = tf->_rate;
+				e.dir[0] = tf->_direction.x; e.dir[1] = tf->_direction.y; e.dir[2] = tf->_direction.z;
+				e.pos0[0] = tf->_pos0.x; e.pos0[1] = tf->_pos0.y; e.pos0[2] = tf->_pos0.z;
+			}
+			else {
+				throw oxDNAException("Only ConstantRate (string), MutualTrap and MovingTrap forces are supported by the oxdna_b200 CUDA backend at the moment.\n");
+			}
+			table.push_back(e);
+		}
+	}
+	// unlike the reference (MD_CUDABackend.cu:110-112) external forces may be combined with CUDA_sort_every > 0:
+	// the table holds original particle ids, the device maps them through its slot table
+	oxb_check(_ctx, oxb_set_ext_forces(_ctx, (int) table.size(), table.data()), "set_ext_forces");
+}
+
+void MD_CUDABackend::_flush() {
+	if(_pending_steps == 0) return;
+	oxb_check(_ctx, oxb_set_step(_ctx, _first_pending_step), "set_step");
+	llint n = _pending_steps;
+	_pending_steps = 0;
+	int rc = oxb_run(_ctx, n);
+	long long updates = 0;
+	oxb_get_stats(_ctx, &updates, nullptr, nullptr, nullptr);
+	_N_updates = (int) updates;
+	if(rc != 0) throw oxDNAException("%s", oxb_last_error(_ctx));
+	if(_print_energy) {
+		double U = 0., K = 0.;
+		oxb_check(_ctx, oxb_energy(_ctx, &U, &K), "energy");
+		_backend_info = Utils::sformat("\tCUDA_energy: %lf", U / N());
+	}
+}
+
+void MD_CUDABackend::sim_step() {
+	_mytimer->resume();
+	if(_pending_steps == 0) _first_pending_step = current_step();
+	_pending_steps++;
+	if(_pending_steps >= _max_pending) _flush();
+	_mytimer->pause();
+}
+
+void MD_CUDABackend::apply_simulation_data_changes() {
+	_flush();
+	_gpu_to_host();
+	_cuda_interaction->sync_host();
+	if(!_avoid_cpu_calculations) {
+		_lists->global_update(true);
+	}
+}
+
+void MD_CUDABackend::apply_changes_to_simulation_data() {
+	_host_to_gpu();
+	_apply_external_forces_changes();
+	_cuda_interaction->sync_GPU();
+}
+
+void MD_CUDABackend::_on_T_update() {
+	// steps queued at the old temperature must run before the operators re-derive their constants
+	if(_ctx != nullptr) _flush();
+	MDBackend::_on_T_update();
+}

@@ -1,0 +1,134 @@
+"""Drop-in test of the C++ host side: the reference's own main()/SimManager/input parser linked with OUR BackendFactory,
+MD_CUDABackend and operator classes (oxdna_b200/host) runs a stock input file with `backend = CUDA`, and the trajectory
+is compared with the unmodified reference CPU binary (oracle/_ref/oxDNA, `backend = CPU`, analytic DNA2_nomesh potential)
+started from the same files and seed.  Config C1 of BASELINE.json (examples/HAIRPIN, 18 nt, max_backbone_force = 10).
+
+Both executables are build artefacts of this container (they link the reference's objects) and travel to the GPU box;
+where they are missing the test is skipped.  Tolerances: FP32 pair arithmetic vs FP64 over 300 NVE steps of a chaotic
+system -> positions 2e-3, CPU-evaluated energies of the two trajectories 2e-4 per nucleotide."""
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from oxdna_b200 import io as oio
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OURS = os.path.join(ROOT, "oxdna_b200", "host", "_build", "oxDNA_b200")
+REF = os.path.join(ROOT, "oracle", "_ref", "oxDNA")
+FIX = os.path.join(ROOT, "tests", "golden", "hairpin")
+
+INPUT = """backend = {backend}
+backend_precision = mixed
+sim_type = MD
+interaction_type = {itype}
+salt_concentration = 0.5
+T = 334K
+dt = 0.003
+steps = {steps}
+thermostat = {thermostat}
+newtonian_steps = 103
+diff_coeff = 2.5
+verlet_skin = 0.05
+max_backbone_force = 10
+CUDA_list = verlet
+CUDA_sort_every = {sort_every}
+use_edge = {use_edge}
+seed = 42
+refresh_vel = 1
+topology = initial.top
+conf_file = initial.conf
+trajectory_file = trajectory.dat
+lastconf_file = last_conf.dat
+energy_file = energy.dat
+print_energy_every = 100
+print_conf_interval = 100000
+restart_step_counter = 1
+time_scale = linear
+no_stdout_energy = 1
+{extra}
+"""
+
+FORCES = """{
+type = mutual_trap
+particle = 0
+ref_particle = 17
+stiff = 0.5
+r0 = 1.5
+PBC = 1
+}
+{
+type = mutual_trap
+particle = 17
+ref_particle = 0
+stiff = 0.5
+r0 = 1.5
+PBC = 1
+}
+"""
+
+
+def run(binary, d, **kw):
+    os.makedirs(d, exist_ok=True)
+    for f in ("initial.top", "initial.conf"):
+        shutil.copy(os.path.join(FIX, f), d)
+    with open(os.path.join(d, "forces.txt"), "w") as f:
+        f.write(FORCES)
+    with open(os.path.join(d, "input"), "w") as f:
+        f.write(INPUT.format(**kw))
+    p = subprocess.run([binary, "input"], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    return p
+
+
+def energies(d):
+    return np.loadtxt(os.path.join(d, "energy.dat"), ndmin=2)
+
+
+needs_binaries = pytest.mark.skipif(not (os.path.exists(OURS) and os.path.exists(REF)), reason="drop-in executables not built (need /root/reference)")
+
+
+@pytest.mark.gpu
+@needs_binaries
+@pytest.mark.parametrize("use_edge,sort_every,extra", [(1, 1, ""), (0, 0, ""), (1, 1, "external_forces = 1\nexternal_forces_file = forces.txt")])
+def test_stock_input_file_matches_reference_cpu(tmp_path, use_edge, sort_every, extra):
+    a = run(OURS, str(tmp_path / "ours"), backend="CUDA", itype="DNA2", steps=300, thermostat="no", use_edge=use_edge, sort_every=sort_every, extra=extra)
+    assert a.returncode == 0, a.stdout[-2000:]
+    b = run(REF, str(tmp_path / "ref"), backend="CPU", itype="DNA2_nomesh", steps=300, thermostat="no", use_edge=0, sort_every=0, extra=extra)
+    assert b.returncode == 0, b.stdout[-2000:]
+    ca, cb = oio.read_conf(str(tmp_path / "ours" / "last_conf.dat")), oio.read_conf(str(tmp_path / "ref" / "last_conf.dat"))
+    assert np.abs(ca["pos"] - cb["pos"]).max() < 2e-3
+    assert np.abs(ca["a1"] - cb["a1"]).max() < 5e-3
+    ea, eb = energies(str(tmp_path / "ours")), energies(str(tmp_path / "ref"))
+    assert ea.shape == eb.shape and ea.shape[0] >= 3
+    assert np.abs(ea[:, 1:] - eb[:, 1:]).max() < 2e-4
+
+
+@pytest.mark.gpu
+@needs_binaries
+def test_stock_input_file_thermostat_and_errors(tmp_path):
+    a = run(OURS, str(tmp_path / "t"), backend="CUDA", itype="DNA2", steps=5000, thermostat="brownian", use_edge=1, sort_every=1, extra="")
+    assert a.returncode == 0, a.stdout[-2000:]
+    e = energies(str(tmp_path / "t"))
+    assert np.all(np.isfinite(e)) and e.shape[0] >= 40
+    # the strained start structure (max_backbone_force) dumps ~6 units of energy per nucleotide into kinetic energy; the
+    # Andersen-like thermostat (pt = 0.0137 every 103 steps -> relaxation time ~7500 steps) must be draining it
+    assert e[-5:, 2].mean() < 0.8 * e[:5, 2].mean()
+    # reference incompatibilities are reported as the reference reports them (fatal oxDNAException, non-zero exit)
+    bad = run(OURS, str(tmp_path / "bad"), backend="CUDA", itype="DNA2", steps=10, thermostat="no", use_edge=1, sort_every=0, extra="CUDA_list = no")
+    assert bad.returncode != 0 and "incompatible" in bad.stdout
+    bad = run(OURS, str(tmp_path / "bad2"), backend="CUDA", itype="DNA2", steps=10, thermostat="no", use_edge=1, sort_every=0, extra="reload_from = x")
+    assert bad.returncode != 0 and "checkpoints" in bad.stdout
+    bad = run(OURS, str(tmp_path / "bad3"), backend="CUDA", itype="RNA2", steps=10, thermostat="no", use_edge=1, sort_every=0, extra="")
+    assert bad.returncode != 0
+
+
+@needs_binaries
+def test_no_cpu_fallback_in_the_dropin_binary(tmp_path):
+    """Without a CUDA device the backend must refuse to run (this test is meaningful on the CPU-only container)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    a = run(OURS, str(tmp_path / "nogpu"), backend="CUDA", itype="DNA2", steps=10, thermostat="no", use_edge=1, sort_every=0, extra="")
+    assert a.returncode != 0 and "no CPU fallback" in a.stdout
