@@ -24,6 +24,9 @@ sys.path.insert(0, ROOT)
 
 T_STR, SALT, DT = "300K", 0.5, 0.003
 FLOP_FAR, FLOP_DH, FLOP_CONTACT, FLOP_BONDED = 170.0, 60.0, 1500.0, 900.0  # SURVEY 8(d) per-pair figures
+# ncu dram__bytes_read.sum + dram__bytes_write.sum of one force pass (near + HB/CRST + coaxial + bonded + DH kernels)
+NCU_FORCE_PASS_DRAM_BYTES_C2 = None
+NCU_FORCE_PASS_DRAM_BYTES_C4 = int((58.02 + 0.93 + 75.63 + 1.32 + 0.02 + 84.21 + 5.47 + 88.0 + 3.0) * 1e6)
 
 
 def workload(name):
@@ -334,8 +337,11 @@ def ours(args):
             flops = N * (2 * (FLOP_FAR * ps["listed"] + FLOP_DH * ps["dh"] + FLOP_CONTACT * ps["contact"]) + 2 * FLOP_BONDED)
         sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
         fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
-        integ_bytes = N * 336.0  # first_step_mixed: 176 B read + 160 B written per particle; second half-kick fused
+        # first_step_mixed: 176 B read + 160 B written per particle, second half-kick fused; + 16 B Fb read in edge mode
+        integ_bytes = N * (336.0 + (16.0 if args.use_edge else 0.0))
         integ_gbs = integ_bytes / (t_integ * 1e-3) / 1e9
+        # DRAM bytes of one force pass from the committed ncu --set full capture of the same workload (sum over its kernels)
+        traffic = {"c2": NCU_FORCE_PASS_DRAM_BYTES_C2, "c4": NCU_FORCE_PASS_DRAM_BYTES_C4}.get(args.workload) if args.use_edge else None
         step_ms = total_ms / (args.steps * md)
         rebuild_every = md * args.steps / max(stats1["n_list_updates"] - stats0["n_list_updates"], 1)
 
@@ -385,7 +391,8 @@ def ours(args):
                            "pairs_per_particle": ps},
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
                 "roofline": {"kernel": "forces (edge non-bonded + bonded)" if args.use_edge else "forces (particle-centric)", "bound": "hbm", "achieved": force_gbs, "peak": hbm_peak,
-                             "unit": "GB/s", "frac": force_gbs / hbm_peak, "traffic": None, "peak_source": peak_src, "ms": t_force,
+                             "unit": "GB/s", "frac": force_gbs / hbm_peak, "traffic": traffic,
+                             "traffic_source": "profiles/summary_r01f.txt (C2) / summary_r01e.txt (C4): dram__bytes_read.sum + dram__bytes_write.sum summed over the kernels of one force pass", "peak_source": peak_src, "ms": t_force,
                              "share_of_step": t_force / step_ms,
                              "note": "the force kernel is FP32/SFU-bound, not HBM-bound (see roofline_fp32); HBM figure given as the contract asks"},
                 "roofline_fp32": {"achieved_tflops": flops / (t_force * 1e-3) / 1e12, "peak_tflops": fp32_peak, "frac": flops / (t_force * 1e-3) / 1e12 / fp32_peak,

@@ -71,9 +71,9 @@ struct oxb_ctx {
 	int edge_hint = 0;
 	int *dh_nbr = nullptr, *dh_nnbr = nullptr;
 	int max_dh = 0;
-	int2 *hb_list = nullptr, *cx_list = nullptr;
-	int *counters = nullptr;
-	int hb_cap = 0, cx_cap = 0;
+	int2 *hb_list = nullptr, *cx_list = nullptr, *cr_list = nullptr;
+	int *seg_counts = nullptr;
+	int n_seg = 1, hb_seg = 1, cx_seg = 1, cr_seg = 1;
 	void *cub_tmp = nullptr;
 	size_t cub_tmp_bytes = 0;
 	unsigned *hkeys = nullptr, *hkeys_sorted = nullptr;
@@ -143,10 +143,10 @@ void free_lists(oxb_ctx *c) {
 	cudaFree(c->dh_nbr); cudaFree(c->dh_nnbr); cudaFree(c->near_mask);
 	c->near_mask = nullptr;
 	c->slots_cell_ordered = false;
-	cudaFree(c->hb_list); cudaFree(c->cx_list); cudaFree(c->counters);
+	cudaFree(c->hb_list); cudaFree(c->cx_list); cudaFree(c->cr_list); cudaFree(c->seg_counts);
 	c->cell_key = c->cell_key_sorted = c->cell_val = c->cell_val_sorted = c->cell_start = c->nbr = c->nnbr = c->edge_offsets = c->n_edges = nullptr;
-	c->counters = c->dh_nbr = c->dh_nnbr = nullptr;
-	c->edges = c->hb_list = c->cx_list = nullptr;
+	c->seg_counts = c->dh_nbr = c->dh_nnbr = nullptr;
+	c->edges = c->hb_list = c->cx_list = c->cr_list = nullptr;
 	c->cub_tmp = nullptr;
 	c->lists_allocated = false;
 }
@@ -180,10 +180,16 @@ int alloc_lists(oxb_ctx *c, int max_neigh) {
 	CU(cudaMemset(c->n_edges, 0, 2 * sizeof(int)));
 	c->max_dh = max_neigh;
 	CU(dalloc(&c->dh_nbr, (size_t) c->max_dh * N)); CU(dalloc(&c->dh_nnbr, N));
-	c->hb_cap = c->use_edge ? 6 * N + 1024 : 1;
-	c->cx_cap = c->use_edge ? 3 * N + 1024 : 1;
-	CU(dalloc(&c->hb_list, (size_t) c->hb_cap)); CU(dalloc(&c->cx_list, (size_t) c->cx_cap)); CU(dalloc(&c->counters, 2));
-	CU(cudaMemset(c->counters, 0, 2 * sizeof(int)));
+	// segmented work lists of the edge pipeline: one segment per block of the near-edge kernel, sized ~4x the expected load
+	// (hydrogen-bonding pairs ~0.5 N, cross-stacking-only pairs ~1.2 N, coaxial pairs << N) plus a floor for tiny systems
+	// ~3.3 near edges per particle, one producer block per 128 edges up to 16 blocks per SM (grid-stride beyond that)
+	c->n_seg = c->use_edge ? (int) std::max<long long>(1, std::min<long long>(16ll * c->n_sm, (33ll * N / 10 + 127) / 128)) : 1;
+	c->hb_seg = c->use_edge ? (int) (6ll * N / c->n_seg) + 128 : 1;
+	c->cr_seg = 1; // the cross-stacking-only list is not produced (see forces.cu)
+	c->cx_seg = c->use_edge ? (int) (2ll * N / c->n_seg) + 64 : 1;
+	CU(dalloc(&c->hb_list, (size_t) c->hb_seg * c->n_seg)); CU(dalloc(&c->cx_list, (size_t) c->cx_seg * c->n_seg));
+	CU(dalloc(&c->cr_list, (size_t) c->cr_seg * c->n_seg)); CU(dalloc(&c->seg_counts, (size_t) 3 * c->n_seg));
+	CU(cudaMemset(c->seg_counts, 0, sizeof(int) * 3 * (size_t) c->n_seg));
 	c->edge_capacity = c->use_edge ? ((long long) N * max_neigh) / 4 + N : 1;
 	CU(dalloc(&c->edges, (size_t) c->edge_capacity));
 	c->cub_tmp_bytes = std::max(oxb::lists_tmp_bytes(N, (int) ncells), oxb::sort_tmp_bytes(N));
@@ -324,27 +330,28 @@ int launch_forces(oxb_ctx *c, int hw, bool clear, long long step) {
 		if(clear) {
 			CU(cudaMemsetAsync(c->F[a], 0, sizeof(float4) * (size_t) c->N, m));
 			CU(cudaMemsetAsync(c->T[a], 0, sizeof(float4) * (size_t) c->N, m));
-			CU(cudaMemsetAsync(c->counters, 0, 2 * sizeof(int), m));
 		}
 		oxb::EdgeArgs e;
 		e.N = c->N; e.ipos = c->ipos[a]; e.iback = c->iback[a]; e.quat = c->quat[a]; e.bonds = c->bonds[a]; e.edges = c->edges;
 		e.n_edges = c->n_edges; e.dh_nbr = c->dh_nbr; e.dh_nnbr = c->dh_nnbr;
-		e.F = c->F[a]; e.T = c->T[a]; e.Fb = c->Fb; e.hb_list = c->hb_list; e.cx_list = c->cx_list; e.counters = c->counters;
-		e.hb_cap = c->hb_cap; e.cx_cap = c->cx_cap;
+		e.F = c->F[a]; e.T = c->T[a]; e.Fb = c->Fb; e.hb_list = c->hb_list; e.cx_list = c->cx_list; e.cr_list = c->cr_list; e.seg_counts = c->seg_counts;
+		e.n_seg = c->n_seg; e.hb_seg = c->hb_seg; e.cx_seg = c->cx_seg; e.cr_seg = c->cr_seg;
+		// ~1.7 items per particle in that list; aim at ~2 items per consumer thread
+		e.hb_split = (int) std::max<long long>(1, std::min<long long>(8, (17ll * c->N / 10 / c->n_seg + 64) / 128));
 		CU(cudaEventRecord(c->ev_fork, m));
 		CU(cudaStreamWaitEvent(c->aux[0], c->ev_fork, 0));
 		CU(cudaStreamWaitEvent(c->aux[1], c->ev_fork, 0));
-		oxb::launch_edge_stage(c->aux[0], 0, c->model, c->boxf, e, c->flags, hw, c->n_sm);
-		oxb::launch_edge_stage(c->aux[1], 4, c->model, c->boxf, e, c->flags, hw, c->n_sm);
-		oxb::launch_edge_stage(m, 1, c->model, c->boxf, e, c->flags, hw, c->n_sm);
+		oxb::launch_edge_stage(c->aux[0], 0, c->model, c->boxf, e, c->flags, hw);
+		oxb::launch_edge_stage(c->aux[1], 4, c->model, c->boxf, e, c->flags, hw);
+		oxb::launch_edge_stage(m, 1, c->model, c->boxf, e, c->flags, hw);
 		CU(cudaEventRecord(c->ev_near, m));
-		oxb::launch_edge_stage(m, 2, c->model, c->boxf, e, c->flags, hw, c->n_sm);
+		oxb::launch_edge_stage(m, 2, c->model, c->boxf, e, c->flags, hw);
 		if(c->n_ext > 0) {
 			oxb::launch_ext_forces(c->aux[1], c->n_ext, c->ext, c->slot_of, c->ipos[a], c->posd[a], c->boxf, step, c->cur_step, c->F[a], c->flags, hw);
 			c->launches += 1;
 		}
 		CU(cudaStreamWaitEvent(c->aux[1], c->ev_near, 0));
-		oxb::launch_edge_stage(c->aux[1], 3, c->model, c->boxf, e, c->flags, hw, c->n_sm);
+		oxb::launch_edge_stage(c->aux[1], 3, c->model, c->boxf, e, c->flags, hw);
 		CU(cudaEventRecord(c->ev_join[0], c->aux[0]));
 		CU(cudaEventRecord(c->ev_join[1], c->aux[1]));
 		CU(cudaStreamWaitEvent(m, c->ev_join[0], 0));
@@ -375,7 +382,7 @@ oxb::IntegrateArgs integ_args(oxb_ctx *c, long long step) {
 	a.F = c->F[k]; a.T = c->T[k]; a.Fb = c->use_edge ? c->Fb : nullptr; a.iback = c->iback[k]; a.list_iback = c->list_iback[k]; a.list_ibase = c->list_ibase[k];
 	a.back_a1 = c->model.back_a1; a.back_a2 = c->model.back_a2; a.base_a1 = c->model.base_a1;
 	a.flags = c->flags; a.sums = c->sums; a.th = c->th; a.step = step;
-	a.cur_step = c->cur_step; a.counters = c->use_edge ? c->counters : nullptr;
+	a.cur_step = c->cur_step;
 	return a;
 }
 
@@ -928,6 +935,9 @@ int oxb_run(oxb_ctx *c, long long n_steps) {
 		c->step += done;
 		remaining -= done;
 		since_rebuild += done;
+		if(c->error_flags & OXB_ERR_EDGE_OVERFLOW) {
+			return fail(c, 8, "a work-list segment of the edge pipeline overflowed around step %lld (local density far above the average)", c->step);
+		}
 		if(c->error_flags & OXB_ERR_FENE_BROKEN) {
 			return fail(c, 6, "the distance between bonded neighbors exceeded acceptable values (FENE range) around step %lld", c->step);
 		}
@@ -1096,6 +1106,13 @@ int oxb_time_kernel(oxb_ctx *c, int which, int reps, float *ms) {
 	CU(cudaEventCreate(&e1));
 	rc = reset_batch_flags(c);
 	if(rc) return rc;
+	if(which == 1) {
+		// untimed first launch: with lazy module loading the first use of a kernel variant costs milliseconds
+		oxb::IntegrateArgs a = integ_args(c, c->step);
+		a.dt = 0.;
+		oxb::launch_integrate_epoch(c->stream, a, OXB_PH_SECOND | OXB_PH_FIRST | OXB_PH_COUNT_STEP, 0);
+		c->launches++;
+	}
 	CU(cudaStreamSynchronize(c->stream));
 	CU(cudaEventRecord(e0, c->stream));
 	for(int r = 0; r < reps; r++) {
@@ -1124,7 +1141,10 @@ int oxb_time_kernel(oxb_ctx *c, int which, int reps, float *ms) {
 	*ms = t / reps;
 	cudaEventDestroy(e0);
 	cudaEventDestroy(e1);
-	if(which != 0) { if(which != 1) c->lists_valid = false; c->forces_valid = false; rc = ensure_forces(c); if(rc) return rc; }
+	if(which >= 2) c->lists_valid = false;
+	c->forces_valid = false;
+	rc = ensure_forces(c);
+	if(rc) return rc;
 	CU(cudaStreamSynchronize(c->stream));
 	return 0;
 }

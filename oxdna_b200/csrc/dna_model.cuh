@@ -298,26 +298,20 @@ OXB_HD float dna2_dh(const oxb_dna2_params &M, float rbb2, bool p_end, bool q_en
 // device-only variant with SFU intrinsics (rsqrt, ex2): no IEEE division / square root on the most frequent path.
 // Relative error ~2e-7, far inside the 1e-5 force tolerance.
 __device__ __forceinline__ float dna2_dh_fast(const oxb_dna2_params &M, float rbb2, bool p_end, bool q_end, float &fs) {
-	fs = 0.f;
-	if(rbb2 >= M.dh_rc * M.dh_rc) return 0.f;
+	// both radial regimes are evaluated and selected (ex2 and rsqrt are single SFU instructions): no divergent branch in
+	// the most frequently executed loop of the step
 	float inv = rsqrtf(rbb2);
 	float m = rbb2 * inv;
-	float cut = 1.f;
+	float cut = (rbb2 < M.dh_rc * M.dh_rc) ? 1.f : 0.f;
 	if(M.dh_half_charged_ends) {
 		if(p_end) cut *= 0.5f;
 		if(q_end) cut *= 0.5f;
 	}
-	float en, f;
-	if(m < M.dh_rhigh) {
-		float ex = __expf(m * M.dh_minus_kappa) * M.dh_prefactor * inv;
-		en = ex;
-		f = -ex * (M.dh_minus_kappa - inv);
-	}
-	else {
-		float x = m - M.dh_rc;
-		en = M.dh_b * x * x;
-		f = -2.f * M.dh_b * x;
-	}
+	float ex = __expf(m * M.dh_minus_kappa) * M.dh_prefactor * inv;
+	float x = m - M.dh_rc;
+	bool inner = m < M.dh_rhigh;
+	float en = inner ? ex : M.dh_b * x * x;
+	float f = inner ? -ex * (M.dh_minus_kappa - inv) : -2.f * M.dh_b * x;
 	fs = f * cut * inv;
 	return en * cut;
 }
@@ -367,6 +361,7 @@ OXB_HD bool dna2_cxst_may_act(const oxb_dna2_params &M, v3 h, const Axes &A, con
 }
 
 // rb = base-base vector.  Returns total energy (HB + cross stacking), ehb = the HB part.
+template<bool WITH_HB = true>
 OXB_HD float dna2_hbcr(const oxb_dna2_params &M, v3 rb, float rbm2, const Axes &A, const Axes &B, int btp, int btq, bool hb_on, bool cr_on,
 		PairAcc &acc, float &ehb) {
 	const float cb = M.base_a1;
@@ -382,7 +377,7 @@ OXB_HD float dna2_hbcr(const oxb_dna2_params &M, v3 rb, float rbm2, const Axes &
 	Angle t7 = make_angle(-B.a3, h);
 	Angle t8 = make_angle(A.a3, h);
 	float g1 = 0.f, g2 = 0.f, g3 = 0.f, g4 = 0.f, g7 = 0.f, g8 = 0.f, grad = 0.f;
-	if(hb_on) {
+	if(WITH_HB && hb_on) {
 		int ti = btype_to_type(btq) * 5 + btype_to_type(btp);
 		float mult = (abs(btq) >= 300 && abs(btp) >= 300) ? M.hb_multiplier : 1.f;
 		RadVal f1 = f1_r(M.hb, M.hb_eps[ti], M.hb_shift[ti], m);

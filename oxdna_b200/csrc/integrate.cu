@@ -46,8 +46,6 @@ __global__ void __launch_bounds__(256) k_integrate(oxb::IntegrateArgs a, int epo
 	if(i == 0) {
 		if(PH & OXB_PH_COUNT_STEP) atomicAdd(flags + OXB_FLAG_STEPS_DONE, 1);
 		a.cur_step[(epoch + 1) & 1] = step + ((PH & OXB_PH_COUNT_STEP) ? 1 : 0);
-		// this launch runs after every consumer of the heavy work lists of the current force pass: reset their lengths
-		if((PH & OXB_PH_FIRST) && a.counters != nullptr) { a.counters[0] = 0; a.counters[1] = 0; }
 	}
 
 	double sv[5] = { 0., 0., 0., 0., 0. };
@@ -119,9 +117,19 @@ __global__ void __launch_bounds__(256) k_integrate(oxb::IntegrateArgs a, int epo
 			double n2 = L.x * L.x + L.y * L.y + L.z * L.z;
 			double4 qn = a.quatd[i];
 			if(n2 > 0.) {
-				double n = sqrt(n2), sh, ch;
-				sincos(0.5 * a.dt * n, &sh, &ch);
-				double k = sh / n;
+				// half angle th = dt |L| / 2 is ~1e-3: sin(th)/|L| and cos(th) from their Taylor series (remainder < 1e-20 for
+				// th < 0.03) -- no square root, no division, no slow-path double sincos; the general path stays for huge |L|
+				const double h = 0.5 * a.dt, t2 = h * h * n2;
+				double k, ch;
+				if(t2 < 9e-4) {
+					k = h * (1. + t2 * (-1. / 6. + t2 * (1. / 120. + t2 * (-1. / 5040. + t2 * (1. / 362880.)))));
+					ch = 1. + t2 * (-0.5 + t2 * (1. / 24. + t2 * (-1. / 720. + t2 * (1. / 40320. - t2 * (1. / 3628800.)))));
+				}
+				else {
+					double n = sqrt(n2), sh;
+					sincos(h * n, &sh, &ch);
+					k = sh / n;
+				}
 				double bx = L.x * k, by = L.y * k, bz = L.z * k, bw = ch;
 				double4 q = qn, o;
 				o.w = q.w * bw - q.x * bx - q.y * by - q.z * bz;

@@ -57,11 +57,14 @@ struct EdgeArgs {
 	const int *n_edges;
 	const int *dh_nbr, *dh_nnbr; // Debye-Hueckel neighbour matrix, column-major, stride N
 	float4 *F, *T, *Fb;
-	int2 *hb_list, *cx_list;
-	int *counters; // [0] hb/cross-stacking work items, [1] coaxial work items
-	int hb_cap, cx_cap;
+	// work lists segmented by producer block (n_seg blocks): hydrogen-bonding pairs, coaxial-stacking pairs, cross-stacking-only
+	// pairs; seg_counts[l * n_seg + b] = length of block b's segment of list l
+	int2 *hb_list, *cx_list, *cr_list;
+	int *seg_counts;
+	int n_seg, hb_seg, cx_seg, cr_seg;
+	int hb_split; // consumer blocks per segment of the hydrogen-bonding / cross-stacking list
 };
-void launch_edge_stage(cudaStream_t s, int which, const oxb_dna2_params &M, BoxF box, const EdgeArgs &a, int *flags, int hw, int n_sm);
+void launch_edge_stage(cudaStream_t s, int which, const oxb_dna2_params &M, BoxF box, const EdgeArgs &a, int *flags, int hw);
 void launch_ext_forces(cudaStream_t s, int n, const DevExtForce *ef, const int *slot_of, const int4 *ipos, const double4 *posd, BoxF box,
 		long long step, const long long *cur_step, float4 *F, const int *flags, int hw);
 
@@ -84,7 +87,6 @@ struct IntegrateArgs {
 	ThermostatCfg th;
 	long long step;      // step index of the thermostat application, or < 0: read it from cur_step (graph-launched batches)
 	long long *cur_step; // two device words, see k_integrate
-	int *counters;       // work-list lengths of the edge pipeline (reset here), or nullptr
 };
 void launch_integrate_epoch(cudaStream_t s, const IntegrateArgs &a, int phases, int epoch);
 void launch_bussi_update_epoch(cudaStream_t s, KinSums *sums, int N, ThermostatCfg th, long long step, const int *flags, int epoch);

@@ -180,12 +180,16 @@ __global__ void __launch_bounds__(128) k_build_neigh(oxb::ListArgs a, const int 
 		}
 	}
 	if(!active) return;
+	{
+		// one same-address atomic per warp, not per thread
+		const unsigned am = __activemask();
+		const int wmax = __reduce_max_sync(am, count);
+		if((int) (threadIdx.x & 31) == (__ffs(am) - 1)) atomicMax(a.flags + OXB_FLAG_MAX_NEIGH_SEEN, wmax);
+	}
 	if(count > a.max_neigh) {
 		atomicOr(a.flags + OXB_FLAG_ERROR, OXB_ERR_NEIGH_OVERFLOW);
-		atomicMax(a.flags + OXB_FLAG_MAX_NEIGH_SEEN, count);
 		count = a.max_neigh;
 	}
-	else atomicMax(a.flags + OXB_FLAG_MAX_NEIGH_SEEN, count);
 	if(ndh > a.max_dh) {
 		atomicOr(a.flags + OXB_FLAG_ERROR, OXB_ERR_NEIGH_OVERFLOW);
 		ndh = a.max_dh;

