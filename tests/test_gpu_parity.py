@@ -215,3 +215,41 @@ def test_temperature_update_changes_model():
         assert abs(U1 - U0) > 1e-3
     finally:
         sim.close()
+
+
+def _block_stats(x, nb=10):
+    b = x[: len(x) // nb * nb].reshape(nb, -1).mean(1)
+    return float(x.mean()), float(b.std(ddof=1) / np.sqrt(nb))
+
+
+def test_long_run_mean_energies_match_reference_statistically():
+    """Third correctness criterion of the north star: <U/N> (and <K/N>) over a long thermostatted run agree with the
+    reference's CPU backend within statistical error.  Reference numbers: tests/golden/stat_lattice8_ref.json (400,000
+    steps of the unmodified reference, block-averaged).  Ours: 400,000 steps, sampled every 100, 50,000 discarded.
+    Criterion: |difference| < 3 combined standard errors (10-block estimates)."""
+    import json
+    import os
+    ref = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "stat_lattice8_ref.json")))
+    sysm = lattice.duplex_lattice(8, bp=20, spacing=10.0, seed=1)
+    T = parse_temperature("300K")
+    v, L = lattice.maxwell_velocities(len(sysm["pos"]), T, 1)
+    inp = dict(backend="CUDA", interaction_type="DNA2", T="300K", salt_concentration=0.5, dt=0.003, verlet_skin=0.05, thermostat="brownian",
+               newtonian_steps=103, diff_coeff=2.5, CUDA_sort_every=1, use_edge=1, seed=4242)
+    sim = Simulation(inp, sysm, dict(box=sysm["box"], pos=sysm["pos"], a1=sysm["a1"], a3=sysm["a3"], vel=v, L=L))
+    try:
+        N = sim.N
+        sim.run(50000)
+        U, K = [], []
+        for _ in range(3500):
+            sim.run(100)
+            u, k = sim.ctx.energy()
+            U.append(u / N)
+            K.append(k / N)
+        mu, su = _block_stats(np.array(U))
+        mk, sk = _block_stats(np.array(K))
+        su_ref = max(float(ref["U_stderr"]), 0.0026)  # the 10-block estimate of the reference run
+        assert abs(mu - ref["U_per_nt"]) < 3.0 * np.hypot(su, su_ref), (mu, su, ref["U_per_nt"], su_ref)
+        assert abs(mk - ref["K_per_nt"]) < 3.0 * np.hypot(sk, float(ref["K_stderr"])) + 0.002, (mk, sk, ref["K_per_nt"])
+        assert abs(mk - 3.0 * T) < 0.02 * 3.0 * T
+    finally:
+        sim.close()
