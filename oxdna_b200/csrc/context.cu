@@ -79,6 +79,10 @@ struct oxb_ctx {
 	unsigned *hkeys = nullptr, *hkeys_sorted = nullptr;
 	int *hvals = nullptr, *hvals_sorted = nullptr, *hinv = nullptr;
 	bool lists_allocated = false, lists_valid = false, forces_valid = false;
+	// what the current lists were built for: they stay usable for a model with radii that are not larger (a replica-exchange
+	// energy evaluation at a lower temperature), but only an exact match reproduces the reference's pair set
+	double lists_rv = 0., lists_dh_rc = 0.;
+	long long ncells_alloc = 0;
 	long long n_list_updates = 0, n_sorts = 0;
 	int error_flags = 0;
 
@@ -96,7 +100,7 @@ struct oxb_ctx {
 	cudaStream_t aux[2] = { nullptr, nullptr };
 	cudaEvent_t ev_fork = nullptr, ev_near = nullptr, ev_join[2] = { nullptr, nullptr };
 	long long *cur_step = nullptr; // device, 2 words (see k_integrate)
-	struct BatchGraph { int units, cur; cudaGraphExec_t exec; };
+	struct BatchGraph { int units, cur; unsigned long long cfg; cudaGraphExec_t exec; };
 	std::vector<BatchGraph> graphs;
 	bool use_graphs = true;
 	long long graph_launches = 0;
@@ -148,11 +152,12 @@ void free_lists(oxb_ctx *c) {
 	c->seg_counts = c->dh_nbr = c->dh_nnbr = nullptr;
 	c->edges = c->hb_list = c->cx_list = c->cr_list = nullptr;
 	c->cub_tmp = nullptr;
+	c->ncells_alloc = 0;
 	c->lists_allocated = false;
 }
 
-int alloc_lists(oxb_ctx *c, int max_neigh) {
-	free_lists(c);
+// cell grid for the current cutoff; the cell table is the only allocation that depends on it
+int ensure_cells(oxb_ctx *c) {
 	const int N = c->N;
 	double rv = c->rcut + 2. * c->skin;
 	long long ncells = 1;
@@ -172,9 +177,25 @@ int alloc_lists(oxb_ctx *c, int max_neigh) {
 			ncells *= c->ncell[k];
 		}
 	}
+	if(ncells > c->ncells_alloc) {
+		CU(cudaStreamSynchronize(c->stream));
+		cudaFree(c->cell_start); cudaFree(c->cub_tmp);
+		c->cell_start = nullptr; c->cub_tmp = nullptr;
+		c->ncells_alloc = ncells + ncells / 8;
+		CU(dalloc(&c->cell_start, 2 * (size_t) c->ncells_alloc));
+		c->cub_tmp_bytes = std::max(oxb::lists_tmp_bytes(N, (int) c->ncells_alloc), oxb::sort_tmp_bytes(N));
+		CU(cudaMalloc(&c->cub_tmp, c->cub_tmp_bytes));
+	}
+	return 0;
+}
+
+int alloc_lists(oxb_ctx *c, int max_neigh) {
+	free_lists(c);
+	const int N = c->N;
+	c->ncells_alloc = 0;
+	{ int rc = ensure_cells(c); if(rc) return rc; }
 	c->max_neigh = max_neigh;
 	CU(dalloc(&c->cell_key, N)); CU(dalloc(&c->cell_key_sorted, N)); CU(dalloc(&c->cell_val, N)); CU(dalloc(&c->cell_val_sorted, N));
-	CU(dalloc(&c->cell_start, 2 * (size_t) ncells));
 	CU(dalloc(&c->nbr, (size_t) max_neigh * N)); CU(dalloc(&c->nnbr, N));
 	CU(dalloc(&c->edge_offsets, (size_t) N + 1)); CU(dalloc(&c->n_edges, 2)); CU(dalloc(&c->near_mask, (size_t) N));
 	CU(cudaMemset(c->n_edges, 0, 2 * sizeof(int)));
@@ -192,8 +213,6 @@ int alloc_lists(oxb_ctx *c, int max_neigh) {
 	CU(cudaMemset(c->seg_counts, 0, sizeof(int) * 3 * (size_t) c->n_seg));
 	c->edge_capacity = c->use_edge ? ((long long) N * max_neigh) / 4 + N : 1;
 	CU(dalloc(&c->edges, (size_t) c->edge_capacity));
-	c->cub_tmp_bytes = std::max(oxb::lists_tmp_bytes(N, (int) ncells), oxb::sort_tmp_bytes(N));
-	CU(cudaMalloc(&c->cub_tmp, c->cub_tmp_bytes));
 	c->lists_allocated = true;
 	return 0;
 }
@@ -248,6 +267,7 @@ int read_flags(oxb_ctx *c) {
 
 int do_sort(oxb_ctx *c) {
 	if(!c->lists_allocated) { int rc = alloc_lists(c, c->max_neigh > 0 ? c->max_neigh : 64); if(rc) return rc; }
+	{ int rc = ensure_cells(c); if(rc) return rc; }
 	const int N = c->N, a = c->cur, b = 1 - c->cur;
 	if(c->hkeys == nullptr) {
 		CU(dalloc(&c->hkeys, N)); CU(dalloc(&c->hkeys_sorted, N)); CU(dalloc(&c->hvals, N)); CU(dalloc(&c->hvals_sorted, N)); CU(dalloc(&c->hinv, N));
@@ -285,6 +305,7 @@ int do_sort(oxb_ctx *c) {
 
 int do_build(oxb_ctx *c) {
 	if(!c->lists_allocated) { int rc = alloc_lists(c, 64); if(rc) return rc; }
+	{ int rc = ensure_cells(c); if(rc) return rc; }
 	for(int attempt = 0; attempt < 6; attempt++) {
 		CU(cudaMemsetAsync(c->flags + OXB_FLAG_ERROR, 0, sizeof(int), c->stream));
 		oxb::launch_build_lists(c->stream, list_args(c));
@@ -296,6 +317,8 @@ int do_build(oxb_ctx *c) {
 		if((c->h_flags[OXB_FLAG_ERROR] & (OXB_ERR_NEIGH_OVERFLOW | OXB_ERR_EDGE_OVERFLOW)) == 0) {
 			c->error_flags &= ~(OXB_ERR_NEIGH_OVERFLOW | OXB_ERR_EDGE_OVERFLOW);
 			c->lists_valid = true;
+			c->lists_rv = c->rcut + 2. * c->skin;
+			c->lists_dh_rc = (double) c->model.dh_rc;
 			c->slots_cell_ordered = false; // particles move on: the next build bins them itself unless a re-sort precedes it
 			c->n_list_updates++;
 			return 0;
@@ -470,8 +493,24 @@ int launch_unit(oxb_ctx *c, int epoch, long long step, bool with_first) {
 }
 
 // cached graph of `units` consecutive full units starting at an even launch index, for the current state buffers
+unsigned long long config_hash(const oxb_ctx *c) {
+	// FNV-1a over the by-value kernel arguments a captured batch freezes: model constants, thermostat, time step, skin
+	unsigned long long h = 1469598103934665603ull;
+	auto mix = [&](const void *p, size_t n) {
+		const unsigned char *b = (const unsigned char *) p;
+		for(size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; }
+	};
+	mix(&c->model, sizeof(c->model));
+	mix(&c->th.type, sizeof(int)); mix(&c->th.every, sizeof(int)); mix(&c->th.a, 4 * sizeof(float)); mix(&c->th.seed, sizeof(c->th.seed));
+	mix(&c->dt, sizeof(double)); mix(&c->skin, sizeof(double));
+	return h;
+}
+
 int batch_graph(oxb_ctx *c, int units, cudaGraphExec_t *out) {
-	for(auto &g : c->graphs) if(g.units == units && g.cur == c->cur) { *out = g.exec; return 0; }
+	// temperature changes (replica exchange) alternate between a few configurations: graphs are kept per configuration
+	const unsigned long long cfg = config_hash(c);
+	for(auto &g : c->graphs) if(g.units == units && g.cur == c->cur && g.cfg == cfg) { *out = g.exec; return 0; }
+	if(c->graphs.size() >= 48) drop_graphs(c);
 	cudaGraph_t graph = nullptr;
 	const long long launches0 = c->launches;
 	CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
@@ -485,7 +524,7 @@ int batch_graph(oxb_ctx *c, int units, cudaGraphExec_t *out) {
 	e = cudaGraphInstantiate(&exec, graph, 0);
 	cudaGraphDestroy(graph);
 	if(e != cudaSuccess) return fail(c, 100 + (int) e, "graph instantiation failed: %s", cudaGetErrorString(e));
-	c->graphs.push_back({ units, c->cur, exec });
+	c->graphs.push_back({ units, c->cur, cfg, exec });
 	*out = exec;
 	return 0;
 }
@@ -645,15 +684,14 @@ int oxb_set_topology(oxb_ctx *c, const int *btype, const int *n3, const int *n5,
 int oxb_set_model_dna2(oxb_ctx *c, const oxb_dna2_params *P, double rcut) {
 	if(c == nullptr || P == nullptr) return 1;
 	c->model = *P;
-	drop_graphs(c);
-	bool rcut_changed = (rcut != c->rcut);
 	c->rcut = rcut;
 	c->have_model = true;
 	c->forces_valid = false;
-	if(rcut_changed) {
-		c->lists_valid = false;
-		if(c->lists_allocated) free_lists(c);
-	}
+	// Lists built for radii that are not smaller than the new model's stay valid for forces and energies (every pair inside
+	// the new cutoffs is listed, the kernels re-test the distances): a replica-exchange energy evaluation under the partner's
+	// colder Hamiltonian costs one force pass, no rebuild and no reallocation.  oxb_update_lists / oxb_get_pairs rebuild for
+	// the exact radius when it differs.
+	if(c->lists_valid && (rcut + 2. * c->skin > c->lists_rv || (double) P->dh_rc > c->lists_dh_rc)) c->lists_valid = false;
 	return 0;
 }
 
@@ -670,7 +708,6 @@ int oxb_set_lists(oxb_ctx *c, double verlet_skin, int use_edge, int sort_every, 
 int oxb_set_dt(oxb_ctx *c, double dt) {
 	if(c == nullptr) return 1;
 	c->dt = dt;
-	drop_graphs(c);
 	return 0;
 }
 
@@ -681,7 +718,6 @@ int oxb_set_thermostat(oxb_ctx *c, int type, int every, double a, double b, doub
 	c->th.type = type; c->th.every = every < 1 ? 1 : every;
 	c->th.a = (float) a; c->th.b = (float) b; c->th.c = (float) cc; c->th.d = (float) d; c->th.seed = seed;
 	c->bussi_init = false;
-	drop_graphs(c);
 	return 0;
 }
 
@@ -1032,6 +1068,7 @@ int oxb_get_pairs(oxb_ctx *c, int *pairs, long long max_pairs, long long *n_pair
 	if(c == nullptr || n_pairs == nullptr) return 1;
 	int rc = check_ready(c);
 	if(rc) return rc;
+	if(c->lists_valid && c->lists_rv != c->rcut + 2. * c->skin) c->lists_valid = false; // the pair set is defined by the exact radius
 	rc = ensure_lists(c);
 	if(rc) return rc;
 	const int N = c->N;
