@@ -89,7 +89,96 @@ def lattice_case(name, n_duplex, spacing, steps, T="300K", salt=0.5, seed=3, nve
     print("wrote", path, "N =", len(st0["pos"]), "U/N =", f0["U"] / len(st0["pos"]), "pairs =", len(base["pairs"]))
 
 
+SEQDEP_RNA = "/root/reference/rna_sequence_dependent_parameters.txt"
+
+
+def read_seq_dep_rna(path=SEQDEP_RNA):
+    vals = {}
+    for line in open(path):
+        if "=" in line:
+            k, v = line.split("=")
+            vals[k.strip()] = float(v)
+    B = "AGCT"
+    return dict(stck=np.array([vals[f"STCK_{a}_{b}"] for a in B for b in B]), cross=np.array([vals[f"CROSS_{a}_{b}"] for a in B for b in B]),
+                st_t_dep=vals["ST_T_DEP"], hb_AT=vals["HYDR_A_T"], hb_GC=vals["HYDR_C_G"], hb_GT=vals["HYDR_G_T"])
+
+
+def force_field_rna():
+    """test/RNA/FORCE_FIELD of the reference: the 16-nt configuration, its golden per-term energies, and the full CPU output."""
+    import shutil
+    src = "/root/reference/test/RNA/FORCE_FIELD"
+    dst = os.path.join(GOLD, "force_field_rna")
+    os.makedirs(dst, exist_ok=True)
+    for f in ("init.top", "init.dat"):
+        shutil.copy(os.path.join(src, f), os.path.join(dst, f))
+    shutil.copy(os.path.join(src, "AVG_SEQ", "reference.dat"), os.path.join(dst, "reference_avg_seq.dat"))
+    top, conf = os.path.join(dst, "init.top"), os.path.join(dst, "init.dat")
+    r = Reference(top, conf, interaction_type="RNA2", salt_concentration=1.0, T="20C")
+    dump(r, r.topology(), os.path.join(dst, "ref_rna2.npz"), dict(T="20C", salt=1.0))
+    r.close()
+    r = Reference(top, conf, interaction_type="RNA2", salt_concentration=1.0, T="20C", use_average_seq=0, seq_dep_file=SEQDEP_RNA)
+    sd = read_seq_dep_rna()
+    dump(r, r.topology(), os.path.join(dst, "ref_rna2_seqdep.npz"), dict(T="20C", salt=1.0, **{"sd_" + k: v for k, v in sd.items()}))
+    r.close()
+
+
+def rna_lattice_case(name, n_duplex, steps, T="300K", salt=0.5, seed=3, nve_steps=100, no_hb=False, seq_dep=False, mismatch=None):
+    """A-form RNA duplex lattice thermalised by the reference CPU backend (RNA2), then forces + an NVE segment from the
+    thermalised state.  no_hb: same state re-evaluated with an all-A sequence (no hydrogen bonding => no meshed term, so
+    forces and trajectories pin the restatement to rounding)."""
+    sysm = lattice.rna_duplex_lattice(n_duplex, bp=16, spacing=10.0, seed=seed)
+    d = tempfile.mkdtemp()
+    top, conf = os.path.join(d, "l.top"), os.path.join(d, "l.dat")
+    oio.write_topology(top, sysm["btype"], sysm["n3"], sysm["n5"], sysm["strand"])
+    from oxdna_b200.sim import parse_temperature
+    v, L = lattice.maxwell_velocities(len(sysm["pos"]), parse_temperature(T), 5)
+    oio.write_conf(conf, sysm["box"], sysm["pos"], sysm["a1"], sysm["a3"], v, L)
+    keys = dict(interaction_type="RNA2", salt_concentration=salt, T=T)
+    if seq_dep:
+        keys.update(use_average_seq=0, seq_dep_file=SEQDEP_RNA)
+    if mismatch is not None:
+        keys.update(mismatch_repulsion=1, mismatch_repulsion_strength=mismatch)
+    r = Reference(top, conf, thermostat="brownian", newtonian_steps=103, diff_coeff=2.5, seed=7, **keys)
+    r.step(steps)
+    st = r.state()
+    r.close()
+    if no_hb:
+        oio.write_topology(top, np.zeros_like(sysm["btype"]), sysm["n3"], sysm["n5"], sysm["strand"])
+    conf2 = os.path.join(d, "t.dat")
+    oio.write_conf(conf2, sysm["box"], st["pos"], st["a1"], st["a3"], st["vel"], st["L"])
+    r = Reference(top, conf2, thermostat="no", dt=0.003, **keys)
+    topo = r.topology()
+    st0 = r.state()
+    RH.lib().oxref_rebuild_lists()
+    f0 = r.compute_forces()
+    base = dict(pos=st0["pos"], a1=st0["a1"], a3=st0["a3"], vel=st0["vel"], L=st0["L"], box=r.box(), rcut=r.rcut(),
+                btype=topo["btype"], n3=topo["n3"], n5=topo["n5"], strand=topo["strand"], force=f0["force"],
+                torque_body=f0["torque_body"], torque_lab=f0["torque_lab"], U=f0["U"], energy_split=r.energy_split(), pairs=r.pairs(),
+                T=T, salt=salt, seq_dep=int(seq_dep), mismatch=-1.0 if mismatch is None else float(mismatch))
+    if seq_dep:
+        base.update({"sd_" + k: v for k, v in read_seq_dep_rna().items()})
+    r.step(nve_steps)
+    st1 = r.state()
+    base.update(nve_steps=nve_steps, pos1=st1["pos"], a11=st1["a1"], a31=st1["a3"], vel1=st1["vel"], L1=st1["L"],
+                U1=r.system_energy(), n_updates=r.n_updates())
+    r.close()
+    path = os.path.join(GOLD, name + ".npz")
+    np.savez_compressed(path, **base)
+    print("wrote", path, "N =", len(st0["pos"]), "U/N =", f0["U"] / len(st0["pos"]), "pairs =", len(base["pairs"]),
+          "terms/N", np.round(base["energy_split"] / len(st0["pos"]), 4))
+
+
+def rna():
+    force_field_rna()
+    rna_lattice_case("rna_lattice8", 8, 3000)
+    rna_lattice_case("rna_lattice8_nohb", 8, 3000, no_hb=True)
+    rna_lattice_case("rna_lattice8_seqdep", 8, 3000, T="310K", salt=1.0, seq_dep=True, mismatch=1.0)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "rna":
+        rna()
+        sys.exit(0)
     force_field()
     lattice_case("lattice8", 8, 10.0, 3000)
     lattice_case("lattice27_dense", 27, 8.5, 4000, T="330K")

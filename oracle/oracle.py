@@ -10,7 +10,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "liboxoracle.so")
 _SRC = [os.path.join(_HERE, "oxdna_oracle.c")]
-_HDR = [os.path.join(_HERE, "oxdna_oracle.h")]
+_HDR = [os.path.join(_HERE, "oxdna_oracle.h"), os.path.join(_HERE, "oxrna_oracle.inc")]
 
 NTERMS = 8
 TERM_NAMES = ["FENE", "BEXC", "STCK", "NEXC", "HB", "CRSTCK", "CXSTCK", "DH"]
@@ -57,6 +57,24 @@ class DNA2Params(C.Structure):
         + [("cxst_t1_sa", C.c_double), ("cxst_t1_sb", C.c_double), ("stck_phi1", _F5), ("stck_phi2", _F5)]
         + [(n, C.c_double) for n in "dh_minus_kappa dh_prefactor dh_rhigh dh_rc dh_b".split()]
         + [("dh_half_charged_ends", C.c_int), ("hb_multiplier", C.c_double), ("rcut", C.c_double)]
+    )
+
+
+class RNA2Params(C.Structure):
+    _fields_ = (
+        [("back", C.c_double * 3), ("stack_a1", C.c_double), ("base_a1", C.c_double), ("stack3", C.c_double * 2),
+         ("stack5", C.c_double * 2), ("p3", C.c_double * 3), ("p5", C.c_double * 3)]
+        + [(n, C.c_double) for n in "T fene_eps fene_r0 fene_delta fene_delta2".split()]
+        + [("use_mbf", C.c_int)]
+        + [(n, C.c_double) for n in "mbf_xmax mbf_fmax mbf_finf".split()]
+        + [("excl", _Excl * 4), ("excl_eps", C.c_double), ("hb", _F1), ("stck", _F1), ("crst", _F2), ("cxst", _F2),
+           ("crst_kfac", (C.c_double * 5) * 5)]
+        + [(n, _F4) for n in ("stck_t5 stck_t6 stck_tb1 stck_tb2 hb_t1 hb_t2 hb_t3 hb_t4 hb_t7 hb_t8 crst_t1 crst_t2 crst_t3 crst_t7 "
+                              "crst_t8 cxst_t1 cxst_t4 cxst_t5 cxst_t6").split()]
+        + [(n, _F5) for n in "stck_phi1 stck_phi2 cxst_phi3 cxst_phi4".split()]
+        + [(n, C.c_double) for n in "dh_minus_kappa dh_prefactor dh_rhigh dh_rc dh_b".split()]
+        + [("dh_half_charged_ends", C.c_int), ("average", C.c_int), ("mismatch_repulsion", C.c_int), ("mis_eps", C.c_double),
+           ("mis_shift", C.c_double), ("cpu_quirks", C.c_int), ("rcut", C.c_double)]
     )
 
 
@@ -121,6 +139,26 @@ def dna2_params_seqdep(P, stck16, stck_fact_eps, hb_AT, hb_GC):
     return P
 
 
+def rna2_params(T, salt=1.0, dh_half_charged_ends=True, max_backbone_force=None, max_backbone_force_far=0.04,
+                mismatch_repulsion=False, mismatch_repulsion_strength=1.0, cpu_quirks=False):
+    """oxRNA2 parameters.  cpu_quirks=True reproduces the two spots where the reference CPU class's force is not the gradient
+    of its energy (see oxdna_oracle.h); the reference's CUDA kernels -- and ours -- use the gradient."""
+    P = RNA2Params()
+    mbf = max_backbone_force is not None
+    lib().oxo_rna2_params_init(C.byref(P), C.c_double(T), C.c_double(salt), int(dh_half_charged_ends), int(mbf),
+                               C.c_double(max_backbone_force if mbf else 0.0),
+                               C.c_double(float(np.float32(max_backbone_force_far))), int(mismatch_repulsion),
+                               C.c_double(mismatch_repulsion_strength))
+    P.cpu_quirks = int(cpu_quirks)
+    return P
+
+
+def rna2_params_seqdep(P, stck16, st_t_dep, cross16, hb_AT, hb_GC, hb_GT):
+    s, c = _d(stck16).reshape(16), _d(cross16).reshape(16)
+    lib().oxo_rna2_params_seqdep(C.byref(P), _p(s), C.c_double(st_t_dep), _p(c), C.c_double(hb_AT), C.c_double(hb_GC), C.c_double(hb_GT))
+    return P
+
+
 def axes_from_a1a3(a1, a3):
     a1, a3 = _d(a1), _d(a3)
     N = a1.shape[0]
@@ -147,7 +185,8 @@ def forces(P, pos, axes, btype, n3, n5, box, pairs):
     N = pos.shape[0]
     f, tl, tb = np.zeros((N, 3)), np.zeros((N, 3)), np.zeros((N, 3))
     et, ep = np.zeros(NTERMS), np.zeros(N)
-    lib().oxo_dna2_forces(C.byref(P), N, _p(pos), _p(axes), _p(btype), _p(n3), _p(n5), _p(box), _p(pairs),
+    fn = lib().oxo_rna2_forces if isinstance(P, RNA2Params) else lib().oxo_dna2_forces
+    fn(C.byref(P), N, _p(pos), _p(axes), _p(btype), _p(n3), _p(n5), _p(box), _p(pairs),
                           C.c_longlong(pairs.shape[0]), _p(f), _p(tl), _p(tb), _p(et), _p(ep))
     return dict(force=f, torque_lab=tl, torque_body=tb, eterms=et, epart=ep, U=et.sum())
 
@@ -204,10 +243,12 @@ class MD:
         self.pairs[: len(p)] = p
         S.npairs = len(p)
         self.list_pos[:] = self.pos
-        lib().oxo_md_compute_forces(C.byref(P), C.byref(S))
+        rna = isinstance(P, RNA2Params)
+        self._steps = lib().oxo_rna2_md_steps if rna else lib().oxo_md_steps
+        (lib().oxo_rna2_md_compute_forces if rna else lib().oxo_md_compute_forces)(C.byref(P), C.byref(S))
 
     def step(self, n=1):
-        return lib().oxo_md_steps(C.byref(self.P), C.byref(self.S), int(n))
+        return self._steps(C.byref(self.P), C.byref(self.S), int(n))
 
     @property
     def U(self):

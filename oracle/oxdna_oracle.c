@@ -623,10 +623,18 @@ void oxo_axes_from_a1a3(int N, const double *a1, const double *a3, double *axes)
 }
 
 /* ------------------------------------------------------------------ MD step */
-void oxo_md_compute_forces(const oxo_dna2_params *P, oxo_md *S) {
+typedef void (*forces_cb)(const void *P, int N, const double *pos, const double *axes, const int *btype, const int *n3, const int *n5,
+		const double *box, const int *pairs, long long npairs, double *force, double *tl, double *et);
+
+static void dna_forces_cb(const void *P, int N, const double *pos, const double *axes, const int *btype, const int *n3, const int *n5,
+		const double *box, const int *pairs, long long npairs, double *force, double *tl, double *et) {
+	oxo_dna2_forces((const oxo_dna2_params *) P, N, pos, axes, btype, n3, n5, box, pairs, npairs, force, tl, NULL, et, NULL);
+}
+
+static void md_compute_forces_generic(const void *P, forces_cb cb, oxo_md *S) {
 	double et[OXO_NTERMS];
 	double *tl = (double *) calloc(3 * (size_t) S->N, sizeof(double));
-	oxo_dna2_forces(P, S->N, S->pos, S->axes, S->btype, S->n3, S->n5, S->box, S->pairs, S->npairs, S->force, tl, NULL, et, NULL);
+	cb(P, S->N, S->pos, S->axes, S->btype, S->n3, S->n5, S->box, S->pairs, S->npairs, S->force, tl, et);
 	/* external forces enter before the interactions in the reference (MD_CPUBackend.cpp:149-153); addition commutes */
 	if(S->nf > 0) oxo_ext_forces(S->nf, S->ef, S->N, S->pos, S->box, S->step, S->force);
 	for(int i = 0; i < S->N; i++) {
@@ -638,12 +646,14 @@ void oxo_md_compute_forces(const oxo_dna2_params *P, oxo_md *S) {
 	free(tl);
 }
 
-static void rebuild(const oxo_dna2_params *P, oxo_md *S) {
-	S->npairs = oxo_verlet_pairs(S->N, S->pos, S->n3, S->n5, S->box, P->rcut + 2 * S->skin, S->pairs, S->max_pairs);
+void oxo_md_compute_forces(const oxo_dna2_params *P, oxo_md *S) { md_compute_forces_generic(P, dna_forces_cb, S); }
+
+static void rebuild(double rcut, oxo_md *S) {
+	S->npairs = oxo_verlet_pairs(S->N, S->pos, S->n3, S->n5, S->box, rcut + 2 * S->skin, S->pairs, S->max_pairs);
 	memcpy(S->list_pos, S->pos, 3 * (size_t) S->N * sizeof(double));
 }
 
-int oxo_md_steps(const oxo_dna2_params *P, oxo_md *S, int nsteps) {
+static int md_steps_generic(const void *P, double rcut, forces_cb cb, oxo_md *S, int nsteps) {
 	int rebuilds = 0;
 	const double dt = S->dt;
 	for(int it = 0; it < nsteps; it++) {
@@ -668,8 +678,8 @@ int oxo_md_steps(const oxo_dna2_params *P, oxo_md *S, int nsteps) {
 			double d[3] = { x[0] - S->list_pos[3 * i], x[1] - S->list_pos[3 * i + 1], x[2] - S->list_pos[3 * i + 2] };
 			if(dot3(d, d) > SQ(S->skin)) stale = 1;
 		}
-		if(stale) { rebuild(P, S); rebuilds++; }
-		oxo_md_compute_forces(P, S);
+		if(stale) { rebuild(rcut, S); rebuilds++; }
+		md_compute_forces_generic(P, cb, S);
 		for(int i = 0; i < S->N; i++) for(int k = 0; k < 3; k++) {
 			S->vel[3 * i + k] += S->force[3 * i + k] * dt * 0.5;
 			S->L[3 * i + k] += S->torque_body[3 * i + k] * dt * 0.5;
@@ -678,6 +688,8 @@ int oxo_md_steps(const oxo_dna2_params *P, oxo_md *S, int nsteps) {
 	}
 	return rebuilds;
 }
+
+int oxo_md_steps(const oxo_dna2_params *P, oxo_md *S, int nsteps) { return md_steps_generic(P, P->rcut, dna_forces_cb, S, nsteps); }
 
 /* ------------------------------------------------------------------ thermostat parameters */
 void oxo_brownian_params(double T, double dt_in, int ns, double pt_in, double diff_coeff, double *pt, double *pr, double *rescale) {
@@ -699,3 +711,5 @@ void oxo_langevin_params(double T, double dt, double gamma_in, double diff_in, d
 	*rt = sqrt(2. * g * T / dt);
 	*rr = sqrt(2. * (*gr) * T / dt);
 }
+
+#include "oxrna_oracle.inc"

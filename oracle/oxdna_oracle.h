@@ -1,5 +1,5 @@
 /* TEST INFRASTRUCTURE ONLY -- CPU restatement (plain C, double precision) of the reference's algorithm for
- * the oxDNA2 MD step.  Used only by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg as the
+ * the oxDNA2 / oxRNA2 MD step.  Used only by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg as the
  * checker; the product (oxdna_b200/) never includes, links or calls anything in this directory.
  *
  * Pinning: validated against (i) the reference's golden vector test/DNA/FORCE_FIELD/AVG_SEQ/reference.dat
@@ -92,6 +92,46 @@ typedef struct {
 } oxo_md;
 int oxo_md_steps(const oxo_dna2_params *P, oxo_md *S, int nsteps);
 void oxo_md_compute_forces(const oxo_dna2_params *P, oxo_md *S);
+
+/* ------------------------------------------------------------------ oxRNA2 (src/Interactions/RNAInteraction.cpp, RNAInteraction2.cpp, rna_model.h) */
+typedef struct {
+	/* sites, src/Particles/RNANucleotide.h:27-52: BACK = back[0] a1 + back[1] a2 + back[2] a3; STACK = stack_a1 a1; BASE = base_a1 a1;
+	 * STACK_3 / STACK_5 = (a1, a2) coefficients; BBVECTOR_3 / _5 = p3 / p5 on (a1, a2, a3) */
+	double back[3], stack_a1, base_a1, stack3[2], stack5[2], p3[3], p5[3];
+	double T;
+	double fene_eps, fene_r0, fene_delta, fene_delta2;
+	int use_mbf;
+	double mbf_xmax, mbf_fmax, mbf_finf;
+	oxo_excl excl[4]; /* 0: back-back, 1: base-base, 2: base(p)-back(q), 3: back(p)-base(q) */
+	double excl_eps;
+	oxo_f1 hb, stck;
+	oxo_f2 crst, cxst;
+	double crst_kfac[5][5]; /* sequence-dependent cross-stacking multiplier [type p][type q], RNAInteraction.cpp:365-372,901-905 */
+	oxo_f4 stck_t5, stck_t6, stck_tb1, stck_tb2, hb_t1, hb_t2, hb_t3, hb_t4, hb_t7, hb_t8, crst_t1, crst_t2, crst_t3, crst_t7, crst_t8,
+		cxst_t1, cxst_t4, cxst_t5, cxst_t6;
+	oxo_f5 stck_phi1, stck_phi2, cxst_phi3, cxst_phi4;
+	double dh_minus_kappa, dh_prefactor, dh_rhigh, dh_rc, dh_b;
+	int dh_half_charged_ends;
+	int average;            /* use_average_seq: G-U wobble pairs exist only when 0 */
+	int mismatch_repulsion; /* RNAInteraction2.cpp:43-55,96-101 */
+	double mis_eps, mis_shift;
+	/* 1: reproduce two places where the CPU class's force is NOT the gradient of its energy (the reference's CUDA kernels
+	 * use the gradient): the phi2 stacking term lacks the thetaB1/B2 factors (RNAInteraction.cpp:620) and the mirrored
+	 * coaxial theta1 term has the opposite sign (RNAInteraction.cpp:1046 vs :1302 and CUDA_RNA.cuh:896).  0: gradient. */
+	int cpu_quirks;
+	double rcut;
+} oxo_rna2_params;
+
+void oxo_rna2_params_init(oxo_rna2_params *P, double T, double salt, int dh_half_charged_ends, int use_mbf, double mbf_fmax,
+		double mbf_finf, int mismatch_repulsion, double mismatch_strength);
+/* sequence-dependent strengths (RNAInteraction.cpp:345-391): stck_raw16 / cross_raw16 = STCK_X_Y / CROSS_X_Y (order A, G, C, T=U) */
+void oxo_rna2_params_seqdep(oxo_rna2_params *P, const double *stck_raw16, double st_t_dep, const double *cross_raw16, double hb_AT,
+		double hb_GC, double hb_GT);
+void oxo_rna2_forces(const oxo_rna2_params *P, int N, const double *pos, const double *axes, const int *btype,
+		const int *n3, const int *n5, const double *box, const int *pairs, long long npairs,
+		double *force, double *torque_lab, double *torque_body, double *eterms, double *epart);
+int oxo_rna2_md_steps(const oxo_rna2_params *P, oxo_md *S, int nsteps);
+void oxo_rna2_md_compute_forces(const oxo_rna2_params *P, oxo_md *S);
 
 /* thermostat parameter derivation (src/Backends/Thermostats/{Brownian,Langevin,Bussi}Thermostat.cpp) */
 void oxo_brownian_params(double T, double dt, int newtonian_steps, double pt_in, double diff_coeff, double *pt, double *pr, double *rescale);

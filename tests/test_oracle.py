@@ -110,3 +110,141 @@ def test_oracle_matches_live_reference_after_perturbation(tmp_path):
             assert abs(out["U"] - ref["U"]) < 1e-9 * max(1.0, abs(ref["U"]))
     finally:
         r.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------- oxRNA2
+def _rna_params(g, cpu_quirks=True):
+    mis = float(g["mismatch"]) if "mismatch" in g else -1.0
+    P = O.rna2_params(parse_temperature(str(g["T"])), float(g["salt"]), cpu_quirks=cpu_quirks, mismatch_repulsion=mis >= 0,
+                      mismatch_repulsion_strength=max(mis, 0.0))
+    if "sd_stck" in g:
+        O.rna2_params_seqdep(P, g["sd_stck"], float(g["sd_st_t_dep"]), g["sd_cross"], float(g["sd_hb_AT"]), float(g["sd_hb_GC"]), float(g["sd_hb_GT"]))
+    return P
+
+
+def test_rna_reference_golden_vector_file(which="avg_seq"):
+    """test/RNA/FORCE_FIELD/AVG_SEQ/reference.dat of the reference: per-term energies per nucleotide (6 decimals).  (The
+    reference's SEQ_DEP test sets use_average_seq = true and holds the same numbers; the sequence-dependent tables are
+    pinned by the ref_rna2_seqdep fixture below.)  The CPU class meshes the hydrogen-bonding f4 factors; the analytic form
+    (what the CUDA kernels evaluate) differs from it in the 6th digit of that term only."""
+    d = os.path.join(GOLD, "force_field_rna")
+    ref = np.loadtxt(os.path.join(d, f"reference_{which}.dat"))
+    g = load_golden("force_field_rna/ref_rna2" + ("_seqdep" if which == "seq_dep" else ""))
+    t = oio.read_topology(os.path.join(d, "init.top"))
+    c = oio.read_conf(os.path.join(d, "init.dat"))
+    for k in ("btype", "n3", "n5"):
+        assert (t[k] == g[k]).all()
+    P = _rna_params(g)
+    ax = O.axes_from_a1a3(c["a1"], c["a3"])
+    pairs = O.verlet_pairs(c["pos"], t["n3"], t["n5"], c["box"], P.rcut + 0.1)
+    out = O.forces(P, c["pos"], ax, t["btype"], t["n3"], t["n5"], c["box"], pairs)
+    assert np.allclose(out["eterms"] / t["N"], ref, atol=2.5e-6), (out["eterms"] / t["N"], ref)
+
+
+@pytest.mark.parametrize("case", ["force_field_rna/ref_rna2", "force_field_rna/ref_rna2_seqdep", "rna_lattice8", "rna_lattice8_nohb", "rna_lattice8_seqdep"])
+def test_rna_oracle_matches_reference_fixture(case):
+    """Fixtures written by the unmodified reference CPU backend (interaction_type = RNA2).  Everything but the meshed
+    hydrogen-bonding term agrees to rounding (cpu_quirks: see oxdna_oracle.h); that term agrees to mesh accuracy."""
+    g = load_golden(case)
+    P = _rna_params(g)
+    assert P.rcut == float(g["rcut"])
+    ax = O.axes_from_a1a3(g["a1"], g["a3"])
+    pairs = O.verlet_pairs(g["pos"], g["n3"], g["n5"], g["box"], P.rcut + 2 * 0.05)
+    assert pair_set(pairs) == pair_set(g["pairs"])
+    out = O.forces(P, g["pos"], ax, g["btype"], g["n3"], g["n5"], g["box"], pairs)
+    d = out["eterms"] - g["energy_split"]
+    hb = 4
+    assert np.abs(np.delete(d, hb)).max() < 1e-10
+    has_hb = abs(g["energy_split"][hb]) > 0
+    # the mesh derivative is the least accurate part of the CPU class; mismatched pairs sit anywhere in the angular windows
+    # (also on the coarse ends of the meshes), Watson-Crick pairs near the well centres
+    tol = (2e-3 if float(g.get("mismatch", -1.0)) >= 0 else 1e-4) if has_hb else 1e-9
+    assert abs(d[hb]) <= 1e-4 * abs(g["energy_split"][hb])
+    for k in ("force", "torque_lab", "torque_body"):
+        assert np.abs(out[k] - g[k]).max() < tol * max(1.0, np.abs(g[k]).max()), k
+
+
+def test_rna_oracle_nve_matches_reference_fixture():
+    g = load_golden("rna_lattice8_nohb")
+    P = _rna_params(g)
+    md = O.MD(P, g["pos"], O.axes_from_a1a3(g["a1"], g["a3"]), g["vel"], g["L"], g["btype"], g["n3"], g["n5"], g["box"], 0.003, 0.05)
+    md.step(int(g["nve_steps"]))
+    assert np.abs(md.pos - g["pos1"]).max() < 1e-9
+    assert np.abs(md.vel - g["vel1"]).max() < 1e-9
+    assert np.abs(md.L - g["L1"]).max() < 1e-9
+    assert np.abs(md.axes[:, 0:3] - g["a11"]).max() < 1e-9
+
+
+def _rotate(ax9, axis, angle):
+    """rigid rotation of one particle's axes about a lab-frame axis"""
+    k = axis / np.linalg.norm(axis)
+    K = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    R = np.eye(3) + np.sin(angle) * K + (1 - np.cos(angle)) * K @ K
+    return (ax9.reshape(3, 3) @ R.T).reshape(9)
+
+
+@pytest.mark.parametrize("model", ["rna", "dna"])
+def test_oracle_gradient_form_is_the_gradient(model):
+    """With cpu_quirks = 0 the restated force and torque ARE minus the gradient of the restated energy (central differences).
+    This is the form the CUDA kernels are held to (the reference's own CUDA kernels use the gradient as well)."""
+    rng = np.random.default_rng(5)
+    if model == "rna":
+        g = load_golden("rna_lattice8_seqdep")
+        P = _rna_params(g, cpu_quirks=False)
+    else:
+        g = load_golden("lattice8")
+        P = _params(g)
+    pos = g["pos"] + rng.normal(scale=0.03, size=g["pos"].shape)
+    ax = O.axes_from_a1a3(g["a1"] + rng.normal(scale=0.1, size=g["a1"].shape), g["a3"] + rng.normal(scale=0.1, size=g["a3"].shape))
+    pairs = O.verlet_pairs(pos, g["n3"], g["n5"], g["box"], P.rcut + 0.2)
+    args = (g["btype"], g["n3"], g["n5"], g["box"], pairs)
+    out = O.forces(P, pos, ax, *args)
+    h = 1e-6
+    worst_f = worst_t = 0.0
+    for i in rng.choice(len(pos), size=24, replace=False):
+        for k in range(3):
+            e = np.zeros(3)
+            e[k] = 1.0
+            pp, pm = pos.copy(), pos.copy()
+            pp[i] += h * e
+            pm[i] -= h * e
+            fd = -(O.forces(P, pp, ax, *args)["U"] - O.forces(P, pm, ax, *args)["U"]) / (2 * h)
+            worst_f = max(worst_f, abs(fd - out["force"][i, k]))
+            ap, am = ax.copy(), ax.copy()
+            ap[i] = _rotate(ax[i], e, h)
+            am[i] = _rotate(ax[i], e, -h)
+            td = -(O.forces(P, pos, ap, *args)["U"] - O.forces(P, pos, am, *args)["U"]) / (2 * h)
+            worst_t = max(worst_t, abs(td - out["torque_lab"][i, k]))
+    scale = max(1.0, np.abs(out["force"]).max())
+    assert worst_f < 2e-6 * scale and worst_t < 2e-6 * scale, (worst_f, worst_t, scale)
+
+
+@pytest.mark.skipif(not RH.available(), reason="oracle/_ref not built (needs /root/reference)")
+def test_rna_oracle_matches_live_reference_without_meshed_term(tmp_path):
+    """All-A sequence (no hydrogen bonding, hence no meshed factor): 60 strongly perturbed configurations of the reference's
+    16-nt RNA test system, restatement (cpu_quirks = 1) against the live reference CPU class to rounding."""
+    rng = np.random.default_rng(1)
+    top = str(tmp_path / "aaaa.top")
+    with open(top, "w") as f:
+        f.write("16 3 5->3\nAAAA circular=False type=RNA\nAAAA circular=False type=RNA\nAAAAAAAA circular=False type=RNA\n")
+    conf = os.path.join(GOLD, "force_field_rna", "init.dat")
+    r = RH.Reference(top, conf, interaction_type="RNA2", salt_concentration=0.3, T="37C")
+    try:
+        st, topo = r.state(), r.topology()
+        P = O.rna2_params(O.celsius(37.0), 0.3, cpu_quirks=True)
+        assert P.rcut == r.rcut()
+        worst = 0.0
+        for it in range(60):
+            sc = 0.05 * (it % 8)
+            pos = st["pos"] + rng.normal(scale=sc / 2, size=st["pos"].shape)
+            ax = O.axes_from_a1a3(st["a1"] + rng.normal(scale=sc, size=st["a1"].shape), st["a3"] + rng.normal(scale=sc, size=st["a3"].shape))
+            r.set_state(pos, ax[:, 0:3], ax[:, 6:9])
+            ref, es = r.compute_forces(), r.energy_split()
+            pairs = O.verlet_pairs(pos, topo["n3"], topo["n5"], r.box(), P.rcut + 0.1)
+            out = O.forces(P, pos, ax, topo["btype"], topo["n3"], topo["n5"], r.box(), pairs)
+            worst = max(worst, np.abs(out["eterms"] - es).max() / max(1.0, np.abs(es).max()))
+            for k in ("force", "torque_lab", "torque_body"):
+                worst = max(worst, np.abs(out[k] - ref[k]).max() / max(1.0, np.abs(ref[k]).max()))
+        assert worst < 1e-10, worst
+    finally:
+        r.close()
