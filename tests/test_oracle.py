@@ -158,7 +158,8 @@ def test_rna_oracle_matches_reference_fixture(case):
     has_hb = abs(g["energy_split"][hb]) > 0
     # the mesh derivative is the least accurate part of the CPU class; mismatched pairs sit anywhere in the angular windows
     # (also on the coarse ends of the meshes), Watson-Crick pairs near the well centres
-    tol = (2e-3 if float(g.get("mismatch", -1.0)) >= 0 else 1e-4) if has_hb else 1e-9
+    # (6- and 12-point meshes, rna_model.h:1124-1129)
+    tol = (5e-3 if float(g.get("mismatch", -1.0)) >= 0 else 1e-4) if has_hb else 1e-9
     assert abs(d[hb]) <= 1e-4 * abs(g["energy_split"][hb])
     for k in ("force", "torque_lab", "torque_body"):
         assert np.abs(out[k] - g[k]).max() < tol * max(1.0, np.abs(g[k]).max()), k
