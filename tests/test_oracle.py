@@ -195,8 +195,8 @@ def test_oracle_gradient_form_is_the_gradient(model):
     else:
         g = load_golden("lattice8")
         P = _params(g)
-    pos = g["pos"] + rng.normal(scale=0.03, size=g["pos"].shape)
-    ax = O.axes_from_a1a3(g["a1"] + rng.normal(scale=0.1, size=g["a1"].shape), g["a3"] + rng.normal(scale=0.1, size=g["a3"].shape))
+    pos = g["pos"] + rng.normal(scale=0.01, size=g["pos"].shape)
+    ax = O.axes_from_a1a3(g["a1"] + rng.normal(scale=0.05, size=g["a1"].shape), g["a3"] + rng.normal(scale=0.05, size=g["a3"].shape))
     pairs = O.verlet_pairs(pos, g["n3"], g["n5"], g["box"], P.rcut + 0.2)
     args = (g["btype"], g["n3"], g["n5"], g["box"], pairs)
     out = O.forces(P, pos, ax, *args)
