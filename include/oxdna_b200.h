@@ -64,6 +64,50 @@ int oxb_dna2_params_init(oxb_dna2_params *P, double T, double salt_concentration
  * stck_raw[4][4] are the STCK_X_Y entries of the parameter file (order A, G, C, T). */
 int oxb_dna2_params_seqdep(oxb_dna2_params *P, double T, const double *stck_raw16, double stck_fact_eps, double hb_AT, double hb_GC);
 
+/* ---- oxRNA2 parameter block.  Replaces the `CUDAModel rnamodel` constant upload of
+ * src/CUDA/Interactions/CUDARNAInteraction.cu:43-230,278-385 (values from src/Interactions/rna_model.h through the CPU
+ * RNA2Interaction).  Same table conventions as the DNA block; every angular factor keeps its own entry because the
+ * reference's `external_model` file may set theta2/theta3, theta7/theta8, theta5/theta6 independently. */
+enum { OXB_RF4_STCK_T5 = 0, OXB_RF4_STCK_T6, OXB_RF4_STCK_TB1, OXB_RF4_STCK_TB2, OXB_RF4_HB_T1, OXB_RF4_HB_T2, OXB_RF4_HB_T3,
+	OXB_RF4_HB_T4, OXB_RF4_HB_T7, OXB_RF4_HB_T8, OXB_RF4_CRST_T1, OXB_RF4_CRST_T2, OXB_RF4_CRST_T3, OXB_RF4_CRST_T7, OXB_RF4_CRST_T8,
+	OXB_RF4_CXST_T1, OXB_RF4_CXST_T4, OXB_RF4_CXST_T5, OXB_RF4_CXST_T6, OXB_NRF4 };
+
+typedef struct {
+	/* sites (src/Particles/RNANucleotide.h:27-52): BACK = back_a1 a1 + back_a2 a2 + back_a3 a3, STACK = stack_a1 a1,
+	 * BASE = base_a1 a1, STACK_3 / STACK_5 on (a1, a2), backbone-direction unit vectors p3 / p5 on (a1, a2, a3) */
+	float back_a1, back_a2, back_a3, stack_a1, base_a1;
+	float stack3_a1, stack3_a2, stack5_a1, stack5_a2;
+	float p3[3], p5[3];
+	float fene_eps, fene_r0, fene_delta, fene_delta2;
+	int use_mbf;
+	float mbf_xmax, mbf_fmax, mbf_finf, mbf_e0;
+	float excl_eps;
+	oxb_excl excl[4]; /* back-back, base-base, base(p)-back(q), back(p)-base(q) */
+	oxb_f1 hb, stck;
+	float hb_eps[25], hb_shift[25], stck_eps[25], stck_shift[25]; /* [type_n3 * 5 + type_n5] */
+	oxb_f2 crst, cxst;
+	float crst_kfac[25]; /* sequence-dependent cross-stacking multiplier [type_p * 5 + type_q] (1 for the average model) */
+	oxb_f4 f4[OXB_NRF4];
+	float f4_cmin[OXB_NRF4], f4_cmax[OXB_NRF4];
+	oxb_f5 phi1, phi2, phi3, phi4;
+	float dh_minus_kappa, dh_prefactor, dh_rhigh, dh_rc, dh_b;
+	int dh_half_charged_ends;
+	int average;            /* use_average_seq: G-U wobble pairs hydrogen-bond only when 0 */
+	int mismatch_repulsion; /* src/Interactions/RNAInteraction2.cpp:43-55,96-101 */
+	float mis_eps, mis_shift;
+	float hb_multiplier;
+	float rcut, rcut_near;
+} oxb_rna2_params;
+
+/* RNA2Interaction::get_settings/init (src/Interactions/RNAInteraction.cpp:60-397, RNAInteraction2.cpp:31-102) */
+int oxb_rna2_params_init(oxb_rna2_params *P, double T, double salt_concentration, int dh_half_charged_ends,
+		int use_max_backbone_force, double max_backbone_force, double max_backbone_force_far, int mismatch_repulsion,
+		double mismatch_repulsion_strength, double *rcut_out);
+/* rna_sequence_dependent_parameters.txt (RNAInteraction.cpp:345-391): STCK_X_Y, ST_T_DEP, CROSS_X_Y, HYDR_A_T, HYDR_C_G,
+ * HYDR_G_T; 4 x 4 tables in the order A, G, C, U.  Clears `average`. */
+int oxb_rna2_params_seqdep(oxb_rna2_params *P, double T, const double *stck_raw16, double st_t_dep, const double *cross_raw16,
+		double hb_AT, double hb_GC, double hb_GT);
+
 typedef struct {
 	int type;      /* OXB_EXT_* */
 	int particle;  /* original index */
@@ -84,6 +128,7 @@ int oxb_set_stream(oxb_ctx *ctx, void *cuda_stream);
 int oxb_set_box(oxb_ctx *ctx, const double box[3]);                                           /* CUDABox, src/CUDA/cuda_utils/CUDABox.h */
 int oxb_set_topology(oxb_ctx *ctx, const int *btype, const int *n3, const int *n5, const int *strand);
 int oxb_set_model_dna2(oxb_ctx *ctx, const oxb_dna2_params *P, double rcut);                  /* CUDADNAInteraction::cuda_init */
+int oxb_set_model_rna2(oxb_ctx *ctx, const oxb_rna2_params *P, double rcut);                  /* CUDARNAInteraction::cuda_init */
 /* CUDASimpleVerletList::get_settings/init (src/CUDA/Lists/CUDASimpleVerletList.cu:47-56,165-202) + CUDA_sort_every, use_edge */
 int oxb_set_lists(oxb_ctx *ctx, double verlet_skin, int use_edge, int sort_every, double max_density_multiplier);
 int oxb_set_dt(oxb_ctx *ctx, double dt);

@@ -51,12 +51,32 @@ class DNA2Params(C.Structure):
     )
 
 
+NRF4 = 19
+
+
+class RNA2Params(C.Structure):
+    _fields_ = (
+        [(n, C.c_float) for n in "back_a1 back_a2 back_a3 stack_a1 base_a1 stack3_a1 stack3_a2 stack5_a1 stack5_a2".split()]
+        + [("p3", C.c_float * 3), ("p5", C.c_float * 3)]
+        + [(n, C.c_float) for n in "fene_eps fene_r0 fene_delta fene_delta2".split()]
+        + [("use_mbf", C.c_int)]
+        + [(n, C.c_float) for n in "mbf_xmax mbf_fmax mbf_finf mbf_e0 excl_eps".split()]
+        + [("excl", Excl * 4), ("hb", F1), ("stck", F1)]
+        + [(n, C.c_float * 25) for n in "hb_eps hb_shift stck_eps stck_shift".split()]
+        + [("crst", F2), ("cxst", F2), ("crst_kfac", C.c_float * 25), ("f4", F4 * NRF4), ("f4_cmin", C.c_float * NRF4), ("f4_cmax", C.c_float * NRF4)]
+        + [(n, F5) for n in "phi1 phi2 phi3 phi4".split()]
+        + [(n, C.c_float) for n in "dh_minus_kappa dh_prefactor dh_rhigh dh_rc dh_b".split()]
+        + [("dh_half_charged_ends", C.c_int), ("average", C.c_int), ("mismatch_repulsion", C.c_int), ("mis_eps", C.c_float),
+           ("mis_shift", C.c_float), ("hb_multiplier", C.c_float), ("rcut", C.c_float), ("rcut_near", C.c_float)]
+    )
+
+
 class ExtForce(C.Structure):
     _fields_ = [("type", C.c_int), ("particle", C.c_int), ("ref", C.c_int), ("pbc", C.c_int)] + [
         (n, C.c_double) for n in "stiff r0 rate stiff_rate F0".split()] + [("dir", C.c_double * 3), ("pos0", C.c_double * 3)]
 
 
-EXPORTED = """oxb_dna2_params_init oxb_dna2_params_seqdep oxb_create oxb_destroy oxb_last_error oxb_set_stream oxb_set_box
+EXPORTED = """oxb_dna2_params_init oxb_dna2_params_seqdep oxb_rna2_params_init oxb_rna2_params_seqdep oxb_set_model_rna2 oxb_create oxb_destroy oxb_last_error oxb_set_stream oxb_set_box
 oxb_set_topology oxb_set_model_dna2 oxb_set_lists oxb_set_dt oxb_set_thermostat oxb_set_ext_forces oxb_set_state oxb_get_state
 oxb_set_step oxb_get_step oxb_sort oxb_update_lists oxb_compute_forces oxb_first_step oxb_second_step oxb_thermostat oxb_run
 oxb_synchronize oxb_get_forces oxb_energy oxb_get_pairs oxb_get_stats oxb_device_views oxb_launch_count oxb_time_kernel""".split()
@@ -109,6 +129,36 @@ def dna2_params(T, salt=0.5, dh_half_charged_ends=True, max_backbone_force=None,
     return P, rc.value
 
 
+def dna2_params_seqdep(P, T, stck16, stck_fact_eps, hb_AT, hb_GC):
+    """oxb_dna2_params_seqdep: STCK_X_Y table (A, G, C, T order), STCK_FACT_EPS, HYDR_A_T, HYDR_C_G of oxDNA2_sequence_dependent_parameters.txt."""
+    s = _d(np.asarray(stck16).reshape(16))
+    if lib().oxb_dna2_params_seqdep(C.byref(P), C.c_double(T), _p(s), C.c_double(stck_fact_eps), C.c_double(hb_AT), C.c_double(hb_GC)) != 0:
+        raise OxbError("oxb_dna2_params_seqdep failed")
+    return P
+
+
+def rna2_params(T, salt=1.0, dh_half_charged_ends=True, max_backbone_force=None, max_backbone_force_far=0.04, mismatch_repulsion=False,
+                mismatch_repulsion_strength=1.0):
+    """oxb_rna2_params_init.  Returns (params, rcut)."""
+    P = RNA2Params()
+    rc = C.c_double()
+    mbf = max_backbone_force is not None
+    r = lib().oxb_rna2_params_init(C.byref(P), C.c_double(T), C.c_double(salt), int(dh_half_charged_ends), int(mbf),
+                                   C.c_double(max_backbone_force if mbf else 0.0), C.c_double(max_backbone_force_far),
+                                   int(mismatch_repulsion), C.c_double(mismatch_repulsion_strength), C.byref(rc))
+    if r != 0:
+        raise OxbError("oxb_rna2_params_init failed")
+    return P, rc.value
+
+
+def rna2_params_seqdep(P, T, stck16, st_t_dep, cross16, hb_AT, hb_GC, hb_GT):
+    s, x = _d(np.asarray(stck16).reshape(16)), _d(np.asarray(cross16).reshape(16))
+    if lib().oxb_rna2_params_seqdep(C.byref(P), C.c_double(T), _p(s), C.c_double(st_t_dep), _p(x), C.c_double(hb_AT), C.c_double(hb_GC),
+                                    C.c_double(hb_GT)) != 0:
+        raise OxbError("oxb_rna2_params_seqdep failed")
+    return P
+
+
 class Context:
     """One simulated system on one GPU (opaque oxb_ctx*)."""
 
@@ -147,6 +197,9 @@ class Context:
 
     def set_model_dna2(self, P, rcut):
         self._ck(self._L.oxb_set_model_dna2(self._h, C.byref(P), C.c_double(rcut)))
+
+    def set_model_rna2(self, P, rcut):
+        self._ck(self._L.oxb_set_model_rna2(self._h, C.byref(P), C.c_double(rcut)))
 
     def set_lists(self, verlet_skin=0.05, use_edge=False, sort_every=0, max_density_multiplier=3.0):
         self._ck(self._L.oxb_set_lists(self._h, C.c_double(verlet_skin), int(use_edge), int(sort_every), C.c_double(max_density_multiplier)))

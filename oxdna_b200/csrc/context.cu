@@ -53,8 +53,14 @@ struct oxb_ctx {
 	double *h_scalars = nullptr; // pinned
 
 	// model
+	// exactly one force field is active.  For oxRNA2 the fields of `model` that the context itself reads (site offsets,
+	// radial ranges for the list radii, dh_rc, rcut_near) are mirrored from `rmodel`; the kernels get the RNA block.
 	oxb_dna2_params model;
+	oxb_rna2_params rmodel;
+	bool is_rna = false;
+	float back_a3 = 0.f;
 	double rcut = 0.;
+	oxb::ModelRef mref() const { return is_rna ? oxb::ModelRef{ nullptr, &rmodel } : oxb::ModelRef{ &model, nullptr }; }
 
 	// lists
 	double skin = 0.05, max_density_multiplier = 3.;
@@ -364,17 +370,17 @@ int launch_forces(oxb_ctx *c, int hw, bool clear, long long step) {
 		CU(cudaEventRecord(c->ev_fork, m));
 		CU(cudaStreamWaitEvent(c->aux[0], c->ev_fork, 0));
 		CU(cudaStreamWaitEvent(c->aux[1], c->ev_fork, 0));
-		oxb::launch_edge_stage(c->aux[0], 0, c->model, c->boxf, e, c->flags, hw);
-		oxb::launch_edge_stage(c->aux[1], 4, c->model, c->boxf, e, c->flags, hw);
-		oxb::launch_edge_stage(m, 1, c->model, c->boxf, e, c->flags, hw);
+		oxb::launch_edge_stage(c->aux[0], 0, c->mref(), c->boxf, e, c->flags, hw);
+		oxb::launch_edge_stage(c->aux[1], 4, c->mref(), c->boxf, e, c->flags, hw);
+		oxb::launch_edge_stage(m, 1, c->mref(), c->boxf, e, c->flags, hw);
 		CU(cudaEventRecord(c->ev_near, m));
-		oxb::launch_edge_stage(m, 2, c->model, c->boxf, e, c->flags, hw);
+		oxb::launch_edge_stage(m, 2, c->mref(), c->boxf, e, c->flags, hw);
 		if(c->n_ext > 0) {
 			oxb::launch_ext_forces(c->aux[1], c->n_ext, c->ext, c->slot_of, c->ipos[a], c->posd[a], c->boxf, step, c->cur_step, c->F[a], c->flags, hw);
 			c->launches += 1;
 		}
 		CU(cudaStreamWaitEvent(c->aux[1], c->ev_near, 0));
-		oxb::launch_edge_stage(c->aux[1], 3, c->model, c->boxf, e, c->flags, hw);
+		oxb::launch_edge_stage(c->aux[1], 3, c->mref(), c->boxf, e, c->flags, hw);
 		CU(cudaEventRecord(c->ev_join[0], c->aux[0]));
 		CU(cudaEventRecord(c->ev_join[1], c->aux[1]));
 		CU(cudaStreamWaitEvent(m, c->ev_join[0], 0));
@@ -382,7 +388,7 @@ int launch_forces(oxb_ctx *c, int hw, bool clear, long long step) {
 		c->launches += 5;
 	}
 	else {
-		oxb::launch_forces_particle(m, c->model, c->boxf, c->N, c->ipos[a], c->quat[a], c->bonds[a], c->nbr, c->nnbr, c->N, c->F[a], c->T[a],
+		oxb::launch_forces_particle(m, c->mref(), c->boxf, c->N, c->ipos[a], c->quat[a], c->bonds[a], c->nbr, c->nnbr, c->N, c->F[a], c->T[a],
 				c->flags, hw);
 		c->launches += 1;
 		if(c->n_ext > 0) {
@@ -403,7 +409,7 @@ oxb::IntegrateArgs integ_args(oxb_ctx *c, long long step) {
 	a.posd = c->posd[k]; a.veld = c->veld[k]; a.Ld = c->Ld[k]; a.quatd = c->quatd[k];
 	a.ipos = c->ipos[k]; a.quat = c->quat[k]; a.list_ipos = c->list_ipos[k];
 	a.F = c->F[k]; a.T = c->T[k]; a.Fb = c->use_edge ? c->Fb : nullptr; a.iback = c->iback[k]; a.list_iback = c->list_iback[k]; a.list_ibase = c->list_ibase[k];
-	a.back_a1 = c->model.back_a1; a.back_a2 = c->model.back_a2; a.base_a1 = c->model.base_a1;
+	a.back_a1 = c->model.back_a1; a.back_a2 = c->model.back_a2; a.back_a3 = c->back_a3; a.base_a1 = c->model.base_a1;
 	a.flags = c->flags; a.sums = c->sums; a.th = c->th; a.step = step;
 	a.cur_step = c->cur_step;
 	return a;
@@ -683,7 +689,10 @@ int oxb_set_topology(oxb_ctx *c, const int *btype, const int *n3, const int *n5,
 
 int oxb_set_model_dna2(oxb_ctx *c, const oxb_dna2_params *P, double rcut) {
 	if(c == nullptr || P == nullptr) return 1;
+	if(c->is_rna) { drop_graphs(c); c->lists_valid = false; }
 	c->model = *P;
+	c->is_rna = false;
+	c->back_a3 = 0.f;
 	c->rcut = rcut;
 	c->have_model = true;
 	c->forces_valid = false;
@@ -691,6 +700,26 @@ int oxb_set_model_dna2(oxb_ctx *c, const oxb_dna2_params *P, double rcut) {
 	// the new cutoffs is listed, the kernels re-test the distances): a replica-exchange energy evaluation under the partner's
 	// colder Hamiltonian costs one force pass, no rebuild and no reallocation.  oxb_update_lists / oxb_get_pairs rebuild for
 	// the exact radius when it differs.
+	if(c->lists_valid && (rcut + 2. * c->skin > c->lists_rv || (double) P->dh_rc > c->lists_dh_rc)) c->lists_valid = false;
+	return 0;
+}
+
+int oxb_set_model_rna2(oxb_ctx *c, const oxb_rna2_params *P, double rcut) {
+	if(c == nullptr || P == nullptr) return 1;
+	if(!c->is_rna && c->have_model) { drop_graphs(c); c->lists_valid = false; }
+	c->rmodel = *P;
+	c->is_rna = true;
+	// the subset the context reads (list radii, site offsets)
+	oxb_dna2_params &M = c->model;
+	std::memset(&M, 0, sizeof(M));
+	M.back_a1 = P->back_a1; M.back_a2 = P->back_a2; c->back_a3 = P->back_a3;
+	M.base_a1 = P->base_a1; M.stack_a1 = P->stack_a1;
+	for(int k = 0; k < 4; k++) M.excl[k] = P->excl[k];
+	M.hb = P->hb; M.crst = P->crst; M.cxst = P->cxst;
+	M.dh_rc = P->dh_rc; M.rcut = P->rcut; M.rcut_near = P->rcut_near;
+	c->rcut = rcut;
+	c->have_model = true;
+	c->forces_valid = false;
 	if(c->lists_valid && (rcut + 2. * c->skin > c->lists_rv || (double) P->dh_rc > c->lists_dh_rc)) c->lists_valid = false;
 	return 0;
 }
@@ -786,10 +815,10 @@ int oxb_set_state(oxb_ctx *c, const double *pos, const double *a1, const double 
 		hi[i].w = pack_word(c->h_btype[i], i);
 		{
 			// backbone site (grooved): r + back_a1 a1 + back_a2 a2, from the same float-rounded constants the kernels use
-			double b1 = c->model.back_a1, b2 = c->model.back_a2;
-			hk[i].x = (int) to_fixed(pos[3 * i] + b1 * v1[0] + b2 * v2[0], 1. / c->box[0]);
-			hk[i].y = (int) to_fixed(pos[3 * i + 1] + b1 * v1[1] + b2 * v2[1], 1. / c->box[1]);
-			hk[i].z = (int) to_fixed(pos[3 * i + 2] + b1 * v1[2] + b2 * v2[2], 1. / c->box[2]);
+			double b1 = c->model.back_a1, b2 = c->model.back_a2, b3 = c->back_a3;
+			hk[i].x = (int) to_fixed(pos[3 * i] + b1 * v1[0] + b2 * v2[0] + b3 * v3_[0], 1. / c->box[0]);
+			hk[i].y = (int) to_fixed(pos[3 * i + 1] + b1 * v1[1] + b2 * v2[1] + b3 * v3_[1], 1. / c->box[1]);
+			hk[i].z = (int) to_fixed(pos[3 * i + 2] + b1 * v1[2] + b2 * v2[2] + b3 * v3_[2], 1. / c->box[2]);
 			hk[i].w = (c->h_n3[i] < 0 || c->h_n5[i] < 0) ? 1 : 0;
 		}
 		hb[i] = make_int2(c->h_n3[i], c->h_n5[i]);
@@ -1025,7 +1054,7 @@ int oxb_get_forces(oxb_ctx *c, double *force, double *torque_body, double *torqu
 			double x1[3], x2[3], x3[3];
 			axes_from_quatd(q, x1, x2, x3);
 			double bk[3], g[3] = { hB[s].x, hB[s].y, hB[s].z };
-			for(int d = 0; d < 3; d++) bk[d] = (double) c->model.back_a1 * x1[d] + (double) c->model.back_a2 * x2[d];
+			for(int d = 0; d < 3; d++) bk[d] = (double) c->model.back_a1 * x1[d] + (double) c->model.back_a2 * x2[d] + (double) c->back_a3 * x3[d];
 			hF[s].x += hB[s].x; hF[s].y += hB[s].y; hF[s].z += hB[s].z; hF[s].w += hB[s].w;
 			hT[s].x += (float) (bk[1] * g[2] - bk[2] * g[1]); hT[s].y += (float) (bk[2] * g[0] - bk[0] * g[2]); hT[s].z += (float) (bk[0] * g[1] - bk[1] * g[0]);
 		}

@@ -210,6 +210,8 @@ struct PairAcc {
 	OXB_HD void site_ak(v3 f, float cp) { F += f; axpy(Pa, cp, f); Qk += f; }
 	OXB_HD void site_ka(v3 f, float cq) { F += f; Pk += f; axpy(Qa, cq, f); }
 	OXB_HD void site_kk(v3 f) { F += f; Pk += f; Qk += f; }
+	// arbitrary lever arms (oxRNA's 3'/5' stacking sites)
+	OXB_HD void site_gg(v3 f, v3 sp, v3 sq) { F += f; Tp -= cross(sp, f); Tq += cross(sq, f); }
 	// lab-frame torques including lever arms
 	OXB_HD v3 torque_p(const Axes &A, v3 pback) const { return Tp - cross(A.a1, Pa) - cross(pback, Pk); }
 	OXB_HD v3 torque_q(const Axes &B, v3 qback) const { return Tq + cross(B.a1, Qa) + cross(qback, Qk); }
@@ -240,8 +242,8 @@ OXB_HD Angle make_angle_cos(v3 u, v3 v) {
 	return a;
 }
 
-OXB_HD bool in_window(const oxb_dna2_params &M, int k, float c) { return c > M.f4_cmin[k] && c < M.f4_cmax[k]; }
-OXB_HD bool in_window_sym(const oxb_dna2_params &M, int k, float c) { return in_window(M, k, c) || in_window(M, k, -c); }
+template<class PB> OXB_HD bool in_window(const PB &M, int k, float c) { return c > M.f4_cmin[k] && c < M.f4_cmax[k]; }
+template<class PB> OXB_HD bool in_window_sym(const PB &M, int k, float c) { return in_window(M, k, c) || in_window(M, k, -c); }
 
 // chain rule, c = u.v with u on p and v on q, g = dE/dc
 OXB_HD void chain_bb(PairAcc &A, float g, const Angle &a) {
@@ -270,7 +272,7 @@ struct PairEnergy {
 // ---------------------------------------------------------------------------------------------------------------
 
 // returns the DH energy; fs such that force-on-q = fs * rbb (zero outside the range)
-OXB_HD float dna2_dh(const oxb_dna2_params &M, float rbb2, bool p_end, bool q_end, float &fs) {
+template<class PB> OXB_HD float dna2_dh(const PB &M, float rbb2, bool p_end, bool q_end, float &fs) {
 	fs = 0.f;
 	if(rbb2 >= M.dh_rc * M.dh_rc) return 0.f;
 	float m = sqrtf(rbb2);
@@ -297,7 +299,7 @@ OXB_HD float dna2_dh(const oxb_dna2_params &M, float rbb2, bool p_end, bool q_en
 #ifdef __CUDACC__
 // device-only variant with SFU intrinsics (rsqrt, ex2): no IEEE division / square root on the most frequent path.
 // Relative error ~2e-7, far inside the 1e-5 force tolerance.
-__device__ __forceinline__ float dna2_dh_fast(const oxb_dna2_params &M, float rbb2, bool p_end, bool q_end, float &fs) {
+template<class PB> __device__ __forceinline__ float dna2_dh_fast(const PB &M, float rbb2, bool p_end, bool q_end, float &fs) {
 	// both radial regimes are evaluated and selected (ex2 and rsqrt are single SFU instructions): no divergent branch in
 	// the most frequently executed loop of the step
 	float inv = rsqrtf(rbb2);
@@ -317,7 +319,7 @@ __device__ __forceinline__ float dna2_dh_fast(const oxb_dna2_params &M, float rb
 }
 #endif
 
-OXB_HD float dna2_excl(const oxb_dna2_params &M, v3 r, v3 rbb, v3 rb, const Axes &A, const Axes &B, v3 pback, v3 qback, PairAcc &acc) {
+template<class PB> OXB_HD float dna2_excl(const PB &M, v3 r, v3 rbb, v3 rb, const Axes &A, const Axes &B, v3 pback, v3 qback, PairAcc &acc) {
 	const float cb = M.base_a1;
 	float s, E = 0.f;
 	float en = excl_s(M.excl[0], M.excl_eps, rbb, s);
@@ -497,15 +499,12 @@ OXB_HD PairEnergy dna2_nonbonded(const oxb_dna2_params &M, v3 r, const Axes &A, 
 	return E;
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Bonded pair p -> q = n3(p).  r = q - p.  Terms: FENE backbone, bonded excluded volume (3 site pairs), stacking.
-// Returns energy; sets *broken when the bond is outside the FENE range (reference throws; we flag).
-// ---------------------------------------------------------------------------------------------------------------
-OXB_HD float dna2_bonded(const oxb_dna2_params &M, v3 r, const Axes &A, const Axes &B, int btp, int btq, v3 pback,
-		v3 qback, PairAcc &acc, bool &broken) {
+// FENE backbone + bonded excluded volume (3 site pairs): the same functional form in oxDNA2 and oxRNA2
+// (DNAInteraction.cpp:415-528, RNAInteraction.cpp:431-531)
+template<class PB>
+OXB_HD float bonded_fene_excl(const PB &M, v3 r, const Axes &A, const Axes &B, v3 pback, v3 qback, PairAcc &acc, bool &broken) {
 	float E = 0.f;
-	const float cb = M.base_a1, cs = M.stack_a1, cr = M.backref_a1;
-
+	const float cb = M.base_a1;
 	// FENE
 	{
 		v3 d = r + qback - pback;
@@ -546,6 +545,19 @@ OXB_HD float dna2_bonded(const oxb_dna2_params &M, v3 r, const Axes &A, const Ax
 		en = excl_s(M.excl[3], M.excl_eps, d, s);
 		if(en != 0.f) { E += en; acc.site_ka(d * s, cb); }
 	}
+	return E;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Bonded pair p -> q = n3(p).  r = q - p.  Terms: FENE backbone, bonded excluded volume (3 site pairs), stacking.
+// Returns energy; sets *broken when the bond is outside the FENE range (reference throws; we flag).
+// ---------------------------------------------------------------------------------------------------------------
+OXB_HD float dna2_bonded(const oxb_dna2_params &M, v3 r, const Axes &A, const Axes &B, int btp, int btq, v3 pback,
+		v3 qback, PairAcc &acc, bool &broken) {
+	float E = 0.f;
+	const float cb = M.base_a1, cs = M.stack_a1, cr = M.backref_a1;
+
+	E += bonded_fene_excl(M, r, A, B, pback, qback, acc, broken);
 	// stacking
 	{
 		v3 rs = r + B.a1 * cs - A.a1 * cs;

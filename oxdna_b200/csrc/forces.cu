@@ -4,7 +4,7 @@
 //
 // Data: ipos int4 (fixed-point position, .w = btype<<22 | original index), quat float4, bonds int2 (n3, n5 slots),
 // neighbour matrix column-major nbr[k * stride + i], forces/torques float4 (.w = energy / HB energy as in the reference).
-#include "dna_model.cuh"
+#include "models.cuh"
 #include "kernels.h"
 
 #include <algorithm>
@@ -18,11 +18,12 @@ struct Particle {
 	int btype;
 };
 
-__device__ __forceinline__ Particle load_particle(const oxb_dna2_params &M, const int4 *__restrict__ ipos, const float4 *__restrict__ quat, int i) {
+template<class MD>
+__device__ __forceinline__ Particle load_particle(const typename MD::Params &M, const int4 *__restrict__ ipos, const float4 *__restrict__ quat, int i) {
 	Particle P;
 	P.ip = __ldg(ipos + i);
 	P.ax = axes_from_quat(__ldg(quat + i));
-	P.back = P.ax.a1 * M.back_a1 + P.ax.a2 * M.back_a2;
+	P.back = MD::back(M, P.ax);
 	P.btype = word_btype(P.ip.w);
 	return P;
 }
@@ -30,14 +31,15 @@ __device__ __forceinline__ Particle load_particle(const oxb_dna2_params &M, cons
 // ------------------------------------------------------------------------------------------------------------
 // Particle-centric: one thread per particle, every listed pair evaluated from both ends, no atomics, deterministic.
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_forces_particle(const __grid_constant__ oxb_dna2_params M, BoxF box, int N, const int4 *__restrict__ ipos,
+template<class MD>
+__global__ void __launch_bounds__(128) k_forces_particle(const __grid_constant__ typename MD::Params M, BoxF box, int N, const int4 *__restrict__ ipos,
 		const float4 *__restrict__ quat, const int2 *__restrict__ bonds, const int *__restrict__ nbr, const int *__restrict__ nnbr, int stride,
 		float4 *__restrict__ F, float4 *__restrict__ T, int *__restrict__ flags, int hw) {
 	if(flags[hw]) return;
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= N) return;
 
-	Particle P = load_particle(M, ipos, quat, i);
+	Particle P = load_particle<MD>(M, ipos, quat, i);
 	int2 b = __ldg(bonds + i);
 	bool p_end = (b.x < 0 || b.y < 0);
 
@@ -46,18 +48,18 @@ __global__ void __launch_bounds__(128) k_forces_particle(const __grid_constant__
 	bool broken = false;
 
 	if(b.x >= 0) { // I am the 5' side of the bond (p), q = my n3
-		Particle Q = load_particle(M, ipos, quat, b.x);
+		Particle Q = load_particle<MD>(M, ipos, quat, b.x);
 		PairAcc acc;
 		acc.clear();
-		e += dna2_bonded(M, min_image_fixed(box, P.ip, Q.ip), P.ax, Q.ax, P.btype, Q.btype, P.back, Q.back, acc, broken);
+		e += MD::bonded(M, min_image_fixed(box, P.ip, Q.ip), P.ax, Q.ax, P.btype, Q.btype, P.back, Q.back, acc, broken);
 		f -= acc.F;
 		t += acc.torque_p(P.ax, P.back);
 	}
 	if(b.y >= 0) { // my n5 neighbour is p, I am q
-		Particle Q = load_particle(M, ipos, quat, b.y);
+		Particle Q = load_particle<MD>(M, ipos, quat, b.y);
 		PairAcc acc;
 		acc.clear();
-		e += dna2_bonded(M, min_image_fixed(box, Q.ip, P.ip), Q.ax, P.ax, Q.btype, P.btype, Q.back, P.back, acc, broken);
+		e += MD::bonded(M, min_image_fixed(box, Q.ip, P.ip), Q.ax, P.ax, Q.btype, P.btype, Q.back, P.back, acc, broken);
 		f += acc.F;
 		t += acc.torque_q(P.ax, P.back);
 	}
@@ -65,11 +67,11 @@ __global__ void __launch_bounds__(128) k_forces_particle(const __grid_constant__
 	int nn = __ldg(nnbr + i);
 	for(int k = 0; k < nn; k++) {
 		int j = __ldg(nbr + (size_t) k * stride + i);
-		Particle Q = load_particle(M, ipos, quat, j);
+		Particle Q = load_particle<MD>(M, ipos, quat, j);
 		int2 bq = __ldg(bonds + j);
 		PairAcc acc;
 		acc.clear();
-		PairEnergy pe = dna2_nonbonded(M, min_image_fixed(box, P.ip, Q.ip), P.ax, Q.ax, P.btype, Q.btype, p_end, (bq.x < 0 || bq.y < 0), P.back,
+		PairEnergy pe = MD::nonbonded(M, min_image_fixed(box, P.ip, Q.ip), P.ax, Q.ax, P.btype, Q.btype, p_end, (bq.x < 0 || bq.y < 0), P.back,
 				Q.back, acc);
 		e += pe.total;
 		ehb += pe.hb;
@@ -122,7 +124,8 @@ __device__ __forceinline__ bool segmented_reduce(int key, unsigned lane, float (
 // Debye-Hueckel, particle-centric over its own neighbour matrix (selected on the backbone-site distance): per neighbour one
 // coalesced index load + one 16-byte gather of a fixed-point backbone site; no atomics, deterministic.  Writes the
 // backbone-site force sum Fb (.w = energy); k_bonded_finalize folds it into force and torque.
-__global__ void __launch_bounds__(128) k_dh_particle(const __grid_constant__ oxb_dna2_params M, BoxF box, int N, const int4 *__restrict__ iback,
+template<class MD>
+__global__ void __launch_bounds__(128) k_dh_particle(const __grid_constant__ typename MD::Params M, BoxF box, int N, const int4 *__restrict__ iback,
 		const int *__restrict__ dh_nbr, const int *__restrict__ dh_nnbr, float4 *__restrict__ Fb, const int *__restrict__ flags, int hw) {
 	if(flags[hw]) return;
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -164,7 +167,8 @@ __device__ __forceinline__ void block_append(bool flag, int2 item, int2 *__restr
 	}
 }
 
-__global__ void __launch_bounds__(128) k_edge_near(const __grid_constant__ oxb_dna2_params M, BoxF box, const int *__restrict__ n_edges,
+template<class MD>
+__global__ void __launch_bounds__(128) k_edge_near(const __grid_constant__ typename MD::Params M, BoxF box, const int *__restrict__ n_edges,
 		const int2 *__restrict__ edges, const int4 *__restrict__ ipos, const float4 *__restrict__ quat, float4 *__restrict__ F, float4 *__restrict__ T,
 		int2 *__restrict__ hb_list, int2 *__restrict__ cx_list, int2 *__restrict__ cr_list, int *__restrict__ seg_counts, int hb_seg, int cx_seg,
 		int cr_seg, int *__restrict__ flags, int hw) {
@@ -185,8 +189,8 @@ __global__ void __launch_bounds__(128) k_edge_near(const __grid_constant__ oxb_d
 		float ve = 0.f;
 		bool want_hb = false, want_cx = false, want_cr = false;
 		if(valid) {
-			Particle P = load_particle(M, ipos, quat, ed.x);
-			Particle Q = load_particle(M, ipos, quat, ed.y);
+			Particle P = load_particle<MD>(M, ipos, quat, ed.x);
+			Particle Q = load_particle<MD>(M, ipos, quat, ed.y);
 			v3 r = min_image_fixed(box, P.ip, Q.ip);
 			if(dot(r, r) < M.rcut_near * M.rcut_near) {
 				v3 rbb = r + Q.back - P.back;
@@ -205,17 +209,17 @@ __global__ void __launch_bounds__(128) k_edge_near(const __grid_constant__ oxb_d
 				// radial range first, then the cosine windows of every angular factor: only pairs whose product can be
 				// non-zero reach the heavy kernels
 				float rbm2 = dot(rb, rb);
-				bool hb_on = dna2_hb_in_range(M, rbm2, P.btype, Q.btype), cr_on = dna2_crst_in_range(M, rbm2);
+				bool hb_on = MD::hb_in_range(M, rbm2, P.btype, Q.btype), cr_on = MD::crst_in_range(M, rbm2);
 				if(hb_on || cr_on) {
 					// pairs that can hydrogen-bond go to the full kernel, the (more numerous) cross-stacking-only pairs to a
 					// specialised one: both lists are warp-uniform
 					// (splitting this list into a hydrogen-bonding and a cross-stacking-only list with specialised kernels was
 					// measured SLOWER, 53 + 39 us against 83 us at 1M particles, and is kept only as MODE 2 below)
-					want_hb = dna2_hbcr_may_act(M, rb * rsqrtf(rbm2), P.ax, Q.ax, hb_on, cr_on);
+					want_hb = MD::hbcr_may_act(M, rb * rsqrtf(rbm2), P.ax, Q.ax, hb_on, cr_on);
 				}
 				v3 rs = r + (Q.ax.a1 - P.ax.a1) * M.stack_a1;
 				float rs2 = dot(rs, rs);
-				if(dna2_cxst_in_range(M, rs2)) want_cx = dna2_cxst_may_act(M, rs * rsqrtf(rs2), P.ax, Q.ax);
+				if(MD::cxst_in_range(M, rs2)) want_cx = MD::cxst_may_act(M, rs * rsqrtf(rs2), P.ax, Q.ax);
 			}
 		}
 		block_append(want_hb, ed, hb_list, &s_cnt[0], hb_seg, flags);
@@ -239,8 +243,8 @@ __global__ void __launch_bounds__(128) k_edge_near(const __grid_constant__ oxb_d
 }
 
 // MODE 0: hydrogen bonding (+ cross stacking where also in range) | 1: coaxial stacking | 2: cross stacking only
-template<int MODE>
-__global__ void __launch_bounds__(64) k_edge_heavy(const __grid_constant__ oxb_dna2_params M, BoxF box, const int *__restrict__ seg_counts,
+template<class MD, int MODE>
+__global__ void __launch_bounds__(64) k_edge_heavy(const __grid_constant__ typename MD::Params M, BoxF box, const int *__restrict__ seg_counts,
 		const int2 *__restrict__ list, int seg, const int4 *__restrict__ ipos, const float4 *__restrict__ quat, float4 *__restrict__ F,
 		float4 *__restrict__ T, const int *__restrict__ flags, int hw) {
 	if(flags[hw]) return;
@@ -250,21 +254,21 @@ __global__ void __launch_bounds__(64) k_edge_heavy(const __grid_constant__ oxb_d
 	list += (size_t) blockIdx.x * seg;
 	for(int k = blockIdx.y * blockDim.x + threadIdx.x; k < n; k += blockDim.x * gridDim.y) {
 		int2 ed = __ldg(list + k);
-		Particle P = load_particle(M, ipos, quat, ed.x);
-		Particle Q = load_particle(M, ipos, quat, ed.y);
+		Particle P = load_particle<MD>(M, ipos, quat, ed.x);
+		Particle Q = load_particle<MD>(M, ipos, quat, ed.y);
 		v3 r = min_image_fixed(box, P.ip, Q.ip);
 		PairAcc acc;
 		acc.clear();
 		float en, ehb = 0.f;
 		if(MODE == 1) {
 			v3 rs = r + (Q.ax.a1 - P.ax.a1) * M.stack_a1;
-			en = dna2_cxst(M, rs, dot(rs, rs), P.ax, Q.ax, acc);
+			en = MD::cxst(M, rs, dot(rs, rs), r + Q.back - P.back, P.ax, Q.ax, acc);
 		}
 		else {
 			v3 rb = r + (Q.ax.a1 - P.ax.a1) * M.base_a1;
 			float rbm2 = dot(rb, rb);
-			if(MODE == 0) en = dna2_hbcr<true>(M, rb, rbm2, P.ax, Q.ax, P.btype, Q.btype, dna2_hb_in_range(M, rbm2, P.btype, Q.btype), dna2_crst_in_range(M, rbm2), acc, ehb);
-			else en = dna2_hbcr<false>(M, rb, rbm2, P.ax, Q.ax, P.btype, Q.btype, false, true, acc, ehb);
+			if(MODE == 0) en = MD::template hbcr<true>(M, rb, rbm2, P.ax, Q.ax, P.btype, Q.btype, MD::hb_in_range(M, rbm2, P.btype, Q.btype), MD::crst_in_range(M, rbm2), acc, ehb);
+			else en = MD::template hbcr<false>(M, rb, rbm2, P.ax, Q.ax, P.btype, Q.btype, false, true, acc, ehb);
 		}
 		if(en != 0.f) {
 			v3 tp = acc.torque_p(P.ax, P.back), tq = acc.torque_q(Q.ax, Q.back);
@@ -278,19 +282,20 @@ __global__ void __launch_bounds__(64) k_edge_heavy(const __grid_constant__ oxb_d
 
 // per particle: bonded interaction with its n3 neighbour (each bond evaluated once).  Independent of the other kernels of
 // the force pass (it only adds into F/T), so it runs concurrently with them on its own stream.
-__global__ void __launch_bounds__(128) k_bonded(const __grid_constant__ oxb_dna2_params M, BoxF box, int N, const int4 *__restrict__ ipos,
+template<class MD>
+__global__ void __launch_bounds__(128) k_bonded(const __grid_constant__ typename MD::Params M, BoxF box, int N, const int4 *__restrict__ ipos,
 		const float4 *__restrict__ quat, const int2 *__restrict__ bonds, float4 *__restrict__ F, float4 *__restrict__ T, int *__restrict__ flags, int hw) {
 	if(flags[hw]) return;
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= N) return;
 	int2 b = __ldg(bonds + i);
 	if(b.x < 0) return;
-	Particle P = load_particle(M, ipos, quat, i);
-	Particle Q = load_particle(M, ipos, quat, b.x);
+	Particle P = load_particle<MD>(M, ipos, quat, i);
+	Particle Q = load_particle<MD>(M, ipos, quat, b.x);
 	PairAcc acc;
 	acc.clear();
 	bool broken = false;
-	float en = dna2_bonded(M, min_image_fixed(box, P.ip, Q.ip), P.ax, Q.ax, P.btype, Q.btype, P.back, Q.back, acc, broken);
+	float en = MD::bonded(M, min_image_fixed(box, P.ip, Q.ip), P.ax, Q.ax, P.btype, Q.btype, P.back, Q.back, acc, broken);
 	v3 tp = acc.torque_p(P.ax, P.back), tq = acc.torque_q(Q.ax, Q.back);
 	atomic_add4(F + i, -acc.F.x, -acc.F.y, -acc.F.z, en);
 	atomic_add4(T + i, tp.x, tp.y, tp.z, 0.f);
@@ -350,30 +355,37 @@ __global__ void k_ext_forces(int n, const DevExtForce *__restrict__ ef, const in
 
 namespace oxb {
 
-void launch_forces_particle(cudaStream_t s, const oxb_dna2_params &M, BoxF box, int N, const int4 *ipos, const float4 *quat, const int2 *bonds,
+void launch_forces_particle(cudaStream_t s, const ModelRef &MR, BoxF box, int N, const int4 *ipos, const float4 *quat, const int2 *bonds,
 		const int *nbr, const int *nnbr, int stride, float4 *F, float4 *T, int *flags, int hw) {
 	int tpb = 128;
-	k_forces_particle<<<(N + tpb - 1) / tpb, tpb, 0, s>>>(M, box, N, ipos, quat, bonds, nbr, nnbr, stride, F, T, flags, hw);
+	if(MR.rna) k_forces_particle<RnaModel><<<(N + tpb - 1) / tpb, tpb, 0, s>>>(*MR.rna, box, N, ipos, quat, bonds, nbr, nnbr, stride, F, T, flags, hw);
+	else k_forces_particle<DnaModel><<<(N + tpb - 1) / tpb, tpb, 0, s>>>(*MR.dna, box, N, ipos, quat, bonds, nbr, nnbr, stride, F, T, flags, hw);
 }
 
 // the kernels of the edge pipeline, launched one by one so that the context can place them on concurrent streams:
 //   which = 0 Debye-Hueckel (writes Fb) | 1 near edges (F, T, work lists) | 2 HB (+ cross stacking) | 3 coaxial stacking | 4 bonds
 //           5 cross stacking only
-void launch_edge_stage(cudaStream_t s, int which, const oxb_dna2_params &M, BoxF box, const EdgeArgs &a, int *flags, int hw) {
+template<class MD>
+static void launch_edge_stage_t(cudaStream_t s, int which, const typename MD::Params &M, BoxF box, const EdgeArgs &a, int *flags, int hw) {
 	auto blocks_for = [&](long long items) { return (int) std::max<long long>(1, (items + 127) / 128); };
 	switch(which) {
-	case 0: k_dh_particle<<<blocks_for(a.N), 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, flags, hw); break;
+	case 0: k_dh_particle<MD><<<blocks_for(a.N), 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, flags, hw); break;
 	// the producer and the three consumers of the segmented work lists share one fixed grid (a.n_seg blocks, grid-stride
 	// inside): nothing here depends on device-side counts, so a captured graph stays valid across list rebuilds
 	case 1:
-		k_edge_near<<<a.n_seg, 128, 0, s>>>(M, box, a.n_edges, a.edges, a.ipos, a.quat, a.F, a.T, a.hb_list, a.cx_list, a.cr_list, a.seg_counts, a.hb_seg,
+		k_edge_near<MD><<<a.n_seg, 128, 0, s>>>(M, box, a.n_edges, a.edges, a.ipos, a.quat, a.F, a.T, a.hb_list, a.cx_list, a.cr_list, a.seg_counts, a.hb_seg,
 				a.cx_seg, a.cr_seg, flags, hw);
 		break;
-	case 2: k_edge_heavy<0><<<dim3(a.n_seg, a.hb_split), 64, 0, s>>>(M, box, a.seg_counts, a.hb_list, a.hb_seg, a.ipos, a.quat, a.F, a.T, flags, hw); break;
-	case 3: k_edge_heavy<1><<<a.n_seg, 64, 0, s>>>(M, box, a.seg_counts, a.cx_list, a.cx_seg, a.ipos, a.quat, a.F, a.T, flags, hw); break;
-	case 5: k_edge_heavy<2><<<dim3(a.n_seg, a.hb_split), 64, 0, s>>>(M, box, a.seg_counts, a.cr_list, a.cr_seg, a.ipos, a.quat, a.F, a.T, flags, hw); break;
-	default: k_bonded<<<blocks_for(a.N), 128, 0, s>>>(M, box, a.N, a.ipos, a.quat, a.bonds, a.F, a.T, flags, hw); break;
+	case 2: k_edge_heavy<MD, 0><<<dim3(a.n_seg, a.hb_split), 64, 0, s>>>(M, box, a.seg_counts, a.hb_list, a.hb_seg, a.ipos, a.quat, a.F, a.T, flags, hw); break;
+	case 3: k_edge_heavy<MD, 1><<<a.n_seg, 64, 0, s>>>(M, box, a.seg_counts, a.cx_list, a.cx_seg, a.ipos, a.quat, a.F, a.T, flags, hw); break;
+	case 5: k_edge_heavy<MD, 2><<<dim3(a.n_seg, a.hb_split), 64, 0, s>>>(M, box, a.seg_counts, a.cr_list, a.cr_seg, a.ipos, a.quat, a.F, a.T, flags, hw); break;
+	default: k_bonded<MD><<<blocks_for(a.N), 128, 0, s>>>(M, box, a.N, a.ipos, a.quat, a.bonds, a.F, a.T, flags, hw); break;
 	}
+}
+
+void launch_edge_stage(cudaStream_t s, int which, const ModelRef &MR, BoxF box, const EdgeArgs &a, int *flags, int hw) {
+	if(MR.rna) launch_edge_stage_t<RnaModel>(s, which, *MR.rna, box, a, flags, hw);
+	else launch_edge_stage_t<DnaModel>(s, which, *MR.dna, box, a, flags, hw);
 }
 
 void launch_ext_forces(cudaStream_t s, int n, const DevExtForce *ef, const int *slot_of, const int4 *ipos, const double4 *posd, BoxF box,

@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(256) k_integrate(oxb::IntegrateArgs a, int epo
 				float4 fb = a.Fb[i];
 				v3 g = mk3(fb.x, fb.y, fb.z);
 				F.x += g.x; F.y += g.y; F.z += g.z;
-				tl += cross(A.a1 * a.back_a1 + A.a2 * a.back_a2, g);
+				tl += cross(A.a1 * a.back_a1 + A.a2 * a.back_a2 + A.a3 * a.back_a3, g);
 			}
 			T.x = dot(A.a1, tl); T.y = dot(A.a2, tl); T.z = dot(A.a3, tl);
 		}
@@ -144,10 +144,10 @@ __global__ void __launch_bounds__(256) k_integrate(oxb::IntegrateArgs a, int epo
 				// fixed-point backbone-site position for the Debye-Hueckel kernel: r + back_a1 a1 + back_a2 a2
 				double sqx = qn.x * qn.x, sqy = qn.y * qn.y, sqz = qn.z * qn.z, sqw = qn.w * qn.w;
 				double xy = qn.x * qn.y, xz = qn.x * qn.z, xw = qn.x * qn.w, yz = qn.y * qn.z, yw = qn.y * qn.w, zw = qn.z * qn.w;
-				double b1 = a.back_a1, b2 = a.back_a2;
-				double bx = r.x + b1 * (sqx - sqy - sqz + sqw) + b2 * (2. * (xy - zw));
-				double by = r.y + b1 * (2. * (xy + zw)) + b2 * (-sqx + sqy - sqz + sqw);
-				double bz = r.z + b1 * (2. * (xz - yw)) + b2 * (2. * (yz + xw));
+				double b1 = a.back_a1, b2 = a.back_a2, b3 = a.back_a3;
+				double bx = r.x + b1 * (sqx - sqy - sqz + sqw) + b2 * (2. * (xy - zw)) + b3 * (2. * (xz + yw));
+				double by = r.y + b1 * (2. * (xy + zw)) + b2 * (-sqx + sqy - sqz + sqw) + b3 * (2. * (yz - xw));
+				double bz = r.z + b1 * (2. * (xz - yw)) + b2 * (2. * (yz + xw)) + b3 * (-sqx - sqy + sqz + sqw);
 				int4 ib = a.iback[i];
 				ib.x = (int) to_fixed(bx, a.box_inv[0]); ib.y = (int) to_fixed(by, a.box_inv[1]); ib.z = (int) to_fixed(bz, a.box_inv[2]);
 				a.iback[i] = ib;

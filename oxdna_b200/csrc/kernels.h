@@ -46,8 +46,14 @@ enum { OXB_PH_SECOND = 1, OXB_PH_THERMO = 2, OXB_PH_FIRST = 4, OXB_PH_BUSSI_SUMS
 
 namespace oxb {
 
+// the force field of a context: exactly one of the two blocks is set
+struct ModelRef {
+	const oxb_dna2_params *dna;
+	const oxb_rna2_params *rna;
+};
+
 // ---- forces.cu
-void launch_forces_particle(cudaStream_t s, const oxb_dna2_params &M, BoxF box, int N, const int4 *ipos, const float4 *quat, const int2 *bonds,
+void launch_forces_particle(cudaStream_t s, const ModelRef &M, BoxF box, int N, const int4 *ipos, const float4 *quat, const int2 *bonds,
 		const int *nbr, const int *nnbr, int stride, float4 *F, float4 *T, int *flags, int hw);
 struct EdgeArgs {
 	int N;
@@ -64,7 +70,7 @@ struct EdgeArgs {
 	int n_seg, hb_seg, cx_seg, cr_seg;
 	int hb_split; // consumer blocks per segment of the hydrogen-bonding / cross-stacking list
 };
-void launch_edge_stage(cudaStream_t s, int which, const oxb_dna2_params &M, BoxF box, const EdgeArgs &a, int *flags, int hw);
+void launch_edge_stage(cudaStream_t s, int which, const ModelRef &M, BoxF box, const EdgeArgs &a, int *flags, int hw);
 void launch_ext_forces(cudaStream_t s, int n, const DevExtForce *ef, const int *slot_of, const int4 *ipos, const double4 *posd, BoxF box,
 		long long step, const long long *cur_step, float4 *F, const int *flags, int hw);
 
@@ -81,7 +87,7 @@ struct IntegrateArgs {
 	const int4 *list_ipos, *list_iback, *list_ibase;
 	float4 *F, *T, *Fb; // lab-frame force / torque accumulators (zeroed by the first-half phase once consumed)
 	int4 *iback;        // fixed-point backbone-site position, .w bit 0 = strand end
-	float back_a1, back_a2, base_a1;
+	float back_a1, back_a2, back_a3, base_a1;
 	int *flags;
 	KinSums *sums;
 	ThermostatCfg th;

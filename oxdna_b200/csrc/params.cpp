@@ -160,3 +160,149 @@ extern "C" int oxb_dna2_params_seqdep(oxb_dna2_params *P, double T, const double
 	P->hb_shift[5 * G + C] = P->hb_shift[5 * C + G] = (float) (hb_GC * morse_shift(kHB));
 	return 0;
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// oxRNA2.  Constants: src/Interactions/rna_model.h (struct Model, all members float); derivations:
+// RNAInteraction::init (src/Interactions/RNAInteraction.cpp:194-397), RNA2Interaction::get_settings/init
+// (src/Interactions/RNAInteraction2.cpp:31-102).
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr WellF1 kRnaHB = { 8.f, 0.75f, 0.4f, -126.243f, -7.87708f, 0.34f, 0.7f, 0.276908f, 0.783775f };
+constexpr WellF1 kRnaSTCK = { 6.f, 0.93f, 0.43f, -68.1857f, -3.12992f, 0.35f, 0.78f, 0.26239f, 0.986f };
+constexpr float kRnaHbEps = 0.870439f;
+
+void put_f4(oxb_rna2_params *P, int k, float a, float b, float t0, float ts, float tc) {
+	P->f4[k] = oxb_f4{ a, b, t0, ts, tc };
+	double lo = std::fmax(0., (double) t0 - tc), hi = std::fmin(3.14159265358979323846, (double) t0 + tc);
+	P->f4_cmin[k] = (float) (std::cos(hi) - 1e-4);
+	P->f4_cmax[k] = (float) (std::cos(lo) + 1e-4);
+}
+
+} // namespace
+
+extern "C" int oxb_rna2_params_init(oxb_rna2_params *P, double T, double salt, int dh_half_charged_ends, int use_mbf, double mbf_fmax,
+		double mbf_finf, int mismatch_repulsion, double mismatch_strength, double *rcut_out) {
+	if(P == nullptr || !(T > 0) || !(salt > 0)) return 1;
+	std::memset(P, 0, sizeof(*P));
+	P->average = 1;
+
+	// interaction sites, rna_model.h:313-350
+	P->back_a1 = -0.4f; P->back_a2 = 0.0f; P->back_a3 = 0.2f;
+	P->stack_a1 = 0.34f; P->base_a1 = 0.4f;
+	P->stack3_a1 = 0.4f; P->stack3_a2 = 0.1f;
+	P->stack5_a1 = 0.124906078525f; P->stack5_a2 = -0.00866274917473f;
+	P->p5[0] = -0.104402f; P->p5[1] = -0.841783f; P->p5[2] = 0.529624f;
+	P->p3[0] = -0.462510f; P->p3[1] = -0.528218f; P->p3[2] = 0.712089f;
+
+	P->fene_eps = 2.0f; P->fene_r0 = 0.761070781051f; P->fene_delta = 0.25f; P->fene_delta2 = 0.0625f;
+	P->use_mbf = use_mbf ? 1 : 0;
+	if(use_mbf) {
+		double eps = 2.0, d2 = 0.0625;
+		double xmax = (-eps + std::sqrt(eps * eps + 4. * mbf_fmax * mbf_fmax * d2)) / (2. * mbf_fmax);
+		double fene_xmax = -(eps / 2.) * std::log(1. - xmax * xmax / d2);
+		double long_xmax = (mbf_fmax - mbf_finf) * xmax * std::log(xmax) + mbf_finf * xmax;
+		P->mbf_xmax = (float) xmax; P->mbf_fmax = (float) mbf_fmax; P->mbf_finf = (float) mbf_finf;
+		P->mbf_e0 = (float) (fene_xmax - long_xmax);
+	}
+
+	P->excl_eps = 2.0f;
+	put_excl(P->excl[0], 0.70f, 0.675f, 892.016223343f, 0.711879214356f);
+	put_excl(P->excl[1], 0.33f, 0.32f, 4119.70450017f, 0.335388426126f);
+	put_excl(P->excl[2], 0.515f, 0.50f, 1707.30627298f, 0.52329943261f);
+	put_excl(P->excl[3], 0.515f, 0.50f, 1707.30627298f, 0.52329943261f);
+
+	put_f1(P->hb, kRnaHB);
+	put_f1(P->stck, kRnaSTCK);
+	const double eps_hb = kRnaHbEps;
+	const double eps_st = 1.40206f + 2.77f * T; // RNAInteraction.cpp:331
+	for(int i = 0; i < 25; i++) {
+		P->hb_eps[i] = (float) eps_hb;
+		P->hb_shift[i] = (float) (eps_hb * morse_shift(kRnaHB));
+		P->stck_eps[i] = (float) eps_st;
+		P->stck_shift[i] = (float) (eps_st * morse_shift(kRnaSTCK));
+		P->crst_kfac[i] = 1.f;
+	}
+	P->crst = oxb_f2{ 59.9626f, 0.6f, 0.5f, -0.888889f, 0.42f, 0.375f, -0.888889f, 0.58f, 0.625f };
+	P->cxst = oxb_f2{ 80.f, 0.6f, 0.5f, -0.888889f, 0.42f, 0.375f, -0.888889f, 0.58f, 0.625f };
+
+	put_f4(P, OXB_RF4_STCK_T5, 0.9f, 3.89361f, 0.f, 0.95f, 1.16959f);
+	put_f4(P, OXB_RF4_STCK_T6, 0.9f, 3.89361f, 0.f, 0.95f, 1.16959f);
+	put_f4(P, OXB_RF4_STCK_TB1, 1.3f, 6.4381f, 0.f, 0.8f, 0.961538f);
+	put_f4(P, OXB_RF4_STCK_TB2, 1.3f, 6.4381f, 0.f, 0.8f, 0.961538f);
+	put_f4(P, OXB_RF4_HB_T1, 1.5f, 4.16038f, 0.f, 0.7f, 0.952381f);
+	put_f4(P, OXB_RF4_HB_T2, 1.5f, 4.16038f, 0.f, 0.7f, 0.952381f);
+	put_f4(P, OXB_RF4_HB_T3, 1.5f, 4.16038f, 0.f, 0.7f, 0.952381f);
+	put_f4(P, OXB_RF4_HB_T4, 0.46f, 0.133855f, kPi, 0.7f, 3.10559f);
+	put_f4(P, OXB_RF4_HB_T7, 4.f, 17.0526f, kPi * 0.5f, 0.45f, 0.555556f);
+	put_f4(P, OXB_RF4_HB_T8, 4.f, 17.0526f, kPi * 0.5f, 0.45f, 0.555556f);
+	put_f4(P, OXB_RF4_CRST_T1, 2.25f, 7.00545f, 0.505f, 0.58f, 0.766284f);
+	put_f4(P, OXB_RF4_CRST_T2, 1.70f, 6.2469f, 1.266f, 0.68f, 0.865052f);
+	put_f4(P, OXB_RF4_CRST_T3, 1.70f, 6.2469f, 1.266f, 0.68f, 0.865052f);
+	put_f4(P, OXB_RF4_CRST_T7, 1.70f, 6.2469f, 0.309f, 0.68f, 0.865052f);
+	put_f4(P, OXB_RF4_CRST_T8, 1.70f, 6.2469f, 0.309f, 0.68f, 0.865052f);
+	put_f4(P, OXB_RF4_CXST_T1, 2.f, 10.9032f, 2.592f, 0.65f, 0.769231f);
+	put_f4(P, OXB_RF4_CXST_T4, 1.3f, 6.4381f, 0.151f, 0.8f, 0.961538f);
+	put_f4(P, OXB_RF4_CXST_T5, 0.9f, 3.89361f, 0.685f, 0.95f, 1.16959f);
+	put_f4(P, OXB_RF4_CXST_T6, 0.9f, 3.89361f, 0.685f, 0.95f, 1.16959f);
+	P->phi1 = oxb_f5{ 2.0f, 10.9032f, -0.769231f, -0.65f };
+	P->phi2 = P->phi1; P->phi3 = P->phi1; P->phi4 = P->phi1;
+
+	// Debye-Hueckel: both get_settings and init use the float 0.1f here (unlike DNA2)
+	const double lfac = 0.3667258, q = 0.0858;
+	salt = (double) (float) salt;
+	const double lambda = lfac * std::sqrt(T / 0.1f) / std::sqrt(salt);
+	const double x = 3.0 * lambda, l = lambda;
+	const double B = -(std::exp(-x / l) * q * q * (x + l) * (x + l)) / (4. * x * x * x * l * l * (-q));
+	const double RC = x * (q * x + 3. * q * l) / (q * (x + l));
+	P->dh_minus_kappa = (float) (-1.0 / lambda);
+	P->dh_prefactor = (float) q;
+	P->dh_rhigh = (float) x;
+	P->dh_rc = (float) RC;
+	P->dh_b = (float) B;
+	P->dh_half_charged_ends = dh_half_charged_ends ? 1 : 0;
+	P->hb_multiplier = 1.f;
+
+	P->mismatch_repulsion = mismatch_repulsion ? 1 : 0;
+	if(mismatch_repulsion) {
+		const float temp = -1.0f * (float) mismatch_strength / kRnaHbEps; // RNAInteraction2.cpp:97
+		P->mis_eps = (float) (eps_hb * temp);
+		P->mis_shift = (float) (eps_hb * morse_shift(kRnaHB) * temp);
+	}
+
+	const float b2 = P->back_a1 * P->back_a1 + P->back_a2 * P->back_a2 + P->back_a3 * P->back_a3;
+	const double back_len = std::sqrt((double) b2);
+	const double rcutback = 2 * back_len + (double) 0.711879214356f;
+	const double rcutbase = 2 * std::fabs((double) P->base_a1) + std::fmax((double) kRnaHB.rchigh, (double) P->crst.rchigh);
+	double rcut_near = std::fmax(rcutback, rcutbase);
+	double rcut = rcut_near;
+	const double debyecut = 2. * back_len + RC;
+	if(debyecut > rcut) rcut = debyecut;
+	P->rcut = (float) rcut;
+	P->rcut_near = (float) rcut_near;
+	if(rcut_out != nullptr) *rcut_out = rcut;
+	return 0;
+}
+
+extern "C" int oxb_rna2_params_seqdep(oxb_rna2_params *P, double T, const double *stck_raw16, double st_t_dep, const double *cross_raw16,
+		double hb_AT, double hb_GC, double hb_GT) {
+	if(P == nullptr || stck_raw16 == nullptr || cross_raw16 == nullptr) return 1;
+	P->average = 0;
+	for(int i = 0; i < 4; i++) {
+		for(int j = 0; j < 4; j++) {
+			double eps = (double) (float) stck_raw16[4 * i + j] * (1.0 + T * (double) (float) st_t_dep);
+			P->stck_eps[5 * i + j] = (float) eps;
+			P->stck_shift[5 * i + j] = (float) (eps * morse_shift(kRnaSTCK));
+			P->crst_kfac[5 * i + j] = (float) cross_raw16[4 * i + j] / P->crst.k;
+		}
+	}
+	const int A = 0, G = 1, C = 2, U = 3;
+	const int ij[3][2] = { { A, U }, { G, C }, { G, U } };
+	const double v[3] = { (double) (float) hb_AT, (double) (float) hb_GC, (double) (float) hb_GT };
+	for(int k = 0; k < 3; k++) {
+		int i = ij[k][0], j = ij[k][1];
+		P->hb_eps[5 * i + j] = P->hb_eps[5 * j + i] = (float) v[k];
+		P->hb_shift[5 * i + j] = P->hb_shift[5 * j + i] = (float) (v[k] * morse_shift(kRnaHB));
+	}
+	return 0;
+}

@@ -55,6 +55,23 @@ def langevin_params(T, dt, gamma_trans=0.0, diff_coeff=0.0):
     return g, gr, np.sqrt(2.0 * g * T / dt), np.sqrt(2.0 * gr * T / dt)
 
 
+def read_seq_dep(path_or_dict):
+    """`seq_dep_file` (key = value lines, e.g. oxDNA2_sequence_dependent_parameters.txt / rna_sequence_dependent_parameters.txt),
+    or an already parsed dict."""
+    if isinstance(path_or_dict, dict):
+        return path_or_dict
+    if path_or_dict is None:
+        raise ValueError("use_average_seq = false needs seq_dep_file")
+    out = {}
+    with open(path_or_dict) as f:
+        for line in f:
+            line = line.split("#")[0]
+            if "=" in line:
+                k, v = line.split("=", 1)
+                out[k.strip()] = float(np.float32(v))  # the reference reads these with getInputFloat
+    return out
+
+
 class Simulation:
     def __init__(self, inp, topology, conf, device=0):
         """topology: dict(btype, n3, n5, strand); conf: dict(box, pos, a1, a3[, vel, L])."""
@@ -63,8 +80,9 @@ class Simulation:
         if str(g("backend", "CUDA")).upper() != "CUDA":
             raise ValueError("oxdna_b200 only implements backend = CUDA")
         itype = str(g("interaction_type", "DNA2"))
-        if itype not in ("DNA2", "DNA2_nomesh"):
-            raise ValueError(f"interaction_type = {itype} is not available in this build (DNA2 only)")
+        if itype not in ("DNA2", "DNA2_nomesh", "RNA2"):
+            raise ValueError(f"interaction_type = {itype} is not available in this build (DNA2, RNA2)")
+        self.itype = itype
         prec = str(g("backend_precision", "mixed"))
         if prec not in ("mixed",):
             raise ValueError(f"backend_precision = {prec} is not available in this build")
@@ -94,8 +112,28 @@ class Simulation:
     def _set_model(self):
         g = self.inp.get
         mbf = g("max_backbone_force", None)
-        self.params, self.rcut = capi.dna2_params(self.T, float(g("salt_concentration", 0.5)), _bool(g("dh_half_charged_ends", 1)),
-                                                  None if mbf is None else float(mbf), float(g("max_backbone_force_far", 0.04)))
+        mbf = None if mbf is None else float(mbf)
+        average = _bool(g("use_average_seq", 1))
+        sd = None if average else read_seq_dep(g("seq_dep_file"))
+        if self.itype == "RNA2":
+            # RNA2Interaction::get_settings: salt defaults to 1.0 (src/Interactions/RNAInteraction2.cpp:34-37)
+            self.params, self.rcut = capi.rna2_params(self.T, float(g("salt_concentration", 1.0)), _bool(g("dh_half_charged_ends", 1)), mbf,
+                                                      float(g("max_backbone_force_far", 0.04)), _bool(g("mismatch_repulsion", 0)),
+                                                      float(g("mismatch_repulsion_strength", 1.0)))
+            if sd is not None:
+                B = "AGCT"
+                hb = lambda a, b: sd.get(f"HYDR_{a}_{b}", sd.get(f"HYDR_{b}_{a}"))
+                capi.rna2_params_seqdep(self.params, self.T, [sd[f"STCK_{a}_{b}"] for a in B for b in B], sd["ST_T_DEP"],
+                                        [sd[f"CROSS_{a}_{b}"] for a in B for b in B], hb("A", "T"), hb("G", "C"), hb("G", "T"))
+            self.ctx.set_model_rna2(self.params, self.rcut)
+            return
+        self.params, self.rcut = capi.dna2_params(self.T, float(g("salt_concentration", 0.5)), _bool(g("dh_half_charged_ends", 1)), mbf,
+                                                  float(g("max_backbone_force_far", 0.04)))
+        if sd is not None:
+            # DNAInteraction.cpp:329-375
+            B = "AGCT"
+            hb = lambda a, b: sd.get(f"HYDR_{a}_{b}", sd.get(f"HYDR_{b}_{a}"))
+            capi.dna2_params_seqdep(self.params, self.T, [sd[f"STCK_{a}_{b}"] for a in B for b in B], sd["STCK_FACT_EPS"], hb("A", "T"), hb("G", "C"))
         self.ctx.set_model_dna2(self.params, self.rcut)
 
     def _set_thermostat(self):

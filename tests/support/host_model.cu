@@ -1,14 +1,14 @@
 // TEST SUPPORT: runs the product's FP32 pair-potential functions (oxdna_b200/csrc/dna_model.cuh, compiled for the
 // host by nvcc) over a pair list, so their formulation can be checked against the oracle on a machine without a GPU.
 // This is a unit test of device code's arithmetic, not a product code path.
-#include "../../oxdna_b200/csrc/dna_model.cuh"
+#include "../../oxdna_b200/csrc/models.cuh"
 
 #include <cmath>
 #include <vector>
 
-extern "C" void host_dna2_forces(const oxb_dna2_params *Mp, int N, const double *pos, const double *axes, const int *btype, const int *n3,
+template<class MD>
+static void host_forces(const typename MD::Params &M, int N, const double *pos, const double *axes, const int *btype, const int *n3,
 		const int *n5, const double *box, const int *pairs, long long npairs, double *F, double *Tlab, double *epart) {
-	const oxb_dna2_params &M = *Mp;
 	BoxF b;
 	b.lx = (float) box[0]; b.ly = (float) box[1]; b.lz = (float) box[2];
 	b.sx = (float) (box[0] / 4294967296.0); b.sy = (float) (box[1] / 4294967296.0); b.sz = (float) (box[2] / 4294967296.0);
@@ -23,7 +23,7 @@ extern "C" void host_dna2_forces(const oxb_dna2_params *Mp, int N, const double 
 		quatd q = quat_from_axes(axes + 9 * i, axes + 9 * i + 3, axes + 9 * i + 6);
 		float4 qf = make_float4((float) q.x, (float) q.y, (float) q.z, (float) q.w);
 		ax[i] = axes_from_quat(qf);
-		back[i] = ax[i].a1 * M.back_a1 + ax[i].a2 * M.back_a2;
+		back[i] = MD::back(M, ax[i]);
 	}
 	for(int i = 0; i < 3 * N; i++) F[i] = Tlab[i] = 0.;
 	for(int i = 0; i < N; i++) epart[i] = 0.;
@@ -41,14 +41,24 @@ extern "C" void host_dna2_forces(const oxb_dna2_params *Mp, int N, const double 
 		v3 r = min_image_fixed(b, ip[p], ip[q]);
 		PairAcc acc; acc.clear();
 		bool broken = false;
-		float e = dna2_bonded(M, r, ax[p], ax[q], btype[p], btype[q], back[p], back[q], acc, broken);
+		float e = MD::bonded(M, r, ax[p], ax[q], btype[p], btype[q], back[p], back[q], acc, broken);
 		scatter(p, q, acc, e);
 	}
 	for(long long k = 0; k < npairs; k++) {
 		int p = pairs[2 * k + 1], q = pairs[2 * k];
 		v3 r = min_image_fixed(b, ip[p], ip[q]);
 		PairAcc acc; acc.clear();
-		PairEnergy e = dna2_nonbonded(M, r, ax[p], ax[q], btype[p], btype[q], n3[p] < 0 || n5[p] < 0, n3[q] < 0 || n5[q] < 0, back[p], back[q], acc);
+		PairEnergy e = MD::nonbonded(M, r, ax[p], ax[q], btype[p], btype[q], n3[p] < 0 || n5[p] < 0, n3[q] < 0 || n5[q] < 0, back[p], back[q], acc);
 		scatter(p, q, acc, e.total);
 	}
+}
+
+extern "C" void host_dna2_forces(const oxb_dna2_params *M, int N, const double *pos, const double *axes, const int *btype, const int *n3,
+		const int *n5, const double *box, const int *pairs, long long npairs, double *F, double *Tlab, double *epart) {
+	host_forces<DnaModel>(*M, N, pos, axes, btype, n3, n5, box, pairs, npairs, F, Tlab, epart);
+}
+
+extern "C" void host_rna2_forces(const oxb_rna2_params *M, int N, const double *pos, const double *axes, const int *btype, const int *n3,
+		const int *n5, const double *box, const int *pairs, long long npairs, double *F, double *Tlab, double *epart) {
+	host_forces<RnaModel>(*M, N, pos, axes, btype, n3, n5, box, pairs, npairs, F, Tlab, epart);
 }

@@ -19,7 +19,7 @@ SO = os.path.join(ROOT, "tests", "support", "_build", "libhostmodel.so")
 def hostlib():
     os.makedirs(os.path.dirname(SO), exist_ok=True)
     src = os.path.join(ROOT, "tests", "support", "host_model.cu")
-    deps = [src, os.path.join(ROOT, "oxdna_b200", "csrc", "dna_model.cuh"), os.path.join(ROOT, "oxdna_b200", "csrc", "common.cuh")]
+    deps = [src] + [os.path.join(ROOT, "oxdna_b200", "csrc", f) for f in ("dna_model.cuh", "rna_model.cuh", "models.cuh", "common.cuh", "params.cpp")]
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-Xcompiler", "-fPIC", "-shared", "-o", SO, src,
                                os.path.join(ROOT, "oxdna_b200", "csrc", "params.cpp")])
@@ -44,3 +44,162 @@ def test_fp32_formulation_within_mixed_tolerance(hostlib, case):
     assert np.linalg.norm(F - g["force"], axis=1).max() <= 1e-5 * fmax
     assert np.linalg.norm(Tl - g["torque_lab"], axis=1).max() <= 1e-5 * tmax
     assert abs(ep.sum() - float(g["U"])) <= 1e-6 * abs(float(g["U"]))
+
+
+def rna_models(g):
+    """(product FP32 block, oracle block in its gradient form) for an RNA fixture"""
+    T, salt = parse_temperature(str(g["T"])), float(g["salt"])
+    mis = float(g["mismatch"]) if "mismatch" in g else -1.0
+    M, rcut = capi.rna2_params(T, salt, mismatch_repulsion=mis >= 0, mismatch_repulsion_strength=max(mis, 0.0))
+    P = O.rna2_params(T, salt, cpu_quirks=False, mismatch_repulsion=mis >= 0, mismatch_repulsion_strength=max(mis, 0.0))
+    if "sd_stck" in g:
+        sd = [g["sd_stck"], float(g["sd_st_t_dep"]), g["sd_cross"], float(g["sd_hb_AT"]), float(g["sd_hb_GC"]), float(g["sd_hb_GT"])]
+        capi.rna2_params_seqdep(M, T, *sd)
+        O.rna2_params_seqdep(P, *sd)
+    return M, rcut, P
+
+
+def test_rna_parameter_block_matches_oracle():
+    g = load_golden("rna_lattice8_seqdep")
+    M, rcut, P = rna_models(g)
+    assert rcut == P.rcut == float(g["rcut"])
+    assert abs(M.dh_rc - P.dh_rc) < 1e-6 and abs(M.dh_b - P.dh_b) < 1e-7 * abs(P.dh_b) + 1e-9
+    for i in range(4):
+        for j in range(4):
+            assert abs(M.stck_eps[5 * i + j] - P.stck.eps[i][j]) < 2e-7 and abs(M.hb_eps[5 * i + j] - P.hb.eps[i][j]) < 2e-7
+            assert abs(M.stck_shift[5 * i + j] - P.stck.shift[i][j]) < 2e-7 and abs(M.crst_kfac[5 * i + j] - P.crst_kfac[i][j]) < 2e-7
+    assert abs(M.mis_eps - P.mis_eps) < 2e-7 and abs(M.mis_shift - P.mis_shift) < 2e-7
+    names = ("stck_t5 stck_t6 stck_tb1 stck_tb2 hb_t1 hb_t2 hb_t3 hb_t4 hb_t7 hb_t8 crst_t1 crst_t2 crst_t3 crst_t7 crst_t8 cxst_t1 cxst_t4 "
+             "cxst_t5 cxst_t6").split()
+    for k, n in enumerate(names):
+        o = getattr(P, n)
+        for f in "a b t0 ts tc".split():
+            assert abs(getattr(M.f4[k], f) - getattr(o, f)) < 1e-6, (n, f)
+
+
+@pytest.mark.parametrize("case", ["force_field_rna/ref_rna2", "force_field_rna/ref_rna2_seqdep", "rna_lattice8", "rna_lattice8_nohb", "rna_lattice8_seqdep"])
+@pytest.mark.parametrize("perturb", [0.0, 0.06])
+def test_rna_fp32_formulation_within_mixed_tolerance(hostlib, case, perturb):
+    """oxRNA2: FP32 device functions against the restatement in its gradient form (cpu_quirks = 0, what the reference's CUDA
+    kernels evaluate).  `perturb` shakes the orientations so that the rarely visited branches (phi factors, mirrored theta1,
+    mismatch repulsion) are exercised as well."""
+    g = load_golden(case)
+    M, rcut, P = rna_models(g)
+    N = len(g["pos"])
+    rng = np.random.default_rng(11)
+    ax = np.ascontiguousarray(O.axes_from_a1a3(g["a1"] + rng.normal(scale=perturb, size=g["a1"].shape), g["a3"] + rng.normal(scale=perturb, size=g["a3"].shape)))
+    pos, box = np.ascontiguousarray(g["pos"]), np.ascontiguousarray(g["box"], dtype=np.float64)
+    bt, n3, n5 = (np.ascontiguousarray(g[k], dtype=np.int32) for k in ("btype", "n3", "n5"))
+    pairs = np.ascontiguousarray(O.verlet_pairs(pos, n3, n5, box, P.rcut + 0.1), dtype=np.int32)
+    ref = O.forces(P, pos, ax, bt, n3, n5, box, pairs)
+    F, Tl, ep = np.zeros((N, 3)), np.zeros((N, 3)), np.zeros(N)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    hostlib.host_rna2_forces(C.byref(M), N, p(pos), p(ax), p(bt), p(n3), p(n5), p(box), p(pairs), C.c_longlong(len(pairs)), p(F), p(Tl), p(ep))
+    fmax = np.linalg.norm(ref["force"], axis=1).max()
+    tmax = np.linalg.norm(ref["torque_lab"], axis=1).max()
+    # Thermalised fixtures: the north star's 1e-5.  Shaken (unphysical) orientations push bases into the quadratic smoothing
+    # zone of the base-base excluded volume, whose stiffness 2 eps b = 1.6e4 turns the 4e-8 rounding of an FP32 orientation
+    # into ~7e-4 of absolute force error whatever the formulation (the reference's float quaternions included): allow it.
+    stiff = 1e-3 if perturb > 0 else 0.0
+    assert np.linalg.norm(F - ref["force"], axis=1).max() <= 1e-5 * fmax + stiff
+    assert np.linalg.norm(Tl - ref["torque_lab"], axis=1).max() <= 1e-5 * tmax + stiff
+    assert abs(ep.sum() - ref["U"]) <= 2e-6 * abs(ref["U"]) + 1e-2 * stiff
+    assert np.abs(ep - ref["epart"]).max() <= 1e-5 * max(1.0, np.abs(ref["epart"]).max()) + 1e-2 * stiff
+
+
+def _random_rotations(rng, n):
+    q = rng.normal(size=(n, 4))
+    q /= np.linalg.norm(q, axis=1)[:, None]
+    w, x, y, z = q.T
+    R = np.empty((n, 3, 3))
+    R[:, 0, 0], R[:, 0, 1], R[:, 0, 2] = 1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)
+    R[:, 1, 0], R[:, 1, 1], R[:, 1, 2] = 2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)
+    R[:, 2, 0], R[:, 2, 1], R[:, 2, 2] = 2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)
+    return R  # columns = a1, a2, a3
+
+
+def _pair_cloud(rng, n_pairs, site_p, site_q, dmin, dmax, spread=None):
+    """n_pairs isolated two-particle systems on a grid: q placed so that |site_q(q) - site_p(p)| is uniform in (dmin, dmax).
+    site_*: coefficients on (a1, a2, a3).  spread: if set, q's frame is p's frame times a random rotation of at most that angle."""
+    Rp = _random_rotations(rng, n_pairs)
+    if spread is None:
+        Rq = _random_rotations(rng, n_pairs)
+    else:
+        ax = rng.normal(size=(n_pairs, 3))
+        ax /= np.linalg.norm(ax, axis=1)[:, None]
+        ang = rng.uniform(0, spread, size=n_pairs)
+        K = np.zeros((n_pairs, 3, 3))
+        K[:, 0, 1], K[:, 0, 2], K[:, 1, 0], K[:, 1, 2], K[:, 2, 0], K[:, 2, 1] = -ax[:, 2], ax[:, 1], ax[:, 2], -ax[:, 0], -ax[:, 1], ax[:, 0]
+        dR = np.eye(3)[None] + np.sin(ang)[:, None, None] * K + (1 - np.cos(ang))[:, None, None] * (K @ K)
+        Rq = Rp @ dR
+    u = rng.normal(size=(n_pairs, 3))
+    u /= np.linalg.norm(u, axis=1)[:, None]
+    d = rng.uniform(dmin, dmax, size=n_pairs)
+    side = int(np.ceil(n_pairs ** (1 / 3)))
+    k = np.arange(n_pairs)
+    grid = np.stack([k % side, (k // side) % side, k // (side * side)], axis=1) * 6.0 + 3.0
+    sp = Rp @ np.asarray(site_p)
+    sq = Rq @ np.asarray(site_q)
+    xp = grid
+    xq = grid + sp + u * d[:, None] - sq
+    pos = np.empty((2 * n_pairs, 3))
+    pos[0::2], pos[1::2] = xp, xq
+    R = np.empty((2 * n_pairs, 3, 3))
+    R[0::2], R[1::2] = Rp, Rq
+    axes = np.ascontiguousarray(np.concatenate([R[:, :, 0], R[:, :, 1], R[:, :, 2]], axis=1))
+    box = np.array([side * 6.0] * 3)
+    return pos, axes, box
+
+
+@pytest.mark.parametrize("kind", ["base", "stack", "bonded"])
+def test_rna_fp32_pair_cloud_covers_rare_branches(hostlib, kind):
+    """Isolated random pairs placed inside the radial window of (base) hydrogen bonding / mismatch repulsion / cross stacking,
+    (stack) coaxial stacking incl. the phi3/phi4 triple products and the mirrored theta1, (bonded) 3'-5' stacking incl. the
+    thetaB and phi factors.  Excluded volume is switched off in both models (it is the DNA code path, tested above, and its
+    r^-13 wall would drown the angular terms in random overlaps)."""
+    rng = np.random.default_rng({"base": 1, "stack": 2, "bonded": 3}[kind])
+    T = parse_temperature("310K")
+    M, rcut = capi.rna2_params(T, 0.5, mismatch_repulsion=True, mismatch_repulsion_strength=1.3)
+    P = O.rna2_params(T, 0.5, cpu_quirks=False, mismatch_repulsion=True, mismatch_repulsion_strength=1.3)
+    sd = [np.linspace(1.1, 1.7, 16), 1.97561, np.linspace(50.0, 70.0, 16), 0.82, 1.06, 0.51]
+    capi.rna2_params_seqdep(M, T, *sd)
+    O.rna2_params_seqdep(P, *sd)
+    M.excl_eps = 0.0
+    P.excl_eps = 0.0
+    n = 60000
+    if kind == "base":
+        pos, axes, box = _pair_cloud(rng, n, (0.4, 0, 0), (0.4, 0, 0), 0.2, 0.8)
+    elif kind == "stack":
+        pos, axes, box = _pair_cloud(rng, n, (0.34, 0, 0), (0.34, 0, 0), 0.36, 0.64)
+    else:
+        pos, axes, box = _pair_cloud(rng, n, (-0.4, 0, 0.2), (-0.4, 0, 0.2), 0.761 - 0.2, 0.761 + 0.2, spread=1.2)
+    N = 2 * n
+    bt = rng.integers(0, 4, size=N).astype(np.int32)
+    n3 = np.full(N, -1, dtype=np.int32)
+    n5 = np.full(N, -1, dtype=np.int32)
+    if kind == "bonded":
+        n3[0::2] = np.arange(1, N, 2)
+        n5[1::2] = np.arange(0, N, 2)
+        pairs = np.zeros((0, 2), dtype=np.int32)
+    else:
+        pairs = np.ascontiguousarray(np.stack([np.arange(0, N, 2), np.arange(1, N, 2)], axis=1), dtype=np.int32)
+    ref = O.forces(P, pos, axes, bt, n3, n5, box, pairs)
+    F, Tl, ep = np.zeros((N, 3)), np.zeros((N, 3)), np.zeros(N)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    hostlib.host_rna2_forces(C.byref(M), N, p(pos), p(axes), p(bt), p(n3), p(n5), p(box), p(pairs), C.c_longlong(len(pairs)), p(F), p(Tl), p(ep))
+    active = np.abs(ref["epart"]) > 1e-4
+    # coverage: the sample must actually reach the branches it is meant for
+    if kind == "base":
+        assert active.sum() > 400
+    elif kind == "stack":
+        assert (np.abs(ref["epart"]) > 1e-3).sum() > 400 and ref["eterms"][6] < -1.0
+    else:
+        assert ref["eterms"][2] < -100.0
+    fn, tn = np.linalg.norm(ref["force"], axis=1), np.linalg.norm(ref["torque_lab"], axis=1)
+    scale = np.maximum(np.maximum(fn, tn), 1.0)
+    # pair-wise bound against the pair's own force scale (floor 1, reduced units; cf. SURVEY 8(d) F_floor): 99.9 % of the
+    # 120,000 particles inside 3e-6, the worst one inside 2e-5
+    for got, want in ((F, ref["force"]), (Tl, ref["torque_lab"])):
+        err = np.linalg.norm(got - want, axis=1) / scale
+        assert np.quantile(err, 0.999) <= 3e-6 and err.max() <= 2e-5, (np.quantile(err, 0.999), err.max())
+    assert (np.abs(ep - ref["epart"]) / np.maximum(np.abs(ref["epart"]), 1.0)).max() <= 1e-5
