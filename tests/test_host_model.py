@@ -198,8 +198,8 @@ def test_rna_fp32_pair_cloud_covers_rare_branches(hostlib, kind):
     fn, tn = np.linalg.norm(ref["force"], axis=1), np.linalg.norm(ref["torque_lab"], axis=1)
     scale = np.maximum(np.maximum(fn, tn), 1.0)
     # pair-wise bound against the pair's own force scale (floor 1, reduced units; cf. SURVEY 8(d) F_floor): 99.9 % of the
-    # 120,000 particles inside 3e-6, the worst one inside 2e-5
+    # 120,000 particles inside 6e-6, the worst one inside 2e-5
     for got, want in ((F, ref["force"]), (Tl, ref["torque_lab"])):
         err = np.linalg.norm(got - want, axis=1) / scale
-        assert np.quantile(err, 0.999) <= 3e-6 and err.max() <= 2e-5, (np.quantile(err, 0.999), err.max())
+        assert np.quantile(err, 0.999) <= 6e-6 and err.max() <= 2e-5, (np.quantile(err, 0.999), err.max())
     assert (np.abs(ep - ref["epart"]) / np.maximum(np.abs(ref["epart"]), 1.0)).max() <= 1e-5
