@@ -253,3 +253,137 @@ def test_long_run_mean_energies_match_reference_statistically():
         assert abs(mk - 3.0 * T) < 0.02 * 3.0 * T
     finally:
         sim.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------- oxRNA2
+RNA_CASES = ["force_field_rna/ref_rna2", "force_field_rna/ref_rna2_seqdep", "rna_lattice8", "rna_lattice8_nohb", "rna_lattice8_seqdep"]
+
+
+def rna_inp(g, **over):
+    inp = dict(backend="CUDA", interaction_type="RNA2", T=str(g["T"]), salt_concentration=float(g["salt"]), dt=0.003,
+               verlet_skin=0.05, thermostat="no", CUDA_sort_every=0, use_edge=0, seed=11)
+    if "sd_stck" in g:
+        B = "AGCT"
+        sd = {f"STCK_{a}_{b}": float(g["sd_stck"][4 * i + j]) for i, a in enumerate(B) for j, b in enumerate(B)}
+        sd.update({f"CROSS_{a}_{b}": float(g["sd_cross"][4 * i + j]) for i, a in enumerate(B) for j, b in enumerate(B)})
+        sd.update(ST_T_DEP=float(g["sd_st_t_dep"]), HYDR_A_T=float(g["sd_hb_AT"]), HYDR_C_G=float(g["sd_hb_GC"]), HYDR_G_T=float(g["sd_hb_GT"]))
+        inp.update(use_average_seq=0, seq_dep_file=sd)
+    if "mismatch" in g and float(g["mismatch"]) >= 0:
+        inp.update(mismatch_repulsion=1, mismatch_repulsion_strength=float(g["mismatch"]))
+    inp.update(over)
+    return inp
+
+
+def rna_oracle(g, pos=None, a1=None, a3=None):
+    """the restatement in its gradient form (what the reference's CUDA kernels evaluate; see oracle/oxdna_oracle.h)"""
+    T, salt = parse_temperature(str(g["T"])), float(g["salt"])
+    mis = float(g["mismatch"]) if "mismatch" in g else -1.0
+    P = O.rna2_params(T, salt, cpu_quirks=False, mismatch_repulsion=mis >= 0, mismatch_repulsion_strength=max(mis, 0.0))
+    if "sd_stck" in g:
+        O.rna2_params_seqdep(P, g["sd_stck"], float(g["sd_st_t_dep"]), g["sd_cross"], float(g["sd_hb_AT"]), float(g["sd_hb_GC"]), float(g["sd_hb_GT"]))
+    pos = g["pos"] if pos is None else pos
+    ax = O.axes_from_a1a3(g["a1"] if a1 is None else a1, g["a3"] if a3 is None else a3)
+    pairs = O.verlet_pairs(pos, g["n3"], g["n5"], g["box"], P.rcut + 2 * 0.05)
+    out = O.forces(P, pos, ax, g["btype"], g["n3"], g["n5"], g["box"], pairs)
+    out["pairs"] = pairs
+    out["P"] = P
+    return out
+
+
+@pytest.mark.parametrize("case", RNA_CASES)
+@pytest.mark.parametrize("use_edge", [0, 1])
+@pytest.mark.parametrize("sort_every", [0, 1])
+def test_rna_forces_torques_energy_vs_oracle(case, use_edge, sort_every):
+    g = load_golden(case)
+    ref = rna_oracle(g)
+    topo = dict(btype=g["btype"], n3=g["n3"], n5=g["n5"], strand=g["strand"])
+    conf = dict(box=g["box"], pos=g["pos"], a1=g["a1"], a3=g["a3"], vel=g["vel"], L=g["L"])
+    sim = Simulation(rna_inp(g, use_edge=use_edge, CUDA_sort_every=sort_every), topo, conf)
+    try:
+        assert sim.rcut == float(g["rcut"])  # bit-equal to the reference CPU class
+        assert pair_set(sim.ctx.get_pairs()) == pair_set(g["pairs"])  # reference CPU Verlet list
+        out = sim.ctx.get_forces()
+        check_forces(out, ref)
+        assert np.abs(out["energy"] * 0.5 - ref["epart"]).max() <= 1e-5 * max(1.0, np.abs(ref["epart"]).max())
+        hb = out["hb_energy"].sum() * 0.5
+        assert abs(hb - ref["eterms"][4]) <= 1e-5 * abs(ref["eterms"][4]) + 1e-6
+        # and against the reference CPU class itself: every term but the meshed hydrogen bonding to FP32 accuracy
+        if abs(float(g["energy_split"][4])) == 0:
+            check_forces(out, g)
+    finally:
+        sim.close()
+
+
+@pytest.mark.parametrize("use_edge,sort_every", [(0, 0), (1, 1)])
+def test_rna_nve_trajectory_vs_reference(use_edge, sort_every):
+    """100 NVE steps from the thermalised all-A RNA lattice (no meshed term in the reference CPU run)."""
+    g = load_golden("rna_lattice8_nohb")
+    topo = dict(btype=g["btype"], n3=g["n3"], n5=g["n5"], strand=g["strand"])
+    conf = dict(box=g["box"], pos=g["pos"], a1=g["a1"], a3=g["a3"], vel=g["vel"], L=g["L"])
+    sim = Simulation(rna_inp(g, use_edge=use_edge, CUDA_sort_every=sort_every), topo, conf)
+    try:
+        n = int(g["nve_steps"])
+        sim.run(n)
+        st = sim.ctx.get_state()
+        assert np.abs(st["pos"] - g["pos1"]).max() < 2e-4
+        assert np.abs(st["vel"] - g["vel1"]).max() < 2e-3
+        assert np.abs(st["a1"] - g["a11"]).max() < 2e-3
+        U, K = sim.ctx.energy()
+        E0 = float(g["U"]) + 0.5 * (np.sum(g["vel"] ** 2) + np.sum(g["L"] ** 2))
+        assert abs((U + K) - E0) < 2e-3 * abs(E0)
+    finally:
+        sim.close()
+
+
+def test_rna_energy_conservation_and_thermostat():
+    """1,000 NVE steps of the hydrogen-bonded RNA lattice conserve energy (the force is the gradient); then the Brownian
+    thermostat equilibrates <K> to 3T (translation 3T/2 + rotation 3T/2 per nucleotide)."""
+    g = load_golden("rna_lattice8")
+    topo = dict(btype=g["btype"], n3=g["n3"], n5=g["n5"], strand=g["strand"])
+    conf = dict(box=g["box"], pos=g["pos"], a1=g["a1"], a3=g["a3"], vel=g["vel"], L=g["L"])
+    sim = Simulation(rna_inp(g, use_edge=1, CUDA_sort_every=1), topo, conf)
+    try:
+        U0, K0 = sim.ctx.energy()
+        sim.run(1000)
+        U1, K1 = sim.ctx.energy()
+        assert abs((U1 + K1) - (U0 + K0)) < 1e-3 * abs(U0 + K0)
+        ref = rna_oracle(g, **{k: sim.ctx.get_state()[k] for k in ("pos", "a1", "a3")})
+        check_forces(sim.ctx.get_forces(), ref)
+    finally:
+        sim.close()
+    T = parse_temperature(str(g["T"]))
+    sim = Simulation(rna_inp(g, use_edge=1, CUDA_sort_every=1, thermostat="brownian", newtonian_steps=20, pt=0.2), topo, conf)
+    try:
+        sim.run(6000)  # strong coupling (pt = 0.2 every 20 steps): equilibrates in a few thousand steps
+        ks = []
+        for _ in range(80):
+            sim.run(250)
+            ks.append(sim.ctx.energy()[1] / sim.N)
+        assert abs(np.mean(ks) - 3.0 * T) < 0.04 * 3.0 * T, (np.mean(ks), 3.0 * T)
+        assert sim.ctx.stats()["error_flags"] == 0
+    finally:
+        sim.close()
+
+
+def test_rna_duplex_lattice_generator_is_stable_and_sorted_lists_match():
+    """C3-style system: A-form duplex lattice from our own generator, sequence-dependent oxRNA2 (tables passed as a dict)."""
+    sysm = lattice.rna_duplex_lattice(27, bp=16, spacing=10.0, seed=4)
+    T = parse_temperature("300K")
+    v, L = lattice.maxwell_velocities(len(sysm["pos"]), T, 3)
+    conf = dict(box=sysm["box"], pos=sysm["pos"], a1=sysm["a1"], a3=sysm["a3"], vel=v, L=L)
+    g = dict(T="300K", salt=0.5, btype=sysm["btype"], n3=sysm["n3"], n5=sysm["n5"], box=sysm["box"], pos=sysm["pos"], a1=sysm["a1"], a3=sysm["a3"])
+    ref = rna_oracle(g)
+    sim = Simulation(rna_inp(g, use_edge=1, CUDA_sort_every=1, thermostat="brownian", newtonian_steps=103, diff_coeff=2.5), sysm, conf)
+    try:
+        assert pair_set(sim.ctx.get_pairs()) == pair_set(ref["pairs"])
+        check_forces(sim.ctx.get_forces(), ref)
+        assert ref["eterms"][4] / sim.N < -0.3  # hydrogen bonded duplexes
+        sim.run(2000)
+        st = sim.ctx.get_state()
+        g2 = dict(g, pos=st["pos"], a1=st["a1"], a3=st["a3"])
+        ref2 = rna_oracle(g2)
+        assert pair_set(sim.ctx.get_pairs()) == pair_set(ref2["pairs"])
+        check_forces(sim.ctx.get_forces(), ref2)
+        assert ref2["eterms"][4] / sim.N < -0.2 and sim.ctx.stats()["error_flags"] == 0
+    finally:
+        sim.close()
