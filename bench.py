@@ -37,6 +37,9 @@ def workload(name):
     elif name == "c4":
         sysm = lattice.duplex_lattice(25000, bp=20, spacing=10.0, seed=12345, sites_per_side=30)
         desc = "C4: oxDNA2 1M-nt lattice (25,000 x 20-bp), L=300, salt 0.5, 50,000 mutual traps"
+    elif name == "c3":
+        sysm = lattice.rna_duplex_lattice(2048, bp=16, spacing=10.0, seed=12345)  # 13^3 sites, L = 130
+        desc = "C3: oxRNA2 synthetic lattice of 2,048 x 16-bp A-form duplexes (65,536 nt), sequence-dependent parameters, L=130, salt 0.5, T=300K"
     elif name == "small":
         sysm = lattice.duplex_lattice(64, bp=20, spacing=10.0, seed=12345)
         desc = "small: 64 x 20-bp duplexes (2,560 nt)"
@@ -45,10 +48,21 @@ def workload(name):
     return sysm, desc
 
 
+def model_keys(name, tmpdir=None):
+    """interaction keys of the workload; with tmpdir the sequence-dependent table is written to a file (reference binaries)"""
+    if name != "c3":
+        return dict(interaction_type="DNA2")
+    from oxdna_b200 import seqdep
+    sd = seqdep.RNA_SEQ_DEP if tmpdir is None else seqdep.write_file(os.path.join(tmpdir, "rna_seq_dep.txt"), seqdep.RNA_SEQ_DEP)
+    return dict(interaction_type="RNA2", use_average_seq=0, seq_dep_file=sd)
+
+
 def base_input(args, T=T_STR):
-    return dict(backend="CUDA", backend_precision="mixed", interaction_type="DNA2", T=T, salt_concentration=SALT, dt=DT,
-                verlet_skin=0.05, thermostat="brownian", newtonian_steps=103, diff_coeff=2.5, CUDA_list="verlet",
-                CUDA_sort_every=args.sort_every, use_edge=args.use_edge, seed=42)
+    d = dict(backend="CUDA", backend_precision="mixed", T=T, salt_concentration=SALT, dt=DT,
+             verlet_skin=0.05, thermostat="brownian", newtonian_steps=103, diff_coeff=2.5, CUDA_list="verlet",
+             CUDA_sort_every=args.sort_every, use_edge=args.use_edge, seed=42)
+    d.update(model_keys(args.workload))
+    return d
 
 
 class ClockSampler:
@@ -97,7 +111,8 @@ def pair_statistics(sim, sysm):
     N = sim.N
     from oxdna_b200 import io as oio
     ax = oio.orthonormal_axes(st["a1"], st["a3"])
-    back = st["pos"] + ax[:, 0:3] * (-0.34) + ax[:, 3:6] * 0.3408
+    P = sim.params
+    back = st["pos"] + ax[:, 0:3] * float(P.back_a1) + ax[:, 3:6] * float(P.back_a2) + ax[:, 6:9] * float(getattr(P, "back_a3", 0.0))
     box = sysm["box"]
     d = back[pairs[:, 1]] - back[pairs[:, 0]]
     d -= np.rint(d / box) * box
@@ -124,20 +139,27 @@ def write_case(sysm, T, d, state=None):
     return top, conf
 
 
-def _ref_worker(kind, top, conf, md_steps, warm, steps, barrier, q):
+def _ref_worker(kind, top, conf, md_steps, warm, steps, barrier, q, keys=None):
     """One single-threaded CPU MD process (the reference is single-threaded by design)."""
     try:
         if kind == "reference":
             from oracle.refharness import Reference
-            r = Reference(top, conf, interaction_type="DNA2", salt_concentration=SALT, T=T_STR, thermostat="brownian", newtonian_steps=103,
-                          diff_coeff=2.5, dt=DT, seed=42)
+            r = Reference(top, conf, salt_concentration=SALT, T=T_STR, thermostat="brownian", newtonian_steps=103,
+                          diff_coeff=2.5, dt=DT, seed=42, **(keys or dict(interaction_type="DNA2")))
             stepper = r.step
         else:
             from oracle import oracle as O
             from oxdna_b200 import io as oio
             from oxdna_b200.sim import parse_temperature
             t, c = oio.read_topology(top), oio.read_conf(conf)
-            P = O.dna2_params(parse_temperature(T_STR), SALT)
+            if keys and keys.get("interaction_type") == "RNA2":
+                from oxdna_b200.sim import read_seq_dep
+                sd, B = read_seq_dep(keys["seq_dep_file"]), "AGCT"
+                P = O.rna2_params(parse_temperature(T_STR), SALT, cpu_quirks=True)
+                O.rna2_params_seqdep(P, [sd[f"STCK_{a}_{b}"] for a in B for b in B], sd["ST_T_DEP"], [sd[f"CROSS_{a}_{b}"] for a in B for b in B],
+                                     sd["HYDR_A_T"], sd["HYDR_C_G"], sd["HYDR_G_T"])
+            else:
+                P = O.dna2_params(parse_temperature(T_STR), SALT)
             md = O.MD(P, c["pos"], O.axes_from_a1a3(c["a1"], c["a3"]), c["vel"], c["L"], t["btype"], t["n3"], t["n5"], c["box"], DT, 0.05)
             stepper = md.step
         barrier.wait()
@@ -156,7 +178,7 @@ def _ref_worker(kind, top, conf, md_steps, warm, steps, barrier, q):
             pass
 
 
-def run_cpu(sysm, md_steps, warm, steps, procs):
+def run_cpu(sysm, md_steps, warm, steps, procs, workload_name="c2", state=None):
     """Times `procs` independent single-threaded CPU simulations of the workload.  Returns (particle-steps/s, kind, seconds)."""
     import multiprocessing as mp
     from oracle import refharness
@@ -166,10 +188,11 @@ def run_cpu(sysm, md_steps, warm, steps, procs):
         O.build()
     ctx = mp.get_context("spawn")
     d = tempfile.mkdtemp()
-    top, conf = write_case(sysm, T_STR, d)
+    top, conf = write_case(sysm, T_STR, d, state)
+    keys = model_keys(workload_name, d)
     barrier = ctx.Barrier(procs + 1)
     q = ctx.Queue()
-    ps = [ctx.Process(target=_ref_worker, args=(kind, top, conf, md_steps, warm, steps, barrier, q)) for _ in range(procs)]
+    ps = [ctx.Process(target=_ref_worker, args=(kind, top, conf, md_steps, warm, steps, barrier, q, keys)) for _ in range(procs)]
     for p in ps:
         p.start()
     barrier.wait()
@@ -202,7 +225,8 @@ def run_ref_cuda(sysm, workload_name, steps_a, steps_b, state):
         # the reference refuses external forces together with CUDA_sort_every > 0 (MD_CUDABackend.cu:110-112)
         res = R.time_reference_cuda(top, conf, N, steps_a, steps_b, [(1, 0), (0, 0)], T=T_STR, salt=SALT, dt=DT, ext_forces=lattice.mutual_traps(sysm))
     else:
-        res = R.time_reference_cuda(top, conf, N, steps_a, steps_b, [(1, 1), (0, 1), (1, 0), (0, 0)], T=T_STR, salt=SALT, dt=DT)
+        res = R.time_reference_cuda(top, conf, N, steps_a, steps_b, [(1, 1), (0, 1), (1, 0), (0, 0)], T=T_STR, salt=SALT, dt=DT,
+                                    model_keys=model_keys(workload_name, d))
     best = res["best"]
     return {"value": best["value"] if best else None, "unit": "particle-steps/s", "best": best, "runs": res["runs"], "method": res["method"],
             "build": "unmodified /root/reference/src/CUDA, nvcc -arch=sm_100 -O3 -use_fast_math (oracle/Makefile.refcuda), backend_precision = mixed"}
@@ -222,7 +246,7 @@ def reference_arm(args):
     sysm, desc = workload(args.workload)
     procs = args.ref_procs or min(host_cores(), 32)
     md = args.ref_md_steps
-    val, kind, secs = run_cpu(sysm, md, args.warmup, args.steps, procs)
+    val, kind, secs = run_cpu(sysm, md, args.warmup, args.steps, procs, args.workload)
     N = len(sysm["pos"])
     line = {"impl": "reference", "metric": "particle-steps/s", "value": val, "unit": "particle-steps/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -367,7 +391,7 @@ def ours(args):
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             try:
-                cval, kind, secs = run_cpu(sysm, args.cpu_md_steps, 0, 1, 1)
+                cval, kind, secs = run_cpu(sysm, args.cpu_md_steps, 0, 1, 1, args.workload, sim.ctx.get_state())
                 cpu = {"value": cval, "unit": "particle-steps/s", "cores": 1, "kind": kind,
                        "sample": f"{args.cpu_md_steps} MD steps of the same {N}-nt system on one host core ({secs:.1f} s), host has {host_cores()} cores"}
             except Exception as e:  # pragma: no cover
@@ -414,7 +438,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cuda"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c4", "small"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "small"])
     ap.add_argument("--md-steps", type=int, default=1000, help="MD steps per bench step")
     ap.add_argument("--equil", type=int, default=10000, help="untimed equilibration MD steps")
     ap.add_argument("--use-edge", type=int, default=1)

@@ -25,7 +25,7 @@ def available():
 TEMPLATE = """backend = CUDA
 backend_precision = mixed
 sim_type = MD
-interaction_type = DNA2
+{model}
 salt_concentration = {salt}
 T = {T}
 dt = {dt}
@@ -67,10 +67,11 @@ def write_forces_file(path, forces):
             f.write("}\n")
 
 
-def _run(d, top, conf, steps, use_edge, sort_every, T, salt, dt, ext_path):
+def _run(d, top, conf, steps, use_edge, sort_every, T, salt, dt, ext_path, model_keys=None):
     inp = os.path.join(d, f"input_{steps}")
     with open(inp, "w") as f:
-        f.write(TEMPLATE.format(salt=salt, T=T, dt=dt, steps=steps, sort_every=sort_every, use_edge=use_edge, top=top, conf=conf, d=d,
+        model = "\n".join(f"{k} = {v}" for k, v in (model_keys or {"interaction_type": "DNA2"}).items())
+        f.write(TEMPLATE.format(model=model, salt=salt, T=T, dt=dt, steps=steps, sort_every=sort_every, use_edge=use_edge, top=top, conf=conf, d=d,
                                 ext=1 if ext_path else 0, extfile=f"external_forces_file = {ext_path}" if ext_path else ""))
     t0 = time.perf_counter()
     p = subprocess.run([BIN, inp], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
@@ -88,7 +89,7 @@ def _run(d, top, conf, steps, use_edge, sort_every, T, salt, dt, ext_path):
     return (float(m.group(1)) if m else t1 - t0), ("SimBackend timer" if m else "wall clock"), (int(u.group(1)) if u else None)
 
 
-def time_reference_cuda(top, conf, N, steps_a, steps_b, variants, T="300K", salt=0.5, dt=0.003, ext_forces=None):
+def time_reference_cuda(top, conf, N, steps_a, steps_b, variants, T="300K", salt=0.5, dt=0.003, ext_forces=None, model_keys=None):
     """variants: list of (use_edge, CUDA_sort_every).  Returns dict(best=..., runs=[...]) in particle-steps/s."""
     d = tempfile.mkdtemp(prefix="refcuda_")
     ext_path = None
@@ -98,8 +99,8 @@ def time_reference_cuda(top, conf, N, steps_a, steps_b, variants, T="300K", salt
     runs = []
     for (use_edge, sort_every) in variants:
         try:
-            ta, how, ua = _run(d, top, conf, steps_a, use_edge, sort_every, T, salt, dt, ext_path)
-            tb, how, ub = _run(d, top, conf, steps_b, use_edge, sort_every, T, salt, dt, ext_path)
+            ta, how, ua = _run(d, top, conf, steps_a, use_edge, sort_every, T, salt, dt, ext_path, model_keys)
+            tb, how, ub = _run(d, top, conf, steps_b, use_edge, sort_every, T, salt, dt, ext_path, model_keys)
             val = N * (steps_b - steps_a) / max(tb - ta, 1e-9)
             runs.append(dict(use_edge=use_edge, CUDA_sort_every=sort_every, value=val, ms_per_md_step=1e3 * (tb - ta) / (steps_b - steps_a),
                              loop_s=[ta, tb], clock=how,

@@ -382,6 +382,7 @@ def test_rna_duplex_lattice_generator_is_stable_and_sorted_lists_match():
         st = sim.ctx.get_state()
         g2 = dict(g, pos=st["pos"], a1=st["a1"], a3=st["a3"])
         ref2 = rna_oracle(g2)
+        sim.ctx.update_lists()  # the list in use dates from the last rebuild; rebuild it for the current configuration
         assert pair_set(sim.ctx.get_pairs()) == pair_set(ref2["pairs"])
         check_forces(sim.ctx.get_forces(), ref2)
         assert ref2["eterms"][4] / sim.N < -0.2 and sim.ctx.stats()["error_flags"] == 0
