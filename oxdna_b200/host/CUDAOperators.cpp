@@ -103,11 +103,149 @@ void CUDADNAInteraction::_on_T_update() {
 	}
 }
 
+void CUDARNAInteraction::get_settings(input_file &inp) {
+	RNA2Interaction::get_settings(inp);
+}
+
+void CUDARNAInteraction::cuda_init(oxb_ctx *ctx, int N) {
+	CUDABaseInteraction::cuda_init(ctx, N);
+	Logger::instance()->disable_log("CUDARNAInteraction");
+	RNA2Interaction::init();
+	Logger::instance()->enable_log("CUDARNAInteraction");
+	_upload();
+}
+
+static void put_f4(oxb_rna2_params &P, int k, float a, float b, float t0, float ts, float tc) {
+	P.f4[k] = oxb_f4 { a, b, t0, ts, tc };
+	double lo = std::fmax(0., (double) t0 - tc), hi = std::fmin(3.14159265358979323846, (double) t0 + tc);
+	P.f4_cmin[k] = (float) (std::cos(hi) - 1e-4);
+	P.f4_cmax[k] = (float) (std::cos(lo) + 1e-4);
+}
+
+static void put_excl(oxb_excl &e, float sigma, float rstar, float b, float rc) {
+	e.sigma2 = (float) ((double) sigma * sigma);
+	e.rstar2 = (float) ((double) rstar * rstar);
+	e.b = b;
+	e.rc = rc;
+	e.rc2 = (float) ((double) rc * rc);
+}
+
+void CUDARNAInteraction::_upload() {
+	if(_ctx == nullptr) return;
+	oxb_rna2_params P;
+	double rcut = 0.;
+	int rc = oxb_rna2_params_init(&P, (double) this->_T, (double) _salt_concentration, _debye_huckel_half_charged_ends ? 1 : 0, _use_mbf ? 1 : 0,
+			(double) _mbf_fmax, (double) _mbf_finf, _mismatch_repulsion ? 1 : 0, (double) _RNA_HYDR_MIS, &rcut);
+	if(rc != 0) throw oxDNAException("oxb_rna2_params_init failed (T = %lf, salt = %f)", (double) this->_T, _salt_concentration);
+	// everything the input file (or an `external_model` file) can change comes from the CPU class that parsed it
+	const Model &m = *model;
+	P.back_a1 = m.RNA_POS_BACK_a1; P.back_a2 = m.RNA_POS_BACK_a2; P.back_a3 = m.RNA_POS_BACK_a3;
+	P.stack_a1 = m.RNA_POS_STACK; P.base_a1 = m.RNA_POS_BASE;
+	P.stack3_a1 = m.RNA_POS_STACK_3_a1; P.stack3_a2 = m.RNA_POS_STACK_3_a2;
+	P.stack5_a1 = m.RNA_POS_STACK_5_a1; P.stack5_a2 = m.RNA_POS_STACK_5_a2;
+	P.p3[0] = m.p3_x; P.p3[1] = m.p3_y; P.p3[2] = m.p3_z;
+	P.p5[0] = m.p5_x; P.p5[1] = m.p5_y; P.p5[2] = m.p5_z;
+	P.fene_eps = m.RNA_FENE_EPS; P.fene_r0 = m.RNA_FENE_R0; P.fene_delta = m.RNA_FENE_DELTA; P.fene_delta2 = m.RNA_FENE_DELTA2;
+	if(_use_mbf) {
+		double xmax = (double) _mbf_xmax, fmax = (double) _mbf_fmax, finf = (double) _mbf_finf;
+		P.mbf_xmax = (float) xmax;
+		P.mbf_e0 = (float) (-(m.RNA_FENE_EPS / 2.) * std::log(1. - xmax * xmax / m.RNA_FENE_DELTA2) - ((fmax - finf) * xmax * std::log(xmax) + finf * xmax));
+	}
+	P.excl_eps = m.RNA_EXCL_EPS;
+	put_excl(P.excl[0], m.RNA_EXCL_S1, m.RNA_EXCL_R1, m.RNA_EXCL_B1, m.RNA_EXCL_RC1);
+	put_excl(P.excl[1], m.RNA_EXCL_S2, m.RNA_EXCL_R2, m.RNA_EXCL_B2, m.RNA_EXCL_RC2);
+	put_excl(P.excl[2], m.RNA_EXCL_S3, m.RNA_EXCL_R3, m.RNA_EXCL_B3, m.RNA_EXCL_RC3);
+	put_excl(P.excl[3], m.RNA_EXCL_S4, m.RNA_EXCL_R4, m.RNA_EXCL_B4, m.RNA_EXCL_RC4);
+	auto put_f1 = [&](oxb_f1 &d, int t) {
+		d.a = (float) F1_A[t]; d.rc = (float) F1_RC[t]; d.r0 = (float) F1_R0[t]; d.blow = (float) F1_BLOW[t]; d.bhigh = (float) F1_BHIGH[t];
+		d.rlow = (float) F1_RLOW[t]; d.rhigh = (float) F1_RHIGH[t]; d.rclow = (float) F1_RCLOW[t]; d.rchigh = (float) F1_RCHIGH[t];
+	};
+	put_f1(P.hb, RNA_HYDR_F1);
+	put_f1(P.stck, RNA_STCK_F1);
+	auto put_f2 = [&](oxb_f2 &d, int t) {
+		d.k = (float) F2_K[t]; d.rc = (float) F2_RC[t]; d.r0 = (float) F2_R0[t]; d.blow = (float) F2_BLOW[t]; d.rlow = (float) F2_RLOW[t];
+		d.rclow = (float) F2_RCLOW[t]; d.bhigh = (float) F2_BHIGH[t]; d.rhigh = (float) F2_RHIGH[t]; d.rchigh = (float) F2_RCHIGH[t];
+	};
+	put_f2(P.crst, RNA_CRST_F2);
+	put_f2(P.cxst, RNA_CXST_F2);
+	// mismatch repulsion rescaled entry [0][0] of the HB table in init() (RNAInteraction2.cpp:96-101): keep it apart
+	const float hb_eps_default = m.RNA_HYDR_EPS;
+	const double hb_shift_unit = F1_SHIFT[RNA_HYDR_F1][1][1] / F1_EPS[RNA_HYDR_F1][1][1];
+	for(int i = 0; i < 5; i++) {
+		for(int j = 0; j < 5; j++) {
+			P.hb_eps[5 * i + j] = (float) F1_EPS[RNA_HYDR_F1][i][j];
+			P.hb_shift[5 * i + j] = (float) F1_SHIFT[RNA_HYDR_F1][i][j];
+			P.stck_eps[5 * i + j] = (float) F1_EPS[RNA_STCK_F1][i][j];
+			P.stck_shift[5 * i + j] = (float) F1_SHIFT[RNA_STCK_F1][i][j];
+			P.crst_kfac[5 * i + j] = (float) _cross_seq_dep_K[i][j];
+		}
+	}
+	P.mismatch_repulsion = _mismatch_repulsion ? 1 : 0;
+	if(_mismatch_repulsion) {
+		P.mis_eps = (float) F1_EPS[RNA_HYDR_F1][0][0];
+		P.mis_shift = (float) F1_SHIFT[RNA_HYDR_F1][0][0];
+		P.hb_eps[0] = hb_eps_default; // A-A never hydrogen-bonds; restore the unscaled default
+		P.hb_shift[0] = (float) (hb_eps_default * hb_shift_unit);
+	}
+	P.average = _average ? 1 : 0;
+	put_f4(P, OXB_RF4_STCK_T5, m.RNA_STCK_THETA5_A, m.RNA_STCK_THETA5_B, m.RNA_STCK_THETA5_T0, m.RNA_STCK_THETA5_TS, m.RNA_STCK_THETA5_TC);
+	put_f4(P, OXB_RF4_STCK_T6, m.RNA_STCK_THETA6_A, m.RNA_STCK_THETA6_B, m.RNA_STCK_THETA6_T0, m.RNA_STCK_THETA6_TS, m.RNA_STCK_THETA6_TC);
+	put_f4(P, OXB_RF4_STCK_TB1, m.STCK_THETAB1_A, m.STCK_THETAB1_B, m.STCK_THETAB1_T0, m.STCK_THETAB1_TS, m.STCK_THETAB1_TC);
+	put_f4(P, OXB_RF4_STCK_TB2, m.STCK_THETAB2_A, m.STCK_THETAB2_B, m.STCK_THETAB2_T0, m.STCK_THETAB2_TS, m.STCK_THETAB2_TC);
+	put_f4(P, OXB_RF4_HB_T1, m.RNA_HYDR_THETA1_A, m.RNA_HYDR_THETA1_B, m.RNA_HYDR_THETA1_T0, m.RNA_HYDR_THETA1_TS, m.RNA_HYDR_THETA1_TC);
+	put_f4(P, OXB_RF4_HB_T2, m.RNA_HYDR_THETA2_A, m.RNA_HYDR_THETA2_B, m.RNA_HYDR_THETA2_T0, m.RNA_HYDR_THETA2_TS, m.RNA_HYDR_THETA2_TC);
+	put_f4(P, OXB_RF4_HB_T3, m.RNA_HYDR_THETA3_A, m.RNA_HYDR_THETA3_B, m.RNA_HYDR_THETA3_T0, m.RNA_HYDR_THETA3_TS, m.RNA_HYDR_THETA3_TC);
+	put_f4(P, OXB_RF4_HB_T4, m.RNA_HYDR_THETA4_A, m.RNA_HYDR_THETA4_B, m.RNA_HYDR_THETA4_T0, m.RNA_HYDR_THETA4_TS, m.RNA_HYDR_THETA4_TC);
+	put_f4(P, OXB_RF4_HB_T7, m.RNA_HYDR_THETA7_A, m.RNA_HYDR_THETA7_B, m.RNA_HYDR_THETA7_T0, m.RNA_HYDR_THETA7_TS, m.RNA_HYDR_THETA7_TC);
+	put_f4(P, OXB_RF4_HB_T8, m.RNA_HYDR_THETA8_A, m.RNA_HYDR_THETA8_B, m.RNA_HYDR_THETA8_T0, m.RNA_HYDR_THETA8_TS, m.RNA_HYDR_THETA8_TC);
+	put_f4(P, OXB_RF4_CRST_T1, m.RNA_CRST_THETA1_A, m.RNA_CRST_THETA1_B, m.RNA_CRST_THETA1_T0, m.RNA_CRST_THETA1_TS, m.RNA_CRST_THETA1_TC);
+	put_f4(P, OXB_RF4_CRST_T2, m.RNA_CRST_THETA2_A, m.RNA_CRST_THETA2_B, m.RNA_CRST_THETA2_T0, m.RNA_CRST_THETA2_TS, m.RNA_CRST_THETA2_TC);
+	put_f4(P, OXB_RF4_CRST_T3, m.RNA_CRST_THETA3_A, m.RNA_CRST_THETA3_B, m.RNA_CRST_THETA3_T0, m.RNA_CRST_THETA3_TS, m.RNA_CRST_THETA3_TC);
+	put_f4(P, OXB_RF4_CRST_T7, m.RNA_CRST_THETA7_A, m.RNA_CRST_THETA7_B, m.RNA_CRST_THETA7_T0, m.RNA_CRST_THETA7_TS, m.RNA_CRST_THETA7_TC);
+	put_f4(P, OXB_RF4_CRST_T8, m.RNA_CRST_THETA8_A, m.RNA_CRST_THETA8_B, m.RNA_CRST_THETA8_T0, m.RNA_CRST_THETA8_TS, m.RNA_CRST_THETA8_TC);
+	put_f4(P, OXB_RF4_CXST_T1, m.RNA_CXST_THETA1_A, m.RNA_CXST_THETA1_B, m.RNA_CXST_THETA1_T0, m.RNA_CXST_THETA1_TS, m.RNA_CXST_THETA1_TC);
+	put_f4(P, OXB_RF4_CXST_T4, m.RNA_CXST_THETA4_A, m.RNA_CXST_THETA4_B, m.RNA_CXST_THETA4_T0, m.RNA_CXST_THETA4_TS, m.RNA_CXST_THETA4_TC);
+	put_f4(P, OXB_RF4_CXST_T5, m.RNA_CXST_THETA5_A, m.RNA_CXST_THETA5_B, m.RNA_CXST_THETA5_T0, m.RNA_CXST_THETA5_TS, m.RNA_CXST_THETA5_TC);
+	put_f4(P, OXB_RF4_CXST_T6, m.RNA_CXST_THETA6_A, m.RNA_CXST_THETA6_B, m.RNA_CXST_THETA6_T0, m.RNA_CXST_THETA6_TS, m.RNA_CXST_THETA6_TC);
+	P.phi1 = oxb_f5 { m.RNA_STCK_PHI1_A, m.RNA_STCK_PHI1_B, m.RNA_STCK_PHI1_XC, m.RNA_STCK_PHI1_XS };
+	P.phi2 = oxb_f5 { m.RNA_STCK_PHI2_A, m.RNA_STCK_PHI2_B, m.RNA_STCK_PHI2_XC, m.RNA_STCK_PHI2_XS };
+	P.phi3 = oxb_f5 { m.RNA_CXST_PHI3_A, m.RNA_CXST_PHI3_B, m.RNA_CXST_PHI3_XC, m.RNA_CXST_PHI3_XS };
+	P.phi4 = oxb_f5 { m.RNA_CXST_PHI4_A, m.RNA_CXST_PHI4_B, m.RNA_CXST_PHI4_XC, m.RNA_CXST_PHI4_XS };
+	P.dh_minus_kappa = (float) _minus_kappa;
+	P.dh_prefactor = (float) _debye_huckel_prefactor;
+	P.dh_rhigh = (float) _debye_huckel_RHIGH;
+	P.dh_rc = (float) _debye_huckel_RC;
+	P.dh_b = (float) _debye_huckel_B;
+	// cutoffs: the Verlet radius must be the CPU class's own double-precision cutoff (bit-exact pair sets)
+	const double back_len = std::sqrt((double) (m.RNA_POS_BACK_a1 * m.RNA_POS_BACK_a1 + m.RNA_POS_BACK_a2 * m.RNA_POS_BACK_a2 + m.RNA_POS_BACK_a3 * m.RNA_POS_BACK_a3));
+	const double near_back = 2. * back_len + m.RNA_EXCL_RC1;
+	const double near_base = 2. * std::fabs((double) m.RNA_POS_BASE) + std::fmax(std::fmax((double) m.RNA_HYDR_RCHIGH, (double) m.RNA_CRST_RCHIGH), (double) m.RNA_EXCL_RC2);
+	const double near_mixed = back_len + std::fabs((double) m.RNA_POS_BASE) + std::fmax((double) m.RNA_EXCL_RC3, (double) m.RNA_EXCL_RC4);
+	const double near_stack = 2. * std::fabs((double) m.RNA_POS_STACK) + m.RNA_CXST_RCHIGH;
+	P.rcut_near = (float) (std::fmax(std::fmax(near_back, near_base), std::fmax(near_mixed, near_stack)) * (1. + 1e-6));
+	rcut = (double) this->_rcut;
+	P.rcut = (float) rcut;
+	if(P.rcut_near > P.rcut) P.rcut_near = P.rcut;
+	oxb_check(_ctx, oxb_set_model_rna2(_ctx, &P, rcut), "set_model_rna2");
+}
+
+void CUDARNAInteraction::_on_T_update() {
+	// CUDARNAInteraction.cu:421-423 re-runs cuda_init -> RNA2Interaction::init()
+	this->_T = CONFIG_INFO->temperature();
+	if(_ctx != nullptr) {
+		Logger::instance()->disable_log("CUDARNAInteraction");
+		RNA2Interaction::init();
+		Logger::instance()->enable_log("CUDARNAInteraction");
+		_upload();
+	}
+}
+
 std::shared_ptr<CUDABaseInteraction> CUDAInteractionFactory::make_interaction(input_file &inp) {
 	std::string inter_type("DNA");
 	getInputString(&inp, "interaction_type", inter_type, 0);
 	if(inter_type == "DNA2") return std::make_shared<CUDADNAInteraction>();
-	throw oxDNAException("CUDA interaction '%s' not found in the oxdna_b200 backend (available: DNA2). Aborting", inter_type.c_str());
+	if(inter_type == "RNA2") return std::make_shared<CUDARNAInteraction>();
+	throw oxDNAException("CUDA interaction '%s' not found in the oxdna_b200 backend (available: DNA2, RNA2). Aborting", inter_type.c_str());
 }
 
 // ---------------------------------------------------------------------------------------------------------- lists

@@ -6,6 +6,7 @@
 //   class here                      replaces (reference file)
 //   CUDABaseInteraction             src/CUDA/Interactions/CUDABaseInteraction.h:20-64
 //   CUDADNAInteraction              src/CUDA/Interactions/CUDADNAInteraction.{h,cu}
+//   CUDARNAInteraction              src/CUDA/Interactions/CUDARNAInteraction.{h,cu}
 //   CUDAInteractionFactory          src/CUDA/Interactions/CUDAInteractionFactory.cu:28-53
 //   CUDABaseList / CUDASimpleVerletList / CUDAListFactory   src/CUDA/Lists/*.{h,cu}
 //   CUDABaseThermostat, CUDA{No,Brownian,Langevin,Bussi}Thermostat, CUDAThermostatFactory   src/CUDA/Thermostats/*.{h,cu}
@@ -24,6 +25,7 @@
 #include "Backends/Thermostats/NoThermostat.h"
 #include "Boxes/BaseBox.h"
 #include "Interactions/DNA2Interaction.h"
+#include "Interactions/RNAInteraction2.h"
 #include "Utilities/oxDNAException.h"
 
 #include <memory>
@@ -69,6 +71,25 @@ protected:
 public:
 	CUDADNAInteraction();
 	virtual ~CUDADNAInteraction();
+
+	void get_settings(input_file &inp) override;
+	void cuda_init(oxb_ctx *ctx, int N) override;
+	number get_cuda_rcut() override {
+		return this->get_rcut();
+	}
+};
+
+/// interaction_type = RNA2: constants from the CPU RNA2Interaction and its Model block (rna_model.h; `external_model`,
+/// `use_average_seq` / `seq_dep_file`, `mismatch_repulsion[_strength]`, salt and dh_* keys, max_backbone_force), as the
+/// reference's CUDARNAInteraction copies them into its `CUDAModel` (CUDARNAInteraction.cu:43-230,278-385)
+class CUDARNAInteraction: public CUDABaseInteraction, public RNA2Interaction {
+protected:
+	void _upload();
+	void _on_T_update() override;
+
+public:
+	CUDARNAInteraction() {}
+	virtual ~CUDARNAInteraction() {}
 
 	void get_settings(input_file &inp) override;
 	void cuda_init(oxb_ctx *ctx, int N) override;

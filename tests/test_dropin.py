@@ -70,10 +70,10 @@ PBC = 1
 """
 
 
-def run(binary, d, **kw):
+def run(binary, d, fix=FIX, files=("initial.top", "initial.conf"), **kw):
     os.makedirs(d, exist_ok=True)
-    for f in ("initial.top", "initial.conf"):
-        shutil.copy(os.path.join(FIX, f), d)
+    for f, name in zip(files, ("initial.top", "initial.conf")):
+        shutil.copy(os.path.join(fix, f), os.path.join(d, name))
     with open(os.path.join(d, "forces.txt"), "w") as f:
         f.write(FORCES)
     with open(os.path.join(d, "input"), "w") as f:
@@ -120,8 +120,34 @@ def test_stock_input_file_thermostat_and_errors(tmp_path):
     assert bad.returncode != 0 and "incompatible" in bad.stdout
     bad = run(OURS, str(tmp_path / "bad2"), backend="CUDA", itype="DNA2", steps=10, thermostat="no", use_edge=1, sort_every=0, extra="reload_from = x")
     assert bad.returncode != 0
-    bad = run(OURS, str(tmp_path / "bad3"), backend="CUDA", itype="RNA2", steps=10, thermostat="no", use_edge=1, sort_every=0, extra="")
-    assert bad.returncode != 0
+    bad = run(OURS, str(tmp_path / "bad3"), backend="CUDA", itype="LJ", steps=10, thermostat="no", use_edge=1, sort_every=0, extra="")
+    assert bad.returncode != 0 and "not found in the oxdna_b200 backend" in bad.stdout
+
+
+@pytest.mark.gpu
+@needs_binaries
+@pytest.mark.parametrize("use_edge,sort_every,extra", [(1, 1, ""), (0, 0, "use_average_seq = 0\nseq_dep_file = seq.txt\nmismatch_repulsion = 1")])
+def test_stock_rna_input_file_matches_reference_cpu(tmp_path, use_edge, sort_every, extra):
+    """interaction_type = RNA2 through the drop-in executable (CUDARNAInteraction on the reference's RNA2Interaction), on the
+    16-nt system of the reference's test/RNA/FORCE_FIELD, against the reference CPU binary.  The CPU class interpolates the
+    hydrogen-bonding factors on 6-12 point meshes and its force deviates from the gradient in two places (oracle/oxdna_oracle.h),
+    so the trajectories part faster than for DNA: 100 steps, looser bounds."""
+    from oxdna_b200 import seqdep
+    rfix = os.path.join(ROOT, "tests", "golden", "force_field_rna")
+    kw = dict(fix=rfix, files=("init.top", "init.dat"), steps=100, thermostat="no", extra=extra)
+    for d in ("ours", "ref"):
+        os.makedirs(str(tmp_path / d), exist_ok=True)
+        seqdep.write_file(str(tmp_path / d / "seq.txt"), seqdep.RNA_SEQ_DEP)
+    a = run(OURS, str(tmp_path / "ours"), backend="CUDA", itype="RNA2", use_edge=use_edge, sort_every=sort_every, **kw)
+    assert a.returncode == 0, a.stdout[-2000:]
+    b = run(REF, str(tmp_path / "ref"), backend="CPU", itype="RNA2", use_edge=0, sort_every=0, **kw)
+    assert b.returncode == 0, b.stdout[-2000:]
+    ca, cb = oio.read_conf(str(tmp_path / "ours" / "last_conf.dat")), oio.read_conf(str(tmp_path / "ref" / "last_conf.dat"))
+    assert np.abs(ca["pos"] - cb["pos"]).max() < 5e-3
+    assert np.abs(ca["a1"] - cb["a1"]).max() < 2e-2
+    ea, eb = energies(str(tmp_path / "ours")), energies(str(tmp_path / "ref"))
+    assert ea.shape == eb.shape
+    assert np.abs(ea[:, 1:] - eb[:, 1:]).max() < 1e-3
 
 
 @needs_binaries
