@@ -432,6 +432,83 @@ def ours(args):
             dist.destroy_process_group()
 
 
+def ours_ensemble(args):
+    """Config C5: `--replicas-per-gpu` temperature replicas of the workload on every GPU (64 in total at 8 x 8), advanced
+    concurrently (one host thread and one set of CUDA streams per replica), one exchange attempt per bench step."""
+    import torch
+    import torch.distributed as dist
+    from oxdna_b200 import lattice
+    from oxdna_b200.remd import ReplicaExchange, TorchComm, geometric_ladder
+    from oxdna_b200.sim import Simulation, parse_temperature
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: oxdna_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    sysm, desc = workload(args.workload)
+    N, md, nl = len(sysm["pos"]), args.md_steps, args.replicas_per_gpu
+    R = world * nl
+    ladder_K = geometric_ladder(290.0, 350.0, R)
+    sims = []
+    for k in range(nl):
+        g = rank * nl + k
+        T = f"{ladder_K[g]:.6f}K"
+        v, L = lattice.maxwell_velocities(N, parse_temperature(T), 5 + g)
+        sims.append(Simulation(base_input(args, T), sysm, dict(box=sysm["box"], pos=sysm["pos"], a1=sysm["a1"], a3=sysm["a3"], vel=v, L=L), device=local_rank))
+    remd = ReplicaExchange(sims, ladder_K * 0.1 / 300.0, TorchComm(torch.device("cuda", local_rank)) if world > 1 else None, seed=42,
+                           concurrent=not args.sequential_replicas)
+    remd.advance(args.equil)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    for _ in range(args.warmup):
+        remd.advance(md)
+        remd.exchange()
+    launches0 = sum(s.ctx.launch_count() for s in sims)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    total_ms = 0.0
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        remd.advance(md)
+        remd.exchange()
+        torch.cuda.synchronize()  # the replicas run on their own streams: bracket with device-wide synchronisation
+        e1.record()
+        e1.synchronize()
+        total_ms += e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        dist.barrier()
+        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    launches = sum(s.ctx.launch_count() for s in sims) - launches0
+    if rank == 0:
+        value = R * N * md * args.steps / (total_ms * 1e-3)
+        line = {"metric": "particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32 forces / f64 integration (mixed)", "data": "synthetic",
+                "config": {"workload": "C5-style ensemble: " + desc, "md_steps_per_step": md, "replicas": R, "replicas_per_gpu": nl,
+                           "parallelism": f"{nl} replicas per GPU advanced {'sequentially' if args.sequential_replicas else 'concurrently (one host thread + CUDA streams each)'}, "
+                                          "replica exchange (temperature swap) every bench step, NCCL all_gather of 2 doubles per replica",
+                           "ladder_K": [float(ladder_K[0]), float(ladder_K[-1])], "use_edge": int(args.use_edge), "CUDA_sort_every": args.sort_every,
+                           "l2": "256 MiB buffer written between timed iterations", "exchange_acceptance": float(np.mean(remd.rates()))},
+                "gpu_launches": int(launches), "clocks": clocks, "e2e": None, "roofline": None, "cpu_baseline": None}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -446,6 +523,8 @@ def main():
     ap.add_argument("--ref-md-steps", type=int, default=4, help="MD steps per bench step of the CPU reference arm")
     ap.add_argument("--ref-procs", type=int, default=0)
     ap.add_argument("--cpu-md-steps", type=int, default=40)
+    ap.add_argument("--replicas-per-gpu", type=int, default=1, help="> 1: C5-style replica ensemble (64 replicas = 8 per GPU on 8 GPUs)")
+    ap.add_argument("--sequential-replicas", action="store_true", help="ensemble mode: advance the local replicas one after the other (comparison)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip the reference-CUDA-backend comparator leg")
     ap.add_argument("--ref-cuda-steps", type=int, nargs=2, default=[10000, 20000], help="steps=A and steps=B runs of the reference CLI")
@@ -466,6 +545,8 @@ def main():
             r = run_ref_cuda(sysm, args.workload, a, b, state)
             print(json.dumps({"impl": "reference-cuda", "metric": "particle-steps/s", "value": r.get("value"), "unit": "particle-steps/s", "n_gpus": 1,
                               "higher_is_better": True, "config": {"workload": desc}, "reference_cuda": r}), flush=True)
+    elif args.replicas_per_gpu > 1:
+        ours_ensemble(args)
     else:
         ours(args)
 

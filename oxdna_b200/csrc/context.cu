@@ -450,6 +450,8 @@ int init_bussi(oxb_ctx *c) {
 }
 
 int check_ready(oxb_ctx *c) {
+	// any host thread may drive a context (replica ensembles run one thread per local replica): bind the calling thread
+	cudaSetDevice(c->device);
 	if(!c->have_topology) return fail(c, 2, "topology not set");
 	if(!c->have_box) return fail(c, 2, "box not set");
 	if(!c->have_model) return fail(c, 2, "interaction model not set");

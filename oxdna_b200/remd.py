@@ -59,8 +59,12 @@ class ReplicaExchange:
     temperatures: the global ladder (simulation units), len = world_size * len(replicas).
     Global replica id g = rank * n_local + k; initially replica g sits on ladder position g."""
 
-    def __init__(self, replicas, temperatures, comm=None, seed=0):
+    def __init__(self, replicas, temperatures, comm=None, seed=0, concurrent=True):
         self.comm = comm or LocalComm()
+        # local replicas advance CONCURRENTLY: one host thread per replica, each blocked inside the C ABI (ctypes drops the
+        # GIL), each context on its own CUDA streams -- an 81,920-nt replica alone cannot fill 148 SMs
+        self.concurrent = concurrent and len(replicas) > 1
+        self._pool = None
         self.replicas = list(replicas)
         self.nl = len(self.replicas)
         self.T = np.asarray(temperatures, dtype=np.float64)
@@ -82,15 +86,18 @@ class ReplicaExchange:
         pairs = attempted_pairs(self.round, self.R)
         at = {int(self.location[g]): g for g in range(self.R)}  # ladder position -> replica
         local = np.zeros((self.nl, 2))
-        for k, rep in enumerate(self.replicas):
-            g = self._gid(k)
-            pos = int(self.location[g])
+
+        def energies(k):
+            rep = self.replicas[k]
+            pos = int(self.location[self._gid(k)])
             local[k, 0] = rep.system_energy()
             if any(pos == b for (_, b) in pairs):
                 # upper member of an attempted pair: energy with the partner's (lower) temperature Hamiltonian
                 rep.update_temperature(self.T[pos - 1])
                 local[k, 1] = rep.system_energy()
                 rep.update_temperature(self.T[pos])
+
+        self._map(energies, range(self.nl))
         E = self.comm.all_gather(local.reshape(-1)).reshape(self.R, 2)
         rng = np.random.default_rng([self.seed, self.round])
         u = rng.random(self.R)
@@ -113,10 +120,21 @@ class ReplicaExchange:
         self.round += 1
         return accepted
 
+    def _map(self, fn, items):
+        if not self.concurrent:
+            return [fn(x) for x in items]
+        if self._pool is None:
+            from concurrent.futures import ThreadPoolExecutor
+            self._pool = ThreadPoolExecutor(max_workers=self.nl)
+        return list(self._pool.map(fn, items))
+
+    def advance(self, steps):
+        """`steps` MD steps of every local replica"""
+        self._map(lambda rep: rep.run(steps), self.replicas)
+
     def run(self, rounds, pt_move_every):
         for _ in range(rounds):
-            for rep in self.replicas:
-                rep.run(pt_move_every)
+            self.advance(pt_move_every)
             self.exchange()
 
     def rates(self):
