@@ -165,6 +165,10 @@ int oxb_synchronize(oxb_ctx *ctx);
 int oxb_get_forces(oxb_ctx *ctx, double *force, double *torque_body, double *torque_lab, double *energy, double *hb_energy);
 /* potential energy U and kinetic energy K of the whole system (GpuUtils::sum_c_number4_to_double_on_GPU, CUDA_print_energy) */
 int oxb_energy(oxb_ctx *ctx, double *U, double *K);
+/* potential energy of the whole system split into the reference's terms, terms[OXB_NTERMS] in the order of OXB_TERM_*
+ * (BaseInteraction::get_system_energy_split, src/Interactions/BaseInteraction.cpp:61-90; the `potential_energy` observable
+ * with split = true, src/Observables/PotentialEnergy.cpp), evaluated on the device for the current positions */
+int oxb_energy_split(oxb_ctx *ctx, double *terms);
 /* unique Verlet pairs (i < j, original ids); call with pairs = NULL to get the count */
 int oxb_get_pairs(oxb_ctx *ctx, int *pairs, long long max_pairs, long long *n_pairs);
 /* number of list rebuilds / sorts so far; current neighbour-matrix capacity; overflow flags (0 = ok) */

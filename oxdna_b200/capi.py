@@ -79,7 +79,7 @@ class ExtForce(C.Structure):
 EXPORTED = """oxb_dna2_params_init oxb_dna2_params_seqdep oxb_rna2_params_init oxb_rna2_params_seqdep oxb_set_model_rna2 oxb_create oxb_destroy oxb_last_error oxb_set_stream oxb_set_box
 oxb_set_topology oxb_set_model_dna2 oxb_set_lists oxb_set_dt oxb_set_thermostat oxb_set_ext_forces oxb_set_state oxb_get_state
 oxb_set_step oxb_get_step oxb_sort oxb_update_lists oxb_compute_forces oxb_first_step oxb_second_step oxb_thermostat oxb_run
-oxb_synchronize oxb_get_forces oxb_energy oxb_get_pairs oxb_get_stats oxb_device_views oxb_launch_count oxb_time_kernel""".split()
+oxb_synchronize oxb_get_forces oxb_energy oxb_energy_split oxb_get_pairs oxb_get_stats oxb_device_views oxb_launch_count oxb_time_kernel""".split()
 
 _lib = None
 
@@ -280,6 +280,12 @@ class Context:
         U, K = C.c_double(), C.c_double()
         self._ck(self._L.oxb_energy(self._h, C.byref(U), C.byref(K)))
         return U.value, K.value
+
+    def energy_split(self):
+        """per-term potential energies (FENE, BEXC, STCK, NEXC, HB, CRSTCK, CXSTCK, DH), summed on the device"""
+        out = np.zeros(NTERMS)
+        self._ck(self._L.oxb_energy_split(self._h, _p(out)))
+        return out
 
     def get_pairs(self):
         n = C.c_longlong()

@@ -502,7 +502,7 @@ OXB_HD PairEnergy dna2_nonbonded(const oxb_dna2_params &M, v3 r, const Axes &A, 
 // FENE backbone + bonded excluded volume (3 site pairs): the same functional form in oxDNA2 and oxRNA2
 // (DNAInteraction.cpp:415-528, RNAInteraction.cpp:431-531)
 template<class PB>
-OXB_HD float bonded_fene_excl(const PB &M, v3 r, const Axes &A, const Axes &B, v3 pback, v3 qback, PairAcc &acc, bool &broken) {
+OXB_HD float bonded_fene_excl(const PB &M, v3 r, const Axes &A, const Axes &B, v3 pback, v3 qback, PairAcc &acc, bool &broken, float *esplit = nullptr) {
 	float E = 0.f;
 	const float cb = M.base_a1;
 	// FENE
@@ -529,6 +529,7 @@ OXB_HD float bonded_fene_excl(const PB &M, v3 r, const Axes &A, const Axes &B, v
 			s = -OXB_DIV(M.fene_eps * x, den) * invm;
 		}
 		E += en;
+		if(esplit) esplit[0] += en;
 		acc.site_kk(d * s);
 	}
 	// bonded excluded volume
@@ -537,13 +538,13 @@ OXB_HD float bonded_fene_excl(const PB &M, v3 r, const Axes &A, const Axes &B, v
 		v3 pbase = A.a1 * cb, qbase = B.a1 * cb;
 		v3 d = r + qbase - pbase;
 		float en = excl_s(M.excl[1], M.excl_eps, d, s);
-		if(en != 0.f) { E += en; acc.site_aa(d * s, cb, cb); }
+		if(en != 0.f) { E += en; if(esplit) esplit[1] += en; acc.site_aa(d * s, cb, cb); }
 		d = r + qback - pbase;
 		en = excl_s(M.excl[2], M.excl_eps, d, s);
-		if(en != 0.f) { E += en; acc.site_ak(d * s, cb); }
+		if(en != 0.f) { E += en; if(esplit) esplit[1] += en; acc.site_ak(d * s, cb); }
 		d = r + qbase - pback;
 		en = excl_s(M.excl[3], M.excl_eps, d, s);
-		if(en != 0.f) { E += en; acc.site_ka(d * s, cb); }
+		if(en != 0.f) { E += en; if(esplit) esplit[1] += en; acc.site_ka(d * s, cb); }
 	}
 	return E;
 }
@@ -553,11 +554,11 @@ OXB_HD float bonded_fene_excl(const PB &M, v3 r, const Axes &A, const Axes &B, v
 // Returns energy; sets *broken when the bond is outside the FENE range (reference throws; we flag).
 // ---------------------------------------------------------------------------------------------------------------
 OXB_HD float dna2_bonded(const oxb_dna2_params &M, v3 r, const Axes &A, const Axes &B, int btp, int btq, v3 pback,
-		v3 qback, PairAcc &acc, bool &broken) {
+		v3 qback, PairAcc &acc, bool &broken, float *esplit = nullptr) {
 	float E = 0.f;
 	const float cb = M.base_a1, cs = M.stack_a1, cr = M.backref_a1;
 
-	E += bonded_fene_excl(M, r, A, B, pback, qback, acc, broken);
+	E += bonded_fene_excl(M, r, A, B, pback, qback, acc, broken, esplit);
 	// stacking
 	{
 		v3 rs = r + B.a1 * cs - A.a1 * cs;
@@ -585,6 +586,7 @@ OXB_HD float dna2_bonded(const oxb_dna2_params &M, v3 r, const Axes &A, const Ax
 			float e = f1.v * p456 * pb;
 			if(e != 0.f) {
 				E += e;
+				if(esplit) esplit[2] += e;
 				v3 f = h * (-(f1.d * p456 * pb));
 				float fb = f1.v * pb;
 				chain_bb(acc, fb * a4.dc * a5.v * a6.v, t4);

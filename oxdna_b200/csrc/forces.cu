@@ -305,6 +305,74 @@ __global__ void __launch_bounds__(128) k_bonded(const __grid_constant__ typename
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Observable: potential energy split into the reference's eight terms (FENE, bonded excluded volume, stacking, non-bonded
+// excluded volume, hydrogen bonding, cross stacking, coaxial stacking, Debye-Hueckel), summed on the device in double.
+// Replaces the CPU get_system_energy_split() the reference runs after a D2H copy and a CPU list rebuild
+// (src/Interactions/BaseInteraction.cpp:61-90).  One thread per particle over the full Verlet matrix,
+// every unique pair once (from its lower slot); forces are not needed and are eliminated by the compiler.
+// ------------------------------------------------------------------------------------------------------------
+template<class MD>
+__global__ void __launch_bounds__(128) k_energy_split(const __grid_constant__ typename MD::Params M, BoxF box, int N, const int4 *__restrict__ ipos,
+		const float4 *__restrict__ quat, const int2 *__restrict__ bonds, const int *__restrict__ nbr, const int *__restrict__ nnbr, int stride,
+		double *__restrict__ out) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	float e[OXB_NTERMS];
+#pragma unroll
+	for(int t = 0; t < OXB_NTERMS; t++) e[t] = 0.f;
+	if(i < N) {
+		Particle P = load_particle<MD>(M, ipos, quat, i);
+		int2 b = __ldg(bonds + i);
+		bool p_end = (b.x < 0 || b.y < 0);
+		PairAcc acc;
+		acc.clear();
+		if(b.x >= 0) {
+			Particle Q = load_particle<MD>(M, ipos, quat, b.x);
+			bool broken = false;
+			MD::bonded(M, min_image_fixed(box, P.ip, Q.ip), P.ax, Q.ax, P.btype, Q.btype, P.back, Q.back, acc, broken, e);
+		}
+		int nn = __ldg(nnbr + i);
+		for(int k = 0; k < nn; k++) {
+			int j = __ldg(nbr + (size_t) k * stride + i);
+			if(j < i) continue;
+			Particle Q = load_particle<MD>(M, ipos, quat, j);
+			v3 r = min_image_fixed(box, P.ip, Q.ip);
+			float r2 = dot(r, r);
+			if(r2 >= M.rcut * M.rcut) continue;
+			int2 bq = __ldg(bonds + j);
+			v3 rbb = r + Q.back - P.back;
+			float fs;
+			e[OXB_TERM_DH] += dna2_dh(M, dot(rbb, rbb), p_end, (bq.x < 0 || bq.y < 0), fs);
+			if(r2 >= M.rcut_near * M.rcut_near) continue;
+			v3 rb = r + (Q.ax.a1 - P.ax.a1) * M.base_a1;
+			e[OXB_TERM_NEXC] += dna2_excl(M, r, rbb, rb, P.ax, Q.ax, P.back, Q.back, acc);
+			float rbm2 = dot(rb, rb);
+			bool hb_on = MD::hb_in_range(M, rbm2, P.btype, Q.btype), cr_on = MD::crst_in_range(M, rbm2);
+			if(hb_on || cr_on) {
+				float ehb;
+				float tot = MD::template hbcr<true>(M, rb, rbm2, P.ax, Q.ax, P.btype, Q.btype, hb_on, cr_on, acc, ehb);
+				e[OXB_TERM_HB] += ehb;
+				e[OXB_TERM_CRST] += tot - ehb;
+			}
+			v3 rs = r + (Q.ax.a1 - P.ax.a1) * M.stack_a1;
+			float rs2 = dot(rs, rs);
+			if(MD::cxst_in_range(M, rs2)) e[OXB_TERM_CXST] += MD::cxst(M, rs, rs2, rbb, P.ax, Q.ax, acc);
+		}
+	}
+	__shared__ double sh[OXB_NTERMS][4];
+#pragma unroll
+	for(int t = 0; t < OXB_NTERMS; t++) {
+		double x = (double) e[t];
+		for(int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+		if((threadIdx.x & 31) == 0) sh[t][threadIdx.x >> 5] = x;
+	}
+	__syncthreads();
+	if(threadIdx.x < OXB_NTERMS) {
+		double x = sh[threadIdx.x][0] + sh[threadIdx.x][1] + sh[threadIdx.x][2] + sh[threadIdx.x][3];
+		if(x != 0.) atomicAdd(out + threadIdx.x, x);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // External forces: one thread per force entry (compact table, not 15 slots x N as in the reference).  Runs after the
 // interaction kernels and adds into F.  Particle ids in the table are ORIGINAL ids, mapped through slot_of, so the
 // Hilbert re-sort needs no table rewrite (the reference forbids sort + external forces, MD_CUDABackend.cu:110-112).
@@ -386,6 +454,14 @@ static void launch_edge_stage_t(cudaStream_t s, int which, const typename MD::Pa
 void launch_edge_stage(cudaStream_t s, int which, const ModelRef &MR, BoxF box, const EdgeArgs &a, int *flags, int hw) {
 	if(MR.rna) launch_edge_stage_t<RnaModel>(s, which, *MR.rna, box, a, flags, hw);
 	else launch_edge_stage_t<DnaModel>(s, which, *MR.dna, box, a, flags, hw);
+}
+
+void launch_energy_split(cudaStream_t s, const ModelRef &MR, BoxF box, int N, const int4 *ipos, const float4 *quat, const int2 *bonds, const int *nbr,
+		const int *nnbr, int stride, double *out) {
+	cudaMemsetAsync(out, 0, sizeof(double) * OXB_NTERMS, s);
+	int tpb = 128;
+	if(MR.rna) k_energy_split<RnaModel><<<(N + tpb - 1) / tpb, tpb, 0, s>>>(*MR.rna, box, N, ipos, quat, bonds, nbr, nnbr, stride, out);
+	else k_energy_split<DnaModel><<<(N + tpb - 1) / tpb, tpb, 0, s>>>(*MR.dna, box, N, ipos, quat, bonds, nbr, nnbr, stride, out);
 }
 
 void launch_ext_forces(cudaStream_t s, int n, const DevExtForce *ef, const int *slot_of, const int4 *ipos, const double4 *posd, BoxF box,

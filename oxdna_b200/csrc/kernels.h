@@ -71,6 +71,8 @@ struct EdgeArgs {
 	int hb_split; // consumer blocks per segment of the hydrogen-bonding / cross-stacking list
 };
 void launch_edge_stage(cudaStream_t s, int which, const ModelRef &M, BoxF box, const EdgeArgs &a, int *flags, int hw);
+void launch_energy_split(cudaStream_t s, const ModelRef &M, BoxF box, int N, const int4 *ipos, const float4 *quat, const int2 *bonds, const int *nbr,
+		const int *nnbr, int stride, double *out);
 void launch_ext_forces(cudaStream_t s, int n, const DevExtForce *ef, const int *slot_of, const int4 *ipos, const double4 *posd, BoxF box,
 		long long step, const long long *cur_step, float4 *F, const int *flags, int hw);
 

@@ -43,8 +43,9 @@ std::shared_ptr<SimBackend> BackendFactory::make_backend(input_file &inp) {
 		else if(backend_opt == "CUDA") {
 			if(precision_state == KEY_NOT_FOUND) backend_prec = "mixed";
 			if(backend_prec == "mixed") new_backend = new CUDAMixedBackend();
+			else if(backend_prec == "float") new_backend = new MD_CUDABackend(); // BackendFactory.cpp:62-64; served by the mixed kernels
 			else {
-				throw oxDNAException("Backend precision '%s' is not allowed, as the oxdna_b200 backend has been compiled with 'mixed' support only", backend_prec.c_str());
+				throw oxDNAException("Backend precision '%s' is not allowed, as the oxdna_b200 backend has been compiled with 'float' and 'mixed' support only", backend_prec.c_str());
 			}
 			OX_LOG(Logger::LOG_INFO, "CUDA backend precision: %s", backend_prec.c_str());
 		}

@@ -14,7 +14,7 @@
 class MD_CUDABackend: public MDBackend {
 protected:
 	oxb_ctx *_ctx = nullptr;
-	int _precision = OXB_PRECISION_MIXED;
+	int _precision = OXB_PRECISION_FLOAT; // plain MD_CUDABackend = backend_precision float, as in the reference's factory
 	int _device_number = -1;
 	int _sort_every = 0;
 	int _threads_per_block = 0; // accepted, unused: launch shapes are fixed per kernel

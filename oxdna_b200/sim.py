@@ -84,8 +84,10 @@ class Simulation:
             raise ValueError(f"interaction_type = {itype} is not available in this build (DNA2, RNA2)")
         self.itype = itype
         prec = str(g("backend_precision", "mixed"))
-        if prec not in ("mixed",):
-            raise ValueError(f"backend_precision = {prec} is not available in this build")
+        if prec not in ("mixed", "float"):
+            raise ValueError(f"backend_precision = {prec} is not available (float and mixed are; float is served by the mixed kernels)")
+        if prec == "double" and _bool(g("use_edge", 0)):
+            raise ValueError("use_edge and double precision are not compatible")  # MD_CUDABackend.cu:625-632
         if "reload_from" in self.inp:
             # CUDABaseBackend.cu:137-140
             raise ValueError("The CUDA backend does not support checkpoints (reload_from)")
@@ -95,7 +97,7 @@ class Simulation:
         self.T = parse_temperature(g("T"))
         self.dt = float(g("dt", 0.003))
         self.N = N = len(topology["btype"])
-        self.ctx = capi.Context(N, device=device)
+        self.ctx = capi.Context(N, device=device, precision=capi.PRECISION_FLOAT if prec == "float" else capi.PRECISION_MIXED)
         c = self.ctx
         c.set_box(conf["box"])
         c.set_topology(topology["btype"], topology["n3"], topology["n5"], topology.get("strand"))

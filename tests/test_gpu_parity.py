@@ -388,3 +388,27 @@ def test_rna_duplex_lattice_generator_is_stable_and_sorted_lists_match():
         assert ref2["eterms"][4] / sim.N < -0.2 and sim.ctx.stats()["error_flags"] == 0
     finally:
         sim.close()
+
+
+def test_backend_precision_float_and_split_energy_observable():
+    """backend_precision = float is accepted and served by the mixed kernels (tolerance of the float criterion: 1e-4); the
+    device-side split-energy observable reproduces the reference's per-term energies (get_system_energy_split)."""
+    for case, rna in (("lattice27_dense", False), ("rna_lattice8_seqdep", True), ("force_field_rna/ref_rna2", True)):
+        g = load_golden(case)
+        topo = dict(btype=g["btype"], n3=g["n3"], n5=g["n5"], strand=g["strand"])
+        conf = dict(box=g["box"], pos=g["pos"], a1=g["a1"], a3=g["a3"], vel=g["vel"], L=g["L"])
+        if rna:
+            ref = rna_oracle(g)
+            sim = Simulation(rna_inp(g, use_edge=1, CUDA_sort_every=1, backend_precision="float"), topo, conf)
+        else:
+            ref = dict(force=g["force"], torque_lab=g["torque_lab"], torque_body=g["torque_body"], U=float(g["U"]), eterms=g["energy_split"])
+            sim = make_sim(g, use_edge=1, CUDA_sort_every=1, backend_precision="float")
+        try:
+            check_forces(sim.ctx.get_forces(), ref, tol=1e-4)
+            terms = sim.ctx.energy_split()
+            assert np.abs(terms - ref["eterms"]).max() <= 2e-6 * np.abs(ref["eterms"]).max() + 1e-6, (terms, ref["eterms"])
+            assert abs(terms.sum() - sim.ctx.energy()[0]) <= 2e-6 * abs(terms.sum())
+            sim.run(50)
+            assert sim.ctx.stats()["error_flags"] == 0
+        finally:
+            sim.close()
