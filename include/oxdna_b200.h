@@ -19,7 +19,8 @@ typedef struct oxb_ctx oxb_ctx;
 
 enum { OXB_PRECISION_FLOAT = 0, OXB_PRECISION_MIXED = 1 };
 enum { OXB_THERMOSTAT_NONE = 0, OXB_THERMOSTAT_BROWNIAN = 1, OXB_THERMOSTAT_LANGEVIN = 2, OXB_THERMOSTAT_BUSSI = 3 };
-enum { OXB_EXT_STRING = 0, OXB_EXT_TRAP = 1, OXB_EXT_MUTUAL_TRAP = 2 };
+enum { OXB_EXT_STRING = 0, OXB_EXT_TRAP = 1, OXB_EXT_MUTUAL_TRAP = 2, OXB_EXT_LOWDIM_TRAP = 3, OXB_EXT_REPULSION_PLANE = 4,
+	OXB_EXT_ATTRACTION_PLANE = 5, OXB_EXT_SPHERE = 6, OXB_EXT_LJ_WALL = 7, OXB_EXT_NTYPES };
 enum { OXB_TERM_FENE = 0, OXB_TERM_BEXC, OXB_TERM_STCK, OXB_TERM_NEXC, OXB_TERM_HB, OXB_TERM_CRST, OXB_TERM_CXST, OXB_TERM_DH, OXB_NTERMS };
 
 /* ---- force-field parameters (device constant block).  Replaces the __constant__ upload of
@@ -108,13 +109,26 @@ int oxb_rna2_params_init(oxb_rna2_params *P, double T, double salt_concentration
 int oxb_rna2_params_seqdep(oxb_rna2_params *P, double T, const double *stck_raw16, double st_t_dep, const double *cross_raw16,
 		double hb_AT, double hb_GC, double hb_GT);
 
+/* One external force acting on one particle -- or on every particle when particle = -1 (`particle = all`), in which case
+ * the entry is kept once and evaluated per particle (the reference stores 15 union slots per particle).
+ *   type                 reference class (src/Forces/)   fields used
+ *   STRING               ConstantRateForce               F0, rate, dir
+ *   TRAP                 MovingTrap                      stiff, rate, dir, pos0
+ *   MUTUAL_TRAP          MutualTrap                      ref, pbc, stiff, r0, rate, stiff_rate
+ *   LOWDIM_TRAP          LowdimMovingTrap                stiff, rate, dir, pos0, iaux = visibility mask (bit 0 x, 1 y, 2 z)
+ *   REPULSION_PLANE      RepulsionPlane                  stiff, dir, aux[0] = position, aux[1] = v, aux[2] = end_position
+ *   ATTRACTION_PLANE     AttractionPlane                 stiff, dir, aux[0] = position
+ *   SPHERE               RepulsiveSphere                 stiff, r0, rate, pos0 = center, aux[0] = r_ext
+ *   LJ_WALL              LJWall                          stiff, dir, aux[0] = position, aux[1] = sigma, aux[2] = cutoff, iaux = n */
 typedef struct {
 	int type;      /* OXB_EXT_* */
-	int particle;  /* original index */
+	int particle;  /* original index, or -1 = all particles */
 	int ref;       /* mutual trap partner, original index */
 	int pbc;
 	double stiff, r0, rate, stiff_rate, F0;
 	double dir[3], pos0[3];
+	double aux[4];
+	int iaux;
 } oxb_ext_force;
 
 /* ---- life cycle.  Replaces MD_CUDABackend / CUDAMixedBackend construction + init_cuda

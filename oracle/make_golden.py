@@ -168,6 +168,54 @@ def rna_lattice_case(name, n_duplex, steps, T="300K", salt=0.5, seed=3, nve_step
           "terms/N", np.round(base["energy_split"] / len(st0["pos"]), 4))
 
 
+def ext2_forces(pos):
+    """the five further external-force types, placed so that each one acts on the thermalised lattice8"""
+    xmin, zmin = float(pos[:, 0].min()), float(pos[:, 2].min())
+    return [dict(type="repulsion_plane", particle="all", stiff=1.5, dir=(0.0, 0.0, 1.0), position=-(zmin + 1.5), v=0.002, end_position=-(zmin + 1.6)),
+            dict(type="attraction_plane", particle=17, stiff=0.3, dir=(0.0, 1.0, 0.0), position=-3.0),
+            dict(type="attraction_plane", particle=200, stiff=0.3, dir=(0.0, 1.0, 0.0), position=-30.0),
+            dict(type="sphere", particle="all", stiff=2.0, r0=7.0, rate=-0.001, center=(10.0, 10.0, 10.0)),
+            dict(type="sphere", particle=5, stiff=1.0, r0=0.5, r_ext=3.0, center=(1.0, 19.0, 2.0)),
+            dict(type="LJ_wall", particle="all", stiff=0.5, dir=(1.0, 0.0, 0.0), position=-(xmin - 1.0), sigma=1.0, n=6, only_repulsive=1),
+            dict(type="lowdim_trap", particle=33, stiff=0.7, rate=0.001, pos0=(5.0, 5.0, 5.0), dir=(1.0, 1.0, 0.0), visibility=(1, 0, 1)),
+            dict(type="mutual_trap", particle=0, ref_particle=39, stiff=0.1, r0=1.2, PBC=1)]
+
+
+def ext2_case():
+    """lattice8 state + forces file with the further force types, evaluated and stepped by the reference CPU backend"""
+    g = dict(np.load(os.path.join(GOLD, "lattice8.npz")))
+    d = tempfile.mkdtemp()
+    top, conf = os.path.join(d, "l.top"), os.path.join(d, "l.dat")
+    oio.write_topology(top, g["btype"], g["n3"], g["n5"], g["strand"])
+    oio.write_conf(conf, g["box"], g["pos"], g["a1"], g["a3"], g["vel"], g["L"])
+    ext = ext2_forces(g["pos"])
+    fpath = os.path.join(d, "forces.txt")
+    with open(fpath, "w") as f:
+        for e in ext:
+            f.write("{\n")
+            for k, val in e.items():
+                if isinstance(val, (tuple, list)):
+                    val = ",".join(str(x) for x in val)
+                f.write(f"{k} = {val}\n")
+            f.write("}\n")
+    r = Reference(top, conf, interaction_type="DNA2_nomesh", salt_concentration=float(g["salt"]), T=str(g["T"]), thermostat="no", dt=0.003,
+                  external_forces=1, external_forces_file=fpath)
+    st0 = r.state()
+    RH.lib().oxref_rebuild_lists()
+    f0 = r.compute_forces()
+    base = {k: g[k] for k in ("btype", "n3", "n5", "strand", "box", "T", "salt")}
+    base.update(pos=st0["pos"], a1=st0["a1"], a3=st0["a3"], vel=st0["vel"], L=st0["L"], rcut=r.rcut(), force=f0["force"], torque_lab=f0["torque_lab"],
+                force_noext=g["force"], U=f0["U"])
+    n = 100
+    r.step(n)
+    st1 = r.state()
+    base.update(nve_steps=n, pos1=st1["pos"], a11=st1["a1"], vel1=st1["vel"], L1=st1["L"])
+    r.close()
+    np.savez_compressed(os.path.join(GOLD, "lattice8_ext2.npz"), **base)
+    dF = np.abs(base["force"] - base["force_noext"])
+    print("wrote lattice8_ext2: particles feeling an external force:", int((dF.max(axis=1) > 1e-12).sum()), "max |dF|", dF.max())
+
+
 def rna():
     force_field_rna()
     rna_lattice_case("rna_lattice8", 8, 3000)
@@ -178,6 +226,9 @@ def rna():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "rna":
         rna()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "ext2":
+        ext2_case()
         sys.exit(0)
     force_field()
     lattice_case("lattice8", 8, 10.0, 3000)

@@ -80,7 +80,46 @@ class RNA2Params(C.Structure):
 
 class ExtForce(C.Structure):
     _fields_ = [("type", C.c_int), ("particle", C.c_int), ("ref", C.c_int), ("pbc", C.c_int)] + [
-        (n, C.c_double) for n in "stiff r0 rate stiff_rate F0".split()] + [("dir", C.c_double * 3), ("pos0", C.c_double * 3)]
+        (n, C.c_double) for n in "stiff r0 rate stiff_rate F0".split()] + [("dir", C.c_double * 3), ("pos0", C.c_double * 3),
+                                                                              ("aux", C.c_double * 4), ("iaux", C.c_int)]
+
+EXT_TYPES = {"string": 0, "trap": 1, "mutual_trap": 2, "lowdim_trap": 3, "repulsion_plane": 4, "attraction_plane": 5, "sphere": 6, "LJ_wall": 7}
+
+
+def fill_ext_entry(e, d):
+    """dict with the reference's external-force keys (docs/source/forces.md) -> one table entry (oxb_ext_force / oxo_ext_force)"""
+    e.type = EXT_TYPES[d["type"]]
+    part = d.get("particle", -1)
+    e.particle = -1 if str(part) in ("-1", "all") else int(part)
+    e.ref = int(d.get("ref_particle", -1))
+    e.pbc = int(d.get("PBC", 0))
+    e.stiff, e.r0, e.rate = float(d.get("stiff", 1.0 if d["type"] == "LJ_wall" else 0.0)), float(d.get("r0", 0.0)), float(d.get("rate", 0.0))
+    e.stiff_rate, e.F0 = float(d.get("stiff_rate", 0.0)), float(d.get("F0", 0.0))
+    dr = np.array(d.get("dir", (1, 0, 0) if d["type"] != "mutual_trap" else (0, 0, 1)), dtype=np.float64)
+    if d["type"] != "mutual_trap" and np.linalg.norm(dr) > 0:
+        dr = dr / np.linalg.norm(dr)
+    centre = d.get("center", d.get("pos0", (0, 0, 0)))
+    for c in range(3):
+        e.dir[c] = dr[c]
+        e.pos0[c] = float(centre[c])
+    aux = [0.0, 0.0, 0.0, 0.0]
+    e.iaux = 0
+    if d["type"] == "lowdim_trap":
+        vis = d.get("visibility", (1, 1, 1))
+        e.iaux = (1 if vis[0] else 0) | (2 if vis[1] else 0) | (4 if vis[2] else 0)
+    elif d["type"] == "repulsion_plane":
+        aux[0], aux[1], aux[2] = float(d["position"]), float(d.get("v", 0.0)), float(d.get("end_position", 1e6))
+    elif d["type"] == "attraction_plane":
+        aux[0] = float(d["position"])
+    elif d["type"] == "sphere":
+        aux[0] = float(d.get("r_ext", 1e10))
+    elif d["type"] == "LJ_wall":
+        n = int(d.get("n", 6))
+        aux[0], aux[1] = float(d["position"]), float(d.get("sigma", 1.0))
+        aux[2] = 2.0 ** (1.0 / n) if int(d.get("only_repulsive", 0)) else 1e6
+        e.iaux = n
+    for c in range(4):
+        e.aux[c] = aux[c]
 
 
 EXT_STRING, EXT_TRAP, EXT_MUTUAL = 0, 1, 2
@@ -194,19 +233,7 @@ def forces(P, pos, axes, btype, n3, n5, box, pairs):
 def make_ext(forces_list):
     arr = (ExtForce * max(len(forces_list), 1))()
     for k, d in enumerate(forces_list):
-        e = arr[k]
-        e.type = {"string": EXT_STRING, "trap": EXT_TRAP, "mutual_trap": EXT_MUTUAL}[d["type"]]
-        e.particle = d["particle"]
-        e.ref = d.get("ref_particle", -1)
-        e.pbc = int(d.get("PBC", 0))
-        e.stiff, e.r0, e.rate = d.get("stiff", 0.0), d.get("r0", 0.0), d.get("rate", 0.0)
-        e.stiff_rate, e.F0 = d.get("stiff_rate", 0.0), d.get("F0", 0.0)
-        dr = np.array(d.get("dir", (0, 0, 1)), dtype=np.float64)
-        if e.type != EXT_MUTUAL:
-            dr = dr / np.linalg.norm(dr)
-        for c in range(3):
-            e.dir[c] = dr[c]
-            e.pos0[c] = d.get("pos0", (0, 0, 0))[c]
+        fill_ext_entry(arr[k], d)
     return arr
 
 

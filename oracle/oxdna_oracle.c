@@ -521,31 +521,70 @@ void oxo_dna2_forces(const oxo_dna2_params *P, int N, const double *pos, const d
 }
 
 /* ------------------------------------------------------------------ external forces */
+static void ext_one(const oxo_ext_force *f, const double *pos, int p, const double *box, long long step, double *force) {
+	const double *pp = pos + 3 * (size_t) p;
+	double *F = force + 3 * (size_t) p;
+	if(f->type == OXO_EXT_STRING) {
+		/* src/Forces/ConstantRateForce.cpp:52-61 */
+		double s = f->F0 + f->rate * step;
+		axpy3(s, f->dir, F);
+	}
+	else if(f->type == OXO_EXT_TRAP) {
+		/* src/Forces/MovingTrap.cpp:50-64 */
+		for(int k = 0; k < 3; k++) F[k] += -f->stiff * (pp[k] - (f->pos0[k] + (f->rate * step) * f->dir[k]));
+	}
+	else if(f->type == OXO_EXT_LOWDIM) {
+		/* src/Forces/LowdimMovingTrap.cpp:68-82 */
+		for(int k = 0; k < 3; k++) {
+			double trap = ((f->iaux >> k) & 1) ? f->pos0[k] + (f->rate * step) * f->dir[k] : pp[k];
+			F[k] += -f->stiff * (pp[k] - trap);
+		}
+	}
+	else if(f->type == OXO_EXT_MUTUAL) {
+		/* src/Forces/MutualTrap.cpp:54-66 */
+		const double *qq = pos + 3 * (size_t) f->ref;
+		double dr[3];
+		if(f->pbc) min_image(box, pp, qq, dr);
+		else for(int k = 0; k < 3; k++) dr[k] = qq[k] - pp[k];
+		double m = sqrt(dot3(dr, dr));
+		double s = (m - (f->r0 + (f->rate * step))) * (f->stiff + (f->stiff_rate * step));
+		for(int k = 0; k < 3; k++) F[k] += (dr[k] / m) * s;
+	}
+	else if(f->type == OXO_EXT_REPULSION_PLANE) {
+		/* src/Forces/RepulsionPlane.cpp:44-58 */
+		double position = f->aux[0] + f->aux[1] * step, end = f->aux[2], start = f->aux[0];
+		if(end > start && position > end) position = end;
+		if(end < start && position < end) position = end;
+		double d = dot3(f->dir, pp) + position;
+		if(d < 0.) axpy3(-(d * f->stiff), f->dir, F);
+	}
+	else if(f->type == OXO_EXT_ATTRACTION_PLANE) {
+		/* src/Forces/AttractionPlane.cpp:45-55 */
+		double d = dot3(f->dir, pp) + f->aux[0];
+		if(d >= 0.) axpy3(-f->stiff * 1.0, f->dir, F);
+		else axpy3(-(d * f->stiff), f->dir, F);
+	}
+	else if(f->type == OXO_EXT_SPHERE) {
+		/* src/Forces/RepulsiveSphere.cpp:46-53 */
+		double d[3];
+		min_image(box, f->pos0, pp, d);
+		double m = sqrt(dot3(d, d)), radius = f->r0 + f->rate * (double) step;
+		if(!(m <= radius || m >= f->aux[0])) axpy3(-f->stiff * (1. - radius / m), d, F);
+	}
+	else if(f->type == OXO_EXT_LJ_WALL) {
+		/* src/Forces/LJWall.cpp:62-68 */
+		double d = dot3(f->dir, pp) + f->aux[0], rel = d / f->aux[1];
+		if(!(rel > f->aux[2])) {
+			double lj = pow(rel, -f->iaux);
+			axpy3(4 * f->iaux * f->stiff * (2 * SQ(lj) - lj) / d, f->dir, F);
+		}
+	}
+}
+
 void oxo_ext_forces(int nf, const oxo_ext_force *ef, int N, const double *pos, const double *box, long long step, double *force) {
-	(void) N;
 	for(int i = 0; i < nf; i++) {
-		const oxo_ext_force *f = &ef[i];
-		const double *pp = pos + 3 * (size_t) f->particle;
-		double *F = force + 3 * (size_t) f->particle;
-		if(f->type == OXO_EXT_STRING) {
-			/* src/Forces/ConstantRateForce.cpp:52-61 */
-			double s = f->F0 + f->rate * step;
-			axpy3(s, f->dir, F);
-		}
-		else if(f->type == OXO_EXT_TRAP) {
-			/* src/Forces/MovingTrap.cpp:50-64 */
-			for(int k = 0; k < 3; k++) F[k] += -f->stiff * (pp[k] - (f->pos0[k] + (f->rate * step) * f->dir[k]));
-		}
-		else if(f->type == OXO_EXT_MUTUAL) {
-			/* src/Forces/MutualTrap.cpp:54-66 */
-			const double *qq = pos + 3 * (size_t) f->ref;
-			double dr[3];
-			if(f->pbc) min_image(box, pp, qq, dr);
-			else for(int k = 0; k < 3; k++) dr[k] = qq[k] - pp[k];
-			double m = sqrt(dot3(dr, dr));
-			double s = (m - (f->r0 + (f->rate * step))) * (f->stiff + (f->stiff_rate * step));
-			for(int k = 0; k < 3; k++) F[k] += (dr[k] / m) * s;
-		}
+		if(ef[i].particle >= 0) ext_one(&ef[i], pos, ef[i].particle, box, step, force);
+		else for(int p = 0; p < N; p++) ext_one(&ef[i], pos, p, box, step, force);
 	}
 }
 

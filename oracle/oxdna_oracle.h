@@ -55,8 +55,10 @@ void oxo_dna2_params_init(oxo_dna2_params *P, double T, double salt, int dh_half
 		int use_mbf, double mbf_fmax, double mbf_finf);
 void oxo_dna2_params_seqdep(oxo_dna2_params *P, const double *stck_raw16, double stck_fact_eps, double hb_AT, double hb_GC);
 
-typedef struct { int type; int particle; int ref; int pbc; double stiff, r0, rate, stiff_rate, F0; double dir[3], pos0[3]; } oxo_ext_force;
-enum { OXO_EXT_STRING = 0, OXO_EXT_TRAP = 1, OXO_EXT_MUTUAL = 2 };
+/* particle = -1: every particle.  aux / iaux: see the table in include/oxdna_b200.h (same conventions) */
+typedef struct { int type; int particle; int ref; int pbc; double stiff, r0, rate, stiff_rate, F0; double dir[3], pos0[3]; double aux[4]; int iaux; } oxo_ext_force;
+enum { OXO_EXT_STRING = 0, OXO_EXT_TRAP = 1, OXO_EXT_MUTUAL = 2, OXO_EXT_LOWDIM = 3, OXO_EXT_REPULSION_PLANE = 4, OXO_EXT_ATTRACTION_PLANE = 5,
+	OXO_EXT_SPHERE = 6, OXO_EXT_LJ_WALL = 7 };
 
 /* axes: N x 9 doubles = a1(3) a2(3) a3(3).  pairs: npairs x 2 ints (non-bonded candidates, each unique pair once).
  * Outputs (any may be NULL): force N x 3 (lab), torque_lab N x 3, torque_body N x 3, eterms[OXO_NTERMS] totals,
@@ -65,7 +67,8 @@ void oxo_dna2_forces(const oxo_dna2_params *P, int N, const double *pos, const d
 		const int *n3, const int *n5, const double *box, const int *pairs, long long npairs,
 		double *force, double *torque_lab, double *torque_body, double *eterms, double *epart);
 
-/* external forces (src/Forces/{ConstantRateForce,MovingTrap,MutualTrap}.cpp), added to force (lab frame) */
+/* external forces (src/Forces/{ConstantRateForce,MovingTrap,MutualTrap,LowdimMovingTrap,RepulsionPlane,AttractionPlane,
+ * RepulsiveSphere,LJWall}.cpp), added to force (lab frame) */
 void oxo_ext_forces(int nf, const oxo_ext_force *ef, int N, const double *pos, const double *box, long long step, double *force);
 
 /* Verlet list exactly as src/Lists/Cells.cpp:120-181 + VerletList.cpp:35-66: unique pairs (q<p), not bonded,

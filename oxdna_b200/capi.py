@@ -13,7 +13,7 @@ SO_PATH = os.path.join(_HERE, "liboxdna_b200.so")
 
 PRECISION_FLOAT, PRECISION_MIXED = 0, 1
 THERMOSTAT_NONE, THERMOSTAT_BROWNIAN, THERMOSTAT_LANGEVIN, THERMOSTAT_BUSSI = 0, 1, 2, 3
-EXT_STRING, EXT_TRAP, EXT_MUTUAL_TRAP = 0, 1, 2
+EXT_STRING, EXT_TRAP, EXT_MUTUAL_TRAP, EXT_LOWDIM_TRAP, EXT_REPULSION_PLANE, EXT_ATTRACTION_PLANE, EXT_SPHERE, EXT_LJ_WALL = range(8)
 NTERMS = 8
 NF4 = 13
 
@@ -73,7 +73,46 @@ class RNA2Params(C.Structure):
 
 class ExtForce(C.Structure):
     _fields_ = [("type", C.c_int), ("particle", C.c_int), ("ref", C.c_int), ("pbc", C.c_int)] + [
-        (n, C.c_double) for n in "stiff r0 rate stiff_rate F0".split()] + [("dir", C.c_double * 3), ("pos0", C.c_double * 3)]
+        (n, C.c_double) for n in "stiff r0 rate stiff_rate F0".split()] + [("dir", C.c_double * 3), ("pos0", C.c_double * 3),
+                                                                              ("aux", C.c_double * 4), ("iaux", C.c_int)]
+
+EXT_TYPES = {"string": 0, "trap": 1, "mutual_trap": 2, "lowdim_trap": 3, "repulsion_plane": 4, "attraction_plane": 5, "sphere": 6, "LJ_wall": 7}
+
+
+def fill_ext_entry(e, d):
+    """dict with the reference's external-force keys (docs/source/forces.md) -> one table entry (oxb_ext_force / oxo_ext_force)"""
+    e.type = EXT_TYPES[d["type"]]
+    part = d.get("particle", -1)
+    e.particle = -1 if str(part) in ("-1", "all") else int(part)
+    e.ref = int(d.get("ref_particle", -1))
+    e.pbc = int(d.get("PBC", 0))
+    e.stiff, e.r0, e.rate = float(d.get("stiff", 1.0 if d["type"] == "LJ_wall" else 0.0)), float(d.get("r0", 0.0)), float(d.get("rate", 0.0))
+    e.stiff_rate, e.F0 = float(d.get("stiff_rate", 0.0)), float(d.get("F0", 0.0))
+    dr = np.array(d.get("dir", (1, 0, 0) if d["type"] != "mutual_trap" else (0, 0, 1)), dtype=np.float64)
+    if d["type"] != "mutual_trap" and np.linalg.norm(dr) > 0:
+        dr = dr / np.linalg.norm(dr)
+    centre = d.get("center", d.get("pos0", (0, 0, 0)))
+    for c in range(3):
+        e.dir[c] = dr[c]
+        e.pos0[c] = float(centre[c])
+    aux = [0.0, 0.0, 0.0, 0.0]
+    e.iaux = 0
+    if d["type"] == "lowdim_trap":
+        vis = d.get("visibility", (1, 1, 1))
+        e.iaux = (1 if vis[0] else 0) | (2 if vis[1] else 0) | (4 if vis[2] else 0)
+    elif d["type"] == "repulsion_plane":
+        aux[0], aux[1], aux[2] = float(d["position"]), float(d.get("v", 0.0)), float(d.get("end_position", 1e6))
+    elif d["type"] == "attraction_plane":
+        aux[0] = float(d["position"])
+    elif d["type"] == "sphere":
+        aux[0] = float(d.get("r_ext", 1e10))
+    elif d["type"] == "LJ_wall":
+        n = int(d.get("n", 6))
+        aux[0], aux[1] = float(d["position"]), float(d.get("sigma", 1.0))
+        aux[2] = 2.0 ** (1.0 / n) if int(d.get("only_repulsive", 0)) else 1e6
+        e.iaux = n
+    for c in range(4):
+        e.aux[c] = aux[c]
 
 
 EXPORTED = """oxb_dna2_params_init oxb_dna2_params_seqdep oxb_rna2_params_init oxb_rna2_params_seqdep oxb_set_model_rna2 oxb_create oxb_destroy oxb_last_error oxb_set_stream oxb_set_box
@@ -215,16 +254,7 @@ class Context:
         n = len(forces)
         arr = (ExtForce * max(n, 1))()
         for k, f in enumerate(forces):
-            e = arr[k]
-            e.type = {"string": EXT_STRING, "trap": EXT_TRAP, "mutual_trap": EXT_MUTUAL_TRAP}[f["type"]]
-            e.particle = int(f["particle"])
-            e.ref = int(f.get("ref_particle", -1))
-            e.pbc = int(f.get("PBC", 0))
-            e.stiff, e.r0, e.rate = float(f.get("stiff", 0.0)), float(f.get("r0", 0.0)), float(f.get("rate", 0.0))
-            e.stiff_rate, e.F0 = float(f.get("stiff_rate", 0.0)), float(f.get("F0", 0.0))
-            for x in range(3):
-                e.dir[x] = float(f.get("dir", (0, 0, 1))[x])
-                e.pos0[x] = float(f.get("pos0", (0, 0, 0))[x])
+            fill_ext_entry(arr[k], f)
         self._ck(self._L.oxb_set_ext_forces(self._h, n, arr))
 
     # ---- state

@@ -98,8 +98,8 @@ struct oxb_ctx {
 	bool mid_step = false; // positions already advanced for `step`, forces pending
 	ThermostatCfg th;
 	bool bussi_init = false;
-	int n_ext = 0;
-	DevExtForce *ext = nullptr;
+	int n_ext = 0, n_ext_all = 0; // entries bound to one particle / entries acting on every particle
+	DevExtForce *ext = nullptr, *ext_all = nullptr;
 	double avg_interval = 8.;
 
 	// concurrency inside one force pass (independent kernels on forked streams) and graph-captured batches of steps
@@ -379,6 +379,10 @@ int launch_forces(oxb_ctx *c, int hw, bool clear, long long step) {
 			oxb::launch_ext_forces(c->aux[1], c->n_ext, c->ext, c->slot_of, c->ipos[a], c->posd[a], c->boxf, step, c->cur_step, c->F[a], c->flags, hw);
 			c->launches += 1;
 		}
+		if(c->n_ext_all > 0) {
+			oxb::launch_ext_forces_all(c->aux[1], c->N, c->n_ext_all, c->ext_all, c->ipos[a], c->posd[a], c->boxf, step, c->cur_step, c->F[a], c->flags, hw);
+			c->launches += 1;
+		}
 		CU(cudaStreamWaitEvent(c->aux[1], c->ev_near, 0));
 		oxb::launch_edge_stage(c->aux[1], 3, c->mref(), c->boxf, e, c->flags, hw);
 		CU(cudaEventRecord(c->ev_join[0], c->aux[0]));
@@ -393,6 +397,10 @@ int launch_forces(oxb_ctx *c, int hw, bool clear, long long step) {
 		c->launches += 1;
 		if(c->n_ext > 0) {
 			oxb::launch_ext_forces(m, c->n_ext, c->ext, c->slot_of, c->ipos[a], c->posd[a], c->boxf, step, c->cur_step, c->F[a], c->flags, hw);
+			c->launches += 1;
+		}
+		if(c->n_ext_all > 0) {
+			oxb::launch_ext_forces_all(m, c->N, c->n_ext_all, c->ext_all, c->ipos[a], c->posd[a], c->boxf, step, c->cur_step, c->F[a], c->flags, hw);
 			c->launches += 1;
 		}
 	}
@@ -542,7 +550,7 @@ int batch_graph(oxb_ctx *c, int units, cudaGraphExec_t *out) {
 // stream launches.
 int launch_full_units(oxb_ctx *c, long long n, long long step0, int &epoch) {
 	const bool graphable = c->use_graphs && c->th.type != OXB_THERMOSTAT_BUSSI;
-	const int per_unit = (c->use_edge ? 5 : 1) + (c->n_ext > 0 ? 1 : 0) + 1;
+	const int per_unit = (c->use_edge ? 5 : 1) + (c->n_ext > 0 ? 1 : 0) + (c->n_ext_all > 0 ? 1 : 0) + 1;
 	long long k = 0;
 	while(k < n) {
 		int chunk = 0;
@@ -645,7 +653,7 @@ void oxb_destroy(oxb_ctx *c) {
 		cudaFree(c->quat[k]); cudaFree(c->F[k]); cudaFree(c->T[k]); cudaFree(c->bonds[k]); cudaFree(c->iback[k]); cudaFree(c->list_iback[k]); cudaFree(c->list_ibase[k]);
 	}
 	cudaFree(c->Fb);
-	cudaFree(c->slot_of); cudaFree(c->flags); cudaFree(c->sums); cudaFree(c->d_energy); cudaFree(c->ext); cudaFree(c->pos_f4);
+	cudaFree(c->slot_of); cudaFree(c->flags); cudaFree(c->sums); cudaFree(c->d_energy); cudaFree(c->ext); cudaFree(c->ext_all); cudaFree(c->pos_f4);
 	cudaFree(c->hkeys); cudaFree(c->hkeys_sorted); cudaFree(c->hvals); cudaFree(c->hvals_sorted); cudaFree(c->hinv);
 	free_lists(c);
 	if(c->h_flags) cudaFreeHost(c->h_flags);
@@ -758,12 +766,15 @@ int oxb_set_thermostat(oxb_ctx *c, int type, int every, double a, double b, doub
 
 int oxb_set_ext_forces(oxb_ctx *c, int n, const oxb_ext_force *f) {
 	if(c == nullptr || n < 0 || (n > 0 && f == nullptr)) return 1;
-	std::vector<DevExtForce> h(std::max(n, 1));
+	std::vector<DevExtForce> h, hall;
 	for(int k = 0; k < n; k++) {
-		if(f[k].particle < 0 || f[k].particle >= c->N) return fail(c, 1, "external force %d: invalid particle %d", k, f[k].particle);
+		if(f[k].type < OXB_EXT_STRING || f[k].type >= OXB_EXT_NTYPES) return fail(c, 1, "external force %d: unsupported type %d", k, f[k].type);
+		if(f[k].particle < -1 || f[k].particle >= c->N) return fail(c, 1, "external force %d: invalid particle %d", k, f[k].particle);
 		if(f[k].type == OXB_EXT_MUTUAL_TRAP && (f[k].ref < 0 || f[k].ref >= c->N)) return fail(c, 1, "Invalid reference particle %d for Mutual Trap", f[k].ref);
-		if(f[k].type < OXB_EXT_STRING || f[k].type > OXB_EXT_MUTUAL_TRAP) return fail(c, 1, "external force %d: unsupported type %d", k, f[k].type);
-		DevExtForce &d = h[k];
+		if(f[k].type == OXB_EXT_MUTUAL_TRAP && f[k].particle < 0) return fail(c, 1, "external force %d: a mutual trap needs one particle", k);
+		if(f[k].type == OXB_EXT_LJ_WALL && (f[k].iaux % 2 != 0 || f[k].iaux <= 0)) return fail(c, 1, "LJWall: n (%d) should be an even integer. Aborting", f[k].iaux);
+		DevExtForce d;
+		std::memset(&d, 0, sizeof(d));
 		d.type = f[k].type; d.particle = f[k].particle; d.ref = f[k].ref < 0 ? 0 : f[k].ref; d.pbc = f[k].pbc;
 		d.stiff = (float) f[k].stiff; d.r0 = (float) f[k].r0; d.rate = (float) f[k].rate; d.stiff_rate = (float) f[k].stiff_rate; d.F0 = (float) f[k].F0;
 		double nrm = std::sqrt(f[k].dir[0] * f[k].dir[0] + f[k].dir[1] * f[k].dir[1] + f[k].dir[2] * f[k].dir[2]);
@@ -771,12 +782,19 @@ int oxb_set_ext_forces(oxb_ctx *c, int n, const oxb_ext_force *f) {
 			d.dir[x] = (float) ((f[k].type != OXB_EXT_MUTUAL_TRAP && nrm > 0) ? f[k].dir[x] / nrm : f[k].dir[x]);
 			d.pos0[x] = f[k].pos0[x];
 		}
+		for(int x = 0; x < 4; x++) d.aux[x] = (float) f[k].aux[x];
+		d.iaux = f[k].iaux;
+		(f[k].particle < 0 ? hall : h).push_back(d);
 	}
 	cudaFree(c->ext);
-	c->ext = nullptr;
-	CU(dalloc(&c->ext, (size_t) std::max(n, 1)));
-	if(n > 0) CU(cudaMemcpy(c->ext, h.data(), sizeof(DevExtForce) * n, cudaMemcpyHostToDevice));
-	c->n_ext = n;
+	cudaFree(c->ext_all);
+	c->ext = c->ext_all = nullptr;
+	CU(dalloc(&c->ext, std::max<size_t>(h.size(), 1)));
+	CU(dalloc(&c->ext_all, std::max<size_t>(hall.size(), 1)));
+	if(!h.empty()) CU(cudaMemcpy(c->ext, h.data(), sizeof(DevExtForce) * h.size(), cudaMemcpyHostToDevice));
+	if(!hall.empty()) CU(cudaMemcpy(c->ext_all, hall.data(), sizeof(DevExtForce) * hall.size(), cudaMemcpyHostToDevice));
+	c->n_ext = (int) h.size();
+	c->n_ext_all = (int) hall.size();
 	c->forces_valid = false;
 	drop_graphs(c);
 	return 0;
@@ -879,7 +897,7 @@ int oxb_get_state(oxb_ctx *c, double *pos, double *a1, double *a3, double *vel, 
 int oxb_set_step(oxb_ctx *c, long long step) {
 	if(c == nullptr) return 1;
 	c->step = step;
-	c->forces_valid = c->forces_valid && (c->n_ext == 0);
+	c->forces_valid = c->forces_valid && (c->n_ext == 0) && (c->n_ext_all == 0);
 	return 0;
 }
 

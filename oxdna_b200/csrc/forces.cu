@@ -377,6 +377,67 @@ __global__ void __launch_bounds__(128) k_energy_split(const __grid_constant__ ty
 // interaction kernels and adds into F.  Particle ids in the table are ORIGINAL ids, mapped through slot_of, so the
 // Hilbert re-sort needs no table rewrite (the reference forbids sort + external forces, MD_CUDABackend.cu:110-112).
 // ------------------------------------------------------------------------------------------------------------
+// force of a single-particle entry on a particle at absolute position p (double, unwrapped: what the reference's CPU classes see)
+__device__ __forceinline__ v3 ext_single(const DevExtForce &e, double4 p, int4 ip, BoxF box, long long step) {
+	const float st = (float) step;
+	switch(e.type) {
+	case OXB_EXT_STRING: {
+		// ConstantRateForce.cpp:52-61
+		float s = e.F0 + e.rate * st;
+		return mk3(e.dir[0] * s, e.dir[1] * s, e.dir[2] * s);
+	}
+	case OXB_EXT_TRAP:
+	case OXB_EXT_LOWDIM_TRAP: {
+		// MovingTrap.cpp:50-64, LowdimMovingTrap.cpp:68-82: absolute (unwrapped) position, kept in double
+		double rs = (double) e.rate * (double) step;
+		v3 f = mk3((float) (-(double) e.stiff * (p.x - (e.pos0[0] + rs * e.dir[0]))), (float) (-(double) e.stiff * (p.y - (e.pos0[1] + rs * e.dir[1]))),
+				(float) (-(double) e.stiff * (p.z - (e.pos0[2] + rs * e.dir[2]))));
+		if(e.type == OXB_EXT_LOWDIM_TRAP) {
+			if(!(e.iaux & 1)) f.x = 0.f;
+			if(!(e.iaux & 2)) f.y = 0.f;
+			if(!(e.iaux & 4)) f.z = 0.f;
+		}
+		return f;
+	}
+	case OXB_EXT_REPULSION_PLANE: {
+		// RepulsionPlane.cpp:44-58
+		double pos = (double) e.aux[0] + (double) e.aux[1] * (double) step, end = e.aux[2], start = e.aux[0];
+		if(end > start && pos > end) pos = end;
+		if(end < start && pos < end) pos = end;
+		double d = e.dir[0] * p.x + e.dir[1] * p.y + e.dir[2] * p.z + pos;
+		if(d >= 0.) return mk3(0.f, 0.f, 0.f);
+		float s = (float) (-d * (double) e.stiff);
+		return mk3(e.dir[0] * s, e.dir[1] * s, e.dir[2] * s);
+	}
+	case OXB_EXT_ATTRACTION_PLANE: {
+		// AttractionPlane.cpp:45-55
+		double d = e.dir[0] * p.x + e.dir[1] * p.y + e.dir[2] * p.z + (double) e.aux[0];
+		float s = (d >= 0.) ? -e.stiff : (float) (-d * (double) e.stiff);
+		return mk3(e.dir[0] * s, e.dir[1] * s, e.dir[2] * s);
+	}
+	case OXB_EXT_SPHERE: {
+		// RepulsiveSphere.cpp:46-53: minimum image of (pos - center)
+		int4 ic;
+		ic.x = (int) to_fixed(e.pos0[0], 1. / (double) box.lx); ic.y = (int) to_fixed(e.pos0[1], 1. / (double) box.ly); ic.z = (int) to_fixed(e.pos0[2], 1. / (double) box.lz);
+		v3 d = min_image_fixed(box, ic, ip);
+		float m = sqrtf(dot(d, d));
+		float radius = e.r0 + e.rate * st;
+		if(m <= radius || m >= e.aux[0]) return mk3(0.f, 0.f, 0.f);
+		return d * (-e.stiff * (1.f - radius / m));
+	}
+	case OXB_EXT_LJ_WALL: {
+		// LJWall.cpp:62-68
+		double d = e.dir[0] * p.x + e.dir[1] * p.y + e.dir[2] * p.z + (double) e.aux[0];
+		float rel = (float) d / e.aux[1];
+		if(rel > e.aux[2]) return mk3(0.f, 0.f, 0.f);
+		float lj = powf(rel, -(float) e.iaux);
+		float s = 4.f * (float) e.iaux * e.stiff * (2.f * lj * lj - lj) / (float) d;
+		return mk3(e.dir[0] * s, e.dir[1] * s, e.dir[2] * s);
+	}
+	default: return mk3(0.f, 0.f, 0.f);
+	}
+}
+
 __global__ void k_ext_forces(int n, const DevExtForce *__restrict__ ef, const int *__restrict__ slot_of, const int4 *__restrict__ ipos,
 		const double4 *__restrict__ posd, BoxF box, long long step, const long long *__restrict__ cur_step, float4 *__restrict__ F,
 		const int *__restrict__ flags, int hw) {
@@ -387,22 +448,10 @@ __global__ void k_ext_forces(int n, const DevExtForce *__restrict__ ef, const in
 	if(k >= n) return;
 	DevExtForce e = ef[k];
 	int i = slot_of[e.particle];
-	float st = (float) step;
 	v3 f;
-	if(e.type == OXB_EXT_STRING) {
-		// ConstantRateForce.cpp:52-61
-		float s = e.F0 + e.rate * st;
-		f = mk3(e.dir[0] * s, e.dir[1] * s, e.dir[2] * s);
-	}
-	else if(e.type == OXB_EXT_TRAP) {
-		// MovingTrap.cpp:50-64: uses the absolute (unwrapped) position, kept in double
-		double4 p = posd[i];
-		double rs = (double) e.rate * (double) step;
-		f = mk3((float) (-(double) e.stiff * (p.x - (e.pos0[0] + rs * e.dir[0]))), (float) (-(double) e.stiff * (p.y - (e.pos0[1] + rs * e.dir[1]))),
-				(float) (-(double) e.stiff * (p.z - (e.pos0[2] + rs * e.dir[2]))));
-	}
-	else {
+	if(e.type == OXB_EXT_MUTUAL_TRAP) {
 		// MutualTrap.cpp:54-66
+		float st = (float) step;
 		int j = slot_of[e.ref];
 		v3 dr;
 		if(e.pbc) dr = min_image_fixed(box, ipos[i], ipos[j]);
@@ -414,6 +463,23 @@ __global__ void k_ext_forces(int n, const DevExtForce *__restrict__ ef, const in
 		float s = (m - (e.r0 + e.rate * st)) * (e.stiff + e.stiff_rate * st) / m;
 		f = dr * s;
 	}
+	else f = ext_single(e, posd[i], ipos[i], box, step);
+	atomicAdd(&F[i].x, f.x);
+	atomicAdd(&F[i].y, f.y);
+	atomicAdd(&F[i].z, f.z);
+}
+
+__global__ void k_ext_forces_all(int N, int n_all, const DevExtForce *__restrict__ ef, const int4 *__restrict__ ipos, const double4 *__restrict__ posd,
+		BoxF box, long long step, const long long *__restrict__ cur_step, float4 *__restrict__ F, const int *__restrict__ flags, int hw) {
+	if(flags[hw]) return;
+	if(step < 0) step = cur_step[hw & 1];
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= N) return;
+	double4 p = posd[i];
+	int4 ip = ipos[i];
+	v3 f = mk3(0.f, 0.f, 0.f);
+	for(int k = 0; k < n_all; k++) f += ext_single(ef[k], p, ip, box, step);
+	// the interaction kernels add into F concurrently (other streams): atomics
 	atomicAdd(&F[i].x, f.x);
 	atomicAdd(&F[i].y, f.y);
 	atomicAdd(&F[i].z, f.z);
@@ -469,6 +535,13 @@ void launch_ext_forces(cudaStream_t s, int n, const DevExtForce *ef, const int *
 	if(n <= 0) return;
 	int tpb = 128;
 	k_ext_forces<<<(n + tpb - 1) / tpb, tpb, 0, s>>>(n, ef, slot_of, ipos, posd, box, step, cur_step, F, flags, hw);
+}
+
+void launch_ext_forces_all(cudaStream_t s, int N, int n_all, const DevExtForce *ef_all, const int4 *ipos, const double4 *posd, BoxF box,
+		long long step, const long long *cur_step, float4 *F, const int *flags, int hw) {
+	if(n_all <= 0) return;
+	int tpb = 128;
+	k_ext_forces_all<<<(N + tpb - 1) / tpb, tpb, 0, s>>>(N, n_all, ef_all, ipos, posd, box, step, cur_step, F, flags, hw);
 }
 
 } // namespace oxb

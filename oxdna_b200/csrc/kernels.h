@@ -23,6 +23,8 @@ struct DevExtForce {
 	float stiff, r0, rate, stiff_rate, F0;
 	float dir[3];
 	double pos0[3];
+	float aux[4];
+	int iaux;
 };
 
 struct ThermostatCfg {
@@ -74,6 +76,9 @@ void launch_edge_stage(cudaStream_t s, int which, const ModelRef &M, BoxF box, c
 void launch_energy_split(cudaStream_t s, const ModelRef &M, BoxF box, int N, const int4 *ipos, const float4 *quat, const int2 *bonds, const int *nbr,
 		const int *nnbr, int stride, double *out);
 void launch_ext_forces(cudaStream_t s, int n, const DevExtForce *ef, const int *slot_of, const int4 *ipos, const double4 *posd, BoxF box,
+		long long step, const long long *cur_step, float4 *F, const int *flags, int hw);
+// entries that act on every particle (particle = all): one thread per particle, no atomics
+void launch_ext_forces_all(cudaStream_t s, int N, int n_all, const DevExtForce *ef_all, const int4 *ipos, const double4 *posd, BoxF box,
 		long long step, const long long *cur_step, float4 *F, const int *flags, int hw);
 
 // ---- integrate.cu

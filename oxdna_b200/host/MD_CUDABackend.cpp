@@ -2,6 +2,15 @@
 // src/CUDA/Backends/MD_CUDABackend.cu:231-394,567-747; the device work goes through the C ABI (include/oxdna_b200.h).
 #include "MD_CUDABackend.h"
 
+#include "Forces/AttractionPlane.h"
+#include "Forces/LJWall.h"
+#include "Forces/LowdimMovingTrap.h"
+#include "Forces/RepulsionPlane.h"
+#include "Forces/RepulsiveSphere.h"
+
+#include <map>
+#include <set>
+
 #include "Forces/ConstantRateForce.h"
 #include "Forces/MovingTrap.h"
 #include "Forces/MutualTrap.h"
@@ -171,6 +180,11 @@ void MD_CUDABackend::_gpu_to_host() {
 void MD_CUDABackend::_apply_external_forces_changes() {
 	if(!_external_forces) return;
 	std::vector<oxb_ext_force> table;
+	// a force given with `particle = all` is the same object attached to every particle: keep it as ONE table entry
+	// (particle = -1) instead of N copies (the reference keeps 15 union slots per particle)
+	std::map<BaseForce *, int> uses;
+	for(int i = 0; i < N(); i++) for(auto f : _particles[i]->ext_forces) uses[f]++;
+	std::set<BaseForce *> emitted;
 	for(int i = 0; i < N(); i++) {
 		BaseParticle *p = _particles[i];
 		for(auto f : p->ext_forces) {
@@ -178,6 +192,7 @@ void MD_CUDABackend::_apply_external_forces_changes() {
 			memset(&e, 0, sizeof(e));
 			e.particle = i;
 			auto &ft = typeid(*f);
+			bool single_particle_type = true;
 			if(ft == typeid(ConstantRateForce)) {
 				ConstantRateForce *cf = static_cast<ConstantRateForce *>(f);
 				if(cf->dir_as_centre) throw oxDNAException("ConstantRateForce with dir_as_centre = true is not supported by the oxdna_b200 CUDA backend");
@@ -187,6 +202,7 @@ void MD_CUDABackend::_apply_external_forces_changes() {
 			}
 			else if(ft == typeid(MutualTrap)) {
 				MutualTrap *mf = static_cast<MutualTrap *>(f);
+				single_particle_type = false;
 				e.type = OXB_EXT_MUTUAL_TRAP;
 				e.ref = mf->_p_ptr->index;
 				e.pbc = mf->PBC ? 1 : 0;
@@ -199,8 +215,50 @@ void MD_CUDABackend::_apply_external_forces_changes() {
 				e.dir[0] = tf->_direction.x; e.dir[1] = tf->_direction.y; e.dir[2] = tf->_direction.z;
 				e.pos0[0] = tf->_pos0.x; e.pos0[1] = tf->_pos0.y; e.pos0[2] = tf->_pos0.z;
 			}
+			else if(ft == typeid(LowdimMovingTrap)) {
+				LowdimMovingTrap *tf = static_cast<LowdimMovingTrap *>(f);
+				e.type = OXB_EXT_LOWDIM_TRAP;
+				e.stiff = tf->_stiff; e.rate = tf->_rate;
+				e.dir[0] = tf->_direction.x; e.dir[1] = tf->_direction.y; e.dir[2] = tf->_direction.z;
+				e.pos0[0] = tf->_pos0.x; e.pos0[1] = tf->_pos0.y; e.pos0[2] = tf->_pos0.z;
+				e.iaux = (tf->_visX ? 1 : 0) | (tf->_visY ? 2 : 0) | (tf->_visZ ? 4 : 0);
+			}
+			else if(ft == typeid(RepulsionPlane)) {
+				RepulsionPlane *pf = static_cast<RepulsionPlane *>(f);
+				e.type = OXB_EXT_REPULSION_PLANE;
+				e.stiff = pf->_stiff;
+				e.dir[0] = pf->_direction.x; e.dir[1] = pf->_direction.y; e.dir[2] = pf->_direction.z;
+				e.aux[0] = pf->_starting_position; e.aux[1] = pf->_v; e.aux[2] = pf->_end_position;
+			}
+			else if(ft == typeid(AttractionPlane)) {
+				AttractionPlane *pf = static_cast<AttractionPlane *>(f);
+				e.type = OXB_EXT_ATTRACTION_PLANE;
+				e.stiff = pf->_stiff;
+				e.dir[0] = pf->_direction.x; e.dir[1] = pf->_direction.y; e.dir[2] = pf->_direction.z;
+				e.aux[0] = pf->_position;
+			}
+			else if(ft == typeid(RepulsiveSphere)) {
+				RepulsiveSphere *sf = static_cast<RepulsiveSphere *>(f);
+				e.type = OXB_EXT_SPHERE;
+				e.stiff = sf->_stiff; e.r0 = sf->_r0; e.rate = sf->_rate;
+				e.pos0[0] = sf->_center.x; e.pos0[1] = sf->_center.y; e.pos0[2] = sf->_center.z;
+				e.aux[0] = sf->_r_ext;
+			}
+			else if(ft == typeid(LJWall)) {
+				LJWall *wf = static_cast<LJWall *>(f);
+				e.type = OXB_EXT_LJ_WALL;
+				e.stiff = wf->_stiff;
+				e.dir[0] = wf->_direction.x; e.dir[1] = wf->_direction.y; e.dir[2] = wf->_direction.z;
+				e.aux[0] = wf->_position; e.aux[1] = wf->_sigma; e.aux[2] = wf->_cutoff;
+				e.iaux = wf->_n;
+			}
 			else {
-				throw oxDNAException("Only ConstantRate (string), MutualTrap and MovingTrap forces are supported by the oxdna_b200 CUDA backend at the moment.\n");
+				throw oxDNAException("Only string, trap, mutual_trap, lowdim_trap, repulsion_plane, attraction_plane, sphere and LJ_wall forces are supported by the oxdna_b200 CUDA backend at the moment.\n");
+			}
+			if(single_particle_type && N() > 1 && uses[f] == N()) {
+				if(emitted.count(f)) continue;
+				emitted.insert(f);
+				e.particle = -1;
 			}
 			table.push_back(e);
 		}

@@ -70,12 +70,56 @@ PBC = 1
 """
 
 
+FORCES2 = """{
+type = repulsion_plane
+particle = all
+stiff = 1.0
+dir = 0,0,1
+position = -23.5
+}
+{
+type = sphere
+particle = all
+stiff = 2.0
+r0 = 4.0
+center = 25.,25.,25.
+}
+{
+type = LJ_wall
+particle = 3
+stiff = 0.4
+dir = 1,0,0
+position = -20.0
+sigma = 1.5
+n = 4
+}
+{
+type = lowdim_trap
+particle = 9
+stiff = 0.5
+rate = 0.001
+pos0 = 25., 25., 25.
+dir = 0., 1., 0.
+visibility = 0, 1, 1
+}
+{
+type = attraction_plane
+particle = 0
+stiff = 0.2
+dir = 0,1,0
+position = -20.
+}
+"""
+
+
 def run(binary, d, fix=FIX, files=("initial.top", "initial.conf"), **kw):
     os.makedirs(d, exist_ok=True)
     for f, name in zip(files, ("initial.top", "initial.conf")):
         shutil.copy(os.path.join(fix, f), os.path.join(d, name))
     with open(os.path.join(d, "forces.txt"), "w") as f:
         f.write(FORCES)
+    with open(os.path.join(d, "forces2.txt"), "w") as f:
+        f.write(FORCES2)
     with open(os.path.join(d, "input"), "w") as f:
         f.write(INPUT.format(**kw))
     p = subprocess.run([binary, "input"], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
@@ -91,7 +135,8 @@ needs_binaries = pytest.mark.skipif(not (os.path.exists(OURS) and os.path.exists
 
 @pytest.mark.gpu
 @needs_binaries
-@pytest.mark.parametrize("use_edge,sort_every,extra", [(1, 1, ""), (0, 0, ""), (1, 1, "external_forces = 1\nexternal_forces_file = forces.txt")])
+@pytest.mark.parametrize("use_edge,sort_every,extra", [(1, 1, ""), (0, 0, ""), (1, 1, "external_forces = 1\nexternal_forces_file = forces.txt"),
+                                                       (1, 1, "external_forces = 1\nexternal_forces_file = forces2.txt")])
 def test_stock_input_file_matches_reference_cpu(tmp_path, use_edge, sort_every, extra):
     a = run(OURS, str(tmp_path / "ours"), backend="CUDA", itype="DNA2", steps=300, thermostat="no", use_edge=use_edge, sort_every=sort_every, extra=extra)
     assert a.returncode == 0, a.stdout[-2000:]

@@ -6,7 +6,7 @@ arithmetic), energies relative 1e-6; NVE trajectories against the double-precisi
 import numpy as np
 import pytest
 
-from conftest import load_golden, pair_set
+from conftest import ext2_forces, load_golden, pair_set
 from oracle import oracle as O
 from oxdna_b200 import capi, lattice
 from oxdna_b200.sim import Simulation, parse_temperature
@@ -412,3 +412,24 @@ def test_backend_precision_float_and_split_energy_observable():
             assert sim.ctx.stats()["error_flags"] == 0
         finally:
             sim.close()
+
+
+@pytest.mark.parametrize("use_edge,sort_every", [(0, 0), (1, 1)])
+def test_further_external_forces_vs_reference(use_edge, sort_every):
+    """SURVEY 8f rank 2 (first batch): repulsion_plane, attraction_plane, sphere, LJ_wall, lowdim_trap, `particle = all` entries
+    kept once in the table -- against the reference CPU run (forces at step 0, 100 steps of dynamics with moving plane / sphere)."""
+    g = load_golden("lattice8_ext2")
+    sim = make_sim(g, use_edge=use_edge, CUDA_sort_every=sort_every, external_forces_list=ext2_forces(g["pos"]))
+    try:
+        out = sim.ctx.get_forces()
+        fmax = np.linalg.norm(g["force"], axis=1).max()
+        assert np.linalg.norm(out["force"] - g["force"], axis=1).max() <= 1e-5 * fmax
+        ext_part = out["force"] - (g["force_noext"] - 0.0)
+        assert np.abs((ext_part - (g["force"] - g["force_noext"]))).max() <= 2e-5 * fmax
+        n = int(g["nve_steps"])
+        sim.run(n)
+        st = sim.ctx.get_state()
+        assert np.abs(st["pos"] - g["pos1"]).max() < 2e-4
+        assert np.abs(st["vel"] - g["vel1"]).max() < 2e-3
+    finally:
+        sim.close()

@@ -5,7 +5,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLD, load_golden, pair_set
+from conftest import GOLD, ext2_forces, load_golden, pair_set
 from oracle import oracle as O
 from oracle import refharness as RH
 from oxdna_b200 import io as oio
@@ -67,6 +67,20 @@ def test_oracle_external_forces_fixture():
            dict(type="mutual_trap", particle=39, ref_particle=0, stiff=0.1, r0=1.2, PBC=1),
            dict(type="trap", particle=45, pos0=(5.0, 5.0, 5.0), stiff=0.5, rate=0.001, dir=(1.0, 0.0, 0.0)),
            dict(type="string", particle=80, F0=0.2, rate=0.0001, dir=(0.0, 1.0, 1.0))]
+    md = O.MD(P, g["pos"], O.axes_from_a1a3(g["a1"], g["a3"]), g["vel"], g["L"], g["btype"], g["n3"], g["n5"], g["box"], 0.003, 0.05, ext=ext)
+    assert np.abs(md.force - g["force"]).max() < 1e-9
+    md.step(int(g["nve_steps"]))
+    assert np.abs(md.pos - g["pos1"]).max() < 1e-9
+    assert np.abs(md.vel - g["vel1"]).max() < 1e-9
+
+
+def test_oracle_further_external_forces_fixture():
+    """repulsion_plane (moving, clamped), attraction_plane (both branches), sphere (shrinking, r_ext), LJ_wall (only_repulsive),
+    lowdim_trap (visibility mask), with `particle = all` entries -- forces at step 0 and 100 steps against the reference CPU run"""
+    g = load_golden("lattice8_ext2")
+    P = _params(g)
+    ext = ext2_forces(g["pos"])
+    assert np.abs(O.ext_forces(ext, g["pos"], g["box"], 0) - (g["force"] - g["force_noext"])).max() < 1e-9
     md = O.MD(P, g["pos"], O.axes_from_a1a3(g["a1"], g["a3"]), g["vel"], g["L"], g["btype"], g["n3"], g["n5"], g["box"], 0.003, 0.05, ext=ext)
     assert np.abs(md.force - g["force"]).max() < 1e-9
     md.step(int(g["nve_steps"]))
