@@ -183,7 +183,8 @@ void put_f4(oxb_rna2_params *P, int k, float a, float b, float t0, float ts, flo
 
 extern "C" int oxb_rna2_params_init(oxb_rna2_params *P, double T, double salt, int dh_half_charged_ends, int use_mbf, double mbf_fmax,
 		double mbf_finf, int mismatch_repulsion, double mismatch_strength, double *rcut_out) {
-	if(P == nullptr || !(T > 0) || !(salt > 0)) return 1;
+	if(P == nullptr || !(T > 0)) return 1;
+	const bool with_dh = salt > 0; // salt <= 0: first-generation oxRNA (interaction_type = RNA), no Debye-Hueckel term
 	std::memset(P, 0, sizeof(*P));
 	P->average = 1;
 
@@ -250,16 +251,19 @@ extern "C" int oxb_rna2_params_init(oxb_rna2_params *P, double T, double salt, i
 
 	// Debye-Hueckel: both get_settings and init use the float 0.1f here (unlike DNA2)
 	const double lfac = 0.3667258, q = 0.0858;
-	salt = (double) (float) salt;
-	const double lambda = lfac * std::sqrt(T / 0.1f) / std::sqrt(salt);
-	const double x = 3.0 * lambda, l = lambda;
-	const double B = -(std::exp(-x / l) * q * q * (x + l) * (x + l)) / (4. * x * x * x * l * l * (-q));
-	const double RC = x * (q * x + 3. * q * l) / (q * (x + l));
-	P->dh_minus_kappa = (float) (-1.0 / lambda);
-	P->dh_prefactor = (float) q;
-	P->dh_rhigh = (float) x;
-	P->dh_rc = (float) RC;
-	P->dh_b = (float) B;
+	double RC = 0.;
+	if(with_dh) {
+		salt = (double) (float) salt;
+		const double lambda = lfac * std::sqrt(T / 0.1f) / std::sqrt(salt);
+		const double x = 3.0 * lambda, l = lambda;
+		const double B = -(std::exp(-x / l) * q * q * (x + l) * (x + l)) / (4. * x * x * x * l * l * (-q));
+		RC = x * (q * x + 3. * q * l) / (q * (x + l));
+		P->dh_minus_kappa = (float) (-1.0 / lambda);
+		P->dh_prefactor = (float) q;
+		P->dh_rhigh = (float) x;
+		P->dh_rc = (float) RC;
+		P->dh_b = (float) B;
+	}
 	P->dh_half_charged_ends = dh_half_charged_ends ? 1 : 0;
 	P->hb_multiplier = 1.f;
 
@@ -277,7 +281,7 @@ extern "C" int oxb_rna2_params_init(oxb_rna2_params *P, double T, double salt, i
 	double rcut_near = std::fmax(rcutback, rcutbase);
 	double rcut = rcut_near;
 	const double debyecut = 2. * back_len + RC;
-	if(debyecut > rcut) rcut = debyecut;
+	if(with_dh && debyecut > rcut) rcut = debyecut;
 	P->rcut = (float) rcut;
 	P->rcut_near = (float) rcut_near;
 	if(rcut_out != nullptr) *rcut_out = rcut;

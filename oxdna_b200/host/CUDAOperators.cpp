@@ -104,13 +104,15 @@ void CUDADNAInteraction::_on_T_update() {
 }
 
 void CUDARNAInteraction::get_settings(input_file &inp) {
-	RNA2Interaction::get_settings(inp);
+	if(_v1) RNAInteraction::get_settings(inp);
+	else RNA2Interaction::get_settings(inp);
 }
 
 void CUDARNAInteraction::cuda_init(oxb_ctx *ctx, int N) {
 	CUDABaseInteraction::cuda_init(ctx, N);
 	Logger::instance()->disable_log("CUDARNAInteraction");
-	RNA2Interaction::init();
+	if(_v1) RNAInteraction::init();
+	else RNA2Interaction::init();
 	Logger::instance()->enable_log("CUDARNAInteraction");
 	_upload();
 }
@@ -134,8 +136,9 @@ void CUDARNAInteraction::_upload() {
 	if(_ctx == nullptr) return;
 	oxb_rna2_params P;
 	double rcut = 0.;
-	int rc = oxb_rna2_params_init(&P, (double) this->_T, (double) _salt_concentration, _debye_huckel_half_charged_ends ? 1 : 0, _use_mbf ? 1 : 0,
-			(double) _mbf_fmax, (double) _mbf_finf, _mismatch_repulsion ? 1 : 0, (double) _RNA_HYDR_MIS, &rcut);
+	const bool mismatch = !_v1 && _mismatch_repulsion;
+	int rc = oxb_rna2_params_init(&P, (double) this->_T, _v1 ? 0. : (double) _salt_concentration, (!_v1 && _debye_huckel_half_charged_ends) ? 1 : 0, _use_mbf ? 1 : 0,
+			(double) _mbf_fmax, (double) _mbf_finf, mismatch ? 1 : 0, mismatch ? (double) _RNA_HYDR_MIS : 0., &rcut);
 	if(rc != 0) throw oxDNAException("oxb_rna2_params_init failed (T = %lf, salt = %f)", (double) this->_T, _salt_concentration);
 	// everything the input file (or an `external_model` file) can change comes from the CPU class that parsed it
 	const Model &m = *model;
@@ -180,8 +183,8 @@ void CUDARNAInteraction::_upload() {
 			P.crst_kfac[5 * i + j] = (float) _cross_seq_dep_K[i][j];
 		}
 	}
-	P.mismatch_repulsion = _mismatch_repulsion ? 1 : 0;
-	if(_mismatch_repulsion) {
+	P.mismatch_repulsion = mismatch ? 1 : 0;
+	if(mismatch) {
 		P.mis_eps = (float) F1_EPS[RNA_HYDR_F1][0][0];
 		P.mis_shift = (float) F1_SHIFT[RNA_HYDR_F1][0][0];
 		P.hb_eps[0] = hb_eps_default; // A-A never hydrogen-bonds; restore the unscaled default
@@ -211,11 +214,13 @@ void CUDARNAInteraction::_upload() {
 	P.phi2 = oxb_f5 { m.RNA_STCK_PHI2_A, m.RNA_STCK_PHI2_B, m.RNA_STCK_PHI2_XC, m.RNA_STCK_PHI2_XS };
 	P.phi3 = oxb_f5 { m.RNA_CXST_PHI3_A, m.RNA_CXST_PHI3_B, m.RNA_CXST_PHI3_XC, m.RNA_CXST_PHI3_XS };
 	P.phi4 = oxb_f5 { m.RNA_CXST_PHI4_A, m.RNA_CXST_PHI4_B, m.RNA_CXST_PHI4_XC, m.RNA_CXST_PHI4_XS };
-	P.dh_minus_kappa = (float) _minus_kappa;
-	P.dh_prefactor = (float) _debye_huckel_prefactor;
-	P.dh_rhigh = (float) _debye_huckel_RHIGH;
-	P.dh_rc = (float) _debye_huckel_RC;
-	P.dh_b = (float) _debye_huckel_B;
+	if(!_v1) {
+		P.dh_minus_kappa = (float) _minus_kappa;
+		P.dh_prefactor = (float) _debye_huckel_prefactor;
+		P.dh_rhigh = (float) _debye_huckel_RHIGH;
+		P.dh_rc = (float) _debye_huckel_RC;
+		P.dh_b = (float) _debye_huckel_B;
+	}
 	// cutoffs: the Verlet radius must be the CPU class's own double-precision cutoff (bit-exact pair sets)
 	const double back_len = std::sqrt((double) (m.RNA_POS_BACK_a1 * m.RNA_POS_BACK_a1 + m.RNA_POS_BACK_a2 * m.RNA_POS_BACK_a2 + m.RNA_POS_BACK_a3 * m.RNA_POS_BACK_a3));
 	const double near_back = 2. * back_len + m.RNA_EXCL_RC1;
@@ -234,7 +239,8 @@ void CUDARNAInteraction::_on_T_update() {
 	this->_T = CONFIG_INFO->temperature();
 	if(_ctx != nullptr) {
 		Logger::instance()->disable_log("CUDARNAInteraction");
-		RNA2Interaction::init();
+		if(_v1) RNAInteraction::init();
+		else RNA2Interaction::init();
 		Logger::instance()->enable_log("CUDARNAInteraction");
 		_upload();
 	}
@@ -245,7 +251,8 @@ std::shared_ptr<CUDABaseInteraction> CUDAInteractionFactory::make_interaction(in
 	getInputString(&inp, "interaction_type", inter_type, 0);
 	if(inter_type == "DNA2") return std::make_shared<CUDADNAInteraction>();
 	if(inter_type == "RNA2") return std::make_shared<CUDARNAInteraction>();
-	throw oxDNAException("CUDA interaction '%s' not found in the oxdna_b200 backend (available: DNA2, RNA2). Aborting", inter_type.c_str());
+	if(inter_type == "RNA") return std::make_shared<CUDARNAInteraction>(true);
+	throw oxDNAException("CUDA interaction '%s' not found in the oxdna_b200 backend (available: DNA2, RNA2, RNA). Aborting", inter_type.c_str());
 }
 
 // ---------------------------------------------------------------------------------------------------------- lists

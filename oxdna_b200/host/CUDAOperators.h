@@ -84,11 +84,14 @@ public:
 /// reference's CUDARNAInteraction copies them into its `CUDAModel` (CUDARNAInteraction.cu:43-230,278-385)
 class CUDARNAInteraction: public CUDABaseInteraction, public RNA2Interaction {
 protected:
+	/// interaction_type = RNA (first-generation oxRNA, class RNAInteraction): the same model without the Debye-Hueckel and
+	/// mismatch terms; only the RNAInteraction part of the CPU class is configured and initialised
+	bool _v1 = false;
 	void _upload();
 	void _on_T_update() override;
 
 public:
-	CUDARNAInteraction() {}
+	explicit CUDARNAInteraction(bool first_generation = false) : _v1(first_generation) {}
 	virtual ~CUDARNAInteraction() {}
 
 	void get_settings(input_file &inp) override;

@@ -80,8 +80,8 @@ class Simulation:
         if str(g("backend", "CUDA")).upper() != "CUDA":
             raise ValueError("oxdna_b200 only implements backend = CUDA")
         itype = str(g("interaction_type", "DNA2"))
-        if itype not in ("DNA2", "DNA2_nomesh", "RNA2"):
-            raise ValueError(f"interaction_type = {itype} is not available in this build (DNA2, RNA2)")
+        if itype not in ("DNA2", "DNA2_nomesh", "RNA2", "RNA"):
+            raise ValueError(f"interaction_type = {itype} is not available in this build (DNA2, RNA2, RNA)")
         self.itype = itype
         prec = str(g("backend_precision", "mixed"))
         if prec not in ("mixed", "float"):
@@ -117,10 +117,12 @@ class Simulation:
         mbf = None if mbf is None else float(mbf)
         average = _bool(g("use_average_seq", 1))
         sd = None if average else read_seq_dep(g("seq_dep_file"))
-        if self.itype == "RNA2":
-            # RNA2Interaction::get_settings: salt defaults to 1.0 (src/Interactions/RNAInteraction2.cpp:34-37)
-            self.params, self.rcut = capi.rna2_params(self.T, float(g("salt_concentration", 1.0)), _bool(g("dh_half_charged_ends", 1)), mbf,
-                                                      float(g("max_backbone_force_far", 0.04)), _bool(g("mismatch_repulsion", 0)),
+        if self.itype in ("RNA2", "RNA"):
+            # RNA2Interaction::get_settings: salt defaults to 1.0 (src/Interactions/RNAInteraction2.cpp:34-37); interaction_type = RNA
+            # (class RNAInteraction) is the same model without the Debye-Hueckel and mismatch terms: salt 0 switches them off
+            v2 = self.itype == "RNA2"
+            self.params, self.rcut = capi.rna2_params(self.T, float(g("salt_concentration", 1.0)) if v2 else 0.0, _bool(g("dh_half_charged_ends", 1)), mbf,
+                                                      float(g("max_backbone_force_far", 0.04)), v2 and _bool(g("mismatch_repulsion", 0)),
                                                       float(g("mismatch_repulsion_strength", 1.0)))
             if sd is not None:
                 B = "AGCT"

@@ -433,3 +433,26 @@ def test_further_external_forces_vs_reference(use_edge, sort_every):
         assert np.abs(st["vel"] - g["vel1"]).max() < 2e-3
     finally:
         sim.close()
+
+
+@pytest.mark.parametrize("use_edge", [0, 1])
+def test_first_generation_oxrna(use_edge):
+    """interaction_type = RNA (class RNAInteraction): oxRNA without the Debye-Hueckel term, shorter cutoff"""
+    g = load_golden("rna_lattice8")
+    P = O.rna2_params(parse_temperature(str(g["T"])), 0.0, cpu_quirks=False)
+    ax = O.axes_from_a1a3(g["a1"], g["a3"])
+    pairs = O.verlet_pairs(g["pos"], g["n3"], g["n5"], g["box"], P.rcut + 2 * 0.05)
+    ref = O.forces(P, g["pos"], ax, g["btype"], g["n3"], g["n5"], g["box"], pairs)
+    assert ref["eterms"][7] == 0.0
+    topo = dict(btype=g["btype"], n3=g["n3"], n5=g["n5"], strand=g["strand"])
+    conf = dict(box=g["box"], pos=g["pos"], a1=g["a1"], a3=g["a3"], vel=g["vel"], L=g["L"])
+    sim = Simulation(rna_inp(g, interaction_type="RNA", use_edge=use_edge, CUDA_sort_every=1), topo, conf)
+    try:
+        assert sim.rcut == P.rcut
+        assert pair_set(sim.ctx.get_pairs()) == pair_set(pairs)
+        check_forces(sim.ctx.get_forces(), ref)
+        assert np.abs(sim.ctx.energy_split() - ref["eterms"]).max() <= 2e-6 * np.abs(ref["eterms"]).max()
+        sim.run(200)
+        assert sim.ctx.stats()["error_flags"] == 0
+    finally:
+        sim.close()

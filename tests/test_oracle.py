@@ -263,3 +263,23 @@ def test_rna_oracle_matches_live_reference_without_meshed_term(tmp_path):
         assert worst < 1e-10, worst
     finally:
         r.close()
+
+
+@pytest.mark.skipif(not RH.available(), reason="oracle/_ref not built (needs /root/reference)")
+def test_first_generation_oxrna_oracle_matches_live_reference():
+    """interaction_type = RNA (no Debye-Hueckel): cutoff bit-equal, every term but the meshed hydrogen bonding to rounding"""
+    top, conf = os.path.join(GOLD, "force_field_rna", "init.top"), os.path.join(GOLD, "force_field_rna", "init.dat")
+    r = RH.Reference(top, conf, interaction_type="RNA", T="30C")
+    try:
+        P = O.rna2_params(O.celsius(30.0), 0.0, cpu_quirks=True)
+        assert P.rcut == r.rcut()
+        st, topo = r.state(), r.topology()
+        r.compute_forces()
+        es = r.energy_split()
+        pairs = O.verlet_pairs(st["pos"], topo["n3"], topo["n5"], r.box(), P.rcut + 0.1)
+        assert pair_set(pairs) == pair_set(r.pairs())
+        out = O.forces(P, st["pos"], O.axes_from_a1a3(st["a1"], st["a3"]), topo["btype"], topo["n3"], topo["n5"], r.box(), pairs)
+        d = out["eterms"][:7] - es[:7]
+        assert np.abs(np.delete(d, 4)).max() < 1e-10 and abs(d[4]) < 1e-4 * abs(es[4]) and out["eterms"][7] == 0.0
+    finally:
+        r.close()
