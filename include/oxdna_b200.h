@@ -53,6 +53,11 @@ typedef struct {
 	float hb_multiplier;
 	float rcut; /* global interaction cutoff on the centre-of-mass distance */
 	float rcut_near; /* centre-of-mass distance beyond which only Debye-Hueckel can act */
+	/* first-generation oxDNA (interaction_type = DNA / DNA_nomesh, class DNAInteraction): coaxial stacking with the mirrored
+	 * f4(2 pi - theta1) and the f5(cos phi3)^2 factor (src/CUDA/Interactions/CUDA_DNA.cuh:612-719 with grooving off), no
+	 * Debye-Hueckel */
+	int v1;
+	oxb_f5 phi3;
 } oxb_dna2_params;
 
 /* Host-side derivation of the oxDNA2 parameter block at temperature T (simulation units, K/3000) and molar
@@ -61,6 +66,9 @@ typedef struct {
  * `rcut_out` receives the double-precision cutoff used for the Verlet radius. */
 int oxb_dna2_params_init(oxb_dna2_params *P, double T, double salt_concentration, int dh_half_charged_ends,
 		int use_max_backbone_force, double max_backbone_force, double max_backbone_force_far, double *rcut_out);
+/* interaction_type = DNA (src/Interactions/DNAInteraction.cpp:12-228,295-328); grooving = the major_minor_grooving key */
+int oxb_dna1_params_init(oxb_dna2_params *P, double T, int major_minor_grooving, int use_max_backbone_force, double max_backbone_force,
+		double max_backbone_force_far, double *rcut_out);
 /* sequence-dependent stacking / HB strengths (src/Interactions/DNAInteraction.cpp:329-375):
  * stck_raw[4][4] are the STCK_X_Y entries of the parameter file (order A, G, C, T). */
 int oxb_dna2_params_seqdep(oxb_dna2_params *P, double T, const double *stck_raw16, double stck_fact_eps, double hb_AT, double hb_GC);
@@ -130,6 +138,10 @@ typedef struct {
 	double aux[4];
 	int iaux;
 } oxb_ext_force;
+
+/* sizeof() of the ABI structures as compiled into the library (0: oxb_dna2_params, 1: oxb_rna2_params, 2: oxb_ext_force), so that
+ * foreign-language bindings can assert their mirrors */
+int oxb_sizeof(int which);
 
 /* ---- life cycle.  Replaces MD_CUDABackend / CUDAMixedBackend construction + init_cuda
  * (src/CUDA/Backends/CUDABaseBackend.cu:143-242, MD_CUDABackend.cu:674-747). */

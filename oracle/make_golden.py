@@ -42,7 +42,7 @@ def force_field():
     r.close()
 
 
-def lattice_case(name, n_duplex, spacing, steps, T="300K", salt=0.5, seed=3, nve_steps=200, ext=None):
+def lattice_case(name, n_duplex, spacing, steps, T="300K", salt=0.5, seed=3, nve_steps=200, ext=None, itype="DNA2_nomesh"):
     sysm = lattice.duplex_lattice(n_duplex, bp=20, spacing=spacing, seed=seed)
     d = tempfile.mkdtemp()
     top, conf = os.path.join(d, "l.top"), os.path.join(d, "l.dat")
@@ -50,7 +50,7 @@ def lattice_case(name, n_duplex, spacing, steps, T="300K", salt=0.5, seed=3, nve
     from oxdna_b200.sim import parse_temperature
     v, L = lattice.maxwell_velocities(len(sysm["pos"]), parse_temperature(T), 5)
     oio.write_conf(conf, sysm["box"], sysm["pos"], sysm["a1"], sysm["a3"], v, L)
-    r = Reference(top, conf, interaction_type="DNA2_nomesh", salt_concentration=salt, T=T, thermostat="brownian",
+    r = Reference(top, conf, interaction_type=itype, salt_concentration=salt, T=T, thermostat="brownian",
                   newtonian_steps=103, diff_coeff=2.5, seed=7)
     r.step(steps)
     st = r.state()
@@ -59,7 +59,7 @@ def lattice_case(name, n_duplex, spacing, steps, T="300K", salt=0.5, seed=3, nve
     # restart without thermostat from the thermalised state: forces + an NVE segment
     conf2 = os.path.join(d, "t.dat")
     oio.write_conf(conf2, sysm["box"], st["pos"], st["a1"], st["a3"], st["vel"], st["L"])
-    keys = dict(interaction_type="DNA2_nomesh", salt_concentration=salt, T=T, thermostat="no", dt=0.003)
+    keys = dict(interaction_type=itype, salt_concentration=salt, T=T, thermostat="no", dt=0.003)
     if ext:
         fpath = os.path.join(d, "forces.txt")
         with open(fpath, "w") as f:
@@ -226,6 +226,9 @@ def rna():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "rna":
         rna()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "dna1":
+        lattice_case("lattice8_dna1", 8, 8.0, 3000, T="310K", itype="DNA_nomesh", nve_steps=100)
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "ext2":
         ext2_case()

@@ -111,6 +111,29 @@ void oxo_dna2_params_init(oxo_dna2_params *P, double T, double salt, int dh_half
 	if(debyecut > P->rcut) P->rcut = debyecut;
 }
 
+void oxo_dna1_params_init(oxo_dna2_params *P, double T, int grooving, int use_mbf, double mbf_fmax, double mbf_finf) {
+	/* first-generation oxDNA (interaction_type = DNA, class DNAInteraction): src/Interactions/DNAInteraction.cpp:12-228,295-328 */
+	oxo_dna2_params_init(P, T, 1.0, 0, use_mbf, mbf_fmax, mbf_finf);
+	P->v1 = 1;
+	if(!grooving) {
+		/* DNANucleotide.cpp:83-87: STACK = BACK * (POS_STACK / POS_BACK), BASE = STACK * (POS_BASE / POS_STACK), float ratios */
+		P->back_a1 = -0.4f; P->back_a2 = 0.;
+		P->stack_a1 = (double) -0.4f * (double) (0.34f / -0.4f);
+		P->base_a1 = P->stack_a1 * (double) (0.4f / 0.34f);
+	}
+	P->fene_r0 = 0.7525f;
+	fill_f1(&P->hb, 1.077f);
+	fill_f1(&P->stck, 1.3448f + 2.6568f * T);
+	P->cxst.k = 46.0f;
+	set_f4(&P->cxst_t1, 2.f, 10.9032f, (OXO_PI - 0.60f), 0.65f, 0.769231f);
+	P->cxst_phi3 = (oxo_f5){ 2.0f, 10.9032f, -0.769231f, -0.65f };
+	P->dh_prefactor = 0; P->dh_b = 0; P->dh_rc = 0; P->dh_rhigh = 0; P->dh_minus_kappa = 0;
+	double rcutback = grooving ? 2 * sqrt((double) ((-0.3400f) * (-0.3400f) + (0.3408f) * (0.3408f))) + (double) 0.711879214356f
+			: 2 * fabs((double) -0.4f) + (double) 0.711879214356f;
+	double rcutbase = 2 * fabs((double) 0.4f) + (double) 0.783775f;
+	P->rcut = fmax(rcutback, rcutbase);
+}
+
 void oxo_dna2_params_seqdep(oxo_dna2_params *P, const double *stck_raw16, double stck_fact_eps, double hb_AT, double hb_GC) {
 	/* DNAInteraction.cpp:329-375; base order A=0 G=1 C=2 T=3 (src/defs.h) */
 	double sh_st = SQ(1 - exp(-(double) ((float) (P->stck.rc - P->stck.r0) * (float) P->stck.a)));
@@ -232,6 +255,47 @@ static void chain_body_dir(pacc *A, double g, const double *u, const double *rha
 	axpy3(-g, x, onq ? A->Tq : A->Tp);
 }
 
+/* ------------------------------------------------------------------ angular factors, angle based (RNAInteraction.cpp:1304-1371) */
+static double rna_acos(double c) { return (c > 1) ? 0. : ((c < -1) ? (double) OXO_PI : acos(c)); } /* LRACOS, src/defs.h:17 */
+
+static double f4_val(const oxo_f4 *f, double t) {
+	t -= f->t0;
+	if(t < 0) t = -t;
+	if(t < f->tc) return (t > f->ts) ? f->b * SQ(f->tc - t) : 1. - f->a * SQ(t);
+	return 0;
+}
+
+/* f4'(t) / sin(t) with the reference's small-angle guard */
+static double f4_dsin(const oxo_f4 *f, double t) {
+	double x = t - f->t0, m = 1;
+	if(x < 0) { x = -x; m = -1; }
+	if(x < f->tc) {
+		double s = sin(t);
+		if(x > f->ts) return m * 2 * f->b * (x - f->tc) / s;
+		return (SQ(s) > 1e-8) ? -m * 2 * f->a * x / s : -m * 2 * f->a;
+	}
+	return 0;
+}
+
+
+/* c = shat . (bhat x u), u a body vector of p (onq = 0) or q (onq = 1); shat between the stacking sites, bhat between the
+ * backbone sites; g = dE/dc.  RNAInteraction.cpp:1093-1142 */
+static void chain_triple(pacc *A, double g, const double *u, int onq, const double *sh, double sm, const double *ssp, const double *ssq,
+		const double *bh, double bm, const double *bsp, const double *bsq) {
+	double bu[3], us[3], sb[3], F[3], x[3];
+	cross3(bh, u, bu);  /* c = shat . bu */
+	cross3(u, sh, us);  /* c = bhat . us */
+	cross3(sh, bh, sb); /* c = u . sb    */
+	double c = dot3(sh, bu);
+	for(int k = 0; k < 3; k++) F[k] = -g * (bu[k] - c * sh[k]) / sm;
+	site_force(A, ssp, ssq, F);
+	for(int k = 0; k < 3; k++) F[k] = -g * (us[k] - c * bh[k]) / bm;
+	site_force(A, bsp, bsq, F);
+	cross3(u, sb, x);
+	axpy3(-g, x, onq ? A->Tq : A->Tp);
+}
+
+
 static double excl_eval(const oxo_dna2_params *P, const oxo_excl *e, const double *r, double *F) {
 	/* DNAInteraction.cpp:1182-1205; F = force on q */
 	double r2 = dot3(r, r), en = 0;
@@ -261,7 +325,7 @@ static void make_sites(const oxo_dna2_params *P, const double *ax, sites_t *S) {
 	for(int k = 0; k < 3; k++) {
 		S->back[k] = S->a1[k] * P->back_a1 + S->a2[k] * P->back_a2;
 		S->stack[k] = S->a1[k] * P->stack_a1;
-		S->base[k] = S->stack[k] * ((double) 0.4f / (double) 0.34f);
+		S->base[k] = S->stack[k] * (P->base_a1 / P->stack_a1);
 		S->backref[k] = S->a1[k] * P->backref_a1;
 	}
 }
@@ -416,10 +480,26 @@ static void nonbonded_pair(const oxo_dna2_params *P, const double *r, const site
 		double c5 = dot3(sp->a3, h), c6 = dot3(mb3, h);
 		double f2, f2d, g[4], d[4];
 		f2_eval(&P->cxst, m, &f2, &f2d);
-		f4_cxst_t1(P, c1, &g[0], &d[0]);
+		if(P->v1) {
+			/* oxDNA1: f4(t1) + f4(2 PI - t1) (DNAInteraction.cpp:1331-1352) */
+			double t = rna_acos(c1);
+			g[0] = f4_val(&P->cxst_t1, t) + f4_val(&P->cxst_t1, 2 * OXO_PI - t);
+			d[0] = -f4_dsin(&P->cxst_t1, t) - f4_dsin(&P->cxst_t1, 2 * OXO_PI - t);
+		}
+		else f4_cxst_t1(P, c1, &g[0], &d[0]);
 		f4_eval(&P->cxst_t4, c4, &g[1], &d[1]);
 		f4_sym(&P->cxst_t5, c5, &g[2], &d[2]);
 		f4_sym(&P->cxst_t5, c6, &g[3], &d[3]);
+		/* oxDNA1: times f5(cos phi3)^2, cos phi3 = shat . (bhat_ref x a1) with bhat_ref between the UNGROOVED backbone
+		 * reference sites (DNAInteraction.cpp:1049-1062) */
+		double wv[3], wm = 1, wh[3] = { 0, 0, 0 }, f5v = 1, f5d = 0;
+		if(P->v1) {
+			double x3[3];
+			site_sep(r, sp->backref, sq->backref, wv, &wm, wh);
+			cross3(wh, sp->a1, x3);
+			f5_eval(&P->cxst_phi3, dot3(h, x3), &f5v, &f5d);
+			f2 *= f5v * f5v; f2d *= f5v * f5v;
+		}
 		double E = f2 * g[0] * g[1] * g[2] * g[3];
 		e[OXO_CXST] += E;
 		if(E != 0.) {
@@ -431,6 +511,7 @@ static void nonbonded_pair(const oxo_dna2_params *P, const double *r, const site
 			chain_body_body(A, rest[1], sp->a3, sq->a3);
 			chain_body_dir(A, rest[2], sp->a3, h, m, c5, 0, sp->stack, sq->stack);
 			chain_body_dir(A, rest[3], mb3, h, m, c6, 1, sp->stack, sq->stack);
+			if(P->v1 && f5d != 0.) chain_triple(A, (E / f5v) * 2 * f5d, sp->a1, 0, h, m, sp->stack, sq->stack, wh, wm, sp->backref, sq->backref);
 		}
 	}
 

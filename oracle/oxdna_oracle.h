@@ -46,6 +46,9 @@ typedef struct {
 	int dh_half_charged_ends;
 	double hb_multiplier;
 	double rcut;
+	/* first-generation oxDNA (interaction_type = DNA): mirrored coaxial theta1 and the phi3 factor, no Debye-Hueckel */
+	int v1;
+	oxo_f5 cxst_phi3;
 } oxo_dna2_params;
 
 /* average-sequence oxDNA2 parameters at temperature T (simulation units) and molar salt.
@@ -53,6 +56,8 @@ typedef struct {
  * values STCK_X_Y) + stck_fact_eps + hb_eps_AT, hb_eps_GC are taken from the arguments. */
 void oxo_dna2_params_init(oxo_dna2_params *P, double T, double salt, int dh_half_charged_ends,
 		int use_mbf, double mbf_fmax, double mbf_finf);
+/* interaction_type = DNA (class DNAInteraction); grooving = the major_minor_grooving key */
+void oxo_dna1_params_init(oxo_dna2_params *P, double T, int grooving, int use_mbf, double mbf_fmax, double mbf_finf);
 void oxo_dna2_params_seqdep(oxo_dna2_params *P, const double *stck_raw16, double stck_fact_eps, double hb_AT, double hb_GC);
 
 /* particle = -1: every particle.  aux / iaux: see the table in include/oxdna_b200.h (same conventions) */

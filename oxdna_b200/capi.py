@@ -47,7 +47,7 @@ class DNA2Params(C.Structure):
         + [(n, C.c_float * 25) for n in "hb_eps hb_shift stck_eps stck_shift".split()]
         + [("crst", F2), ("cxst", F2), ("f4", F4 * NF4), ("f4_cmin", C.c_float * NF4), ("f4_cmax", C.c_float * NF4), ("cxst_t1_sa", C.c_float), ("cxst_t1_sb", C.c_float), ("phi1", F5), ("phi2", F5)]
         + [(n, C.c_float) for n in "dh_minus_kappa dh_prefactor dh_rhigh dh_rc dh_b".split()]
-        + [("dh_half_charged_ends", C.c_int), ("hb_multiplier", C.c_float), ("rcut", C.c_float), ("rcut_near", C.c_float)]
+        + [("dh_half_charged_ends", C.c_int), ("hb_multiplier", C.c_float), ("rcut", C.c_float), ("rcut_near", C.c_float), ("v1", C.c_int), ("phi3", F5)]
     )
 
 
@@ -115,7 +115,7 @@ def fill_ext_entry(e, d):
         e.aux[c] = aux[c]
 
 
-EXPORTED = """oxb_dna2_params_init oxb_dna2_params_seqdep oxb_rna2_params_init oxb_rna2_params_seqdep oxb_set_model_rna2 oxb_create oxb_destroy oxb_last_error oxb_set_stream oxb_set_box
+EXPORTED = """oxb_sizeof oxb_dna2_params_init oxb_dna1_params_init oxb_dna2_params_seqdep oxb_rna2_params_init oxb_rna2_params_seqdep oxb_set_model_rna2 oxb_create oxb_destroy oxb_last_error oxb_set_stream oxb_set_box
 oxb_set_topology oxb_set_model_dna2 oxb_set_lists oxb_set_dt oxb_set_thermostat oxb_set_ext_forces oxb_set_state oxb_get_state
 oxb_set_step oxb_get_step oxb_sort oxb_update_lists oxb_compute_forces oxb_first_step oxb_second_step oxb_thermostat oxb_run
 oxb_synchronize oxb_get_forces oxb_energy oxb_energy_split oxb_get_pairs oxb_get_stats oxb_device_views oxb_launch_count oxb_time_kernel""".split()
@@ -136,6 +136,9 @@ def lib():
         L.oxb_last_error.argtypes = [C.c_void_p]
         L.oxb_destroy.argtypes = [C.c_void_p]
         L.oxb_destroy.restype = None
+        for which, mirror in enumerate((DNA2Params, RNA2Params, ExtForce)):
+            if L.oxb_sizeof(which) != C.sizeof(mirror):
+                raise RuntimeError(f"ABI mismatch: {mirror.__name__} is {C.sizeof(mirror)} bytes here, {L.oxb_sizeof(which)} in {SO_PATH}")
         _lib = L
     return _lib
 
@@ -165,6 +168,18 @@ def dna2_params(T, salt=0.5, dh_half_charged_ends=True, max_backbone_force=None,
                                    C.c_double(max_backbone_force if mbf else 0.0), C.c_double(max_backbone_force_far), C.byref(rc))
     if r != 0:
         raise OxbError("oxb_dna2_params_init failed")
+    return P, rc.value
+
+
+def dna1_params(T, grooving=False, max_backbone_force=None, max_backbone_force_far=0.04):
+    """oxb_dna1_params_init (interaction_type = DNA / DNA_nomesh).  Returns (params, rcut)."""
+    P = DNA2Params()
+    rc = C.c_double()
+    mbf = max_backbone_force is not None
+    r = lib().oxb_dna1_params_init(C.byref(P), C.c_double(T), int(grooving), int(mbf), C.c_double(max_backbone_force if mbf else 0.0),
+                                   C.c_double(max_backbone_force_far), C.byref(rc))
+    if r != 0:
+        raise OxbError("oxb_dna1_params_init failed")
     return P, rc.value
 
 

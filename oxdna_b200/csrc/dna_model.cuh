@@ -100,6 +100,16 @@ OXB_HD AngVal f4_ts_cxst_t1(const oxb_dna2_params &M, float t, float s) {
 	return r;
 }
 
+// coaxial theta1 of oxDNA (first generation) and oxRNA: f4(theta) + f4(2 pi - theta)
+// (DNAInteraction.cpp:1331-1352, RNAInteraction.cpp:1026,1298-1303); sin(2 pi - theta) = -sin(theta)
+OXB_HD AngVal f4_ts_rna_cxst_t1(const oxb_f4 &f, float t, float s) {
+	AngVal p = f4_ts(f, t, s), n = f4_ts(f, 2.f * OXB_PI_F - t, s);
+	AngVal r;
+	r.v = p.v + n.v;
+	r.dc = p.dc - n.dc;
+	return r;
+}
+
 OXB_HD AngVal f5_c(const oxb_f5 &f, float c) {
 	AngVal r;
 	r.v = 0.f;
@@ -256,6 +266,23 @@ OXB_HD v3 chain_bd(PairAcc &A, float g, v3 u, v3 rhat, float inv_r, const Angle 
 	if(ON_Q) axpy(A.Tq, -g, a.x);
 	else axpy(A.Tp, -g, a.x);
 	return (u - rhat * a.c) * (-g * inv_r);
+}
+
+// chain rule for c = shat . (bhat x u): u a body axis of p (ON_Q = false) or q; shat between the stacking sites (a1-collinear,
+// coefficient cs), bhat between the backbone sites -- the true (grooved / a3-displaced) ones, or with BACK_A1 the a1-collinear
+// reference sites of coefficient cr (oxDNA).  g = dE/dc.  RNAInteraction.cpp:1093-1142, DNAInteraction.cpp:1105-1160
+template<bool ON_Q, bool BACK_A1>
+OXB_HD void chain_triple(PairAcc &acc, float g, v3 u, v3 sh, float sinv, float cs, v3 bh, float binv, float cr) {
+	v3 bu = cross(bh, u);
+	float c = dot(sh, bu);
+	acc.site_aa((bu - sh * c) * (-g * sinv), cs, cs);
+	v3 us = cross(u, sh);
+	v3 fb = (us - bh * c) * (-g * binv);
+	if(BACK_A1) acc.site_aa(fb, cr, cr);
+	else acc.site_kk(fb);
+	v3 t = cross(u, cross(sh, bh));
+	if(ON_Q) axpy(acc.Tq, -g, t);
+	else axpy(acc.Tp, -g, t);
 }
 
 struct PairEnergy {
@@ -454,12 +481,24 @@ OXB_HD float dna2_cxst(const oxb_dna2_params &M, v3 rs, float rs2, const Axes &A
 	Angle t5 = make_angle(A.a3, h);
 	Angle t6 = make_angle(-B.a3, h);
 	RadVal f2 = f2_r(M.cxst, m);
-	AngVal a1 = f4_ts_cxst_t1(M, t1.t, t1.s);
+	AngVal a1 = M.v1 ? f4_ts_rna_cxst_t1(M.f4[OXB_F4_CXST_T1], t1.t, t1.s) : f4_ts_cxst_t1(M, t1.t, t1.s);
 	AngVal a4 = f4_ts(M.f4[OXB_F4_CXST_T4], t4.t, t4.s);
 	AngVal a5 = f4_ts_sym(M.f4[OXB_F4_CXST_T5], t5.t, t5.s);
 	AngVal a6 = f4_ts_sym(M.f4[OXB_F4_CXST_T5], t6.t, t6.s);
 	float p14 = a1.v * a4.v, p56 = a5.v * a6.v;
 	float e = f2.v * p14 * p56;
+	if(M.v1 && e != 0.f) {
+		// oxDNA: times f5(cos phi3)^2, cos phi3 = shat . (bhat_ref x a1), bhat_ref between the ungrooved backbone reference sites
+		v3 w = rs + (B.a1 - A.a1) * (M.backref_a1 - cs);
+		float winv = OXB_RSQRT(dot(w, w));
+		v3 wh = w * winv;
+		AngVal b3 = f5_c(M.phi3, dot(h, cross(wh, A.a1)));
+		float e0 = e;
+		e *= b3.v * b3.v;
+		f2.v *= b3.v * b3.v;
+		f2.d *= b3.v * b3.v;
+		if(e != 0.f && b3.dc != 0.f) chain_triple<false, true>(acc, e0 * 2.f * b3.v * b3.dc, A.a1, h, inv, cs, wh, winv, M.backref_a1);
+	}
 	if(e != 0.f) {
 		v3 f = h * (-(f2.d * p14 * p56));
 		chain_bb(acc, f2.v * p56 * a1.dc * a4.v, t1);

@@ -142,6 +142,51 @@ extern "C" int oxb_dna2_params_init(oxb_dna2_params *P, double T, double salt, i
 	return 0;
 }
 
+extern "C" int oxb_dna1_params_init(oxb_dna2_params *P, double T, int grooving, int use_mbf, double mbf_fmax, double mbf_finf, double *rcut_out) {
+	// everything oxDNA and oxDNA2 share comes from the oxDNA2 block; then the first-generation differences (src/model.h:48,91,152-154,362,377)
+	int rc = oxb_dna2_params_init(P, T, 1.0, 0, use_mbf, mbf_fmax, mbf_finf, nullptr);
+	if(rc != 0) return rc;
+	P->v1 = 1;
+	if(!grooving) {
+		// DNANucleotide.cpp:83-87: STACK = BACK * (POS_STACK / POS_BACK), BASE = STACK * (POS_BASE / POS_STACK)
+		P->back_a1 = -0.4f; P->back_a2 = 0.f;
+		const double stack = (double) -0.4f * (double) (0.34f / -0.4f);
+		P->stack_a1 = (float) stack;
+		P->base_a1 = (float) (stack * (double) (0.4f / 0.34f));
+	}
+	P->fene_r0 = 0.7525f;
+	if(use_mbf) {
+		// the energy offset of the log tail does not depend on r0
+	}
+	const double eps_hb = 1.077f;
+	const double eps_st = 1.3448f + 2.6568f * T; // DNAInteraction.cpp:317
+	for(int i = 0; i < 25; i++) {
+		P->hb_eps[i] = (float) eps_hb;
+		P->hb_shift[i] = (float) (eps_hb * morse_shift(kHB));
+		P->stck_eps[i] = (float) eps_st;
+		P->stck_shift[i] = (float) (eps_st * morse_shift(kSTCK));
+	}
+	P->cxst.k = 46.0f;
+	{
+		const float t0 = kPi - 0.60f, tc = 0.769231f;
+		P->f4[OXB_F4_CXST_T1] = oxb_f4{ 2.f, 10.9032f, t0, 0.65f, tc };
+		// f4(theta) + f4(2 pi - theta): support theta > t0 - tc (the mirror's support lies inside)
+		P->f4_cmin[OXB_F4_CXST_T1] = -1.f - 1e-4f;
+		P->f4_cmax[OXB_F4_CXST_T1] = (float) (std::cos((double) t0 - tc) + 1e-4);
+	}
+	P->phi3 = oxb_f5{ 2.0f, 10.9032f, -0.769231f, -0.65f };
+	P->dh_minus_kappa = 0.f; P->dh_prefactor = 0.f; P->dh_rhigh = 0.f; P->dh_rc = 0.f; P->dh_b = 0.f;
+	P->dh_half_charged_ends = 0;
+	const double rcutback = grooving ? 2 * std::sqrt((double) ((-0.3400f) * (-0.3400f) + (0.3408f) * (0.3408f))) + (double) 0.711879214356f
+			: 2 * std::fabs((double) -0.4f) + (double) 0.711879214356f;
+	const double rcutbase = 2 * std::fabs((double) 0.4f) + (double) kHB.rchigh;
+	const double rcut = std::fmax(rcutback, rcutbase);
+	P->rcut = (float) rcut;
+	P->rcut_near = (float) rcut;
+	if(rcut_out != nullptr) *rcut_out = rcut;
+	return 0;
+}
+
 extern "C" int oxb_dna2_params_seqdep(oxb_dna2_params *P, double T, const double *stck_raw16, double stck_fact_eps, double hb_AT,
 		double hb_GC) {
 	if(P == nullptr || stck_raw16 == nullptr) return 1;
@@ -309,4 +354,13 @@ extern "C" int oxb_rna2_params_seqdep(oxb_rna2_params *P, double T, const double
 		P->hb_shift[5 * i + j] = P->hb_shift[5 * j + i] = (float) (v[k] * morse_shift(kRnaHB));
 	}
 	return 0;
+}
+
+extern "C" int oxb_sizeof(int which) {
+	switch(which) {
+	case 0: return (int) sizeof(oxb_dna2_params);
+	case 1: return (int) sizeof(oxb_rna2_params);
+	case 2: return (int) sizeof(oxb_ext_force);
+	default: return -1;
+	}
 }

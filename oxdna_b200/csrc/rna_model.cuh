@@ -20,15 +20,6 @@ OXB_HD AngVal f4_ts_mirror(const oxb_f4 &f, float t, float s) {
 	return n;
 }
 
-// coaxial theta1: f4(theta) + f4(2 pi - theta) (RNAInteraction.cpp:1026,1298-1303)
-OXB_HD AngVal f4_ts_rna_cxst_t1(const oxb_f4 &f, float t, float s) {
-	AngVal p = f4_ts(f, t, s), n = f4_ts(f, 2.f * OXB_PI_F - t, s);
-	AngVal r;
-	r.v = p.v + n.v;
-	r.dc = p.dc - n.dc;
-	return r;
-}
-
 // 0: no hydrogen-bonding-type term, 1: Watson-Crick or (sequence-dependent model) G-U wobble pair, 2: mismatch repulsion
 OXB_HD int rna2_hb_kind(const oxb_rna2_params &M, int btp, int btq) {
 	bool pair = (btp + btq == 3);
@@ -178,20 +169,6 @@ OXB_HD float rna2_hbcr(const oxb_rna2_params &M, v3 rb, float rbm2, const Axes &
 	return E;
 }
 
-// chain rule for c = shat . (bhat x u): u a body axis of p (ON_Q = false) or q; shat between the stacking sites (a1-collinear,
-// coefficient cs), bhat between the backbone sites.  g = dE/dc.  RNAInteraction.cpp:1093-1142
-template<bool ON_Q>
-OXB_HD void chain_triple(PairAcc &acc, float g, v3 u, v3 sh, float sinv, float cs, v3 bh, float binv) {
-	v3 bu = cross(bh, u);
-	float c = dot(sh, bu);
-	acc.site_aa((bu - sh * c) * (-g * sinv), cs, cs);
-	v3 us = cross(u, sh);
-	acc.site_kk((us - bh * c) * (-g * binv));
-	v3 t = cross(u, cross(sh, bh));
-	if(ON_Q) axpy(acc.Tq, -g, t);
-	else axpy(acc.Tp, -g, t);
-}
-
 // coaxial stacking on the stack-stack vector rs; rbk = backbone-backbone vector (for phi3 / phi4)
 OXB_HD float rna2_cxst(const oxb_rna2_params &M, v3 rs, float rs2, v3 rbk, const Axes &A, const Axes &B, PairAcc &acc) {
 	const float cs = M.stack_a1;
@@ -224,8 +201,8 @@ OXB_HD float rna2_cxst(const oxb_rna2_params &M, v3 rs, float rs2, v3 rbk, const
 		f += chain_bd<false>(acc, fb * p14 * a5.dc * a6.v, A.a3, h, inv, t5);
 		f += chain_bd<true>(acc, fb * p14 * a5.v * a6.dc, -B.a3, h, inv, t6);
 		acc.site_aa(f, cs, cs);
-		if(b3.dc != 0.f) chain_triple<false>(acc, e0 * b3.dc * b4.v, A.a1, h, inv, cs, bh, binv);
-		if(b4.dc != 0.f) chain_triple<true>(acc, e0 * b3.v * b4.dc, B.a1, h, inv, cs, bh, binv);
+		if(b3.dc != 0.f) chain_triple<false, false>(acc, e0 * b3.dc * b4.v, A.a1, h, inv, cs, bh, binv, 0.f);
+		if(b4.dc != 0.f) chain_triple<true, false>(acc, e0 * b3.v * b4.dc, B.a1, h, inv, cs, bh, binv, 0.f);
 	}
 	return e;
 }

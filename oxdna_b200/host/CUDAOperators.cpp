@@ -103,6 +103,46 @@ void CUDADNAInteraction::_on_T_update() {
 	}
 }
 
+void CUDADNA1Interaction::cuda_init(oxb_ctx *ctx, int N) {
+	CUDABaseInteraction::cuda_init(ctx, N);
+	Logger::instance()->disable_log("CUDADNAInteraction");
+	DNAInteraction::init();
+	Logger::instance()->enable_log("CUDADNAInteraction");
+	_upload();
+}
+
+void CUDADNA1Interaction::_upload() {
+	if(_ctx == nullptr) return;
+	oxb_dna2_params P;
+	double rcut = 0.;
+	int rc = oxb_dna1_params_init(&P, (double) this->_T, _grooving ? 1 : 0, _use_mbf ? 1 : 0, (double) _mbf_fmax, (double) _mbf_finf, &rcut);
+	if(rc != 0) throw oxDNAException("oxb_dna1_params_init failed (T = %lf)", (double) this->_T);
+	for(int i = 0; i < 5; i++) {
+		for(int j = 0; j < 5; j++) {
+			P.hb_eps[5 * i + j] = (float) F1_EPS[HYDR_F1][i][j];
+			P.hb_shift[5 * i + j] = (float) F1_SHIFT[HYDR_F1][i][j];
+			P.stck_eps[5 * i + j] = (float) F1_EPS[STCK_F1][i][j];
+			P.stck_shift[5 * i + j] = (float) F1_SHIFT[STCK_F1][i][j];
+		}
+	}
+	P.hb_multiplier = (float) _hb_multiplier;
+	if(_use_mbf) P.mbf_xmax = (float) _mbf_xmax;
+	rcut = (double) this->_rcut;
+	P.rcut = (float) rcut;
+	P.rcut_near = (float) rcut;
+	oxb_check(_ctx, oxb_set_model_dna2(_ctx, &P, rcut), "set_model_dna2");
+}
+
+void CUDADNA1Interaction::_on_T_update() {
+	this->_T = CONFIG_INFO->temperature();
+	if(_ctx != nullptr) {
+		Logger::instance()->disable_log("CUDADNAInteraction");
+		DNAInteraction::init();
+		Logger::instance()->enable_log("CUDADNAInteraction");
+		_upload();
+	}
+}
+
 void CUDARNAInteraction::get_settings(input_file &inp) {
 	if(_v1) RNAInteraction::get_settings(inp);
 	else RNA2Interaction::get_settings(inp);
@@ -252,7 +292,8 @@ std::shared_ptr<CUDABaseInteraction> CUDAInteractionFactory::make_interaction(in
 	if(inter_type == "DNA2") return std::make_shared<CUDADNAInteraction>();
 	if(inter_type == "RNA2") return std::make_shared<CUDARNAInteraction>();
 	if(inter_type == "RNA") return std::make_shared<CUDARNAInteraction>(true);
-	throw oxDNAException("CUDA interaction '%s' not found in the oxdna_b200 backend (available: DNA2, RNA2, RNA). Aborting", inter_type.c_str());
+	if(inter_type == "DNA" || inter_type == "DNA_nomesh") return std::make_shared<CUDADNA1Interaction>();
+	throw oxDNAException("CUDA interaction '%s' not found in the oxdna_b200 backend (available: DNA, DNA2, RNA, RNA2). Aborting", inter_type.c_str());
 }
 
 // ---------------------------------------------------------------------------------------------------------- lists

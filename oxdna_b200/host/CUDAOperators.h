@@ -79,6 +79,23 @@ public:
 	}
 };
 
+/// interaction_type = DNA / DNA_nomesh (first-generation oxDNA): constants from the CPU DNAInteraction
+class CUDADNA1Interaction: public CUDABaseInteraction, public DNAInteraction {
+protected:
+	void _upload();
+	void _on_T_update() override;
+
+public:
+	CUDADNA1Interaction() {}
+	virtual ~CUDADNA1Interaction() {}
+
+	void get_settings(input_file &inp) override { DNAInteraction::get_settings(inp); }
+	void cuda_init(oxb_ctx *ctx, int N) override;
+	number get_cuda_rcut() override {
+		return this->get_rcut();
+	}
+};
+
 /// interaction_type = RNA2: constants from the CPU RNA2Interaction and its Model block (rna_model.h; `external_model`,
 /// `use_average_seq` / `seq_dep_file`, `mismatch_repulsion[_strength]`, salt and dh_* keys, max_backbone_force), as the
 /// reference's CUDARNAInteraction copies them into its `CUDAModel` (CUDARNAInteraction.cu:43-230,278-385)

@@ -80,8 +80,8 @@ class Simulation:
         if str(g("backend", "CUDA")).upper() != "CUDA":
             raise ValueError("oxdna_b200 only implements backend = CUDA")
         itype = str(g("interaction_type", "DNA2"))
-        if itype not in ("DNA2", "DNA2_nomesh", "RNA2", "RNA"):
-            raise ValueError(f"interaction_type = {itype} is not available in this build (DNA2, RNA2, RNA)")
+        if itype not in ("DNA2", "DNA2_nomesh", "DNA", "DNA_nomesh", "RNA2", "RNA"):
+            raise ValueError(f"interaction_type = {itype} is not available in this build (DNA, DNA2, RNA, RNA2)")
         self.itype = itype
         prec = str(g("backend_precision", "mixed"))
         if prec not in ("mixed", "float"):
@@ -131,8 +131,11 @@ class Simulation:
                                         [sd[f"CROSS_{a}_{b}"] for a in B for b in B], hb("A", "T"), hb("G", "C"), hb("G", "T"))
             self.ctx.set_model_rna2(self.params, self.rcut)
             return
-        self.params, self.rcut = capi.dna2_params(self.T, float(g("salt_concentration", 0.5)), _bool(g("dh_half_charged_ends", 1)), mbf,
-                                                  float(g("max_backbone_force_far", 0.04)))
+        if self.itype in ("DNA", "DNA_nomesh"):
+            self.params, self.rcut = capi.dna1_params(self.T, _bool(g("major_minor_grooving", 0)), mbf, float(g("max_backbone_force_far", 0.04)))
+        else:
+            self.params, self.rcut = capi.dna2_params(self.T, float(g("salt_concentration", 0.5)), _bool(g("dh_half_charged_ends", 1)), mbf,
+                                                      float(g("max_backbone_force_far", 0.04)))
         if sd is not None:
             # DNAInteraction.cpp:329-375
             B = "AGCT"

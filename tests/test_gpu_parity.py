@@ -456,3 +456,34 @@ def test_first_generation_oxrna(use_edge):
         assert sim.ctx.stats()["error_flags"] == 0
     finally:
         sim.close()
+
+
+@pytest.mark.parametrize("use_edge", [0, 1])
+def test_first_generation_oxdna(use_edge):
+    """interaction_type = DNA (class DNAInteraction): against the reference CPU fixture (DNA_nomesh) -- pair set, forces, split
+    energies, 100 NVE steps; then the shaken configuration against the oracle (coaxial stacking with the phi3 factor)"""
+    g = load_golden("lattice8_dna1")
+    sim = make_sim(g, interaction_type="DNA", use_edge=use_edge, CUDA_sort_every=1)
+    try:
+        assert sim.rcut == float(g["rcut"])
+        assert pair_set(sim.ctx.get_pairs()) == pair_set(g["pairs"])
+        check_forces(sim.ctx.get_forces(), g)
+        es = np.zeros(8)
+        es[:7] = g["energy_split"][:7]
+        assert np.abs(sim.ctx.energy_split() - es).max() <= 2e-6 * np.abs(es).max()
+        n = int(g["nve_steps"])
+        sim.run(n)
+        st = sim.ctx.get_state()
+        assert np.abs(st["pos"] - g["pos1"]).max() < 2e-4 and np.abs(st["vel"] - g["vel1"]).max() < 2e-3
+        # shaken orientations: exercises the rarely visited branches
+        rng = np.random.default_rng(4)
+        P = O.dna1_params(parse_temperature(str(g["T"])))
+        ax = O.axes_from_a1a3(g["a1"] + rng.normal(scale=0.06, size=g["a1"].shape), g["a3"] + rng.normal(scale=0.06, size=g["a3"].shape))
+        sim.ctx.set_state(g["pos"], ax[:, 0:3], ax[:, 6:9], g["vel"], g["L"])
+        pairs = O.verlet_pairs(g["pos"], g["n3"], g["n5"], g["box"], P.rcut + 0.1)
+        ref = O.forces(P, g["pos"], ax, g["btype"], g["n3"], g["n5"], g["box"], pairs)
+        out = sim.ctx.get_forces()
+        assert np.linalg.norm(out["force"] - ref["force"], axis=1).max() <= 1e-5 * np.linalg.norm(ref["force"], axis=1).max() + 1e-3
+        assert np.linalg.norm(out["torque_lab"] - ref["torque_lab"], axis=1).max() <= 1e-5 * np.linalg.norm(ref["torque_lab"], axis=1).max() + 1e-3
+    finally:
+        sim.close()

@@ -203,3 +203,52 @@ def test_rna_fp32_pair_cloud_covers_rare_branches(hostlib, kind):
         err = np.linalg.norm(got - want, axis=1) / scale
         assert np.quantile(err, 0.999) <= 6e-6 and err.max() <= 2e-5, (np.quantile(err, 0.999), err.max())
     assert (np.abs(ep - ref["epart"]) / np.maximum(np.abs(ref["epart"]), 1.0)).max() <= 1e-5
+
+
+def test_first_generation_oxdna_fp32_formulation(hostlib):
+    """interaction_type = DNA: FP32 device functions against the reference fixture (and, shaken, against the oracle)"""
+    g = load_golden("lattice8_dna1")
+    T = parse_temperature(str(g["T"]))
+    M, rcut = capi.dna1_params(T)
+    P = O.dna1_params(T)
+    assert rcut == P.rcut == float(g["rcut"]) and M.v1 == 1
+    N = len(g["pos"])
+    rng = np.random.default_rng(2)
+    pos, box = np.ascontiguousarray(g["pos"]), np.ascontiguousarray(g["box"], dtype=np.float64)
+    bt, n3, n5 = (np.ascontiguousarray(g[k], dtype=np.int32) for k in ("btype", "n3", "n5"))
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    for perturb in (0.0, 0.06):
+        ax = np.ascontiguousarray(O.axes_from_a1a3(g["a1"] + rng.normal(scale=perturb, size=g["a1"].shape), g["a3"] + rng.normal(scale=perturb, size=g["a3"].shape)))
+        pairs = np.ascontiguousarray(O.verlet_pairs(pos, n3, n5, box, P.rcut + 0.1), dtype=np.int32)
+        ref = O.forces(P, pos, ax, bt, n3, n5, box, pairs)
+        F, Tl, ep = np.zeros((N, 3)), np.zeros((N, 3)), np.zeros(N)
+        hostlib.host_dna2_forces(C.byref(M), N, p(pos), p(ax), p(bt), p(n3), p(n5), p(box), p(pairs), C.c_longlong(len(pairs)), p(F), p(Tl), p(ep))
+        stiff = 1e-3 if perturb > 0 else 0.0
+        assert np.linalg.norm(F - ref["force"], axis=1).max() <= 1e-5 * np.linalg.norm(ref["force"], axis=1).max() + stiff
+        assert np.linalg.norm(Tl - ref["torque_lab"], axis=1).max() <= 1e-5 * np.linalg.norm(ref["torque_lab"], axis=1).max() + stiff
+        assert abs(ep.sum() - ref["U"]) <= 2e-6 * abs(ref["U"]) + 1e-2 * stiff
+
+
+def test_oxdna1_coaxial_pair_cloud(hostlib):
+    """isolated random pairs inside the coaxial-stacking radial window: mirrored theta1 + f5(cos phi3)^2 of oxDNA"""
+    rng = np.random.default_rng(7)
+    T = parse_temperature("310K")
+    M, rcut = capi.dna1_params(T)
+    P = O.dna1_params(T)
+    M.excl_eps = 0.0
+    P.excl_eps = 0.0
+    n = 60000
+    pos, axes, box = _pair_cloud(rng, n, (0.34, 0, 0), (0.34, 0, 0), 0.19, 0.61)
+    N = 2 * n
+    bt = rng.integers(0, 4, size=N).astype(np.int32)
+    none = np.full(N, -1, dtype=np.int32)
+    pairs = np.ascontiguousarray(np.stack([np.arange(0, N, 2), np.arange(1, N, 2)], axis=1), dtype=np.int32)
+    ref = O.forces(P, pos, axes, bt, none, none, box, pairs)
+    F, Tl, ep = np.zeros((N, 3)), np.zeros((N, 3)), np.zeros(N)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    hostlib.host_dna2_forces(C.byref(M), N, p(pos), p(axes), p(bt), p(none), p(none), p(box), p(pairs), C.c_longlong(len(pairs)), p(F), p(Tl), p(ep))
+    assert ref["eterms"][6] < -1.0 and (np.abs(ref["epart"]) > 1e-3).sum() > 200
+    scale = np.maximum(np.maximum(np.linalg.norm(ref["force"], axis=1), np.linalg.norm(ref["torque_lab"], axis=1)), 1.0)
+    for got, want in ((F, ref["force"]), (Tl, ref["torque_lab"])):
+        err = np.linalg.norm(got - want, axis=1) / scale
+        assert np.quantile(err, 0.999) <= 6e-6 and err.max() <= 2e-5, (np.quantile(err, 0.999), err.max())

@@ -283,3 +283,52 @@ def test_first_generation_oxrna_oracle_matches_live_reference():
         assert np.abs(np.delete(d, 4)).max() < 1e-10 and abs(d[4]) < 1e-4 * abs(es[4]) and out["eterms"][7] == 0.0
     finally:
         r.close()
+
+
+def test_first_generation_oxdna_oracle_matches_reference_fixture():
+    """interaction_type = DNA_nomesh (class DNAInteraction): fixture written by the reference CPU backend"""
+    g = load_golden("lattice8_dna1")
+    P = O.dna1_params(parse_temperature(str(g["T"])))
+    assert P.rcut == float(g["rcut"])
+    ax = O.axes_from_a1a3(g["a1"], g["a3"])
+    pairs = O.verlet_pairs(g["pos"], g["n3"], g["n5"], g["box"], P.rcut + 2 * 0.05)
+    assert pair_set(pairs) == pair_set(g["pairs"])
+    out = O.forces(P, g["pos"], ax, g["btype"], g["n3"], g["n5"], g["box"], pairs)
+    assert np.abs(out["eterms"][:7] - g["energy_split"][:7]).max() < 1e-10
+    # the fixture keeps a1 and a3 of the reference's (slightly non-orthonormal after 3,000 steps) orientation matrices; rebuilding
+    # the axes from them moves the sites by ~1e-12, which the stiff excluded volume turns into ~1e-8 (the live test below feeds
+    # identical axes to both sides and holds 1e-10)
+    assert np.abs(out["force"] - g["force"]).max() < 1e-7 and np.abs(out["torque_lab"] - g["torque_lab"]).max() < 1e-7
+    md = O.MD(P, g["pos"], ax, g["vel"], g["L"], g["btype"], g["n3"], g["n5"], g["box"], 0.003, 0.05)
+    md.step(int(g["nve_steps"]))
+    assert np.abs(md.pos - g["pos1"]).max() < 1e-8 and np.abs(md.vel - g["vel1"]).max() < 1e-7
+
+
+@pytest.mark.skipif(not RH.available(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("grooving", [0, 1])
+def test_first_generation_oxdna_oracle_matches_live_reference(grooving):
+    """120 perturbed configurations of the reference's 16-nt DNA test system (most of them with coaxial stacking active:
+    mirrored theta1 and the phi3 factor), with and without major_minor_grooving"""
+    rng = np.random.default_rng(3)
+    top, conf = os.path.join(GOLD, "force_field_dna", "init.top"), os.path.join(GOLD, "force_field_dna", "init.dat")
+    r = RH.Reference(top, conf, interaction_type="DNA_nomesh", T="30C", major_minor_grooving=grooving, max_backbone_force=10)
+    try:
+        P = O.dna1_params(O.celsius(30.0), grooving=bool(grooving), max_backbone_force=10.0)
+        assert P.rcut == r.rcut()
+        st, topo = r.state(), r.topology()
+        worst, coax = 0.0, 0
+        for it in range(120):
+            sc = 0.04 * (it % 8)
+            pos = st["pos"] + rng.normal(scale=sc / 2, size=st["pos"].shape)
+            ax = O.axes_from_a1a3(st["a1"] + rng.normal(scale=sc, size=st["a1"].shape), st["a3"] + rng.normal(scale=sc, size=st["a3"].shape))
+            r.set_state(pos, ax[:, 0:3], ax[:, 6:9])
+            ref, es = r.compute_forces(), r.energy_split()
+            pairs = O.verlet_pairs(pos, topo["n3"], topo["n5"], r.box(), P.rcut + 0.1)
+            out = O.forces(P, pos, ax, topo["btype"], topo["n3"], topo["n5"], r.box(), pairs)
+            worst = max(worst, np.abs(out["eterms"][:7] - es[:7]).max() / max(1.0, np.abs(es).max()))
+            for k in ("force", "torque_lab"):
+                worst = max(worst, np.abs(out[k] - ref[k]).max() / max(1.0, np.abs(ref[k]).max()))
+            coax += es[6] != 0
+        assert worst < 1e-10 and coax > 50, (worst, coax)
+    finally:
+        r.close()
