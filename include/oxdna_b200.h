@@ -20,7 +20,8 @@ typedef struct oxb_ctx oxb_ctx;
 enum { OXB_PRECISION_FLOAT = 0, OXB_PRECISION_MIXED = 1 };
 enum { OXB_THERMOSTAT_NONE = 0, OXB_THERMOSTAT_BROWNIAN = 1, OXB_THERMOSTAT_LANGEVIN = 2, OXB_THERMOSTAT_BUSSI = 3 };
 enum { OXB_EXT_STRING = 0, OXB_EXT_TRAP = 1, OXB_EXT_MUTUAL_TRAP = 2, OXB_EXT_LOWDIM_TRAP = 3, OXB_EXT_REPULSION_PLANE = 4,
-	OXB_EXT_ATTRACTION_PLANE = 5, OXB_EXT_SPHERE = 6, OXB_EXT_LJ_WALL = 7, OXB_EXT_NTYPES };
+	OXB_EXT_ATTRACTION_PLANE = 5, OXB_EXT_SPHERE = 6, OXB_EXT_LJ_WALL = 7, OXB_EXT_TWIST = 8, OXB_EXT_SPHERE_SMOOTH = 9, OXB_EXT_ELLIPSOID = 10,
+	OXB_EXT_NTYPES };
 enum { OXB_TERM_FENE = 0, OXB_TERM_BEXC, OXB_TERM_STCK, OXB_TERM_NEXC, OXB_TERM_HB, OXB_TERM_CRST, OXB_TERM_CXST, OXB_TERM_DH, OXB_NTERMS };
 
 /* ---- force-field parameters (device constant block).  Replaces the __constant__ upload of
@@ -127,7 +128,10 @@ int oxb_rna2_params_seqdep(oxb_rna2_params *P, double T, const double *stck_raw1
  *   REPULSION_PLANE      RepulsionPlane                  stiff, dir, aux[0] = position, aux[1] = v, aux[2] = end_position
  *   ATTRACTION_PLANE     AttractionPlane                 stiff, dir, aux[0] = position
  *   SPHERE               RepulsiveSphere                 stiff, r0, rate, pos0 = center, aux[0] = r_ext
- *   LJ_WALL              LJWall                          stiff, dir, aux[0] = position, aux[1] = sigma, aux[2] = cutoff, iaux = n */
+ *   LJ_WALL              LJWall                          stiff, dir, aux[0] = position, aux[1] = sigma, aux[2] = cutoff, iaux = n
+ *   TWIST                ConstantRateTorque              stiff, rate, F0 = base, dir = axis, pos0, aux[0..2] = center, aux[3..5] = mask
+ *   SPHERE_SMOOTH        RepulsiveSphereSmooth           stiff, r0, pos0 = center, aux[0] = r_ext, aux[1] = smooth, aux[2] = alpha
+ *   ELLIPSOID            RepulsiveEllipsoid              stiff, pos0 = center, aux[0..2] = r_2 (inner), aux[3..5] = r_1 (outer) */
 typedef struct {
 	int type;      /* OXB_EXT_* */
 	int particle;  /* original index, or -1 = all particles */
@@ -135,7 +139,7 @@ typedef struct {
 	int pbc;
 	double stiff, r0, rate, stiff_rate, F0;
 	double dir[3], pos0[3];
-	double aux[4];
+	double aux[8];
 	int iaux;
 } oxb_ext_force;
 

@@ -168,17 +168,7 @@ def rna_lattice_case(name, n_duplex, steps, T="300K", salt=0.5, seed=3, nve_step
           "terms/N", np.round(base["energy_split"] / len(st0["pos"]), 4))
 
 
-def ext2_forces(pos):
-    """the five further external-force types, placed so that each one acts on the thermalised lattice8"""
-    xmin, zmin = float(pos[:, 0].min()), float(pos[:, 2].min())
-    return [dict(type="repulsion_plane", particle="all", stiff=1.5, dir=(0.0, 0.0, 1.0), position=-(zmin + 1.5), v=0.002, end_position=-(zmin + 1.6)),
-            dict(type="attraction_plane", particle=17, stiff=0.3, dir=(0.0, 1.0, 0.0), position=-3.0),
-            dict(type="attraction_plane", particle=200, stiff=0.3, dir=(0.0, 1.0, 0.0), position=-30.0),
-            dict(type="sphere", particle="all", stiff=2.0, r0=7.0, rate=-0.001, center=(10.0, 10.0, 10.0)),
-            dict(type="sphere", particle=5, stiff=1.0, r0=0.5, r_ext=3.0, center=(1.0, 19.0, 2.0)),
-            dict(type="LJ_wall", particle="all", stiff=0.5, dir=(1.0, 0.0, 0.0), position=-(xmin - 1.0), sigma=1.0, n=6, only_repulsive=1),
-            dict(type="lowdim_trap", particle=33, stiff=0.7, rate=0.001, pos0=(5.0, 5.0, 5.0), dir=(1.0, 1.0, 0.0), visibility=(1, 0, 1)),
-            dict(type="mutual_trap", particle=0, ref_particle=39, stiff=0.1, r0=1.2, PBC=1)]
+from oracle.fixtures import ext2_forces  # noqa: E402
 
 
 def ext2_case():

@@ -660,6 +660,38 @@ static void ext_one(const oxo_ext_force *f, const double *pos, int p, const doub
 			axpy3(4 * f->iaux * f->stiff * (2 * SQ(lj) - lj) / d, f->dir, F);
 		}
 	}
+	else if(f->type == OXO_EXT_TWIST) {
+		/* src/Forces/ConstantRateTorque.cpp:76-103 */
+		double t = f->F0 + f->rate * (double) step, sn = sin(t), cs = cos(t), oc = 1. - cs;
+		const double *a = f->dir, *c = f->aux, *mask = f->aux + 3;
+		double v[3] = { f->pos0[0] - c[0], f->pos0[1] - c[1], f->pos0[2] - c[2] };
+		double R[3][3] = { { a[0] * a[0] * oc + cs, a[0] * a[1] * oc - a[2] * sn, a[0] * a[2] * oc + a[1] * sn },
+				{ a[0] * a[1] * oc + a[2] * sn, a[1] * a[1] * oc + cs, a[1] * a[2] * oc - a[0] * sn },
+				{ a[0] * a[2] * oc - a[1] * sn, a[1] * a[2] * oc + a[0] * sn, a[2] * a[2] * oc + cs } };
+		for(int k = 0; k < 3; k++) {
+			double trap = R[k][0] * v[0] + R[k][1] * v[1] + R[k][2] * v[2] + c[k];
+			F[k] += -f->stiff * (pp[k] - trap) * mask[k];
+		}
+	}
+	else if(f->type == OXO_EXT_SPHERE_SMOOTH) {
+		/* src/Forces/RepulsiveSphereSmooth.cpp:48-63 */
+		double d[3];
+		min_image(box, f->pos0, pp, d);
+		double m = sqrt(dot3(d, d)), r_ext = f->aux[0], smooth = f->aux[1], alpha = f->aux[2];
+		if(!(m < f->r0 || m > r_ext)) {
+			if(m >= alpha && m <= r_ext) axpy3(-(f->stiff * 0.5 * exp((m - alpha) / smooth)) / m, d, F);
+			else axpy3(-(f->stiff * m - f->stiff * 0.5 * exp(-(m - alpha) / smooth)) / m, d, F);
+		}
+	}
+	else if(f->type == OXO_EXT_ELLIPSOID) {
+		/* src/Forces/RepulsiveEllipsoid.cpp:55-67 */
+		double d[3];
+		min_image(box, f->pos0, pp, d);
+		const double *r2 = f->aux, *r1 = f->aux + 3;
+		double in = SQ(d[0]) / SQ(r2[0]) + SQ(d[1]) / SQ(r2[1]) + SQ(d[2]) / SQ(r2[2]);
+		double out = SQ(d[0]) / SQ(r1[0]) + SQ(d[1]) / SQ(r1[1]) + SQ(d[2]) / SQ(r1[2]);
+		if(!(in < 1. && out > 1.)) axpy3(-f->stiff / sqrt(dot3(d, d)), d, F);
+	}
 }
 
 void oxo_ext_forces(int nf, const oxo_ext_force *ef, int N, const double *pos, const double *box, long long step, double *force) {

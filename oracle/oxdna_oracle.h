@@ -61,9 +61,9 @@ void oxo_dna1_params_init(oxo_dna2_params *P, double T, int grooving, int use_mb
 void oxo_dna2_params_seqdep(oxo_dna2_params *P, const double *stck_raw16, double stck_fact_eps, double hb_AT, double hb_GC);
 
 /* particle = -1: every particle.  aux / iaux: see the table in include/oxdna_b200.h (same conventions) */
-typedef struct { int type; int particle; int ref; int pbc; double stiff, r0, rate, stiff_rate, F0; double dir[3], pos0[3]; double aux[4]; int iaux; } oxo_ext_force;
+typedef struct { int type; int particle; int ref; int pbc; double stiff, r0, rate, stiff_rate, F0; double dir[3], pos0[3]; double aux[8]; int iaux; } oxo_ext_force;
 enum { OXO_EXT_STRING = 0, OXO_EXT_TRAP = 1, OXO_EXT_MUTUAL = 2, OXO_EXT_LOWDIM = 3, OXO_EXT_REPULSION_PLANE = 4, OXO_EXT_ATTRACTION_PLANE = 5,
-	OXO_EXT_SPHERE = 6, OXO_EXT_LJ_WALL = 7 };
+	OXO_EXT_SPHERE = 6, OXO_EXT_LJ_WALL = 7, OXO_EXT_TWIST = 8, OXO_EXT_SPHERE_SMOOTH = 9, OXO_EXT_ELLIPSOID = 10 };
 
 /* axes: N x 9 doubles = a1(3) a2(3) a3(3).  pairs: npairs x 2 ints (non-bonded candidates, each unique pair once).
  * Outputs (any may be NULL): force N x 3 (lab), torque_lab N x 3, torque_body N x 3, eterms[OXO_NTERMS] totals,

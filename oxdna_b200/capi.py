@@ -74,9 +74,9 @@ class RNA2Params(C.Structure):
 class ExtForce(C.Structure):
     _fields_ = [("type", C.c_int), ("particle", C.c_int), ("ref", C.c_int), ("pbc", C.c_int)] + [
         (n, C.c_double) for n in "stiff r0 rate stiff_rate F0".split()] + [("dir", C.c_double * 3), ("pos0", C.c_double * 3),
-                                                                              ("aux", C.c_double * 4), ("iaux", C.c_int)]
+                                                                              ("aux", C.c_double * 8), ("iaux", C.c_int)]
 
-EXT_TYPES = {"string": 0, "trap": 1, "mutual_trap": 2, "lowdim_trap": 3, "repulsion_plane": 4, "attraction_plane": 5, "sphere": 6, "LJ_wall": 7}
+EXT_TYPES = {"string": 0, "trap": 1, "mutual_trap": 2, "lowdim_trap": 3, "repulsion_plane": 4, "attraction_plane": 5, "sphere": 6, "LJ_wall": 7, "twist": 8, "sphere_smooth": 9, "ellipsoid": 10}
 
 
 def fill_ext_entry(e, d):
@@ -88,14 +88,14 @@ def fill_ext_entry(e, d):
     e.pbc = int(d.get("PBC", 0))
     e.stiff, e.r0, e.rate = float(d.get("stiff", 1.0 if d["type"] == "LJ_wall" else 0.0)), float(d.get("r0", 0.0)), float(d.get("rate", 0.0))
     e.stiff_rate, e.F0 = float(d.get("stiff_rate", 0.0)), float(d.get("F0", 0.0))
-    dr = np.array(d.get("dir", (1, 0, 0) if d["type"] != "mutual_trap" else (0, 0, 1)), dtype=np.float64)
+    dr = np.array(d.get("axis", d.get("dir", (1, 0, 0) if d["type"] != "mutual_trap" else (0, 0, 1))), dtype=np.float64)
     if d["type"] != "mutual_trap" and np.linalg.norm(dr) > 0:
         dr = dr / np.linalg.norm(dr)
-    centre = d.get("center", d.get("pos0", (0, 0, 0)))
+    centre = d.get("pos0", (0, 0, 0)) if d["type"] == "twist" else d.get("center", d.get("pos0", (0, 0, 0)))
     for c in range(3):
         e.dir[c] = dr[c]
         e.pos0[c] = float(centre[c])
-    aux = [0.0, 0.0, 0.0, 0.0]
+    aux = [0.0] * 8
     e.iaux = 0
     if d["type"] == "lowdim_trap":
         vis = d.get("visibility", (1, 1, 1))
@@ -111,7 +111,18 @@ def fill_ext_entry(e, d):
         aux[0], aux[1] = float(d["position"]), float(d.get("sigma", 1.0))
         aux[2] = 2.0 ** (1.0 / n) if int(d.get("only_repulsive", 0)) else 1e6
         e.iaux = n
-    for c in range(4):
+    elif d["type"] == "twist":
+        e.F0 = float(d.get("base", 0.0))
+        aux[0:3] = [float(x) for x in d["center"]]
+        aux[3:6] = [float(x) for x in d.get("mask", (0.0, 0.0, 0.0))]
+    elif d["type"] == "sphere_smooth":
+        # the reference reads `smooth` and `alpha` from the r_ext key as well (RepulsiveSphereSmooth.cpp:27-29)
+        aux[0] = float(d["r_ext"])
+        aux[1], aux[2] = float(d.get("smooth", aux[0])), float(d.get("alpha", aux[0]))
+    elif d["type"] == "ellipsoid":
+        aux[0:3] = [float(x) for x in d["r_2"]]
+        aux[3:6] = [float(x) for x in d.get("r_1", (1e-6, 1e-6, 1e-6))]
+    for c in range(8):
         e.aux[c] = aux[c]
 
 

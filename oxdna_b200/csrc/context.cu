@@ -779,10 +779,10 @@ int oxb_set_ext_forces(oxb_ctx *c, int n, const oxb_ext_force *f) {
 		d.stiff = (float) f[k].stiff; d.r0 = (float) f[k].r0; d.rate = (float) f[k].rate; d.stiff_rate = (float) f[k].stiff_rate; d.F0 = (float) f[k].F0;
 		double nrm = std::sqrt(f[k].dir[0] * f[k].dir[0] + f[k].dir[1] * f[k].dir[1] + f[k].dir[2] * f[k].dir[2]);
 		for(int x = 0; x < 3; x++) {
-			d.dir[x] = (float) ((f[k].type != OXB_EXT_MUTUAL_TRAP && nrm > 0) ? f[k].dir[x] / nrm : f[k].dir[x]);
+			d.dir[x] = (float) ((f[k].type != OXB_EXT_MUTUAL_TRAP && nrm > 0) ? f[k].dir[x] / nrm : f[k].dir[x]); // unit direction / axis
 			d.pos0[x] = f[k].pos0[x];
 		}
-		for(int x = 0; x < 4; x++) d.aux[x] = (float) f[k].aux[x];
+		for(int x = 0; x < 8; x++) d.aux[x] = (float) f[k].aux[x];
 		d.iaux = f[k].iaux;
 		(f[k].particle < 0 ? hall : h).push_back(d);
 	}

@@ -434,6 +434,38 @@ __device__ __forceinline__ v3 ext_single(const DevExtForce &e, double4 p, int4 i
 		float s = 4.f * (float) e.iaux * e.stiff * (2.f * lj * lj - lj) / (float) d;
 		return mk3(e.dir[0] * s, e.dir[1] * s, e.dir[2] * s);
 	}
+	case OXB_EXT_TWIST: {
+		// ConstantRateTorque.cpp:76-103: trap at pos0 rotated by (base + rate t) about the axis through `center`, masked
+		double t = (double) e.F0 + (double) e.rate * (double) step;
+		double sn, cs;
+		sincos(t, &sn, &cs);
+		double oc = 1. - cs, ax = e.dir[0], ay = e.dir[1], az = e.dir[2];
+		double vx = e.pos0[0] - (double) e.aux[0], vy = e.pos0[1] - (double) e.aux[1], vz = e.pos0[2] - (double) e.aux[2];
+		double tx = (ax * ax * oc + cs) * vx + (ax * ay * oc - az * sn) * vy + (ax * az * oc + ay * sn) * vz + (double) e.aux[0];
+		double ty = (ax * ay * oc + az * sn) * vx + (ay * ay * oc + cs) * vy + (ay * az * oc - ax * sn) * vz + (double) e.aux[1];
+		double tz = (ax * az * oc - ay * sn) * vx + (ay * az * oc + ax * sn) * vy + (az * az * oc + cs) * vz + (double) e.aux[2];
+		return mk3((float) (-(double) e.stiff * (p.x - tx) * (double) e.aux[3]), (float) (-(double) e.stiff * (p.y - ty) * (double) e.aux[4]),
+				(float) (-(double) e.stiff * (p.z - tz) * (double) e.aux[5]));
+	}
+	case OXB_EXT_SPHERE_SMOOTH:
+	case OXB_EXT_ELLIPSOID: {
+		int4 ic;
+		ic.x = (int) to_fixed(e.pos0[0], 1. / (double) box.lx); ic.y = (int) to_fixed(e.pos0[1], 1. / (double) box.ly); ic.z = (int) to_fixed(e.pos0[2], 1. / (double) box.lz);
+		v3 d = min_image_fixed(box, ic, ip);
+		float m = sqrtf(dot(d, d));
+		if(e.type == OXB_EXT_SPHERE_SMOOTH) {
+			// RepulsiveSphereSmooth.cpp:48-63
+			if(m < e.r0 || m > e.aux[0]) return mk3(0.f, 0.f, 0.f);
+			float s = (m >= e.aux[2]) ? -(e.stiff * 0.5f * expf((m - e.aux[2]) / e.aux[1])) / m
+					: -(e.stiff * m - e.stiff * 0.5f * expf(-(m - e.aux[2]) / e.aux[1])) / m;
+			return d * s;
+		}
+		// RepulsiveEllipsoid.cpp:55-67
+		float in = d.x * d.x / (e.aux[0] * e.aux[0]) + d.y * d.y / (e.aux[1] * e.aux[1]) + d.z * d.z / (e.aux[2] * e.aux[2]);
+		float out = d.x * d.x / (e.aux[3] * e.aux[3]) + d.y * d.y / (e.aux[4] * e.aux[4]) + d.z * d.z / (e.aux[5] * e.aux[5]);
+		if(in < 1.f && out > 1.f) return mk3(0.f, 0.f, 0.f);
+		return d * (-e.stiff / m);
+	}
 	default: return mk3(0.f, 0.f, 0.f);
 	}
 }

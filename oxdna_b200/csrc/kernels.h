@@ -23,7 +23,7 @@ struct DevExtForce {
 	float stiff, r0, rate, stiff_rate, F0;
 	float dir[3];
 	double pos0[3];
-	float aux[4];
+	float aux[8];
 	int iaux;
 };
 

@@ -3,6 +3,9 @@
 #include "MD_CUDABackend.h"
 
 #include "Forces/AttractionPlane.h"
+#include "Forces/ConstantRateTorque.h"
+#include "Forces/RepulsiveEllipsoid.h"
+#include "Forces/RepulsiveSphereSmooth.h"
 #include "Forces/LJWall.h"
 #include "Forces/LowdimMovingTrap.h"
 #include "Forces/RepulsionPlane.h"
@@ -252,8 +255,32 @@ void MD_CUDABackend::_apply_external_forces_changes() {
 				e.aux[0] = wf->_position; e.aux[1] = wf->_sigma; e.aux[2] = wf->_cutoff;
 				e.iaux = wf->_n;
 			}
+			else if(ft == typeid(ConstantRateTorque)) {
+				ConstantRateTorque *tf = static_cast<ConstantRateTorque *>(f);
+				e.type = OXB_EXT_TWIST;
+				e.stiff = tf->_stiff; e.rate = tf->_rate; e.F0 = tf->_F0;
+				e.dir[0] = tf->_axis.x; e.dir[1] = tf->_axis.y; e.dir[2] = tf->_axis.z;
+				e.pos0[0] = tf->_pos0.x; e.pos0[1] = tf->_pos0.y; e.pos0[2] = tf->_pos0.z;
+				e.aux[0] = tf->_center.x; e.aux[1] = tf->_center.y; e.aux[2] = tf->_center.z;
+				e.aux[3] = tf->_mask.x; e.aux[4] = tf->_mask.y; e.aux[5] = tf->_mask.z;
+			}
+			else if(ft == typeid(RepulsiveSphereSmooth)) {
+				RepulsiveSphereSmooth *sf = static_cast<RepulsiveSphereSmooth *>(f);
+				e.type = OXB_EXT_SPHERE_SMOOTH;
+				e.stiff = sf->_stiff; e.r0 = sf->_r0;
+				e.pos0[0] = sf->_center.x; e.pos0[1] = sf->_center.y; e.pos0[2] = sf->_center.z;
+				e.aux[0] = sf->_r_ext; e.aux[1] = sf->_smooth; e.aux[2] = sf->_alpha;
+			}
+			else if(ft == typeid(RepulsiveEllipsoid)) {
+				RepulsiveEllipsoid *ef = static_cast<RepulsiveEllipsoid *>(f);
+				e.type = OXB_EXT_ELLIPSOID;
+				e.stiff = ef->_stiff;
+				e.pos0[0] = ef->_centre.x; e.pos0[1] = ef->_centre.y; e.pos0[2] = ef->_centre.z;
+				e.aux[0] = ef->_r_2.x; e.aux[1] = ef->_r_2.y; e.aux[2] = ef->_r_2.z;
+				e.aux[3] = ef->_r_1.x; e.aux[4] = ef->_r_1.y; e.aux[5] = ef->_r_1.z;
+			}
 			else {
-				throw oxDNAException("Only string, trap, mutual_trap, lowdim_trap, repulsion_plane, attraction_plane, sphere and LJ_wall forces are supported by the oxdna_b200 CUDA backend at the moment.\n");
+				throw oxDNAException("Only string, trap, mutual_trap, lowdim_trap, twist, repulsion_plane, attraction_plane, sphere, sphere_smooth, ellipsoid and LJ_wall forces are supported by the oxdna_b200 CUDA backend at the moment.\n");
 			}
 			if(single_particle_type && N() > 1 && uses[f] == N()) {
 				if(emitted.count(f)) continue;

@@ -109,6 +109,24 @@ stiff = 0.2
 dir = 0,1,0
 position = -20.
 }
+{
+type = twist
+particle = 17
+stiff = 0.3
+rate = 0.001
+base = 0.2
+axis = 0., 0., 1.
+pos0 = 8., 13., 36.
+center = 7., 12., 36.
+mask = 1., 1., 0.
+}
+{
+type = ellipsoid
+particle = all
+stiff = 0.05
+r_2 = 3., 4., 3.
+center = 8., 13., 36.
+}
 """
 
 
