@@ -487,3 +487,35 @@ def test_first_generation_oxdna(use_edge):
         assert np.linalg.norm(out["torque_lab"] - ref["torque_lab"], axis=1).max() <= 1e-5 * np.linalg.norm(ref["torque_lab"], axis=1).max() + 1e-3
     finally:
         sim.close()
+
+
+def test_rna_long_run_mean_energies_match_reference_statistically():
+    """Third correctness criterion for oxRNA2: <U/N>, <K/N> over 400,000 thermostatted steps against the unmodified reference CPU
+    backend (tests/golden/stat_rna_lattice8_ref.json, written by oracle/make_stat_fixture.py).  The reference CPU class meshes the
+    hydrogen-bonding factors (5e-6 of that term) -- far below the statistical error."""
+    import json
+    import os
+    ref = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "stat_rna_lattice8_ref.json")))
+    sysm = lattice.rna_duplex_lattice(8, bp=16, spacing=10.0, seed=1)
+    T = parse_temperature("300K")
+    v, L = lattice.maxwell_velocities(len(sysm["pos"]), T, 1)
+    inp = dict(backend="CUDA", interaction_type="RNA2", T="300K", salt_concentration=0.5, dt=0.003, verlet_skin=0.05, thermostat="brownian",
+               newtonian_steps=103, diff_coeff=2.5, CUDA_sort_every=1, use_edge=1, seed=4242)
+    sim = Simulation(inp, sysm, dict(box=sysm["box"], pos=sysm["pos"], a1=sysm["a1"], a3=sysm["a3"], vel=v, L=L))
+    try:
+        N = sim.N
+        sim.run(50000)
+        U, K = [], []
+        for _ in range(3500):
+            sim.run(100)
+            u, k = sim.ctx.energy()
+            U.append(u / N)
+            K.append(k / N)
+        mu, su = _block_stats(np.array(U))
+        mk, sk = _block_stats(np.array(K))
+        su_ref = max(float(ref["U_stderr"]), 0.0026)
+        assert abs(mu - ref["U_per_nt"]) < 3.0 * np.hypot(su, su_ref), (mu, su, ref["U_per_nt"], su_ref)
+        assert abs(mk - ref["K_per_nt"]) < 3.0 * np.hypot(sk, float(ref["K_stderr"])) + 0.002, (mk, sk, ref["K_per_nt"])
+        assert abs(mk - 3.0 * T) < 0.02 * 3.0 * T
+    finally:
+        sim.close()
