@@ -174,6 +174,11 @@ int oxb_set_ext_forces(oxb_ctx *ctx, int n, const oxb_ext_force *forces);
  * (src/CUDA/Backends/MD_CUDABackend.cu:231-394).  pos, a1, a3, vel, L: N x 3 doubles, original order. */
 int oxb_set_state(oxb_ctx *ctx, const double *pos, const double *a1, const double *a3, const double *vel, const double *L);
 int oxb_get_state(oxb_ctx *ctx, double *pos, double *a1, double *a3, double *vel, double *L);
+/* trajectory / last_conf frame in the reference's text format (docs/source/configurations.md:14-34; Configuration::_headers and
+ * ::_particle, src/Observables/Configurations/Configuration.cpp:85-140) straight from the device state, without the BaseParticle
+ * round trip and CPU energy evaluation of SimBackend::print_conf: "t = step / b = box / E = Etot U K (per particle)" + one line
+ * per particle (original order): pos a1 a3 [vel L].  append != 0 adds a frame to an existing trajectory file. */
+int oxb_write_conf(oxb_ctx *ctx, const char *path, int append, int print_momenta);
 int oxb_set_step(oxb_ctx *ctx, long long step);
 long long oxb_get_step(const oxb_ctx *ctx);
 

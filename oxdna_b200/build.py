@@ -7,7 +7,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "liboxdna_b200.so")
 SOURCES = ["context.cu", "forces.cu", "integrate.cu", "lists.cu", "sort.cu", "params.cpp"]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
+# extra -D flags for tuning experiments (profiles/micro/occupancy_sweep.sh)
+EXTRA = os.environ.get("OXB_EXTRA_NVCC", "").split()
+NVCC_FLAGS = EXTRA + ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-O3", "--expt-relaxed-constexpr", "-Wno-deprecated-gpu-targets"]
 
 

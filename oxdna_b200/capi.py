@@ -127,7 +127,7 @@ def fill_ext_entry(e, d):
 
 
 EXPORTED = """oxb_sizeof oxb_dna2_params_init oxb_dna1_params_init oxb_dna2_params_seqdep oxb_rna2_params_init oxb_rna2_params_seqdep oxb_set_model_rna2 oxb_create oxb_destroy oxb_last_error oxb_set_stream oxb_set_box
-oxb_set_topology oxb_set_model_dna2 oxb_set_lists oxb_set_dt oxb_set_thermostat oxb_set_ext_forces oxb_set_state oxb_get_state
+oxb_set_topology oxb_set_model_dna2 oxb_set_lists oxb_set_dt oxb_set_thermostat oxb_set_ext_forces oxb_set_state oxb_get_state oxb_write_conf
 oxb_set_step oxb_get_step oxb_sort oxb_update_lists oxb_compute_forces oxb_first_step oxb_second_step oxb_thermostat oxb_run
 oxb_synchronize oxb_get_forces oxb_energy oxb_energy_split oxb_get_pairs oxb_get_stats oxb_device_views oxb_launch_count oxb_time_kernel""".split()
 
@@ -292,6 +292,10 @@ class Context:
         out = [np.zeros((self.N, 3)) for _ in range(5)]
         self._ck(self._L.oxb_get_state(self._h, *[_p(x) for x in out]))
         return dict(pos=out[0], a1=out[1], a3=out[2], vel=out[3], L=out[4])
+
+    def write_conf(self, path, append=False, print_momenta=True):
+        """one frame in the reference's configuration format, written from the device state"""
+        self._ck(self._L.oxb_write_conf(self._h, str(path).encode(), int(append), int(print_momenta)))
 
     def set_step(self, s):
         self._ck(self._L.oxb_set_step(self._h, C.c_longlong(s)))

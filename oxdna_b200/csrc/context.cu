@@ -894,6 +894,33 @@ int oxb_get_state(oxb_ctx *c, double *pos, double *a1, double *a3, double *vel, 
 	return 0;
 }
 
+int oxb_write_conf(oxb_ctx *c, const char *path, int append, int print_momenta) {
+	if(c == nullptr || path == nullptr) return 1;
+	double U = 0., K = 0.;
+	int rc = oxb_energy(c, &U, &K);
+	if(rc) return rc;
+	const int N = c->N;
+	std::vector<double> pos(3 * (size_t) N), a1(3 * (size_t) N), a3(3 * (size_t) N), vel(3 * (size_t) N), L(3 * (size_t) N);
+	rc = oxb_get_state(c, pos.data(), a1.data(), a3.data(), vel.data(), L.data());
+	if(rc) return rc;
+	FILE *f = std::fopen(path, append ? "a" : "w");
+	if(f == nullptr) return fail(c, 9, "cannot open '%s' for writing", path);
+	std::vector<char> buf(1 << 22);
+	std::setvbuf(f, buf.data(), _IOFBF, buf.size());
+	// header and particle lines exactly as Configuration::_headers / _particle print them (stream precision 15 = %.15g)
+	std::fprintf(f, "t = %lld\nb = %.15g %.15g %.15g\nE = %.15g %.15g %.15g\n", c->step, c->box[0], c->box[1], c->box[2], (U + K) / N, U / N, K / N);
+	for(int i = 0; i < N; i++) {
+		const double *p = &pos[3 * (size_t) i], *x = &a1[3 * (size_t) i], *z = &a3[3 * (size_t) i], *v = &vel[3 * (size_t) i], *l = &L[3 * (size_t) i];
+		if(print_momenta) {
+			std::fprintf(f, "%.15g %.15g %.15g %.15g %.15g %.15g %.15g %.15g %.15g %.15g %.15g %.15g %.15g %.15g %.15g\n", p[0], p[1], p[2], x[0], x[1], x[2], z[0],
+					z[1], z[2], v[0], v[1], v[2], l[0], l[1], l[2]);
+		}
+		else std::fprintf(f, "%.15g %.15g %.15g %.15g %.15g %.15g %.15g %.15g %.15g\n", p[0], p[1], p[2], x[0], x[1], x[2], z[0], z[1], z[2]);
+	}
+	std::fclose(f);
+	return 0;
+}
+
 int oxb_set_step(oxb_ctx *c, long long step) {
 	if(c == nullptr) return 1;
 	c->step = step;

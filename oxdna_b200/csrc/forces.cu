@@ -9,6 +9,18 @@
 
 #include <algorithm>
 
+// minimum resident blocks per SM asked of the compiler for the latency-bound gather kernels (register cap = 65536 / (threads x blocks));
+// tuned on B200 with profiles/micro/occupancy_sweep.sh
+#ifndef OXB_MB_NEAR
+#define OXB_MB_NEAR 1
+#endif
+#ifndef OXB_MB_HEAVY
+#define OXB_MB_HEAVY 1
+#endif
+#ifndef OXB_MB_BONDED
+#define OXB_MB_BONDED 1
+#endif
+
 namespace {
 
 struct Particle {
@@ -168,7 +180,7 @@ __device__ __forceinline__ void block_append(bool flag, int2 item, int2 *__restr
 }
 
 template<class MD>
-__global__ void __launch_bounds__(128) k_edge_near(const __grid_constant__ typename MD::Params M, BoxF box, const int *__restrict__ n_edges,
+__global__ void __launch_bounds__(128, OXB_MB_NEAR) k_edge_near(const __grid_constant__ typename MD::Params M, BoxF box, const int *__restrict__ n_edges,
 		const int2 *__restrict__ edges, const int4 *__restrict__ ipos, const float4 *__restrict__ quat, float4 *__restrict__ F, float4 *__restrict__ T,
 		int2 *__restrict__ hb_list, int2 *__restrict__ cx_list, int2 *__restrict__ cr_list, int *__restrict__ seg_counts, int hb_seg, int cx_seg,
 		int cr_seg, int *__restrict__ flags, int hw) {
@@ -244,7 +256,7 @@ __global__ void __launch_bounds__(128) k_edge_near(const __grid_constant__ typen
 
 // MODE 0: hydrogen bonding (+ cross stacking where also in range) | 1: coaxial stacking | 2: cross stacking only
 template<class MD, int MODE>
-__global__ void __launch_bounds__(64) k_edge_heavy(const __grid_constant__ typename MD::Params M, BoxF box, const int *__restrict__ seg_counts,
+__global__ void __launch_bounds__(64, OXB_MB_HEAVY) k_edge_heavy(const __grid_constant__ typename MD::Params M, BoxF box, const int *__restrict__ seg_counts,
 		const int2 *__restrict__ list, int seg, const int4 *__restrict__ ipos, const float4 *__restrict__ quat, float4 *__restrict__ F,
 		float4 *__restrict__ T, const int *__restrict__ flags, int hw) {
 	if(flags[hw]) return;
@@ -283,7 +295,7 @@ __global__ void __launch_bounds__(64) k_edge_heavy(const __grid_constant__ typen
 // per particle: bonded interaction with its n3 neighbour (each bond evaluated once).  Independent of the other kernels of
 // the force pass (it only adds into F/T), so it runs concurrently with them on its own stream.
 template<class MD>
-__global__ void __launch_bounds__(128) k_bonded(const __grid_constant__ typename MD::Params M, BoxF box, int N, const int4 *__restrict__ ipos,
+__global__ void __launch_bounds__(128, OXB_MB_BONDED) k_bonded(const __grid_constant__ typename MD::Params M, BoxF box, int N, const int4 *__restrict__ ipos,
 		const float4 *__restrict__ quat, const int2 *__restrict__ bonds, float4 *__restrict__ F, float4 *__restrict__ T, int *__restrict__ flags, int hw) {
 	if(flags[hw]) return;
 	int i = blockIdx.x * blockDim.x + threadIdx.x;

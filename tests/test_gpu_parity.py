@@ -519,3 +519,28 @@ def test_rna_long_run_mean_energies_match_reference_statistically():
         assert abs(mk - 3.0 * T) < 0.02 * 3.0 * T
     finally:
         sim.close()
+
+
+def test_write_conf_from_device_state(tmp_path):
+    """oxb_write_conf: the reference's configuration format straight from the device buffers; read back with the same reader
+    the tests use for the reference's own files (15 significant digits)"""
+    from oxdna_b200 import io as oio
+    g = load_golden("lattice8")
+    sim = make_sim(g, use_edge=1, CUDA_sort_every=1)
+    try:
+        sim.run(37)
+        path = tmp_path / "frame.dat"
+        sim.ctx.write_conf(path)
+        sim.ctx.write_conf(tmp_path / "traj.dat")
+        sim.ctx.write_conf(tmp_path / "traj.dat", append=True, print_momenta=True)
+        st, (U, K) = sim.ctx.get_state(), sim.ctx.energy()
+        lines = open(path).read().splitlines()
+        assert lines[0] == "t = 37" and lines[1] == "b = 20 20 20" and len(lines) == 3 + sim.N
+        E = [float(x) for x in lines[2].split("=")[1].split()]
+        assert np.allclose(E, [(U + K) / sim.N, U / sim.N, K / sim.N], rtol=1e-13)
+        c = oio.read_conf(str(path))
+        for k in ("pos", "a1", "a3", "vel", "L"):
+            assert np.allclose(c[k], st[k], rtol=2e-15, atol=1e-15), k
+        assert len(open(tmp_path / "traj.dat").read().splitlines()) == 2 * (3 + sim.N)
+    finally:
+        sim.close()
