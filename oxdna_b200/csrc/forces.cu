@@ -9,16 +9,21 @@
 
 #include <algorithm>
 
-// minimum resident blocks per SM asked of the compiler for the latency-bound gather kernels (register cap = 65536 / (threads x blocks));
-// tuned on B200 with profiles/micro/occupancy_sweep.sh
+// minimum resident blocks per SM asked of the compiler for the latency-bound gather kernels (register cap = 65536 / (threads x blocks)).
+// Tuned on B200 with profiles/micro/occupancy_sweep.sh (profiles/occupancy_sweep_r01.txt): at 92-96 registers these kernels ran at
+// 28 % occupancy with 46-62 % issue utilisation (ncu r01h); capping them at 64 (near, heavy) / 85 (bonded) registers costs a few
+// spilled words and gives +10 % on the 1M-nt step, +5 % at 82k nt.  48 registers (10/20 blocks) is slower again.
 #ifndef OXB_MB_NEAR
-#define OXB_MB_NEAR 1
+#define OXB_MB_NEAR 8
 #endif
 #ifndef OXB_MB_HEAVY
-#define OXB_MB_HEAVY 1
+#define OXB_MB_HEAVY 16
+#endif
+#ifndef OXB_MB_PARTICLE
+#define OXB_MB_PARTICLE 5
 #endif
 #ifndef OXB_MB_BONDED
-#define OXB_MB_BONDED 1
+#define OXB_MB_BONDED 6
 #endif
 
 namespace {
@@ -44,7 +49,7 @@ __device__ __forceinline__ Particle load_particle(const typename MD::Params &M, 
 // Particle-centric: one thread per particle, every listed pair evaluated from both ends, no atomics, deterministic.
 // ------------------------------------------------------------------------------------------------------------
 template<class MD>
-__global__ void __launch_bounds__(128) k_forces_particle(const __grid_constant__ typename MD::Params M, BoxF box, int N, const int4 *__restrict__ ipos,
+__global__ void __launch_bounds__(128, OXB_MB_PARTICLE) k_forces_particle(const __grid_constant__ typename MD::Params M, BoxF box, int N, const int4 *__restrict__ ipos,
 		const float4 *__restrict__ quat, const int2 *__restrict__ bonds, const int *__restrict__ nbr, const int *__restrict__ nnbr, int stride,
 		float4 *__restrict__ F, float4 *__restrict__ T, int *__restrict__ flags, int hw) {
 	if(flags[hw]) return;

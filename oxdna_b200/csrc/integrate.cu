@@ -31,8 +31,12 @@ __device__ __forceinline__ uint4 philox_u4(unsigned long long seed, unsigned id,
 	return Philox::gen(make_uint4(id, (unsigned) step, (unsigned) (step >> 32), draw), make_uint2((unsigned) seed, (unsigned) (seed >> 32)));
 }
 
+#ifndef OXB_MB_INTEGRATE
+#define OXB_MB_INTEGRATE 1
+#endif
+
 template<int PH>
-__global__ void __launch_bounds__(256) k_integrate(oxb::IntegrateArgs a, int epoch) {
+__global__ void __launch_bounds__(256, OXB_MB_INTEGRATE) k_integrate(oxb::IntegrateArgs a, int epoch) {
 	int *flags = a.flags;
 	const int rd = OXB_FLAG_COUNT + (epoch & 1), wr = OXB_FLAG_COUNT + ((epoch + 1) & 1);
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
