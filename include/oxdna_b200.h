@@ -21,7 +21,8 @@ enum { OXB_PRECISION_FLOAT = 0, OXB_PRECISION_MIXED = 1 };
 enum { OXB_THERMOSTAT_NONE = 0, OXB_THERMOSTAT_BROWNIAN = 1, OXB_THERMOSTAT_LANGEVIN = 2, OXB_THERMOSTAT_BUSSI = 3 };
 enum { OXB_EXT_STRING = 0, OXB_EXT_TRAP = 1, OXB_EXT_MUTUAL_TRAP = 2, OXB_EXT_LOWDIM_TRAP = 3, OXB_EXT_REPULSION_PLANE = 4,
 	OXB_EXT_ATTRACTION_PLANE = 5, OXB_EXT_SPHERE = 6, OXB_EXT_LJ_WALL = 7, OXB_EXT_TWIST = 8, OXB_EXT_SPHERE_SMOOTH = 9, OXB_EXT_ELLIPSOID = 10,
-	OXB_EXT_NTYPES };
+	OXB_EXT_REPULSION_PLANE_MOVING = 11, OXB_EXT_GENERIC_CENTRAL = 12, OXB_EXT_LJ_CONE = 13, OXB_EXT_COM = 14, OXB_EXT_YUKAWA_SPHERE = 15,
+	OXB_EXT_SPHERE_MOVING = 16, OXB_EXT_NTYPES };
 enum { OXB_TERM_FENE = 0, OXB_TERM_BEXC, OXB_TERM_STCK, OXB_TERM_NEXC, OXB_TERM_HB, OXB_TERM_CRST, OXB_TERM_CXST, OXB_TERM_DH, OXB_NTERMS };
 
 /* ---- force-field parameters (device constant block).  Replaces the __constant__ upload of
@@ -131,7 +132,17 @@ int oxb_rna2_params_seqdep(oxb_rna2_params *P, double T, const double *stck_raw1
  *   LJ_WALL              LJWall                          stiff, dir, aux[0] = position, aux[1] = sigma, aux[2] = cutoff, iaux = n
  *   TWIST                ConstantRateTorque              stiff, rate, F0 = base, dir = axis, pos0, aux[0..2] = center, aux[3..5] = mask
  *   SPHERE_SMOOTH        RepulsiveSphereSmooth           stiff, r0, pos0 = center, aux[0] = r_ext, aux[1] = smooth, aux[2] = alpha
- *   ELLIPSOID            RepulsiveEllipsoid              stiff, pos0 = center, aux[0..2] = r_2 (inner), aux[3..5] = r_1 (outer) */
+ *   ELLIPSOID            RepulsiveEllipsoid              stiff, pos0 = center, aux[0..2] = r_2 (inner), aux[3..5] = r_1 (outer)
+ *   REPULSION_PLANE_MOVING RepulsionPlaneMoving          stiff, dir, ref = lowest and iaux = highest original index of the (contiguous) ref_particle range
+ *   GENERIC_CENTRAL      GenericCentralForce (gravity)   F0, pos0 = center, aux[0] = inner_cut_off^2, aux[1] = outer_cut_off^2 (0 = none); the
+ *                                                        `interpolated` flavour is CPU-only in the reference as well (forces_defs.cuh:292-310)
+ *   LJ_CONE              LJCone                          stiff, dir, pos0 = apex, aux[0] = sigma, aux[1] = cutoff, aux[2] = alpha, iaux = n
+ *   COM                  COMForce                        ONE entry per force (not per particle): stiff, r0, rate, ref = offset of com_list in
+ *                                                        the index pool (oxb_set_ext_index_pool), iaux = its length, ref_list follows it
+ *                                                        directly and has pbc entries; particle is ignored
+ *   YUKAWA_SPHERE        YukawaSphere                    pos0 = center, r0 = radius, stiff = WCA_epsilon, aux[0] = WCA sigma, aux[1] = WCA cutoff,
+ *                                                        aux[2] = debye_length, aux[3] = debye_A, aux[4] = cutoff, iaux = WCA_n
+ *   SPHERE_MOVING        RepulsiveSphereMoving           stiff, r0, rate, pos0 = origin, aux[0] = r_ext, aux[1..3] = target, aux[4] = steps */
 typedef struct {
 	int type;      /* OXB_EXT_* */
 	int particle;  /* original index, or -1 = all particles */
@@ -169,6 +180,10 @@ int oxb_set_dt(oxb_ctx *ctx, double dt);
 int oxb_set_thermostat(oxb_ctx *ctx, int type, int every, double a, double b, double c, double d, unsigned long long seed);
 /* MD_CUDABackend::_apply_external_forces_changes (src/CUDA/Backends/MD_CUDABackend.cu:108-229) */
 int oxb_set_ext_forces(oxb_ctx *ctx, int n, const oxb_ext_force *forces);
+/* particle-index lists (original indices) referenced by OXB_EXT_COM entries: COMForce::_com_list / _ref_list
+ * (src/Forces/COMForce.cpp:31-44; the reference uploads them per force, src/CUDA/Forces/forces_defs.cuh:367-393).  Call before
+ * oxb_set_ext_forces. */
+int oxb_set_ext_index_pool(oxb_ctx *ctx, int n, const int *indices);
 
 /* ---- state marshalling.  Replaces apply_changes_to_simulation_data / apply_simulation_data_changes
  * (src/CUDA/Backends/MD_CUDABackend.cu:231-394).  pos, a1, a3, vel, L: N x 3 doubles, original order. */

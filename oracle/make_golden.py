@@ -168,17 +168,17 @@ def rna_lattice_case(name, n_duplex, steps, T="300K", salt=0.5, seed=3, nve_step
           "terms/N", np.round(base["energy_split"] / len(st0["pos"]), 4))
 
 
-from oracle.fixtures import ext2_forces  # noqa: E402
+from oracle.fixtures import ext2_forces, ext3_forces  # noqa: E402
 
 
-def ext2_case():
+def ext2_case(name="lattice8_ext2", force_list=ext2_forces):
     """lattice8 state + forces file with the further force types, evaluated and stepped by the reference CPU backend"""
     g = dict(np.load(os.path.join(GOLD, "lattice8.npz")))
     d = tempfile.mkdtemp()
     top, conf = os.path.join(d, "l.top"), os.path.join(d, "l.dat")
     oio.write_topology(top, g["btype"], g["n3"], g["n5"], g["strand"])
     oio.write_conf(conf, g["box"], g["pos"], g["a1"], g["a3"], g["vel"], g["L"])
-    ext = ext2_forces(g["pos"])
+    ext = force_list(g["pos"])
     fpath = os.path.join(d, "forces.txt")
     with open(fpath, "w") as f:
         for e in ext:
@@ -201,9 +201,9 @@ def ext2_case():
     st1 = r.state()
     base.update(nve_steps=n, pos1=st1["pos"], a11=st1["a1"], vel1=st1["vel"], L1=st1["L"])
     r.close()
-    np.savez_compressed(os.path.join(GOLD, "lattice8_ext2.npz"), **base)
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **base)
     dF = np.abs(base["force"] - base["force_noext"])
-    print("wrote lattice8_ext2: particles feeling an external force:", int((dF.max(axis=1) > 1e-12).sum()), "max |dF|", dF.max())
+    print("wrote", name, ": particles feeling an external force:", int((dF.max(axis=1) > 1e-12).sum()), "max |dF|", dF.max())
 
 
 def rna():
@@ -222,6 +222,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "ext2":
         ext2_case()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "ext3":
+        ext2_case("lattice8_ext3", ext3_forces)
         sys.exit(0)
     force_field()
     lattice_case("lattice8", 8, 10.0, 3000)

@@ -83,15 +83,32 @@ class ExtForce(C.Structure):
         (n, C.c_double) for n in "stiff r0 rate stiff_rate F0".split()] + [("dir", C.c_double * 3), ("pos0", C.c_double * 3),
                                                                               ("aux", C.c_double * 8), ("iaux", C.c_int)]
 
-EXT_TYPES = {"string": 0, "trap": 1, "mutual_trap": 2, "lowdim_trap": 3, "repulsion_plane": 4, "attraction_plane": 5, "sphere": 6, "LJ_wall": 7, "twist": 8, "sphere_smooth": 9, "ellipsoid": 10}
+EXT_TYPES = {"string": 0, "trap": 1, "mutual_trap": 2, "lowdim_trap": 3, "repulsion_plane": 4, "attraction_plane": 5, "sphere": 6, "LJ_wall": 7, "twist": 8, "sphere_smooth": 9, "ellipsoid": 10, "repulsion_plane_moving": 11, "generic_central_force": 12, "LJ_cone": 13, "com": 14, "yukawa_sphere": 15, "repulsive_sphere_moving": 16}
 
 
-def fill_ext_entry(e, d):
+def _index_list(v):
+    """particle lists of the forces file: an int, a sequence, or the reference's "a,b,c" / "a-b" strings (Utils::get_particles_from_string)"""
+    if isinstance(v, (int, np.integer)):
+        return [int(v)]
+    if isinstance(v, str):
+        out = []
+        for tok in v.split(","):
+            tok = tok.strip()
+            if "-" in tok[1:]:
+                a, b = tok.split("-")
+                out.extend(range(int(a), int(b) + 1))
+            else:
+                out.append(int(tok))
+        return out
+    return [int(x) for x in v]
+
+
+def fill_ext_entry(e, d, pool):
     """dict with the reference's external-force keys (docs/source/forces.md) -> one table entry (oxb_ext_force / oxo_ext_force)"""
     e.type = EXT_TYPES[d["type"]]
     part = d.get("particle", -1)
     e.particle = -1 if str(part) in ("-1", "all") else int(part)
-    e.ref = int(d.get("ref_particle", -1))
+    e.ref = int(d.get("ref_particle", -1)) if d["type"] != "repulsion_plane_moving" else -1
     e.pbc = int(d.get("PBC", 0))
     e.stiff, e.r0, e.rate = float(d.get("stiff", 1.0 if d["type"] == "LJ_wall" else 0.0)), float(d.get("r0", 0.0)), float(d.get("rate", 0.0))
     e.stiff_rate, e.F0 = float(d.get("stiff_rate", 0.0)), float(d.get("F0", 0.0))
@@ -129,6 +146,41 @@ def fill_ext_entry(e, d):
     elif d["type"] == "ellipsoid":
         aux[0:3] = [float(x) for x in d["r_2"]]
         aux[3:6] = [float(x) for x in d.get("r_1", (1e-6, 1e-6, 1e-6))]
+    elif d["type"] == "repulsion_plane_moving":
+        refs = sorted(_index_list(d["ref_particle"]))
+        if refs[-1] - refs[0] + 1 != len(refs):
+            raise ValueError("RepulsionPlaneMoving requires the list of ref_particle indices to be contiguous")
+        e.ref, e.iaux = refs[0], refs[-1]
+    elif d["type"] == "generic_central_force":
+        if d.get("force_type", "gravity") != "gravity":
+            raise ValueError("only force_type = gravity runs on the device (as in the reference's CUDA backend)")
+        aux[0], aux[1] = float(d.get("inner_cut_off", 0.0)) ** 2, float(d.get("outer_cut_off", 0.0)) ** 2
+    elif d["type"] == "LJ_cone":
+        n = int(d.get("n", 6))
+        e.stiff = float(d.get("stiff", 1.0))
+        aux[0], aux[2] = float(d.get("sigma", 1.0)), float(d["alpha"])
+        aux[1] = 2.0 ** (1.0 / n) if int(d.get("only_repulsive", 0)) else 1e6
+        e.iaux = n
+    elif d["type"] == "com":
+        com, ref = _index_list(d["com_list"]), _index_list(d["ref_list"])
+        # COMForce keeps std::set<BaseParticle *> lists: duplicates collapse
+        com, ref = sorted(set(com)), sorted(set(ref))
+        e.particle, e.ref, e.iaux, e.pbc = -1, len(pool), len(com), len(ref)
+        pool.extend(com + ref)
+    elif d["type"] == "yukawa_sphere":
+        # YukawaSphere.cpp:22-25 reads WCA_n into sigma (sic); the exponent stays at its default of 6
+        sigma = float(d.get("WCA_n", d.get("WCA_sigma", 1.0)))
+        e.r0, e.stiff, e.iaux = float(d["radius"]), float(d.get("WCA_epsilon", 1.0)), 6
+        aux[0], aux[1] = sigma, sigma * 2.0 ** (1.0 / 6)
+        aux[2], aux[3] = float(d["debye_length"]), float(d["debye_A"])
+        aux[4] = float(d.get("cutoff", 4.0 * aux[2]))
+    elif d["type"] == "repulsive_sphere_moving":
+        org = d.get("origin", d.get("center", (0.0, 0.0, 0.0)))
+        for c in range(3):
+            e.pos0[c] = float(org[c])
+        aux[0] = float(d.get("r_ext", 1e10))
+        aux[1:4] = [float(x) for x in d.get("target", (0.0, 0.0, 0.0))]
+        aux[4] = float(int(float(d.get("steps", d.get("move_steps", 0)))))
     for c in range(8):
         e.aux[c] = aux[c]
 
@@ -250,10 +302,18 @@ def forces(P, pos, axes, btype, n3, n5, box, pairs):
     return dict(force=f, torque_lab=tl, torque_body=tb, eterms=et, epart=ep, U=et.sum())
 
 
+_pool_keep = None
+
+
 def make_ext(forces_list):
+    """table entries; the index pool of the COM forces is handed to the library here (kept alive at module level)"""
+    global _pool_keep
     arr = (ExtForce * max(len(forces_list), 1))()
+    pool = []
     for k, d in enumerate(forces_list):
-        fill_ext_entry(arr[k], d)
+        fill_ext_entry(arr[k], d, pool)
+    _pool_keep = (C.c_int * max(len(pool), 1))(*pool)
+    lib().oxo_set_ext_pool(_pool_keep)
     return arr
 
 

@@ -694,9 +694,113 @@ static void ext_one(const oxo_ext_force *f, const double *pos, int p, const doub
 	}
 }
 
+/* further single-particle types */
+static void ext_more(const oxo_ext_force *f, const double *pos, int p, const double *box, long long step, double *force) {
+	const double *pp = pos + 3 * (size_t) p;
+	double *F = force + 3 * (size_t) p;
+	if(f->type == OXO_EXT_REPULSION_PLANE_MOVING) {
+		/* src/Forces/RepulsionPlaneMoving.cpp:58-66 */
+		for(int idx = f->ref; idx <= f->iaux; idx++) {
+			const double *qq = pos + 3 * (size_t) idx;
+			double d = (pp[0] - qq[0]) * f->dir[0] + (pp[1] - qq[1]) * f->dir[1] + (pp[2] - qq[2]) * f->dir[2];
+			axpy3(-f->stiff * (d < 0. ? d : 0.), f->dir, F);
+		}
+	}
+	else if(f->type == OXO_EXT_GENERIC_CENTRAL) {
+		/* src/Forces/GenericCentralForce.cpp:174-193, gravity */
+		double d[3] = { f->pos0[0] - pp[0], f->pos0[1] - pp[1], f->pos0[2] - pp[2] };
+		double d2 = dot3(d, d);
+		if(d2 < f->aux[0]) return;
+		if(f->aux[1] > 0. && d2 > f->aux[1]) return;
+		axpy3(f->F0 / sqrt(d2), d, F);
+	}
+	else if(f->type == OXO_EXT_LJ_CONE) {
+		/* src/Forces/LJCone.cpp:69-92 */
+		double sigma = f->aux[0], cutoff = f->aux[1], alpha = f->aux[2];
+		double va[3] = { pp[0] - f->pos0[0], pp[1] - f->pos0[1], pp[2] - f->pos0[2] };
+		double d_along = dot3(va, f->dir);
+		double vfa[3] = { f->dir[0] * d_along - va[0], f->dir[1] * d_along - va[1], f->dir[2] * d_along - va[2] };
+		double d_from_axis = sqrt(dot3(vfa, vfa));
+		double d_from_cone = d_along * sin(alpha) - d_from_axis * cos(alpha);
+		double rel = d_from_cone / sigma;
+		if(rel > cutoff) return;
+		double C = d_from_axis * tan(alpha);
+		double nrm[3] = { (d_along + C) * f->dir[0] - va[0], (d_along + C) * f->dir[1] - va[1], (d_along + C) * f->dir[2] - va[2] };
+		double nn = sqrt(dot3(nrm, nrm));
+		double lj = pow(rel, -f->iaux);
+		axpy3(4 * f->iaux * f->stiff * (2 * SQ(lj) - lj) / d_from_cone / nn, nrm, F);
+	}
+	else if(f->type == OXO_EXT_YUKAWA_SPHERE) {
+		/* src/Forces/YukawaSphere.cpp:53-74 */
+		double d[3];
+		min_image(box, f->pos0, pp, d);
+		double m = sqrt(dot3(d, d)), ds = f->r0 - m;
+		if(ds < f->aux[4]) {
+			double s = (f->aux[3] * exp(-ds / f->aux[2])) * (1.0 / (ds * f->aux[2]) + 1.0 / SQ(ds));
+			if(ds < f->aux[1]) {
+				double w = pow(f->aux[0] / ds, 6);
+				s += 4 * f->stiff * f->iaux * (2 * SQ(w) - w) / ds;
+			}
+			axpy3(-s / m, d, F);
+		}
+	}
+	else if(f->type == OXO_EXT_SPHERE_MOVING) {
+		/* src/Forces/RepulsiveSphereMoving.cpp:85-131 */
+		double c[3] = { f->pos0[0], f->pos0[1], f->pos0[2] };
+		if(f->aux[4] > 0.) {
+			double t = (double) step / (double) (long long) f->aux[4];
+			t = t < 0. ? 0. : (t > 1. ? 1. : t);
+			for(int k = 0; k < 3; k++) c[k] = f->pos0[k] + (f->aux[1 + k] - f->pos0[k]) * t;
+		}
+		double d[3];
+		min_image(box, c, pp, d);
+		double m = sqrt(dot3(d, d)), r = m - (f->r0 + f->rate * (double) step);
+		if(r >= f->aux[0] || m <= 0. || r >= pow(2.0, 0.5)) return;
+		double rs = r > 1e-9 ? r : 1e-9;
+		double A = pow(1. / rs, 2);
+		double dUdr = 4.0 * f->stiff * (2.0 * A - 1.0) * (-(2. / rs) * A);
+		axpy3(-dUdr / m, d, F);
+	}
+}
+
+static const int *ext_pool = NULL;
+/* COMForce::_compute_coms caches both centres of mass by step index (COMForce.cpp:48-62, _last_step = -1 initially), so the force
+ * evaluation of the first MD step -- same step index as the one done at initialisation -- sees the centres of mass of the initial
+ * configuration.  Reproduced here (cache keyed by table position, cleared by oxo_set_ext_pool); the reference's CUDA kernel and ours
+ * recompute the sums at every evaluation (CUDA_MD.cuh:441-468). */
+#define OXO_MAX_COM 64
+static struct { long long last_step; double com[3], ref[3]; } com_cache[OXO_MAX_COM];
+/* index lists of the COM forces (COMForce::_com_list, _ref_list) */
+void oxo_set_ext_pool(const int *pool) {
+	ext_pool = pool;
+	for(int k = 0; k < OXO_MAX_COM; k++) com_cache[k].last_step = -1;
+}
+
+static void ext_com(const oxo_ext_force *f, int slot, const double *pos, long long step, double *force) {
+	/* src/Forces/COMForce.cpp:46-71: every particle of com_list feels the spring between the two centres of mass / n_com */
+	const int *cl = ext_pool + f->ref, *rl = cl + f->iaux;
+	double *com = com_cache[slot % OXO_MAX_COM].com, *ref = com_cache[slot % OXO_MAX_COM].ref, d[3];
+	if(step != com_cache[slot % OXO_MAX_COM].last_step) {
+		for(int k = 0; k < 3; k++) com[k] = ref[k] = 0.;
+		for(int k = 0; k < f->iaux; k++) axpy3(1., pos + 3 * (size_t) cl[k], com);
+		for(int k = 0; k < f->pbc; k++) axpy3(1., pos + 3 * (size_t) rl[k], ref);
+		for(int k = 0; k < 3; k++) { com[k] /= f->iaux; ref[k] /= f->pbc; }
+		com_cache[slot % OXO_MAX_COM].last_step = step;
+	}
+	for(int k = 0; k < 3; k++) d[k] = ref[k] - com[k];
+	double m = sqrt(dot3(d, d));
+	double s = (m - (f->r0 + f->rate * step)) * f->stiff / f->iaux;
+	for(int k = 0; k < f->iaux; k++) axpy3(s / m, d, force + 3 * (size_t) cl[k]);
+}
+
 void oxo_ext_forces(int nf, const oxo_ext_force *ef, int N, const double *pos, const double *box, long long step, double *force) {
 	for(int i = 0; i < nf; i++) {
-		if(ef[i].particle >= 0) ext_one(&ef[i], pos, ef[i].particle, box, step, force);
+		if(ef[i].type == OXO_EXT_COM) ext_com(&ef[i], i, pos, step, force);
+		else if(ef[i].type > OXO_EXT_ELLIPSOID) {
+			if(ef[i].particle >= 0) ext_more(&ef[i], pos, ef[i].particle, box, step, force);
+			else for(int p = 0; p < N; p++) ext_more(&ef[i], pos, p, box, step, force);
+		}
+		else if(ef[i].particle >= 0) ext_one(&ef[i], pos, ef[i].particle, box, step, force);
 		else for(int p = 0; p < N; p++) ext_one(&ef[i], pos, p, box, step, force);
 	}
 }

@@ -99,7 +99,10 @@ struct oxb_ctx {
 	ThermostatCfg th;
 	bool bussi_init = false;
 	int n_ext = 0, n_ext_all = 0; // entries bound to one particle / entries acting on every particle
-	DevExtForce *ext = nullptr, *ext_all = nullptr;
+	DevExtForce *ext = nullptr, *ext_all = nullptr, *ext_com = nullptr;
+	int n_ext_com = 0;           // COM forces (one entry per force, evaluated by one block each)
+	int *ext_pool = nullptr;     // com_list / ref_list original indices of the COM forces
+	std::vector<int> ext_pool_h;
 	double avg_interval = 8.;
 
 	// concurrency inside one force pass (independent kernels on forked streams) and graph-captured batches of steps
@@ -380,7 +383,11 @@ int launch_forces(oxb_ctx *c, int hw, bool clear, long long step) {
 			c->launches += 1;
 		}
 		if(c->n_ext_all > 0) {
-			oxb::launch_ext_forces_all(c->aux[1], c->N, c->n_ext_all, c->ext_all, c->ipos[a], c->posd[a], c->boxf, step, c->cur_step, c->F[a], c->flags, hw);
+			oxb::launch_ext_forces_all(c->aux[1], c->N, c->n_ext_all, c->ext_all, c->slot_of, c->ipos[a], c->posd[a], c->boxf, step, c->cur_step, c->F[a], c->flags, hw);
+			c->launches += 1;
+		}
+		if(c->n_ext_com > 0) {
+			oxb::launch_ext_com(c->aux[1], c->n_ext_com, c->ext_com, c->ext_pool, c->slot_of, c->posd[a], step, c->cur_step, c->F[a], c->flags, hw);
 			c->launches += 1;
 		}
 		CU(cudaStreamWaitEvent(c->aux[1], c->ev_near, 0));
@@ -400,7 +407,11 @@ int launch_forces(oxb_ctx *c, int hw, bool clear, long long step) {
 			c->launches += 1;
 		}
 		if(c->n_ext_all > 0) {
-			oxb::launch_ext_forces_all(m, c->N, c->n_ext_all, c->ext_all, c->ipos[a], c->posd[a], c->boxf, step, c->cur_step, c->F[a], c->flags, hw);
+			oxb::launch_ext_forces_all(m, c->N, c->n_ext_all, c->ext_all, c->slot_of, c->ipos[a], c->posd[a], c->boxf, step, c->cur_step, c->F[a], c->flags, hw);
+			c->launches += 1;
+		}
+		if(c->n_ext_com > 0) {
+			oxb::launch_ext_com(m, c->n_ext_com, c->ext_com, c->ext_pool, c->slot_of, c->posd[a], step, c->cur_step, c->F[a], c->flags, hw);
 			c->launches += 1;
 		}
 	}
@@ -550,7 +561,7 @@ int batch_graph(oxb_ctx *c, int units, cudaGraphExec_t *out) {
 // stream launches.
 int launch_full_units(oxb_ctx *c, long long n, long long step0, int &epoch) {
 	const bool graphable = c->use_graphs && c->th.type != OXB_THERMOSTAT_BUSSI;
-	const int per_unit = (c->use_edge ? 5 : 1) + (c->n_ext > 0 ? 1 : 0) + (c->n_ext_all > 0 ? 1 : 0) + 1;
+	const int per_unit = (c->use_edge ? 5 : 1) + (c->n_ext > 0 ? 1 : 0) + (c->n_ext_all > 0 ? 1 : 0) + (c->n_ext_com > 0 ? 1 : 0) + 1;
 	long long k = 0;
 	while(k < n) {
 		int chunk = 0;
@@ -653,7 +664,7 @@ void oxb_destroy(oxb_ctx *c) {
 		cudaFree(c->quat[k]); cudaFree(c->F[k]); cudaFree(c->T[k]); cudaFree(c->bonds[k]); cudaFree(c->iback[k]); cudaFree(c->list_iback[k]); cudaFree(c->list_ibase[k]);
 	}
 	cudaFree(c->Fb);
-	cudaFree(c->slot_of); cudaFree(c->flags); cudaFree(c->sums); cudaFree(c->d_energy); cudaFree(c->ext); cudaFree(c->ext_all); cudaFree(c->pos_f4);
+	cudaFree(c->slot_of); cudaFree(c->flags); cudaFree(c->sums); cudaFree(c->d_energy); cudaFree(c->ext); cudaFree(c->ext_all); cudaFree(c->ext_com); cudaFree(c->ext_pool); cudaFree(c->pos_f4);
 	cudaFree(c->hkeys); cudaFree(c->hkeys_sorted); cudaFree(c->hvals); cudaFree(c->hvals_sorted); cudaFree(c->hinv);
 	free_lists(c);
 	if(c->h_flags) cudaFreeHost(c->h_flags);
@@ -766,13 +777,22 @@ int oxb_set_thermostat(oxb_ctx *c, int type, int every, double a, double b, doub
 
 int oxb_set_ext_forces(oxb_ctx *c, int n, const oxb_ext_force *f) {
 	if(c == nullptr || n < 0 || (n > 0 && f == nullptr)) return 1;
-	std::vector<DevExtForce> h, hall;
+	std::vector<DevExtForce> h, hall, hcom;
 	for(int k = 0; k < n; k++) {
 		if(f[k].type < OXB_EXT_STRING || f[k].type >= OXB_EXT_NTYPES) return fail(c, 1, "external force %d: unsupported type %d", k, f[k].type);
 		if(f[k].particle < -1 || f[k].particle >= c->N) return fail(c, 1, "external force %d: invalid particle %d", k, f[k].particle);
 		if(f[k].type == OXB_EXT_MUTUAL_TRAP && (f[k].ref < 0 || f[k].ref >= c->N)) return fail(c, 1, "Invalid reference particle %d for Mutual Trap", f[k].ref);
 		if(f[k].type == OXB_EXT_MUTUAL_TRAP && f[k].particle < 0) return fail(c, 1, "external force %d: a mutual trap needs one particle", k);
 		if(f[k].type == OXB_EXT_LJ_WALL && (f[k].iaux % 2 != 0 || f[k].iaux <= 0)) return fail(c, 1, "LJWall: n (%d) should be an even integer. Aborting", f[k].iaux);
+		if(f[k].type == OXB_EXT_LJ_CONE && (f[k].iaux % 2 != 0 || f[k].iaux <= 0)) return fail(c, 1, "RepulsiveCone: n (%d) should be an even integer. Aborting", f[k].iaux);
+		if(f[k].type == OXB_EXT_REPULSION_PLANE_MOVING && (f[k].ref < 0 || f[k].iaux < f[k].ref || f[k].iaux >= c->N))
+			return fail(c, 1, "RepulsionPlaneMoving requires the list of ref_particle indices to be contiguous (got %d..%d)", f[k].ref, f[k].iaux);
+		if(f[k].type == OXB_EXT_COM) {
+			const long long lo = f[k].ref, n_com = f[k].iaux, n_ref = f[k].pbc;
+			if(lo < 0 || n_com < 1 || n_ref < 1 || lo + n_com + n_ref > (long long) c->ext_pool_h.size())
+				return fail(c, 1, "external force %d: COM force index lists [%lld, +%lld, +%lld) outside the index pool (%zu entries; call oxb_set_ext_index_pool first)",
+						k, lo, n_com, n_ref, c->ext_pool_h.size());
+		}
 		DevExtForce d;
 		std::memset(&d, 0, sizeof(d));
 		d.type = f[k].type; d.particle = f[k].particle; d.ref = f[k].ref < 0 ? 0 : f[k].ref; d.pbc = f[k].pbc;
@@ -784,11 +804,18 @@ int oxb_set_ext_forces(oxb_ctx *c, int n, const oxb_ext_force *f) {
 		}
 		for(int x = 0; x < 8; x++) d.aux[x] = (float) f[k].aux[x];
 		d.iaux = f[k].iaux;
+		if(f[k].type == OXB_EXT_LJ_CONE) { d.aux[3] = (float) std::sin(f[k].aux[2]); d.aux[4] = (float) std::cos(f[k].aux[2]); d.aux[5] = (float) std::tan(f[k].aux[2]); }
+		if(f[k].type == OXB_EXT_SPHERE_MOVING) d.daux = f[k].aux[4];
+		if(f[k].type == OXB_EXT_COM) { d.ref = f[k].ref; hcom.push_back(d); continue; }
 		(f[k].particle < 0 ? hall : h).push_back(d);
 	}
 	cudaFree(c->ext);
 	cudaFree(c->ext_all);
-	c->ext = c->ext_all = nullptr;
+	cudaFree(c->ext_com);
+	c->ext = c->ext_all = c->ext_com = nullptr;
+	CU(dalloc(&c->ext_com, std::max<size_t>(hcom.size(), 1)));
+	if(!hcom.empty()) CU(cudaMemcpy(c->ext_com, hcom.data(), sizeof(DevExtForce) * hcom.size(), cudaMemcpyHostToDevice));
+	c->n_ext_com = (int) hcom.size();
 	CU(dalloc(&c->ext, std::max<size_t>(h.size(), 1)));
 	CU(dalloc(&c->ext_all, std::max<size_t>(hall.size(), 1)));
 	if(!h.empty()) CU(cudaMemcpy(c->ext, h.data(), sizeof(DevExtForce) * h.size(), cudaMemcpyHostToDevice));
@@ -797,6 +824,18 @@ int oxb_set_ext_forces(oxb_ctx *c, int n, const oxb_ext_force *f) {
 	c->n_ext_all = (int) hall.size();
 	c->forces_valid = false;
 	drop_graphs(c);
+	return 0;
+}
+
+int oxb_set_ext_index_pool(oxb_ctx *c, int n, const int *idx) {
+	if(c == nullptr || n < 0 || (n > 0 && idx == nullptr)) return 1;
+	for(int k = 0; k < n; k++) if(idx[k] < 0 || idx[k] >= c->N) return fail(c, 1, "external-force index pool: invalid particle %d", idx[k]);
+	if(c->n_ext_com > 0) return fail(c, 1, "the index pool cannot change while COM forces that refer to it are set");
+	c->ext_pool_h.assign(idx, idx + n);
+	cudaFree(c->ext_pool);
+	c->ext_pool = nullptr;
+	CU(dalloc(&c->ext_pool, std::max<size_t>((size_t) n, 1)));
+	if(n > 0) CU(cudaMemcpy(c->ext_pool, idx, sizeof(int) * (size_t) n, cudaMemcpyHostToDevice));
 	return 0;
 }
 
@@ -924,7 +963,7 @@ int oxb_write_conf(oxb_ctx *c, const char *path, int append, int print_momenta) 
 int oxb_set_step(oxb_ctx *c, long long step) {
 	if(c == nullptr) return 1;
 	c->step = step;
-	c->forces_valid = c->forces_valid && (c->n_ext == 0) && (c->n_ext_all == 0);
+	c->forces_valid = c->forces_valid && (c->n_ext == 0) && (c->n_ext_all == 0) && (c->n_ext_com == 0);
 	return 0;
 }
 

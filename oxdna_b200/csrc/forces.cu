@@ -395,7 +395,8 @@ __global__ void __launch_bounds__(128) k_energy_split(const __grid_constant__ ty
 // Hilbert re-sort needs no table rewrite (the reference forbids sort + external forces, MD_CUDABackend.cu:110-112).
 // ------------------------------------------------------------------------------------------------------------
 // force of a single-particle entry on a particle at absolute position p (double, unwrapped: what the reference's CPU classes see)
-__device__ __forceinline__ v3 ext_single(const DevExtForce &e, double4 p, int4 ip, BoxF box, long long step) {
+__device__ __forceinline__ v3 ext_single(const DevExtForce &e, double4 p, int4 ip, BoxF box, long long step, const int *__restrict__ slot_of,
+		const double4 *__restrict__ posd) {
 	const float st = (float) step;
 	switch(e.type) {
 	case OXB_EXT_STRING: {
@@ -483,7 +484,109 @@ __device__ __forceinline__ v3 ext_single(const DevExtForce &e, double4 p, int4 i
 		if(in < 1.f && out > 1.f) return mk3(0.f, 0.f, 0.f);
 		return d * (-e.stiff / m);
 	}
+	case OXB_EXT_REPULSION_PLANE_MOVING: {
+		// RepulsionPlaneMoving.cpp:58-66: one plane through every particle of the contiguous ref range (absolute positions)
+		v3 f = mk3(0.f, 0.f, 0.f);
+		for(int idx = e.ref; idx <= e.iaux; idx++) {
+			double4 q = posd[slot_of[idx]];
+			float d = (float) ((p.x - q.x) * (double) e.dir[0] + (p.y - q.y) * (double) e.dir[1] + (p.z - q.z) * (double) e.dir[2]);
+			if(d < 0.f) {
+				float s = -e.stiff * d;
+				f += mk3(e.dir[0] * s, e.dir[1] * s, e.dir[2] * s);
+			}
+		}
+		return f;
+	}
+	case OXB_EXT_GENERIC_CENTRAL: {
+		// GenericCentralForce.cpp:174-193, force_type = gravity
+		v3 d = mk3((float) (e.pos0[0] - p.x), (float) (e.pos0[1] - p.y), (float) (e.pos0[2] - p.z));
+		float d2 = dot(d, d);
+		if(d2 < e.aux[0] || (e.aux[1] > 0.f && d2 > e.aux[1])) return mk3(0.f, 0.f, 0.f);
+		return d * (e.F0 * rsqrtf(d2));
+	}
+	case OXB_EXT_LJ_CONE: {
+		// LJCone.cpp:69-92; aux[3..5] = sin, cos, tan of the half-opening angle
+		v3 dir = mk3(e.dir[0], e.dir[1], e.dir[2]);
+		v3 va = mk3((float) (p.x - e.pos0[0]), (float) (p.y - e.pos0[1]), (float) (p.z - e.pos0[2]));
+		float d_along = dot(va, dir);
+		v3 v_from_axis = dir * d_along - va;
+		float d_from_axis = sqrtf(dot(v_from_axis, v_from_axis));
+		float d_from_cone = d_along * e.aux[3] - d_from_axis * e.aux[4];
+		float rel = d_from_cone / e.aux[0];
+		if(rel > e.aux[1]) return mk3(0.f, 0.f, 0.f);
+		v3 normal = dir * (d_along + d_from_axis * e.aux[5]) - va;
+		normal = normal * rsqrtf(dot(normal, normal));
+		float lj = powf(rel, -(float) e.iaux);
+		return normal * (4.f * (float) e.iaux * e.stiff * (2.f * lj * lj - lj) / d_from_cone);
+	}
+	case OXB_EXT_YUKAWA_SPHERE:
+	case OXB_EXT_SPHERE_MOVING: {
+		double cx = e.pos0[0], cy = e.pos0[1], cz = e.pos0[2];
+		if(e.type == OXB_EXT_SPHERE_MOVING && e.daux > 0.) {
+			// RepulsiveSphereMoving.cpp:85-91: centre interpolated origin -> target over `steps` MD steps
+			double t = (double) step / e.daux;
+			t = t < 0. ? 0. : (t > 1. ? 1. : t);
+			cx += ((double) e.aux[1] - cx) * t; cy += ((double) e.aux[2] - cy) * t; cz += ((double) e.aux[3] - cz) * t;
+		}
+		int4 ic;
+		ic.x = (int) to_fixed(cx, 1. / (double) box.lx); ic.y = (int) to_fixed(cy, 1. / (double) box.ly); ic.z = (int) to_fixed(cz, 1. / (double) box.lz);
+		v3 d = min_image_fixed(box, ic, ip);
+		float m = sqrtf(dot(d, d));
+		if(e.type == OXB_EXT_YUKAWA_SPHERE) {
+			// YukawaSphere.cpp:53-74 (the WCA exponent is 6 whatever WCA_n says, as there)
+			float ds = e.r0 - m;
+			if(!(ds < e.aux[4])) return mk3(0.f, 0.f, 0.f);
+			float s = e.aux[3] * expf(-ds / e.aux[2]) * (1.f / (ds * e.aux[2]) + 1.f / (ds * ds));
+			if(ds < e.aux[1]) {
+				float w = e.aux[0] / ds;
+				w = w * w * w; w = w * w;
+				s += 4.f * e.stiff * (float) e.iaux * (2.f * w * w - w) / ds;
+			}
+			return d * (-s / m);
+		}
+		// RepulsiveSphereMoving.cpp:94-131: WCA (x = 2, sigma = 1, epsilon = stiff) in the surface gap r = |d| - radius
+		float r = m - (e.r0 + e.rate * st);
+		if(r >= e.aux[0] || m <= 0.f || r >= 1.41421356237f) return mk3(0.f, 0.f, 0.f);
+		float rs = fmaxf(r, 1e-9f);
+		float A = 1.f / (rs * rs);
+		float fmag = 4.f * e.stiff * (2.f * A - 1.f) * (2.f / rs) * A;
+		return d * (fmag / m);
+	}
 	default: return mk3(0.f, 0.f, 0.f);
+	}
+}
+
+// COMForce.cpp:46-71: one block per force; centres of mass of com_list and ref_list from the absolute positions, then the
+// spring force shared equally among the com_list particles (the reference recomputes both sums in every thread,
+// CUDA_MD.cuh:441-468).  The ref_list particles feel nothing, as there.
+__global__ void k_ext_com(int n, const DevExtForce *__restrict__ ef, const int *__restrict__ pool, const int *__restrict__ slot_of,
+		const double4 *__restrict__ posd, long long step, const long long *__restrict__ cur_step, float4 *__restrict__ F, const int *__restrict__ flags, int hw) {
+	if(flags[hw]) return;
+	if(step < 0) step = cur_step[hw & 1];
+	__shared__ double sh[6][4];
+	const DevExtForce e = ef[blockIdx.x];
+	const int n_com = e.iaux, n_ref = e.pbc;
+	double acc[6] = { 0., 0., 0., 0., 0., 0. };
+	for(int k = threadIdx.x; k < n_com + n_ref; k += blockDim.x) {
+		double4 q = posd[slot_of[pool[e.ref + k]]];
+		int o = k < n_com ? 0 : 3;
+		acc[o] += q.x; acc[o + 1] += q.y; acc[o + 2] += q.z;
+	}
+	for(int c = 0; c < 6; c++) {
+		double x = acc[c];
+		for(int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+		if((threadIdx.x & 31) == 0) sh[c][threadIdx.x >> 5] = x;
+	}
+	__syncthreads();
+	double d[3];
+	for(int c = 0; c < 3; c++) d[c] = (sh[3 + c][0] + sh[3 + c][1] + sh[3 + c][2] + sh[3 + c][3]) / n_ref - (sh[c][0] + sh[c][1] + sh[c][2] + sh[c][3]) / n_com;
+	double m = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+	double s = (m - ((double) e.r0 + (double) e.rate * (double) step)) * (double) e.stiff / n_com / m;
+	for(int k = threadIdx.x; k < n_com; k += blockDim.x) {
+		int i = slot_of[pool[e.ref + k]];
+		atomicAdd(&F[i].x, (float) (d[0] * s));
+		atomicAdd(&F[i].y, (float) (d[1] * s));
+		atomicAdd(&F[i].z, (float) (d[2] * s));
 	}
 }
 
@@ -512,14 +615,14 @@ __global__ void k_ext_forces(int n, const DevExtForce *__restrict__ ef, const in
 		float s = (m - (e.r0 + e.rate * st)) * (e.stiff + e.stiff_rate * st) / m;
 		f = dr * s;
 	}
-	else f = ext_single(e, posd[i], ipos[i], box, step);
+	else f = ext_single(e, posd[i], ipos[i], box, step, slot_of, posd);
 	atomicAdd(&F[i].x, f.x);
 	atomicAdd(&F[i].y, f.y);
 	atomicAdd(&F[i].z, f.z);
 }
 
-__global__ void k_ext_forces_all(int N, int n_all, const DevExtForce *__restrict__ ef, const int4 *__restrict__ ipos, const double4 *__restrict__ posd,
-		BoxF box, long long step, const long long *__restrict__ cur_step, float4 *__restrict__ F, const int *__restrict__ flags, int hw) {
+__global__ void k_ext_forces_all(int N, int n_all, const DevExtForce *__restrict__ ef, const int *__restrict__ slot_of, const int4 *__restrict__ ipos,
+		const double4 *__restrict__ posd, BoxF box, long long step, const long long *__restrict__ cur_step, float4 *__restrict__ F, const int *__restrict__ flags, int hw) {
 	if(flags[hw]) return;
 	if(step < 0) step = cur_step[hw & 1];
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -527,7 +630,7 @@ __global__ void k_ext_forces_all(int N, int n_all, const DevExtForce *__restrict
 	double4 p = posd[i];
 	int4 ip = ipos[i];
 	v3 f = mk3(0.f, 0.f, 0.f);
-	for(int k = 0; k < n_all; k++) f += ext_single(ef[k], p, ip, box, step);
+	for(int k = 0; k < n_all; k++) f += ext_single(ef[k], p, ip, box, step, slot_of, posd);
 	// the interaction kernels add into F concurrently (other streams): atomics
 	atomicAdd(&F[i].x, f.x);
 	atomicAdd(&F[i].y, f.y);
@@ -586,11 +689,17 @@ void launch_ext_forces(cudaStream_t s, int n, const DevExtForce *ef, const int *
 	k_ext_forces<<<(n + tpb - 1) / tpb, tpb, 0, s>>>(n, ef, slot_of, ipos, posd, box, step, cur_step, F, flags, hw);
 }
 
-void launch_ext_forces_all(cudaStream_t s, int N, int n_all, const DevExtForce *ef_all, const int4 *ipos, const double4 *posd, BoxF box,
+void launch_ext_forces_all(cudaStream_t s, int N, int n_all, const DevExtForce *ef_all, const int *slot_of, const int4 *ipos, const double4 *posd, BoxF box,
 		long long step, const long long *cur_step, float4 *F, const int *flags, int hw) {
 	if(n_all <= 0) return;
 	int tpb = 128;
-	k_ext_forces_all<<<(N + tpb - 1) / tpb, tpb, 0, s>>>(N, n_all, ef_all, ipos, posd, box, step, cur_step, F, flags, hw);
+	k_ext_forces_all<<<(N + tpb - 1) / tpb, tpb, 0, s>>>(N, n_all, ef_all, slot_of, ipos, posd, box, step, cur_step, F, flags, hw);
+}
+
+void launch_ext_com(cudaStream_t s, int n, const DevExtForce *ef_com, const int *pool, const int *slot_of, const double4 *posd, long long step,
+		const long long *cur_step, float4 *F, const int *flags, int hw) {
+	if(n <= 0) return;
+	k_ext_com<<<n, 128, 0, s>>>(n, ef_com, pool, slot_of, posd, step, cur_step, F, flags, hw);
 }
 
 } // namespace oxb

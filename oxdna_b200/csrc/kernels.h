@@ -25,6 +25,7 @@ struct DevExtForce {
 	double pos0[3];
 	float aux[8];
 	int iaux;
+	double daux; // SPHERE_MOVING: number of steps origin -> target
 };
 
 struct ThermostatCfg {
@@ -78,8 +79,11 @@ void launch_energy_split(cudaStream_t s, const ModelRef &M, BoxF box, int N, con
 void launch_ext_forces(cudaStream_t s, int n, const DevExtForce *ef, const int *slot_of, const int4 *ipos, const double4 *posd, BoxF box,
 		long long step, const long long *cur_step, float4 *F, const int *flags, int hw);
 // entries that act on every particle (particle = all): one thread per particle, no atomics
-void launch_ext_forces_all(cudaStream_t s, int N, int n_all, const DevExtForce *ef_all, const int4 *ipos, const double4 *posd, BoxF box,
+void launch_ext_forces_all(cudaStream_t s, int N, int n_all, const DevExtForce *ef_all, const int *slot_of, const int4 *ipos, const double4 *posd, BoxF box,
 		long long step, const long long *cur_step, float4 *F, const int *flags, int hw);
+// COM forces: one block per entry; `pool` holds the com_list / ref_list original indices
+void launch_ext_com(cudaStream_t s, int n, const DevExtForce *ef_com, const int *pool, const int *slot_of, const double4 *posd, long long step,
+		const long long *cur_step, float4 *F, const int *flags, int hw);
 
 // ---- integrate.cu
 struct IntegrateArgs {

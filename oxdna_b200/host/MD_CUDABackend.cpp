@@ -3,6 +3,12 @@
 #include "MD_CUDABackend.h"
 
 #include "Forces/AttractionPlane.h"
+#include "Forces/COMForce.h"
+#include "Forces/GenericCentralForce.h"
+#include "Forces/LJCone.h"
+#include "Forces/RepulsionPlaneMoving.h"
+#include "Forces/RepulsiveSphereMoving.h"
+#include "Forces/YukawaSphere.h"
 #include "Forces/ConstantRateTorque.h"
 #include "Forces/RepulsiveEllipsoid.h"
 #include "Forces/RepulsiveSphereSmooth.h"
@@ -183,6 +189,7 @@ void MD_CUDABackend::_gpu_to_host() {
 void MD_CUDABackend::_apply_external_forces_changes() {
 	if(!_external_forces) return;
 	std::vector<oxb_ext_force> table;
+	std::vector<int> pool; // com_list / ref_list indices of the COM forces
 	// a force given with `particle = all` is the same object attached to every particle: keep it as ONE table entry
 	// (particle = -1) instead of N copies (the reference keeps 15 union slots per particle)
 	std::map<BaseForce *, int> uses;
@@ -279,8 +286,62 @@ void MD_CUDABackend::_apply_external_forces_changes() {
 				e.aux[0] = ef->_r_2.x; e.aux[1] = ef->_r_2.y; e.aux[2] = ef->_r_2.z;
 				e.aux[3] = ef->_r_1.x; e.aux[4] = ef->_r_1.y; e.aux[5] = ef->_r_1.z;
 			}
+			else if(ft == typeid(RepulsionPlaneMoving)) {
+				RepulsionPlaneMoving *pf = static_cast<RepulsionPlaneMoving *>(f);
+				e.type = OXB_EXT_REPULSION_PLANE_MOVING;
+				e.stiff = pf->_stiff;
+				e.dir[0] = pf->_direction.x; e.dir[1] = pf->_direction.y; e.dir[2] = pf->_direction.z;
+				e.ref = pf->low_idx; e.iaux = pf->high_idx;
+			}
+			else if(ft == typeid(GenericCentralForce)) {
+				// as in the reference's CUDA backend (forces_defs.cuh:300-310) only the gravity flavour reaches the device:
+				// an `interpolated` force has F0 = 0 there as well
+				GenericCentralForce *gf = static_cast<GenericCentralForce *>(f);
+				e.type = OXB_EXT_GENERIC_CENTRAL;
+				e.F0 = gf->_F0;
+				e.pos0[0] = gf->center.x; e.pos0[1] = gf->center.y; e.pos0[2] = gf->center.z;
+				e.aux[0] = gf->inner_cut_off_sqr; e.aux[1] = gf->outer_cut_off_sqr;
+			}
+			else if(ft == typeid(LJCone)) {
+				LJCone *cf = static_cast<LJCone *>(f);
+				e.type = OXB_EXT_LJ_CONE;
+				e.stiff = cf->_stiff;
+				e.dir[0] = cf->_direction.x; e.dir[1] = cf->_direction.y; e.dir[2] = cf->_direction.z;
+				e.pos0[0] = cf->_pos0.x; e.pos0[1] = cf->_pos0.y; e.pos0[2] = cf->_pos0.z;
+				e.aux[0] = cf->_sigma; e.aux[1] = cf->_cutoff; e.aux[2] = cf->_alpha;
+				e.iaux = cf->_n;
+			}
+			else if(ft == typeid(COMForce)) {
+				// one table entry per force object (it is attached to every particle of its com_list)
+				if(emitted.count(f)) continue;
+				emitted.insert(f);
+				COMForce *cf = static_cast<COMForce *>(f);
+				single_particle_type = false;
+				e.type = OXB_EXT_COM;
+				e.particle = -1;
+				e.stiff = cf->_stiff; e.r0 = cf->_r0; e.rate = cf->_rate;
+				e.ref = (int) pool.size(); e.iaux = (int) cf->_com_list.size(); e.pbc = (int) cf->_ref_list.size();
+				for(auto q : cf->_com_list) pool.push_back(q->index);
+				for(auto q : cf->_ref_list) pool.push_back(q->index);
+			}
+			else if(ft == typeid(YukawaSphere)) {
+				YukawaSphere *yf = static_cast<YukawaSphere *>(f);
+				e.type = OXB_EXT_YUKAWA_SPHERE;
+				e.pos0[0] = yf->_center.x; e.pos0[1] = yf->_center.y; e.pos0[2] = yf->_center.z;
+				e.r0 = yf->_radius; e.stiff = yf->_epsilon;
+				e.aux[0] = yf->_sigma; e.aux[1] = yf->_WCA_cutoff; e.aux[2] = yf->_debye_length; e.aux[3] = yf->_debye_A; e.aux[4] = yf->_cutoff;
+				e.iaux = yf->_WCA_n;
+			}
+			else if(ft == typeid(RepulsiveSphereMoving)) {
+				RepulsiveSphereMoving *sf = static_cast<RepulsiveSphereMoving *>(f);
+				e.type = OXB_EXT_SPHERE_MOVING;
+				e.stiff = sf->stiff(); e.r0 = sf->r0(); e.rate = sf->rate();
+				LR_vector o = sf->origin(), t = sf->target();
+				e.pos0[0] = o.x; e.pos0[1] = o.y; e.pos0[2] = o.z;
+				e.aux[0] = sf->r_ext(); e.aux[1] = t.x; e.aux[2] = t.y; e.aux[3] = t.z; e.aux[4] = (double) sf->steps();
+			}
 			else {
-				throw oxDNAException("Only string, trap, mutual_trap, lowdim_trap, twist, repulsion_plane, attraction_plane, sphere, sphere_smooth, ellipsoid and LJ_wall forces are supported by the oxdna_b200 CUDA backend at the moment.\n");
+				throw oxDNAException("Only string, trap, mutual_trap, lowdim_trap, twist, repulsion_plane, repulsion_plane_moving, attraction_plane, sphere, sphere_smooth, repulsive_sphere_moving, ellipsoid, LJ_wall, LJ_cone, generic_central_force, com and yukawa_sphere forces are supported by the oxdna_b200 CUDA backend at the moment.\n");
 			}
 			if(single_particle_type && N() > 1 && uses[f] == N()) {
 				if(emitted.count(f)) continue;
@@ -292,6 +353,8 @@ void MD_CUDABackend::_apply_external_forces_changes() {
 	}
 	// unlike the reference (MD_CUDABackend.cu:110-112) external forces may be combined with CUDA_sort_every > 0:
 	// the table holds original particle ids, the device maps them through its slot table
+	oxb_check(_ctx, oxb_set_ext_forces(_ctx, 0, nullptr), "set_ext_forces"); // COM entries refer to the pool: drop them before replacing it
+	oxb_check(_ctx, oxb_set_ext_index_pool(_ctx, (int) pool.size(), pool.data()), "set_ext_index_pool");
 	oxb_check(_ctx, oxb_set_ext_forces(_ctx, (int) table.size(), table.data()), "set_ext_forces");
 }
 

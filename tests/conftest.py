@@ -33,4 +33,4 @@ def pair_set(pairs):
     return set(map(tuple, p.tolist()))
 
 
-from oracle.fixtures import ext2_forces  # noqa: E402,F401  (the force list of the lattice8_ext2 fixture)
+from oracle.fixtures import ext2_forces, ext3_forces  # noqa: E402,F401  (the force lists of the lattice8_ext2 / _ext3 fixtures)

@@ -130,6 +130,59 @@ center = 8., 13., 36.
 """
 
 
+FORCES3 = """{
+type = repulsion_plane_moving
+particle = all
+ref_particle = 9
+stiff = 0.5
+dir = 1,0,0
+}
+{
+type = generic_central_force
+particle = all
+center = 8.9,13.9,34.8
+force_type = gravity
+F0 = 0.02
+inner_cut_off = 0.5
+}
+{
+type = LJ_cone
+particle = all
+stiff = 2.0
+sigma = 4.0
+alpha = 0.5
+n = 6
+dir = 0,0,1
+pos0 = 8.9,13.9,12.0
+}
+{
+type = com
+com_list = 0,1,2
+ref_list = 15,16,17
+stiff = 0.3
+r0 = 1.0
+}
+{
+type = yukawa_sphere
+particle = all
+radius = 9.0
+center = 8.9,13.9,34.8
+debye_length = 2.0
+debye_A = 1.0
+}
+{
+type = repulsive_sphere_moving
+particle = all
+stiff = 0.5
+r0 = 3.8
+rate = 0.0005
+origin = 8.9,13.9,28.0
+target = 8.9,13.9,28.3
+steps = 200
+}
+"""
+
+
 def run(binary, d, fix=FIX, files=("initial.top", "initial.conf"), **kw):
     os.makedirs(d, exist_ok=True)
     for f, name in zip(files, ("initial.top", "initial.conf")):
@@ -138,6 +191,8 @@ def run(binary, d, fix=FIX, files=("initial.top", "initial.conf"), **kw):
         f.write(FORCES)
     with open(os.path.join(d, "forces2.txt"), "w") as f:
         f.write(FORCES2)
+    with open(os.path.join(d, "forces3.txt"), "w") as f:
+        f.write(FORCES3)
     with open(os.path.join(d, "input"), "w") as f:
         f.write(INPUT.format(**kw))
     p = subprocess.run([binary, "input"], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
@@ -154,7 +209,8 @@ needs_binaries = pytest.mark.skipif(not (os.path.exists(OURS) and os.path.exists
 @pytest.mark.gpu
 @needs_binaries
 @pytest.mark.parametrize("use_edge,sort_every,extra", [(1, 1, ""), (0, 0, ""), (1, 1, "external_forces = 1\nexternal_forces_file = forces.txt"),
-                                                       (1, 1, "external_forces = 1\nexternal_forces_file = forces2.txt")])
+                                                       (1, 1, "external_forces = 1\nexternal_forces_file = forces2.txt"),
+                                                       (1, 1, "external_forces = 1\nexternal_forces_file = forces3.txt")])
 def test_stock_input_file_matches_reference_cpu(tmp_path, use_edge, sort_every, extra):
     a = run(OURS, str(tmp_path / "ours"), backend="CUDA", itype="DNA2", steps=300, thermostat="no", use_edge=use_edge, sort_every=sort_every, extra=extra)
     assert a.returncode == 0, a.stdout[-2000:]

@@ -6,7 +6,7 @@ arithmetic), energies relative 1e-6; NVE trajectories against the double-precisi
 import numpy as np
 import pytest
 
-from conftest import ext2_forces, load_golden, pair_set
+from conftest import ext2_forces, ext3_forces, load_golden, pair_set
 from oracle import oracle as O
 from oxdna_b200 import capi, lattice
 from oxdna_b200.sim import Simulation, parse_temperature
@@ -431,6 +431,28 @@ def test_further_external_forces_vs_reference(use_edge, sort_every):
         st = sim.ctx.get_state()
         assert np.abs(st["pos"] - g["pos1"]).max() < 2e-4
         assert np.abs(st["vel"] - g["vel1"]).max() < 2e-3
+    finally:
+        sim.close()
+
+
+@pytest.mark.parametrize("use_edge,sort_every", [(0, 0), (1, 1)])
+def test_external_forces_second_batch_vs_reference(use_edge, sort_every):
+    """SURVEY 8f rank 2 (second batch): repulsion_plane_moving, generic_central_force, LJ_cone, com (index pool, one block per force),
+    yukawa_sphere, repulsive_sphere_moving -- against the reference CPU run (forces at step 0, 100 steps of dynamics)."""
+    g = load_golden("lattice8_ext3")
+    sim = make_sim(g, use_edge=use_edge, CUDA_sort_every=sort_every, external_forces_list=ext3_forces(g["pos"]))
+    try:
+        out = sim.ctx.get_forces()
+        fmax = np.linalg.norm(g["force"], axis=1).max()
+        assert np.linalg.norm(out["force"] - g["force"], axis=1).max() <= 1e-5 * fmax
+        n = int(g["nve_steps"])
+        sim.run(n)
+        st = sim.ctx.get_state()
+        assert np.abs(st["pos"] - g["pos1"]).max() < 2e-4
+        assert np.abs(st["vel"] - g["vel1"]).max() < 2e-3
+        # the table can be replaced while COM forces are set (pool swap) and emptied again
+        sim.ctx.set_ext_forces(ext3_forces(g["pos"])[5:7])
+        sim.ctx.set_ext_forces([])
     finally:
         sim.close()
 

@@ -5,7 +5,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLD, ext2_forces, load_golden, pair_set
+from conftest import GOLD, ext2_forces, ext3_forces, load_golden, pair_set
 from oracle import oracle as O
 from oracle import refharness as RH
 from oxdna_b200 import io as oio
@@ -67,6 +67,26 @@ def test_oracle_external_forces_fixture():
            dict(type="mutual_trap", particle=39, ref_particle=0, stiff=0.1, r0=1.2, PBC=1),
            dict(type="trap", particle=45, pos0=(5.0, 5.0, 5.0), stiff=0.5, rate=0.001, dir=(1.0, 0.0, 0.0)),
            dict(type="string", particle=80, F0=0.2, rate=0.0001, dir=(0.0, 1.0, 1.0))]
+    md = O.MD(P, g["pos"], O.axes_from_a1a3(g["a1"], g["a3"]), g["vel"], g["L"], g["btype"], g["n3"], g["n5"], g["box"], 0.003, 0.05, ext=ext)
+    assert np.abs(md.force - g["force"]).max() < 1e-9
+    md.step(int(g["nve_steps"]))
+    assert np.abs(md.pos - g["pos1"]).max() < 1e-9
+    assert np.abs(md.vel - g["vel1"]).max() < 1e-9
+
+
+def test_oracle_external_forces_second_batch_fixture():
+    """repulsion_plane_moving (range of reference particles, `all` and single), generic_central_force (gravity with both cut-offs, and
+    repulsive without), LJ_cone (only_repulsive), com (two forces with their own index lists), yukawa_sphere (WCA branch active),
+    repulsive_sphere_moving (growing and translating) -- forces at step 0 and 100 steps against the reference CPU run"""
+    g = load_golden("lattice8_ext3")
+    P = _params(g)
+    ext = ext3_forces(g["pos"])
+    ref = g["force"] - g["force_noext"]
+    assert (np.abs(ref).max(axis=1) > 1e-9).sum() >= 250
+    assert np.abs(O.ext_forces(ext, g["pos"], g["box"], 0) - ref).max() < 1e-9
+    # every force type contributes: dropping any entry changes the result
+    for k in range(len(ext)):
+        assert np.abs(O.ext_forces(ext[:k] + ext[k + 1:], g["pos"], g["box"], 0) - ref).max() > 1e-6, ext[k]["type"]
     md = O.MD(P, g["pos"], O.axes_from_a1a3(g["a1"], g["a3"]), g["vel"], g["L"], g["btype"], g["n3"], g["n5"], g["box"], 0.003, 0.05, ext=ext)
     assert np.abs(md.force - g["force"]).max() < 1e-9
     md.step(int(g["nve_steps"]))
