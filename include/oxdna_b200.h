@@ -215,6 +215,22 @@ int oxb_synchronize(oxb_ctx *ctx);
 int oxb_get_forces(oxb_ctx *ctx, double *force, double *torque_body, double *torque_lab, double *energy, double *hb_energy);
 /* potential energy U and kinetic energy K of the whole system (GpuUtils::sum_c_number4_to_double_on_GPU, CUDA_print_energy) */
 int oxb_energy(oxb_ctx *ctx, double *U, double *K);
+
+/* MC barostat: MD_CUDABackend::_apply_barostat (src/CUDA/Backends/MD_CUDABackend.cu:451-516) with its kernels compute_molecular_coms /
+ * rescale_molecular_positions / rescale_positions (src/CUDA/Backends/CUDA_MD.cuh:62-95).  The host draws the new box sides
+ * (L + delta_L (drand48() - 0.5), isotropic or per axis) and the acceptance number u, as the reference does.
+ *   oxb_barostat_move: U(old) -> rescale (molecular: every strand is translated with its centre of mass; atomic: every position is
+ *     scaled) -> rebuild lists -> U(new) -> accept iff exp(-(dE + P dV - N_objs T ln(V'/V)) / T) > u, N_objs = strands or particles;
+ *     a rejected move restores positions and box EXACTLY (device snapshot; the reference applies the inverse scaling in FP32).
+ *   oxb_barostat_trial / _accept / _reject: the same move in pieces, for callers that evaluate their own acceptance rule.
+ * Valid between completed steps (not after oxb_first_step).  Works with use_edge = 1 as well (the reference forbids that
+ * combination, MD_CUDABackend.cu:629-631). */
+int oxb_barostat_move(oxb_ctx *ctx, const double new_box[3], int molecular, double P, double T, double u, int *accepted, double *dE);
+int oxb_barostat_trial(oxb_ctx *ctx, const double new_box[3], int molecular);
+int oxb_barostat_accept(oxb_ctx *ctx);
+int oxb_barostat_reject(oxb_ctx *ctx);
+/* current box sides (they change under the barostat) */
+int oxb_get_box(oxb_ctx *ctx, double box[3]);
 /* potential energy of the whole system split into the reference's terms, terms[OXB_NTERMS] in the order of OXB_TERM_*
  * (BaseInteraction::get_system_energy_split, src/Interactions/BaseInteraction.cpp:61-90; the `potential_energy` observable
  * with split = true, src/Observables/PotentialEnergy.cpp), evaluated on the device for the current positions */

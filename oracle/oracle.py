@@ -376,3 +376,24 @@ def langevin_params(T, dt, gamma_trans=0.0, diff_coeff=0.0):
     v = [C.c_double() for _ in range(4)]
     lib().oxo_langevin_params(C.c_double(T), C.c_double(dt), C.c_double(gamma_trans), C.c_double(diff_coeff), *[C.byref(x) for x in v])
     return tuple(x.value for x in v)
+
+
+def barostat_rescale(pos, strand, box, new_box, molecular):
+    """positions after a volume move: VolumeMove::apply (src/Backends/MCMoves/VolumeMove.cpp:79-90, every position scaled) or
+    MoleculeVolumeMove::apply (src/Backends/MCMoves/MoleculeVolumeMove.cpp:78-104, every strand translated by com * (L'/L - 1));
+    same arithmetic as the CUDA kernels rescale_positions / rescale_molecular_positions (src/CUDA/Backends/CUDA_MD.cuh:62-95)."""
+    pos, box, new_box = _d(pos), _d(box), _d(new_box)
+    if not molecular:
+        return pos * (new_box / box)
+    out = pos.copy()
+    strand = np.asarray(strand)
+    for sid in np.unique(strand):
+        m = strand == sid
+        out[m] += pos[m].mean(axis=0) * (new_box / box - 1.0)
+    return out
+
+
+def barostat_acceptance(dE, P, T, box, new_box, n_objs):
+    """VolumeMove.cpp:98-102 / MD_CUDABackend.cu:488-492: exp(-(dE + P dV - N_objs T ln(V'/V)) / T)"""
+    V0, V1 = float(np.prod(_d(box))), float(np.prod(_d(new_box)))
+    return float(np.exp(-(dE + P * (V1 - V0) - n_objs * T * np.log(V1 / V0)) / T))

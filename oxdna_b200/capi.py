@@ -181,7 +181,7 @@ def fill_ext_entry(e, d, pool):
 EXPORTED = """oxb_sizeof oxb_dna2_params_init oxb_dna1_params_init oxb_dna2_params_seqdep oxb_rna2_params_init oxb_rna2_params_seqdep oxb_set_model_rna2 oxb_create oxb_destroy oxb_last_error oxb_set_stream oxb_set_box
 oxb_set_topology oxb_set_model_dna2 oxb_set_lists oxb_set_dt oxb_set_thermostat oxb_set_ext_forces oxb_set_ext_index_pool oxb_set_state oxb_get_state oxb_write_conf
 oxb_set_step oxb_get_step oxb_sort oxb_update_lists oxb_compute_forces oxb_first_step oxb_second_step oxb_thermostat oxb_run
-oxb_synchronize oxb_get_forces oxb_energy oxb_energy_split oxb_get_pairs oxb_get_stats oxb_device_views oxb_launch_count oxb_time_kernel""".split()
+oxb_synchronize oxb_get_forces oxb_energy oxb_barostat_move oxb_barostat_trial oxb_barostat_accept oxb_barostat_reject oxb_get_box oxb_energy_split oxb_get_pairs oxb_get_stats oxb_device_views oxb_launch_count oxb_time_kernel""".split()
 
 _lib = None
 
@@ -395,6 +395,28 @@ class Context:
         U, K = C.c_double(), C.c_double()
         self._ck(self._L.oxb_energy(self._h, C.byref(U), C.byref(K)))
         return U.value, K.value
+
+    def barostat_move(self, new_box, molecular, P, T, u):
+        """one MC volume move (MD_CUDABackend::_apply_barostat); returns (accepted, dE)"""
+        acc, dE = C.c_int(), C.c_double()
+        b = _d(new_box)
+        self._ck(self._L.oxb_barostat_move(self._h, _p(b), int(bool(molecular)), C.c_double(P), C.c_double(T), C.c_double(u), C.byref(acc), C.byref(dE)))
+        return bool(acc.value), dE.value
+
+    def barostat_trial(self, new_box, molecular):
+        b = _d(new_box)
+        self._ck(self._L.oxb_barostat_trial(self._h, _p(b), int(bool(molecular))))
+
+    def barostat_accept(self):
+        self._ck(self._L.oxb_barostat_accept(self._h))
+
+    def barostat_reject(self):
+        self._ck(self._L.oxb_barostat_reject(self._h))
+
+    def get_box(self):
+        b = np.zeros(3)
+        self._ck(self._L.oxb_get_box(self._h, _p(b)))
+        return b
 
     def energy_split(self):
         """per-term potential energies (FENE, BEXC, STCK, NEXC, HB, CRSTCK, CXSTCK, DH), summed on the device"""

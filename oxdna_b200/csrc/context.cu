@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <map>
 #include <vector>
 
 namespace oxb {
@@ -100,6 +101,14 @@ struct oxb_ctx {
 	bool bussi_init = false;
 	int n_ext = 0, n_ext_all = 0; // entries bound to one particle / entries acting on every particle
 	DevExtForce *ext = nullptr, *ext_all = nullptr, *ext_com = nullptr;
+	// MC barostat (oxb_barostat_*): molecule table, FP64 centres of mass, snapshot of the positions of an open trial
+	int n_mol = 0;
+	int *mol_of = nullptr;
+	double *mol_inv_size = nullptr, *mol_coms = nullptr;
+	double4 *pos_backup = nullptr;
+	int4 *ipos_backup = nullptr, *iback_backup = nullptr;
+	double box_backup[3] = { 0., 0., 0. };
+	bool trial_open = false;
 	int n_ext_com = 0;           // COM forces (one entry per force, evaluated by one block each)
 	int *ext_pool = nullptr;     // com_list / ref_list original indices of the COM forces
 	std::vector<int> ext_pool_h;
@@ -664,7 +673,8 @@ void oxb_destroy(oxb_ctx *c) {
 		cudaFree(c->quat[k]); cudaFree(c->F[k]); cudaFree(c->T[k]); cudaFree(c->bonds[k]); cudaFree(c->iback[k]); cudaFree(c->list_iback[k]); cudaFree(c->list_ibase[k]);
 	}
 	cudaFree(c->Fb);
-	cudaFree(c->slot_of); cudaFree(c->flags); cudaFree(c->sums); cudaFree(c->d_energy); cudaFree(c->ext); cudaFree(c->ext_all); cudaFree(c->ext_com); cudaFree(c->ext_pool); cudaFree(c->pos_f4);
+	cudaFree(c->slot_of); cudaFree(c->flags); cudaFree(c->sums); cudaFree(c->d_energy); cudaFree(c->ext); cudaFree(c->ext_all); cudaFree(c->ext_com); cudaFree(c->ext_pool);
+	cudaFree(c->mol_of); cudaFree(c->mol_inv_size); cudaFree(c->mol_coms); cudaFree(c->pos_backup); cudaFree(c->ipos_backup); cudaFree(c->iback_backup); cudaFree(c->pos_f4);
 	cudaFree(c->hkeys); cudaFree(c->hkeys_sorted); cudaFree(c->hvals); cudaFree(c->hvals_sorted); cudaFree(c->hinv);
 	free_lists(c);
 	if(c->h_flags) cudaFreeHost(c->h_flags);
@@ -709,6 +719,9 @@ int oxb_set_topology(oxb_ctx *c, const int *btype, const int *n3, const int *n5,
 	}
 	c->have_topology = true;
 	c->have_state = false;
+	cudaFree(c->mol_of); cudaFree(c->mol_inv_size); cudaFree(c->mol_coms); cudaFree(c->pos_backup); cudaFree(c->ipos_backup); cudaFree(c->iback_backup);
+	c->mol_of = nullptr; c->mol_inv_size = nullptr; c->mol_coms = nullptr; c->pos_backup = nullptr; c->ipos_backup = c->iback_backup = nullptr;
+	c->trial_open = false;
 	return 0;
 }
 
@@ -900,6 +913,7 @@ int oxb_set_state(oxb_ctx *c, const double *pos, const double *a1, const double 
 	CU(cudaStreamSynchronize(c->stream));
 	c->have_state = true;
 	c->lists_valid = false; c->forces_valid = false; c->mid_step = false;
+	c->trial_open = false;
 	return 0;
 }
 
@@ -1181,6 +1195,108 @@ int oxb_energy(oxb_ctx *c, double *U, double *K) {
 	if(U) *U = 0.5 * c->h_scalars[0];
 	if(K) *K = 0.5 * (hs.v2 + hs.L2);
 	return 0;
+}
+
+// ---- MC barostat (MD_CUDABackend::_apply_barostat, src/CUDA/Backends/MD_CUDABackend.cu:451-516)
+static int barostat_tables(oxb_ctx *c) {
+	if(c->mol_of != nullptr) return 0;
+	const int N = c->N;
+	// molecules = strands (ConfigInfo::molecules() of a nucleic-acid topology); ids compacted in order of first appearance
+	std::map<int, int> ids;
+	std::vector<int> mol(N);
+	for(int i = 0; i < N; i++) {
+		auto it = ids.find(c->h_strand[i]);
+		if(it == ids.end()) it = ids.insert(std::make_pair(c->h_strand[i], (int) ids.size())).first;
+		mol[i] = it->second;
+	}
+	c->n_mol = (int) ids.size();
+	std::vector<double> inv(c->n_mol, 0.);
+	for(int i = 0; i < N; i++) inv[mol[i]] += 1.;
+	for(auto &x : inv) x = 1. / x;
+	CU(dalloc(&c->mol_of, (size_t) N));
+	CU(dalloc(&c->mol_inv_size, (size_t) c->n_mol));
+	CU(dalloc(&c->mol_coms, 3 * (size_t) c->n_mol));
+	CU(dalloc(&c->pos_backup, (size_t) N));
+	CU(dalloc(&c->ipos_backup, (size_t) N));
+	CU(dalloc(&c->iback_backup, (size_t) N));
+	CU(cudaMemcpy(c->mol_of, mol.data(), sizeof(int) * N, cudaMemcpyHostToDevice));
+	CU(cudaMemcpy(c->mol_inv_size, inv.data(), sizeof(double) * c->n_mol, cudaMemcpyHostToDevice));
+	return 0;
+}
+
+int oxb_get_box(oxb_ctx *c, double box[3]) {
+	if(c == nullptr || box == nullptr) return 1;
+	if(!c->have_box) return fail(c, 2, "box not set");
+	for(int k = 0; k < 3; k++) box[k] = c->box[k];
+	return 0;
+}
+
+int oxb_barostat_trial(oxb_ctx *c, const double new_box[3], int molecular) {
+	if(c == nullptr || new_box == nullptr) return 1;
+	int rc = check_ready(c);
+	if(rc) return rc;
+	if(c->mid_step) return fail(c, 2, "a barostat move needs a completed step (call between runs)");
+	if(c->trial_open) return fail(c, 2, "a barostat trial is already open");
+	for(int k = 0; k < 3; k++) if(!(new_box[k] > 0)) return fail(c, 1, "box sides must be positive");
+	rc = barostat_tables(c);
+	if(rc) return rc;
+	const int N = c->N, k = c->cur;
+	CU(cudaMemcpyAsync(c->pos_backup, c->posd[k], sizeof(double4) * N, cudaMemcpyDeviceToDevice, c->stream));
+	CU(cudaMemcpyAsync(c->ipos_backup, c->ipos[k], sizeof(int4) * N, cudaMemcpyDeviceToDevice, c->stream));
+	CU(cudaMemcpyAsync(c->iback_backup, c->iback[k], sizeof(int4) * N, cudaMemcpyDeviceToDevice, c->stream));
+	oxb::RescaleArgs a;
+	a.N = N; a.molecular = molecular ? 1 : 0;
+	for(int d = 0; d < 3; d++) {
+		c->box_backup[d] = c->box[d];
+		a.f[d] = molecular ? new_box[d] / c->box[d] - 1. : new_box[d] / c->box[d];
+		a.box_inv[d] = 1. / new_box[d];
+	}
+	a.posd = c->posd[k]; a.quatd = c->quatd[k]; a.ipos = c->ipos[k]; a.iback = c->iback[k];
+	a.mol_of = c->mol_of; a.coms = c->mol_coms;
+	a.back_a1 = c->model.back_a1; a.back_a2 = c->model.back_a2; a.back_a3 = c->back_a3;
+	if(molecular) { oxb::launch_mol_coms(c->stream, N, c->n_mol, c->ipos[k], c->mol_of, c->mol_inv_size, c->posd[k], c->mol_coms); c->launches++; }
+	oxb::launch_rescale_positions(c->stream, a);
+	c->launches++;
+	CU(cudaGetLastError());
+	c->trial_open = true;
+	return oxb_set_box(c, new_box);
+}
+
+int oxb_barostat_reject(oxb_ctx *c) {
+	if(c == nullptr) return 1;
+	if(!c->trial_open) return fail(c, 2, "no barostat trial is open");
+	const int N = c->N, k = c->cur;
+	CU(cudaMemcpyAsync(c->posd[k], c->pos_backup, sizeof(double4) * N, cudaMemcpyDeviceToDevice, c->stream));
+	CU(cudaMemcpyAsync(c->ipos[k], c->ipos_backup, sizeof(int4) * N, cudaMemcpyDeviceToDevice, c->stream));
+	CU(cudaMemcpyAsync(c->iback[k], c->iback_backup, sizeof(int4) * N, cudaMemcpyDeviceToDevice, c->stream));
+	c->trial_open = false;
+	return oxb_set_box(c, c->box_backup);
+}
+
+int oxb_barostat_accept(oxb_ctx *c) {
+	if(c == nullptr) return 1;
+	if(!c->trial_open) return fail(c, 2, "no barostat trial is open");
+	c->trial_open = false;
+	return 0;
+}
+
+int oxb_barostat_move(oxb_ctx *c, const double new_box[3], int molecular, double P, double T, double u, int *accepted, double *dE_out) {
+	if(c == nullptr || new_box == nullptr) return 1;
+	double U0 = 0., U1 = 0.;
+	int rc = oxb_energy(c, &U0, nullptr);
+	if(rc) return rc;
+	const double V0 = c->box[0] * c->box[1] * c->box[2], V1 = new_box[0] * new_box[1] * new_box[2];
+	rc = oxb_barostat_trial(c, new_box, molecular);
+	if(rc) return rc;
+	rc = oxb_energy(c, &U1, nullptr);
+	if(rc) { oxb_barostat_reject(c); return rc; }
+	const double n_objs = molecular ? (double) c->n_mol : (double) c->N;
+	const double dE = U1 - U0;
+	const double acc = std::exp(-(dE + P * (V1 - V0) - n_objs * T * std::log(V1 / V0)) / T);
+	const bool ok = acc > u;
+	if(dE_out) *dE_out = dE;
+	if(accepted) *accepted = ok ? 1 : 0;
+	return ok ? oxb_barostat_accept(c) : oxb_barostat_reject(c);
 }
 
 int oxb_energy_split(oxb_ctx *c, double *terms) {

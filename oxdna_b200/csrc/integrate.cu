@@ -303,6 +303,43 @@ void launch_ph(cudaStream_t s, const oxb::IntegrateArgs &a, int epoch) {
 	k_integrate<PH><<<(a.N + tpb - 1) / tpb, tpb, 0, s>>>(a, epoch);
 }
 
+// ---- MC barostat support (MD_CUDABackend::_rescale_positions / _rescale_molecular_positions, src/CUDA/Backends/MD_CUDABackend.cu:412-449;
+// kernels compute_molecular_coms / rescale_molecular_positions / rescale_positions, src/CUDA/Backends/CUDA_MD.cuh:62-95), on the FP64 state
+__global__ void k_mol_coms(int N, const int4 *__restrict__ ipos, const int *__restrict__ mol_of, const double *__restrict__ inv_size,
+		const double4 *__restrict__ posd, double *__restrict__ coms) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= N) return;
+	const int m = mol_of[word_index(ipos[i].w)];
+	const double4 r = posd[i];
+	const double w = inv_size[m];
+	atomicAdd(coms + 3 * m, r.x * w); atomicAdd(coms + 3 * m + 1, r.y * w); atomicAdd(coms + 3 * m + 2, r.z * w);
+}
+
+// molecular: r += com(molecule) * shift; atomic: r *= ratio.  Then the fixed-point centre and backbone site are re-encoded for the NEW box.
+__global__ void k_rescale_positions(oxb::RescaleArgs a) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= a.N) return;
+	double4 r = a.posd[i];
+	int4 ip = a.ipos[i];
+	if(a.molecular) {
+		const double *cm = a.coms + 3 * a.mol_of[word_index(ip.w)];
+		r.x += cm[0] * a.f[0]; r.y += cm[1] * a.f[1]; r.z += cm[2] * a.f[2];
+	}
+	else { r.x *= a.f[0]; r.y *= a.f[1]; r.z *= a.f[2]; }
+	a.posd[i] = r;
+	ip.x = (int) to_fixed(r.x, a.box_inv[0]); ip.y = (int) to_fixed(r.y, a.box_inv[1]); ip.z = (int) to_fixed(r.z, a.box_inv[2]);
+	a.ipos[i] = ip;
+	const double4 qn = a.quatd[i];
+	double sqx = qn.x * qn.x, sqy = qn.y * qn.y, sqz = qn.z * qn.z, sqw = qn.w * qn.w;
+	double xy = qn.x * qn.y, xz = qn.x * qn.z, xw = qn.x * qn.w, yz = qn.y * qn.z, yw = qn.y * qn.w, zw = qn.z * qn.w;
+	double b1 = a.back_a1, b2 = a.back_a2, b3 = a.back_a3;
+	int4 ib = a.iback[i];
+	ib.x = (int) to_fixed(r.x + b1 * (sqx - sqy - sqz + sqw) + b2 * (2. * (xy - zw)) + b3 * (2. * (xz + yw)), a.box_inv[0]);
+	ib.y = (int) to_fixed(r.y + b1 * (2. * (xy + zw)) + b2 * (-sqx + sqy - sqz + sqw) + b3 * (2. * (yz - xw)), a.box_inv[1]);
+	ib.z = (int) to_fixed(r.z + b1 * (2. * (xz - yw)) + b2 * (2. * (yz + xw)) + b3 * (-sqx - sqy + sqz + sqw), a.box_inv[2]);
+	a.iback[i] = ib;
+}
+
 } // namespace
 
 namespace oxb {
@@ -337,6 +374,17 @@ void launch_kinetic_sums(cudaStream_t s, int N, const double4 *veld, const doubl
 	k_clear_sums<<<1, 1, 0, s>>>(sums, nullptr, -1);
 	int tpb = 256;
 	k_kinetic_sums<<<(N + tpb - 1) / tpb, tpb, 0, s>>>(N, veld, Ld, sums);
+}
+
+void launch_mol_coms(cudaStream_t s, int N, int n_mol, const int4 *ipos, const int *mol_of, const double *inv_size, const double4 *posd, double *coms) {
+	cudaMemsetAsync(coms, 0, sizeof(double) * 3 * (size_t) n_mol, s);
+	int tpb = 256;
+	k_mol_coms<<<(N + tpb - 1) / tpb, tpb, 0, s>>>(N, ipos, mol_of, inv_size, posd, coms);
+}
+
+void launch_rescale_positions(cudaStream_t s, const RescaleArgs &a) {
+	int tpb = 256;
+	k_rescale_positions<<<(a.N + tpb - 1) / tpb, tpb, 0, s>>>(a);
 }
 
 void launch_energy_sum(cudaStream_t s, int N, const float4 *F, const float4 *Fb, double *out) {

@@ -109,6 +109,20 @@ void launch_integrate_epoch(cudaStream_t s, const IntegrateArgs &a, int phases, 
 void launch_bussi_update_epoch(cudaStream_t s, KinSums *sums, int N, ThermostatCfg th, long long step, const int *flags, int epoch);
 void launch_clear_sums(cudaStream_t s, KinSums *sums, const int *flags, int epoch);
 void launch_kinetic_sums(cudaStream_t s, int N, const double4 *veld, const double4 *Ld, KinSums *sums);
+// MC barostat: molecular centres of mass (FP64, one atomicAdd triple per particle) and position rescaling + fixed-point re-encode
+struct RescaleArgs {
+	int N, molecular;
+	double f[3];        // molecular: shift factor (new/old - 1); atomic: ratio new/old
+	double box_inv[3];  // of the NEW box
+	double4 *posd;
+	const double4 *quatd;
+	int4 *ipos, *iback;
+	const int *mol_of;  // molecule of an original particle id
+	const double *coms; // 3 doubles per molecule
+	float back_a1, back_a2, back_a3;
+};
+void launch_mol_coms(cudaStream_t s, int N, int n_mol, const int4 *ipos, const int *mol_of, const double *inv_size, const double4 *posd, double *coms);
+void launch_rescale_positions(cudaStream_t s, const RescaleArgs &a);
 void launch_energy_sum(cudaStream_t s, int N, const float4 *F, const float4 *Fb, double *out);
 
 // ---- lists.cu

@@ -110,6 +110,15 @@ class Simulation:
         if ext:
             c.set_ext_forces(ext)
         c.set_state(conf["pos"], conf["a1"], conf["a3"], conf.get("vel"), conf.get("L"))
+        # MC barostat, MDBackend::get_settings (src/Backends/MDBackend.cpp:43-59)
+        self.use_barostat = _bool(g("use_barostat", 0))
+        if self.use_barostat:
+            self.P, self.delta_L = float(g("P")), float(g("delta_L"))
+            self.barostat_probability = float(g("barostat_probability"))
+            self.barostat_isotropic = _bool(g("barostat_isotropic", 1))
+            self.barostat_molecular = _bool(g("barostat_molecular", 0))
+            self.barostat_attempts = self.barostat_accepted = 0
+            self._rng = np.random.default_rng(self.seed + 7919)
 
     def _set_model(self):
         g = self.inp.get
@@ -168,7 +177,30 @@ class Simulation:
         self._set_thermostat()
 
     def run(self, steps):
-        self.ctx.run(steps)
+        if not self.use_barostat:
+            self.ctx.run(steps)
+            return
+        # MD_CUDABackend::sim_step (src/CUDA/Backends/MD_CUDABackend.cu:595-599): every step the barostat fires with probability
+        # barostat_probability (MDBackend::_is_barostat_active); the steps in between go out as one fused run
+        fire = np.flatnonzero(self._rng.random(steps) < self.barostat_probability)
+        done = 0
+        for s in fire:
+            self.ctx.run(int(s) + 1 - done)
+            done = int(s) + 1
+            self.barostat_attempt()
+        self.ctx.run(steps - done)
+
+    def barostat_attempt(self):
+        """MD_CUDABackend::_apply_barostat (src/CUDA/Backends/MD_CUDABackend.cu:451-516)"""
+        box = self.ctx.get_box()
+        if self.barostat_isotropic:
+            new = box + self.delta_L * (self._rng.random() - 0.5)
+        else:
+            new = box + self.delta_L * (self._rng.random(3) - 0.5)
+        ok, _ = self.ctx.barostat_move(new, self.barostat_molecular, self.P, self.T, self._rng.random())
+        self.barostat_attempts += 1
+        self.barostat_accepted += int(ok)
+        return ok
 
     def system_energy(self):
         return self.ctx.energy()[0]

@@ -566,3 +566,75 @@ def test_write_conf_from_device_state(tmp_path):
         assert len(open(tmp_path / "traj.dat").read().splitlines()) == 2 * (3 + sim.N)
     finally:
         sim.close()
+
+
+@pytest.mark.parametrize("use_edge,molecular", [(0, 0), (1, 1), (1, 0)])
+def test_mc_barostat_move_vs_oracle(use_edge, molecular):
+    """SURVEY 8f rank 4: one MC volume move (MD_CUDABackend::_apply_barostat).  Rescaled positions, the energy in the new box, the pair
+    set of the rebuilt list and the acceptance decision against the oracle; a rejected move restores the state bit for bit."""
+    g = load_golden("lattice8")
+    sim = make_sim(g, use_edge=use_edge, CUDA_sort_every=1)
+    try:
+        T = parse_temperature(str(g["T"]))
+        P = O.dna2_params(T, float(g["salt"]))
+        ax = O.axes_from_a1a3(g["a1"], g["a3"])
+
+        def oracle_energy(pos, box):
+            pairs = O.verlet_pairs(pos, g["n3"], g["n5"], box, P.rcut + 2 * 0.05)
+            return O.forces(P, pos, ax, g["btype"], g["n3"], g["n5"], box, pairs)["U"], pairs
+
+        box = np.array(g["box"], dtype=np.float64)
+        new_box = box + np.array([-0.31, -0.31, -0.31]) if molecular else box * np.array([0.99, 1.01, 0.985])
+        U0, _ = oracle_energy(g["pos"], box)
+        new_pos = O.barostat_rescale(g["pos"], g["strand"], box, new_box, molecular)
+        U1, pairs1 = oracle_energy(new_pos, new_box)
+        st0 = sim.ctx.get_state()
+        # trial in pieces
+        sim.ctx.barostat_trial(new_box, molecular)
+        st = sim.ctx.get_state()
+        assert np.abs(st["pos"] - new_pos).max() < 1e-12
+        assert np.array_equal(sim.ctx.get_box(), new_box)
+        assert abs(sim.ctx.energy()[0] - U1) <= 2e-6 * abs(U1)
+        assert pair_set(sim.ctx.get_pairs()) == pair_set(pairs1)
+        sim.ctx.barostat_reject()
+        st1 = sim.ctx.get_state()
+        for k in ("pos", "a1", "a3", "vel", "L"):
+            assert np.array_equal(st0[k], st1[k]), k
+        assert np.array_equal(sim.ctx.get_box(), box)
+        assert abs(sim.ctx.energy()[0] - U0) <= 2e-6 * abs(U0)
+        # the full move: decision and dE against the oracle, on both sides of the acceptance number
+        n_objs = len(np.unique(g["strand"])) if molecular else len(g["pos"])
+        press = 0.05
+        acc = O.barostat_acceptance(U1 - U0, press, T, box, new_box, n_objs)
+        for u, expect in ((min(acc, 1.0) * 0.5, True), (min(acc * 2.0 + 1e-3, 2.0), False)):
+            ok, dE = sim.ctx.barostat_move(new_box, molecular, press, T, u)
+            assert ok == expect
+            assert abs(dE - (U1 - U0)) <= 2e-6 * abs(U1) + 1e-6
+            if ok:
+                assert np.array_equal(sim.ctx.get_box(), new_box)
+                sim.ctx.set_box(box)
+                sim.ctx.set_state(g["pos"], g["a1"], g["a3"], g["vel"], g["L"])
+        # dynamics continue in the (restored) box
+        sim.run(20)
+        assert np.isfinite(sim.ctx.energy()[0])
+    finally:
+        sim.close()
+
+
+def test_npt_run_python_mirror():
+    """use_barostat = 1 through the input-key mirror: volume moves interleaved with fused MD batches; at high pressure the box shrinks
+    (molecular moves, Brownian thermostat), acceptance strictly between 0 and 1, trajectory stays finite."""
+    g = load_golden("lattice8")
+    sim = make_sim(g, use_edge=1, CUDA_sort_every=1, thermostat="brownian", newtonian_steps=103, diff_coeff=2.5, use_barostat=1, P=0.5,
+                   delta_L=0.2, barostat_probability=0.1, barostat_molecular=1)
+    try:
+        V0 = np.prod(sim.ctx.get_box())
+        sim.run(1500)
+        V1 = np.prod(sim.ctx.get_box())
+        assert sim.barostat_attempts > 100
+        assert 0 < sim.barostat_accepted < sim.barostat_attempts
+        assert V1 < V0
+        U, K = sim.ctx.energy()
+        assert np.isfinite(U) and np.isfinite(K)
+    finally:
+        sim.close()

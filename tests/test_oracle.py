@@ -352,3 +352,19 @@ def test_first_generation_oxdna_oracle_matches_live_reference(grooving):
         assert worst < 1e-10 and coax > 50, (worst, coax)
     finally:
         r.close()
+
+
+def test_oracle_barostat_rescale_properties():
+    """volume-move restatement: the atomic move scales every coordinate, the molecular move translates each strand rigidly with its
+    centre of mass (intra-strand distances unchanged, strand centres scaled); acceptance formula at dE = 0 reduces to the ideal-gas term"""
+    g = load_golden("lattice8")
+    box, new_box = np.array(g["box"], dtype=float), np.array(g["box"], dtype=float) * np.array([1.02, 0.97, 1.0])
+    a = O.barostat_rescale(g["pos"], g["strand"], box, new_box, False)
+    assert np.allclose(a, g["pos"] * new_box / box, rtol=0, atol=1e-14)
+    m = O.barostat_rescale(g["pos"], g["strand"], box, new_box, True)
+    for sid in np.unique(g["strand"]):
+        sel = g["strand"] == sid
+        assert np.allclose(m[sel] - m[sel].mean(0), g["pos"][sel] - g["pos"][sel].mean(0), atol=1e-12)
+        assert np.allclose(m[sel].mean(0), g["pos"][sel].mean(0) * new_box / box, atol=1e-12)
+    V0, V1 = box.prod(), new_box.prod()
+    assert np.isclose(O.barostat_acceptance(0.0, 0.0, 0.1, box, new_box, 16), (V1 / V0) ** 16)
