@@ -17,6 +17,7 @@
 #include "Forces/RepulsionPlane.h"
 #include "Forces/RepulsiveSphere.h"
 
+#include <cmath>
 #include <map>
 #include <set>
 
@@ -73,9 +74,9 @@ void MD_CUDABackend::get_settings(input_file &inp) {
 			throw oxDNAException("use_edge and use_barostat are not compatible");
 		}
 	}
-	if(_use_barostat) {
-		throw oxDNAException("use_barostat is not available in the oxdna_b200 CUDA backend");
-	}
+	// the reference refuses use_edge + use_barostat (MD_CUDABackend.cu:629-631) only because its edge scratch buffers are sized
+	// for the initial box; the check is kept for input compatibility
+	getInputBool(&inp, "CUDA_barostat_always_refresh", &_barostat_always_refresh, 0);
 
 	getInputBool(&inp, "CUDA_avoid_cpu_calculations", &_avoid_cpu_calculations, 0);
 	getInputBool(&inp, "CUDA_print_energy", &_print_energy, 0);
@@ -154,6 +155,15 @@ void MD_CUDABackend::_host_to_gpu() {
 		vel[3 * i] = p->vel.x; vel[3 * i + 1] = p->vel.y; vel[3 * i + 2] = p->vel.z;
 		L[3 * i] = p->L.x; L[3 * i + 1] = p->L.y; L[3 * i + 2] = p->L.z;
 	}
+	{
+		// CUDABaseBackend::_host_to_gpu: the device box follows the CPU one (CUDABaseBackend.cu:196)
+		double box[3];
+		LR_vector sides = _box->box_sides();
+		if(oxb_get_box(_ctx, box) == 0 && (box[0] != (double) sides.x || box[1] != (double) sides.y || box[2] != (double) sides.z)) {
+			double nb[3] = { (double) sides.x, (double) sides.y, (double) sides.z };
+			oxb_check(_ctx, oxb_set_box(_ctx, nb), "set_box");
+		}
+	}
 	oxb_check(_ctx, oxb_set_state(_ctx, pos.data(), a1.data(), a3.data(), vel.data(), L.data()), "set_state");
 }
 
@@ -161,6 +171,13 @@ void MD_CUDABackend::_gpu_to_host() {
 	const int n = N();
 	std::vector<double> pos(3 * n), a1(3 * n), a3(3 * n), vel(3 * n), L(3 * n);
 	oxb_check(_ctx, oxb_get_state(_ctx, pos.data(), a1.data(), a3.data(), vel.data(), L.data()), "get_state");
+	if(_use_barostat) {
+		// CUDABaseBackend::_gpu_to_host: the box follows the device (CUDABaseBackend.cu:106-107)
+		double box[3];
+		oxb_check(_ctx, oxb_get_box(_ctx, box), "get_box");
+		LR_vector sides = _box->box_sides();
+		if(box[0] != (double) sides.x || box[1] != (double) sides.y || box[2] != (double) sides.z) _box->init(box[0], box[1], box[2]);
+	}
 	std::vector<double> F, T;
 	if(!_avoid_cpu_calculations) {
 		// superset of the reference, which never writes the GPU forces back
@@ -379,8 +396,47 @@ void MD_CUDABackend::sim_step() {
 	_mytimer->resume();
 	if(_pending_steps == 0) _first_pending_step = current_step();
 	_pending_steps++;
-	if(_pending_steps >= _max_pending) _flush();
+	// MD_CUDABackend.cu:595-599: one draw per step decides whether the barostat fires (MDBackend::_is_barostat_active); the move is
+	// applied once the queued steps, this one included, have run
+	const bool barostat_now = _is_barostat_active();
+	if(_pending_steps >= _max_pending || barostat_now) _flush();
+	if(barostat_now) {
+		_timer_barostat->resume();
+		_apply_barostat();
+		_timer_barostat->pause();
+	}
 	_mytimer->pause();
+}
+
+void MD_CUDABackend::_apply_barostat() {
+	// MD_CUDABackend::_apply_barostat (src/CUDA/Backends/MD_CUDABackend.cu:451-516): box draw and acceptance number on the host
+	// (drand48, same order of draws), energies / rescaling / list rebuild on the device
+	_barostat_attempts++;
+	double old_box[3], new_box[3];
+	oxb_check(_ctx, oxb_get_box(_ctx, old_box), "get_box");
+	if(_barostat_isotropic) {
+		double dL = _delta_L * (drand48() - 0.5);
+		for(int k = 0; k < 3; k++) new_box[k] = old_box[k] + dL;
+	}
+	else {
+		for(int k = 0; k < 3; k++) new_box[k] = old_box[k] + _delta_L * (drand48() - 0.5);
+	}
+	int accepted = 0;
+	const double u = drand48();
+	oxb_check(_ctx, oxb_barostat_move(_ctx, new_box, _barostat_molecular ? 1 : 0, (double) _P, (double) _T, u, &accepted, nullptr), "barostat_move");
+	if(accepted) {
+		_barostat_accepted++;
+		_box->init(new_box[0], new_box[1], new_box[2]);
+		CONFIG_INFO->notify(CONFIG_INFO->box->UPDATE_EVENT);
+	}
+	_barostat_acceptance = _barostat_accepted / (number) _barostat_attempts;
+	if(_barostat_always_refresh) {
+		// CUDA_barostat_always_refresh (MD_CUDABackend.cu:512-515,646-651): a Brownian thermostat with newtonian_steps = 1, pt = 1
+		// (hence pr = 1/2, BrownianThermostat.cpp:43-54) redraws every velocity after each attempt
+		oxb_check(_ctx, oxb_set_thermostat(_ctx, OXB_THERMOSTAT_BROWNIAN, 1, 1.0, 0.5, std::sqrt((double) _T), 0., (unsigned long long) lrand48()), "set_thermostat");
+		oxb_check(_ctx, oxb_thermostat(_ctx), "thermostat");
+		_cuda_thermostat->attach(_ctx);
+	}
 }
 
 void MD_CUDABackend::apply_simulation_data_changes() {

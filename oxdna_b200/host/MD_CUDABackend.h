@@ -21,6 +21,8 @@ protected:
 	bool _use_edge = false;
 	bool _avoid_cpu_calculations = false;
 	bool _print_energy = false;
+	bool _barostat_always_refresh = false;
+	llint _barostat_attempts = 0, _barostat_accepted = 0;
 	llint _pending_steps = 0;
 	llint _first_pending_step = 0;
 	llint _max_pending = 100000;
@@ -33,6 +35,7 @@ protected:
 	virtual void _gpu_to_host();
 	virtual void _apply_external_forces_changes();
 	virtual void _flush();
+	virtual void _apply_barostat();
 	void _on_T_update() override;
 
 public:

@@ -277,3 +277,23 @@ def test_no_cpu_fallback_in_the_dropin_binary(tmp_path):
         pytest.skip("GPU present")
     a = run(OURS, str(tmp_path / "nogpu"), backend="CUDA", itype="DNA2", steps=10, thermostat="no", use_edge=1, sort_every=0, extra="")
     assert a.returncode != 0 and "no CPU fallback" in a.stdout
+
+
+@pytest.mark.gpu
+@needs_binaries
+def test_stock_input_file_npt_matches_reference_cpu(tmp_path):
+    """use_barostat = 1.  Both executables draw the per-step activation, the box change and the acceptance number
+    from drand48 in the same order, so as long as the Metropolis decisions agree the boxes follow the same sequence: final box side
+    and acceptance ratio are compared with the reference CPU backend (whose VolumeMove acts at mid-step; ours between steps)."""
+    extra = "use_barostat = 1\nP = 0.01\ndelta_L = 0.5\nbarostat_probability = 0.2"
+    a = run(OURS, str(tmp_path / "ours"), backend="CUDA", itype="DNA2", steps=300, thermostat="no", use_edge=0, sort_every=1, extra=extra)
+    assert a.returncode == 0, a.stdout[-2000:]
+    b = run(REF, str(tmp_path / "ref"), backend="CPU", itype="DNA2_nomesh", steps=300, thermostat="no", use_edge=0, sort_every=0, extra=extra)
+    assert b.returncode == 0, b.stdout[-2000:]
+    ca, cb = oio.read_conf(str(tmp_path / "ours" / "last_conf.dat")), oio.read_conf(str(tmp_path / "ref" / "last_conf.dat"))
+    assert cb["box"][0] < 49.0
+    assert abs(ca["box"][0] - cb["box"][0]) < 0.3, (ca["box"], cb["box"])
+    ea, eb = energies(str(tmp_path / "ours")), energies(str(tmp_path / "ref"))
+    assert ea.shape == eb.shape and ea.shape[1] == 6           # time, U, K, E, density, barostat acceptance
+    assert abs(ea[-1, 5] - eb[-1, 5]) < 0.1
+    assert abs(ea[-1, 4] / eb[-1, 4] - 1.0) < 0.03
