@@ -378,10 +378,8 @@ def ours(args):
         for _ in range(e2e_steps):
             sim.ctx.set_state(pin["pos"], pin["a1"], pin["a3"], pin["vel"], pin["L"])
             sim.run(md)
-            out = sim.ctx.get_state()
+            sim.ctx.get_state(out=pin)  # D2H straight into the pinned host buffers
             U, K = sim.ctx.energy()
-            for k in pin:
-                pin[k][...] = out[k]
         torch.cuda.synchronize()
         e2e_s = (time.perf_counter() - t0) / e2e_steps
         e2e = {"value": N * md / e2e_s, "unit": "particle-steps/s", "h2d_bytes_per_step": N * 172, "d2h_bytes_per_step": N * 144 + 16,

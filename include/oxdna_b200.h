@@ -229,6 +229,12 @@ int oxb_barostat_move(oxb_ctx *ctx, const double new_box[3], int molecular, doub
 int oxb_barostat_trial(oxb_ctx *ctx, const double new_box[3], int molecular);
 int oxb_barostat_accept(oxb_ctx *ctx);
 int oxb_barostat_reject(oxb_ctx *ctx);
+/* SimBackend::fix_diffusion (src/Backends/SimBackend.cpp:786-882; CubicBox::shift_particle, src/Boxes/CubicBox.cpp:70-77) on the device:
+ * every strand is translated by whole box sides so that its centre of mass lies in [0, L), quaternions are renormalised.  Minimum-image
+ * separations, lists and forces are unaffected (no energy check needed, unlike the matrix re-orthonormalisation of the reference).
+ * shifts (may be NULL): 3 ints per particle (original order) = floor(com / L), what the reference adds to BaseParticle::_pos_shift.
+ * As in the reference's CUDA backend, forces that read absolute positions (trap, twist, planes) see the translated coordinates. */
+int oxb_fix_diffusion(oxb_ctx *ctx, int *shifts);
 /* current box sides (they change under the barostat) */
 int oxb_get_box(oxb_ctx *ctx, double box[3]);
 /* potential energy of the whole system split into the reference's terms, terms[OXB_NTERMS] in the order of OXB_TERM_*

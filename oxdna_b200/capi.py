@@ -181,7 +181,7 @@ def fill_ext_entry(e, d, pool):
 EXPORTED = """oxb_sizeof oxb_dna2_params_init oxb_dna1_params_init oxb_dna2_params_seqdep oxb_rna2_params_init oxb_rna2_params_seqdep oxb_set_model_rna2 oxb_create oxb_destroy oxb_last_error oxb_set_stream oxb_set_box
 oxb_set_topology oxb_set_model_dna2 oxb_set_lists oxb_set_dt oxb_set_thermostat oxb_set_ext_forces oxb_set_ext_index_pool oxb_set_state oxb_get_state oxb_write_conf
 oxb_set_step oxb_get_step oxb_sort oxb_update_lists oxb_compute_forces oxb_first_step oxb_second_step oxb_thermostat oxb_run
-oxb_synchronize oxb_get_forces oxb_energy oxb_barostat_move oxb_barostat_trial oxb_barostat_accept oxb_barostat_reject oxb_get_box oxb_energy_split oxb_get_pairs oxb_get_stats oxb_device_views oxb_launch_count oxb_time_kernel""".split()
+oxb_synchronize oxb_get_forces oxb_energy oxb_barostat_move oxb_barostat_trial oxb_barostat_accept oxb_barostat_reject oxb_get_box oxb_fix_diffusion oxb_energy_split oxb_get_pairs oxb_get_stats oxb_device_views oxb_launch_count oxb_time_kernel""".split()
 
 _lib = None
 
@@ -343,10 +343,18 @@ class Context:
         a, b, c, d, e = _d(pos), _d(a1), _d(a3), _d(vel), _d(L)
         self._ck(self._L.oxb_set_state(self._h, _p(a), _p(b), _p(c), _p(d), _p(e)))
 
-    def get_state(self):
-        out = [np.zeros((self.N, 3)) for _ in range(5)]
-        self._ck(self._L.oxb_get_state(self._h, *[_p(x) for x in out]))
-        return dict(pos=out[0], a1=out[1], a3=out[2], vel=out[3], L=out[4])
+    def get_state(self, out=None):
+        """device state -> dict(pos, a1, a3, vel, L) of (N, 3) float64 arrays; `out` may supply the destination arrays (e.g. pinned
+        host memory, which the device copies straight into)"""
+        keys = ("pos", "a1", "a3", "vel", "L")
+        if out is None:
+            out = {k: np.empty((self.N, 3)) for k in keys}
+        for k in keys:
+            a = out[k]
+            if a.dtype != np.float64 or a.shape != (self.N, 3) or not a.flags.c_contiguous:
+                raise ValueError(f"get_state: out['{k}'] must be a C-contiguous float64 array of shape ({self.N}, 3)")
+        self._ck(self._L.oxb_get_state(self._h, *[_p(out[k]) for k in keys]))
+        return out
 
     def write_conf(self, path, append=False, print_momenta=True):
         """one frame in the reference's configuration format, written from the device state"""
@@ -412,6 +420,12 @@ class Context:
 
     def barostat_reject(self):
         self._ck(self._L.oxb_barostat_reject(self._h))
+
+    def fix_diffusion(self):
+        """strands back into the box by whole box sides; returns the (N, 3) int shifts floor(com / L)"""
+        sh = np.zeros((self.N, 3), dtype=np.int32)
+        self._ck(self._L.oxb_fix_diffusion(self._h, _p(sh)))
+        return sh
 
     def get_box(self):
         b = np.zeros(3)

@@ -96,11 +96,16 @@ struct oxb_ctx {
 	// dynamics
 	double dt = 0.003;
 	long long step = 0;
+	bool fork_streams = true; // force pass on three concurrent streams (OXB_FORK=0/1 overrides the size-based default)
 	bool mid_step = false; // positions already advanced for `step`, forces pending
 	ThermostatCfg th;
 	bool bussi_init = false;
 	int n_ext = 0, n_ext_all = 0; // entries bound to one particle / entries acting on every particle
 	DevExtForce *ext = nullptr, *ext_all = nullptr, *ext_com = nullptr;
+	// marshalling on the device (marshal.cu): topology per original id, staging for the flat N x 3 double arrays of set/get_state
+	int4 *d_topo = nullptr;
+	double *d_stage = nullptr; // 15 N doubles: pos, a1, a3, vel, L
+	int *d_marshal_err = nullptr;
 	// MC barostat (oxb_barostat_*): molecule table, FP64 centres of mass, snapshot of the positions of an open trial
 	int n_mol = 0;
 	int *mol_of = nullptr;
@@ -379,32 +384,41 @@ int launch_forces(oxb_ctx *c, int hw, bool clear, long long step) {
 		e.n_seg = c->n_seg; e.hb_seg = c->hb_seg; e.cx_seg = c->cx_seg; e.cr_seg = c->cr_seg;
 		// ~1.7 items per particle in that list; aim at ~2 items per consumer thread
 		e.hb_split = (int) std::max<long long>(1, std::min<long long>(8, (17ll * c->N / 10 / c->n_seg + 64) / 128));
-		CU(cudaEventRecord(c->ev_fork, m));
-		CU(cudaStreamWaitEvent(c->aux[0], c->ev_fork, 0));
-		CU(cudaStreamWaitEvent(c->aux[1], c->ev_fork, 0));
-		oxb::launch_edge_stage(c->aux[0], 0, c->mref(), c->boxf, e, c->flags, hw);
-		oxb::launch_edge_stage(c->aux[1], 4, c->mref(), c->boxf, e, c->flags, hw);
+		// fork = 1: three concurrent streams (pays while one kernel cannot fill the GPU); fork = 0: the same launches in line on the
+		// main stream (large systems: every kernel fills the machine by itself and concurrent kernels only evict each other's
+		// gathers from L2 -- measured at 1M nucleotides, profiles/fork_sweep_r01.txt)
+		const bool fork = c->fork_streams;
+		cudaStream_t s0 = fork ? c->aux[0] : m, s1 = fork ? c->aux[1] : m;
+		if(fork) {
+			CU(cudaEventRecord(c->ev_fork, m));
+			CU(cudaStreamWaitEvent(c->aux[0], c->ev_fork, 0));
+			CU(cudaStreamWaitEvent(c->aux[1], c->ev_fork, 0));
+		}
+		oxb::launch_edge_stage(s0, 0, c->mref(), c->boxf, e, c->flags, hw);
+		oxb::launch_edge_stage(s1, 4, c->mref(), c->boxf, e, c->flags, hw);
 		oxb::launch_edge_stage(m, 1, c->mref(), c->boxf, e, c->flags, hw);
-		CU(cudaEventRecord(c->ev_near, m));
+		if(fork) CU(cudaEventRecord(c->ev_near, m));
 		oxb::launch_edge_stage(m, 2, c->mref(), c->boxf, e, c->flags, hw);
 		if(c->n_ext > 0) {
-			oxb::launch_ext_forces(c->aux[1], c->n_ext, c->ext, c->slot_of, c->ipos[a], c->posd[a], c->boxf, step, c->cur_step, c->F[a], c->flags, hw);
+			oxb::launch_ext_forces(s1, c->n_ext, c->ext, c->slot_of, c->ipos[a], c->posd[a], c->boxf, step, c->cur_step, c->F[a], c->flags, hw);
 			c->launches += 1;
 		}
 		if(c->n_ext_all > 0) {
-			oxb::launch_ext_forces_all(c->aux[1], c->N, c->n_ext_all, c->ext_all, c->slot_of, c->ipos[a], c->posd[a], c->boxf, step, c->cur_step, c->F[a], c->flags, hw);
+			oxb::launch_ext_forces_all(s1, c->N, c->n_ext_all, c->ext_all, c->slot_of, c->ipos[a], c->posd[a], c->boxf, step, c->cur_step, c->F[a], c->flags, hw);
 			c->launches += 1;
 		}
 		if(c->n_ext_com > 0) {
-			oxb::launch_ext_com(c->aux[1], c->n_ext_com, c->ext_com, c->ext_pool, c->slot_of, c->posd[a], step, c->cur_step, c->F[a], c->flags, hw);
+			oxb::launch_ext_com(s1, c->n_ext_com, c->ext_com, c->ext_pool, c->slot_of, c->posd[a], step, c->cur_step, c->F[a], c->flags, hw);
 			c->launches += 1;
 		}
-		CU(cudaStreamWaitEvent(c->aux[1], c->ev_near, 0));
-		oxb::launch_edge_stage(c->aux[1], 3, c->mref(), c->boxf, e, c->flags, hw);
-		CU(cudaEventRecord(c->ev_join[0], c->aux[0]));
-		CU(cudaEventRecord(c->ev_join[1], c->aux[1]));
-		CU(cudaStreamWaitEvent(m, c->ev_join[0], 0));
-		CU(cudaStreamWaitEvent(m, c->ev_join[1], 0));
+		if(fork) CU(cudaStreamWaitEvent(c->aux[1], c->ev_near, 0));
+		oxb::launch_edge_stage(s1, 3, c->mref(), c->boxf, e, c->flags, hw);
+		if(fork) {
+			CU(cudaEventRecord(c->ev_join[0], c->aux[0]));
+			CU(cudaEventRecord(c->ev_join[1], c->aux[1]));
+			CU(cudaStreamWaitEvent(m, c->ev_join[0], 0));
+			CU(cudaStreamWaitEvent(m, c->ev_join[1], 0));
+		}
 		c->launches += 5;
 	}
 	else {
@@ -634,6 +648,8 @@ int oxb_create(oxb_ctx **out, int device, int N, int precision) {
 	{
 		const char *g = getenv("OXB_NO_GRAPHS");
 		c->use_graphs = !(g != nullptr && g[0] == '1');
+		const char *f = getenv("OXB_FORK");
+		if(f != nullptr) c->fork_streams = (f[0] != '0');
 	}
 	for(int k = 0; k < 2; k++) {
 		CU(dalloc(&c->posd[k], N)); CU(dalloc(&c->veld[k], N)); CU(dalloc(&c->Ld[k], N)); CU(dalloc(&c->quatd[k], N));
@@ -674,6 +690,7 @@ void oxb_destroy(oxb_ctx *c) {
 	}
 	cudaFree(c->Fb);
 	cudaFree(c->slot_of); cudaFree(c->flags); cudaFree(c->sums); cudaFree(c->d_energy); cudaFree(c->ext); cudaFree(c->ext_all); cudaFree(c->ext_com); cudaFree(c->ext_pool);
+	cudaFree(c->d_topo); cudaFree(c->d_stage); cudaFree(c->d_marshal_err);
 	cudaFree(c->mol_of); cudaFree(c->mol_inv_size); cudaFree(c->mol_coms); cudaFree(c->pos_backup); cudaFree(c->ipos_backup); cudaFree(c->iback_backup); cudaFree(c->pos_f4);
 	cudaFree(c->hkeys); cudaFree(c->hkeys_sorted); cudaFree(c->hvals); cudaFree(c->hvals_sorted); cudaFree(c->hinv);
 	free_lists(c);
@@ -716,6 +733,12 @@ int oxb_set_topology(oxb_ctx *c, const int *btype, const int *n3, const int *n5,
 	for(int i = 0; i < N; i++) {
 		if(n3[i] >= N || n5[i] >= N) return fail(c, 1, "wrong topology for particle %d (neighbour index out of range)", i);
 		if(btype[i] > 511 || btype[i] < -511) return fail(c, 1, "base type of particle %d does not fit the packed word (|btype| <= 511)", i);
+	}
+	{
+		std::vector<int4> ht(N);
+		for(int i = 0; i < N; i++) ht[i] = make_int4(btype[i], n3[i], n5[i], c->h_strand[i]);
+		if(c->d_topo == nullptr) CU(dalloc(&c->d_topo, (size_t) N));
+		CU(cudaMemcpy(c->d_topo, ht.data(), sizeof(int4) * N, cudaMemcpyHostToDevice));
 	}
 	c->have_topology = true;
 	c->have_state = false;
@@ -817,6 +840,7 @@ int oxb_set_ext_forces(oxb_ctx *c, int n, const oxb_ext_force *f) {
 		}
 		for(int x = 0; x < 8; x++) d.aux[x] = (float) f[k].aux[x];
 		d.iaux = f[k].iaux;
+		d.r0d = f[k].r0;
 		if(f[k].type == OXB_EXT_LJ_CONE) { d.aux[3] = (float) std::sin(f[k].aux[2]); d.aux[4] = (float) std::cos(f[k].aux[2]); d.aux[5] = (float) std::tan(f[k].aux[2]); }
 		if(f[k].type == OXB_EXT_SPHERE_MOVING) d.daux = f[k].aux[4];
 		if(f[k].type == OXB_EXT_COM) { d.ref = f[k].ref; hcom.push_back(d); continue; }
@@ -857,60 +881,36 @@ int oxb_set_state(oxb_ctx *c, const double *pos, const double *a1, const double 
 	if(!c->have_topology) return fail(c, 2, "topology must be set before the state");
 	if(!c->have_box) return fail(c, 2, "box must be set before the state");
 	if(!c->have_model) return fail(c, 2, "interaction model must be set before the state (it fixes the backbone-site geometry)");
-	const int N = c->N;
-	std::vector<double4> hp(N), hv(N), hL(N), hq(N);
-	std::vector<int4> hi(N), hk(N);
-	std::vector<float4> hqf(N);
-	std::vector<int2> hb(N);
-	std::vector<int> hs(N);
-	for(int i = 0; i < N; i++) {
-		hp[i] = make_double4(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], 0.);
-		hv[i] = vel ? make_double4(vel[3 * i], vel[3 * i + 1], vel[3 * i + 2], 0.) : make_double4(0., 0., 0., 0.);
-		hL[i] = L ? make_double4(L[3 * i], L[3 * i + 1], L[3 * i + 2], 0.) : make_double4(0., 0., 0., 0.);
-		// orthonormalise exactly like the reference's configuration reader (src/Backends/SimBackend.cpp:623-629)
-		double v1[3] = { a1[3 * i], a1[3 * i + 1], a1[3 * i + 2] }, v3_[3] = { a3[3 * i], a3[3 * i + 1], a3[3 * i + 2] }, v2[3];
-		double n1 = std::sqrt(v1[0] * v1[0] + v1[1] * v1[1] + v1[2] * v1[2]), n3 = std::sqrt(v3_[0] * v3_[0] + v3_[1] * v3_[1] + v3_[2] * v3_[2]);
-		if(n1 < 0.9 || n3 < 0.9) {
-			// the reader normalises first; a null vector is an error there as well
-			if(n1 == 0. || n3 == 0.) return fail(c, 1, "Invalid orientation for particle %d: at least one of the vectors is a null vector", i);
-		}
-		for(int k = 0; k < 3; k++) { v1[k] /= n1; v3_[k] /= n3; }
-		double d = v1[0] * v3_[0] + v1[1] * v3_[1] + v1[2] * v3_[2];
-		for(int k = 0; k < 3; k++) v1[k] -= v3_[k] * d;
-		n1 = std::sqrt(v1[0] * v1[0] + v1[1] * v1[1] + v1[2] * v1[2]);
-		for(int k = 0; k < 3; k++) v1[k] /= n1;
-		v2[0] = v3_[1] * v1[2] - v3_[2] * v1[1]; v2[1] = v3_[2] * v1[0] - v3_[0] * v1[2]; v2[2] = v3_[0] * v1[1] - v3_[1] * v1[0];
-		double n2 = std::sqrt(v2[0] * v2[0] + v2[1] * v2[1] + v2[2] * v2[2]);
-		for(int k = 0; k < 3; k++) v2[k] /= n2;
-		quatd q = quat_from_axes(v1, v2, v3_);
-		hq[i] = make_double4(q.x, q.y, q.z, q.w);
-		hqf[i] = make_float4((float) q.x, (float) q.y, (float) q.z, (float) q.w);
-		hi[i].x = (int) to_fixed(pos[3 * i], 1. / c->box[0]);
-		hi[i].y = (int) to_fixed(pos[3 * i + 1], 1. / c->box[1]);
-		hi[i].z = (int) to_fixed(pos[3 * i + 2], 1. / c->box[2]);
-		hi[i].w = pack_word(c->h_btype[i], i);
-		{
-			// backbone site (grooved): r + back_a1 a1 + back_a2 a2, from the same float-rounded constants the kernels use
-			double b1 = c->model.back_a1, b2 = c->model.back_a2, b3 = c->back_a3;
-			hk[i].x = (int) to_fixed(pos[3 * i] + b1 * v1[0] + b2 * v2[0] + b3 * v3_[0], 1. / c->box[0]);
-			hk[i].y = (int) to_fixed(pos[3 * i + 1] + b1 * v1[1] + b2 * v2[1] + b3 * v3_[1], 1. / c->box[1]);
-			hk[i].z = (int) to_fixed(pos[3 * i + 2] + b1 * v1[2] + b2 * v2[2] + b3 * v3_[2], 1. / c->box[2]);
-			hk[i].w = (c->h_n3[i] < 0 || c->h_n5[i] < 0) ? 1 : 0;
-		}
-		hb[i] = make_int2(c->h_n3[i], c->h_n5[i]);
-		hs[i] = i;
-	}
+	// flat arrays -> device staging (straight from the caller's buffers: full PCIe rate when they are pinned), conversion on the device
+	const size_t N = (size_t) c->N, n3d = 3 * N;
+	if(c->d_stage == nullptr) CU(dalloc(&c->d_stage, 15 * N));
+	if(c->d_marshal_err == nullptr) CU(dalloc(&c->d_marshal_err, (size_t) 1));
+	double *dp = c->d_stage, *d1 = dp + n3d, *d3 = d1 + n3d, *dv = d3 + n3d, *dL = dv + n3d;
+	CU(cudaMemcpyAsync(dp, pos, sizeof(double) * n3d, cudaMemcpyHostToDevice, c->stream));
+	CU(cudaMemcpyAsync(d1, a1, sizeof(double) * n3d, cudaMemcpyHostToDevice, c->stream));
+	CU(cudaMemcpyAsync(d3, a3, sizeof(double) * n3d, cudaMemcpyHostToDevice, c->stream));
+	if(vel) CU(cudaMemcpyAsync(dv, vel, sizeof(double) * n3d, cudaMemcpyHostToDevice, c->stream));
+	if(L) CU(cudaMemcpyAsync(dL, L, sizeof(double) * n3d, cudaMemcpyHostToDevice, c->stream));
+	int no_err = 0x7fffffff, first_bad = 0;
+	CU(cudaMemcpyAsync(c->d_marshal_err, &no_err, sizeof(int), cudaMemcpyHostToDevice, c->stream));
 	const int k = c->cur;
-	CU(cudaMemcpyAsync(c->posd[k], hp.data(), sizeof(double4) * N, cudaMemcpyHostToDevice, c->stream));
-	CU(cudaMemcpyAsync(c->veld[k], hv.data(), sizeof(double4) * N, cudaMemcpyHostToDevice, c->stream));
-	CU(cudaMemcpyAsync(c->Ld[k], hL.data(), sizeof(double4) * N, cudaMemcpyHostToDevice, c->stream));
-	CU(cudaMemcpyAsync(c->quatd[k], hq.data(), sizeof(double4) * N, cudaMemcpyHostToDevice, c->stream));
-	CU(cudaMemcpyAsync(c->ipos[k], hi.data(), sizeof(int4) * N, cudaMemcpyHostToDevice, c->stream));
-	CU(cudaMemcpyAsync(c->iback[k], hk.data(), sizeof(int4) * N, cudaMemcpyHostToDevice, c->stream));
-	CU(cudaMemcpyAsync(c->quat[k], hqf.data(), sizeof(float4) * N, cudaMemcpyHostToDevice, c->stream));
-	CU(cudaMemcpyAsync(c->bonds[k], hb.data(), sizeof(int2) * N, cudaMemcpyHostToDevice, c->stream));
-	CU(cudaMemcpyAsync(c->slot_of, hs.data(), sizeof(int) * N, cudaMemcpyHostToDevice, c->stream));
+	oxb::MarshalArgs a;
+	a.N = c->N; a.pos = dp; a.a1 = d1; a.a3 = d3; a.vel = vel ? dv : nullptr; a.L = L ? dL : nullptr;
+	a.topo = c->d_topo;
+	for(int d = 0; d < 3; d++) a.box_inv[d] = 1. / c->box[d];
+	a.back_a1 = c->model.back_a1; a.back_a2 = c->model.back_a2; a.back_a3 = c->back_a3;
+	a.posd = c->posd[k]; a.veld = c->veld[k]; a.Ld = c->Ld[k]; a.quatd = c->quatd[k];
+	a.ipos = c->ipos[k]; a.iback = c->iback[k]; a.quat = c->quat[k]; a.bonds = c->bonds[k]; a.slot_of = c->slot_of;
+	a.err = c->d_marshal_err;
+	oxb::launch_state_in(c->stream, a);
+	c->launches++;
+	CU(cudaGetLastError());
+	CU(cudaMemcpyAsync(&first_bad, c->d_marshal_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
 	CU(cudaStreamSynchronize(c->stream));
+	if(first_bad != no_err) {
+		c->have_state = false;
+		return fail(c, 1, "Invalid orientation for particle %d: at least one of the vectors is a null vector", first_bad);
+	}
 	c->have_state = true;
 	c->lists_valid = false; c->forces_valid = false; c->mid_step = false;
 	c->trial_open = false;
@@ -920,30 +920,21 @@ int oxb_set_state(oxb_ctx *c, const double *pos, const double *a1, const double 
 int oxb_get_state(oxb_ctx *c, double *pos, double *a1, double *a3, double *vel, double *L) {
 	if(c == nullptr) return 1;
 	if(!c->have_state) return fail(c, 2, "state not set");
-	const int N = c->N, k = c->cur;
-	std::vector<double4> hp(N), hv(N), hL(N), hq(N);
-	std::vector<int4> hi(N);
-	CU(cudaMemcpyAsync(hp.data(), c->posd[k], sizeof(double4) * N, cudaMemcpyDeviceToHost, c->stream));
-	CU(cudaMemcpyAsync(hv.data(), c->veld[k], sizeof(double4) * N, cudaMemcpyDeviceToHost, c->stream));
-	CU(cudaMemcpyAsync(hL.data(), c->Ld[k], sizeof(double4) * N, cudaMemcpyDeviceToHost, c->stream));
-	CU(cudaMemcpyAsync(hq.data(), c->quatd[k], sizeof(double4) * N, cudaMemcpyDeviceToHost, c->stream));
-	CU(cudaMemcpyAsync(hi.data(), c->ipos[k], sizeof(int4) * N, cudaMemcpyDeviceToHost, c->stream));
+	// slot order -> original order and quaternion -> a1 / a3 on the device, then flat copies straight into the caller's buffers
+	const size_t N = (size_t) c->N, n3d = 3 * N;
+	const int k = c->cur;
+	if(c->d_stage == nullptr) CU(dalloc(&c->d_stage, 15 * N));
+	double *dp = c->d_stage, *d1 = dp + n3d, *d3 = d1 + n3d, *dv = d3 + n3d, *dL = dv + n3d;
+	oxb::launch_state_out(c->stream, c->N, c->ipos[k], c->posd[k], c->veld[k], c->Ld[k], c->quatd[k], pos ? dp : nullptr, a1 ? d1 : nullptr,
+			a3 ? d3 : nullptr, vel ? dv : nullptr, L ? dL : nullptr);
+	c->launches++;
+	CU(cudaGetLastError());
+	if(pos) CU(cudaMemcpyAsync(pos, dp, sizeof(double) * n3d, cudaMemcpyDeviceToHost, c->stream));
+	if(a1) CU(cudaMemcpyAsync(a1, d1, sizeof(double) * n3d, cudaMemcpyDeviceToHost, c->stream));
+	if(a3) CU(cudaMemcpyAsync(a3, d3, sizeof(double) * n3d, cudaMemcpyDeviceToHost, c->stream));
+	if(vel) CU(cudaMemcpyAsync(vel, dv, sizeof(double) * n3d, cudaMemcpyDeviceToHost, c->stream));
+	if(L) CU(cudaMemcpyAsync(L, dL, sizeof(double) * n3d, cudaMemcpyDeviceToHost, c->stream));
 	CU(cudaStreamSynchronize(c->stream));
-	for(int s = 0; s < N; s++) {
-		int i = word_index(hi[s].w);
-		if(pos) { pos[3 * i] = hp[s].x; pos[3 * i + 1] = hp[s].y; pos[3 * i + 2] = hp[s].z; }
-		if(vel) { vel[3 * i] = hv[s].x; vel[3 * i + 1] = hv[s].y; vel[3 * i + 2] = hv[s].z; }
-		if(L) { L[3 * i] = hL[s].x; L[3 * i + 1] = hL[s].y; L[3 * i + 2] = hL[s].z; }
-		if(a1 || a3) {
-			quatd q = { hq[s].x, hq[s].y, hq[s].z, hq[s].w };
-			double x1[3], x2[3], x3[3];
-			axes_from_quatd(q, x1, x2, x3);
-			for(int d = 0; d < 3; d++) {
-				if(a1) a1[3 * i + d] = x1[d];
-				if(a3) a3[3 * i + d] = x3[d];
-			}
-		}
-	}
 	return 0;
 }
 
@@ -1221,6 +1212,30 @@ static int barostat_tables(oxb_ctx *c) {
 	CU(dalloc(&c->iback_backup, (size_t) N));
 	CU(cudaMemcpy(c->mol_of, mol.data(), sizeof(int) * N, cudaMemcpyHostToDevice));
 	CU(cudaMemcpy(c->mol_inv_size, inv.data(), sizeof(double) * c->n_mol, cudaMemcpyHostToDevice));
+	return 0;
+}
+
+int oxb_fix_diffusion(oxb_ctx *c, int *shifts) {
+	if(c == nullptr) return 1;
+	int rc = check_ready(c);
+	if(rc) return rc;
+	if(c->mid_step) return fail(c, 2, "fix_diffusion needs a completed step (call between runs)");
+	rc = barostat_tables(c);
+	if(rc) return rc;
+	const int N = c->N, k = c->cur;
+	int *d_shifts = nullptr;
+	if(shifts) {
+		// staging (15 N doubles) is free between set/get_state calls
+		if(c->d_stage == nullptr) CU(dalloc(&c->d_stage, 15 * (size_t) N));
+		d_shifts = reinterpret_cast<int *>(c->d_stage);
+	}
+	oxb::launch_mol_coms(c->stream, N, c->n_mol, c->ipos[k], c->mol_of, c->mol_inv_size, c->posd[k], c->mol_coms);
+	oxb::launch_fix_diffusion(c->stream, N, c->ipos[k], c->mol_of, c->mol_coms, c->box, c->posd[k], c->quatd[k], c->quat[k], d_shifts);
+	c->launches += 2;
+	CU(cudaGetLastError());
+	if(shifts) CU(cudaMemcpyAsync(shifts, d_shifts, sizeof(int) * 3 * (size_t) N, cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	// positions moved by whole box sides: fixed-point images, lists and forces stay valid
 	return 0;
 }
 

@@ -530,11 +530,16 @@ __device__ __forceinline__ v3 ext_single(const DevExtForce &e, double4 p, int4 i
 		}
 		int4 ic;
 		ic.x = (int) to_fixed(cx, 1. / (double) box.lx); ic.y = (int) to_fixed(cy, 1. / (double) box.ly); ic.z = (int) to_fixed(cz, 1. / (double) box.lz);
-		v3 d = min_image_fixed(box, ic, ip);
-		float m = sqrtf(dot(d, d));
+		// the steep WCA walls act on a DIFFERENCE of lengths (radius - |d|, |d| - radius): |d| in double, the rest in float
+		const double dxd = (double) (int) ((unsigned) ip.x - (unsigned) ic.x) * ((double) box.lx * (1. / 4294967296.));
+		const double dyd = (double) (int) ((unsigned) ip.y - (unsigned) ic.y) * ((double) box.ly * (1. / 4294967296.));
+		const double dzd = (double) (int) ((unsigned) ip.z - (unsigned) ic.z) * ((double) box.lz * (1. / 4294967296.));
+		const double md = sqrt(dxd * dxd + dyd * dyd + dzd * dzd);
+		v3 d = mk3((float) dxd, (float) dyd, (float) dzd);
+		float m = (float) md;
 		if(e.type == OXB_EXT_YUKAWA_SPHERE) {
 			// YukawaSphere.cpp:53-74 (the WCA exponent is 6 whatever WCA_n says, as there)
-			float ds = e.r0 - m;
+			float ds = (float) (e.r0d - md);
 			if(!(ds < e.aux[4])) return mk3(0.f, 0.f, 0.f);
 			float s = e.aux[3] * expf(-ds / e.aux[2]) * (1.f / (ds * e.aux[2]) + 1.f / (ds * ds));
 			if(ds < e.aux[1]) {
@@ -545,7 +550,7 @@ __device__ __forceinline__ v3 ext_single(const DevExtForce &e, double4 p, int4 i
 			return d * (-s / m);
 		}
 		// RepulsiveSphereMoving.cpp:94-131: WCA (x = 2, sigma = 1, epsilon = stiff) in the surface gap r = |d| - radius
-		float r = m - (e.r0 + e.rate * st);
+		float r = (float) (md - (e.r0d + (double) e.rate * (double) step));
 		if(r >= e.aux[0] || m <= 0.f || r >= 1.41421356237f) return mk3(0.f, 0.f, 0.f);
 		float rs = fmaxf(r, 1e-9f);
 		float A = 1.f / (rs * rs);

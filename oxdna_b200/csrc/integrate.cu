@@ -315,6 +315,29 @@ __global__ void k_mol_coms(int N, const int4 *__restrict__ ipos, const int *__re
 	atomicAdd(coms + 3 * m, r.x * w); atomicAdd(coms + 3 * m + 1, r.y * w); atomicAdd(coms + 3 * m + 2, r.z * w);
 }
 
+// SimBackend::fix_diffusion (src/Backends/SimBackend.cpp:786-882) + CubicBox::shift_particle (src/Boxes/CubicBox.cpp:70-77): every strand is
+// translated by whole box sides so that its centre of mass lies inside the box; the unit quaternion is renormalised (the reference
+// orthonormalises the rotation matrix).  A shift by whole box sides leaves every minimum-image separation -- hence energy, forces and
+// Verlet lists -- untouched, so the reference's before/after energy check has nothing to catch here.  shifts (may be null): floor(com / L)
+// per original particle id, for the caller's BaseParticle::_pos_shift.
+__global__ void k_fix_diffusion(int N, const int4 *__restrict__ ipos, const int *__restrict__ mol_of, const double *__restrict__ coms, double lx,
+		double ly, double lz, double4 *__restrict__ posd, double4 *__restrict__ quatd, float4 *__restrict__ quat, int *__restrict__ shifts) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= N) return;
+	const int id = word_index(ipos[i].w);
+	const double *cm = coms + 3 * mol_of[id];
+	const double sx = floor(cm[0] / lx), sy = floor(cm[1] / ly), sz = floor(cm[2] / lz);
+	double4 r = posd[i];
+	r.x -= lx * sx; r.y -= ly * sy; r.z -= lz * sz;
+	posd[i] = r;
+	double4 q = quatd[i];
+	const double n = rsqrt(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+	q.x *= n; q.y *= n; q.z *= n; q.w *= n;
+	quatd[i] = q;
+	quat[i] = make_float4((float) q.x, (float) q.y, (float) q.z, (float) q.w);
+	if(shifts) { shifts[3 * id] = (int) sx; shifts[3 * id + 1] = (int) sy; shifts[3 * id + 2] = (int) sz; }
+}
+
 // molecular: r += com(molecule) * shift; atomic: r *= ratio.  Then the fixed-point centre and backbone site are re-encoded for the NEW box.
 __global__ void k_rescale_positions(oxb::RescaleArgs a) {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -380,6 +403,12 @@ void launch_mol_coms(cudaStream_t s, int N, int n_mol, const int4 *ipos, const i
 	cudaMemsetAsync(coms, 0, sizeof(double) * 3 * (size_t) n_mol, s);
 	int tpb = 256;
 	k_mol_coms<<<(N + tpb - 1) / tpb, tpb, 0, s>>>(N, ipos, mol_of, inv_size, posd, coms);
+}
+
+void launch_fix_diffusion(cudaStream_t s, int N, const int4 *ipos, const int *mol_of, const double *coms, const double *box, double4 *posd,
+		double4 *quatd, float4 *quat, int *shifts) {
+	int tpb = 256;
+	k_fix_diffusion<<<(N + tpb - 1) / tpb, tpb, 0, s>>>(N, ipos, mol_of, coms, box[0], box[1], box[2], posd, quatd, quat, shifts);
 }
 
 void launch_rescale_positions(cudaStream_t s, const RescaleArgs &a) {

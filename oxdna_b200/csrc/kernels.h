@@ -25,7 +25,8 @@ struct DevExtForce {
 	double pos0[3];
 	float aux[8];
 	int iaux;
-	double daux; // SPHERE_MOVING: number of steps origin -> target
+	double daux;  // SPHERE_MOVING: number of steps origin -> target
+	double r0d;   // r0 at full precision (radii of the steep walls)
 };
 
 struct ThermostatCfg {
@@ -109,6 +110,24 @@ void launch_integrate_epoch(cudaStream_t s, const IntegrateArgs &a, int phases, 
 void launch_bussi_update_epoch(cudaStream_t s, KinSums *sums, int N, ThermostatCfg th, long long step, const int *flags, int epoch);
 void launch_clear_sums(cudaStream_t s, KinSums *sums, const int *flags, int epoch);
 void launch_kinetic_sums(cudaStream_t s, int N, const double4 *veld, const double4 *Ld, KinSums *sums);
+// ---- marshal.cu: state marshalling on the device (flat N x 3 double arrays in the order of the original particle ids)
+struct MarshalArgs {
+	int N;
+	const double *pos, *a1, *a3, *vel, *L; // device staging; vel / L may be null (zero momenta)
+	const int4 *topo;                      // btype, n3, n5, strand per original id
+	double box_inv[3];
+	float back_a1, back_a2, back_a3;
+	double4 *posd, *veld, *Ld, *quatd;
+	int4 *ipos, *iback;
+	float4 *quat;
+	int2 *bonds;
+	int *slot_of;
+	int *err; // smallest particle id with a null orientation vector (INT_MAX = none)
+};
+void launch_state_in(cudaStream_t s, const MarshalArgs &a);
+void launch_state_out(cudaStream_t s, int N, const int4 *ipos, const double4 *posd, const double4 *veld, const double4 *Ld, const double4 *quatd,
+		double *pos, double *a1, double *a3, double *vel, double *L);
+
 // MC barostat: molecular centres of mass (FP64, one atomicAdd triple per particle) and position rescaling + fixed-point re-encode
 struct RescaleArgs {
 	int N, molecular;
@@ -123,6 +142,9 @@ struct RescaleArgs {
 };
 void launch_mol_coms(cudaStream_t s, int N, int n_mol, const int4 *ipos, const int *mol_of, const double *inv_size, const double4 *posd, double *coms);
 void launch_rescale_positions(cudaStream_t s, const RescaleArgs &a);
+// fix_diffusion: strands translated by whole box sides back into the box (coms from launch_mol_coms), quaternions renormalised
+void launch_fix_diffusion(cudaStream_t s, int N, const int4 *ipos, const int *mol_of, const double *coms, const double *box, double4 *posd,
+		double4 *quatd, float4 *quat, int *shifts);
 void launch_energy_sum(cudaStream_t s, int N, const float4 *F, const float4 *Fb, double *out);
 
 // ---- lists.cu

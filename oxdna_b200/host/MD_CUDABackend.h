@@ -45,6 +45,7 @@ public:
 	void get_settings(input_file &inp) override;
 	void init() override;
 	void sim_step() override;
+	void fix_diffusion() override;
 	void apply_simulation_data_changes() override;
 	void apply_changes_to_simulation_data() override;
 };

@@ -210,7 +210,8 @@ needs_binaries = pytest.mark.skipif(not (os.path.exists(OURS) and os.path.exists
 @needs_binaries
 @pytest.mark.parametrize("use_edge,sort_every,extra", [(1, 1, ""), (0, 0, ""), (1, 1, "external_forces = 1\nexternal_forces_file = forces.txt"),
                                                        (1, 1, "external_forces = 1\nexternal_forces_file = forces2.txt"),
-                                                       (1, 1, "external_forces = 1\nexternal_forces_file = forces3.txt")])
+                                                       (1, 1, "external_forces = 1\nexternal_forces_file = forces3.txt"),
+                                                       (1, 1, "fix_diffusion_every = 100")])
 def test_stock_input_file_matches_reference_cpu(tmp_path, use_edge, sort_every, extra):
     a = run(OURS, str(tmp_path / "ours"), backend="CUDA", itype="DNA2", steps=300, thermostat="no", use_edge=use_edge, sort_every=sort_every, extra=extra)
     assert a.returncode == 0, a.stdout[-2000:]
