@@ -111,7 +111,6 @@ struct oxb_ctx {
 	int *mol_of = nullptr;
 	double *mol_inv_size = nullptr, *mol_coms = nullptr;
 	double4 *pos_backup = nullptr;
-	int4 *ipos_backup = nullptr, *iback_backup = nullptr;
 	double box_backup[3] = { 0., 0., 0. };
 	bool trial_open = false;
 	int n_ext_com = 0;           // COM forces (one entry per force, evaluated by one block each)
@@ -691,7 +690,7 @@ void oxb_destroy(oxb_ctx *c) {
 	cudaFree(c->Fb);
 	cudaFree(c->slot_of); cudaFree(c->flags); cudaFree(c->sums); cudaFree(c->d_energy); cudaFree(c->ext); cudaFree(c->ext_all); cudaFree(c->ext_com); cudaFree(c->ext_pool);
 	cudaFree(c->d_topo); cudaFree(c->d_stage); cudaFree(c->d_marshal_err);
-	cudaFree(c->mol_of); cudaFree(c->mol_inv_size); cudaFree(c->mol_coms); cudaFree(c->pos_backup); cudaFree(c->ipos_backup); cudaFree(c->iback_backup); cudaFree(c->pos_f4);
+	cudaFree(c->mol_of); cudaFree(c->mol_inv_size); cudaFree(c->mol_coms); cudaFree(c->pos_backup); cudaFree(c->pos_f4);
 	cudaFree(c->hkeys); cudaFree(c->hkeys_sorted); cudaFree(c->hvals); cudaFree(c->hvals_sorted); cudaFree(c->hinv);
 	free_lists(c);
 	if(c->h_flags) cudaFreeHost(c->h_flags);
@@ -742,8 +741,8 @@ int oxb_set_topology(oxb_ctx *c, const int *btype, const int *n3, const int *n5,
 	}
 	c->have_topology = true;
 	c->have_state = false;
-	cudaFree(c->mol_of); cudaFree(c->mol_inv_size); cudaFree(c->mol_coms); cudaFree(c->pos_backup); cudaFree(c->ipos_backup); cudaFree(c->iback_backup);
-	c->mol_of = nullptr; c->mol_inv_size = nullptr; c->mol_coms = nullptr; c->pos_backup = nullptr; c->ipos_backup = c->iback_backup = nullptr;
+	cudaFree(c->mol_of); cudaFree(c->mol_inv_size); cudaFree(c->mol_coms); cudaFree(c->pos_backup);
+	c->mol_of = nullptr; c->mol_inv_size = nullptr; c->mol_coms = nullptr; c->pos_backup = nullptr;
 	c->trial_open = false;
 	return 0;
 }
@@ -1208,8 +1207,6 @@ static int barostat_tables(oxb_ctx *c) {
 	CU(dalloc(&c->mol_inv_size, (size_t) c->n_mol));
 	CU(dalloc(&c->mol_coms, 3 * (size_t) c->n_mol));
 	CU(dalloc(&c->pos_backup, (size_t) N));
-	CU(dalloc(&c->ipos_backup, (size_t) N));
-	CU(dalloc(&c->iback_backup, (size_t) N));
 	CU(cudaMemcpy(c->mol_of, mol.data(), sizeof(int) * N, cudaMemcpyHostToDevice));
 	CU(cudaMemcpy(c->mol_inv_size, inv.data(), sizeof(double) * c->n_mol, cudaMemcpyHostToDevice));
 	return 0;
@@ -1256,10 +1253,8 @@ int oxb_barostat_trial(oxb_ctx *c, const double new_box[3], int molecular) {
 	rc = barostat_tables(c);
 	if(rc) return rc;
 	const int N = c->N, k = c->cur;
-	CU(cudaMemcpyAsync(c->pos_backup, c->posd[k], sizeof(double4) * N, cudaMemcpyDeviceToDevice, c->stream));
-	CU(cudaMemcpyAsync(c->ipos_backup, c->ipos[k], sizeof(int4) * N, cudaMemcpyDeviceToDevice, c->stream));
-	CU(cudaMemcpyAsync(c->iback_backup, c->iback[k], sizeof(int4) * N, cudaMemcpyDeviceToDevice, c->stream));
 	oxb::RescaleArgs a;
+	a.backup = c->pos_backup; a.restore = nullptr;
 	a.N = N; a.molecular = molecular ? 1 : 0;
 	for(int d = 0; d < 3; d++) {
 		c->box_backup[d] = c->box[d];
@@ -1280,10 +1275,18 @@ int oxb_barostat_trial(oxb_ctx *c, const double new_box[3], int molecular) {
 int oxb_barostat_reject(oxb_ctx *c) {
 	if(c == nullptr) return 1;
 	if(!c->trial_open) return fail(c, 2, "no barostat trial is open");
+	// the slots may have been re-sorted since the trial (list rebuild in the new box): restore by original id, then re-encode the
+	// fixed-point centre and backbone site for the old box
 	const int N = c->N, k = c->cur;
-	CU(cudaMemcpyAsync(c->posd[k], c->pos_backup, sizeof(double4) * N, cudaMemcpyDeviceToDevice, c->stream));
-	CU(cudaMemcpyAsync(c->ipos[k], c->ipos_backup, sizeof(int4) * N, cudaMemcpyDeviceToDevice, c->stream));
-	CU(cudaMemcpyAsync(c->iback[k], c->iback_backup, sizeof(int4) * N, cudaMemcpyDeviceToDevice, c->stream));
+	oxb::RescaleArgs a;
+	a.N = N; a.molecular = 0;
+	for(int d = 0; d < 3; d++) { a.f[d] = 1.; a.box_inv[d] = 1. / c->box_backup[d]; }
+	a.posd = c->posd[k]; a.quatd = c->quatd[k]; a.ipos = c->ipos[k]; a.iback = c->iback[k];
+	a.mol_of = c->mol_of; a.coms = c->mol_coms; a.backup = nullptr; a.restore = c->pos_backup;
+	a.back_a1 = c->model.back_a1; a.back_a2 = c->model.back_a2; a.back_a3 = c->back_a3;
+	oxb::launch_rescale_positions(c->stream, a);
+	c->launches++;
+	CU(cudaGetLastError());
 	c->trial_open = false;
 	return oxb_set_box(c, c->box_backup);
 }

@@ -7,6 +7,8 @@
 #include "models.cuh"
 #include "kernels.h"
 
+#include <cstdlib>
+
 #include <algorithm>
 
 // minimum resident blocks per SM asked of the compiler for the latency-bound gather kernels (register cap = 65536 / (threads x blocks)).
@@ -141,19 +143,25 @@ __device__ __forceinline__ bool segmented_reduce(int key, unsigned lane, float (
 // Debye-Hueckel, particle-centric over its own neighbour matrix (selected on the backbone-site distance): per neighbour one
 // coalesced index load + one 16-byte gather of a fixed-point backbone site; no atomics, deterministic.  Writes the
 // backbone-site force sum Fb (.w = energy); k_bonded_finalize folds it into force and torque.
-template<class MD>
+// LPP lanes share one particle (lane s takes neighbours s, s + LPP, ...; partial sums folded with shuffles in a fixed order, so the
+// result stays deterministic): systems that cannot fill the GPU with one thread per particle (C2: 17 warps per SM) get LPP times the
+// loads in flight; index loads stay sector-efficient (LPP rows x 32 / LPP consecutive ints per warp instruction).
+template<class MD, int LPP>
 __global__ void __launch_bounds__(128) k_dh_particle(const __grid_constant__ typename MD::Params M, BoxF box, int N, const int4 *__restrict__ iback,
 		const int *__restrict__ dh_nbr, const int *__restrict__ dh_nnbr, float4 *__restrict__ Fb, const int *__restrict__ flags, int hw) {
 	if(flags[hw]) return;
-	int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if(i >= N) return;
+	const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+	const int sub = gid % LPP;
+	int i = gid / LPP;
+	const bool active = i < N;
+	if(!active) i = N - 1; // whole groups stay in the shuffles
 	const int4 bp = __ldg(iback + i);
-	const int nn = __ldg(dh_nnbr + i);
+	const int nn = active ? __ldg(dh_nnbr + i) : 0;
 	const bool p_end = bp.w & 1;
 	v3 f = mk3(0.f, 0.f, 0.f);
 	float e = 0.f;
 #pragma unroll 4
-	for(int k = 0; k < nn; k++) {
+	for(int k = sub; k < nn; k += LPP) {
 		int j = __ldg(dh_nbr + (size_t) k * N + i);
 		int4 bq = __ldg(iback + j);
 		v3 rbb = min_image_fixed(box, bp, bq);
@@ -162,7 +170,14 @@ __global__ void __launch_bounds__(128) k_dh_particle(const __grid_constant__ typ
 		e += en;
 		axpy(f, -fs, rbb);
 	}
-	Fb[i] = make_float4(f.x, f.y, f.z, e);
+	if(LPP > 1) {
+#pragma unroll
+		for(int o = LPP >> 1; o > 0; o >>= 1) {
+			f.x += __shfl_xor_sync(0xffffffffu, f.x, o); f.y += __shfl_xor_sync(0xffffffffu, f.y, o);
+			f.z += __shfl_xor_sync(0xffffffffu, f.z, o); e += __shfl_xor_sync(0xffffffffu, e, o);
+		}
+	}
+	if(active && sub == 0) Fb[i] = make_float4(f.x, f.y, f.z, e);
 }
 
 // Work lists are SEGMENTED by producer block: block b of k_edge_near owns list[b * seg .. (b + 1) * seg) and publishes its
@@ -656,11 +671,24 @@ void launch_forces_particle(cudaStream_t s, const ModelRef &MR, BoxF box, int N,
 // the kernels of the edge pipeline, launched one by one so that the context can place them on concurrent streams:
 //   which = 0 Debye-Hueckel (writes Fb) | 1 near edges (F, T, work lists) | 2 HB (+ cross stacking) | 3 coaxial stacking | 4 bonds
 //           5 cross stacking only
+static int env_int(const char *name, int dflt) {
+	const char *v = getenv(name);
+	return (v != nullptr && v[0] != 0) ? atoi(v) : dflt;
+}
+
 template<class MD>
 static void launch_edge_stage_t(cudaStream_t s, int which, const typename MD::Params &M, BoxF box, const EdgeArgs &a, int *flags, int hw) {
 	auto blocks_for = [&](long long items) { return (int) std::max<long long>(1, (items + 127) / 128); };
 	switch(which) {
-	case 0: k_dh_particle<MD><<<blocks_for(a.N), 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, flags, hw); break;
+	case 0: {
+		// lanes per particle: 4 below ~300k particles (one thread per particle leaves the SMs short of loads in flight), else 1
+		static const int lpp_env = env_int("OXB_DH_LPP", 0);
+		const int lpp = lpp_env > 0 ? lpp_env : (a.N < 300000 ? 4 : 1);
+		if(lpp >= 4) k_dh_particle<MD, 4><<<blocks_for(4ll * a.N), 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, flags, hw);
+		else if(lpp == 2) k_dh_particle<MD, 2><<<blocks_for(2ll * a.N), 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, flags, hw);
+		else k_dh_particle<MD, 1><<<blocks_for(a.N), 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, flags, hw);
+		break;
+	}
 	// the producer and the three consumers of the segmented work lists share one fixed grid (a.n_seg blocks, grid-stride
 	// inside): nothing here depends on device-side counts, so a captured graph stays valid across list rebuilds
 	case 1:
@@ -670,7 +698,12 @@ static void launch_edge_stage_t(cudaStream_t s, int which, const typename MD::Pa
 	case 2: k_edge_heavy<MD, 0><<<dim3(a.n_seg, a.hb_split), 64, 0, s>>>(M, box, a.seg_counts, a.hb_list, a.hb_seg, a.ipos, a.quat, a.F, a.T, flags, hw); break;
 	case 3: k_edge_heavy<MD, 1><<<a.n_seg, 64, 0, s>>>(M, box, a.seg_counts, a.cx_list, a.cx_seg, a.ipos, a.quat, a.F, a.T, flags, hw); break;
 	case 5: k_edge_heavy<MD, 2><<<dim3(a.n_seg, a.hb_split), 64, 0, s>>>(M, box, a.seg_counts, a.cr_list, a.cr_seg, a.ipos, a.quat, a.F, a.T, flags, hw); break;
-	default: k_bonded<MD><<<blocks_for(a.N), 128, 0, s>>>(M, box, a.N, a.ipos, a.quat, a.bonds, a.F, a.T, flags, hw); break;
+	default: {
+		static const int tpb_env = env_int("OXB_TPB_BONDED", 0);
+		const int tpb = tpb_env > 0 ? tpb_env : 128;
+		k_bonded<MD><<<(a.N + tpb - 1) / tpb, tpb, 0, s>>>(M, box, a.N, a.ipos, a.quat, a.bonds, a.F, a.T, flags, hw);
+		break;
+	}
 	}
 }
 

@@ -13,6 +13,8 @@
 //  * list staleness raises a device flag that turns the rest of a speculative batch of launches into no-ops.
 #include "kernels.h"
 
+#include <cstdlib>
+
 namespace {
 
 __device__ __forceinline__ void philox_gauss4(unsigned long long seed, unsigned id, unsigned long long step, unsigned draw, float g[4]) {
@@ -299,7 +301,9 @@ __global__ void __launch_bounds__(256) k_energy_sum(int N, const float4 *__restr
 
 template<int PH>
 void launch_ph(cudaStream_t s, const oxb::IntegrateArgs &a, int epoch) {
-	int tpb = 256;
+	// small systems: 128-thread blocks halve the tail of the last wave (C2: 320 blocks of 256 on 148 SMs = 2.2 blocks per SM)
+	static const int tpb_env = [] { const char *v = getenv("OXB_TPB_INTEGRATE"); return (v != nullptr && v[0] != 0) ? atoi(v) : 0; }();
+	int tpb = tpb_env > 0 ? tpb_env : 256;
 	k_integrate<PH><<<(a.N + tpb - 1) / tpb, tpb, 0, s>>>(a, epoch);
 }
 
@@ -344,7 +348,9 @@ __global__ void k_rescale_positions(oxb::RescaleArgs a) {
 	if(i >= a.N) return;
 	double4 r = a.posd[i];
 	int4 ip = a.ipos[i];
-	if(a.molecular) {
+	if(a.backup) a.backup[word_index(ip.w)] = r; // snapshot by ORIGINAL id: a re-sort may reorder the slots before a rejection
+	if(a.restore) r = a.restore[word_index(ip.w)];
+	else if(a.molecular) {
 		const double *cm = a.coms + 3 * a.mol_of[word_index(ip.w)];
 		r.x += cm[0] * a.f[0]; r.y += cm[1] * a.f[1]; r.z += cm[2] * a.f[2];
 	}

@@ -138,6 +138,8 @@ struct RescaleArgs {
 	int4 *ipos, *iback;
 	const int *mol_of;  // molecule of an original particle id
 	const double *coms; // 3 doubles per molecule
+	double4 *backup;         // if set: positions before the move, indexed by original id
+	const double4 *restore;  // if set: positions are taken from here (rejected move) instead of being rescaled
 	float back_a1, back_a2, back_a3;
 };
 void launch_mol_coms(cudaStream_t s, int N, int n_mol, const int4 *ipos, const int *mol_of, const double *inv_size, const double4 *posd, double *coms);
