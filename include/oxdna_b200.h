@@ -22,7 +22,7 @@ enum { OXB_THERMOSTAT_NONE = 0, OXB_THERMOSTAT_BROWNIAN = 1, OXB_THERMOSTAT_LANG
 enum { OXB_EXT_STRING = 0, OXB_EXT_TRAP = 1, OXB_EXT_MUTUAL_TRAP = 2, OXB_EXT_LOWDIM_TRAP = 3, OXB_EXT_REPULSION_PLANE = 4,
 	OXB_EXT_ATTRACTION_PLANE = 5, OXB_EXT_SPHERE = 6, OXB_EXT_LJ_WALL = 7, OXB_EXT_TWIST = 8, OXB_EXT_SPHERE_SMOOTH = 9, OXB_EXT_ELLIPSOID = 10,
 	OXB_EXT_REPULSION_PLANE_MOVING = 11, OXB_EXT_GENERIC_CENTRAL = 12, OXB_EXT_LJ_CONE = 13, OXB_EXT_COM = 14, OXB_EXT_YUKAWA_SPHERE = 15,
-	OXB_EXT_SPHERE_MOVING = 16, OXB_EXT_NTYPES };
+	OXB_EXT_SPHERE_MOVING = 16, OXB_EXT_META_COM_TRAP = 17, OXB_EXT_NTYPES };
 enum { OXB_TERM_FENE = 0, OXB_TERM_BEXC, OXB_TERM_STCK, OXB_TERM_NEXC, OXB_TERM_HB, OXB_TERM_CRST, OXB_TERM_CXST, OXB_TERM_DH, OXB_NTERMS };
 
 /* ---- force-field parameters (device constant block).  Replaces the __constant__ upload of
@@ -142,7 +142,11 @@ int oxb_rna2_params_seqdep(oxb_rna2_params *P, double T, const double *stck_raw1
  *                                                        directly and has pbc entries; particle is ignored
  *   YUKAWA_SPHERE        YukawaSphere                    pos0 = center, r0 = radius, stiff = WCA_epsilon, aux[0] = WCA sigma, aux[1] = WCA cutoff,
  *                                                        aux[2] = debye_length, aux[3] = debye_A, aux[4] = cutoff, iaux = WCA_n
- *   SPHERE_MOVING        RepulsiveSphereMoving           stiff, r0, rate, pos0 = origin, aux[0] = r_ext, aux[1..3] = target, aux[4] = steps */
+ *   SPHERE_MOVING        RepulsiveSphereMoving           stiff, r0, rate, pos0 = origin, aux[0] = r_ext, aux[1..3] = target, aux[4] = steps
+ *   META_COM_TRAP        LTCOMTrap (meta_com_trap)       ONE entry per force: ref = offset of p1a in the index pool, iaux = its length, p2a follows with
+ *                                                        pbc entries; aux[0] = xmin, aux[1] = dX, aux[2] = N_grid, aux[3] = mode (1: acts on p1a,
+ *                                                        2: on p2a), aux[4] = offset of potential_grid in the grid pool
+ *                                                        (oxb_set_ext_grid_pool), aux[5] = PBC */
 typedef struct {
 	int type;      /* OXB_EXT_* */
 	int particle;  /* original index, or -1 = all particles */
@@ -184,6 +188,9 @@ int oxb_set_ext_forces(oxb_ctx *ctx, int n, const oxb_ext_force *forces);
  * (src/Forces/COMForce.cpp:31-44; the reference uploads them per force, src/CUDA/Forces/forces_defs.cuh:367-393).  Call before
  * oxb_set_ext_forces. */
 int oxb_set_ext_index_pool(oxb_ctx *ctx, int n, const int *indices);
+/* tabulated bias potentials referenced by OXB_EXT_META_COM_TRAP entries: LTCOMTrap::potential_grid (src/Forces/Metadynamics/LTCOMTrap.cpp:36-41;
+ * uploaded per force by the reference, src/CUDA/Forces/metad_forces.cuh:33-66).  Call before oxb_set_ext_forces. */
+int oxb_set_ext_grid_pool(oxb_ctx *ctx, int n, const double *values);
 
 /* ---- state marshalling.  Replaces apply_changes_to_simulation_data / apply_simulation_data_changes
  * (src/CUDA/Backends/MD_CUDABackend.cu:231-394).  pos, a1, a3, vel, L: N x 3 doubles, original order. */

@@ -46,4 +46,15 @@ def ext3_forces(pos):
             dict(type="com", com_list="300,301", ref_list="310", stiff=1.0, r0=0.5),
             dict(type="yukawa_sphere", particle="all", radius=round(R, 6), center=tuple(centre), debye_length=1.0, debye_A=0.2, WCA_epsilon=1.0, WCA_sigma=1.0),
             dict(type="repulsive_sphere_moving", particle="all", stiff=0.4, r0=round(r0, 6), rate=0.0005, origin=tuple(np.round(org, 6)),
-                 target=tuple(np.round(org + np.array([0.2, 0.1, 0.0]), 6)), steps=400)]
+                 target=tuple(np.round(org + np.array([0.2, 0.1, 0.0]), 6)), steps=400)] + _meta_traps(pos)
+
+
+def _meta_traps(pos):
+    """a metadynamics bias between the two strands of duplex 4 (tabulated Gaussian hill around their current separation), declared
+    once per mode as the reference's metadynamics interface does"""
+    p1a, p2a = list(range(160, 170)), list(range(190, 200))
+    x0 = float(np.linalg.norm(pos[p1a].mean(axis=0) - pos[p2a].mean(axis=0)))
+    xs = np.linspace(0.0, 5.0, 51)
+    grid = ",".join("%.8f" % v for v in 1.5 * np.exp(-0.5 * ((xs - (x0 + 0.15)) / 0.4) ** 2))
+    common = dict(type="meta_com_trap", p1a=",".join(map(str, p1a)), p2a=",".join(map(str, p2a)), xmin=0.0, xmax=5.0, N_grid=51, potential_grid=grid, PBC=1)
+    return [dict(common, mode=1), dict(common, mode=2)]

@@ -83,7 +83,7 @@ class ExtForce(C.Structure):
         (n, C.c_double) for n in "stiff r0 rate stiff_rate F0".split()] + [("dir", C.c_double * 3), ("pos0", C.c_double * 3),
                                                                               ("aux", C.c_double * 8), ("iaux", C.c_int)]
 
-EXT_TYPES = {"string": 0, "trap": 1, "mutual_trap": 2, "lowdim_trap": 3, "repulsion_plane": 4, "attraction_plane": 5, "sphere": 6, "LJ_wall": 7, "twist": 8, "sphere_smooth": 9, "ellipsoid": 10, "repulsion_plane_moving": 11, "generic_central_force": 12, "LJ_cone": 13, "com": 14, "yukawa_sphere": 15, "repulsive_sphere_moving": 16}
+EXT_TYPES = {"string": 0, "trap": 1, "mutual_trap": 2, "lowdim_trap": 3, "repulsion_plane": 4, "attraction_plane": 5, "sphere": 6, "LJ_wall": 7, "twist": 8, "sphere_smooth": 9, "ellipsoid": 10, "repulsion_plane_moving": 11, "generic_central_force": 12, "LJ_cone": 13, "com": 14, "yukawa_sphere": 15, "repulsive_sphere_moving": 16, "meta_com_trap": 17}
 
 
 def _index_list(v):
@@ -103,13 +103,13 @@ def _index_list(v):
     return [int(x) for x in v]
 
 
-def fill_ext_entry(e, d, pool):
+def fill_ext_entry(e, d, pool, grid):
     """dict with the reference's external-force keys (docs/source/forces.md) -> one table entry (oxb_ext_force / oxo_ext_force)"""
     e.type = EXT_TYPES[d["type"]]
     part = d.get("particle", -1)
     e.particle = -1 if str(part) in ("-1", "all") else int(part)
     e.ref = int(d.get("ref_particle", -1)) if d["type"] != "repulsion_plane_moving" else -1
-    e.pbc = int(d.get("PBC", 0))
+    e.pbc = int(d.get("PBC", 0)) if d["type"] != "meta_com_trap" else 0
     e.stiff, e.r0, e.rate = float(d.get("stiff", 1.0 if d["type"] == "LJ_wall" else 0.0)), float(d.get("r0", 0.0)), float(d.get("rate", 0.0))
     e.stiff_rate, e.F0 = float(d.get("stiff_rate", 0.0)), float(d.get("F0", 0.0))
     dr = np.array(d.get("axis", d.get("dir", (1, 0, 0) if d["type"] != "mutual_trap" else (0, 0, 1))), dtype=np.float64)
@@ -181,6 +181,19 @@ def fill_ext_entry(e, d, pool):
         aux[0] = float(d.get("r_ext", 1e10))
         aux[1:4] = [float(x) for x in d.get("target", (0.0, 0.0, 0.0))]
         aux[4] = float(int(float(d.get("steps", d.get("move_steps", 0)))))
+    elif d["type"] == "meta_com_trap":
+        p1a, p2a = _index_list(d["p1a"]), _index_list(d["p2a"])
+        pg = d["potential_grid"]
+        pg = [float(x) for x in (pg.split(",") if isinstance(pg, str) else pg)]
+        n_grid = int(d["N_grid"])
+        if len(pg) != n_grid:
+            raise ValueError("meta_com_trap: potential_grid must hold N_grid values")
+        e.particle, e.ref, e.iaux, e.pbc = -1, len(pool), len(p1a), len(p2a)
+        pool.extend(p1a + p2a)
+        aux[0], aux[1], aux[2] = float(d["xmin"]), (float(d["xmax"]) - float(d["xmin"])) / (n_grid - 1.0), float(n_grid)
+        aux[3], aux[4], aux[5] = float(int(d["mode"])), float(len(grid)), float(int(d.get("PBC", 0)))
+        e.pbc = len(p2a)
+        grid.extend(pg)
     for c in range(8):
         e.aux[c] = aux[c]
 
@@ -309,11 +322,12 @@ def make_ext(forces_list):
     """table entries; the index pool of the COM forces is handed to the library here (kept alive at module level)"""
     global _pool_keep
     arr = (ExtForce * max(len(forces_list), 1))()
-    pool = []
+    pool, grid = [], []
     for k, d in enumerate(forces_list):
-        fill_ext_entry(arr[k], d, pool)
-    _pool_keep = (C.c_int * max(len(pool), 1))(*pool)
-    lib().oxo_set_ext_pool(_pool_keep)
+        fill_ext_entry(arr[k], d, pool, grid)
+    _pool_keep = ((C.c_int * max(len(pool), 1))(*pool), (C.c_double * max(len(grid), 1))(*grid))
+    lib().oxo_set_ext_pool(_pool_keep[0])
+    lib().oxo_set_ext_grid(_pool_keep[1])
     return arr
 
 

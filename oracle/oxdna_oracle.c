@@ -793,9 +793,33 @@ static void ext_com(const oxo_ext_force *f, int slot, const double *pos, long lo
 	for(int k = 0; k < f->iaux; k++) axpy3(s / m, d, force + 3 * (size_t) cl[k]);
 }
 
+static const double *ext_grid = NULL;
+/* tabulated bias potentials of the metadynamics COM traps (LTCOMTrap::potential_grid) */
+void oxo_set_ext_grid(const double *grid) { ext_grid = grid; }
+
+static void ext_meta_com(const oxo_ext_force *f, const double *pos, const double *box, double *force) {
+	/* src/Forces/Metadynamics/LTCOMTrap.cpp:52-78, meta_utils.h:30-34, meta_utils.cpp:18-21 */
+	const int *l1 = ext_pool + f->ref, *l2 = l1 + f->iaux;
+	const int n1 = f->iaux, n2 = f->pbc, mode = (int) f->aux[3], n_grid = (int) f->aux[2];
+	const double xmin = f->aux[0], dX = f->aux[1], *grid = ext_grid + (int) f->aux[4];
+	double c1[3] = { 0, 0, 0 }, c2[3] = { 0, 0, 0 }, dra[3];
+	for(int k = 0; k < n1; k++) axpy3(1., pos + 3 * (size_t) l1[k], c1);
+	for(int k = 0; k < n2; k++) axpy3(1., pos + 3 * (size_t) l2[k], c2);
+	for(int k = 0; k < 3; k++) { c1[k] /= n1; c2[k] /= n2; }
+	if(f->aux[5] != 0.) min_image(box, c2, c1, dra);
+	else for(int k = 0; k < 3; k++) dra[k] = c1[k] - c2[k];
+	double x = sqrt(dot3(dra, dra));
+	int il = (int) floor((x - xmin) / dX), ir = il + 1;
+	double fx = 0.;
+	if(!(il < 0 || ir > n_grid - 1)) fx = -(grid[ir] - grid[il]) / dX;
+	if(mode == 1) for(int k = 0; k < n1; k++) axpy3(fx / x / n1, dra, force + 3 * (size_t) l1[k]);
+	else for(int k = 0; k < n2; k++) axpy3(fx / x / (-1. * n2), dra, force + 3 * (size_t) l2[k]);
+}
+
 void oxo_ext_forces(int nf, const oxo_ext_force *ef, int N, const double *pos, const double *box, long long step, double *force) {
 	for(int i = 0; i < nf; i++) {
-		if(ef[i].type == OXO_EXT_COM) ext_com(&ef[i], i, pos, step, force);
+		if(ef[i].type == OXO_EXT_META_COM_TRAP) ext_meta_com(&ef[i], pos, box, force);
+		else if(ef[i].type == OXO_EXT_COM) ext_com(&ef[i], i, pos, step, force);
 		else if(ef[i].type > OXO_EXT_ELLIPSOID) {
 			if(ef[i].particle >= 0) ext_more(&ef[i], pos, ef[i].particle, box, step, force);
 			else for(int p = 0; p < N; p++) ext_more(&ef[i], pos, p, box, step, force);

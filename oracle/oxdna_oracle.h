@@ -64,7 +64,7 @@ void oxo_dna2_params_seqdep(oxo_dna2_params *P, const double *stck_raw16, double
 typedef struct { int type; int particle; int ref; int pbc; double stiff, r0, rate, stiff_rate, F0; double dir[3], pos0[3]; double aux[8]; int iaux; } oxo_ext_force;
 enum { OXO_EXT_STRING = 0, OXO_EXT_TRAP = 1, OXO_EXT_MUTUAL = 2, OXO_EXT_LOWDIM = 3, OXO_EXT_REPULSION_PLANE = 4, OXO_EXT_ATTRACTION_PLANE = 5,
 	OXO_EXT_SPHERE = 6, OXO_EXT_LJ_WALL = 7, OXO_EXT_TWIST = 8, OXO_EXT_SPHERE_SMOOTH = 9, OXO_EXT_ELLIPSOID = 10,
-	OXO_EXT_REPULSION_PLANE_MOVING = 11, OXO_EXT_GENERIC_CENTRAL = 12, OXO_EXT_LJ_CONE = 13, OXO_EXT_COM = 14, OXO_EXT_YUKAWA_SPHERE = 15, OXO_EXT_SPHERE_MOVING = 16 };
+	OXO_EXT_REPULSION_PLANE_MOVING = 11, OXO_EXT_GENERIC_CENTRAL = 12, OXO_EXT_LJ_CONE = 13, OXO_EXT_COM = 14, OXO_EXT_YUKAWA_SPHERE = 15, OXO_EXT_SPHERE_MOVING = 16, OXO_EXT_META_COM_TRAP = 17 };
 
 /* axes: N x 9 doubles = a1(3) a2(3) a3(3).  pairs: npairs x 2 ints (non-bonded candidates, each unique pair once).
  * Outputs (any may be NULL): force N x 3 (lab), torque_lab N x 3, torque_body N x 3, eterms[OXO_NTERMS] totals,
@@ -77,6 +77,7 @@ void oxo_dna2_forces(const oxo_dna2_params *P, int N, const double *pos, const d
  * RepulsiveSphere,LJWall}.cpp), added to force (lab frame) */
 /* index pool of the COM forces (entry: ref = offset of com_list, iaux = its length, pbc = length of the ref_list that follows) */
 void oxo_set_ext_pool(const int *pool);
+void oxo_set_ext_grid(const double *grid);
 void oxo_ext_forces(int nf, const oxo_ext_force *ef, int N, const double *pos, const double *box, long long step, double *force);
 
 /* Verlet list exactly as src/Lists/Cells.cpp:120-181 + VerletList.cpp:35-66: unique pairs (q<p), not bonded,

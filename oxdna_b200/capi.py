@@ -76,7 +76,7 @@ class ExtForce(C.Structure):
         (n, C.c_double) for n in "stiff r0 rate stiff_rate F0".split()] + [("dir", C.c_double * 3), ("pos0", C.c_double * 3),
                                                                               ("aux", C.c_double * 8), ("iaux", C.c_int)]
 
-EXT_TYPES = {"string": 0, "trap": 1, "mutual_trap": 2, "lowdim_trap": 3, "repulsion_plane": 4, "attraction_plane": 5, "sphere": 6, "LJ_wall": 7, "twist": 8, "sphere_smooth": 9, "ellipsoid": 10, "repulsion_plane_moving": 11, "generic_central_force": 12, "LJ_cone": 13, "com": 14, "yukawa_sphere": 15, "repulsive_sphere_moving": 16}
+EXT_TYPES = {"string": 0, "trap": 1, "mutual_trap": 2, "lowdim_trap": 3, "repulsion_plane": 4, "attraction_plane": 5, "sphere": 6, "LJ_wall": 7, "twist": 8, "sphere_smooth": 9, "ellipsoid": 10, "repulsion_plane_moving": 11, "generic_central_force": 12, "LJ_cone": 13, "com": 14, "yukawa_sphere": 15, "repulsive_sphere_moving": 16, "meta_com_trap": 17}
 
 
 def _index_list(v):
@@ -96,13 +96,13 @@ def _index_list(v):
     return [int(x) for x in v]
 
 
-def fill_ext_entry(e, d, pool):
+def fill_ext_entry(e, d, pool, grid):
     """dict with the reference's external-force keys (docs/source/forces.md) -> one table entry (oxb_ext_force / oxo_ext_force)"""
     e.type = EXT_TYPES[d["type"]]
     part = d.get("particle", -1)
     e.particle = -1 if str(part) in ("-1", "all") else int(part)
     e.ref = int(d.get("ref_particle", -1)) if d["type"] != "repulsion_plane_moving" else -1
-    e.pbc = int(d.get("PBC", 0))
+    e.pbc = int(d.get("PBC", 0)) if d["type"] != "meta_com_trap" else 0
     e.stiff, e.r0, e.rate = float(d.get("stiff", 1.0 if d["type"] == "LJ_wall" else 0.0)), float(d.get("r0", 0.0)), float(d.get("rate", 0.0))
     e.stiff_rate, e.F0 = float(d.get("stiff_rate", 0.0)), float(d.get("F0", 0.0))
     dr = np.array(d.get("axis", d.get("dir", (1, 0, 0) if d["type"] != "mutual_trap" else (0, 0, 1))), dtype=np.float64)
@@ -174,12 +174,25 @@ def fill_ext_entry(e, d, pool):
         aux[0] = float(d.get("r_ext", 1e10))
         aux[1:4] = [float(x) for x in d.get("target", (0.0, 0.0, 0.0))]
         aux[4] = float(int(float(d.get("steps", d.get("move_steps", 0)))))
+    elif d["type"] == "meta_com_trap":
+        p1a, p2a = _index_list(d["p1a"]), _index_list(d["p2a"])
+        pg = d["potential_grid"]
+        pg = [float(x) for x in (pg.split(",") if isinstance(pg, str) else pg)]
+        n_grid = int(d["N_grid"])
+        if len(pg) != n_grid:
+            raise ValueError("meta_com_trap: potential_grid must hold N_grid values")
+        e.particle, e.ref, e.iaux, e.pbc = -1, len(pool), len(p1a), len(p2a)
+        pool.extend(p1a + p2a)
+        aux[0], aux[1], aux[2] = float(d["xmin"]), (float(d["xmax"]) - float(d["xmin"])) / (n_grid - 1.0), float(n_grid)
+        aux[3], aux[4], aux[5] = float(int(d["mode"])), float(len(grid)), float(int(d.get("PBC", 0)))
+        e.pbc = len(p2a)
+        grid.extend(pg)
     for c in range(8):
         e.aux[c] = aux[c]
 
 
 EXPORTED = """oxb_sizeof oxb_dna2_params_init oxb_dna1_params_init oxb_dna2_params_seqdep oxb_rna2_params_init oxb_rna2_params_seqdep oxb_set_model_rna2 oxb_create oxb_destroy oxb_last_error oxb_set_stream oxb_set_box
-oxb_set_topology oxb_set_model_dna2 oxb_set_lists oxb_set_dt oxb_set_thermostat oxb_set_ext_forces oxb_set_ext_index_pool oxb_set_state oxb_get_state oxb_write_conf
+oxb_set_topology oxb_set_model_dna2 oxb_set_lists oxb_set_dt oxb_set_thermostat oxb_set_ext_forces oxb_set_ext_index_pool oxb_set_ext_grid_pool oxb_set_state oxb_get_state oxb_write_conf
 oxb_set_step oxb_get_step oxb_sort oxb_update_lists oxb_compute_forces oxb_first_step oxb_second_step oxb_thermostat oxb_run
 oxb_synchronize oxb_get_forces oxb_energy oxb_barostat_move oxb_barostat_trial oxb_barostat_accept oxb_barostat_reject oxb_get_box oxb_fix_diffusion oxb_energy_split oxb_get_pairs oxb_get_stats oxb_device_views oxb_launch_count oxb_time_kernel""".split()
 
@@ -331,11 +344,12 @@ class Context:
     def set_ext_forces(self, forces):
         n = len(forces)
         arr = (ExtForce * max(n, 1))()
-        pool = []
+        pool, grid = [], []
         for k, f in enumerate(forces):
-            fill_ext_entry(arr[k], f, pool)
-        self._ck(self._L.oxb_set_ext_forces(self._h, 0, arr))  # COM entries refer to the pool: drop them before replacing it
+            fill_ext_entry(arr[k], f, pool, grid)
+        self._ck(self._L.oxb_set_ext_forces(self._h, 0, arr))  # COM entries refer to the pools: drop them before replacing those
         self._ck(self._L.oxb_set_ext_index_pool(self._h, len(pool), (C.c_int * max(len(pool), 1))(*pool)))
+        self._ck(self._L.oxb_set_ext_grid_pool(self._h, len(grid), (C.c_double * max(len(grid), 1))(*grid)))
         self._ck(self._L.oxb_set_ext_forces(self._h, n, arr))
 
     # ---- state

@@ -116,6 +116,8 @@ struct oxb_ctx {
 	int n_ext_com = 0;           // COM forces (one entry per force, evaluated by one block each)
 	int *ext_pool = nullptr;     // com_list / ref_list original indices of the COM forces
 	std::vector<int> ext_pool_h;
+	float *ext_grid = nullptr;   // tabulated bias potentials of the metadynamics COM traps
+	size_t ext_grid_n = 0;
 	double avg_interval = 8.;
 
 	// concurrency inside one force pass (independent kernels on forked streams) and graph-captured batches of steps
@@ -407,7 +409,7 @@ int launch_forces(oxb_ctx *c, int hw, bool clear, long long step) {
 			c->launches += 1;
 		}
 		if(c->n_ext_com > 0) {
-			oxb::launch_ext_com(s1, c->n_ext_com, c->ext_com, c->ext_pool, c->slot_of, c->posd[a], step, c->cur_step, c->F[a], c->flags, hw);
+			oxb::launch_ext_com(s1, c->n_ext_com, c->ext_com, c->ext_pool, c->ext_grid, c->slot_of, c->posd[a], c->box, step, c->cur_step, c->F[a], c->flags, hw);
 			c->launches += 1;
 		}
 		if(fork) CU(cudaStreamWaitEvent(c->aux[1], c->ev_near, 0));
@@ -433,7 +435,7 @@ int launch_forces(oxb_ctx *c, int hw, bool clear, long long step) {
 			c->launches += 1;
 		}
 		if(c->n_ext_com > 0) {
-			oxb::launch_ext_com(m, c->n_ext_com, c->ext_com, c->ext_pool, c->slot_of, c->posd[a], step, c->cur_step, c->F[a], c->flags, hw);
+			oxb::launch_ext_com(m, c->n_ext_com, c->ext_com, c->ext_pool, c->ext_grid, c->slot_of, c->posd[a], c->box, step, c->cur_step, c->F[a], c->flags, hw);
 			c->launches += 1;
 		}
 	}
@@ -688,7 +690,7 @@ void oxb_destroy(oxb_ctx *c) {
 		cudaFree(c->quat[k]); cudaFree(c->F[k]); cudaFree(c->T[k]); cudaFree(c->bonds[k]); cudaFree(c->iback[k]); cudaFree(c->list_iback[k]); cudaFree(c->list_ibase[k]);
 	}
 	cudaFree(c->Fb);
-	cudaFree(c->slot_of); cudaFree(c->flags); cudaFree(c->sums); cudaFree(c->d_energy); cudaFree(c->ext); cudaFree(c->ext_all); cudaFree(c->ext_com); cudaFree(c->ext_pool);
+	cudaFree(c->slot_of); cudaFree(c->flags); cudaFree(c->sums); cudaFree(c->d_energy); cudaFree(c->ext); cudaFree(c->ext_all); cudaFree(c->ext_com); cudaFree(c->ext_pool); cudaFree(c->ext_grid);
 	cudaFree(c->d_topo); cudaFree(c->d_stage); cudaFree(c->d_marshal_err);
 	cudaFree(c->mol_of); cudaFree(c->mol_inv_size); cudaFree(c->mol_coms); cudaFree(c->pos_backup); cudaFree(c->pos_f4);
 	cudaFree(c->hkeys); cudaFree(c->hkeys_sorted); cudaFree(c->hvals); cudaFree(c->hvals_sorted); cudaFree(c->hinv);
@@ -822,7 +824,14 @@ int oxb_set_ext_forces(oxb_ctx *c, int n, const oxb_ext_force *f) {
 		if(f[k].type == OXB_EXT_LJ_CONE && (f[k].iaux % 2 != 0 || f[k].iaux <= 0)) return fail(c, 1, "RepulsiveCone: n (%d) should be an even integer. Aborting", f[k].iaux);
 		if(f[k].type == OXB_EXT_REPULSION_PLANE_MOVING && (f[k].ref < 0 || f[k].iaux < f[k].ref || f[k].iaux >= c->N))
 			return fail(c, 1, "RepulsionPlaneMoving requires the list of ref_particle indices to be contiguous (got %d..%d)", f[k].ref, f[k].iaux);
-		if(f[k].type == OXB_EXT_COM) {
+		if(f[k].type == OXB_EXT_META_COM_TRAP) {
+			const long long ng = (long long) f[k].aux[2], go = (long long) f[k].aux[4];
+			const int mode = (int) f[k].aux[3];
+			if(mode != 1 && mode != 2) return fail(c, 1, "LTCOMTrap: unsupported mode '%d' (should be '1' or '2')", mode);
+			if(ng < 2 || go < 0 || go + ng > (long long) c->ext_grid_n || !(f[k].aux[1] > 0.))
+				return fail(c, 1, "external force %d: potential grid [%lld, +%lld) outside the grid pool (%zu values; call oxb_set_ext_grid_pool first)", k, go, ng, c->ext_grid_n);
+		}
+		if(f[k].type == OXB_EXT_COM || f[k].type == OXB_EXT_META_COM_TRAP) {
 			const long long lo = f[k].ref, n_com = f[k].iaux, n_ref = f[k].pbc;
 			if(lo < 0 || n_com < 1 || n_ref < 1 || lo + n_com + n_ref > (long long) c->ext_pool_h.size())
 				return fail(c, 1, "external force %d: COM force index lists [%lld, +%lld, +%lld) outside the index pool (%zu entries; call oxb_set_ext_index_pool first)",
@@ -842,7 +851,7 @@ int oxb_set_ext_forces(oxb_ctx *c, int n, const oxb_ext_force *f) {
 		d.r0d = f[k].r0;
 		if(f[k].type == OXB_EXT_LJ_CONE) { d.aux[3] = (float) std::sin(f[k].aux[2]); d.aux[4] = (float) std::cos(f[k].aux[2]); d.aux[5] = (float) std::tan(f[k].aux[2]); }
 		if(f[k].type == OXB_EXT_SPHERE_MOVING) d.daux = f[k].aux[4];
-		if(f[k].type == OXB_EXT_COM) { d.ref = f[k].ref; hcom.push_back(d); continue; }
+		if(f[k].type == OXB_EXT_COM || f[k].type == OXB_EXT_META_COM_TRAP) { d.ref = f[k].ref; hcom.push_back(d); continue; }
 		(f[k].particle < 0 ? hall : h).push_back(d);
 	}
 	cudaFree(c->ext);
@@ -860,6 +869,18 @@ int oxb_set_ext_forces(oxb_ctx *c, int n, const oxb_ext_force *f) {
 	c->n_ext_all = (int) hall.size();
 	c->forces_valid = false;
 	drop_graphs(c);
+	return 0;
+}
+
+int oxb_set_ext_grid_pool(oxb_ctx *c, int n, const double *values) {
+	if(c == nullptr || n < 0 || (n > 0 && values == nullptr)) return 1;
+	if(c->n_ext_com > 0) return fail(c, 1, "the grid pool cannot change while forces that refer to it are set");
+	std::vector<float> h(values, values + n);
+	cudaFree(c->ext_grid);
+	c->ext_grid = nullptr;
+	CU(dalloc(&c->ext_grid, std::max<size_t>((size_t) n, 1)));
+	if(n > 0) CU(cudaMemcpy(c->ext_grid, h.data(), sizeof(float) * (size_t) n, cudaMemcpyHostToDevice));
+	c->ext_grid_n = (size_t) n;
 	return 0;
 }
 

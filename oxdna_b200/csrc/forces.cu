@@ -579,8 +579,9 @@ __device__ __forceinline__ v3 ext_single(const DevExtForce &e, double4 p, int4 i
 // COMForce.cpp:46-71: one block per force; centres of mass of com_list and ref_list from the absolute positions, then the
 // spring force shared equally among the com_list particles (the reference recomputes both sums in every thread,
 // CUDA_MD.cuh:441-468).  The ref_list particles feel nothing, as there.
-__global__ void k_ext_com(int n, const DevExtForce *__restrict__ ef, const int *__restrict__ pool, const int *__restrict__ slot_of,
-		const double4 *__restrict__ posd, long long step, const long long *__restrict__ cur_step, float4 *__restrict__ F, const int *__restrict__ flags, int hw) {
+__global__ void k_ext_com(int n, const DevExtForce *__restrict__ ef, const int *__restrict__ pool, const float *__restrict__ grid, const int *__restrict__ slot_of,
+		const double4 *__restrict__ posd, double lx, double ly, double lz, long long step, const long long *__restrict__ cur_step, float4 *__restrict__ F,
+		const int *__restrict__ flags, int hw) {
 	if(flags[hw]) return;
 	if(step < 0) step = cur_step[hw & 1];
 	__shared__ double sh[6][4];
@@ -598,12 +599,31 @@ __global__ void k_ext_com(int n, const DevExtForce *__restrict__ ef, const int *
 		if((threadIdx.x & 31) == 0) sh[c][threadIdx.x >> 5] = x;
 	}
 	__syncthreads();
-	double d[3];
+	double d[3]; // second list's centre of mass - first list's
 	for(int c = 0; c < 3; c++) d[c] = (sh[3 + c][0] + sh[3 + c][1] + sh[3 + c][2] + sh[3 + c][3]) / n_ref - (sh[c][0] + sh[c][1] + sh[c][2] + sh[c][3]) / n_com;
-	double m = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-	double s = (m - ((double) e.r0 + (double) e.rate * (double) step)) * (double) e.stiff / n_com / m;
-	for(int k = threadIdx.x; k < n_com; k += blockDim.x) {
-		int i = slot_of[pool[e.ref + k]];
+	int first = 0, count = n_com;
+	double s;
+	if(e.type == OXB_EXT_META_COM_TRAP) {
+		// LTCOMTrap.cpp:52-78: dra = com(p1a) - com(p2a) (minimum image if PBC), bias force -dV/dx from the tabulated potential by finite
+		// difference of the two grid points around x = |dra| (meta_utils.h:30-34), zero off the grid; mode 1 acts on p1a, mode 2 on p2a
+		if(e.aux[5] != 0.f) { d[0] -= lx * rint(d[0] / lx); d[1] -= ly * rint(d[1] / ly); d[2] -= lz * rint(d[2] / lz); }
+		const double m = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+		const int il = (int) floor((m - (double) e.aux[0]) / (double) e.aux[1]);
+		double fx = 0.;
+		if(il >= 0 && il + 1 <= (int) e.aux[2] - 1) {
+			const float *g = grid + (int) e.aux[4];
+			fx = -((double) g[il + 1] - (double) g[il]) / (double) e.aux[1];
+		}
+		// force on p1a: dra fx / |dra| / n1 with dra = -d; on p2a: the opposite / n2
+		if((int) e.aux[3] == 1) s = -fx / m / n_com;
+		else { s = fx / m / n_ref; first = n_com; count = n_ref; }
+	}
+	else {
+		const double m = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+		s = (m - ((double) e.r0 + (double) e.rate * (double) step)) * (double) e.stiff / n_com / m;
+	}
+	for(int k = threadIdx.x; k < count; k += blockDim.x) {
+		int i = slot_of[pool[e.ref + first + k]];
 		atomicAdd(&F[i].x, (float) (d[0] * s));
 		atomicAdd(&F[i].y, (float) (d[1] * s));
 		atomicAdd(&F[i].z, (float) (d[2] * s));
@@ -681,9 +701,10 @@ static void launch_edge_stage_t(cudaStream_t s, int which, const typename MD::Pa
 	auto blocks_for = [&](long long items) { return (int) std::max<long long>(1, (items + 127) / 128); };
 	switch(which) {
 	case 0: {
-		// lanes per particle: 4 below ~300k particles (one thread per particle leaves the SMs short of loads in flight), else 1
+		// lanes per particle: 1 by default.  2 and 4 were measured neutral to slower at 81,920 and 1M nucleotides
+		// (profiles/smalln_sweep_r01.txt): the kernel is bound by L2 gather bandwidth, not by loads in flight.  OXB_DH_LPP overrides.
 		static const int lpp_env = env_int("OXB_DH_LPP", 0);
-		const int lpp = lpp_env > 0 ? lpp_env : (a.N < 300000 ? 4 : 1);
+		const int lpp = lpp_env > 0 ? lpp_env : 1;
 		if(lpp >= 4) k_dh_particle<MD, 4><<<blocks_for(4ll * a.N), 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, flags, hw);
 		else if(lpp == 2) k_dh_particle<MD, 2><<<blocks_for(2ll * a.N), 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, flags, hw);
 		else k_dh_particle<MD, 1><<<blocks_for(a.N), 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, flags, hw);
@@ -734,10 +755,10 @@ void launch_ext_forces_all(cudaStream_t s, int N, int n_all, const DevExtForce *
 	k_ext_forces_all<<<(N + tpb - 1) / tpb, tpb, 0, s>>>(N, n_all, ef_all, slot_of, ipos, posd, box, step, cur_step, F, flags, hw);
 }
 
-void launch_ext_com(cudaStream_t s, int n, const DevExtForce *ef_com, const int *pool, const int *slot_of, const double4 *posd, long long step,
-		const long long *cur_step, float4 *F, const int *flags, int hw) {
+void launch_ext_com(cudaStream_t s, int n, const DevExtForce *ef_com, const int *pool, const float *grid, const int *slot_of, const double4 *posd,
+		const double *box, long long step, const long long *cur_step, float4 *F, const int *flags, int hw) {
 	if(n <= 0) return;
-	k_ext_com<<<n, 128, 0, s>>>(n, ef_com, pool, slot_of, posd, step, cur_step, F, flags, hw);
+	k_ext_com<<<n, 128, 0, s>>>(n, ef_com, pool, grid, slot_of, posd, box[0], box[1], box[2], step, cur_step, F, flags, hw);
 }
 
 } // namespace oxb

@@ -83,8 +83,8 @@ void launch_ext_forces(cudaStream_t s, int n, const DevExtForce *ef, const int *
 void launch_ext_forces_all(cudaStream_t s, int N, int n_all, const DevExtForce *ef_all, const int *slot_of, const int4 *ipos, const double4 *posd, BoxF box,
 		long long step, const long long *cur_step, float4 *F, const int *flags, int hw);
 // COM forces: one block per entry; `pool` holds the com_list / ref_list original indices
-void launch_ext_com(cudaStream_t s, int n, const DevExtForce *ef_com, const int *pool, const int *slot_of, const double4 *posd, long long step,
-		const long long *cur_step, float4 *F, const int *flags, int hw);
+void launch_ext_com(cudaStream_t s, int n, const DevExtForce *ef_com, const int *pool, const float *grid, const int *slot_of, const double4 *posd,
+		const double *box, long long step, const long long *cur_step, float4 *F, const int *flags, int hw);
 
 // ---- integrate.cu
 struct IntegrateArgs {

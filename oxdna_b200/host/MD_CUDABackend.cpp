@@ -6,6 +6,7 @@
 #include "Forces/COMForce.h"
 #include "Forces/GenericCentralForce.h"
 #include "Forces/LJCone.h"
+#include "Forces/Metadynamics/LTCOMTrap.h"
 #include "Forces/RepulsionPlaneMoving.h"
 #include "Forces/RepulsiveSphereMoving.h"
 #include "Forces/YukawaSphere.h"
@@ -206,7 +207,8 @@ void MD_CUDABackend::_gpu_to_host() {
 void MD_CUDABackend::_apply_external_forces_changes() {
 	if(!_external_forces) return;
 	std::vector<oxb_ext_force> table;
-	std::vector<int> pool; // com_list / ref_list indices of the COM forces
+	std::vector<int> pool;    // com_list / ref_list (p1a / p2a) indices of the COM forces
+	std::vector<double> grid; // tabulated bias potentials of the metadynamics COM traps
 	// a force given with `particle = all` is the same object attached to every particle: keep it as ONE table entry
 	// (particle = -1) instead of N copies (the reference keeps 15 union slots per particle)
 	std::map<BaseForce *, int> uses;
@@ -341,6 +343,20 @@ void MD_CUDABackend::_apply_external_forces_changes() {
 				for(auto q : cf->_com_list) pool.push_back(q->index);
 				for(auto q : cf->_ref_list) pool.push_back(q->index);
 			}
+			else if(ft == typeid(LTCOMTrap)) {
+				// meta_com_trap: one table entry per force object (it is attached to every particle of p1a or of p2a, according to its mode)
+				if(emitted.count(f)) continue;
+				emitted.insert(f);
+				LTCOMTrap *mf = static_cast<LTCOMTrap *>(f);
+				single_particle_type = false;
+				e.type = OXB_EXT_META_COM_TRAP;
+				e.particle = -1;
+				e.ref = (int) pool.size(); e.iaux = (int) mf->_p1a_ptr.size(); e.pbc = (int) mf->_p2a_ptr.size();
+				for(auto q : mf->_p1a_ptr) pool.push_back(q->index);
+				for(auto q : mf->_p2a_ptr) pool.push_back(q->index);
+				e.aux[0] = mf->xmin; e.aux[1] = mf->dX; e.aux[2] = mf->N_grid; e.aux[3] = mf->_mode; e.aux[4] = (double) grid.size(); e.aux[5] = mf->PBC ? 1. : 0.;
+				for(auto v : mf->potential_grid) grid.push_back(v);
+			}
 			else if(ft == typeid(YukawaSphere)) {
 				YukawaSphere *yf = static_cast<YukawaSphere *>(f);
 				e.type = OXB_EXT_YUKAWA_SPHERE;
@@ -358,7 +374,7 @@ void MD_CUDABackend::_apply_external_forces_changes() {
 				e.aux[0] = sf->r_ext(); e.aux[1] = t.x; e.aux[2] = t.y; e.aux[3] = t.z; e.aux[4] = (double) sf->steps();
 			}
 			else {
-				throw oxDNAException("Only string, trap, mutual_trap, lowdim_trap, twist, repulsion_plane, repulsion_plane_moving, attraction_plane, sphere, sphere_smooth, repulsive_sphere_moving, ellipsoid, LJ_wall, LJ_cone, generic_central_force, com and yukawa_sphere forces are supported by the oxdna_b200 CUDA backend at the moment.\n");
+				throw oxDNAException("Only string, trap, mutual_trap, lowdim_trap, twist, repulsion_plane, repulsion_plane_moving, attraction_plane, sphere, sphere_smooth, repulsive_sphere_moving, ellipsoid, LJ_wall, LJ_cone, generic_central_force, com, meta_com_trap and yukawa_sphere forces are supported by the oxdna_b200 CUDA backend at the moment.\n");
 			}
 			if(single_particle_type && N() > 1 && uses[f] == N()) {
 				if(emitted.count(f)) continue;
@@ -372,6 +388,7 @@ void MD_CUDABackend::_apply_external_forces_changes() {
 	// the table holds original particle ids, the device maps them through its slot table
 	oxb_check(_ctx, oxb_set_ext_forces(_ctx, 0, nullptr), "set_ext_forces"); // COM entries refer to the pool: drop them before replacing it
 	oxb_check(_ctx, oxb_set_ext_index_pool(_ctx, (int) pool.size(), pool.data()), "set_ext_index_pool");
+	oxb_check(_ctx, oxb_set_ext_grid_pool(_ctx, (int) grid.size(), grid.data()), "set_ext_grid_pool");
 	oxb_check(_ctx, oxb_set_ext_forces(_ctx, (int) table.size(), table.data()), "set_ext_forces");
 }
 
