@@ -35,6 +35,19 @@
 #include <typeinfo>
 #include <vector>
 
+// `type = total_energy` served from the device: same three columns as src/Observables/TotalEnergy.cpp:33-38
+// (U, K, U + K per particle, BaseObservable's default "%10.6lf" formatter), no particle data needed on the CPU
+class CUDATotalEnergy: public BaseObservable {
+	const double *_UK; // potential, kinetic (totals), owned by the backend
+	int _N;
+public:
+	CUDATotalEnergy(const double *UK, int N) : _UK(UK), _N(N) { }
+	bool require_data_on_CPU() override { return false; }
+	std::string get_output_string(llint curr_step) override {
+		return Utils::sformat("%10.6lf %10.6lf %10.6lf", _UK[0] / _N, _UK[1] / _N, (_UK[0] + _UK[1]) / _N);
+	}
+};
+
 MD_CUDABackend::MD_CUDABackend() :
 				MDBackend() {
 }
@@ -82,6 +95,7 @@ void MD_CUDABackend::get_settings(input_file &inp) {
 	getInputBool(&inp, "CUDA_avoid_cpu_calculations", &_avoid_cpu_calculations, 0);
 	getInputBool(&inp, "CUDA_print_energy", &_print_energy, 0);
 	getInputLLInt(&inp, "CUDA_max_queued_steps", &_max_pending, 0);
+	getInputBool(&inp, "CUDA_device_observables", &_device_observables, 0);
 
 	_cuda_thermostat = CUDAThermostatFactory::make_thermostat(inp, _box.get());
 	_cuda_thermostat->get_settings(inp);
@@ -136,6 +150,8 @@ void MD_CUDABackend::init() {
 	_cuda_thermostat->set_seed(lrand48());
 	_cuda_thermostat->init();
 	_cuda_thermostat->attach(_ctx);
+
+	if(_device_observables) _install_device_observables();
 
 	// copy all the particle related stuff to device memory, then lists and forces for the first step
 	apply_changes_to_simulation_data();
@@ -407,6 +423,56 @@ void MD_CUDABackend::_flush() {
 		oxb_check(_ctx, oxb_energy(_ctx, &U, &K), "energy");
 		_backend_info = Utils::sformat("\tCUDA_energy: %lf", U / N());
 	}
+}
+
+void MD_CUDABackend::_install_device_observables() {
+	// the default energy streams of MDBackend::get_settings (src/Backends/MDBackend.cpp:60-93) with total_energy evaluated on the device
+	auto fill = [&](ObservableOutputPtr out, bool with_plain_step) {
+		if(out == nullptr) return;
+		out->clear();
+		if(with_plain_step) out->add_observable("type = step");
+		out->add_observable("type = step\nunits = MD");
+		out->add_observable(std::make_shared<CUDATotalEnergy>(_device_UK, N()));
+		if(_use_barostat) out->add_observable("type = density");
+		out->add_observable("type = backend_info");
+	};
+	fill(_obs_output_file, false);
+	fill(_obs_output_stdout, true);
+}
+
+void MD_CUDABackend::print_observables() {
+	if(!_device_observables) {
+		MDBackend::print_observables();
+		return;
+	}
+	// SimBackend::print_observables (src/Backends/SimBackend.cpp:728-768) brackets every print with a download, a CPU list rebuild and
+	// an upload.  With device-side energies the default streams need none of that: only the queued steps have to run.
+	bool any = false, only_default = true;
+	for(auto const &out : _obs_outputs) {
+		if(out->is_ready(current_step())) {
+			any = true;
+			if(out != _obs_output_file && out != _obs_output_stdout) only_default = false;
+		}
+	}
+	if(!any) {
+		_backend_info = std::string("");
+		return;
+	}
+	_flush();
+	oxb_check(_ctx, oxb_energy(_ctx, &_device_UK[0], &_device_UK[1]), "energy");
+	if(!only_default) {
+		MDBackend::print_observables(); // some stream wants the particles on the CPU: the reference path
+		return;
+	}
+	_mytimer->resume();
+	_obs_timer->resume();
+	if(_use_barostat) _backend_info.insert(0, Utils::sformat(" %5.3lf", _barostat_acceptance));
+	for(auto const &out : _obs_outputs) {
+		if(out->is_ready(current_step())) out->print_output(current_step());
+	}
+	_backend_info = std::string("");
+	_obs_timer->pause();
+	_mytimer->pause();
 }
 
 void MD_CUDABackend::sim_step() {

@@ -22,6 +22,8 @@ protected:
 	bool _avoid_cpu_calculations = false;
 	bool _print_energy = false;
 	bool _barostat_always_refresh = false;
+	bool _device_observables = false; // CUDA_device_observables: total_energy of the default streams from the device, no CPU round trip
+	double _device_UK[2] = { 0., 0. };
 	llint _barostat_attempts = 0, _barostat_accepted = 0;
 	llint _pending_steps = 0;
 	llint _first_pending_step = 0;
@@ -36,6 +38,7 @@ protected:
 	virtual void _apply_external_forces_changes();
 	virtual void _flush();
 	virtual void _apply_barostat();
+	void _install_device_observables();
 	void _on_T_update() override;
 
 public:
@@ -46,6 +49,7 @@ public:
 	void init() override;
 	void sim_step() override;
 	void fix_diffusion() override;
+	void print_observables() override;
 	void apply_simulation_data_changes() override;
 	void apply_changes_to_simulation_data() override;
 };

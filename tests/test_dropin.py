@@ -298,3 +298,20 @@ def test_stock_input_file_npt_matches_reference_cpu(tmp_path):
     assert ea.shape == eb.shape and ea.shape[1] == 6           # time, U, K, E, density, barostat acceptance
     assert abs(ea[-1, 5] - eb[-1, 5]) < 0.1
     assert abs(ea[-1, 4] / eb[-1, 4] - 1.0) < 0.03
+
+
+@pytest.mark.gpu
+@needs_binaries
+def test_device_side_energy_stream_matches_reference_cpu(tmp_path):
+    """CUDA_device_observables = 1: the default energy streams print U, K, U + K evaluated on the device and the print
+    skips the download / CPU list rebuild / upload bracket of SimBackend::print_observables.  Same columns, same values (FP32 pair
+    arithmetic vs FP64) as the reference CPU binary; the trajectory is unaffected."""
+    a = run(OURS, str(tmp_path / "ours"), backend="CUDA", itype="DNA2", steps=300, thermostat="no", use_edge=1, sort_every=1, extra="CUDA_device_observables = 1")
+    assert a.returncode == 0, a.stdout[-2000:]
+    b = run(REF, str(tmp_path / "ref"), backend="CPU", itype="DNA2_nomesh", steps=300, thermostat="no", use_edge=0, sort_every=0, extra="")
+    assert b.returncode == 0, b.stdout[-2000:]
+    ea, eb = energies(str(tmp_path / "ours")), energies(str(tmp_path / "ref"))
+    assert ea.shape == eb.shape and ea.shape[0] >= 3
+    assert np.abs(ea[:, 1:] - eb[:, 1:]).max() < 2e-4
+    ca, cb = oio.read_conf(str(tmp_path / "ours" / "last_conf.dat")), oio.read_conf(str(tmp_path / "ref" / "last_conf.dat"))
+    assert np.abs(ca["pos"] - cb["pos"]).max() < 2e-3
