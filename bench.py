@@ -23,6 +23,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 T_STR, SALT, DT = "300K", 0.5, 0.003
+_REAL_STDOUT = sys.stdout
 FLOP_FAR, FLOP_DH, FLOP_CONTACT, FLOP_BONDED = 170.0, 60.0, 1500.0, 900.0  # SURVEY 8(d) per-pair figures
 # ncu dram__bytes_read.sum + dram__bytes_write.sum of one force pass (near + HB/CRST + coaxial + bonded + DH kernels)
 NCU_FORCE_PASS_DRAM_BYTES_C2 = None
@@ -257,7 +258,7 @@ def reference_arm(args):
                              "sample": f"{args.steps} x {md} MD steps of {N} nt on each of {procs} cores (aggregate)"},
             "e2e": {"value": val, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_REAL_STDOUT, flush=True)
 
 
 # ----------------------------------------------------------------------------------------------------------- our arm
@@ -424,7 +425,7 @@ def ours(args):
                 "kernels_ms": {"forces": t_force, "integrate": t_integ, "rebuild_incl_sort": t_list, "sort_only": t_sort, "md_step_mean": step_ms,
                                "rebuild_amortised": t_list / rebuild_every},
                 "cpu_baseline": cpu, "reference_cuda": ref_cuda}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_REAL_STDOUT, flush=True)
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
@@ -501,7 +502,7 @@ def ours_ensemble(args):
                            "ladder_K": [float(ladder_K[0]), float(ladder_K[-1])], "use_edge": int(args.use_edge), "CUDA_sort_every": args.sort_every,
                            "l2": "256 MiB buffer written between timed iterations", "exchange_acceptance": float(np.mean(remd.rates()))},
                 "gpu_launches": int(launches), "clocks": clocks, "e2e": None, "roofline": None, "cpu_baseline": None}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_REAL_STDOUT, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -527,6 +528,12 @@ def main():
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip the reference-CUDA-backend comparator leg")
     ap.add_argument("--ref-cuda-steps", type=int, nargs=2, default=[10000, 20000], help="steps=A and steps=B runs of the reference CLI")
     args = ap.parse_args()
+    # the contract is ONE JSON line on stdout: libraries that print banners there (NCCL's version line at communicator creation, torchrun
+    # notices) are sent to stderr for the duration of the run; json lines go to the saved descriptor
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         reference_arm(args)
     elif args.impl == "reference-cuda":
@@ -542,7 +549,7 @@ def main():
             sim.close()
             r = run_ref_cuda(sysm, args.workload, a, b, state)
             print(json.dumps({"impl": "reference-cuda", "metric": "particle-steps/s", "value": r.get("value"), "unit": "particle-steps/s", "n_gpus": 1,
-                              "higher_is_better": True, "config": {"workload": desc}, "reference_cuda": r}), flush=True)
+                              "higher_is_better": True, "config": {"workload": desc}, "reference_cuda": r}), file=_REAL_STDOUT, flush=True)
     elif args.replicas_per_gpu > 1:
         ours_ensemble(args)
     else:
