@@ -282,7 +282,10 @@ def ours(args):
     N = len(sysm["pos"])
     md = args.md_steps
     n_rep = world  # one replica per GPU: weak scaling
-    ladder_K = geometric_ladder(290.0, 350.0, n_rep) if n_rep > 1 else np.array([300.0])
+    # default scaling run: one C2 replica per GPU on a NARROW ladder around the 300 K of the single-GPU workload (geometric 299-301 K:
+    # ~0.3 K spacing at 8 replicas, where 81,920-nt replicas still exchange), so that every rank carries the same work as the N = 1
+    # run; the 290-350 K ladder of config C5 is what --replicas-per-gpu runs (hotter replicas rebuild their lists more often)
+    ladder_K = geometric_ladder(299.0, 301.0, n_rep) if n_rep > 1 else np.array([300.0])
     T_sim = ladder_K * 0.1 / 300.0
     myT = f"{ladder_K[rank]:.6f}K"
     v, L = lattice.maxwell_velocities(N, parse_temperature(myT), 5 + rank)

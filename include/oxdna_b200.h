@@ -201,6 +201,10 @@ int oxb_get_state(oxb_ctx *ctx, double *pos, double *a1, double *a3, double *vel
  * round trip and CPU energy evaluation of SimBackend::print_conf: "t = step / b = box / E = Etot U K (per particle)" + one line
  * per particle (original order): pos a1 a3 [vel L].  append != 0 adds a frame to an existing trajectory file. */
 int oxb_write_conf(oxb_ctx *ctx, const char *path, int append, int print_momenta);
+/* the same frame in the reference's binary format (BinaryConfiguration::_headers / _configuration,
+ * src/Observables/Configurations/BinaryConfiguration.cpp:20-92): step, rng state (3 unsigned shorts, zeros if NULL), box, E U K per
+ * particle, then per particle pos, pos_shift (3 ints per particle, zeros if NULL), a1, a2, a3, vel, L as doubles */
+int oxb_write_conf_binary(oxb_ctx *ctx, const char *path, int append, const unsigned short rng_state[3], const int *pos_shift);
 int oxb_set_step(oxb_ctx *ctx, long long step);
 long long oxb_get_step(const oxb_ctx *ctx);
 

@@ -192,7 +192,7 @@ def fill_ext_entry(e, d, pool, grid):
 
 
 EXPORTED = """oxb_sizeof oxb_dna2_params_init oxb_dna1_params_init oxb_dna2_params_seqdep oxb_rna2_params_init oxb_rna2_params_seqdep oxb_set_model_rna2 oxb_create oxb_destroy oxb_last_error oxb_set_stream oxb_set_box
-oxb_set_topology oxb_set_model_dna2 oxb_set_lists oxb_set_dt oxb_set_thermostat oxb_set_ext_forces oxb_set_ext_index_pool oxb_set_ext_grid_pool oxb_set_state oxb_get_state oxb_write_conf
+oxb_set_topology oxb_set_model_dna2 oxb_set_lists oxb_set_dt oxb_set_thermostat oxb_set_ext_forces oxb_set_ext_index_pool oxb_set_ext_grid_pool oxb_set_state oxb_get_state oxb_write_conf oxb_write_conf_binary
 oxb_set_step oxb_get_step oxb_sort oxb_update_lists oxb_compute_forces oxb_first_step oxb_second_step oxb_thermostat oxb_run
 oxb_synchronize oxb_get_forces oxb_energy oxb_barostat_move oxb_barostat_trial oxb_barostat_accept oxb_barostat_reject oxb_get_box oxb_fix_diffusion oxb_energy_split oxb_get_pairs oxb_get_stats oxb_device_views oxb_launch_count oxb_time_kernel""".split()
 
@@ -373,6 +373,12 @@ class Context:
     def write_conf(self, path, append=False, print_momenta=True):
         """one frame in the reference's configuration format, written from the device state"""
         self._ck(self._L.oxb_write_conf(self._h, str(path).encode(), int(append), int(print_momenta)))
+
+    def write_conf_binary(self, path, append=False, rng_state=None, pos_shift=None):
+        """one frame in the reference's binary configuration format"""
+        seed = None if rng_state is None else (C.c_ushort * 3)(*[int(x) for x in rng_state])
+        sh = None if pos_shift is None else np.ascontiguousarray(pos_shift, dtype=np.int32)
+        self._ck(self._L.oxb_write_conf_binary(self._h, str(path).encode(), int(append), seed, _p(sh)))
 
     def set_step(self, s):
         self._ck(self._L.oxb_set_step(self._h, C.c_longlong(s)))

@@ -985,6 +985,44 @@ int oxb_write_conf(oxb_ctx *c, const char *path, int append, int print_momenta) 
 	return 0;
 }
 
+int oxb_write_conf_binary(oxb_ctx *c, const char *path, int append, const unsigned short rng_state[3], const int *pos_shift) {
+	if(c == nullptr || path == nullptr) return 1;
+	double U = 0., K = 0.;
+	int rc = oxb_energy(c, &U, &K);
+	if(rc) return rc;
+	const int N = c->N;
+	std::vector<double> pos(3 * (size_t) N), a1(3 * (size_t) N), a3(3 * (size_t) N), vel(3 * (size_t) N), L(3 * (size_t) N);
+	rc = oxb_get_state(c, pos.data(), a1.data(), a3.data(), vel.data(), L.data());
+	if(rc) return rc;
+	FILE *f = std::fopen(path, append ? "ab" : "wb");
+	if(f == nullptr) return fail(c, 9, "cannot open '%s' for writing", path);
+	std::vector<char> buf(1 << 22);
+	std::setvbuf(f, buf.data(), _IOFBF, buf.size());
+	// BinaryConfiguration::_headers / _configuration (src/Observables/Configurations/BinaryConfiguration.cpp:20-92): step, rng state,
+	// box, E U K per particle; then per particle pos, pos_shift, the three axes as rows, vel, L -- all native-endian, doubles and ints
+	const long long step = c->step;
+	const unsigned short zero_seed[3] = { 0, 0, 0 };
+	const double e[3] = { (U + K) / N, U / N, K / N };
+	std::fwrite(&step, sizeof(long long), 1, f);
+	std::fwrite(rng_state ? rng_state : zero_seed, sizeof(unsigned short), 3, f);
+	std::fwrite(c->box, sizeof(double), 3, f);
+	std::fwrite(e, sizeof(double), 3, f);
+	for(int i = 0; i < N; i++) {
+		const double *x = &a1[3 * (size_t) i], *z = &a3[3 * (size_t) i];
+		const double y[3] = { z[1] * x[2] - z[2] * x[1], z[2] * x[0] - z[0] * x[2], z[0] * x[1] - z[1] * x[0] }; // a2 = a3 x a1
+		const int none[3] = { 0, 0, 0 };
+		std::fwrite(&pos[3 * (size_t) i], sizeof(double), 3, f);
+		std::fwrite(pos_shift ? pos_shift + 3 * (size_t) i : none, sizeof(int), 3, f);
+		std::fwrite(x, sizeof(double), 3, f);
+		std::fwrite(y, sizeof(double), 3, f);
+		std::fwrite(z, sizeof(double), 3, f);
+		std::fwrite(&vel[3 * (size_t) i], sizeof(double), 3, f);
+		std::fwrite(&L[3 * (size_t) i], sizeof(double), 3, f);
+	}
+	std::fclose(f);
+	return 0;
+}
+
 int oxb_set_step(oxb_ctx *c, long long step) {
 	if(c == nullptr) return 1;
 	c->step = step;

@@ -140,3 +140,17 @@ def axes_from_quaternions(q):
     a2 = np.stack([2 * (x * y - z * w), -x * x + y * y - z * z + w * w, 2 * (y * z + x * w)], axis=1)
     a3 = np.stack([2 * (x * z + y * w), 2 * (y * z - x * w), -x * x - y * y + z * z + w * w], axis=1)
     return np.hstack([a1, a2, a3])
+
+
+def read_binary_conf(path, N, frame=0):
+    """one frame of the reference's binary configuration format (src/Observables/Configurations/BinaryConfiguration.cpp:20-92)"""
+    rec = np.dtype([("pos", "<f8", 3), ("shift", "<i4", 3), ("a1", "<f8", 3), ("a2", "<f8", 3), ("a3", "<f8", 3), ("vel", "<f8", 3), ("L", "<f8", 3)])
+    head = np.dtype([("step", "<i8"), ("rng", "<u2", 3), ("box", "<f8", 3), ("E", "<f8", 3)])
+    size = head.itemsize + N * rec.itemsize
+    with open(path, "rb") as f:
+        f.seek(frame * size)
+        h = np.frombuffer(f.read(head.itemsize), dtype=head)[0]
+        p = np.frombuffer(f.read(N * rec.itemsize), dtype=rec)
+    out = {k: np.array(p[k]) for k in rec.names}
+    out.update(step=int(h["step"]), rng=np.array(h["rng"]), box=np.array(h["box"]), E=np.array(h["E"]))
+    return out

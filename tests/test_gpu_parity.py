@@ -3,6 +3,8 @@
 Tolerances (north star): Verlet pair sets bit-exact; forces/torques |d| <= 1e-5 * max|.| (mixed precision, FP32 pair
 arithmetic), energies relative 1e-6; NVE trajectories against the double-precision CPU step over 200 steps: 2e-4 absolute
 (FP32 force round-off amplified by chaotic dynamics; measured ~1e-5)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -564,6 +566,18 @@ def test_write_conf_from_device_state(tmp_path):
         for k in ("pos", "a1", "a3", "vel", "L"):
             assert np.allclose(c[k], st[k], rtol=1e-14, atol=1e-15), k  # 15 significant digits: relative rounding up to 5e-15
         assert len(open(tmp_path / "traj.dat").read().splitlines()) == 2 * (3 + sim.N)
+        # binary frames (BinaryConfiguration.cpp): bit-exact doubles, record size as the reference's reader expects
+        sh = np.arange(3 * sim.N, dtype=np.int32).reshape(sim.N, 3) % 5 - 2
+        sim.ctx.write_conf_binary(tmp_path / "traj.bin", rng_state=(1, 2, 3), pos_shift=sh)
+        sim.ctx.write_conf_binary(tmp_path / "traj.bin", append=True)
+        assert os.path.getsize(tmp_path / "traj.bin") == 2 * (8 + 6 + 48 + sim.N * (18 * 8 + 12))
+        b0, b1 = oio.read_binary_conf(tmp_path / "traj.bin", sim.N, 0), oio.read_binary_conf(tmp_path / "traj.bin", sim.N, 1)
+        assert b0["step"] == 37 and list(b0["rng"]) == [1, 2, 3] and np.array_equal(b0["box"], [20.0, 20.0, 20.0])
+        assert np.allclose(b0["E"], [(U + K) / sim.N, U / sim.N, K / sim.N], rtol=1e-13)
+        for k in ("pos", "a1", "a3", "vel", "L"):
+            assert np.array_equal(b0[k], st[k]) and np.array_equal(b1[k], st[k]), k
+        assert np.array_equal(b0["shift"], sh) and not b1["shift"].any()
+        assert np.abs(b0["a2"] - np.cross(st["a3"], st["a1"])).max() < 1e-15
     finally:
         sim.close()
 
