@@ -315,3 +315,55 @@ def test_device_side_energy_stream_matches_reference_cpu(tmp_path):
     assert np.abs(ea[:, 1:] - eb[:, 1:]).max() < 2e-4
     ca, cb = oio.read_conf(str(tmp_path / "ours" / "last_conf.dat")), oio.read_conf(str(tmp_path / "ref" / "last_conf.dat"))
     assert np.abs(ca["pos"] - cb["pos"]).max() < 2e-3
+
+
+QUICK_INPUT = """backend = CUDA
+backend_precision = mixed
+CUDA_list = verlet
+CUDA_sort_every = 0
+use_edge = {use_edge}
+CUDA_device_observables = {dev_obs}
+steps = {steps}
+newtonian_steps = 103
+diff_coeff = 2.50
+thermostat = john
+T = {T}
+dt = 0.005
+verlet_skin = 0.05
+topology = {top}
+conf_file = {conf}
+trajectory_file = trajectory.dat
+refresh_vel = 1
+log_file = log.dat
+no_stdout_energy = 1
+restart_step_counter = 1
+energy_file = energy.dat
+print_conf_interval = 1e5
+print_energy_every = 1e3
+time_scale = linear
+external_forces = 0
+"""
+
+
+@pytest.mark.gpu
+@needs_binaries
+@pytest.mark.parametrize("name,T,checks,use_edge,dev_obs", [
+    ("dsdna8", "20C", [(2, -1.37970256144, 0.15)], 1, 0),
+    ("ssdna15", "300K", [(2, -0.700783241758, 0.26), (3, 0.30, 0.015)], 0, 1)])
+def test_reference_quick_md_tests_on_the_gpu_backend(tmp_path, name, T, checks, use_edge, dev_obs):
+    """The reference's OWN statistical MD tests (test/DNA/DSDNA8/MD, test/DNA/SSDNA15/MD: quick_input + quick_compare, ColumnAverage of
+    test/TestSuite.py:141-196) with `backend = CUDA`: stock input keys, first-generation oxDNA, john thermostat, the expected column
+    averages and tolerances are the reference's.  Shortened from 1e6 to 4e5 steps (the tolerance is 10-30 standard errors wide)."""
+    gold = os.path.join(ROOT, "tests", "golden", "quick_md")
+    d = str(tmp_path)
+    shutil.copy(os.path.join(gold, name + ".top"), os.path.join(d, name + ".top"))
+    shutil.copy(os.path.join(gold, name + "_init.dat"), os.path.join(d, "init.dat"))
+    with open(os.path.join(d, "input"), "w") as f:
+        f.write(QUICK_INPUT.format(use_edge=use_edge, dev_obs=dev_obs, steps=400000, T=T, top=name + ".top", conf="init.dat"))
+    p = subprocess.run([OURS, "input"], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-2000:]
+    e = energies(d)
+    assert e.shape[0] >= 400
+    for col, want, tol in checks:
+        avg = e[:, col - 1].mean()
+        assert want - tol <= avg <= want + tol, (name, col, avg, want, tol)
