@@ -777,3 +777,85 @@ def test_single_particle_and_abi_error_paths():
             c.barostat_trial([11.0, 11.0, 11.0], False)  # mid-step
     finally:
         c.close()
+
+
+def _full_size_system(n_duplex, sites=None, equil=300, **inp_over):
+    sysm = lattice.duplex_lattice(n_duplex, bp=20, spacing=10.0, seed=12345, sites_per_side=sites)
+    T = parse_temperature("300K")
+    v, L = lattice.maxwell_velocities(len(sysm["pos"]), T, 5)
+    inp = dict(backend="CUDA", interaction_type="DNA2", T="300K", salt_concentration=0.5, dt=0.003, verlet_skin=0.05, thermostat="brownian",
+               newtonian_steps=103, diff_coeff=2.5, CUDA_sort_every=1, use_edge=1, seed=42)
+    inp.update(inp_over)
+    sim = Simulation(inp, sysm, dict(box=sysm["box"], pos=sysm["pos"], a1=sysm["a1"], a3=sysm["a3"], vel=v, L=L))
+    sim.run(equil)  # off the ideal lattice: thermalised, re-sorted several times
+    return sysm, sim
+
+
+def test_full_size_c2_against_the_oracle():
+    """BASELINE config C2 at its full size (81,920 nt) after 300 thermalising steps with Hilbert re-sorts: pair set bit-exact, forces,
+    torques and energy against the oracle on the downloaded state; edge-centric and particle-centric paths agree."""
+    sysm, sim = _full_size_system(2048)
+    other = None
+    try:
+        st = sim.ctx.get_state()
+        P = O.dna2_params(parse_temperature("300K"), 0.5)
+        pairs = O.verlet_pairs(st["pos"], sysm["n3"], sysm["n5"], sysm["box"], P.rcut + 2 * 0.05)
+        assert pair_set(sim.ctx.get_pairs()) == pair_set(pairs)
+        ref = O.forces(P, st["pos"], O.axes_from_a1a3(st["a1"], st["a3"]), sysm["btype"], sysm["n3"], sysm["n5"], sysm["box"], pairs)
+        sim.ctx.compute_forces()
+        out = sim.ctx.get_forces()
+        fmax, tmax = np.linalg.norm(ref["force"], axis=1).max(), np.linalg.norm(ref["torque_lab"], axis=1).max()
+        assert np.linalg.norm(out["force"] - ref["force"], axis=1).max() <= 1e-5 * fmax
+        assert np.linalg.norm(out["torque_lab"] - ref["torque_lab"], axis=1).max() <= 1e-5 * tmax
+        assert abs(out["U"] - ref["U"]) <= 1e-6 * abs(ref["U"])
+        inp = dict(sim.inp, use_edge=0, thermostat="no")
+        other = Simulation(inp, sysm, dict(box=sysm["box"], pos=st["pos"], a1=st["a1"], a3=st["a3"], vel=st["vel"], L=st["L"]))
+        o2 = other.ctx.get_forces()
+        assert np.linalg.norm(o2["force"] - out["force"], axis=1).max() <= 1e-5 * fmax
+        assert abs(o2["U"] - out["U"]) <= 1e-6 * abs(out["U"])
+    finally:
+        sim.close()
+        if other is not None:
+            other.close()
+
+
+def test_full_size_c4_properties():
+    """BASELINE config C4 at its full size (1,000,000 nt, 50,000 mutual traps, use_edge = 1, Hilbert sort on): the pair set is bit-exact
+    against the oracle's cell list; size-independent properties of the force field hold -- Newton's third law (internal forces sum to
+    zero; the trap pairs are mutual), the energy equals the particle-centric evaluation, and a rigid translation by a non-lattice
+    vector leaves forces and energy unchanged (fixed-point positions: up to the 2^-32 L grid)."""
+    nd = 25000
+    ext = []
+    for d in range(nd):
+        a, b = 40 * d, 40 * d + 39
+        ext.append(dict(type="mutual_trap", particle=a, ref_particle=b, stiff=0.1, r0=1.2, PBC=1))
+        ext.append(dict(type="mutual_trap", particle=b, ref_particle=a, stiff=0.1, r0=1.2, PBC=1))
+    sysm, sim = _full_size_system(nd, sites=30, equil=100, external_forces_list=ext)
+    other = None
+    try:
+        st = sim.ctx.get_state()
+        P = O.dna2_params(parse_temperature("300K"), 0.5)
+        pairs = O.verlet_pairs(st["pos"], sysm["n3"], sysm["n5"], sysm["box"], P.rcut + 2 * 0.05)
+        got = sim.ctx.get_pairs()
+
+        def keys(pp):  # sorted unique (min, max) pairs as one int64 each (a Python set of 12M tuples would take gigabytes)
+            pp = np.asarray(pp, dtype=np.int64)
+            return np.sort(np.minimum(pp[:, 0], pp[:, 1]) * sim.N + np.maximum(pp[:, 0], pp[:, 1]))
+
+        kg, kr = keys(got), keys(pairs)
+        assert len(kg) == len(kr) and len(np.unique(kg)) == len(kg) and np.array_equal(kg, kr)
+        sim.ctx.compute_forces()
+        out = sim.ctx.get_forces()
+        fsum = np.abs(out["force"].sum(axis=0)).max()
+        assert fsum <= 1e-6 * np.abs(out["force"]).sum(), fsum
+        inp = dict(sim.inp, use_edge=0, thermostat="no")
+        shift = np.array([0.123456789, -7.7, 151.31])
+        other = Simulation(inp, sysm, dict(box=sysm["box"], pos=st["pos"] + shift, a1=st["a1"], a3=st["a3"], vel=st["vel"], L=st["L"]))
+        o2 = other.ctx.get_forces()
+        fmax = np.linalg.norm(out["force"], axis=1).max()
+        assert np.linalg.norm(o2["force"] - out["force"], axis=1).max() <= 2e-5 * fmax
+        assert abs(o2["U"] - out["U"]) <= 2e-6 * abs(out["U"])
+    finally:
+        sim.close()
+        if other is not None:
+            other.close()
