@@ -800,6 +800,7 @@ def test_full_size_c2_against_the_oracle():
         st = sim.ctx.get_state()
         P = O.dna2_params(parse_temperature("300K"), 0.5)
         pairs = O.verlet_pairs(st["pos"], sysm["n3"], sysm["n5"], sysm["box"], P.rcut + 2 * 0.05)
+        sim.ctx.update_lists()  # the list in use was built some steps ago: rebuild (and re-sort) at the downloaded configuration
         assert pair_set(sim.ctx.get_pairs()) == pair_set(pairs)
         ref = O.forces(P, st["pos"], O.axes_from_a1a3(st["a1"], st["a3"]), sysm["btype"], sysm["n3"], sysm["n5"], sysm["box"], pairs)
         sim.ctx.compute_forces()
@@ -836,6 +837,7 @@ def test_full_size_c4_properties():
         st = sim.ctx.get_state()
         P = O.dna2_params(parse_temperature("300K"), 0.5)
         pairs = O.verlet_pairs(st["pos"], sysm["n3"], sysm["n5"], sysm["box"], P.rcut + 2 * 0.05)
+        sim.ctx.update_lists()  # the list in use was built some steps ago: rebuild (and re-sort) at the downloaded configuration
         got = sim.ctx.get_pairs()
 
         def keys(pp):  # sorted unique (min, max) pairs as one int64 each (a Python set of 12M tuples would take gigabytes)
