@@ -63,6 +63,7 @@ __host__ __device__ __forceinline__ int btype_to_type(int b) { return (b < 0) ? 
 struct BoxF {
 	float sx, sy, sz;      // L / 2^32
 	float lx, ly, lz;      // L
+	double dsx, dsy, dsz;  // L / 2^32 in double (the FENE distance is taken in double from the fixed-point backbone sites)
 };
 
 OXB_HD v3 min_image_fixed(const BoxF &b, int4 p, int4 q) {
@@ -73,7 +74,8 @@ OXB_HD v3 min_image_fixed(const BoxF &b, int4 p, int4 q) {
 __host__ __device__ __forceinline__ unsigned to_fixed(double x, double invL) {
 	double f = x * invL;
 	f -= floor(f);
-	unsigned long long u = (unsigned long long) (f * 4294967296.0);
+	// round to nearest grid point (half the error of truncation; 2^32 wraps to 0, which is the same point)
+	unsigned long long u = (unsigned long long) (f * 4294967296.0 + 0.5);
 	return (unsigned) (u & 0xFFFFFFFFull);
 }
 

@@ -162,6 +162,7 @@ void drop_graphs(oxb_ctx *c) {
 void set_boxf(oxb_ctx *c) {
 	c->boxf.lx = (float) c->box[0]; c->boxf.ly = (float) c->box[1]; c->boxf.lz = (float) c->box[2];
 	c->boxf.sx = (float) (c->box[0] / 4294967296.0); c->boxf.sy = (float) (c->box[1] / 4294967296.0); c->boxf.sz = (float) (c->box[2] / 4294967296.0);
+	c->boxf.dsx = c->box[0] / 4294967296.0; c->boxf.dsy = c->box[1] / 4294967296.0; c->boxf.dsz = c->box[2] / 4294967296.0;
 }
 
 void free_lists(oxb_ctx *c) {
@@ -423,7 +424,7 @@ int launch_forces(oxb_ctx *c, int hw, bool clear, long long step) {
 		c->launches += 5;
 	}
 	else {
-		oxb::launch_forces_particle(m, c->mref(), c->boxf, c->N, c->ipos[a], c->quat[a], c->bonds[a], c->nbr, c->nnbr, c->N, c->F[a], c->T[a],
+		oxb::launch_forces_particle(m, c->mref(), c->boxf, c->N, c->ipos[a], c->iback[a], c->quat[a], c->bonds[a], c->nbr, c->nnbr, c->N, c->F[a], c->T[a],
 				c->flags, hw);
 		c->launches += 1;
 		if(c->n_ext > 0) {

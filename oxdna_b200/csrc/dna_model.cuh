@@ -540,12 +540,57 @@ OXB_HD PairEnergy dna2_nonbonded(const oxb_dna2_params &M, v3 r, const Axes &A, 
 
 // FENE backbone + bonded excluded volume (3 site pairs): the same functional form in oxDNA2 and oxRNA2
 // (DNAInteraction.cpp:415-528, RNAInteraction.cpp:431-531)
+// The FENE spring is the stiffest term of the model (dF/dr of several thousand for a strained bond): an FP32 backbone-backbone
+// distance (ulp 6e-8 at 0.75) limits its force to ~1e-5 of max|F| in boxes of a few hundred sigma.  The kernels therefore take that one
+// distance in double from the fixed-point backbone sites (exact integer difference x L / 2^32) and hand the result in here.
+struct FeneSite {
+	v3 d;        // backbone(q) - backbone(p)
+	float s, en; // force on q = d * s; energy
+};
+
+#ifdef __CUDACC__
+template<class PB> __device__ __forceinline__ FeneSite fene_from_sites(const PB &M, const BoxF &box, int4 ibp, int4 ibq, bool &broken) {
+	const double dx = (double) (int) ((unsigned) ibq.x - (unsigned) ibp.x) * box.dsx;
+	const double dy = (double) (int) ((unsigned) ibq.y - (unsigned) ibp.y) * box.dsy;
+	const double dz = (double) (int) ((unsigned) ibq.z - (unsigned) ibp.z) * box.dsz;
+	const double m = sqrt(dx * dx + dy * dy + dz * dz);
+	const double x = m - (double) M.fene_r0;
+	double en, s;
+	if(M.use_mbf && fabs(x) > (double) M.mbf_xmax) {
+		const double ax = fabs(x);
+		const double k = ((double) M.mbf_fmax - (double) M.mbf_finf) * (double) M.mbf_xmax;
+		en = k * log(ax) + (double) M.mbf_finf * ax + (double) M.mbf_e0;
+		s = -copysign(1., x) * (k / ax + (double) M.mbf_finf) / m;
+	}
+	else {
+		double den = (double) M.fene_delta2 - x * x;
+		if(den <= 0.) {
+			broken = true;
+			den = 1e-6;
+		}
+		en = -0.5 * (double) M.fene_eps * log(den / (double) M.fene_delta2);
+		s = -(double) M.fene_eps * x / den / m;
+	}
+	FeneSite f;
+	f.d = mk3((float) dx, (float) dy, (float) dz);
+	f.s = (float) s;
+	f.en = (float) en;
+	return f;
+}
+#endif
+
 template<class PB>
-OXB_HD float bonded_fene_excl(const PB &M, v3 r, const Axes &A, const Axes &B, v3 pback, v3 qback, PairAcc &acc, bool &broken, float *esplit = nullptr) {
+OXB_HD float bonded_fene_excl(const PB &M, v3 r, const Axes &A, const Axes &B, v3 pback, v3 qback, PairAcc &acc, bool &broken, float *esplit = nullptr,
+		const FeneSite *fene = nullptr) {
 	float E = 0.f;
 	const float cb = M.base_a1;
 	// FENE
-	{
+	if(fene != nullptr) {
+		E += fene->en;
+		if(esplit) esplit[0] += fene->en;
+		acc.site_kk(fene->d * fene->s);
+	}
+	else {
 		v3 d = r + qback - pback;
 		float d2 = dot(d, d);
 		float invm = OXB_RSQRT(d2);
@@ -593,11 +638,11 @@ OXB_HD float bonded_fene_excl(const PB &M, v3 r, const Axes &A, const Axes &B, v
 // Returns energy; sets *broken when the bond is outside the FENE range (reference throws; we flag).
 // ---------------------------------------------------------------------------------------------------------------
 OXB_HD float dna2_bonded(const oxb_dna2_params &M, v3 r, const Axes &A, const Axes &B, int btp, int btq, v3 pback,
-		v3 qback, PairAcc &acc, bool &broken, float *esplit = nullptr) {
+		v3 qback, PairAcc &acc, bool &broken, float *esplit = nullptr, const FeneSite *fene = nullptr) {
 	float E = 0.f;
 	const float cb = M.base_a1, cs = M.stack_a1, cr = M.backref_a1;
 
-	E += bonded_fene_excl(M, r, A, B, pback, qback, acc, broken, esplit);
+	E += bonded_fene_excl(M, r, A, B, pback, qback, acc, broken, esplit, fene);
 	// stacking
 	{
 		v3 rs = r + B.a1 * cs - A.a1 * cs;

@@ -52,7 +52,7 @@ __device__ __forceinline__ Particle load_particle(const typename MD::Params &M, 
 // ------------------------------------------------------------------------------------------------------------
 template<class MD>
 __global__ void __launch_bounds__(128, OXB_MB_PARTICLE) k_forces_particle(const __grid_constant__ typename MD::Params M, BoxF box, int N, const int4 *__restrict__ ipos,
-		const float4 *__restrict__ quat, const int2 *__restrict__ bonds, const int *__restrict__ nbr, const int *__restrict__ nnbr, int stride,
+		const int4 *__restrict__ iback, const float4 *__restrict__ quat, const int2 *__restrict__ bonds, const int *__restrict__ nbr, const int *__restrict__ nnbr, int stride,
 		float4 *__restrict__ F, float4 *__restrict__ T, int *__restrict__ flags, int hw) {
 	if(flags[hw]) return;
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -70,7 +70,8 @@ __global__ void __launch_bounds__(128, OXB_MB_PARTICLE) k_forces_particle(const 
 		Particle Q = load_particle<MD>(M, ipos, quat, b.x);
 		PairAcc acc;
 		acc.clear();
-		e += MD::bonded(M, min_image_fixed(box, P.ip, Q.ip), P.ax, Q.ax, P.btype, Q.btype, P.back, Q.back, acc, broken);
+		const FeneSite fs = fene_from_sites(M, box, __ldg(iback + i), __ldg(iback + b.x), broken);
+		e += MD::bonded(M, min_image_fixed(box, P.ip, Q.ip), P.ax, Q.ax, P.btype, Q.btype, P.back, Q.back, acc, broken, nullptr, &fs);
 		f -= acc.F;
 		t += acc.torque_p(P.ax, P.back);
 	}
@@ -78,7 +79,8 @@ __global__ void __launch_bounds__(128, OXB_MB_PARTICLE) k_forces_particle(const 
 		Particle Q = load_particle<MD>(M, ipos, quat, b.y);
 		PairAcc acc;
 		acc.clear();
-		e += MD::bonded(M, min_image_fixed(box, Q.ip, P.ip), Q.ax, P.ax, Q.btype, P.btype, Q.back, P.back, acc, broken);
+		const FeneSite fs = fene_from_sites(M, box, __ldg(iback + b.y), __ldg(iback + i), broken);
+		e += MD::bonded(M, min_image_fixed(box, Q.ip, P.ip), Q.ax, P.ax, Q.btype, P.btype, Q.back, P.back, acc, broken, nullptr, &fs);
 		f += acc.F;
 		t += acc.torque_q(P.ax, P.back);
 	}
@@ -219,7 +221,7 @@ __global__ void __launch_bounds__(128, OXB_MB_NEAR) k_edge_near(const __grid_con
 		int2 ed = valid ? __ldg(edges + eidx) : make_int2(-1 - (int) lane, -1);
 		float v[6] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
 		float ve = 0.f;
-		bool want_hb = false, want_cx = false, want_cr = false;
+		bool want_hb = false, want_cx = false, want_cr = false, hb_capable = false;
 		if(valid) {
 			Particle P = load_particle<MD>(M, ipos, quat, ed.x);
 			Particle Q = load_particle<MD>(M, ipos, quat, ed.y);
@@ -248,15 +250,19 @@ __global__ void __launch_bounds__(128, OXB_MB_NEAR) k_edge_near(const __grid_con
 					// (splitting this list into a hydrogen-bonding and a cross-stacking-only list with specialised kernels was
 					// measured SLOWER, 53 + 39 us against 83 us at 1M particles, and is kept only as MODE 2 below)
 					want_hb = MD::hbcr_may_act(M, rb * rsqrtf(rbm2), P.ax, Q.ax, hb_on, cr_on);
+					hb_capable = hb_on;
 				}
 				v3 rs = r + (Q.ax.a1 - P.ax.a1) * M.stack_a1;
 				float rs2 = dot(rs, rs);
 				if(MD::cxst_in_range(M, rs2)) want_cx = MD::cxst_may_act(M, rs * rsqrtf(rs2), P.ax, Q.ax);
 			}
 		}
-		block_append(want_hb, ed, hb_list, &s_cnt[0], hb_seg, flags);
+		// the dense list is kept sorted by kind at no cost: pairs that can hydrogen-bond fill the first third of the block's segment,
+		// cross-stacking-only pairs (about twice as many) the rest, so that the warps of k_edge_heavy<0> are uniform in which of the
+		// two potentials they evaluate (one mixed warp per block at most; ncu r01k: 23.6 of 32 lanes active with the unsorted list)
+		block_append(want_hb && hb_capable, ed, hb_list, &s_cnt[0], hb_seg / 3, flags);
+		block_append(want_hb && !hb_capable, ed, hb_list + hb_seg / 3, &s_cnt[2], hb_seg - hb_seg / 3, flags);
 		block_append(want_cx, ed, cx_list, &s_cnt[1], cx_seg, flags);
-		block_append(want_cr, ed, cr_list, &s_cnt[2], cr_seg, flags);
 		// excluded volume between non-bonded nucleotides is rare: skip the shuffle reduction when the warp has none
 		if(__any_sync(0xffffffffu, ve != 0.f)) {
 			float w[7] = { v[0], v[1], v[2], v[3], v[4], v[5], ve };
@@ -269,7 +275,8 @@ __global__ void __launch_bounds__(128, OXB_MB_NEAR) k_edge_near(const __grid_con
 	}
 	__syncthreads();
 	if(threadIdx.x < 3) {
-		const int seg = (threadIdx.x == 0) ? hb_seg : (threadIdx.x == 1 ? cx_seg : cr_seg);
+		// list 0: hydrogen-bonding-capable pairs (front of the hb segment), 1: coaxial stacking, 2: cross-stacking-only pairs (rest of the hb segment)
+		const int seg = (threadIdx.x == 0) ? hb_seg / 3 : (threadIdx.x == 1 ? cx_seg : hb_seg - hb_seg / 3);
 		seg_counts[threadIdx.x * gridDim.x + blockIdx.x] = min(s_cnt[threadIdx.x], seg);
 	}
 }
@@ -282,10 +289,12 @@ __global__ void __launch_bounds__(64, OXB_MB_HEAVY) k_edge_heavy(const __grid_co
 	if(flags[hw]) return;
 	// list index in seg_counts: 0 hydrogen bonding, 1 coaxial stacking, 2 cross stacking only (same order as MODE)
 	// gridDim.y consumer blocks share one segment (long segments at large N would otherwise serialise on 64 threads)
-	const int n = seg_counts[MODE * gridDim.x + blockIdx.x];
+	// MODE 0 walks both halves of its segment: [0, n_front) and [seg / 3, seg / 3 + n_back)
+	const int n_front = seg_counts[MODE * gridDim.x + blockIdx.x];
+	const int n = n_front + (MODE == 0 ? seg_counts[2 * gridDim.x + blockIdx.x] : 0);
 	list += (size_t) blockIdx.x * seg;
 	for(int k = blockIdx.y * blockDim.x + threadIdx.x; k < n; k += blockDim.x * gridDim.y) {
-		int2 ed = __ldg(list + k);
+		int2 ed = __ldg(list + ((MODE == 0 && k >= n_front) ? seg / 3 + (k - n_front) : k));
 		Particle P = load_particle<MD>(M, ipos, quat, ed.x);
 		Particle Q = load_particle<MD>(M, ipos, quat, ed.y);
 		v3 r = min_image_fixed(box, P.ip, Q.ip);
@@ -316,7 +325,7 @@ __global__ void __launch_bounds__(64, OXB_MB_HEAVY) k_edge_heavy(const __grid_co
 // the force pass (it only adds into F/T), so it runs concurrently with them on its own stream.
 template<class MD>
 __global__ void __launch_bounds__(128, OXB_MB_BONDED) k_bonded(const __grid_constant__ typename MD::Params M, BoxF box, int N, const int4 *__restrict__ ipos,
-		const float4 *__restrict__ quat, const int2 *__restrict__ bonds, float4 *__restrict__ F, float4 *__restrict__ T, int *__restrict__ flags, int hw) {
+		const int4 *__restrict__ iback, const float4 *__restrict__ quat, const int2 *__restrict__ bonds, float4 *__restrict__ F, float4 *__restrict__ T, int *__restrict__ flags, int hw) {
 	if(flags[hw]) return;
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= N) return;
@@ -327,7 +336,8 @@ __global__ void __launch_bounds__(128, OXB_MB_BONDED) k_bonded(const __grid_cons
 	PairAcc acc;
 	acc.clear();
 	bool broken = false;
-	float en = MD::bonded(M, min_image_fixed(box, P.ip, Q.ip), P.ax, Q.ax, P.btype, Q.btype, P.back, Q.back, acc, broken);
+	const FeneSite fs = fene_from_sites(M, box, __ldg(iback + i), __ldg(iback + b.x), broken);
+	float en = MD::bonded(M, min_image_fixed(box, P.ip, Q.ip), P.ax, Q.ax, P.btype, Q.btype, P.back, Q.back, acc, broken, nullptr, &fs);
 	v3 tp = acc.torque_p(P.ax, P.back), tq = acc.torque_q(Q.ax, Q.back);
 	atomic_add4(F + i, -acc.F.x, -acc.F.y, -acc.F.z, en);
 	atomic_add4(T + i, tp.x, tp.y, tp.z, 0.f);
@@ -681,11 +691,11 @@ __global__ void k_ext_forces_all(int N, int n_all, const DevExtForce *__restrict
 
 namespace oxb {
 
-void launch_forces_particle(cudaStream_t s, const ModelRef &MR, BoxF box, int N, const int4 *ipos, const float4 *quat, const int2 *bonds,
+void launch_forces_particle(cudaStream_t s, const ModelRef &MR, BoxF box, int N, const int4 *ipos, const int4 *iback, const float4 *quat, const int2 *bonds,
 		const int *nbr, const int *nnbr, int stride, float4 *F, float4 *T, int *flags, int hw) {
 	int tpb = 128;
-	if(MR.rna) k_forces_particle<RnaModel><<<(N + tpb - 1) / tpb, tpb, 0, s>>>(*MR.rna, box, N, ipos, quat, bonds, nbr, nnbr, stride, F, T, flags, hw);
-	else k_forces_particle<DnaModel><<<(N + tpb - 1) / tpb, tpb, 0, s>>>(*MR.dna, box, N, ipos, quat, bonds, nbr, nnbr, stride, F, T, flags, hw);
+	if(MR.rna) k_forces_particle<RnaModel><<<(N + tpb - 1) / tpb, tpb, 0, s>>>(*MR.rna, box, N, ipos, iback, quat, bonds, nbr, nnbr, stride, F, T, flags, hw);
+	else k_forces_particle<DnaModel><<<(N + tpb - 1) / tpb, tpb, 0, s>>>(*MR.dna, box, N, ipos, iback, quat, bonds, nbr, nnbr, stride, F, T, flags, hw);
 }
 
 // the kernels of the edge pipeline, launched one by one so that the context can place them on concurrent streams:
@@ -718,11 +728,11 @@ static void launch_edge_stage_t(cudaStream_t s, int which, const typename MD::Pa
 		break;
 	case 2: k_edge_heavy<MD, 0><<<dim3(a.n_seg, a.hb_split), 64, 0, s>>>(M, box, a.seg_counts, a.hb_list, a.hb_seg, a.ipos, a.quat, a.F, a.T, flags, hw); break;
 	case 3: k_edge_heavy<MD, 1><<<a.n_seg, 64, 0, s>>>(M, box, a.seg_counts, a.cx_list, a.cx_seg, a.ipos, a.quat, a.F, a.T, flags, hw); break;
-	case 5: k_edge_heavy<MD, 2><<<dim3(a.n_seg, a.hb_split), 64, 0, s>>>(M, box, a.seg_counts, a.cr_list, a.cr_seg, a.ipos, a.quat, a.F, a.T, flags, hw); break;
+	case 5: break; // the separate cross-stacking-only list is no longer produced (slot 2 of seg_counts now counts the back half of the hb segment)
 	default: {
 		static const int tpb_env = env_int("OXB_TPB_BONDED", 0);
 		const int tpb = tpb_env > 0 ? tpb_env : 128;
-		k_bonded<MD><<<(a.N + tpb - 1) / tpb, tpb, 0, s>>>(M, box, a.N, a.ipos, a.quat, a.bonds, a.F, a.T, flags, hw);
+		k_bonded<MD><<<(a.N + tpb - 1) / tpb, tpb, 0, s>>>(M, box, a.N, a.ipos, a.iback, a.quat, a.bonds, a.F, a.T, flags, hw);
 		break;
 	}
 	}

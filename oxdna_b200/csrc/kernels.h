@@ -57,7 +57,7 @@ struct ModelRef {
 };
 
 // ---- forces.cu
-void launch_forces_particle(cudaStream_t s, const ModelRef &M, BoxF box, int N, const int4 *ipos, const float4 *quat, const int2 *bonds,
+void launch_forces_particle(cudaStream_t s, const ModelRef &M, BoxF box, int N, const int4 *ipos, const int4 *iback, const float4 *quat, const int2 *bonds,
 		const int *nbr, const int *nnbr, int stride, float4 *F, float4 *T, int *flags, int hw);
 struct EdgeArgs {
 	int N;

@@ -16,8 +16,8 @@ struct DnaModel {
 		return dna2_hbcr<WITH_HB>(M, rb, rbm2, A, B, btp, btq, hb_on, cr_on, acc, ehb);
 	}
 	static OXB_HD float cxst(const Params &M, v3 rs, float rs2, v3, const Axes &A, const Axes &B, PairAcc &acc) { return dna2_cxst(M, rs, rs2, A, B, acc); }
-	static OXB_HD float bonded(const Params &M, v3 r, const Axes &A, const Axes &B, int btp, int btq, v3 pback, v3 qback, PairAcc &acc, bool &broken, float *esplit = nullptr) {
-		return dna2_bonded(M, r, A, B, btp, btq, pback, qback, acc, broken, esplit);
+	static OXB_HD float bonded(const Params &M, v3 r, const Axes &A, const Axes &B, int btp, int btq, v3 pback, v3 qback, PairAcc &acc, bool &broken, float *esplit = nullptr, const FeneSite *fene = nullptr) {
+		return dna2_bonded(M, r, A, B, btp, btq, pback, qback, acc, broken, esplit, fene);
 	}
 	static OXB_HD PairEnergy nonbonded(const Params &M, v3 r, const Axes &A, const Axes &B, int btp, int btq, bool p_end, bool q_end, v3 pback, v3 qback, PairAcc &acc) {
 		return dna2_nonbonded(M, r, A, B, btp, btq, p_end, q_end, pback, qback, acc);
@@ -37,8 +37,8 @@ struct RnaModel {
 		return rna2_hbcr<WITH_HB>(M, rb, rbm2, A, B, btp, btq, hb_on, cr_on, acc, ehb);
 	}
 	static OXB_HD float cxst(const Params &M, v3 rs, float rs2, v3 rbk, const Axes &A, const Axes &B, PairAcc &acc) { return rna2_cxst(M, rs, rs2, rbk, A, B, acc); }
-	static OXB_HD float bonded(const Params &M, v3 r, const Axes &A, const Axes &B, int btp, int btq, v3 pback, v3 qback, PairAcc &acc, bool &broken, float *esplit = nullptr) {
-		return rna2_bonded(M, r, A, B, btp, btq, pback, qback, acc, broken, esplit);
+	static OXB_HD float bonded(const Params &M, v3 r, const Axes &A, const Axes &B, int btp, int btq, v3 pback, v3 qback, PairAcc &acc, bool &broken, float *esplit = nullptr, const FeneSite *fene = nullptr) {
+		return rna2_bonded(M, r, A, B, btp, btq, pback, qback, acc, broken, esplit, fene);
 	}
 	static OXB_HD PairEnergy nonbonded(const Params &M, v3 r, const Axes &A, const Axes &B, int btp, int btq, bool p_end, bool q_end, v3 pback, v3 qback, PairAcc &acc) {
 		return rna2_nonbonded(M, r, A, B, btp, btq, p_end, q_end, pback, qback, acc);

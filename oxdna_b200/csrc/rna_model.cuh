@@ -238,8 +238,8 @@ OXB_HD PairEnergy rna2_nonbonded(const oxb_rna2_params &M, v3 r, const Axes &A, 
 // bonded pair p -> q = n3(p): FENE, bonded excluded volume, stacking between STACK_3(p) and STACK_5(q)
 // (RNAInteraction.cpp:431-667)
 OXB_HD float rna2_bonded(const oxb_rna2_params &M, v3 r, const Axes &A, const Axes &B, int btp, int btq, v3 pback, v3 qback, PairAcc &acc,
-		bool &broken, float *esplit = nullptr) {
-	float E = bonded_fene_excl(M, r, A, B, pback, qback, acc, broken, esplit);
+		bool &broken, float *esplit = nullptr, const FeneSite *fene = nullptr) {
+	float E = bonded_fene_excl(M, r, A, B, pback, qback, acc, broken, esplit, fene);
 	v3 sp = A.a1 * M.stack3_a1 + A.a2 * M.stack3_a2, sq = B.a1 * M.stack5_a1 + B.a2 * M.stack5_a2;
 	v3 rs = r + sq - sp;
 	float rs2 = dot(rs, rs);
