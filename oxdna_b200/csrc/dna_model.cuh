@@ -210,9 +210,24 @@ OXB_HD float excl_s(const oxb_excl &e, float eps, v3 r, float &s) {
 // Accumulator for one pair (p, q).  F is the force on q (p receives -F).  Forces acting at a1-collinear sites
 // (base, stack, ungrooved backbone reference) are summed pre-multiplied by their offset along a1; forces at the
 // (grooved) backbone site are summed separately.  Tp/Tq collect the pure (non lever-arm) torques, lab frame.
+// Excluded volume is the other stiff piece of the model: d2V/dr2 = 2 eps b ~ 3.6e3 (backbone-backbone) to 1.8e4 (base-base) in the
+// quadratic smoothing shell and about as much on the Lennard-Jones side of r*.  An FP32 site-site distance (ulp 1.2e-7 at 1 sigma,
+// orientation in FP32) then carries ~1e-3 of absolute force error, i.e. more than 1e-5 of max|F| in every large system.  Kernels that
+// can reach the FP64 state hand it in through PairAcc::refine; an ACTIVE excluded-volume term (rare between non-bonded and between
+// bonded nucleotides alike) is then re-evaluated in double from positions and quaternions, and the difference is added.
+struct ExclRefine {
+	const double4 *posd, *quatd; // FP64 state, slot-indexed
+	int sp, sq;                  // slots of p and q
+	double L[3];                 // box sides
+	double b1, b2, b3;           // backbone-site coefficients on a1, a2, a3
+};
+enum { OXB_SITE_KK = 0, OXB_SITE_AA = 1, OXB_SITE_AK = 2, OXB_SITE_KA = 3 }; // (site of p)(site of q): k = backbone, a = on the a1 axis
+
 struct PairAcc {
 	v3 F, Pa, Pk, Qa, Qk, Tp, Tq;
+	const ExclRefine *refine;
 	OXB_HD void clear() {
+		refine = nullptr;
 		F = Pa = Pk = Qa = Qk = Tp = Tq = mk3(0.f, 0.f, 0.f);
 	}
 	// site codes: coefficient along a1, or "backbone" handled by the *_k variants
@@ -226,6 +241,54 @@ struct PairAcc {
 	OXB_HD v3 torque_p(const Axes &A, v3 pback) const { return Tp - cross(A.a1, Pa) - cross(pback, Pk); }
 	OXB_HD v3 torque_q(const Axes &B, v3 qback) const { return Tq + cross(B.a1, Qa) + cross(qback, Qk); }
 };
+
+#ifdef __CUDACC__
+// the force on q of one excluded-volume site pair evaluated in double from the FP64 state.  Deliberately NOT inlined: it runs for the
+// rare active terms only and must not add to the register footprint of the kernels' common path.
+__device__ __noinline__ float3 excl_force_double(const ExclRefine *R, const oxb_excl *e, float eps, int kind, float cb) {
+	const double4 pp = R->posd[R->sp], pq = R->posd[R->sq], qp = R->quatd[R->sp], qq = R->quatd[R->sq];
+	double rd[3] = { pq.x - pp.x, pq.y - pp.y, pq.z - pp.z };
+	for(int k = 0; k < 3; k++) rd[k] -= R->L[k] * rint(rd[k] / R->L[k]);
+	double a1p[3], a2p[3], a3p[3], a1q[3], a2q[3], a3q[3];
+	quatd Qp = { qp.x, qp.y, qp.z, qp.w }, Qq = { qq.x, qq.y, qq.z, qq.w };
+	axes_from_quatd(Qp, a1p, a2p, a3p);
+	axes_from_quatd(Qq, a1q, a2q, a3q);
+	const bool p_back = (kind == OXB_SITE_KK || kind == OXB_SITE_KA), q_back = (kind == OXB_SITE_KK || kind == OXB_SITE_AK);
+	double dd[3];
+	for(int k = 0; k < 3; k++) {
+		const double sp = p_back ? R->b1 * a1p[k] + R->b2 * a2p[k] + R->b3 * a3p[k] : (double) cb * a1p[k];
+		const double sq = q_back ? R->b1 * a1q[k] + R->b2 * a2q[k] + R->b3 * a3q[k] : (double) cb * a1q[k];
+		dd[k] = rd[k] + sq - sp;
+	}
+	const double r2 = dd[0] * dd[0] + dd[1] * dd[1] + dd[2] * dd[2];
+	double sd = 0.;
+	if(r2 < (double) e->rc2) {
+		if(r2 > (double) e->rstar2) {
+			const double m = sqrt(r2);
+			sd = -2. * (double) eps * (double) e->b * (m - (double) e->rc) / m;
+		}
+		else {
+			const double t = (double) e->sigma2 / r2, lj = t * t * t;
+			sd = -24. * (double) eps * (lj - 2. * lj * lj) / r2;
+		}
+	}
+	return make_float3((float) (dd[0] * sd), (float) (dd[1] * sd), (float) (dd[2] * sd));
+}
+#endif
+
+// adds (double-precision force) - (the FP32 force d * s already accumulated) of one active excluded-volume site pair
+OXB_HD void excl_fix(PairAcc &acc, const oxb_excl &e, float eps, v3 d, float s, int kind, float cb) {
+#ifdef __CUDA_ARCH__
+	if(acc.refine == nullptr) return;
+	const float3 fd = excl_force_double(acc.refine, &e, eps, kind, cb);
+	const v3 delta = mk3(fd.x - d.x * s, fd.y - d.y * s, fd.z - d.z * s);
+	if(kind == OXB_SITE_KK) acc.site_kk(delta);
+	else if(kind == OXB_SITE_AA) acc.site_aa(delta, cb, cb);
+	else if(kind == OXB_SITE_AK) acc.site_ak(delta, cb);
+	else acc.site_ka(delta, cb);
+#endif
+}
+
 
 struct Angle {
 	float c, s, t; // cos, sin (>= 0), theta = atan2(sin, cos)
@@ -350,16 +413,29 @@ template<class PB> OXB_HD float dna2_excl(const PB &M, v3 r, v3 rbb, v3 rb, cons
 	const float cb = M.base_a1;
 	float s, E = 0.f;
 	float en = excl_s(M.excl[0], M.excl_eps, rbb, s);
-	if(en != 0.f) { E += en; acc.site_kk(rbb * s); }
+	if(en != 0.f) { E += en; acc.site_kk(rbb * s); excl_fix(acc, M.excl[0], M.excl_eps, rbb, s, OXB_SITE_KK, cb); }
 	en = excl_s(M.excl[1], M.excl_eps, rb, s);
-	if(en != 0.f) { E += en; acc.site_aa(rb * s, cb, cb); }
+	if(en != 0.f) { E += en; acc.site_aa(rb * s, cb, cb); excl_fix(acc, M.excl[1], M.excl_eps, rb, s, OXB_SITE_AA, cb); }
 	v3 d = r + B.a1 * cb - pback; // back(p) - base(q)
 	en = excl_s(M.excl[3], M.excl_eps, d, s);
-	if(en != 0.f) { E += en; acc.site_ka(d * s, cb); }
+	if(en != 0.f) { E += en; acc.site_ka(d * s, cb); excl_fix(acc, M.excl[3], M.excl_eps, d, s, OXB_SITE_KA, cb); }
 	d = r + qback - A.a1 * cb; // base(p) - back(q)
 	en = excl_s(M.excl[2], M.excl_eps, d, s);
-	if(en != 0.f) { E += en; acc.site_ak(d * s, cb); }
+	if(en != 0.f) { E += en; acc.site_ak(d * s, cb); excl_fix(acc, M.excl[2], M.excl_eps, d, s, OXB_SITE_AK, cb); }
 	return E;
+}
+
+// which of the four site pairs are inside their excluded-volume range (bit = OXB_SITE_*)
+template<class PB> OXB_HD int dna2_excl_mask(const PB &M, v3 r, v3 rbb, v3 rb, const Axes &A, const Axes &B, v3 pback, v3 qback) {
+	const float cb = M.base_a1;
+	int m = 0;
+	if(dot(rbb, rbb) < M.excl[0].rc2) m |= 1 << OXB_SITE_KK;
+	if(dot(rb, rb) < M.excl[1].rc2) m |= 1 << OXB_SITE_AA;
+	v3 d = r + B.a1 * cb - pback;
+	if(dot(d, d) < M.excl[3].rc2) m |= 1 << OXB_SITE_KA;
+	d = r + qback - A.a1 * cb;
+	if(dot(d, d) < M.excl[2].rc2) m |= 1 << OXB_SITE_AK;
+	return m;
 }
 
 OXB_HD bool dna2_hb_in_range(const oxb_dna2_params &M, float rbm2, int btp, int btq) {
@@ -546,6 +622,7 @@ OXB_HD PairEnergy dna2_nonbonded(const oxb_dna2_params &M, v3 r, const Axes &A, 
 struct FeneSite {
 	v3 d;        // backbone(q) - backbone(p)
 	float s, en; // force on q = d * s; energy
+	int excl_deferred; // bits OXB_SITE_*: bonded excluded-volume site pairs the caller evaluates itself (in double)
 };
 
 #ifdef __CUDACC__
@@ -575,9 +652,24 @@ template<class PB> __device__ __forceinline__ FeneSite fene_from_sites(const PB 
 	f.d = mk3((float) dx, (float) dy, (float) dz);
 	f.s = (float) s;
 	f.en = (float) en;
+	f.excl_deferred = 0;
 	return f;
 }
 #endif
+
+// bonded pair: which of the three excluded-volume site pairs (base-base, base-back, back-base) are in range
+template<class PB> OXB_HD int bonded_excl_mask(const PB &M, v3 r, const Axes &A, const Axes &B, v3 pback, v3 qback) {
+	const float cb = M.base_a1;
+	v3 pbase = A.a1 * cb, qbase = B.a1 * cb;
+	int m = 0;
+	v3 d = r + qbase - pbase;
+	if(dot(d, d) < M.excl[1].rc2) m |= 1 << OXB_SITE_AA;
+	d = r + qback - pbase;
+	if(dot(d, d) < M.excl[2].rc2) m |= 1 << OXB_SITE_AK;
+	d = r + qbase - pback;
+	if(dot(d, d) < M.excl[3].rc2) m |= 1 << OXB_SITE_KA;
+	return m;
+}
 
 template<class PB>
 OXB_HD float bonded_fene_excl(const PB &M, v3 r, const Axes &A, const Axes &B, v3 pback, v3 qback, PairAcc &acc, bool &broken, float *esplit = nullptr,
@@ -617,18 +709,19 @@ OXB_HD float bonded_fene_excl(const PB &M, v3 r, const Axes &A, const Axes &B, v
 		acc.site_kk(d * s);
 	}
 	// bonded excluded volume
-	{
+	const int deferred = fene != nullptr ? fene->excl_deferred : 0;
+	if(deferred == 0) {
 		float s;
 		v3 pbase = A.a1 * cb, qbase = B.a1 * cb;
 		v3 d = r + qbase - pbase;
 		float en = excl_s(M.excl[1], M.excl_eps, d, s);
-		if(en != 0.f) { E += en; if(esplit) esplit[1] += en; acc.site_aa(d * s, cb, cb); }
+		if(en != 0.f) { E += en; if(esplit) esplit[1] += en; acc.site_aa(d * s, cb, cb); excl_fix(acc, M.excl[1], M.excl_eps, d, s, OXB_SITE_AA, cb); }
 		d = r + qback - pbase;
 		en = excl_s(M.excl[2], M.excl_eps, d, s);
-		if(en != 0.f) { E += en; if(esplit) esplit[1] += en; acc.site_ak(d * s, cb); }
+		if(en != 0.f) { E += en; if(esplit) esplit[1] += en; acc.site_ak(d * s, cb); excl_fix(acc, M.excl[2], M.excl_eps, d, s, OXB_SITE_AK, cb); }
 		d = r + qbase - pback;
 		en = excl_s(M.excl[3], M.excl_eps, d, s);
-		if(en != 0.f) { E += en; if(esplit) esplit[1] += en; acc.site_ka(d * s, cb); }
+		if(en != 0.f) { E += en; if(esplit) esplit[1] += en; acc.site_ka(d * s, cb); excl_fix(acc, M.excl[3], M.excl_eps, d, s, OXB_SITE_KA, cb); }
 	}
 	return E;
 }

@@ -30,6 +30,74 @@
 
 namespace {
 
+template<class MD>
+__device__ __forceinline__ ExclRefine make_refine(const typename MD::Params &M, const BoxF &box, const double4 *posd, const double4 *quatd) {
+	ExclRefine R;
+	R.posd = posd; R.quatd = quatd; R.sp = R.sq = 0;
+	R.L[0] = box.dsx * 4294967296.; R.L[1] = box.dsy * 4294967296.; R.L[2] = box.dsz * 4294967296.;
+	R.b1 = (double) M.back_a1; R.b2 = (double) M.back_a2; R.b3 = (double) MD::back_a3(M);
+	return R;
+}
+
+__device__ __forceinline__ void atomic_add4(float4 *dst, float x, float y, float z, float w) {
+	atomicAdd(dst, make_float4(x, y, z, w));
+}
+
+// One pair whose excluded-volume site pairs `mask` are in range, evaluated entirely in double from the FP64 state and added to F / T
+// (lab frame; .w of F = pair energy, as everywhere).  Runs block-locally AFTER the main loop of the producing kernel, on the few pairs
+// that were parked in shared memory: the hot loops stay free of FP64 and of its registers.
+template<class MD>
+__device__ __noinline__ void excl_double_item(const typename MD::Params &M, const BoxF &box, const double4 *__restrict__ posd, const double4 *__restrict__ qd,
+		int p, int q, int mask, float4 *__restrict__ F, float4 *__restrict__ T) {
+	const double L[3] = { box.dsx * 4294967296., box.dsy * 4294967296., box.dsz * 4294967296. };
+	const double b1 = (double) M.back_a1, b2 = (double) M.back_a2, b3 = (double) MD::back_a3(M), cb = (double) M.base_a1, eps = (double) M.excl_eps;
+	const double4 pp = posd[p], pq = posd[q], qp = qd[p], qq = qd[q];
+	double rd[3] = { pq.x - pp.x, pq.y - pp.y, pq.z - pp.z };
+	for(int k = 0; k < 3; k++) rd[k] -= L[k] * rint(rd[k] / L[k]);
+	double a1p[3], a2p[3], a3p[3], a1q[3], a2q[3], a3q[3];
+	quatd Qp = { qp.x, qp.y, qp.z, qp.w }, Qq = { qq.x, qq.y, qq.z, qq.w };
+	axes_from_quatd(Qp, a1p, a2p, a3p);
+	axes_from_quatd(Qq, a1q, a2q, a3q);
+	double kp[3], kq[3], ap[3], aq[3]; // backbone and base sites relative to the centres
+	for(int k = 0; k < 3; k++) {
+		kp[k] = b1 * a1p[k] + b2 * a2p[k] + b3 * a3p[k]; kq[k] = b1 * a1q[k] + b2 * a2q[k] + b3 * a3q[k];
+		ap[k] = cb * a1p[k]; aq[k] = cb * a1q[k];
+	}
+	double Fq[3] = { 0., 0., 0. }, Tp[3] = { 0., 0., 0. }, Tq[3] = { 0., 0., 0. }, E = 0.;
+	// (kind, parameter block): backbone-backbone 0, base-base 1, base(p)-back(q) 2, back(p)-base(q) 3 -- as in dna2_excl / bonded_fene_excl
+	const int kinds[4] = { OXB_SITE_KK, OXB_SITE_AA, OXB_SITE_AK, OXB_SITE_KA };
+	for(int t = 0; t < 4; t++) {
+		if(!(mask & (1 << kinds[t]))) continue;
+		const oxb_excl &e = M.excl[t];
+		const double *sp = (kinds[t] == OXB_SITE_KK || kinds[t] == OXB_SITE_KA) ? kp : ap;
+		const double *sq = (kinds[t] == OXB_SITE_KK || kinds[t] == OXB_SITE_AK) ? kq : aq;
+		const double d[3] = { rd[0] + sq[0] - sp[0], rd[1] + sq[1] - sp[1], rd[2] + sq[2] - sp[2] };
+		const double r2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+		if(!(r2 < (double) e.rc2)) continue;
+		double sd, en;
+		if(r2 > (double) e.rstar2) {
+			const double m = sqrt(r2), x = m - (double) e.rc;
+			en = eps * (double) e.b * x * x;
+			sd = -2. * eps * (double) e.b * x / m;
+		}
+		else {
+			const double tt = (double) e.sigma2 / r2, lj = tt * tt * tt;
+			en = 4. * eps * (lj * lj - lj);
+			sd = -24. * eps * (lj - 2. * lj * lj) / r2;
+		}
+		const double f[3] = { d[0] * sd, d[1] * sd, d[2] * sd }; // on q, at site sq; -f on p at site sp
+		E += en;
+		for(int k = 0; k < 3; k++) Fq[k] += f[k];
+		Tq[0] += sq[1] * f[2] - sq[2] * f[1]; Tq[1] += sq[2] * f[0] - sq[0] * f[2]; Tq[2] += sq[0] * f[1] - sq[1] * f[0];
+		Tp[0] -= sp[1] * f[2] - sp[2] * f[1]; Tp[1] -= sp[2] * f[0] - sp[0] * f[2]; Tp[2] -= sp[0] * f[1] - sp[1] * f[0];
+	}
+	if(E == 0.) return;
+	atomic_add4(F + q, (float) Fq[0], (float) Fq[1], (float) Fq[2], (float) E);
+	atomic_add4(T + q, (float) Tq[0], (float) Tq[1], (float) Tq[2], 0.f);
+	atomic_add4(F + p, (float) -Fq[0], (float) -Fq[1], (float) -Fq[2], (float) E);
+	atomic_add4(T + p, (float) Tp[0], (float) Tp[1], (float) Tp[2], 0.f);
+}
+
 struct Particle {
 	int4 ip;
 	Axes ax;
@@ -52,7 +120,8 @@ __device__ __forceinline__ Particle load_particle(const typename MD::Params &M, 
 // ------------------------------------------------------------------------------------------------------------
 template<class MD>
 __global__ void __launch_bounds__(128, OXB_MB_PARTICLE) k_forces_particle(const __grid_constant__ typename MD::Params M, BoxF box, int N, const int4 *__restrict__ ipos,
-		const int4 *__restrict__ iback, const float4 *__restrict__ quat, const int2 *__restrict__ bonds, const int *__restrict__ nbr, const int *__restrict__ nnbr, int stride,
+		const int4 *__restrict__ iback, const float4 *__restrict__ quat, const double4 *__restrict__ posd, const double4 *__restrict__ quatd,
+		const int2 *__restrict__ bonds, const int *__restrict__ nbr, const int *__restrict__ nnbr, int stride,
 		float4 *__restrict__ F, float4 *__restrict__ T, int *__restrict__ flags, int hw) {
 	if(flags[hw]) return;
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -65,11 +134,13 @@ __global__ void __launch_bounds__(128, OXB_MB_PARTICLE) k_forces_particle(const 
 	v3 f = mk3(0.f, 0.f, 0.f), t = mk3(0.f, 0.f, 0.f);
 	float e = 0.f, ehb = 0.f;
 	bool broken = false;
+	ExclRefine R = make_refine<MD>(M, box, posd, quatd);
 
 	if(b.x >= 0) { // I am the 5' side of the bond (p), q = my n3
 		Particle Q = load_particle<MD>(M, ipos, quat, b.x);
 		PairAcc acc;
 		acc.clear();
+		R.sp = i; R.sq = b.x; acc.refine = &R;
 		const FeneSite fs = fene_from_sites(M, box, __ldg(iback + i), __ldg(iback + b.x), broken);
 		e += MD::bonded(M, min_image_fixed(box, P.ip, Q.ip), P.ax, Q.ax, P.btype, Q.btype, P.back, Q.back, acc, broken, nullptr, &fs);
 		f -= acc.F;
@@ -79,6 +150,7 @@ __global__ void __launch_bounds__(128, OXB_MB_PARTICLE) k_forces_particle(const 
 		Particle Q = load_particle<MD>(M, ipos, quat, b.y);
 		PairAcc acc;
 		acc.clear();
+		R.sp = b.y; R.sq = i; acc.refine = &R;
 		const FeneSite fs = fene_from_sites(M, box, __ldg(iback + b.y), __ldg(iback + i), broken);
 		e += MD::bonded(M, min_image_fixed(box, Q.ip, P.ip), Q.ax, P.ax, Q.btype, P.btype, Q.back, P.back, acc, broken, nullptr, &fs);
 		f += acc.F;
@@ -92,6 +164,7 @@ __global__ void __launch_bounds__(128, OXB_MB_PARTICLE) k_forces_particle(const 
 		int2 bq = __ldg(bonds + j);
 		PairAcc acc;
 		acc.clear();
+		R.sp = i; R.sq = j; acc.refine = &R;
 		PairEnergy pe = MD::nonbonded(M, min_image_fixed(box, P.ip, Q.ip), P.ax, Q.ax, P.btype, Q.btype, p_end, (bq.x < 0 || bq.y < 0), P.back,
 				Q.back, acc);
 		e += pe.total;
@@ -122,9 +195,6 @@ __global__ void __launch_bounds__(128, OXB_MB_PARTICLE) k_forces_particle(const 
 // segment head issues the 128-bit vector atomic (red.global.add.v4.f32).  F/T/Fb hold lab-frame sums; the integrator
 // rotates the torque into the body frame.
 // ------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void atomic_add4(float4 *dst, float x, float y, float z, float w) {
-	atomicAdd(dst, make_float4(x, y, z, w));
-}
 
 template<int NV>
 __device__ __forceinline__ bool segmented_reduce(int key, unsigned lane, float (&v)[NV]) {
@@ -203,8 +273,8 @@ __device__ __forceinline__ void block_append(bool flag, int2 item, int2 *__restr
 
 template<class MD>
 __global__ void __launch_bounds__(128, OXB_MB_NEAR) k_edge_near(const __grid_constant__ typename MD::Params M, BoxF box, const int *__restrict__ n_edges,
-		const int2 *__restrict__ edges, const int4 *__restrict__ ipos, const float4 *__restrict__ quat, float4 *__restrict__ F, float4 *__restrict__ T,
-		int2 *__restrict__ hb_list, int2 *__restrict__ cx_list, int2 *__restrict__ cr_list, int *__restrict__ seg_counts, int hb_seg, int cx_seg,
+		const int2 *__restrict__ edges, const int4 *__restrict__ ipos, const float4 *__restrict__ quat, const double4 *__restrict__ posd,
+		const double4 *__restrict__ quatd, float4 *__restrict__ F, float4 *__restrict__ T, int2 *__restrict__ hb_list, int2 *__restrict__ cx_list, int2 *__restrict__ cr_list, int *__restrict__ seg_counts, int hb_seg, int cx_seg,
 		int cr_seg, int *__restrict__ flags, int hw) {
 	if(flags[hw]) return;
 	__shared__ int s_cnt[3];
@@ -215,6 +285,12 @@ __global__ void __launch_bounds__(128, OXB_MB_NEAR) k_edge_near(const __grid_con
 	cr_list += (size_t) blockIdx.x * cr_seg;
 	const int ne = *n_edges;
 	const unsigned lane = threadIdx.x & 31;
+	// pairs with an excluded-volume site pair in range are parked here and evaluated in double after the loop (excl_double_item)
+	constexpr int EXN = 384;
+	__shared__ int s_ex[EXN][3];
+	__shared__ int s_nex;
+	if(threadIdx.x == 0) s_nex = 0;
+	__syncthreads();
 	for(int base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < ne; base += gridDim.x * blockDim.x) {
 		int eidx = base + lane;
 		bool valid = eidx < ne;
@@ -231,7 +307,13 @@ __global__ void __launch_bounds__(128, OXB_MB_NEAR) k_edge_near(const __grid_con
 				v3 rb = r + (Q.ax.a1 - P.ax.a1) * M.base_a1;
 				PairAcc acc;
 				acc.clear();
-				float en = dna2_excl(M, r, rbb, rb, P.ax, Q.ax, P.back, Q.back, acc);
+				float en = 0.f;
+				const int xmask = dna2_excl_mask(M, r, rbb, rb, P.ax, Q.ax, P.back, Q.back);
+				if(xmask != 0) {
+					const int slot = atomicAdd(&s_nex, 1);
+					if(slot < EXN) { s_ex[slot][0] = ed.x; s_ex[slot][1] = ed.y; s_ex[slot][2] = xmask; }
+					else en = dna2_excl(M, r, rbb, rb, P.ax, Q.ax, P.back, Q.back, acc); // buffer full: FP32 evaluation in place
+				}
 				if(en != 0.f) {
 					v3 tq = acc.torque_q(Q.ax, Q.back), tp = acc.torque_p(P.ax, P.back);
 					atomic_add4(F + ed.y, acc.F.x, acc.F.y, acc.F.z, en);
@@ -274,6 +356,7 @@ __global__ void __launch_bounds__(128, OXB_MB_NEAR) k_edge_near(const __grid_con
 		}
 	}
 	__syncthreads();
+	for(int k = threadIdx.x; k < min(s_nex, EXN); k += blockDim.x) excl_double_item<MD>(M, box, posd, quatd, s_ex[k][0], s_ex[k][1], s_ex[k][2], F, T);
 	if(threadIdx.x < 3) {
 		// list 0: hydrogen-bonding-capable pairs (front of the hb segment), 1: coaxial stacking, 2: cross-stacking-only pairs (rest of the hb segment)
 		const int seg = (threadIdx.x == 0) ? hb_seg / 3 : (threadIdx.x == 1 ? cx_seg : hb_seg - hb_seg / 3);
@@ -325,28 +408,41 @@ __global__ void __launch_bounds__(64, OXB_MB_HEAVY) k_edge_heavy(const __grid_co
 // the force pass (it only adds into F/T), so it runs concurrently with them on its own stream.
 template<class MD>
 __global__ void __launch_bounds__(128, OXB_MB_BONDED) k_bonded(const __grid_constant__ typename MD::Params M, BoxF box, int N, const int4 *__restrict__ ipos,
-		const int4 *__restrict__ iback, const float4 *__restrict__ quat, const int2 *__restrict__ bonds, float4 *__restrict__ F, float4 *__restrict__ T, int *__restrict__ flags, int hw) {
+		const int4 *__restrict__ iback, const float4 *__restrict__ quat, const double4 *__restrict__ posd, const double4 *__restrict__ quatd,
+		const int2 *__restrict__ bonds, float4 *__restrict__ F, float4 *__restrict__ T, int *__restrict__ flags, int hw) {
 	if(flags[hw]) return;
-	int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if(i >= N) return;
-	int2 b = __ldg(bonds + i);
-	if(b.x < 0) return;
-	Particle P = load_particle<MD>(M, ipos, quat, i);
-	Particle Q = load_particle<MD>(M, ipos, quat, b.x);
-	PairAcc acc;
-	acc.clear();
-	bool broken = false;
-	const FeneSite fs = fene_from_sites(M, box, __ldg(iback + i), __ldg(iback + b.x), broken);
-	float en = MD::bonded(M, min_image_fixed(box, P.ip, Q.ip), P.ax, Q.ax, P.btype, Q.btype, P.back, Q.back, acc, broken, nullptr, &fs);
-	v3 tp = acc.torque_p(P.ax, P.back), tq = acc.torque_q(Q.ax, Q.back);
-	atomic_add4(F + i, -acc.F.x, -acc.F.y, -acc.F.z, en);
-	atomic_add4(T + i, tp.x, tp.y, tp.z, 0.f);
-	atomic_add4(F + b.x, acc.F.x, acc.F.y, acc.F.z, en);
-	atomic_add4(T + b.x, tq.x, tq.y, tq.z, 0.f);
-	if(broken) atomicOr(flags + OXB_FLAG_ERROR, OXB_ERR_FENE_BROKEN);
+	// bonds with an excluded-volume site pair in range: parked, then evaluated in double (every thread can park one: never full)
+	__shared__ int s_ex[128][3];
+	__shared__ int s_nex;
+	if(threadIdx.x == 0) s_nex = 0;
+	__syncthreads();
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	const int2 b = (i < N) ? __ldg(bonds + i) : make_int2(-1, -1);
+	if(b.x >= 0) {
+		Particle P = load_particle<MD>(M, ipos, quat, i);
+		Particle Q = load_particle<MD>(M, ipos, quat, b.x);
+		PairAcc acc;
+		acc.clear();
+		bool broken = false;
+		const v3 r = min_image_fixed(box, P.ip, Q.ip);
+		FeneSite fs = fene_from_sites(M, box, __ldg(iback + i), __ldg(iback + b.x), broken);
+		fs.excl_deferred = bonded_excl_mask(M, r, P.ax, Q.ax, P.back, Q.back);
+		if(fs.excl_deferred != 0) {
+			const int slot = atomicAdd(&s_nex, 1);
+			s_ex[slot][0] = i; s_ex[slot][1] = b.x; s_ex[slot][2] = fs.excl_deferred;
+		}
+		float en = MD::bonded(M, r, P.ax, Q.ax, P.btype, Q.btype, P.back, Q.back, acc, broken, nullptr, &fs);
+		v3 tp = acc.torque_p(P.ax, P.back), tq = acc.torque_q(Q.ax, Q.back);
+		atomic_add4(F + i, -acc.F.x, -acc.F.y, -acc.F.z, en);
+		atomic_add4(T + i, tp.x, tp.y, tp.z, 0.f);
+		atomic_add4(F + b.x, acc.F.x, acc.F.y, acc.F.z, en);
+		atomic_add4(T + b.x, tq.x, tq.y, tq.z, 0.f);
+		if(broken) atomicOr(flags + OXB_FLAG_ERROR, OXB_ERR_FENE_BROKEN);
+	}
+	__syncthreads();
+	for(int k = threadIdx.x; k < s_nex; k += blockDim.x) excl_double_item<MD>(M, box, posd, quatd, s_ex[k][0], s_ex[k][1], s_ex[k][2], F, T);
 }
 
-// ------------------------------------------------------------------------------------------------------------
 // Observable: potential energy split into the reference's eight terms (FENE, bonded excluded volume, stacking, non-bonded
 // excluded volume, hydrogen bonding, cross stacking, coaxial stacking, Debye-Hueckel), summed on the device in double.
 // Replaces the CPU get_system_energy_split() the reference runs after a D2H copy and a CPU list rebuild
@@ -691,11 +787,12 @@ __global__ void k_ext_forces_all(int N, int n_all, const DevExtForce *__restrict
 
 namespace oxb {
 
-void launch_forces_particle(cudaStream_t s, const ModelRef &MR, BoxF box, int N, const int4 *ipos, const int4 *iback, const float4 *quat, const int2 *bonds,
+void launch_forces_particle(cudaStream_t s, const ModelRef &MR, BoxF box, int N, const int4 *ipos, const int4 *iback, const float4 *quat,
+		const double4 *posd, const double4 *quatd, const int2 *bonds,
 		const int *nbr, const int *nnbr, int stride, float4 *F, float4 *T, int *flags, int hw) {
 	int tpb = 128;
-	if(MR.rna) k_forces_particle<RnaModel><<<(N + tpb - 1) / tpb, tpb, 0, s>>>(*MR.rna, box, N, ipos, iback, quat, bonds, nbr, nnbr, stride, F, T, flags, hw);
-	else k_forces_particle<DnaModel><<<(N + tpb - 1) / tpb, tpb, 0, s>>>(*MR.dna, box, N, ipos, iback, quat, bonds, nbr, nnbr, stride, F, T, flags, hw);
+	if(MR.rna) k_forces_particle<RnaModel><<<(N + tpb - 1) / tpb, tpb, 0, s>>>(*MR.rna, box, N, ipos, iback, quat, posd, quatd, bonds, nbr, nnbr, stride, F, T, flags, hw);
+	else k_forces_particle<DnaModel><<<(N + tpb - 1) / tpb, tpb, 0, s>>>(*MR.dna, box, N, ipos, iback, quat, posd, quatd, bonds, nbr, nnbr, stride, F, T, flags, hw);
 }
 
 // the kernels of the edge pipeline, launched one by one so that the context can place them on concurrent streams:
@@ -723,7 +820,7 @@ static void launch_edge_stage_t(cudaStream_t s, int which, const typename MD::Pa
 	// the producer and the three consumers of the segmented work lists share one fixed grid (a.n_seg blocks, grid-stride
 	// inside): nothing here depends on device-side counts, so a captured graph stays valid across list rebuilds
 	case 1:
-		k_edge_near<MD><<<a.n_seg, 128, 0, s>>>(M, box, a.n_edges, a.edges, a.ipos, a.quat, a.F, a.T, a.hb_list, a.cx_list, a.cr_list, a.seg_counts, a.hb_seg,
+		k_edge_near<MD><<<a.n_seg, 128, 0, s>>>(M, box, a.n_edges, a.edges, a.ipos, a.quat, a.posd, a.quatd, a.F, a.T, a.hb_list, a.cx_list, a.cr_list, a.seg_counts, a.hb_seg,
 				a.cx_seg, a.cr_seg, flags, hw);
 		break;
 	case 2: k_edge_heavy<MD, 0><<<dim3(a.n_seg, a.hb_split), 64, 0, s>>>(M, box, a.seg_counts, a.hb_list, a.hb_seg, a.ipos, a.quat, a.F, a.T, flags, hw); break;
@@ -732,7 +829,7 @@ static void launch_edge_stage_t(cudaStream_t s, int which, const typename MD::Pa
 	default: {
 		static const int tpb_env = env_int("OXB_TPB_BONDED", 0);
 		const int tpb = tpb_env > 0 ? tpb_env : 128;
-		k_bonded<MD><<<(a.N + tpb - 1) / tpb, tpb, 0, s>>>(M, box, a.N, a.ipos, a.iback, a.quat, a.bonds, a.F, a.T, flags, hw);
+		k_bonded<MD><<<(a.N + tpb - 1) / tpb, tpb, 0, s>>>(M, box, a.N, a.ipos, a.iback, a.quat, a.posd, a.quatd, a.bonds, a.F, a.T, flags, hw);
 		break;
 	}
 	}

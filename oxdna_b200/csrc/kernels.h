@@ -57,12 +57,14 @@ struct ModelRef {
 };
 
 // ---- forces.cu
-void launch_forces_particle(cudaStream_t s, const ModelRef &M, BoxF box, int N, const int4 *ipos, const int4 *iback, const float4 *quat, const int2 *bonds,
+void launch_forces_particle(cudaStream_t s, const ModelRef &M, BoxF box, int N, const int4 *ipos, const int4 *iback, const float4 *quat,
+		const double4 *posd, const double4 *quatd, const int2 *bonds,
 		const int *nbr, const int *nnbr, int stride, float4 *F, float4 *T, int *flags, int hw);
 struct EdgeArgs {
 	int N;
 	const int4 *ipos, *iback;
 	const float4 *quat;
+	const double4 *posd, *quatd; // FP64 state: read only where an excluded-volume term is active (ExclRefine)
 	const int2 *bonds, *edges; // near edges
 	const int *n_edges;
 	const int *dh_nbr, *dh_nnbr; // Debye-Hueckel neighbour matrix, column-major, stride N

@@ -6,6 +6,7 @@
 struct DnaModel {
 	typedef oxb_dna2_params Params;
 	static OXB_HD v3 back(const Params &M, const Axes &A) { return A.a1 * M.back_a1 + A.a2 * M.back_a2; }
+	static OXB_HD float back_a3(const Params &M) { return 0.f; }
 	static OXB_HD bool hb_in_range(const Params &M, float rbm2, int btp, int btq) { return dna2_hb_in_range(M, rbm2, btp, btq); }
 	static OXB_HD bool crst_in_range(const Params &M, float rbm2) { return dna2_crst_in_range(M, rbm2); }
 	static OXB_HD bool cxst_in_range(const Params &M, float rs2) { return dna2_cxst_in_range(M, rs2); }
@@ -27,6 +28,7 @@ struct DnaModel {
 struct RnaModel {
 	typedef oxb_rna2_params Params;
 	static OXB_HD v3 back(const Params &M, const Axes &A) { return rna2_back(M, A); }
+	static OXB_HD float back_a3(const Params &M) { return M.back_a3; }
 	static OXB_HD bool hb_in_range(const Params &M, float rbm2, int btp, int btq) { return rna2_hb_in_range(M, rbm2, btp, btq); }
 	static OXB_HD bool crst_in_range(const Params &M, float rbm2) { return rna2_crst_in_range(M, rbm2); }
 	static OXB_HD bool cxst_in_range(const Params &M, float rs2) { return rna2_cxst_in_range(M, rs2); }
