@@ -79,6 +79,9 @@ struct oxb_ctx {
 	int *dh_nbr = nullptr, *dh_nnbr = nullptr;
 	int max_dh = 0;
 	int2 *hb_list = nullptr, *cx_list = nullptr, *cr_list = nullptr;
+	int4 *ex_list = nullptr;
+	int *ex_counts = nullptr, *ex_bonded = nullptr;
+	int ex_seg = 1;
 	int *seg_counts = nullptr;
 	int n_seg = 1, hb_seg = 1, cx_seg = 1, cr_seg = 1;
 	void *cub_tmp = nullptr;
@@ -173,6 +176,8 @@ void free_lists(oxb_ctx *c) {
 	c->near_mask = nullptr;
 	c->slots_cell_ordered = false;
 	cudaFree(c->hb_list); cudaFree(c->cx_list); cudaFree(c->cr_list); cudaFree(c->seg_counts);
+	cudaFree(c->ex_list); cudaFree(c->ex_counts); cudaFree(c->ex_bonded);
+	c->ex_list = nullptr; c->ex_counts = c->ex_bonded = nullptr;
 	c->cell_key = c->cell_key_sorted = c->cell_val = c->cell_val_sorted = c->cell_start = c->nbr = c->nnbr = c->edge_offsets = c->n_edges = nullptr;
 	c->seg_counts = c->dh_nbr = c->dh_nnbr = nullptr;
 	c->edges = c->hb_list = c->cx_list = c->cr_list = nullptr;
@@ -234,6 +239,10 @@ int alloc_lists(oxb_ctx *c, int max_neigh) {
 	c->cr_seg = 1; // the cross-stacking-only list is not produced (see forces.cu)
 	c->cx_seg = c->use_edge ? (int) (2ll * N / c->n_seg) + 64 : 1;
 	CU(dalloc(&c->hb_list, (size_t) c->hb_seg * c->n_seg)); CU(dalloc(&c->cx_list, (size_t) c->cx_seg * c->n_seg));
+	c->ex_seg = c->use_edge ? (int) (2ll * N / c->n_seg) + 64 : 1;
+	CU(dalloc(&c->ex_list, (size_t) c->ex_seg * c->n_seg)); CU(dalloc(&c->ex_counts, (size_t) c->n_seg)); CU(dalloc(&c->ex_bonded, (size_t) N));
+	CU(cudaMemset(c->ex_counts, 0, sizeof(int) * (size_t) c->n_seg));
+	CU(cudaMemset(c->ex_bonded, 0, sizeof(int) * (size_t) N));
 	CU(dalloc(&c->cr_list, (size_t) c->cr_seg * c->n_seg)); CU(dalloc(&c->seg_counts, (size_t) 3 * c->n_seg));
 	CU(cudaMemset(c->seg_counts, 0, sizeof(int) * 3 * (size_t) c->n_seg));
 	c->edge_capacity = c->use_edge ? ((long long) N * max_neigh) / 4 + N : 1;
@@ -383,6 +392,7 @@ int launch_forces(oxb_ctx *c, int hw, bool clear, long long step) {
 		e.N = c->N; e.ipos = c->ipos[a]; e.iback = c->iback[a]; e.quat = c->quat[a]; e.posd = c->posd[a]; e.quatd = c->quatd[a]; e.bonds = c->bonds[a]; e.edges = c->edges;
 		e.n_edges = c->n_edges; e.dh_nbr = c->dh_nbr; e.dh_nnbr = c->dh_nnbr;
 		e.F = c->F[a]; e.T = c->T[a]; e.Fb = c->Fb; e.hb_list = c->hb_list; e.cx_list = c->cx_list; e.cr_list = c->cr_list; e.seg_counts = c->seg_counts;
+		e.ex_list = c->ex_list; e.ex_counts = c->ex_counts; e.ex_bonded = c->ex_bonded; e.ex_seg = c->ex_seg;
 		e.n_seg = c->n_seg; e.hb_seg = c->hb_seg; e.cx_seg = c->cx_seg; e.cr_seg = c->cr_seg;
 		// ~1.7 items per particle in that list; aim at ~2 items per consumer thread
 		e.hb_split = (int) std::max<long long>(1, std::min<long long>(8, (17ll * c->N / 10 / c->n_seg + 64) / 128));
@@ -415,13 +425,14 @@ int launch_forces(oxb_ctx *c, int hw, bool clear, long long step) {
 		}
 		if(fork) CU(cudaStreamWaitEvent(c->aux[1], c->ev_near, 0));
 		oxb::launch_edge_stage(s1, 3, c->mref(), c->boxf, e, c->flags, hw);
+		oxb::launch_edge_stage(s1, 6, c->mref(), c->boxf, e, c->flags, hw); // excluded volume in double for the parked pairs (after near + bonded)
 		if(fork) {
 			CU(cudaEventRecord(c->ev_join[0], c->aux[0]));
 			CU(cudaEventRecord(c->ev_join[1], c->aux[1]));
 			CU(cudaStreamWaitEvent(m, c->ev_join[0], 0));
 			CU(cudaStreamWaitEvent(m, c->ev_join[1], 0));
 		}
-		c->launches += 5;
+		c->launches += 6;
 	}
 	else {
 		oxb::launch_forces_particle(m, c->mref(), c->boxf, c->N, c->ipos[a], c->iback[a], c->quat[a], c->posd[a], c->quatd[a], c->bonds[a], c->nbr, c->nnbr, c->N, c->F[a], c->T[a],
@@ -586,7 +597,7 @@ int batch_graph(oxb_ctx *c, int units, cudaGraphExec_t *out) {
 // stream launches.
 int launch_full_units(oxb_ctx *c, long long n, long long step0, int &epoch) {
 	const bool graphable = c->use_graphs && c->th.type != OXB_THERMOSTAT_BUSSI;
-	const int per_unit = (c->use_edge ? 5 : 1) + (c->n_ext > 0 ? 1 : 0) + (c->n_ext_all > 0 ? 1 : 0) + (c->n_ext_com > 0 ? 1 : 0) + 1;
+	const int per_unit = (c->use_edge ? 6 : 1) + (c->n_ext > 0 ? 1 : 0) + (c->n_ext_all > 0 ? 1 : 0) + (c->n_ext_com > 0 ? 1 : 0) + 1;
 	long long k = 0;
 	while(k < n) {
 		int chunk = 0;

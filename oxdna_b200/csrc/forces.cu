@@ -275,7 +275,7 @@ template<class MD>
 __global__ void __launch_bounds__(128, OXB_MB_NEAR) k_edge_near(const __grid_constant__ typename MD::Params M, BoxF box, const int *__restrict__ n_edges,
 		const int2 *__restrict__ edges, const int4 *__restrict__ ipos, const float4 *__restrict__ quat, const double4 *__restrict__ posd,
 		const double4 *__restrict__ quatd, float4 *__restrict__ F, float4 *__restrict__ T, int2 *__restrict__ hb_list, int2 *__restrict__ cx_list, int2 *__restrict__ cr_list, int *__restrict__ seg_counts, int hb_seg, int cx_seg,
-		int cr_seg, int *__restrict__ flags, int hw) {
+		int cr_seg, int4 *__restrict__ ex_list, int *__restrict__ ex_counts, int ex_seg, int *__restrict__ flags, int hw) {
 	if(flags[hw]) return;
 	__shared__ int s_cnt[3];
 	if(threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
@@ -285,12 +285,11 @@ __global__ void __launch_bounds__(128, OXB_MB_NEAR) k_edge_near(const __grid_con
 	cr_list += (size_t) blockIdx.x * cr_seg;
 	const int ne = *n_edges;
 	const unsigned lane = threadIdx.x & 31;
-	// pairs with an excluded-volume site pair in range are parked here and evaluated in double after the loop (excl_double_item)
-	constexpr int EXN = 384;
-	__shared__ int s_ex[EXN][3];
+	// pairs with an excluded-volume site pair in range are parked in this block's segment of ex_list; k_excl_fix evaluates them in double
 	__shared__ int s_nex;
 	if(threadIdx.x == 0) s_nex = 0;
 	__syncthreads();
+	ex_list += (size_t) blockIdx.x * ex_seg;
 	for(int base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < ne; base += gridDim.x * blockDim.x) {
 		int eidx = base + lane;
 		bool valid = eidx < ne;
@@ -311,7 +310,7 @@ __global__ void __launch_bounds__(128, OXB_MB_NEAR) k_edge_near(const __grid_con
 				const int xmask = dna2_excl_mask(M, r, rbb, rb, P.ax, Q.ax, P.back, Q.back);
 				if(xmask != 0) {
 					const int slot = atomicAdd(&s_nex, 1);
-					if(slot < EXN) { s_ex[slot][0] = ed.x; s_ex[slot][1] = ed.y; s_ex[slot][2] = xmask; }
+					if(slot < ex_seg) ex_list[slot] = make_int4(ed.x, ed.y, xmask, 0);
 					else en = dna2_excl(M, r, rbb, rb, P.ax, Q.ax, P.back, Q.back, acc); // buffer full: FP32 evaluation in place
 				}
 				if(en != 0.f) {
@@ -356,7 +355,7 @@ __global__ void __launch_bounds__(128, OXB_MB_NEAR) k_edge_near(const __grid_con
 		}
 	}
 	__syncthreads();
-	for(int k = threadIdx.x; k < min(s_nex, EXN); k += blockDim.x) excl_double_item<MD>(M, box, posd, quatd, s_ex[k][0], s_ex[k][1], s_ex[k][2], F, T);
+	if(threadIdx.x == 0) ex_counts[blockIdx.x] = min(s_nex, ex_seg);
 	if(threadIdx.x < 3) {
 		// list 0: hydrogen-bonding-capable pairs (front of the hb segment), 1: coaxial stacking, 2: cross-stacking-only pairs (rest of the hb segment)
 		const int seg = (threadIdx.x == 0) ? hb_seg / 3 : (threadIdx.x == 1 ? cx_seg : hb_seg - hb_seg / 3);
@@ -408,39 +407,53 @@ __global__ void __launch_bounds__(64, OXB_MB_HEAVY) k_edge_heavy(const __grid_co
 // the force pass (it only adds into F/T), so it runs concurrently with them on its own stream.
 template<class MD>
 __global__ void __launch_bounds__(128, OXB_MB_BONDED) k_bonded(const __grid_constant__ typename MD::Params M, BoxF box, int N, const int4 *__restrict__ ipos,
-		const int4 *__restrict__ iback, const float4 *__restrict__ quat, const double4 *__restrict__ posd, const double4 *__restrict__ quatd,
-		const int2 *__restrict__ bonds, float4 *__restrict__ F, float4 *__restrict__ T, int *__restrict__ flags, int hw) {
+		const int4 *__restrict__ iback, const float4 *__restrict__ quat, const int2 *__restrict__ bonds, float4 *__restrict__ F, float4 *__restrict__ T,
+		int *__restrict__ ex_bonded, int *__restrict__ flags, int hw) {
 	if(flags[hw]) return;
-	// bonds with an excluded-volume site pair in range: parked, then evaluated in double (every thread can park one: never full)
-	__shared__ int s_ex[128][3];
-	__shared__ int s_nex;
-	if(threadIdx.x == 0) s_nex = 0;
-	__syncthreads();
-	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	const int2 b = (i < N) ? __ldg(bonds + i) : make_int2(-1, -1);
-	if(b.x >= 0) {
-		Particle P = load_particle<MD>(M, ipos, quat, i);
-		Particle Q = load_particle<MD>(M, ipos, quat, b.x);
-		PairAcc acc;
-		acc.clear();
-		bool broken = false;
-		const v3 r = min_image_fixed(box, P.ip, Q.ip);
-		FeneSite fs = fene_from_sites(M, box, __ldg(iback + i), __ldg(iback + b.x), broken);
-		fs.excl_deferred = bonded_excl_mask(M, r, P.ax, Q.ax, P.back, Q.back);
-		if(fs.excl_deferred != 0) {
-			const int slot = atomicAdd(&s_nex, 1);
-			s_ex[slot][0] = i; s_ex[slot][1] = b.x; s_ex[slot][2] = fs.excl_deferred;
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= N) return;
+	int2 b = __ldg(bonds + i);
+	if(b.x < 0) { ex_bonded[i] = 0; return; }
+	Particle P = load_particle<MD>(M, ipos, quat, i);
+	Particle Q = load_particle<MD>(M, ipos, quat, b.x);
+	PairAcc acc;
+	acc.clear();
+	bool broken = false;
+	const v3 r = min_image_fixed(box, P.ip, Q.ip);
+	FeneSite fs = fene_from_sites(M, box, __ldg(iback + i), __ldg(iback + b.x), broken);
+	// bonded excluded-volume site pairs in range are left to k_excl_fix (double); one mask per particle
+	fs.excl_deferred = bonded_excl_mask(M, r, P.ax, Q.ax, P.back, Q.back);
+	ex_bonded[i] = fs.excl_deferred;
+	float en = MD::bonded(M, r, P.ax, Q.ax, P.btype, Q.btype, P.back, Q.back, acc, broken, nullptr, &fs);
+	v3 tp = acc.torque_p(P.ax, P.back), tq = acc.torque_q(Q.ax, Q.back);
+	atomic_add4(F + i, -acc.F.x, -acc.F.y, -acc.F.z, en);
+	atomic_add4(T + i, tp.x, tp.y, tp.z, 0.f);
+	atomic_add4(F + b.x, acc.F.x, acc.F.y, acc.F.z, en);
+	atomic_add4(T + b.x, tq.x, tq.y, tq.z, 0.f);
+	if(broken) atomicOr(flags + OXB_FLAG_ERROR, OXB_ERR_FENE_BROKEN);
+}
+
+// Excluded volume in double for the parked pairs: blocks [0, n_seg) walk the near-edge segments, the following blocks scan the
+// per-particle masks of the bonds (256 particles each).  Runs after k_edge_near and k_bonded, next to the coaxial-stacking kernel.
+template<class MD>
+__global__ void __launch_bounds__(128) k_excl_fix(const __grid_constant__ typename MD::Params M, BoxF box, int N, int n_seg, const int4 *__restrict__ ex_list,
+		const int *__restrict__ ex_counts, int ex_seg, const int *__restrict__ ex_bonded, const int2 *__restrict__ bonds, const double4 *__restrict__ posd,
+		const double4 *__restrict__ quatd, float4 *__restrict__ F, float4 *__restrict__ T, const int *__restrict__ flags, int hw) {
+	if(flags[hw]) return;
+	if((int) blockIdx.x < n_seg) {
+		const int n = ex_counts[blockIdx.x];
+		const int4 *seg = ex_list + (size_t) blockIdx.x * ex_seg;
+		for(int k = threadIdx.x; k < n; k += blockDim.x) {
+			const int4 it = __ldg(seg + k);
+			excl_double_item<MD>(M, box, posd, quatd, it.x, it.y, it.z, F, T);
 		}
-		float en = MD::bonded(M, r, P.ax, Q.ax, P.btype, Q.btype, P.back, Q.back, acc, broken, nullptr, &fs);
-		v3 tp = acc.torque_p(P.ax, P.back), tq = acc.torque_q(Q.ax, Q.back);
-		atomic_add4(F + i, -acc.F.x, -acc.F.y, -acc.F.z, en);
-		atomic_add4(T + i, tp.x, tp.y, tp.z, 0.f);
-		atomic_add4(F + b.x, acc.F.x, acc.F.y, acc.F.z, en);
-		atomic_add4(T + b.x, tq.x, tq.y, tq.z, 0.f);
-		if(broken) atomicOr(flags + OXB_FLAG_ERROR, OXB_ERR_FENE_BROKEN);
 	}
-	__syncthreads();
-	for(int k = threadIdx.x; k < s_nex; k += blockDim.x) excl_double_item<MD>(M, box, posd, quatd, s_ex[k][0], s_ex[k][1], s_ex[k][2], F, T);
+	else {
+		for(int i = ((int) blockIdx.x - n_seg) * 256 + threadIdx.x, e = min(N, ((int) blockIdx.x - n_seg + 1) * 256); i < e; i += blockDim.x) {
+			const int mask = __ldg(ex_bonded + i);
+			if(mask != 0) excl_double_item<MD>(M, box, posd, quatd, i, __ldg(bonds + i).x, mask, F, T);
+		}
+	}
 }
 
 // Observable: potential energy split into the reference's eight terms (FENE, bonded excluded volume, stacking, non-bonded
@@ -821,15 +834,19 @@ static void launch_edge_stage_t(cudaStream_t s, int which, const typename MD::Pa
 	// inside): nothing here depends on device-side counts, so a captured graph stays valid across list rebuilds
 	case 1:
 		k_edge_near<MD><<<a.n_seg, 128, 0, s>>>(M, box, a.n_edges, a.edges, a.ipos, a.quat, a.posd, a.quatd, a.F, a.T, a.hb_list, a.cx_list, a.cr_list, a.seg_counts, a.hb_seg,
-				a.cx_seg, a.cr_seg, flags, hw);
+				a.cx_seg, a.cr_seg, a.ex_list, a.ex_counts, a.ex_seg, flags, hw);
 		break;
 	case 2: k_edge_heavy<MD, 0><<<dim3(a.n_seg, a.hb_split), 64, 0, s>>>(M, box, a.seg_counts, a.hb_list, a.hb_seg, a.ipos, a.quat, a.F, a.T, flags, hw); break;
 	case 3: k_edge_heavy<MD, 1><<<a.n_seg, 64, 0, s>>>(M, box, a.seg_counts, a.cx_list, a.cx_seg, a.ipos, a.quat, a.F, a.T, flags, hw); break;
+	case 6:
+		k_excl_fix<MD><<<a.n_seg + (a.N + 255) / 256, 128, 0, s>>>(M, box, a.N, a.n_seg, a.ex_list, a.ex_counts, a.ex_seg, a.ex_bonded, a.bonds, a.posd, a.quatd, a.F, a.T,
+				flags, hw);
+		break;
 	case 5: break; // the separate cross-stacking-only list is no longer produced (slot 2 of seg_counts now counts the back half of the hb segment)
 	default: {
 		static const int tpb_env = env_int("OXB_TPB_BONDED", 0);
 		const int tpb = tpb_env > 0 ? tpb_env : 128;
-		k_bonded<MD><<<(a.N + tpb - 1) / tpb, tpb, 0, s>>>(M, box, a.N, a.ipos, a.iback, a.quat, a.posd, a.quatd, a.bonds, a.F, a.T, flags, hw);
+		k_bonded<MD><<<(a.N + tpb - 1) / tpb, tpb, 0, s>>>(M, box, a.N, a.ipos, a.iback, a.quat, a.bonds, a.F, a.T, a.ex_bonded, flags, hw);
 		break;
 	}
 	}

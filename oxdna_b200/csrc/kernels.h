@@ -75,6 +75,11 @@ struct EdgeArgs {
 	int *seg_counts;
 	int n_seg, hb_seg, cx_seg, cr_seg;
 	int hb_split; // consumer blocks per segment of the hydrogen-bonding / cross-stacking list
+	// pairs with an excluded-volume site pair in range, evaluated in double by k_excl_fix: near edges (p, q, mask, -) segmented by
+	// producer block like the lists above (ex_counts[b] entries in block b's segment of ex_seg), bonds as one mask per particle
+	int4 *ex_list;
+	int *ex_counts, *ex_bonded;
+	int ex_seg;
 };
 void launch_edge_stage(cudaStream_t s, int which, const ModelRef &M, BoxF box, const EdgeArgs &a, int *flags, int hw);
 void launch_energy_split(cudaStream_t s, const ModelRef &M, BoxF box, int N, const int4 *ipos, const float4 *quat, const int2 *bonds, const int *nbr,
