@@ -393,6 +393,7 @@ int launch_forces(oxb_ctx *c, int hw, bool clear, long long step) {
 		e.n_edges = c->n_edges; e.dh_nbr = c->dh_nbr; e.dh_nnbr = c->dh_nnbr;
 		e.F = c->F[a]; e.T = c->T[a]; e.Fb = c->Fb; e.hb_list = c->hb_list; e.cx_list = c->cx_list; e.cr_list = c->cr_list; e.seg_counts = c->seg_counts;
 		e.ex_list = c->ex_list; e.ex_counts = c->ex_counts; e.ex_bonded = c->ex_bonded; e.ex_seg = c->ex_seg;
+		e.refine = (c->precision == OXB_PRECISION_MIXED) ? 1 : 0;
 		e.n_seg = c->n_seg; e.hb_seg = c->hb_seg; e.cx_seg = c->cx_seg; e.cr_seg = c->cr_seg;
 		// ~1.7 items per particle in that list; aim at ~2 items per consumer thread
 		e.hb_split = (int) std::max<long long>(1, std::min<long long>(8, (17ll * c->N / 10 / c->n_seg + 64) / 128));
@@ -425,17 +426,18 @@ int launch_forces(oxb_ctx *c, int hw, bool clear, long long step) {
 		}
 		if(fork) CU(cudaStreamWaitEvent(c->aux[1], c->ev_near, 0));
 		oxb::launch_edge_stage(s1, 3, c->mref(), c->boxf, e, c->flags, hw);
-		oxb::launch_edge_stage(s1, 6, c->mref(), c->boxf, e, c->flags, hw); // excluded volume in double for the parked pairs (after near + bonded)
+		if(e.refine) oxb::launch_edge_stage(s1, 6, c->mref(), c->boxf, e, c->flags, hw); // excluded volume in double for the parked pairs (after near + bonded)
 		if(fork) {
 			CU(cudaEventRecord(c->ev_join[0], c->aux[0]));
 			CU(cudaEventRecord(c->ev_join[1], c->aux[1]));
 			CU(cudaStreamWaitEvent(m, c->ev_join[0], 0));
 			CU(cudaStreamWaitEvent(m, c->ev_join[1], 0));
 		}
-		c->launches += 6;
+		c->launches += e.refine ? 6 : 5;
 	}
 	else {
-		oxb::launch_forces_particle(m, c->mref(), c->boxf, c->N, c->ipos[a], c->iback[a], c->quat[a], c->posd[a], c->quatd[a], c->bonds[a], c->nbr, c->nnbr, c->N, c->F[a], c->T[a],
+		oxb::launch_forces_particle(m, c->mref(), c->boxf, c->N, c->ipos[a], c->iback[a], c->quat[a],
+				c->precision == OXB_PRECISION_MIXED ? c->posd[a] : nullptr, c->quatd[a], c->bonds[a], c->nbr, c->nnbr, c->N, c->F[a], c->T[a],
 				c->flags, hw);
 		c->launches += 1;
 		if(c->n_ext > 0) {
@@ -597,7 +599,7 @@ int batch_graph(oxb_ctx *c, int units, cudaGraphExec_t *out) {
 // stream launches.
 int launch_full_units(oxb_ctx *c, long long n, long long step0, int &epoch) {
 	const bool graphable = c->use_graphs && c->th.type != OXB_THERMOSTAT_BUSSI;
-	const int per_unit = (c->use_edge ? 6 : 1) + (c->n_ext > 0 ? 1 : 0) + (c->n_ext_all > 0 ? 1 : 0) + (c->n_ext_com > 0 ? 1 : 0) + 1;
+	const int per_unit = (c->use_edge ? (c->precision == OXB_PRECISION_MIXED ? 6 : 5) : 1) + (c->n_ext > 0 ? 1 : 0) + (c->n_ext_all > 0 ? 1 : 0) + (c->n_ext_com > 0 ? 1 : 0) + 1;
 	long long k = 0;
 	while(k < n) {
 		int chunk = 0;
@@ -639,10 +641,9 @@ int oxb_create(oxb_ctx **out, int device, int N, int precision) {
 	c->device = device; c->N = N; c->precision = precision;
 	std::memset(&c->th, 0, sizeof(c->th));
 	c->th.every = 1;
-	// backend_precision = float is SERVED BY THE MIXED PATH: FP32 pair arithmetic either way; the state stays FP64.  The
-	// reference's all-float state (CUDA_MD.cuh:26-60,556-578) exists to spare FP64 throughput on consumer GPUs; on B200 the
-	// integrator is HBM-bound and the FP64 state is what keeps positions exact at L = 300 (fixed-point + exact list predicate),
-	// so a float request gets strictly better accuracy (well inside its 1e-4 force tolerance) at the mixed path's speed.
+	// backend_precision: both keep the FP64 state and FP32 pair arithmetic.  mixed (the reference default) additionally takes the two
+	// stiff pieces of the model -- the FENE distance and every excluded-volume term that is in range -- in double (1e-5 force
+	// criterion at any box size); float skips that refinement (pure FP32 pair arithmetic, 1e-4 criterion, ~5 % faster).
 	if(precision != OXB_PRECISION_MIXED && precision != OXB_PRECISION_FLOAT) return fail(c, 4, "backend_precision must be mixed or float (double is not available)");
 	int ndev = 0;
 	cudaError_t e = cudaGetDeviceCount(&ndev);

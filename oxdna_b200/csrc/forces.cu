@@ -135,14 +135,16 @@ __global__ void __launch_bounds__(128, OXB_MB_PARTICLE) k_forces_particle(const 
 	float e = 0.f, ehb = 0.f;
 	bool broken = false;
 	ExclRefine R = make_refine<MD>(M, box, posd, quatd);
+	const bool refine = posd != nullptr; // backend_precision = mixed
 
 	if(b.x >= 0) { // I am the 5' side of the bond (p), q = my n3
 		Particle Q = load_particle<MD>(M, ipos, quat, b.x);
 		PairAcc acc;
 		acc.clear();
-		R.sp = i; R.sq = b.x; acc.refine = &R;
-		const FeneSite fs = fene_from_sites(M, box, __ldg(iback + i), __ldg(iback + b.x), broken);
-		e += MD::bonded(M, min_image_fixed(box, P.ip, Q.ip), P.ax, Q.ax, P.btype, Q.btype, P.back, Q.back, acc, broken, nullptr, &fs);
+		R.sp = i; R.sq = b.x; acc.refine = refine ? &R : nullptr;
+		FeneSite fs;
+		if(refine) fs = fene_from_sites(M, box, __ldg(iback + i), __ldg(iback + b.x), broken);
+		e += MD::bonded(M, min_image_fixed(box, P.ip, Q.ip), P.ax, Q.ax, P.btype, Q.btype, P.back, Q.back, acc, broken, nullptr, refine ? &fs : nullptr);
 		f -= acc.F;
 		t += acc.torque_p(P.ax, P.back);
 	}
@@ -150,9 +152,10 @@ __global__ void __launch_bounds__(128, OXB_MB_PARTICLE) k_forces_particle(const 
 		Particle Q = load_particle<MD>(M, ipos, quat, b.y);
 		PairAcc acc;
 		acc.clear();
-		R.sp = b.y; R.sq = i; acc.refine = &R;
-		const FeneSite fs = fene_from_sites(M, box, __ldg(iback + b.y), __ldg(iback + i), broken);
-		e += MD::bonded(M, min_image_fixed(box, Q.ip, P.ip), Q.ax, P.ax, Q.btype, P.btype, Q.back, P.back, acc, broken, nullptr, &fs);
+		R.sp = b.y; R.sq = i; acc.refine = refine ? &R : nullptr;
+		FeneSite fs;
+		if(refine) fs = fene_from_sites(M, box, __ldg(iback + b.y), __ldg(iback + i), broken);
+		e += MD::bonded(M, min_image_fixed(box, Q.ip, P.ip), Q.ax, P.ax, Q.btype, P.btype, Q.back, P.back, acc, broken, nullptr, refine ? &fs : nullptr);
 		f += acc.F;
 		t += acc.torque_q(P.ax, P.back);
 	}
@@ -164,7 +167,7 @@ __global__ void __launch_bounds__(128, OXB_MB_PARTICLE) k_forces_particle(const 
 		int2 bq = __ldg(bonds + j);
 		PairAcc acc;
 		acc.clear();
-		R.sp = i; R.sq = j; acc.refine = &R;
+		R.sp = i; R.sq = j; acc.refine = refine ? &R : nullptr;
 		PairEnergy pe = MD::nonbonded(M, min_image_fixed(box, P.ip, Q.ip), P.ax, Q.ax, P.btype, Q.btype, p_end, (bq.x < 0 || bq.y < 0), P.back,
 				Q.back, acc);
 		e += pe.total;
@@ -275,7 +278,7 @@ template<class MD>
 __global__ void __launch_bounds__(128, OXB_MB_NEAR) k_edge_near(const __grid_constant__ typename MD::Params M, BoxF box, const int *__restrict__ n_edges,
 		const int2 *__restrict__ edges, const int4 *__restrict__ ipos, const float4 *__restrict__ quat, const double4 *__restrict__ posd,
 		const double4 *__restrict__ quatd, float4 *__restrict__ F, float4 *__restrict__ T, int2 *__restrict__ hb_list, int2 *__restrict__ cx_list, int2 *__restrict__ cr_list, int *__restrict__ seg_counts, int hb_seg, int cx_seg,
-		int cr_seg, int4 *__restrict__ ex_list, int *__restrict__ ex_counts, int ex_seg, int *__restrict__ flags, int hw) {
+		int cr_seg, int4 *__restrict__ ex_list, int *__restrict__ ex_counts, int ex_seg, int refine, int *__restrict__ flags, int hw) {
 	if(flags[hw]) return;
 	__shared__ int s_cnt[3];
 	if(threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
@@ -309,7 +312,7 @@ __global__ void __launch_bounds__(128, OXB_MB_NEAR) k_edge_near(const __grid_con
 				float en = 0.f;
 				const int xmask = dna2_excl_mask(M, r, rbb, rb, P.ax, Q.ax, P.back, Q.back);
 				if(xmask != 0) {
-					const int slot = atomicAdd(&s_nex, 1);
+					const int slot = refine ? atomicAdd(&s_nex, 1) : ex_seg;
 					if(slot < ex_seg) ex_list[slot] = make_int4(ed.x, ed.y, xmask, 0);
 					else en = dna2_excl(M, r, rbb, rb, P.ax, Q.ax, P.back, Q.back, acc); // buffer full: FP32 evaluation in place
 				}
@@ -408,23 +411,27 @@ __global__ void __launch_bounds__(64, OXB_MB_HEAVY) k_edge_heavy(const __grid_co
 template<class MD>
 __global__ void __launch_bounds__(128, OXB_MB_BONDED) k_bonded(const __grid_constant__ typename MD::Params M, BoxF box, int N, const int4 *__restrict__ ipos,
 		const int4 *__restrict__ iback, const float4 *__restrict__ quat, const int2 *__restrict__ bonds, float4 *__restrict__ F, float4 *__restrict__ T,
-		int *__restrict__ ex_bonded, int *__restrict__ flags, int hw) {
+		int *__restrict__ ex_bonded, int refine, int *__restrict__ flags, int hw) {
 	if(flags[hw]) return;
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= N) return;
 	int2 b = __ldg(bonds + i);
-	if(b.x < 0) { ex_bonded[i] = 0; return; }
+	if(b.x < 0) { if(refine) ex_bonded[i] = 0; return; }
 	Particle P = load_particle<MD>(M, ipos, quat, i);
 	Particle Q = load_particle<MD>(M, ipos, quat, b.x);
 	PairAcc acc;
 	acc.clear();
 	bool broken = false;
 	const v3 r = min_image_fixed(box, P.ip, Q.ip);
-	FeneSite fs = fene_from_sites(M, box, __ldg(iback + i), __ldg(iback + b.x), broken);
-	// bonded excluded-volume site pairs in range are left to k_excl_fix (double); one mask per particle
-	fs.excl_deferred = bonded_excl_mask(M, r, P.ax, Q.ax, P.back, Q.back);
-	ex_bonded[i] = fs.excl_deferred;
-	float en = MD::bonded(M, r, P.ax, Q.ax, P.btype, Q.btype, P.back, Q.back, acc, broken, nullptr, &fs);
+	float en;
+	if(refine) {
+		FeneSite fs = fene_from_sites(M, box, __ldg(iback + i), __ldg(iback + b.x), broken);
+		// bonded excluded-volume site pairs in range are left to k_excl_fix (double); one mask per particle
+		fs.excl_deferred = bonded_excl_mask(M, r, P.ax, Q.ax, P.back, Q.back);
+		ex_bonded[i] = fs.excl_deferred;
+		en = MD::bonded(M, r, P.ax, Q.ax, P.btype, Q.btype, P.back, Q.back, acc, broken, nullptr, &fs);
+	}
+	else en = MD::bonded(M, r, P.ax, Q.ax, P.btype, Q.btype, P.back, Q.back, acc, broken);
 	v3 tp = acc.torque_p(P.ax, P.back), tq = acc.torque_q(Q.ax, Q.back);
 	atomic_add4(F + i, -acc.F.x, -acc.F.y, -acc.F.z, en);
 	atomic_add4(T + i, tp.x, tp.y, tp.z, 0.f);
@@ -834,7 +841,7 @@ static void launch_edge_stage_t(cudaStream_t s, int which, const typename MD::Pa
 	// inside): nothing here depends on device-side counts, so a captured graph stays valid across list rebuilds
 	case 1:
 		k_edge_near<MD><<<a.n_seg, 128, 0, s>>>(M, box, a.n_edges, a.edges, a.ipos, a.quat, a.posd, a.quatd, a.F, a.T, a.hb_list, a.cx_list, a.cr_list, a.seg_counts, a.hb_seg,
-				a.cx_seg, a.cr_seg, a.ex_list, a.ex_counts, a.ex_seg, flags, hw);
+				a.cx_seg, a.cr_seg, a.ex_list, a.ex_counts, a.ex_seg, a.refine, flags, hw);
 		break;
 	case 2: k_edge_heavy<MD, 0><<<dim3(a.n_seg, a.hb_split), 64, 0, s>>>(M, box, a.seg_counts, a.hb_list, a.hb_seg, a.ipos, a.quat, a.F, a.T, flags, hw); break;
 	case 3: k_edge_heavy<MD, 1><<<a.n_seg, 64, 0, s>>>(M, box, a.seg_counts, a.cx_list, a.cx_seg, a.ipos, a.quat, a.F, a.T, flags, hw); break;
@@ -846,7 +853,7 @@ static void launch_edge_stage_t(cudaStream_t s, int which, const typename MD::Pa
 	default: {
 		static const int tpb_env = env_int("OXB_TPB_BONDED", 0);
 		const int tpb = tpb_env > 0 ? tpb_env : 128;
-		k_bonded<MD><<<(a.N + tpb - 1) / tpb, tpb, 0, s>>>(M, box, a.N, a.ipos, a.iback, a.quat, a.bonds, a.F, a.T, a.ex_bonded, flags, hw);
+		k_bonded<MD><<<(a.N + tpb - 1) / tpb, tpb, 0, s>>>(M, box, a.N, a.ipos, a.iback, a.quat, a.bonds, a.F, a.T, a.ex_bonded, a.refine, flags, hw);
 		break;
 	}
 	}

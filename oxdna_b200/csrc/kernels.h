@@ -80,6 +80,7 @@ struct EdgeArgs {
 	int4 *ex_list;
 	int *ex_counts, *ex_bonded;
 	int ex_seg;
+	int refine; // 1 (backend_precision = mixed): FENE and excluded volume in double; 0 (float): FP32 pair arithmetic throughout
 };
 void launch_edge_stage(cudaStream_t s, int which, const ModelRef &M, BoxF box, const EdgeArgs &a, int *flags, int hw);
 void launch_energy_split(cudaStream_t s, const ModelRef &M, BoxF box, int N, const int4 *ipos, const float4 *quat, const int2 *bonds, const int *nbr,

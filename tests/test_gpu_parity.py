@@ -393,7 +393,7 @@ def test_rna_duplex_lattice_generator_is_stable_and_sorted_lists_match():
 
 
 def test_backend_precision_float_and_split_energy_observable():
-    """backend_precision = float is accepted and served by the mixed kernels (tolerance of the float criterion: 1e-4); the
+    """backend_precision = float: FP32 pair arithmetic throughout, no FP64 refinement of FENE / excluded volume (float criterion: 1e-4); the
     device-side split-energy observable reproduces the reference's per-term energies (get_system_energy_split)."""
     for case, rna in (("lattice27_dense", False), ("rna_lattice8_seqdep", True), ("force_field_rna/ref_rna2", True)):
         g = load_golden(case)
