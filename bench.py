@@ -26,9 +26,10 @@ T_STR, SALT, DT = "300K", 0.5, 0.003
 _REAL_STDOUT = sys.stdout
 FLOP_FAR, FLOP_DH, FLOP_CONTACT, FLOP_BONDED = 170.0, 60.0, 1500.0, 900.0  # SURVEY 8(d) per-pair figures
 # ncu dram__bytes_read.sum + dram__bytes_write.sum of one force pass (near + HB/CRST + coaxial + bonded + DH kernels)
-# (profiles/summary_r01k.txt, one `ncu --set full` capture per workload, cold cache: compulsory traffic of one pass)
-NCU_FORCE_PASS_DRAM_BYTES_C2 = int((6.925 + 5.923 + 4.772 + 6.499 + 0.055 + 0.028) * 1e6)  # DH, bonded, near, HB/CRST, coaxial
-NCU_FORCE_PASS_DRAM_BYTES_C4 = int((84.21 + 5.90 + 72.03 + 0.73 + 58.02 + 1.58 + 76.37 + 6.89 + 0.03) * 1e6)
+# (profiles/summary_r01n.txt, one `ncu --set full` capture per workload, cold cache: compulsory traffic of one pass;
+#  kernels: Debye-Hueckel, bonded, near edges, HB / cross stacking, coaxial stacking, excluded volume in double)
+NCU_FORCE_PASS_DRAM_BYTES_C2 = int((6.92 + 7.60 + 4.77 + 6.64 + 0.03 + 0.38) * 1e6)
+NCU_FORCE_PASS_DRAM_BYTES_C4 = int((88.77 + 92.25 + 59.75 + 83.87 + 0.03 + 4.03) * 1e6)
 
 
 def workload(name):
@@ -419,7 +420,7 @@ def ours(args):
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
                 "roofline": {"kernel": "forces (edge non-bonded + bonded)" if args.use_edge else "forces (particle-centric)", "bound": "hbm", "achieved": force_gbs, "peak": hbm_peak,
                              "unit": "GB/s", "frac": force_gbs / hbm_peak, "traffic": traffic,
-                             "traffic_source": "profiles/summary_r01k.txt: dram__bytes_read.sum + dram__bytes_write.sum summed over the kernels of one force pass", "peak_source": peak_src, "ms": t_force,
+                             "traffic_source": "profiles/summary_r01n.txt: dram__bytes_read.sum + dram__bytes_write.sum summed over the kernels of one force pass", "peak_source": peak_src, "ms": t_force,
                              "share_of_step": t_force / step_ms,
                              "note": "the force kernel is FP32/SFU-bound, not HBM-bound (see roofline_fp32); HBM figure given as the contract asks"},
                 "roofline_fp32": {"achieved_tflops": flops / (t_force * 1e-3) / 1e12, "peak_tflops": fp32_peak, "frac": flops / (t_force * 1e-3) / 1e12 / fp32_peak,

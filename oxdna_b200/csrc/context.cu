@@ -99,6 +99,8 @@ struct oxb_ctx {
 	// dynamics
 	double dt = 0.003;
 	long long step = 0;
+	bool defer_build_checks = true; // OXB_DEFER_BUILD_CHECK=0 restores one host synchronisation per rebuild
+	bool build_unchecked = false; // a list rebuild was launched without waiting for its overflow flags (oxb_run); the next batch checks
 	bool fork_streams = true; // force pass on three concurrent streams (OXB_FORK=0/1 overrides the size-based default)
 	bool mid_step = false; // positions already advanced for `step`, forces pending
 	ThermostatCfg th;
@@ -337,14 +339,26 @@ int do_sort(oxb_ctx *c) {
 	return 0;
 }
 
-int do_build(oxb_ctx *c) {
-	if(!c->lists_allocated) { int rc = alloc_lists(c, 64); if(rc) return rc; }
+// deferred: launch the rebuild and return WITHOUT reading its overflow flags (one host synchronisation less per rebuild inside
+// oxb_run).  The batch that follows starts with k_batch_begin(check = 1), which turns an overflow into a halt: every kernel of the
+// batch is then a no-op, oxb_run sees "halted with zero steps done + overflow bits" and repeats the rebuild on the checked path.
+int do_build(oxb_ctx *c, bool deferred = false) {
+	if(!c->lists_allocated) { int rc = alloc_lists(c, 64); if(rc) return rc; deferred = false; }
 	{ int rc = ensure_cells(c); if(rc) return rc; }
 	for(int attempt = 0; attempt < 6; attempt++) {
 		CU(cudaMemsetAsync(c->flags + OXB_FLAG_ERROR, 0, sizeof(int), c->stream));
 		oxb::launch_build_lists(c->stream, list_args(c));
 		c->launches += c->use_edge ? 7 : 4;
 		CU(cudaGetLastError());
+		if(deferred) {
+			c->lists_valid = true;
+			c->lists_rv = c->rcut + 2. * c->skin;
+			c->lists_dh_rc = (double) c->model.dh_rc;
+			c->slots_cell_ordered = false;
+			c->n_list_updates++;
+			c->build_unchecked = true;
+			return 0;
+		}
 		int rc = read_flags(c);
 		if(rc) return rc;
 		int seen = c->h_flags[OXB_FLAG_MAX_NEIGH_SEEN];
@@ -366,14 +380,14 @@ int do_build(oxb_ctx *c) {
 	return fail(c, 3, "neighbour list does not fit after repeated growth (max_neigh = %d)", c->max_neigh);
 }
 
-int ensure_lists(oxb_ctx *c) {
+int ensure_lists(oxb_ctx *c, bool deferred = false) {
 	if(c->lists_valid) return 0;
 	if(!c->have_state || !c->have_model || !c->have_box) return fail(c, 2, "box, model and state must be set before building lists");
 	if(c->sort_every > 0 && (c->n_list_updates % c->sort_every) == 0) {
 		int rc = do_sort(c);
 		if(rc) return rc;
 	}
-	return do_build(c);
+	return do_build(c, deferred);
 }
 
 // hw: index of the halt word the launched kernels must honour; clear: F/T are not known to be zero; step < 0: kernels read
@@ -472,17 +486,19 @@ oxb::IntegrateArgs integ_args(oxb_ctx *c, long long step) {
 	return a;
 }
 
-__global__ void k_batch_begin(int *flags, long long *cur_step, long long step) {
+__global__ void k_batch_begin(int *flags, long long *cur_step, long long step, int check_build) {
+	// check_build: the list rebuild in front of this batch was not checked by the host; an overflow halts the whole batch
+	const int halt = (check_build && (flags[OXB_FLAG_ERROR] & (OXB_ERR_NEIGH_OVERFLOW | OXB_ERR_EDGE_OVERFLOW))) ? 1 : 0;
 	flags[OXB_FLAG_STEPS_DONE] = 0;
-	flags[OXB_FLAG_COUNT] = 0;
-	flags[OXB_FLAG_COUNT + 1] = 0;
+	flags[OXB_FLAG_COUNT] = halt;
+	flags[OXB_FLAG_COUNT + 1] = halt;
 	cur_step[0] = step;
 	cur_step[1] = step;
 }
 
 // start of a batch of launches: clears the halt words and the completed-step counter, seeds the device-side step index
 int reset_batch_flags(oxb_ctx *c) {
-	k_batch_begin<<<1, 1, 0, c->stream>>>(c->flags, c->cur_step, c->step);
+	k_batch_begin<<<1, 1, 0, c->stream>>>(c->flags, c->cur_step, c->step, c->build_unchecked ? 1 : 0);
 	c->launches++;
 	CU(cudaGetLastError());
 	return 0;
@@ -662,6 +678,8 @@ int oxb_create(oxb_ctx **out, int device, int N, int precision) {
 	{
 		const char *g = getenv("OXB_NO_GRAPHS");
 		c->use_graphs = !(g != nullptr && g[0] == '1');
+		const char *db = getenv("OXB_DEFER_BUILD_CHECK");
+		if(db != nullptr) c->defer_build_checks = (db[0] != '0');
 		const char *f = getenv("OXB_FORK");
 		if(f != nullptr) c->fork_streams = (f[0] != '0');
 	}
@@ -1129,9 +1147,12 @@ int oxb_run(oxb_ctx *c, long long n_steps) {
 	if(c->th.type == OXB_THERMOSTAT_BUSSI && !c->bussi_init) { rc = init_bussi(c); if(rc) return rc; }
 	long long remaining = n_steps;
 	long long since_rebuild = 0;
+	bool since_rebuild_valid = false;
 	while(remaining > 0) {
-		rc = ensure_lists(c);
+		// rebuilds in the middle of a run are launched unchecked (see do_build); the first one of a run is checked
+		rc = ensure_lists(c, c->defer_build_checks && since_rebuild_valid);
 		if(rc) return rc;
+		since_rebuild_valid = true;
 		rc = reset_batch_flags(c);
 		if(rc) return rc;
 		const long long step0 = c->step;
@@ -1163,6 +1184,19 @@ int oxb_run(oxb_ctx *c, long long n_steps) {
 		if(rc) return rc;
 		const int done = c->h_flags[OXB_FLAG_STEPS_DONE];
 		const bool halted = c->h_flags[OXB_FLAG_COUNT] || c->h_flags[OXB_FLAG_COUNT + 1];
+		if(c->build_unchecked) {
+			c->build_unchecked = false;
+			if(halted && done == 0 && (c->h_flags[OXB_FLAG_ERROR] & (OXB_ERR_NEIGH_OVERFLOW | OXB_ERR_EDGE_OVERFLOW))) {
+				// the unchecked rebuild overflowed and k_batch_begin halted the batch: nothing ran.  Redo it on the checked path
+				// (which grows the arrays); it is the same list update, not a new one
+				c->error_flags &= ~(OXB_ERR_NEIGH_OVERFLOW | OXB_ERR_EDGE_OVERFLOW);
+				c->lists_valid = false;
+				c->n_list_updates--;
+				rc = do_build(c, false);
+				if(rc) return rc;
+				continue;
+			}
+		}
 		c->step += done;
 		remaining -= done;
 		since_rebuild += done;

@@ -863,3 +863,35 @@ def test_full_size_c4_properties():
         sim.close()
         if other is not None:
             other.close()
+
+
+def test_list_overflow_in_the_middle_of_a_run_takes_the_checked_path():
+    """Mid-run list rebuilds are launched without waiting for their overflow flags; an overflow halts the following batch and the
+    rebuild is repeated on the checked path, which grows the arrays.  A shrinking repulsive sphere compresses the lattice until the
+    neighbour matrix must grow; the trajectory is bit-identical (particle-centric path: deterministic) to the one with a host
+    synchronisation after every rebuild (OXB_DEFER_BUILD_CHECK=0)."""
+    g = load_golden("lattice8")
+    ext = [dict(type="sphere", particle="all", stiff=3.0, r0=9.0, rate=-0.0012, center=(10.0, 10.0, 10.0))]
+    outs = []
+    for defer in ("1", "0"):
+        os.environ["OXB_DEFER_BUILD_CHECK"] = defer
+        try:
+            sim = make_sim(g, use_edge=0, CUDA_sort_every=1, thermostat="brownian", newtonian_steps=53, diff_coeff=2.5, external_forces_list=ext,
+                           max_density_multiplier=1.0)
+        finally:
+            del os.environ["OXB_DEFER_BUILD_CHECK"]
+        try:
+            sim.run(10)
+            n0 = sim.ctx.stats()
+            sim.run(4000)
+            st, n1 = sim.ctx.get_state(), sim.ctx.stats()
+            assert n1["error_flags"] == 0
+            assert np.isfinite(sim.ctx.energy()[0])
+            outs.append((st, n0, n1))
+        finally:
+            sim.close()
+    (a, a0, a1), (b, b0, b1) = outs
+    assert a1["max_neigh"] > a0["max_neigh"], (a0, a1)  # the matrix did grow during the run
+    assert a1["max_neigh"] == b1["max_neigh"] and a1["n_list_updates"] == b1["n_list_updates"]
+    for k in ("pos", "vel", "a1", "L"):
+        assert np.array_equal(a[k], b[k]), k
