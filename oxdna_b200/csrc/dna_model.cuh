@@ -622,6 +622,7 @@ OXB_HD PairEnergy dna2_nonbonded(const oxb_dna2_params &M, v3 r, const Axes &A, 
 struct FeneSite {
 	v3 d;        // backbone(q) - backbone(p)
 	float s, en; // force on q = d * s; energy
+	int has_fene; // 0: d, s, en are not set, the FP32 FENE expression is used (bonds far from the stiff end of the FENE range)
 	int excl_deferred; // bits OXB_SITE_*: bonded excluded-volume site pairs the caller evaluates itself (in double)
 };
 
@@ -652,6 +653,7 @@ template<class PB> __device__ __forceinline__ FeneSite fene_from_sites(const PB 
 	f.d = mk3((float) dx, (float) dy, (float) dz);
 	f.s = (float) s;
 	f.en = (float) en;
+	f.has_fene = 1;
 	f.excl_deferred = 0;
 	return f;
 }
@@ -677,7 +679,7 @@ OXB_HD float bonded_fene_excl(const PB &M, v3 r, const Axes &A, const Axes &B, v
 	float E = 0.f;
 	const float cb = M.base_a1;
 	// FENE
-	if(fene != nullptr) {
+	if(fene != nullptr && fene->has_fene) {
 		E += fene->en;
 		if(esplit) esplit[0] += fene->en;
 		acc.site_kk(fene->d * fene->s);

@@ -309,12 +309,15 @@ __global__ void __launch_bounds__(128, OXB_MB_NEAR) k_edge_near(const __grid_con
 				v3 rb = r + (Q.ax.a1 - P.ax.a1) * M.base_a1;
 				PairAcc acc;
 				acc.clear();
-				float en = 0.f;
-				const int xmask = dna2_excl_mask(M, r, rbb, rb, P.ax, Q.ax, P.back, Q.back);
-				if(xmask != 0) {
-					const int slot = refine ? atomicAdd(&s_nex, 1) : ex_seg;
-					if(slot < ex_seg) ex_list[slot] = make_int4(ed.x, ed.y, xmask, 0);
-					else en = dna2_excl(M, r, rbb, rb, P.ax, Q.ax, P.back, Q.back, acc); // buffer full: FP32 evaluation in place
+				// common path unchanged: the FP32 evaluation tells whether any site pair is in range at all.  If one is (a few per
+				// cent of the edges) and the refinement is on, the pair is parked for k_excl_fix and the FP32 result is dropped
+				float en = dna2_excl(M, r, rbb, rb, P.ax, Q.ax, P.back, Q.back, acc);
+				if(en != 0.f && refine) {
+					const int slot = atomicAdd(&s_nex, 1);
+					if(slot < ex_seg) {
+						ex_list[slot] = make_int4(ed.x, ed.y, dna2_excl_mask(M, r, rbb, rb, P.ax, Q.ax, P.back, Q.back), 0);
+						en = 0.f;
+					}
 				}
 				if(en != 0.f) {
 					v3 tq = acc.torque_q(Q.ax, Q.back), tp = acc.torque_p(P.ax, P.back);
@@ -425,7 +428,15 @@ __global__ void __launch_bounds__(128, OXB_MB_BONDED) k_bonded(const __grid_cons
 	const v3 r = min_image_fixed(box, P.ip, Q.ip);
 	float en;
 	if(refine) {
-		FeneSite fs = fene_from_sites(M, box, __ldg(iback + i), __ldg(iback + b.x), broken);
+		// d2V/dr2 of the FENE spring is eps / Delta^2 = 32 at rest and grows as (1 + u) / (1 - u)^2, u = x^2 / Delta^2: the FP32
+		// distance (~1e-7) is good for 1e-5 of the force until u ~ 0.5; bonds stretched further take the distance in double
+		FeneSite fs;
+		fs.has_fene = 0;
+		{
+			const v3 dbb = r + Q.back - P.back;
+			const float x = sqrtf(dot(dbb, dbb)) - M.fene_r0;
+			if(x * x > 0.4f * M.fene_delta2) fs = fene_from_sites(M, box, __ldg(iback + i), __ldg(iback + b.x), broken);
+		}
 		// bonded excluded-volume site pairs in range are left to k_excl_fix (double); one mask per particle
 		fs.excl_deferred = bonded_excl_mask(M, r, P.ax, Q.ax, P.back, Q.back);
 		ex_bonded[i] = fs.excl_deferred;

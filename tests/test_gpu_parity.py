@@ -871,13 +871,13 @@ def test_list_overflow_in_the_middle_of_a_run_takes_the_checked_path():
     neighbour matrix must grow; the trajectory is bit-identical (particle-centric path: deterministic) to the one with a host
     synchronisation after every rebuild (OXB_DEFER_BUILD_CHECK=0)."""
     g = load_golden("lattice8")
-    ext = [dict(type="sphere", particle="all", stiff=3.0, r0=9.0, rate=-0.0012, center=(10.0, 10.0, 10.0))]
+    ext = [dict(type="sphere", particle="all", stiff=1.0, r0=9.0, rate=-0.0006, center=(10.0, 10.0, 10.0))]
     outs = []
     for defer in ("1", "0"):
         os.environ["OXB_DEFER_BUILD_CHECK"] = defer
         try:
             sim = make_sim(g, use_edge=0, CUDA_sort_every=1, thermostat="brownian", newtonian_steps=53, diff_coeff=2.5, external_forces_list=ext,
-                           max_density_multiplier=1.0)
+                           max_density_multiplier=1.0, max_backbone_force=5.0)
         finally:
             del os.environ["OXB_DEFER_BUILD_CHECK"]
         try:
