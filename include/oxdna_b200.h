@@ -246,6 +246,10 @@ int oxb_barostat_reject(oxb_ctx *ctx);
  * shifts (may be NULL): 3 ints per particle (original order) = floor(com / L), what the reference adds to BaseParticle::_pos_shift.
  * As in the reference's CUDA backend, forces that read absolute positions (trap, twist, planes) see the translated coordinates. */
 int oxb_fix_diffusion(oxb_ctx *ctx, int *shifts);
+/* How the host thread waits for the device at the end of a batch of steps inside oxb_run: 0 (default) spins in the driver (lowest
+ * latency: one system per GPU), 1 sleeps on a blocking-sync event (replica ensembles that run more host threads than the box has
+ * cores: 64 replicas on 8 GPUs are 64 driver threads).  No counterpart in the reference (one process per replica, examples/OXPY_REMD). */
+int oxb_set_host_wait(oxb_ctx *ctx, int blocking);
 /* current box sides (they change under the barostat) */
 int oxb_get_box(oxb_ctx *ctx, double box[3]);
 /* potential energy of the whole system split into the reference's terms, terms[OXB_NTERMS] in the order of OXB_TERM_*

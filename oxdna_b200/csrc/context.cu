@@ -99,6 +99,8 @@ struct oxb_ctx {
 	// dynamics
 	double dt = 0.003;
 	long long step = 0;
+	bool blocking_wait = false;     // oxb_set_host_wait
+	cudaEvent_t ev_wait = nullptr;
 	bool defer_build_checks = true; // OXB_DEFER_BUILD_CHECK=0 restores one host synchronisation per rebuild
 	bool build_unchecked = false; // a list rebuild was launched without waiting for its overflow flags (oxb_run); the next batch checks
 	bool fork_streams = true; // force pass on three concurrent streams (OXB_FORK=0/1 overrides the size-based default)
@@ -296,7 +298,13 @@ oxb::ListArgs list_args(oxb_ctx *c) {
 
 int read_flags(oxb_ctx *c) {
 	CU(cudaMemcpyAsync(c->h_flags, c->flags, sizeof(int) * OXB_FLAG_WORDS, cudaMemcpyDeviceToHost, c->stream));
-	CU(cudaStreamSynchronize(c->stream));
+	if(c->blocking_wait) {
+		// replica ensembles with more host threads than cores: sleep on a blocking-sync event instead of spinning in the driver
+		if(c->ev_wait == nullptr) CU(cudaEventCreateWithFlags(&c->ev_wait, cudaEventBlockingSync | cudaEventDisableTiming));
+		CU(cudaEventRecord(c->ev_wait, c->stream));
+		CU(cudaEventSynchronize(c->ev_wait));
+	}
+	else CU(cudaStreamSynchronize(c->stream));
 	c->error_flags |= c->h_flags[OXB_FLAG_ERROR];
 	return 0;
 }
@@ -715,6 +723,7 @@ void oxb_destroy(oxb_ctx *c) {
 	}
 	if(c->ev_fork) cudaEventDestroy(c->ev_fork);
 	if(c->ev_near) cudaEventDestroy(c->ev_near);
+	if(c->ev_wait) cudaEventDestroy(c->ev_wait);
 	cudaFree(c->cur_step);
 	for(int k = 0; k < 2; k++) {
 		cudaFree(c->posd[k]); cudaFree(c->veld[k]); cudaFree(c->Ld[k]); cudaFree(c->quatd[k]); cudaFree(c->ipos[k]); cudaFree(c->list_ipos[k]);
@@ -1339,6 +1348,12 @@ int oxb_fix_diffusion(oxb_ctx *c, int *shifts) {
 	if(shifts) CU(cudaMemcpyAsync(shifts, d_shifts, sizeof(int) * 3 * (size_t) N, cudaMemcpyDeviceToHost, c->stream));
 	CU(cudaStreamSynchronize(c->stream));
 	// positions moved by whole box sides: fixed-point images, lists and forces stay valid
+	return 0;
+}
+
+int oxb_set_host_wait(oxb_ctx *c, int blocking) {
+	if(c == nullptr) return 1;
+	c->blocking_wait = blocking != 0;
 	return 0;
 }
 

@@ -65,6 +65,16 @@ class ReplicaExchange:
         # GIL), each context on its own CUDA streams -- an 81,920-nt replica alone cannot fill 148 SMs
         self.concurrent = concurrent and len(replicas) > 1
         self._pool = None
+        if self.concurrent:
+            # one driver thread per local replica on every rank of the node: once they outnumber the cores, spinning waits starve
+            # each other (64 replicas on 8 GPUs of a 16-core host), so the threads sleep on blocking-sync events instead
+            import os
+            n_threads = len(replicas) * int(os.environ.get("LOCAL_WORLD_SIZE", self.comm.world_size))
+            if n_threads > (os.cpu_count() or 1):
+                for rep in replicas:
+                    ctx = getattr(rep, "ctx", None)
+                    if ctx is not None and hasattr(ctx, "set_host_wait"):
+                        ctx.set_host_wait(True)
         self.replicas = list(replicas)
         self.nl = len(self.replicas)
         self.T = np.asarray(temperatures, dtype=np.float64)
