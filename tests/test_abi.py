@@ -56,3 +56,38 @@ def test_parameter_block_matches_oracle():
         assert abs(P.hb_shift[3] - Q.hb.shift[0][3]) < 1e-6
         assert abs(P.f4[capi.NF4 - 3].t0 - Q.cxst_t1.t0) < 1e-7 and abs(P.cxst_t1_sb - Q.cxst_t1_sb) < 1e-7
         assert np.isclose(P.base_a1, Q.base_a1) and np.isclose(P.back_a2, Q.back_a2)
+
+
+def test_external_force_table_mapping_matches_the_oracle_side():
+    """The dict -> table-entry mapping exists twice on purpose (the product must not import oracle/): both copies have to fill identical
+    entries, index pools and bias-table pools for every force type of the fixtures, and reject the same malformed input."""
+    import ctypes as C
+
+    import numpy as np
+
+    from conftest import ext2_forces, ext3_forces, load_golden
+    from oracle import oracle as O
+    from oxdna_b200 import capi
+
+    g = load_golden("lattice8")
+    forces = ext2_forces(g["pos"]) + ext3_forces(g["pos"]) + [dict(type="string", particle=3, F0=0.1, rate=0.01, dir=(0, 0, 2.0)),
+                                                               dict(type="trap", particle=4, stiff=1.0, rate=0.0, pos0=(1, 2, 3), dir=(1, 0, 0))]
+    assert set(capi.EXT_TYPES) == set(O.EXT_TYPES) and all(capi.EXT_TYPES[k] == O.EXT_TYPES[k] for k in capi.EXT_TYPES)
+    assert {f["type"] for f in forces} == set(capi.EXT_TYPES)  # every type the library knows is exercised by a fixture
+    pool_a, grid_a, pool_b, grid_b = [], [], [], []
+    for f in forces:
+        a, b = capi.ExtForce(), O.ExtForce()
+        capi.fill_ext_entry(a, f, pool_a, grid_a)
+        O.fill_ext_entry(b, f, pool_b, grid_b)
+        assert C.sizeof(a) == C.sizeof(b) == capi.lib().oxb_sizeof(2)
+        assert bytes(a) == bytes(b), f["type"]
+    assert pool_a == pool_b and np.array_equal(grid_a, grid_b) and len(pool_a) > 0 and len(grid_a) > 0
+    for bad in (dict(type="repulsion_plane_moving", particle=0, ref_particle="3,5", stiff=1.0, dir=(1, 0, 0)),
+                dict(type="generic_central_force", particle=0, center=(0, 0, 0), force_type="interpolated", potential_file="x", interpolated_N=10),
+                dict(type="meta_com_trap", p1a="0", p2a="1", xmin=0, xmax=1, N_grid=3, potential_grid="0,1", mode=1)):
+        for fill, E in ((capi.fill_ext_entry, capi.ExtForce), (O.fill_ext_entry, O.ExtForce)):
+            try:
+                fill(E(), bad, [], [])
+            except ValueError:
+                continue
+            raise AssertionError(f"{bad['type']}: malformed entry accepted")
