@@ -190,10 +190,12 @@ __global__ void __launch_bounds__(128, OXB_MB_PARTICLE) k_forces_particle(const 
 //                 detection of pairs inside the hydrogen-bonding / cross-stacking / coaxial-stacking radial ranges AND
 //                 inside the cosine window of every angular factor; those are appended (warp-aggregated) to two
 //                 compact work lists
-//   k_edge_hbcr   dense list of base-base contacts: hydrogen bonding + cross stacking
-//   k_edge_cxst   dense list of stack-stack contacts: coaxial stacking
-//   k_bonded_finalize  per particle: FENE + bonded excluded volume + stacking with its n3 neighbour (each bond once),
-//                 and folding of the backbone-site force sum Fb into force and torque
+//                 (excluded-volume terms that are in range are parked for k_excl_fix when the refinement is on)
+//   k_edge_heavy<0>  dense list of base-base contacts: hydrogen bonding + cross stacking
+//   k_edge_heavy<1>  dense list of stack-stack contacts: coaxial stacking
+//   k_bonded      per particle: FENE + bonded excluded volume + stacking with its n3 neighbour (each bond once)
+//   k_excl_fix    the parked excluded-volume pairs of k_edge_near and k_bonded in double (backend_precision = mixed)
+// (the integrator folds the backbone-site force sum Fb of k_dh_particle into force and torque)
 // Edges are grouped by `from`, so lanes sharing `from` first reduce with shuffles (segmented suffix sum) and only the
 // segment head issues the 128-bit vector atomic (red.global.add.v4.f32).  F/T/Fb hold lab-frame sums; the integrator
 // rotates the torque into the body frame.
@@ -217,7 +219,7 @@ __device__ __forceinline__ bool segmented_reduce(int key, unsigned lane, float (
 
 // Debye-Hueckel, particle-centric over its own neighbour matrix (selected on the backbone-site distance): per neighbour one
 // coalesced index load + one 16-byte gather of a fixed-point backbone site; no atomics, deterministic.  Writes the
-// backbone-site force sum Fb (.w = energy); k_bonded_finalize folds it into force and torque.
+// backbone-site force sum Fb (.w = energy); the integrator folds it into force and torque.
 // LPP lanes share one particle (lane s takes neighbours s, s + LPP, ...; partial sums folded with shuffles in a fixed order, so the
 // result stays deterministic): systems that cannot fill the GPU with one thread per particle (C2: 17 warps per SM) get LPP times the
 // loads in flight; index loads stay sector-efficient (LPP rows x 32 / LPP consecutive ints per warp instruction).
