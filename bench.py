@@ -412,7 +412,8 @@ def ours(args):
         line = {"metric": "particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 forces / f64 integration (mixed)",
                 "data": "synthetic",
-                "config": {"workload": desc, "md_steps_per_step": md, "replicas": n_rep, "parallelism": "1 replica per GPU, replica exchange every step" if world > 1 else "single system",
+                "config": {"workload": desc, "md_steps_per_step": md, "replicas": n_rep, "parallelism": (f"1 replica per GPU, temperatures geometric {float(ladder_K[0]):.1f}-{float(ladder_K[-1]):.1f} K, replica-exchange attempt (NCCL all_gather of "
+                                           "2 doubles per replica) every bench step") if world > 1 else "single system",
                            "use_edge": int(args.use_edge), "CUDA_sort_every": args.sort_every, "thermostat": "brownian (newtonian_steps 103)", "dt": DT, "verlet_skin": 0.05,
                            "equilibration_md_steps": args.equil, "l2": "256 MiB buffer written between timed iterations (L2 flush)",
                            "ns_per_day": 86400.0 / (step_ms * 1e-3) * DT * 3.03e-3, "md_steps_per_s": 1e3 / step_ms, "list_rebuild_every_md_steps": rebuild_every,
