@@ -99,6 +99,8 @@ struct oxb_ctx {
 	// dynamics
 	double dt = 0.003;
 	long long step = 0;
+	double spec_factor = 1.0;       // speculative batch length in units of the running mean rebuild interval (OXB_SPEC_FACTOR;
+	                                // profiles/spec_sweep_r01.txt: 1.0 beats 0.8 by 3 % at 81,920 nt, 0.5 % at 1M)
 	bool blocking_wait = false;     // oxb_set_host_wait
 	cudaEvent_t ev_wait = nullptr;
 	bool defer_build_checks = true; // OXB_DEFER_BUILD_CHECK=0 restores one host synchronisation per rebuild
@@ -686,6 +688,8 @@ int oxb_create(oxb_ctx **out, int device, int N, int precision) {
 	{
 		const char *g = getenv("OXB_NO_GRAPHS");
 		c->use_graphs = !(g != nullptr && g[0] == '1');
+		const char *sf = getenv("OXB_SPEC_FACTOR");
+		if(sf != nullptr && atof(sf) > 0.) c->spec_factor = atof(sf);
 		const char *db = getenv("OXB_DEFER_BUILD_CHECK");
 		if(db != nullptr) c->defer_build_checks = (db[0] != '0');
 		const char *f = getenv("OXB_FORK");
@@ -1174,9 +1178,9 @@ int oxb_run(oxb_ctx *c, long long n_steps) {
 		}
 		// the batch: `full` units that end with the first half of the following step, then (only at the very end of the run)
 		// one closing unit without it
-		// speculate up to ~0.8 x the running mean rebuild interval past the last rebuild, then in pairs (launches behind a halt are
+		// speculate up to ~1.0 x the running mean rebuild interval past the last rebuild, then in pairs (launches behind a halt are
 		// no-ops but still cost their launch latency); even sizes keep the graph path usable
-		long long budget = (long long) (0.8 * c->avg_interval + 0.5) - since_rebuild;
+		long long budget = (long long) (c->spec_factor * c->avg_interval + 0.5) - since_rebuild;
 		budget = std::max<long long>(2, std::min<long long>(64, budget)) & ~1ll;
 		const bool closes = (remaining <= budget);
 		long long full = closes ? remaining - 1 : budget;
