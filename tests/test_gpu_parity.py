@@ -895,3 +895,30 @@ def test_list_overflow_in_the_middle_of_a_run_takes_the_checked_path():
     assert a1["max_neigh"] == b1["max_neigh"] and a1["n_list_updates"] == b1["n_list_updates"]
     for k in ("pos", "vel", "a1", "L"):
         assert np.array_equal(a[k], b[k]), k
+
+
+def test_full_size_c3_against_the_oracle():
+    """BASELINE config C3 at its full size (65,536 nt of oxRNA2 with the published sequence-dependent tables) after 300 thermalising
+    steps with Hilbert re-sorts: pair set bit-exact, forces, torques and energy against the oracle (gradient form, as the reference's
+    CUDA kernels) on the downloaded state."""
+    from oxdna_b200 import seqdep
+    sysm = lattice.rna_duplex_lattice(2048, bp=16, spacing=10.0, seed=12345)
+    B = "AGCT"
+    sd = seqdep.RNA_SEQ_DEP
+    g = dict(T="300K", salt=0.5, btype=sysm["btype"], n3=sysm["n3"], n5=sysm["n5"], box=sysm["box"], pos=sysm["pos"], a1=sysm["a1"], a3=sysm["a3"],
+             sd_stck=np.array([sd[f"STCK_{a}_{b}"] for a in B for b in B]), sd_cross=np.array([sd[f"CROSS_{a}_{b}"] for a in B for b in B]),
+             sd_st_t_dep=sd["ST_T_DEP"], sd_hb_AT=sd["HYDR_A_T"], sd_hb_GC=sd["HYDR_C_G"], sd_hb_GT=sd["HYDR_G_T"])
+    v, L = lattice.maxwell_velocities(len(sysm["pos"]), parse_temperature("300K"), 5)
+    conf = dict(box=sysm["box"], pos=sysm["pos"], a1=sysm["a1"], a3=sysm["a3"], vel=v, L=L)
+    sim = Simulation(rna_inp(g, use_edge=1, CUDA_sort_every=1, thermostat="brownian", newtonian_steps=103, diff_coeff=2.5, seed=42), sysm, conf)
+    try:
+        sim.run(300)
+        st = sim.ctx.get_state()
+        ref = rna_oracle(dict(g, pos=st["pos"], a1=st["a1"], a3=st["a3"]))
+        sim.ctx.update_lists()
+        assert pair_set(sim.ctx.get_pairs()) == pair_set(ref["pairs"])
+        sim.ctx.compute_forces()
+        check_forces(sim.ctx.get_forces(), ref)
+        assert sim.ctx.stats()["error_flags"] == 0
+    finally:
+        sim.close()
