@@ -278,8 +278,8 @@ __device__ __forceinline__ void block_append(bool flag, int2 item, int2 *__restr
 
 template<class MD>
 __global__ void __launch_bounds__(128, OXB_MB_NEAR) k_edge_near(const __grid_constant__ typename MD::Params M, BoxF box, const int *__restrict__ n_edges,
-		const int2 *__restrict__ edges, const int4 *__restrict__ ipos, const float4 *__restrict__ quat, const double4 *__restrict__ posd,
-		const double4 *__restrict__ quatd, float4 *__restrict__ F, float4 *__restrict__ T, int2 *__restrict__ hb_list, int2 *__restrict__ cx_list, int2 *__restrict__ cr_list, int *__restrict__ seg_counts, int hb_seg, int cx_seg,
+		const int2 *__restrict__ edges, const int4 *__restrict__ ipos, const float4 *__restrict__ quat, float4 *__restrict__ F, float4 *__restrict__ T,
+		int2 *__restrict__ hb_list, int2 *__restrict__ cx_list, int2 *__restrict__ cr_list, int *__restrict__ seg_counts, int hb_seg, int cx_seg,
 		int cr_seg, int4 *__restrict__ ex_list, int *__restrict__ ex_counts, int ex_seg, int refine, int *__restrict__ flags, int hw) {
 	if(flags[hw]) return;
 	__shared__ int s_cnt[3];
@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(128, OXB_MB_NEAR) k_edge_near(const __grid_con
 		int2 ed = valid ? __ldg(edges + eidx) : make_int2(-1 - (int) lane, -1);
 		float v[6] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
 		float ve = 0.f;
-		bool want_hb = false, want_cx = false, want_cr = false, hb_capable = false;
+		bool want_hb = false, want_cx = false, hb_capable = false;
 		if(valid) {
 			Particle P = load_particle<MD>(M, ipos, quat, ed.x);
 			Particle Q = load_particle<MD>(M, ipos, quat, ed.y);
@@ -853,7 +853,7 @@ static void launch_edge_stage_t(cudaStream_t s, int which, const typename MD::Pa
 	// the producer and the three consumers of the segmented work lists share one fixed grid (a.n_seg blocks, grid-stride
 	// inside): nothing here depends on device-side counts, so a captured graph stays valid across list rebuilds
 	case 1:
-		k_edge_near<MD><<<a.n_seg, 128, 0, s>>>(M, box, a.n_edges, a.edges, a.ipos, a.quat, a.posd, a.quatd, a.F, a.T, a.hb_list, a.cx_list, a.cr_list, a.seg_counts, a.hb_seg,
+		k_edge_near<MD><<<a.n_seg, 128, 0, s>>>(M, box, a.n_edges, a.edges, a.ipos, a.quat, a.F, a.T, a.hb_list, a.cx_list, a.cr_list, a.seg_counts, a.hb_seg,
 				a.cx_seg, a.cr_seg, a.ex_list, a.ex_counts, a.ex_seg, a.refine, flags, hw);
 		break;
 	case 2: k_edge_heavy<MD, 0><<<dim3(a.n_seg, a.hb_split), 64, 0, s>>>(M, box, a.seg_counts, a.hb_list, a.hb_seg, a.ipos, a.quat, a.F, a.T, flags, hw); break;
