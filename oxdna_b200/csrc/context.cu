@@ -401,7 +401,7 @@ int ensure_lists(oxb_ctx *c, bool deferred = false) {
 }
 
 // hw: index of the halt word the launched kernels must honour; clear: F/T are not known to be zero; step < 0: kernels read
-// the step index from the device counter.  Edge pipeline = 5 kernels on 3 streams:
+// the step index from the device counter.  Edge pipeline = 5 kernels (6 in mixed precision: + k_excl_fix on aux1) on 3 streams:
 //   main: near edges -> hydrogen bonding / cross stacking      aux0: Debye-Hueckel      aux1: bonds, external forces, coaxial stacking
 // joined back into main before the integrator.  Under stream capture the same calls become the fork/join edges of a graph.
 int launch_forces(oxb_ctx *c, int hw, bool clear, long long step) {
