@@ -17,6 +17,10 @@ extern "C" {
 
 typedef struct oxb_ctx oxb_ctx;
 
+/* backend_precision (src/Backends/BackendFactory.cpp:55-81).  Both keep an FP64 state and FP32 pair arithmetic.  MIXED (the
+ * reference default) additionally evaluates the stiff terms in double -- the FENE distance of strongly stretched bonds and every
+ * excluded-volume site pair in range -- so that forces stay within 1e-5 of the FP64 CPU interaction at any box size; FLOAT skips
+ * that (1e-4 criterion, ~5 % faster). */
 enum { OXB_PRECISION_FLOAT = 0, OXB_PRECISION_MIXED = 1 };
 enum { OXB_THERMOSTAT_NONE = 0, OXB_THERMOSTAT_BROWNIAN = 1, OXB_THERMOSTAT_LANGEVIN = 2, OXB_THERMOSTAT_BUSSI = 3 };
 enum { OXB_EXT_STRING = 0, OXB_EXT_TRAP = 1, OXB_EXT_MUTUAL_TRAP = 2, OXB_EXT_LOWDIM_TRAP = 3, OXB_EXT_REPULSION_PLANE = 4,
