@@ -411,3 +411,32 @@ def barostat_acceptance(dE, P, T, box, new_box, n_objs):
     """VolumeMove.cpp:98-102 / MD_CUDABackend.cu:488-492: exp(-(dE + P dV - N_objs T ln(V'/V)) / T)"""
     V0, V1 = float(np.prod(_d(box))), float(np.prod(_d(new_box)))
     return float(np.exp(-(dE + P * (V1 - V0) - n_objs * T * np.log(V1 / V0)) / T))
+
+
+class Coord(C.Structure):
+    _fields_ = [("mode", C.c_int), ("mixed_weight", C.c_double), ("hb_energy_cutoff", C.c_double), ("hb_transition_width", C.c_double),
+                ("d0", C.c_double), ("r0", C.c_double), ("n", C.c_int), ("coord_min", C.c_double), ("coord_max", C.c_double), ("N_grid", C.c_int),
+                ("grid", C.POINTER(C.c_double)), ("n_pairs", C.c_int), ("pairs", C.POINTER(C.c_int))]
+
+
+def meta_coordination(d, pos, axes, btype, box):
+    """meta_coordination force of the forces file (keys of LTCoordination::init and CoordSettings::get_settings; `pairs` = the hydrogen-bond
+    pairs of the op_file).  Returns dict(coordination, force, torque_lab)."""
+    pairs = _i(np.asarray(d["pairs"]).reshape(-1, 2))
+    grid = _d(d["potential_grid"])
+    c = Coord()
+    c.mode = {"hb_cutoff": 0, "switching_function": 1, "mixed": 2}[d.get("coordination_type", "hb_cutoff")]
+    c.mixed_weight = float(d.get("mixed_weight", 0.0))
+    c.hb_energy_cutoff, c.hb_transition_width = float(d.get("hb_energy_cutoff", -0.2)), float(d.get("hb_transition_width", 0.1))
+    c.d0, c.r0, c.n = float(d.get("d0", 0.4)), float(d.get("r0", 0.5)), int(d.get("n", 6))
+    c.coord_min, c.coord_max = float(d.get("coord_min", 0.0)), float(d.get("coord_max", len(pairs) * 1.01))
+    c.N_grid = len(grid)
+    c.grid = grid.ctypes.data_as(C.POINTER(C.c_double))
+    c.n_pairs = len(pairs)
+    c.pairs = pairs.ctypes.data_as(C.POINTER(C.c_int))
+    pos, axes, box, btype = _d(pos), _d(axes), _d(box), _i(btype)
+    f, t = np.zeros_like(pos), np.zeros_like(pos)
+    fn = lib().oxo_meta_coordination
+    fn.restype = C.c_double
+    val = fn(C.byref(c), pos.shape[0], _p(pos), _p(axes), _p(btype), _p(box), _p(f), _p(t))
+    return dict(coordination=val, force=f, torque_lab=t)

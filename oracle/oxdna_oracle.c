@@ -829,6 +829,140 @@ void oxo_ext_forces(int nf, const oxo_ext_force *ef, int N, const double *pos, c
 	}
 }
 
+/* ------------------------------------------------------------------ metadynamics coordination bias
+ * LTCoordination (src/Forces/Metadynamics/LTCoordination.cpp:94-221) over the helpers of src/Forces/Metadynamics/meta_utils.{h,cpp}:
+ * a smooth count of formed base pairs among a list of candidate pairs, biased by a tabulated potential.  The hydrogen-bond energy is
+ * the unsmoothed oxDNA2 expression of meta_utils.cpp:252-366 (its constants are the float literals of src/model.h). */
+static double mc_f1(double r) {
+	/* meta_utils.cpp:215-232; `shift` is evaluated with a float argument to exp there */
+	const double shift = 1.0678f * SQ(1.0 - (double) expf(-(0.75f - 0.4f) * 8.f));
+	if(!(r < 0.783775f)) return 0.;
+	double tmp = 1.0 - exp(-(r - 0.4f) * 8.f);
+	return 1.0678f * SQ(tmp) - shift;
+}
+static double mc_f1D(double r) {
+	if(!(r < 0.783775f)) return 0.;
+	double tmp = exp(-(r - 0.4f) * 8.f);
+	return 2.0 * 1.0678f * (1 - tmp) * tmp * 8.f;
+}
+static double mc_f4(double t, double t0, double a) {
+	t -= t0;
+	if(t < 0.0) t *= -1.0;
+	return (t < 1.0 / sqrt(a)) ? 1.0 - a * SQ(t) : 0.;
+}
+static double mc_f4Dsin(double t, double t0, double a) {
+	/* meta_utils.cpp:246-267 */
+	double m = 1.0, tt0 = t - t0;
+	if(tt0 < 0.0) { tt0 *= -1.0; m = -1.0; }
+	if(!(tt0 < 1.0 / sqrt(a))) return 0.;
+	double sint = sin(t);
+	return (sint > 1e-10) ? m * 2.0 * a * tt0 / sint : m * 2.0 * a;
+}
+static double safe_acos_(double x) { return acos(fmax(-1.0, fmin(1.0, x))); }
+
+/* energy of the pair (p, q); force on p and lab-frame torque on p if wanted (meta_utils.cpp:269-366) */
+static double mc_hb(const double *pos, const double *axes, const int *btype, const double *box, int p, int q, double *force, double *torque, int want) {
+	const float PIf = 3.141592653589793238462643f;
+	const double T0[6] = { 0.f, 0.f, 0.f, PIf, PIf * 0.5f, PIf * 0.5f }, A[6] = { 1.5f, 1.5f, 1.5f, 0.46f, 4.f, 4.f };
+	for(int k = 0; k < 3; k++) force[k] = torque[k] = 0.;
+	if(btype[p] + btype[q] != 3) return 0.;
+	const double *a1 = axes + 9 * (size_t) p, *a3 = a1 + 6, *b1 = axes + 9 * (size_t) q, *b3 = b1 + 6;
+	double r[3], rh[3];
+	min_image(box, pos + 3 * (size_t) p, pos + 3 * (size_t) q, r);
+	for(int k = 0; k < 3; k++) rh[k] = r[k] + 0.4f * b1[k] - 0.4f * a1[k];
+	double m = sqrt(dot3(rh, rh));
+	if(!(0.276908f < m && m < 0.783775f)) return 0.;
+	double h[3] = { rh[0] / m, rh[1] / m, rh[2] / m };
+	double c[6] = { -dot3(a1, b1), -dot3(b1, h), dot3(a1, h), dot3(a3, b3), -dot3(b3, h), dot3(a3, h) };
+	double t[6], f4[6], f1 = mc_f1(m), e = f1;
+	for(int k = 0; k < 6; k++) { t[k] = safe_acos_(c[k]); f4[k] = mc_f4(t[k], T0[k], A[k]); e *= f4[k]; }
+	if(!want || e == 0.) return e;
+	const double sgn[6] = { 1., 1., -1., -1., 1., -1. }; /* f4t1Dsin, f4t2Dsin, -f4t3Dsin, -f4t4Dsin, f4t7Dsin, -f4t8Dsin */
+	double D[6], prod_wo[6];
+	for(int k = 0; k < 6; k++) {
+		D[k] = sgn[k] * mc_f4Dsin(t[k], T0[k], A[k]);
+		prod_wo[k] = f1;
+		for(int j = 0; j < 6; j++) prod_wo[k] *= (j == k) ? D[k] : f4[j];
+	}
+	double all4 = f4[0] * f4[1] * f4[2] * f4[3] * f4[4] * f4[5], dir[3];
+	axpy3(-(mc_f1D(m) * all4), h, force);                          /* radial */
+	cross3(a3, b3, dir); axpy3(-prod_wo[3], dir, torque);          /* theta4 */
+	cross3(a1, b1, dir); axpy3(-prod_wo[0], dir, torque);          /* theta1 */
+	for(int k = 0; k < 3; k++) force[k] += (b1[k] + h[k] * c[1]) * (prod_wo[1] / m);      /* theta2 (torque on q only) */
+	for(int k = 0; k < 3; k++) force[k] += (a1[k] - h[k] * c[2]) * (prod_wo[2] / m);      /* theta3 */
+	cross3(h, a1, dir); axpy3(prod_wo[2], dir, torque);
+	for(int k = 0; k < 3; k++) force[k] += (b3[k] + h[k] * c[4]) * (prod_wo[4] / m);      /* theta7 (torque on q only) */
+	for(int k = 0; k < 3; k++) force[k] += (a3[k] - h[k] * c[5]) * (prod_wo[5] / m);      /* theta8 */
+	cross3(h, a3, dir); axpy3(prod_wo[5], dir, torque);
+	double base[3] = { 0.4f * a1[0], 0.4f * a1[1], 0.4f * a1[2] };
+	cross3(base, force, dir); axpy3(1., dir, torque);
+	return e;
+}
+static double mc_smooth(double cut, double width, double e) {
+	double x = (cut - e) / width;
+	if(x > 10.0) return 1.0;
+	if(x < -10.0) return 0.0;
+	return 0.5 * (1.0 + tanh(x));
+}
+static double mc_dsmooth(double cut, double width, double e) {
+	double x = (cut - e) / width;
+	if(x > 10.0 || x < -10.0) return 0.0;
+	double th = tanh(x);
+	return -0.5 * (1.0 - SQ(th)) / width;
+}
+static void mc_base_vec(const double *pos, const double *axes, const double *box, int p, int q, double *r) {
+	double bp[3], bq[3];
+	for(int k = 0; k < 3; k++) { bp[k] = pos[3 * (size_t) p + k] + 0.4f * axes[9 * (size_t) p + k]; bq[k] = pos[3 * (size_t) q + k] + 0.4f * axes[9 * (size_t) q + k]; }
+	min_image(box, bp, bq, r);
+}
+static double mc_pair_contribution(const oxo_coord *C, const double *pos, const double *axes, const int *btype, const double *box, int p, int q) {
+	/* meta_utils.cpp:127-157 */
+	double f[3], t[3], hbc = 0., sw = 0.;
+	if(C->mode != 1) hbc = mc_smooth(C->hb_energy_cutoff, C->hb_transition_width, mc_hb(pos, axes, btype, box, p, q, f, t, 0));
+	if(C->mode != 0) {
+		double r[3];
+		mc_base_vec(pos, axes, box, p, q, r);
+		sw = 1.0 / (1.0 + pow((sqrt(dot3(r, r)) - C->d0) / C->r0, C->n));
+	}
+	return C->mode == 0 ? hbc : (C->mode == 1 ? sw : C->mixed_weight * hbc + (1.0 - C->mixed_weight) * sw);
+}
+
+double oxo_meta_coordination(const oxo_coord *C, int N, const double *pos, const double *axes, const int *btype, const double *box,
+		double *force, double *torque_lab) {
+	(void) N;
+	double coord = 0.;
+	for(int k = 0; k < C->n_pairs; k++) coord += mc_pair_contribution(C, pos, axes, btype, box, C->pairs[2 * k], C->pairs[2 * k + 1]);
+	/* LTCoordination::_coordination clamps; ::force reads -dV/dcoord off the grid by finite difference (meta_utils.h:30-34) */
+	double cl = coord < C->coord_min ? C->coord_min : (coord > C->coord_max ? C->coord_max : coord);
+	double dc = (C->coord_max - C->coord_min) / (C->N_grid - 1.0);
+	int il = (int) floor((cl - C->coord_min) / dc), ir = il + 1;
+	double df = 0.;
+	if(!(il < 0 || ir > C->N_grid - 1)) df = -(C->grid[ir] - C->grid[il]) / dc;
+	for(int k = 0; k < C->n_pairs; k++) for(int side = 0; side < 2; side++) {
+		/* meta_utils.cpp:159-205 with current = p, other = q */
+		int p = C->pairs[2 * k + side], q = C->pairs[2 * k + 1 - side];
+		double f[3] = { 0, 0, 0 }, t[3] = { 0, 0, 0 }, fs[3] = { 0, 0, 0 }, ts[3] = { 0, 0, 0 };
+		if(C->mode != 1) {
+			double e = mc_hb(pos, axes, btype, box, p, q, f, t, 1), d = mc_dsmooth(C->hb_energy_cutoff, C->hb_transition_width, e);
+			for(int x = 0; x < 3; x++) { f[x] *= d; t[x] *= d; }
+		}
+		if(C->mode != 0) {
+			double r[3], base[3];
+			mc_base_vec(pos, axes, box, p, q, r);
+			double rm = sqrt(dot3(r, r)), xx = (rm - C->d0) / C->r0, xn = pow(xx, C->n);
+			double dcdr = (C->n / C->r0) * pow(xx, C->n - 1) / SQ(1.0 + xn);
+			for(int x = 0; x < 3; x++) { fs[x] = r[x] / rm * dcdr; base[x] = 0.4f * axes[9 * (size_t) p + x]; }
+			cross3(base, fs, ts);
+		}
+		double w = C->mode == 2 ? C->mixed_weight : (C->mode == 0 ? 1. : 0.);
+		for(int x = 0; x < 3; x++) {
+			force[3 * (size_t) p + x] += df * (w * f[x] + (1. - w) * fs[x]);
+			torque_lab[3 * (size_t) p + x] += df * (w * t[x] + (1. - w) * ts[x]);
+		}
+	}
+	return coord;
+}
+
 /* ------------------------------------------------------------------ Verlet list */
 static int cell_of(const double *box, const int *nc, const double *p) {
 	/* src/Lists/Cells.h:60-65 */

@@ -78,6 +78,12 @@ void oxo_dna2_forces(const oxo_dna2_params *P, int N, const double *pos, const d
 /* index pool of the COM forces (entry: ref = offset of com_list, iaux = its length, pbc = length of the ref_list that follows) */
 void oxo_set_ext_pool(const int *pool);
 void oxo_set_ext_grid(const double *grid);
+/* metadynamics coordination bias (meta_coordination, LTCoordination): mode 0 hb_cutoff, 1 switching_function, 2 mixed; pairs = n_pairs x 2
+ * particle indices.  Adds force and lab-frame torque on every particle of the pairs; returns the (unclamped) coordination. */
+typedef struct { int mode; double mixed_weight, hb_energy_cutoff, hb_transition_width, d0, r0; int n; double coord_min, coord_max; int N_grid; const double *grid;
+	int n_pairs; const int *pairs; } oxo_coord;
+double oxo_meta_coordination(const oxo_coord *C, int N, const double *pos, const double *axes, const int *btype, const double *box,
+		double *force, double *torque_lab);
 void oxo_ext_forces(int nf, const oxo_ext_force *ef, int N, const double *pos, const double *box, long long step, double *force);
 
 /* Verlet list exactly as src/Lists/Cells.cpp:120-181 + VerletList.cpp:35-66: unique pairs (q<p), not bonded,

@@ -368,3 +368,41 @@ def test_oracle_barostat_rescale_properties():
         assert np.allclose(m[sel].mean(0), g["pos"][sel].mean(0) * new_box / box, atol=1e-12)
     V0, V1 = box.prod(), new_box.prod()
     assert np.isclose(O.barostat_acceptance(0.0, 0.0, 0.1, box, new_box, 16), (V1 / V0) ** 16)
+
+
+@pytest.mark.skipif(not RH.available(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("mode,extra", [("hb_cutoff", {}), ("switching_function", dict(d0=0.35, r0=0.45, n=6)),
+                                        ("mixed", dict(mixed_weight=0.7, hb_energy_cutoff=-0.1, d0=0.4, r0=0.5, n=4))])
+def test_meta_coordination_restatement_matches_live_reference(tmp_path, mode, extra):
+    """The last external force of the reference's CUDA backend that the device side does not evaluate yet: its
+    oracle is in place and pinned.  LTCoordination (smooth count of formed base pairs + tabulated bias) on the thermalised lattice8
+    state: force and lab-frame torque on every particle of the 20 candidate pairs of duplex 0 against the unmodified reference CPU
+    class, for the three coordination types."""
+    g = load_golden("lattice8")
+    top, conf, opf, ff = (str(tmp_path / n) for n in ("l.top", "l.dat", "op.txt", "forces.txt"))
+    oio.write_topology(top, g["btype"], g["n3"], g["n5"], g["strand"])
+    oio.write_conf(conf, g["box"], g["pos"], g["a1"], g["a3"], g["vel"], g["L"])
+    pairs = [(k, 39 - k) for k in range(20)]
+    with open(opf, "w") as f:
+        f.write("{\norder_parameter = bond\nname = all_native_bonds\n" + "".join(f"pair{k + 1} = {a}, {b}\n" for k, (a, b) in enumerate(pairs)) + "}\n")
+    xs = np.linspace(0.0, 20.2, 102)
+    grid = 0.05 * (xs - 12.0) ** 2
+    d = dict(coordination_type=mode, coord_min=0.0, coord_max=20.2, N_grid=len(grid), **extra)
+    with open(ff, "w") as f:
+        f.write("{\ntype = meta_coordination\nop_file = " + opf + "\n" + "".join(f"{k} = {v}\n" for k, v in d.items()) +
+                "potential_grid = " + ",".join("%.10f" % v for v in grid) + "\n}\n")
+    r = RH.Reference(top, conf, interaction_type="DNA2_nomesh", salt_concentration=float(g["salt"]), T=str(g["T"]), thermostat="no", dt=0.003,
+                     external_forces=1, external_forces_file=ff)
+    try:
+        RH.lib().oxref_rebuild_lists()
+        ref = r.compute_forces()
+    finally:
+        r.close()
+    ax = O.axes_from_a1a3(g["a1"], g["a3"])
+    out = O.meta_coordination(dict(d, pairs=pairs, potential_grid=[float("%.10f" % v) for v in grid]), g["pos"], ax, g["btype"], g["box"])
+    dF, dT = ref["force"] - g["force"], ref["torque_lab"] - g["torque_lab"]
+    assert 5.0 < out["coordination"] < 20.0
+    assert np.abs(dF).max() > 1e-3 and np.abs(dT).max() > 1e-4          # the bias does act
+    assert not np.abs(dF[40:]).max() > 1e-12                            # and only on the particles of the pairs
+    assert np.abs(out["force"] - dF).max() < 1e-9
+    assert np.abs(out["torque_lab"] - dT).max() < 1e-9
