@@ -26,7 +26,7 @@ enum { OXB_THERMOSTAT_NONE = 0, OXB_THERMOSTAT_BROWNIAN = 1, OXB_THERMOSTAT_LANG
 enum { OXB_EXT_STRING = 0, OXB_EXT_TRAP = 1, OXB_EXT_MUTUAL_TRAP = 2, OXB_EXT_LOWDIM_TRAP = 3, OXB_EXT_REPULSION_PLANE = 4,
 	OXB_EXT_ATTRACTION_PLANE = 5, OXB_EXT_SPHERE = 6, OXB_EXT_LJ_WALL = 7, OXB_EXT_TWIST = 8, OXB_EXT_SPHERE_SMOOTH = 9, OXB_EXT_ELLIPSOID = 10,
 	OXB_EXT_REPULSION_PLANE_MOVING = 11, OXB_EXT_GENERIC_CENTRAL = 12, OXB_EXT_LJ_CONE = 13, OXB_EXT_COM = 14, OXB_EXT_YUKAWA_SPHERE = 15,
-	OXB_EXT_SPHERE_MOVING = 16, OXB_EXT_META_COM_TRAP = 17, OXB_EXT_NTYPES };
+	OXB_EXT_SPHERE_MOVING = 16, OXB_EXT_META_COM_TRAP = 17, OXB_EXT_META_COORDINATION = 18, OXB_EXT_NTYPES };
 enum { OXB_TERM_FENE = 0, OXB_TERM_BEXC, OXB_TERM_STCK, OXB_TERM_NEXC, OXB_TERM_HB, OXB_TERM_CRST, OXB_TERM_CXST, OXB_TERM_DH, OXB_NTERMS };
 
 /* ---- force-field parameters (device constant block).  Replaces the __constant__ upload of
@@ -150,7 +150,13 @@ int oxb_rna2_params_seqdep(oxb_rna2_params *P, double T, const double *stck_raw1
  *   META_COM_TRAP        LTCOMTrap (meta_com_trap)       ONE entry per force: ref = offset of p1a in the index pool, iaux = its length, p2a follows with
  *                                                        pbc entries; aux[0] = xmin, aux[1] = dX, aux[2] = N_grid, aux[3] = mode (1: acts on p1a,
  *                                                        2: on p2a), aux[4] = offset of potential_grid in the grid pool
- *                                                        (oxb_set_ext_grid_pool), aux[5] = PBC */
+ *                                                        (oxb_set_ext_grid_pool), aux[5] = PBC
+ *   META_COORDINATION    LTCoordination (meta_coordination) ONE entry per force: ref = offset of the hydrogen-bond candidate pairs in the index pool
+ *                                                        (p0, q0, p1, q1, ...), iaux = number of pairs; aux[0] = coord_min, aux[1] = d_coord,
+ *                                                        aux[2] = N_grid, aux[3] = coordination type (0 hb_cutoff, 1 switching_function, 2 mixed),
+ *                                                        aux[4] = offset of potential_grid in the grid pool, aux[5] = mixed_weight,
+ *                                                        aux[6] = hb_energy_cutoff, aux[7] = hb_transition_width, r0 = d0, stiff = r0 (of the
+ *                                                        switching function), pbc = n, F0 = coord_max.  Adds forces AND lab-frame torques. */
 typedef struct {
 	int type;      /* OXB_EXT_* */
 	int particle;  /* original index, or -1 = all particles */

@@ -76,7 +76,7 @@ class ExtForce(C.Structure):
         (n, C.c_double) for n in "stiff r0 rate stiff_rate F0".split()] + [("dir", C.c_double * 3), ("pos0", C.c_double * 3),
                                                                               ("aux", C.c_double * 8), ("iaux", C.c_int)]
 
-EXT_TYPES = {"string": 0, "trap": 1, "mutual_trap": 2, "lowdim_trap": 3, "repulsion_plane": 4, "attraction_plane": 5, "sphere": 6, "LJ_wall": 7, "twist": 8, "sphere_smooth": 9, "ellipsoid": 10, "repulsion_plane_moving": 11, "generic_central_force": 12, "LJ_cone": 13, "com": 14, "yukawa_sphere": 15, "repulsive_sphere_moving": 16, "meta_com_trap": 17}
+EXT_TYPES = {"string": 0, "trap": 1, "mutual_trap": 2, "lowdim_trap": 3, "repulsion_plane": 4, "attraction_plane": 5, "sphere": 6, "LJ_wall": 7, "twist": 8, "sphere_smooth": 9, "ellipsoid": 10, "repulsion_plane_moving": 11, "generic_central_force": 12, "LJ_cone": 13, "com": 14, "yukawa_sphere": 15, "repulsive_sphere_moving": 16, "meta_com_trap": 17, "meta_coordination": 18}
 
 
 def _index_list(v):
@@ -102,7 +102,7 @@ def fill_ext_entry(e, d, pool, grid):
     part = d.get("particle", -1)
     e.particle = -1 if str(part) in ("-1", "all") else int(part)
     e.ref = int(d.get("ref_particle", -1)) if d["type"] != "repulsion_plane_moving" else -1
-    e.pbc = int(d.get("PBC", 0)) if d["type"] != "meta_com_trap" else 0
+    e.pbc = int(d.get("PBC", 0)) if d["type"] not in ("meta_com_trap", "meta_coordination") else 0
     e.stiff, e.r0, e.rate = float(d.get("stiff", 1.0 if d["type"] == "LJ_wall" else 0.0)), float(d.get("r0", 0.0)), float(d.get("rate", 0.0))
     e.stiff_rate, e.F0 = float(d.get("stiff_rate", 0.0)), float(d.get("F0", 0.0))
     dr = np.array(d.get("axis", d.get("dir", (1, 0, 0) if d["type"] != "mutual_trap" else (0, 0, 1))), dtype=np.float64)
@@ -186,6 +186,25 @@ def fill_ext_entry(e, d, pool, grid):
         aux[0], aux[1], aux[2] = float(d["xmin"]), (float(d["xmax"]) - float(d["xmin"])) / (n_grid - 1.0), float(n_grid)
         aux[3], aux[4], aux[5] = float(int(d["mode"])), float(len(grid)), float(int(d.get("PBC", 0)))
         e.pbc = len(p2a)
+        grid.extend(pg)
+    elif d["type"] == "meta_coordination":
+        # `pairs`: the hydrogen-bond candidate pairs of the op_file (LTCoordination::init reads them from there)
+        pairs = [(int(a), int(b)) for a, b in d["pairs"]]
+        flat = [x for ab in pairs for x in ab]
+        if len(set(flat)) != len(flat):
+            raise ValueError("LTCoordination assumes each particle appears only once")
+        pg = d["potential_grid"]
+        pg = [float(x) for x in (pg.split(",") if isinstance(pg, str) else pg)]
+        n_grid = int(d["N_grid"])
+        if len(pg) != n_grid:
+            raise ValueError("LTCoordination: potential_grid size != N_grid")
+        mode = {"hb_cutoff": 0, "switching_function": 1, "mixed": 2}[d.get("coordination_type", "hb_cutoff")]
+        cmin, cmax = float(d.get("coord_min", 0.0)), float(d.get("coord_max", len(pairs) * 1.01))
+        e.particle, e.ref, e.iaux, e.pbc = -1, len(pool), len(pairs), int(d.get("n", 6))
+        pool.extend(flat)
+        e.r0, e.stiff, e.F0 = float(d.get("d0", 0.4)), float(d.get("r0", 0.5)), cmax
+        aux[0], aux[1], aux[2], aux[3], aux[4] = cmin, (cmax - cmin) / (n_grid - 1.0), float(n_grid), float(mode), float(len(grid))
+        aux[5], aux[6], aux[7] = float(d.get("mixed_weight", 0.0)), float(d.get("hb_energy_cutoff", -0.2)), float(d.get("hb_transition_width", 0.1))
         grid.extend(pg)
     for c in range(8):
         e.aux[c] = aux[c]

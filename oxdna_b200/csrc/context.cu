@@ -445,7 +445,7 @@ int launch_forces(oxb_ctx *c, int hw, bool clear, long long step) {
 			c->launches += 1;
 		}
 		if(c->n_ext_com > 0) {
-			oxb::launch_ext_com(s1, c->n_ext_com, c->ext_com, c->ext_pool, c->ext_grid, c->slot_of, c->posd[a], c->box, step, c->cur_step, c->F[a], c->flags, hw);
+			oxb::launch_ext_com(s1, c->n_ext_com, c->ext_com, c->ext_pool, c->ext_grid, c->slot_of, c->posd[a], c->quatd[a], c->ipos[a], c->box, step, c->cur_step, c->F[a], c->T[a], c->flags, hw);
 			c->launches += 1;
 		}
 		if(fork) CU(cudaStreamWaitEvent(c->aux[1], c->ev_near, 0));
@@ -473,7 +473,7 @@ int launch_forces(oxb_ctx *c, int hw, bool clear, long long step) {
 			c->launches += 1;
 		}
 		if(c->n_ext_com > 0) {
-			oxb::launch_ext_com(m, c->n_ext_com, c->ext_com, c->ext_pool, c->ext_grid, c->slot_of, c->posd[a], c->box, step, c->cur_step, c->F[a], c->flags, hw);
+			oxb::launch_ext_com(m, c->n_ext_com, c->ext_com, c->ext_pool, c->ext_grid, c->slot_of, c->posd[a], c->quatd[a], c->ipos[a], c->box, step, c->cur_step, c->F[a], c->T[a], c->flags, hw);
 			c->launches += 1;
 		}
 	}
@@ -875,6 +875,16 @@ int oxb_set_ext_forces(oxb_ctx *c, int n, const oxb_ext_force *f) {
 			if(ng < 2 || go < 0 || go + ng > (long long) c->ext_grid_n || !(f[k].aux[1] > 0.))
 				return fail(c, 1, "external force %d: potential grid [%lld, +%lld) outside the grid pool (%zu values; call oxb_set_ext_grid_pool first)", k, go, ng, c->ext_grid_n);
 		}
+		if(f[k].type == OXB_EXT_META_COORDINATION) {
+			const long long ng = (long long) f[k].aux[2], go = (long long) f[k].aux[4], lo = f[k].ref, np_ = f[k].iaux;
+			const int mode = (int) f[k].aux[3];
+			if(mode < 0 || mode > 2) return fail(c, 1, "Coordination: unknown coordination_type %d (0 hb_cutoff, 1 switching_function, 2 mixed)", mode);
+			if(mode != 0 && (f[k].pbc % 2) != 0) return fail(c, 1, "LTCoordination: exponent n must be an even integer");
+			if(ng < 2 || go < 0 || go + ng > (long long) c->ext_grid_n || !(f[k].aux[1] > 0.))
+				return fail(c, 1, "external force %d: potential grid [%lld, +%lld) outside the grid pool (%zu values; call oxb_set_ext_grid_pool first)", k, go, ng, c->ext_grid_n);
+			if(lo < 0 || np_ < 1 || lo + 2 * np_ > (long long) c->ext_pool_h.size())
+				return fail(c, 1, "external force %d: pair list [%lld, +2 x %lld) outside the index pool (%zu entries)", k, lo, np_, c->ext_pool_h.size());
+		}
 		if(f[k].type == OXB_EXT_COM || f[k].type == OXB_EXT_META_COM_TRAP) {
 			const long long lo = f[k].ref, n_com = f[k].iaux, n_ref = f[k].pbc;
 			if(lo < 0 || n_com < 1 || n_ref < 1 || lo + n_com + n_ref > (long long) c->ext_pool_h.size())
@@ -895,7 +905,7 @@ int oxb_set_ext_forces(oxb_ctx *c, int n, const oxb_ext_force *f) {
 		d.r0d = f[k].r0;
 		if(f[k].type == OXB_EXT_LJ_CONE) { d.aux[3] = (float) std::sin(f[k].aux[2]); d.aux[4] = (float) std::cos(f[k].aux[2]); d.aux[5] = (float) std::tan(f[k].aux[2]); }
 		if(f[k].type == OXB_EXT_SPHERE_MOVING) d.daux = f[k].aux[4];
-		if(f[k].type == OXB_EXT_COM || f[k].type == OXB_EXT_META_COM_TRAP) { d.ref = f[k].ref; hcom.push_back(d); continue; }
+		if(f[k].type == OXB_EXT_COM || f[k].type == OXB_EXT_META_COM_TRAP || f[k].type == OXB_EXT_META_COORDINATION) { d.ref = f[k].ref; hcom.push_back(d); continue; }
 		(f[k].particle < 0 ? hall : h).push_back(d);
 	}
 	cudaFree(c->ext);

@@ -718,13 +718,152 @@ __device__ __forceinline__ v3 ext_single(const DevExtForce &e, double4 p, int4 i
 // COMForce.cpp:46-71: one block per force; centres of mass of com_list and ref_list from the absolute positions, then the
 // spring force shared equally among the com_list particles (the reference recomputes both sums in every thread,
 // CUDA_MD.cuh:441-468).  The ref_list particles feel nothing, as there.
+// ---- metadynamics coordination bias (LTCoordination, src/Forces/Metadynamics/LTCoordination.cpp:94-221 over meta_utils.cpp:119-366;
+// the reference's device version: src/CUDA/Forces/metad_forces.cuh:138-470).  Double precision from the FP64 state; constants are the
+// float literals of src/model.h.  One block per force: the coordination (sum over the candidate pairs) by block reduction, then every
+// pair adds bias force and lab-frame torque to both of its particles (the reference recomputes the whole sum in every thread).
+__device__ __forceinline__ double coord_f4(double t, double t0, double a) {
+	t = fabs(t - t0);
+	return (t < 1.0 / sqrt(a)) ? 1.0 - a * t * t : 0.;
+}
+__device__ __forceinline__ double coord_f4Dsin(double t, double t0, double a) {
+	double m = 1.0, tt0 = t - t0;
+	if(tt0 < 0.0) { tt0 = -tt0; m = -1.0; }
+	if(!(tt0 < 1.0 / sqrt(a))) return 0.;
+	const double sint = sin(t);
+	return (sint > 1e-10) ? m * 2.0 * a * tt0 / sint : m * 2.0 * a;
+}
+// geometry of a pair in double: centre separation r (minimum image), axes a1/a3 of p and b1/b3 of q
+struct CoordPair { double r[3], a1[3], a3[3], b1[3], b3[3]; int pair_types_sum; };
+__device__ inline CoordPair coord_load(const double4 *__restrict__ posd, const double4 *__restrict__ qd, const int4 *__restrict__ ipos, const double *L, int sp, int sq) {
+	CoordPair P;
+	const double4 pp = posd[sp], pq = posd[sq], qp = qd[sp], qq = qd[sq];
+	P.r[0] = pq.x - pp.x; P.r[1] = pq.y - pp.y; P.r[2] = pq.z - pp.z;
+	for(int k = 0; k < 3; k++) P.r[k] -= L[k] * rint(P.r[k] / L[k]);
+	double a2[3];
+	quatd Qp = { qp.x, qp.y, qp.z, qp.w }, Qq = { qq.x, qq.y, qq.z, qq.w };
+	axes_from_quatd(Qp, P.a1, a2, P.a3);
+	axes_from_quatd(Qq, P.b1, a2, P.b3);
+	P.pair_types_sum = word_btype(ipos[sp].w) + word_btype(ipos[sq].w);
+	return P;
+}
+// unsmoothed oxDNA2 hydrogen-bond energy of the pair; force on p and lab-frame torque on p if `want` (meta_utils.cpp:269-366)
+__device__ inline double coord_hb(const CoordPair &P, double *force, double *torque, bool want) {
+	const float PIf = 3.141592653589793238462643f;
+	const double T0[6] = { 0.f, 0.f, 0.f, PIf, PIf * 0.5f, PIf * 0.5f }, A[6] = { 1.5f, 1.5f, 1.5f, 0.46f, 4.f, 4.f };
+	for(int k = 0; k < 3; k++) force[k] = torque[k] = 0.;
+	if(P.pair_types_sum != 3) return 0.;
+	double rh[3];
+	for(int k = 0; k < 3; k++) rh[k] = P.r[k] + 0.4f * P.b1[k] - 0.4f * P.a1[k];
+	const double m = sqrt(rh[0] * rh[0] + rh[1] * rh[1] + rh[2] * rh[2]);
+	if(!(0.276908f < m && m < 0.783775f)) return 0.;
+	const double h[3] = { rh[0] / m, rh[1] / m, rh[2] / m };
+	auto dot = [](const double *a, const double *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; };
+	const double c[6] = { -dot(P.a1, P.b1), -dot(P.b1, h), dot(P.a1, h), dot(P.a3, P.b3), -dot(P.b3, h), dot(P.a3, h) };
+	// f1 without the smoothing branches (meta_utils.cpp:215-232); the shift is evaluated in float there
+	const double shift = 1.0678f * (1.0 - (double) expf(-(0.75f - 0.4f) * 8.f)) * (1.0 - (double) expf(-(0.75f - 0.4f) * 8.f));
+	const double ex = exp(-(m - 0.4f) * 8.f);
+	const double f1 = 1.0678f * (1.0 - ex) * (1.0 - ex) - shift, f1D = 2.0 * 1.0678f * (1 - ex) * ex * 8.f;
+	double t[6], f4[6], e = f1;
+	for(int k = 0; k < 6; k++) { t[k] = acos(fmax(-1.0, fmin(1.0, c[k]))); f4[k] = coord_f4(t[k], T0[k], A[k]); e *= f4[k]; }
+	if(!want || e == 0.) return e;
+	const double sgn[6] = { 1., 1., -1., -1., 1., -1. };
+	double pw[6];
+	for(int k = 0; k < 6; k++) {
+		pw[k] = f1 * sgn[k] * coord_f4Dsin(t[k], T0[k], A[k]);
+		for(int j = 0; j < 6; j++) if(j != k) pw[k] *= f4[j];
+	}
+	const double all = f4[0] * f4[1] * f4[2] * f4[3] * f4[4] * f4[5];
+	auto cross_add = [](double s, const double *a, const double *b, double *o) {
+		o[0] += s * (a[1] * b[2] - a[2] * b[1]); o[1] += s * (a[2] * b[0] - a[0] * b[2]); o[2] += s * (a[0] * b[1] - a[1] * b[0]);
+	};
+	for(int k = 0; k < 3; k++) {
+		force[k] = -h[k] * (f1D * all) + (P.b1[k] + h[k] * c[1]) * (pw[1] / m) + (P.a1[k] - h[k] * c[2]) * (pw[2] / m) + (P.b3[k] + h[k] * c[4]) * (pw[4] / m) +
+				(P.a3[k] - h[k] * c[5]) * (pw[5] / m);
+	}
+	cross_add(-pw[3], P.a3, P.b3, torque);
+	cross_add(-pw[0], P.a1, P.b1, torque);
+	cross_add(pw[2], h, P.a1, torque);
+	cross_add(pw[5], h, P.a3, torque);
+	const double base[3] = { 0.4f * P.a1[0], 0.4f * P.a1[1], 0.4f * P.a1[2] };
+	cross_add(1., base, force, torque);
+	return e;
+}
+struct CoordCfg { int mode, n; double w, cut, width, d0, r0; };
+__device__ inline double coord_switch_vec(const CoordPair &P, double *r) { // base(q) - base(p), returns its length
+	for(int k = 0; k < 3; k++) r[k] = P.r[k] + 0.4f * P.b1[k] - 0.4f * P.a1[k];
+	return sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+}
+__device__ inline double coord_contribution(const CoordCfg &C, const CoordPair &P) {
+	double f[3], t[3], hbc = 0., sw = 0.;
+	if(C.mode != 1) {
+		const double x = (C.cut - coord_hb(P, f, t, false)) / C.width;
+		hbc = x > 10.0 ? 1.0 : (x < -10.0 ? 0.0 : 0.5 * (1.0 + tanh(x)));
+	}
+	if(C.mode != 0) {
+		double r[3];
+		sw = 1.0 / (1.0 + pow((coord_switch_vec(P, r) - C.d0) / C.r0, (double) C.n));
+	}
+	return C.mode == 0 ? hbc : (C.mode == 1 ? sw : C.w * hbc + (1.0 - C.w) * sw);
+}
+// d(contribution)/d(position of p) and d/d(rotation of p) (lab frame), meta_utils.cpp:159-205 with current = p
+__device__ inline void coord_gradient(const CoordCfg &C, const CoordPair &P, double *force, double *torque) {
+	double f[3] = { 0., 0., 0. }, t[3] = { 0., 0., 0. }, fs[3] = { 0., 0., 0. }, ts[3] = { 0., 0., 0. };
+	if(C.mode != 1) {
+		const double e = coord_hb(P, f, t, true), x = (C.cut - e) / C.width;
+		double d = 0.;
+		if(!(x > 10.0 || x < -10.0)) { const double th = tanh(x); d = -0.5 * (1.0 - th * th) / C.width; }
+		for(int k = 0; k < 3; k++) { f[k] *= d; t[k] *= d; }
+	}
+	if(C.mode != 0) {
+		double r[3];
+		const double rm = coord_switch_vec(P, r), xx = (rm - C.d0) / C.r0, xn = pow(xx, (double) C.n);
+		const double dcdr = ((double) C.n / C.r0) * pow(xx, (double) (C.n - 1)) / ((1.0 + xn) * (1.0 + xn));
+		for(int k = 0; k < 3; k++) fs[k] = r[k] / rm * dcdr;
+		const double b[3] = { 0.4f * P.a1[0], 0.4f * P.a1[1], 0.4f * P.a1[2] };
+		ts[0] = b[1] * fs[2] - b[2] * fs[1]; ts[1] = b[2] * fs[0] - b[0] * fs[2]; ts[2] = b[0] * fs[1] - b[1] * fs[0];
+	}
+	const double w = C.mode == 2 ? C.w : (C.mode == 0 ? 1. : 0.);
+	for(int k = 0; k < 3; k++) { force[k] = w * f[k] + (1. - w) * fs[k]; torque[k] = w * t[k] + (1. - w) * ts[k]; }
+}
+
 __global__ void k_ext_com(int n, const DevExtForce *__restrict__ ef, const int *__restrict__ pool, const float *__restrict__ grid, const int *__restrict__ slot_of,
-		const double4 *__restrict__ posd, double lx, double ly, double lz, long long step, const long long *__restrict__ cur_step, float4 *__restrict__ F,
-		const int *__restrict__ flags, int hw) {
+		const double4 *__restrict__ posd, const double4 *__restrict__ qd, const int4 *__restrict__ ipos, double lx, double ly, double lz, long long step,
+		const long long *__restrict__ cur_step, float4 *__restrict__ F, float4 *__restrict__ T, const int *__restrict__ flags, int hw) {
 	if(flags[hw]) return;
 	if(step < 0) step = cur_step[hw & 1];
 	__shared__ double sh[6][4];
 	const DevExtForce e = ef[blockIdx.x];
+	if(e.type == OXB_EXT_META_COORDINATION) {
+		CoordCfg C;
+		C.mode = (int) e.aux[3]; C.n = e.pbc; C.w = (double) e.aux[5]; C.cut = (double) e.aux[6]; C.width = (double) e.aux[7]; C.d0 = (double) e.r0; C.r0 = (double) e.stiff;
+		const double L[3] = { lx, ly, lz };
+		const int n_pairs = e.iaux;
+		double part = 0.;
+		for(int k = threadIdx.x; k < n_pairs; k += blockDim.x)
+			part += coord_contribution(C, coord_load(posd, qd, ipos, L, slot_of[pool[e.ref + 2 * k]], slot_of[pool[e.ref + 2 * k + 1]]));
+		for(int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+		if((threadIdx.x & 31) == 0) sh[0][threadIdx.x >> 5] = part;
+		__syncthreads();
+		double coord = sh[0][0] + sh[0][1] + sh[0][2] + sh[0][3];
+		// LTCoordination::_coordination clamps to [coord_min, coord_max]; -dV/dcoord by finite difference on the grid, zero off it
+		const double cmin = (double) e.aux[0], dc = (double) e.aux[1], cmax = (double) e.F0;
+		coord = fmin(fmax(coord, cmin), cmax);
+		const int il = (int) floor((coord - cmin) / dc);
+		double df = 0.;
+		if(il >= 0 && il + 1 <= (int) e.aux[2] - 1) {
+			const float *g = grid + (int) e.aux[4];
+			df = -((double) g[il + 1] - (double) g[il]) / dc;
+		}
+		for(int k = threadIdx.x; k < 2 * n_pairs; k += blockDim.x) {
+			const int sp = slot_of[pool[e.ref + k]], sq = slot_of[pool[e.ref + (k ^ 1)]];
+			double f[3], t[3];
+			coord_gradient(C, coord_load(posd, qd, ipos, L, sp, sq), f, t);
+			atomicAdd(&F[sp].x, (float) (df * f[0])); atomicAdd(&F[sp].y, (float) (df * f[1])); atomicAdd(&F[sp].z, (float) (df * f[2]));
+			atomicAdd(&T[sp].x, (float) (df * t[0])); atomicAdd(&T[sp].y, (float) (df * t[1])); atomicAdd(&T[sp].z, (float) (df * t[2]));
+		}
+		return;
+	}
 	const int n_com = e.iaux, n_ref = e.pbc;
 	double acc[6] = { 0., 0., 0., 0., 0., 0. };
 	for(int k = threadIdx.x; k < n_com + n_ref; k += blockDim.x) {
@@ -900,9 +1039,9 @@ void launch_ext_forces_all(cudaStream_t s, int N, int n_all, const DevExtForce *
 }
 
 void launch_ext_com(cudaStream_t s, int n, const DevExtForce *ef_com, const int *pool, const float *grid, const int *slot_of, const double4 *posd,
-		const double *box, long long step, const long long *cur_step, float4 *F, const int *flags, int hw) {
+		const double4 *quatd, const int4 *ipos, const double *box, long long step, const long long *cur_step, float4 *F, float4 *T, const int *flags, int hw) {
 	if(n <= 0) return;
-	k_ext_com<<<n, 128, 0, s>>>(n, ef_com, pool, grid, slot_of, posd, box[0], box[1], box[2], step, cur_step, F, flags, hw);
+	k_ext_com<<<n, 128, 0, s>>>(n, ef_com, pool, grid, slot_of, posd, quatd, ipos, box[0], box[1], box[2], step, cur_step, F, T, flags, hw);
 }
 
 } // namespace oxb

@@ -92,7 +92,7 @@ void launch_ext_forces_all(cudaStream_t s, int N, int n_all, const DevExtForce *
 		long long step, const long long *cur_step, float4 *F, const int *flags, int hw);
 // COM forces: one block per entry; `pool` holds the com_list / ref_list original indices
 void launch_ext_com(cudaStream_t s, int n, const DevExtForce *ef_com, const int *pool, const float *grid, const int *slot_of, const double4 *posd,
-		const double *box, long long step, const long long *cur_step, float4 *F, const int *flags, int hw);
+		const double4 *quatd, const int4 *ipos, const double *box, long long step, const long long *cur_step, float4 *F, float4 *T, const int *flags, int hw);
 
 // ---- integrate.cu
 struct IntegrateArgs {

@@ -71,7 +71,9 @@ def test_external_force_table_mapping_matches_the_oracle_side():
 
     g = load_golden("lattice8")
     forces = ext2_forces(g["pos"]) + ext3_forces(g["pos"]) + [dict(type="string", particle=3, F0=0.1, rate=0.01, dir=(0, 0, 2.0)),
-                                                               dict(type="trap", particle=4, stiff=1.0, rate=0.0, pos0=(1, 2, 3), dir=(1, 0, 0))]
+                                                               dict(type="trap", particle=4, stiff=1.0, rate=0.0, pos0=(1, 2, 3), dir=(1, 0, 0)),
+                                                               dict(type="meta_coordination", pairs=[(0, 39), (1, 38)], coordination_type="mixed", mixed_weight=0.7,
+                                                                    N_grid=3, potential_grid="0,1,4", coord_max=2.02, d0=0.35, r0=0.45, n=4)]
     assert set(capi.EXT_TYPES) == set(O.EXT_TYPES) and all(capi.EXT_TYPES[k] == O.EXT_TYPES[k] for k in capi.EXT_TYPES)
     assert {f["type"] for f in forces} == set(capi.EXT_TYPES)  # every type the library knows is exercised by a fixture
     pool_a, grid_a, pool_b, grid_b = [], [], [], []

@@ -922,3 +922,29 @@ def test_full_size_c3_against_the_oracle():
         assert sim.ctx.stats()["error_flags"] == 0
     finally:
         sim.close()
+
+
+@pytest.mark.parametrize("mode,extra", [("hb_cutoff", {}), ("switching_function", dict(d0=0.35, r0=0.45, n=6)),
+                                        ("mixed", dict(mixed_weight=0.7, hb_energy_cutoff=-0.1, d0=0.4, r0=0.5, n=4))])
+def test_meta_coordination_bias_vs_oracle(mode, extra):
+    """meta_coordination (LTCoordination): bias force AND lab-frame torque on the particles of the 20 candidate base pairs of duplex 0,
+    against the oracle that is pinned to the reference CPU class (tests/test_oracle.py); then a short run."""
+    g = load_golden("lattice8")
+    pairs = [(k, 39 - k) for k in range(20)]
+    xs = np.linspace(0.0, 20.2, 102)
+    d = dict(type="meta_coordination", pairs=pairs, coordination_type=mode, coord_min=0.0, coord_max=20.2, N_grid=len(xs),
+             potential_grid=[float(v) for v in 0.01 * (xs - 12.0) ** 2], **extra)
+    ref = O.meta_coordination(d, g["pos"], O.axes_from_a1a3(g["a1"], g["a3"]), g["btype"], g["box"])
+    assert np.abs(ref["force"]).max() > 1e-4 and np.abs(ref["torque_lab"]).max() > 1e-5
+    sim = make_sim(g, use_edge=1, CUDA_sort_every=1, external_forces_list=[d])
+    try:
+        out = sim.ctx.get_forces()
+        fmax, tmax = np.linalg.norm(g["force"], axis=1).max(), np.linalg.norm(g["torque_lab"], axis=1).max()
+        assert np.linalg.norm(out["force"] - (g["force"] + ref["force"]), axis=1).max() <= 1e-5 * fmax
+        assert np.linalg.norm(out["torque_lab"] - (g["torque_lab"] + ref["torque_lab"]), axis=1).max() <= 1e-5 * tmax
+        # the bias itself, isolated from the interaction forces, to its own scale
+        assert np.abs((out["force"] - g["force"]) - ref["force"]).max() <= 2e-5 * fmax
+        sim.run(50)
+        assert np.isfinite(sim.ctx.energy()[0]) and sim.ctx.stats()["error_flags"] == 0
+    finally:
+        sim.close()
