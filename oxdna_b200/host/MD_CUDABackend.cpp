@@ -7,6 +7,7 @@
 #include "Forces/GenericCentralForce.h"
 #include "Forces/LJCone.h"
 #include "Forces/Metadynamics/LTCOMTrap.h"
+#include "Forces/Metadynamics/LTCoordination.h"
 #include "Forces/RepulsionPlaneMoving.h"
 #include "Forces/RepulsiveSphereMoving.h"
 #include "Forces/YukawaSphere.h"
@@ -373,6 +374,23 @@ void MD_CUDABackend::_apply_external_forces_changes() {
 				e.aux[0] = mf->xmin; e.aux[1] = mf->dX; e.aux[2] = mf->N_grid; e.aux[3] = mf->_mode; e.aux[4] = (double) grid.size(); e.aux[5] = mf->PBC ? 1. : 0.;
 				for(auto v : mf->potential_grid) grid.push_back(v);
 			}
+			else if(ft == typeid(LTCoordination)) {
+				// meta_coordination: one table entry per force object (it is attached to every particle of its hydrogen-bond pairs)
+				if(emitted.count(f)) continue;
+				emitted.insert(f);
+				LTCoordination *cf = static_cast<LTCoordination *>(f);
+				single_particle_type = false;
+				e.type = OXB_EXT_META_COORDINATION;
+				e.particle = -1;
+				e.ref = (int) pool.size(); e.iaux = (int) cf->all_pairs.size();
+				for(auto &pr : cf->all_pairs) { pool.push_back(pr.first->index); pool.push_back(pr.second->index); }
+				const int mode = static_cast<int>(cf->settings.coord_mode); // HB_ENERGY, SWITCHING_FUNCTION, MIXED = 0, 1, 2
+				e.pbc = cf->settings.n; e.r0 = cf->settings.d0; e.stiff = cf->settings.r0; e.F0 = cf->coord_max;
+				e.aux[0] = cf->coord_min; e.aux[1] = cf->d_coord; e.aux[2] = cf->N_grid; e.aux[3] = mode; e.aux[4] = (double) grid.size();
+				e.aux[5] = (mode == 2) ? cf->settings.mixed_weight : 0.; // only set by the parser for the mixed type
+				e.aux[6] = cf->settings.hb_energy_cutoff; e.aux[7] = cf->settings.hb_transition_width;
+				for(auto v : cf->potential_grid) grid.push_back(v);
+			}
 			else if(ft == typeid(YukawaSphere)) {
 				YukawaSphere *yf = static_cast<YukawaSphere *>(f);
 				e.type = OXB_EXT_YUKAWA_SPHERE;
@@ -390,7 +408,7 @@ void MD_CUDABackend::_apply_external_forces_changes() {
 				e.aux[0] = sf->r_ext(); e.aux[1] = t.x; e.aux[2] = t.y; e.aux[3] = t.z; e.aux[4] = (double) sf->steps();
 			}
 			else {
-				throw oxDNAException("Only string, trap, mutual_trap, lowdim_trap, twist, repulsion_plane, repulsion_plane_moving, attraction_plane, sphere, sphere_smooth, repulsive_sphere_moving, ellipsoid, LJ_wall, LJ_cone, generic_central_force, com, meta_com_trap and yukawa_sphere forces are supported by the oxdna_b200 CUDA backend at the moment.\n");
+				throw oxDNAException("Only string, trap, mutual_trap, lowdim_trap, twist, repulsion_plane, repulsion_plane_moving, attraction_plane, sphere, sphere_smooth, repulsive_sphere_moving, ellipsoid, LJ_wall, LJ_cone, generic_central_force, com, meta_com_trap, meta_coordination and yukawa_sphere forces are supported by the oxdna_b200 CUDA backend at the moment.\n");
 			}
 			if(single_particle_type && N() > 1 && uses[f] == N()) {
 				if(emitted.count(f)) continue;

@@ -183,6 +183,24 @@ steps = 200
 """
 
 
+OP_FILE = "{\norder_parameter = bond\nname = stem\n" + "".join(f"pair{k + 1} = {k}, {17 - k}\n" for k in range(6)) + "}\n"
+FORCES4 = """{
+type = meta_coordination
+op_file = op.txt
+coordination_type = mixed
+mixed_weight = 0.7
+hb_energy_cutoff = -0.1
+d0 = 0.4
+r0 = 0.5
+n = 6
+coord_min = 0.0
+coord_max = 6.06
+N_grid = 31
+potential_grid = """ + ",".join("%.8f" % (0.5 * (x - 3.0) ** 2) for x in np.linspace(0.0, 6.06, 31)) + """
+}
+"""
+
+
 def run(binary, d, fix=FIX, files=("initial.top", "initial.conf"), **kw):
     os.makedirs(d, exist_ok=True)
     for f, name in zip(files, ("initial.top", "initial.conf")):
@@ -193,6 +211,10 @@ def run(binary, d, fix=FIX, files=("initial.top", "initial.conf"), **kw):
         f.write(FORCES2)
     with open(os.path.join(d, "forces3.txt"), "w") as f:
         f.write(FORCES3)
+    with open(os.path.join(d, "forces4.txt"), "w") as f:
+        f.write(FORCES4)
+    with open(os.path.join(d, "op.txt"), "w") as f:
+        f.write(OP_FILE)
     with open(os.path.join(d, "input"), "w") as f:
         f.write(INPUT.format(**kw))
     p = subprocess.run([binary, "input"], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
@@ -211,7 +233,8 @@ needs_binaries = pytest.mark.skipif(not (os.path.exists(OURS) and os.path.exists
 @pytest.mark.parametrize("use_edge,sort_every,extra", [(1, 1, ""), (0, 0, ""), (1, 1, "external_forces = 1\nexternal_forces_file = forces.txt"),
                                                        (1, 1, "external_forces = 1\nexternal_forces_file = forces2.txt"),
                                                        (1, 1, "external_forces = 1\nexternal_forces_file = forces3.txt"),
-                                                       (1, 1, "fix_diffusion_every = 100")])
+                                                       (1, 1, "fix_diffusion_every = 100"),
+                                                       (1, 1, "external_forces = 1\nexternal_forces_file = forces4.txt")])
 def test_stock_input_file_matches_reference_cpu(tmp_path, use_edge, sort_every, extra):
     a = run(OURS, str(tmp_path / "ours"), backend="CUDA", itype="DNA2", steps=300, thermostat="no", use_edge=use_edge, sort_every=sort_every, extra=extra)
     assert a.returncode == 0, a.stdout[-2000:]
