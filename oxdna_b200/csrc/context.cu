@@ -1168,6 +1168,11 @@ int oxb_run(oxb_ctx *c, long long n_steps) {
 	int rc = check_ready(c);
 	if(rc) return rc;
 	if(c->th.type == OXB_THERMOSTAT_BUSSI && !c->bussi_init) { rc = init_bussi(c); if(rc) return rc; }
+	if(c->build_unchecked) {
+		// a previous run ended (on an error) between an unchecked rebuild and the batch that would have checked it: rebuild on the checked path
+		c->build_unchecked = false;
+		c->lists_valid = false;
+	}
 	long long remaining = n_steps;
 	long long since_rebuild = 0;
 	bool since_rebuild_valid = false;
