@@ -1,9 +1,11 @@
 #!/usr/bin/env python
 """Benchmark of the oxDNA GPU MD step (BASELINE.json metric: particle-steps/s).
 
-  python bench.py --gpus 1 --steps K --warmup W              our CUDA path, N = 1: config C2 (81,920 nt duplex lattice)
-  torchrun ... bench.py --gpus N ...                          N > 1: one C2 replica per GPU, replica exchange over NCCL
-  python bench.py --impl reference ...                        the reference's own CPU implementation on the host cores
+  python bench.py --gpus 1 --steps K --warmup W              our CUDA path, N = 1: config C4 (1M-nt duplex lattice, DH, 50,000 mutual traps) as
+                                                              the headline; C2, C3 and C5-on-one-GPU under "extras"
+  torchrun ... bench.py --gpus N ...                          N > 1: config C5 -- 64 temperature replicas of C2 (290-350 K), 64/N per GPU as
+                                                              replica batches, replica exchange over NCCL every bench step
+  python bench.py --impl reference ...                        the reference's own CPU implementation of the same workload on the host cores
 
 One bench "step" = one block of `md_steps_per_step` MD steps (the unit the reference's OxpyManager.run(steps) /
 REMD pt_move_every works in); value = N_particles * md_steps / device time.  Prints ONE JSON line on rank 0.
@@ -212,7 +214,7 @@ def run_cpu(sysm, md_steps, warm, steps, procs, workload_name="c2", state=None):
     return procs * N * md_steps * steps / (t1 - t0), kind, t1 - t0
 
 
-def run_ref_cuda(sysm, workload_name, steps_a, steps_b, state):
+def run_ref_cuda(sysm, workload_name, steps_a, steps_b, state, quick=False):
     """The reference's own CUDA backend on this GPU, same workload, via its stock CLI (oracle/ref_cuda_bench.py).
     It starts from `state`, a thermalised configuration produced by our engine: on the IDEAL lattice (exactly parallel
     base normals) the reference's GPU kernels normalise a zero cross product and fill the system with NaNs at step 0
@@ -224,15 +226,24 @@ def run_ref_cuda(sysm, workload_name, steps_a, steps_b, state):
     d = tempfile.mkdtemp()
     top, conf = write_case(sysm, T_STR, d, state)
     N = len(sysm["pos"])
+    kw = dict(T=T_STR, salt=SALT, dt=DT)
     if workload_name == "c4":
         # the reference refuses external forces together with CUDA_sort_every > 0 (MD_CUDABackend.cu:110-112)
-        res = R.time_reference_cuda(top, conf, N, steps_a, steps_b, [(1, 0), (0, 0)], T=T_STR, salt=SALT, dt=DT, ext_forces=lattice.mutual_traps(sysm))
+        variants = [(1, 0)] if quick else [(1, 0), (0, 0)]
+        kw["ext_forces"] = lattice.mutual_traps(sysm)
     else:
-        res = R.time_reference_cuda(top, conf, N, steps_a, steps_b, [(1, 1), (0, 1), (1, 0), (0, 0)], T=T_STR, salt=SALT, dt=DT,
-                                    model_keys=model_keys(workload_name, d))
+        variants = [(1, 0)] if quick else [(1, 1), (0, 1), (1, 0), (0, 0)]
+        kw["model_keys"] = model_keys(workload_name, d)
+    res = R.time_reference_cuda(top, conf, N, steps_a, steps_b, variants, **kw)
     best = res["best"]
-    return {"value": best["value"] if best else None, "unit": "particle-steps/s", "best": best, "runs": res["runs"], "method": res["method"],
-            "build": "unmodified /root/reference/src/CUDA, nvcc -arch=sm_100 -O3 -use_fast_math (oracle/Makefile.refcuda), backend_precision = mixed"}
+    out = {"value": best["value"] if best else None, "unit": "particle-steps/s", "best": best, "runs": res["runs"], "method": res["method"],
+           "build": "unmodified /root/reference/src/CUDA, nvcc -arch=sm_100 -O3 -use_fast_math (oracle/Makefile.refcuda), backend_precision = mixed"}
+    # second comparator: the same build with Timings.cpp compiled -DNOCUDA, i.e. WITHOUT a cudaDeviceSynchronize per timer
+    # (src/Utilities/Timings.cpp:15-19,53-61) -- the reference's kernels and host logic with the timer synchronisation taken out
+    if best and os.path.exists(R.BIN_NOSYNC):
+        ns = R.time_reference_cuda(top, conf, N, steps_a, steps_b, [(best["use_edge"], best["CUDA_sort_every"])], binary=R.BIN_NOSYNC, **kw)
+        out["no_timer_sync"] = {"value": ns["best"]["value"] if ns["best"] else None, "best": ns["best"], "method": ns["method"]}
+    return out
 
 
 def host_cores():
@@ -246,10 +257,13 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sysm, desc = workload(args.workload)
+    wl = args.workload or ("c4" if args.gpus == 1 else "c2")
+    sysm, desc = workload(wl)
+    if args.gpus > 1:
+        desc = "C5: 64 temperature replicas (290-350 K) of " + desc + " -- CPU arm: independent replicas of the same system, one per core"
     procs = args.ref_procs or min(host_cores(), 32)
-    md = args.ref_md_steps
-    val, kind, secs = run_cpu(sysm, md, args.warmup, args.steps, procs, args.workload)
+    md = args.ref_md_steps or (1 if wl == "c4" else 4)
+    val, kind, secs = run_cpu(sysm, md, args.warmup, args.steps, procs, wl)
     N = len(sysm["pos"])
     line = {"impl": "reference", "metric": "particle-steps/s", "value": val, "unit": "particle-steps/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -264,123 +278,129 @@ def reference_arm(args):
 
 
 # ----------------------------------------------------------------------------------------------------------- our arm
-def ours(args):
+def load_peaks():
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        peaks = {}
+    return float(peaks.get("hbm_gbs", 6650.0)), ("measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)")
+
+
+# DRAM bytes of one force pass / one integrate launch from the committed `ncu --set full` capture of the same workload (cold cache: the
+# compulsory traffic; profiles/summary_r02*.txt): dram__bytes_read.sum + dram__bytes_write.sum summed over the kernels of the pass
+NCU_DRAM_BYTES = {"c2": dict(force=NCU_FORCE_PASS_DRAM_BYTES_C2, integrate=22.0e6), "c4": dict(force=NCU_FORCE_PASS_DRAM_BYTES_C4, integrate=423.0e6)}
+
+
+def measure_single(args, wl, steps, warmup, equil, md, full, local_rank=0):
+    """One system on one GPU: `steps` bench steps of `md` MD steps, CUDA events on the launching stream, device-side phase timeline
+    (oxb_set_profile) over the SAME timed region.  full: add e2e, CPU baseline, reference-CUDA comparators."""
+    import ctypes
+
     import torch
-    import torch.distributed as dist
     from oxdna_b200 import capi, lattice
-    from oxdna_b200.remd import ReplicaExchange, TorchComm, geometric_ladder
     from oxdna_b200.sim import Simulation, parse_temperature
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py needs a CUDA device: oxdna_b200 has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    sysm, desc = workload(args.workload)
+    sysm, desc = workload(wl)
     N = len(sysm["pos"])
-    md = args.md_steps
-    n_rep = world  # one replica per GPU: weak scaling
-    # default scaling run: one C2 replica per GPU on a NARROW ladder around the 300 K of the single-GPU workload (geometric 299-301 K:
-    # ~0.3 K spacing at 8 replicas, where 81,920-nt replicas still exchange), so that every rank carries the same work as the N = 1
-    # run; the 290-350 K ladder of config C5 is what --replicas-per-gpu runs (hotter replicas rebuild their lists more often)
-    ladder_K = geometric_ladder(299.0, 301.0, n_rep) if n_rep > 1 else np.array([300.0])
-    T_sim = ladder_K * 0.1 / 300.0
-    myT = f"{ladder_K[rank]:.6f}K"
-    v, L = lattice.maxwell_velocities(N, parse_temperature(myT), 5 + rank)
+    v, L = lattice.maxwell_velocities(N, parse_temperature(T_STR), 5)
     conf = dict(box=sysm["box"], pos=sysm["pos"], a1=sysm["a1"], a3=sysm["a3"], vel=v, L=L)
-    inp = base_input(args, myT)
-    if args.workload == "c4":
+    wargs = argparse.Namespace(**vars(args))
+    wargs.workload = wl
+    inp = base_input(wargs, T_STR)
+    if wl == "c4":
         inp["external_forces_list"] = lattice.mutual_traps(sysm)
     sim = Simulation(inp, sysm, conf, device=local_rank)
     stream = torch.cuda.Stream()
     # the context launches on torch's stream so that torch.cuda.Event brackets exactly our kernels
-    sim.ctx._ck(capi.lib().oxb_set_stream(sim.ctx._h, __import__("ctypes").c_void_p(stream.cuda_stream)))
-    remd = ReplicaExchange([sim], T_sim, TorchComm(torch.device("cuda", local_rank)) if world > 1 else None, seed=42) if world > 1 else None
-
+    sim.ctx._ck(capi.lib().oxb_set_stream(sim.ctx._h, ctypes.c_void_p(stream.cuda_stream)))
+    out = {}
     with torch.cuda.stream(stream):
-        sim.run(args.equil)
+        sim.run(equil)
         flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
-
-        def one_step():
+        sim.ctx.set_profile(True)
+        for _ in range(warmup):
             sim.run(md)
-            if remd is not None:
-                remd.exchange()
-
-        for _ in range(args.warmup):
-            one_step()
-        stats0 = sim.ctx.stats()
-        launches0 = sim.ctx.launch_count()
+        sim.ctx.set_profile(True)  # zeroes the accumulators
+        stats0, launches0 = sim.ctx.stats(), sim.ctx.launch_count()
         torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
         sampler = ClockSampler(local_rank)
-        if rank == 0:
-            sampler.start()
+        sampler.start()
         total_ms = 0.0
-        for _ in range(args.steps):
-            flush.zero_()  # L2 flush between timed iterations (state of C2 is smaller than the 126 MB L2)
+        for _ in range(steps):
+            flush.zero_()  # L2 flush between timed iterations
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            one_step()
+            sim.run(md)
             e1.record(stream)
             e1.synchronize()
             total_ms += e0.elapsed_time(e1)
         torch.cuda.synchronize()
-        clocks = sampler.stop() if rank == 0 else None
-        if world > 1:
-            dist.barrier()
-            t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            total_ms = float(t.item())
+        clocks = sampler.stop()
+        prof = sim.ctx.get_profile()
+        sim.ctx.set_profile(False)
         launches = sim.ctx.launch_count() - launches0
         stats1 = sim.ctx.stats()
-        value = n_rep * N * md * args.steps / (total_ms * 1e-3)
-
-        if rank != 0:
-            if world > 1:
-                dist.barrier()
-                dist.destroy_process_group()
-            return
-
-        # ---- per-kernel roofline figures, measured live with CUDA events on the launching stream
-        t_force = sim.ctx.time_kernel(0, 20)
-        t_integ = sim.ctx.time_kernel(1, 20)
-        t_list = sim.ctx.time_kernel(2, 5)
-        t_sort = sim.ctx.time_kernel(3, 5)
+        n_md = md * steps
+        n_reb = max(stats1["n_list_updates"] - stats0["n_list_updates"], 1)
+        n_sort = max(stats1["n_sorts"] - stats0["n_sorts"], 1)
+        value = N * n_md / (total_ms * 1e-3)
+        step_ms = total_ms / n_md
+        # ---- phase times from the device timeline of the timed region (they add up to it; launch gaps belong to the phase that was open)
+        t_force, t_integ = prof["force"][0] / n_md, prof["integrate"][0] / n_md
+        t_build, t_sort, t_wait = prof["build"][0] / n_reb, prof["sort"][0] / n_sort, prof["wait"][0] / n_reb
+        prof_total = sum(v[0] for v in prof.values())
         ps = pair_statistics(sim, sysm)
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
-        # algorithmic bytes per particle of the force pass: 40 B state read + 32 B F,T write + 8 B per listed unique pair
-        force_bytes = N * (40.0 + 32.0 + 8.0 * ps["listed"])
-        force_gbs = force_bytes / (t_force * 1e-3) / 1e9
+        hbm_peak, peak_src = load_peaks()
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
         flops = N * (FLOP_FAR * ps["listed"] + FLOP_DH * ps["dh"] + FLOP_CONTACT * ps["contact"] + FLOP_BONDED * 1.0)
         if not args.use_edge:
             flops = N * (2 * (FLOP_FAR * ps["listed"] + FLOP_DH * ps["dh"] + FLOP_CONTACT * ps["contact"]) + 2 * FLOP_BONDED)
-        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
-        fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
-        # first_step_mixed: 176 B read + 160 B written per particle, second half-kick fused; + 16 B Fb read in edge mode
+        tf = flops / (t_force * 1e-3) / 1e12
+        # algorithmic bytes (SURVEY 8d): force pass 40 B state read + 32 B F,T write + 8 B per listed unique pair; integrate 336 B (+ 16 B
+        # Debye-Hueckel site force in edge mode); list rebuild 140 B per particle; Hilbert sort 470 B per particle
+        force_bytes = N * (40.0 + 32.0 + 8.0 * ps["listed"])
         integ_bytes = N * (336.0 + (16.0 if args.use_edge else 0.0))
-        integ_gbs = integ_bytes / (t_integ * 1e-3) / 1e9
-        # DRAM bytes of one force pass from the committed ncu --set full capture of the same workload (sum over its kernels)
-        traffic = {"c2": NCU_FORCE_PASS_DRAM_BYTES_C2, "c4": NCU_FORCE_PASS_DRAM_BYTES_C4}.get(args.workload) if args.use_edge else None
-        step_ms = total_ms / (args.steps * md)
-        rebuild_every = md * args.steps / max(stats1["n_list_updates"] - stats0["n_list_updates"], 1)
+        gbs = lambda b, ms: b / (ms * 1e-3) / 1e9 if ms > 0 else None
+        ncu = NCU_DRAM_BYTES.get(wl, {}) if args.use_edge else {}
+        out.update({
+            "value": value, "ms_per_step": total_ms / steps, "gpu_launches": int(launches), "clocks": clocks, "N": N, "desc": desc, "pairs_per_particle": ps,
+            "step_ms": step_ms, "list_rebuild_every_md_steps": n_md / n_reb,
+            "roofline": {"kernel": "force pass (Debye-Hueckel + near edges + HB/cross stacking + coaxial + bonded)" if args.use_edge else "forces (particle-centric)",
+                         "bound": "fp32", "achieved": tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tf / fp32_peak, "traffic": ncu.get("force"),
+                         "model": "SURVEY 8(d) algorithmic FLOP per pair class x measured pair counts", "sm_mhz": sm_mhz, "ms": t_force,
+                         "share_of_step": t_force / step_ms,
+                         "hbm": {"achieved": gbs(force_bytes, t_force), "peak": hbm_peak, "unit": "GB/s", "frac": gbs(force_bytes, t_force) / hbm_peak,
+                                 "algorithmic_bytes": force_bytes, "peak_source": peak_src},
+                         "timing": "device-side %globaltimer phase timeline inside the timed region (oxb_set_profile)"},
+            "roofline_integrate": {"kernel": "k_integrate: second half-kick + thermostat + first half-kick/drift/rotate + staleness", "bound": "hbm",
+                                   "achieved": gbs(integ_bytes, t_integ), "peak": hbm_peak, "unit": "GB/s", "frac": gbs(integ_bytes, t_integ) / hbm_peak,
+                                   "traffic": ncu.get("integrate"), "ms": t_integ, "share_of_step": t_integ / step_ms, "peak_source": peak_src},
+            "roofline_list": {"kernel": "list rebuild (binning + 27-cell scan + DH matrix + edge list)", "bound": "hbm", "achieved": gbs(N * 140.0, t_build),
+                              "peak": hbm_peak, "unit": "GB/s", "frac": gbs(N * 140.0, t_build) / hbm_peak, "ms": t_build, "per_md_step_ms": t_build * n_reb / n_md},
+            "roofline_sort": {"kernel": "Hilbert re-sort (keys + radix sort + one gather pass)", "bound": "hbm", "achieved": gbs(N * 470.0, t_sort),
+                              "peak": hbm_peak, "unit": "GB/s", "frac": gbs(N * 470.0, t_sort) / hbm_peak if t_sort > 0 else None, "ms": t_sort,
+                              "per_md_step_ms": t_sort * n_sort / n_md},
+            "kernels_ms": {"force_pass": t_force, "integrate": t_integ, "list_build_per_rebuild": t_build, "sort_per_sort": t_sort,
+                           "halt_and_host_wait_per_rebuild": t_wait, "other_per_md_step": prof["other"][0] / n_md, "md_step_mean": step_ms,
+                           "sum_of_phases_per_md_step": prof_total / n_md, "rebuilds": n_reb, "sorts": n_sort,
+                           "source": "device-side phase timeline of the timed region; phases add up to md_step_mean"},
+        })
+        if not full:
+            if args.extras_ref_cuda:
+                try:
+                    out["reference_cuda"] = run_ref_cuda(sysm, wl, 5000, 15000, sim.ctx.get_state(), quick=True)
+                except Exception as e:  # pragma: no cover
+                    out["reference_cuda"] = {"value": None, "unavailable": repr(e)[-300:]}
+            sim.close()
+            return out
 
         # ---- end to end through the public API with host buffers (OxpyManager.run semantics: H2D, steps, D2H)
         st = sim.ctx.get_state()
         pin = {k: torch.from_numpy(st[k]).pin_memory().numpy() for k in ("pos", "a1", "a3", "vel", "L")}
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        e2e_steps = max(1, min(args.steps, 3))
+        e2e_steps = max(1, min(steps, 3))
         for _ in range(e2e_steps):
             sim.ctx.set_state(pin["pos"], pin["a1"], pin["a3"], pin["vel"], pin["L"])
             sim.run(md)
@@ -388,63 +408,153 @@ def ours(args):
             U, K = sim.ctx.energy()
         torch.cuda.synchronize()
         e2e_s = (time.perf_counter() - t0) / e2e_steps
-        e2e = {"value": N * md / e2e_s, "unit": "particle-steps/s", "h2d_bytes_per_step": N * 172, "d2h_bytes_per_step": N * 144 + 16,
-               "api": "set_state (H2D) + run(md_steps) + get_state + energy (D2H), wall clock, n_gpus=1 leg", "U_per_particle": U / N, "K_per_particle": K / N}
+        out["e2e"] = {"value": N * md / e2e_s, "unit": "particle-steps/s", "h2d_bytes_per_step": N * 120, "d2h_bytes_per_step": N * 120 + 16,
+                      "api": "set_state (H2D from pinned host buffers) + run(md_steps) + get_state + energy (D2H), host wall clock", "U_per_particle": U / N,
+                      "K_per_particle": K / N}
+        state = sim.ctx.get_state()
+        sim.close()
+        del flush
+        torch.cuda.empty_cache()
 
-        # ---- CPU baseline on a bounded sample of the same workload (rank 0, N = 1 only)
-        cpu = None
-        if world == 1 and not args.no_cpu_baseline:
-            try:
-                cval, kind, secs = run_cpu(sysm, args.cpu_md_steps, 0, 1, 1, args.workload, sim.ctx.get_state())
-                cpu = {"value": cval, "unit": "particle-steps/s", "cores": 1, "kind": kind,
-                       "sample": f"{args.cpu_md_steps} MD steps of the same {N}-nt system on one host core ({secs:.1f} s), host has {host_cores()} cores"}
-            except Exception as e:  # pragma: no cover
-                cpu = {"value": None, "unit": "particle-steps/s", "cores": 1, "kind": "port", "sample": "failed: " + repr(e)}
-
-        ref_cuda = None
-        if world == 1 and not args.no_ref_cuda:
-            try:
-                a, b = args.ref_cuda_steps
-                ref_cuda = run_ref_cuda(sysm, args.workload, a, b, sim.ctx.get_state())
-            except Exception as e:  # pragma: no cover
-                ref_cuda = {"value": None, "unavailable": repr(e)[-300:]}
-
-        line = {"metric": "particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 forces / f64 integration (mixed)",
-                "data": "synthetic",
-                "config": {"workload": desc, "md_steps_per_step": md, "replicas": n_rep, "parallelism": (f"1 replica per GPU, temperatures geometric {float(ladder_K[0]):.1f}-{float(ladder_K[-1]):.1f} K, replica-exchange attempt (NCCL all_gather of "
-                                           "2 doubles per replica) every bench step") if world > 1 else "single system",
-                           "use_edge": int(args.use_edge), "CUDA_sort_every": args.sort_every, "thermostat": "brownian (newtonian_steps 103)", "dt": DT, "verlet_skin": 0.05,
-                           "equilibration_md_steps": args.equil, "l2": "256 MiB buffer written between timed iterations (L2 flush)",
-                           "ns_per_day": 86400.0 / (step_ms * 1e-3) * DT * 3.03e-3, "md_steps_per_s": 1e3 / step_ms, "list_rebuild_every_md_steps": rebuild_every,
-                           "pairs_per_particle": ps},
-                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-                "roofline": {"kernel": "forces (edge non-bonded + bonded)" if args.use_edge else "forces (particle-centric)", "bound": "hbm", "achieved": force_gbs, "peak": hbm_peak,
-                             "unit": "GB/s", "frac": force_gbs / hbm_peak, "traffic": traffic,
-                             "traffic_source": "profiles/summary_r01n.txt: dram__bytes_read.sum + dram__bytes_write.sum summed over the kernels of one force pass", "peak_source": peak_src, "ms": t_force,
-                             "share_of_step": t_force / step_ms,
-                             "note": "the force kernel is FP32/SFU-bound, not HBM-bound (see roofline_fp32); HBM figure given as the contract asks"},
-                "roofline_fp32": {"achieved_tflops": flops / (t_force * 1e-3) / 1e12, "peak_tflops": fp32_peak, "frac": flops / (t_force * 1e-3) / 1e12 / fp32_peak,
-                                  "model": "SURVEY 8(d) algorithmic FLOP per pair class", "sm_mhz": sm_mhz},
-                "roofline_integrate": {"kernel": "fused second half-kick + thermostat + first half-kick/drift/rotate", "bound": "hbm", "achieved": integ_gbs, "peak": hbm_peak,
-                                       "unit": "GB/s", "frac": integ_gbs / hbm_peak, "ms": t_integ, "share_of_step": t_integ / step_ms},
-                "kernels_ms": {"forces": t_force, "integrate": t_integ, "rebuild_incl_sort": t_list, "sort_only": t_sort, "md_step_mean": step_ms,
-                               "rebuild_amortised": t_list / rebuild_every},
-                "cpu_baseline": cpu, "reference_cuda": ref_cuda}
-        print(json.dumps(line), file=_REAL_STDOUT, flush=True)
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
+    # ---- CPU baseline on a bounded sample of the same workload
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            cmd = args.cpu_md_steps or (6 if wl == "c4" else 40)
+            cval, kind, secs = run_cpu(sysm, cmd, 0, 1, 1, wl, state)
+            cpu = {"value": cval, "unit": "particle-steps/s", "cores": 1, "kind": kind,
+                   "sample": f"{cmd} MD steps of the same {N}-nt system on one host core ({secs:.1f} s), host has {host_cores()} cores"}
+        except Exception as e:  # pragma: no cover
+            cpu = {"value": None, "unit": "particle-steps/s", "cores": 1, "kind": "port", "sample": "failed: " + repr(e)}
+    out["cpu_baseline"] = cpu
+    ref_cuda = None
+    if not args.no_ref_cuda:
+        try:
+            a, b = args.ref_cuda_steps or ([3000, 9000] if wl == "c4" else [10000, 20000])
+            ref_cuda = run_ref_cuda(sysm, wl, a, b, state)
+        except Exception as e:  # pragma: no cover
+            ref_cuda = {"value": None, "unavailable": repr(e)[-300:]}
+    out["reference_cuda"] = ref_cuda
+    return out
 
 
-def ours_ensemble(args):
-    """Config C5: `--replicas-per-gpu` temperature replicas of the workload on every GPU (64 in total at 8 x 8), advanced
-    concurrently (one host thread and one set of CUDA streams per replica), one exchange attempt per bench step."""
+def measure_ensemble(args, R_total, steps, warmup, equil, md, world, rank, local_rank, dist=None, e2e=True):
+    """Config C5: R_total temperature replicas of C2 (geometric 290-350 K), R_total / world per GPU held as replica BATCHES (one context,
+    one launch per kernel for all local replicas), one exchange attempt (NCCL all_gather of 2 doubles per replica) per bench step."""
     import torch
-    import torch.distributed as dist
     from oxdna_b200 import lattice
     from oxdna_b200.remd import ReplicaExchange, TorchComm, geometric_ladder
-    from oxdna_b200.sim import Simulation, parse_temperature
+    from oxdna_b200.sim import make_batches, parse_temperature
+
+    sysm, desc = workload("c2")
+    N = len(sysm["pos"])
+    nl = R_total // world
+    ladder_K = geometric_ladder(290.0, 350.0, R_total)
+    ladder = ladder_K * 0.1 / 300.0
+    confs = []
+    for k in range(nl):
+        g = rank * nl + k
+        v, L = lattice.maxwell_velocities(N, float(ladder[g]), 5 + g)
+        confs.append(dict(box=sysm["box"], pos=sysm["pos"], a1=sysm["a1"], a3=sysm["a3"], vel=v, L=L))
+    wargs = argparse.Namespace(**vars(args))
+    wargs.workload = "c2"
+    inp = base_input(wargs, T_STR)
+    inp.pop("T")
+    batches = make_batches(inp, sysm, confs, ladder[rank * nl:(rank + 1) * nl], device=local_rank, ladder_max=float(ladder[-1]))
+    comm = TorchComm(torch.device("cuda", local_rank)) if world > 1 else None
+    remd = ReplicaExchange(batches, ladder, comm, seed=42)
+    remd.advance(equil)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    for _ in range(warmup):
+        remd.advance(md)
+        remd.exchange()
+    launches0 = sum(b.ctx.launch_count() for b in batches)
+    stats0 = [b.ctx.stats() for b in batches]
+    for k in remd.timers:
+        remd.timers[k] = 0.0
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    total_ms = 0.0
+    for _ in range(steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        remd.advance(md)
+        remd.exchange()
+        torch.cuda.synchronize()  # the batches run on their own streams: bracket with device-wide synchronisation
+        e1.record()
+        e1.synchronize()
+        total_ms += e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    my_ms = total_ms
+    timers = dict(remd.timers)
+    launches = sum(b.ctx.launch_count() for b in batches) - launches0
+    stats1 = [b.ctx.stats() for b in batches]
+    rebuilds = sum(s1["n_list_updates"] - s0["n_list_updates"] for s0, s1 in zip(stats0, stats1))
+    # ---- end to end at N GPUs: every bench step uploads the local replicas' states from pinned host memory, advances, exchanges, reads back
+    e2e_ms = None
+    if e2e:
+        pins = []
+        for b in batches:
+            st = b.ctx.get_state()
+            pins.append({k: torch.from_numpy(st[k]).pin_memory().numpy() for k in ("pos", "a1", "a3", "vel", "L")})
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        n_e2e = max(1, min(steps, 3))
+        for _ in range(n_e2e):
+            for b, pin in zip(batches, pins):
+                b.ctx.set_state(pin["pos"], pin["a1"], pin["a3"], pin["vel"], pin["L"])
+            remd.advance(md)
+            remd.exchange()
+            for b, pin in zip(batches, pins):
+                b.ctx.get_state(out=pin)
+        torch.cuda.synchronize()
+        e2e_ms = 1e3 * (time.perf_counter() - t0) / n_e2e
+    per_rank = [dict(rank=rank, device_ms_per_step=my_ms / steps, md_ms=1e3 * timers["md"] / steps, exchange_ms=1e3 * (timers["energy"] + timers["update"]) / steps,
+                     host_wait_ms=1e3 * timers["comm"] / steps, list_rebuilds_per_replica_batch=rebuilds / max(len(batches), 1) / steps)]
+    if world > 1:
+        t = torch.tensor([total_ms, e2e_ms or 0.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_max = float(t[0].item()), float(t[1].item())
+        e2e_ms = e2e_max if e2e else None
+        gathered = [None] * world
+        dist.all_gather_object(gathered, per_rank[0])
+        per_rank = gathered
+        la = torch.tensor([launches], dtype=torch.float64, device="cuda")
+        dist.all_reduce(la)
+        launches = int(la.item())
+    value = R_total * N * md * steps / (total_ms * 1e-3)
+    res = {"value": value, "ms_per_step": total_ms / steps, "gpu_launches": int(launches), "clocks": clocks, "per_rank": per_rank,
+           "config": {"workload": "C5: replica-exchange MD, %d temperature replicas (geometric 290-350 K) of " % R_total + desc, "md_steps_per_step": md,
+                      "replicas": R_total, "replicas_per_gpu": nl, "batches_per_gpu": len(batches),
+                      "parallelism": f"{nl} replicas per GPU as {len(batches)} replica batch(es): one context, one launch per kernel for all replicas of a batch "
+                                     "(replica = grid offset, per-replica constant table); replica exchange (temperature swap) every bench step, NCCL all_gather of "
+                                     "2 doubles per replica; no data-path collective",
+                      "ladder_K": [float(ladder_K[0]), float(ladder_K[-1])], "use_edge": int(args.use_edge), "CUDA_sort_every": args.sort_every,
+                      "thermostat": "brownian (newtonian_steps 103)", "dt": DT, "verlet_skin": 0.05, "equilibration_md_steps": equil,
+                      "l2": "256 MiB buffer written between timed iterations (L2 flush)", "exchange_acceptance": float(np.mean(remd.rates()))}}
+    if e2e_ms:
+        res["e2e"] = {"value": R_total * N * md / (e2e_ms * 1e-3), "unit": "particle-steps/s", "h2d_bytes_per_step": R_total * N * 120,
+                      "d2h_bytes_per_step": R_total * N * 120 + 16 * R_total, "n_gpus": world,
+                      "api": "per bench step on every rank: set_state of the local replica batches (H2D from pinned host buffers) + run(md_steps) + exchange "
+                             "(energies D2H, NCCL all_gather) + get_state (D2H); host wall clock, max over ranks"}
+    for b in batches:
+        b.close()
+    del flush
+    torch.cuda.empty_cache()
+    return res
+
+
+def ours(args):
+    import torch
+    import torch.distributed as dist
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -454,64 +564,54 @@ def ours_ensemble(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    sysm, desc = workload(args.workload)
-    N, md, nl = len(sysm["pos"]), args.md_steps, args.replicas_per_gpu
-    R = world * nl
-    ladder_K = geometric_ladder(290.0, 350.0, R)
-    sims = []
-    for k in range(nl):
-        g = rank * nl + k
-        T = f"{ladder_K[g]:.6f}K"
-        v, L = lattice.maxwell_velocities(N, parse_temperature(T), 5 + g)
-        sims.append(Simulation(base_input(args, T), sysm, dict(box=sysm["box"], pos=sysm["pos"], a1=sysm["a1"], a3=sysm["a3"], vel=v, L=L), device=local_rank))
-    remd = ReplicaExchange(sims, ladder_K * 0.1 / 300.0, TorchComm(torch.device("cuda", local_rank)) if world > 1 else None, seed=42,
-                           concurrent=not args.sequential_replicas)
-    remd.advance(args.equil)
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
-    for _ in range(args.warmup):
-        remd.advance(md)
-        remd.exchange()
-    launches0 = sum(s.ctx.launch_count() for s in sims)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    total_ms = 0.0
-    for _ in range(args.steps):
-        flush.zero_()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        remd.advance(md)
-        remd.exchange()
-        torch.cuda.synchronize()  # the replicas run on their own streams: bracket with device-wide synchronisation
-        e1.record()
-        e1.synchronize()
-        total_ms += e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        dist.barrier()
-        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-    launches = sum(s.ctx.launch_count() for s in sims) - launches0
-    if rank == 0:
-        value = R * N * md * args.steps / (total_ms * 1e-3)
-        line = {"metric": "particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32 forces / f64 integration (mixed)", "data": "synthetic",
-                "config": {"workload": "C5-style ensemble: " + desc, "md_steps_per_step": md, "replicas": R, "replicas_per_gpu": nl,
-                           "parallelism": f"{nl} replicas per GPU advanced {'sequentially' if args.sequential_replicas else 'concurrently (one host thread + CUDA streams each)'}, "
-                                          "replica exchange (temperature swap) every bench step, NCCL all_gather of 2 doubles per replica",
-                           "ladder_K": [float(ladder_K[0]), float(ladder_K[-1])], "use_edge": int(args.use_edge), "CUDA_sort_every": args.sort_every,
-                           "l2": "256 MiB buffer written between timed iterations", "exchange_acceptance": float(np.mean(remd.rates()))},
-                "gpu_launches": int(launches), "clocks": clocks, "e2e": None, "roofline": None, "cpu_baseline": None}
-        print(json.dumps(line), file=_REAL_STDOUT, flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    base = {"metric": "particle-steps/s", "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
+            "vs_baseline": None, "dtype": "f32 forces / f64 integration (mixed)", "data": "synthetic"}
+    if world > 1 or args.workload == "c5":
+        R = args.replicas or 64
+        if R % world:
+            raise ValueError(f"{R} replicas do not divide over {world} GPUs")
+        r = measure_ensemble(args, R, args.steps, args.warmup, args.equil, args.md_steps, world, rank, local_rank, dist)
+        if rank == 0:
+            line = dict(base, value=r["value"], ms_per_step=r["ms_per_step"], scaling="strong", config=r["config"], gpu_launches=r["gpu_launches"], clocks=r["clocks"],
+                        e2e=r.get("e2e"), per_rank=r["per_rank"], roofline=None, cpu_baseline=None,
+                        note="strong scaling: the 64 replicas of C5 are divided over the GPUs; the single-GPU C5 figure (64 replicas on one GPU) is extras.c5_one_gpu "
+                             "of the --gpus 1 line, whose headline is C4")
+            print(json.dumps(line), file=_REAL_STDOUT, flush=True)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+    wl = args.workload or "c4"
+    m = measure_single(args, wl, args.steps, args.warmup, args.equil, args.md_steps, True, local_rank)
+    ps, step_ms = m.pop("pairs_per_particle"), m.pop("step_ms")
+    line = dict(base, value=m.pop("value"), ms_per_step=m.pop("ms_per_step"), scaling="weak",
+                config={"workload": m.pop("desc"), "md_steps_per_step": args.md_steps, "replicas": 1, "parallelism": "single system (a single system does not shard: replicas only)",
+                        "use_edge": int(args.use_edge), "CUDA_sort_every": args.sort_every, "thermostat": "brownian (newtonian_steps 103)", "dt": DT, "verlet_skin": 0.05,
+                        "equilibration_md_steps": args.equil, "l2": "256 MiB buffer written between timed iterations (L2 flush)",
+                        "ns_per_day": 86400.0 / (step_ms * 1e-3) * DT * 3.03e-3, "md_steps_per_s": 1e3 / step_ms,
+                        "list_rebuild_every_md_steps": m.pop("list_rebuild_every_md_steps"), "pairs_per_particle": ps})
+    m.pop("N")
+    line.update(m)
+    # ---- the other BASELINE configs, bounded: C2 and C3 (single systems) and C5 on ONE GPU (64 replicas, two batches)
+    extras = {}
+    if not args.no_extras and wl == "c4":
+        for name in ("c2", "c3"):
+            try:
+                x = measure_single(args, name, 5, 3, 10000, 1000, False, local_rank)
+                extras[name] = {"workload": x["desc"], "value": x["value"], "unit": "particle-steps/s", "md_step_ms": x["step_ms"], "kernels_ms": x["kernels_ms"],
+                                "roofline_fp32_frac": x["roofline"]["frac"], "list_rebuild_every_md_steps": x["list_rebuild_every_md_steps"],
+                                "reference_cuda": x.get("reference_cuda")}
+            except Exception as e:  # pragma: no cover
+                extras[name] = {"error": repr(e)[-300:]}
+        try:
+            x = measure_ensemble(args, args.replicas or 64, 3, 2, 3000, 1000, 1, 0, local_rank, None, e2e=False)
+            extras["c5_one_gpu"] = {"workload": x["config"]["workload"], "value": x["value"], "unit": "particle-steps/s", "ms_per_step": x["ms_per_step"],
+                                    "batches": x["config"]["batches_per_gpu"], "per_rank": x["per_rank"], "exchange_acceptance": x["config"]["exchange_acceptance"],
+                                    "note": "the strong-scaling base of the --gpus N runs (64 replicas on one GPU)"}
+        except Exception as e:  # pragma: no cover
+            extras["c5_one_gpu"] = {"error": repr(e)[-300:]}
+    line["extras"] = extras
+    print(json.dumps(line), file=_REAL_STDOUT, flush=True)
 
 
 def main():
@@ -520,19 +620,20 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cuda"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "small"])
+    ap.add_argument("--workload", default=None, choices=["c2", "c3", "c4", "c5", "small"], help="default: c4 on one GPU, c5 (replica ensemble) on several")
     ap.add_argument("--md-steps", type=int, default=1000, help="MD steps per bench step")
     ap.add_argument("--equil", type=int, default=10000, help="untimed equilibration MD steps")
     ap.add_argument("--use-edge", type=int, default=1)
     ap.add_argument("--sort-every", type=int, default=1)
-    ap.add_argument("--ref-md-steps", type=int, default=4, help="MD steps per bench step of the CPU reference arm")
+    ap.add_argument("--replicas", type=int, default=0, help="C5: total number of temperature replicas (default 64)")
+    ap.add_argument("--ref-md-steps", type=int, default=0, help="MD steps per bench step of the CPU reference arm (default: 1 at C4, 4 otherwise)")
     ap.add_argument("--ref-procs", type=int, default=0)
-    ap.add_argument("--cpu-md-steps", type=int, default=40)
-    ap.add_argument("--replicas-per-gpu", type=int, default=1, help="> 1: C5-style replica ensemble (64 replicas = 8 per GPU on 8 GPUs)")
-    ap.add_argument("--sequential-replicas", action="store_true", help="ensemble mode: advance the local replicas one after the other (comparison)")
+    ap.add_argument("--cpu-md-steps", type=int, default=0, help="MD steps of the one-core CPU baseline sample (default: 6 at C4, 40 otherwise)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-ref-cuda", action="store_true", help="skip the reference-CUDA-backend comparator leg")
-    ap.add_argument("--ref-cuda-steps", type=int, nargs=2, default=[10000, 20000], help="steps=A and steps=B runs of the reference CLI")
+    ap.add_argument("--no-ref-cuda", action="store_true", help="skip the reference-CUDA-backend comparator legs")
+    ap.add_argument("--no-extras", action="store_true", help="N = 1: skip the bounded C2 / C3 / C5-on-one-GPU legs")
+    ap.add_argument("--extras-ref-cuda", type=int, default=1, help="reference-CUDA comparator (one variant) for the C2 / C3 extras")
+    ap.add_argument("--ref-cuda-steps", type=int, nargs=2, default=None, help="steps=A and steps=B runs of the reference CLI")
     args = ap.parse_args()
     # the contract is ONE JSON line on stdout: libraries that print banners there (NCCL's version line at communicator creation, torchrun
     # notices) are sent to stderr for the duration of the run; json lines go to the saved descriptor
@@ -546,18 +647,19 @@ def main():
         if int(os.environ.get("RANK", "0")) == 0:
             from oxdna_b200 import lattice
             from oxdna_b200.sim import Simulation, parse_temperature
-            sysm, desc = workload(args.workload)
-            a, b = args.ref_cuda_steps
+            wl = args.workload or "c4"
+            sysm, desc = workload(wl)
+            a, b = args.ref_cuda_steps or [10000, 20000]
             v, L = lattice.maxwell_velocities(len(sysm["pos"]), parse_temperature(T_STR), 5)
-            sim = Simulation(base_input(args), sysm, dict(box=sysm["box"], pos=sysm["pos"], a1=sysm["a1"], a3=sysm["a3"], vel=v, L=L))
+            wargs = argparse.Namespace(**vars(args))
+            wargs.workload = wl
+            sim = Simulation(base_input(wargs), sysm, dict(box=sysm["box"], pos=sysm["pos"], a1=sysm["a1"], a3=sysm["a3"], vel=v, L=L))
             sim.run(args.equil)
             state = sim.ctx.get_state()
             sim.close()
-            r = run_ref_cuda(sysm, args.workload, a, b, state)
+            r = run_ref_cuda(sysm, wl, a, b, state)
             print(json.dumps({"impl": "reference-cuda", "metric": "particle-steps/s", "value": r.get("value"), "unit": "particle-steps/s", "n_gpus": 1,
                               "higher_is_better": True, "config": {"workload": desc}, "reference_cuda": r}), file=_REAL_STDOUT, flush=True)
-    elif args.replicas_per_gpu > 1:
-        ours_ensemble(args)
     else:
         ours(args)
 

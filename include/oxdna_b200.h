@@ -168,8 +168,22 @@ typedef struct {
 	int iaux;
 } oxb_ext_force;
 
-/* sizeof() of the ABI structures as compiled into the library (0: oxb_dna2_params, 1: oxb_rna2_params, 2: oxb_ext_force), so that
- * foreign-language bindings can assert their mirrors */
+/* ---- replica batching (examples/OXPY_REMD/remd.py runs one process + one GPU context per temperature replica).
+ * A context can hold R independent replicas of one system as ONE batch: particles [r * N/R, (r + 1) * N/R) of the context belong to
+ * replica r, every kernel of the step is launched once for all of them (the replica is a grid offset: slots stay replica-contiguous,
+ * the cell table and the Hilbert key carry the replica index, so no pair ever crosses replicas).  Replicas share box, topology and
+ * every temperature-independent constant; what depends on the temperature lives in a device table of one oxb_replica_consts per
+ * replica that the kernels index by replica -- a temperature swap rewrites 2 table rows and touches neither kernel arguments nor
+ * captured graphs (the reference re-initialises interaction and thermostat and re-uploads constant memory, remd.py:104-147). */
+typedef struct {
+	float stck_eps[25], stck_shift[25];                           /* stacking strength f1(eps(T)), DNAInteraction.cpp:329-375 */
+	float dh_minus_kappa, dh_prefactor, dh_rhigh, dh_rc, dh_b;    /* Debye-Hueckel, DNA2Interaction.cpp:99-149 */
+	float rcut2;                                                  /* squared interaction cutoff of this replica's Hamiltonian */
+	float th_a, th_b, th_c, th_d;                                 /* thermostat constants, meaning as in oxb_set_thermostat */
+} oxb_replica_consts;
+
+/* sizeof() of the ABI structures as compiled into the library (0: oxb_dna2_params, 1: oxb_rna2_params, 2: oxb_ext_force,
+ * 3: oxb_replica_consts), so that foreign-language bindings can assert their mirrors */
 int oxb_sizeof(int which);
 
 /* ---- life cycle.  Replaces MD_CUDABackend / CUDAMixedBackend construction + init_cuda
@@ -184,6 +198,19 @@ int oxb_set_box(oxb_ctx *ctx, const double box[3]);                             
 int oxb_set_topology(oxb_ctx *ctx, const int *btype, const int *n3, const int *n5, const int *strand);
 int oxb_set_model_dna2(oxb_ctx *ctx, const oxb_dna2_params *P, double rcut);                  /* CUDADNAInteraction::cuda_init */
 int oxb_set_model_rna2(oxb_ctx *ctx, const oxb_rna2_params *P, double rcut);                  /* CUDARNAInteraction::cuda_init */
+/* Replica batching: declare that the N particles are n_replicas copies of one N / n_replicas-particle system (topology, state and
+ * external forces are given for all N particles, replica after replica; bonds must not cross replicas).  The model set with
+ * oxb_set_model_* fixes the list radii and must be the one of the HOTTEST temperature any replica will visit (largest Debye-Hueckel
+ * range); oxb_set_replica_consts installs the per-replica temperature-dependent constants (n = n_replicas rows; oxb_replica_consts_dna2 /
+ * _rna2 fill a row from a parameter block and the thermostat constants a..d of oxb_set_thermostat at that temperature).
+ * oxb_replica_energies: potential energy of every replica for the current table (one force pass if the forces are not current, then
+ * a segmented reduction), what OxpyManager::system_energy() returns per process in the reference's REMD driver.
+ * Not available with the Bussi thermostat (one global kinetic energy) and oxb_energy_split. */
+int oxb_set_replicas(oxb_ctx *ctx, int n_replicas);
+int oxb_set_replica_consts(oxb_ctx *ctx, int n, const oxb_replica_consts *rows);
+int oxb_replica_energies(oxb_ctx *ctx, double *U);
+void oxb_replica_consts_dna2(const oxb_dna2_params *P, double th_a, double th_b, double th_c, double th_d, oxb_replica_consts *out);
+void oxb_replica_consts_rna2(const oxb_rna2_params *P, double th_a, double th_b, double th_c, double th_d, oxb_replica_consts *out);
 /* CUDASimpleVerletList::get_settings/init (src/CUDA/Lists/CUDASimpleVerletList.cu:47-56,165-202) + CUDA_sort_every, use_edge */
 int oxb_set_lists(oxb_ctx *ctx, double verlet_skin, int use_edge, int sort_every, double max_density_multiplier);
 int oxb_set_dt(oxb_ctx *ctx, double dt);
@@ -282,6 +309,16 @@ long long oxb_launch_count(const oxb_ctx *ctx);
  * the context's stream; returns milliseconds per launch.  which: 0 = non-bonded+bonded force pass, 1 = integrate (first
  * step), 2 = list rebuild, 3 = sort */
 int oxb_time_kernel(oxb_ctx *ctx, int which, int reps, float *ms_per_launch);
+/* Timeline of the hot loop measured INSIDE oxb_run (graph-launched batches included): while enabled, the first thread of the kernel
+ * that opens each phase of the step stamps %globaltimer on the device and the time since the previous stamp is charged to the phase
+ * that was open, so the phases add up to the device time of the run (launch gaps and host-synchronisation bubbles included).
+ * Phases (OXB_PROF_*): 0 other, 1 force pass, 2 integrate, 3 halted launches + host wait before a rebuild, 4 Hilbert sort, 5 list build.
+ * Replaces the reference's TimingManager around sim_step (src/Utilities/Timings.cpp, MD_CUDABackend.cu:567-619), which needs a
+ * cudaDeviceSynchronize per timer.  oxb_set_profile zeroes the accumulators; oxb_get_profile returns milliseconds and the number of
+ * times each phase was entered (6 values each). */
+#define OXB_PROF_NPHASES 6
+int oxb_set_profile(oxb_ctx *ctx, int enable);
+int oxb_get_profile(oxb_ctx *ctx, double *ms, long long *entries);
 
 #ifdef __cplusplus
 }

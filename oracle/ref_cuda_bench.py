@@ -16,6 +16,8 @@ import time
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 BIN = os.path.join(_HERE, "_ref", "oxDNA_cuda")
+# same objects with Timings.cpp compiled -DNOCUDA: no cudaDeviceSynchronize per timer (src/Utilities/Timings.cpp:15-19,53-61)
+BIN_NOSYNC = os.path.join(_HERE, "_ref", "oxDNA_cuda_nosync")
 
 
 def available():
@@ -67,14 +69,14 @@ def write_forces_file(path, forces):
             f.write("}\n")
 
 
-def _run(d, top, conf, steps, use_edge, sort_every, T, salt, dt, ext_path, model_keys=None):
+def _run(d, top, conf, steps, use_edge, sort_every, T, salt, dt, ext_path, model_keys=None, binary=BIN):
     inp = os.path.join(d, f"input_{steps}")
     with open(inp, "w") as f:
         model = "\n".join(f"{k} = {v}" for k, v in (model_keys or {"interaction_type": "DNA2"}).items())
         f.write(TEMPLATE.format(model=model, salt=salt, T=T, dt=dt, steps=steps, sort_every=sort_every, use_edge=use_edge, top=top, conf=conf, d=d,
                                 ext=1 if ext_path else 0, extfile=f"external_forces_file = {ext_path}" if ext_path else ""))
     t0 = time.perf_counter()
-    p = subprocess.run([BIN, inp], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    p = subprocess.run([binary, inp], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     t1 = time.perf_counter()
     if p.returncode != 0:
         raise RuntimeError("reference CUDA backend failed:\n" + p.stdout[-2000:])
@@ -89,7 +91,7 @@ def _run(d, top, conf, steps, use_edge, sort_every, T, salt, dt, ext_path, model
     return (float(m.group(1)) if m else t1 - t0), ("SimBackend timer" if m else "wall clock"), (int(u.group(1)) if u else None)
 
 
-def time_reference_cuda(top, conf, N, steps_a, steps_b, variants, T="300K", salt=0.5, dt=0.003, ext_forces=None, model_keys=None):
+def time_reference_cuda(top, conf, N, steps_a, steps_b, variants, T="300K", salt=0.5, dt=0.003, ext_forces=None, model_keys=None, binary=BIN):
     """variants: list of (use_edge, CUDA_sort_every).  Returns dict(best=..., runs=[...]) in particle-steps/s."""
     d = tempfile.mkdtemp(prefix="refcuda_")
     ext_path = None
@@ -99,8 +101,8 @@ def time_reference_cuda(top, conf, N, steps_a, steps_b, variants, T="300K", salt
     runs = []
     for (use_edge, sort_every) in variants:
         try:
-            ta, how, ua = _run(d, top, conf, steps_a, use_edge, sort_every, T, salt, dt, ext_path, model_keys)
-            tb, how, ub = _run(d, top, conf, steps_b, use_edge, sort_every, T, salt, dt, ext_path, model_keys)
+            ta, how, ua = _run(d, top, conf, steps_a, use_edge, sort_every, T, salt, dt, ext_path, model_keys, binary)
+            tb, how, ub = _run(d, top, conf, steps_b, use_edge, sort_every, T, salt, dt, ext_path, model_keys, binary)
             val = N * (steps_b - steps_a) / max(tb - ta, 1e-9)
             runs.append(dict(use_edge=use_edge, CUDA_sort_every=sort_every, value=val, ms_per_md_step=1e3 * (tb - ta) / (steps_b - steps_a),
                              loop_s=[ta, tb], clock=how,
@@ -111,4 +113,4 @@ def time_reference_cuda(top, conf, N, steps_a, steps_b, variants, T="300K", salt
     best = max(ok, key=lambda r: r["value"]) if ok else None
     return dict(best=best, runs=runs, unit="particle-steps/s",
                 method=f"stock CLI; difference of the reference's own 'Total Running Time' (SimBackend timer: simulation loop only) between a steps={steps_b} and a "
-                       f"steps={steps_a} run, i.e. MD steps {steps_a}..{steps_b} after equilibration; timers on, default threads_per_block")
+                       f"steps={steps_a} run, i.e. MD steps {steps_a}..{steps_b} after equilibration; " + ("timers WITHOUT device synchronisation (Timings.cpp -DNOCUDA)" if binary == BIN_NOSYNC else "timers on (a cudaDeviceSynchronize each), as users run it") + ", default threads_per_block")

@@ -71,6 +71,12 @@ class RNA2Params(C.Structure):
     )
 
 
+class ReplicaConsts(C.Structure):
+    """oxb_replica_consts: the temperature-dependent constants of one replica of a batch"""
+    _fields_ = ([("stck_eps", C.c_float * 25), ("stck_shift", C.c_float * 25)]
+                + [(n, C.c_float) for n in "dh_minus_kappa dh_prefactor dh_rhigh dh_rc dh_b rcut2 th_a th_b th_c th_d".split()])
+
+
 class ExtForce(C.Structure):
     _fields_ = [("type", C.c_int), ("particle", C.c_int), ("ref", C.c_int), ("pbc", C.c_int)] + [
         (n, C.c_double) for n in "stiff r0 rate stiff_rate F0".split()] + [("dir", C.c_double * 3), ("pos0", C.c_double * 3),
@@ -213,7 +219,8 @@ def fill_ext_entry(e, d, pool, grid):
 EXPORTED = """oxb_sizeof oxb_dna2_params_init oxb_dna1_params_init oxb_dna2_params_seqdep oxb_rna2_params_init oxb_rna2_params_seqdep oxb_set_model_rna2 oxb_create oxb_destroy oxb_last_error oxb_set_stream oxb_set_box
 oxb_set_topology oxb_set_model_dna2 oxb_set_lists oxb_set_dt oxb_set_thermostat oxb_set_ext_forces oxb_set_ext_index_pool oxb_set_ext_grid_pool oxb_set_state oxb_get_state oxb_write_conf oxb_write_conf_binary
 oxb_set_step oxb_get_step oxb_sort oxb_update_lists oxb_compute_forces oxb_first_step oxb_second_step oxb_thermostat oxb_run
-oxb_synchronize oxb_get_forces oxb_energy oxb_barostat_move oxb_barostat_trial oxb_barostat_accept oxb_barostat_reject oxb_get_box oxb_set_host_wait oxb_fix_diffusion oxb_energy_split oxb_get_pairs oxb_get_stats oxb_device_views oxb_launch_count oxb_time_kernel""".split()
+oxb_synchronize oxb_get_forces oxb_energy oxb_barostat_move oxb_barostat_trial oxb_barostat_accept oxb_barostat_reject oxb_get_box oxb_set_host_wait oxb_fix_diffusion oxb_energy_split oxb_get_pairs oxb_get_stats oxb_device_views oxb_launch_count oxb_time_kernel oxb_set_profile oxb_get_profile
+oxb_set_replicas oxb_set_replica_consts oxb_replica_energies oxb_replica_consts_dna2 oxb_replica_consts_rna2""".split()
 
 _lib = None
 
@@ -231,7 +238,9 @@ def lib():
         L.oxb_last_error.argtypes = [C.c_void_p]
         L.oxb_destroy.argtypes = [C.c_void_p]
         L.oxb_destroy.restype = None
-        for which, mirror in enumerate((DNA2Params, RNA2Params, ExtForce)):
+        L.oxb_replica_consts_dna2.restype = None
+        L.oxb_replica_consts_rna2.restype = None
+        for which, mirror in enumerate((DNA2Params, RNA2Params, ExtForce, ReplicaConsts)):
             if L.oxb_sizeof(which) != C.sizeof(mirror):
                 raise RuntimeError(f"ABI mismatch: {mirror.__name__} is {C.sizeof(mirror)} bytes here, {L.oxb_sizeof(which)} in {SO_PATH}")
         _lib = L
@@ -300,6 +309,14 @@ def rna2_params(T, salt=1.0, dh_half_charged_ends=True, max_backbone_force=None,
     return P, rc.value
 
 
+def replica_consts(P, th=(0.0, 0.0, 0.0, 0.0)):
+    """oxb_replica_consts_dna2 / _rna2: the temperature-dependent subset of a parameter block + thermostat constants a..d"""
+    out = ReplicaConsts()
+    fn = lib().oxb_replica_consts_rna2 if isinstance(P, RNA2Params) else lib().oxb_replica_consts_dna2
+    fn(C.byref(P), C.c_double(th[0]), C.c_double(th[1]), C.c_double(th[2]), C.c_double(th[3]), C.byref(out))
+    return out
+
+
 def rna2_params_seqdep(P, T, stck16, st_t_dep, cross16, hb_AT, hb_GC, hb_GT):
     s, x = _d(np.asarray(stck16).reshape(16)), _d(np.asarray(cross16).reshape(16))
     if lib().oxb_rna2_params_seqdep(C.byref(P), C.c_double(T), _p(s), C.c_double(st_t_dep), _p(x), C.c_double(hb_AT), C.c_double(hb_GC),
@@ -349,6 +366,19 @@ class Context:
 
     def set_model_rna2(self, P, rcut):
         self._ck(self._L.oxb_set_model_rna2(self._h, C.byref(P), C.c_double(rcut)))
+
+    def set_replicas(self, n):
+        self._ck(self._L.oxb_set_replicas(self._h, int(n)))
+        self.n_replicas = int(n)
+
+    def set_replica_consts(self, rows):
+        arr = (ReplicaConsts * len(rows))(*rows)
+        self._ck(self._L.oxb_set_replica_consts(self._h, len(rows), arr))
+
+    def replica_energies(self):
+        out = np.zeros(getattr(self, "n_replicas", 1))
+        self._ck(self._L.oxb_replica_energies(self._h, _p(out)))
+        return out
 
     def set_lists(self, verlet_skin=0.05, use_edge=False, sort_every=0, max_density_multiplier=3.0):
         self._ck(self._L.oxb_set_lists(self._h, C.c_double(verlet_skin), int(use_edge), int(sort_every), C.c_double(max_density_multiplier)))
@@ -494,6 +524,17 @@ class Context:
 
     def launch_count(self):
         return self._L.oxb_launch_count(self._h)
+
+    PROF_PHASES = ("other", "force", "integrate", "wait", "sort", "build")
+
+    def set_profile(self, enable=True):
+        self._ck(self._L.oxb_set_profile(self._h, int(bool(enable))))
+
+    def get_profile(self):
+        """{phase: (milliseconds, entries)} accumulated inside run() since set_profile(True)"""
+        ms, n = (C.c_double * 6)(), (C.c_longlong * 6)()
+        self._ck(self._L.oxb_get_profile(self._h, ms, n))
+        return {k: (ms[i], n[i]) for i, k in enumerate(self.PROF_PHASES)}
 
     def time_kernel(self, which, reps=10):
         ms = C.c_float()

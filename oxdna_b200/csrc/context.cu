@@ -63,6 +63,12 @@ struct oxb_ctx {
 	double rcut = 0.;
 	oxb::ModelRef mref() const { return is_rna ? oxb::ModelRef{ nullptr, &rmodel } : oxb::ModelRef{ &model, nullptr }; }
 
+	// replica batching (oxb_set_replicas): n_rep replicas of n_per particles, one row of temperature-dependent constants each
+	int n_rep = 1, n_per = 0;
+	oxb_replica_consts *rep = nullptr; // device table, n_rep rows (null while n_rep == 1)
+	bool have_rep_consts = false;
+	double *d_rep_energy = nullptr, *h_rep_energy = nullptr;
+
 	// lists
 	double skin = 0.05, max_density_multiplier = 3.;
 	int use_edge = 0, sort_every = 0;
@@ -74,6 +80,7 @@ struct oxb_ctx {
 	int *edge_offsets = nullptr, *n_edges = nullptr;
 	ulonglong2 *near_mask = nullptr;
 	bool slots_cell_ordered = false; // the last re-sort ordered the slots by cell and left the cell ids in cell_key_sorted
+	int sort_ncell[3] = { 0, 0, 0 }; // ... for this cell grid (a model change in between invalidates the shortcut)
 	long long edge_capacity = 0;
 	int edge_hint = 0;
 	int *dh_nbr = nullptr, *dh_nnbr = nullptr;
@@ -137,6 +144,7 @@ struct oxb_ctx {
 	std::vector<BatchGraph> graphs;
 	bool use_graphs = true;
 	long long graph_launches = 0;
+	bool profiling = false; // oxb_set_profile: device-side phase timeline (kernels.h, prof_mark)
 };
 
 namespace {
@@ -206,12 +214,20 @@ int ensure_cells(oxb_ctx *c) {
 		ncells *= n;
 	}
 	// keep the cell table bounded for huge dilute boxes: coarsen uniformly (cells only need to be >= r_verlet wide)
-	while(ncells > 8ll * N + 4096) {
+	while(ncells > 8ll * (N / c->n_rep) + 4096) {
 		ncells = 1;
 		for(int k = 0; k < 3; k++) {
 			c->ncell[k] = std::max(3, (c->ncell[k] * 4) / 5);
 			ncells *= c->ncell[k];
 		}
+	}
+	if(c->n_rep > 1) {
+		// one copy of the grid per replica; the replica index also forms the top bits of the 32-bit Hilbert key
+		int bits = 1, rep_bits = 0;
+		while((1 << bits) < std::max(c->ncell[0], std::max(c->ncell[1], c->ncell[2]))) bits++;
+		while((1 << rep_bits) < c->n_rep) rep_bits++;
+		if(3 * bits + rep_bits > 32) return fail(c, 1, "replica batching: %d replicas x a %d x %d x %d cell grid do not fit the 32-bit sort key", c->n_rep, c->ncell[0], c->ncell[1], c->ncell[2]);
+		ncells *= c->n_rep;
 	}
 	if(ncells > c->ncells_alloc) {
 		CU(cudaStreamSynchronize(c->stream));
@@ -260,6 +276,7 @@ int alloc_lists(oxb_ctx *c, int max_neigh) {
 oxb::ListArgs list_args(oxb_ctx *c) {
 	oxb::ListArgs a;
 	a.N = c->N;
+	a.n_rep = c->n_rep; a.n_per = c->n_per;
 	for(int k = 0; k < 3; k++) { a.box[k] = c->box[k]; a.ncell[k] = c->ncell[k]; }
 	a.boxf = c->boxf;
 	a.rv = c->rcut + 2. * c->skin;
@@ -294,7 +311,7 @@ oxb::ListArgs list_args(oxb_ctx *c) {
 	a.cub_tmp = c->cub_tmp; a.cub_tmp_bytes = c->cub_tmp_bytes;
 	a.build_edges = c->use_edge != 0;
 	a.near_mask = c->near_mask;
-	a.direct = c->slots_cell_ordered;
+	a.direct = c->slots_cell_ordered && c->sort_ncell[0] == c->ncell[0] && c->sort_ncell[1] == c->ncell[1] && c->sort_ncell[2] == c->ncell[2];
 	return a;
 }
 
@@ -320,11 +337,13 @@ int do_sort(oxb_ctx *c) {
 	}
 	oxb::SortArgs s;
 	s.N = N;
+	s.n_rep = c->n_rep; s.n_per = c->n_per;
 	for(int k = 0; k < 3; k++) s.box[k] = c->box[k];
 	s.posd = c->posd[a];
 	for(int k = 0; k < 3; k++) s.ncell[k] = c->ncell[k];
 	s.keys = c->hkeys; s.keys_sorted = c->hkeys_sorted; s.vals = c->hvals; s.vals_sorted = c->hvals_sorted; s.inv = c->hinv;
 	s.cub_tmp = c->cub_tmp; s.cub_tmp_bytes = c->cub_tmp_bytes;
+	s.flags = c->flags;
 	oxb::launch_hilbert_order(c->stream, s);
 	oxb::PermuteArgs p;
 	p.N = N; p.perm = c->hvals_sorted; p.inv = c->hinv;
@@ -337,9 +356,11 @@ int do_sort(oxb_ctx *c) {
 	p.bonds_in = c->bonds[a]; p.bonds_out = c->bonds[b];
 	p.slot_of = c->slot_of;
 	p.cell_lin = c->cell_key_sorted;
+	p.n_per = c->n_per;
 	for(int k = 0; k < 3; k++) { p.box[k] = c->box[k]; p.ncell[k] = c->ncell[k]; }
 	oxb::launch_permute(c->stream, p);
 	c->slots_cell_ordered = true; // consumed (and cleared) by the list build that follows
+	for(int k = 0; k < 3; k++) c->sort_ncell[k] = c->ncell[k];
 	c->launches += 5;
 	c->cur = b;
 	c->n_sorts++;
@@ -413,6 +434,7 @@ int launch_forces(oxb_ctx *c, int hw, bool clear, long long step) {
 			CU(cudaMemsetAsync(c->T[a], 0, sizeof(float4) * (size_t) c->N, m));
 		}
 		oxb::EdgeArgs e;
+		e.rep = c->rep; e.n_per = c->n_per;
 		e.N = c->N; e.ipos = c->ipos[a]; e.iback = c->iback[a]; e.quat = c->quat[a]; e.posd = c->posd[a]; e.quatd = c->quatd[a]; e.bonds = c->bonds[a]; e.edges = c->edges;
 		e.n_edges = c->n_edges; e.dh_nbr = c->dh_nbr; e.dh_nnbr = c->dh_nnbr;
 		e.F = c->F[a]; e.T = c->T[a]; e.Fb = c->Fb; e.hb_list = c->hb_list; e.cx_list = c->cx_list; e.cr_list = c->cr_list; e.seg_counts = c->seg_counts;
@@ -462,7 +484,7 @@ int launch_forces(oxb_ctx *c, int hw, bool clear, long long step) {
 	else {
 		oxb::launch_forces_particle(m, c->mref(), c->boxf, c->N, c->ipos[a], c->iback[a], c->quat[a],
 				c->precision == OXB_PRECISION_MIXED ? c->posd[a] : nullptr, c->quatd[a], c->bonds[a], c->nbr, c->nnbr, c->N, c->F[a], c->T[a],
-				c->flags, hw);
+				c->rep, c->n_per, c->flags, hw);
 		c->launches += 1;
 		if(c->n_ext > 0) {
 			oxb::launch_ext_forces(m, c->n_ext, c->ext, c->slot_of, c->ipos[a], c->posd[a], c->boxf, step, c->cur_step, c->F[a], c->flags, hw);
@@ -492,6 +514,7 @@ oxb::IntegrateArgs integ_args(oxb_ctx *c, long long step) {
 	a.F = c->F[k]; a.T = c->T[k]; a.Fb = c->use_edge ? c->Fb : nullptr; a.iback = c->iback[k]; a.list_iback = c->list_iback[k]; a.list_ibase = c->list_ibase[k];
 	a.back_a1 = c->model.back_a1; a.back_a2 = c->model.back_a2; a.back_a3 = c->back_a3; a.base_a1 = c->model.base_a1;
 	a.flags = c->flags; a.sums = c->sums; a.th = c->th; a.step = step;
+	a.rep = c->rep; a.n_per = c->n_per;
 	a.cur_step = c->cur_step;
 	return a;
 }
@@ -505,6 +528,8 @@ __global__ void k_batch_begin(int *flags, long long *cur_step, long long step, i
 	cur_step[0] = step;
 	cur_step[1] = step;
 }
+
+__global__ void k_prof_mark(int *flags, int phase, int reset) { prof_mark(flags, phase, reset != 0); }
 
 // start of a batch of launches: clears the halt words and the completed-step counter, seeds the device-side step index
 int reset_batch_flags(oxb_ctx *c) {
@@ -539,6 +564,10 @@ int check_ready(oxb_ctx *c) {
 	if(!c->have_box) return fail(c, 2, "box not set");
 	if(!c->have_model) return fail(c, 2, "interaction model not set");
 	if(!c->have_state) return fail(c, 2, "state not set");
+	if(c->n_rep > 1) {
+		if(!c->have_rep_consts) return fail(c, 2, "replica batching: oxb_set_replica_consts has not been called");
+		if(c->th.type == OXB_THERMOSTAT_BUSSI) return fail(c, 1, "replica batching is not available with the Bussi thermostat");
+	}
 	return 0;
 }
 
@@ -592,6 +621,10 @@ unsigned long long config_hash(const oxb_ctx *c) {
 		for(size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; }
 	};
 	mix(&c->model, sizeof(c->model));
+	// oxRNA: `model` only mirrors what the context reads; the kernels freeze the full RNA block (stacking strengths, sequence-dependent
+	// tables, mismatch repulsion ...) by value
+	if(c->is_rna) { mix(&c->rmodel, sizeof(c->rmodel)); mix(&c->back_a3, sizeof(float)); }
+	mix(&c->precision, sizeof(int));
 	mix(&c->th.type, sizeof(int)); mix(&c->th.every, sizeof(int)); mix(&c->th.a, 4 * sizeof(float)); mix(&c->th.seed, sizeof(c->th.seed));
 	mix(&c->dt, sizeof(double)); mix(&c->skin, sizeof(double));
 	return h;
@@ -665,6 +698,7 @@ int oxb_create(oxb_ctx **out, int device, int N, int precision) {
 	oxb_ctx *c = new oxb_ctx();
 	*out = c;
 	c->device = device; c->N = N; c->precision = precision;
+	c->n_per = N;
 	std::memset(&c->th, 0, sizeof(c->th));
 	c->th.every = 1;
 	// backend_precision: both keep the FP64 state and FP32 pair arithmetic.  mixed (the reference default) additionally takes the two
@@ -706,8 +740,8 @@ int oxb_create(oxb_ctx **out, int device, int N, int precision) {
 	CU(dalloc(&c->slot_of, N));
 	CU(dalloc(&c->Fb, N));
 	CU(cudaMemset(c->Fb, 0, sizeof(float4) * N));
-	CU(dalloc(&c->flags, OXB_FLAG_WORDS));
-	CU(cudaMemset(c->flags, 0, sizeof(int) * OXB_FLAG_WORDS));
+	CU(dalloc(&c->flags, OXB_FLAG_ALLOC));
+	CU(cudaMemset(c->flags, 0, sizeof(int) * OXB_FLAG_ALLOC));
 	CU(cudaMallocHost((void **) &c->h_flags, sizeof(int) * OXB_FLAG_WORDS));
 	CU(dalloc(&c->sums, 1));
 	CU(cudaMemset(c->sums, 0, sizeof(KinSums)));
@@ -734,6 +768,8 @@ void oxb_destroy(oxb_ctx *c) {
 		cudaFree(c->quat[k]); cudaFree(c->F[k]); cudaFree(c->T[k]); cudaFree(c->bonds[k]); cudaFree(c->iback[k]); cudaFree(c->list_iback[k]); cudaFree(c->list_ibase[k]);
 	}
 	cudaFree(c->Fb);
+	cudaFree(c->rep); cudaFree(c->d_rep_energy);
+	if(c->h_rep_energy) cudaFreeHost(c->h_rep_energy);
 	cudaFree(c->slot_of); cudaFree(c->flags); cudaFree(c->sums); cudaFree(c->d_energy); cudaFree(c->ext); cudaFree(c->ext_all); cudaFree(c->ext_com); cudaFree(c->ext_pool); cudaFree(c->ext_grid);
 	cudaFree(c->d_topo); cudaFree(c->d_stage); cudaFree(c->d_marshal_err);
 	cudaFree(c->mol_of); cudaFree(c->mol_inv_size); cudaFree(c->mol_coms); cudaFree(c->pos_backup); cudaFree(c->pos_f4);
@@ -778,6 +814,8 @@ int oxb_set_topology(oxb_ctx *c, const int *btype, const int *n3, const int *n5,
 	for(int i = 0; i < N; i++) {
 		if(n3[i] >= N || n5[i] >= N) return fail(c, 1, "wrong topology for particle %d (neighbour index out of range)", i);
 		if(btype[i] > 511 || btype[i] < -511) return fail(c, 1, "base type of particle %d does not fit the packed word (|btype| <= 511)", i);
+		if(c->n_rep > 1 && ((n3[i] >= 0 && n3[i] / c->n_per != i / c->n_per) || (n5[i] >= 0 && n5[i] / c->n_per != i / c->n_per)))
+			return fail(c, 1, "replica batching: particle %d is bonded across replicas", i);
 	}
 	{
 		std::vector<int4> ht(N);
@@ -827,6 +865,67 @@ int oxb_set_model_rna2(oxb_ctx *c, const oxb_rna2_params *P, double rcut) {
 	c->have_model = true;
 	c->forces_valid = false;
 	if(c->lists_valid && (rcut + 2. * c->skin > c->lists_rv || (double) P->dh_rc > c->lists_dh_rc)) c->lists_valid = false;
+	return 0;
+}
+
+int oxb_set_replicas(oxb_ctx *c, int n_replicas) {
+	if(c == nullptr) return 1;
+	if(n_replicas < 1 || c->N % n_replicas != 0) return fail(c, 1, "the number of particles (%d) is not a multiple of the number of replicas (%d)", c->N, n_replicas);
+	cudaSetDevice(c->device);
+	const int n_per = c->N / n_replicas;
+	if(c->have_topology) {
+		for(int i = 0; i < c->N; i++) {
+			if((c->h_n3[i] >= 0 && c->h_n3[i] / n_per != i / n_per) || (c->h_n5[i] >= 0 && c->h_n5[i] / n_per != i / n_per))
+				return fail(c, 1, "replica batching: particle %d is bonded across replicas", i);
+		}
+	}
+	CU(cudaStreamSynchronize(c->stream));
+	drop_graphs(c);
+	cudaFree(c->rep); cudaFree(c->d_rep_energy);
+	if(c->h_rep_energy) cudaFreeHost(c->h_rep_energy);
+	c->rep = nullptr; c->d_rep_energy = nullptr; c->h_rep_energy = nullptr;
+	c->n_rep = n_replicas; c->n_per = n_per;
+	c->have_rep_consts = false;
+	if(n_replicas > 1) {
+		CU(dalloc(&c->rep, (size_t) n_replicas));
+		CU(dalloc(&c->d_rep_energy, (size_t) n_replicas));
+		CU(cudaMallocHost((void **) &c->h_rep_energy, sizeof(double) * (size_t) n_replicas));
+	}
+	c->lists_valid = false; c->forces_valid = false;
+	if(c->lists_allocated) free_lists(c);
+	return 0;
+}
+
+int oxb_set_replica_consts(oxb_ctx *c, int n, const oxb_replica_consts *rows) {
+	if(c == nullptr || rows == nullptr) return 1;
+	if(c->n_rep < 2 || n != c->n_rep) return fail(c, 1, "oxb_set_replica_consts: %d rows for %d replicas (call oxb_set_replicas first)", n, c->n_rep);
+	if(!c->have_model) return fail(c, 2, "the interaction model (hottest replica: list radii) must be set before the replica constants");
+	cudaSetDevice(c->device);
+	for(int r = 0; r < n; r++) {
+		// the lists are built for the radii of the model block: no replica may reach further
+		if(rows[r].dh_rc > c->model.dh_rc * (1.f + 1e-6f) || rows[r].rcut2 > (float) (c->rcut * c->rcut) * (1.f + 1e-6f))
+			return fail(c, 1, "replica %d: Debye-Hueckel range %g / cutoff %g exceed those of the model block (%g / %g): set the model of the hottest temperature", r,
+					(double) rows[r].dh_rc, std::sqrt((double) rows[r].rcut2), (double) c->model.dh_rc, c->rcut);
+	}
+	// stream-ordered: kernels already queued keep the old table
+	CU(cudaMemcpyAsync(c->rep, rows, sizeof(oxb_replica_consts) * (size_t) n, cudaMemcpyHostToDevice, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	c->have_rep_consts = true;
+	c->forces_valid = false;
+	return 0;
+}
+
+int oxb_replica_energies(oxb_ctx *c, double *U) {
+	if(c == nullptr || U == nullptr) return 1;
+	if(c->n_rep < 2) return oxb_energy(c, U, nullptr);
+	int rc = ensure_forces(c);
+	if(rc) return rc;
+	const int k = c->cur;
+	oxb::launch_energy_sum_replicas(c->stream, c->N, c->n_rep, c->n_per, c->F[k], c->use_edge ? c->Fb : nullptr, c->d_rep_energy);
+	c->launches += 1;
+	CU(cudaMemcpyAsync(c->h_rep_energy, c->d_rep_energy, sizeof(double) * (size_t) c->n_rep, cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	for(int r = 0; r < c->n_rep; r++) U[r] = 0.5 * c->h_rep_energy[r];
 	return 0;
 }
 
@@ -988,6 +1087,8 @@ int oxb_set_state(oxb_ctx *c, const double *pos, const double *a1, const double 
 	c->have_state = true;
 	c->lists_valid = false; c->forces_valid = false; c->mid_step = false;
 	c->trial_open = false;
+	c->slots_cell_ordered = false; // the slots were rewritten in identity order
+	c->error_flags = 0;            // errors (a broken FENE bond ...) belonged to the previous state
 	return 0;
 }
 
@@ -1173,6 +1274,7 @@ int oxb_run(oxb_ctx *c, long long n_steps) {
 		c->build_unchecked = false;
 		c->lists_valid = false;
 	}
+	if(c->profiling) { k_prof_mark<<<1, 1, 0, c->stream>>>(c->flags, OXB_PROF_OTHER, 1); c->launches++; } // time between runs is nobody's
 	long long remaining = n_steps;
 	long long since_rebuild = 0;
 	bool since_rebuild_valid = false;
@@ -1247,6 +1349,7 @@ int oxb_run(oxb_ctx *c, long long n_steps) {
 			if(done != batch) return fail(c, 7, "internal error: batch of %lld steps completed %d without a halt", batch, done);
 		}
 	}
+	if(c->profiling) { k_prof_mark<<<1, 1, 0, c->stream>>>(c->flags, OXB_PROF_OTHER, 0); c->launches++; } // closes the last integrate launch
 	// at the end of a run the forces in memory belong to the last completed step's positions: still valid
 	c->forces_valid = true;
 	c->mid_step = false;
@@ -1459,6 +1562,7 @@ int oxb_barostat_move(oxb_ctx *c, const double new_box[3], int molecular, double
 
 int oxb_energy_split(oxb_ctx *c, double *terms) {
 	if(c == nullptr || terms == nullptr) return 1;
+	if(c->n_rep > 1) return fail(c, 1, "oxb_energy_split is not available for a replica batch");
 	int rc = check_ready(c);
 	if(rc) return rc;
 	rc = ensure_lists(c);
@@ -1542,6 +1646,30 @@ int oxb_device_views(oxb_ctx *c, void **poss_f4, void **orientations_f4, void **
 }
 
 long long oxb_launch_count(const oxb_ctx *c) { return c ? c->launches : 0; }
+
+int oxb_set_profile(oxb_ctx *c, int enable) {
+	if(c == nullptr) return 1;
+	cudaSetDevice(c->device);
+	CU(cudaStreamSynchronize(c->stream));
+	CU(cudaMemset(c->flags + OXB_PROF_OFFSET, 0, sizeof(unsigned long long) * (2 + 2 * OXB_PROF_NPHASE)));
+	const int on = enable ? 1 : 0;
+	CU(cudaMemcpy(c->flags + OXB_FLAG_PROF_ON, &on, sizeof(int), cudaMemcpyHostToDevice));
+	c->profiling = on != 0;
+	return 0;
+}
+
+int oxb_get_profile(oxb_ctx *c, double *ms, long long *entries) {
+	if(c == nullptr) return 1;
+	cudaSetDevice(c->device);
+	unsigned long long h[2 + 2 * OXB_PROF_NPHASE];
+	CU(cudaStreamSynchronize(c->stream));
+	CU(cudaMemcpy(h, c->flags + OXB_PROF_OFFSET, sizeof(h), cudaMemcpyDeviceToHost));
+	for(int p = 0; p < OXB_PROF_NPHASE; p++) {
+		if(ms) ms[p] = 1e-6 * (double) h[2 + p];
+		if(entries) entries[p] = (long long) h[2 + OXB_PROF_NPHASE + p];
+	}
+	return 0;
+}
 
 int oxb_time_kernel(oxb_ctx *c, int which, int reps, float *ms) {
 	if(c == nullptr || ms == nullptr || reps < 1) return 1;

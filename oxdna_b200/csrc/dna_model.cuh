@@ -226,8 +226,10 @@ enum { OXB_SITE_KK = 0, OXB_SITE_AA = 1, OXB_SITE_AK = 2, OXB_SITE_KA = 3 }; // 
 struct PairAcc {
 	v3 F, Pa, Pk, Qa, Qk, Tp, Tq;
 	const ExclRefine *refine;
+	const oxb_replica_consts *rep; // replica batching: the temperature-dependent constants of this pair's replica (null = those of the model block)
 	OXB_HD void clear() {
 		refine = nullptr;
+		rep = nullptr;
 		F = Pa = Pk = Qa = Qk = Tp = Tq = mk3(0.f, 0.f, 0.f);
 	}
 	// site codes: coefficient along a1, or "backbone" handled by the *_k variants
@@ -360,6 +362,19 @@ struct PairEnergy {
 //   dna2_cxst      coaxial stacking (oxDNA2 form: no phi3 term, harmonic add-on to theta1)
 // r = min-image(q - p) between centres of mass; forces are "on q".
 // ---------------------------------------------------------------------------------------------------------------
+
+// the Debye-Hueckel constants as a value: either the model block's or a replica's row (same field names: dna2_dh / dna2_dh_fast take both)
+struct DhView {
+	float dh_minus_kappa, dh_prefactor, dh_rhigh, dh_rc, dh_b;
+	int dh_half_charged_ends;
+};
+template<class PB> OXB_HD DhView dh_view(const PB &M, const oxb_replica_consts *rep) {
+	DhView D;
+	D.dh_half_charged_ends = M.dh_half_charged_ends;
+	if(rep != nullptr) { D.dh_minus_kappa = rep->dh_minus_kappa; D.dh_prefactor = rep->dh_prefactor; D.dh_rhigh = rep->dh_rhigh; D.dh_rc = rep->dh_rc; D.dh_b = rep->dh_b; }
+	else { D.dh_minus_kappa = M.dh_minus_kappa; D.dh_prefactor = M.dh_prefactor; D.dh_rhigh = M.dh_rhigh; D.dh_rc = M.dh_rc; D.dh_b = M.dh_b; }
+	return D;
+}
 
 // returns the DH energy; fs such that force-on-q = fs * rbb (zero outside the range)
 template<class PB> OXB_HD float dna2_dh(const PB &M, float rbb2, bool p_end, bool q_end, float &fs) {
@@ -593,10 +608,10 @@ OXB_HD PairEnergy dna2_nonbonded(const oxb_dna2_params &M, v3 r, const Axes &A, 
 	E.total = 0.f;
 	E.hb = 0.f;
 	float r2 = dot(r, r);
-	if(r2 >= M.rcut * M.rcut) return E; // DNA2Interaction.cpp:46-48
+	if(r2 >= (acc.rep ? acc.rep->rcut2 : M.rcut * M.rcut)) return E; // DNA2Interaction.cpp:46-48
 	v3 rbb = r + qback - pback;
 	float fs;
-	float en = dna2_dh(M, dot(rbb, rbb), p_end, q_end, fs);
+	float en = acc.rep ? dna2_dh(dh_view(M, acc.rep), dot(rbb, rbb), p_end, q_end, fs) : dna2_dh(M, dot(rbb, rbb), p_end, q_end, fs);
 	if(en != 0.f) { E.total += en; acc.site_kk(rbb * fs); }
 	if(r2 >= M.rcut_near * M.rcut_near) return E;
 	v3 rb = r + (B.a1 - A.a1) * M.base_a1;
@@ -745,7 +760,7 @@ OXB_HD float dna2_bonded(const oxb_dna2_params &M, v3 r, const Axes &A, const Ax
 		float inv = OXB_RSQRT(rs2);
 		float m = rs2 * inv;
 		int ti = btype_to_type(btq) * 5 + btype_to_type(btp);
-		RadVal f1 = f1_r(M.stck, M.stck_eps[ti], M.stck_shift[ti], m);
+		RadVal f1 = acc.rep ? f1_r(M.stck, acc.rep->stck_eps[ti], acc.rep->stck_shift[ti], m) : f1_r(M.stck, M.stck_eps[ti], M.stck_shift[ti], m);
 		if(f1.v != 0.f || f1.d != 0.f) {
 			v3 h = rs * inv;
 			v3 w = r + B.a1 * cr - A.a1 * cr;

@@ -122,7 +122,8 @@ template<class MD>
 __global__ void __launch_bounds__(128, OXB_MB_PARTICLE) k_forces_particle(const __grid_constant__ typename MD::Params M, BoxF box, int N, const int4 *__restrict__ ipos,
 		const int4 *__restrict__ iback, const float4 *__restrict__ quat, const double4 *__restrict__ posd, const double4 *__restrict__ quatd,
 		const int2 *__restrict__ bonds, const int *__restrict__ nbr, const int *__restrict__ nnbr, int stride,
-		float4 *__restrict__ F, float4 *__restrict__ T, int *__restrict__ flags, int hw) {
+		float4 *__restrict__ F, float4 *__restrict__ T, const oxb_replica_consts *__restrict__ rep, int n_per, int *__restrict__ flags, int hw) {
+	if(blockIdx.x == 0 && threadIdx.x == 0) prof_mark(flags, flags[hw] ? OXB_PROF_WAIT : OXB_PROF_FORCE);
 	if(flags[hw]) return;
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= N) return;
@@ -136,12 +137,14 @@ __global__ void __launch_bounds__(128, OXB_MB_PARTICLE) k_forces_particle(const 
 	bool broken = false;
 	ExclRefine R = make_refine<MD>(M, box, posd, quatd);
 	const bool refine = posd != nullptr; // backend_precision = mixed
+	if(rep != nullptr) rep += i / n_per;   // replica batching: slots are replica-contiguous
 
 	if(b.x >= 0) { // I am the 5' side of the bond (p), q = my n3
 		Particle Q = load_particle<MD>(M, ipos, quat, b.x);
 		PairAcc acc;
 		acc.clear();
 		R.sp = i; R.sq = b.x; acc.refine = refine ? &R : nullptr;
+		acc.rep = rep;
 		FeneSite fs;
 		if(refine) fs = fene_from_sites(M, box, __ldg(iback + i), __ldg(iback + b.x), broken);
 		e += MD::bonded(M, min_image_fixed(box, P.ip, Q.ip), P.ax, Q.ax, P.btype, Q.btype, P.back, Q.back, acc, broken, nullptr, refine ? &fs : nullptr);
@@ -153,6 +156,7 @@ __global__ void __launch_bounds__(128, OXB_MB_PARTICLE) k_forces_particle(const 
 		PairAcc acc;
 		acc.clear();
 		R.sp = b.y; R.sq = i; acc.refine = refine ? &R : nullptr;
+		acc.rep = rep;
 		FeneSite fs;
 		if(refine) fs = fene_from_sites(M, box, __ldg(iback + b.y), __ldg(iback + i), broken);
 		e += MD::bonded(M, min_image_fixed(box, Q.ip, P.ip), Q.ax, P.ax, Q.btype, P.btype, Q.back, P.back, acc, broken, nullptr, refine ? &fs : nullptr);
@@ -168,6 +172,7 @@ __global__ void __launch_bounds__(128, OXB_MB_PARTICLE) k_forces_particle(const 
 		PairAcc acc;
 		acc.clear();
 		R.sp = i; R.sq = j; acc.refine = refine ? &R : nullptr;
+		acc.rep = rep;
 		PairEnergy pe = MD::nonbonded(M, min_image_fixed(box, P.ip, Q.ip), P.ax, Q.ax, P.btype, Q.btype, p_end, (bq.x < 0 || bq.y < 0), P.back,
 				Q.back, acc);
 		e += pe.total;
@@ -223,15 +228,20 @@ __device__ __forceinline__ bool segmented_reduce(int key, unsigned lane, float (
 // LPP lanes share one particle (lane s takes neighbours s, s + LPP, ...; partial sums folded with shuffles in a fixed order, so the
 // result stays deterministic): systems that cannot fill the GPU with one thread per particle (C2: 17 warps per SM) get LPP times the
 // loads in flight; index loads stay sector-efficient (LPP rows x 32 / LPP consecutive ints per warp instruction).
-template<class MD, int LPP>
+// REP (replica batching): the constants come from the row of the particle's replica, as register values; the single-system
+// instantiation keeps them as constant-bank operands.
+template<class MD, int LPP, bool REP>
 __global__ void __launch_bounds__(128) k_dh_particle(const __grid_constant__ typename MD::Params M, BoxF box, int N, const int4 *__restrict__ iback,
-		const int *__restrict__ dh_nbr, const int *__restrict__ dh_nnbr, float4 *__restrict__ Fb, const int *__restrict__ flags, int hw) {
+		const int *__restrict__ dh_nbr, const int *__restrict__ dh_nnbr, float4 *__restrict__ Fb, const oxb_replica_consts *__restrict__ rep, int n_per,
+		const int *__restrict__ flags, int hw) {
 	if(flags[hw]) return;
 	const int gid = blockIdx.x * blockDim.x + threadIdx.x;
 	const int sub = gid % LPP;
 	int i = gid / LPP;
 	const bool active = i < N;
 	if(!active) i = N - 1; // whole groups stay in the shuffles
+	DhView D;
+	if(REP) D = dh_view(M, rep + i / n_per);
 	const int4 bp = __ldg(iback + i);
 	const int nn = active ? __ldg(dh_nnbr + i) : 0;
 	const bool p_end = bp.w & 1;
@@ -243,7 +253,7 @@ __global__ void __launch_bounds__(128) k_dh_particle(const __grid_constant__ typ
 		int4 bq = __ldg(iback + j);
 		v3 rbb = min_image_fixed(box, bp, bq);
 		float fs;
-		float en = dna2_dh_fast(M, dot(rbb, rbb), p_end, bq.w & 1, fs);
+		float en = REP ? dna2_dh_fast(D, dot(rbb, rbb), p_end, bq.w & 1, fs) : dna2_dh_fast(M, dot(rbb, rbb), p_end, bq.w & 1, fs);
 		e += en;
 		axpy(f, -fs, rbb);
 	}
@@ -281,6 +291,7 @@ __global__ void __launch_bounds__(128, OXB_MB_NEAR) k_edge_near(const __grid_con
 		const int2 *__restrict__ edges, const int4 *__restrict__ ipos, const float4 *__restrict__ quat, float4 *__restrict__ F, float4 *__restrict__ T,
 		int2 *__restrict__ hb_list, int2 *__restrict__ cx_list, int2 *__restrict__ cr_list, int *__restrict__ seg_counts, int hb_seg, int cx_seg,
 		int cr_seg, int4 *__restrict__ ex_list, int *__restrict__ ex_counts, int ex_seg, int refine, int *__restrict__ flags, int hw) {
+	if(blockIdx.x == 0 && threadIdx.x == 0) prof_mark(flags, flags[hw] ? OXB_PROF_WAIT : OXB_PROF_FORCE);
 	if(flags[hw]) return;
 	__shared__ int s_cnt[3];
 	if(threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
@@ -416,7 +427,7 @@ __global__ void __launch_bounds__(64, OXB_MB_HEAVY) k_edge_heavy(const __grid_co
 template<class MD>
 __global__ void __launch_bounds__(128, OXB_MB_BONDED) k_bonded(const __grid_constant__ typename MD::Params M, BoxF box, int N, const int4 *__restrict__ ipos,
 		const int4 *__restrict__ iback, const float4 *__restrict__ quat, const int2 *__restrict__ bonds, float4 *__restrict__ F, float4 *__restrict__ T,
-		int *__restrict__ ex_bonded, int refine, int *__restrict__ flags, int hw) {
+		int *__restrict__ ex_bonded, int refine, const oxb_replica_consts *__restrict__ rep, int n_per, int *__restrict__ flags, int hw) {
 	if(flags[hw]) return;
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= N) return;
@@ -426,6 +437,7 @@ __global__ void __launch_bounds__(128, OXB_MB_BONDED) k_bonded(const __grid_cons
 	Particle Q = load_particle<MD>(M, ipos, quat, b.x);
 	PairAcc acc;
 	acc.clear();
+	if(rep != nullptr) acc.rep = rep + i / n_per; // replica batching: this replica's stacking strength
 	bool broken = false;
 	const v3 r = min_image_fixed(box, P.ip, Q.ip);
 	float en;
@@ -961,10 +973,10 @@ namespace oxb {
 
 void launch_forces_particle(cudaStream_t s, const ModelRef &MR, BoxF box, int N, const int4 *ipos, const int4 *iback, const float4 *quat,
 		const double4 *posd, const double4 *quatd, const int2 *bonds,
-		const int *nbr, const int *nnbr, int stride, float4 *F, float4 *T, int *flags, int hw) {
+		const int *nbr, const int *nnbr, int stride, float4 *F, float4 *T, const oxb_replica_consts *rep, int n_per, int *flags, int hw) {
 	int tpb = 128;
-	if(MR.rna) k_forces_particle<RnaModel><<<(N + tpb - 1) / tpb, tpb, 0, s>>>(*MR.rna, box, N, ipos, iback, quat, posd, quatd, bonds, nbr, nnbr, stride, F, T, flags, hw);
-	else k_forces_particle<DnaModel><<<(N + tpb - 1) / tpb, tpb, 0, s>>>(*MR.dna, box, N, ipos, iback, quat, posd, quatd, bonds, nbr, nnbr, stride, F, T, flags, hw);
+	if(MR.rna) k_forces_particle<RnaModel><<<(N + tpb - 1) / tpb, tpb, 0, s>>>(*MR.rna, box, N, ipos, iback, quat, posd, quatd, bonds, nbr, nnbr, stride, F, T, rep, n_per, flags, hw);
+	else k_forces_particle<DnaModel><<<(N + tpb - 1) / tpb, tpb, 0, s>>>(*MR.dna, box, N, ipos, iback, quat, posd, quatd, bonds, nbr, nnbr, stride, F, T, rep, n_per, flags, hw);
 }
 
 // the kernels of the edge pipeline, launched one by one so that the context can place them on concurrent streams:
@@ -984,9 +996,10 @@ static void launch_edge_stage_t(cudaStream_t s, int which, const typename MD::Pa
 		// (profiles/smalln_sweep_r01.txt): the kernel is bound by L2 gather bandwidth, not by loads in flight.  OXB_DH_LPP overrides.
 		static const int lpp_env = env_int("OXB_DH_LPP", 0);
 		const int lpp = lpp_env > 0 ? lpp_env : 1;
-		if(lpp >= 4) k_dh_particle<MD, 4><<<blocks_for(4ll * a.N), 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, flags, hw);
-		else if(lpp == 2) k_dh_particle<MD, 2><<<blocks_for(2ll * a.N), 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, flags, hw);
-		else k_dh_particle<MD, 1><<<blocks_for(a.N), 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, flags, hw);
+		if(a.rep != nullptr) k_dh_particle<MD, 1, true><<<blocks_for(a.N), 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, a.rep, a.n_per, flags, hw);
+		else if(lpp >= 4) k_dh_particle<MD, 4, false><<<blocks_for(4ll * a.N), 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, nullptr, 1, flags, hw);
+		else if(lpp == 2) k_dh_particle<MD, 2, false><<<blocks_for(2ll * a.N), 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, nullptr, 1, flags, hw);
+		else k_dh_particle<MD, 1, false><<<blocks_for(a.N), 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, nullptr, 1, flags, hw);
 		break;
 	}
 	// the producer and the three consumers of the segmented work lists share one fixed grid (a.n_seg blocks, grid-stride
@@ -1005,7 +1018,7 @@ static void launch_edge_stage_t(cudaStream_t s, int which, const typename MD::Pa
 	default: {
 		static const int tpb_env = env_int("OXB_TPB_BONDED", 0);
 		const int tpb = tpb_env > 0 ? tpb_env : 128;
-		k_bonded<MD><<<(a.N + tpb - 1) / tpb, tpb, 0, s>>>(M, box, a.N, a.ipos, a.iback, a.quat, a.bonds, a.F, a.T, a.ex_bonded, a.refine, flags, hw);
+		k_bonded<MD><<<(a.N + tpb - 1) / tpb, tpb, 0, s>>>(M, box, a.N, a.ipos, a.iback, a.quat, a.bonds, a.F, a.T, a.ex_bonded, a.refine, a.rep, a.n_per, flags, hw);
 		break;
 	}
 	}

@@ -43,9 +43,10 @@ __global__ void __launch_bounds__(256, OXB_MB_INTEGRATE) k_integrate(oxb::Integr
 	const int rd = OXB_FLAG_COUNT + (epoch & 1), wr = OXB_FLAG_COUNT + ((epoch + 1) & 1);
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if(flags[rd]) { // halted earlier in this batch: stay halted (sticky), do nothing
-		if(i == 0) flags[wr] = 1;
+		if(i == 0) { flags[wr] = 1; prof_mark(flags, OXB_PROF_WAIT); }
 		return;
 	}
+	if(i == 0) prof_mark(flags, OXB_PROF_INTEG);
 	// step index: explicit (stream-launched paths) or the device-side counter (graph-launched batches, where kernel
 	// arguments are frozen): word (epoch & 1) is read, word ((epoch + 1) & 1) is written -- never the same word
 	const long long step = (a.step >= 0) ? a.step : a.cur_step[epoch & 1];
@@ -90,6 +91,11 @@ __global__ void __launch_bounds__(256, OXB_MB_INTEGRATE) k_integrate(oxb::Integr
 		}
 		if((PH & OXB_PH_THERMO) && (a.th.type == OXB_THERMOSTAT_LANGEVIN || (step % a.th.every) == 0)) {
 			unsigned id = (unsigned) word_index(a.ipos[i].w);
+			if(a.rep != nullptr) {
+				// replica batching: the thermostat constants of this particle's replica (slots are replica-contiguous)
+				const oxb_replica_consts *rc = a.rep + i / a.n_per;
+				a.th.a = rc->th_a; a.th.b = rc->th_b; a.th.c = rc->th_c; a.th.d = rc->th_d;
+			}
 			if(a.th.type == OXB_THERMOSTAT_BROWNIAN) {
 				uint4 u = philox_u4(a.th.seed, id, (unsigned long long) step, 0u);
 				bool rt = u01(u.x) < a.th.a, rr = u01(u.y) < a.th.b;
@@ -299,6 +305,28 @@ __global__ void __launch_bounds__(256) k_energy_sum(int N, const float4 *__restr
 	}
 }
 
+// per-replica potential energy: slots [r * n_per, (r + 1) * n_per) belong to replica r; a block that lies inside one replica reduces
+// in shared memory and issues one atomic, a block that straddles a boundary falls back to one atomic per warp / lane
+__global__ void __launch_bounds__(256) k_energy_sum_replicas(int N, int n_per, const float4 *__restrict__ F, const float4 *__restrict__ Fb, double *out) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	double x = (i < N) ? (double) F[i].w : 0.;
+	if(Fb != nullptr && i < N) x += (double) Fb[i].w;
+	const int first = blockIdx.x * blockDim.x, last = min(N, first + (int) blockDim.x) - 1;
+	const int r = min(i, N - 1) / n_per;
+	if(first / n_per == last / n_per) {
+		for(int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+		__shared__ double sh[8];
+		if((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = x;
+		__syncthreads();
+		if(threadIdx.x == 0) {
+			double s = 0.;
+			for(int w = 0; w < (int) (blockDim.x >> 5); w++) s += sh[w];
+			atomicAdd(out + r, s);
+		}
+	}
+	else if(i < N) atomicAdd(out + r, x);
+}
+
 template<int PH>
 void launch_ph(cudaStream_t s, const oxb::IntegrateArgs &a, int epoch) {
 	// small systems: 128-thread blocks halve the tail of the last wave (C2: 320 blocks of 256 on 148 SMs = 2.2 blocks per SM)
@@ -426,6 +454,12 @@ void launch_energy_sum(cudaStream_t s, int N, const float4 *F, const float4 *Fb,
 	cudaMemsetAsync(out, 0, sizeof(double), s);
 	int tpb = 256;
 	k_energy_sum<<<(N + tpb - 1) / tpb, tpb, 0, s>>>(N, F, Fb, out);
+}
+
+void launch_energy_sum_replicas(cudaStream_t s, int N, int n_rep, int n_per, const float4 *F, const float4 *Fb, double *out) {
+	cudaMemsetAsync(out, 0, sizeof(double) * (size_t) n_rep, s);
+	int tpb = 256;
+	k_energy_sum_replicas<<<(N + tpb - 1) / tpb, tpb, 0, s>>>(N, n_per, F, Fb, out);
 }
 
 } // namespace oxb

@@ -15,8 +15,30 @@ enum : int {
 	// and turns into a no-op, so a speculative batch of launches stops at the step that needs a list rebuild without any
 	// host synchronisation inside the batch.  No kernel ever reads a word that it can write itself.
 	OXB_FLAG_COUNT = 8,
-	OXB_FLAG_WORDS = 16,
+	OXB_FLAG_PROF_ON = 12,   // 1 = the first thread of the step's kernels stamps %globaltimer into the profile area (oxb_set_profile)
+	OXB_FLAG_WORDS = 16,     // words copied back by read_flags
+	OXB_PROF_OFFSET = 32,    // profile area (unsigned long long words) starts at this int offset
+	OXB_FLAG_ALLOC = 96,
 };
+
+// Device-side timeline of the hot loop: every kernel that opens a phase of the step has its first thread stamp %globaltimer; the time
+// since the previous stamp is charged to the phase that was open.  Works inside graph-launched batches and costs one thread a few
+// global accesses, so the decomposition is measured IN the timed region (bench.py roofline), launch gaps included: the phases sum to
+// the device time line of the run.  Layout (unsigned long long): [0] last stamp, [1] open phase, [2 + p] ns in phase p, [2 + NPHASE + p] entries into p.
+enum { OXB_PROF_OTHER = 0, OXB_PROF_FORCE = 1, OXB_PROF_INTEG = 2, OXB_PROF_WAIT = 3, OXB_PROF_SORT = 4, OXB_PROF_BUILD = 5, OXB_PROF_NPHASE = 6 };
+#ifdef __CUDACC__
+__device__ __forceinline__ void prof_mark(int *flags, int phase, bool reset = false) {
+	if(flags[OXB_FLAG_PROF_ON] == 0) return;
+	unsigned long long *prof = reinterpret_cast<unsigned long long *>(flags + OXB_PROF_OFFSET);
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	const unsigned long long open = prof[1];
+	if(!reset && prof[0] != 0ull) prof[2 + open] += t - prof[0];
+	if(reset || open != (unsigned long long) phase) prof[2 + OXB_PROF_NPHASE + phase] += 1ull;
+	prof[0] = t;
+	prof[1] = (unsigned long long) phase;
+}
+#endif
 
 struct DevExtForce {
 	int type, particle, ref, pbc;
@@ -59,9 +81,11 @@ struct ModelRef {
 // ---- forces.cu
 void launch_forces_particle(cudaStream_t s, const ModelRef &M, BoxF box, int N, const int4 *ipos, const int4 *iback, const float4 *quat,
 		const double4 *posd, const double4 *quatd, const int2 *bonds,
-		const int *nbr, const int *nnbr, int stride, float4 *F, float4 *T, int *flags, int hw);
+		const int *nbr, const int *nnbr, int stride, float4 *F, float4 *T, const oxb_replica_consts *rep, int n_per, int *flags, int hw);
 struct EdgeArgs {
 	int N;
+	const oxb_replica_consts *rep; // replica batching: one row per replica (null: single system), n_per particles per replica
+	int n_per;
 	const int4 *ipos, *iback;
 	const float4 *quat;
 	const double4 *posd, *quatd; // FP64 state: read only where an excluded-volume term is active (ExclRefine)
@@ -111,6 +135,8 @@ struct IntegrateArgs {
 	int *flags;
 	KinSums *sums;
 	ThermostatCfg th;
+	const oxb_replica_consts *rep; // replica batching: per-replica thermostat constants (null: th applies to every particle)
+	int n_per;
 	long long step;      // step index of the thermostat application, or < 0: read it from cur_step (graph-launched batches)
 	long long *cur_step; // two device words, see k_integrate
 };
@@ -156,10 +182,13 @@ void launch_rescale_positions(cudaStream_t s, const RescaleArgs &a);
 void launch_fix_diffusion(cudaStream_t s, int N, const int4 *ipos, const int *mol_of, const double *coms, const double *box, double4 *posd,
 		double4 *quatd, float4 *quat, int *shifts);
 void launch_energy_sum(cudaStream_t s, int N, const float4 *F, const float4 *Fb, double *out);
+// per-replica potential energies: out[r] = sum over the slots of replica r (n_rep doubles, zeroed here)
+void launch_energy_sum_replicas(cudaStream_t s, int N, int n_rep, int n_per, const float4 *F, const float4 *Fb, double *out);
 
 // ---- lists.cu
 struct ListArgs {
 	int N;
+	int n_rep, n_per; // replica batching: the cell table holds n_rep copies of the grid, cell id = replica * ncells + cell
 	double box[3];
 	BoxF boxf;
 	int ncell[3];
@@ -198,6 +227,7 @@ void launch_build_lists(cudaStream_t s, const ListArgs &a);
 // ---- sort.cu
 struct SortArgs {
 	int N;
+	int n_rep, n_per; // replica batching: the replica index forms the top bits of the key (slots stay replica-contiguous)
 	double box[3];
 	const double4 *posd;
 	int ncell[3];            // > 0: sort by the Hilbert index of the list builder's cell coordinates (binning for free)
@@ -206,6 +236,7 @@ struct SortArgs {
 	int *inv;                // inv[old_slot] = new_slot
 	void *cub_tmp;
 	size_t cub_tmp_bytes;
+	int *flags;
 };
 size_t sort_tmp_bytes(int N);
 void launch_hilbert_order(cudaStream_t s, const SortArgs &a);
@@ -223,6 +254,7 @@ struct PermuteArgs {
 	int2 *bonds_out;
 	int *slot_of; // slot_of[original id] = new slot
 	int *cell_lin; // optional: linear cell id of every new slot (what the list builder's binning would have produced)
+	int n_per;     // replica batching: particles per replica (cell ids are offset by replica * ncells)
 	double box[3];
 	int ncell[3];
 };

@@ -23,18 +23,21 @@ __device__ __forceinline__ int cell_coord(double x, double L, int n) {
 	return min(c, n - 1);
 }
 
-__global__ void __launch_bounds__(256) k_cell_keys(int N, const double4 *__restrict__ posd, double Lx, double Ly, double Lz, int nx, int ny, int nz,
-		int *__restrict__ key, int *__restrict__ val) {
+__global__ void __launch_bounds__(256) k_cell_keys(int N, int n_per, const double4 *__restrict__ posd, double Lx, double Ly, double Lz, int nx, int ny, int nz,
+		int *__restrict__ key, int *__restrict__ val, int *__restrict__ flags) {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i == 0) prof_mark(flags, OXB_PROF_BUILD);
 	if(i >= N) return;
 	double4 p = posd[i];
 	int cx = cell_coord(p.x, Lx, nx), cy = cell_coord(p.y, Ly, ny), cz = cell_coord(p.z, Lz, nz);
-	key[i] = cx + nx * (cy + ny * cz);
+	key[i] = cx + nx * (cy + ny * cz) + (i / n_per) * (nx * ny * nz); // replica batching: one copy of the grid per replica
 	val[i] = i;
 }
 
-__global__ void __launch_bounds__(256) k_cell_ranges(int N, const int *__restrict__ key_sorted, int *__restrict__ cell_start, int *__restrict__ cell_end) {
+__global__ void __launch_bounds__(256) k_cell_ranges(int N, const int *__restrict__ key_sorted, int *__restrict__ cell_start, int *__restrict__ cell_end,
+		int *__restrict__ flags) {
 	int j = blockIdx.x * blockDim.x + threadIdx.x;
+	if(j == 0) prof_mark(flags, OXB_PROF_BUILD);
 	if(j >= N) return;
 	int k = key_sorted[j];
 	if(j == 0 || key_sorted[j - 1] != k) cell_start[k] = j;
@@ -90,6 +93,7 @@ __global__ void __launch_bounds__(128) k_build_neigh(oxb::ListArgs a, const int 
 	const int nx = a.ncell[0], ny = a.ncell[1], nz = a.ncell[2];
 	const double4 pd = a.posd[i];
 	const int cx = cell_coord(pd.x, a.box[0], nx), cy = cell_coord(pd.y, a.box[1], ny), cz = cell_coord(pd.z, a.box[2], nz);
+	const int coff = (a.n_rep > 1) ? (i / a.n_per) * (nx * ny * nz) : 0; // this replica's copy of the grid
 	// phase 1: the 27 ranges as independent loads; only the non-empty ones are kept (in scan order, which keeps the neighbour
 	// order deterministic), so that all lanes of a warp walk through candidates instead of through mostly empty cells
 	int n_rg = 0;
@@ -105,7 +109,7 @@ __global__ void __launch_bounds__(128) k_build_neigh(oxb::ListArgs a, const int 
 #pragma unroll
 				for(int dx = -1; dx <= 1; dx++) {
 					int xc = cx + dx; xc += (xc < 0) ? nx : 0; xc -= (xc >= nx) ? nx : 0;
-					int c = xc + nx * (yc + ny * zc);
+					int c = coff + xc + nx * (yc + ny * zc);
 					rg[q] = make_int2(__ldg(cell_start + c), __ldg(cell_end + c));
 					q++;
 				}
@@ -168,7 +172,9 @@ __global__ void __launch_bounds__(128) k_build_neigh(oxb::ListArgs a, const int 
 			v3 db = min_image_fixed(a.boxf, ib, ibm);
 			if(m > i && d2 < a.rnear2 && near_pair(a, d, a1p, a1_of(__ldg(a.quat + m)), bkp, min_image_fixed(a.boxf, ipm, ibm))) {
 				higher_near++;
-				if(count < 64) mask0 |= 1ull << count;
+				// rows that overflow max_neigh are rebuilt after the matrix has grown: never flag an entry that was not written
+				if(count >= a.max_neigh) mask_overflow = true;
+				else if(count < 64) mask0 |= 1ull << count;
 				else if(count < 128) mask1 |= 1ull << (count - 64);
 				else mask_overflow = true;
 			}
@@ -221,7 +227,7 @@ __global__ void __launch_bounds__(128) k_fill_edges(oxb::ListArgs a) {
 	int off = a.edge_offsets[i];
 	const int nn = a.nnbr[i];
 	ulonglong2 mk = a.near_mask[i];
-	if(nn <= 127 || !(mk.y >> 63)) {
+	if(!(mk.y >> 63)) {
 		unsigned long long w = mk.x;
 		while(w) {
 			int k = __ffsll((long long) w) - 1;
@@ -281,18 +287,18 @@ size_t lists_tmp_bytes(int N, int ncells) {
 // cell_start has room for 2 * ncells ints: starts then ends
 void launch_build_lists(cudaStream_t s, const ListArgs &a) {
 	const int N = a.N;
-	const int ncells = a.ncell[0] * a.ncell[1] * a.ncell[2];
+	const int ncells = a.ncell[0] * a.ncell[1] * a.ncell[2] * a.n_rep;
 	int *cell_start = a.cell_start, *cell_end = a.cell_start + ncells;
 	int tpb = 256;
 	size_t tmp = a.cub_tmp_bytes;
 	if(!a.direct) {
 		// binning = stable sort of (cell, slot); with a.direct the re-sort that has just run left the particles ordered by
 		// cell and wrote each slot's cell id into cell_key_sorted (sort.cu: k_permute)
-		k_cell_keys<<<(N + tpb - 1) / tpb, tpb, 0, s>>>(N, a.posd, a.box[0], a.box[1], a.box[2], a.ncell[0], a.ncell[1], a.ncell[2], a.cell_key, a.cell_val);
+		k_cell_keys<<<(N + tpb - 1) / tpb, tpb, 0, s>>>(N, a.n_per, a.posd, a.box[0], a.box[1], a.box[2], a.ncell[0], a.ncell[1], a.ncell[2], a.cell_key, a.cell_val, a.flags);
 		cub::DeviceRadixSort::SortPairs(a.cub_tmp, tmp, a.cell_key, a.cell_key_sorted, a.cell_val, a.cell_val_sorted, N, 0, bits_for(ncells), s);
 	}
 	cudaMemsetAsync(cell_start, 0, sizeof(int) * 2 * (size_t) ncells, s);
-	k_cell_ranges<<<(N + tpb - 1) / tpb, tpb, 0, s>>>(N, a.cell_key_sorted, cell_start, cell_end);
+	k_cell_ranges<<<(N + tpb - 1) / tpb, tpb, 0, s>>>(N, a.cell_key_sorted, cell_start, cell_end, a.flags);
 	cudaMemsetAsync(a.flags + OXB_FLAG_MAX_NEIGH_SEEN, 0, sizeof(int), s);
 	if(a.direct) k_build_neigh<true><<<(N + 127) / 128, 128, 0, s>>>(a, cell_start, cell_end);
 	else k_build_neigh<false><<<(N + 127) / 128, 128, 0, s>>>(a, cell_start, cell_end);

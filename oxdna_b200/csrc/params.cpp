@@ -361,6 +361,18 @@ extern "C" int oxb_sizeof(int which) {
 	case 0: return (int) sizeof(oxb_dna2_params);
 	case 1: return (int) sizeof(oxb_rna2_params);
 	case 2: return (int) sizeof(oxb_ext_force);
+	case 3: return (int) sizeof(oxb_replica_consts);
 	default: return -1;
 	}
 }
+
+// the temperature-dependent subset of a parameter block (see oxb_replica_consts): stacking strength and Debye-Hueckel
+template<class PB>
+static void replica_consts_from(const PB *P, double a, double b, double c, double d, oxb_replica_consts *out) {
+	for(int i = 0; i < 25; i++) { out->stck_eps[i] = P->stck_eps[i]; out->stck_shift[i] = P->stck_shift[i]; }
+	out->dh_minus_kappa = P->dh_minus_kappa; out->dh_prefactor = P->dh_prefactor; out->dh_rhigh = P->dh_rhigh; out->dh_rc = P->dh_rc; out->dh_b = P->dh_b;
+	out->rcut2 = P->rcut * P->rcut;
+	out->th_a = (float) a; out->th_b = (float) b; out->th_c = (float) c; out->th_d = (float) d;
+}
+extern "C" void oxb_replica_consts_dna2(const oxb_dna2_params *P, double a, double b, double c, double d, oxb_replica_consts *out) { replica_consts_from(P, a, b, c, d, out); }
+extern "C" void oxb_replica_consts_rna2(const oxb_rna2_params *P, double a, double b, double c, double d, oxb_replica_consts *out) { replica_consts_from(P, a, b, c, d, out); }

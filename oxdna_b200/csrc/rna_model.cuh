@@ -214,10 +214,10 @@ OXB_HD PairEnergy rna2_nonbonded(const oxb_rna2_params &M, v3 r, const Axes &A, 
 	E.total = 0.f;
 	E.hb = 0.f;
 	float r2 = dot(r, r);
-	if(r2 >= M.rcut * M.rcut) return E; // RNAInteraction2.cpp:20-22
+	if(r2 >= (acc.rep ? acc.rep->rcut2 : M.rcut * M.rcut)) return E; // RNAInteraction2.cpp:20-22
 	v3 rbb = r + qback - pback;
 	float fs;
-	float en = dna2_dh(M, dot(rbb, rbb), p_end, q_end, fs);
+	float en = acc.rep ? dna2_dh(dh_view(M, acc.rep), dot(rbb, rbb), p_end, q_end, fs) : dna2_dh(M, dot(rbb, rbb), p_end, q_end, fs);
 	if(en != 0.f) { E.total += en; acc.site_kk(rbb * fs); }
 	if(r2 >= M.rcut_near * M.rcut_near) return E;
 	v3 rb = r + (B.a1 - A.a1) * M.base_a1;
@@ -246,7 +246,7 @@ OXB_HD float rna2_bonded(const oxb_rna2_params &M, v3 r, const Axes &A, const Ax
 	float inv = OXB_RSQRT(rs2);
 	float m = rs2 * inv;
 	int ti = btype_to_type(btq) * 5 + btype_to_type(btp);
-	RadVal f1 = f1_r(M.stck, M.stck_eps[ti], M.stck_shift[ti], m);
+	RadVal f1 = acc.rep ? f1_r(M.stck, acc.rep->stck_eps[ti], acc.rep->stck_shift[ti], m) : f1_r(M.stck, M.stck_eps[ti], M.stck_shift[ti], m);
 	if(f1.v != 0.f || f1.d != 0.f) {
 		v3 h = rs * inv;
 		v3 rbk = r + qback - pback;

@@ -43,14 +43,15 @@ __device__ __forceinline__ unsigned hilbert_key(unsigned x, unsigned y, unsigned
 	return key;
 }
 
-__global__ void __launch_bounds__(256) k_hilbert_keys(int N, const double4 *__restrict__ posd, double Lx, double Ly, double Lz, unsigned *__restrict__ keys,
-		int *__restrict__ vals) {
+__global__ void __launch_bounds__(256) k_hilbert_keys(int N, int n_per, const double4 *__restrict__ posd, double Lx, double Ly, double Lz, unsigned *__restrict__ keys,
+		int *__restrict__ vals, int *__restrict__ flags) {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i == 0) prof_mark(flags, OXB_PROF_SORT);
 	if(i >= N) return;
 	double4 p = posd[i];
-	const int bits = 10;
+	const int bits = (n_per < N) ? 8 : 10; // replica batching: the replica index takes the top bits of the 32-bit key
 	unsigned x = to_fixed(p.x, 1. / Lx) >> (32 - bits), y = to_fixed(p.y, 1. / Ly) >> (32 - bits), z = to_fixed(p.z, 1. / Lz) >> (32 - bits);
-	keys[i] = hilbert_key(x, y, z, bits);
+	keys[i] = hilbert_key(x, y, z, bits) | ((unsigned) (i / n_per) << (3 * bits));
 	vals[i] = i;
 }
 
@@ -63,12 +64,14 @@ __device__ __forceinline__ int cell_coord_s(double x, double L, int n) {
 	return min(c, n - 1);
 }
 
-__global__ void __launch_bounds__(256) k_cell_hilbert_keys(int N, const double4 *__restrict__ posd, double Lx, double Ly, double Lz, int nx, int ny, int nz,
-		int bits, unsigned *__restrict__ keys, int *__restrict__ vals) {
+__global__ void __launch_bounds__(256) k_cell_hilbert_keys(int N, int n_per, const double4 *__restrict__ posd, double Lx, double Ly, double Lz, int nx, int ny, int nz,
+		int bits, unsigned *__restrict__ keys, int *__restrict__ vals, int *__restrict__ flags) {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i == 0) prof_mark(flags, OXB_PROF_SORT);
 	if(i >= N) return;
 	double4 p = posd[i];
-	keys[i] = hilbert_key((unsigned) cell_coord_s(p.x, Lx, nx), (unsigned) cell_coord_s(p.y, Ly, ny), (unsigned) cell_coord_s(p.z, Lz, nz), bits);
+	keys[i] = hilbert_key((unsigned) cell_coord_s(p.x, Lx, nx), (unsigned) cell_coord_s(p.y, Ly, ny), (unsigned) cell_coord_s(p.z, Lz, nz), bits)
+			| ((unsigned) (i / n_per) << (3 * bits));
 	vals[i] = i;
 }
 
@@ -101,7 +104,8 @@ __global__ void __launch_bounds__(256) k_permute(oxb::PermuteArgs a) {
 	a.slot_of[word_index(ip.w)] = n;
 	if(a.cell_lin != nullptr) {
 		double4 p = a.posd_in[o];
-		a.cell_lin[n] = cell_coord_s(p.x, a.box[0], a.ncell[0]) + a.ncell[0] * (cell_coord_s(p.y, a.box[1], a.ncell[1]) + a.ncell[1] * cell_coord_s(p.z, a.box[2], a.ncell[2]));
+		a.cell_lin[n] = cell_coord_s(p.x, a.box[0], a.ncell[0]) + a.ncell[0] * (cell_coord_s(p.y, a.box[1], a.ncell[1]) + a.ncell[1] * cell_coord_s(p.z, a.box[2], a.ncell[2]))
+				+ (n / a.n_per) * (a.ncell[0] * a.ncell[1] * a.ncell[2]);
 	}
 }
 
@@ -111,22 +115,24 @@ namespace oxb {
 
 size_t sort_tmp_bytes(int N) {
 	size_t a = 0;
-	cub::DeviceRadixSort::SortPairs(nullptr, a, (unsigned *) nullptr, (unsigned *) nullptr, (int *) nullptr, (int *) nullptr, N, 0, 30);
+	cub::DeviceRadixSort::SortPairs(nullptr, a, (unsigned *) nullptr, (unsigned *) nullptr, (int *) nullptr, (int *) nullptr, N, 0, 32);
 	return a + 256;
 }
 
 void launch_hilbert_order(cudaStream_t s, const SortArgs &a) {
 	int tpb = 256, nb = (a.N + tpb - 1) / tpb;
 	size_t tmp = a.cub_tmp_bytes;
+	int rep_bits = 0;
+	while((1 << rep_bits) < a.n_rep) rep_bits++;
 	if(a.ncell[0] > 0) {
 		int bits = 1;
 		while((1 << bits) < std::max(a.ncell[0], std::max(a.ncell[1], a.ncell[2]))) bits++;
-		k_cell_hilbert_keys<<<nb, tpb, 0, s>>>(a.N, a.posd, a.box[0], a.box[1], a.box[2], a.ncell[0], a.ncell[1], a.ncell[2], bits, a.keys, a.vals);
-		cub::DeviceRadixSort::SortPairs(a.cub_tmp, tmp, a.keys, a.keys_sorted, a.vals, a.vals_sorted, a.N, 0, 3 * bits, s);
+		k_cell_hilbert_keys<<<nb, tpb, 0, s>>>(a.N, a.n_per, a.posd, a.box[0], a.box[1], a.box[2], a.ncell[0], a.ncell[1], a.ncell[2], bits, a.keys, a.vals, a.flags);
+		cub::DeviceRadixSort::SortPairs(a.cub_tmp, tmp, a.keys, a.keys_sorted, a.vals, a.vals_sorted, a.N, 0, 3 * bits + rep_bits, s);
 	}
 	else {
-		k_hilbert_keys<<<nb, tpb, 0, s>>>(a.N, a.posd, a.box[0], a.box[1], a.box[2], a.keys, a.vals);
-		cub::DeviceRadixSort::SortPairs(a.cub_tmp, tmp, a.keys, a.keys_sorted, a.vals, a.vals_sorted, a.N, 0, 30, s);
+		k_hilbert_keys<<<nb, tpb, 0, s>>>(a.N, a.n_per, a.posd, a.box[0], a.box[1], a.box[2], a.keys, a.vals, a.flags);
+		cub::DeviceRadixSort::SortPairs(a.cub_tmp, tmp, a.keys, a.keys_sorted, a.vals, a.vals_sorted, a.N, 0, (a.n_rep > 1 ? 24 : 30) + rep_bits, s);
 	}
 	k_invert<<<nb, tpb, 0, s>>>(a.N, a.vals_sorted, a.inv);
 }

@@ -120,7 +120,8 @@ class Simulation:
             self.barostat_attempts = self.barostat_accepted = 0
             self._rng = np.random.default_rng(self.seed + 7919)
 
-    def _set_model(self):
+    def _model_for(self, T):
+        """(parameter block, rcut) of the configured interaction at temperature T (simulation units)"""
         g = self.inp.get
         mbf = g("max_backbone_force", None)
         mbf = None if mbf is None else float(mbf)
@@ -130,45 +131,55 @@ class Simulation:
             # RNA2Interaction::get_settings: salt defaults to 1.0 (src/Interactions/RNAInteraction2.cpp:34-37); interaction_type = RNA
             # (class RNAInteraction) is the same model without the Debye-Hueckel and mismatch terms: salt 0 switches them off
             v2 = self.itype == "RNA2"
-            self.params, self.rcut = capi.rna2_params(self.T, float(g("salt_concentration", 1.0)) if v2 else 0.0, _bool(g("dh_half_charged_ends", 1)), mbf,
-                                                      float(g("max_backbone_force_far", 0.04)), v2 and _bool(g("mismatch_repulsion", 0)),
-                                                      float(g("mismatch_repulsion_strength", 1.0)))
+            params, rcut = capi.rna2_params(T, float(g("salt_concentration", 1.0)) if v2 else 0.0, _bool(g("dh_half_charged_ends", 1)), mbf,
+                                            float(g("max_backbone_force_far", 0.04)), v2 and _bool(g("mismatch_repulsion", 0)),
+                                            float(g("mismatch_repulsion_strength", 1.0)))
             if sd is not None:
                 B = "AGCT"
                 hb = lambda a, b: sd.get(f"HYDR_{a}_{b}", sd.get(f"HYDR_{b}_{a}"))
-                capi.rna2_params_seqdep(self.params, self.T, [sd[f"STCK_{a}_{b}"] for a in B for b in B], sd["ST_T_DEP"],
+                capi.rna2_params_seqdep(params, T, [sd[f"STCK_{a}_{b}"] for a in B for b in B], sd["ST_T_DEP"],
                                         [sd[f"CROSS_{a}_{b}"] for a in B for b in B], hb("A", "T"), hb("G", "C"), hb("G", "T"))
-            self.ctx.set_model_rna2(self.params, self.rcut)
-            return
+            return params, rcut
         if self.itype in ("DNA", "DNA_nomesh"):
-            self.params, self.rcut = capi.dna1_params(self.T, _bool(g("major_minor_grooving", 0)), mbf, float(g("max_backbone_force_far", 0.04)))
+            params, rcut = capi.dna1_params(T, _bool(g("major_minor_grooving", 0)), mbf, float(g("max_backbone_force_far", 0.04)))
         else:
-            self.params, self.rcut = capi.dna2_params(self.T, float(g("salt_concentration", 0.5)), _bool(g("dh_half_charged_ends", 1)), mbf,
-                                                      float(g("max_backbone_force_far", 0.04)))
+            params, rcut = capi.dna2_params(T, float(g("salt_concentration", 0.5)), _bool(g("dh_half_charged_ends", 1)), mbf,
+                                            float(g("max_backbone_force_far", 0.04)))
         if sd is not None:
             # DNAInteraction.cpp:329-375
             B = "AGCT"
             hb = lambda a, b: sd.get(f"HYDR_{a}_{b}", sd.get(f"HYDR_{b}_{a}"))
-            capi.dna2_params_seqdep(self.params, self.T, [sd[f"STCK_{a}_{b}"] for a in B for b in B], sd["STCK_FACT_EPS"], hb("A", "T"), hb("G", "C"))
-        self.ctx.set_model_dna2(self.params, self.rcut)
+            capi.dna2_params_seqdep(params, T, [sd[f"STCK_{a}_{b}"] for a in B for b in B], sd["STCK_FACT_EPS"], hb("A", "T"), hb("G", "C"))
+        return params, rcut
 
-    def _set_thermostat(self):
+    def _set_model(self):
+        self.params, self.rcut = self._model_for(self.T)
+        if self.itype in ("RNA2", "RNA"):
+            self.ctx.set_model_rna2(self.params, self.rcut)
+        else:
+            self.ctx.set_model_dna2(self.params, self.rcut)
+
+    def _thermostat_for(self, T):
+        """(type, every, a, b, c, d) of oxb_set_thermostat for the configured thermostat at temperature T"""
         g = self.inp.get
         kind = str(g("thermostat", "no")).lower()
         if kind == "no":
-            self.ctx.set_thermostat(capi.THERMOSTAT_NONE)
-        elif kind in ("john", "brownian"):  # synonyms, CUDAThermostatFactory.cu:23-28
+            return (capi.THERMOSTAT_NONE, 1, 0.0, 0.0, 0.0, 0.0)
+        if kind in ("john", "brownian"):  # synonyms, CUDAThermostatFactory.cu:23-28
             ns = int(g("newtonian_steps"))
-            pt, pr, resc = brownian_params(self.T, self.dt, ns, float(g("pt", 0.0)), float(g("diff_coeff", 0.0)))
-            self.ctx.set_thermostat(capi.THERMOSTAT_BROWNIAN, ns, pt, pr, resc, 0.0, self.seed)
-        elif kind == "langevin":
-            gt, gr, rt, rr = langevin_params(self.T, self.dt, float(g("gamma_trans", 0.0)), float(g("diff_coeff", 0.0)))
-            self.ctx.set_thermostat(capi.THERMOSTAT_LANGEVIN, 1, gt, gr, rt, rr, self.seed)
-        elif kind == "bussi":
+            pt, pr, resc = brownian_params(T, self.dt, ns, float(g("pt", 0.0)), float(g("diff_coeff", 0.0)))
+            return (capi.THERMOSTAT_BROWNIAN, ns, pt, pr, resc, 0.0)
+        if kind == "langevin":
+            gt, gr, rt, rr = langevin_params(T, self.dt, float(g("gamma_trans", 0.0)), float(g("diff_coeff", 0.0)))
+            return (capi.THERMOSTAT_LANGEVIN, 1, gt, gr, rt, rr)
+        if kind == "bussi":
             ns, tau = int(g("newtonian_steps")), int(g("bussi_tau"))
-            self.ctx.set_thermostat(capi.THERMOSTAT_BUSSI, ns, self.T, np.exp(-ns / float(tau)), 0.0, 0.0, self.seed)
-        else:
-            raise ValueError(f"Invalid thermostat '{kind}'")
+            return (capi.THERMOSTAT_BUSSI, ns, T, np.exp(-ns / float(tau)), 0.0, 0.0)
+        raise ValueError(f"Invalid thermostat '{kind}'")
+
+    def _set_thermostat(self):
+        kind, every, a, b, c, d = self._thermostat_for(self.T)
+        self.ctx.set_thermostat(kind, every, a, b, c, d, self.seed)
 
     def update_temperature(self, T):
         """ConfigInfo::update_temperature -> interaction re-init + thermostat re-init (SURVEY 3.4)."""
@@ -207,3 +218,102 @@ class Simulation:
 
     def close(self):
         self.ctx.close()
+
+
+class ReplicaBatch(Simulation):
+    """R temperature replicas of one system in ONE GPU context (replica batching, include/oxdna_b200.h oxb_set_replicas): every kernel of
+    the step is launched once for all replicas; the temperature-dependent constants (stacking strength, Debye-Hueckel, thermostat) live
+    in a per-replica device table, so a temperature swap rewrites table rows and nothing else.  The reference runs one process and one
+    GPU context per replica (examples/OXPY_REMD/remd.py:67-102) and re-initialises interaction + thermostat on every accepted swap.
+
+    topology: ONE replica's topology; confs: one conf dict per replica (same box); temperatures: simulation units, one per replica;
+    ladder_max: hottest temperature any replica may be given later (fixes the list radii; default max(temperatures))."""
+
+    def __init__(self, inp, topology, confs, temperatures, device=0, ladder_max=None):
+        R, n = len(confs), len(topology["btype"])
+        if len(temperatures) != R:
+            raise ValueError("one temperature per replica")
+        self.n_replicas, self.n_per = R, n
+        off = (np.arange(R) * n)[:, None]
+
+        def rep_idx(a):  # neighbour indices: -1 stays -1
+            a = np.asarray(a)[None, :]
+            return np.where(a >= 0, a + off, a).reshape(-1)
+
+        nstrand = int(np.max(topology.get("strand", np.zeros(n, dtype=int)))) + 1
+        top = dict(btype=np.tile(np.asarray(topology["btype"]), R), n3=rep_idx(topology["n3"]), n5=rep_idx(topology["n5"]),
+                   strand=(np.asarray(topology.get("strand", np.zeros(n, dtype=int)))[None, :] + (np.arange(R) * nstrand)[:, None]).reshape(-1))
+        cat = lambda k: None if confs[0].get(k) is None else np.concatenate([np.asarray(c[k], dtype=np.float64) for c in confs])
+        conf = dict(box=confs[0]["box"], pos=cat("pos"), a1=cat("a1"), a3=cat("a3"), vel=cat("vel"), L=cat("L"))
+        inp = dict(inp)
+        if str(inp.get("thermostat", "no")).lower() == "bussi":
+            raise ValueError("replica batching is not available with the Bussi thermostat")
+        ext = inp.get("external_forces_list")
+        if ext:
+            full = []
+            for r in range(R):
+                for e in ext:
+                    e = dict(e)
+                    for key in ("particle", "ref_particle"):
+                        if isinstance(e.get(key), (int, np.integer)) and e[key] >= 0:
+                            e[key] = int(e[key]) + r * n
+                        elif key in e and not isinstance(e[key], (int, np.integer)):
+                            raise ValueError("replica batching: external forces must name single particles")
+                    full.append(e)
+            inp["external_forces_list"] = full
+        self.temps = np.asarray(temperatures, dtype=np.float64)
+        inp["T"] = float(max(float(np.max(self.temps)), ladder_max or 0.0))  # list radii: the hottest Hamiltonian of the ladder
+        super().__init__(inp, top, conf, device=device)
+        self.ctx.set_replicas(R)
+        self._rows = {}
+        self._table = None
+        self.set_temperatures(self.temps)
+
+    def _row(self, T):
+        key = float(T)
+        if key not in self._rows:
+            P, _ = self._model_for(key)
+            self._rows[key] = capi.replica_consts(P, self._thermostat_for(key)[2:])
+        return self._rows[key]
+
+    def set_temperatures(self, T, first=False):
+        T = np.asarray(T, dtype=np.float64)
+        if self._table is None or not np.array_equal(T, self._table):
+            self.ctx.set_replica_consts([self._row(t) for t in T])
+            self._table = T.copy()
+        self.temps = T.copy()
+
+    def energies(self):
+        return self.ctx.replica_energies()
+
+    def energies_at(self, T, mask=None):
+        """potential energy of every replica under the Hamiltonian of temperature T[r] (one force pass for the whole batch); the table
+        stays at T until set_temperatures is called"""
+        T = np.asarray(T, dtype=np.float64)
+        if not np.array_equal(T, self._table):
+            self.ctx.set_replica_consts([self._row(t) for t in T])
+            self._table = T.copy()
+        return self.ctx.replica_energies()
+
+    def system_energy(self):
+        return float(np.sum(self.energies()))
+
+    def update_temperature(self, T):
+        raise ValueError("a replica batch takes one temperature per replica: set_temperatures")
+
+    def get_states(self):
+        st = self.ctx.get_state()
+        n = self.n_per
+        return [{k: v[r * n:(r + 1) * n] for k, v in st.items()} for r in range(self.n_replicas)]
+
+
+def make_batches(inp, topology, confs, temperatures, device=0, ladder_max=None, max_particles=4000000):
+    """Splits the local replicas into as few ReplicaBatch contexts as the 22-bit particle index allows (64 x 81,920 nt = 2 batches)."""
+    R, n = len(confs), len(topology["btype"])
+    per = max(1, min(R, max_particles // n))
+    n_batches = (R + per - 1) // per
+    per = (R + n_batches - 1) // n_batches
+    out = []
+    for b in range(0, R, per):
+        out.append(ReplicaBatch(inp, topology, confs[b:b + per], temperatures[b:b + per], device=device, ladder_max=ladder_max))
+    return out

@@ -820,9 +820,11 @@ def test_full_size_c2_against_the_oracle():
             other.close()
 
 
-def test_full_size_c4_properties():
-    """BASELINE config C4 at its full size (1,000,000 nt, 50,000 mutual traps, use_edge = 1, Hilbert sort on): the pair set is bit-exact
-    against the oracle's cell list; size-independent properties of the force field hold -- Newton's third law (internal forces sum to
+def test_full_size_c4_forces_against_the_oracle():
+    """BASELINE config C4 at its full size (1,000,000 nt, 50,000 mutual traps, use_edge = 1, Hilbert sort on) after 150 thermalising
+    steps with re-sorts, i.e. with the launch shape of the headline benchmark: the pair set is bit-exact against the oracle's cell list
+    (12.3 M pairs); forces (mutual traps included), lab-frame torques <= 1e-5 * max|.| and the potential energy <= 1e-6 against the
+    oracle on the downloaded state; size-independent properties of the force field hold -- Newton's third law (internal forces sum to
     zero; the trap pairs are mutual), the energy equals the particle-centric evaluation, and a rigid translation by a non-lattice
     vector leaves forces and energy unchanged (fixed-point positions: up to the 2^-32 L grid)."""
     nd = 25000
@@ -831,12 +833,28 @@ def test_full_size_c4_properties():
         a, b = 40 * d, 40 * d + 39
         ext.append(dict(type="mutual_trap", particle=a, ref_particle=b, stiff=0.1, r0=1.2, PBC=1))
         ext.append(dict(type="mutual_trap", particle=b, ref_particle=a, stiff=0.1, r0=1.2, PBC=1))
-    sysm, sim = _full_size_system(nd, sites=30, equil=100, external_forces_list=ext)
+    sysm, sim = _full_size_system(nd, sites=30, equil=150, external_forces_list=ext)
     other = None
     try:
+        # forces of the state the run left behind, computed with the lists the RUN built (several steps old) -- the production launch shape
+        run_out = sim.ctx.get_forces()
         st = sim.ctx.get_state()
         P = O.dna2_params(parse_temperature("300K"), 0.5)
         pairs = O.verlet_pairs(st["pos"], sysm["n3"], sysm["n5"], sysm["box"], P.rcut + 2 * 0.05)
+        ref = O.forces(P, st["pos"], O.axes_from_a1a3(st["a1"], st["a3"]), sysm["btype"], sysm["n3"], sysm["n5"], sysm["box"], pairs)
+        # mutual traps (src/Forces/MutualTrap.cpp:54-66): F_p = stiff (|dr| - r0) dr / |dr|, dr = min-image(r_ref - r_p)
+        pa, pb = np.array([e["particle"] for e in ext]), np.array([e["ref_particle"] for e in ext])
+        dr = st["pos"][pb] - st["pos"][pa]
+        dr -= np.rint(dr / sysm["box"]) * sysm["box"]
+        m = np.linalg.norm(dr, axis=1)
+        fref = ref["force"].copy()
+        np.add.at(fref, pa, dr * (0.1 * (m - 1.2) / m)[:, None])
+        fmax0, tmax0 = np.linalg.norm(fref, axis=1).max(), np.linalg.norm(ref["torque_lab"], axis=1).max()
+        dF = np.linalg.norm(run_out["force"] - fref, axis=1).max()
+        dT = np.linalg.norm(run_out["torque_lab"] - ref["torque_lab"], axis=1).max()
+        assert dF <= 1e-5 * fmax0, (dF, fmax0)
+        assert dT <= 1e-5 * tmax0, (dT, tmax0)
+        assert abs(run_out["U"] - ref["U"]) <= 1e-6 * abs(ref["U"]), (run_out["U"], ref["U"])
         sim.ctx.update_lists()  # the list in use was built some steps ago: rebuild (and re-sort) at the downloaded configuration
         got = sim.ctx.get_pairs()
 
@@ -848,6 +866,10 @@ def test_full_size_c4_properties():
         assert len(kg) == len(kr) and len(np.unique(kg)) == len(kg) and np.array_equal(kg, kr)
         sim.ctx.compute_forces()
         out = sim.ctx.get_forces()
+        # same comparison on the freshly rebuilt lists
+        assert np.linalg.norm(out["force"] - fref, axis=1).max() <= 1e-5 * fmax0
+        assert np.linalg.norm(out["torque_lab"] - ref["torque_lab"], axis=1).max() <= 1e-5 * tmax0
+        assert abs(out["U"] - ref["U"]) <= 1e-6 * abs(ref["U"])
         fsum = np.abs(out["force"].sum(axis=0)).max()
         assert fsum <= 1e-6 * np.abs(out["force"]).sum(), fsum
         inp = dict(sim.inp, use_edge=0, thermostat="no")
