@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/oxdna_b200.h"
 
@@ -78,6 +79,27 @@ __host__ __device__ __forceinline__ unsigned to_fixed(double x, double invL) {
 	unsigned long long u = (unsigned long long) (f * 4294967296.0 + 0.5);
 	return (unsigned) (u & 0xFFFFFFFFull);
 }
+
+// ---- staleness references of the Verlet lists.  The list builder records where the centre, the backbone site and the base site of
+// every particle were; the integrator compares against them every step.  They live in the otherwise unused .w lanes of the FP64
+// position / velocity / angular-momentum elements (which the integrator streams anyway: the three int4 arrays they replace cost it
+// 48 B of reads per particle-step) as 3 x 21-bit fixed point, rounded to nearest: resolution L / 2^21, error <= L / 2^22 per axis,
+// which the integrator's threshold is tightened by.
+OXB_HD double pack_ref(int4 p) {
+	const unsigned long long x = (((unsigned) p.x + 0x400u) >> 11) & 0x1FFFFFu, y = (((unsigned) p.y + 0x400u) >> 11) & 0x1FFFFFu, z = (((unsigned) p.z + 0x400u) >> 11) & 0x1FFFFFu;
+	const unsigned long long w = x | (y << 21) | (z << 42);
+#ifdef __CUDA_ARCH__
+	return __longlong_as_double((long long) w);
+#else
+	double d; memcpy(&d, &w, 8); return d;
+#endif
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ int4 unpack_ref(double d) {
+	const unsigned long long w = (unsigned long long) __double_as_longlong(d);
+	return make_int4((int) ((unsigned) (w & 0x1FFFFFull) << 11), (int) ((unsigned) ((w >> 21) & 0x1FFFFFull) << 11), (int) ((unsigned) ((w >> 42) & 0x1FFFFFull) << 11), 0);
+}
+#endif
 
 // ---- Philox4x32-10 counter-based RNG (Salmon et al., SC'11).  Stateless: stream = (seed, original particle id),
 // counter = (step, draw index), so the Hilbert re-sort and temperature changes never touch RNG state.

@@ -39,7 +39,7 @@ struct oxb_ctx {
 	// double-buffered state (slot order)
 	int cur = 0;
 	double4 *posd[2] = { nullptr, nullptr }, *veld[2] = { nullptr, nullptr }, *Ld[2] = { nullptr, nullptr }, *quatd[2] = { nullptr, nullptr };
-	int4 *ipos[2] = { nullptr, nullptr }, *list_ipos[2] = { nullptr, nullptr }, *iback[2] = { nullptr, nullptr }, *list_iback[2] = { nullptr, nullptr }, *list_ibase[2] = { nullptr, nullptr };
+	int4 *ipos[2] = { nullptr, nullptr }, *iback[2] = { nullptr, nullptr };
 	float4 *Fb = nullptr;
 	float4 *quat[2] = { nullptr, nullptr }, *F[2] = { nullptr, nullptr }, *T[2] = { nullptr, nullptr };
 	int2 *bonds[2] = { nullptr, nullptr };
@@ -112,6 +112,7 @@ struct oxb_ctx {
 	cudaEvent_t ev_wait = nullptr;
 	bool defer_build_checks = true; // OXB_DEFER_BUILD_CHECK=0 restores one host synchronisation per rebuild
 	bool build_unchecked = false; // a list rebuild was launched without waiting for its overflow flags (oxb_run); the next batch checks
+	bool dh_half = true; // Debye-Hueckel matrix with every pair in one row + partner atomics (OXB_DH_HALF=0: full matrix, no atomics)
 	bool fork_streams = true; // force pass on three concurrent streams (OXB_FORK=0/1 overrides the size-based default)
 	bool mid_step = false; // positions already advanced for `step`, forces pending
 	ThermostatCfg th;
@@ -285,7 +286,8 @@ oxb::ListArgs list_args(oxb_ctx *c) {
 	a.cell_start = c->cell_start;
 	a.nbr = c->nbr; a.nnbr = c->nnbr; a.max_neigh = c->max_neigh; a.stride = c->N;
 	a.edges = c->edges; a.edge_offsets = c->edge_offsets; a.n_edges = c->n_edges; a.edge_capacity = c->edge_capacity;
-	a.iback = c->iback[c->cur]; a.list_iback = c->list_iback[c->cur]; a.list_ibase = c->list_ibase[c->cur]; a.quat = c->quat[c->cur];
+	a.iback = c->iback[c->cur]; a.quat = c->quat[c->cur];
+	a.ref_pos = c->posd[c->cur]; a.ref_vel = c->veld[c->cur]; a.ref_L = c->Ld[c->cur];
 	a.base_a1 = c->model.base_a1; a.stack_a1 = c->model.stack_a1;
 	{
 		const oxb_dna2_params &M = c->model;
@@ -296,6 +298,7 @@ oxb::ListArgs list_args(oxb_ctx *c) {
 		a.r2_bk = sq(std::max((double) M.excl[2].rc, (double) M.excl[3].rc) + pad);
 		a.r2_stack = sq((double) M.cxst.rchigh + pad);
 	} a.dh_nbr = c->dh_nbr; a.dh_nnbr = c->dh_nnbr; a.max_dh = c->max_dh;
+	a.dh_half = c->dh_half && c->use_edge;
 	{
 		double rd = (double) c->model.dh_rc + 2. * c->skin + 0.02;
 		a.rdh2 = (float) (rd * rd);
@@ -306,7 +309,6 @@ oxb::ListArgs list_args(oxb_ctx *c) {
 		double rn = (double) c->model.rcut_near + 2. * c->skin + 0.02;
 		a.rnear2 = (float) (rn * rn);
 	}
-	a.list_ipos = c->list_ipos[c->cur];
 	a.flags = c->flags;
 	a.cub_tmp = c->cub_tmp; a.cub_tmp_bytes = c->cub_tmp_bytes;
 	a.build_edges = c->use_edge != 0;
@@ -349,9 +351,8 @@ int do_sort(oxb_ctx *c) {
 	p.N = N; p.perm = c->hvals_sorted; p.inv = c->hinv;
 	p.posd_in = c->posd[a]; p.veld_in = c->veld[a]; p.Ld_in = c->Ld[a]; p.quatd_in = c->quatd[a];
 	p.posd_out = c->posd[b]; p.veld_out = c->veld[b]; p.Ld_out = c->Ld[b]; p.quatd_out = c->quatd[b];
-	p.ipos_in = c->ipos[a]; p.list_ipos_in = c->list_ipos[a]; p.ipos_out = c->ipos[b]; p.list_ipos_out = c->list_ipos[b];
-	p.iback_in = c->iback[a]; p.iback_out = c->iback[b]; p.list_iback_in = c->list_iback[a]; p.list_iback_out = c->list_iback[b];
-	p.list_ibase_in = c->list_ibase[a]; p.list_ibase_out = c->list_ibase[b];
+	p.ipos_in = c->ipos[a]; p.ipos_out = c->ipos[b];
+	p.iback_in = c->iback[a]; p.iback_out = c->iback[b];
 	p.quat_in = c->quat[a]; p.F_in = c->F[a]; p.T_in = c->T[a]; p.quat_out = c->quat[b]; p.F_out = c->F[b]; p.T_out = c->T[b];
 	p.bonds_in = c->bonds[a]; p.bonds_out = c->bonds[b];
 	p.slot_of = c->slot_of;
@@ -432,6 +433,7 @@ int launch_forces(oxb_ctx *c, int hw, bool clear, long long step) {
 		if(clear) {
 			CU(cudaMemsetAsync(c->F[a], 0, sizeof(float4) * (size_t) c->N, m));
 			CU(cudaMemsetAsync(c->T[a], 0, sizeof(float4) * (size_t) c->N, m));
+			if(c->dh_half) CU(cudaMemsetAsync(c->Fb, 0, sizeof(float4) * (size_t) c->N, m));
 		}
 		oxb::EdgeArgs e;
 		e.rep = c->rep; e.n_per = c->n_per;
@@ -440,6 +442,7 @@ int launch_forces(oxb_ctx *c, int hw, bool clear, long long step) {
 		e.F = c->F[a]; e.T = c->T[a]; e.Fb = c->Fb; e.hb_list = c->hb_list; e.cx_list = c->cx_list; e.cr_list = c->cr_list; e.seg_counts = c->seg_counts;
 		e.ex_list = c->ex_list; e.ex_counts = c->ex_counts; e.ex_bonded = c->ex_bonded; e.ex_seg = c->ex_seg;
 		e.refine = (c->precision == OXB_PRECISION_MIXED) ? 1 : 0;
+		e.dh_half = c->dh_half ? 1 : 0;
 		e.n_seg = c->n_seg; e.hb_seg = c->hb_seg; e.cx_seg = c->cx_seg; e.cr_seg = c->cr_seg;
 		// ~1.7 items per particle in that list; aim at ~2 items per consumer thread
 		e.hb_split = (int) std::max<long long>(1, std::min<long long>(8, (17ll * c->N / 10 / c->n_seg + 64) / 128));
@@ -507,14 +510,20 @@ oxb::IntegrateArgs integ_args(oxb_ctx *c, long long step) {
 	const int k = c->cur;
 	a.N = c->N; a.dt = c->dt;
 	for(int d = 0; d < 3; d++) a.box_inv[d] = 1. / c->box[d];
-	a.skin2 = (float) (c->skin * c->skin);
+	{
+		// the staleness references are 21-bit fixed point (common.cuh, pack_ref): tighten the threshold by their worst-case error
+		const double lmax = std::max(c->box[0], std::max(c->box[1], c->box[2]));
+		const double s_eff = std::max(c->skin - 1.7321 * lmax / 4194304., 0.5 * c->skin);
+		a.skin2 = (float) (s_eff * s_eff);
+	}
 	a.box = c->boxf;
 	a.posd = c->posd[k]; a.veld = c->veld[k]; a.Ld = c->Ld[k]; a.quatd = c->quatd[k];
-	a.ipos = c->ipos[k]; a.quat = c->quat[k]; a.list_ipos = c->list_ipos[k];
-	a.F = c->F[k]; a.T = c->T[k]; a.Fb = c->use_edge ? c->Fb : nullptr; a.iback = c->iback[k]; a.list_iback = c->list_iback[k]; a.list_ibase = c->list_ibase[k];
+	a.ipos = c->ipos[k]; a.quat = c->quat[k];
+	a.F = c->F[k]; a.T = c->T[k]; a.Fb = c->use_edge ? c->Fb : nullptr; a.iback = c->iback[k];
 	a.back_a1 = c->model.back_a1; a.back_a2 = c->model.back_a2; a.back_a3 = c->back_a3; a.base_a1 = c->model.base_a1;
 	a.flags = c->flags; a.sums = c->sums; a.th = c->th; a.step = step;
 	a.rep = c->rep; a.n_per = c->n_per;
+	a.zero_Fb = (c->use_edge && c->dh_half) ? 1 : 0;
 	a.cur_step = c->cur_step;
 	return a;
 }
@@ -726,16 +735,17 @@ int oxb_create(oxb_ctx **out, int device, int N, int precision) {
 		if(sf != nullptr && atof(sf) > 0.) c->spec_factor = atof(sf);
 		const char *db = getenv("OXB_DEFER_BUILD_CHECK");
 		if(db != nullptr) c->defer_build_checks = (db[0] != '0');
+		const char *dhh = getenv("OXB_DH_HALF");
+		if(dhh != nullptr) c->dh_half = (dhh[0] != '0');
 		const char *f = getenv("OXB_FORK");
 		if(f != nullptr) c->fork_streams = (f[0] != '0');
 	}
 	for(int k = 0; k < 2; k++) {
 		CU(dalloc(&c->posd[k], N)); CU(dalloc(&c->veld[k], N)); CU(dalloc(&c->Ld[k], N)); CU(dalloc(&c->quatd[k], N));
-		CU(dalloc(&c->ipos[k], N)); CU(dalloc(&c->list_ipos[k], N)); CU(dalloc(&c->iback[k], N)); CU(dalloc(&c->list_iback[k], N)); CU(dalloc(&c->list_ibase[k], N));
-		CU(cudaMemset(c->list_iback[k], 0, sizeof(int4) * N)); CU(cudaMemset(c->list_ibase[k], 0, sizeof(int4) * N)); CU(dalloc(&c->quat[k], N)); CU(dalloc(&c->F[k], N)); CU(dalloc(&c->T[k], N));
+		CU(dalloc(&c->ipos[k], N)); CU(dalloc(&c->iback[k], N));
+		CU(dalloc(&c->quat[k], N)); CU(dalloc(&c->F[k], N)); CU(dalloc(&c->T[k], N));
 		CU(dalloc(&c->bonds[k], N));
 		CU(cudaMemset(c->F[k], 0, sizeof(float4) * N)); CU(cudaMemset(c->T[k], 0, sizeof(float4) * N));
-		CU(cudaMemset(c->list_ipos[k], 0, sizeof(int4) * N));
 	}
 	CU(dalloc(&c->slot_of, N));
 	CU(dalloc(&c->Fb, N));
@@ -764,8 +774,8 @@ void oxb_destroy(oxb_ctx *c) {
 	if(c->ev_wait) cudaEventDestroy(c->ev_wait);
 	cudaFree(c->cur_step);
 	for(int k = 0; k < 2; k++) {
-		cudaFree(c->posd[k]); cudaFree(c->veld[k]); cudaFree(c->Ld[k]); cudaFree(c->quatd[k]); cudaFree(c->ipos[k]); cudaFree(c->list_ipos[k]);
-		cudaFree(c->quat[k]); cudaFree(c->F[k]); cudaFree(c->T[k]); cudaFree(c->bonds[k]); cudaFree(c->iback[k]); cudaFree(c->list_iback[k]); cudaFree(c->list_ibase[k]);
+		cudaFree(c->posd[k]); cudaFree(c->veld[k]); cudaFree(c->Ld[k]); cudaFree(c->quatd[k]); cudaFree(c->ipos[k]);
+		cudaFree(c->quat[k]); cudaFree(c->F[k]); cudaFree(c->T[k]); cudaFree(c->bonds[k]); cudaFree(c->iback[k]);
 	}
 	cudaFree(c->Fb);
 	cudaFree(c->rep); cudaFree(c->d_rep_energy);

@@ -230,10 +230,14 @@ __device__ __forceinline__ bool segmented_reduce(int key, unsigned lane, float (
 // loads in flight; index loads stay sector-efficient (LPP rows x 32 / LPP consecutive ints per warp instruction).
 // REP (replica batching): the constants come from the row of the particle's replica, as register values; the single-system
 // instantiation keeps them as constant-bank operands.
-template<class MD, int LPP, bool REP>
+// HALF: the matrix lists every pair in ONE of its two rows; the thread evaluates it once, keeps its own share in registers and sends
+// the partner's with one 128-bit red.global.add (half the evaluations and half the index traffic of the full matrix; Fb is then an
+// accumulator that the integrator zeroes, and the sum is no longer order-deterministic -- like the rest of the edge pipeline).
+template<class MD, int LPP, bool REP, bool HALF>
 __global__ void __launch_bounds__(128) k_dh_particle(const __grid_constant__ typename MD::Params M, BoxF box, int N, const int4 *__restrict__ iback,
 		const int *__restrict__ dh_nbr, const int *__restrict__ dh_nnbr, float4 *__restrict__ Fb, const oxb_replica_consts *__restrict__ rep, int n_per,
-		const int *__restrict__ flags, int hw) {
+		int *__restrict__ flags, int hw) {
+	if(blockIdx.x == 0 && threadIdx.x == 0) prof_mark(flags, flags[hw] ? OXB_PROF_WAIT : OXB_PROF_FORCE);
 	if(flags[hw]) return;
 	const int gid = blockIdx.x * blockDim.x + threadIdx.x;
 	const int sub = gid % LPP;
@@ -256,6 +260,7 @@ __global__ void __launch_bounds__(128) k_dh_particle(const __grid_constant__ typ
 		float en = REP ? dna2_dh_fast(D, dot(rbb, rbb), p_end, bq.w & 1, fs) : dna2_dh_fast(M, dot(rbb, rbb), p_end, bq.w & 1, fs);
 		e += en;
 		axpy(f, -fs, rbb);
+		if(HALF && en != 0.f) atomic_add4(Fb + j, fs * rbb.x, fs * rbb.y, fs * rbb.z, en);
 	}
 	if(LPP > 1) {
 #pragma unroll
@@ -264,7 +269,8 @@ __global__ void __launch_bounds__(128) k_dh_particle(const __grid_constant__ typ
 			f.z += __shfl_xor_sync(0xffffffffu, f.z, o); e += __shfl_xor_sync(0xffffffffu, e, o);
 		}
 	}
-	if(active && sub == 0) Fb[i] = make_float4(f.x, f.y, f.z, e);
+	if(HALF) { if(active && sub == 0 && e != 0.f) atomic_add4(Fb + i, f.x, f.y, f.z, e); }
+	else if(active && sub == 0) Fb[i] = make_float4(f.x, f.y, f.z, e);
 }
 
 // Work lists are SEGMENTED by producer block: block b of k_edge_near owns list[b * seg .. (b + 1) * seg) and publishes its
@@ -428,6 +434,7 @@ template<class MD>
 __global__ void __launch_bounds__(128, OXB_MB_BONDED) k_bonded(const __grid_constant__ typename MD::Params M, BoxF box, int N, const int4 *__restrict__ ipos,
 		const int4 *__restrict__ iback, const float4 *__restrict__ quat, const int2 *__restrict__ bonds, float4 *__restrict__ F, float4 *__restrict__ T,
 		int *__restrict__ ex_bonded, int refine, const oxb_replica_consts *__restrict__ rep, int n_per, int *__restrict__ flags, int hw) {
+	if(blockIdx.x == 0 && threadIdx.x == 0) prof_mark(flags, flags[hw] ? OXB_PROF_WAIT : OXB_PROF_FORCE);
 	if(flags[hw]) return;
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= N) return;
@@ -996,10 +1003,14 @@ static void launch_edge_stage_t(cudaStream_t s, int which, const typename MD::Pa
 		// (profiles/smalln_sweep_r01.txt): the kernel is bound by L2 gather bandwidth, not by loads in flight.  OXB_DH_LPP overrides.
 		static const int lpp_env = env_int("OXB_DH_LPP", 0);
 		const int lpp = lpp_env > 0 ? lpp_env : 1;
-		if(a.rep != nullptr) k_dh_particle<MD, 1, true><<<blocks_for(a.N), 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, a.rep, a.n_per, flags, hw);
-		else if(lpp >= 4) k_dh_particle<MD, 4, false><<<blocks_for(4ll * a.N), 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, nullptr, 1, flags, hw);
-		else if(lpp == 2) k_dh_particle<MD, 2, false><<<blocks_for(2ll * a.N), 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, nullptr, 1, flags, hw);
-		else k_dh_particle<MD, 1, false><<<blocks_for(a.N), 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, nullptr, 1, flags, hw);
+		if(a.rep != nullptr) {
+			if(a.dh_half) k_dh_particle<MD, 1, true, true><<<blocks_for(a.N), 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, a.rep, a.n_per, flags, hw);
+			else k_dh_particle<MD, 1, true, false><<<blocks_for(a.N), 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, a.rep, a.n_per, flags, hw);
+		}
+		else if(a.dh_half) k_dh_particle<MD, 1, false, true><<<blocks_for(a.N), 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, nullptr, 1, flags, hw);
+		else if(lpp >= 4) k_dh_particle<MD, 4, false, false><<<blocks_for(4ll * a.N), 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, nullptr, 1, flags, hw);
+		else if(lpp == 2) k_dh_particle<MD, 2, false, false><<<blocks_for(2ll * a.N), 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, nullptr, 1, flags, hw);
+		else k_dh_particle<MD, 1, false, false><<<blocks_for(a.N), 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, nullptr, 1, flags, hw);
 		break;
 	}
 	// the producer and the three consumers of the segmented work lists share one fixed grid (a.n_seg blocks, grid-stride

@@ -62,7 +62,9 @@ __global__ void __launch_bounds__(256, OXB_MB_INTEGRATE) k_integrate(oxb::Integr
 		if(PH & (OXB_PH_SECOND | OXB_PH_FIRST)) {
 			// the force kernels accumulate the torque in the lab frame: rotate it into the body frame (L is a body-frame
 			// angular momentum with unit inertia, src/CUDA/Interactions/CUDA_DNA.cuh:896)
-			Axes A = axes_from_quat(a.quat[i]);
+			// (the FP32 copy of the quaternion is not read: it is re-derived from the FP64 one that the first-half phase streams anyway)
+			const double4 qd0 = a.quatd[i];
+			Axes A = axes_from_quat(make_float4((float) qd0.x, (float) qd0.y, (float) qd0.z, (float) qd0.w));
 			v3 tl = mk3(T.x, T.y, T.z);
 			if(a.Fb != nullptr) {
 				// edge pipeline: the Debye-Hueckel kernel leaves its force sum, acting at the backbone site, in Fb
@@ -164,20 +166,21 @@ __global__ void __launch_bounds__(256, OXB_MB_INTEGRATE) k_integrate(oxb::Integr
 				ib.x = (int) to_fixed(bx, a.box_inv[0]); ib.y = (int) to_fixed(by, a.box_inv[1]); ib.z = (int) to_fixed(bz, a.box_inv[2]);
 				a.iback[i] = ib;
 				// rotational staleness: neither the backbone site nor the base site may have moved further than the skin
-				v3 db = min_image_fixed(a.box, a.list_iback[i], ib);
+				v3 db = min_image_fixed(a.box, unpack_ref(v.w), ib);
 				if(dot(db, db) > a.skin2) flags[wr] = 1;
 				double c1 = a.base_a1;
 				int4 is = ib;
 				is.x = (int) to_fixed(r.x + c1 * (sqx - sqy - sqz + sqw), a.box_inv[0]);
 				is.y = (int) to_fixed(r.y + c1 * (2. * (xy + zw)), a.box_inv[1]);
 				is.z = (int) to_fixed(r.z + c1 * (2. * (xz - yw)), a.box_inv[2]);
-				v3 ds = min_image_fixed(a.box, a.list_ibase[i], is);
+				v3 ds = min_image_fixed(a.box, unpack_ref(L.w), is);
 				if(dot(ds, ds) > a.skin2) flags[wr] = 1;
 			}
 			// forces are consumed: leave zeroed accumulators for the next force pass
 			a.F[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 			a.T[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-			v3 d = min_image_fixed(a.box, a.list_ipos[i], ip);
+			if(a.zero_Fb) a.Fb[i] = make_float4(0.f, 0.f, 0.f, 0.f); // half-matrix Debye-Hueckel kernel: Fb is an accumulator
+			v3 d = min_image_fixed(a.box, unpack_ref(r.w), ip);
 			if(dot(d, d) > a.skin2) flags[wr] = 1;
 		}
 		a.veld[i] = v;

@@ -30,13 +30,15 @@ enum { OXB_PROF_OTHER = 0, OXB_PROF_FORCE = 1, OXB_PROF_INTEG = 2, OXB_PROF_WAIT
 __device__ __forceinline__ void prof_mark(int *flags, int phase, bool reset = false) {
 	if(flags[OXB_FLAG_PROF_ON] == 0) return;
 	unsigned long long *prof = reinterpret_cast<unsigned long long *>(flags + OXB_PROF_OFFSET);
+	// the kernels of one force pass start concurrently on forked streams: whichever arrives first opens the phase (atomic exchange of the
+	// open-phase word), the others find it open and leave; the bookkeeping below then has a single writer
+	const unsigned long long open = atomicExch(prof + 1, (unsigned long long) phase);
+	if(!reset && open == (unsigned long long) phase) return;
 	unsigned long long t;
 	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-	const unsigned long long open = prof[1];
 	if(!reset && prof[0] != 0ull) prof[2 + open] += t - prof[0];
-	if(reset || open != (unsigned long long) phase) prof[2 + OXB_PROF_NPHASE + phase] += 1ull;
+	prof[2 + OXB_PROF_NPHASE + phase] += 1ull;
 	prof[0] = t;
-	prof[1] = (unsigned long long) phase;
 }
 #endif
 
@@ -98,6 +100,7 @@ struct EdgeArgs {
 	int2 *hb_list, *cx_list, *cr_list;
 	int *seg_counts;
 	int n_seg, hb_seg, cx_seg, cr_seg;
+	int dh_half;  // the Debye-Hueckel matrix holds every pair once: the kernel adds the partner's share atomically, Fb must be zero on entry
 	int hb_split; // consumer blocks per segment of the hydrogen-bonding / cross-stacking list
 	// pairs with an excluded-volume site pair in range, evaluated in double by k_excl_fix: near edges (p, q, mask, -) segmented by
 	// producer block like the lists above (ex_counts[b] entries in block b's segment of ex_seg), bonds as one mask per particle
@@ -123,13 +126,13 @@ struct IntegrateArgs {
 	int N;
 	double dt;
 	double box_inv[3];
-	float skin2;
+	float skin2;        // (skin - quantisation error of the packed references)^2
 	BoxF box;
 	double4 *posd, *veld, *Ld, *quatd;
 	int4 *ipos;
 	float4 *quat;
-	const int4 *list_ipos, *list_iback, *list_ibase;
 	float4 *F, *T, *Fb; // lab-frame force / torque accumulators (zeroed by the first-half phase once consumed)
+	int zero_Fb;        // Fb is an accumulator too (dh_half)
 	int4 *iback;        // fixed-point backbone-site position, .w bit 0 = strand end
 	float back_a1, back_a2, back_a3, base_a1;
 	int *flags;
@@ -207,15 +210,15 @@ struct ListArgs {
 	float rnear2;      // (rcut_near + 2 skin + margin)^2
 	// Debye-Hueckel neighbour matrix (full, both directions), selected on the backbone-site distance
 	const int4 *iback;
-	int4 *list_iback, *list_ibase;
+	double4 *ref_pos, *ref_vel, *ref_L; // the FP64 state arrays whose .w lanes take the staleness references (common.cuh, pack_ref)
 	const float4 *quat;
 	float base_a1, stack_a1;
 	float r2_bb, r2_base, r2_bk, r2_stack; // squared site-site selection radii of the near-edge list (range + 2 skin + margin)
 	int *dh_nbr, *dh_nnbr;
 	int max_dh;
+	bool dh_half;      // each Debye-Hueckel pair appears in one row only (see k_dh_particle)
 	float rdh2;        // (dh_rc + 2 skin + margin)^2
 	long long edge_capacity;
-	int4 *list_ipos;
 	int *flags;
 	void *cub_tmp;
 	size_t cub_tmp_bytes;
@@ -246,8 +249,8 @@ struct PermuteArgs {
 	const int *inv;  // inv[old] = new
 	const double4 *posd_in, *veld_in, *Ld_in, *quatd_in;
 	double4 *posd_out, *veld_out, *Ld_out, *quatd_out;
-	const int4 *ipos_in, *list_ipos_in, *iback_in, *list_iback_in, *list_ibase_in;
-	int4 *ipos_out, *list_ipos_out, *iback_out, *list_iback_out, *list_ibase_out;
+	const int4 *ipos_in, *iback_in;
+	int4 *ipos_out, *iback_out;
 	const float4 *quat_in, *F_in, *T_in;
 	float4 *quat_out, *F_out, *T_out;
 	const int2 *bonds_in;

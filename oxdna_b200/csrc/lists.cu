@@ -23,6 +23,10 @@ __device__ __forceinline__ int cell_coord(double x, double L, int n) {
 	return min(c, n - 1);
 }
 
+__device__ __forceinline__ v3 a1_of(float4 q) {
+	return mk3(q.x * q.x - q.y * q.y - q.z * q.z + q.w * q.w, 2.f * (q.x * q.y + q.z * q.w), 2.f * (q.x * q.z - q.y * q.w));
+}
+
 __global__ void __launch_bounds__(256) k_cell_keys(int N, int n_per, const double4 *__restrict__ posd, double Lx, double Ly, double Lz, int nx, int ny, int nz,
 		int *__restrict__ key, int *__restrict__ val, int *__restrict__ flags) {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -34,11 +38,25 @@ __global__ void __launch_bounds__(256) k_cell_keys(int N, int n_per, const doubl
 	val[i] = i;
 }
 
+// (also records the staleness references of slot j -- where its centre, backbone site and base site are at this rebuild -- in the .w lanes
+// of the FP64 state; done here and not in k_build_neigh, which reads other particles' positions while it runs)
 __global__ void __launch_bounds__(256) k_cell_ranges(int N, const int *__restrict__ key_sorted, int *__restrict__ cell_start, int *__restrict__ cell_end,
-		int *__restrict__ flags) {
+		const int4 *__restrict__ ipos, const int4 *__restrict__ iback, const float4 *__restrict__ quat, float base_a1, BoxF boxf,
+		double4 *__restrict__ ref_pos, double4 *__restrict__ ref_vel, double4 *__restrict__ ref_L, int *__restrict__ flags) {
 	int j = blockIdx.x * blockDim.x + threadIdx.x;
 	if(j == 0) prof_mark(flags, OXB_PROF_BUILD);
 	if(j >= N) return;
+	{
+		const int4 ip = ipos[j];
+		const v3 a1p = a1_of(quat[j]);
+		int4 bs = ip;
+		bs.x = (int) ((unsigned) ip.x + (unsigned) (int) rintf(a1p.x * base_a1 / boxf.sx));
+		bs.y = (int) ((unsigned) ip.y + (unsigned) (int) rintf(a1p.y * base_a1 / boxf.sy));
+		bs.z = (int) ((unsigned) ip.z + (unsigned) (int) rintf(a1p.z * base_a1 / boxf.sz));
+		ref_pos[j].w = pack_ref(ip);
+		ref_vel[j].w = pack_ref(iback[j]);
+		ref_L[j].w = pack_ref(bs);
+	}
 	int k = key_sorted[j];
 	if(j == 0 || key_sorted[j - 1] != k) cell_start[k] = j;
 	if(j == N - 1 || key_sorted[j + 1] != k) cell_end[k] = j + 1;
@@ -68,10 +86,6 @@ __device__ __forceinline__ bool near_pair(const oxb::ListArgs &a, v3 r, v3 a1p, 
 	if(dot(d1, d1) < a.r2_bk) return true;
 	v3 d2 = r + a1q * a.base_a1 - bkp; // back(p) - base(q)
 	return dot(d2, d2) < a.r2_bk;
-}
-
-__device__ __forceinline__ v3 a1_of(float4 q) {
-	return mk3(q.x * q.x - q.y * q.y - q.z * q.z + q.w * q.w, 2.f * (q.x * q.y + q.z * q.w), 2.f * (q.x * q.z - q.y * q.w));
 }
 
 // One thread per particle: visit the 27 surrounding cells, keep non-bonded particles closer than rv.
@@ -178,7 +192,9 @@ __global__ void __launch_bounds__(128) k_build_neigh(oxb::ListArgs a, const int 
 				else if(count < 128) mask1 |= 1ull << (count - 64);
 				else mask_overflow = true;
 			}
-			if(dot(db, db) < a.rdh2) {
+			// dh_half: every Debye-Hueckel pair is kept by ONE of its particles (by the parity of i + m, so that rows stay balanced); the
+			// kernel adds the partner's share with one vector atomic.  Full rows (both directions, no atomics) otherwise.
+			if(dot(db, db) < a.rdh2 && (!a.dh_half || ((((i + m) & 1) == 0) == (i < m)))) {
 				if(ndh < a.max_dh) a.dh_nbr[(size_t) ndh * a.stride + i] = m;
 				ndh++;
 			}
@@ -202,15 +218,6 @@ __global__ void __launch_bounds__(128) k_build_neigh(oxb::ListArgs a, const int 
 	}
 	a.nnbr[i] = count;
 	a.dh_nnbr[i] = ndh;
-	a.list_ipos[i] = ip;
-	a.list_iback[i] = ib;
-	{
-		int4 bs = ip;
-		bs.x = (int) ((unsigned) ip.x + (unsigned) (int) rintf(a1p.x * a.base_a1 / a.boxf.sx));
-		bs.y = (int) ((unsigned) ip.y + (unsigned) (int) rintf(a1p.y * a.base_a1 / a.boxf.sy));
-		bs.z = (int) ((unsigned) ip.z + (unsigned) (int) rintf(a1p.z * a.base_a1 / a.boxf.sz));
-		a.list_ibase[i] = bs;
-	}
 	if(a.build_edges) {
 		a.edge_offsets[i] = higher_near;
 		// rows longer than the mask fall back to the geometric test in k_fill_edges (top bit of word 1 doubles as the marker:
@@ -298,7 +305,8 @@ void launch_build_lists(cudaStream_t s, const ListArgs &a) {
 		cub::DeviceRadixSort::SortPairs(a.cub_tmp, tmp, a.cell_key, a.cell_key_sorted, a.cell_val, a.cell_val_sorted, N, 0, bits_for(ncells), s);
 	}
 	cudaMemsetAsync(cell_start, 0, sizeof(int) * 2 * (size_t) ncells, s);
-	k_cell_ranges<<<(N + tpb - 1) / tpb, tpb, 0, s>>>(N, a.cell_key_sorted, cell_start, cell_end, a.flags);
+	k_cell_ranges<<<(N + tpb - 1) / tpb, tpb, 0, s>>>(N, a.cell_key_sorted, cell_start, cell_end, a.ipos, a.iback, a.quat, a.base_a1, a.boxf, a.ref_pos, a.ref_vel,
+			a.ref_L, a.flags);
 	cudaMemsetAsync(a.flags + OXB_FLAG_MAX_NEIGH_SEEN, 0, sizeof(int), s);
 	if(a.direct) k_build_neigh<true><<<(N + 127) / 128, 128, 0, s>>>(a, cell_start, cell_end);
 	else k_build_neigh<false><<<(N + 127) / 128, 128, 0, s>>>(a, cell_start, cell_end);

@@ -90,10 +90,7 @@ __global__ void __launch_bounds__(256) k_permute(oxb::PermuteArgs a) {
 	a.quatd_out[n] = a.quatd_in[o];
 	int4 ip = a.ipos_in[o];
 	a.ipos_out[n] = ip;
-	a.list_ipos_out[n] = a.list_ipos_in[o];
 	a.iback_out[n] = a.iback_in[o];
-	a.list_iback_out[n] = a.list_iback_in[o];
-	a.list_ibase_out[n] = a.list_ibase_in[o];
 	a.quat_out[n] = a.quat_in[o];
 	a.F_out[n] = a.F_in[o];
 	a.T_out[n] = a.T_in[o];
