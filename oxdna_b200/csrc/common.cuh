@@ -52,6 +52,33 @@ __host__ __device__ __forceinline__ Axes axes_from_quat(float4 q) {
 	return A;
 }
 
+// ---- FP32 orientation record of a particle: its a1 and a3 axes in 32 bytes = ONE sector,
+//   axf[2 i] = (a1.x, a1.y, a1.z, a3.x), axf[2 i + 1] = (a3.y, a3.z, 0, 0);  a2 = a3 x a1.
+// The integrator writes it from the FP64 quaternion (it forms these products anyway for the backbone site); every pair kernel reads it
+// with two 128-bit loads of the same sector instead of gathering a quaternion (half a sector) and expanding it (~35 instructions per
+// particle and pair: the pair kernels are instruction-issue bound).
+OXB_HD void store_axes(float4 *axf, int i, double a1x, double a1y, double a1z, double a3x, double a3y, double a3z) {
+	axf[2 * (size_t) i] = make_float4((float) a1x, (float) a1y, (float) a1z, (float) a3x);
+	axf[2 * (size_t) i + 1] = make_float4((float) a3y, (float) a3z, 0.f, 0.f);
+}
+OXB_HD void store_axes_from_quatd(float4 *axf, int i, double x, double y, double z, double w) {
+	store_axes(axf, i, x * x - y * y - z * z + w * w, 2. * (x * y + z * w), 2. * (x * z - y * w), 2. * (x * z + y * w), 2. * (y * z - x * w), -x * x - y * y + z * z + w * w);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ Axes load_axes(const float4 *__restrict__ axf, int i) {
+	const float4 u = __ldg(axf + 2 * (size_t) i), w = __ldg(axf + 2 * (size_t) i + 1);
+	Axes A;
+	A.a1 = mk3(u.x, u.y, u.z);
+	A.a3 = mk3(u.w, w.x, w.y);
+	A.a2 = cross(A.a3, A.a1);
+	return A;
+}
+__device__ __forceinline__ v3 load_a1(const float4 *__restrict__ axf, int i) {
+	const float4 u = __ldg(axf + 2 * (size_t) i);
+	return mk3(u.x, u.y, u.z);
+}
+#endif
+
 // ---- packed particle word: (btype << 22) | original index, as in the reference (MD_CUDABackend.cu:243-254)
 __host__ __device__ __forceinline__ int pack_word(int btype, int index) { return (btype << 22) | (index & 0x003FFFFF); }
 __host__ __device__ __forceinline__ int word_btype(int w) { return w >> 22; }

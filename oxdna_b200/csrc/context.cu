@@ -41,7 +41,9 @@ struct oxb_ctx {
 	double4 *posd[2] = { nullptr, nullptr }, *veld[2] = { nullptr, nullptr }, *Ld[2] = { nullptr, nullptr }, *quatd[2] = { nullptr, nullptr };
 	int4 *ipos[2] = { nullptr, nullptr }, *iback[2] = { nullptr, nullptr };
 	float4 *Fb = nullptr;
-	float4 *quat[2] = { nullptr, nullptr }, *F[2] = { nullptr, nullptr }, *T[2] = { nullptr, nullptr };
+	float4 *axf[2] = { nullptr, nullptr }; // FP32 orientation records (a1, a3): 2 float4 per particle (common.cuh)
+	float4 *quat_f4 = nullptr;             // optional reference-layout quaternion view, filled on demand
+	float4 *F[2] = { nullptr, nullptr }, *T[2] = { nullptr, nullptr };
 	int2 *bonds[2] = { nullptr, nullptr };
 	int *slot_of = nullptr;
 	float4 *pos_f4 = nullptr; // optional reference-layout view, filled on demand
@@ -286,7 +288,7 @@ oxb::ListArgs list_args(oxb_ctx *c) {
 	a.cell_start = c->cell_start;
 	a.nbr = c->nbr; a.nnbr = c->nnbr; a.max_neigh = c->max_neigh; a.stride = c->N;
 	a.edges = c->edges; a.edge_offsets = c->edge_offsets; a.n_edges = c->n_edges; a.edge_capacity = c->edge_capacity;
-	a.iback = c->iback[c->cur]; a.quat = c->quat[c->cur];
+	a.iback = c->iback[c->cur]; a.axf = c->axf[c->cur];
 	a.ref_pos = c->posd[c->cur]; a.ref_vel = c->veld[c->cur]; a.ref_L = c->Ld[c->cur];
 	a.base_a1 = c->model.base_a1; a.stack_a1 = c->model.stack_a1;
 	{
@@ -353,7 +355,7 @@ int do_sort(oxb_ctx *c) {
 	p.posd_out = c->posd[b]; p.veld_out = c->veld[b]; p.Ld_out = c->Ld[b]; p.quatd_out = c->quatd[b];
 	p.ipos_in = c->ipos[a]; p.ipos_out = c->ipos[b];
 	p.iback_in = c->iback[a]; p.iback_out = c->iback[b];
-	p.quat_in = c->quat[a]; p.F_in = c->F[a]; p.T_in = c->T[a]; p.quat_out = c->quat[b]; p.F_out = c->F[b]; p.T_out = c->T[b];
+	p.axf_in = c->axf[a]; p.F_in = c->F[a]; p.T_in = c->T[a]; p.axf_out = c->axf[b]; p.F_out = c->F[b]; p.T_out = c->T[b];
 	p.bonds_in = c->bonds[a]; p.bonds_out = c->bonds[b];
 	p.slot_of = c->slot_of;
 	p.cell_lin = c->cell_key_sorted;
@@ -437,7 +439,7 @@ int launch_forces(oxb_ctx *c, int hw, bool clear, long long step) {
 		}
 		oxb::EdgeArgs e;
 		e.rep = c->rep; e.n_per = c->n_per;
-		e.N = c->N; e.ipos = c->ipos[a]; e.iback = c->iback[a]; e.quat = c->quat[a]; e.posd = c->posd[a]; e.quatd = c->quatd[a]; e.bonds = c->bonds[a]; e.edges = c->edges;
+		e.N = c->N; e.ipos = c->ipos[a]; e.iback = c->iback[a]; e.axf = c->axf[a]; e.posd = c->posd[a]; e.quatd = c->quatd[a]; e.bonds = c->bonds[a]; e.edges = c->edges;
 		e.n_edges = c->n_edges; e.dh_nbr = c->dh_nbr; e.dh_nnbr = c->dh_nnbr;
 		e.F = c->F[a]; e.T = c->T[a]; e.Fb = c->Fb; e.hb_list = c->hb_list; e.cx_list = c->cx_list; e.cr_list = c->cr_list; e.seg_counts = c->seg_counts;
 		e.ex_list = c->ex_list; e.ex_counts = c->ex_counts; e.ex_bonded = c->ex_bonded; e.ex_seg = c->ex_seg;
@@ -485,7 +487,7 @@ int launch_forces(oxb_ctx *c, int hw, bool clear, long long step) {
 		c->launches += e.refine ? 6 : 5;
 	}
 	else {
-		oxb::launch_forces_particle(m, c->mref(), c->boxf, c->N, c->ipos[a], c->iback[a], c->quat[a],
+		oxb::launch_forces_particle(m, c->mref(), c->boxf, c->N, c->ipos[a], c->iback[a], c->axf[a],
 				c->precision == OXB_PRECISION_MIXED ? c->posd[a] : nullptr, c->quatd[a], c->bonds[a], c->nbr, c->nnbr, c->N, c->F[a], c->T[a],
 				c->rep, c->n_per, c->flags, hw);
 		c->launches += 1;
@@ -518,7 +520,7 @@ oxb::IntegrateArgs integ_args(oxb_ctx *c, long long step) {
 	}
 	a.box = c->boxf;
 	a.posd = c->posd[k]; a.veld = c->veld[k]; a.Ld = c->Ld[k]; a.quatd = c->quatd[k];
-	a.ipos = c->ipos[k]; a.quat = c->quat[k];
+	a.ipos = c->ipos[k]; a.axf = c->axf[k];
 	a.F = c->F[k]; a.T = c->T[k]; a.Fb = c->use_edge ? c->Fb : nullptr; a.iback = c->iback[k];
 	a.back_a1 = c->model.back_a1; a.back_a2 = c->model.back_a2; a.back_a3 = c->back_a3; a.base_a1 = c->model.base_a1;
 	a.flags = c->flags; a.sums = c->sums; a.th = c->th; a.step = step;
@@ -743,7 +745,7 @@ int oxb_create(oxb_ctx **out, int device, int N, int precision) {
 	for(int k = 0; k < 2; k++) {
 		CU(dalloc(&c->posd[k], N)); CU(dalloc(&c->veld[k], N)); CU(dalloc(&c->Ld[k], N)); CU(dalloc(&c->quatd[k], N));
 		CU(dalloc(&c->ipos[k], N)); CU(dalloc(&c->iback[k], N));
-		CU(dalloc(&c->quat[k], N)); CU(dalloc(&c->F[k], N)); CU(dalloc(&c->T[k], N));
+		CU(dalloc(&c->axf[k], 2 * (size_t) N)); CU(dalloc(&c->F[k], N)); CU(dalloc(&c->T[k], N));
 		CU(dalloc(&c->bonds[k], N));
 		CU(cudaMemset(c->F[k], 0, sizeof(float4) * N)); CU(cudaMemset(c->T[k], 0, sizeof(float4) * N));
 	}
@@ -775,14 +777,14 @@ void oxb_destroy(oxb_ctx *c) {
 	cudaFree(c->cur_step);
 	for(int k = 0; k < 2; k++) {
 		cudaFree(c->posd[k]); cudaFree(c->veld[k]); cudaFree(c->Ld[k]); cudaFree(c->quatd[k]); cudaFree(c->ipos[k]);
-		cudaFree(c->quat[k]); cudaFree(c->F[k]); cudaFree(c->T[k]); cudaFree(c->bonds[k]); cudaFree(c->iback[k]);
+		cudaFree(c->axf[k]); cudaFree(c->F[k]); cudaFree(c->T[k]); cudaFree(c->bonds[k]); cudaFree(c->iback[k]);
 	}
 	cudaFree(c->Fb);
 	cudaFree(c->rep); cudaFree(c->d_rep_energy);
 	if(c->h_rep_energy) cudaFreeHost(c->h_rep_energy);
 	cudaFree(c->slot_of); cudaFree(c->flags); cudaFree(c->sums); cudaFree(c->d_energy); cudaFree(c->ext); cudaFree(c->ext_all); cudaFree(c->ext_com); cudaFree(c->ext_pool); cudaFree(c->ext_grid);
 	cudaFree(c->d_topo); cudaFree(c->d_stage); cudaFree(c->d_marshal_err);
-	cudaFree(c->mol_of); cudaFree(c->mol_inv_size); cudaFree(c->mol_coms); cudaFree(c->pos_backup); cudaFree(c->pos_f4);
+	cudaFree(c->mol_of); cudaFree(c->mol_inv_size); cudaFree(c->mol_coms); cudaFree(c->pos_backup); cudaFree(c->pos_f4); cudaFree(c->quat_f4);
 	cudaFree(c->hkeys); cudaFree(c->hkeys_sorted); cudaFree(c->hvals); cudaFree(c->hvals_sorted); cudaFree(c->hinv);
 	free_lists(c);
 	if(c->h_flags) cudaFreeHost(c->h_flags);
@@ -1083,7 +1085,7 @@ int oxb_set_state(oxb_ctx *c, const double *pos, const double *a1, const double 
 	for(int d = 0; d < 3; d++) a.box_inv[d] = 1. / c->box[d];
 	a.back_a1 = c->model.back_a1; a.back_a2 = c->model.back_a2; a.back_a3 = c->back_a3;
 	a.posd = c->posd[k]; a.veld = c->veld[k]; a.Ld = c->Ld[k]; a.quatd = c->quatd[k];
-	a.ipos = c->ipos[k]; a.iback = c->iback[k]; a.quat = c->quat[k]; a.bonds = c->bonds[k]; a.slot_of = c->slot_of;
+	a.ipos = c->ipos[k]; a.iback = c->iback[k]; a.axf = c->axf[k]; a.bonds = c->bonds[k]; a.slot_of = c->slot_of;
 	a.err = c->d_marshal_err;
 	oxb::launch_state_in(c->stream, a);
 	c->launches++;
@@ -1474,7 +1476,7 @@ int oxb_fix_diffusion(oxb_ctx *c, int *shifts) {
 		d_shifts = reinterpret_cast<int *>(c->d_stage);
 	}
 	oxb::launch_mol_coms(c->stream, N, c->n_mol, c->ipos[k], c->mol_of, c->mol_inv_size, c->posd[k], c->mol_coms);
-	oxb::launch_fix_diffusion(c->stream, N, c->ipos[k], c->mol_of, c->mol_coms, c->box, c->posd[k], c->quatd[k], c->quat[k], d_shifts);
+	oxb::launch_fix_diffusion(c->stream, N, c->ipos[k], c->mol_of, c->mol_coms, c->box, c->posd[k], c->quatd[k], c->axf[k], d_shifts);
 	c->launches += 2;
 	CU(cudaGetLastError());
 	if(shifts) CU(cudaMemcpyAsync(shifts, d_shifts, sizeof(int) * 3 * (size_t) N, cudaMemcpyDeviceToHost, c->stream));
@@ -1578,7 +1580,7 @@ int oxb_energy_split(oxb_ctx *c, double *terms) {
 	rc = ensure_lists(c);
 	if(rc) return rc;
 	const int k = c->cur;
-	oxb::launch_energy_split(c->stream, c->mref(), c->boxf, c->N, c->ipos[k], c->quat[k], c->bonds[k], c->nbr, c->nnbr, c->N, c->d_energy + 2);
+	oxb::launch_energy_split(c->stream, c->mref(), c->boxf, c->N, c->ipos[k], c->axf[k], c->bonds[k], c->nbr, c->nnbr, c->N, c->d_energy + 2);
 	c->launches += 1;
 	CU(cudaGetLastError());
 	CU(cudaMemcpyAsync(c->h_scalars + 2, c->d_energy + 2, sizeof(double) * OXB_NTERMS, cudaMemcpyDeviceToHost, c->stream));
@@ -1632,6 +1634,12 @@ __global__ void k_pos_view(int N, const double4 *__restrict__ posd, const int4 *
 	double4 p = posd[i];
 	out[i] = make_float4((float) p.x, (float) p.y, (float) p.z, __int_as_float(ipos[i].w));
 }
+__global__ void k_quat_view(int N, const double4 *__restrict__ quatd, float4 *__restrict__ out) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= N) return;
+	double4 q = quatd[i];
+	out[i] = make_float4((float) q.x, (float) q.y, (float) q.z, (float) q.w);
+}
 } // namespace
 
 int oxb_device_views(oxb_ctx *c, void **poss_f4, void **orientations_f4, void **matrix_neighs, void **number_neighs, void **edge_list, void **n_edges) {
@@ -1647,7 +1655,14 @@ int oxb_device_views(oxb_ctx *c, void **poss_f4, void **orientations_f4, void **
 		CU(cudaStreamSynchronize(c->stream));
 		*poss_f4 = c->pos_f4;
 	}
-	if(orientations_f4) *orientations_f4 = c->quat[c->cur];
+	if(orientations_f4) {
+		// GPU_quat view (src/CUDA/cuda_defs.h:58-97) of the FP64 quaternions
+		if(c->quat_f4 == nullptr) CU(dalloc(&c->quat_f4, c->N));
+		k_quat_view<<<(c->N + 255) / 256, 256, 0, c->stream>>>(c->N, c->quatd[c->cur], c->quat_f4);
+		c->launches++;
+		CU(cudaStreamSynchronize(c->stream));
+		*orientations_f4 = c->quat_f4;
+	}
 	if(matrix_neighs) *matrix_neighs = c->nbr;
 	if(number_neighs) *number_neighs = c->nnbr;
 	if(edge_list) *edge_list = c->edges;

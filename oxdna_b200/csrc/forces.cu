@@ -2,7 +2,7 @@
 // sum_edge_forces_torques and set_external_forces of the reference (src/CUDA/Interactions/CUDA_DNA.cuh:727-904,
 // src/CUDA/Interactions/CUDABaseInteraction.cu:21-48, src/CUDA/Backends/CUDA_MD.cuh:97-554).
 //
-// Data: ipos int4 (fixed-point position, .w = btype<<22 | original index), quat float4, bonds int2 (n3, n5 slots),
+// Data: ipos int4 (fixed-point position, .w = btype<<22 | original index), axf = FP32 orientation record (a1, a3; common.cuh), bonds int2 (n3, n5 slots),
 // neighbour matrix column-major nbr[k * stride + i], forces/torques float4 (.w = energy / HB energy as in the reference).
 #include "models.cuh"
 #include "kernels.h"
@@ -106,10 +106,10 @@ struct Particle {
 };
 
 template<class MD>
-__device__ __forceinline__ Particle load_particle(const typename MD::Params &M, const int4 *__restrict__ ipos, const float4 *__restrict__ quat, int i) {
+__device__ __forceinline__ Particle load_particle(const typename MD::Params &M, const int4 *__restrict__ ipos, const float4 *__restrict__ axf, int i) {
 	Particle P;
 	P.ip = __ldg(ipos + i);
-	P.ax = axes_from_quat(__ldg(quat + i));
+	P.ax = load_axes(axf, i);
 	P.back = MD::back(M, P.ax);
 	P.btype = word_btype(P.ip.w);
 	return P;
@@ -120,7 +120,7 @@ __device__ __forceinline__ Particle load_particle(const typename MD::Params &M, 
 // ------------------------------------------------------------------------------------------------------------
 template<class MD>
 __global__ void __launch_bounds__(128, OXB_MB_PARTICLE) k_forces_particle(const __grid_constant__ typename MD::Params M, BoxF box, int N, const int4 *__restrict__ ipos,
-		const int4 *__restrict__ iback, const float4 *__restrict__ quat, const double4 *__restrict__ posd, const double4 *__restrict__ quatd,
+		const int4 *__restrict__ iback, const float4 *__restrict__ axf, const double4 *__restrict__ posd, const double4 *__restrict__ quatd,
 		const int2 *__restrict__ bonds, const int *__restrict__ nbr, const int *__restrict__ nnbr, int stride,
 		float4 *__restrict__ F, float4 *__restrict__ T, const oxb_replica_consts *__restrict__ rep, int n_per, int *__restrict__ flags, int hw) {
 	if(blockIdx.x == 0 && threadIdx.x == 0) prof_mark(flags, flags[hw] ? OXB_PROF_WAIT : OXB_PROF_FORCE);
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(128, OXB_MB_PARTICLE) k_forces_particle(const 
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= N) return;
 
-	Particle P = load_particle<MD>(M, ipos, quat, i);
+	Particle P = load_particle<MD>(M, ipos, axf, i);
 	int2 b = __ldg(bonds + i);
 	bool p_end = (b.x < 0 || b.y < 0);
 
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(128, OXB_MB_PARTICLE) k_forces_particle(const 
 	if(rep != nullptr) rep += i / n_per;   // replica batching: slots are replica-contiguous
 
 	if(b.x >= 0) { // I am the 5' side of the bond (p), q = my n3
-		Particle Q = load_particle<MD>(M, ipos, quat, b.x);
+		Particle Q = load_particle<MD>(M, ipos, axf, b.x);
 		PairAcc acc;
 		acc.clear();
 		R.sp = i; R.sq = b.x; acc.refine = refine ? &R : nullptr;
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(128, OXB_MB_PARTICLE) k_forces_particle(const 
 		t += acc.torque_p(P.ax, P.back);
 	}
 	if(b.y >= 0) { // my n5 neighbour is p, I am q
-		Particle Q = load_particle<MD>(M, ipos, quat, b.y);
+		Particle Q = load_particle<MD>(M, ipos, axf, b.y);
 		PairAcc acc;
 		acc.clear();
 		R.sp = b.y; R.sq = i; acc.refine = refine ? &R : nullptr;
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(128, OXB_MB_PARTICLE) k_forces_particle(const 
 	int nn = __ldg(nnbr + i);
 	for(int k = 0; k < nn; k++) {
 		int j = __ldg(nbr + (size_t) k * stride + i);
-		Particle Q = load_particle<MD>(M, ipos, quat, j);
+		Particle Q = load_particle<MD>(M, ipos, axf, j);
 		int2 bq = __ldg(bonds + j);
 		PairAcc acc;
 		acc.clear();
@@ -294,7 +294,7 @@ __device__ __forceinline__ void block_append(bool flag, int2 item, int2 *__restr
 
 template<class MD>
 __global__ void __launch_bounds__(128, OXB_MB_NEAR) k_edge_near(const __grid_constant__ typename MD::Params M, BoxF box, const int *__restrict__ n_edges,
-		const int2 *__restrict__ edges, const int4 *__restrict__ ipos, const float4 *__restrict__ quat, float4 *__restrict__ F, float4 *__restrict__ T,
+		const int2 *__restrict__ edges, const int4 *__restrict__ ipos, const float4 *__restrict__ axf, float4 *__restrict__ F, float4 *__restrict__ T,
 		int2 *__restrict__ hb_list, int2 *__restrict__ cx_list, int2 *__restrict__ cr_list, int *__restrict__ seg_counts, int hb_seg, int cx_seg,
 		int cr_seg, int4 *__restrict__ ex_list, int *__restrict__ ex_counts, int ex_seg, int refine, int *__restrict__ flags, int hw) {
 	if(blockIdx.x == 0 && threadIdx.x == 0) prof_mark(flags, flags[hw] ? OXB_PROF_WAIT : OXB_PROF_FORCE);
@@ -320,8 +320,8 @@ __global__ void __launch_bounds__(128, OXB_MB_NEAR) k_edge_near(const __grid_con
 		float ve = 0.f;
 		bool want_hb = false, want_cx = false, hb_capable = false;
 		if(valid) {
-			Particle P = load_particle<MD>(M, ipos, quat, ed.x);
-			Particle Q = load_particle<MD>(M, ipos, quat, ed.y);
+			Particle P = load_particle<MD>(M, ipos, axf, ed.x);
+			Particle Q = load_particle<MD>(M, ipos, axf, ed.y);
 			v3 r = min_image_fixed(box, P.ip, Q.ip);
 			if(dot(r, r) < M.rcut_near * M.rcut_near) {
 				v3 rbb = r + Q.back - P.back;
@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(128, OXB_MB_NEAR) k_edge_near(const __grid_con
 // MODE 0: hydrogen bonding (+ cross stacking where also in range) | 1: coaxial stacking | 2: cross stacking only
 template<class MD, int MODE>
 __global__ void __launch_bounds__(64, OXB_MB_HEAVY) k_edge_heavy(const __grid_constant__ typename MD::Params M, BoxF box, const int *__restrict__ seg_counts,
-		const int2 *__restrict__ list, int seg, const int4 *__restrict__ ipos, const float4 *__restrict__ quat, float4 *__restrict__ F,
+		const int2 *__restrict__ list, int seg, const int4 *__restrict__ ipos, const float4 *__restrict__ axf, float4 *__restrict__ F,
 		float4 *__restrict__ T, const int *__restrict__ flags, int hw) {
 	if(flags[hw]) return;
 	// list index in seg_counts: 0 hydrogen bonding, 1 coaxial stacking, 2 cross stacking only (same order as MODE)
@@ -402,8 +402,8 @@ __global__ void __launch_bounds__(64, OXB_MB_HEAVY) k_edge_heavy(const __grid_co
 	list += (size_t) blockIdx.x * seg;
 	for(int k = blockIdx.y * blockDim.x + threadIdx.x; k < n; k += blockDim.x * gridDim.y) {
 		int2 ed = __ldg(list + ((MODE == 0 && k >= n_front) ? seg / 3 + (k - n_front) : k));
-		Particle P = load_particle<MD>(M, ipos, quat, ed.x);
-		Particle Q = load_particle<MD>(M, ipos, quat, ed.y);
+		Particle P = load_particle<MD>(M, ipos, axf, ed.x);
+		Particle Q = load_particle<MD>(M, ipos, axf, ed.y);
 		v3 r = min_image_fixed(box, P.ip, Q.ip);
 		PairAcc acc;
 		acc.clear();
@@ -432,7 +432,7 @@ __global__ void __launch_bounds__(64, OXB_MB_HEAVY) k_edge_heavy(const __grid_co
 // the force pass (it only adds into F/T), so it runs concurrently with them on its own stream.
 template<class MD>
 __global__ void __launch_bounds__(128, OXB_MB_BONDED) k_bonded(const __grid_constant__ typename MD::Params M, BoxF box, int N, const int4 *__restrict__ ipos,
-		const int4 *__restrict__ iback, const float4 *__restrict__ quat, const int2 *__restrict__ bonds, float4 *__restrict__ F, float4 *__restrict__ T,
+		const int4 *__restrict__ iback, const float4 *__restrict__ axf, const int2 *__restrict__ bonds, float4 *__restrict__ F, float4 *__restrict__ T,
 		int *__restrict__ ex_bonded, int refine, const oxb_replica_consts *__restrict__ rep, int n_per, int *__restrict__ flags, int hw) {
 	if(blockIdx.x == 0 && threadIdx.x == 0) prof_mark(flags, flags[hw] ? OXB_PROF_WAIT : OXB_PROF_FORCE);
 	if(flags[hw]) return;
@@ -440,8 +440,8 @@ __global__ void __launch_bounds__(128, OXB_MB_BONDED) k_bonded(const __grid_cons
 	if(i >= N) return;
 	int2 b = __ldg(bonds + i);
 	if(b.x < 0) { if(refine) ex_bonded[i] = 0; return; }
-	Particle P = load_particle<MD>(M, ipos, quat, i);
-	Particle Q = load_particle<MD>(M, ipos, quat, b.x);
+	Particle P = load_particle<MD>(M, ipos, axf, i);
+	Particle Q = load_particle<MD>(M, ipos, axf, b.x);
 	PairAcc acc;
 	acc.clear();
 	if(rep != nullptr) acc.rep = rep + i / n_per; // replica batching: this replica's stacking strength
@@ -503,20 +503,20 @@ __global__ void __launch_bounds__(128) k_excl_fix(const __grid_constant__ typena
 // ------------------------------------------------------------------------------------------------------------
 template<class MD>
 __global__ void __launch_bounds__(128) k_energy_split(const __grid_constant__ typename MD::Params M, BoxF box, int N, const int4 *__restrict__ ipos,
-		const float4 *__restrict__ quat, const int2 *__restrict__ bonds, const int *__restrict__ nbr, const int *__restrict__ nnbr, int stride,
+		const float4 *__restrict__ axf, const int2 *__restrict__ bonds, const int *__restrict__ nbr, const int *__restrict__ nnbr, int stride,
 		double *__restrict__ out) {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	float e[OXB_NTERMS];
 #pragma unroll
 	for(int t = 0; t < OXB_NTERMS; t++) e[t] = 0.f;
 	if(i < N) {
-		Particle P = load_particle<MD>(M, ipos, quat, i);
+		Particle P = load_particle<MD>(M, ipos, axf, i);
 		int2 b = __ldg(bonds + i);
 		bool p_end = (b.x < 0 || b.y < 0);
 		PairAcc acc;
 		acc.clear();
 		if(b.x >= 0) {
-			Particle Q = load_particle<MD>(M, ipos, quat, b.x);
+			Particle Q = load_particle<MD>(M, ipos, axf, b.x);
 			bool broken = false;
 			MD::bonded(M, min_image_fixed(box, P.ip, Q.ip), P.ax, Q.ax, P.btype, Q.btype, P.back, Q.back, acc, broken, e);
 		}
@@ -524,7 +524,7 @@ __global__ void __launch_bounds__(128) k_energy_split(const __grid_constant__ ty
 		for(int k = 0; k < nn; k++) {
 			int j = __ldg(nbr + (size_t) k * stride + i);
 			if(j < i) continue;
-			Particle Q = load_particle<MD>(M, ipos, quat, j);
+			Particle Q = load_particle<MD>(M, ipos, axf, j);
 			v3 r = min_image_fixed(box, P.ip, Q.ip);
 			float r2 = dot(r, r);
 			if(r2 >= M.rcut * M.rcut) continue;
@@ -978,12 +978,12 @@ __global__ void k_ext_forces_all(int N, int n_all, const DevExtForce *__restrict
 
 namespace oxb {
 
-void launch_forces_particle(cudaStream_t s, const ModelRef &MR, BoxF box, int N, const int4 *ipos, const int4 *iback, const float4 *quat,
+void launch_forces_particle(cudaStream_t s, const ModelRef &MR, BoxF box, int N, const int4 *ipos, const int4 *iback, const float4 *axf,
 		const double4 *posd, const double4 *quatd, const int2 *bonds,
 		const int *nbr, const int *nnbr, int stride, float4 *F, float4 *T, const oxb_replica_consts *rep, int n_per, int *flags, int hw) {
 	int tpb = 128;
-	if(MR.rna) k_forces_particle<RnaModel><<<(N + tpb - 1) / tpb, tpb, 0, s>>>(*MR.rna, box, N, ipos, iback, quat, posd, quatd, bonds, nbr, nnbr, stride, F, T, rep, n_per, flags, hw);
-	else k_forces_particle<DnaModel><<<(N + tpb - 1) / tpb, tpb, 0, s>>>(*MR.dna, box, N, ipos, iback, quat, posd, quatd, bonds, nbr, nnbr, stride, F, T, rep, n_per, flags, hw);
+	if(MR.rna) k_forces_particle<RnaModel><<<(N + tpb - 1) / tpb, tpb, 0, s>>>(*MR.rna, box, N, ipos, iback, axf, posd, quatd, bonds, nbr, nnbr, stride, F, T, rep, n_per, flags, hw);
+	else k_forces_particle<DnaModel><<<(N + tpb - 1) / tpb, tpb, 0, s>>>(*MR.dna, box, N, ipos, iback, axf, posd, quatd, bonds, nbr, nnbr, stride, F, T, rep, n_per, flags, hw);
 }
 
 // the kernels of the edge pipeline, launched one by one so that the context can place them on concurrent streams:
@@ -1016,11 +1016,11 @@ static void launch_edge_stage_t(cudaStream_t s, int which, const typename MD::Pa
 	// the producer and the three consumers of the segmented work lists share one fixed grid (a.n_seg blocks, grid-stride
 	// inside): nothing here depends on device-side counts, so a captured graph stays valid across list rebuilds
 	case 1:
-		k_edge_near<MD><<<a.n_seg, 128, 0, s>>>(M, box, a.n_edges, a.edges, a.ipos, a.quat, a.F, a.T, a.hb_list, a.cx_list, a.cr_list, a.seg_counts, a.hb_seg,
+		k_edge_near<MD><<<a.n_seg, 128, 0, s>>>(M, box, a.n_edges, a.edges, a.ipos, a.axf, a.F, a.T, a.hb_list, a.cx_list, a.cr_list, a.seg_counts, a.hb_seg,
 				a.cx_seg, a.cr_seg, a.ex_list, a.ex_counts, a.ex_seg, a.refine, flags, hw);
 		break;
-	case 2: k_edge_heavy<MD, 0><<<dim3(a.n_seg, a.hb_split), 64, 0, s>>>(M, box, a.seg_counts, a.hb_list, a.hb_seg, a.ipos, a.quat, a.F, a.T, flags, hw); break;
-	case 3: k_edge_heavy<MD, 1><<<a.n_seg, 64, 0, s>>>(M, box, a.seg_counts, a.cx_list, a.cx_seg, a.ipos, a.quat, a.F, a.T, flags, hw); break;
+	case 2: k_edge_heavy<MD, 0><<<dim3(a.n_seg, a.hb_split), 64, 0, s>>>(M, box, a.seg_counts, a.hb_list, a.hb_seg, a.ipos, a.axf, a.F, a.T, flags, hw); break;
+	case 3: k_edge_heavy<MD, 1><<<a.n_seg, 64, 0, s>>>(M, box, a.seg_counts, a.cx_list, a.cx_seg, a.ipos, a.axf, a.F, a.T, flags, hw); break;
 	case 6:
 		k_excl_fix<MD><<<a.n_seg + (a.N + 255) / 256, 128, 0, s>>>(M, box, a.N, a.n_seg, a.ex_list, a.ex_counts, a.ex_seg, a.ex_bonded, a.bonds, a.posd, a.quatd, a.F, a.T,
 				flags, hw);
@@ -1029,7 +1029,7 @@ static void launch_edge_stage_t(cudaStream_t s, int which, const typename MD::Pa
 	default: {
 		static const int tpb_env = env_int("OXB_TPB_BONDED", 0);
 		const int tpb = tpb_env > 0 ? tpb_env : 128;
-		k_bonded<MD><<<(a.N + tpb - 1) / tpb, tpb, 0, s>>>(M, box, a.N, a.ipos, a.iback, a.quat, a.bonds, a.F, a.T, a.ex_bonded, a.refine, a.rep, a.n_per, flags, hw);
+		k_bonded<MD><<<(a.N + tpb - 1) / tpb, tpb, 0, s>>>(M, box, a.N, a.ipos, a.iback, a.axf, a.bonds, a.F, a.T, a.ex_bonded, a.refine, a.rep, a.n_per, flags, hw);
 		break;
 	}
 	}
@@ -1040,12 +1040,12 @@ void launch_edge_stage(cudaStream_t s, int which, const ModelRef &MR, BoxF box, 
 	else launch_edge_stage_t<DnaModel>(s, which, *MR.dna, box, a, flags, hw);
 }
 
-void launch_energy_split(cudaStream_t s, const ModelRef &MR, BoxF box, int N, const int4 *ipos, const float4 *quat, const int2 *bonds, const int *nbr,
+void launch_energy_split(cudaStream_t s, const ModelRef &MR, BoxF box, int N, const int4 *ipos, const float4 *axf, const int2 *bonds, const int *nbr,
 		const int *nnbr, int stride, double *out) {
 	cudaMemsetAsync(out, 0, sizeof(double) * OXB_NTERMS, s);
 	int tpb = 128;
-	if(MR.rna) k_energy_split<RnaModel><<<(N + tpb - 1) / tpb, tpb, 0, s>>>(*MR.rna, box, N, ipos, quat, bonds, nbr, nnbr, stride, out);
-	else k_energy_split<DnaModel><<<(N + tpb - 1) / tpb, tpb, 0, s>>>(*MR.dna, box, N, ipos, quat, bonds, nbr, nnbr, stride, out);
+	if(MR.rna) k_energy_split<RnaModel><<<(N + tpb - 1) / tpb, tpb, 0, s>>>(*MR.rna, box, N, ipos, axf, bonds, nbr, nnbr, stride, out);
+	else k_energy_split<DnaModel><<<(N + tpb - 1) / tpb, tpb, 0, s>>>(*MR.dna, box, N, ipos, axf, bonds, nbr, nnbr, stride, out);
 }
 
 void launch_ext_forces(cudaStream_t s, int n, const DevExtForce *ef, const int *slot_of, const int4 *ipos, const double4 *posd, BoxF box,

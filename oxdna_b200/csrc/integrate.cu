@@ -62,9 +62,12 @@ __global__ void __launch_bounds__(256, OXB_MB_INTEGRATE) k_integrate(oxb::Integr
 		if(PH & (OXB_PH_SECOND | OXB_PH_FIRST)) {
 			// the force kernels accumulate the torque in the lab frame: rotate it into the body frame (L is a body-frame
 			// angular momentum with unit inertia, src/CUDA/Interactions/CUDA_DNA.cuh:896)
-			// (the FP32 copy of the quaternion is not read: it is re-derived from the FP64 one that the first-half phase streams anyway)
-			const double4 qd0 = a.quatd[i];
-			Axes A = axes_from_quat(make_float4((float) qd0.x, (float) qd0.y, (float) qd0.z, (float) qd0.w));
+			Axes A;
+			{
+				// plain loads: this thread rewrites the record below
+				const float4 u = a.axf[2 * (size_t) i], w = a.axf[2 * (size_t) i + 1];
+				A.a1 = mk3(u.x, u.y, u.z); A.a3 = mk3(u.w, w.x, w.y); A.a2 = cross(A.a3, A.a1);
+			}
 			v3 tl = mk3(T.x, T.y, T.z);
 			if(a.Fb != nullptr) {
 				// edge pipeline: the Debye-Hueckel kernel leaves its force sum, acting at the backbone site, in Fb
@@ -151,13 +154,14 @@ __global__ void __launch_bounds__(256, OXB_MB_INTEGRATE) k_integrate(oxb::Integr
 				o.y = q.w * by - q.x * bz + q.y * bw + q.z * bx;
 				o.z = q.w * bz + q.x * by - q.y * bx + q.z * bw;
 				a.quatd[i] = o;
-				a.quat[i] = make_float4((float) o.x, (float) o.y, (float) o.z, (float) o.w);
 				qn = o;
 			}
 			{
 				// fixed-point backbone-site position for the Debye-Hueckel kernel: r + back_a1 a1 + back_a2 a2
 				double sqx = qn.x * qn.x, sqy = qn.y * qn.y, sqz = qn.z * qn.z, sqw = qn.w * qn.w;
 				double xy = qn.x * qn.y, xz = qn.x * qn.z, xw = qn.x * qn.w, yz = qn.y * qn.z, yw = qn.y * qn.w, zw = qn.z * qn.w;
+				// FP32 orientation record for the pair kernels (a1, a3), from the same double products
+				if(n2 > 0.) store_axes(a.axf, i, sqx - sqy - sqz + sqw, 2. * (xy + zw), 2. * (xz - yw), 2. * (xz + yw), 2. * (yz - xw), -sqx - sqy + sqz + sqw);
 				double b1 = a.back_a1, b2 = a.back_a2, b3 = a.back_a3;
 				double bx = r.x + b1 * (sqx - sqy - sqz + sqw) + b2 * (2. * (xy - zw)) + b3 * (2. * (xz + yw));
 				double by = r.y + b1 * (2. * (xy + zw)) + b2 * (-sqx + sqy - sqz + sqw) + b3 * (2. * (yz - xw));
@@ -356,7 +360,7 @@ __global__ void k_mol_coms(int N, const int4 *__restrict__ ipos, const int *__re
 // Verlet lists -- untouched, so the reference's before/after energy check has nothing to catch here.  shifts (may be null): floor(com / L)
 // per original particle id, for the caller's BaseParticle::_pos_shift.
 __global__ void k_fix_diffusion(int N, const int4 *__restrict__ ipos, const int *__restrict__ mol_of, const double *__restrict__ coms, double lx,
-		double ly, double lz, double4 *__restrict__ posd, double4 *__restrict__ quatd, float4 *__restrict__ quat, int *__restrict__ shifts) {
+		double ly, double lz, double4 *__restrict__ posd, double4 *__restrict__ quatd, float4 *__restrict__ axf, int *__restrict__ shifts) {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= N) return;
 	const int id = word_index(ipos[i].w);
@@ -369,7 +373,7 @@ __global__ void k_fix_diffusion(int N, const int4 *__restrict__ ipos, const int 
 	const double n = rsqrt(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
 	q.x *= n; q.y *= n; q.z *= n; q.w *= n;
 	quatd[i] = q;
-	quat[i] = make_float4((float) q.x, (float) q.y, (float) q.z, (float) q.w);
+	store_axes_from_quatd(axf, i, q.x, q.y, q.z, q.w);
 	if(shifts) { shifts[3 * id] = (int) sx; shifts[3 * id + 1] = (int) sy; shifts[3 * id + 2] = (int) sz; }
 }
 
@@ -443,9 +447,9 @@ void launch_mol_coms(cudaStream_t s, int N, int n_mol, const int4 *ipos, const i
 }
 
 void launch_fix_diffusion(cudaStream_t s, int N, const int4 *ipos, const int *mol_of, const double *coms, const double *box, double4 *posd,
-		double4 *quatd, float4 *quat, int *shifts) {
+		double4 *quatd, float4 *axf, int *shifts) {
 	int tpb = 256;
-	k_fix_diffusion<<<(N + tpb - 1) / tpb, tpb, 0, s>>>(N, ipos, mol_of, coms, box[0], box[1], box[2], posd, quatd, quat, shifts);
+	k_fix_diffusion<<<(N + tpb - 1) / tpb, tpb, 0, s>>>(N, ipos, mol_of, coms, box[0], box[1], box[2], posd, quatd, axf, shifts);
 }
 
 void launch_rescale_positions(cudaStream_t s, const RescaleArgs &a) {

@@ -81,7 +81,7 @@ struct ModelRef {
 };
 
 // ---- forces.cu
-void launch_forces_particle(cudaStream_t s, const ModelRef &M, BoxF box, int N, const int4 *ipos, const int4 *iback, const float4 *quat,
+void launch_forces_particle(cudaStream_t s, const ModelRef &M, BoxF box, int N, const int4 *ipos, const int4 *iback, const float4 *axf,
 		const double4 *posd, const double4 *quatd, const int2 *bonds,
 		const int *nbr, const int *nnbr, int stride, float4 *F, float4 *T, const oxb_replica_consts *rep, int n_per, int *flags, int hw);
 struct EdgeArgs {
@@ -89,7 +89,7 @@ struct EdgeArgs {
 	const oxb_replica_consts *rep; // replica batching: one row per replica (null: single system), n_per particles per replica
 	int n_per;
 	const int4 *ipos, *iback;
-	const float4 *quat;
+	const float4 *axf;
 	const double4 *posd, *quatd; // FP64 state: read only where an excluded-volume term is active (ExclRefine)
 	const int2 *bonds, *edges; // near edges
 	const int *n_edges;
@@ -110,7 +110,7 @@ struct EdgeArgs {
 	int refine; // 1 (backend_precision = mixed): FENE and excluded volume in double; 0 (float): FP32 pair arithmetic throughout
 };
 void launch_edge_stage(cudaStream_t s, int which, const ModelRef &M, BoxF box, const EdgeArgs &a, int *flags, int hw);
-void launch_energy_split(cudaStream_t s, const ModelRef &M, BoxF box, int N, const int4 *ipos, const float4 *quat, const int2 *bonds, const int *nbr,
+void launch_energy_split(cudaStream_t s, const ModelRef &M, BoxF box, int N, const int4 *ipos, const float4 *axf, const int2 *bonds, const int *nbr,
 		const int *nnbr, int stride, double *out);
 void launch_ext_forces(cudaStream_t s, int n, const DevExtForce *ef, const int *slot_of, const int4 *ipos, const double4 *posd, BoxF box,
 		long long step, const long long *cur_step, float4 *F, const int *flags, int hw);
@@ -130,7 +130,7 @@ struct IntegrateArgs {
 	BoxF box;
 	double4 *posd, *veld, *Ld, *quatd;
 	int4 *ipos;
-	float4 *quat;
+	float4 *axf;
 	float4 *F, *T, *Fb; // lab-frame force / torque accumulators (zeroed by the first-half phase once consumed)
 	int zero_Fb;        // Fb is an accumulator too (dh_half)
 	int4 *iback;        // fixed-point backbone-site position, .w bit 0 = strand end
@@ -156,7 +156,7 @@ struct MarshalArgs {
 	float back_a1, back_a2, back_a3;
 	double4 *posd, *veld, *Ld, *quatd;
 	int4 *ipos, *iback;
-	float4 *quat;
+	float4 *axf;
 	int2 *bonds;
 	int *slot_of;
 	int *err; // smallest particle id with a null orientation vector (INT_MAX = none)
@@ -183,7 +183,7 @@ void launch_mol_coms(cudaStream_t s, int N, int n_mol, const int4 *ipos, const i
 void launch_rescale_positions(cudaStream_t s, const RescaleArgs &a);
 // fix_diffusion: strands translated by whole box sides back into the box (coms from launch_mol_coms), quaternions renormalised
 void launch_fix_diffusion(cudaStream_t s, int N, const int4 *ipos, const int *mol_of, const double *coms, const double *box, double4 *posd,
-		double4 *quatd, float4 *quat, int *shifts);
+		double4 *quatd, float4 *axf, int *shifts);
 void launch_energy_sum(cudaStream_t s, int N, const float4 *F, const float4 *Fb, double *out);
 // per-replica potential energies: out[r] = sum over the slots of replica r (n_rep doubles, zeroed here)
 void launch_energy_sum_replicas(cudaStream_t s, int N, int n_rep, int n_per, const float4 *F, const float4 *Fb, double *out);
@@ -211,7 +211,7 @@ struct ListArgs {
 	// Debye-Hueckel neighbour matrix (full, both directions), selected on the backbone-site distance
 	const int4 *iback;
 	double4 *ref_pos, *ref_vel, *ref_L; // the FP64 state arrays whose .w lanes take the staleness references (common.cuh, pack_ref)
-	const float4 *quat;
+	const float4 *axf;
 	float base_a1, stack_a1;
 	float r2_bb, r2_base, r2_bk, r2_stack; // squared site-site selection radii of the near-edge list (range + 2 skin + margin)
 	int *dh_nbr, *dh_nnbr;
@@ -251,8 +251,8 @@ struct PermuteArgs {
 	double4 *posd_out, *veld_out, *Ld_out, *quatd_out;
 	const int4 *ipos_in, *iback_in;
 	int4 *ipos_out, *iback_out;
-	const float4 *quat_in, *F_in, *T_in;
-	float4 *quat_out, *F_out, *T_out;
+	const float4 *axf_in, *F_in, *T_in;
+	float4 *axf_out, *F_out, *T_out;
 	const int2 *bonds_in;
 	int2 *bonds_out;
 	int *slot_of; // slot_of[original id] = new slot

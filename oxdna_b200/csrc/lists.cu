@@ -23,10 +23,6 @@ __device__ __forceinline__ int cell_coord(double x, double L, int n) {
 	return min(c, n - 1);
 }
 
-__device__ __forceinline__ v3 a1_of(float4 q) {
-	return mk3(q.x * q.x - q.y * q.y - q.z * q.z + q.w * q.w, 2.f * (q.x * q.y + q.z * q.w), 2.f * (q.x * q.z - q.y * q.w));
-}
-
 __global__ void __launch_bounds__(256) k_cell_keys(int N, int n_per, const double4 *__restrict__ posd, double Lx, double Ly, double Lz, int nx, int ny, int nz,
 		int *__restrict__ key, int *__restrict__ val, int *__restrict__ flags) {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -41,14 +37,14 @@ __global__ void __launch_bounds__(256) k_cell_keys(int N, int n_per, const doubl
 // (also records the staleness references of slot j -- where its centre, backbone site and base site are at this rebuild -- in the .w lanes
 // of the FP64 state; done here and not in k_build_neigh, which reads other particles' positions while it runs)
 __global__ void __launch_bounds__(256) k_cell_ranges(int N, const int *__restrict__ key_sorted, int *__restrict__ cell_start, int *__restrict__ cell_end,
-		const int4 *__restrict__ ipos, const int4 *__restrict__ iback, const float4 *__restrict__ quat, float base_a1, BoxF boxf,
+		const int4 *__restrict__ ipos, const int4 *__restrict__ iback, const float4 *__restrict__ axf, float base_a1, BoxF boxf,
 		double4 *__restrict__ ref_pos, double4 *__restrict__ ref_vel, double4 *__restrict__ ref_L, int *__restrict__ flags) {
 	int j = blockIdx.x * blockDim.x + threadIdx.x;
 	if(j == 0) prof_mark(flags, OXB_PROF_BUILD);
 	if(j >= N) return;
 	{
 		const int4 ip = ipos[j];
-		const v3 a1p = a1_of(quat[j]);
+		const v3 a1p = load_a1(axf, j);
 		int4 bs = ip;
 		bs.x = (int) ((unsigned) ip.x + (unsigned) (int) rintf(a1p.x * base_a1 / boxf.sx));
 		bs.y = (int) ((unsigned) ip.y + (unsigned) (int) rintf(a1p.y * base_a1 / boxf.sy));
@@ -142,7 +138,7 @@ __global__ void __launch_bounds__(128) k_build_neigh(oxb::ListArgs a, const int 
 	const float band = 1e-4f * rv2f;
 	const double rv2 = a.rv * a.rv;
 	const int4 ib = a.iback[i];
-	const v3 a1p = a1_of(a.quat[i]);
+	const v3 a1p = load_a1(a.axf, i);
 	const v3 bkp = min_image_fixed(a.boxf, ip, ib);
 	int count = 0, higher_near = 0, ndh = 0;
 	unsigned long long mask0 = 0ull, mask1 = 0ull;
@@ -184,7 +180,7 @@ __global__ void __launch_bounds__(128) k_build_neigh(oxb::ListArgs a, const int 
 			// next rebuild (both the centre and the backbone site of every particle move less than `skin`)
 			const int4 ibm = __ldg(a.iback + m);
 			v3 db = min_image_fixed(a.boxf, ib, ibm);
-			if(m > i && d2 < a.rnear2 && near_pair(a, d, a1p, a1_of(__ldg(a.quat + m)), bkp, min_image_fixed(a.boxf, ipm, ibm))) {
+			if(m > i && d2 < a.rnear2 && near_pair(a, d, a1p, load_a1(a.axf, m), bkp, min_image_fixed(a.boxf, ipm, ibm))) {
 				higher_near++;
 				// rows that overflow max_neigh are rebuilt after the matrix has grown: never flag an entry that was not written
 				if(count >= a.max_neigh) mask_overflow = true;
@@ -254,14 +250,14 @@ __global__ void __launch_bounds__(128) k_fill_edges(oxb::ListArgs a) {
 		// very long row: redo the geometric selection (same predicate as in k_build_neigh)
 		const int4 ip = a.ipos[i];
 		const int4 ib = a.iback[i];
-		const v3 a1p = a1_of(a.quat[i]);
+		const v3 a1p = load_a1(a.axf, i);
 		const v3 bkp = min_image_fixed(a.boxf, ip, ib);
 		for(int k = 0; k < nn; k++) {
 			int m = a.nbr[(size_t) k * a.stride + i];
 			if(m > i) {
 				const int4 ipm = __ldg(a.ipos + m);
 				v3 d = min_image_fixed(a.boxf, ip, ipm);
-				if(dot(d, d) < a.rnear2 && near_pair(a, d, a1p, a1_of(__ldg(a.quat + m)), bkp, min_image_fixed(a.boxf, ipm, __ldg(a.iback + m)))) {
+				if(dot(d, d) < a.rnear2 && near_pair(a, d, a1p, load_a1(a.axf, m), bkp, min_image_fixed(a.boxf, ipm, __ldg(a.iback + m)))) {
 					if(off < a.edge_capacity) a.edges[off] = make_int2(i, m);
 					off++;
 				}
@@ -305,7 +301,7 @@ void launch_build_lists(cudaStream_t s, const ListArgs &a) {
 		cub::DeviceRadixSort::SortPairs(a.cub_tmp, tmp, a.cell_key, a.cell_key_sorted, a.cell_val, a.cell_val_sorted, N, 0, bits_for(ncells), s);
 	}
 	cudaMemsetAsync(cell_start, 0, sizeof(int) * 2 * (size_t) ncells, s);
-	k_cell_ranges<<<(N + tpb - 1) / tpb, tpb, 0, s>>>(N, a.cell_key_sorted, cell_start, cell_end, a.ipos, a.iback, a.quat, a.base_a1, a.boxf, a.ref_pos, a.ref_vel,
+	k_cell_ranges<<<(N + tpb - 1) / tpb, tpb, 0, s>>>(N, a.cell_key_sorted, cell_start, cell_end, a.ipos, a.iback, a.axf, a.base_a1, a.boxf, a.ref_pos, a.ref_vel,
 			a.ref_L, a.flags);
 	cudaMemsetAsync(a.flags + OXB_FLAG_MAX_NEIGH_SEEN, 0, sizeof(int), s);
 	if(a.direct) k_build_neigh<true><<<(N + 127) / 128, 128, 0, s>>>(a, cell_start, cell_end);

@@ -34,7 +34,7 @@ __global__ void k_state_in(MarshalArgs a) {
 	for(int k = 0; k < 3; k++) v2[k] /= n2;
 	quatd q = quat_from_axes(v1, v2, v3_);
 	a.quatd[i] = make_double4(q.x, q.y, q.z, q.w);
-	a.quat[i] = make_float4((float) q.x, (float) q.y, (float) q.z, (float) q.w);
+	store_axes_from_quatd(a.axf, i, q.x, q.y, q.z, q.w); // from the quaternion, exactly as the integrator derives it
 	const int4 t = a.topo[i]; // btype, n3, n5, strand
 	int4 ip;
 	ip.x = (int) to_fixed(p[0], a.box_inv[0]); ip.y = (int) to_fixed(p[1], a.box_inv[1]); ip.z = (int) to_fixed(p[2], a.box_inv[2]);

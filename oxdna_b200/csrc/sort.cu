@@ -91,7 +91,8 @@ __global__ void __launch_bounds__(256) k_permute(oxb::PermuteArgs a) {
 	int4 ip = a.ipos_in[o];
 	a.ipos_out[n] = ip;
 	a.iback_out[n] = a.iback_in[o];
-	a.quat_out[n] = a.quat_in[o];
+	a.axf_out[2 * (size_t) n] = a.axf_in[2 * (size_t) o];
+	a.axf_out[2 * (size_t) n + 1] = a.axf_in[2 * (size_t) o + 1];
 	a.F_out[n] = a.F_in[o];
 	a.T_out[n] = a.T_in[o];
 	int2 b = a.bonds_in[o];
