@@ -114,6 +114,7 @@ struct oxb_ctx {
 	cudaEvent_t ev_wait = nullptr;
 	bool defer_build_checks = true; // OXB_DEFER_BUILD_CHECK=0 restores one host synchronisation per rebuild
 	bool build_unchecked = false; // a list rebuild was launched without waiting for its overflow flags (oxb_run); the next batch checks
+	bool fold_tails = true; // coaxial stacking + FP64 excluded volume in the tails of the producing kernels (OXB_FOLD=0: separate launches)
 	bool dh_half = true; // Debye-Hueckel matrix with every pair in one row + partner atomics (OXB_DH_HALF=0: full matrix, no atomics)
 	bool fork_streams = true; // force pass on three concurrent streams (OXB_FORK=0/1 overrides the size-based default)
 	bool mid_step = false; // positions already advanced for `step`, forces pending
@@ -445,6 +446,7 @@ int launch_forces(oxb_ctx *c, int hw, bool clear, long long step) {
 		e.ex_list = c->ex_list; e.ex_counts = c->ex_counts; e.ex_bonded = c->ex_bonded; e.ex_seg = c->ex_seg;
 		e.refine = (c->precision == OXB_PRECISION_MIXED) ? 1 : 0;
 		e.dh_half = c->dh_half ? 1 : 0;
+		e.fold = c->fold_tails ? 1 : 0;
 		e.n_seg = c->n_seg; e.hb_seg = c->hb_seg; e.cx_seg = c->cx_seg; e.cr_seg = c->cr_seg;
 		// ~1.7 items per particle in that list; aim at ~2 items per consumer thread
 		e.hb_split = (int) std::max<long long>(1, std::min<long long>(8, (17ll * c->N / 10 / c->n_seg + 64) / 128));
@@ -476,15 +478,17 @@ int launch_forces(oxb_ctx *c, int hw, bool clear, long long step) {
 			c->launches += 1;
 		}
 		if(fork) CU(cudaStreamWaitEvent(c->aux[1], c->ev_near, 0));
-		oxb::launch_edge_stage(s1, 3, c->mref(), c->boxf, e, c->flags, hw);
-		if(e.refine) oxb::launch_edge_stage(s1, 6, c->mref(), c->boxf, e, c->flags, hw); // excluded volume in double for the parked pairs (after near + bonded)
+		if(!e.fold) {
+			oxb::launch_edge_stage(s1, 3, c->mref(), c->boxf, e, c->flags, hw);
+			if(e.refine) oxb::launch_edge_stage(s1, 6, c->mref(), c->boxf, e, c->flags, hw); // excluded volume in double for the parked pairs (after near + bonded)
+		}
 		if(fork) {
 			CU(cudaEventRecord(c->ev_join[0], c->aux[0]));
 			CU(cudaEventRecord(c->ev_join[1], c->aux[1]));
 			CU(cudaStreamWaitEvent(m, c->ev_join[0], 0));
 			CU(cudaStreamWaitEvent(m, c->ev_join[1], 0));
 		}
-		c->launches += e.refine ? 6 : 5;
+		c->launches += e.fold ? 4 : (e.refine ? 6 : 5);
 	}
 	else {
 		oxb::launch_forces_particle(m, c->mref(), c->boxf, c->N, c->ipos[a], c->iback[a], c->axf[a],
@@ -669,7 +673,7 @@ int batch_graph(oxb_ctx *c, int units, cudaGraphExec_t *out) {
 // stream launches.
 int launch_full_units(oxb_ctx *c, long long n, long long step0, int &epoch) {
 	const bool graphable = c->use_graphs && c->th.type != OXB_THERMOSTAT_BUSSI;
-	const int per_unit = (c->use_edge ? (c->precision == OXB_PRECISION_MIXED ? 6 : 5) : 1) + (c->n_ext > 0 ? 1 : 0) + (c->n_ext_all > 0 ? 1 : 0) + (c->n_ext_com > 0 ? 1 : 0) + 1;
+	const int per_unit = (c->use_edge ? (c->fold_tails ? 4 : (c->precision == OXB_PRECISION_MIXED ? 6 : 5)) : 1) + (c->n_ext > 0 ? 1 : 0) + (c->n_ext_all > 0 ? 1 : 0) + (c->n_ext_com > 0 ? 1 : 0) + 1;
 	long long k = 0;
 	while(k < n) {
 		int chunk = 0;
@@ -737,6 +741,8 @@ int oxb_create(oxb_ctx **out, int device, int N, int precision) {
 		if(sf != nullptr && atof(sf) > 0.) c->spec_factor = atof(sf);
 		const char *db = getenv("OXB_DEFER_BUILD_CHECK");
 		if(db != nullptr) c->defer_build_checks = (db[0] != '0');
+		const char *fo = getenv("OXB_FOLD");
+		if(fo != nullptr) c->fold_tails = (fo[0] != '0');
 		const char *dhh = getenv("OXB_DH_HALF");
 		if(dhh != nullptr) c->dh_half = (dhh[0] != '0');
 		const char *f = getenv("OXB_FORK");

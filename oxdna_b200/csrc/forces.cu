@@ -115,6 +115,28 @@ __device__ __forceinline__ Particle load_particle(const typename MD::Params &M, 
 	return P;
 }
 
+// one coaxial-stacking pair of a block's own work-list segment, evaluated in the TAIL of the producing kernel (fold = 1): the list is tiny
+// (a few hundredths of an entry per particle), so a separate launch costs more than it computes.  Not inlined: the hot loop of the
+// producer keeps its register footprint.
+template<class MD>
+__device__ __noinline__ void cxst_item(const typename MD::Params &M, const BoxF &box, const int4 *__restrict__ ipos, const float4 *__restrict__ axf, int2 ed,
+		float4 *__restrict__ F, float4 *__restrict__ T) {
+	Particle P = load_particle<MD>(M, ipos, axf, ed.x);
+	Particle Q = load_particle<MD>(M, ipos, axf, ed.y);
+	const v3 r = min_image_fixed(box, P.ip, Q.ip);
+	PairAcc acc;
+	acc.clear();
+	const v3 rs = r + (Q.ax.a1 - P.ax.a1) * M.stack_a1;
+	const float en = MD::cxst(M, rs, dot(rs, rs), r + Q.back - P.back, P.ax, Q.ax, acc);
+	if(en != 0.f) {
+		const v3 tp = acc.torque_p(P.ax, P.back), tq = acc.torque_q(Q.ax, Q.back);
+		atomic_add4(F + ed.x, -acc.F.x, -acc.F.y, -acc.F.z, en);
+		atomic_add4(T + ed.x, tp.x, tp.y, tp.z, 0.f);
+		atomic_add4(F + ed.y, acc.F.x, acc.F.y, acc.F.z, en);
+		atomic_add4(T + ed.y, tq.x, tq.y, tq.z, 0.f);
+	}
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // Particle-centric: one thread per particle, every listed pair evaluated from both ends, no atomics, deterministic.
 // ------------------------------------------------------------------------------------------------------------
@@ -296,7 +318,8 @@ template<class MD>
 __global__ void __launch_bounds__(128, OXB_MB_NEAR) k_edge_near(const __grid_constant__ typename MD::Params M, BoxF box, const int *__restrict__ n_edges,
 		const int2 *__restrict__ edges, const int4 *__restrict__ ipos, const float4 *__restrict__ axf, float4 *__restrict__ F, float4 *__restrict__ T,
 		int2 *__restrict__ hb_list, int2 *__restrict__ cx_list, int2 *__restrict__ cr_list, int *__restrict__ seg_counts, int hb_seg, int cx_seg,
-		int cr_seg, int4 *__restrict__ ex_list, int *__restrict__ ex_counts, int ex_seg, int refine, int *__restrict__ flags, int hw) {
+		int cr_seg, int4 *__restrict__ ex_list, int *__restrict__ ex_counts, int ex_seg, int refine, int fold, const double4 *__restrict__ posd,
+		const double4 *__restrict__ quatd, int *__restrict__ flags, int hw) {
 	if(blockIdx.x == 0 && threadIdx.x == 0) prof_mark(flags, flags[hw] ? OXB_PROF_WAIT : OXB_PROF_FORCE);
 	if(flags[hw]) return;
 	__shared__ int s_cnt[3];
@@ -380,6 +403,21 @@ __global__ void __launch_bounds__(128, OXB_MB_NEAR) k_edge_near(const __grid_con
 		}
 	}
 	__syncthreads();
+	if(fold && threadIdx.x < 3) {
+		const int seg = (threadIdx.x == 0) ? hb_seg / 3 : (threadIdx.x == 1 ? cx_seg : hb_seg - hb_seg / 3);
+		seg_counts[threadIdx.x * gridDim.x + blockIdx.x] = min(s_cnt[threadIdx.x], seg);
+	}
+	if(fold) {
+		// tail: this block's own coaxial-stacking pairs and parked excluded-volume pairs (written above, visible after the barrier)
+		const int ncx = min(s_cnt[1], cx_seg);
+		for(int k = threadIdx.x; k < ncx; k += blockDim.x) cxst_item<MD>(M, box, ipos, axf, cx_list[k], F, T);
+		const int nex = min(s_nex, ex_seg);
+		for(int k = threadIdx.x; k < nex; k += blockDim.x) {
+			const int4 it = ex_list[k];
+			excl_double_item<MD>(M, box, posd, quatd, it.x, it.y, it.z, F, T);
+		}
+		return;
+	}
 	if(threadIdx.x == 0) ex_counts[blockIdx.x] = min(s_nex, ex_seg);
 	if(threadIdx.x < 3) {
 		// list 0: hydrogen-bonding-capable pairs (front of the hb segment), 1: coaxial stacking, 2: cross-stacking-only pairs (rest of the hb segment)
@@ -433,13 +471,14 @@ __global__ void __launch_bounds__(64, OXB_MB_HEAVY) k_edge_heavy(const __grid_co
 template<class MD>
 __global__ void __launch_bounds__(128, OXB_MB_BONDED) k_bonded(const __grid_constant__ typename MD::Params M, BoxF box, int N, const int4 *__restrict__ ipos,
 		const int4 *__restrict__ iback, const float4 *__restrict__ axf, const int2 *__restrict__ bonds, float4 *__restrict__ F, float4 *__restrict__ T,
-		int *__restrict__ ex_bonded, int refine, const oxb_replica_consts *__restrict__ rep, int n_per, int *__restrict__ flags, int hw) {
+		int *__restrict__ ex_bonded, int refine, int fold, const double4 *__restrict__ posd, const double4 *__restrict__ quatd,
+		const oxb_replica_consts *__restrict__ rep, int n_per, int *__restrict__ flags, int hw) {
 	if(blockIdx.x == 0 && threadIdx.x == 0) prof_mark(flags, flags[hw] ? OXB_PROF_WAIT : OXB_PROF_FORCE);
 	if(flags[hw]) return;
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= N) return;
 	int2 b = __ldg(bonds + i);
-	if(b.x < 0) { if(refine) ex_bonded[i] = 0; return; }
+	if(b.x < 0) { if(refine && !fold) ex_bonded[i] = 0; return; }
 	Particle P = load_particle<MD>(M, ipos, axf, i);
 	Particle Q = load_particle<MD>(M, ipos, axf, b.x);
 	PairAcc acc;
@@ -448,6 +487,7 @@ __global__ void __launch_bounds__(128, OXB_MB_BONDED) k_bonded(const __grid_cons
 	bool broken = false;
 	const v3 r = min_image_fixed(box, P.ip, Q.ip);
 	float en;
+	int ex_mask = 0;
 	if(refine) {
 		// d2V/dr2 of the FENE spring is eps / Delta^2 = 32 at rest and grows as (1 + u) / (1 - u)^2, u = x^2 / Delta^2: the FP32
 		// distance (~1e-7) is good for 1e-5 of the force until u ~ 0.5; bonds stretched further take the distance in double
@@ -460,7 +500,8 @@ __global__ void __launch_bounds__(128, OXB_MB_BONDED) k_bonded(const __grid_cons
 		}
 		// bonded excluded-volume site pairs in range are left to k_excl_fix (double); one mask per particle
 		fs.excl_deferred = bonded_excl_mask(M, r, P.ax, Q.ax, P.back, Q.back);
-		ex_bonded[i] = fs.excl_deferred;
+		if(!fold) ex_bonded[i] = fs.excl_deferred;
+		ex_mask = fs.excl_deferred;
 		en = MD::bonded(M, r, P.ax, Q.ax, P.btype, Q.btype, P.back, Q.back, acc, broken, nullptr, &fs);
 	}
 	else en = MD::bonded(M, r, P.ax, Q.ax, P.btype, Q.btype, P.back, Q.back, acc, broken);
@@ -470,6 +511,8 @@ __global__ void __launch_bounds__(128, OXB_MB_BONDED) k_bonded(const __grid_cons
 	atomic_add4(F + b.x, acc.F.x, acc.F.y, acc.F.z, en);
 	atomic_add4(T + b.x, tq.x, tq.y, tq.z, 0.f);
 	if(broken) atomicOr(flags + OXB_FLAG_ERROR, OXB_ERR_FENE_BROKEN);
+	// fold = 1: the few bonds with a bonded excluded-volume site pair in range take it in double right here instead of in k_excl_fix
+	if(fold && ex_mask != 0) excl_double_item<MD>(M, box, posd, quatd, i, b.x, ex_mask, F, T);
 }
 
 // Excluded volume in double for the parked pairs: blocks [0, n_seg) walk the near-edge segments, the following blocks scan the
@@ -1017,7 +1060,7 @@ static void launch_edge_stage_t(cudaStream_t s, int which, const typename MD::Pa
 	// inside): nothing here depends on device-side counts, so a captured graph stays valid across list rebuilds
 	case 1:
 		k_edge_near<MD><<<a.n_seg, 128, 0, s>>>(M, box, a.n_edges, a.edges, a.ipos, a.axf, a.F, a.T, a.hb_list, a.cx_list, a.cr_list, a.seg_counts, a.hb_seg,
-				a.cx_seg, a.cr_seg, a.ex_list, a.ex_counts, a.ex_seg, a.refine, flags, hw);
+				a.cx_seg, a.cr_seg, a.ex_list, a.ex_counts, a.ex_seg, a.refine, a.fold, a.posd, a.quatd, flags, hw);
 		break;
 	case 2: k_edge_heavy<MD, 0><<<dim3(a.n_seg, a.hb_split), 64, 0, s>>>(M, box, a.seg_counts, a.hb_list, a.hb_seg, a.ipos, a.axf, a.F, a.T, flags, hw); break;
 	case 3: k_edge_heavy<MD, 1><<<a.n_seg, 64, 0, s>>>(M, box, a.seg_counts, a.cx_list, a.cx_seg, a.ipos, a.axf, a.F, a.T, flags, hw); break;
@@ -1029,7 +1072,7 @@ static void launch_edge_stage_t(cudaStream_t s, int which, const typename MD::Pa
 	default: {
 		static const int tpb_env = env_int("OXB_TPB_BONDED", 0);
 		const int tpb = tpb_env > 0 ? tpb_env : 128;
-		k_bonded<MD><<<(a.N + tpb - 1) / tpb, tpb, 0, s>>>(M, box, a.N, a.ipos, a.iback, a.axf, a.bonds, a.F, a.T, a.ex_bonded, a.refine, a.rep, a.n_per, flags, hw);
+		k_bonded<MD><<<(a.N + tpb - 1) / tpb, tpb, 0, s>>>(M, box, a.N, a.ipos, a.iback, a.axf, a.bonds, a.F, a.T, a.ex_bonded, a.refine, a.fold, a.posd, a.quatd, a.rep, a.n_per, flags, hw);
 		break;
 	}
 	}

@@ -107,6 +107,7 @@ struct EdgeArgs {
 	int4 *ex_list;
 	int *ex_counts, *ex_bonded;
 	int ex_seg;
+	int fold;   // 1: the coaxial-stacking pairs and the parked excluded-volume pairs are evaluated in the tails of k_edge_near / k_bonded (no stage 3 / 6 launches)
 	int refine; // 1 (backend_precision = mixed): FENE and excluded volume in double; 0 (float): FP32 pair arithmetic throughout
 };
 void launch_edge_stage(cudaStream_t s, int which, const ModelRef &M, BoxF box, const EdgeArgs &a, int *flags, int hw);
