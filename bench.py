@@ -382,7 +382,8 @@ def measure_single(args, wl, steps, warmup, equil, md, full, local_rank=0):
                               "peak": hbm_peak, "unit": "GB/s", "frac": gbs(N * 470.0, t_sort) / hbm_peak if t_sort > 0 else None, "ms": t_sort,
                               "per_md_step_ms": t_sort * n_sort / n_md},
             "kernels_ms": {"force_pass": t_force, "integrate": t_integ, "list_build_per_rebuild": t_build, "sort_per_sort": t_sort,
-                           "halt_and_host_wait_per_rebuild": t_wait, "other_per_md_step": prof["other"][0] / n_md, "md_step_mean": step_ms,
+                           "halt_and_host_wait_per_rebuild": t_wait, "batch_launch_gap_per_batch": prof["gap"][0] / max(prof["gap"][1], 1), "batches": prof["gap"][1],
+                           "batch_launch_gap_per_md_step": prof["gap"][0] / n_md, "other_per_md_step": prof["other"][0] / n_md, "md_step_mean": step_ms,
                            "sum_of_phases_per_md_step": prof_total / n_md, "rebuilds": n_reb, "sorts": n_sort,
                            "source": "device-side phase timeline of the timed region; phases add up to md_step_mean"},
         })

@@ -126,7 +126,8 @@ int oxb_rna2_params_seqdep(oxb_rna2_params *P, double T, const double *stck_raw1
 /* One external force acting on one particle -- or on every particle when particle = -1 (`particle = all`), in which case
  * the entry is kept once and evaluated per particle (the reference stores 15 union slots per particle).
  *   type                 reference class (src/Forces/)   fields used
- *   STRING               ConstantRateForce               F0, rate, dir
+ *   STRING               ConstantRateForce               F0, rate, dir; pbc = 1 is the reference's dir_as_centre: the force points from the
+ *                                                        particle to the point pos0 (src/CUDA/Backends/CUDA_MD.cuh:114-130)
  *   TRAP                 MovingTrap                      stiff, rate, dir, pos0
  *   MUTUAL_TRAP          MutualTrap                      ref, pbc, stiff, r0, rate, stiff_rate
  *   LOWDIM_TRAP          LowdimMovingTrap                stiff, rate, dir, pos0, iaux = visibility mask (bit 0 x, 1 y, 2 z)
@@ -312,11 +313,12 @@ int oxb_time_kernel(oxb_ctx *ctx, int which, int reps, float *ms_per_launch);
 /* Timeline of the hot loop measured INSIDE oxb_run (graph-launched batches included): while enabled, the first thread of the kernel
  * that opens each phase of the step stamps %globaltimer on the device and the time since the previous stamp is charged to the phase
  * that was open, so the phases add up to the device time of the run (launch gaps and host-synchronisation bubbles included).
- * Phases (OXB_PROF_*): 0 other, 1 force pass, 2 integrate, 3 halted launches + host wait before a rebuild, 4 Hilbert sort, 5 list build.
+ * Phases (OXB_PROF_*): 0 other, 1 force pass, 2 integrate, 3 halted launches + host wait before a rebuild, 4 Hilbert sort, 5 list build,
+ * 6 gap between the start of a batch (k_batch_begin) and its first force kernel (launch latency of the batch).
  * Replaces the reference's TimingManager around sim_step (src/Utilities/Timings.cpp, MD_CUDABackend.cu:567-619), which needs a
  * cudaDeviceSynchronize per timer.  oxb_set_profile zeroes the accumulators; oxb_get_profile returns milliseconds and the number of
- * times each phase was entered (6 values each). */
-#define OXB_PROF_NPHASES 6
+ * times each phase was entered (7 values each). */
+#define OXB_PROF_NPHASES 7
 int oxb_set_profile(oxb_ctx *ctx, int enable);
 int oxb_get_profile(oxb_ctx *ctx, double *ms, long long *entries);
 

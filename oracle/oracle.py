@@ -116,6 +116,11 @@ def fill_ext_entry(e, d, pool, grid):
     if d["type"] != "mutual_trap" and np.linalg.norm(dr) > 0:
         dr = dr / np.linalg.norm(dr)
     centre = d.get("pos0", (0, 0, 0)) if d["type"] == "twist" else d.get("center", d.get("pos0", (0, 0, 0)))
+    if d["type"] == "string" and int(d.get("dir_as_centre", 0)):
+        # ConstantRateForce with dir_as_centre (src/Forces/ConstantRateForce.cpp:31,44-46,54-61): `dir` is a point, kept unnormalised in
+        # pos0; the force points from the particle towards it.  Flagged in the (otherwise unused) pbc field.
+        centre = d["dir"]
+        e.pbc = 1
     for c in range(3):
         e.dir[c] = dr[c]
         e.pos0[c] = float(centre[c])

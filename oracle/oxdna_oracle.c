@@ -608,7 +608,13 @@ static void ext_one(const oxo_ext_force *f, const double *pos, int p, const doub
 	if(f->type == OXO_EXT_STRING) {
 		/* src/Forces/ConstantRateForce.cpp:52-61 */
 		double s = f->F0 + f->rate * step;
-		axpy3(s, f->dir, F);
+		if(f->pbc) {
+			/* dir_as_centre: the force points from the particle to the point pos0 (ConstantRateForce.cpp:54-61) */
+			double d[3] = { f->pos0[0] - pp[0], f->pos0[1] - pp[1], f->pos0[2] - pp[2] };
+			double m = sqrt(dot3(d, d));
+			for(int k = 0; k < 3; k++) F[k] += s * d[k] / m;
+		}
+		else axpy3(s, f->dir, F);
 	}
 	else if(f->type == OXO_EXT_TRAP) {
 		/* src/Forces/MovingTrap.cpp:50-64 */

@@ -115,6 +115,11 @@ def fill_ext_entry(e, d, pool, grid):
     if d["type"] != "mutual_trap" and np.linalg.norm(dr) > 0:
         dr = dr / np.linalg.norm(dr)
     centre = d.get("pos0", (0, 0, 0)) if d["type"] == "twist" else d.get("center", d.get("pos0", (0, 0, 0)))
+    if d["type"] == "string" and int(d.get("dir_as_centre", 0)):
+        # ConstantRateForce with dir_as_centre (src/Forces/ConstantRateForce.cpp:31,44-46,54-61): `dir` is a point, kept unnormalised in
+        # pos0; the force points from the particle towards it.  Flagged in the (otherwise unused) pbc field.
+        centre = d["dir"]
+        e.pbc = 1
     for c in range(3):
         e.dir[c] = dr[c]
         e.pos0[c] = float(centre[c])
@@ -525,14 +530,14 @@ class Context:
     def launch_count(self):
         return self._L.oxb_launch_count(self._h)
 
-    PROF_PHASES = ("other", "force", "integrate", "wait", "sort", "build")
+    PROF_PHASES = ("other", "force", "integrate", "wait", "sort", "build", "gap")
 
     def set_profile(self, enable=True):
         self._ck(self._L.oxb_set_profile(self._h, int(bool(enable))))
 
     def get_profile(self):
         """{phase: (milliseconds, entries)} accumulated inside run() since set_profile(True)"""
-        ms, n = (C.c_double * 6)(), (C.c_longlong * 6)()
+        ms, n = (C.c_double * 7)(), (C.c_longlong * 7)()
         self._ck(self._L.oxb_get_profile(self._h, ms, n))
         return {k: (ms[i], n[i]) for i, k in enumerate(self.PROF_PHASES)}
 

@@ -535,6 +535,7 @@ oxb::IntegrateArgs integ_args(oxb_ctx *c, long long step) {
 }
 
 __global__ void k_batch_begin(int *flags, long long *cur_step, long long step, int check_build) {
+	prof_mark(flags, OXB_PROF_GAP); // from here to the first kernel of the force pass: launch latency of the batch (graph launch included)
 	// check_build: the list rebuild in front of this batch was not checked by the host; an overflow halts the whole batch
 	const int halt = (check_build && (flags[OXB_FLAG_ERROR] & (OXB_ERR_NEIGH_OVERFLOW | OXB_ERR_EDGE_OVERFLOW))) ? 1 : 0;
 	flags[OXB_FLAG_STEPS_DONE] = 0;

@@ -616,8 +616,13 @@ __device__ __forceinline__ v3 ext_single(const DevExtForce &e, double4 p, int4 i
 	const float st = (float) step;
 	switch(e.type) {
 	case OXB_EXT_STRING: {
-		// ConstantRateForce.cpp:52-61
+		// ConstantRateForce.cpp:52-61; dir_as_centre (flag in pbc): towards the point pos0 (CUDA_MD.cuh:114-130)
 		float s = e.F0 + e.rate * st;
+		if(e.pbc) {
+			const double dx = e.pos0[0] - p.x, dy = e.pos0[1] - p.y, dz = e.pos0[2] - p.z;
+			const double inv = (double) s / sqrt(dx * dx + dy * dy + dz * dz);
+			return mk3((float) (dx * inv), (float) (dy * inv), (float) (dz * inv));
+		}
 		return mk3(e.dir[0] * s, e.dir[1] * s, e.dir[2] * s);
 	}
 	case OXB_EXT_TRAP:

@@ -59,12 +59,18 @@ __global__ void __launch_bounds__(256, OXB_MB_INTEGRATE) k_integrate(oxb::Integr
 	if(i < a.N) {
 		const double hdt = 0.5 * a.dt;
 		float4 F = a.F[i], T = a.T[i];
+		double4 qd0 = make_double4(0., 0., 0., 1.);
 		if(PH & (OXB_PH_SECOND | OXB_PH_FIRST)) {
 			// the force kernels accumulate the torque in the lab frame: rotate it into the body frame (L is a body-frame
 			// angular momentum with unit inertia, src/CUDA/Interactions/CUDA_DNA.cuh:896)
 			Axes A;
-			{
-				// plain loads: this thread rewrites the record below
+			if(PH & OXB_PH_FIRST) {
+				// the first-half phase streams the FP64 quaternion anyway: no second orientation read
+				qd0 = a.quatd[i];
+				A = axes_from_quat(make_float4((float) qd0.x, (float) qd0.y, (float) qd0.z, (float) qd0.w));
+			}
+			else {
+				// plain loads (not __ldg): other variants of this kernel rewrite the record
 				const float4 u = a.axf[2 * (size_t) i], w = a.axf[2 * (size_t) i + 1];
 				A.a1 = mk3(u.x, u.y, u.z); A.a3 = mk3(u.w, w.x, w.y); A.a2 = cross(A.a3, A.a1);
 			}
@@ -132,7 +138,7 @@ __global__ void __launch_bounds__(256, OXB_MB_INTEGRATE) k_integrate(oxb::Integr
 			a.ipos[i] = ip;
 			// body-frame rotation by |L| dt about L: q <- q (x) (Lhat sin(th/2), cos(th/2))
 			double n2 = L.x * L.x + L.y * L.y + L.z * L.z;
-			double4 qn = a.quatd[i];
+			double4 qn = qd0;
 			if(n2 > 0.) {
 				// half angle th = dt |L| / 2 is ~1e-3: sin(th)/|L| and cos(th) from their Taylor series (remainder < 1e-20 for
 				// th < 0.03) -- no square root, no division, no slow-path double sincos; the general path stays for huge |L|

@@ -18,14 +18,14 @@ enum : int {
 	OXB_FLAG_PROF_ON = 12,   // 1 = the first thread of the step's kernels stamps %globaltimer into the profile area (oxb_set_profile)
 	OXB_FLAG_WORDS = 16,     // words copied back by read_flags
 	OXB_PROF_OFFSET = 32,    // profile area (unsigned long long words) starts at this int offset
-	OXB_FLAG_ALLOC = 96,
+	OXB_FLAG_ALLOC = 128,
 };
 
 // Device-side timeline of the hot loop: every kernel that opens a phase of the step has its first thread stamp %globaltimer; the time
 // since the previous stamp is charged to the phase that was open.  Works inside graph-launched batches and costs one thread a few
 // global accesses, so the decomposition is measured IN the timed region (bench.py roofline), launch gaps included: the phases sum to
 // the device time line of the run.  Layout (unsigned long long): [0] last stamp, [1] open phase, [2 + p] ns in phase p, [2 + NPHASE + p] entries into p.
-enum { OXB_PROF_OTHER = 0, OXB_PROF_FORCE = 1, OXB_PROF_INTEG = 2, OXB_PROF_WAIT = 3, OXB_PROF_SORT = 4, OXB_PROF_BUILD = 5, OXB_PROF_NPHASE = 6 };
+enum { OXB_PROF_OTHER = 0, OXB_PROF_FORCE = 1, OXB_PROF_INTEG = 2, OXB_PROF_WAIT = 3, OXB_PROF_SORT = 4, OXB_PROF_BUILD = 5, OXB_PROF_GAP = 6, OXB_PROF_NPHASE = 7 };
 #ifdef __CUDACC__
 __device__ __forceinline__ void prof_mark(int *flags, int phase, bool reset = false) {
 	if(flags[OXB_FLAG_PROF_ON] == 0) return;

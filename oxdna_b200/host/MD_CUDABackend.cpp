@@ -241,10 +241,14 @@ void MD_CUDABackend::_apply_external_forces_changes() {
 			bool single_particle_type = true;
 			if(ft == typeid(ConstantRateForce)) {
 				ConstantRateForce *cf = static_cast<ConstantRateForce *>(f);
-				if(cf->dir_as_centre) throw oxDNAException("ConstantRateForce with dir_as_centre = true is not supported by the oxdna_b200 CUDA backend");
 				e.type = OXB_EXT_STRING;
 				e.F0 = cf->_F0; e.rate = cf->_rate;
 				e.dir[0] = cf->_direction.x; e.dir[1] = cf->_direction.y; e.dir[2] = cf->_direction.z;
+				if(cf->dir_as_centre) {
+					// the "direction" is a point: the force pulls towards it (src/CUDA/Backends/CUDA_MD.cuh:117-122)
+					e.pbc = 1;
+					e.pos0[0] = cf->_direction.x; e.pos0[1] = cf->_direction.y; e.pos0[2] = cf->_direction.z;
+				}
 			}
 			else if(ft == typeid(MutualTrap)) {
 				MutualTrap *mf = static_cast<MutualTrap *>(f);

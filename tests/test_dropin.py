@@ -261,6 +261,12 @@ def test_stock_input_file_thermostat_and_errors(tmp_path):
     # reference incompatibilities are reported as the reference reports them (fatal oxDNAException, non-zero exit)
     bad = run(OURS, str(tmp_path / "bad"), backend="CUDA", itype="DNA2", steps=10, thermostat="no", use_edge=1, sort_every=0, extra="CUDA_list = no")
     assert bad.returncode != 0 and "incompatible" in bad.stdout
+    # CUDA_list = no (src/CUDA/Lists/CUDANoList.cu) without use_edge is accepted: same forces as the Verlet list, so the NVE energies of a
+    # short run are identical to the CUDA_list = verlet run (the later key overrides the template's)
+    nl = run(OURS, str(tmp_path / "nolist"), backend="CUDA", itype="DNA2", steps=300, thermostat="no", use_edge=0, sort_every=0, extra="CUDA_list = no")
+    vl = run(OURS, str(tmp_path / "verlet"), backend="CUDA", itype="DNA2", steps=300, thermostat="no", use_edge=0, sort_every=0, extra="")
+    assert nl.returncode == 0 and vl.returncode == 0, nl.stdout[-1500:]
+    assert np.array_equal(energies(str(tmp_path / "nolist")), energies(str(tmp_path / "verlet")))
     bad = run(OURS, str(tmp_path / "bad2"), backend="CUDA", itype="DNA2", steps=10, thermostat="no", use_edge=1, sort_every=0, extra="reload_from = x")
     assert bad.returncode != 0
     bad = run(OURS, str(tmp_path / "bad3"), backend="CUDA", itype="LJ", steps=10, thermostat="no", use_edge=1, sort_every=0, extra="")

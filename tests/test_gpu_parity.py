@@ -164,6 +164,25 @@ def test_external_forces_vs_reference():
             sim.close()
 
 
+@pytest.mark.parametrize("use_edge,sort_every", [(0, 0), (1, 1)])
+def test_string_force_dir_as_centre(use_edge, sort_every):
+    """`string` with dir_as_centre = true (src/CUDA/Backends/CUDA_MD.cuh:114-130) against the oracle, at a later step (rate != 0)"""
+    g = load_golden("lattice8")
+    ext = [dict(type="string", particle=7, F0=0.3, rate=0.002, dir=(4.0, -2.0, 11.0), dir_as_centre=1),
+           dict(type="string", particle="all", F0=0.05, rate=0.0, dir=(10.0, 10.0, 10.0), dir_as_centre=1),
+           dict(type="string", particle=9, F0=0.1, rate=0.0, dir=(0.0, 0.0, 2.0))]
+    sim = make_sim(g, use_edge=use_edge, CUDA_sort_every=sort_every, external_forces_list=ext)
+    bare = make_sim(g, use_edge=use_edge, CUDA_sort_every=sort_every)
+    try:
+        sim.ctx.set_step(50)
+        got = sim.ctx.get_forces()["force"] - bare.ctx.get_forces()["force"]
+        ref = O.ext_forces(ext, g["pos"], g["box"], 50)
+        assert np.abs(got - ref).max() < 2e-6, np.abs(got - ref).max()
+    finally:
+        sim.close()
+        bare.close()
+
+
 def test_run_is_deterministic_particle_centric():
     g = load_golden("lattice8")
     outs = []

@@ -108,6 +108,19 @@ def test_oracle_further_external_forces_fixture():
     assert np.abs(md.vel - g["vel1"]).max() < 1e-9
 
 
+def test_oracle_string_force_dir_as_centre():
+    """ConstantRateForce with dir_as_centre = true (src/Forces/ConstantRateForce.cpp:54-61; src/CUDA/Backends/CUDA_MD.cuh:114-130): the
+    force (F0 + rate * step) points from the particle towards the point given as `dir`."""
+    g = load_golden("lattice8")
+    ext = [dict(type="string", particle=7, F0=0.3, rate=0.002, dir=(4.0, -2.0, 11.0), dir_as_centre=1),
+           dict(type="string", particle=9, F0=0.1, rate=0.0, dir=(0.0, 0.0, 2.0))]
+    F = O.ext_forces(ext, g["pos"], g["box"], 50)
+    d = np.array([4.0, -2.0, 11.0]) - g["pos"][7]
+    assert np.allclose(F[7], (0.3 + 0.002 * 50) * d / np.linalg.norm(d), atol=1e-14)
+    assert np.allclose(F[9], [0.0, 0.0, 0.1], atol=1e-15)
+    assert np.count_nonzero(np.abs(F).sum(axis=1)) == 2
+
+
 def test_thermostat_parameter_restatement():
     T = parse_temperature("300K")
     from oxdna_b200.sim import brownian_params, langevin_params
