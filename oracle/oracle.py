@@ -289,15 +289,15 @@ def dna2_params_seqdep(P, stck16, stck_fact_eps, hb_AT, hb_GC):
 
 def rna2_params(T, salt=1.0, dh_half_charged_ends=True, max_backbone_force=None, max_backbone_force_far=0.04,
                 mismatch_repulsion=False, mismatch_repulsion_strength=1.0, cpu_quirks=False):
-    """oxRNA2 parameters.  cpu_quirks=True reproduces the two spots where the reference CPU class's force is not the gradient
-    of its energy (see oxdna_oracle.h); the reference's CUDA kernels -- and ours -- use the gradient."""
+    """oxRNA2 parameters.  cpu_quirks=True (= 3; 1 and 2 select one of them) reproduces the two spots where the reference CPU class's
+    force is not the gradient of its energy (see oxdna_oracle.h); the reference's CUDA kernels -- and ours -- use the gradient."""
     P = RNA2Params()
     mbf = max_backbone_force is not None
     lib().oxo_rna2_params_init(C.byref(P), C.c_double(T), C.c_double(salt), int(dh_half_charged_ends), int(mbf),
                                C.c_double(max_backbone_force if mbf else 0.0),
                                C.c_double(float(np.float32(max_backbone_force_far))), int(mismatch_repulsion),
                                C.c_double(mismatch_repulsion_strength))
-    P.cpu_quirks = int(cpu_quirks)
+    P.cpu_quirks = 3 if cpu_quirks is True else int(cpu_quirks)  # bit 0: phi2 stacking term, bit 1: mirrored coaxial theta1 term
     return P
 
 

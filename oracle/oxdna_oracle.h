@@ -133,9 +133,9 @@ typedef struct {
 	int average;            /* use_average_seq: G-U wobble pairs exist only when 0 */
 	int mismatch_repulsion; /* RNAInteraction2.cpp:43-55,96-101 */
 	double mis_eps, mis_shift;
-	/* 1: reproduce two places where the CPU class's force is NOT the gradient of its energy (the reference's CUDA kernels
-	 * use the gradient): the phi2 stacking term lacks the thetaB1/B2 factors (RNAInteraction.cpp:620) and the mirrored
-	 * coaxial theta1 term has the opposite sign (RNAInteraction.cpp:1046 vs :1302 and CUDA_RNA.cuh:896).  0: gradient. */
+	/* bit mask: reproduce two places where the CPU class's force is NOT the gradient of its energy (the reference's CUDA kernels
+	 * use the gradient): bit 0 -- the phi2 stacking term lacks the thetaB1/B2 factors (RNAInteraction.cpp:620); bit 1 -- the mirrored
+	 * coaxial theta1 term has the opposite sign (RNAInteraction.cpp:1046 vs :1302 and CUDA_RNA.cuh:896).  3: the CPU class; 0: gradient. */
 	int cpu_quirks;
 	double rcut;
 } oxo_rna2_params;

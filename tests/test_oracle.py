@@ -188,6 +188,35 @@ def test_rna_reference_golden_vector_file(which="avg_seq"):
     assert np.allclose(out["eterms"] / t["N"], ref, atol=2.5e-6), (out["eterms"] / t["N"], ref)
 
 
+def test_rna_cpu_quirk_term_is_active_on_the_quirks_fixture():
+    """tests/golden/rna_quirks.npz (oracle/make_golden.py rna_quirks): a strongly perturbed all-A configuration of the reference's 16-nt
+    RNA system on which the reference CPU class's force is visibly NOT the gradient of its energy: the mirrored coaxial theta1 term
+    (src/Interactions/RNAInteraction.cpp:1046; cpu_quirks bit 1).  The restatement with cpu_quirks = 3 reproduces the live CPU class
+    to rounding; with cpu_quirks = 0 (the gradient, what src/CUDA/Interactions/CUDA_RNA.cuh:896 evaluates) the energy is identical
+    and the torques differ by 2.5 %.  The second such spot (phi2 stacking term, RNAInteraction.cpp:620; bit 0) is dormant with the
+    stock parameters: inside the theta-B2 window cos(phi2) >= 0.04, where f5 is flat -- it changes nothing here or anywhere we looked."""
+    g = load_golden("rna_quirks")
+    assert float(g["energy_split"][4]) == 0.0  # no hydrogen bonding: no meshed factor in the CPU numbers
+    ax = O.axes_from_a1a3(g["a1"], g["a3"])
+    out = {}
+    for q in (3, 2, 1, 0):
+        P = _rna_params(g, cpu_quirks=q)
+        pairs = O.verlet_pairs(g["pos"], g["n3"], g["n5"], g["box"], P.rcut + 2 * 0.05)
+        assert pair_set(pairs) == pair_set(g["pairs"])
+        out[q] = O.forces(P, g["pos"], ax, g["btype"], g["n3"], g["n5"], g["box"], pairs)
+    fmax = np.linalg.norm(g["force"], axis=1).max()
+    tmax = np.linalg.norm(g["torque_lab"], axis=1).max()
+    assert np.abs(out[3]["force"] - g["force"]).max() < 1e-10 * fmax
+    assert np.abs(out[3]["torque_lab"] - g["torque_lab"]).max() < 1e-10 * tmax
+    assert abs(out[3]["U"] - float(g["U"])) < 1e-10 * abs(float(g["U"]))
+    assert abs(out[0]["U"] - out[3]["U"]) < 1e-12 * abs(out[3]["U"])  # the energy has no quirk
+    dT = np.linalg.norm(out[0]["torque_lab"] - out[3]["torque_lab"], axis=1).max() / tmax
+    assert dT > 1e-2, dT  # three orders of magnitude above the 1e-5 GPU criterion
+    # the phi2 term is dormant: bit 0 changes nothing
+    assert np.array_equal(out[2]["torque_lab"], out[3]["torque_lab"]) and np.array_equal(out[1]["torque_lab"], out[0]["torque_lab"])
+    assert np.array_equal(out[2]["force"], out[3]["force"])
+
+
 @pytest.mark.parametrize("case", ["force_field_rna/ref_rna2", "force_field_rna/ref_rna2_seqdep", "rna_lattice8", "rna_lattice8_nohb", "rna_lattice8_seqdep"])
 def test_rna_oracle_matches_reference_fixture(case):
     """Fixtures written by the unmodified reference CPU backend (interaction_type = RNA2).  Everything but the meshed
