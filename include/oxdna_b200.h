@@ -303,6 +303,32 @@ int oxb_get_stats(oxb_ctx *ctx, long long *n_list_updates, long long *n_sorts, i
  * unique pairs closer than rcut_near + 2 skin at the last rebuild (the pairs that can feel more than Debye-Hueckel) */
 int oxb_device_views(oxb_ctx *ctx, void **poss_f4, void **orientations_f4, void **matrix_neighs, void **number_neighs,
 		void **edge_list, void **n_edges);
+/* ---- plugin seam: a third-party interaction replaces the built-in force field.  Replaces the call
+ * CUDABaseInteraction::compute_forces(lists, d_poss, d_orientations, d_forces, d_torques, d_bonds, d_box) that the reference's backend
+ * makes on whatever CUDAInteractionFactory returned -- for unknown interaction types the class that PluginManager finds in
+ * CUDA<type>.so through make_CUDA<type> (src/CUDA/Interactions/CUDAInteractionFactory.cu:44-51, src/PluginManagement/PluginManager.cpp:89-180,
+ * src/CUDA/Interactions/CUDABaseInteraction.h:60).  The callback is invoked on the host wherever the built-in force pass would be launched
+ * (first forces, every MD step inside oxb_run, energy read-backs); it must enqueue its kernels on views->stream and return 0.  Arrays are
+ * in the reference's layouts, indexed by slot (the Hilbert order of the last re-sort): poss float4 (absolute position, .w = btype << 22 |
+ * original index, MD_CUDABackend.cu:243-254), orientations float4 quaternions (GPU_quat), matrix_neighs column-major
+ * (matrix_neighs[k * stride + i], k < number_neighs[i], both directions of every pair, bonded neighbours excluded), bonds int2 (n3, n5
+ * slots, -1 = none).  forces / torques are float4 accumulators, zero on entry: x, y, z in the LAB frame (the integrator rotates the
+ * torque into the body frame; the reference's kernels do that themselves), forces .w = the particle's share of the potential energy
+ * summed from both ends of every pair (U = sum / 2, as in the reference), torques .w = hydrogen-bonding energy or 0.
+ * Setting a callback defines the interaction: rcut fixes the Verlet radius, no built-in model is needed; use_edge and captured graphs
+ * are not available with it.  fn = NULL removes it. */
+typedef struct oxb_force_views {
+	int N, stride;
+	const void *poss, *orientations;
+	const int *matrix_neighs, *number_neighs;
+	const void *bonds;
+	void *forces, *torques;
+	double box[3];
+	long long step;
+	void *stream; /* cudaStream_t */
+} oxb_force_views;
+typedef int (*oxb_force_callback)(void *user, const oxb_force_views *views);
+int oxb_set_force_callback(oxb_ctx *ctx, oxb_force_callback fn, void *user, double rcut);
 /* number of kernel launches issued by this context so far (bench.py's gpu_launches claim) */
 long long oxb_launch_count(const oxb_ctx *ctx);
 

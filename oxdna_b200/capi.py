@@ -221,11 +221,20 @@ def fill_ext_entry(e, d, pool, grid):
         e.aux[c] = aux[c]
 
 
+class ForceViews(C.Structure):
+    """oxb_force_views (include/oxdna_b200.h): device pointers in the reference's layouts, handed to a plugged-in force pass"""
+    _fields_ = [("N", C.c_int), ("stride", C.c_int), ("poss", C.c_void_p), ("orientations", C.c_void_p), ("matrix_neighs", C.c_void_p),
+                ("number_neighs", C.c_void_p), ("bonds", C.c_void_p), ("forces", C.c_void_p), ("torques", C.c_void_p), ("box", C.c_double * 3),
+                ("step", C.c_longlong), ("stream", C.c_void_p)]
+
+
+FORCE_CALLBACK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(ForceViews))
+
 EXPORTED = """oxb_sizeof oxb_dna2_params_init oxb_dna1_params_init oxb_dna2_params_seqdep oxb_rna2_params_init oxb_rna2_params_seqdep oxb_set_model_rna2 oxb_create oxb_destroy oxb_last_error oxb_set_stream oxb_set_box
 oxb_set_topology oxb_set_model_dna2 oxb_set_lists oxb_set_dt oxb_set_thermostat oxb_set_ext_forces oxb_set_ext_index_pool oxb_set_ext_grid_pool oxb_set_state oxb_get_state oxb_write_conf oxb_write_conf_binary
 oxb_set_step oxb_get_step oxb_sort oxb_update_lists oxb_compute_forces oxb_first_step oxb_second_step oxb_thermostat oxb_run
 oxb_synchronize oxb_get_forces oxb_energy oxb_barostat_move oxb_barostat_trial oxb_barostat_accept oxb_barostat_reject oxb_get_box oxb_set_host_wait oxb_fix_diffusion oxb_energy_split oxb_get_pairs oxb_get_stats oxb_device_views oxb_launch_count oxb_time_kernel oxb_set_profile oxb_get_profile
-oxb_set_replicas oxb_set_replica_consts oxb_replica_energies oxb_replica_consts_dna2 oxb_replica_consts_rna2""".split()
+oxb_set_replicas oxb_set_replica_consts oxb_replica_energies oxb_replica_consts_dna2 oxb_replica_consts_rna2 oxb_set_force_callback""".split()
 
 _lib = None
 
@@ -521,6 +530,29 @@ class Context:
         out = np.zeros((max(n.value, 1), 2), dtype=np.int32)
         self._ck(self._L.oxb_get_pairs(self._h, _p(out), C.c_longlong(n.value), C.byref(n)))
         return out[: n.value]
+
+    def device_views(self):
+        """oxb_device_views: raw device pointers (ints) of the reference-layout views, for zero-copy consumers (plugin seam)"""
+        p = [C.c_void_p() for _ in range(6)]
+        self._ck(self._L.oxb_device_views(self._h, *[C.byref(x) for x in p]))
+        return dict(zip(("poss", "orientations", "matrix_neighs", "number_neighs", "edge_list", "n_edges"), [x.value for x in p]))
+
+    def set_force_callback(self, fn, rcut):
+        """oxb_set_force_callback: fn(views: ForceViews) -> int enqueues a third-party force pass on views.stream (None removes it)"""
+        if fn is None:
+            self._force_cb = None
+            self._ck(self._L.oxb_set_force_callback(self._h, None, None, C.c_double(0.0)))
+            return
+
+        def tramp(_user, vp):
+            try:
+                return int(fn(vp.contents) or 0)
+            except Exception:  # an exception cannot cross the C frame
+                import traceback
+                traceback.print_exc()
+                return 1
+        self._force_cb = FORCE_CALLBACK(tramp)  # keep the thunk alive
+        self._ck(self._L.oxb_set_force_callback(self._h, self._force_cb, None, C.c_double(rcut)))
 
     def stats(self):
         a, b, c, d = C.c_longlong(), C.c_longlong(), C.c_int(), C.c_int()

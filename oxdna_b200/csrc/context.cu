@@ -98,6 +98,9 @@ struct oxb_ctx {
 	unsigned *hkeys = nullptr, *hkeys_sorted = nullptr;
 	int *hvals = nullptr, *hvals_sorted = nullptr, *hinv = nullptr;
 	bool lists_allocated = false, lists_valid = false, forces_valid = false;
+	bool need_full_matrix = false; // a consumer of both directions of every pair (oxb_device_views) has shown up: no half-shell builds any more
+	bool half_shell_ok = true;     // OXB_HALF_SHELL=0 switches the half-shell scan off
+	bool nbr_is_half = false;      // what the current lists hold
 	// what the current lists were built for: they stay usable for a model with radii that are not larger (a replica-exchange
 	// energy evaluation at a lower temperature), but only an exact match reproduces the reference's pair set
 	double lists_rv = 0., lists_dh_rc = 0.;
@@ -149,6 +152,9 @@ struct oxb_ctx {
 	bool use_graphs = true;
 	long long graph_launches = 0;
 	bool profiling = false; // oxb_set_profile: device-side phase timeline (kernels.h, prof_mark)
+	// plugin seam (oxb_set_force_callback): a third-party force pass in place of the built-in kernels
+	oxb_force_callback force_cb = nullptr;
+	void *force_cb_user = nullptr;
 };
 
 namespace {
@@ -260,7 +266,11 @@ int alloc_lists(oxb_ctx *c, int max_neigh) {
 	// segmented work lists of the edge pipeline: one segment per block of the near-edge kernel, sized ~4x the expected load
 	// (hydrogen-bonding pairs ~0.5 N, cross-stacking-only pairs ~1.2 N, coaxial pairs << N) plus a floor for tiny systems
 	// ~3.3 near edges per particle, one producer block per 128 edges up to 16 blocks per SM (grid-stride beyond that)
-	c->n_seg = c->use_edge ? (int) std::max<long long>(1, std::min<long long>(16ll * c->n_sm, (33ll * N / 10 + 127) / 128)) : 1;
+	{
+		const char *e = getenv("OXB_PB_NEAR"); // blocks per SM of the near-edge kernel and of its work-list segments (default 16)
+		const int pb = (e != nullptr && atoi(e) > 0) ? atoi(e) : 16;
+		c->n_seg = c->use_edge ? (int) std::max<long long>(1, std::min<long long>((long long) pb * c->n_sm, (33ll * N / 10 + 127) / 128)) : 1;
+	}
 	c->hb_seg = c->use_edge ? (int) (6ll * N / c->n_seg) + 128 : 1;
 	c->cr_seg = 1; // the cross-stacking-only list is not produced (see forces.cu)
 	c->cx_seg = c->use_edge ? (int) (2ll * N / c->n_seg) + 64 : 1;
@@ -302,6 +312,9 @@ oxb::ListArgs list_args(oxb_ctx *c) {
 		a.r2_stack = sq((double) M.cxst.rchigh + pad);
 	} a.dh_nbr = c->dh_nbr; a.dh_nnbr = c->dh_nnbr; a.max_dh = c->max_dh;
 	a.dh_half = c->dh_half && c->use_edge;
+	// the edge pipeline consumes every pair once (near edges from the lower slot, half Debye-Hueckel matrix): scan half a shell and leave the
+	// upper triangle of the Verlet matrix only.  The full matrix (plugin seam) is built when somebody asks for it (oxb_device_views)
+	a.half_shell = a.dh_half && !c->need_full_matrix && c->half_shell_ok;
 	{
 		double rd = (double) c->model.dh_rc + 2. * c->skin + 0.02;
 		a.rdh2 = (float) (rd * rd);
@@ -317,6 +330,7 @@ oxb::ListArgs list_args(oxb_ctx *c) {
 	a.build_edges = c->use_edge != 0;
 	a.near_mask = c->near_mask;
 	a.direct = c->slots_cell_ordered && c->sort_ncell[0] == c->ncell[0] && c->sort_ncell[1] == c->ncell[1] && c->sort_ncell[2] == c->ncell[2];
+	a.ranges_done = a.direct;
 	return a;
 }
 
@@ -362,6 +376,9 @@ int do_sort(oxb_ctx *c) {
 	p.cell_lin = c->cell_key_sorted;
 	p.n_per = c->n_per;
 	for(int k = 0; k < 3; k++) { p.box[k] = c->box[k]; p.ncell[k] = c->ncell[k]; }
+	p.ncells_total = (long long) c->ncell[0] * c->ncell[1] * c->ncell[2] * c->n_rep;
+	p.keys_sorted = c->hkeys_sorted; p.cell_start = c->cell_start; p.cell_end = c->cell_start + p.ncells_total;
+	p.base_a1 = c->model.base_a1; p.boxf = c->boxf;
 	oxb::launch_permute(c->stream, p);
 	c->slots_cell_ordered = true; // consumed (and cleared) by the list build that follows
 	for(int k = 0; k < 3; k++) c->sort_ncell[k] = c->ncell[k];
@@ -382,8 +399,13 @@ int do_build(oxb_ctx *c, bool deferred = false) {
 	{ int rc = ensure_cells(c); if(rc) return rc; }
 	for(int attempt = 0; attempt < 6; attempt++) {
 		CU(cudaMemsetAsync(c->flags + OXB_FLAG_ERROR, 0, sizeof(int), c->stream));
-		oxb::launch_build_lists(c->stream, list_args(c));
-		c->launches += c->use_edge ? 7 : 4;
+		{
+			const oxb::ListArgs la = list_args(c);
+			oxb::launch_build_lists(c->stream, la);
+			c->nbr_is_half = la.half_shell;
+			// neighbour scan (+ scan + edge fill); without a preceding re-sort also cell keys, radix sort (>= 3 kernels), cell ranges
+			c->launches += (c->use_edge ? 4 : 1) + (la.direct ? 0 : 5);
+		}
 		CU(cudaGetLastError());
 		if(deferred) {
 			c->lists_valid = true;
@@ -425,6 +447,47 @@ int ensure_lists(oxb_ctx *c, bool deferred = false) {
 	return do_build(c, deferred);
 }
 
+__global__ void k_pos_view(int N, const double4 *__restrict__ posd, const int4 *__restrict__ ipos, float4 *__restrict__ out) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= N) return;
+	double4 p = posd[i];
+	out[i] = make_float4((float) p.x, (float) p.y, (float) p.z, __int_as_float(ipos[i].w));
+}
+__global__ void k_quat_view(int N, const double4 *__restrict__ quatd, float4 *__restrict__ out) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= N) return;
+	double4 q = quatd[i];
+	out[i] = make_float4((float) q.x, (float) q.y, (float) q.z, (float) q.w);
+}
+
+// plugin seam: reference-layout views of the current state, then the third-party force pass on the context's stream.  The accumulators
+// are cleared first in every case: launches behind a halt are no-ops for the built-in kernels but not for a plugin's.
+int launch_forces_callback(oxb_ctx *c, long long step) {
+	const int a = c->cur, N = c->N;
+	cudaStream_t m = c->stream;
+	if(c->pos_f4 == nullptr) CU(dalloc(&c->pos_f4, N));
+	if(c->quat_f4 == nullptr) CU(dalloc(&c->quat_f4, N));
+	CU(cudaMemsetAsync(c->F[a], 0, sizeof(float4) * (size_t) N, m));
+	CU(cudaMemsetAsync(c->T[a], 0, sizeof(float4) * (size_t) N, m));
+	k_pos_view<<<(N + 255) / 256, 256, 0, m>>>(N, c->posd[a], c->ipos[a], c->pos_f4);
+	k_quat_view<<<(N + 255) / 256, 256, 0, m>>>(N, c->quatd[a], c->quat_f4);
+	c->launches += 2;
+	oxb_force_views v;
+	v.N = N; v.stride = N;
+	v.poss = c->pos_f4; v.orientations = c->quat_f4;
+	v.matrix_neighs = c->nbr; v.number_neighs = c->nnbr;
+	v.bonds = c->bonds[a];
+	v.forces = c->F[a]; v.torques = c->T[a];
+	for(int k = 0; k < 3; k++) v.box[k] = c->box[k];
+	v.step = step < 0 ? c->step : step;
+	v.stream = (void *) m;
+	const int rc = c->force_cb(c->force_cb_user, &v);
+	if(rc != 0) return fail(c, 10, "the force callback of the plugged-in interaction failed with code %d", rc);
+	c->launches += 1;
+	CU(cudaGetLastError());
+	return 0;
+}
+
 // hw: index of the halt word the launched kernels must honour; clear: F/T are not known to be zero; step < 0: kernels read
 // the step index from the device counter.  Edge pipeline = 5 kernels (6 in mixed precision: + k_excl_fix on aux1) on 3 streams:
 //   main: near edges -> hydrogen bonding / cross stacking      aux0: Debye-Hueckel      aux1: bonds, external forces, coaxial stacking
@@ -440,6 +503,7 @@ int launch_forces(oxb_ctx *c, int hw, bool clear, long long step) {
 		}
 		oxb::EdgeArgs e;
 		e.rep = c->rep; e.n_per = c->n_per;
+		e.n_sm = c->n_sm;
 		e.N = c->N; e.ipos = c->ipos[a]; e.iback = c->iback[a]; e.axf = c->axf[a]; e.posd = c->posd[a]; e.quatd = c->quatd[a]; e.bonds = c->bonds[a]; e.edges = c->edges;
 		e.n_edges = c->n_edges; e.dh_nbr = c->dh_nbr; e.dh_nnbr = c->dh_nnbr;
 		e.F = c->F[a]; e.T = c->T[a]; e.Fb = c->Fb; e.hb_list = c->hb_list; e.cx_list = c->cx_list; e.cr_list = c->cr_list; e.seg_counts = c->seg_counts;
@@ -491,10 +555,11 @@ int launch_forces(oxb_ctx *c, int hw, bool clear, long long step) {
 		c->launches += e.fold ? 4 : (e.refine ? 6 : 5);
 	}
 	else {
-		oxb::launch_forces_particle(m, c->mref(), c->boxf, c->N, c->ipos[a], c->iback[a], c->axf[a],
+		if(c->force_cb != nullptr) { int rc = launch_forces_callback(c, step); if(rc) return rc; }
+		else oxb::launch_forces_particle(m, c->mref(), c->boxf, c->N, c->ipos[a], c->iback[a], c->axf[a],
 				c->precision == OXB_PRECISION_MIXED ? c->posd[a] : nullptr, c->quatd[a], c->bonds[a], c->nbr, c->nnbr, c->N, c->F[a], c->T[a],
 				c->rep, c->n_per, c->flags, hw);
-		c->launches += 1;
+		if(c->force_cb == nullptr) c->launches += 1;
 		if(c->n_ext > 0) {
 			oxb::launch_ext_forces(m, c->n_ext, c->ext, c->slot_of, c->ipos[a], c->posd[a], c->boxf, step, c->cur_step, c->F[a], c->flags, hw);
 			c->launches += 1;
@@ -673,7 +738,7 @@ int batch_graph(oxb_ctx *c, int units, cudaGraphExec_t *out) {
 // in chunks of 8/4/2 units (even sizes keep the frozen parity valid) while the index is even; the rest goes out as plain
 // stream launches.
 int launch_full_units(oxb_ctx *c, long long n, long long step0, int &epoch) {
-	const bool graphable = c->use_graphs && c->th.type != OXB_THERMOSTAT_BUSSI;
+	const bool graphable = c->use_graphs && c->th.type != OXB_THERMOSTAT_BUSSI && c->force_cb == nullptr;
 	const int per_unit = (c->use_edge ? (c->fold_tails ? 4 : (c->precision == OXB_PRECISION_MIXED ? 6 : 5)) : 1) + (c->n_ext > 0 ? 1 : 0) + (c->n_ext_all > 0 ? 1 : 0) + (c->n_ext_com > 0 ? 1 : 0) + 1;
 	long long k = 0;
 	while(k < n) {
@@ -746,6 +811,8 @@ int oxb_create(oxb_ctx **out, int device, int N, int precision) {
 		if(fo != nullptr) c->fold_tails = (fo[0] != '0');
 		const char *dhh = getenv("OXB_DH_HALF");
 		if(dhh != nullptr) c->dh_half = (dhh[0] != '0');
+		const char *hs = getenv("OXB_HALF_SHELL");
+		if(hs != nullptr) c->half_shell_ok = (hs[0] != '0');
 		const char *f = getenv("OXB_FORK");
 		if(f != nullptr) c->fork_streams = (f[0] != '0');
 	}
@@ -884,6 +951,27 @@ int oxb_set_model_rna2(oxb_ctx *c, const oxb_rna2_params *P, double rcut) {
 	c->have_model = true;
 	c->forces_valid = false;
 	if(c->lists_valid && (rcut + 2. * c->skin > c->lists_rv || (double) P->dh_rc > c->lists_dh_rc)) c->lists_valid = false;
+	return 0;
+}
+
+int oxb_set_force_callback(oxb_ctx *c, oxb_force_callback fn, void *user, double rcut) {
+	if(c == nullptr) return 1;
+	if(fn != nullptr && !(rcut > 0.)) return fail(c, 1, "oxb_set_force_callback: the interaction cutoff must be positive");
+	if(fn != nullptr && c->n_rep > 1) return fail(c, 1, "a plugged-in interaction cannot be combined with replica batching");
+	cudaSetDevice(c->device);
+	CU(cudaStreamSynchronize(c->stream));
+	drop_graphs(c);
+	c->force_cb = fn; c->force_cb_user = user;
+	c->forces_valid = false; c->lists_valid = false;
+	if(fn != nullptr) {
+		// the context only needs the Verlet radius: an all-zero built-in block with this cutoff (no Debye-Hueckel rows, no site geometry)
+		std::memset(&c->model, 0, sizeof(c->model));
+		c->model.rcut = (float) rcut; c->model.rcut_near = (float) rcut;
+		c->is_rna = false; c->back_a3 = 0.f;
+		c->rcut = rcut;
+		c->have_model = true;
+	}
+	else c->have_model = false;
 	return 0;
 }
 
@@ -1615,8 +1703,9 @@ int oxb_get_pairs(oxb_ctx *c, int *pairs, long long max_pairs, long long *n_pair
 		int i = word_index(hi[s].w);
 		for(int k = 0; k < hn[s]; k++) {
 			int j = word_index(hi[hm[(size_t) k * N + s]].w);
-			if(i < j) {
-				if(pairs != nullptr && n < max_pairs) { pairs[2 * n] = i; pairs[2 * n + 1] = j; }
+			// full matrix: every pair shows up from both ends, keep it once; half matrix: every entry is a pair
+			if(i < j || c->nbr_is_half) {
+				if(pairs != nullptr && n < max_pairs) { pairs[2 * n] = std::min(i, j); pairs[2 * n + 1] = std::max(i, j); }
 				n++;
 			}
 		}
@@ -1634,25 +1723,15 @@ int oxb_get_stats(oxb_ctx *c, long long *n_list_updates, long long *n_sorts, int
 	return 0;
 }
 
-namespace {
-__global__ void k_pos_view(int N, const double4 *__restrict__ posd, const int4 *__restrict__ ipos, float4 *__restrict__ out) {
-	int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if(i >= N) return;
-	double4 p = posd[i];
-	out[i] = make_float4((float) p.x, (float) p.y, (float) p.z, __int_as_float(ipos[i].w));
-}
-__global__ void k_quat_view(int N, const double4 *__restrict__ quatd, float4 *__restrict__ out) {
-	int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if(i >= N) return;
-	double4 q = quatd[i];
-	out[i] = make_float4((float) q.x, (float) q.y, (float) q.z, (float) q.w);
-}
-} // namespace
-
 int oxb_device_views(oxb_ctx *c, void **poss_f4, void **orientations_f4, void **matrix_neighs, void **number_neighs, void **edge_list, void **n_edges) {
 	if(c == nullptr) return 1;
 	int rc = check_ready(c);
 	if(rc) return rc;
+	if((matrix_neighs || number_neighs) && !c->need_full_matrix) {
+		// the reference's matrix holds both directions of every pair: from now on the builds produce it
+		c->need_full_matrix = true;
+		if(c->nbr_is_half) c->lists_valid = false;
+	}
 	rc = ensure_lists(c);
 	if(rc) return rc;
 	if(poss_f4) {

@@ -86,6 +86,7 @@ void launch_forces_particle(cudaStream_t s, const ModelRef &M, BoxF box, int N, 
 		const int *nbr, const int *nnbr, int stride, float4 *F, float4 *T, const oxb_replica_consts *rep, int n_per, int *flags, int hw);
 struct EdgeArgs {
 	int N;
+	int n_sm; // SM count, for the co-resident launch grids (0: one block per 128 items)
 	const oxb_replica_consts *rep; // replica batching: one row per replica (null: single system), n_per particles per replica
 	int n_per;
 	const int4 *ipos, *iback;
@@ -207,6 +208,7 @@ struct ListArgs {
 	int *edge_offsets; // N + 1
 	ulonglong2 *near_mask; // per row: which entries are near edges to a higher slot
 	bool direct;       // particle arrays are ordered by cell: cell members are the slots [start, end) themselves
+	bool ranges_done;  // ... and the re-sort's gather pass already filled the cell table and the staleness references
 	int *n_edges;      // device-side length of `edges`
 	float rnear2;      // (rcut_near + 2 skin + margin)^2
 	// Debye-Hueckel neighbour matrix (full, both directions), selected on the backbone-site distance
@@ -218,6 +220,7 @@ struct ListArgs {
 	int *dh_nbr, *dh_nnbr;
 	int max_dh;
 	bool dh_half;      // each Debye-Hueckel pair appears in one row only (see k_dh_particle)
+	bool half_shell;   // edge pipeline: only partners in higher slots are scanned; nbr / nnbr / dh_nbr hold every pair once (row of the lower slot)
 	float rdh2;        // (dh_rc + 2 skin + margin)^2
 	long long edge_capacity;
 	int *flags;
@@ -258,6 +261,12 @@ struct PermuteArgs {
 	int2 *bonds_out;
 	int *slot_of; // slot_of[original id] = new slot
 	int *cell_lin; // optional: linear cell id of every new slot (what the list builder's binning would have produced)
+	// optional (with cell_lin): the list builder's cell table and staleness references are produced by the same pass (sort.cu: k_permute)
+	const unsigned *keys_sorted; // the sorted Hilbert keys of the cells: equal keys = equal cell
+	int *cell_start, *cell_end;  // ncells_total entries each, contiguous (cell_end = cell_start + ncells_total), zeroed by launch_permute
+	long long ncells_total;
+	float base_a1;
+	BoxF boxf;
 	int n_per;     // replica batching: particles per replica (cell ids are offset by replica * ncells)
 	double box[3];
 	int ncell[3];

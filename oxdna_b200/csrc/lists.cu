@@ -14,6 +14,8 @@
 
 #include <cub/cub.cuh>
 
+#include <cstdlib>
+
 namespace {
 
 __device__ __forceinline__ int cell_coord(double x, double L, int n) {
@@ -95,6 +97,7 @@ __device__ __forceinline__ bool near_pair(const oxb::ListArgs &a, v3 r, v3 a1p, 
 template<bool DIRECT>
 __global__ void __launch_bounds__(128) k_build_neigh(oxb::ListArgs a, const int *__restrict__ cell_start, const int *__restrict__ cell_end) {
 	__shared__ int2 s_range[27][128];
+	if(blockIdx.x == 0 && threadIdx.x == 0) prof_mark(a.flags, OXB_PROF_BUILD);
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	const bool active = i < a.N;
 	if(!active) i = a.N - 1;
@@ -121,6 +124,8 @@ __global__ void __launch_bounds__(128) k_build_neigh(oxb::ListArgs a, const int 
 					int xc = cx + dx; xc += (xc < 0) ? nx : 0; xc -= (xc >= nx) ? nx : 0;
 					int c = coff + xc + nx * (yc + ny * zc);
 					rg[q] = make_int2(__ldg(cell_start + c), __ldg(cell_end + c));
+					// half shell: only partners in higher slots are wanted; with cell-ordered slots whole cells (about half of the 27) drop out
+					if(DIRECT && a.half_shell) rg[q].x = max(rg[q].x, i + 1);
 					q++;
 				}
 			}
@@ -142,7 +147,7 @@ __global__ void __launch_bounds__(128) k_build_neigh(oxb::ListArgs a, const int 
 	const v3 bkp = min_image_fixed(a.boxf, ip, ib);
 	int count = 0, higher_near = 0, ndh = 0;
 	unsigned long long mask0 = 0ull, mask1 = 0ull;
-	bool mask_overflow = false;
+	bool mask_overflow = false, dh_overflow = false;
 	// phase 2: one flat loop over this particle's candidates (cursor = range r, slot j), next candidate prefetched
 	int r = 0, j = 0, jend = 0;
 	int m_next = 0;
@@ -169,7 +174,7 @@ __global__ void __launch_bounds__(128) k_build_neigh(oxb::ListArgs a, const int 
 			m_next = DIRECT ? j : __ldg(a.cell_val_sorted + j);
 			ip_next = __ldg(a.ipos + m_next);
 		}
-		if(m == i || m == b.x || m == b.y) continue;
+		if(m == i || m == b.x || m == b.y || (a.half_shell && m < i)) continue;
 		v3 d = min_image_fixed(a.boxf, ip, ipm);
 		float d2 = dot(d, d);
 		bool in = d2 < rv2f;
@@ -188,11 +193,22 @@ __global__ void __launch_bounds__(128) k_build_neigh(oxb::ListArgs a, const int 
 				else if(count < 128) mask1 |= 1ull << (count - 64);
 				else mask_overflow = true;
 			}
-			// dh_half: every Debye-Hueckel pair is kept by ONE of its particles (by the parity of i + m, so that rows stay balanced); the
-			// kernel adds the partner's share with one vector atomic.  Full rows (both directions, no atomics) otherwise.
-			if(dot(db, db) < a.rdh2 && (!a.dh_half || ((((i + m) & 1) == 0) == (i < m)))) {
-				if(ndh < a.max_dh) a.dh_nbr[(size_t) ndh * a.stride + i] = m;
-				ndh++;
+			if(dot(db, db) < a.rdh2) {
+				if(a.half_shell) {
+					// this scan sees every pair once (m > i); rows filled from the lower slot only would be as long as a particle has
+					// partners AFTER it on the Hilbert curve -- 0 to twice the mean within one warp of k_dh_particle (+ 10 us per force pass at
+					// 1M nt).  The same parity rule as below picks the owner; rows are appended through their counters (zeroed by the launcher)
+					const int owner = ((i + m) & 1) == 0 ? i : m, other = i + m - owner;
+					const int pos = atomicAdd(a.dh_nnbr + owner, 1);
+					if(pos < a.max_dh) a.dh_nbr[(size_t) pos * a.stride + owner] = other;
+					else dh_overflow = true;
+				}
+				// dh_half: every Debye-Hueckel pair is kept by ONE of its particles (by the parity of i + m, so that rows stay balanced); the
+				// kernel adds the partner's share with one vector atomic.  Full rows (both directions, no atomics) otherwise.
+				else if(!a.dh_half || ((((i + m) & 1) == 0) == (i < m))) {
+					if(ndh < a.max_dh) a.dh_nbr[(size_t) ndh * a.stride + i] = m;
+					ndh++;
+				}
 			}
 			count++;
 		}
@@ -202,22 +218,175 @@ __global__ void __launch_bounds__(128) k_build_neigh(oxb::ListArgs a, const int 
 		// one same-address atomic per warp, not per thread
 		const unsigned am = __activemask();
 		const int wmax = __reduce_max_sync(am, count);
-		if((int) (threadIdx.x & 31) == (__ffs(am) - 1)) atomicMax(a.flags + OXB_FLAG_MAX_NEIGH_SEEN, wmax);
+		if((int) (threadIdx.x & 31) == (__ffs(am) - 1) && wmax > a.max_neigh) atomicMax(a.flags + OXB_FLAG_MAX_NEIGH_SEEN, wmax);
 	}
 	if(count > a.max_neigh) {
 		atomicOr(a.flags + OXB_FLAG_ERROR, OXB_ERR_NEIGH_OVERFLOW);
 		count = a.max_neigh;
 	}
-	if(ndh > a.max_dh) {
+	if(ndh > a.max_dh || dh_overflow) {
 		atomicOr(a.flags + OXB_FLAG_ERROR, OXB_ERR_NEIGH_OVERFLOW);
 		ndh = a.max_dh;
 	}
 	a.nnbr[i] = count;
-	a.dh_nnbr[i] = ndh;
+	if(!a.half_shell) a.dh_nnbr[i] = ndh;
 	if(a.build_edges) {
 		a.edge_offsets[i] = higher_near;
 		// rows longer than the mask fall back to the geometric test in k_fill_edges (top bit of word 1 doubles as the marker:
 		// entry 127 can only be flagged together with an overflow, which takes the fallback anyway)
+		if(mask_overflow) mask1 |= 1ull << 63;
+		a.near_mask[i] = make_ulonglong2(mask0, mask1);
+	}
+}
+
+// G lanes per particle (G = 4, 8, 16).  The thread-per-particle kernel above pays one exposed L2 latency per candidate (iback / axf of a
+// candidate can only be requested after its distance test) and walks ~60 candidates serially: 434 us at 1M nucleotides with the
+// issue slots nearly idle.  Here the G lanes of a group split the candidates of ONE particle:
+//  * the 27 cell ranges are fetched by the group in one round (lane g takes cells g, g + G, ...), prefix-summed in scan order with
+//    width-G shuffles and parked in shared memory: the candidates of the particle form one flat index space [0, T);
+//  * round r tests candidates r G ... r G + G - 1, one per lane (independent loads: G times the memory parallelism, a G-th of the
+//    serial depth); hits are compacted in candidate order with a ballot, so every row of the neighbour matrix, of the Debye-Hueckel
+//    matrix and every near-edge mask is bit-identical to what the serial kernel writes.
+template<bool DIRECT, int G>
+__global__ void __launch_bounds__(256, 4) k_build_neigh_g(oxb::ListArgs a, const int *__restrict__ cell_start, const int *__restrict__ cell_end) {
+	constexpr int PPB = 256 / G;
+	__shared__ int s_start[PPB][28], s_pref[PPB][28];
+	if(blockIdx.x == 0 && threadIdx.x == 0) prof_mark(a.flags, OXB_PROF_BUILD);
+	const int grp = threadIdx.x / G, g = threadIdx.x % G;
+	const unsigned lane = threadIdx.x & 31;
+	const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << (lane / G * G);
+	const unsigned lt = gmask & ((1u << lane) - 1u); // lanes of my group below me
+	int i = blockIdx.x * PPB + grp;
+	const bool active = i < a.N;
+	if(!active) i = a.N - 1;
+	const int4 ip = __ldg(a.ipos + i);
+	const int2 b = __ldg(a.bonds + i);
+	const int nx = a.ncell[0], ny = a.ncell[1], nz = a.ncell[2];
+	const double4 pd = a.posd[i];
+	const int cx = cell_coord(pd.x, a.box[0], nx), cy = cell_coord(pd.y, a.box[1], ny), cz = cell_coord(pd.z, a.box[2], nz);
+	const int coff = (a.n_rep > 1) ? (i / a.n_per) * (nx * ny * nz) : 0; // this replica's copy of the grid
+	int T = 0;
+	{
+		int carry = 0;
+#pragma unroll
+		for(int t = 0; t < (27 + G - 1) / G; t++) {
+			const int q = g + G * t;
+			int st = 0, len = 0;
+			if(q < 27) {
+				int zc = cz + q / 9 - 1; zc += (zc < 0) ? nz : 0; zc -= (zc >= nz) ? nz : 0;
+				int yc = cy + (q / 3) % 3 - 1; yc += (yc < 0) ? ny : 0; yc -= (yc >= ny) ? ny : 0;
+				int xc = cx + q % 3 - 1; xc += (xc < 0) ? nx : 0; xc -= (xc >= nx) ? nx : 0;
+				const int c = coff + xc + nx * (yc + ny * zc);
+				st = __ldg(cell_start + c);
+				const int en = __ldg(cell_end + c);
+				if(DIRECT && a.half_shell) st = max(st, i + 1); // half shell, see k_build_neigh
+				len = max(en - st, 0);
+			}
+			int incl = len;
+#pragma unroll
+			for(int d = 1; d < G; d <<= 1) {
+				const int v = __shfl_up_sync(0xffffffffu, incl, d, G);
+				if(g >= d) incl += v;
+			}
+			if(q < 27) { s_start[grp][q] = st; s_pref[grp][q] = carry + incl - len; }
+			carry += __shfl_sync(0xffffffffu, incl, G - 1, G);
+		}
+		if(g == 0) s_pref[grp][27] = carry;
+		T = active ? carry : 0;
+	}
+	__syncwarp();
+	const float rv2f = (float) (a.rv * a.rv);
+	const float band = 1e-4f * rv2f;
+	const double rv2 = a.rv * a.rv;
+	const int4 ib = __ldg(a.iback + i);
+	const v3 a1p = load_a1(a.axf, i);
+	const v3 bkp = min_image_fixed(a.boxf, ip, ib);
+	int count = 0, ndh = 0, higher_near = 0;
+	unsigned long long mask0 = 0ull, mask1 = 0ull;
+	bool mask_overflow = false, dh_overflow = false;
+	const int Tw = __reduce_max_sync(0xffffffffu, T);
+	int c = 0;
+	for(int k0 = 0; k0 < Tw; k0 += G) {
+		const int k = k0 + g;
+		bool in = false;
+		int m = -1;
+		int4 ipm = ip;
+		float d2 = 0.f;
+		v3 d = mk3(0.f, 0.f, 0.f);
+		if(k < T) {
+			while(k >= s_pref[grp][c + 1]) c++;
+			const int j = s_start[grp][c] + (k - s_pref[grp][c]);
+			m = DIRECT ? j : __ldg(a.cell_val_sorted + j);
+			ipm = __ldg(a.ipos + m);
+			if(m != i && m != b.x && m != b.y && !(a.half_shell && m < i)) {
+				d = min_image_fixed(a.boxf, ip, ipm);
+				d2 = dot(d, d);
+				in = d2 < rv2f;
+				if(fabsf(d2 - rv2f) < band) in = within_exact(pd, a.posd[m], a.box[0], a.box[1], a.box[2], rv2);
+			}
+		}
+		const unsigned bal = __ballot_sync(0xffffffffu, in) & gmask;
+		bool is_dh = false;
+		if(in) {
+			const int row = count + __popc(bal & lt);
+			if(row < a.max_neigh) a.nbr[(size_t) row * a.stride + i] = m;
+			const int4 ibm = __ldg(a.iback + m);
+			const v3 db = min_image_fixed(a.boxf, ib, ibm);
+			if(m > i && d2 < a.rnear2 && near_pair(a, d, a1p, load_a1(a.axf, m), bkp, min_image_fixed(a.boxf, ipm, ibm))) {
+				higher_near++;
+				// rows that overflow max_neigh are rebuilt after the matrix has grown: never flag an entry that was not written
+				if(row >= a.max_neigh) mask_overflow = true;
+				else if(row < 64) mask0 |= 1ull << row;
+				else if(row < 128) mask1 |= 1ull << (row - 64);
+				else mask_overflow = true;
+			}
+			// dh_half: every Debye-Hueckel pair is kept by ONE of its particles (by the parity of i + m, so that rows stay balanced)
+			is_dh = dot(db, db) < a.rdh2 && (!a.dh_half || a.half_shell || ((((i + m) & 1) == 0) == (i < m)));
+			if(is_dh && a.half_shell) {
+				// half shell: rows are appended through their counters, owner by the same parity rule (see k_build_neigh)
+				const int owner = ((i + m) & 1) == 0 ? i : m, other = i + m - owner;
+				const int pos = atomicAdd(a.dh_nnbr + owner, 1);
+				if(pos < a.max_dh) a.dh_nbr[(size_t) pos * a.stride + owner] = other;
+				else dh_overflow = true;
+				is_dh = false;
+			}
+		}
+		count += __popc(bal);
+		const unsigned bdh = __ballot_sync(0xffffffffu, is_dh) & gmask;
+		if(is_dh) {
+			const int row = ndh + __popc(bdh & lt);
+			if(row < a.max_dh) a.dh_nbr[(size_t) row * a.stride + i] = m;
+		}
+		ndh += __popc(bdh);
+	}
+	// fold the per-lane near-edge bookkeeping over the group
+#pragma unroll
+	for(int o = G >> 1; o > 0; o >>= 1) {
+		mask0 |= __shfl_xor_sync(0xffffffffu, mask0, o);
+		mask1 |= __shfl_xor_sync(0xffffffffu, mask1, o);
+		higher_near += __shfl_xor_sync(0xffffffffu, higher_near, o);
+		mask_overflow = (__shfl_xor_sync(0xffffffffu, (int) mask_overflow, o) != 0) || mask_overflow;
+		dh_overflow = (__shfl_xor_sync(0xffffffffu, (int) dh_overflow, o) != 0) || dh_overflow;
+	}
+	{
+		// the longest row only matters when one overflowed (it sizes the regrown matrix): no same-address atomic otherwise -- one per warp
+		// is 250,000 serialised atomics at 1M particles and G = 8, which tripled the time of this kernel
+		const int wmax = __reduce_max_sync(0xffffffffu, active ? count : 0);
+		if(lane == 0 && wmax > a.max_neigh) atomicMax(a.flags + OXB_FLAG_MAX_NEIGH_SEEN, wmax);
+	}
+	if(!active || g != 0) return;
+	if(count > a.max_neigh) {
+		atomicOr(a.flags + OXB_FLAG_ERROR, OXB_ERR_NEIGH_OVERFLOW);
+		count = a.max_neigh;
+	}
+	if(ndh > a.max_dh || dh_overflow) {
+		atomicOr(a.flags + OXB_FLAG_ERROR, OXB_ERR_NEIGH_OVERFLOW);
+		ndh = a.max_dh;
+	}
+	a.nnbr[i] = count;
+	if(!a.half_shell) a.dh_nnbr[i] = ndh;
+	if(a.build_edges) {
+		a.edge_offsets[i] = higher_near;
 		if(mask_overflow) mask1 |= 1ull << 63;
 		a.near_mask[i] = make_ulonglong2(mask0, mask1);
 	}
@@ -300,12 +469,28 @@ void launch_build_lists(cudaStream_t s, const ListArgs &a) {
 		k_cell_keys<<<(N + tpb - 1) / tpb, tpb, 0, s>>>(N, a.n_per, a.posd, a.box[0], a.box[1], a.box[2], a.ncell[0], a.ncell[1], a.ncell[2], a.cell_key, a.cell_val, a.flags);
 		cub::DeviceRadixSort::SortPairs(a.cub_tmp, tmp, a.cell_key, a.cell_key_sorted, a.cell_val, a.cell_val_sorted, N, 0, bits_for(ncells), s);
 	}
-	cudaMemsetAsync(cell_start, 0, sizeof(int) * 2 * (size_t) ncells, s);
-	k_cell_ranges<<<(N + tpb - 1) / tpb, tpb, 0, s>>>(N, a.cell_key_sorted, cell_start, cell_end, a.ipos, a.iback, a.axf, a.base_a1, a.boxf, a.ref_pos, a.ref_vel,
-			a.ref_L, a.flags);
+	if(!(a.direct && a.ranges_done)) {
+		cudaMemsetAsync(cell_start, 0, sizeof(int) * 2 * (size_t) ncells, s);
+		k_cell_ranges<<<(N + tpb - 1) / tpb, tpb, 0, s>>>(N, a.cell_key_sorted, cell_start, cell_end, a.ipos, a.iback, a.axf, a.base_a1, a.boxf, a.ref_pos, a.ref_vel,
+				a.ref_L, a.flags);
+	}
 	cudaMemsetAsync(a.flags + OXB_FLAG_MAX_NEIGH_SEEN, 0, sizeof(int), s);
-	if(a.direct) k_build_neigh<true><<<(N + 127) / 128, 128, 0, s>>>(a, cell_start, cell_end);
-	else k_build_neigh<false><<<(N + 127) / 128, 128, 0, s>>>(a, cell_start, cell_end);
+	if(a.half_shell) cudaMemsetAsync(a.dh_nnbr, 0, sizeof(int) * (size_t) N, s); // the rows of the Debye-Hueckel matrix are appended through their counters
+	// lanes per particle of the neighbour scan (OXB_BUILD_G = 1: the thread-per-particle kernel)
+	// (measured on B200, gpurun_out r2e: 8 lanes win while the system cannot fill the machine with one thread per particle -- 82 against 98 us
+	// at 81,920 nt --, the serial kernel wins at 1M nt -- it executes 2.3 x fewer instructions, ncu r02f -- and both are issue-bound there)
+	static const int G_env = [] { const char *e = getenv("OXB_BUILD_G"); int g = e ? atoi(e) : 0; return (g == 1 || g == 4 || g == 8 || g == 16) ? g : 0; }();
+	const int G = G_env ? G_env : (N < 300000 ? 8 : 1);
+#define OXB_BUILD_LAUNCH(D)                                                                                              \
+	do {                                                                                                                 \
+		if(G == 4) k_build_neigh_g<D, 4><<<(N + 63) / 64, 256, 0, s>>>(a, cell_start, cell_end);                         \
+		else if(G == 8) k_build_neigh_g<D, 8><<<(N + 31) / 32, 256, 0, s>>>(a, cell_start, cell_end);                    \
+		else if(G == 16) k_build_neigh_g<D, 16><<<(N + 15) / 16, 256, 0, s>>>(a, cell_start, cell_end);                  \
+		else k_build_neigh<D><<<(N + 127) / 128, 128, 0, s>>>(a, cell_start, cell_end);                                  \
+	} while(0)
+	if(a.direct) OXB_BUILD_LAUNCH(true);
+	else OXB_BUILD_LAUNCH(false);
+#undef OXB_BUILD_LAUNCH
 	if(a.build_edges) {
 		tmp = a.cub_tmp_bytes;
 		// in-place exclusive scan over N + 1 entries (the last input entry is ignored: its output is the total)

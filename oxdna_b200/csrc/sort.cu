@@ -80,31 +80,51 @@ __global__ void __launch_bounds__(256) k_invert(int N, const int *__restrict__ p
 	if(n < N) inv[perm[n]] = n;
 }
 
+// One gather pass into the second state buffer.  When the sort key is the Hilbert index of the list builder's cells (a.cell_lin set), the
+// pass also does the list builder's bookkeeping for the new slots, which would otherwise cost a second pass over the particles
+// (lists.cu: k_cell_ranges): linear cell id, the (start, end) slot range of every cell (equal keys = equal cell, the table is zeroed by
+// the caller) and the staleness references in the .w lanes of the FP64 state.  F and T come out zero: a re-sort invalidates the forces
+// (mid-step they have been consumed and zeroed by the integrator), so gathering them would move 64 B per particle for nothing.
 __global__ void __launch_bounds__(256) k_permute(oxb::PermuteArgs a) {
 	int n = blockIdx.x * blockDim.x + threadIdx.x;
 	if(n >= a.N) return;
 	int o = a.perm[n];
-	a.posd_out[n] = a.posd_in[o];
-	a.veld_out[n] = a.veld_in[o];
-	a.Ld_out[n] = a.Ld_in[o];
-	a.quatd_out[n] = a.quatd_in[o];
+	double4 pd = a.posd_in[o], vd = a.veld_in[o], ld = a.Ld_in[o];
 	int4 ip = a.ipos_in[o];
+	const int4 ib = a.iback_in[o];
+	const float4 ax0 = a.axf_in[2 * (size_t) o], ax1 = a.axf_in[2 * (size_t) o + 1];
+	if(a.cell_lin != nullptr) {
+		const int cl = cell_coord_s(pd.x, a.box[0], a.ncell[0]) + a.ncell[0] * (cell_coord_s(pd.y, a.box[1], a.ncell[1]) + a.ncell[1] * cell_coord_s(pd.z, a.box[2], a.ncell[2]))
+				+ (n / a.n_per) * (a.ncell[0] * a.ncell[1] * a.ncell[2]);
+		a.cell_lin[n] = cl;
+		if(a.cell_start != nullptr) {
+			const unsigned k = a.keys_sorted[n];
+			if(n == 0 || a.keys_sorted[n - 1] != k) a.cell_start[cl] = n;
+			if(n == a.N - 1 || a.keys_sorted[n + 1] != k) a.cell_end[cl] = n + 1;
+			int4 bs = ip;
+			bs.x = (int) ((unsigned) ip.x + (unsigned) (int) rintf(ax0.x * a.base_a1 / a.boxf.sx));
+			bs.y = (int) ((unsigned) ip.y + (unsigned) (int) rintf(ax0.y * a.base_a1 / a.boxf.sy));
+			bs.z = (int) ((unsigned) ip.z + (unsigned) (int) rintf(ax0.z * a.base_a1 / a.boxf.sz));
+			pd.w = pack_ref(ip);
+			vd.w = pack_ref(ib);
+			ld.w = pack_ref(bs);
+		}
+	}
+	a.posd_out[n] = pd;
+	a.veld_out[n] = vd;
+	a.Ld_out[n] = ld;
+	a.quatd_out[n] = a.quatd_in[o];
 	a.ipos_out[n] = ip;
-	a.iback_out[n] = a.iback_in[o];
-	a.axf_out[2 * (size_t) n] = a.axf_in[2 * (size_t) o];
-	a.axf_out[2 * (size_t) n + 1] = a.axf_in[2 * (size_t) o + 1];
-	a.F_out[n] = a.F_in[o];
-	a.T_out[n] = a.T_in[o];
+	a.iback_out[n] = ib;
+	a.axf_out[2 * (size_t) n] = ax0;
+	a.axf_out[2 * (size_t) n + 1] = ax1;
+	a.F_out[n] = make_float4(0.f, 0.f, 0.f, 0.f);
+	a.T_out[n] = make_float4(0.f, 0.f, 0.f, 0.f);
 	int2 b = a.bonds_in[o];
 	b.x = (b.x >= 0) ? a.inv[b.x] : b.x;
 	b.y = (b.y >= 0) ? a.inv[b.y] : b.y;
 	a.bonds_out[n] = b;
 	a.slot_of[word_index(ip.w)] = n;
-	if(a.cell_lin != nullptr) {
-		double4 p = a.posd_in[o];
-		a.cell_lin[n] = cell_coord_s(p.x, a.box[0], a.ncell[0]) + a.ncell[0] * (cell_coord_s(p.y, a.box[1], a.ncell[1]) + a.ncell[1] * cell_coord_s(p.z, a.box[2], a.ncell[2]))
-				+ (n / a.n_per) * (a.ncell[0] * a.ncell[1] * a.ncell[2]);
-	}
 }
 
 } // namespace
@@ -137,6 +157,7 @@ void launch_hilbert_order(cudaStream_t s, const SortArgs &a) {
 
 void launch_permute(cudaStream_t s, const PermuteArgs &a) {
 	int tpb = 256;
+	if(a.cell_lin != nullptr && a.cell_start != nullptr) cudaMemsetAsync(a.cell_start, 0, sizeof(int) * 2 * (size_t) a.ncells_total, s);
 	k_permute<<<(a.N + tpb - 1) / tpb, tpb, 0, s>>>(a);
 }
 

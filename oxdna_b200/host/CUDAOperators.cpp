@@ -3,6 +3,8 @@
 // work is forwarded to liboxdna_b200.so.
 #include "CUDAOperators.h"
 
+#include "PluginManagement/PluginManager.h"
+
 #include "Utilities/ConfigInfo.h"
 #include "Utilities/Logger.h"
 #include "Utilities/Utils.h"
@@ -35,6 +37,29 @@ void CUDABaseInteraction::cuda_init(oxb_ctx *ctx, int N) {
 
 void CUDABaseInteraction::compute_forces(oxb_ctx *ctx) {
 	oxb_check(ctx, oxb_compute_forces(ctx), "compute_forces");
+}
+
+void CUDABaseInteraction::compute_forces_views(const oxb_force_views &) {
+	throw oxDNAException("this CUDA interaction does not implement compute_forces_views()");
+}
+
+namespace {
+// C trampoline of the plugin seam: exceptions must not unwind through the C frames of liboxdna_b200.so
+int plugin_force_pass(void *user, const oxb_force_views *views) {
+	try {
+		static_cast<CUDABaseInteraction *>(user)->compute_forces_views(*views);
+	}
+	catch(oxDNAException &e) {
+		OX_LOG(Logger::LOG_ERROR, "plugged-in CUDA interaction: %s", e.what());
+		return 1;
+	}
+	return 0;
+}
+} // namespace
+
+void CUDABaseInteraction::attach_as_plugin(oxb_ctx *ctx) {
+	if(_use_edge) throw oxDNAException("use_edge is not available with a plugged-in CUDA interaction");
+	oxb_check(ctx, oxb_set_force_callback(ctx, plugin_force_pass, this, (double) get_cuda_rcut()), "set_force_callback");
 }
 
 CUDADNAInteraction::CUDADNAInteraction() {}
@@ -293,7 +318,12 @@ std::shared_ptr<CUDABaseInteraction> CUDAInteractionFactory::make_interaction(in
 	if(inter_type == "RNA2") return std::make_shared<CUDARNAInteraction>();
 	if(inter_type == "RNA") return std::make_shared<CUDARNAInteraction>(true);
 	if(inter_type == "DNA" || inter_type == "DNA_nomesh") return std::make_shared<CUDADNA1Interaction>();
-	throw oxDNAException("CUDA interaction '%s' not found in the oxdna_b200 backend (available: DNA, DNA2, RNA, RNA2). Aborting", inter_type.c_str());
+	// anything else: CUDA<type>.so on the plugin search path, entry point make_CUDA<type> (or make / make_interaction), exactly as the
+	// reference looks it up (CUDAInteractionFactory.cu:44-51, PluginManager.cpp:89-180); the object must be one of OUR CUDABaseInteraction
+	std::string cuda_name = "CUDA" + inter_type;
+	std::shared_ptr<CUDABaseInteraction> res = std::dynamic_pointer_cast<CUDABaseInteraction>(PluginManager::instance()->get_interaction(cuda_name));
+	if(res == nullptr) throw oxDNAException("CUDA interaction '%s' not found. Aborting", cuda_name.c_str());
+	return res;
 }
 
 // ---------------------------------------------------------------------------------------------------------- lists

@@ -59,6 +59,16 @@ public:
 	bool use_edge() const { return _use_edge; }
 	/// forces, torques and per-particle energies for the context's current positions and lists
 	virtual void compute_forces(oxb_ctx *ctx);
+
+	// ---- plugin seam (reference: CUDAInteractionFactory falls back to PluginManager::get_interaction("CUDA" + type),
+	// src/CUDA/Interactions/CUDAInteractionFactory.cu:44-51, and the backend calls compute_forces(lists, d_poss, d_orientations,
+	// d_forces, d_torques, d_bonds, d_box) on whatever came back, CUDABaseInteraction.h:60).  A third-party interaction derives from
+	// this class and from a CPU BaseInteraction, overrides compute_forces_views() -- the same raw device arrays in the reference's
+	// layouts, see oxb_force_views in include/oxdna_b200.h -- and calls attach_as_plugin() from its cuda_init().
+	/// enqueue the force pass on views.stream; forces / torques are zeroed accumulators (lab frame, .w = energy share)
+	virtual void compute_forces_views(const oxb_force_views &views);
+	/// makes compute_forces_views() the context's force pass, with get_cuda_rcut() as the Verlet cutoff
+	void attach_as_plugin(oxb_ctx *ctx);
 };
 
 /// interaction_type = DNA2: the CPU DNA2Interaction supplies every constant (sequence dependence, salt, dh_* keys,

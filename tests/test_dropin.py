@@ -249,6 +249,36 @@ def test_stock_input_file_matches_reference_cpu(tmp_path, use_edge, sort_every, 
 
 
 @pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(os.path.join(os.path.dirname(OURS), "plugins", "CUDAToy.so")), reason="toy plugin not built (needs /root/reference)")
+def test_third_party_interaction_through_the_plugin_manager(tmp_path):
+    """The plugin seam of the drop-in backend: `interaction_type = Toy` is unknown to both factories, so the reference's
+    InteractionFactory loads Toy.so (make_Toy) and our CUDAInteractionFactory loads CUDAToy.so (make_CUDAToy) through the reference's
+    own PluginManager (src/CUDA/Interactions/CUDAInteractionFactory.cu:44-51, src/PluginManagement/PluginManager.cpp:89-180).  The toy
+    interaction (tests/plugin) computes a soft repulsion with its own kernel from the raw device arrays (poss float4, column-major
+    matrix_neighs, number_neighs); 300 NVE steps are compared with a plain numpy velocity-Verlet run of the same potential."""
+    from conftest import load_golden
+    from test_gpu_plugin_seam import toy_reference
+    g = load_golden("lattice8")
+    src = tmp_path / "src"
+    os.makedirs(src)
+    oio.write_topology(str(src / "t.top"), g["btype"], g["n3"], g["n5"], g["strand"])
+    oio.write_conf(str(src / "t.conf"), g["box"], g["pos"], g["a1"], g["a3"], g["vel"], g["L"])
+    plug = os.path.join(os.path.dirname(OURS), "plugins")
+    d = str(tmp_path / "toy")
+    a = run(OURS, d, fix=str(src), files=("t.top", "t.conf"), backend="CUDA", itype="Toy", steps=300, thermostat="no", use_edge=0, sort_every=1,
+            extra=f"plugin_search_path = {plug}\nrefresh_vel = 0\ntoy_k = 3.0\ntoy_rc = 1.4\n")
+    assert a.returncode == 0, a.stdout[-2000:]
+    last = oio.read_conf(os.path.join(d, "last_conf.dat"))
+    p_ref, v_ref, _ = toy_reference(g["pos"], g["vel"], g["n3"], g["n5"], g["box"], 0.003, 300)
+    assert np.abs(last["pos"] - p_ref).max() < 2e-5 and np.abs(last["vel"] - v_ref).max() < 2e-5
+    assert np.abs(last["pos"] - g["pos"]).max() > 1e-2  # it did move
+    # an interaction nobody provides fails the way the reference fails
+    bad = run(OURS, str(tmp_path / "none"), fix=str(src), files=("t.top", "t.conf"), backend="CUDA", itype="DNA2", steps=10, thermostat="no", use_edge=0,
+              sort_every=0, extra=f"plugin_search_path = {plug}\ninteraction_type = Nope\n")
+    assert bad.returncode != 0
+
+
+@pytest.mark.gpu
 @needs_binaries
 def test_stock_input_file_thermostat_and_errors(tmp_path):
     a = run(OURS, str(tmp_path / "t"), backend="CUDA", itype="DNA2", steps=5000, thermostat="brownian", use_edge=1, sort_every=1, extra="")
@@ -270,7 +300,7 @@ def test_stock_input_file_thermostat_and_errors(tmp_path):
     bad = run(OURS, str(tmp_path / "bad2"), backend="CUDA", itype="DNA2", steps=10, thermostat="no", use_edge=1, sort_every=0, extra="reload_from = x")
     assert bad.returncode != 0
     bad = run(OURS, str(tmp_path / "bad3"), backend="CUDA", itype="LJ", steps=10, thermostat="no", use_edge=1, sort_every=0, extra="")
-    assert bad.returncode != 0 and "not found in the oxdna_b200 backend" in bad.stdout
+    assert bad.returncode != 0 and "CUDA interaction 'CUDALJ' not found" in bad.stdout  # the reference's own message (CUDAInteractionFactory.cu:49)
 
 
 @pytest.mark.gpu
