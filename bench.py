@@ -347,7 +347,9 @@ def measure_single(args, wl, steps, warmup, equil, md, full, local_rank=0):
         step_ms = total_ms / n_md
         # ---- phase times from the device timeline of the timed region (they add up to it; launch gaps belong to the phase that was open)
         t_force, t_integ = prof["force"][0] / n_md, prof["integrate"][0] / n_md
-        t_build, t_sort, t_wait = prof["build"][0] / n_reb, prof["sort"][0] / n_sort, prof["wait"][0] / n_reb
+        t_build, t_sort, t_wait = (prof["build"][0] + prof["edges"][0]) / n_reb, (prof["sort"][0] + prof["permute"][0]) / n_sort, prof["wait"][0] / n_reb
+        t_parts = {"sort_keys_radix_invert": prof["sort"][0] / n_sort, "sort_gather_pass": prof["permute"][0] / n_sort,
+                   "build_neighbour_scan": prof["build"][0] / n_reb, "build_edge_scan_fill": prof["edges"][0] / n_reb}
         prof_total = sum(v[0] for v in prof.values())
         ps = pair_statistics(sim, sysm)
         hbm_peak, peak_src = load_peaks()
@@ -381,7 +383,7 @@ def measure_single(args, wl, steps, warmup, equil, md, full, local_rank=0):
             "roofline_sort": {"kernel": "Hilbert re-sort (keys + radix sort + one gather pass)", "bound": "hbm", "achieved": gbs(N * 470.0, t_sort),
                               "peak": hbm_peak, "unit": "GB/s", "frac": gbs(N * 470.0, t_sort) / hbm_peak if t_sort > 0 else None, "ms": t_sort,
                               "per_md_step_ms": t_sort * n_sort / n_md},
-            "kernels_ms": {"force_pass": t_force, "integrate": t_integ, "list_build_per_rebuild": t_build, "sort_per_sort": t_sort,
+            "kernels_ms": {"force_pass": t_force, "integrate": t_integ, "list_build_per_rebuild": t_build, "sort_per_sort": t_sort, "rebuild_parts": t_parts,
                            "halt_and_host_wait_per_rebuild": t_wait, "batch_launch_gap_per_batch": prof["gap"][0] / max(prof["gap"][1], 1), "batches": prof["gap"][1],
                            "batch_launch_gap_per_md_step": prof["gap"][0] / n_md, "other_per_md_step": prof["other"][0] / n_md, "md_step_mean": step_ms,
                            "sum_of_phases_per_md_step": prof_total / n_md, "rebuilds": n_reb, "sorts": n_sort,

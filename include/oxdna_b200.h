@@ -340,11 +340,12 @@ int oxb_time_kernel(oxb_ctx *ctx, int which, int reps, float *ms_per_launch);
  * that opens each phase of the step stamps %globaltimer on the device and the time since the previous stamp is charged to the phase
  * that was open, so the phases add up to the device time of the run (launch gaps and host-synchronisation bubbles included).
  * Phases (OXB_PROF_*): 0 other, 1 force pass, 2 integrate, 3 halted launches + host wait before a rebuild, 4 Hilbert sort, 5 list build,
- * 6 gap between the start of a batch (k_batch_begin) and its first force kernel (launch latency of the batch).
+ * 6 gap between the start of a batch (k_batch_begin) and its first force kernel (launch latency of the batch), 7 the gather pass of the
+ * re-sort (4 = keys + radix sort + inverse permutation), 8 edge-list scan + fill (5 = cell binning + neighbour scan).
  * Replaces the reference's TimingManager around sim_step (src/Utilities/Timings.cpp, MD_CUDABackend.cu:567-619), which needs a
  * cudaDeviceSynchronize per timer.  oxb_set_profile zeroes the accumulators; oxb_get_profile returns milliseconds and the number of
- * times each phase was entered (7 values each). */
-#define OXB_PROF_NPHASES 7
+ * times each phase was entered (OXB_PROF_NPHASES values each). */
+#define OXB_PROF_NPHASES 9
 int oxb_set_profile(oxb_ctx *ctx, int enable);
 int oxb_get_profile(oxb_ctx *ctx, double *ms, long long *entries);
 

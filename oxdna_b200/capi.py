@@ -562,14 +562,14 @@ class Context:
     def launch_count(self):
         return self._L.oxb_launch_count(self._h)
 
-    PROF_PHASES = ("other", "force", "integrate", "wait", "sort", "build", "gap")
+    PROF_PHASES = ("other", "force", "integrate", "wait", "sort", "build", "gap", "permute", "edges")
 
     def set_profile(self, enable=True):
         self._ck(self._L.oxb_set_profile(self._h, int(bool(enable))))
 
     def get_profile(self):
         """{phase: (milliseconds, entries)} accumulated inside run() since set_profile(True)"""
-        ms, n = (C.c_double * 7)(), (C.c_longlong * 7)()
+        ms, n = (C.c_double * len(self.PROF_PHASES))(), (C.c_longlong * len(self.PROF_PHASES))()
         self._ck(self._L.oxb_get_profile(self._h, ms, n))
         return {k: (ms[i], n[i]) for i, k in enumerate(self.PROF_PHASES)}
 

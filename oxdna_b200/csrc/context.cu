@@ -373,6 +373,7 @@ int do_sort(oxb_ctx *c) {
 	p.axf_in = c->axf[a]; p.F_in = c->F[a]; p.T_in = c->T[a]; p.axf_out = c->axf[b]; p.F_out = c->F[b]; p.T_out = c->T[b];
 	p.bonds_in = c->bonds[a]; p.bonds_out = c->bonds[b];
 	p.slot_of = c->slot_of;
+	p.flags = c->flags;
 	p.cell_lin = c->cell_key_sorted;
 	p.n_per = c->n_per;
 	for(int k = 0; k < 3; k++) { p.box[k] = c->box[k]; p.ncell[k] = c->ncell[k]; }
@@ -503,7 +504,6 @@ int launch_forces(oxb_ctx *c, int hw, bool clear, long long step) {
 		}
 		oxb::EdgeArgs e;
 		e.rep = c->rep; e.n_per = c->n_per;
-		e.n_sm = c->n_sm;
 		e.N = c->N; e.ipos = c->ipos[a]; e.iback = c->iback[a]; e.axf = c->axf[a]; e.posd = c->posd[a]; e.quatd = c->quatd[a]; e.bonds = c->bonds[a]; e.edges = c->edges;
 		e.n_edges = c->n_edges; e.dh_nbr = c->dh_nbr; e.dh_nnbr = c->dh_nnbr;
 		e.F = c->F[a]; e.T = c->T[a]; e.Fb = c->Fb; e.hb_list = c->hb_list; e.cx_list = c->cx_list; e.cr_list = c->cr_list; e.seg_counts = c->seg_counts;

@@ -261,9 +261,7 @@ __global__ void __launch_bounds__(128) k_dh_particle(const __grid_constant__ typ
 		int *__restrict__ flags, int hw) {
 	if(blockIdx.x == 0 && threadIdx.x == 0) prof_mark(flags, flags[hw] ? OXB_PROF_WAIT : OXB_PROF_FORCE);
 	if(flags[hw]) return;
-	// grid-stride: with a grid of a few blocks per SM (launch_edge_stage_t, "co-resident" launch) the kernel shares every SM with the other
-	// kernels of the force pass for its whole duration instead of taking the machine in turns with them
-	for(int gid = blockIdx.x * blockDim.x + threadIdx.x; gid / LPP < ((N + 31) & ~31); gid += gridDim.x * blockDim.x) {
+	const int gid = blockIdx.x * blockDim.x + threadIdx.x;
 	const int sub = gid % LPP;
 	int i = gid / LPP;
 	const bool active = i < N;
@@ -295,7 +293,6 @@ __global__ void __launch_bounds__(128) k_dh_particle(const __grid_constant__ typ
 	}
 	if(HALF) { if(active && sub == 0 && e != 0.f) atomic_add4(Fb + i, f.x, f.y, f.z, e); }
 	else if(active && sub == 0) Fb[i] = make_float4(f.x, f.y, f.z, e);
-	}
 }
 
 // Work lists are SEGMENTED by producer block: block b of k_edge_near owns list[b * seg .. (b + 1) * seg) and publishes its
@@ -478,15 +475,16 @@ __global__ void __launch_bounds__(128, OXB_MB_BONDED) k_bonded(const __grid_cons
 		const oxb_replica_consts *__restrict__ rep, int n_per, int *__restrict__ flags, int hw) {
 	if(blockIdx.x == 0 && threadIdx.x == 0) prof_mark(flags, flags[hw] ? OXB_PROF_WAIT : OXB_PROF_FORCE);
 	if(flags[hw]) return;
-	bool broken = false;
-	for(int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) { // grid-stride, see k_dh_particle
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= N) return;
 	int2 b = __ldg(bonds + i);
-	if(b.x < 0) { if(refine && !fold) ex_bonded[i] = 0; continue; }
+	if(b.x < 0) { if(refine && !fold) ex_bonded[i] = 0; return; }
 	Particle P = load_particle<MD>(M, ipos, axf, i);
 	Particle Q = load_particle<MD>(M, ipos, axf, b.x);
 	PairAcc acc;
 	acc.clear();
 	if(rep != nullptr) acc.rep = rep + i / n_per; // replica batching: this replica's stacking strength
+	bool broken = false;
 	const v3 r = min_image_fixed(box, P.ip, Q.ip);
 	float en;
 	int ex_mask = 0;
@@ -512,10 +510,9 @@ __global__ void __launch_bounds__(128, OXB_MB_BONDED) k_bonded(const __grid_cons
 	atomic_add4(T + i, tp.x, tp.y, tp.z, 0.f);
 	atomic_add4(F + b.x, acc.F.x, acc.F.y, acc.F.z, en);
 	atomic_add4(T + b.x, tq.x, tq.y, tq.z, 0.f);
+	if(broken) atomicOr(flags + OXB_FLAG_ERROR, OXB_ERR_FENE_BROKEN);
 	// fold = 1: the few bonds with a bonded excluded-volume site pair in range take it in double right here instead of in k_excl_fix
 	if(fold && ex_mask != 0) excl_double_item<MD>(M, box, posd, quatd, i, b.x, ex_mask, F, T);
-	}
-	if(broken) atomicOr(flags + OXB_FLAG_ERROR, OXB_ERR_FENE_BROKEN);
 }
 
 // Excluded volume in double for the parked pairs: blocks [0, n_seg) walk the near-edge segments, the following blocks scan the
@@ -1047,13 +1044,7 @@ static int env_int(const char *name, int dflt) {
 
 template<class MD>
 static void launch_edge_stage_t(cudaStream_t s, int which, const typename MD::Params &M, BoxF box, const EdgeArgs &a, int *flags, int hw) {
-	// co-resident launch (a.n_sm > 0 and OXB_PB_* blocks per SM): the Debye-Hueckel and bonded kernels get a grid of a few blocks per SM and
-	// stride over the particles, so that on the forked streams all kernels of the pass live on every SM at the same time
-	static const int pb_dh = env_int("OXB_PB_DH", 0), pb_bonded = env_int("OXB_PB_BONDED", 0);
-	auto blocks_for = [&](long long items, int per_sm = 0) {
-		const long long full = std::max<long long>(1, (items + 127) / 128);
-		return (int) ((per_sm > 0 && a.n_sm > 0) ? std::min<long long>(full, (long long) per_sm * a.n_sm) : full);
-	};
+	auto blocks_for = [&](long long items) { return (int) std::max<long long>(1, (items + 127) / 128); };
 	switch(which) {
 	case 0: {
 		// lanes per particle: 1 by default.  2 and 4 were measured neutral to slower at 81,920 and 1M nucleotides
@@ -1061,10 +1052,10 @@ static void launch_edge_stage_t(cudaStream_t s, int which, const typename MD::Pa
 		static const int lpp_env = env_int("OXB_DH_LPP", 0);
 		const int lpp = lpp_env > 0 ? lpp_env : 1;
 		if(a.rep != nullptr) {
-			if(a.dh_half) k_dh_particle<MD, 1, true, true><<<blocks_for(a.N, pb_dh), 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, a.rep, a.n_per, flags, hw);
-			else k_dh_particle<MD, 1, true, false><<<blocks_for(a.N, pb_dh), 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, a.rep, a.n_per, flags, hw);
+			if(a.dh_half) k_dh_particle<MD, 1, true, true><<<blocks_for(a.N), 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, a.rep, a.n_per, flags, hw);
+			else k_dh_particle<MD, 1, true, false><<<blocks_for(a.N), 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, a.rep, a.n_per, flags, hw);
 		}
-		else if(a.dh_half) k_dh_particle<MD, 1, false, true><<<blocks_for(a.N, pb_dh), 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, nullptr, 1, flags, hw);
+		else if(a.dh_half) k_dh_particle<MD, 1, false, true><<<blocks_for(a.N), 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, nullptr, 1, flags, hw);
 		else if(lpp >= 4) k_dh_particle<MD, 4, false, false><<<blocks_for(4ll * a.N), 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, nullptr, 1, flags, hw);
 		else if(lpp == 2) k_dh_particle<MD, 2, false, false><<<blocks_for(2ll * a.N), 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, nullptr, 1, flags, hw);
 		else k_dh_particle<MD, 1, false, false><<<blocks_for(a.N), 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, nullptr, 1, flags, hw);
@@ -1086,8 +1077,7 @@ static void launch_edge_stage_t(cudaStream_t s, int which, const typename MD::Pa
 	default: {
 		static const int tpb_env = env_int("OXB_TPB_BONDED", 0);
 		const int tpb = tpb_env > 0 ? tpb_env : 128;
-		const int nb_full = (a.N + tpb - 1) / tpb;
-		k_bonded<MD><<<(pb_bonded > 0 && a.n_sm > 0) ? std::min(nb_full, pb_bonded * a.n_sm) : nb_full, tpb, 0, s>>>(M, box, a.N, a.ipos, a.iback, a.axf, a.bonds, a.F, a.T, a.ex_bonded, a.refine, a.fold, a.posd, a.quatd, a.rep, a.n_per, flags, hw);
+		k_bonded<MD><<<(a.N + tpb - 1) / tpb, tpb, 0, s>>>(M, box, a.N, a.ipos, a.iback, a.axf, a.bonds, a.F, a.T, a.ex_bonded, a.refine, a.fold, a.posd, a.quatd, a.rep, a.n_per, flags, hw);
 		break;
 	}
 	}

@@ -25,7 +25,8 @@ enum : int {
 // since the previous stamp is charged to the phase that was open.  Works inside graph-launched batches and costs one thread a few
 // global accesses, so the decomposition is measured IN the timed region (bench.py roofline), launch gaps included: the phases sum to
 // the device time line of the run.  Layout (unsigned long long): [0] last stamp, [1] open phase, [2 + p] ns in phase p, [2 + NPHASE + p] entries into p.
-enum { OXB_PROF_OTHER = 0, OXB_PROF_FORCE = 1, OXB_PROF_INTEG = 2, OXB_PROF_WAIT = 3, OXB_PROF_SORT = 4, OXB_PROF_BUILD = 5, OXB_PROF_GAP = 6, OXB_PROF_NPHASE = 7 };
+enum { OXB_PROF_OTHER = 0, OXB_PROF_FORCE = 1, OXB_PROF_INTEG = 2, OXB_PROF_WAIT = 3, OXB_PROF_SORT = 4, OXB_PROF_BUILD = 5, OXB_PROF_GAP = 6, OXB_PROF_PERMUTE = 7,
+	OXB_PROF_EDGES = 8, OXB_PROF_NPHASE = 9 };
 #ifdef __CUDACC__
 __device__ __forceinline__ void prof_mark(int *flags, int phase, bool reset = false) {
 	if(flags[OXB_FLAG_PROF_ON] == 0) return;
@@ -86,7 +87,6 @@ void launch_forces_particle(cudaStream_t s, const ModelRef &M, BoxF box, int N, 
 		const int *nbr, const int *nnbr, int stride, float4 *F, float4 *T, const oxb_replica_consts *rep, int n_per, int *flags, int hw);
 struct EdgeArgs {
 	int N;
-	int n_sm; // SM count, for the co-resident launch grids (0: one block per 128 items)
 	const oxb_replica_consts *rep; // replica batching: one row per replica (null: single system), n_per particles per replica
 	int n_per;
 	const int4 *ipos, *iback;
@@ -260,6 +260,7 @@ struct PermuteArgs {
 	const int2 *bonds_in;
 	int2 *bonds_out;
 	int *slot_of; // slot_of[original id] = new slot
+	int *flags;   // device control words (phase timeline)
 	int *cell_lin; // optional: linear cell id of every new slot (what the list builder's binning would have produced)
 	// optional (with cell_lin): the list builder's cell table and staleness references are produced by the same pass (sort.cu: k_permute)
 	const unsigned *keys_sorted; // the sorted Hilbert keys of the cells: equal keys = equal cell

@@ -96,6 +96,9 @@ __device__ __forceinline__ bool near_pair(const oxb::ListArgs &a, v3 r, v3 a1p, 
 //    (bit k = row entry k), from which k_fill_edges emits the edge list without touching any geometry again.
 template<bool DIRECT>
 __global__ void __launch_bounds__(128) k_build_neigh(oxb::ListArgs a, const int *__restrict__ cell_start, const int *__restrict__ cell_end) {
+	// (staging the rows in shared-memory columns and flushing them row by row -- whole sectors instead of 4-byte pieces scattered over as
+	// many rows as the lanes have different counts -- was measured: it halves the 0.45 ms that the 35-us edge fill takes behind a
+	// FULL-shell build on the device timeline, but costs occupancy: 0.41 against 0.39 ms for the half-shell build, gpurun_out r2i-r2k)
 	__shared__ int2 s_range[27][128];
 	if(blockIdx.x == 0 && threadIdx.x == 0) prof_mark(a.flags, OXB_PROF_BUILD);
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -181,38 +184,43 @@ __global__ void __launch_bounds__(128) k_build_neigh(oxb::ListArgs a, const int 
 		if(fabsf(d2 - rv2f) < band) in = within_exact(pd, a.posd[m], a.box[0], a.box[1], a.box[2], rv2);
 		if(in) {
 			if(count < a.max_neigh) a.nbr[(size_t) count * a.stride + i] = m;
-			// Debye-Hueckel acts between backbone sites: keep m if the sites can come within dh_rc before the
-			// next rebuild (both the centre and the backbone site of every particle move less than `skin`)
-			const int4 ibm = __ldg(a.iback + m);
-			v3 db = min_image_fixed(a.boxf, ib, ibm);
-			if(m > i && d2 < a.rnear2 && near_pair(a, d, a1p, load_a1(a.axf, m), bkp, min_image_fixed(a.boxf, ipm, ibm))) {
-				higher_near++;
-				// rows that overflow max_neigh are rebuilt after the matrix has grown: never flag an entry that was not written
-				if(count >= a.max_neigh) mask_overflow = true;
-				else if(count < 64) mask0 |= 1ull << count;
-				else if(count < 128) mask1 |= 1ull << (count - 64);
-				else mask_overflow = true;
-			}
-			if(dot(db, db) < a.rdh2) {
-				if(a.half_shell) {
-					// this scan sees every pair once (m > i); rows filled from the lower slot only would be as long as a particle has
-					// partners AFTER it on the Hilbert curve -- 0 to twice the mean within one warp of k_dh_particle (+ 10 us per force pass at
-					// 1M nt).  The same parity rule as below picks the owner; rows are appended through their counters (zeroed by the launcher)
-					const int owner = ((i + m) & 1) == 0 ? i : m, other = i + m - owner;
-					const int pos = atomicAdd(a.dh_nnbr + owner, 1);
-					if(pos < a.max_dh) a.dh_nbr[(size_t) pos * a.stride + owner] = other;
-					else dh_overflow = true;
-				}
-				// dh_half: every Debye-Hueckel pair is kept by ONE of its particles (by the parity of i + m, so that rows stay balanced); the
-				// kernel adds the partner's share with one vector atomic.  Full rows (both directions, no atomics) otherwise.
-				else if(!a.dh_half || ((((i + m) & 1) == 0) == (i < m))) {
-					if(ndh < a.max_dh) a.dh_nbr[(size_t) ndh * a.stride + i] = m;
-					ndh++;
-				}
-			}
 			count++;
 		}
 	}
+	// phase 3: classification of the row just written (near edge? Debye-Hueckel row?).  Kept out of the candidate loop: there nearly
+	// every warp iteration has a hit on SOME lane, so the ~100 instructions of this block ran for every candidate (57 per particle)
+	// with a few lanes active; here the lanes walk rows of similar length together (ncu r02f: 6,900 warp instructions per warp before)
+	const int nrow = min(count, a.max_neigh);
+	for(int k = 0; k < nrow; k++) {
+		const int m = a.nbr[(size_t) k * a.stride + i]; // this thread's own store (plain load, program order)
+		const int4 ipm = __ldg(a.ipos + m);
+		const int4 ibm = __ldg(a.iback + m);
+		const v3 d = min_image_fixed(a.boxf, ip, ipm);
+		const float d2 = dot(d, d);
+		// Debye-Hueckel acts between backbone sites: keep m if the sites can come within dh_rc before the
+		// next rebuild (both the centre and the backbone site of every particle move less than `skin`)
+		const v3 db = min_image_fixed(a.boxf, ib, ibm);
+		if(m > i && d2 < a.rnear2 && near_pair(a, d, a1p, load_a1(a.axf, m), bkp, min_image_fixed(a.boxf, ipm, ibm))) {
+			higher_near++;
+			if(k < 64) mask0 |= 1ull << k;
+			else if(k < 128) mask1 |= 1ull << (k - 64);
+			else mask_overflow = true;
+		}
+		if(dot(db, db) < a.rdh2) {
+			// dh_half: every Debye-Hueckel pair is kept by ONE of its particles (by the parity of i + m, so that rows stay balanced); the
+			// kernel adds the partner's share with one vector atomic.  Full rows (both directions, no atomics) otherwise.
+			// half shell: this scan sees every pair once (m > i) and the lower slot keeps it.  Rows are then as long as a particle has
+			// partners AFTER it on the Hilbert curve (0 to twice the mean inside one warp of k_dh_particle: + 10 us per force pass at
+			// 1M nt); balancing them by appending to the partner's row through an atomic counter was measured and costs 0.3 ms per
+			// rebuild (gpurun_out r2h) -- three times what it gains
+			if(a.half_shell || !a.dh_half || ((((i + m) & 1) == 0) == (i < m))) {
+				if(ndh < a.max_dh) a.dh_nbr[(size_t) ndh * a.stride + i] = m;
+				ndh++;
+			}
+		}
+	}
+	// rows that overflow max_neigh are rebuilt after the matrix has grown (the entries beyond it were never written: not classified)
+	if(count > a.max_neigh) mask_overflow = true;
 	if(!active) return;
 	{
 		// one same-address atomic per warp, not per thread
@@ -229,7 +237,7 @@ __global__ void __launch_bounds__(128) k_build_neigh(oxb::ListArgs a, const int 
 		ndh = a.max_dh;
 	}
 	a.nnbr[i] = count;
-	if(!a.half_shell) a.dh_nnbr[i] = ndh;
+	a.dh_nnbr[i] = ndh;
 	if(a.build_edges) {
 		a.edge_offsets[i] = higher_near;
 		// rows longer than the mask fall back to the geometric test in k_fill_edges (top bit of word 1 doubles as the marker:
@@ -342,14 +350,7 @@ __global__ void __launch_bounds__(256, 4) k_build_neigh_g(oxb::ListArgs a, const
 			}
 			// dh_half: every Debye-Hueckel pair is kept by ONE of its particles (by the parity of i + m, so that rows stay balanced)
 			is_dh = dot(db, db) < a.rdh2 && (!a.dh_half || a.half_shell || ((((i + m) & 1) == 0) == (i < m)));
-			if(is_dh && a.half_shell) {
-				// half shell: rows are appended through their counters, owner by the same parity rule (see k_build_neigh)
-				const int owner = ((i + m) & 1) == 0 ? i : m, other = i + m - owner;
-				const int pos = atomicAdd(a.dh_nnbr + owner, 1);
-				if(pos < a.max_dh) a.dh_nbr[(size_t) pos * a.stride + owner] = other;
-				else dh_overflow = true;
-				is_dh = false;
-			}
+
 		}
 		count += __popc(bal);
 		const unsigned bdh = __ballot_sync(0xffffffffu, is_dh) & gmask;
@@ -384,7 +385,7 @@ __global__ void __launch_bounds__(256, 4) k_build_neigh_g(oxb::ListArgs a, const
 		ndh = a.max_dh;
 	}
 	a.nnbr[i] = count;
-	if(!a.half_shell) a.dh_nnbr[i] = ndh;
+	a.dh_nnbr[i] = ndh;
 	if(a.build_edges) {
 		a.edge_offsets[i] = higher_near;
 		if(mask_overflow) mask1 |= 1ull << 63;
@@ -395,6 +396,7 @@ __global__ void __launch_bounds__(256, 4) k_build_neigh_g(oxb::ListArgs a, const
 // near edge (i, m) for every flagged row entry; rows are contiguous in the output (grouped by `from`)
 __global__ void __launch_bounds__(128) k_fill_edges(oxb::ListArgs a) {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i == 0) prof_mark(a.flags, OXB_PROF_EDGES);
 	if(i >= a.N) return;
 	int off = a.edge_offsets[i];
 	const int nn = a.nnbr[i];
@@ -475,7 +477,7 @@ void launch_build_lists(cudaStream_t s, const ListArgs &a) {
 				a.ref_L, a.flags);
 	}
 	cudaMemsetAsync(a.flags + OXB_FLAG_MAX_NEIGH_SEEN, 0, sizeof(int), s);
-	if(a.half_shell) cudaMemsetAsync(a.dh_nnbr, 0, sizeof(int) * (size_t) N, s); // the rows of the Debye-Hueckel matrix are appended through their counters
+
 	// lanes per particle of the neighbour scan (OXB_BUILD_G = 1: the thread-per-particle kernel)
 	// (measured on B200, gpurun_out r2e: 8 lanes win while the system cannot fill the machine with one thread per particle -- 82 against 98 us
 	// at 81,920 nt --, the serial kernel wins at 1M nt -- it executes 2.3 x fewer instructions, ncu r02f -- and both are issue-bound there)

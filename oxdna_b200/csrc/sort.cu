@@ -87,6 +87,7 @@ __global__ void __launch_bounds__(256) k_invert(int N, const int *__restrict__ p
 // (mid-step they have been consumed and zeroed by the integrator), so gathering them would move 64 B per particle for nothing.
 __global__ void __launch_bounds__(256) k_permute(oxb::PermuteArgs a) {
 	int n = blockIdx.x * blockDim.x + threadIdx.x;
+	if(n == 0 && a.flags != nullptr) prof_mark(a.flags, OXB_PROF_PERMUTE);
 	if(n >= a.N) return;
 	int o = a.perm[n];
 	double4 pd = a.posd_in[o], vd = a.veld_in[o], ld = a.Ld_in[o];
