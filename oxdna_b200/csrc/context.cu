@@ -97,6 +97,8 @@ struct oxb_ctx {
 	size_t cub_tmp_bytes = 0;
 	unsigned *hkeys = nullptr, *hkeys_sorted = nullptr;
 	int *hvals = nullptr, *hvals_sorted = nullptr, *hinv = nullptr;
+	int *sort_small = nullptr; // scratch of the one-launch ordering of small systems (sort.cu: k_sort_small)
+	size_t sort_small_bytes = 0;
 	bool lists_allocated = false, lists_valid = false, forces_valid = false;
 	bool need_full_matrix = false; // a consumer of both directions of every pair (oxb_device_views) has shown up: no half-shell builds any more
 	bool half_shell_ok = true;     // OXB_HALF_SHELL=0 switches the half-shell scan off
@@ -361,6 +363,17 @@ int do_sort(oxb_ctx *c) {
 	s.posd = c->posd[a];
 	for(int k = 0; k < 3; k++) s.ncell[k] = c->ncell[k];
 	s.keys = c->hkeys; s.keys_sorted = c->hkeys_sorted; s.vals = c->hvals; s.vals_sorted = c->hvals_sorted; s.inv = c->hinv;
+	{
+		const size_t need = oxb::sort_small_bytes(N, c->ncell, c->n_rep);
+		if(need > c->sort_small_bytes) {
+			CU(cudaStreamSynchronize(c->stream));
+			cudaFree(c->sort_small);
+			c->sort_small = nullptr;
+			CU(cudaMalloc((void **) &c->sort_small, need));
+			c->sort_small_bytes = need;
+		}
+		s.small_tmp = need > 0 ? c->sort_small : nullptr;
+	}
 	s.cub_tmp = c->cub_tmp; s.cub_tmp_bytes = c->cub_tmp_bytes;
 	s.flags = c->flags;
 	oxb::launch_hilbert_order(c->stream, s);
@@ -859,7 +872,7 @@ void oxb_destroy(oxb_ctx *c) {
 	cudaFree(c->slot_of); cudaFree(c->flags); cudaFree(c->sums); cudaFree(c->d_energy); cudaFree(c->ext); cudaFree(c->ext_all); cudaFree(c->ext_com); cudaFree(c->ext_pool); cudaFree(c->ext_grid);
 	cudaFree(c->d_topo); cudaFree(c->d_stage); cudaFree(c->d_marshal_err);
 	cudaFree(c->mol_of); cudaFree(c->mol_inv_size); cudaFree(c->mol_coms); cudaFree(c->pos_backup); cudaFree(c->pos_f4); cudaFree(c->quat_f4);
-	cudaFree(c->hkeys); cudaFree(c->hkeys_sorted); cudaFree(c->hvals); cudaFree(c->hvals_sorted); cudaFree(c->hinv);
+	cudaFree(c->hkeys); cudaFree(c->hkeys_sorted); cudaFree(c->hvals); cudaFree(c->hvals_sorted); cudaFree(c->hinv); cudaFree(c->sort_small);
 	free_lists(c);
 	if(c->h_flags) cudaFreeHost(c->h_flags);
 	if(c->h_scalars) cudaFreeHost(c->h_scalars);

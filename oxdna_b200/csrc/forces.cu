@@ -273,18 +273,53 @@ __global__ void __launch_bounds__(128) k_dh_particle(const __grid_constant__ typ
 	const bool p_end = bp.w & 1;
 	v3 f = mk3(0.f, 0.f, 0.f);
 	float e = 0.f;
+	if(LPP == 1) {
+		// Row lengths differ a lot inside a warp -- with the half-shell lists a particle keeps the partners that come AFTER it on the Hilbert
+		// curve, 0 to twice the mean -- and a warp lasts as long as its longest row (ncu r02m: 14.7 of 32 lanes active).  Lanes l and 31 - l
+		// therefore share their two rows evenly: the one with the shorter row takes the tail of the other's and hands the partial force
+		// back with one shuffle at the end.  The schedule is fixed by the row lengths, so the full-matrix variant stays deterministic.
+		const unsigned lane = threadIdx.x & 31;
+		const int pl = 31 - (int) lane;
+		const int nn_o = __shfl_sync(0xffffffffu, nn, pl), i_o = __shfl_sync(0xffffffffu, i, pl);
+		int4 bo;
+		bo.x = __shfl_sync(0xffffffffu, bp.x, pl); bo.y = __shfl_sync(0xffffffffu, bp.y, pl); bo.z = __shfl_sync(0xffffffffu, bp.z, pl); bo.w = __shfl_sync(0xffffffffu, bp.w, pl);
+		DhView Do;
+		if(REP) Do = dh_view(M, rep + i_o / n_per);
+		const int half = (nn + nn_o + 1) >> 1;
+		const int n_own = (nn > nn_o) ? nn - (half - nn_o) : nn;  // the longer row gives its tail away ...
+		const int n_help = (nn < nn_o) ? half - nn : 0;           // ... to the lane with the shorter one
+		const int k_help0 = nn_o - n_help;
+		v3 g = mk3(0.f, 0.f, 0.f);
+		float eg = 0.f;
+		const int n_all = n_own + n_help;
 #pragma unroll 4
-	for(int k = sub; k < nn; k += LPP) {
-		int j = __ldg(dh_nbr + (size_t) k * N + i);
-		int4 bq = __ldg(iback + j);
-		v3 rbb = min_image_fixed(box, bp, bq);
-		float fs;
-		float en = REP ? dna2_dh_fast(D, dot(rbb, rbb), p_end, bq.w & 1, fs) : dna2_dh_fast(M, dot(rbb, rbb), p_end, bq.w & 1, fs);
-		e += en;
-		axpy(f, -fs, rbb);
-		if(HALF && en != 0.f) atomic_add4(Fb + j, fs * rbb.x, fs * rbb.y, fs * rbb.z, en);
+		for(int t = 0; t < n_all; t++) {
+			const bool mine = t < n_own;
+			const int j = __ldg(dh_nbr + (size_t) (mine ? t : k_help0 + (t - n_own)) * N + (mine ? i : i_o));
+			const int4 b0 = mine ? bp : bo;
+			const int4 bq = __ldg(iback + j);
+			const v3 rbb = min_image_fixed(box, b0, bq);
+			float fs;
+			const float en = REP ? dna2_dh_fast(mine ? D : Do, dot(rbb, rbb), b0.w & 1, bq.w & 1, fs) : dna2_dh_fast(M, dot(rbb, rbb), b0.w & 1, bq.w & 1, fs);
+			if(mine) { e += en; axpy(f, -fs, rbb); }
+			else { eg += en; axpy(g, -fs, rbb); }
+			if(HALF && en != 0.f) atomic_add4(Fb + j, fs * rbb.x, fs * rbb.y, fs * rbb.z, en);
+		}
+		f.x += __shfl_sync(0xffffffffu, g.x, pl); f.y += __shfl_sync(0xffffffffu, g.y, pl); f.z += __shfl_sync(0xffffffffu, g.z, pl);
+		e += __shfl_sync(0xffffffffu, eg, pl);
 	}
-	if(LPP > 1) {
+	else {
+#pragma unroll 4
+		for(int k = sub; k < nn; k += LPP) {
+			int j = __ldg(dh_nbr + (size_t) k * N + i);
+			int4 bq = __ldg(iback + j);
+			v3 rbb = min_image_fixed(box, bp, bq);
+			float fs;
+			float en = REP ? dna2_dh_fast(D, dot(rbb, rbb), p_end, bq.w & 1, fs) : dna2_dh_fast(M, dot(rbb, rbb), p_end, bq.w & 1, fs);
+			e += en;
+			axpy(f, -fs, rbb);
+			if(HALF && en != 0.f) atomic_add4(Fb + j, fs * rbb.x, fs * rbb.y, fs * rbb.z, en);
+		}
 #pragma unroll
 		for(int o = LPP >> 1; o > 0; o >>= 1) {
 			f.x += __shfl_xor_sync(0xffffffffu, f.x, o); f.y += __shfl_xor_sync(0xffffffffu, f.y, o);

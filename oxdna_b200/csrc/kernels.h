@@ -244,8 +244,10 @@ struct SortArgs {
 	void *cub_tmp;
 	size_t cub_tmp_bytes;
 	int *flags;
+	int *small_tmp; // scratch of the one-launch ordering of small systems (sort_small_bytes), or null: radix sort
 };
 size_t sort_tmp_bytes(int N);
+size_t sort_small_bytes(int N, const int ncell[3], int n_rep);
 void launch_hilbert_order(cudaStream_t s, const SortArgs &a);
 struct PermuteArgs {
 	int N;

@@ -10,8 +10,10 @@
 #include "kernels.h"
 
 #include <cub/cub.cuh>
+#include <cooperative_groups.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace {
 
@@ -73,6 +75,100 @@ __global__ void __launch_bounds__(256) k_cell_hilbert_keys(int N, int n_per, con
 	keys[i] = hilbert_key((unsigned) cell_coord_s(p.x, Lx, nx), (unsigned) cell_coord_s(p.y, Ly, ny), (unsigned) cell_coord_s(p.z, Lz, nz), bits)
 			| ((unsigned) (i / n_per) << (3 * bits));
 	vals[i] = i;
+}
+
+// Small systems: the whole ordering step -- cell keys, stable sort by key, inverse permutation -- in ONE cooperative launch.  At 81,920
+// particles the seven launches of the key kernel + cub::DeviceRadixSort + inversion take 73 us on the device timeline for ~20 us of work
+// (each of the tiny kernels has a floor of 3-4 us plus launch latency behind a host synchronisation).  Counting sort over the Hilbert
+// keys of the cells (2^(3 bits) bins): histogram with atomics, three-stage exclusive scan, scatter; ties are then put in the order of
+// the old slots (a bin holds the few members of one cell), so the permutation is the same STABLE sort the radix path produces and
+// everything downstream stays bit-identical.  Grid = resident blocks only (cooperative launch), grid-stride loops throughout.
+__global__ void __launch_bounds__(256) k_sort_small(oxb::SortArgs a, int bits, int nbins, int *__restrict__ hist, int *__restrict__ block_sums, int *__restrict__ tmp) {
+	namespace cg = cooperative_groups;
+	cg::grid_group grid = cg::this_grid();
+	const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+	if(tid == 0) prof_mark(a.flags, OXB_PROF_SORT);
+	for(int b = tid; b < nbins; b += nthr) hist[b] = 0;
+	grid.sync();
+	// keys + occupancy of the bins (the atomic's return value is NOT used as the rank: it depends on the scheduling)
+	for(int i = tid; i < a.N; i += nthr) {
+		const double4 p = a.posd[i];
+		const unsigned key = hilbert_key((unsigned) cell_coord_s(p.x, a.box[0], a.ncell[0]), (unsigned) cell_coord_s(p.y, a.box[1], a.ncell[1]),
+				(unsigned) cell_coord_s(p.z, a.box[2], a.ncell[2]), bits);
+		a.keys[i] = key;
+		atomicAdd(hist + key, 1);
+	}
+	grid.sync();
+	// exclusive scan of the bins: every block scans one contiguous chunk, block 0 scans the chunk totals, every block adds its offset
+	__shared__ int s_warp[8];
+	__shared__ int s_carry;
+	const int chunk = (nbins + gridDim.x - 1) / gridDim.x;
+	const int c0 = blockIdx.x * chunk, c1 = min(c0 + chunk, nbins);
+	if(threadIdx.x == 0) s_carry = 0;
+	__syncthreads();
+	for(int base = c0; base < c1; base += blockDim.x) {
+		const int b = base + threadIdx.x;
+		const int v = (b < c1) ? hist[b] : 0;
+		int x = v;
+		for(int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if((threadIdx.x & 31) >= o) x += y; }
+		if((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = x;
+		__syncthreads();
+		int woff = 0;
+		for(int w = 0; w < (int) (threadIdx.x >> 5); w++) woff += s_warp[w];
+		const int carry = s_carry;
+		if(b < c1) hist[b] = carry + woff + x - v; // exclusive, relative to the chunk
+		__syncthreads();
+		if(threadIdx.x == blockDim.x - 1) s_carry = carry + woff + x;
+		__syncthreads();
+	}
+	if(threadIdx.x == 0) block_sums[blockIdx.x] = s_carry;
+	grid.sync();
+	if(blockIdx.x == 0) {
+		// gridDim.x totals (a few hundred): one block, same warp-scan scheme
+		if(threadIdx.x == 0) s_carry = 0;
+		__syncthreads();
+		for(int base = 0; base < (int) gridDim.x; base += blockDim.x) {
+			const int b = base + threadIdx.x;
+			const int v = (b < (int) gridDim.x) ? block_sums[b] : 0;
+			int x = v;
+			for(int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if((threadIdx.x & 31) >= o) x += y; }
+			if((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = x;
+			__syncthreads();
+			int woff = 0;
+			for(int w = 0; w < (int) (threadIdx.x >> 5); w++) woff += s_warp[w];
+			const int carry = s_carry;
+			if(b < (int) gridDim.x) block_sums[b] = carry + woff + x - v;
+			__syncthreads();
+			if(threadIdx.x == blockDim.x - 1) s_carry = carry + woff + x;
+			__syncthreads();
+		}
+	}
+	grid.sync();
+	{
+		const int off = block_sums[blockIdx.x];
+		for(int b = c0 + threadIdx.x; b < c1; b += blockDim.x) hist[b] += off;
+	}
+	grid.sync();
+	// scatter in arbitrary order inside each bin (second counter array: tmp[N ...] would do, the bins' cursors live behind the N slots)
+	int *cursor = tmp + a.N;
+	for(int b = tid; b < nbins; b += nthr) cursor[b] = 0;
+	grid.sync();
+	for(int i = tid; i < a.N; i += nthr) {
+		const unsigned key = a.keys[i];
+		tmp[hist[key] + atomicAdd(cursor + key, 1)] = i;
+	}
+	grid.sync();
+	// stable order inside the bins: rank = members with a smaller old slot
+	for(int i = tid; i < a.N; i += nthr) {
+		const unsigned key = a.keys[i];
+		const int s0 = hist[key], n = cursor[key];
+		int rank = 0;
+		for(int k = 0; k < n; k++) rank += (tmp[s0 + k] < i) ? 1 : 0;
+		const int pos = s0 + rank;
+		a.vals_sorted[pos] = i;
+		a.inv[i] = pos;
+		a.keys_sorted[pos] = key;
+	}
 }
 
 __global__ void __launch_bounds__(256) k_invert(int N, const int *__restrict__ perm, int *__restrict__ inv) {
@@ -138,8 +234,38 @@ size_t sort_tmp_bytes(int N) {
 	return a + 256;
 }
 
+// scratch of the one-launch ordering of small systems: bins + chunk totals + (N + bins) ints; 0 if the system does not qualify
+size_t sort_small_bytes(int N, const int ncell[3], int n_rep) {
+	static const bool off = [] { const char *e = getenv("OXB_SORT_SMALL"); return e != nullptr && e[0] == '0'; }();
+	if(off || n_rep > 1 || ncell[0] <= 0 || N > 400000) return 0;
+	int bits = 1;
+	while((1 << bits) < std::max(ncell[0], std::max(ncell[1], ncell[2]))) bits++;
+	const long long nbins = 1ll << (3 * bits);
+	if(nbins > (1ll << 21) || nbins > 16ll * N + 4096) return 0; // very dilute boxes: the radix sort does not care about empty bins
+	return sizeof(int) * (size_t) (2 * nbins + 4096 + N);
+}
+
 void launch_hilbert_order(cudaStream_t s, const SortArgs &a) {
 	int tpb = 256, nb = (a.N + tpb - 1) / tpb;
+	if(a.small_tmp != nullptr) {
+		int bits = 1;
+		while((1 << bits) < std::max(a.ncell[0], std::max(a.ncell[1], a.ncell[2]))) bits++;
+		int nbins = 1 << (3 * bits);
+		static int max_blocks = 0;
+		if(max_blocks == 0) {
+			int per_sm = 0, dev = 0, sms = 0;
+			cudaGetDevice(&dev);
+			cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+			cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sort_small, 256, 0);
+			max_blocks = std::max(1, per_sm * sms);
+		}
+		int grid = std::min(max_blocks, std::min(4096, std::max(nb, (nbins + 255) / 256)));
+		int *hist = a.small_tmp, *block_sums = hist + nbins, *tmp = block_sums + 4096;
+		SortArgs aa = a;
+		void *args[] = { (void *) &aa, (void *) &bits, (void *) &nbins, (void *) &hist, (void *) &block_sums, (void *) &tmp };
+		cudaLaunchCooperativeKernel((const void *) k_sort_small, dim3(grid), dim3(256), args, 0, s);
+		return;
+	}
 	size_t tmp = a.cub_tmp_bytes;
 	int rep_bits = 0;
 	while((1 << rep_bits) < a.n_rep) rep_bits++;
