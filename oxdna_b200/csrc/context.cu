@@ -119,6 +119,8 @@ struct oxb_ctx {
 	cudaEvent_t ev_wait = nullptr;
 	bool defer_build_checks = true; // OXB_DEFER_BUILD_CHECK=0 restores one host synchronisation per rebuild
 	bool build_unchecked = false; // a list rebuild was launched without waiting for its overflow flags (oxb_run); the next batch checks
+	bool fold_hb = false;  // ... and hydrogen bonding / cross stacking in the tail of k_edge_near (OXB_FOLD_HB=0/1; default: systems below 300,000 particles)
+	bool fold_hb_set = false;
 	bool fold_tails = true; // coaxial stacking + FP64 excluded volume in the tails of the producing kernels (OXB_FOLD=0: separate launches)
 	bool dh_half = true; // Debye-Hueckel matrix with every pair in one row + partner atomics (OXB_DH_HALF=0: full matrix, no atomics)
 	bool fork_streams = true; // force pass on three concurrent streams (OXB_FORK=0/1 overrides the size-based default)
@@ -523,7 +525,8 @@ int launch_forces(oxb_ctx *c, int hw, bool clear, long long step) {
 		e.ex_list = c->ex_list; e.ex_counts = c->ex_counts; e.ex_bonded = c->ex_bonded; e.ex_seg = c->ex_seg;
 		e.refine = (c->precision == OXB_PRECISION_MIXED) ? 1 : 0;
 		e.dh_half = c->dh_half ? 1 : 0;
-		e.fold = c->fold_tails ? 1 : 0;
+		// bit 0: coaxial stacking + FP64 excluded volume in the tails of the producers; bit 1: hydrogen bonding / cross stacking too (no stage 2 launch)
+		e.fold = c->fold_tails ? (c->fold_hb ? 3 : 1) : 0;
 		e.n_seg = c->n_seg; e.hb_seg = c->hb_seg; e.cx_seg = c->cx_seg; e.cr_seg = c->cr_seg;
 		// ~1.7 items per particle in that list; aim at ~2 items per consumer thread
 		e.hb_split = (int) std::max<long long>(1, std::min<long long>(8, (17ll * c->N / 10 / c->n_seg + 64) / 128));
@@ -541,7 +544,7 @@ int launch_forces(oxb_ctx *c, int hw, bool clear, long long step) {
 		oxb::launch_edge_stage(s1, 4, c->mref(), c->boxf, e, c->flags, hw);
 		oxb::launch_edge_stage(m, 1, c->mref(), c->boxf, e, c->flags, hw);
 		if(fork) CU(cudaEventRecord(c->ev_near, m));
-		oxb::launch_edge_stage(m, 2, c->mref(), c->boxf, e, c->flags, hw);
+		if(!(e.fold & 2)) oxb::launch_edge_stage(m, 2, c->mref(), c->boxf, e, c->flags, hw);
 		if(c->n_ext > 0) {
 			oxb::launch_ext_forces(s1, c->n_ext, c->ext, c->slot_of, c->ipos[a], c->posd[a], c->boxf, step, c->cur_step, c->F[a], c->flags, hw);
 			c->launches += 1;
@@ -565,7 +568,7 @@ int launch_forces(oxb_ctx *c, int hw, bool clear, long long step) {
 			CU(cudaStreamWaitEvent(m, c->ev_join[0], 0));
 			CU(cudaStreamWaitEvent(m, c->ev_join[1], 0));
 		}
-		c->launches += e.fold ? 4 : (e.refine ? 6 : 5);
+		c->launches += (e.fold & 2) ? 3 : (e.fold ? 4 : (e.refine ? 6 : 5));
 	}
 	else {
 		if(c->force_cb != nullptr) { int rc = launch_forces_callback(c, step); if(rc) return rc; }
@@ -752,7 +755,7 @@ int batch_graph(oxb_ctx *c, int units, cudaGraphExec_t *out) {
 // stream launches.
 int launch_full_units(oxb_ctx *c, long long n, long long step0, int &epoch) {
 	const bool graphable = c->use_graphs && c->th.type != OXB_THERMOSTAT_BUSSI && c->force_cb == nullptr;
-	const int per_unit = (c->use_edge ? (c->fold_tails ? 4 : (c->precision == OXB_PRECISION_MIXED ? 6 : 5)) : 1) + (c->n_ext > 0 ? 1 : 0) + (c->n_ext_all > 0 ? 1 : 0) + (c->n_ext_com > 0 ? 1 : 0) + 1;
+	const int per_unit = (c->use_edge ? (c->fold_tails ? (c->fold_hb ? 3 : 4) : (c->precision == OXB_PRECISION_MIXED ? 6 : 5)) : 1) + (c->n_ext > 0 ? 1 : 0) + (c->n_ext_all > 0 ? 1 : 0) + (c->n_ext_com > 0 ? 1 : 0) + 1;
 	long long k = 0;
 	while(k < n) {
 		int chunk = 0;
@@ -824,6 +827,9 @@ int oxb_create(oxb_ctx **out, int device, int N, int precision) {
 		if(fo != nullptr) c->fold_tails = (fo[0] != '0');
 		const char *dhh = getenv("OXB_DH_HALF");
 		if(dhh != nullptr) c->dh_half = (dhh[0] != '0');
+		const char *fh = getenv("OXB_FOLD_HB");
+		if(fh != nullptr) { c->fold_hb = (fh[0] != '0'); c->fold_hb_set = true; }
+		if(!c->fold_hb_set) c->fold_hb = N < 300000;
 		const char *hs = getenv("OXB_HALF_SHELL");
 		if(hs != nullptr) c->half_shell_ok = (hs[0] != '0');
 		const char *f = getenv("OXB_FORK");

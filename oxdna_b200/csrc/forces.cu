@@ -137,6 +137,29 @@ __device__ __noinline__ void cxst_item(const typename MD::Params &M, const BoxF 
 	}
 }
 
+// one pair of a block's own hydrogen-bonding / cross-stacking segment, evaluated in the tail of the producing kernel (fold & 2: small
+// systems, where the consumer launch behind the producer costs more in latency than the separate grid gains in balance)
+template<class MD>
+__device__ __noinline__ void hbcr_item(const typename MD::Params &M, const BoxF &box, const int4 *__restrict__ ipos, const float4 *__restrict__ axf, int2 ed,
+		float4 *__restrict__ F, float4 *__restrict__ T) {
+	Particle P = load_particle<MD>(M, ipos, axf, ed.x);
+	Particle Q = load_particle<MD>(M, ipos, axf, ed.y);
+	const v3 r = min_image_fixed(box, P.ip, Q.ip);
+	PairAcc acc;
+	acc.clear();
+	float ehb = 0.f;
+	const v3 rb = r + (Q.ax.a1 - P.ax.a1) * M.base_a1;
+	const float rbm2 = dot(rb, rb);
+	const float en = MD::template hbcr<true>(M, rb, rbm2, P.ax, Q.ax, P.btype, Q.btype, MD::hb_in_range(M, rbm2, P.btype, Q.btype), MD::crst_in_range(M, rbm2), acc, ehb);
+	if(en != 0.f) {
+		const v3 tp = acc.torque_p(P.ax, P.back), tq = acc.torque_q(Q.ax, Q.back);
+		atomic_add4(F + ed.x, -acc.F.x, -acc.F.y, -acc.F.z, en);
+		atomic_add4(T + ed.x, tp.x, tp.y, tp.z, ehb);
+		atomic_add4(F + ed.y, acc.F.x, acc.F.y, acc.F.z, en);
+		atomic_add4(T + ed.y, tq.x, tq.y, tq.z, ehb);
+	}
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // Particle-centric: one thread per particle, every listed pair evaluated from both ends, no atomics, deterministic.
 // ------------------------------------------------------------------------------------------------------------
@@ -450,6 +473,11 @@ __global__ void __launch_bounds__(128, OXB_MB_NEAR) k_edge_near(const __grid_con
 		for(int k = threadIdx.x; k < nex; k += blockDim.x) {
 			const int4 it = ex_list[k];
 			excl_double_item<MD>(M, box, posd, quatd, it.x, it.y, it.z, F, T);
+		}
+		if(fold & 2) {
+			// ... and its hydrogen-bonding / cross-stacking pairs: front third of the segment, then the cross-stacking-only pairs behind it
+			const int n_front = min(s_cnt[0], hb_seg / 3), n_hb = n_front + min(s_cnt[2], hb_seg - hb_seg / 3);
+			for(int k = threadIdx.x; k < n_hb; k += blockDim.x) hbcr_item<MD>(M, box, ipos, axf, hb_list[(k >= n_front) ? hb_seg / 3 + (k - n_front) : k], F, T);
 		}
 		return;
 	}

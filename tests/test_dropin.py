@@ -401,28 +401,31 @@ print_conf_interval = 1e5
 print_energy_every = 1e3
 time_scale = linear
 external_forces = 0
+seed = 20261017
 """
 
 
 @pytest.mark.gpu
 @needs_binaries
-@pytest.mark.parametrize("name,T,checks,use_edge,dev_obs", [
-    ("dsdna8", "20C", [(2, -1.37970256144, 0.15)], 1, 0),
-    ("ssdna15", "300K", [(2, -0.700783241758, 0.26), (3, 0.30, 0.015)], 0, 1)])
-def test_reference_quick_md_tests_on_the_gpu_backend(tmp_path, name, T, checks, use_edge, dev_obs):
+@pytest.mark.parametrize("name,T,checks,use_edge,dev_obs,steps", [
+    ("dsdna8", "20C", [(2, -1.37970256144, 0.15)], 1, 0, 400000),
+    ("ssdna15", "300K", [(2, -0.700783241758, 0.26), (3, 0.30, 0.015)], 0, 1, 1000000)])
+def test_reference_quick_md_tests_on_the_gpu_backend(tmp_path, name, T, checks, use_edge, dev_obs, steps):
     """The reference's OWN statistical MD tests (test/DNA/DSDNA8/MD, test/DNA/SSDNA15/MD: quick_input + quick_compare, ColumnAverage of
     test/TestSuite.py:141-196) with `backend = CUDA`: stock input keys, first-generation oxDNA, john thermostat, the expected column
-    averages and tolerances are the reference's.  Shortened from 1e6 to 4e5 steps (the tolerance is 10-30 standard errors wide)."""
+    averages and tolerances are the reference's.  The duplex is shortened from 1e6 to 4e5 steps (its tolerance is tens of standard errors
+    wide); the 15-nt single strand folds and unfolds transient hairpins, so it keeps the reference's 1e6 steps (at 4e5 steps and a
+    time-based seed one run in five or so lands outside the reference's tolerance) and both runs carry a fixed seed."""
     gold = os.path.join(ROOT, "tests", "golden", "quick_md")
     d = str(tmp_path)
     shutil.copy(os.path.join(gold, name + ".top"), os.path.join(d, name + ".top"))
     shutil.copy(os.path.join(gold, name + "_init.dat"), os.path.join(d, "init.dat"))
     with open(os.path.join(d, "input"), "w") as f:
-        f.write(QUICK_INPUT.format(use_edge=use_edge, dev_obs=dev_obs, steps=400000, T=T, top=name + ".top", conf="init.dat"))
+        f.write(QUICK_INPUT.format(use_edge=use_edge, dev_obs=dev_obs, steps=steps, T=T, top=name + ".top", conf="init.dat"))
     p = subprocess.run([OURS, "input"], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-2000:]
     e = energies(d)
-    assert e.shape[0] >= 400
+    assert e.shape[0] >= steps // 1000
     for col, want, tol in checks:
         avg = e[:, col - 1].mean()
         assert want - tol <= avg <= want + tol, (name, col, avg, want, tol)
