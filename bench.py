@@ -243,6 +243,21 @@ def run_ref_cuda(sysm, workload_name, steps_a, steps_b, state, quick=False):
     if best and os.path.exists(R.BIN_NOSYNC):
         ns = R.time_reference_cuda(top, conf, N, steps_a, steps_b, [(best["use_edge"], best["CUDA_sort_every"])], binary=R.BIN_NOSYNC, **kw)
         out["no_timer_sync"] = {"value": ns["best"]["value"] if ns["best"] else None, "best": ns["best"], "method": ns["method"]}
+        # MD_CUDABackend::sim_step reads the pinned flag _d_are_lists_old[0] right behind the launch of its first-step kernel
+        # (src/CUDA/Backends/MD_CUDABackend.cu:570-581); the only thing that orders the read behind the kernel is the cudaDeviceSynchronize
+        # of the timer that is paused in between (src/Utilities/Timings.cpp:53-61).  Without it the host reads a stale flag and the lists
+        # are rebuilt late: such a run is faster and WRONG (pairs enter the cutoff unlisted).  The figure is kept as an upper bound only.
+        try:
+            ra, rb = ns["best"]["list_rebuild_every_md_steps"], best["list_rebuild_every_md_steps"]
+            if ra > 2.0 * rb:
+                out["no_timer_sync"]["valid"] = False
+                out["no_timer_sync"]["note"] = (f"lists rebuilt every {ra:.0f} steps instead of every {rb:.1f}: without the timers' cudaDeviceSynchronize the reference "
+                                                "reads its lists-are-old flag before the kernel has written it (MD_CUDABackend.cu:570-581) -- an upper bound from an "
+                                                "incorrect run, not a comparator")
+            else:
+                out["no_timer_sync"]["valid"] = True
+        except Exception:
+            pass
     return out
 
 

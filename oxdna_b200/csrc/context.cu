@@ -684,6 +684,18 @@ int ensure_forces(oxb_ctx *c) {
 	return 0;
 }
 
+// Force passes launched outside oxb_run (energies, force read-backs, barostat trials) must not swallow a work-list segment overflow: the
+// pass has dropped interactions and the number would be silently wrong (a barostat trial could accept on it).  One 64-byte read-back
+// behind the synchronisation these callers do anyway.  A FENE bond out of range is NOT an error here: the reference's CPU energy of such
+// a state is a huge number that a barostat trial simply rejects; oxb_run reports it for states it would integrate.
+int check_force_flags(oxb_ctx *c, const char *what) {
+	CU(cudaMemcpyAsync(c->h_flags, c->flags, sizeof(int) * OXB_FLAG_WORDS, cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	if(c->h_flags[OXB_FLAG_ERROR] & OXB_ERR_EDGE_OVERFLOW)
+		return fail(c, 8, "%s: a work-list segment of the edge pipeline overflowed (local density far above the average): interactions were dropped", what);
+	return 0;
+}
+
 // One unit of the hot loop with launch index `epoch`: force pass for the pending positions, then ONE integrate launch doing
 // the second half-kick + thermostat of step s and (with_first) the first half-kick + drift + rotation of step s + 1.
 // step < 0: graph capture, the kernels take the step index from the device counter.
@@ -1333,8 +1345,7 @@ int oxb_compute_forces(oxb_ctx *c) {
 	c->forces_valid = false;
 	int rc = ensure_forces(c);
 	if(rc) return rc;
-	CU(cudaStreamSynchronize(c->stream));
-	return 0;
+	return check_force_flags(c, "compute_forces");
 }
 
 int oxb_first_step(oxb_ctx *c) {
@@ -1544,7 +1555,8 @@ int oxb_energy(oxb_ctx *c, double *U, double *K) {
 	c->launches += 3;
 	CU(cudaMemcpyAsync(c->h_scalars, c->d_energy, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
 	CU(cudaMemcpyAsync(&hs, c->sums, sizeof(KinSums), cudaMemcpyDeviceToHost, c->stream));
-	CU(cudaStreamSynchronize(c->stream));
+	rc = check_force_flags(c, "energy");
+	if(rc) return rc;
 	if(U) *U = 0.5 * c->h_scalars[0];
 	if(K) *K = 0.5 * (hs.v2 + hs.L2);
 	return 0;

@@ -190,6 +190,8 @@ __global__ void __launch_bounds__(128) k_build_neigh(oxb::ListArgs a, const int 
 	// phase 3: classification of the row just written (near edge? Debye-Hueckel row?).  Kept out of the candidate loop: there nearly
 	// every warp iteration has a hit on SOME lane, so the ~100 instructions of this block ran for every candidate (57 per particle)
 	// with a few lanes active; here the lanes walk rows of similar length together (ncu r02f: 6,900 warp instructions per warp before)
+	// (sharing the rows between lanes l and 31 - l as k_dh_particle does was measured here too: 0.44 against 0.39 ms at 1M nt -- the extra
+	// selects and registers cost more than the balance gains, gpurun_out r2r)
 	const int nrow = min(count, a.max_neigh);
 	for(int k = 0; k < nrow; k++) {
 		const int m = a.nbr[(size_t) k * a.stride + i]; // this thread's own store (plain load, program order)

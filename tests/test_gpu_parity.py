@@ -1018,3 +1018,38 @@ def test_meta_coordination_bias_vs_oracle(mode, extra):
         assert np.isfinite(sim.ctx.energy()[0]) and sim.ctx.stats()["error_flags"] == 0
     finally:
         sim.close()
+
+
+def test_one_launch_ordering_of_small_systems_equals_the_radix_sort(tmp_path):
+    """The cooperative counting sort that orders small systems (csrc/sort.cu: k_sort_small) must produce the permutation of the stable radix
+    sort it replaces (keys = Hilbert index of the list builder's cells, ties in the order of the old slots; src/CUDA/CUDA_sort.cu:106-193 is
+    the reference's version of the step).  The switch is read once per process, so the radix run happens in a child process."""
+    import subprocess
+    import sys
+    script = r'''
+import sys, numpy as np
+sys.path.insert(0, %r)
+from conftest import load_golden
+from oxdna_b200.sim import Simulation
+g = load_golden("lattice27_dense")
+inp = dict(backend="CUDA", interaction_type="DNA2", T=str(g["T"]), salt_concentration=float(g["salt"]), dt=0.003, verlet_skin=0.05, thermostat="no",
+           CUDA_sort_every=1, use_edge=0, seed=11)
+sim = Simulation(inp, dict(btype=g["btype"], n3=g["n3"], n5=g["n5"], strand=g["strand"]), dict(box=g["box"], pos=g["pos"], a1=g["a1"], a3=g["a3"], vel=g["vel"], L=g["L"]))
+sim.run(40)   # several re-sorts of a moving system
+import torch
+v = sim.ctx.device_views()
+class D:
+    def __init__(s, p, n): s.__cuda_array_interface__ = dict(shape=(n, 4), typestr="<f4", data=(int(p), False), version=3, strides=None)
+w = torch.as_tensor(D(v["poss"], len(g["pos"])), device="cuda")[:, 3].contiguous().cpu().numpy().view(np.int32) & 0x003FFFFF
+assert sim.ctx.stats()["n_sorts"] >= 2
+np.save(sys.argv[1], w)
+''' % (os.path.join(os.path.dirname(os.path.abspath(__file__))),)
+    out = {}
+    for tag, env in (("small", {}), ("radix", {"OXB_SORT_SMALL": "0"})):
+        f = str(tmp_path / (tag + ".npy"))
+        p = subprocess.run([sys.executable, "-c", script, f], env=dict(os.environ, **env), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+        assert p.returncode == 0, p.stdout[-2000:]
+        out[tag] = np.load(f)
+    assert sorted(out["small"].tolist()) == list(range(len(out["small"])))
+    # (particle-centric forces: the two 40-step trajectories are bit-identical, so the orders must be too)
+    assert np.array_equal(out["small"], out["radix"])
