@@ -271,8 +271,11 @@ int alloc_lists(oxb_ctx *c, int max_neigh) {
 	// (hydrogen-bonding pairs ~0.5 N, cross-stacking-only pairs ~1.2 N, coaxial pairs << N) plus a floor for tiny systems
 	// ~3.3 near edges per particle, one producer block per 128 edges up to 16 blocks per SM (grid-stride beyond that)
 	{
-		const char *e = getenv("OXB_PB_NEAR"); // blocks per SM of the near-edge kernel and of its work-list segments (default 16)
-		const int pb = (e != nullptr && atoi(e) > 0) ? atoi(e) : 16;
+		// blocks per SM of the near-edge kernel and of its work-list segments: 8 = what an SM holds of this kernel (64 registers x 128
+		// threads), i.e. ONE full wave that strides over the edges, no tail wave.  Sweep on B200 (gpurun_out r2t / r2u): at 81,920 nt 8 gives
+		// 1.58e9 particle-steps/s against 1.48e9 for 10, 12 and 16 and 1.44e9 for 4; neutral at 1M nt
+		const char *e = getenv("OXB_PB_NEAR");
+		const int pb = (e != nullptr && atoi(e) > 0) ? atoi(e) : 8;
 		c->n_seg = c->use_edge ? (int) std::max<long long>(1, std::min<long long>((long long) pb * c->n_sm, (33ll * N / 10 + 127) / 128)) : 1;
 	}
 	c->hb_seg = c->use_edge ? (int) (6ll * N / c->n_seg) + 128 : 1;

@@ -33,10 +33,10 @@ for rep in sorted(f for f in os.listdir(os.path.join(root, "gpurun_out")) if f.e
                 lines.append(f"  {m} = {r[idx[m]]} {units[idx[m]]}")
     lines.append("")
 
-lp = os.path.join(root, "gpurun_out", f"launches_{tag}.csv")
-if os.path.exists(lp):
+import glob
+for lp in sorted(glob.glob(os.path.join(root, "gpurun_out", f"launches_{tag}.csv")) + glob.glob(os.path.join(root, "gpurun_out", f"launches_*_{tag}.csv"))):
     agg = {}
-    with open(lp) as f:
+    with open(lp, errors="ignore") as f:
         rd = csv.reader(l for l in f if l.startswith('"'))
         hdr = next(rd)
         ik, iv = hdr.index("Kernel Name"), hdr.index("Metric Value")
@@ -53,9 +53,13 @@ if os.path.exists(lp):
             n, t = agg.get(name, (0, 0.0))
             agg[name] = (n + 1, t + v)
     tot = sum(t for _, t in agg.values())
-    lines.append(f"## launches_{tag}.csv: per-kernel device time (gpu__time_duration.sum, ns; cold-cache, serialised => compare shares)")
+    lines.append(f"## {os.path.basename(lp)}: per-kernel device time (gpu__time_duration.sum, ns; cold-cache, serialised => compare shares)")
     for name, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         lines.append(f"  {name:60s} launches={n:5d} mean_ns={t / n:10.0f} share={100 * t / tot:5.1f}%")
+    lines.append("")
+    # tracked copy of the launch list itself
+    import shutil
+    shutil.copy(lp, os.path.join(out, os.path.basename(lp)))
 with open(os.path.join(out, f"summary_{tag}.txt"), "w") as f:
     f.write("\n".join(lines) + "\n")
 print("\n".join(lines[-25:]))
