@@ -79,6 +79,12 @@ __device__ __forceinline__ v3 load_a1(const float4 *__restrict__ axf, int i) {
 }
 #endif
 
+// ---- classes of a near edge: which families of site pairs can come into range before the next list rebuild (decided by the list builder
+// with the same 2 x skin padding that selects the near edges; the near-edge kernel evaluates only the flagged families).  In the edge list
+// and -- half-shell builds only, where the matrix is private to the edge pipeline -- in the Verlet matrix entry the class sits above the
+// 22-bit slot index.
+enum : int { OXB_CLS_BB = 1, OXB_CLS_EB = 2, OXB_CLS_HBCR = 4, OXB_CLS_ST = 8, OXB_CLS_BK = 16, OXB_CLS_ALL = 31, OXB_CLS_SHIFT = 24, OXB_SLOT_MASK = 0x003FFFFF };
+
 // ---- packed particle word: (btype << 22) | original index, as in the reference (MD_CUDABackend.cu:243-254)
 __host__ __device__ __forceinline__ int pack_word(int btype, int index) { return (btype << 22) | (index & 0x003FFFFF); }
 __host__ __device__ __forceinline__ int word_btype(int w) { return w >> 22; }

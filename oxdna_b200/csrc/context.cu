@@ -314,7 +314,8 @@ oxb::ListArgs list_args(oxb_ctx *c) {
 		double pad = 2. * c->skin + 0.02;
 		auto sq = [](double x) { return (float) (x * x); };
 		a.r2_bb = sq(M.excl[0].rc + pad);
-		a.r2_base = sq(std::max(std::max((double) M.hb.rchigh, (double) M.crst.rchigh), (double) M.excl[1].rc) + pad);
+		a.r2_base = sq(std::max((double) M.hb.rchigh, (double) M.crst.rchigh) + pad);
+		a.r2_eb = sq((double) M.excl[1].rc + pad);
 		a.r2_bk = sq(std::max((double) M.excl[2].rc, (double) M.excl[3].rc) + pad);
 		a.r2_stack = sq((double) M.cxst.rchigh + pad);
 	} a.dh_nbr = c->dh_nbr; a.dh_nnbr = c->dh_nnbr; a.max_dh = c->max_dh;
@@ -1736,7 +1737,7 @@ int oxb_get_pairs(oxb_ctx *c, int *pairs, long long max_pairs, long long *n_pair
 	for(int s = 0; s < N; s++) {
 		int i = word_index(hi[s].w);
 		for(int k = 0; k < hn[s]; k++) {
-			int j = word_index(hi[hm[(size_t) k * N + s]].w);
+			int j = word_index(hi[hm[(size_t) k * N + s] & OXB_SLOT_MASK].w); // (half-shell entries carry the near-edge class above the slot)
 			// full matrix: every pair shows up from both ends, keep it once; half matrix: every entry is a pair
 			if(i < j || c->nbr_is_half) {
 				if(pairs != nullptr && n < max_pairs) { pairs[2 * n] = std::min(i, j); pairs[2 * n + 1] = std::max(i, j); }

@@ -440,6 +440,29 @@ template<class PB> OXB_HD float dna2_excl(const PB &M, v3 r, v3 rbb, v3 rb, cons
 	return E;
 }
 
+// the same with the families the list builder has ruled out until the next rebuild skipped (cls: OXB_CLS_* bits of the near edge)
+template<class PB> OXB_HD float dna2_excl_cls(const PB &M, int cls, v3 r, v3 rbb, v3 rb, const Axes &A, const Axes &B, v3 pback, v3 qback, PairAcc &acc) {
+	const float cb = M.base_a1;
+	float s, E = 0.f, en;
+	if(cls & OXB_CLS_BB) {
+		en = excl_s(M.excl[0], M.excl_eps, rbb, s);
+		if(en != 0.f) { E += en; acc.site_kk(rbb * s); excl_fix(acc, M.excl[0], M.excl_eps, rbb, s, OXB_SITE_KK, cb); }
+	}
+	if(cls & OXB_CLS_EB) {
+		en = excl_s(M.excl[1], M.excl_eps, rb, s);
+		if(en != 0.f) { E += en; acc.site_aa(rb * s, cb, cb); excl_fix(acc, M.excl[1], M.excl_eps, rb, s, OXB_SITE_AA, cb); }
+	}
+	if(cls & OXB_CLS_BK) {
+		v3 d = r + B.a1 * cb - pback; // back(p) - base(q)
+		en = excl_s(M.excl[3], M.excl_eps, d, s);
+		if(en != 0.f) { E += en; acc.site_ka(d * s, cb); excl_fix(acc, M.excl[3], M.excl_eps, d, s, OXB_SITE_KA, cb); }
+		d = r + qback - A.a1 * cb; // base(p) - back(q)
+		en = excl_s(M.excl[2], M.excl_eps, d, s);
+		if(en != 0.f) { E += en; acc.site_ak(d * s, cb); excl_fix(acc, M.excl[2], M.excl_eps, d, s, OXB_SITE_AK, cb); }
+	}
+	return E;
+}
+
 // which of the four site pairs are inside their excluded-volume range (bit = OXB_SITE_*)
 template<class PB> OXB_HD int dna2_excl_mask(const PB &M, v3 r, v3 rbb, v3 rb, const Axes &A, const Axes &B, v3 pback, v3 qback) {
 	const float cb = M.base_a1;

@@ -397,6 +397,9 @@ __global__ void __launch_bounds__(128, OXB_MB_NEAR) k_edge_near(const __grid_con
 		int eidx = base + lane;
 		bool valid = eidx < ne;
 		int2 ed = valid ? __ldg(edges + eidx) : make_int2(-1 - (int) lane, -1);
+		// the list builder's verdict on which families of site pairs can come into range before the next rebuild (common.cuh, OXB_CLS_*)
+		const int cls = valid ? (int) ((unsigned) ed.y >> OXB_CLS_SHIFT) : 0;
+		if(valid) ed.y &= OXB_SLOT_MASK;
 		float v[6] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
 		float ve = 0.f;
 		bool want_hb = false, want_cx = false, hb_capable = false;
@@ -411,7 +414,7 @@ __global__ void __launch_bounds__(128, OXB_MB_NEAR) k_edge_near(const __grid_con
 				acc.clear();
 				// common path unchanged: the FP32 evaluation tells whether any site pair is in range at all.  If one is (a few per
 				// cent of the edges) and the refinement is on, the pair is parked for k_excl_fix and the FP32 result is dropped
-				float en = dna2_excl(M, r, rbb, rb, P.ax, Q.ax, P.back, Q.back, acc);
+				float en = (cls & (OXB_CLS_BB | OXB_CLS_EB | OXB_CLS_BK)) ? dna2_excl_cls(M, cls, r, rbb, rb, P.ax, Q.ax, P.back, Q.back, acc) : 0.f;
 				if(en != 0.f && refine) {
 					const int slot = atomicAdd(&s_nex, 1);
 					if(slot < ex_seg) {
@@ -430,7 +433,8 @@ __global__ void __launch_bounds__(128, OXB_MB_NEAR) k_edge_near(const __grid_con
 				// radial range first, then the cosine windows of every angular factor: only pairs whose product can be
 				// non-zero reach the heavy kernels
 				float rbm2 = dot(rb, rb);
-				bool hb_on = MD::hb_in_range(M, rbm2, P.btype, Q.btype), cr_on = MD::crst_in_range(M, rbm2);
+				const bool base_on = (cls & OXB_CLS_HBCR) != 0;
+				bool hb_on = base_on && MD::hb_in_range(M, rbm2, P.btype, Q.btype), cr_on = base_on && MD::crst_in_range(M, rbm2);
 				if(hb_on || cr_on) {
 					// pairs that can hydrogen-bond go to the full kernel, the (more numerous) cross-stacking-only pairs to a
 					// specialised one: both lists are warp-uniform
@@ -439,9 +443,11 @@ __global__ void __launch_bounds__(128, OXB_MB_NEAR) k_edge_near(const __grid_con
 					want_hb = MD::hbcr_may_act(M, rb * rsqrtf(rbm2), P.ax, Q.ax, hb_on, cr_on);
 					hb_capable = hb_on;
 				}
-				v3 rs = r + (Q.ax.a1 - P.ax.a1) * M.stack_a1;
-				float rs2 = dot(rs, rs);
-				if(MD::cxst_in_range(M, rs2)) want_cx = MD::cxst_may_act(M, rs * rsqrtf(rs2), P.ax, Q.ax);
+				if(cls & OXB_CLS_ST) {
+					v3 rs = r + (Q.ax.a1 - P.ax.a1) * M.stack_a1;
+					float rs2 = dot(rs, rs);
+					if(MD::cxst_in_range(M, rs2)) want_cx = MD::cxst_may_act(M, rs * rsqrtf(rs2), P.ax, Q.ax);
+				}
 			}
 		}
 		// the dense list is kept sorted by kind at no cost: pairs that can hydrogen-bond fill the first third of the block's segment,
@@ -628,7 +634,7 @@ __global__ void __launch_bounds__(128) k_energy_split(const __grid_constant__ ty
 		}
 		int nn = __ldg(nnbr + i);
 		for(int k = 0; k < nn; k++) {
-			int j = __ldg(nbr + (size_t) k * stride + i);
+			int j = __ldg(nbr + (size_t) k * stride + i) & OXB_SLOT_MASK; // (half-shell entries carry the near-edge class above the slot)
 			if(j < i) continue;
 			Particle Q = load_particle<MD>(M, ipos, axf, j);
 			v3 r = min_image_fixed(box, P.ip, Q.ip);

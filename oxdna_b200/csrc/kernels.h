@@ -216,7 +216,9 @@ struct ListArgs {
 	double4 *ref_pos, *ref_vel, *ref_L; // the FP64 state arrays whose .w lanes take the staleness references (common.cuh, pack_ref)
 	const float4 *axf;
 	float base_a1, stack_a1;
-	float r2_bb, r2_base, r2_bk, r2_stack; // squared site-site selection radii of the near-edge list (range + 2 skin + margin)
+	// squared site-site selection radii of the near-edge list (range + 2 skin + margin): backbone-backbone and base-base excluded volume,
+	// base-base hydrogen bonding / cross stacking (r2_base), base-backbone excluded volume, stack-stack coaxial stacking
+	float r2_bb, r2_eb, r2_base, r2_bk, r2_stack;
 	int *dh_nbr, *dh_nnbr;
 	int max_dh;
 	bool dh_half;      // each Debye-Hueckel pair appears in one row only (see k_dh_particle)

@@ -72,18 +72,22 @@ __device__ __forceinline__ bool within_exact(double4 p, double4 q, double Lx, do
 // Site-based selection of the "near" edges: a pair can feel something other than Debye-Hueckel before the next rebuild
 // only if one of its site-site distances is within the range of the corresponding term plus twice the skin (every site
 // -- centre, backbone, base and, being between centre and base, stack -- moves less than `skin` between rebuilds).
-__device__ __forceinline__ bool near_pair(const oxb::ListArgs &a, v3 r, v3 a1p, v3 a1q, v3 bkp, v3 bkq) {
+// Returns the CLASS of the pair: one bit per family of site pairs that can come into range (OXB_CLS_*, common.cuh); 0 = not a near edge.
+__device__ __forceinline__ int near_pair(const oxb::ListArgs &a, v3 r, v3 a1p, v3 a1q, v3 bkp, v3 bkq) {
+	int cls = 0;
 	v3 rbb = r + bkq - bkp;
-	if(dot(rbb, rbb) < a.r2_bb) return true;
+	if(dot(rbb, rbb) < a.r2_bb) cls |= OXB_CLS_BB;
 	v3 da = a1q - a1p;
 	v3 rb = r + da * a.base_a1;
-	if(dot(rb, rb) < a.r2_base) return true;
+	const float rb2 = dot(rb, rb);
+	if(rb2 < a.r2_eb) cls |= OXB_CLS_EB;
+	if(rb2 < a.r2_base) cls |= OXB_CLS_HBCR;
 	v3 rs = r + da * a.stack_a1;
-	if(dot(rs, rs) < a.r2_stack) return true;
+	if(dot(rs, rs) < a.r2_stack) cls |= OXB_CLS_ST;
 	v3 d1 = r + bkq - a1p * a.base_a1; // base(p) - back(q)
-	if(dot(d1, d1) < a.r2_bk) return true;
 	v3 d2 = r + a1q * a.base_a1 - bkp; // back(p) - base(q)
-	return dot(d2, d2) < a.r2_bk;
+	if(dot(d1, d1) < a.r2_bk || dot(d2, d2) < a.r2_bk) cls |= OXB_CLS_BK;
+	return cls;
 }
 
 // One thread per particle: visit the 27 surrounding cells, keep non-bonded particles closer than rv.
@@ -202,11 +206,14 @@ __global__ void __launch_bounds__(128) k_build_neigh(oxb::ListArgs a, const int 
 		// Debye-Hueckel acts between backbone sites: keep m if the sites can come within dh_rc before the
 		// next rebuild (both the centre and the backbone site of every particle move less than `skin`)
 		const v3 db = min_image_fixed(a.boxf, ib, ibm);
-		if(m > i && d2 < a.rnear2 && near_pair(a, d, a1p, load_a1(a.axf, m), bkp, min_image_fixed(a.boxf, ipm, ibm))) {
+		const int cls = (m > i && d2 < a.rnear2) ? near_pair(a, d, a1p, load_a1(a.axf, m), bkp, min_image_fixed(a.boxf, ipm, ibm)) : 0;
+		if(cls != 0) {
 			higher_near++;
 			if(k < 64) mask0 |= 1ull << k;
 			else if(k < 128) mask1 |= 1ull << (k - 64);
 			else mask_overflow = true;
+			// half shell: the matrix is private to the edge pipeline, the entry carries the class to k_fill_edges
+			if(a.half_shell) a.nbr[(size_t) k * a.stride + i] = m | (cls << OXB_CLS_SHIFT);
 		}
 		if(dot(db, db) < a.rdh2) {
 			// dh_half: every Debye-Hueckel pair is kept by ONE of its particles (by the parity of i + m, so that rows stay balanced); the
@@ -339,10 +346,12 @@ __global__ void __launch_bounds__(256, 4) k_build_neigh_g(oxb::ListArgs a, const
 		bool is_dh = false;
 		if(in) {
 			const int row = count + __popc(bal & lt);
-			if(row < a.max_neigh) a.nbr[(size_t) row * a.stride + i] = m;
 			const int4 ibm = __ldg(a.iback + m);
 			const v3 db = min_image_fixed(a.boxf, ib, ibm);
-			if(m > i && d2 < a.rnear2 && near_pair(a, d, a1p, load_a1(a.axf, m), bkp, min_image_fixed(a.boxf, ipm, ibm))) {
+			const int cls = (m > i && d2 < a.rnear2) ? near_pair(a, d, a1p, load_a1(a.axf, m), bkp, min_image_fixed(a.boxf, ipm, ibm)) : 0;
+			// (half shell: the matrix is private to the edge pipeline, the entry carries the near-edge class to k_fill_edges)
+			if(row < a.max_neigh) a.nbr[(size_t) row * a.stride + i] = a.half_shell ? (m | (cls << OXB_CLS_SHIFT)) : m;
+			if(cls != 0) {
 				higher_near++;
 				// rows that overflow max_neigh are rebuilt after the matrix has grown: never flag an entry that was not written
 				if(row >= a.max_neigh) mask_overflow = true;
@@ -403,19 +412,22 @@ __global__ void __launch_bounds__(128) k_fill_edges(oxb::ListArgs a) {
 	int off = a.edge_offsets[i];
 	const int nn = a.nnbr[i];
 	ulonglong2 mk = a.near_mask[i];
+	// edge = (from, to | class << 24).  Half-shell builds left the class in the matrix entry; a full (public, reference-layout) matrix holds
+	// plain slots and its edges are marked with every class
+	const int cls_all = a.half_shell ? 0 : (OXB_CLS_ALL << OXB_CLS_SHIFT);
 	if(!(mk.y >> 63)) {
 		unsigned long long w = mk.x;
 		while(w) {
 			int k = __ffsll((long long) w) - 1;
 			w &= w - 1;
-			if(off < a.edge_capacity) a.edges[off] = make_int2(i, a.nbr[(size_t) k * a.stride + i]);
+			if(off < a.edge_capacity) a.edges[off] = make_int2(i, a.nbr[(size_t) k * a.stride + i] | cls_all);
 			off++;
 		}
 		w = mk.y;
 		while(w) {
 			int k = 64 + __ffsll((long long) w) - 1;
 			w &= w - 1;
-			if(off < a.edge_capacity) a.edges[off] = make_int2(i, a.nbr[(size_t) k * a.stride + i]);
+			if(off < a.edge_capacity) a.edges[off] = make_int2(i, a.nbr[(size_t) k * a.stride + i] | cls_all);
 			off++;
 		}
 	}
@@ -426,12 +438,13 @@ __global__ void __launch_bounds__(128) k_fill_edges(oxb::ListArgs a) {
 		const v3 a1p = load_a1(a.axf, i);
 		const v3 bkp = min_image_fixed(a.boxf, ip, ib);
 		for(int k = 0; k < nn; k++) {
-			int m = a.nbr[(size_t) k * a.stride + i];
+			int m = a.nbr[(size_t) k * a.stride + i] & OXB_SLOT_MASK;
 			if(m > i) {
 				const int4 ipm = __ldg(a.ipos + m);
 				v3 d = min_image_fixed(a.boxf, ip, ipm);
-				if(dot(d, d) < a.rnear2 && near_pair(a, d, a1p, load_a1(a.axf, m), bkp, min_image_fixed(a.boxf, ipm, __ldg(a.iback + m)))) {
-					if(off < a.edge_capacity) a.edges[off] = make_int2(i, m);
+				const int cls = (dot(d, d) < a.rnear2) ? near_pair(a, d, a1p, load_a1(a.axf, m), bkp, min_image_fixed(a.boxf, ipm, __ldg(a.iback + m))) : 0;
+				if(cls != 0) {
+					if(off < a.edge_capacity) a.edges[off] = make_int2(i, m | (cls << OXB_CLS_SHIFT));
 					off++;
 				}
 			}
