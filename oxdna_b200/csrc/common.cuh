@@ -16,6 +16,8 @@ enum : int {
 	OXB_ERR_FENE_BROKEN = 2,    // a backbone bond left the FENE range
 	OXB_ERR_EDGE_OVERFLOW = 4,
 	OXB_ERR_NAN = 8,
+	OXB_ERR_SEG_OVERFLOW = 16,  // a work-list segment of the edge pipeline overflowed during a force pass: the pass is incomplete, the
+	                            // integrator launch behind it turns into a halt and the host grows the segments and repeats the pass
 };
 
 struct v3 {

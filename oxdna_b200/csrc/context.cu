@@ -119,6 +119,8 @@ struct oxb_ctx {
 	cudaEvent_t ev_wait = nullptr;
 	bool defer_build_checks = true; // OXB_DEFER_BUILD_CHECK=0 restores one host synchronisation per rebuild
 	bool build_unchecked = false; // a list rebuild was launched without waiting for its overflow flags (oxb_run); the next batch checks
+	double seg_scale = 1.;   // growth factor of the work-list segments (doubled whenever one overflows; OXB_SEG_SCALE sets the start value)
+	bool dirty_acc = false;  // F / T / Fb hold the partial sums of an incomplete force pass: clear them before the next one
 	bool fold_hb = false;  // ... and hydrogen bonding / cross stacking in the tail of k_edge_near (OXB_FOLD_HB=0/1; default: systems below 300,000 particles)
 	bool fold_hb_set = false;
 	bool fold_tails = true; // coaxial stacking + FP64 excluded volume in the tails of the producing kernels (OXB_FOLD=0: separate launches)
@@ -278,11 +280,11 @@ int alloc_lists(oxb_ctx *c, int max_neigh) {
 		const int pb = (e != nullptr && atoi(e) > 0) ? atoi(e) : 8;
 		c->n_seg = c->use_edge ? (int) std::max<long long>(1, std::min<long long>((long long) pb * c->n_sm, (33ll * N / 10 + 127) / 128)) : 1;
 	}
-	c->hb_seg = c->use_edge ? (int) (6ll * N / c->n_seg) + 128 : 1;
+	c->hb_seg = c->use_edge ? (int) (c->seg_scale * (double) (6ll * N / c->n_seg + 128)) + 3 : 1;
 	c->cr_seg = 1; // the cross-stacking-only list is not produced (see forces.cu)
-	c->cx_seg = c->use_edge ? (int) (2ll * N / c->n_seg) + 64 : 1;
+	c->cx_seg = c->use_edge ? (int) (c->seg_scale * (double) (2ll * N / c->n_seg + 64)) + 1 : 1;
 	CU(dalloc(&c->hb_list, (size_t) c->hb_seg * c->n_seg)); CU(dalloc(&c->cx_list, (size_t) c->cx_seg * c->n_seg));
-	c->ex_seg = c->use_edge ? (int) (2ll * N / c->n_seg) + 64 : 1;
+	c->ex_seg = c->use_edge ? (int) (c->seg_scale * (double) (2ll * N / c->n_seg + 64)) + 1 : 1;
 	CU(dalloc(&c->ex_list, (size_t) c->ex_seg * c->n_seg)); CU(dalloc(&c->ex_counts, (size_t) c->n_seg)); CU(dalloc(&c->ex_bonded, (size_t) N));
 	CU(cudaMemset(c->ex_counts, 0, sizeof(int) * (size_t) c->n_seg));
 	CU(cudaMemset(c->ex_bonded, 0, sizeof(int) * (size_t) N));
@@ -684,20 +686,47 @@ int ensure_forces(oxb_ctx *c) {
 		if(rc) return rc;
 		CU(cudaGetLastError());
 		c->forces_valid = true;
+		c->dirty_acc = false; // (the pass started from cleared accumulators)
 	}
 	return 0;
 }
 
-// Force passes launched outside oxb_run (energies, force read-backs, barostat trials) must not swallow a work-list segment overflow: the
-// pass has dropped interactions and the number would be silently wrong (a barostat trial could accept on it).  One 64-byte read-back
-// behind the synchronisation these callers do anyway.  A FENE bond out of range is NOT an error here: the reference's CPU energy of such
-// a state is a huge number that a barostat trial simply rejects; oxb_run reports it for states it would integrate.
+// A force pass that overflowed a work-list segment has dropped pairs.  The segments are sized from N-averaged heuristics; a dense aggregate
+// (compact origami, high-pressure NPT) can exceed them.  Recovery, like the neighbour matrix and the edge list: double the segments
+// (the lists are rebuilt: every array of the edge pipeline is reallocated) and repeat the pass.
+int grow_segments(oxb_ctx *c, const char *what) {
+	c->error_flags &= ~OXB_ERR_SEG_OVERFLOW;
+	if(c->seg_scale > 256.) return fail(c, 8, "%s: a work-list segment of the edge pipeline overflowed even at %g x its default size", what, c->seg_scale);
+	c->seg_scale *= 2.;
+	int rc = alloc_lists(c, c->max_neigh > 0 ? c->max_neigh : 64);
+	if(rc) return rc;
+	c->lists_valid = false; c->forces_valid = false;
+	c->dirty_acc = true;
+	return 0;
+}
+
+// Force passes launched outside oxb_run (energies, force read-backs, barostat trials) must not swallow such an overflow either (a barostat
+// trial could accept on an energy with dropped pairs).  One 64-byte read-back behind the synchronisation these callers do anyway.  A FENE
+// bond out of range is NOT an error here: the reference's CPU energy of such a state is a huge number that a barostat trial simply
+// rejects; oxb_run reports it for states it would integrate.  Returns -1 if the pass has to be repeated.
 int check_force_flags(oxb_ctx *c, const char *what) {
 	CU(cudaMemcpyAsync(c->h_flags, c->flags, sizeof(int) * OXB_FLAG_WORDS, cudaMemcpyDeviceToHost, c->stream));
 	CU(cudaStreamSynchronize(c->stream));
-	if(c->h_flags[OXB_FLAG_ERROR] & OXB_ERR_EDGE_OVERFLOW)
-		return fail(c, 8, "%s: a work-list segment of the edge pipeline overflowed (local density far above the average): interactions were dropped", what);
+	if(c->h_flags[OXB_FLAG_ERROR] & OXB_ERR_SEG_OVERFLOW) {
+		int rc = grow_segments(c, what);
+		return rc ? rc : -1;
+	}
 	return 0;
+}
+
+int ensure_forces_checked(oxb_ctx *c, const char *what) {
+	for(int attempt = 0; attempt < 12; attempt++) {
+		int rc = ensure_forces(c);
+		if(rc) return rc;
+		rc = check_force_flags(c, what);
+		if(rc != -1) return rc;
+	}
+	return fail(c, 8, "%s: work-list segments keep overflowing", what);
 }
 
 // One unit of the hot loop with launch index `epoch`: force pass for the pending positions, then ONE integrate launch doing
@@ -843,6 +872,8 @@ int oxb_create(oxb_ctx **out, int device, int N, int precision) {
 		if(fo != nullptr) c->fold_tails = (fo[0] != '0');
 		const char *dhh = getenv("OXB_DH_HALF");
 		if(dhh != nullptr) c->dh_half = (dhh[0] != '0');
+		const char *ss = getenv("OXB_SEG_SCALE");
+		if(ss != nullptr && atof(ss) > 0.) c->seg_scale = atof(ss);
 		const char *fh = getenv("OXB_FOLD_HB");
 		if(fh != nullptr) { c->fold_hb = (fh[0] != '0'); c->fold_hb_set = true; }
 		if(!c->fold_hb_set) c->fold_hb = N < 300000;
@@ -1060,7 +1091,7 @@ int oxb_set_replica_consts(oxb_ctx *c, int n, const oxb_replica_consts *rows) {
 int oxb_replica_energies(oxb_ctx *c, double *U) {
 	if(c == nullptr || U == nullptr) return 1;
 	if(c->n_rep < 2) return oxb_energy(c, U, nullptr);
-	int rc = ensure_forces(c);
+	int rc = ensure_forces_checked(c, "replica_energies");
 	if(rc) return rc;
 	const int k = c->cur;
 	oxb::launch_energy_sum_replicas(c->stream, c->N, c->n_rep, c->n_per, c->F[k], c->use_edge ? c->Fb : nullptr, c->d_rep_energy);
@@ -1347,14 +1378,12 @@ int oxb_update_lists(oxb_ctx *c) {
 int oxb_compute_forces(oxb_ctx *c) {
 	if(c == nullptr) return 1;
 	c->forces_valid = false;
-	int rc = ensure_forces(c);
-	if(rc) return rc;
-	return check_force_flags(c, "compute_forces");
+	return ensure_forces_checked(c, "compute_forces");
 }
 
 int oxb_first_step(oxb_ctx *c) {
 	if(c == nullptr) return 1;
-	int rc = ensure_forces(c);
+	int rc = ensure_forces_checked(c, "first_step");
 	if(rc) return rc;
 	rc = reset_batch_flags(c);
 	if(rc) return rc;
@@ -1370,7 +1399,7 @@ int oxb_first_step(oxb_ctx *c) {
 
 int oxb_second_step(oxb_ctx *c) {
 	if(c == nullptr) return 1;
-	int rc = ensure_forces(c);
+	int rc = ensure_forces_checked(c, "second_step");
 	if(rc) return rc;
 	rc = reset_batch_flags(c);
 	if(rc) return rc;
@@ -1427,6 +1456,15 @@ int oxb_run(oxb_ctx *c, long long n_steps) {
 		rc = reset_batch_flags(c);
 		if(rc) return rc;
 		const long long step0 = c->step;
+		const bool started_mid = c->mid_step;
+		if(c->dirty_acc) {
+			// an incomplete force pass left partial sums behind
+			const int k = c->cur;
+			CU(cudaMemsetAsync(c->F[k], 0, sizeof(float4) * (size_t) c->N, c->stream));
+			CU(cudaMemsetAsync(c->T[k], 0, sizeof(float4) * (size_t) c->N, c->stream));
+			CU(cudaMemsetAsync(c->Fb, 0, sizeof(float4) * (size_t) c->N, c->stream));
+			c->dirty_acc = false;
+		}
 		if(!c->mid_step) {
 			// start of a run: forces for the current positions, then the first half-kick + drift.  Launch index -1: reads halt
 			// word 1, writes word 0, so that the first full unit below always has index 0 (captured graphs freeze the parity)
@@ -1471,8 +1509,17 @@ int oxb_run(oxb_ctx *c, long long n_steps) {
 		c->step += done;
 		remaining -= done;
 		since_rebuild += done;
+		if(c->error_flags & OXB_ERR_SEG_OVERFLOW) {
+			// a force pass of this batch dropped pairs: the integrator launch behind it halted the batch without using the forces.  Enlarge
+			// the segments and repeat that pass
+			rc = grow_segments(c, "run");
+			if(rc) return rc;
+			c->mid_step = started_mid || done > 0;
+			since_rebuild = 0;
+			continue;
+		}
 		if(c->error_flags & OXB_ERR_EDGE_OVERFLOW) {
-			return fail(c, 8, "a work-list segment of the edge pipeline overflowed around step %lld (local density far above the average)", c->step);
+			return fail(c, 8, "the edge list overflowed around step %lld after repeated growth", c->step);
 		}
 		if(c->error_flags & OXB_ERR_FENE_BROKEN) {
 			return fail(c, 6, "the distance between bonded neighbors exceeded acceptable values (FENE range) around step %lld", c->step);
@@ -1505,7 +1552,7 @@ int oxb_synchronize(oxb_ctx *c) {
 
 int oxb_get_forces(oxb_ctx *c, double *force, double *torque_body, double *torque_lab, double *energy, double *hb_energy) {
 	if(c == nullptr) return 1;
-	int rc = ensure_forces(c);
+	int rc = ensure_forces_checked(c, "get_forces");
 	if(rc) return rc;
 	const int N = c->N, k = c->cur;
 	std::vector<float4> hF(N), hT(N), hB(N, make_float4(0.f, 0.f, 0.f, 0.f));
@@ -1549,7 +1596,7 @@ int oxb_get_forces(oxb_ctx *c, double *force, double *torque_body, double *torqu
 
 int oxb_energy(oxb_ctx *c, double *U, double *K) {
 	if(c == nullptr) return 1;
-	int rc = ensure_forces(c);
+	int rc = ensure_forces_checked(c, "energy");
 	if(rc) return rc;
 	const int k = c->cur;
 	oxb::launch_energy_sum(c->stream, c->N, c->F[k], c->use_edge ? c->Fb : nullptr, c->d_energy);
@@ -1559,8 +1606,7 @@ int oxb_energy(oxb_ctx *c, double *U, double *K) {
 	c->launches += 3;
 	CU(cudaMemcpyAsync(c->h_scalars, c->d_energy, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
 	CU(cudaMemcpyAsync(&hs, c->sums, sizeof(KinSums), cudaMemcpyDeviceToHost, c->stream));
-	rc = check_force_flags(c, "energy");
-	if(rc) return rc;
+	CU(cudaStreamSynchronize(c->stream));
 	if(U) *U = 0.5 * c->h_scalars[0];
 	if(K) *K = 0.5 * (hs.v2 + hs.L2);
 	return 0;

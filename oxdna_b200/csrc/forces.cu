@@ -368,7 +368,7 @@ __device__ __forceinline__ void block_append(bool flag, int2 item, int2 *__restr
 	if(flag) {
 		int pos = base + __popc(mask & ((1u << lane) - 1u));
 		if(pos < seg) seg_base[pos] = item;
-		else atomicOr(flags + OXB_FLAG_ERROR, OXB_ERR_EDGE_OVERFLOW);
+		else atomicOr(flags + OXB_FLAG_ERROR, OXB_ERR_SEG_OVERFLOW);
 	}
 }
 

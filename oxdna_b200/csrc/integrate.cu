@@ -42,7 +42,9 @@ __global__ void __launch_bounds__(256, OXB_MB_INTEGRATE) k_integrate(oxb::Integr
 	int *flags = a.flags;
 	const int rd = OXB_FLAG_COUNT + (epoch & 1), wr = OXB_FLAG_COUNT + ((epoch + 1) & 1);
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if(flags[rd]) { // halted earlier in this batch: stay halted (sticky), do nothing
+	// halted earlier in this batch: stay halted (sticky), do nothing.  An incomplete force pass (a work-list segment overflowed) halts the
+	// batch the same way: the forces must not be integrated; the host enlarges the segments and repeats the pass
+	if(flags[rd] || (flags[OXB_FLAG_ERROR] & OXB_ERR_SEG_OVERFLOW)) {
 		if(i == 0) { flags[wr] = 1; prof_mark(flags, OXB_PROF_WAIT); }
 		return;
 	}

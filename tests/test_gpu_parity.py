@@ -1053,3 +1053,50 @@ np.save(sys.argv[1], w)
     assert sorted(out["small"].tolist()) == list(range(len(out["small"])))
     # (particle-centric forces: the two 40-step trajectories are bit-identical, so the orders must be too)
     assert np.array_equal(out["small"], out["radix"])
+
+
+@pytest.mark.parametrize("case", ["lattice27_dense", "rna_lattice8"])
+def test_work_list_segment_overflow_is_recovered(case, monkeypatch):
+    """The work lists of the edge pipeline (hydrogen-bonding / cross-stacking and coaxial pairs per producer block) are sized from N-averaged
+    heuristics.  With the segments shrunk to a fiftieth (OXB_SEG_SCALE) the very first force pass overflows them: the pass is repeated with
+    doubled segments until it fits -- out of a run (get_forces) and in the middle of one (the integrator launch behind an incomplete pass
+    halts the batch) -- and nothing is lost: forces against the reference fixture / the oracle, and a 150-step NVE run against the same run
+    with default segments."""
+    g = load_golden(case)
+    rna = case.startswith("rna")
+
+    def make(**over):
+        if rna:
+            topo = dict(btype=g["btype"], n3=g["n3"], n5=g["n5"], strand=g["strand"])
+            conf = dict(box=g["box"], pos=g["pos"], a1=g["a1"], a3=g["a3"], vel=g["vel"], L=g["L"])
+            return Simulation(rna_inp(g, use_edge=1, CUDA_sort_every=1, **over), topo, conf)
+        return make_sim(g, use_edge=1, CUDA_sort_every=1, **over)
+
+    ref_sim = make()
+    try:
+        ref_sim.run(150)
+        want = ref_sim.ctx.get_state()
+    finally:
+        ref_sim.close()
+    monkeypatch.setenv("OXB_SEG_SCALE", "0.02")
+    sim = make()
+    try:
+        out = sim.ctx.get_forces()
+        if rna:
+            check_forces(out, rna_oracle(g))
+        else:
+            check_forces(out, g)
+        sim.run(150)
+        got = sim.ctx.get_state()
+        # (float atomics of the edge pipeline: the two runs agree to round-off amplified over 150 steps, not bit for bit)
+        assert np.abs(got["pos"] - want["pos"]).max() < 1e-4 and np.abs(got["vel"] - want["vel"]).max() < 2e-3
+    finally:
+        sim.close()
+    # a run that starts on tiny segments (no force evaluation before it) recovers inside oxb_run
+    sim = make()
+    try:
+        sim.run(150)
+        got = sim.ctx.get_state()
+        assert np.abs(got["pos"] - want["pos"]).max() < 1e-4
+    finally:
+        sim.close()
