@@ -27,12 +27,12 @@ sys.path.insert(0, ROOT)
 T_STR, SALT, DT = "300K", 0.5, 0.003
 _REAL_STDOUT = sys.stdout
 FLOP_FAR, FLOP_DH, FLOP_CONTACT, FLOP_BONDED = 170.0, 60.0, 1500.0, 900.0  # SURVEY 8(d) per-pair figures
-# ncu dram__bytes_read.sum + dram__bytes_write.sum of one force pass (near + HB/CRST + coaxial + bonded + DH kernels)
-# (profiles/summary_r01n.txt, one `ncu --set full` capture per workload, cold cache: compulsory traffic of one pass;
-#  kernels: Debye-Hueckel, bonded, near edges, HB / cross stacking, coaxial stacking, excluded volume in double)
-NCU_FORCE_PASS_DRAM_BYTES_C2 = int((6.92 + 7.60 + 4.77 + 6.64 + 0.03 + 0.38) * 1e6)
-NCU_FORCE_PASS_DRAM_BYTES_C4 = int((88.77 + 92.25 + 59.75 + 83.87 + 0.03 + 4.03) * 1e6)
-
+# ncu dram__bytes_read.sum + dram__bytes_write.sum of one force pass, summed over its kernels (profiles/summary_r02a.txt: one
+# `ncu --set full` capture per workload, cold cache: the compulsory traffic of one pass)
+#   C2: Debye-Hueckel, bonded, near edges incl. the folded HB / cross-stacking / coaxial / FP64 excluded-volume tails
+#   C4: Debye-Hueckel, bonded, near edges incl. coaxial / FP64 excluded-volume tails, HB + cross stacking, mutual traps
+NCU_FORCE_PASS_DRAM_BYTES_C2 = int((7.80 + 7.29 + 9.01) * 1e6)
+NCU_FORCE_PASS_DRAM_BYTES_C4 = int((101.40 + 93.96 + 79.87 + 120.61 + 18.98) * 1e6)
 
 def workload(name):
     from oxdna_b200 import lattice
@@ -303,7 +303,9 @@ def load_peaks():
 
 # DRAM bytes of one force pass / one integrate launch from the committed `ncu --set full` capture of the same workload (cold cache: the
 # compulsory traffic; profiles/summary_r02*.txt): dram__bytes_read.sum + dram__bytes_write.sum summed over the kernels of the pass
-NCU_DRAM_BYTES = {"c2": dict(force=NCU_FORCE_PASS_DRAM_BYTES_C2, integrate=22.0e6), "c4": dict(force=NCU_FORCE_PASS_DRAM_BYTES_C4, integrate=423.0e6)}
+# (list: k_build_neigh half shell 247.3 MB + k_fill_edges 121.6 MB, ncu r02l; sort: the gather pass k_permute 407.7 MB, ncu r02f)
+NCU_DRAM_BYTES = {"c2": dict(force=NCU_FORCE_PASS_DRAM_BYTES_C2, integrate=15.77e6),
+                  "c4": dict(force=NCU_FORCE_PASS_DRAM_BYTES_C4, integrate=379.15e6, list=368.9e6, sort=407.7e6)}
 
 
 def measure_single(args, wl, steps, warmup, equil, md, full, local_rank=0):
@@ -394,9 +396,10 @@ def measure_single(args, wl, steps, warmup, equil, md, full, local_rank=0):
                                    "achieved": gbs(integ_bytes, t_integ), "peak": hbm_peak, "unit": "GB/s", "frac": gbs(integ_bytes, t_integ) / hbm_peak,
                                    "traffic": ncu.get("integrate"), "ms": t_integ, "share_of_step": t_integ / step_ms, "peak_source": peak_src},
             "roofline_list": {"kernel": "list rebuild (binning + 27-cell scan + DH matrix + edge list)", "bound": "hbm", "achieved": gbs(N * 140.0, t_build),
-                              "peak": hbm_peak, "unit": "GB/s", "frac": gbs(N * 140.0, t_build) / hbm_peak, "ms": t_build, "per_md_step_ms": t_build * n_reb / n_md},
+                              "peak": hbm_peak, "unit": "GB/s", "frac": gbs(N * 140.0, t_build) / hbm_peak, "traffic": ncu.get("list"), "ms": t_build,
+                              "per_md_step_ms": t_build * n_reb / n_md, "note": "issue-bound on divergence, not on bytes (DESIGN 3)"},
             "roofline_sort": {"kernel": "Hilbert re-sort (keys + radix sort + one gather pass)", "bound": "hbm", "achieved": gbs(N * 470.0, t_sort),
-                              "peak": hbm_peak, "unit": "GB/s", "frac": gbs(N * 470.0, t_sort) / hbm_peak if t_sort > 0 else None, "ms": t_sort,
+                              "peak": hbm_peak, "unit": "GB/s", "frac": gbs(N * 470.0, t_sort) / hbm_peak if t_sort > 0 else None, "traffic": ncu.get("sort"), "ms": t_sort,
                               "per_md_step_ms": t_sort * n_sort / n_md},
             "kernels_ms": {"force_pass": t_force, "integrate": t_integ, "list_build_per_rebuild": t_build, "sort_per_sort": t_sort, "rebuild_parts": t_parts,
                            "halt_and_host_wait_per_rebuild": t_wait, "batch_launch_gap_per_batch": prof["gap"][0] / max(prof["gap"][1], 1), "batches": prof["gap"][1],
