@@ -121,6 +121,7 @@ struct oxb_ctx {
 	bool build_unchecked = false; // a list rebuild was launched without waiting for its overflow flags (oxb_run); the next batch checks
 	double seg_scale = 1.;   // growth factor of the work-list segments (doubled whenever one overflows; OXB_SEG_SCALE sets the start value)
 	bool dirty_acc = false;  // F / T / Fb hold the partial sums of an incomplete force pass: clear them before the next one
+	bool near_tile = false;  // OXB_NEAR_TILE=1: tile-staged variant of the near-edge kernel (experiment)
 	bool fold_hb = false;  // ... and hydrogen bonding / cross stacking in the tail of k_edge_near (OXB_FOLD_HB=0/1; default: systems below 300,000 particles)
 	bool fold_hb_set = false;
 	bool fold_tails = true; // coaxial stacking + FP64 excluded volume in the tails of the producing kernels (OXB_FOLD=0: separate launches)
@@ -279,6 +280,7 @@ int alloc_lists(oxb_ctx *c, int max_neigh) {
 		const char *e = getenv("OXB_PB_NEAR");
 		const int pb = (e != nullptr && atoi(e) > 0) ? atoi(e) : 8;
 		c->n_seg = c->use_edge ? (int) std::max<long long>(1, std::min<long long>((long long) pb * c->n_sm, (33ll * N / 10 + 127) / 128)) : 1;
+		if(c->use_edge && c->near_tile) c->n_seg = (N + 127) / 128; // one block (and one work-list segment) per tile of 128 slots
 	}
 	c->hb_seg = c->use_edge ? (int) (c->seg_scale * (double) (6ll * N / c->n_seg + 128)) + 3 : 1;
 	c->cr_seg = 1; // the cross-stacking-only list is not produced (see forces.cu)
@@ -527,6 +529,7 @@ int launch_forces(oxb_ctx *c, int hw, bool clear, long long step) {
 		e.rep = c->rep; e.n_per = c->n_per;
 		e.N = c->N; e.ipos = c->ipos[a]; e.iback = c->iback[a]; e.axf = c->axf[a]; e.posd = c->posd[a]; e.quatd = c->quatd[a]; e.bonds = c->bonds[a]; e.edges = c->edges;
 		e.n_edges = c->n_edges; e.dh_nbr = c->dh_nbr; e.dh_nnbr = c->dh_nnbr;
+		e.edge_offsets = c->edge_offsets; e.near_tile = c->near_tile ? 1 : 0;
 		e.F = c->F[a]; e.T = c->T[a]; e.Fb = c->Fb; e.hb_list = c->hb_list; e.cx_list = c->cx_list; e.cr_list = c->cr_list; e.seg_counts = c->seg_counts;
 		e.ex_list = c->ex_list; e.ex_counts = c->ex_counts; e.ex_bonded = c->ex_bonded; e.ex_seg = c->ex_seg;
 		e.refine = (c->precision == OXB_PRECISION_MIXED) ? 1 : 0;
@@ -872,6 +875,8 @@ int oxb_create(oxb_ctx **out, int device, int N, int precision) {
 		if(fo != nullptr) c->fold_tails = (fo[0] != '0');
 		const char *dhh = getenv("OXB_DH_HALF");
 		if(dhh != nullptr) c->dh_half = (dhh[0] != '0');
+		const char *nt = getenv("OXB_NEAR_TILE");
+		if(nt != nullptr) c->near_tile = (nt[0] != '0');
 		const char *ss = getenv("OXB_SEG_SCALE");
 		if(ss != nullptr && atof(ss) > 0.) c->seg_scale = atof(ss);
 		const char *fh = getenv("OXB_FOLD_HB");

@@ -372,8 +372,12 @@ __device__ __forceinline__ void block_append(bool flag, int2 item, int2 *__restr
 	}
 }
 
-template<class MD>
+// TILE (OXB_NEAR_TILE=1, an experiment kept switchable): block b owns the 128 consecutive `from` slots [128 b, 128 b + 128) and their edges
+// (edge_offsets), stages those particles -- position, the three axes, the backbone site -- in shared memory once and takes both ends of an
+// edge from there whenever they fall into the tile: the "shared-memory staging of neighbour data" variant of this kernel.
+template<class MD, bool TILE>
 __global__ void __launch_bounds__(128, OXB_MB_NEAR) k_edge_near(const __grid_constant__ typename MD::Params M, BoxF box, const int *__restrict__ n_edges,
+		const int *__restrict__ edge_offsets, int N,
 		const int2 *__restrict__ edges, const int4 *__restrict__ ipos, const float4 *__restrict__ axf, float4 *__restrict__ F, float4 *__restrict__ T,
 		int2 *__restrict__ hb_list, int2 *__restrict__ cx_list, int2 *__restrict__ cr_list, int *__restrict__ seg_counts, int hb_seg, int cx_seg,
 		int cr_seg, int4 *__restrict__ ex_list, int *__restrict__ ex_counts, int ex_seg, int refine, int fold, const double4 *__restrict__ posd,
@@ -393,9 +397,37 @@ __global__ void __launch_bounds__(128, OXB_MB_NEAR) k_edge_near(const __grid_con
 	if(threadIdx.x == 0) s_nex = 0;
 	__syncthreads();
 	ex_list += (size_t) blockIdx.x * ex_seg;
-	for(int base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < ne; base += gridDim.x * blockDim.x) {
+	// TILE: the staged particles, 64 bytes each: (a1, back.x), (a2, back.y), (a3, back.z) and the fixed-point position
+	constexpr int TP = 128;
+	__shared__ float4 s_ax[TILE ? 3 * TP : 1];
+	__shared__ int4 s_ip[TILE ? TP : 1];
+	const int p0 = blockIdx.x * TP;
+	int e_begin = (blockIdx.x * blockDim.x + threadIdx.x) - lane, e_end = ne, e_step = gridDim.x * blockDim.x;
+	if(TILE) {
+		for(int t = threadIdx.x; t < TP && p0 + t < N; t += blockDim.x) {
+			const Particle S = load_particle<MD>(M, ipos, axf, p0 + t);
+			s_ip[t] = S.ip;
+			s_ax[3 * t] = make_float4(S.ax.a1.x, S.ax.a1.y, S.ax.a1.z, S.back.x);
+			s_ax[3 * t + 1] = make_float4(S.ax.a2.x, S.ax.a2.y, S.ax.a2.z, S.back.y);
+			s_ax[3 * t + 2] = make_float4(S.ax.a3.x, S.ax.a3.y, S.ax.a3.z, S.back.z);
+		}
+		__syncthreads();
+		const int o0 = __ldg(edge_offsets + min(p0, N)), o1 = __ldg(edge_offsets + min(p0 + TP, N));
+		e_begin = o0 + (int) threadIdx.x - (int) lane; e_end = min(o1, ne); e_step = blockDim.x;
+	}
+	auto staged = [&](int slot) {
+		Particle S;
+		const int t = slot - p0;
+		const float4 u = s_ax[3 * t], v = s_ax[3 * t + 1], w = s_ax[3 * t + 2];
+		S.ip = s_ip[t];
+		S.ax.a1 = mk3(u.x, u.y, u.z); S.ax.a2 = mk3(v.x, v.y, v.z); S.ax.a3 = mk3(w.x, w.y, w.z);
+		S.back = mk3(u.w, v.w, w.w);
+		S.btype = word_btype(S.ip.w);
+		return S;
+	};
+	for(int base = e_begin; base < e_end; base += e_step) {
 		int eidx = base + lane;
-		bool valid = eidx < ne;
+		bool valid = eidx < e_end;
 		int2 ed = valid ? __ldg(edges + eidx) : make_int2(-1 - (int) lane, -1);
 		// the list builder's verdict on which families of site pairs can come into range before the next rebuild (common.cuh, OXB_CLS_*)
 		const int cls = valid ? (int) ((unsigned) ed.y >> OXB_CLS_SHIFT) : 0;
@@ -404,8 +436,16 @@ __global__ void __launch_bounds__(128, OXB_MB_NEAR) k_edge_near(const __grid_con
 		float ve = 0.f;
 		bool want_hb = false, want_cx = false, hb_capable = false;
 		if(valid) {
-			Particle P = load_particle<MD>(M, ipos, axf, ed.x);
-			Particle Q = load_particle<MD>(M, ipos, axf, ed.y);
+			Particle P, Q;
+			if(TILE) {
+				P = staged(ed.x);
+				if((unsigned) (ed.y - p0) < (unsigned) TP) Q = staged(ed.y);
+				else Q = load_particle<MD>(M, ipos, axf, ed.y);
+			}
+			else {
+				P = load_particle<MD>(M, ipos, axf, ed.x);
+				Q = load_particle<MD>(M, ipos, axf, ed.y);
+			}
 			v3 r = min_image_fixed(box, P.ip, Q.ip);
 			if(dot(r, r) < M.rcut_near * M.rcut_near) {
 				v3 rbb = r + Q.back - P.back;
@@ -1133,8 +1173,10 @@ static void launch_edge_stage_t(cudaStream_t s, int which, const typename MD::Pa
 	// the producer and the three consumers of the segmented work lists share one fixed grid (a.n_seg blocks, grid-stride
 	// inside): nothing here depends on device-side counts, so a captured graph stays valid across list rebuilds
 	case 1:
-		k_edge_near<MD><<<a.n_seg, 128, 0, s>>>(M, box, a.n_edges, a.edges, a.ipos, a.axf, a.F, a.T, a.hb_list, a.cx_list, a.cr_list, a.seg_counts, a.hb_seg,
-				a.cx_seg, a.cr_seg, a.ex_list, a.ex_counts, a.ex_seg, a.refine, a.fold, a.posd, a.quatd, flags, hw);
+		if(a.near_tile) k_edge_near<MD, true><<<a.n_seg, 128, 0, s>>>(M, box, a.n_edges, a.edge_offsets, a.N, a.edges, a.ipos, a.axf, a.F, a.T, a.hb_list, a.cx_list, a.cr_list,
+				a.seg_counts, a.hb_seg, a.cx_seg, a.cr_seg, a.ex_list, a.ex_counts, a.ex_seg, a.refine, a.fold, a.posd, a.quatd, flags, hw);
+		else k_edge_near<MD, false><<<a.n_seg, 128, 0, s>>>(M, box, a.n_edges, a.edge_offsets, a.N, a.edges, a.ipos, a.axf, a.F, a.T, a.hb_list, a.cx_list, a.cr_list,
+				a.seg_counts, a.hb_seg, a.cx_seg, a.cr_seg, a.ex_list, a.ex_counts, a.ex_seg, a.refine, a.fold, a.posd, a.quatd, flags, hw);
 		break;
 	case 2: k_edge_heavy<MD, 0><<<dim3(a.n_seg, a.hb_split), 64, 0, s>>>(M, box, a.seg_counts, a.hb_list, a.hb_seg, a.ipos, a.axf, a.F, a.T, flags, hw); break;
 	case 3: k_edge_heavy<MD, 1><<<a.n_seg, 64, 0, s>>>(M, box, a.seg_counts, a.cx_list, a.cx_seg, a.ipos, a.axf, a.F, a.T, flags, hw); break;

@@ -94,6 +94,8 @@ struct EdgeArgs {
 	const double4 *posd, *quatd; // FP64 state: read only where an excluded-volume term is active (ExclRefine)
 	const int2 *bonds, *edges; // near edges
 	const int *n_edges;
+	const int *edge_offsets; // N + 1 entries: first near edge of every `from` slot (the tile variant of the near-edge kernel)
+	int near_tile;           // 1: one block of the near-edge kernel per tile of 128 `from` slots, staged in shared memory (n_seg = tiles)
 	const int *dh_nbr, *dh_nnbr; // Debye-Hueckel neighbour matrix, column-major, stride N
 	float4 *F, *T, *Fb;
 	// work lists segmented by producer block (n_seg blocks): hydrogen-bonding pairs, coaxial-stacking pairs, cross-stacking-only
