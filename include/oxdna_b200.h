@@ -302,7 +302,8 @@ int oxb_get_stats(oxb_ctx *ctx, long long *n_list_updates, long long *n_sorts, i
  * (btype<<22 | index) in .w, float4 quaternions, column-major neighbour matrix, neighbour counts, and the int2 list of
  * unique pairs closer than rcut_near + 2 skin at the last rebuild (the pairs that can feel more than Debye-Hueckel; .x = from slot,
  * .y = to slot | class << 24, the class being the list builder's bit mask of the site-pair families that can come into range before the
- * next rebuild).  Asking for matrix_neighs / number_neighs switches the context to full builds (both directions of every pair, plain
+ * next rebuild; the list comes in three segments by class group -- n_edges[0] = total, n_edges[1..3] = the segment lengths -- each grouped
+ * by `from` in slot order).  Asking for matrix_neighs / number_neighs switches the context to full builds (both directions of every pair, plain
  * slots), which the edge pipeline's own half-shell builds do not produce. */
 int oxb_device_views(oxb_ctx *ctx, void **poss_f4, void **orientations_f4, void **matrix_neighs, void **number_neighs,
 		void **edge_list, void **n_edges);

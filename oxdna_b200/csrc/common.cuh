@@ -87,6 +87,11 @@ __device__ __forceinline__ v3 load_a1(const float4 *__restrict__ axf, int i) {
 // 22-bit slot index.
 enum : int { OXB_CLS_BB = 1, OXB_CLS_EB = 2, OXB_CLS_HBCR = 4, OXB_CLS_ST = 8, OXB_CLS_BK = 16, OXB_CLS_ALL = 31, OXB_CLS_SHIFT = 24, OXB_SLOT_MASK = 0x003FFFFF };
 
+// The edge list is laid out in three segments by class GROUP, each grouped by `from` in slot order: 0 = hydrogen bonding / cross stacking
+// only, 1 = + coaxial stacking, 2 = any excluded-volume family.  Warps of the near-edge kernel are then uniform in which families they test
+// (with one list every warp holds some edge of every class and executes all of the screening code with a part of its lanes).
+OXB_HD int cls_group(int cls) { return (cls & (OXB_CLS_BB | OXB_CLS_EB | OXB_CLS_BK)) ? 2 : ((cls & OXB_CLS_ST) ? 1 : 0); }
+
 // ---- packed particle word: (btype << 22) | original index, as in the reference (MD_CUDABackend.cu:243-254)
 __host__ __device__ __forceinline__ int pack_word(int btype, int index) { return (btype << 22) | (index & 0x003FFFFF); }
 __host__ __device__ __forceinline__ int word_btype(int w) { return w >> 22; }

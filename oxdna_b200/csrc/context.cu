@@ -79,7 +79,8 @@ struct oxb_ctx {
 	int *cell_key = nullptr, *cell_key_sorted = nullptr, *cell_val = nullptr, *cell_val_sorted = nullptr, *cell_start = nullptr;
 	int *nbr = nullptr, *nnbr = nullptr;
 	int2 *edges = nullptr;
-	int *edge_offsets = nullptr, *n_edges = nullptr;
+	int4 *edge_cnt = nullptr;
+	int *n_edges = nullptr;
 	ulonglong2 *near_mask = nullptr;
 	bool slots_cell_ordered = false; // the last re-sort ordered the slots by cell and left the cell ids in cell_key_sorted
 	int sort_ncell[3] = { 0, 0, 0 }; // ... for this cell grid (a model change in between invalidates the shortcut)
@@ -121,6 +122,7 @@ struct oxb_ctx {
 	bool build_unchecked = false; // a list rebuild was launched without waiting for its overflow flags (oxb_run); the next batch checks
 	double seg_scale = 1.;   // growth factor of the work-list segments (doubled whenever one overflows; OXB_SEG_SCALE sets the start value)
 	bool dirty_acc = false;  // F / T / Fb hold the partial sums of an incomplete force pass: clear them before the next one
+	bool class_groups = true; // edge list in three segments by class group (OXB_CLASS_GROUPS=0: one segment)
 	bool near_tile = false;  // OXB_NEAR_TILE=1: tile-staged variant of the near-edge kernel (experiment)
 	bool fold_hb = false;  // ... and hydrogen bonding / cross stacking in the tail of k_edge_near (OXB_FOLD_HB=0/1; default: systems below 300,000 particles)
 	bool fold_hb_set = false;
@@ -202,14 +204,15 @@ void set_boxf(oxb_ctx *c) {
 void free_lists(oxb_ctx *c) {
 	drop_graphs(c);
 	cudaFree(c->cell_key); cudaFree(c->cell_key_sorted); cudaFree(c->cell_val); cudaFree(c->cell_val_sorted); cudaFree(c->cell_start);
-	cudaFree(c->nbr); cudaFree(c->nnbr); cudaFree(c->edges); cudaFree(c->edge_offsets); cudaFree(c->n_edges); cudaFree(c->cub_tmp);
+	cudaFree(c->nbr); cudaFree(c->nnbr); cudaFree(c->edges); cudaFree(c->edge_cnt); cudaFree(c->n_edges); cudaFree(c->cub_tmp);
 	cudaFree(c->dh_nbr); cudaFree(c->dh_nnbr); cudaFree(c->near_mask);
 	c->near_mask = nullptr;
 	c->slots_cell_ordered = false;
 	cudaFree(c->hb_list); cudaFree(c->cx_list); cudaFree(c->cr_list); cudaFree(c->seg_counts);
 	cudaFree(c->ex_list); cudaFree(c->ex_counts); cudaFree(c->ex_bonded);
 	c->ex_list = nullptr; c->ex_counts = c->ex_bonded = nullptr;
-	c->cell_key = c->cell_key_sorted = c->cell_val = c->cell_val_sorted = c->cell_start = c->nbr = c->nnbr = c->edge_offsets = c->n_edges = nullptr;
+	c->cell_key = c->cell_key_sorted = c->cell_val = c->cell_val_sorted = c->cell_start = c->nbr = c->nnbr = c->n_edges = nullptr;
+	c->edge_cnt = nullptr;
 	c->seg_counts = c->dh_nbr = c->dh_nnbr = nullptr;
 	c->edges = c->hb_list = c->cx_list = c->cr_list = nullptr;
 	c->cub_tmp = nullptr;
@@ -266,8 +269,9 @@ int alloc_lists(oxb_ctx *c, int max_neigh) {
 	c->max_neigh = max_neigh;
 	CU(dalloc(&c->cell_key, N)); CU(dalloc(&c->cell_key_sorted, N)); CU(dalloc(&c->cell_val, N)); CU(dalloc(&c->cell_val_sorted, N));
 	CU(dalloc(&c->nbr, (size_t) max_neigh * N)); CU(dalloc(&c->nnbr, N));
-	CU(dalloc(&c->edge_offsets, (size_t) N + 1)); CU(dalloc(&c->n_edges, 2)); CU(dalloc(&c->near_mask, (size_t) N));
-	CU(cudaMemset(c->n_edges, 0, 2 * sizeof(int)));
+	CU(dalloc(&c->edge_cnt, (size_t) N + 1)); CU(dalloc(&c->n_edges, 4)); CU(dalloc(&c->near_mask, (size_t) N));
+	CU(cudaMemset(c->edge_cnt, 0, sizeof(int4) * ((size_t) N + 1)));
+	CU(cudaMemset(c->n_edges, 0, 4 * sizeof(int)));
 	c->max_dh = max_neigh;
 	CU(dalloc(&c->dh_nbr, (size_t) c->max_dh * N)); CU(dalloc(&c->dh_nnbr, N));
 	// segmented work lists of the edge pipeline: one segment per block of the near-edge kernel, sized ~4x the expected load
@@ -309,7 +313,7 @@ oxb::ListArgs list_args(oxb_ctx *c) {
 	a.cell_key = c->cell_key; a.cell_key_sorted = c->cell_key_sorted; a.cell_val = c->cell_val; a.cell_val_sorted = c->cell_val_sorted;
 	a.cell_start = c->cell_start;
 	a.nbr = c->nbr; a.nnbr = c->nnbr; a.max_neigh = c->max_neigh; a.stride = c->N;
-	a.edges = c->edges; a.edge_offsets = c->edge_offsets; a.n_edges = c->n_edges; a.edge_capacity = c->edge_capacity;
+	a.edges = c->edges; a.edge_cnt = c->edge_cnt; a.n_edges = c->n_edges; a.edge_capacity = c->edge_capacity;
 	a.iback = c->iback[c->cur]; a.axf = c->axf[c->cur];
 	a.ref_pos = c->posd[c->cur]; a.ref_vel = c->veld[c->cur]; a.ref_L = c->Ld[c->cur];
 	a.base_a1 = c->model.base_a1; a.stack_a1 = c->model.stack_a1;
@@ -340,6 +344,7 @@ oxb::ListArgs list_args(oxb_ctx *c) {
 	a.flags = c->flags;
 	a.cub_tmp = c->cub_tmp; a.cub_tmp_bytes = c->cub_tmp_bytes;
 	a.build_edges = c->use_edge != 0;
+	a.class_groups = c->class_groups && !c->near_tile; // (the tile variant of the near-edge kernel walks one segment by `from`)
 	a.near_mask = c->near_mask;
 	a.direct = c->slots_cell_ordered && c->sort_ncell[0] == c->ncell[0] && c->sort_ncell[1] == c->ncell[1] && c->sort_ncell[2] == c->ncell[2];
 	a.ranges_done = a.direct;
@@ -529,7 +534,7 @@ int launch_forces(oxb_ctx *c, int hw, bool clear, long long step) {
 		e.rep = c->rep; e.n_per = c->n_per;
 		e.N = c->N; e.ipos = c->ipos[a]; e.iback = c->iback[a]; e.axf = c->axf[a]; e.posd = c->posd[a]; e.quatd = c->quatd[a]; e.bonds = c->bonds[a]; e.edges = c->edges;
 		e.n_edges = c->n_edges; e.dh_nbr = c->dh_nbr; e.dh_nnbr = c->dh_nnbr;
-		e.edge_offsets = c->edge_offsets; e.near_tile = c->near_tile ? 1 : 0;
+		e.edge_cnt = c->edge_cnt; e.near_tile = c->near_tile ? 1 : 0;
 		e.F = c->F[a]; e.T = c->T[a]; e.Fb = c->Fb; e.hb_list = c->hb_list; e.cx_list = c->cx_list; e.cr_list = c->cr_list; e.seg_counts = c->seg_counts;
 		e.ex_list = c->ex_list; e.ex_counts = c->ex_counts; e.ex_bonded = c->ex_bonded; e.ex_seg = c->ex_seg;
 		e.refine = (c->precision == OXB_PRECISION_MIXED) ? 1 : 0;
@@ -875,6 +880,8 @@ int oxb_create(oxb_ctx **out, int device, int N, int precision) {
 		if(fo != nullptr) c->fold_tails = (fo[0] != '0');
 		const char *dhh = getenv("OXB_DH_HALF");
 		if(dhh != nullptr) c->dh_half = (dhh[0] != '0');
+		const char *cg = getenv("OXB_CLASS_GROUPS");
+		if(cg != nullptr) c->class_groups = (cg[0] != '0');
 		const char *nt = getenv("OXB_NEAR_TILE");
 		if(nt != nullptr) c->near_tile = (nt[0] != '0');
 		const char *ss = getenv("OXB_SEG_SCALE");

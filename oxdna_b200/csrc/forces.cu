@@ -377,7 +377,7 @@ __device__ __forceinline__ void block_append(bool flag, int2 item, int2 *__restr
 // edge from there whenever they fall into the tile: the "shared-memory staging of neighbour data" variant of this kernel.
 template<class MD, bool TILE>
 __global__ void __launch_bounds__(128, OXB_MB_NEAR) k_edge_near(const __grid_constant__ typename MD::Params M, BoxF box, const int *__restrict__ n_edges,
-		const int *__restrict__ edge_offsets, int N,
+		const int4 *__restrict__ edge_cnt, int N,
 		const int2 *__restrict__ edges, const int4 *__restrict__ ipos, const float4 *__restrict__ axf, float4 *__restrict__ F, float4 *__restrict__ T,
 		int2 *__restrict__ hb_list, int2 *__restrict__ cx_list, int2 *__restrict__ cr_list, int *__restrict__ seg_counts, int hb_seg, int cx_seg,
 		int cr_seg, int4 *__restrict__ ex_list, int *__restrict__ ex_counts, int ex_seg, int refine, int fold, const double4 *__restrict__ posd,
@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(128, OXB_MB_NEAR) k_edge_near(const __grid_con
 			s_ax[3 * t + 2] = make_float4(S.ax.a3.x, S.ax.a3.y, S.ax.a3.z, S.back.z);
 		}
 		__syncthreads();
-		const int o0 = __ldg(edge_offsets + min(p0, N)), o1 = __ldg(edge_offsets + min(p0 + TP, N));
+		const int o0 = __ldg(edge_cnt + min(p0, N)).x, o1 = __ldg(edge_cnt + min(p0 + TP, N)).x;
 		e_begin = o0 + (int) threadIdx.x - (int) lane; e_end = min(o1, ne); e_step = blockDim.x;
 	}
 	auto staged = [&](int slot) {
@@ -1173,9 +1173,9 @@ static void launch_edge_stage_t(cudaStream_t s, int which, const typename MD::Pa
 	// the producer and the three consumers of the segmented work lists share one fixed grid (a.n_seg blocks, grid-stride
 	// inside): nothing here depends on device-side counts, so a captured graph stays valid across list rebuilds
 	case 1:
-		if(a.near_tile) k_edge_near<MD, true><<<a.n_seg, 128, 0, s>>>(M, box, a.n_edges, a.edge_offsets, a.N, a.edges, a.ipos, a.axf, a.F, a.T, a.hb_list, a.cx_list, a.cr_list,
+		if(a.near_tile) k_edge_near<MD, true><<<a.n_seg, 128, 0, s>>>(M, box, a.n_edges, a.edge_cnt, a.N, a.edges, a.ipos, a.axf, a.F, a.T, a.hb_list, a.cx_list, a.cr_list,
 				a.seg_counts, a.hb_seg, a.cx_seg, a.cr_seg, a.ex_list, a.ex_counts, a.ex_seg, a.refine, a.fold, a.posd, a.quatd, flags, hw);
-		else k_edge_near<MD, false><<<a.n_seg, 128, 0, s>>>(M, box, a.n_edges, a.edge_offsets, a.N, a.edges, a.ipos, a.axf, a.F, a.T, a.hb_list, a.cx_list, a.cr_list,
+		else k_edge_near<MD, false><<<a.n_seg, 128, 0, s>>>(M, box, a.n_edges, a.edge_cnt, a.N, a.edges, a.ipos, a.axf, a.F, a.T, a.hb_list, a.cx_list, a.cr_list,
 				a.seg_counts, a.hb_seg, a.cx_seg, a.cr_seg, a.ex_list, a.ex_counts, a.ex_seg, a.refine, a.fold, a.posd, a.quatd, flags, hw);
 		break;
 	case 2: k_edge_heavy<MD, 0><<<dim3(a.n_seg, a.hb_split), 64, 0, s>>>(M, box, a.seg_counts, a.hb_list, a.hb_seg, a.ipos, a.axf, a.F, a.T, flags, hw); break;

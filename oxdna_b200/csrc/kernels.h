@@ -94,7 +94,7 @@ struct EdgeArgs {
 	const double4 *posd, *quatd; // FP64 state: read only where an excluded-volume term is active (ExclRefine)
 	const int2 *bonds, *edges; // near edges
 	const int *n_edges;
-	const int *edge_offsets; // N + 1 entries: first near edge of every `from` slot (the tile variant of the near-edge kernel)
+	const int4 *edge_cnt;    // N + 1 entries, .x = first near edge of every `from` slot when the list is one segment (the tile variant of the near-edge kernel)
 	int near_tile;           // 1: one block of the near-edge kernel per tile of 128 `from` slots, staged in shared memory (n_seg = tiles)
 	const int *dh_nbr, *dh_nnbr; // Debye-Hueckel neighbour matrix, column-major, stride N
 	float4 *F, *T, *Fb;
@@ -207,7 +207,8 @@ struct ListArgs {
 	int *nbr, *nnbr;
 	int max_neigh, stride;
 	int2 *edges;       // unique pairs that can come within rcut_near before the next rebuild ("near" edges), grouped by `from`
-	int *edge_offsets; // N + 1
+	int4 *edge_cnt;    // N + 1: near edges of every `from` slot per class group (x, y, z), exclusive-scanned in place; entry N = totals
+	bool class_groups; // lay the edge list out in three segments by class group (common.cuh: cls_group); false: one segment
 	ulonglong2 *near_mask; // per row: which entries are near edges to a higher slot
 	bool direct;       // particle arrays are ordered by cell: cell members are the slots [start, end) themselves
 	bool ranges_done;  // ... and the re-sort's gather pass already filled the cell table and the staleness references

@@ -153,6 +153,7 @@ __global__ void __launch_bounds__(128) k_build_neigh(oxb::ListArgs a, const int 
 	const v3 a1p = load_a1(a.axf, i);
 	const v3 bkp = min_image_fixed(a.boxf, ip, ib);
 	int count = 0, higher_near = 0, ndh = 0;
+	int ng0 = 0, ng1 = 0, ng2 = 0; // near edges of this row per class group
 	unsigned long long mask0 = 0ull, mask1 = 0ull;
 	bool mask_overflow = false, dh_overflow = false;
 	// phase 2: one flat loop over this particle's candidates (cursor = range r, slot j), next candidate prefetched
@@ -209,6 +210,8 @@ __global__ void __launch_bounds__(128) k_build_neigh(oxb::ListArgs a, const int 
 		const int cls = (m > i && d2 < a.rnear2) ? near_pair(a, d, a1p, load_a1(a.axf, m), bkp, min_image_fixed(a.boxf, ipm, ibm)) : 0;
 		if(cls != 0) {
 			higher_near++;
+			const int grp = a.class_groups ? (a.half_shell ? cls_group(cls) : 2) : 0; // (full builds mark their edges with every class)
+			ng0 += grp == 0; ng1 += grp == 1; ng2 += grp == 2;
 			if(k < 64) mask0 |= 1ull << k;
 			else if(k < 128) mask1 |= 1ull << (k - 64);
 			else mask_overflow = true;
@@ -248,7 +251,8 @@ __global__ void __launch_bounds__(128) k_build_neigh(oxb::ListArgs a, const int 
 	a.nnbr[i] = count;
 	a.dh_nnbr[i] = ndh;
 	if(a.build_edges) {
-		a.edge_offsets[i] = higher_near;
+		// (a row that takes the geometric fallback of k_fill_edges is counted there again: same classes, same counts)
+		a.edge_cnt[i] = make_int4(ng0, ng1, ng2, higher_near);
 		// rows longer than the mask fall back to the geometric test in k_fill_edges (top bit of word 1 doubles as the marker:
 		// entry 127 can only be flagged together with an overflow, which takes the fallback anyway)
 		if(mask_overflow) mask1 |= 1ull << 63;
@@ -319,6 +323,7 @@ __global__ void __launch_bounds__(256, 4) k_build_neigh_g(oxb::ListArgs a, const
 	const v3 a1p = load_a1(a.axf, i);
 	const v3 bkp = min_image_fixed(a.boxf, ip, ib);
 	int count = 0, ndh = 0, higher_near = 0;
+	int ng0 = 0, ng1 = 0, ng2 = 0; // near edges of this row per class group
 	unsigned long long mask0 = 0ull, mask1 = 0ull;
 	bool mask_overflow = false, dh_overflow = false;
 	const int Tw = __reduce_max_sync(0xffffffffu, T);
@@ -353,6 +358,8 @@ __global__ void __launch_bounds__(256, 4) k_build_neigh_g(oxb::ListArgs a, const
 			if(row < a.max_neigh) a.nbr[(size_t) row * a.stride + i] = a.half_shell ? (m | (cls << OXB_CLS_SHIFT)) : m;
 			if(cls != 0) {
 				higher_near++;
+				const int grp = a.class_groups ? (a.half_shell ? cls_group(cls) : 2) : 0; // (full builds mark their edges with every class)
+				ng0 += grp == 0; ng1 += grp == 1; ng2 += grp == 2;
 				// rows that overflow max_neigh are rebuilt after the matrix has grown: never flag an entry that was not written
 				if(row >= a.max_neigh) mask_overflow = true;
 				else if(row < 64) mask0 |= 1ull << row;
@@ -377,6 +384,7 @@ __global__ void __launch_bounds__(256, 4) k_build_neigh_g(oxb::ListArgs a, const
 		mask0 |= __shfl_xor_sync(0xffffffffu, mask0, o);
 		mask1 |= __shfl_xor_sync(0xffffffffu, mask1, o);
 		higher_near += __shfl_xor_sync(0xffffffffu, higher_near, o);
+		ng0 += __shfl_xor_sync(0xffffffffu, ng0, o); ng1 += __shfl_xor_sync(0xffffffffu, ng1, o); ng2 += __shfl_xor_sync(0xffffffffu, ng2, o);
 		mask_overflow = (__shfl_xor_sync(0xffffffffu, (int) mask_overflow, o) != 0) || mask_overflow;
 		dh_overflow = (__shfl_xor_sync(0xffffffffu, (int) dh_overflow, o) != 0) || dh_overflow;
 	}
@@ -398,37 +406,48 @@ __global__ void __launch_bounds__(256, 4) k_build_neigh_g(oxb::ListArgs a, const
 	a.nnbr[i] = count;
 	a.dh_nnbr[i] = ndh;
 	if(a.build_edges) {
-		a.edge_offsets[i] = higher_near;
+		a.edge_cnt[i] = make_int4(ng0, ng1, ng2, higher_near);
 		if(mask_overflow) mask1 |= 1ull << 63;
 		a.near_mask[i] = make_ulonglong2(mask0, mask1);
 	}
 }
 
-// near edge (i, m) for every flagged row entry; rows are contiguous in the output (grouped by `from`)
+// near edge (i, m) for every flagged row entry.  The list has three segments by class group (common.cuh: cls_group), each grouped by `from`
+// in slot order; edge_cnt holds the exclusive scan of the per-row counts (entry N = totals).
+struct Cnt4Sum {
+	__host__ __device__ __forceinline__ int4 operator()(const int4 &x, const int4 &y) const { return make_int4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w); }
+};
+
 __global__ void __launch_bounds__(128) k_fill_edges(oxb::ListArgs a) {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if(i == 0) prof_mark(a.flags, OXB_PROF_EDGES);
 	if(i >= a.N) return;
-	int off = a.edge_offsets[i];
+	const int4 tot = a.edge_cnt[a.N];
+	const int4 o = a.edge_cnt[i];
+	int off[3] = { o.x, tot.x + o.y, tot.x + tot.y + o.z }; // cursor of this row in each segment
 	const int nn = a.nnbr[i];
 	ulonglong2 mk = a.near_mask[i];
 	// edge = (from, to | class << 24).  Half-shell builds left the class in the matrix entry; a full (public, reference-layout) matrix holds
 	// plain slots and its edges are marked with every class
 	const int cls_all = a.half_shell ? 0 : (OXB_CLS_ALL << OXB_CLS_SHIFT);
+	auto emit = [&](int entry) {
+		const int e = entry | cls_all;
+		const int g = a.class_groups ? cls_group((int) ((unsigned) e >> OXB_CLS_SHIFT)) : 0;
+		const int pos = (g == 0) ? off[0]++ : (g == 1 ? off[1]++ : off[2]++);
+		if(pos < a.edge_capacity) a.edges[pos] = make_int2(i, e);
+	};
 	if(!(mk.y >> 63)) {
 		unsigned long long w = mk.x;
 		while(w) {
 			int k = __ffsll((long long) w) - 1;
 			w &= w - 1;
-			if(off < a.edge_capacity) a.edges[off] = make_int2(i, a.nbr[(size_t) k * a.stride + i] | cls_all);
-			off++;
+			emit(a.nbr[(size_t) k * a.stride + i]);
 		}
 		w = mk.y;
 		while(w) {
 			int k = 64 + __ffsll((long long) w) - 1;
 			w &= w - 1;
-			if(off < a.edge_capacity) a.edges[off] = make_int2(i, a.nbr[(size_t) k * a.stride + i] | cls_all);
-			off++;
+			emit(a.nbr[(size_t) k * a.stride + i]);
 		}
 	}
 	else {
@@ -443,16 +462,15 @@ __global__ void __launch_bounds__(128) k_fill_edges(oxb::ListArgs a) {
 				const int4 ipm = __ldg(a.ipos + m);
 				v3 d = min_image_fixed(a.boxf, ip, ipm);
 				const int cls = (dot(d, d) < a.rnear2) ? near_pair(a, d, a1p, load_a1(a.axf, m), bkp, min_image_fixed(a.boxf, ipm, __ldg(a.iback + m))) : 0;
-				if(cls != 0) {
-					if(off < a.edge_capacity) a.edges[off] = make_int2(i, m | (cls << OXB_CLS_SHIFT));
-					off++;
-				}
+				if(cls != 0) emit(a.half_shell ? (m | (cls << OXB_CLS_SHIFT)) : m);
 			}
 		}
 	}
-	if(i == a.N - 1) {
-		a.n_edges[0] = (off <= a.edge_capacity) ? off : (int) a.edge_capacity;
-		if(off > a.edge_capacity) atomicOr(a.flags + OXB_FLAG_ERROR, OXB_ERR_EDGE_OVERFLOW);
+	if(i == 0) {
+		const long long total = (long long) tot.x + tot.y + tot.z;
+		a.n_edges[0] = (total <= a.edge_capacity) ? (int) total : (int) a.edge_capacity;
+		a.n_edges[1] = tot.x; a.n_edges[2] = tot.y; a.n_edges[3] = tot.z;
+		if(total > a.edge_capacity) atomicOr(a.flags + OXB_FLAG_ERROR, OXB_ERR_EDGE_OVERFLOW);
 	}
 }
 
@@ -469,7 +487,7 @@ namespace oxb {
 size_t lists_tmp_bytes(int N, int ncells) {
 	size_t a = 0, b = 0;
 	cub::DeviceRadixSort::SortPairs(nullptr, a, (int *) nullptr, (int *) nullptr, (int *) nullptr, (int *) nullptr, N, 0, bits_for(ncells));
-	cub::DeviceScan::ExclusiveSum(nullptr, b, (int *) nullptr, (int *) nullptr, N + 1);
+	cub::DeviceScan::ExclusiveScan(nullptr, b, (int4 *) nullptr, (int4 *) nullptr, Cnt4Sum(), make_int4(0, 0, 0, 0), N + 1);
 	return (a > b ? a : b) + 256;
 }
 
@@ -511,7 +529,7 @@ void launch_build_lists(cudaStream_t s, const ListArgs &a) {
 	if(a.build_edges) {
 		tmp = a.cub_tmp_bytes;
 		// in-place exclusive scan over N + 1 entries (the last input entry is ignored: its output is the total)
-		cub::DeviceScan::ExclusiveSum(a.cub_tmp, tmp, a.edge_offsets, a.edge_offsets, N + 1, s);
+		cub::DeviceScan::ExclusiveScan(a.cub_tmp, tmp, a.edge_cnt, a.edge_cnt, Cnt4Sum(), make_int4(0, 0, 0, 0), N + 1, s);
 		k_fill_edges<<<(N + 127) / 128, 128, 0, s>>>(a);
 	}
 }
