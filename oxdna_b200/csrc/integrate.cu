@@ -62,6 +62,16 @@ __global__ void __launch_bounds__(256, OXB_MB_INTEGRATE) k_integrate(oxb::Integr
 		const double hdt = 0.5 * a.dt;
 		float4 F = a.F[i], T = a.T[i];
 		double4 qd0 = make_double4(0., 0., 0., 1.);
+		// every load of the launch is issued here, before the first store: the arrays of IntegrateArgs may alias as far as the compiler
+		// knows, so a load written behind a store is issued behind it and its latency is exposed (position, fixed-point position and
+		// backbone site were fetched one after the other in the middle of the arithmetic)
+		double4 r0 = make_double4(0., 0., 0., 0.);
+		int4 ip0 = make_int4(0, 0, 0, 0), ib0 = make_int4(0, 0, 0, 0);
+		if(PH & OXB_PH_FIRST) { r0 = a.posd[i]; ip0 = a.ipos[i]; ib0 = a.iback[i]; }
+		else if(PH & OXB_PH_THERMO) ip0 = a.ipos[i];
+		const double4 v0 = a.veld[i], L0 = a.Ld[i];
+		float4 fb0 = make_float4(0.f, 0.f, 0.f, 0.f);
+		if((PH & (OXB_PH_SECOND | OXB_PH_FIRST)) && a.Fb != nullptr) fb0 = a.Fb[i];
 		if(PH & (OXB_PH_SECOND | OXB_PH_FIRST)) {
 			// the force kernels accumulate the torque in the lab frame: rotate it into the body frame (L is a body-frame
 			// angular momentum with unit inertia, src/CUDA/Interactions/CUDA_DNA.cuh:896)
@@ -79,14 +89,14 @@ __global__ void __launch_bounds__(256, OXB_MB_INTEGRATE) k_integrate(oxb::Integr
 			v3 tl = mk3(T.x, T.y, T.z);
 			if(a.Fb != nullptr) {
 				// edge pipeline: the Debye-Hueckel kernel leaves its force sum, acting at the backbone site, in Fb
-				float4 fb = a.Fb[i];
+				const float4 fb = fb0;
 				v3 g = mk3(fb.x, fb.y, fb.z);
 				F.x += g.x; F.y += g.y; F.z += g.z;
 				tl += cross(A.a1 * a.back_a1 + A.a2 * a.back_a2 + A.a3 * a.back_a3, g);
 			}
 			T.x = dot(A.a1, tl); T.y = dot(A.a2, tl); T.z = dot(A.a3, tl);
 		}
-		double4 v = a.veld[i], L = a.Ld[i];
+		double4 v = v0, L = L0;
 		if(PH & OXB_PH_SECOND) {
 			v.x += F.x * hdt; v.y += F.y * hdt; v.z += F.z * hdt;
 			L.x += T.x * hdt; L.y += T.y * hdt; L.z += T.z * hdt;
@@ -103,7 +113,7 @@ __global__ void __launch_bounds__(256, OXB_MB_INTEGRATE) k_integrate(oxb::Integr
 			L.x *= S.factor_r; L.y *= S.factor_r; L.z *= S.factor_r;
 		}
 		if((PH & OXB_PH_THERMO) && (a.th.type == OXB_THERMOSTAT_LANGEVIN || (step % a.th.every) == 0)) {
-			unsigned id = (unsigned) word_index(a.ipos[i].w);
+			unsigned id = (unsigned) word_index(ip0.w);
 			if(a.rep != nullptr) {
 				// replica batching: the thermostat constants of this particle's replica (slots are replica-contiguous)
 				const oxb_replica_consts *rc = a.rep + i / a.n_per;
@@ -132,10 +142,10 @@ __global__ void __launch_bounds__(256, OXB_MB_INTEGRATE) k_integrate(oxb::Integr
 		if(PH & OXB_PH_FIRST) {
 			v.x += F.x * hdt; v.y += F.y * hdt; v.z += F.z * hdt;
 			L.x += T.x * hdt; L.y += T.y * hdt; L.z += T.z * hdt;
-			double4 r = a.posd[i];
+			double4 r = r0;
 			r.x += v.x * a.dt; r.y += v.y * a.dt; r.z += v.z * a.dt;
 			a.posd[i] = r;
-			int4 ip = a.ipos[i];
+			int4 ip = ip0;
 			ip.x = (int) to_fixed(r.x, a.box_inv[0]); ip.y = (int) to_fixed(r.y, a.box_inv[1]); ip.z = (int) to_fixed(r.z, a.box_inv[2]);
 			a.ipos[i] = ip;
 			// body-frame rotation by |L| dt about L: q <- q (x) (Lhat sin(th/2), cos(th/2))
@@ -174,7 +184,7 @@ __global__ void __launch_bounds__(256, OXB_MB_INTEGRATE) k_integrate(oxb::Integr
 				double bx = r.x + b1 * (sqx - sqy - sqz + sqw) + b2 * (2. * (xy - zw)) + b3 * (2. * (xz + yw));
 				double by = r.y + b1 * (2. * (xy + zw)) + b2 * (-sqx + sqy - sqz + sqw) + b3 * (2. * (yz - xw));
 				double bz = r.z + b1 * (2. * (xz - yw)) + b2 * (2. * (yz + xw)) + b3 * (-sqx - sqy + sqz + sqw);
-				int4 ib = a.iback[i];
+				int4 ib = ib0;
 				ib.x = (int) to_fixed(bx, a.box_inv[0]); ib.y = (int) to_fixed(by, a.box_inv[1]); ib.z = (int) to_fixed(bz, a.box_inv[2]);
 				a.iback[i] = ib;
 				// rotational staleness: neither the backbone site nor the base site may have moved further than the skin

@@ -5,6 +5,7 @@ mkdir -p gpurun_out
 TAG=${1:-r02}
 ( time timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -15 ) > gpurun_out/tests_${TAG}.log 2>&1
 tail -4 gpurun_out/tests_${TAG}.log
+( python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 ) | tee gpurun_out/smoke_${TAG}.log
 ( time timeout 1500 python bench.py > gpurun_out/bench_${TAG}_default.json 2> gpurun_out/bench_${TAG}_default.err ) 2>&1 | tail -3
 ( time timeout 900 python bench.py --impl reference > gpurun_out/bench_${TAG}_reference.json 2> gpurun_out/bench_${TAG}_reference.err ) 2>&1 | tail -3
 Q="--no-cpu-baseline --no-ref-cuda --no-extras"
