@@ -27,12 +27,12 @@ sys.path.insert(0, ROOT)
 T_STR, SALT, DT = "300K", 0.5, 0.003
 _REAL_STDOUT = sys.stdout
 FLOP_FAR, FLOP_DH, FLOP_CONTACT, FLOP_BONDED = 170.0, 60.0, 1500.0, 900.0  # SURVEY 8(d) per-pair figures
-# ncu dram__bytes_read.sum + dram__bytes_write.sum of one force pass, summed over its kernels (profiles/summary_r02a.txt: one
+# ncu dram__bytes_read.sum + dram__bytes_write.sum of one force pass, summed over its kernels (profiles/summary_r02c.txt: one
 # `ncu --set full` capture per workload, cold cache: the compulsory traffic of one pass)
 #   C2: Debye-Hueckel, bonded, near edges incl. the folded HB / cross-stacking / coaxial / FP64 excluded-volume tails
 #   C4: Debye-Hueckel, bonded, near edges incl. coaxial / FP64 excluded-volume tails, HB + cross stacking, mutual traps
-NCU_FORCE_PASS_DRAM_BYTES_C2 = int((7.80 + 7.29 + 9.01) * 1e6)
-NCU_FORCE_PASS_DRAM_BYTES_C4 = int((101.40 + 93.96 + 79.87 + 120.61 + 18.98) * 1e6)
+NCU_FORCE_PASS_DRAM_BYTES_C2 = int((7.80 + 7.29 + 9.08) * 1e6)
+NCU_FORCE_PASS_DRAM_BYTES_C4 = int((99.73 + 94.58 + 88.36 + 127.72 + 18.99) * 1e6)
 
 def workload(name):
     from oxdna_b200 import lattice
