@@ -42,7 +42,7 @@ def force_field():
     r.close()
 
 
-def lattice_case(name, n_duplex, spacing, steps, T="300K", salt=0.5, seed=3, nve_steps=200, ext=None, itype="DNA2_nomesh"):
+def lattice_case(name, n_duplex, spacing, steps, T="300K", salt=0.5, seed=3, nve_steps=200, ext=None, itype="DNA2_nomesh", more_keys=None, dna3=False):
     sysm = lattice.duplex_lattice(n_duplex, bp=20, spacing=spacing, seed=seed)
     d = tempfile.mkdtemp()
     top, conf = os.path.join(d, "l.top"), os.path.join(d, "l.dat")
@@ -51,7 +51,7 @@ def lattice_case(name, n_duplex, spacing, steps, T="300K", salt=0.5, seed=3, nve
     v, L = lattice.maxwell_velocities(len(sysm["pos"]), parse_temperature(T), 5)
     oio.write_conf(conf, sysm["box"], sysm["pos"], sysm["a1"], sysm["a3"], v, L)
     r = Reference(top, conf, interaction_type=itype, salt_concentration=salt, T=T, thermostat="brownian",
-                  newtonian_steps=103, diff_coeff=2.5, seed=7)
+                  newtonian_steps=103, diff_coeff=2.5, seed=7, **(more_keys or {}))
     r.step(steps)
     st = r.state()
     topo = r.topology()
@@ -59,7 +59,7 @@ def lattice_case(name, n_duplex, spacing, steps, T="300K", salt=0.5, seed=3, nve
     # restart without thermostat from the thermalised state: forces + an NVE segment
     conf2 = os.path.join(d, "t.dat")
     oio.write_conf(conf2, sysm["box"], st["pos"], st["a1"], st["a3"], st["vel"], st["L"])
-    keys = dict(interaction_type=itype, salt_concentration=salt, T=T, thermostat="no", dt=0.003)
+    keys = dict(interaction_type=itype, salt_concentration=salt, T=T, thermostat="no", dt=0.003, **(more_keys or {}))
     if ext:
         fpath = os.path.join(d, "forces.txt")
         with open(fpath, "w") as f:
@@ -79,6 +79,12 @@ def lattice_case(name, n_duplex, spacing, steps, T="300K", salt=0.5, seed=3, nve
                 btype=topo["btype"], n3=topo["n3"], n5=topo["n5"], strand=topo["strand"], force=f0["force"],
                 torque_body=f0["torque_body"], torque_lab=f0["torque_lab"], U=f0["U"], energy_split=r.energy_split(), pairs=r.pairs(),
                 T=T, salt=salt)
+    if dna3:
+        # the tetramer-indexed tables + scalars the live DNA3Interaction holds after init() (what CUDADNA3Interaction::cuda_init uploads)
+        tab, sc = np.zeros((215, 900)), np.zeros(40)
+        k = RH.lib().oxref_dna3_tables(RH._p(tab), RH._p(sc))
+        assert k == 29
+        base.update(dna3_tables=tab, dna3_scalars=sc[:k])
     r.step(nve_steps)
     st1 = r.state()
     base.update(nve_steps=nve_steps, pos1=st1["pos"], a11=st1["a1"], a31=st1["a3"], vel1=st1["vel"], L1=st1["L"],
@@ -271,6 +277,12 @@ if __name__ == "__main__":
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "dna1":
         lattice_case("lattice8_dna1", 8, 8.0, 3000, T="310K", itype="DNA_nomesh", nve_steps=100)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "dna3":
+        # oxDNA3 (DNA3Interaction_nomesh: the class the CUDA backend instantiates, InteractionFactory.cpp:63-65), sequence-dependent tables
+        sd = dict(use_average_seq=0, seq_dep_file="/root/reference/oxDNA3_sequence_dependent_parameters.txt")
+        lattice_case("dna3_lattice8", 8, 10.0, 3000, itype="DNA3_nomesh", more_keys=sd, dna3=True, nve_steps=100)
+        lattice_case("dna3_lattice27_dense", 27, 8.5, 4000, T="330K", salt=0.2, itype="DNA3_nomesh", more_keys=sd, dna3=True, nve_steps=100)
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "ext2":
         ext2_case()

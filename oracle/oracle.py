@@ -10,7 +10,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "liboxoracle.so")
 _SRC = [os.path.join(_HERE, "oxdna_oracle.c")]
-_HDR = [os.path.join(_HERE, "oxdna_oracle.h"), os.path.join(_HERE, "oxrna_oracle.inc")]
+_HDR = [os.path.join(_HERE, "oxdna_oracle.h"), os.path.join(_HERE, "oxrna_oracle.inc"), os.path.join(_HERE, "oxdna3_oracle.inc")]
 
 NTERMS = 8
 TERM_NAMES = ["FENE", "BEXC", "STCK", "NEXC", "HB", "CRSTCK", "CXSTCK", "DH"]
@@ -76,6 +76,18 @@ class RNA2Params(C.Structure):
         + [("dh_half_charged_ends", C.c_int), ("average", C.c_int), ("mismatch_repulsion", C.c_int), ("mis_eps", C.c_double),
            ("mis_shift", C.c_double), ("cpu_quirks", C.c_int), ("rcut", C.c_double)]
     )
+
+
+class DNA3Params(C.Structure):
+    """oxDNA3: tetramer-indexed tables (a pointer into `tables`, kept alive by the wrapper) + scalars; see oxdna_oracle.h"""
+    _fields_ = ([("tab", C.c_void_p), ("fene_eps", C.c_double), ("use_mbf", C.c_int)]
+                + [(n, C.c_double) for n in "mbf_fmax mbf_finf hb_multiplier dh_rc dh_rhigh dh_prefactor dh_b dh_minus_kappa".split()]
+                + [("dh_half_charged_ends", C.c_int), ("rcut", C.c_double), ("cxst_t1", _F4), ("cxst_t4", _F4), ("cxst_t5", _F4)]
+                + [(n, C.c_double) for n in "cxst_t1_sa cxst_t1_sb excl_eps back_a1 back_a2 backref_a1".split()]
+                + [("pos_stack", C.c_double * 5), ("pos_base", C.c_double * 5), ("ref_form", C.c_int)])
+
+
+DNA3_NTAB, DNA3_TSIZE, DNA3_NSCALARS = 215, 900, 29
 
 
 class ExtForce(C.Structure):
@@ -307,6 +319,15 @@ def rna2_params_seqdep(P, stck16, st_t_dep, cross16, hb_AT, hb_GC, hb_GT):
     return P
 
 
+def dna3_params(tables, scalars):
+    """tables: (215, 900) doubles, scalars: the block of oxref_dna3_tables -- both as stored in tests/golden/dna3_*.npz"""
+    P = DNA3Params()
+    P._tables = np.ascontiguousarray(tables, dtype=np.float64).reshape(DNA3_NTAB, DNA3_TSIZE)
+    P._scalars = np.ascontiguousarray(scalars, dtype=np.float64)
+    lib().oxo_dna3_params_fill(C.byref(P), _p(P._tables), _p(P._scalars))
+    return P
+
+
 def axes_from_a1a3(a1, a3):
     a1, a3 = _d(a1), _d(a3)
     N = a1.shape[0]
@@ -333,7 +354,7 @@ def forces(P, pos, axes, btype, n3, n5, box, pairs):
     N = pos.shape[0]
     f, tl, tb = np.zeros((N, 3)), np.zeros((N, 3)), np.zeros((N, 3))
     et, ep = np.zeros(NTERMS), np.zeros(N)
-    fn = lib().oxo_rna2_forces if isinstance(P, RNA2Params) else lib().oxo_dna2_forces
+    fn = lib().oxo_rna2_forces if isinstance(P, RNA2Params) else (lib().oxo_dna3_forces if isinstance(P, DNA3Params) else lib().oxo_dna2_forces)
     fn(C.byref(P), N, _p(pos), _p(axes), _p(btype), _p(n3), _p(n5), _p(box), _p(pairs),
                           C.c_longlong(pairs.shape[0]), _p(f), _p(tl), _p(tb), _p(et), _p(ep))
     return dict(force=f, torque_lab=tl, torque_body=tb, eterms=et, epart=ep, U=et.sum())
@@ -388,9 +409,9 @@ class MD:
         self.pairs[: len(p)] = p
         S.npairs = len(p)
         self.list_pos[:] = self.pos
-        rna = isinstance(P, RNA2Params)
-        self._steps = lib().oxo_rna2_md_steps if rna else lib().oxo_md_steps
-        (lib().oxo_rna2_md_compute_forces if rna else lib().oxo_md_compute_forces)(C.byref(P), C.byref(S))
+        kind = "rna2_" if isinstance(P, RNA2Params) else ("dna3_" if isinstance(P, DNA3Params) else "")
+        self._steps = getattr(lib(), f"oxo_{kind}md_steps")
+        getattr(lib(), f"oxo_{kind}md_compute_forces")(C.byref(P), C.byref(S))
 
     def step(self, n=1):
         return self._steps(C.byref(self.P), C.byref(self.S), int(n))

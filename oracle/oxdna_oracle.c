@@ -1133,3 +1133,4 @@ void oxo_langevin_params(double T, double dt, double gamma_in, double diff_in, d
 }
 
 #include "oxrna_oracle.inc"
+#include "oxdna3_oracle.inc"

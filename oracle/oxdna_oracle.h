@@ -151,6 +151,34 @@ void oxo_rna2_forces(const oxo_rna2_params *P, int N, const double *pos, const d
 int oxo_rna2_md_steps(const oxo_rna2_params *P, oxo_md *S, int nsteps);
 void oxo_rna2_md_compute_forces(const oxo_rna2_params *P, oxo_md *S);
 
+/* ------------------------------------------------------------------ oxDNA3 (src/Interactions/DNA3Interaction.cpp, class DNA3Interaction_nomesh)
+ * tab: OXO_DNA3_NTAB tables of OXO_DNA3_TSIZE = 6 x 5 x 5 x 6 doubles, entry ((n3_2 * 5 + n3_1) * 5 + n5_1) * 6 + n5_2 (5 = no neighbour;
+ * src/Utilities/oxdna3_utils.h:18-33), in this order (the member arrays of DNA3Interaction.h:70-113, array index fastest within a group):
+ *   0 fene_r0, 1 fene_delta, 2 fene_delta2, 3 mbf_xmax, 4.. excl_s[7], 11.. excl_r[7], 18.. excl_b[7], 25.. excl_rc[7],
+ *   32.. F1 {EPS, A, RC, R0, BLOW, BHIGH, RLOW, RHIGH, RCLOW, RCHIGH, SHIFT}[2], 54.. F2 {K, K_SYMM, RC, R0, BLOW, RLOW, RCLOW, BHIGH, RCHIGH, RHIGH}[4],
+ *   94.. F4 {A, B, T0, TS, TC}[21], 199.. F5 {A, B, XC, XS}[4] */
+enum { OXO3_FENE_R0 = 0, OXO3_FENE_DELTA = 1, OXO3_FENE_DELTA2 = 2, OXO3_MBF_XMAX = 3, OXO3_EXCL_S = 4, OXO3_EXCL_R = 11, OXO3_EXCL_B = 18, OXO3_EXCL_RC = 25,
+	OXO3_F1 = 32, OXO3_F2 = 54, OXO3_F4 = 94, OXO3_F5 = 199, OXO_DNA3_NTAB = 215, OXO_DNA3_TSIZE = 900 };
+typedef struct {
+	const double *tab;
+	double fene_eps; int use_mbf; double mbf_fmax, mbf_finf, hb_multiplier;
+	double dh_rc, dh_rhigh, dh_prefactor, dh_b, dh_minus_kappa; int dh_half_charged_ends;
+	double rcut;
+	oxo_f4 cxst_t1, cxst_t4, cxst_t5; double cxst_t1_sa, cxst_t1_sb; /* scalar angular set of the coaxial stacking (DNA2Interaction) */
+	double excl_eps;
+	double back_a1, back_a2, backref_a1, pos_stack[5], pos_base[5]; /* per-type stacking / base site offsets, src/model.h:15-39 */
+	/* 1 (default): the stacking phi1 / phi2 force exactly as the reference writes it (CPU class and CUDA kernel), with the oxDNA2 lever
+	 * gamma = 0.74 -- NOT the gradient of the energy for the oxDNA3 stacking site at 0.37; 0: the gradient (finite-difference checks) */
+	int ref_form;
+} oxo_dna3_params;
+/* scalars: the block written by oxref_dna3_tables (oracle/ref_harness.cpp), also stored in the fixtures */
+void oxo_dna3_params_fill(oxo_dna3_params *P, const double *tab, const double *scalars);
+void oxo_dna3_forces(const oxo_dna3_params *P, int N, const double *pos, const double *axes, const int *btype,
+		const int *n3, const int *n5, const double *box, const int *pairs, long long npairs,
+		double *force, double *torque_lab, double *torque_body, double *eterms, double *epart);
+int oxo_dna3_md_steps(const oxo_dna3_params *P, oxo_md *S, int nsteps);
+void oxo_dna3_md_compute_forces(const oxo_dna3_params *P, oxo_md *S);
+
 /* thermostat parameter derivation (src/Backends/Thermostats/{Brownian,Langevin,Bussi}Thermostat.cpp) */
 void oxo_brownian_params(double T, double dt, int newtonian_steps, double pt_in, double diff_coeff, double *pt, double *pr, double *rescale);
 void oxo_langevin_params(double T, double dt, double gamma_trans_in, double diff_coeff_in, double *gamma_t, double *gamma_r, double *resc_t, double *resc_r);

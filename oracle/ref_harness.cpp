@@ -16,6 +16,7 @@
 #include <Utilities/Timings.h>
 #include <Utilities/oxDNAException.h>
 #include <Interactions/BaseInteraction.h>
+#include <Interactions/DNA3Interaction.h>
 #include <Lists/BaseList.h>
 #include <Boxes/BaseBox.h>
 #include <Particles/BaseParticle.h>
@@ -274,6 +275,62 @@ int oxref_N_updates() {
 
 void oxref_update_temperature(double T) {
 	CONFIG_INFO->update_temperature(T);
+}
+
+// ---- oxDNA3: the tetramer-indexed parameter tables of the live DNA3Interaction, in the table order of include/oxdna_b200.h
+// (OXB_DNA3_*), i.e. what CUDADNA3Interaction::cuda_init uploads (src/CUDA/Interactions/CUDADNA3Interaction.cu:46-150).
+namespace {
+typedef MultiDimArray<TETRAMER_DIM_A, TETRAMER_DIM_B, TETRAMER_DIM_B, TETRAMER_DIM_A> Tab;
+struct Dna3Peek: public DNA3Interaction {
+	// pointers to protected members may be formed inside a derived class
+	static Tab &r0(DNA3Interaction &d) { return d.*(&Dna3Peek::_fene_r0_SD); }
+	static Tab &delta(DNA3Interaction &d) { return d.*(&Dna3Peek::_fene_delta_SD); }
+	static Tab &delta2(DNA3Interaction &d) { return d.*(&Dna3Peek::_fene_delta2_SD); }
+	static Tab &xmax(DNA3Interaction &d) { return d.*(&Dna3Peek::_mbf_xmax_SD); }
+	static double fene_eps(DNA3Interaction &d) { return d.*(&Dna3Peek::_fene_eps); }
+	static double hb_multi(DNA3Interaction &d) { return d.*(&Dna3Peek::_hb_multiplier); }
+	static bool use_mbf(DNA3Interaction &d) { return d.*(&Dna3Peek::_use_mbf); }
+	static double mbf_fmax(DNA3Interaction &d) { return d.*(&Dna3Peek::_mbf_fmax); }
+	static double mbf_finf(DNA3Interaction &d) { return d.*(&Dna3Peek::_mbf_finf); }
+	static double dh_rc(DNA3Interaction &d) { return d.*(&Dna3Peek::_debye_huckel_RC); }
+	static double dh_rhigh(DNA3Interaction &d) { return d.*(&Dna3Peek::_debye_huckel_RHIGH); }
+	static double dh_pref(DNA3Interaction &d) { return d.*(&Dna3Peek::_debye_huckel_prefactor); }
+	static double dh_b(DNA3Interaction &d) { return d.*(&Dna3Peek::_debye_huckel_B); }
+	static double dh_mk(DNA3Interaction &d) { return d.*(&Dna3Peek::_minus_kappa); }
+	static bool dh_half(DNA3Interaction &d) { return d.*(&Dna3Peek::_debye_huckel_half_charged_ends); }
+};
+void put(double *&o, const Tab *t, int n) {
+	for(int i = 0; i < n; i++) { std::memcpy(o, t[i].data, sizeof(double) * Tab::total_size); o += Tab::total_size; }
+}
+}
+
+// tables: 215 x 900 doubles; scalars: 40 doubles (see oracle/oracle.py: DNA3_SCALARS).  Returns 0, or -1 if the interaction is not oxDNA3.
+int oxref_dna3_tables(double *tables, double *scalars) {
+	DNA3Interaction *d = dynamic_cast<DNA3Interaction *>(CONFIG_INFO->interaction);
+	if(d == nullptr) return -1;
+	double *o = tables;
+	put(o, &Dna3Peek::r0(*d), 1); put(o, &Dna3Peek::delta(*d), 1); put(o, &Dna3Peek::delta2(*d), 1); put(o, &Dna3Peek::xmax(*d), 1);
+	put(o, d->_excl_s, 7); put(o, d->_excl_r, 7); put(o, d->_excl_b, 7); put(o, d->_excl_rc, 7);
+	put(o, d->F1_SD_EPS, 2); put(o, d->F1_SD_A, 2); put(o, d->F1_SD_RC, 2); put(o, d->F1_SD_R0, 2); put(o, d->F1_SD_BLOW, 2); put(o, d->F1_SD_BHIGH, 2);
+	put(o, d->F1_SD_RLOW, 2); put(o, d->F1_SD_RHIGH, 2); put(o, d->F1_SD_RCLOW, 2); put(o, d->F1_SD_RCHIGH, 2); put(o, d->F1_SD_SHIFT, 2);
+	put(o, d->F2_SD_K, 4); put(o, d->F2_SD_K_SYMM, 4); put(o, d->F2_SD_RC, 4); put(o, d->F2_SD_R0, 4); put(o, d->F2_SD_BLOW, 4); put(o, d->F2_SD_RLOW, 4);
+	put(o, d->F2_SD_RCLOW, 4); put(o, d->F2_SD_BHIGH, 4); put(o, d->F2_SD_RCHIGH, 4); put(o, d->F2_SD_RHIGH, 4);
+	put(o, d->F4_SD_THETA_A, 21); put(o, d->F4_SD_THETA_B, 21); put(o, d->F4_SD_THETA_T0, 21); put(o, d->F4_SD_THETA_TS, 21); put(o, d->F4_SD_THETA_TC, 21);
+	put(o, d->F5_SD_PHI_A, 4); put(o, d->F5_SD_PHI_B, 4); put(o, d->F5_SD_PHI_XC, 4); put(o, d->F5_SD_PHI_XS, 4);
+	double *s = scalars;
+	int k = 0;
+	s[k++] = Dna3Peek::fene_eps(*d); s[k++] = Dna3Peek::use_mbf(*d) ? 1. : 0.; s[k++] = Dna3Peek::mbf_fmax(*d); s[k++] = Dna3Peek::mbf_finf(*d);
+	s[k++] = Dna3Peek::hb_multi(*d);
+	s[k++] = Dna3Peek::dh_rc(*d); s[k++] = Dna3Peek::dh_rhigh(*d); s[k++] = Dna3Peek::dh_pref(*d); s[k++] = Dna3Peek::dh_b(*d); s[k++] = Dna3Peek::dh_mk(*d);
+	s[k++] = Dna3Peek::dh_half(*d) ? 1. : 0.;
+	s[k++] = d->get_rcut();
+	// the scalar f4 set of the coaxial stacking (DNA2Interaction members): theta1 (+ pure harmonic), theta4, theta5 = theta6
+	const int ids[3] = { CXST_F4_THETA1, CXST_F4_THETA4, CXST_F4_THETA5 };
+	for(int i = 0; i < 3; i++) {
+		s[k++] = d->F4_THETA_A[ids[i]]; s[k++] = d->F4_THETA_B[ids[i]]; s[k++] = d->F4_THETA_T0[ids[i]]; s[k++] = d->F4_THETA_TS[ids[i]]; s[k++] = d->F4_THETA_TC[ids[i]];
+	}
+	s[k++] = d->F4_THETA_SA[CXST_F4_THETA1]; s[k++] = d->F4_THETA_SB[CXST_F4_THETA1];
+	return k;
 }
 
 } // extern "C"
