@@ -199,6 +199,30 @@ int oxb_set_box(oxb_ctx *ctx, const double box[3]);                             
 int oxb_set_topology(oxb_ctx *ctx, const int *btype, const int *n3, const int *n5, const int *strand);
 int oxb_set_model_dna2(oxb_ctx *ctx, const oxb_dna2_params *P, double rcut);                  /* CUDADNAInteraction::cuda_init */
 int oxb_set_model_rna2(oxb_ctx *ctx, const oxb_rna2_params *P, double rcut);                  /* CUDARNAInteraction::cuda_init */
+
+/* ---- oxDNA3 (interaction_type = DNA3; src/Interactions/DNA3Interaction.{h,cpp}, src/CUDA/Interactions/CUDADNA3Interaction.cu, CUDA_DNA3.cuh).
+ * Every parameter of the oxDNA2 functional forms is a table over the tetramer (n3_2, n3_1, n5_1, n5_2): 6 x 5 x 5 x 6 = 900 entries,
+ * entry ((n3_2 * 5 + n3_1) * 5 + n5_1) * 6 + n5_2, 5 = no such neighbour (src/Utilities/oxdna3_utils.h:18-33).  The tables are INPUT: the host
+ * hands over what DNA3Interaction::init leaves in the class -- exactly the arrays CUDADNA3Interaction::cuda_init uploads
+ * (CUDADNA3Interaction.cu:46-150) -- as OXB_DNA3_NTAB tables of OXB_DNA3_TSIZE doubles in this order (array index fastest within a group):
+ *   0 _fene_r0_SD, 1 _fene_delta_SD, 2 _fene_delta2_SD, 3 _mbf_xmax_SD, 4.. _excl_s[7], 11.. _excl_r[7], 18.. _excl_b[7], 25.. _excl_rc[7],
+ *   32.. F1_SD_{EPS, A, RC, R0, BLOW, BHIGH, RLOW, RHIGH, RCLOW, RCHIGH, SHIFT}[2],
+ *   54.. F2_SD_{K, K_SYMM, RC, R0, BLOW, RLOW, RCLOW, BHIGH, RCHIGH, RHIGH}[4], 94.. F4_SD_THETA_{A, B, T0, TS, TC}[21], 199.. F5_SD_PHI_{A, B, XC, XS}[4]
+ * The library repacks them into per-tetramer records (csrc/dna3_model.cuh).  Both force variants of the reference (use_edge = 0 / 1) are
+ * served by one particle-centric kernel; replica batching is not available for this interaction. */
+enum { OXB_DNA3_FENE_R0 = 0, OXB_DNA3_FENE_DELTA = 1, OXB_DNA3_FENE_DELTA2 = 2, OXB_DNA3_MBF_XMAX = 3, OXB_DNA3_EXCL_S = 4, OXB_DNA3_EXCL_R = 11,
+	OXB_DNA3_EXCL_B = 18, OXB_DNA3_EXCL_RC = 25, OXB_DNA3_F1 = 32, OXB_DNA3_F2 = 54, OXB_DNA3_F4 = 94, OXB_DNA3_F5 = 199, OXB_DNA3_NTAB = 215, OXB_DNA3_TSIZE = 900 };
+typedef struct {
+	double fene_eps;                 /* _fene_eps */
+	double use_mbf, mbf_fmax, mbf_finf; /* max_backbone_force (non-zero = on), DNAInteraction.h:35-38 */
+	double hb_multiplier;
+	double dh_rc, dh_rhigh, dh_prefactor, dh_b, dh_minus_kappa, dh_half_charged_ends; /* DNA2Interaction.h:32-40 */
+	double rcut;                     /* get_rcut() */
+	double cxst_t1[5], cxst_t4[5], cxst_t5[5]; /* {A, B, T0, TS, TC} of the scalar F4_THETA_* at CXST_F4_THETA1 / 4 / 5: coaxial stacking keeps the oxDNA2 angular set */
+	double cxst_t1_sa, cxst_t1_sb;   /* F4_THETA_SA / SB [CXST_F4_THETA1], DNA2Interaction.h:111-112 */
+} oxb_dna3_scalars;
+int oxb_set_model_dna3(oxb_ctx *ctx, const double *tables, const oxb_dna3_scalars *S);       /* CUDADNA3Interaction::cuda_init */
+
 /* Replica batching: declare that the N particles are n_replicas copies of one N / n_replicas-particle system (topology, state and
  * external forces are given for all N particles, replica after replica; bonds must not cross replicas).  The model set with
  * oxb_set_model_* fixes the list radii and must be the one of the HOTTEST temperature any replica will visit (largest Debye-Hueckel

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "liboxdna_b200.so")
-SOURCES = ["context.cu", "forces.cu", "integrate.cu", "lists.cu", "sort.cu", "marshal.cu", "params.cpp"]
+SOURCES = ["context.cu", "forces.cu", "forces_dna3.cu", "integrate.cu", "lists.cu", "sort.cu", "marshal.cu", "params.cpp"]
 # extra -D flags for tuning experiments (profiles/micro/occupancy_sweep.sh)
 EXTRA = os.environ.get("OXB_EXTRA_NVCC", "").split()
 NVCC_FLAGS = EXTRA + ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-ftz=true", "-lineinfo", "-Xcompiler", "-fPIC",

@@ -228,9 +228,26 @@ class ForceViews(C.Structure):
                 ("step", C.c_longlong), ("stream", C.c_void_p)]
 
 
+class DNA3Scalars(C.Structure):
+    """oxb_dna3_scalars (include/oxdna_b200.h): 29 doubles, the order of the block oracle/ref_harness.cpp:oxref_dna3_tables writes"""
+    _fields_ = ([(n, C.c_double) for n in ("fene_eps use_mbf mbf_fmax mbf_finf hb_multiplier dh_rc dh_rhigh dh_prefactor dh_b dh_minus_kappa "
+                                           "dh_half_charged_ends rcut").split()]
+                + [("cxst_t1", C.c_double * 5), ("cxst_t4", C.c_double * 5), ("cxst_t5", C.c_double * 5), ("cxst_t1_sa", C.c_double), ("cxst_t1_sb", C.c_double)])
+
+
+DNA3_NTAB, DNA3_TSIZE = 215, 900
+
+
+def dna3_scalars(block):
+    """from the flat block of 29 doubles (fixtures, reference harness)"""
+    b = np.ascontiguousarray(block, dtype=np.float64)
+    assert b.size == C.sizeof(DNA3Scalars) // 8
+    return DNA3Scalars.from_buffer_copy(b.tobytes())
+
+
 FORCE_CALLBACK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(ForceViews))
 
-EXPORTED = """oxb_sizeof oxb_dna2_params_init oxb_dna1_params_init oxb_dna2_params_seqdep oxb_rna2_params_init oxb_rna2_params_seqdep oxb_set_model_rna2 oxb_create oxb_destroy oxb_last_error oxb_set_stream oxb_set_box
+EXPORTED = """oxb_sizeof oxb_dna2_params_init oxb_dna1_params_init oxb_dna2_params_seqdep oxb_rna2_params_init oxb_rna2_params_seqdep oxb_set_model_rna2 oxb_set_model_dna3 oxb_create oxb_destroy oxb_last_error oxb_set_stream oxb_set_box
 oxb_set_topology oxb_set_model_dna2 oxb_set_lists oxb_set_dt oxb_set_thermostat oxb_set_ext_forces oxb_set_ext_index_pool oxb_set_ext_grid_pool oxb_set_state oxb_get_state oxb_write_conf oxb_write_conf_binary
 oxb_set_step oxb_get_step oxb_sort oxb_update_lists oxb_compute_forces oxb_first_step oxb_second_step oxb_thermostat oxb_run
 oxb_synchronize oxb_get_forces oxb_energy oxb_barostat_move oxb_barostat_trial oxb_barostat_accept oxb_barostat_reject oxb_get_box oxb_set_host_wait oxb_fix_diffusion oxb_energy_split oxb_get_pairs oxb_get_stats oxb_device_views oxb_launch_count oxb_time_kernel oxb_set_profile oxb_get_profile
@@ -380,6 +397,14 @@ class Context:
 
     def set_model_rna2(self, P, rcut):
         self._ck(self._L.oxb_set_model_rna2(self._h, C.byref(P), C.c_double(rcut)))
+
+    def set_model_dna3(self, tables, scalars):
+        """tables: (215, 900) doubles in the order of include/oxdna_b200.h; scalars: DNA3Scalars or the flat block of 29 doubles"""
+        t = np.ascontiguousarray(tables, dtype=np.float64)
+        if t.size != DNA3_NTAB * DNA3_TSIZE:
+            raise ValueError(f"oxDNA3 needs {DNA3_NTAB} tables of {DNA3_TSIZE} entries")
+        S = scalars if isinstance(scalars, DNA3Scalars) else dna3_scalars(scalars)
+        self._ck(self._L.oxb_set_model_dna3(self._h, _p(t), C.byref(S)))
 
     def set_replicas(self, n):
         self._ck(self._L.oxb_set_replicas(self._h, int(n)))

@@ -8,6 +8,7 @@
 // synchronises once, rebuilds (sort + cells + Verlet list) and resumes at the pending force evaluation.  The reference
 // synchronises >= 6 times per step (timers) and reads a pinned flag every step.
 #include "kernels.h"
+#include "dna3_pack.h"
 
 #include <algorithm>
 #include <cmath>
@@ -63,7 +64,17 @@ struct oxb_ctx {
 	bool is_rna = false;
 	float back_a3 = 0.f;
 	double rcut = 0.;
-	oxb::ModelRef mref() const { return is_rna ? oxb::ModelRef{ nullptr, &rmodel } : oxb::ModelRef{ &model, nullptr }; }
+	// oxDNA3: `model` mirrors site offsets and radii as for oxRNA2; the kernels get the packed records (d3; one device allocation d3_buf)
+	bool is_dna3 = false;
+	oxb_dna3_dev d3;
+	float4 *d3_buf = nullptr;
+	int *d3_tcode = nullptr;
+	bool d3_tcode_valid = false;
+	int use_edge_asked = 0; // what oxb_set_lists was given (oxDNA3 is served by the particle-centric pass whatever it says)
+	oxb::ModelRef mref() const {
+		if(is_dna3) return oxb::ModelRef{ nullptr, nullptr, &d3 };
+		return is_rna ? oxb::ModelRef{ nullptr, &rmodel, nullptr } : oxb::ModelRef{ &model, nullptr, nullptr };
+	}
 
 	// replica batching (oxb_set_replicas): n_rep replicas of n_per particles, one row of temperature-dependent constants each
 	int n_rep = 1, n_per = 0;
@@ -668,6 +679,26 @@ int init_bussi(oxb_ctx *c) {
 	return 0;
 }
 
+// the per-particle type word of the oxDNA3 kernels (by ORIGINAL id): type | n3 type << 3 | n5 type << 6 | (btype == 4) << 9, 5 = no neighbour
+// (neigh_types of the reference, CUDA_DNA3.cuh:96-108; DNANucleotide::set_positions for the dummy base, DNANucleotide.cpp:71-79)
+int dna3_upload_codes(oxb_ctx *c) {
+	if(c->d3_tcode_valid) return 0;
+	if(!c->have_topology) return fail(c, 2, "the topology must be set before oxDNA3 forces are evaluated");
+	const int N = c->N;
+	std::vector<int> code(N);
+	for(int i = 0; i < N; i++) {
+		const int t = btype_to_type(c->h_btype[i]);
+		const int t3 = c->h_n3[i] >= 0 ? btype_to_type(c->h_btype[c->h_n3[i]]) : 5;
+		const int t5 = c->h_n5[i] >= 0 ? btype_to_type(c->h_btype[c->h_n5[i]]) : 5;
+		code[i] = t | (t3 << 3) | (t5 << 6) | ((c->h_btype[i] == 4) ? (1 << 9) : 0);
+	}
+	if(c->d3_tcode == nullptr) CU(dalloc(&c->d3_tcode, (size_t) N));
+	CU(cudaMemcpy(c->d3_tcode, code.data(), sizeof(int) * N, cudaMemcpyHostToDevice));
+	c->d3.tcode = c->d3_tcode;
+	c->d3_tcode_valid = true;
+	return 0;
+}
+
 int check_ready(oxb_ctx *c) {
 	// any host thread may drive a context (replica ensembles run one thread per local replica): bind the calling thread
 	cudaSetDevice(c->device);
@@ -678,7 +709,9 @@ int check_ready(oxb_ctx *c) {
 	if(c->n_rep > 1) {
 		if(!c->have_rep_consts) return fail(c, 2, "replica batching: oxb_set_replica_consts has not been called");
 		if(c->th.type == OXB_THERMOSTAT_BUSSI) return fail(c, 1, "replica batching is not available with the Bussi thermostat");
+		if(c->is_dna3) return fail(c, 1, "replica batching is not available for oxDNA3");
 	}
+	if(c->is_dna3) return dna3_upload_codes(c);
 	return 0;
 }
 
@@ -774,6 +807,7 @@ unsigned long long config_hash(const oxb_ctx *c) {
 	// oxRNA: `model` only mirrors what the context reads; the kernels freeze the full RNA block (stacking strengths, sequence-dependent
 	// tables, mismatch repulsion ...) by value
 	if(c->is_rna) { mix(&c->rmodel, sizeof(c->rmodel)); mix(&c->back_a3, sizeof(float)); }
+	if(c->is_dna3) mix(&c->d3, sizeof(c->d3)); // scalars by value, tables behind stable pointers (re-uploaded in place)
 	mix(&c->precision, sizeof(int));
 	mix(&c->th.type, sizeof(int)); mix(&c->th.every, sizeof(int)); mix(&c->th.a, 4 * sizeof(float)); mix(&c->th.seed, sizeof(c->th.seed));
 	mix(&c->dt, sizeof(double)); mix(&c->skin, sizeof(double));
@@ -933,6 +967,7 @@ void oxb_destroy(oxb_ctx *c) {
 	}
 	cudaFree(c->Fb);
 	cudaFree(c->rep); cudaFree(c->d_rep_energy);
+	cudaFree(c->d3_buf); cudaFree(c->d3_tcode);
 	if(c->h_rep_energy) cudaFreeHost(c->h_rep_energy);
 	cudaFree(c->slot_of); cudaFree(c->flags); cudaFree(c->sums); cudaFree(c->d_energy); cudaFree(c->ext); cudaFree(c->ext_all); cudaFree(c->ext_com); cudaFree(c->ext_pool); cudaFree(c->ext_grid);
 	cudaFree(c->d_topo); cudaFree(c->d_stage); cudaFree(c->d_marshal_err);
@@ -988,6 +1023,7 @@ int oxb_set_topology(oxb_ctx *c, const int *btype, const int *n3, const int *n5,
 		CU(cudaMemcpy(c->d_topo, ht.data(), sizeof(int4) * N, cudaMemcpyHostToDevice));
 	}
 	c->have_topology = true;
+	c->d3_tcode_valid = false;
 	c->have_state = false;
 	cudaFree(c->mol_of); cudaFree(c->mol_inv_size); cudaFree(c->mol_coms); cudaFree(c->pos_backup);
 	c->mol_of = nullptr; c->mol_inv_size = nullptr; c->mol_coms = nullptr; c->pos_backup = nullptr;
@@ -995,9 +1031,19 @@ int oxb_set_topology(oxb_ctx *c, const int *btype, const int *n3, const int *n5,
 	return 0;
 }
 
+// oxDNA3 is served by the particle-centric pass: entering / leaving the model switches the edge pipeline off / back to what was asked
+static void leave_dna3(oxb_ctx *c) {
+	c->is_dna3 = false;
+	if(c->use_edge != c->use_edge_asked) {
+		c->use_edge = c->use_edge_asked;
+		if(c->lists_allocated) free_lists(c);
+	}
+}
+
 int oxb_set_model_dna2(oxb_ctx *c, const oxb_dna2_params *P, double rcut) {
 	if(c == nullptr || P == nullptr) return 1;
-	if(c->is_rna) { drop_graphs(c); c->lists_valid = false; }
+	if(c->is_rna || c->is_dna3) { drop_graphs(c); c->lists_valid = false; }
+	if(c->is_dna3) leave_dna3(c);
 	c->model = *P;
 	c->is_rna = false;
 	c->back_a3 = 0.f;
@@ -1015,6 +1061,7 @@ int oxb_set_model_dna2(oxb_ctx *c, const oxb_dna2_params *P, double rcut) {
 int oxb_set_model_rna2(oxb_ctx *c, const oxb_rna2_params *P, double rcut) {
 	if(c == nullptr || P == nullptr) return 1;
 	if(!c->is_rna && c->have_model) { drop_graphs(c); c->lists_valid = false; }
+	if(c->is_dna3) leave_dna3(c);
 	c->rmodel = *P;
 	c->is_rna = true;
 	// the subset the context reads (list radii, site offsets)
@@ -1029,6 +1076,38 @@ int oxb_set_model_rna2(oxb_ctx *c, const oxb_rna2_params *P, double rcut) {
 	c->have_model = true;
 	c->forces_valid = false;
 	if(c->lists_valid && (rcut + 2. * c->skin > c->lists_rv || (double) P->dh_rc > c->lists_dh_rc)) c->lists_valid = false;
+	return 0;
+}
+
+int oxb_set_model_dna3(oxb_ctx *c, const double *tab, const oxb_dna3_scalars *S) {
+	if(c == nullptr || tab == nullptr || S == nullptr) return 1;
+	if(c->n_rep > 1) return fail(c, 1, "replica batching is not available for oxDNA3");
+	cudaSetDevice(c->device);
+	CU(cudaStreamSynchronize(c->stream));
+	const bool entering = !c->is_dna3;
+	if(entering && c->have_model) { drop_graphs(c); c->lists_valid = false; }
+	std::vector<float> h;
+	oxb_dna3_dev &D = c->d3;
+	const int *keep_tcode = c->d3_tcode_valid ? c->d3_tcode : nullptr;
+	size_t off[5];
+	dna3_pack(tab, S, h, D, off);
+	if(c->d3_buf == nullptr) CU(dalloc(&c->d3_buf, h.size() / 4));
+	CU(cudaMemcpy(c->d3_buf, h.data(), sizeof(float) * h.size(), cudaMemcpyHostToDevice));
+	D.bonded = c->d3_buf + off[0]; D.crst = c->d3_buf + off[1]; D.cxst = c->d3_buf + off[2]; D.hb = c->d3_buf + off[3]; D.nexcl = c->d3_buf + off[4];
+	D.tcode = keep_tcode;
+	// the subset the context itself reads (list radii, site offsets for the integrator's fixed-point sites)
+	oxb_dna2_params &M = c->model;
+	std::memset(&M, 0, sizeof(M));
+	M.back_a1 = D.back_a1; M.back_a2 = D.back_a2; c->back_a3 = 0.f;
+	M.base_a1 = 0.43f; M.stack_a1 = 0.37f; M.backref_a1 = D.backref_a1;
+	M.dh_rc = D.dh_rc; M.rcut = (float) S->rcut; M.rcut_near = (float) S->rcut;
+	c->is_rna = false;
+	c->is_dna3 = true;
+	if(c->use_edge) { c->use_edge = 0; if(c->lists_allocated) free_lists(c); c->lists_valid = false; }
+	c->rcut = S->rcut;
+	c->have_model = true;
+	c->forces_valid = false;
+	if(c->lists_valid && (S->rcut + 2. * c->skin > c->lists_rv || (double) D.dh_rc > c->lists_dh_rc)) c->lists_valid = false;
 	return 0;
 }
 
@@ -1117,7 +1196,7 @@ int oxb_replica_energies(oxb_ctx *c, double *U) {
 int oxb_set_lists(oxb_ctx *c, double verlet_skin, int use_edge, int sort_every, double max_density_multiplier) {
 	if(c == nullptr) return 1;
 	if(!(verlet_skin > 0)) return fail(c, 1, "verlet_skin must be > 0");
-	c->skin = verlet_skin; c->use_edge = use_edge ? 1 : 0; c->sort_every = sort_every < 0 ? 0 : sort_every;
+	c->skin = verlet_skin; c->use_edge_asked = use_edge ? 1 : 0; c->use_edge = (use_edge && !c->is_dna3) ? 1 : 0; c->sort_every = sort_every < 0 ? 0 : sort_every;
 	c->max_density_multiplier = max_density_multiplier;
 	c->lists_valid = false; c->forces_valid = false;
 	if(c->lists_allocated) free_lists(c);

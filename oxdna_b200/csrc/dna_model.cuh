@@ -247,7 +247,7 @@ struct PairAcc {
 #ifdef __CUDACC__
 // the force on q of one excluded-volume site pair evaluated in double from the FP64 state.  Deliberately NOT inlined: it runs for the
 // rare active terms only and must not add to the register footprint of the kernels' common path.
-__device__ __noinline__ float3 excl_force_double(const ExclRefine *R, const oxb_excl *e, float eps, int kind, float cb) {
+static __device__ __noinline__ float3 excl_force_double(const ExclRefine *R, const oxb_excl *e, float eps, int kind, float cbp, float cbq) {
 	const double4 pp = R->posd[R->sp], pq = R->posd[R->sq], qp = R->quatd[R->sp], qq = R->quatd[R->sq];
 	double rd[3] = { pq.x - pp.x, pq.y - pp.y, pq.z - pp.z };
 	for(int k = 0; k < 3; k++) rd[k] -= R->L[k] * rint(rd[k] / R->L[k]);
@@ -258,8 +258,8 @@ __device__ __noinline__ float3 excl_force_double(const ExclRefine *R, const oxb_
 	const bool p_back = (kind == OXB_SITE_KK || kind == OXB_SITE_KA), q_back = (kind == OXB_SITE_KK || kind == OXB_SITE_AK);
 	double dd[3];
 	for(int k = 0; k < 3; k++) {
-		const double sp = p_back ? R->b1 * a1p[k] + R->b2 * a2p[k] + R->b3 * a3p[k] : (double) cb * a1p[k];
-		const double sq = q_back ? R->b1 * a1q[k] + R->b2 * a2q[k] + R->b3 * a3q[k] : (double) cb * a1q[k];
+		const double sp = p_back ? R->b1 * a1p[k] + R->b2 * a2p[k] + R->b3 * a3p[k] : (double) cbp * a1p[k];
+		const double sq = q_back ? R->b1 * a1q[k] + R->b2 * a2q[k] + R->b3 * a3q[k] : (double) cbq * a1q[k];
 		dd[k] = rd[k] + sq - sp;
 	}
 	const double r2 = dd[0] * dd[0] + dd[1] * dd[1] + dd[2] * dd[2];
@@ -278,18 +278,20 @@ __device__ __noinline__ float3 excl_force_double(const ExclRefine *R, const oxb_
 }
 #endif
 
-// adds (double-precision force) - (the FP32 force d * s already accumulated) of one active excluded-volume site pair
-OXB_HD void excl_fix(PairAcc &acc, const oxb_excl &e, float eps, v3 d, float s, int kind, float cb) {
+// adds (double-precision force) - (the FP32 force d * s already accumulated) of one active excluded-volume site pair; cbp / cbq: offsets of
+// the base sites of p and q along a1 (oxDNA3: per type)
+OXB_HD void excl_fix2(PairAcc &acc, const oxb_excl &e, float eps, v3 d, float s, int kind, float cbp, float cbq) {
 #ifdef __CUDA_ARCH__
 	if(acc.refine == nullptr) return;
-	const float3 fd = excl_force_double(acc.refine, &e, eps, kind, cb);
+	const float3 fd = excl_force_double(acc.refine, &e, eps, kind, cbp, cbq);
 	const v3 delta = mk3(fd.x - d.x * s, fd.y - d.y * s, fd.z - d.z * s);
 	if(kind == OXB_SITE_KK) acc.site_kk(delta);
-	else if(kind == OXB_SITE_AA) acc.site_aa(delta, cb, cb);
-	else if(kind == OXB_SITE_AK) acc.site_ak(delta, cb);
-	else acc.site_ka(delta, cb);
+	else if(kind == OXB_SITE_AA) acc.site_aa(delta, cbp, cbq);
+	else if(kind == OXB_SITE_AK) acc.site_ak(delta, cbp);
+	else acc.site_ka(delta, cbq);
 #endif
 }
+OXB_HD void excl_fix(PairAcc &acc, const oxb_excl &e, float eps, v3 d, float s, int kind, float cb) { excl_fix2(acc, e, eps, d, s, kind, cb, cb); }
 
 
 struct Angle {

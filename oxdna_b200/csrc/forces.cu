@@ -1139,7 +1139,8 @@ void launch_forces_particle(cudaStream_t s, const ModelRef &MR, BoxF box, int N,
 		const double4 *posd, const double4 *quatd, const int2 *bonds,
 		const int *nbr, const int *nnbr, int stride, float4 *F, float4 *T, const oxb_replica_consts *rep, int n_per, int *flags, int hw) {
 	int tpb = 128;
-	if(MR.rna) k_forces_particle<RnaModel><<<(N + tpb - 1) / tpb, tpb, 0, s>>>(*MR.rna, box, N, ipos, iback, axf, posd, quatd, bonds, nbr, nnbr, stride, F, T, rep, n_per, flags, hw);
+	if(MR.dna3) launch_forces_dna3(s, *MR.dna3, box, N, ipos, iback, axf, posd, quatd, bonds, nbr, nnbr, stride, F, T, flags, hw);
+	else if(MR.rna) k_forces_particle<RnaModel><<<(N + tpb - 1) / tpb, tpb, 0, s>>>(*MR.rna, box, N, ipos, iback, axf, posd, quatd, bonds, nbr, nnbr, stride, F, T, rep, n_per, flags, hw);
 	else k_forces_particle<DnaModel><<<(N + tpb - 1) / tpb, tpb, 0, s>>>(*MR.dna, box, N, ipos, iback, axf, posd, quatd, bonds, nbr, nnbr, stride, F, T, rep, n_per, flags, hw);
 }
 
@@ -1201,6 +1202,7 @@ void launch_edge_stage(cudaStream_t s, int which, const ModelRef &MR, BoxF box, 
 
 void launch_energy_split(cudaStream_t s, const ModelRef &MR, BoxF box, int N, const int4 *ipos, const float4 *axf, const int2 *bonds, const int *nbr,
 		const int *nnbr, int stride, double *out) {
+	if(MR.dna3) { launch_energy_split_dna3(s, *MR.dna3, box, N, ipos, axf, bonds, nbr, nnbr, stride, out); return; }
 	cudaMemsetAsync(out, 0, sizeof(double) * OXB_NTERMS, s);
 	int tpb = 128;
 	if(MR.rna) k_energy_split<RnaModel><<<(N + tpb - 1) / tpb, tpb, 0, s>>>(*MR.rna, box, N, ipos, axf, bonds, nbr, nnbr, stride, out);

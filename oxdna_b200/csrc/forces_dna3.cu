@@ -1,0 +1,157 @@
+// oxDNA3 force pass (sm_100a).  Replaces DNA3_forces / DNA3_forces_edge_nonbonded / DNA3_forces_edge_bonded of the reference
+// (src/CUDA/Interactions/CUDA_DNA3.cuh:880-1085, CUDADNA3Interaction.cu:171-212).  One thread per particle over the full Verlet matrix,
+// every listed pair evaluated from both ends: no atomics, deterministic, the same launch shape as k_forces_particle (forces.cu).  Both of
+// the reference's variants (`use_edge` = 0 / 1) are served by this kernel: their results are identical by construction.
+//
+// Data: as forces.cu, plus the packed parameter records and the per-particle type word of dna3_model.cuh.
+#include "dna3_model.cuh"
+#include "kernels.h"
+
+namespace {
+
+struct P3 {
+	int4 ip;
+	Axes ax;
+	v3 back;
+	int btype;
+	Nuc3 n;
+};
+
+__device__ __forceinline__ P3 load_p3(const oxb_dna3_dev &M, const int4 *__restrict__ ipos, const float4 *__restrict__ axf, int i) {
+	P3 P;
+	P.ip = __ldg(ipos + i);
+	P.ax = load_axes(axf, i);
+	P.back = P.ax.a1 * M.back_a1 + P.ax.a2 * M.back_a2;
+	P.btype = word_btype(P.ip.w);
+	P.n = nuc3_from_code(__ldg(M.tcode + word_index(P.ip.w)));
+	return P;
+}
+
+__device__ __forceinline__ ExclRefine refine3(const oxb_dna3_dev &M, const BoxF &box, const double4 *posd, const double4 *quatd) {
+	ExclRefine R;
+	R.posd = posd; R.quatd = quatd; R.sp = R.sq = 0;
+	R.L[0] = box.dsx * 4294967296.; R.L[1] = box.dsy * 4294967296.; R.L[2] = box.dsz * 4294967296.;
+	R.b1 = (double) M.back_a1; R.b2 = (double) M.back_a2; R.b3 = 0.;
+	return R;
+}
+
+// the bond p -> q = n3(p): record of the tetramer (n3(q), q, p, n5(p)); FENE in double from the fixed-point backbone sites (mixed precision)
+__device__ __forceinline__ float bond3(const oxb_dna3_dev &M, const BoxF &box, const P3 &P, const P3 &Q, const int4 *__restrict__ iback, int sp, int sq,
+		bool refine, PairAcc &acc, bool &broken, float *esplit) {
+	float rec[OXB3_REC_BONDED];
+	load_rec<OXB3_REC_BONDED / 4>(M.bonded + ix4(Q.n.n3t, Q.n.type, P.n.type, P.n.n5t) * (OXB3_REC_BONDED / 4), rec);
+	FeneSite fs;
+	if(refine) fs = fene_from_sites(fene3_of(M, rec), box, __ldg(iback + sp), __ldg(iback + sq), broken);
+	return dna3_bonded(M, rec, min_image_fixed(box, P.ip, Q.ip), P.ax, Q.ax, P.n, Q.n, P.back, Q.back, acc, broken, esplit, refine ? &fs : nullptr);
+}
+
+__global__ void __launch_bounds__(128, 4) k_forces_dna3(const __grid_constant__ oxb_dna3_dev M, BoxF box, int N, const int4 *__restrict__ ipos,
+		const int4 *__restrict__ iback, const float4 *__restrict__ axf, const double4 *__restrict__ posd, const double4 *__restrict__ quatd,
+		const int2 *__restrict__ bonds, const int *__restrict__ nbr, const int *__restrict__ nnbr, int stride,
+		float4 *__restrict__ F, float4 *__restrict__ T, int *__restrict__ flags, int hw) {
+	if(blockIdx.x == 0 && threadIdx.x == 0) prof_mark(flags, flags[hw] ? OXB_PROF_WAIT : OXB_PROF_FORCE);
+	if(flags[hw]) return;
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= N) return;
+	const P3 P = load_p3(M, ipos, axf, i);
+	const int2 b = __ldg(bonds + i);
+	v3 f = mk3(0.f, 0.f, 0.f), t = mk3(0.f, 0.f, 0.f);
+	float e = 0.f, ehb = 0.f;
+	bool broken = false;
+	ExclRefine R = refine3(M, box, posd, quatd);
+	const bool refine = posd != nullptr; // backend_precision = mixed
+	if(b.x >= 0) { // I am the 5' side of the bond (p), q = my n3
+		const P3 Q = load_p3(M, ipos, axf, b.x);
+		PairAcc acc;
+		acc.clear();
+		R.sp = i; R.sq = b.x; acc.refine = refine ? &R : nullptr;
+		e += bond3(M, box, P, Q, iback, i, b.x, refine, acc, broken, nullptr);
+		f -= acc.F;
+		t += acc.torque_p(P.ax, P.back);
+	}
+	if(b.y >= 0) { // my n5 neighbour is p, I am q
+		const P3 Q = load_p3(M, ipos, axf, b.y);
+		PairAcc acc;
+		acc.clear();
+		R.sp = b.y; R.sq = i; acc.refine = refine ? &R : nullptr;
+		e += bond3(M, box, Q, P, iback, b.y, i, refine, acc, broken, nullptr);
+		f += acc.F;
+		t += acc.torque_q(P.ax, P.back);
+	}
+	const int nn = __ldg(nnbr + i);
+	for(int k = 0; k < nn; k++) {
+		const int j = __ldg(nbr + (size_t) k * stride + i);
+		const P3 Q = load_p3(M, ipos, axf, j);
+		PairAcc acc;
+		acc.clear();
+		R.sp = i; R.sq = j; acc.refine = refine ? &R : nullptr;
+		const PairEnergy pe = dna3_nonbonded(M, min_image_fixed(box, P.ip, Q.ip), P.ax, Q.ax, P.btype, Q.btype, P.n, Q.n, P.back, Q.back, acc);
+		e += pe.total;
+		ehb += pe.hb;
+		f -= acc.F;
+		t += acc.torque_p(P.ax, P.back);
+	}
+	// torque stays in the lab frame; the integrator rotates it into the body frame
+	F[i] = make_float4(f.x, f.y, f.z, e);
+	T[i] = make_float4(t.x, t.y, t.z, ehb);
+	if(broken) atomicOr(flags + OXB_FLAG_ERROR, OXB_ERR_FENE_BROKEN);
+}
+
+// per-term energies (the CPU get_system_energy_split of the reference, BaseInteraction.cpp:61-90): every unique pair once, from its lower slot
+__global__ void __launch_bounds__(128) k_energy_split_dna3(const __grid_constant__ oxb_dna3_dev M, BoxF box, int N, const int4 *__restrict__ ipos,
+		const float4 *__restrict__ axf, const int2 *__restrict__ bonds, const int *__restrict__ nbr, const int *__restrict__ nnbr, int stride,
+		double *__restrict__ out) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	float e[OXB_NTERMS];
+#pragma unroll
+	for(int t = 0; t < OXB_NTERMS; t++) e[t] = 0.f;
+	if(i < N) {
+		const P3 P = load_p3(M, ipos, axf, i);
+		const int2 b = __ldg(bonds + i);
+		PairAcc acc;
+		acc.clear();
+		bool broken = false;
+		if(b.x >= 0) {
+			const P3 Q = load_p3(M, ipos, axf, b.x);
+			bond3(M, box, P, Q, nullptr, i, b.x, false, acc, broken, e);
+		}
+		const int nn = __ldg(nnbr + i);
+		for(int k = 0; k < nn; k++) {
+			const int j = __ldg(nbr + (size_t) k * stride + i) & OXB_SLOT_MASK;
+			if(j < i) continue;
+			const P3 Q = load_p3(M, ipos, axf, j);
+			dna3_nonbonded(M, min_image_fixed(box, P.ip, Q.ip), P.ax, Q.ax, P.btype, Q.btype, P.n, Q.n, P.back, Q.back, acc, e);
+		}
+	}
+	__shared__ double sh[OXB_NTERMS][4];
+#pragma unroll
+	for(int t = 0; t < OXB_NTERMS; t++) {
+		double x = (double) e[t];
+		for(int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+		if((threadIdx.x & 31) == 0) sh[t][threadIdx.x >> 5] = x;
+	}
+	__syncthreads();
+	if(threadIdx.x < OXB_NTERMS) {
+		const double x = sh[threadIdx.x][0] + sh[threadIdx.x][1] + sh[threadIdx.x][2] + sh[threadIdx.x][3];
+		if(x != 0.) atomicAdd(out + threadIdx.x, x);
+	}
+}
+
+} // namespace
+
+namespace oxb {
+
+void launch_forces_dna3(cudaStream_t s, const oxb_dna3_dev &M, BoxF box, int N, const int4 *ipos, const int4 *iback, const float4 *axf,
+		const double4 *posd, const double4 *quatd, const int2 *bonds, const int *nbr, const int *nnbr, int stride, float4 *F, float4 *T, int *flags, int hw) {
+	const int tpb = 128;
+	k_forces_dna3<<<(N + tpb - 1) / tpb, tpb, 0, s>>>(M, box, N, ipos, iback, axf, posd, quatd, bonds, nbr, nnbr, stride, F, T, flags, hw);
+}
+
+void launch_energy_split_dna3(cudaStream_t s, const oxb_dna3_dev &M, BoxF box, int N, const int4 *ipos, const float4 *axf, const int2 *bonds,
+		const int *nbr, const int *nnbr, int stride, double *out) {
+	cudaMemsetAsync(out, 0, sizeof(double) * OXB_NTERMS, s);
+	const int tpb = 128;
+	k_energy_split_dna3<<<(N + tpb - 1) / tpb, tpb, 0, s>>>(M, box, N, ipos, axf, bonds, nbr, nnbr, stride, out);
+}
+
+} // namespace oxb

@@ -73,13 +73,43 @@ struct KinSums {
 // phases: bit 0 = second half-kick of step `step`, bit 1 = thermostat of step `step`, bit 2 = first half-kick + drift of step+1
 enum { OXB_PH_SECOND = 1, OXB_PH_THERMO = 2, OXB_PH_FIRST = 4, OXB_PH_BUSSI_SUMS = 8, OXB_PH_BUSSI_APPLY = 16, OXB_PH_COUNT_STEP = 32 };
 
+// ---- oxDNA3 (dna3_model.cuh, forces_dna3.cu): packed parameter records, see dna3_model.cuh for the layout
+enum { OXB3_REC_BONDED = 48, OXB3_REC_CRST = 32, OXB3_REC_CXST = 12, OXB3_REC_HB = 32, OXB3_REC_NEXCL = 16 };
+
+// kernel argument (by value): device pointers to the packed records + the scalars of the model
+struct oxb_dna3_dev {
+	const float4 *bonded; // 900 x 12 float4: fene {r0, delta2, xmax, e0} | excl 4, 5, 6 {sigma2, rstar2, b, rc} | stacking f1 (12) | f4 theta4, theta5 (12) | f5 phi1, phi2 (8)
+	const float4 *crst;   // 2 x 900 x 8 float4 (3'3' diagonal, then 5'5'): f2 (12) | f4 theta1, theta2, theta4, theta7 (20)
+	const float4 *cxst;   // 900 x 3 float4: f2 with K, K_SYMM in slot 9
+	const float4 *hb;     // 25 x 8 float4 [type q * 5 + type p]: f1 (12) | f4 theta1, theta2, theta4, theta7 (20)
+	const float4 *nexcl;  // 25 x 4 float4 [type q * 5 + type p]: excl 0..3 {sigma2, rstar2, b, rc}
+	const int *tcode;     // per ORIGINAL id: type | n3 type << 3 | n5 type << 6 | (btype == 4) << 9   (5 = no neighbour)
+	float fene_eps, mbf_fmax, mbf_finf, hb_multiplier, excl_eps;
+	int use_mbf;
+	float dh_minus_kappa, dh_prefactor, dh_rhigh, dh_rc, dh_b;
+	int dh_half_charged_ends;
+	float rcut2;
+	float r2_excl_max, r2_base_max, r2_stack_max; // squares of: longest excluded-volume range + both levers; longest HB / cross-stacking range; longest coaxial range
+	oxb_f4 cxst_t1, cxst_t4, cxst_t5;
+	float cxst_t1_sa, cxst_t1_sb;
+	float back_a1, back_a2, backref_a1, gamma;
+	float pos_stack[5], pos_base[5];
+};
+
 namespace oxb {
 
 // the force field of a context: exactly one of the two blocks is set
 struct ModelRef {
 	const oxb_dna2_params *dna;
 	const oxb_rna2_params *rna;
+	const oxb_dna3_dev *dna3; // oxDNA3: particle-centric pass only (forces_dna3.cu)
 };
+
+// ---- forces_dna3.cu
+void launch_forces_dna3(cudaStream_t s, const oxb_dna3_dev &M, BoxF box, int N, const int4 *ipos, const int4 *iback, const float4 *axf,
+		const double4 *posd, const double4 *quatd, const int2 *bonds, const int *nbr, const int *nnbr, int stride, float4 *F, float4 *T, int *flags, int hw);
+void launch_energy_split_dna3(cudaStream_t s, const oxb_dna3_dev &M, BoxF box, int N, const int4 *ipos, const float4 *axf, const int2 *bonds,
+		const int *nbr, const int *nnbr, int stride, double *out);
 
 // ---- forces.cu
 void launch_forces_particle(cudaStream_t s, const ModelRef &M, BoxF box, int N, const int4 *ipos, const int4 *iback, const float4 *axf,

@@ -168,6 +168,70 @@ void CUDADNA1Interaction::_on_T_update() {
 	}
 }
 
+// ---- oxDNA3
+void CUDADNA3Interaction::get_settings(input_file &inp) {
+	Logger::instance()->disable_log("CUDADNA3Interaction");
+	DNA3Interaction::get_settings(inp);
+	Logger::instance()->enable_log("CUDADNA3Interaction");
+}
+
+void CUDADNA3Interaction::cuda_init(oxb_ctx *ctx, int N) {
+	CUDABaseInteraction::cuda_init(ctx, N);
+	Logger::instance()->disable_log("CUDADNA3Interaction");
+	DNA3Interaction::init();
+	Logger::instance()->enable_log("CUDADNA3Interaction");
+	_upload();
+}
+
+void CUDADNA3Interaction::_upload() {
+	if(_ctx == nullptr) return;
+	typedef MultiDimArray<TETRAMER_DIM_A, TETRAMER_DIM_B, TETRAMER_DIM_B, TETRAMER_DIM_A> Tab;
+	static_assert(Tab::total_size == OXB_DNA3_TSIZE, "tetramer table size");
+	std::vector<double> tables((size_t) OXB_DNA3_NTAB * OXB_DNA3_TSIZE);
+	double *o = tables.data();
+	auto put = [&o](const Tab *t, int n) {
+		for(int i = 0; i < n; i++) {
+			for(size_t k = 0; k < Tab::total_size; k++) o[k] = (double) t[i].data[k];
+			o += Tab::total_size;
+		}
+	};
+	// the order of include/oxdna_b200.h (OXB_DNA3_*)
+	put(&_fene_r0_SD, 1); put(&_fene_delta_SD, 1); put(&_fene_delta2_SD, 1); put(&_mbf_xmax_SD, 1);
+	put(_excl_s, 7); put(_excl_r, 7); put(_excl_b, 7); put(_excl_rc, 7);
+	put(F1_SD_EPS, 2); put(F1_SD_A, 2); put(F1_SD_RC, 2); put(F1_SD_R0, 2); put(F1_SD_BLOW, 2); put(F1_SD_BHIGH, 2); put(F1_SD_RLOW, 2);
+	put(F1_SD_RHIGH, 2); put(F1_SD_RCLOW, 2); put(F1_SD_RCHIGH, 2); put(F1_SD_SHIFT, 2);
+	put(F2_SD_K, 4); put(F2_SD_K_SYMM, 4); put(F2_SD_RC, 4); put(F2_SD_R0, 4); put(F2_SD_BLOW, 4); put(F2_SD_RLOW, 4); put(F2_SD_RCLOW, 4);
+	put(F2_SD_BHIGH, 4); put(F2_SD_RCHIGH, 4); put(F2_SD_RHIGH, 4);
+	put(F4_SD_THETA_A, 21); put(F4_SD_THETA_B, 21); put(F4_SD_THETA_T0, 21); put(F4_SD_THETA_TS, 21); put(F4_SD_THETA_TC, 21);
+	put(F5_SD_PHI_A, 4); put(F5_SD_PHI_B, 4); put(F5_SD_PHI_XC, 4); put(F5_SD_PHI_XS, 4);
+	oxb_dna3_scalars S;
+	S.fene_eps = (double) _fene_eps;
+	S.use_mbf = _use_mbf ? 1. : 0.; S.mbf_fmax = (double) _mbf_fmax; S.mbf_finf = (double) _mbf_finf;
+	S.hb_multiplier = (double) _hb_multiplier;
+	S.dh_rc = (double) _debye_huckel_RC; S.dh_rhigh = (double) _debye_huckel_RHIGH; S.dh_prefactor = (double) _debye_huckel_prefactor;
+	S.dh_b = (double) _debye_huckel_B; S.dh_minus_kappa = (double) _minus_kappa; S.dh_half_charged_ends = _debye_huckel_half_charged_ends ? 1. : 0.;
+	S.rcut = (double) this->_rcut;
+	const int ids[3] = { CXST_F4_THETA1, CXST_F4_THETA4, CXST_F4_THETA5 };
+	double *dst[3] = { S.cxst_t1, S.cxst_t4, S.cxst_t5 };
+	for(int i = 0; i < 3; i++) {
+		dst[i][0] = (double) F4_THETA_A[ids[i]]; dst[i][1] = (double) F4_THETA_B[ids[i]]; dst[i][2] = (double) F4_THETA_T0[ids[i]];
+		dst[i][3] = (double) F4_THETA_TS[ids[i]]; dst[i][4] = (double) F4_THETA_TC[ids[i]];
+	}
+	S.cxst_t1_sa = (double) F4_THETA_SA[CXST_F4_THETA1]; S.cxst_t1_sb = (double) F4_THETA_SB[CXST_F4_THETA1];
+	oxb_check(_ctx, oxb_set_model_dna3(_ctx, tables.data(), &S), "set_model_dna3");
+}
+
+void CUDADNA3Interaction::_on_T_update() {
+	// CUDADNA3Interaction.cu:152-154 re-runs cuda_init -> DNA3Interaction::init()
+	this->_T = CONFIG_INFO->temperature();
+	if(_ctx != nullptr) {
+		Logger::instance()->disable_log("CUDADNA3Interaction");
+		DNA3Interaction::init();
+		Logger::instance()->enable_log("CUDADNA3Interaction");
+		_upload();
+	}
+}
+
 void CUDARNAInteraction::get_settings(input_file &inp) {
 	if(_v1) RNAInteraction::get_settings(inp);
 	else RNA2Interaction::get_settings(inp);
@@ -318,6 +382,7 @@ std::shared_ptr<CUDABaseInteraction> CUDAInteractionFactory::make_interaction(in
 	if(inter_type == "RNA2") return std::make_shared<CUDARNAInteraction>();
 	if(inter_type == "RNA") return std::make_shared<CUDARNAInteraction>(true);
 	if(inter_type == "DNA" || inter_type == "DNA_nomesh") return std::make_shared<CUDADNA1Interaction>();
+	if(inter_type == "DNA3") return std::make_shared<CUDADNA3Interaction>(); // CUDAInteractionFactory.cu:41
 	// anything else: CUDA<type>.so on the plugin search path, entry point make_CUDA<type> (or make / make_interaction), exactly as the
 	// reference looks it up (CUDAInteractionFactory.cu:44-51, PluginManager.cpp:89-180); the object must be one of OUR CUDABaseInteraction
 	std::string cuda_name = "CUDA" + inter_type;

@@ -25,6 +25,7 @@
 #include "Backends/Thermostats/NoThermostat.h"
 #include "Boxes/BaseBox.h"
 #include "Interactions/DNA2Interaction.h"
+#include "Interactions/DNA3Interaction.h"
 #include "Interactions/RNAInteraction2.h"
 #include "Utilities/oxDNAException.h"
 
@@ -100,6 +101,25 @@ public:
 	virtual ~CUDADNA1Interaction() {}
 
 	void get_settings(input_file &inp) override { DNAInteraction::get_settings(inp); }
+	void cuda_init(oxb_ctx *ctx, int N) override;
+	number get_cuda_rcut() override {
+		return this->get_rcut();
+	}
+};
+
+/// interaction_type = DNA3 (oxDNA3): the CPU DNA3Interaction_nomesh parses the sequence-dependent parameter file and derives the 214
+/// tetramer-indexed tables; they are handed to the device library as they stand (the reference's CUDADNA3Interaction::cuda_init uploads the
+/// same member arrays, src/CUDA/Interactions/CUDADNA3Interaction.cu:46-150).  use_edge = 1 is accepted: one kernel serves both variants.
+class CUDADNA3Interaction: public CUDABaseInteraction, public DNA3Interaction_nomesh {
+protected:
+	void _upload();
+	void _on_T_update() override;
+
+public:
+	CUDADNA3Interaction() {}
+	virtual ~CUDADNA3Interaction() {}
+
+	void get_settings(input_file &inp) override;
 	void cuda_init(oxb_ctx *ctx, int N) override;
 	number get_cuda_rcut() override {
 		return this->get_rcut();

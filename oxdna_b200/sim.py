@@ -80,8 +80,8 @@ class Simulation:
         if str(g("backend", "CUDA")).upper() != "CUDA":
             raise ValueError("oxdna_b200 only implements backend = CUDA")
         itype = str(g("interaction_type", "DNA2"))
-        if itype not in ("DNA2", "DNA2_nomesh", "DNA", "DNA_nomesh", "RNA2", "RNA"):
-            raise ValueError(f"interaction_type = {itype} is not available in this build (DNA, DNA2, RNA, RNA2)")
+        if itype not in ("DNA2", "DNA2_nomesh", "DNA", "DNA_nomesh", "RNA2", "RNA", "DNA3", "DNA3_nomesh"):
+            raise ValueError(f"interaction_type = {itype} is not available in this build (DNA, DNA2, DNA3, RNA, RNA2)")
         self.itype = itype
         prec = str(g("backend_precision", "mixed"))
         if prec not in ("mixed", "float"):
@@ -153,6 +153,16 @@ class Simulation:
         return params, rcut
 
     def _set_model(self):
+        if self.itype in ("DNA3", "DNA3_nomesh"):
+            # oxDNA3: the tetramer-indexed tables are input (what DNA3Interaction::init leaves in the class and CUDADNA3Interaction::cuda_init
+            # uploads, CUDADNA3Interaction.cu:46-150): keys dna3_tables (215 x 900) and dna3_scalars (29 doubles, capi.DNA3Scalars)
+            tab, sc = self.inp.get("dna3_tables"), self.inp.get("dna3_scalars")
+            if tab is None or sc is None:
+                raise ValueError("interaction_type = DNA3 needs the parameter tables of DNA3Interaction (dna3_tables, dna3_scalars)")
+            self.params = capi.dna3_scalars(sc) if not isinstance(sc, capi.DNA3Scalars) else sc
+            self.rcut = float(self.params.rcut)
+            self.ctx.set_model_dna3(tab, self.params)
+            return
         self.params, self.rcut = self._model_for(self.T)
         if self.itype in ("RNA2", "RNA"):
             self.ctx.set_model_rna2(self.params, self.rcut)

@@ -429,3 +429,34 @@ def test_reference_quick_md_tests_on_the_gpu_backend(tmp_path, name, T, checks, 
     for col, want, tol in checks:
         avg = e[:, col - 1].mean()
         assert want - tol <= avg <= want + tol, (name, col, avg, want, tol)
+
+
+SEQ3 = "/root/reference/oxDNA3_sequence_dependent_parameters.txt"
+
+
+@pytest.mark.gpu
+@needs_binaries
+@pytest.mark.parametrize("use_edge,sort_every,seqdep", [(0, 0, False), (1, 1, False), (1, 1, True)])
+def test_stock_input_file_oxdna3_matches_reference_cpu(tmp_path, use_edge, sort_every, seqdep):
+    """interaction_type = DNA3 through the drop-in executable (CUDADNA3Interaction on the reference's DNA3Interaction_nomesh: the tables the
+    CPU class derives are handed to oxb_set_model_dna3) against the reference CPU binary with DNA3_nomesh: 300 NVE steps from the thermalised
+    oxDNA3 fixture (8 duplexes).  Average-sequence tables everywhere; the sequence-dependent parameter file only where /root/reference is
+    mounted."""
+    if seqdep and not os.path.exists(SEQ3):
+        pytest.skip("oxDNA3 parameter file not available (needs /root/reference)")
+    g = np.load(os.path.join(ROOT, "tests", "golden", "dna3_lattice8.npz"))
+    fix = str(tmp_path / "fix")
+    os.makedirs(fix)
+    oio.write_topology(os.path.join(fix, "initial.top"), g["btype"], g["n3"], g["n5"], g["strand"])
+    oio.write_conf(os.path.join(fix, "initial.conf"), g["box"], g["pos"], g["a1"], g["a3"], g["vel"], g["L"])
+    extra = "refresh_vel = 0\n" + (f"use_average_seq = 0\nseq_dep_file = {SEQ3}" if seqdep else "")
+    a = run(OURS, str(tmp_path / "ours"), fix=fix, backend="CUDA", itype="DNA3", steps=300, thermostat="no", use_edge=use_edge, sort_every=sort_every, extra=extra)
+    assert a.returncode == 0, a.stdout[-2000:]
+    b = run(REF, str(tmp_path / "ref"), fix=fix, backend="CPU", itype="DNA3_nomesh", steps=300, thermostat="no", use_edge=0, sort_every=0, extra=extra)
+    assert b.returncode == 0, b.stdout[-2000:]
+    ca, cb = oio.read_conf(str(tmp_path / "ours" / "last_conf.dat")), oio.read_conf(str(tmp_path / "ref" / "last_conf.dat"))
+    assert np.abs(ca["pos"] - cb["pos"]).max() < 2e-3
+    assert np.abs(ca["a1"] - cb["a1"]).max() < 5e-3
+    ea, eb = energies(str(tmp_path / "ours")), energies(str(tmp_path / "ref"))
+    assert ea.shape == eb.shape and ea.shape[0] >= 3
+    assert np.abs(ea[:, 1:] - eb[:, 1:]).max() < 2e-4

@@ -19,7 +19,7 @@ SO = os.path.join(ROOT, "tests", "support", "_build", "libhostmodel.so")
 def hostlib():
     os.makedirs(os.path.dirname(SO), exist_ok=True)
     src = os.path.join(ROOT, "tests", "support", "host_model.cu")
-    deps = [src] + [os.path.join(ROOT, "oxdna_b200", "csrc", f) for f in ("dna_model.cuh", "rna_model.cuh", "models.cuh", "common.cuh", "params.cpp")]
+    deps = [src] + [os.path.join(ROOT, "oxdna_b200", "csrc", f) for f in ("dna_model.cuh", "rna_model.cuh", "models.cuh", "common.cuh", "params.cpp", "dna3_model.cuh", "dna3_pack.h", "kernels.h")]
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-Xcompiler", "-fPIC", "-shared", "-o", SO, src,
                                os.path.join(ROOT, "oxdna_b200", "csrc", "params.cpp")])
@@ -252,3 +252,52 @@ def test_oxdna1_coaxial_pair_cloud(hostlib):
     for got, want in ((F, ref["force"]), (Tl, ref["torque_lab"])):
         err = np.linalg.norm(got - want, axis=1) / scale
         assert np.quantile(err, 0.999) <= 6e-6 and err.max() <= 2e-5, (np.quantile(err, 0.999), err.max())
+
+
+@pytest.mark.parametrize("case", ["dna3_lattice8", "dna3_lattice27_dense"])
+def test_dna3_fp32_formulation_within_mixed_tolerance(hostlib, case):
+    """oxDNA3: the packed per-tetramer records + the FP32 device functions (csrc/dna3_model.cuh, dna3_pack.h) compiled for the host,
+    against the fixture of the reference CPU class (DNA3Interaction_nomesh) and, with a nick that switches coaxial stacking on, the oracle"""
+    g = load_golden(case)
+    N = len(g["pos"])
+    tab = np.ascontiguousarray(g["dna3_tables"], dtype=np.float64)
+    S = capi.dna3_scalars(g["dna3_scalars"])
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    pos, box = np.ascontiguousarray(g["pos"]), np.ascontiguousarray(g["box"], dtype=np.float64)
+    ax = np.ascontiguousarray(O.axes_from_a1a3(g["a1"], g["a3"]))
+    pairs = np.ascontiguousarray(g["pairs"], dtype=np.int32)
+    bt = np.ascontiguousarray(g["btype"], dtype=np.int32)
+
+    def run(n3, n5, pairs):
+        n3, n5, pairs = (np.ascontiguousarray(x, dtype=np.int32) for x in (n3, n5, pairs))
+        F, Tl, ep, es = np.zeros((N, 3)), np.zeros((N, 3)), np.zeros(N), np.zeros(8)
+        hostlib.host_dna3_forces(p(tab), C.byref(S), N, p(pos), p(ax), p(bt), p(n3), p(n5), p(box), p(pairs), C.c_longlong(len(pairs)), p(F), p(Tl),
+                                 p(ep), p(es))
+        return F, Tl, ep, es
+
+    F, Tl, ep, es = run(g["n3"], g["n5"], pairs)
+    fmax = np.linalg.norm(g["force"], axis=1).max()
+    tmax = np.linalg.norm(g["torque_lab"], axis=1).max()
+    assert np.linalg.norm(F - g["force"], axis=1).max() <= 1e-5 * fmax
+    assert np.linalg.norm(Tl - g["torque_lab"], axis=1).max() <= 1e-5 * tmax
+    assert abs(ep.sum() - float(g["U"])) <= 1e-6 * abs(float(g["U"]))
+    assert np.abs(es - g["energy_split"]).max() <= 2e-6 * abs(float(g["U"]))
+    # nicked strands: the stacked neighbours across the nick become a non-bonded pair inside the coaxial-stacking window
+    n3, n5 = g["n3"].copy(), g["n5"].copy()
+    starts = np.flatnonzero(g["n3"] < 0)
+    cut = []
+    for k, first in enumerate(starts[::3]):
+        i = first + (1 if k % 3 == 0 else 9)
+        j = n5[i]
+        n5[i], n3[j] = -1, -1
+        cut.append((min(i, j), max(i, j)))
+    pairs2 = np.vstack([pairs, np.array(cut, dtype=np.int32)])
+    P = O.dna3_params(g["dna3_tables"], g["dna3_scalars"])
+    ref = O.forces(P, pos, ax, bt, n3, n5, box, pairs2)
+    assert abs(ref["eterms"][6]) > 1e-2
+    F, Tl, ep, es = run(n3, n5, pairs2)
+    fmax = np.linalg.norm(ref["force"], axis=1).max()
+    tmax = np.linalg.norm(ref["torque_lab"], axis=1).max()
+    assert np.linalg.norm(F - ref["force"], axis=1).max() <= 1e-5 * fmax
+    assert np.linalg.norm(Tl - ref["torque_lab"], axis=1).max() <= 1e-5 * tmax
+    assert np.abs(es - ref["eterms"]).max() <= 2e-6 * abs(ref["U"])
