@@ -45,6 +45,9 @@ def workload(name):
     elif name == "c3":
         sysm = lattice.rna_duplex_lattice(2048, bp=16, spacing=10.0, seed=12345)  # 13^3 sites, L = 130
         desc = "C3: oxRNA2 synthetic lattice of 2,048 x 16-bp A-form duplexes (65,536 nt), sequence-dependent parameters, L=130, salt 0.5, T=300K"
+    elif name == "c2_dna3":
+        sysm = lattice.duplex_lattice(2048, bp=20, spacing=10.0, seed=12345)
+        desc = "C2 geometry under oxDNA3 (interaction_type = DNA3, average-sequence tetramer tables): 2,048 x 20-bp duplexes (81,920 nt), L=130, salt 0.5, T=300K"
     elif name == "small":
         sysm = lattice.duplex_lattice(64, bp=20, spacing=10.0, seed=12345)
         desc = "small: 64 x 20-bp duplexes (2,560 nt)"
@@ -55,6 +58,13 @@ def workload(name):
 
 def model_keys(name, tmpdir=None):
     """interaction keys of the workload; with tmpdir the sequence-dependent table is written to a file (reference binaries)"""
+    if name == "c2_dna3":
+        # oxDNA3 with use_average_seq = 1 (the reference binaries fill their tables without a parameter file); our side takes the tables the
+        # reference CPU class derives for T = 300 K, salt 0.5 from the committed fixture (oracle/make_golden.py dna3)
+        if tmpdir is not None:
+            return dict(interaction_type="DNA3")
+        g = np.load(os.path.join(ROOT, "tests", "golden", "dna3_tables_avg_300K_salt05.npz"))
+        return dict(interaction_type="DNA3", dna3_tables=g["dna3_tables"], dna3_scalars=g["dna3_scalars"])
     if name != "c3":
         return dict(interaction_type="DNA2")
     from oxdna_b200 import seqdep
@@ -373,7 +383,8 @@ def measure_single(args, wl, steps, warmup, equil, md, full, local_rank=0):
         sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
         fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
         flops = N * (FLOP_FAR * ps["listed"] + FLOP_DH * ps["dh"] + FLOP_CONTACT * ps["contact"] + FLOP_BONDED * 1.0)
-        if not args.use_edge:
+        particle_centric = (not args.use_edge) or wl == "c2_dna3"  # oxDNA3: one particle-centric kernel serves both use_edge settings
+        if particle_centric:
             flops = N * (2 * (FLOP_FAR * ps["listed"] + FLOP_DH * ps["dh"] + FLOP_CONTACT * ps["contact"]) + 2 * FLOP_BONDED)
         tf = flops / (t_force * 1e-3) / 1e12
         # algorithmic bytes: force pass 40 B state read + 32 B F,T write + 8 B per listed unique pair; integrate 336 B (+ 16 B
@@ -385,7 +396,7 @@ def measure_single(args, wl, steps, warmup, equil, md, full, local_rank=0):
         out.update({
             "value": value, "ms_per_step": total_ms / steps, "gpu_launches": int(launches), "clocks": clocks, "N": N, "desc": desc, "pairs_per_particle": ps,
             "step_ms": step_ms, "list_rebuild_every_md_steps": n_md / n_reb,
-            "roofline": {"kernel": "force pass (Debye-Hueckel + near edges + HB/cross stacking + coaxial + bonded)" if args.use_edge else "forces (particle-centric)",
+            "roofline": {"kernel": "force pass (Debye-Hueckel + near edges + HB/cross stacking + coaxial + bonded)" if not particle_centric else "forces (particle-centric)",
                          "bound": "fp32", "achieved": tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tf / fp32_peak, "traffic": ncu.get("force"),
                          "model": "SURVEY 8(d) algorithmic FLOP per pair class x measured pair counts", "sm_mhz": sm_mhz, "ms": t_force,
                          "share_of_step": t_force / step_ms,
@@ -616,7 +627,7 @@ def ours(args):
     # ---- the other BASELINE configs, bounded: C2 and C3 (single systems) and C5 on ONE GPU (64 replicas, two batches)
     extras = {}
     if not args.no_extras and wl == "c4":
-        for name in ("c2", "c3"):
+        for name in ("c2", "c3", "c2_dna3"):
             try:
                 x = measure_single(args, name, 5, 3, 10000, 1000, False, local_rank)
                 extras[name] = {"workload": x["desc"], "value": x["value"], "unit": "particle-steps/s", "md_step_ms": x["step_ms"], "kernels_ms": x["kernels_ms"],
@@ -641,7 +652,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cuda"])
-    ap.add_argument("--workload", default=None, choices=["c2", "c3", "c4", "c5", "small"], help="default: c4 on one GPU, c5 (replica ensemble) on several")
+    ap.add_argument("--workload", default=None, choices=["c2", "c3", "c4", "c5", "small", "c2_dna3"], help="default: c4 on one GPU, c5 (replica ensemble) on several")
     ap.add_argument("--md-steps", type=int, default=1000, help="MD steps per bench step")
     ap.add_argument("--equil", type=int, default=10000, help="untimed equilibration MD steps")
     ap.add_argument("--use-edge", type=int, default=1)

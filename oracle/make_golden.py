@@ -283,6 +283,18 @@ if __name__ == "__main__":
         sd = dict(use_average_seq=0, seq_dep_file="/root/reference/oxDNA3_sequence_dependent_parameters.txt")
         lattice_case("dna3_lattice8", 8, 10.0, 3000, itype="DNA3_nomesh", more_keys=sd, dna3=True, nve_steps=100)
         lattice_case("dna3_lattice27_dense", 27, 8.5, 4000, T="330K", salt=0.2, itype="DNA3_nomesh", more_keys=sd, dna3=True, nve_steps=100)
+        # the average-sequence tables (use_average_seq = 1: no parameter file) at the bench's temperature and salt: bench.py --workload c2_dna3
+        sysm = lattice.duplex_lattice(8, bp=20, spacing=10.0, seed=3)
+        d = tempfile.mkdtemp()
+        top, conf = os.path.join(d, "l.top"), os.path.join(d, "l.dat")
+        oio.write_topology(top, sysm["btype"], sysm["n3"], sysm["n5"], sysm["strand"])
+        v, L = lattice.maxwell_velocities(len(sysm["pos"]), 0.1, 5)
+        oio.write_conf(conf, sysm["box"], sysm["pos"], sysm["a1"], sysm["a3"], v, L)
+        r = Reference(top, conf, interaction_type="DNA3_nomesh", salt_concentration=0.5, T="300K")
+        tab, sc = np.zeros((215, 900)), np.zeros(40)
+        k = RH.lib().oxref_dna3_tables(RH._p(tab), RH._p(sc))
+        r.close()
+        np.savez_compressed(os.path.join(GOLD, "dna3_tables_avg_300K_salt05.npz"), dna3_tables=tab, dna3_scalars=sc[:k], T="300K", salt=0.5)
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "ext2":
         ext2_case()

@@ -5,6 +5,8 @@ src/CUDA/Backends/CUDABaseBackend.cu:110-141, MD_CUDABackend.cu:621-672, CUDAThe
 the C ABI.  It is the host-side convenience used by tests, bench.py and the REMD driver; the C++ host classes in
 oxdna_b200/host mirror the same interface for linking against the reference's SimManager.
 """
+import types
+
 import numpy as np
 
 from . import capi
@@ -159,9 +161,11 @@ class Simulation:
             tab, sc = self.inp.get("dna3_tables"), self.inp.get("dna3_scalars")
             if tab is None or sc is None:
                 raise ValueError("interaction_type = DNA3 needs the parameter tables of DNA3Interaction (dna3_tables, dna3_scalars)")
-            self.params = capi.dna3_scalars(sc) if not isinstance(sc, capi.DNA3Scalars) else sc
-            self.rcut = float(self.params.rcut)
-            self.ctx.set_model_dna3(tab, self.params)
+            S = capi.dna3_scalars(sc) if not isinstance(sc, capi.DNA3Scalars) else sc
+            self.rcut = float(S.rcut)
+            self.ctx.set_model_dna3(tab, S)
+            # what callers read from a parameter block (bench.pair_statistics): backbone-site offsets (src/model.h:16-17) and radii
+            self.params = types.SimpleNamespace(scalars=S, back_a1=-0.34, back_a2=0.3408, dh_rc=float(S.dh_rc), rcut=self.rcut, rcut_near=self.rcut)
             return
         self.params, self.rcut = self._model_for(self.T)
         if self.itype in ("RNA2", "RNA"):
