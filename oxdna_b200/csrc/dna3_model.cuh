@@ -113,135 +113,153 @@ OXB_HD void six_add(Six &S, RadVal f, const oxb_f4 &p1, const oxb_f4 &p2, const 
 	}
 }
 
-// Non-bonded pair (p, q): DNA3Interaction.cpp:1137-1228 (excluded volume), 1477-1598 (hydrogen bonding), 1600-1755 (cross stacking),
-// 1758-1883 (coaxial stacking), DNA2Interaction.cpp:157-210 (Debye-Hueckel).  esplit (optional): per-term energies in the order of OXB_TERM_*.
+// ---- non-bonded pair (p, q), in the three pieces the force kernel runs as separate uniform loops (forces_dna3.cu); r = min-image(q - p)
+// between the centres, forces are "on q".  esplit (optional): per-term energies in the order of OXB_TERM_*.
+
+// the four excluded-volume site pairs, parameters of the tetramer (-, q, p, -): DNA3Interaction.cpp:1137-1228
+OXB_HD float dna3_excl4(const oxb_dna3_dev &M, v3 r, v3 rbb, v3 rb, const Axes &A, const Axes &B, const Nuc3 &np, const Nuc3 &nq, v3 pback, v3 qback,
+		PairAcc &acc) {
+	const float cbp = M.pos_base[np.si], cbq = M.pos_base[nq.si];
+	float rec[OXB3_REC_NEXCL];
+	load_rec<OXB3_REC_NEXCL / 4>(M.nexcl + (nq.type * 5 + np.type) * (OXB3_REC_NEXCL / 4), rec);
+	float en = excl3(M, excl_rec(rec + 4), rb, OXB_SITE_AA, cbp, cbq, acc);
+	en += excl3(M, excl_rec(rec + 12), r + B.a1 * cbq - pback, OXB_SITE_KA, cbp, cbq, acc);
+	en += excl3(M, excl_rec(rec + 8), r + qback - A.a1 * cbp, OXB_SITE_AK, cbp, cbq, acc);
+	en += excl3(M, excl_rec(rec), rbb, OXB_SITE_KK, cbp, cbq, acc);
+	return en;
+}
+
+// hydrogen bonding (parameters of (0, q, p, 0), DNA3Interaction.cpp:1477-1598) + cross stacking (3'3' diagonal: tetramer (n3(q), q, p, n3(p)),
+// 5'5' diagonal: (n5(q), q, p, n5(p)); DNA3Interaction.cpp:1600-1755) on the base-base vector rb; returns the total, ehb = the HB part
+OXB_HD float dna3_hbcr(const oxb_dna3_dev &M, v3 rb, float rbm2, const Axes &A, const Axes &B, int btp, int btq, const Nuc3 &np, const Nuc3 &nq,
+		PairAcc &acc, float &ehb, float *esplit = nullptr) {
+	ehb = 0.f;
+	const float cbp = M.pos_base[np.si], cbq = M.pos_base[nq.si];
+	const float inv = OXB_RSQRT(rbm2);
+	const float m = rbm2 * inv;
+	const v3 h = rb * inv;
+	const float c7 = -dot(B.a3, h), c8 = dot(A.a3, h);
+	float rh[OXB3_REC_HB];
+	bool hb_on = (btp + btq == 3);
+	if(hb_on) {
+		load_rec<OXB3_REC_HB / 4>(M.hb + (nq.type * 5 + np.type) * (OXB3_REC_HB / 4), rh);
+		hb_on = rh[7] < m && m < rh[8];
+	}
+	const int ix33 = ix4(nq.n3t, nq.type, np.type, np.n3t), ix55 = ix4(nq.n5t, nq.type, np.type, np.n5t);
+	float r33[12], r55[12];
+	load_rec<3>(M.crst + ix33 * (OXB3_REC_CRST / 4), r33); // first 12 floats of the record: f2
+	load_rec<3>(M.crst + (900 + ix55) * (OXB3_REC_CRST / 4), r55);
+	const bool in33 = c7 > 0.f && c8 > 0.f && r33[5] < m && m < r33[8];
+	const bool in55 = c7 < 0.f && c8 < 0.f && r55[5] < m && m < r55[8];
+	if(!(hb_on || in33 || in55)) return 0.f;
+	Six S;
+	S.t1 = make_angle(-A.a1, B.a1); S.t2 = make_angle(-B.a1, h); S.t3 = make_angle(A.a1, h);
+	S.t4 = make_angle(A.a3, B.a3); S.t7 = make_angle(-B.a3, h); S.t8 = make_angle(A.a3, h);
+	S.g1 = S.g2 = S.g3 = S.g4 = S.g7 = S.g8 = S.grad = S.E = 0.f;
+	if(hb_on) {
+		const float mult = (abs(btq) >= 300 && abs(btp) >= 300) ? M.hb_multiplier : 1.f;
+		RadVal f1 = f1_rec(rh, m);
+		f1.v *= mult; f1.d *= mult;
+		float e;
+		six_add(S, f1, f4_rec(rh + 12), f4_rec(rh + 17), f4_rec(rh + 22), f4_rec(rh + 27), e);
+		ehb += e;
+		if(esplit) esplit[4] += e;
+	}
+	if(in33 || in55) {
+		// both diagonals are evaluated once either gate is open, as the reference does (DNA3Interaction.cpp:1640-1665): each f2 has its own range
+		float rr[OXB3_REC_CRST - 12], e;
+		load_rec<(OXB3_REC_CRST - 12) / 4>(M.crst + ix33 * (OXB3_REC_CRST / 4) + 3, rr);
+		six_add(S, f2_r(f2_rec(r33), m), f4_rec(rr), f4_rec(rr + 5), f4_rec(rr + 10), f4_rec(rr + 15), e);
+		if(esplit) esplit[5] += e;
+		load_rec<(OXB3_REC_CRST - 12) / 4>(M.crst + (900 + ix55) * (OXB3_REC_CRST / 4) + 3, rr);
+		six_add(S, f2_r(f2_rec(r55), m), f4_rec(rr), f4_rec(rr + 5), f4_rec(rr + 10), f4_rec(rr + 15), e);
+		if(esplit) esplit[5] += e;
+	}
+	if(S.E != 0.f) {
+		v3 f = h * (-S.grad);
+		chain_bb(acc, S.g1, S.t1);
+		f += chain_bd<true>(acc, S.g2, -B.a1, h, inv, S.t2);
+		f += chain_bd<false>(acc, S.g3, A.a1, h, inv, S.t3);
+		chain_bb(acc, S.g4, S.t4);
+		f += chain_bd<true>(acc, S.g7, -B.a3, h, inv, S.t7);
+		f += chain_bd<false>(acc, S.g8, A.a3, h, inv, S.t8);
+		acc.site_aa(f, cbp, cbq);
+	}
+	return S.E;
+}
+
+// coaxial stacking on the stack-stack vector rs: radial part per tetramer (three K branches, DNA3Interaction.cpp:1814-1825), angular part the
+// scalar oxDNA2 set (DNA3Interaction.cpp:1758-1883)
+OXB_HD float dna3_cxst(const oxb_dna3_dev &M, v3 rs, float rs2, const Axes &A, const Axes &B, const Nuc3 &np, const Nuc3 &nq, PairAcc &acc) {
+	const float csp = M.pos_stack[np.si], csq = M.pos_stack[nq.si];
+	float r0[OXB3_REC_CXST];
+	load_rec<OXB3_REC_CXST / 4>(M.cxst + ix4(0, nq.type, np.type, 0) * (OXB3_REC_CXST / 4), r0);
+	const float inv = OXB_RSQRT(rs2);
+	const float m = rs2 * inv;
+	if(!(r0[5] < m && m < r0[8])) return 0.f;
+	int ix;
+	bool symm = false;
+	if(!np.has_n3 && !nq.has_n5) ix = ix4(nq.n3t, nq.type, np.type, np.n5t);
+	else if(!np.has_n5 && !nq.has_n3) ix = ix4(np.n5t, np.type, nq.type, nq.n3t);
+	else { ix = ix4(nq.n3t, nq.type, np.type, np.n5t); symm = true; }
+	float rc[OXB3_REC_CXST];
+	load_rec<OXB3_REC_CXST / 4>(M.cxst + ix * (OXB3_REC_CXST / 4), rc);
+	oxb_f2 fp = f2_rec(rc);
+	if(symm) fp.k = rc[9];
+	const RadVal f2 = f2_r(fp, m);
+	const v3 h = rs * inv;
+	const Angle t1 = make_angle(-A.a1, B.a1), t4 = make_angle(A.a3, B.a3), t5 = make_angle(A.a3, h), t6 = make_angle(-B.a3, h);
+	AngVal a1 = f4_ts(M.cxst_t1, t1.t, t1.s);
+	{
+		const float x = t1.t - M.cxst_t1_sb;
+		if(x >= 0.f) {
+			a1.v += M.cxst_t1_sa * x * x;
+			a1.dc -= (t1.s * t1.s > 1e-8f) ? OXB_DIV(2.f * M.cxst_t1_sa * x, t1.s) : 2.f * M.cxst_t1_sa;
+		}
+	}
+	const AngVal a4 = f4_ts(M.cxst_t4, t4.t, t4.s), a5 = f4_ts_sym(M.cxst_t5, t5.t, t5.s), a6 = f4_ts_sym(M.cxst_t5, t6.t, t6.s);
+	const float p14 = a1.v * a4.v, p56 = a5.v * a6.v;
+	const float e = f2.v * p14 * p56;
+	if(e != 0.f) {
+		v3 f = h * (-(f2.d * p14 * p56));
+		chain_bb(acc, f2.v * p56 * a1.dc * a4.v, t1);
+		chain_bb(acc, f2.v * p56 * a1.v * a4.dc, t4);
+		f += chain_bd<false>(acc, f2.v * p14 * a5.dc * a6.v, A.a3, h, inv, t5);
+		f += chain_bd<true>(acc, f2.v * p14 * a5.v * a6.dc, -B.a3, h, inv, t6);
+		acc.site_aa(f, csp, csq);
+	}
+	return e;
+}
+
+// the whole non-bonded interaction of one pair (split-energy kernel, host-side unit test); Debye-Hueckel inherited from DNA2Interaction.cpp:157-210
 OXB_HD PairEnergy dna3_nonbonded(const oxb_dna3_dev &M, v3 r, const Axes &A, const Axes &B, int btp, int btq, const Nuc3 &np, const Nuc3 &nq,
 		v3 pback, v3 qback, PairAcc &acc, float *esplit = nullptr) {
 	PairEnergy E;
 	E.total = 0.f;
 	E.hb = 0.f;
-	if(dot(r, r) >= M.rcut2) return E;
+	const float r2 = dot(r, r);
+	if(r2 >= M.rcut2) return E;
 	const v3 rbb = r + qback - pback;
 	{
 		float fs;
 		const float en = dna2_dh(M, dot(rbb, rbb), !(np.has_n3 && np.has_n5), !(nq.has_n3 && nq.has_n5), fs);
 		if(en != 0.f) { E.total += en; acc.site_kk(rbb * fs); if(esplit) esplit[7] += en; }
 	}
-	const float cbp = M.pos_base[np.si], cbq = M.pos_base[nq.si], csp = M.pos_stack[np.si], csq = M.pos_stack[nq.si];
-	const v3 rb = r + B.a1 * cbq - A.a1 * cbp;
+	if(r2 >= M.r2_near_max) return E; // no site pair of any other term can be in range
+	const v3 rb = r + B.a1 * M.pos_base[nq.si] - A.a1 * M.pos_base[np.si];
 	const float rbm2 = dot(rb, rb);
-	const int tt = nq.type * 5 + np.type;
-	// nothing but Debye-Hueckel beyond the longest excluded-volume range of the tables + the two longest levers (set by the host)
-	if(dot(r, r) < M.r2_excl_max) {
-		float rec[OXB3_REC_NEXCL];
-		load_rec<OXB3_REC_NEXCL / 4>(M.nexcl + tt * (OXB3_REC_NEXCL / 4), rec);
-		float en = excl3(M, excl_rec(rec + 4), rb, OXB_SITE_AA, cbp, cbq, acc);
-		en += excl3(M, excl_rec(rec + 12), r + B.a1 * cbq - pback, OXB_SITE_KA, cbp, cbq, acc);
-		en += excl3(M, excl_rec(rec + 8), r + qback - A.a1 * cbp, OXB_SITE_AK, cbp, cbq, acc);
-		en += excl3(M, excl_rec(rec), rbb, OXB_SITE_KK, cbp, cbq, acc);
+	if(r2 < M.r2_excl_max) {
+		const float en = dna3_excl4(M, r, rbb, rb, A, B, np, nq, pback, qback, acc);
 		E.total += en;
 		if(esplit) esplit[3] += en;
 	}
-	if(rbm2 < M.r2_base_max) {
-		// hydrogen bonding: parameters of (0, q, p, 0); cross stacking: 3'3' diagonal (n3(q), q, p, n3(p)), 5'5' diagonal (n5(q), q, p, n5(p))
-		const float inv = OXB_RSQRT(rbm2);
-		const float m = rbm2 * inv;
-		const v3 h = rb * inv;
-		const float c7 = -dot(B.a3, h), c8 = dot(A.a3, h);
-		float rh[OXB3_REC_HB];
-		bool hb_on = (btp + btq == 3);
-		if(hb_on) {
-			load_rec<OXB3_REC_HB / 4>(M.hb + tt * (OXB3_REC_HB / 4), rh);
-			hb_on = rh[7] < m && m < rh[8];
-		}
-		const int ix33 = ix4(nq.n3t, nq.type, np.type, np.n3t), ix55 = ix4(nq.n5t, nq.type, np.type, np.n5t);
-		float r33[12], r55[12];
-		load_rec<3>(M.crst + ix33 * (OXB3_REC_CRST / 4), r33); // first 12 floats of the record: f2
-		load_rec<3>(M.crst + (900 + ix55) * (OXB3_REC_CRST / 4), r55);
-		const bool in33 = c7 > 0.f && c8 > 0.f && r33[5] < m && m < r33[8];
-		const bool in55 = c7 < 0.f && c8 < 0.f && r55[5] < m && m < r55[8];
-		if(hb_on || in33 || in55) {
-			Six S;
-			S.t1 = make_angle(-A.a1, B.a1); S.t2 = make_angle(-B.a1, h); S.t3 = make_angle(A.a1, h);
-			S.t4 = make_angle(A.a3, B.a3); S.t7 = make_angle(-B.a3, h); S.t8 = make_angle(A.a3, h);
-			S.g1 = S.g2 = S.g3 = S.g4 = S.g7 = S.g8 = S.grad = S.E = 0.f;
-			if(hb_on) {
-				const float mult = (abs(btq) >= 300 && abs(btp) >= 300) ? M.hb_multiplier : 1.f;
-				RadVal f1 = f1_rec(rh, m);
-				f1.v *= mult; f1.d *= mult;
-				float e;
-				six_add(S, f1, f4_rec(rh + 12), f4_rec(rh + 17), f4_rec(rh + 22), f4_rec(rh + 27), e);
-				E.hb += e;
-				if(esplit) esplit[4] += e;
-			}
-			if(in33 || in55) {
-				// both diagonals are evaluated once either gate is open, as the reference does (DNA3Interaction.cpp:1640-1665): each f2 has its own range
-				float rr[OXB3_REC_CRST], e;
-				load_rec<OXB3_REC_CRST / 4>(M.crst + ix33 * (OXB3_REC_CRST / 4), rr);
-				six_add(S, f2_r(f2_rec(rr), m), f4_rec(rr + 12), f4_rec(rr + 17), f4_rec(rr + 22), f4_rec(rr + 27), e);
-				if(esplit) esplit[5] += e;
-				load_rec<OXB3_REC_CRST / 4>(M.crst + (900 + ix55) * (OXB3_REC_CRST / 4), rr);
-				six_add(S, f2_r(f2_rec(rr), m), f4_rec(rr + 12), f4_rec(rr + 17), f4_rec(rr + 22), f4_rec(rr + 27), e);
-				if(esplit) esplit[5] += e;
-			}
-			if(S.E != 0.f) {
-				E.total += S.E;
-				v3 f = h * (-S.grad);
-				chain_bb(acc, S.g1, S.t1);
-				f += chain_bd<true>(acc, S.g2, -B.a1, h, inv, S.t2);
-				f += chain_bd<false>(acc, S.g3, A.a1, h, inv, S.t3);
-				chain_bb(acc, S.g4, S.t4);
-				f += chain_bd<true>(acc, S.g7, -B.a3, h, inv, S.t7);
-				f += chain_bd<false>(acc, S.g8, A.a3, h, inv, S.t8);
-				acc.site_aa(f, cbp, cbq);
-			}
-		}
-	}
-	{
-		// coaxial stacking: radial part per tetramer (three K branches, DNA3Interaction.cpp:1814-1825), angular part the scalar oxDNA2 set
-		const v3 rs = r + B.a1 * csq - A.a1 * csp;
-		const float rs2 = dot(rs, rs);
-		if(rs2 < M.r2_stack_max) {
-			float r0[OXB3_REC_CXST];
-			load_rec<OXB3_REC_CXST / 4>(M.cxst + ix4(0, nq.type, np.type, 0) * (OXB3_REC_CXST / 4), r0);
-			const float inv = OXB_RSQRT(rs2);
-			const float m = rs2 * inv;
-			if(r0[5] < m && m < r0[8]) {
-				int ix;
-				bool symm = false;
-				if(!np.has_n3 && !nq.has_n5) ix = ix4(nq.n3t, nq.type, np.type, np.n5t);
-				else if(!np.has_n5 && !nq.has_n3) ix = ix4(np.n5t, np.type, nq.type, nq.n3t);
-				else { ix = ix4(nq.n3t, nq.type, np.type, np.n5t); symm = true; }
-				float rc[OXB3_REC_CXST];
-				load_rec<OXB3_REC_CXST / 4>(M.cxst + ix * (OXB3_REC_CXST / 4), rc);
-				oxb_f2 fp = f2_rec(rc);
-				if(symm) fp.k = rc[9];
-				const RadVal f2 = f2_r(fp, m);
-				const v3 h = rs * inv;
-				const Angle t1 = make_angle(-A.a1, B.a1), t4 = make_angle(A.a3, B.a3), t5 = make_angle(A.a3, h), t6 = make_angle(-B.a3, h);
-				AngVal a1 = f4_ts(M.cxst_t1, t1.t, t1.s);
-				{
-					const float x = t1.t - M.cxst_t1_sb;
-					if(x >= 0.f) {
-						a1.v += M.cxst_t1_sa * x * x;
-						a1.dc -= (t1.s * t1.s > 1e-8f) ? OXB_DIV(2.f * M.cxst_t1_sa * x, t1.s) : 2.f * M.cxst_t1_sa;
-					}
-				}
-				const AngVal a4 = f4_ts(M.cxst_t4, t4.t, t4.s), a5 = f4_ts_sym(M.cxst_t5, t5.t, t5.s), a6 = f4_ts_sym(M.cxst_t5, t6.t, t6.s);
-				const float p14 = a1.v * a4.v, p56 = a5.v * a6.v;
-				const float e = f2.v * p14 * p56;
-				if(e != 0.f) {
-					E.total += e;
-					if(esplit) esplit[6] += e;
-					v3 f = h * (-(f2.d * p14 * p56));
-					chain_bb(acc, f2.v * p56 * a1.dc * a4.v, t1);
-					chain_bb(acc, f2.v * p56 * a1.v * a4.dc, t4);
-					f += chain_bd<false>(acc, f2.v * p14 * a5.dc * a6.v, A.a3, h, inv, t5);
-					f += chain_bd<true>(acc, f2.v * p14 * a5.v * a6.dc, -B.a3, h, inv, t6);
-					acc.site_aa(f, csp, csq);
-				}
-			}
-		}
+	if(rbm2 < M.r2_base_max) E.total += dna3_hbcr(M, rb, rbm2, A, B, btp, btq, np, nq, acc, E.hb, esplit);
+	const v3 rs = r + B.a1 * M.pos_stack[nq.si] - A.a1 * M.pos_stack[np.si];
+	const float rs2 = dot(rs, rs);
+	if(rs2 < M.r2_stack_max) {
+		const float en = dna3_cxst(M, rs, rs2, A, B, np, nq, acc);
+		E.total += en;
+		if(esplit) esplit[6] += en;
 	}
 	return E;
 }

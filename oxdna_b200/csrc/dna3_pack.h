@@ -83,4 +83,5 @@ inline void dna3_pack(const double *tab, const oxb_dna3_scalars *S, std::vector<
 	D.r2_excl_max = (float) std::pow(max_excl_rc + 2. * lever + 0.01, 2);
 	D.r2_base_max = (float) std::pow(max_base + 1e-3, 2);
 	D.r2_stack_max = (float) std::pow(max_stack + 1e-3, 2);
+	D.r2_near_max = (float) std::pow(std::max(max_excl_rc + 2. * lever, std::max(max_base + 2. * 0.43, max_stack + 2. * 0.37)) + 0.01, 2);
 }

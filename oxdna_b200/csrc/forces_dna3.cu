@@ -7,6 +7,8 @@
 #include "dna3_model.cuh"
 #include "kernels.h"
 
+#include <cstdlib>
+
 namespace {
 
 struct P3 {
@@ -45,7 +47,15 @@ __device__ __forceinline__ float bond3(const oxb_dna3_dev &M, const BoxF &box, c
 	return dna3_bonded(M, rec, min_image_fixed(box, P.ip, Q.ip), P.ax, Q.ax, P.n, Q.n, P.back, Q.back, acc, broken, esplit, refine ? &fs : nullptr);
 }
 
-__global__ void __launch_bounds__(128, 4) k_forces_dna3(const __grid_constant__ oxb_dna3_dev M, BoxF box, int N, const int4 *__restrict__ ipos,
+// The neighbour loop is split by COST into uniform passes (the single loop ran with 8.9 of 32 lanes active: one lane inside the six-angle
+// hydrogen-bonding code held the 31 others; ncu r02af): per chunk of 64 neighbours
+//   pass 1  every listed pair: fixed-point centre + backbone site of the neighbour (2 x 16 B), Debye-Hueckel, "near" bit if any other term can reach
+//   pass 2  near pairs: full particle record, the four excluded-volume site pairs, bits for "bases in range" / "stacking sites in range"
+//   pass 3  base-base contacts: hydrogen bonding + cross stacking        pass 4  stack-stack contacts: coaxial stacking
+// The p-side accumulators (force, lever sums, pure torque) are linear in the pairs: one PairAcc is carried through all passes and the two
+// cross products of the torque are taken once.
+template<int MB>
+__global__ void __launch_bounds__(128, MB) k_forces_dna3(const __grid_constant__ oxb_dna3_dev M, BoxF box, int N, const int4 *__restrict__ ipos,
 		const int4 *__restrict__ iback, const float4 *__restrict__ axf, const double4 *__restrict__ posd, const double4 *__restrict__ quatd,
 		const int2 *__restrict__ bonds, const int *__restrict__ nbr, const int *__restrict__ nnbr, int stride,
 		float4 *__restrict__ F, float4 *__restrict__ T, int *__restrict__ flags, int hw) {
@@ -54,44 +64,89 @@ __global__ void __launch_bounds__(128, 4) k_forces_dna3(const __grid_constant__ 
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= N) return;
 	const P3 P = load_p3(M, ipos, axf, i);
+	const int4 ibp = __ldg(iback + i);
 	const int2 b = __ldg(bonds + i);
-	v3 f = mk3(0.f, 0.f, 0.f), t = mk3(0.f, 0.f, 0.f);
+	const bool p_end = (b.x < 0 || b.y < 0);
 	float e = 0.f, ehb = 0.f;
 	bool broken = false;
 	ExclRefine R = refine3(M, box, posd, quatd);
 	const bool refine = posd != nullptr; // backend_precision = mixed
+	PairAcc acc; // everything in which this particle is "p"
+	acc.clear();
+	acc.refine = refine ? &R : nullptr;
+	v3 fq = mk3(0.f, 0.f, 0.f), tq = mk3(0.f, 0.f, 0.f); // the bond in which it is "q"
 	if(b.x >= 0) { // I am the 5' side of the bond (p), q = my n3
 		const P3 Q = load_p3(M, ipos, axf, b.x);
-		PairAcc acc;
-		acc.clear();
-		R.sp = i; R.sq = b.x; acc.refine = refine ? &R : nullptr;
+		R.sp = i; R.sq = b.x;
 		e += bond3(M, box, P, Q, iback, i, b.x, refine, acc, broken, nullptr);
-		f -= acc.F;
-		t += acc.torque_p(P.ax, P.back);
 	}
 	if(b.y >= 0) { // my n5 neighbour is p, I am q
 		const P3 Q = load_p3(M, ipos, axf, b.y);
-		PairAcc acc;
-		acc.clear();
-		R.sp = b.y; R.sq = i; acc.refine = refine ? &R : nullptr;
-		e += bond3(M, box, Q, P, iback, b.y, i, refine, acc, broken, nullptr);
-		f += acc.F;
-		t += acc.torque_q(P.ax, P.back);
+		PairAcc a2;
+		a2.clear();
+		R.sp = b.y; R.sq = i; a2.refine = refine ? &R : nullptr;
+		e += bond3(M, box, Q, P, iback, b.y, i, refine, a2, broken, nullptr);
+		fq = a2.F;
+		tq = a2.torque_q(P.ax, P.back);
 	}
+	R.sp = i;
 	const int nn = __ldg(nnbr + i);
-	for(int k = 0; k < nn; k++) {
-		const int j = __ldg(nbr + (size_t) k * stride + i);
-		const P3 Q = load_p3(M, ipos, axf, j);
-		PairAcc acc;
-		acc.clear();
-		R.sp = i; R.sq = j; acc.refine = refine ? &R : nullptr;
-		const PairEnergy pe = dna3_nonbonded(M, min_image_fixed(box, P.ip, Q.ip), P.ax, Q.ax, P.btype, Q.btype, P.n, Q.n, P.back, Q.back, acc);
-		e += pe.total;
-		ehb += pe.hb;
-		f -= acc.F;
-		t += acc.torque_p(P.ax, P.back);
+	for(int base = 0; base < nn; base += 64) {
+		const int cnt = min(64, nn - base);
+		const int *__restrict__ row = nbr + (size_t) base * stride + i;
+		unsigned long long near = 0ull, mb = 0ull, ms = 0ull;
+#pragma unroll 4
+		for(int k = 0; k < cnt; k++) {
+			const int j = __ldg(row + (size_t) k * stride);
+			const int4 ipq = __ldg(ipos + j);
+			const int4 ibq = __ldg(iback + j);
+			const v3 r = min_image_fixed(box, P.ip, ipq);
+			const float r2 = dot(r, r);
+			const v3 rbb = min_image_fixed(box, ibp, ibq);
+			float fs;
+			float en = dna2_dh_fast(M, dot(rbb, rbb), p_end, ibq.w & 1, fs);
+			if(r2 >= M.rcut2) { en = 0.f; fs = 0.f; } // no interaction beyond the centre-centre cutoff (DNA2Interaction.cpp:46-48)
+			e += en;
+			acc.site_kk(rbb * fs);
+			if(r2 < M.r2_near_max) near |= 1ull << k;
+		}
+		while(near) {
+			const int k = __ffsll((long long) near) - 1;
+			near &= near - 1ull;
+			const int j = __ldg(row + (size_t) k * stride);
+			const P3 Q = load_p3(M, ipos, axf, j);
+			const v3 r = min_image_fixed(box, P.ip, Q.ip);
+			const v3 a1d_b = Q.ax.a1 * M.pos_base[Q.n.si] - P.ax.a1 * M.pos_base[P.n.si];
+			const v3 rb = r + a1d_b;
+			const v3 rs = r + Q.ax.a1 * M.pos_stack[Q.n.si] - P.ax.a1 * M.pos_stack[P.n.si];
+			if(dot(r, r) < M.r2_excl_max) {
+				R.sq = j;
+				e += dna3_excl4(M, r, r + Q.back - P.back, rb, P.ax, Q.ax, P.n, Q.n, P.back, Q.back, acc);
+			}
+			if(dot(rb, rb) < M.r2_base_max) mb |= 1ull << k;
+			if(dot(rs, rs) < M.r2_stack_max) ms |= 1ull << k;
+		}
+		while(mb) {
+			const int k = __ffsll((long long) mb) - 1;
+			mb &= mb - 1ull;
+			const int j = __ldg(row + (size_t) k * stride);
+			const P3 Q = load_p3(M, ipos, axf, j);
+			const v3 rb = min_image_fixed(box, P.ip, Q.ip) + Q.ax.a1 * M.pos_base[Q.n.si] - P.ax.a1 * M.pos_base[P.n.si];
+			float eh;
+			e += dna3_hbcr(M, rb, dot(rb, rb), P.ax, Q.ax, P.btype, Q.btype, P.n, Q.n, acc, eh);
+			ehb += eh;
+		}
+		while(ms) {
+			const int k = __ffsll((long long) ms) - 1;
+			ms &= ms - 1ull;
+			const int j = __ldg(row + (size_t) k * stride);
+			const P3 Q = load_p3(M, ipos, axf, j);
+			const v3 rs = min_image_fixed(box, P.ip, Q.ip) + Q.ax.a1 * M.pos_stack[Q.n.si] - P.ax.a1 * M.pos_stack[P.n.si];
+			e += dna3_cxst(M, rs, dot(rs, rs), P.ax, Q.ax, P.n, Q.n, acc);
+		}
 	}
 	// torque stays in the lab frame; the integrator rotates it into the body frame
+	const v3 f = fq - acc.F, t = tq + acc.torque_p(P.ax, P.back);
 	F[i] = make_float4(f.x, f.y, f.z, e);
 	T[i] = make_float4(t.x, t.y, t.z, ehb);
 	if(broken) atomicOr(flags + OXB_FLAG_ERROR, OXB_ERR_FENE_BROKEN);
@@ -144,7 +199,13 @@ namespace oxb {
 void launch_forces_dna3(cudaStream_t s, const oxb_dna3_dev &M, BoxF box, int N, const int4 *ipos, const int4 *iback, const float4 *axf,
 		const double4 *posd, const double4 *quatd, const int2 *bonds, const int *nbr, const int *nnbr, int stride, float4 *F, float4 *T, int *flags, int hw) {
 	const int tpb = 128;
-	k_forces_dna3<<<(N + tpb - 1) / tpb, tpb, 0, s>>>(M, box, N, ipos, iback, axf, posd, quatd, bonds, nbr, nnbr, stride, F, T, flags, hw);
+	// minimum resident blocks per SM asked of the compiler = register cap (4: 128 registers, 790 B of spills; 3: 168, 230 B; 2: 250, none).
+	// Measured on B200 (profiles/sweeps_r02.txt, ag): OXB_DNA3_MB overrides
+	static const int mb = [] { const char *v = getenv("OXB_DNA3_MB"); return (v != nullptr && v[0] != 0) ? atoi(v) : 3; }();
+	const int blocks = (N + tpb - 1) / tpb;
+	if(mb >= 4) k_forces_dna3<4><<<blocks, tpb, 0, s>>>(M, box, N, ipos, iback, axf, posd, quatd, bonds, nbr, nnbr, stride, F, T, flags, hw);
+	else if(mb == 3) k_forces_dna3<3><<<blocks, tpb, 0, s>>>(M, box, N, ipos, iback, axf, posd, quatd, bonds, nbr, nnbr, stride, F, T, flags, hw);
+	else k_forces_dna3<2><<<blocks, tpb, 0, s>>>(M, box, N, ipos, iback, axf, posd, quatd, bonds, nbr, nnbr, stride, F, T, flags, hw);
 }
 
 void launch_energy_split_dna3(cudaStream_t s, const oxb_dna3_dev &M, BoxF box, int N, const int4 *ipos, const float4 *axf, const int2 *bonds,
