@@ -54,15 +54,19 @@ __device__ __forceinline__ float bond3(const oxb_dna3_dev &M, const BoxF &box, c
 //   pass 3  base-base contacts: hydrogen bonding + cross stacking        pass 4  stack-stack contacts: coaxial stacking
 // The p-side accumulators (force, lever sums, pure torque) are linear in the pairs: one PairAcc is carried through all passes and the two
 // cross products of the torque are taken once.
-template<int MB>
+template<int MB, int LPP>
 __global__ void __launch_bounds__(128, MB) k_forces_dna3(const __grid_constant__ oxb_dna3_dev M, BoxF box, int N, const int4 *__restrict__ ipos,
 		const int4 *__restrict__ iback, const float4 *__restrict__ axf, const double4 *__restrict__ posd, const double4 *__restrict__ quatd,
 		const int2 *__restrict__ bonds, const int *__restrict__ nbr, const int *__restrict__ nnbr, int stride,
 		float4 *__restrict__ F, float4 *__restrict__ T, int *__restrict__ flags, int hw) {
 	if(blockIdx.x == 0 && threadIdx.x == 0) prof_mark(flags, flags[hw] ? OXB_PROF_WAIT : OXB_PROF_FORCE);
 	if(flags[hw]) return;
-	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	// LPP = 2: lanes 2m and 2m + 1 share particle m -- alternate neighbours in every pass, one bond each -- and add their sums with shuffles:
+	// half the dependent chain per thread, twice the blocks (82k nucleotides are 1.4 waves of 128-thread blocks at 3 blocks per SM)
+	const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+	const int i = LPP == 2 ? gid >> 1 : gid, sub = LPP == 2 ? gid & 1 : 0;
 	if(i >= N) return;
+	const unsigned am = __activemask(); // the lanes that take part in the final shuffles (both lanes of a particle leave together)
 	const P3 P = load_p3(M, ipos, axf, i);
 	const int4 ibp = __ldg(iback + i);
 	const int2 b = __ldg(bonds + i);
@@ -75,12 +79,12 @@ __global__ void __launch_bounds__(128, MB) k_forces_dna3(const __grid_constant__
 	acc.clear();
 	acc.refine = refine ? &R : nullptr;
 	v3 fq = mk3(0.f, 0.f, 0.f), tq = mk3(0.f, 0.f, 0.f); // the bond in which it is "q"
-	if(b.x >= 0) { // I am the 5' side of the bond (p), q = my n3
+	if(b.x >= 0 && sub == 0) { // I am the 5' side of the bond (p), q = my n3
 		const P3 Q = load_p3(M, ipos, axf, b.x);
 		R.sp = i; R.sq = b.x;
 		e += bond3(M, box, P, Q, iback, i, b.x, refine, acc, broken, nullptr);
 	}
-	if(b.y >= 0) { // my n5 neighbour is p, I am q
+	if(b.y >= 0 && sub == LPP - 1) { // my n5 neighbour is p, I am q
 		const P3 Q = load_p3(M, ipos, axf, b.y);
 		PairAcc a2;
 		a2.clear();
@@ -96,7 +100,7 @@ __global__ void __launch_bounds__(128, MB) k_forces_dna3(const __grid_constant__
 		const int *__restrict__ row = nbr + (size_t) base * stride + i;
 		unsigned long long near = 0ull, mb = 0ull, ms = 0ull;
 #pragma unroll 4
-		for(int k = 0; k < cnt; k++) {
+		for(int k = sub; k < cnt; k += LPP) {
 			const int j = __ldg(row + (size_t) k * stride);
 			const int4 ipq = __ldg(ipos + j);
 			const int4 ibq = __ldg(iback + j);
@@ -146,9 +150,16 @@ __global__ void __launch_bounds__(128, MB) k_forces_dna3(const __grid_constant__
 		}
 	}
 	// torque stays in the lab frame; the integrator rotates it into the body frame
-	const v3 f = fq - acc.F, t = tq + acc.torque_p(P.ax, P.back);
-	F[i] = make_float4(f.x, f.y, f.z, e);
-	T[i] = make_float4(t.x, t.y, t.z, ehb);
+	v3 f = fq - acc.F, t = tq + acc.torque_p(P.ax, P.back);
+	if(LPP == 2) {
+		f.x += __shfl_xor_sync(am, f.x, 1); f.y += __shfl_xor_sync(am, f.y, 1); f.z += __shfl_xor_sync(am, f.z, 1);
+		t.x += __shfl_xor_sync(am, t.x, 1); t.y += __shfl_xor_sync(am, t.y, 1); t.z += __shfl_xor_sync(am, t.z, 1);
+		e += __shfl_xor_sync(am, e, 1); ehb += __shfl_xor_sync(am, ehb, 1);
+	}
+	if(sub == 0) {
+		F[i] = make_float4(f.x, f.y, f.z, e);
+		T[i] = make_float4(t.x, t.y, t.z, ehb);
+	}
 	if(broken) atomicOr(flags + OXB_FLAG_ERROR, OXB_ERR_FENE_BROKEN);
 }
 
@@ -202,10 +213,15 @@ void launch_forces_dna3(cudaStream_t s, const oxb_dna3_dev &M, BoxF box, int N, 
 	// minimum resident blocks per SM asked of the compiler = register cap (4: 128 registers, 790 B of spills; 3: 168, 230 B; 2: 250, none).
 	// Measured on B200 (profiles/sweeps_r02.txt, ag): OXB_DNA3_MB overrides
 	static const int mb = [] { const char *v = getenv("OXB_DNA3_MB"); return (v != nullptr && v[0] != 0) ? atoi(v) : 3; }();
-	const int blocks = (N + tpb - 1) / tpb;
-	if(mb >= 4) k_forces_dna3<4><<<blocks, tpb, 0, s>>>(M, box, N, ipos, iback, axf, posd, quatd, bonds, nbr, nnbr, stride, F, T, flags, hw);
-	else if(mb == 3) k_forces_dna3<3><<<blocks, tpb, 0, s>>>(M, box, N, ipos, iback, axf, posd, quatd, bonds, nbr, nnbr, stride, F, T, flags, hw);
-	else k_forces_dna3<2><<<blocks, tpb, 0, s>>>(M, box, N, ipos, iback, axf, posd, quatd, bonds, nbr, nnbr, stride, F, T, flags, hw);
+	static const int lpp = [] { const char *v = getenv("OXB_DNA3_LPP"); return (v != nullptr && v[0] != 0) ? atoi(v) : 1; }();
+	const int blocks = (int) (((long long) N * (lpp == 2 ? 2 : 1) + tpb - 1) / tpb);
+	if(lpp == 2) {
+		if(mb >= 4) k_forces_dna3<4, 2><<<blocks, tpb, 0, s>>>(M, box, N, ipos, iback, axf, posd, quatd, bonds, nbr, nnbr, stride, F, T, flags, hw);
+		else k_forces_dna3<3, 2><<<blocks, tpb, 0, s>>>(M, box, N, ipos, iback, axf, posd, quatd, bonds, nbr, nnbr, stride, F, T, flags, hw);
+	}
+	else if(mb >= 4) k_forces_dna3<4, 1><<<blocks, tpb, 0, s>>>(M, box, N, ipos, iback, axf, posd, quatd, bonds, nbr, nnbr, stride, F, T, flags, hw);
+	else if(mb == 3) k_forces_dna3<3, 1><<<blocks, tpb, 0, s>>>(M, box, N, ipos, iback, axf, posd, quatd, bonds, nbr, nnbr, stride, F, T, flags, hw);
+	else k_forces_dna3<2, 1><<<blocks, tpb, 0, s>>>(M, box, N, ipos, iback, axf, posd, quatd, bonds, nbr, nnbr, stride, F, T, flags, hw);
 }
 
 void launch_energy_split_dna3(cudaStream_t s, const oxb_dna3_dev &M, BoxF box, int N, const int4 *ipos, const float4 *axf, const int2 *bonds,
