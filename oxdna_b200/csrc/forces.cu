@@ -232,6 +232,122 @@ __global__ void __launch_bounds__(128, OXB_MB_PARTICLE) k_forces_particle(const 
 	if(broken) atomicOr(flags + OXB_FLAG_ERROR, OXB_ERR_FENE_BROKEN);
 }
 
+// The same pass with the neighbour loop split by COST into uniform sub-passes (as k_forces_dna3, forces_dna3.cu): a single loop runs with a
+// third of the lanes active, because one lane inside the six-angle hydrogen-bonding code holds the 31 others.  Per chunk of 64 neighbours:
+//   pass 1  every listed pair: fixed-point centre + backbone site of the neighbour (2 x 16 B), Debye-Hueckel, "near" bit
+//   pass 2  near pairs: full particle record, the four excluded-volume site pairs, radial + cosine-window screening -> bits
+//   pass 3  hydrogen bonding + cross stacking        pass 4  coaxial stacking
+// The p-side sums are linear in the pairs: one PairAcc is carried through all passes, the torque's cross products are taken once.
+// Still no atomics: deterministic.  OXB_PARTICLE_SPLIT=0 selects the single loop.
+template<class MD, int MB>
+__global__ void __launch_bounds__(128, MB) k_forces_particle_split(const __grid_constant__ typename MD::Params M, BoxF box, int N,
+		const int4 *__restrict__ ipos, const int4 *__restrict__ iback, const float4 *__restrict__ axf, const double4 *__restrict__ posd,
+		const double4 *__restrict__ quatd, const int2 *__restrict__ bonds, const int *__restrict__ nbr, const int *__restrict__ nnbr, int stride,
+		float4 *__restrict__ F, float4 *__restrict__ T, const oxb_replica_consts *__restrict__ rep, int n_per, int *__restrict__ flags, int hw) {
+	if(blockIdx.x == 0 && threadIdx.x == 0) prof_mark(flags, flags[hw] ? OXB_PROF_WAIT : OXB_PROF_FORCE);
+	if(flags[hw]) return;
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= N) return;
+	const Particle P = load_particle<MD>(M, ipos, axf, i);
+	const int4 ibp = __ldg(iback + i);
+	const int2 b = __ldg(bonds + i);
+	const bool p_end = (b.x < 0 || b.y < 0);
+	float e = 0.f, ehb = 0.f;
+	bool broken = false;
+	ExclRefine R = make_refine<MD>(M, box, posd, quatd);
+	const bool refine = posd != nullptr; // backend_precision = mixed
+	if(rep != nullptr) rep += i / n_per;   // replica batching: slots are replica-contiguous
+	const DhView D = dh_view(M, rep);
+	const float rcut2 = rep ? rep->rcut2 : M.rcut * M.rcut;
+	PairAcc acc; // everything in which this particle is "p"
+	acc.clear();
+	acc.refine = refine ? &R : nullptr;
+	acc.rep = rep;
+	v3 fq = mk3(0.f, 0.f, 0.f), tq = mk3(0.f, 0.f, 0.f); // the bond in which it is "q"
+	if(b.x >= 0) { // I am the 5' side of the bond (p), q = my n3
+		const Particle Q = load_particle<MD>(M, ipos, axf, b.x);
+		R.sp = i; R.sq = b.x;
+		FeneSite fs;
+		if(refine) fs = fene_from_sites(M, box, ibp, __ldg(iback + b.x), broken);
+		e += MD::bonded(M, min_image_fixed(box, P.ip, Q.ip), P.ax, Q.ax, P.btype, Q.btype, P.back, Q.back, acc, broken, nullptr, refine ? &fs : nullptr);
+	}
+	if(b.y >= 0) { // my n5 neighbour is p, I am q
+		const Particle Q = load_particle<MD>(M, ipos, axf, b.y);
+		PairAcc a2;
+		a2.clear();
+		R.sp = b.y; R.sq = i; a2.refine = refine ? &R : nullptr;
+		a2.rep = rep;
+		FeneSite fs;
+		if(refine) fs = fene_from_sites(M, box, __ldg(iback + b.y), ibp, broken);
+		e += MD::bonded(M, min_image_fixed(box, Q.ip, P.ip), Q.ax, P.ax, Q.btype, P.btype, Q.back, P.back, a2, broken, nullptr, refine ? &fs : nullptr);
+		fq = a2.F;
+		tq = a2.torque_q(P.ax, P.back);
+	}
+	R.sp = i;
+	const float rnear2 = M.rcut_near * M.rcut_near;
+	const int nn = __ldg(nnbr + i);
+	for(int base = 0; base < nn; base += 64) {
+		const int cnt = min(64, nn - base);
+		const int *__restrict__ row = nbr + (size_t) base * stride + i;
+		unsigned long long near = 0ull, mb = 0ull, ms = 0ull;
+#pragma unroll 4
+		for(int k = 0; k < cnt; k++) {
+			const int j = __ldg(row + (size_t) k * stride);
+			const int4 ipq = __ldg(ipos + j);
+			const int4 ibq = __ldg(iback + j);
+			const v3 r = min_image_fixed(box, P.ip, ipq);
+			const float r2 = dot(r, r);
+			const v3 rbb = min_image_fixed(box, ibp, ibq);
+			float fs;
+			float en = dna2_dh_fast(D, dot(rbb, rbb), p_end, ibq.w & 1, fs);
+			if(r2 >= rcut2) { en = 0.f; fs = 0.f; } // no interaction beyond the centre-centre cutoff (DNA2Interaction.cpp:46-48)
+			e += en;
+			acc.site_kk(rbb * fs);
+			if(r2 < rnear2 && r2 < rcut2) near |= 1ull << k;
+		}
+		while(near) {
+			const int k = __ffsll((long long) near) - 1;
+			near &= near - 1ull;
+			const int j = __ldg(row + (size_t) k * stride);
+			const Particle Q = load_particle<MD>(M, ipos, axf, j);
+			const v3 r = min_image_fixed(box, P.ip, Q.ip);
+			const v3 da = Q.ax.a1 - P.ax.a1;
+			const v3 rb = r + da * M.base_a1, rs = r + da * M.stack_a1;
+			R.sq = j;
+			e += dna2_excl(M, r, r + Q.back - P.back, rb, P.ax, Q.ax, P.back, Q.back, acc);
+			const float rbm2 = dot(rb, rb), rs2 = dot(rs, rs);
+			const bool hb_on = MD::hb_in_range(M, rbm2, P.btype, Q.btype), cr_on = MD::crst_in_range(M, rbm2);
+			if((hb_on || cr_on) && MD::hbcr_may_act(M, rb * rsqrtf(rbm2), P.ax, Q.ax, hb_on, cr_on)) mb |= 1ull << k;
+			if(MD::cxst_in_range(M, rs2) && MD::cxst_may_act(M, rs * rsqrtf(rs2), P.ax, Q.ax)) ms |= 1ull << k;
+		}
+		while(mb) {
+			const int k = __ffsll((long long) mb) - 1;
+			mb &= mb - 1ull;
+			const int j = __ldg(row + (size_t) k * stride);
+			const Particle Q = load_particle<MD>(M, ipos, axf, j);
+			const v3 rb = min_image_fixed(box, P.ip, Q.ip) + (Q.ax.a1 - P.ax.a1) * M.base_a1;
+			const float rbm2 = dot(rb, rb);
+			float eh;
+			e += MD::template hbcr<true>(M, rb, rbm2, P.ax, Q.ax, P.btype, Q.btype, MD::hb_in_range(M, rbm2, P.btype, Q.btype), MD::crst_in_range(M, rbm2), acc, eh);
+			ehb += eh;
+		}
+		while(ms) {
+			const int k = __ffsll((long long) ms) - 1;
+			ms &= ms - 1ull;
+			const int j = __ldg(row + (size_t) k * stride);
+			const Particle Q = load_particle<MD>(M, ipos, axf, j);
+			const v3 r = min_image_fixed(box, P.ip, Q.ip);
+			const v3 rs = r + (Q.ax.a1 - P.ax.a1) * M.stack_a1;
+			e += MD::cxst(M, rs, dot(rs, rs), r + Q.back - P.back, P.ax, Q.ax, acc);
+		}
+	}
+	// torque stays in the lab frame; the integrator rotates it into the body frame
+	const v3 f = fq - acc.F, t = tq + acc.torque_p(P.ax, P.back);
+	F[i] = make_float4(f.x, f.y, f.z, e);
+	T[i] = make_float4(t.x, t.y, t.z, ehb);
+	if(broken) atomicOr(flags + OXB_FLAG_ERROR, OXB_ERR_FENE_BROKEN);
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // Edge-centric, staged.  One thread per unique pair, but the pair population is split by COST so that every kernel is
 // (nearly) uniform across a warp -- the single-kernel version ran with 8 of 32 lanes active (ncu r01):
@@ -1135,11 +1251,28 @@ __global__ void k_ext_forces_all(int N, int n_all, const DevExtForce *__restrict
 
 namespace oxb {
 
+static int env_int(const char *name, int dflt);
+static bool particle_split() {
+	static const bool on = [] { const char *v = getenv("OXB_PARTICLE_SPLIT"); return v == nullptr || v[0] != '0'; }();
+	return on;
+}
+
 void launch_forces_particle(cudaStream_t s, const ModelRef &MR, BoxF box, int N, const int4 *ipos, const int4 *iback, const float4 *axf,
 		const double4 *posd, const double4 *quatd, const int2 *bonds,
 		const int *nbr, const int *nnbr, int stride, float4 *F, float4 *T, const oxb_replica_consts *rep, int n_per, int *flags, int hw) {
 	int tpb = 128;
 	if(MR.dna3) launch_forces_dna3(s, *MR.dna3, box, N, ipos, iback, axf, posd, quatd, bonds, nbr, nnbr, stride, F, T, flags, hw);
+	else if(particle_split()) {
+		// register cap as resident blocks per SM: 3 = 168 registers (the kernel wants ~250; at 96 it spills 700 B).  OXB_PARTICLE_MB = 4: 128
+		static const int mb = env_int("OXB_PARTICLE_MB", 3);
+		const int blocks = (N + tpb - 1) / tpb;
+		if(MR.rna) {
+			if(mb >= 4) k_forces_particle_split<RnaModel, 4><<<blocks, tpb, 0, s>>>(*MR.rna, box, N, ipos, iback, axf, posd, quatd, bonds, nbr, nnbr, stride, F, T, rep, n_per, flags, hw);
+			else k_forces_particle_split<RnaModel, 3><<<blocks, tpb, 0, s>>>(*MR.rna, box, N, ipos, iback, axf, posd, quatd, bonds, nbr, nnbr, stride, F, T, rep, n_per, flags, hw);
+		}
+		else if(mb >= 4) k_forces_particle_split<DnaModel, 4><<<blocks, tpb, 0, s>>>(*MR.dna, box, N, ipos, iback, axf, posd, quatd, bonds, nbr, nnbr, stride, F, T, rep, n_per, flags, hw);
+		else k_forces_particle_split<DnaModel, 3><<<blocks, tpb, 0, s>>>(*MR.dna, box, N, ipos, iback, axf, posd, quatd, bonds, nbr, nnbr, stride, F, T, rep, n_per, flags, hw);
+	}
 	else if(MR.rna) k_forces_particle<RnaModel><<<(N + tpb - 1) / tpb, tpb, 0, s>>>(*MR.rna, box, N, ipos, iback, axf, posd, quatd, bonds, nbr, nnbr, stride, F, T, rep, n_per, flags, hw);
 	else k_forces_particle<DnaModel><<<(N + tpb - 1) / tpb, tpb, 0, s>>>(*MR.dna, box, N, ipos, iback, axf, posd, quatd, bonds, nbr, nnbr, stride, F, T, rep, n_per, flags, hw);
 }
