@@ -129,3 +129,30 @@ def test_dna3_model_switch_on_one_context():
         assert abs(sim.ctx.energy()[0] - U2) <= 1e-6 * abs(U2)
     finally:
         sim.close()
+
+
+def test_dna3_full_size_c2_geometry_against_the_oracle():
+    """81,920 nucleotides (the C2 lattice, L = 130) under oxDNA3 with the sequence-dependent tables of the fixture, after 300 thermalising
+    steps with Hilbert re-sorts: pair set bit-exact (rcut of oxDNA3), forces, lab torques and energy against the oracle on the downloaded state"""
+    from oxdna_b200 import lattice
+    from oxdna_b200.sim import parse_temperature
+    g = load_golden("dna3_lattice8")
+    sysm = lattice.duplex_lattice(2048, bp=20, spacing=10.0, seed=12345)
+    N = len(sysm["pos"])
+    v, L = lattice.maxwell_velocities(N, parse_temperature("300K"), 5)
+    inp = dict(backend="CUDA", interaction_type="DNA3", T="300K", salt_concentration=0.5, dt=0.003, verlet_skin=0.05, thermostat="brownian",
+               newtonian_steps=103, diff_coeff=2.5, CUDA_sort_every=1, use_edge=1, seed=11, dna3_tables=g["dna3_tables"], dna3_scalars=g["dna3_scalars"])
+    sim = Simulation(inp, sysm, dict(box=sysm["box"], pos=sysm["pos"], a1=sysm["a1"], a3=sysm["a3"], vel=v, L=L))
+    try:
+        sim.run(300)
+        st = sim.ctx.get_state()
+        P = O.dna3_params(g["dna3_tables"], g["dna3_scalars"])
+        pairs = O.verlet_pairs(st["pos"], sysm["n3"], sysm["n5"], sysm["box"], P.rcut + 2 * 0.05)
+        sim.ctx.update_lists()
+        assert pair_set(sim.ctx.get_pairs()) == pair_set(pairs)
+        ref = O.forces(P, st["pos"], O.axes_from_a1a3(st["a1"], st["a3"]), sysm["btype"], sysm["n3"], sysm["n5"], sysm["box"], pairs)
+        sim.ctx.compute_forces()
+        check_forces(sim.ctx.get_forces(), ref)
+        assert np.abs(np.asarray(sim.ctx.energy_split())[:8] - ref["eterms"]).max() <= 2e-6 * abs(ref["U"])
+    finally:
+        sim.close()
