@@ -93,7 +93,12 @@ struct Six {
 	Angle t1, t2, t3, t4, t7, t8;
 	float g1, g2, g3, g4, g7, g8, grad, E;
 };
-OXB_HD void six_add(Six &S, RadVal f, const oxb_f4 &p1, const oxb_f4 &p2, const oxb_f4 &p4, const oxb_f4 &p7, float &e_out) {
+// f4 block of a record: theta1, theta2 (= theta3), theta4, theta7 (= theta8), 5 floats each, fetched where it is used (the records are not
+// held in registers across the evaluation: the kernel is register-bound)
+OXB_HD void six_add(Six &S, RadVal f, const float4 *f4blk, float &e_out) {
+	float q[20];
+	load_rec<5>(f4blk, q);
+	const oxb_f4 p1 = f4_rec(q), p2 = f4_rec(q + 5), p4 = f4_rec(q + 10), p7 = f4_rec(q + 15);
 	const AngVal a1 = f4_ts(p1, S.t1.t, S.t1.s), a2 = f4_ts(p2, S.t2.t, S.t2.s), a3 = f4_ts(p2, S.t3.t, S.t3.s);
 	const AngVal a4 = f4_ts(p4, S.t4.t, S.t4.s), a7 = f4_ts(p7, S.t7.t, S.t7.s), a8 = f4_ts(p7, S.t8.t, S.t8.s);
 	const float p12 = a1.v * a2.v, p34 = a3.v * a4.v, p78 = a7.v * a8.v;
@@ -139,18 +144,19 @@ OXB_HD float dna3_hbcr(const oxb_dna3_dev &M, v3 rb, float rbm2, const Axes &A, 
 	const float m = rbm2 * inv;
 	const v3 h = rb * inv;
 	const float c7 = -dot(B.a3, h), c8 = dot(A.a3, h);
-	float rh[OXB3_REC_HB];
+	// gates first, from the two float4 of each record that hold rclow / rchigh (floats 7, 8 of an f1 record, 5, 8 of an f2 record)
+	const float4 *hbr = M.hb + (nq.type * 5 + np.type) * (OXB3_REC_HB / 4);
 	bool hb_on = (btp + btq == 3);
 	if(hb_on) {
-		load_rec<OXB3_REC_HB / 4>(M.hb + (nq.type * 5 + np.type) * (OXB3_REC_HB / 4), rh);
-		hb_on = rh[7] < m && m < rh[8];
+		float g[8];
+		load_rec<2>(hbr + 1, g);
+		hb_on = g[3] < m && m < g[4];
 	}
-	const int ix33 = ix4(nq.n3t, nq.type, np.type, np.n3t), ix55 = ix4(nq.n5t, nq.type, np.type, np.n5t);
-	float r33[12], r55[12];
-	load_rec<3>(M.crst + ix33 * (OXB3_REC_CRST / 4), r33); // first 12 floats of the record: f2
-	load_rec<3>(M.crst + (900 + ix55) * (OXB3_REC_CRST / 4), r55);
-	const bool in33 = c7 > 0.f && c8 > 0.f && r33[5] < m && m < r33[8];
-	const bool in55 = c7 < 0.f && c8 < 0.f && r55[5] < m && m < r55[8];
+	const float4 *c33 = M.crst + ix4(nq.n3t, nq.type, np.type, np.n3t) * (OXB3_REC_CRST / 4);
+	const float4 *c55 = M.crst + (900 + ix4(nq.n5t, nq.type, np.type, np.n5t)) * (OXB3_REC_CRST / 4);
+	bool in33 = c7 > 0.f && c8 > 0.f, in55 = c7 < 0.f && c8 < 0.f;
+	if(in33) { float g[8]; load_rec<2>(c33 + 1, g); in33 = g[1] < m && m < g[4]; }
+	if(in55) { float g[8]; load_rec<2>(c55 + 1, g); in55 = g[1] < m && m < g[4]; }
 	if(!(hb_on || in33 || in55)) return 0.f;
 	Six S;
 	S.t1 = make_angle(-A.a1, B.a1); S.t2 = make_angle(-B.a1, h); S.t3 = make_angle(A.a1, h);
@@ -158,21 +164,23 @@ OXB_HD float dna3_hbcr(const oxb_dna3_dev &M, v3 rb, float rbm2, const Axes &A, 
 	S.g1 = S.g2 = S.g3 = S.g4 = S.g7 = S.g8 = S.grad = S.E = 0.f;
 	if(hb_on) {
 		const float mult = (abs(btq) >= 300 && abs(btp) >= 300) ? M.hb_multiplier : 1.f;
-		RadVal f1 = f1_rec(rh, m);
+		float fr[12];
+		load_rec<3>(hbr, fr);
+		RadVal f1 = f1_rec(fr, m);
 		f1.v *= mult; f1.d *= mult;
 		float e;
-		six_add(S, f1, f4_rec(rh + 12), f4_rec(rh + 17), f4_rec(rh + 22), f4_rec(rh + 27), e);
+		six_add(S, f1, hbr + 3, e);
 		ehb += e;
 		if(esplit) esplit[4] += e;
 	}
 	if(in33 || in55) {
 		// both diagonals are evaluated once either gate is open, as the reference does (DNA3Interaction.cpp:1640-1665): each f2 has its own range
-		float rr[OXB3_REC_CRST - 12], e;
-		load_rec<(OXB3_REC_CRST - 12) / 4>(M.crst + ix33 * (OXB3_REC_CRST / 4) + 3, rr);
-		six_add(S, f2_r(f2_rec(r33), m), f4_rec(rr), f4_rec(rr + 5), f4_rec(rr + 10), f4_rec(rr + 15), e);
+		float fr[12], e;
+		load_rec<3>(c33, fr);
+		six_add(S, f2_r(f2_rec(fr), m), c33 + 3, e);
 		if(esplit) esplit[5] += e;
-		load_rec<(OXB3_REC_CRST - 12) / 4>(M.crst + (900 + ix55) * (OXB3_REC_CRST / 4) + 3, rr);
-		six_add(S, f2_r(f2_rec(r55), m), f4_rec(rr), f4_rec(rr + 5), f4_rec(rr + 10), f4_rec(rr + 15), e);
+		load_rec<3>(c55, fr);
+		six_add(S, f2_r(f2_rec(fr), m), c55 + 3, e);
 		if(esplit) esplit[5] += e;
 	}
 	if(S.E != 0.f) {
@@ -269,7 +277,9 @@ struct Fene3 {
 	float fene_r0, fene_delta2, fene_eps, mbf_xmax, mbf_fmax, mbf_finf, mbf_e0;
 	int use_mbf;
 };
-OXB_HD Fene3 fene3_of(const oxb_dna3_dev &M, const float *rec) {
+OXB_HD Fene3 fene3_of(const oxb_dna3_dev &M, const float4 *rec4) {
+	float rec[4];
+	load_rec<1>(rec4, rec);
 	Fene3 f;
 	f.fene_r0 = rec[0]; f.fene_delta2 = rec[1]; f.mbf_xmax = rec[2]; f.mbf_e0 = rec[3];
 	f.fene_eps = M.fene_eps; f.mbf_fmax = M.mbf_fmax; f.mbf_finf = M.mbf_finf; f.use_mbf = M.use_mbf;
@@ -278,7 +288,7 @@ OXB_HD Fene3 fene3_of(const oxb_dna3_dev &M, const float *rec) {
 
 // Bonded pair p -> q = n3(p): DNA3Interaction.cpp:1230-1287 (FENE), 1057-1135 (excluded volume), 1289-1475 (stacking).
 // rec: the bonded record of the tetramer (n3(q), q, p, n5(p)).
-OXB_HD float dna3_bonded(const oxb_dna3_dev &M, const float *rec, v3 r, const Axes &A, const Axes &B, const Nuc3 &np, const Nuc3 &nq, v3 pback, v3 qback,
+OXB_HD float dna3_bonded(const oxb_dna3_dev &M, const float4 *rec4, v3 r, const Axes &A, const Axes &B, const Nuc3 &np, const Nuc3 &nq, v3 pback, v3 qback,
 		PairAcc &acc, bool &broken, float *esplit = nullptr, const FeneSite *fene = nullptr) {
 	float E = 0.f;
 	const float cbp = M.pos_base[np.si], cbq = M.pos_base[nq.si], csp = M.pos_stack[np.si], csq = M.pos_stack[nq.si], cr = M.backref_a1;
@@ -288,7 +298,7 @@ OXB_HD float dna3_bonded(const oxb_dna3_dev &M, const float *rec, v3 r, const Ax
 		acc.site_kk(fene->d * fene->s);
 	}
 	else {
-		const Fene3 F = fene3_of(M, rec);
+		const Fene3 F = fene3_of(M, rec4);
 		const v3 d = r + qback - pback;
 		const float d2 = dot(d, d);
 		const float invm = OXB_RSQRT(d2);
@@ -310,9 +320,11 @@ OXB_HD float dna3_bonded(const oxb_dna3_dev &M, const float *rec, v3 r, const Ax
 		acc.site_kk(d * s);
 	}
 	{
-		float en = excl3(M, excl_rec(rec + 4), r + B.a1 * cbq - A.a1 * cbp, OXB_SITE_AA, cbp, cbq, acc);
-		en += excl3(M, excl_rec(rec + 8), r + qback - A.a1 * cbp, OXB_SITE_AK, cbp, cbq, acc);
-		en += excl3(M, excl_rec(rec + 12), r + B.a1 * cbq - pback, OXB_SITE_KA, cbp, cbq, acc);
+		float ex[12];
+		load_rec<3>(rec4 + 1, ex);
+		float en = excl3(M, excl_rec(ex), r + B.a1 * cbq - A.a1 * cbp, OXB_SITE_AA, cbp, cbq, acc);
+		en += excl3(M, excl_rec(ex + 4), r + qback - A.a1 * cbp, OXB_SITE_AK, cbp, cbq, acc);
+		en += excl3(M, excl_rec(ex + 8), r + B.a1 * cbq - pback, OXB_SITE_KA, cbp, cbq, acc);
 		E += en;
 		if(esplit) esplit[1] += en;
 	}
@@ -320,8 +332,15 @@ OXB_HD float dna3_bonded(const oxb_dna3_dev &M, const float *rec, v3 r, const Ax
 	const float rs2 = dot(rs, rs);
 	const float inv = OXB_RSQRT(rs2);
 	const float m = rs2 * inv;
-	const RadVal f1 = f1_rec(rec + 16, m);
+	RadVal f1;
+	{
+		float fr[12];
+		load_rec<3>(rec4 + 4, fr);
+		f1 = f1_rec(fr, m);
+	}
 	if(f1.v != 0.f || f1.d != 0.f) {
+		float rec[20]; // f4 theta4 (0..4), theta5 (5..9), - , f5 phi1 (12..15), phi2 (16..19)
+		load_rec<5>(rec4 + 7, rec);
 		const v3 h = rs * inv;
 		const v3 w = r + (B.a1 - A.a1) * cr;
 		const float w2 = dot(w, w);
@@ -329,9 +348,9 @@ OXB_HD float dna3_bonded(const oxb_dna3_dev &M, const float *rec, v3 r, const Ax
 		const v3 wh = w * winv;
 		const Angle t4 = make_angle(A.a3, B.a3), t5 = make_angle(-A.a3, h), t6 = make_angle(-B.a3, h);
 		const float cp1 = dot(A.a2, wh), cp2 = dot(B.a2, wh);
-		const oxb_f4 p5 = f4_rec(rec + 33);
-		const AngVal a4 = f4_ts(f4_rec(rec + 28), t4.t, t4.s), a5 = f4_ts(p5, t5.t, t5.s), a6 = f4_ts(p5, t6.t, t6.s);
-		const AngVal b1 = f5_c(f5_rec(rec + 40), cp1), b2 = f5_c(f5_rec(rec + 44), cp2);
+		const oxb_f4 p5 = f4_rec(rec + 5);
+		const AngVal a4 = f4_ts(f4_rec(rec), t4.t, t4.s), a5 = f4_ts(p5, t5.t, t5.s), a6 = f4_ts(p5, t6.t, t6.s);
+		const AngVal b1 = f5_c(f5_rec(rec + 12), cp1), b2 = f5_c(f5_rec(rec + 16), cp2);
 		const float p456 = a4.v * a5.v * a6.v, pb = b1.v * b2.v;
 		const float e = f1.v * p456 * pb;
 		if(e != 0.f) {

@@ -40,8 +40,7 @@ __device__ __forceinline__ ExclRefine refine3(const oxb_dna3_dev &M, const BoxF 
 // the bond p -> q = n3(p): record of the tetramer (n3(q), q, p, n5(p)); FENE in double from the fixed-point backbone sites (mixed precision)
 __device__ __forceinline__ float bond3(const oxb_dna3_dev &M, const BoxF &box, const P3 &P, const P3 &Q, const int4 *__restrict__ iback, int sp, int sq,
 		bool refine, PairAcc &acc, bool &broken, float *esplit) {
-	float rec[OXB3_REC_BONDED];
-	load_rec<OXB3_REC_BONDED / 4>(M.bonded + ix4(Q.n.n3t, Q.n.type, P.n.type, P.n.n5t) * (OXB3_REC_BONDED / 4), rec);
+	const float4 *rec = M.bonded + ix4(Q.n.n3t, Q.n.type, P.n.type, P.n.n5t) * (OXB3_REC_BONDED / 4);
 	FeneSite fs;
 	if(refine) fs = fene_from_sites(fene3_of(M, rec), box, __ldg(iback + sp), __ldg(iback + sq), broken);
 	return dna3_bonded(M, rec, min_image_fixed(box, P.ip, Q.ip), P.ax, Q.ax, P.n, Q.n, P.back, Q.back, acc, broken, esplit, refine ? &fs : nullptr);

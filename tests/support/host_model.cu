@@ -107,8 +107,7 @@ extern "C" void host_dna3_forces(const double *tables, const oxb_dna3_scalars *S
 	for(int p = 0; p < N; p++) {
 		int q = n3[p];
 		if(q < 0) continue;
-		float rec[OXB3_REC_BONDED];
-		load_rec<OXB3_REC_BONDED / 4>(M.bonded + ix4(nuc[q].n3t, nuc[q].type, nuc[p].type, nuc[p].n5t) * (OXB3_REC_BONDED / 4), rec);
+		const float4 *rec = M.bonded + ix4(nuc[q].n3t, nuc[q].type, nuc[p].type, nuc[p].n5t) * (OXB3_REC_BONDED / 4);
 		PairAcc acc; acc.clear();
 		bool broken = false;
 		float e = dna3_bonded(M, rec, min_image_fixed(b, ip[p], ip[q]), ax[p], ax[q], nuc[p], nuc[q], back[p], back[q], acc, broken, es);
