@@ -195,8 +195,13 @@ class Simulation:
         kind, every, a, b, c, d = self._thermostat_for(self.T)
         self.ctx.set_thermostat(kind, every, a, b, c, d, self.seed)
 
-    def update_temperature(self, T):
-        """ConfigInfo::update_temperature -> interaction re-init + thermostat re-init (SURVEY 3.4)."""
+    def update_temperature(self, T, dna3_tables=None, dna3_scalars=None):
+        """ConfigInfo::update_temperature -> interaction re-init + thermostat re-init (SURVEY 3.4).  oxDNA3: the tables depend on T
+        (stacking strengths) and are input here -- hand in the ones DNA3Interaction::init derives for the new temperature."""
+        if self.itype in ("DNA3", "DNA3_nomesh"):
+            if dna3_tables is None or dna3_scalars is None:
+                raise ValueError("interaction_type = DNA3: update_temperature needs the parameter tables for the new temperature")
+            self.inp["dna3_tables"], self.inp["dna3_scalars"] = dna3_tables, dna3_scalars
         self.T = parse_temperature(T)
         self._set_model()
         self._set_thermostat()

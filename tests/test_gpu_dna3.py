@@ -156,3 +156,24 @@ def test_dna3_full_size_c2_geometry_against_the_oracle():
         assert np.abs(np.asarray(sim.ctx.energy_split())[:8] - ref["eterms"]).max() <= 2e-6 * abs(ref["U"])
     finally:
         sim.close()
+
+
+def test_dna3_refuses_what_it_does_not_serve():
+    """replica batches and a temperature change without new tables are explicit errors (the tables depend on T and are input)"""
+    from oxdna_b200 import capi
+    g = load_golden("dna3_lattice8")
+    sim = make_sim(g)
+    try:
+        with pytest.raises(ValueError):
+            sim.update_temperature("310K")
+        sim.update_temperature("300K", g["dna3_tables"], g["dna3_scalars"])
+        check_forces(sim.ctx.get_forces(), g)
+    finally:
+        sim.close()
+    c = capi.Context(len(g["pos"]))
+    try:
+        c.set_replicas(2)
+        with pytest.raises(capi.OxbError):
+            c.set_model_dna3(g["dna3_tables"], g["dna3_scalars"])
+    finally:
+        c.close()
