@@ -280,6 +280,7 @@ int alloc_lists(oxb_ctx *c, int max_neigh) {
 	c->max_neigh = max_neigh;
 	CU(dalloc(&c->cell_key, N)); CU(dalloc(&c->cell_key_sorted, N)); CU(dalloc(&c->cell_val, N)); CU(dalloc(&c->cell_val_sorted, N));
 	CU(dalloc(&c->nbr, (size_t) max_neigh * N)); CU(dalloc(&c->nnbr, N));
+	CU(cudaMemset(c->nbr, 0, sizeof(int) * (size_t) max_neigh * N)); // (oxb_get_pairs downloads whole rows: keep the unwritten tails defined)
 	CU(dalloc(&c->edge_cnt, (size_t) N + 1)); CU(dalloc(&c->n_edges, 4)); CU(dalloc(&c->near_mask, (size_t) N));
 	CU(cudaMemset(c->edge_cnt, 0, sizeof(int4) * ((size_t) N + 1)));
 	CU(cudaMemset(c->n_edges, 0, 4 * sizeof(int)));
