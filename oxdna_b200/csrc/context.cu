@@ -70,7 +70,7 @@ struct oxb_ctx {
 	float4 *d3_buf = nullptr;
 	int *d3_tcode = nullptr;
 	bool d3_tcode_valid = false;
-	int use_edge_asked = 0; // what oxb_set_lists was given (oxDNA3 is served by the particle-centric pass whatever it says)
+	int use_edge_asked = 0; // what oxb_set_lists was given
 	oxb::ModelRef mref() const {
 		if(is_dna3) return oxb::ModelRef{ nullptr, nullptr, &d3 };
 		return is_rna ? oxb::ModelRef{ nullptr, &rmodel, nullptr } : oxb::ModelRef{ &model, nullptr, nullptr };
@@ -552,7 +552,7 @@ int launch_forces(oxb_ctx *c, int hw, bool clear, long long step) {
 		e.refine = (c->precision == OXB_PRECISION_MIXED) ? 1 : 0;
 		e.dh_half = c->dh_half ? 1 : 0;
 		// bit 0: coaxial stacking + FP64 excluded volume in the tails of the producers; bit 1: hydrogen bonding / cross stacking too (no stage 2 launch)
-		e.fold = c->fold_tails ? (c->fold_hb ? 3 : 1) : 0;
+		e.fold = c->is_dna3 ? 0 : (c->fold_tails ? (c->fold_hb ? 3 : 1) : 0); // (oxDNA3: every stage is its own launch, forces.cu)
 		e.n_seg = c->n_seg; e.hb_seg = c->hb_seg; e.cx_seg = c->cx_seg; e.cr_seg = c->cr_seg;
 		// ~1.7 items per particle in that list; aim at ~2 items per consumer thread
 		e.hb_split = (int) std::max<long long>(1, std::min<long long>(8, (17ll * c->N / 10 / c->n_seg + 64) / 128));
@@ -586,7 +586,7 @@ int launch_forces(oxb_ctx *c, int hw, bool clear, long long step) {
 		if(fork) CU(cudaStreamWaitEvent(c->aux[1], c->ev_near, 0));
 		if(!e.fold) {
 			oxb::launch_edge_stage(s1, 3, c->mref(), c->boxf, e, c->flags, hw);
-			if(e.refine) oxb::launch_edge_stage(s1, 6, c->mref(), c->boxf, e, c->flags, hw); // excluded volume in double for the parked pairs (after near + bonded)
+			if(e.refine && !c->is_dna3) oxb::launch_edge_stage(s1, 6, c->mref(), c->boxf, e, c->flags, hw); // excluded volume in double for the parked pairs (after near + bonded)
 		}
 		if(fork) {
 			CU(cudaEventRecord(c->ev_join[0], c->aux[0]));
@@ -594,7 +594,7 @@ int launch_forces(oxb_ctx *c, int hw, bool clear, long long step) {
 			CU(cudaStreamWaitEvent(m, c->ev_join[0], 0));
 			CU(cudaStreamWaitEvent(m, c->ev_join[1], 0));
 		}
-		c->launches += (e.fold & 2) ? 3 : (e.fold ? 4 : (e.refine ? 6 : 5));
+		c->launches += c->is_dna3 ? 5 : ((e.fold & 2) ? 3 : (e.fold ? 4 : (e.refine ? 6 : 5)));
 	}
 	else {
 		if(c->force_cb != nullptr) { int rc = launch_forces_callback(c, step); if(rc) return rc; }
@@ -843,7 +843,7 @@ int batch_graph(oxb_ctx *c, int units, cudaGraphExec_t *out) {
 // stream launches.
 int launch_full_units(oxb_ctx *c, long long n, long long step0, int &epoch) {
 	const bool graphable = c->use_graphs && c->th.type != OXB_THERMOSTAT_BUSSI && c->force_cb == nullptr;
-	const int per_unit = (c->use_edge ? (c->fold_tails ? (c->fold_hb ? 3 : 4) : (c->precision == OXB_PRECISION_MIXED ? 6 : 5)) : 1) + (c->n_ext > 0 ? 1 : 0) + (c->n_ext_all > 0 ? 1 : 0) + (c->n_ext_com > 0 ? 1 : 0) + 1;
+	const int per_unit = (c->use_edge ? (c->is_dna3 ? 5 : (c->fold_tails ? (c->fold_hb ? 3 : 4) : (c->precision == OXB_PRECISION_MIXED ? 6 : 5))) : 1) + (c->n_ext > 0 ? 1 : 0) + (c->n_ext_all > 0 ? 1 : 0) + (c->n_ext_com > 0 ? 1 : 0) + 1;
 	long long k = 0;
 	while(k < n) {
 		int chunk = 0;
@@ -1032,13 +1032,8 @@ int oxb_set_topology(oxb_ctx *c, const int *btype, const int *n3, const int *n5,
 	return 0;
 }
 
-// oxDNA3 is served by the particle-centric pass: entering / leaving the model switches the edge pipeline off / back to what was asked
 static void leave_dna3(oxb_ctx *c) {
 	c->is_dna3 = false;
-	if(c->use_edge != c->use_edge_asked) {
-		c->use_edge = c->use_edge_asked;
-		if(c->lists_allocated) free_lists(c);
-	}
 }
 
 int oxb_set_model_dna2(oxb_ctx *c, const oxb_dna2_params *P, double rcut) {
@@ -1101,10 +1096,17 @@ int oxb_set_model_dna3(oxb_ctx *c, const double *tab, const oxb_dna3_scalars *S)
 	std::memset(&M, 0, sizeof(M));
 	M.back_a1 = D.back_a1; M.back_a2 = D.back_a2; c->back_a3 = 0.f;
 	M.base_a1 = 0.43f; M.stack_a1 = 0.37f; M.backref_a1 = D.backref_a1;
-	M.dh_rc = D.dh_rc; M.rcut = (float) S->rcut; M.rcut_near = (float) S->rcut;
+	M.dh_rc = D.dh_rc; M.rcut = (float) S->rcut;
+	// thresholds of the list builder's near-edge selection (list_args): the longest range of any tetramer per family of site pairs.  The
+	// builder places every base site at 0.43 a1 and every stacking site at 0.37 a1; the true offsets are 0.37 ... 0.43 (0.34 for a dummy
+	// base): a base-base distance is off by at most 0.12, a base-backbone or stack-stack distance by at most 0.06
+	M.rcut_near = std::min((float) S->rcut, std::sqrt(D.r2_near_max));
+	M.excl[0].rc = D.range_bb; M.excl[1].rc = D.range_eb + 0.12f; M.excl[2].rc = M.excl[3].rc = D.range_bk + 0.06f;
+	M.hb.rchigh = M.crst.rchigh = std::sqrt(D.r2_base_max) + 0.12f;
+	M.cxst.rchigh = std::sqrt(D.r2_stack_max) + 0.06f;
 	c->is_rna = false;
 	c->is_dna3 = true;
-	if(c->use_edge) { c->use_edge = 0; if(c->lists_allocated) free_lists(c); c->lists_valid = false; }
+	c->lists_valid = false;
 	c->rcut = S->rcut;
 	c->have_model = true;
 	c->forces_valid = false;
@@ -1197,7 +1199,7 @@ int oxb_replica_energies(oxb_ctx *c, double *U) {
 int oxb_set_lists(oxb_ctx *c, double verlet_skin, int use_edge, int sort_every, double max_density_multiplier) {
 	if(c == nullptr) return 1;
 	if(!(verlet_skin > 0)) return fail(c, 1, "verlet_skin must be > 0");
-	c->skin = verlet_skin; c->use_edge_asked = use_edge ? 1 : 0; c->use_edge = (use_edge && !c->is_dna3) ? 1 : 0; c->sort_every = sort_every < 0 ? 0 : sort_every;
+	c->skin = verlet_skin; c->use_edge_asked = use_edge ? 1 : 0; c->use_edge = use_edge ? 1 : 0; c->sort_every = sort_every < 0 ? 0 : sort_every;
 	c->max_density_multiplier = max_density_multiplier;
 	c->lists_valid = false; c->forces_valid = false;
 	if(c->lists_allocated) free_lists(c);

@@ -34,7 +34,7 @@ inline void dna3_pack(const double *tab, const oxb_dna3_scalars *S, std::vector<
 	auto put_f4 = [&](float *o, int ty, int ix) { for(int par = 0; par < 5; par++) o[par] = (float) T(OXB_DNA3_F4 + par * 21 + ty, ix); };
 	auto put_f5 = [&](float *o, int ty, int ix) { for(int par = 0; par < 4; par++) o[par] = (float) T(OXB_DNA3_F5 + par * 4 + ty, ix); };
 	const bool use_mbf = S->use_mbf != 0.;
-	double max_excl_rc = 0., max_base = 0., max_stack = 0.;
+	double max_excl_rc = 0., max_base = 0., max_stack = 0., max_bb = 0., max_eb = 0., max_bk = 0.;
 	for(int ix = 0; ix < 900; ix++) {
 		float *o = hb_ + (size_t) ix * OXB3_REC_BONDED;
 		const double xmax = T(OXB_DNA3_MBF_XMAX, ix), d2 = T(OXB_DNA3_FENE_DELTA2, ix);
@@ -64,6 +64,8 @@ inline void dna3_pack(const double *tab, const oxb_dna3_scalars *S, std::vector<
 		max_base = std::max(max_base, T(OXB_DNA3_F1 + 9 * 2 + 0, ix0));
 		float *e = he + (size_t) (tq * 5 + tp) * OXB3_REC_NEXCL;
 		for(int w = 0; w < 4; w++) put_excl(e + 4 * w, w, ix5);
+		max_bb = std::max(max_bb, T(OXB_DNA3_EXCL_RC + 0, ix5)); max_eb = std::max(max_eb, T(OXB_DNA3_EXCL_RC + 1, ix5));
+		max_bk = std::max(max_bk, std::max(T(OXB_DNA3_EXCL_RC + 2, ix5), T(OXB_DNA3_EXCL_RC + 3, ix5)));
 	}
 	std::memset(&D, 0, sizeof(D));
 	off[0] = 0; off[1] = NB; off[2] = (size_t) NB + NC; off[3] = (size_t) NB + NC + NX; off[4] = (size_t) NB + NC + NX + NH;
@@ -83,5 +85,6 @@ inline void dna3_pack(const double *tab, const oxb_dna3_scalars *S, std::vector<
 	D.r2_excl_max = (float) std::pow(max_excl_rc + 2. * lever + 0.01, 2);
 	D.r2_base_max = (float) std::pow(max_base + 1e-3, 2);
 	D.r2_stack_max = (float) std::pow(max_stack + 1e-3, 2);
+	D.range_bb = (float) max_bb; D.range_eb = (float) max_eb; D.range_bk = (float) max_bk;
 	D.r2_near_max = (float) std::pow(std::max(max_excl_rc + 2. * lever, std::max(max_base + 2. * 0.43, max_stack + 2. * 0.37)) + 0.01, 2);
 }

@@ -5,6 +5,7 @@
 // Data: ipos int4 (fixed-point position, .w = btype<<22 | original index), axf = FP32 orientation record (a1, a3; common.cuh), bonds int2 (n3, n5 slots),
 // neighbour matrix column-major nbr[k * stride + i], forces/torques float4 (.w = energy / HB energy as in the reference).
 #include "models.cuh"
+#include "dna3_model.cuh"
 #include "kernels.h"
 
 #include <cstdlib>
@@ -763,6 +764,164 @@ __global__ void __launch_bounds__(128) k_excl_fix(const __grid_constant__ typena
 	}
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// oxDNA3 through the staged edge pipeline (use_edge = 1): the same lists (half Debye-Hueckel matrix, near edges, block-segmented work
+// lists) and the same cost split as above, with the per-tetramer parameter records and per-type site offsets of dna3_model.cuh.
+//   k_dh_particle<Dna3Dh>  Debye-Hueckel (needs the Debye-Hueckel scalars only)
+//   k3_edge_near     near edges: the four excluded-volume site pairs (active ones re-evaluated in double through PairAcc::refine);
+//                    pairs with the bases / the stacking sites inside the longest range of any tetramer go to the two work lists
+//   k3_edge_heavy<0> hydrogen bonding + both cross-stacking diagonals      k3_edge_heavy<1> coaxial stacking
+//   k3_bonded        FENE + bonded excluded volume + stacking, each bond once
+// The near-edge classes of the list builder are not used (every family is screened here): they are thresholds of one parameter set.
+// ------------------------------------------------------------------------------------------------------------
+struct Dna3Dh { typedef oxb_dna3_dev Params; };
+
+struct P3e {
+	int4 ip;
+	Axes ax;
+	v3 back;
+	int btype;
+	Nuc3 n;
+};
+__device__ __forceinline__ P3e load_p3e(const oxb_dna3_dev &M, const int4 *__restrict__ ipos, const float4 *__restrict__ axf, int i) {
+	P3e P;
+	P.ip = __ldg(ipos + i);
+	P.ax = load_axes(axf, i);
+	P.back = P.ax.a1 * M.back_a1 + P.ax.a2 * M.back_a2;
+	P.btype = word_btype(P.ip.w);
+	P.n = nuc3_from_code(__ldg(M.tcode + word_index(P.ip.w)));
+	return P;
+}
+__device__ __forceinline__ ExclRefine refine3e(const oxb_dna3_dev &M, const BoxF &box, const double4 *posd, const double4 *quatd) {
+	ExclRefine R;
+	R.posd = posd; R.quatd = quatd; R.sp = R.sq = 0;
+	R.L[0] = box.dsx * 4294967296.; R.L[1] = box.dsy * 4294967296.; R.L[2] = box.dsz * 4294967296.;
+	R.b1 = (double) M.back_a1; R.b2 = (double) M.back_a2; R.b3 = 0.;
+	return R;
+}
+
+__global__ void __launch_bounds__(128, 4) k3_edge_near(const __grid_constant__ oxb_dna3_dev M, BoxF box, const int *__restrict__ n_edges,
+		const int2 *__restrict__ edges, const int4 *__restrict__ ipos, const float4 *__restrict__ axf, float4 *__restrict__ F, float4 *__restrict__ T,
+		int2 *__restrict__ hb_list, int2 *__restrict__ cx_list, int *__restrict__ seg_counts, int hb_seg, int cx_seg, const double4 *__restrict__ posd,
+		const double4 *__restrict__ quatd, int *__restrict__ flags, int hw) {
+	if(blockIdx.x == 0 && threadIdx.x == 0) prof_mark(flags, flags[hw] ? OXB_PROF_WAIT : OXB_PROF_FORCE);
+	if(flags[hw]) return;
+	__shared__ int s_cnt[2];
+	if(threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+	__syncthreads();
+	hb_list += (size_t) blockIdx.x * hb_seg;
+	cx_list += (size_t) blockIdx.x * cx_seg;
+	const int ne = *n_edges;
+	const unsigned lane = threadIdx.x & 31;
+	ExclRefine R = refine3e(M, box, posd, quatd);
+	for(int base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < ne; base += gridDim.x * blockDim.x) {
+		const int eidx = base + lane;
+		const bool valid = eidx < ne;
+		int2 ed = valid ? __ldg(edges + eidx) : make_int2(-1 - (int) lane, -1);
+		if(valid) ed.y &= OXB_SLOT_MASK;
+		float v[6] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
+		float ve = 0.f;
+		bool want_hb = false, want_cx = false;
+		if(valid) {
+			const P3e P = load_p3e(M, ipos, axf, ed.x), Q = load_p3e(M, ipos, axf, ed.y);
+			const v3 r = min_image_fixed(box, P.ip, Q.ip);
+			const float r2 = dot(r, r);
+			if(r2 < M.r2_near_max && r2 < M.rcut2) {
+				const v3 rb = r + Q.ax.a1 * M.pos_base[Q.n.si] - P.ax.a1 * M.pos_base[P.n.si];
+				const v3 rs = r + Q.ax.a1 * M.pos_stack[Q.n.si] - P.ax.a1 * M.pos_stack[P.n.si];
+				if(r2 < M.r2_excl_max) {
+					PairAcc acc;
+					acc.clear();
+					R.sp = ed.x; R.sq = ed.y; acc.refine = posd != nullptr ? &R : nullptr;
+					const float en = dna3_excl4(M, r, r + Q.back - P.back, rb, P.ax, Q.ax, P.n, Q.n, P.back, Q.back, acc);
+					if(en != 0.f) {
+						const v3 tq = acc.torque_q(Q.ax, Q.back), tp = acc.torque_p(P.ax, P.back);
+						atomic_add4(F + ed.y, acc.F.x, acc.F.y, acc.F.z, en);
+						atomic_add4(T + ed.y, tq.x, tq.y, tq.z, 0.f);
+						v[0] = -acc.F.x; v[1] = -acc.F.y; v[2] = -acc.F.z;
+						v[3] = tp.x; v[4] = tp.y; v[5] = tp.z;
+						ve = en;
+					}
+				}
+				want_hb = dot(rb, rb) < M.r2_base_max;
+				want_cx = dot(rs, rs) < M.r2_stack_max;
+			}
+		}
+		block_append(want_hb, ed, hb_list, &s_cnt[0], hb_seg, flags);
+		block_append(want_cx, ed, cx_list, &s_cnt[1], cx_seg, flags);
+		if(__any_sync(0xffffffffu, ve != 0.f)) {
+			float w[7] = { v[0], v[1], v[2], v[3], v[4], v[5], ve };
+			const bool head = segmented_reduce<7>(ed.x, lane, w);
+			if(valid && head && w[6] != 0.f) {
+				atomic_add4(F + ed.x, w[0], w[1], w[2], w[6]);
+				atomic_add4(T + ed.x, w[3], w[4], w[5], 0.f);
+			}
+		}
+	}
+	__syncthreads();
+	if(threadIdx.x < 3) seg_counts[threadIdx.x * gridDim.x + blockIdx.x] = threadIdx.x == 0 ? min(s_cnt[0], hb_seg) : (threadIdx.x == 1 ? min(s_cnt[1], cx_seg) : 0);
+}
+
+// MODE 0: hydrogen bonding + cross stacking | 1: coaxial stacking, on this producer block's segment of the list (gridDim.y blocks share it)
+template<int MODE>
+__global__ void __launch_bounds__(64, 6) k3_edge_heavy(const __grid_constant__ oxb_dna3_dev M, BoxF box, const int *__restrict__ seg_counts, const int2 *__restrict__ list,
+		int seg, const int4 *__restrict__ ipos, const float4 *__restrict__ axf, float4 *__restrict__ F, float4 *__restrict__ T, int *__restrict__ flags, int hw) {
+	if(flags[hw]) return;
+	const int n = seg_counts[MODE * gridDim.x + blockIdx.x];
+	list += (size_t) blockIdx.x * seg;
+	for(int k = blockIdx.y * blockDim.x + threadIdx.x; k < n; k += blockDim.x * gridDim.y) {
+		const int2 ed = __ldg(list + k);
+		const P3e P = load_p3e(M, ipos, axf, ed.x), Q = load_p3e(M, ipos, axf, ed.y);
+		const v3 r = min_image_fixed(box, P.ip, Q.ip);
+		PairAcc acc;
+		acc.clear();
+		float en, ehb = 0.f;
+		if(MODE == 1) {
+			const v3 rs = r + Q.ax.a1 * M.pos_stack[Q.n.si] - P.ax.a1 * M.pos_stack[P.n.si];
+			en = dna3_cxst(M, rs, dot(rs, rs), P.ax, Q.ax, P.n, Q.n, acc);
+		}
+		else {
+			const v3 rb = r + Q.ax.a1 * M.pos_base[Q.n.si] - P.ax.a1 * M.pos_base[P.n.si];
+			en = dna3_hbcr(M, rb, dot(rb, rb), P.ax, Q.ax, P.btype, Q.btype, P.n, Q.n, acc, ehb);
+		}
+		if(en != 0.f) {
+			const v3 tp = acc.torque_p(P.ax, P.back), tq = acc.torque_q(Q.ax, Q.back);
+			atomic_add4(F + ed.x, -acc.F.x, -acc.F.y, -acc.F.z, en);
+			atomic_add4(T + ed.x, tp.x, tp.y, tp.z, ehb);
+			atomic_add4(F + ed.y, acc.F.x, acc.F.y, acc.F.z, en);
+			atomic_add4(T + ed.y, tq.x, tq.y, tq.z, ehb);
+		}
+	}
+}
+
+__global__ void __launch_bounds__(128, 4) k3_bonded(const __grid_constant__ oxb_dna3_dev M, BoxF box, int N, const int4 *__restrict__ ipos,
+		const int4 *__restrict__ iback, const float4 *__restrict__ axf, const int2 *__restrict__ bonds, float4 *__restrict__ F, float4 *__restrict__ T,
+		const double4 *__restrict__ posd, const double4 *__restrict__ quatd, int *__restrict__ flags, int hw) {
+	if(blockIdx.x == 0 && threadIdx.x == 0) prof_mark(flags, flags[hw] ? OXB_PROF_WAIT : OXB_PROF_FORCE);
+	if(flags[hw]) return;
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= N) return;
+	const int2 b = __ldg(bonds + i);
+	if(b.x < 0) return;
+	const P3e P = load_p3e(M, ipos, axf, i), Q = load_p3e(M, ipos, axf, b.x);
+	const float4 *rec = M.bonded + ix4(Q.n.n3t, Q.n.type, P.n.type, P.n.n5t) * (OXB3_REC_BONDED / 4);
+	PairAcc acc;
+	acc.clear();
+	ExclRefine R = refine3e(M, box, posd, quatd);
+	const bool refine = posd != nullptr;
+	R.sp = i; R.sq = b.x; acc.refine = refine ? &R : nullptr;
+	bool broken = false;
+	FeneSite fs;
+	if(refine) fs = fene_from_sites(fene3_of(M, rec), box, __ldg(iback + i), __ldg(iback + b.x), broken);
+	const float en = dna3_bonded(M, rec, min_image_fixed(box, P.ip, Q.ip), P.ax, Q.ax, P.n, Q.n, P.back, Q.back, acc, broken, nullptr, refine ? &fs : nullptr);
+	const v3 tp = acc.torque_p(P.ax, P.back), tq = acc.torque_q(Q.ax, Q.back);
+	atomic_add4(F + i, -acc.F.x, -acc.F.y, -acc.F.z, en);
+	atomic_add4(T + i, tp.x, tp.y, tp.z, 0.f);
+	atomic_add4(F + b.x, acc.F.x, acc.F.y, acc.F.z, en);
+	atomic_add4(T + b.x, tq.x, tq.y, tq.z, 0.f);
+	if(broken) atomicOr(flags + OXB_FLAG_ERROR, OXB_ERR_FENE_BROKEN);
+}
+
 // Observable: potential energy split into the reference's eight terms (FENE, bonded excluded volume, stacking, non-bonded
 // excluded volume, hydrogen bonding, cross stacking, coaxial stacking, Debye-Hueckel), summed on the device in double.
 // Replaces the CPU get_system_energy_split() the reference runs after a D2H copy and a CPU list rebuild
@@ -1328,7 +1487,27 @@ static void launch_edge_stage_t(cudaStream_t s, int which, const typename MD::Pa
 	}
 }
 
+// oxDNA3: stage numbers as above; stage 6 (parked excluded volume) does not exist -- active terms are refined in place
+static void launch_edge_stage_dna3(cudaStream_t s, int which, const oxb_dna3_dev &M, BoxF box, const EdgeArgs &a, int *flags, int hw) {
+	const int nb = (a.N + 127) / 128;
+	const double4 *posd = a.refine ? a.posd : nullptr;
+	switch(which) {
+	case 0:
+		if(a.dh_half) k_dh_particle<Dna3Dh, 1, false, true><<<nb, 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, nullptr, 1, flags, hw);
+		else k_dh_particle<Dna3Dh, 1, false, false><<<nb, 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, nullptr, 1, flags, hw);
+		break;
+	case 1:
+		k3_edge_near<<<a.n_seg, 128, 0, s>>>(M, box, a.n_edges, a.edges, a.ipos, a.axf, a.F, a.T, a.hb_list, a.cx_list, a.seg_counts, a.hb_seg, a.cx_seg, posd, a.quatd, flags, hw);
+		break;
+	case 2: k3_edge_heavy<0><<<dim3(a.n_seg, a.hb_split), 64, 0, s>>>(M, box, a.seg_counts, a.hb_list, a.hb_seg, a.ipos, a.axf, a.F, a.T, flags, hw); break;
+	case 3: k3_edge_heavy<1><<<a.n_seg, 64, 0, s>>>(M, box, a.seg_counts, a.cx_list, a.cx_seg, a.ipos, a.axf, a.F, a.T, flags, hw); break;
+	case 4: k3_bonded<<<nb, 128, 0, s>>>(M, box, a.N, a.ipos, a.iback, a.axf, a.bonds, a.F, a.T, posd, a.quatd, flags, hw); break;
+	default: break;
+	}
+}
+
 void launch_edge_stage(cudaStream_t s, int which, const ModelRef &MR, BoxF box, const EdgeArgs &a, int *flags, int hw) {
+	if(MR.dna3) { launch_edge_stage_dna3(s, which, *MR.dna3, box, a, flags, hw); return; }
 	if(MR.rna) launch_edge_stage_t<RnaModel>(s, which, *MR.rna, box, a, flags, hw);
 	else launch_edge_stage_t<DnaModel>(s, which, *MR.dna, box, a, flags, hw);
 }

@@ -90,6 +90,7 @@ struct oxb_dna3_dev {
 	int dh_half_charged_ends;
 	float rcut2;
 	float r2_excl_max, r2_base_max, r2_stack_max; // squares of: longest excluded-volume range + both levers; longest HB / cross-stacking range; longest coaxial range
+	float range_bb, range_eb, range_bk; // longest non-bonded excluded-volume ranges: backbone-backbone, base-base, base-backbone (list classification)
 	float r2_near_max;                            // square of the largest centre-centre distance at which any term but Debye-Hueckel can act
 	oxb_f4 cxst_t1, cxst_t4, cxst_t5;
 	float cxst_t1_sa, cxst_t1_sb;
