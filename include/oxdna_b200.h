@@ -208,8 +208,8 @@ int oxb_set_model_rna2(oxb_ctx *ctx, const oxb_rna2_params *P, double rcut);    
  *   0 _fene_r0_SD, 1 _fene_delta_SD, 2 _fene_delta2_SD, 3 _mbf_xmax_SD, 4.. _excl_s[7], 11.. _excl_r[7], 18.. _excl_b[7], 25.. _excl_rc[7],
  *   32.. F1_SD_{EPS, A, RC, R0, BLOW, BHIGH, RLOW, RHIGH, RCLOW, RCHIGH, SHIFT}[2],
  *   54.. F2_SD_{K, K_SYMM, RC, R0, BLOW, RLOW, RCLOW, BHIGH, RCHIGH, RHIGH}[4], 94.. F4_SD_THETA_{A, B, T0, TS, TC}[21], 199.. F5_SD_PHI_{A, B, XC, XS}[4]
- * The library repacks them into per-tetramer records (csrc/dna3_model.cuh).  Both force variants of the reference (use_edge = 0 / 1) are
- * served by one particle-centric kernel; replica batching is not available for this interaction. */
+ * The library repacks them into per-tetramer records (csrc/dna3_model.cuh).  use_edge = 0: one deterministic particle-centric kernel in
+ * cost-split passes; use_edge = 1: the staged edge pipeline (csrc/forces.cu, k3_*).  Replica batching is not available for this interaction. */
 enum { OXB_DNA3_FENE_R0 = 0, OXB_DNA3_FENE_DELTA = 1, OXB_DNA3_FENE_DELTA2 = 2, OXB_DNA3_MBF_XMAX = 3, OXB_DNA3_EXCL_S = 4, OXB_DNA3_EXCL_R = 11,
 	OXB_DNA3_EXCL_B = 18, OXB_DNA3_EXCL_RC = 25, OXB_DNA3_F1 = 32, OXB_DNA3_F2 = 54, OXB_DNA3_F4 = 94, OXB_DNA3_F5 = 199, OXB_DNA3_NTAB = 215, OXB_DNA3_TSIZE = 900 };
 typedef struct {

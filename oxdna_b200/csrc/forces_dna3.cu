@@ -1,7 +1,7 @@
-// oxDNA3 force pass (sm_100a).  Replaces DNA3_forces / DNA3_forces_edge_nonbonded / DNA3_forces_edge_bonded of the reference
+// oxDNA3 force pass, particle-centric (sm_100a; `use_edge = 0`).  Replaces DNA3_forces of the reference
 // (src/CUDA/Interactions/CUDA_DNA3.cuh:880-1085, CUDADNA3Interaction.cu:171-212).  One thread per particle over the full Verlet matrix,
-// every listed pair evaluated from both ends: no atomics, deterministic, the same launch shape as k_forces_particle (forces.cu).  Both of
-// the reference's variants (`use_edge` = 0 / 1) are served by this kernel: their results are identical by construction.
+// every listed pair evaluated from both ends: no atomics, deterministic, the same launch shape as k_forces_particle (forces.cu).
+// (`use_edge = 1`, DNA3_forces_edge_nonbonded / _bonded: the staged edge pipeline, forces.cu k3_*.)
 //
 // Data: as forces.cu, plus the packed parameter records and the per-particle type word of dna3_model.cuh.
 #include "dna3_model.cuh"

@@ -104,7 +104,7 @@ namespace oxb {
 struct ModelRef {
 	const oxb_dna2_params *dna;
 	const oxb_rna2_params *rna;
-	const oxb_dna3_dev *dna3; // oxDNA3: particle-centric pass only (forces_dna3.cu)
+	const oxb_dna3_dev *dna3; // oxDNA3 (forces_dna3.cu: particle-centric pass; forces.cu k3_*: staged edge pipeline)
 };
 
 // ---- forces_dna3.cu

@@ -109,7 +109,7 @@ public:
 
 /// interaction_type = DNA3 (oxDNA3): the CPU DNA3Interaction_nomesh parses the sequence-dependent parameter file and derives the 214
 /// tetramer-indexed tables; they are handed to the device library as they stand (the reference's CUDADNA3Interaction::cuda_init uploads the
-/// same member arrays, src/CUDA/Interactions/CUDADNA3Interaction.cu:46-150).  use_edge = 1 is accepted: one kernel serves both variants.
+/// same member arrays, src/CUDA/Interactions/CUDADNA3Interaction.cu:46-150).  use_edge = 1: staged edge pipeline, use_edge = 0: particle-centric kernel.
 class CUDADNA3Interaction: public CUDABaseInteraction, public DNA3Interaction_nomesh {
 protected:
 	void _upload();
