@@ -301,3 +301,49 @@ def test_dna3_fp32_formulation_within_mixed_tolerance(hostlib, case):
     assert np.linalg.norm(F - ref["force"], axis=1).max() <= 1e-5 * fmax
     assert np.linalg.norm(Tl - ref["torque_lab"], axis=1).max() <= 1e-5 * tmax
     assert np.abs(es - ref["eterms"]).max() <= 2e-6 * abs(ref["U"])
+
+
+@pytest.mark.skipif(not (os.path.exists("/root/reference/oxDNA3_sequence_dependent_parameters.txt") and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "liboxref.so"))),
+                    reason="needs the live reference (oracle/_ref) and its oxDNA3 parameter file")
+def test_dna3_fp32_max_backbone_force_branch(hostlib, tmp_path):
+    """oxDNA3 with max_backbone_force: tables (incl. _mbf_xmax_SD) from the live DNA3Interaction_nomesh, bonds stretched beyond xmax by a
+    perturbation -- the far branch of the FENE term and its energy constant (dna3_pack.h) in the FP32 formulation against the oracle"""
+    from oracle import refharness as RH
+    from oxdna_b200 import io as oio
+    g = load_golden("dna3_lattice8")
+    rng = np.random.default_rng(4)
+    N = len(g["pos"])
+    pos = g["pos"] + rng.normal(0, 0.06, (N, 3))
+    ax = O.axes_from_a1a3(g["a1"] + rng.normal(0, 0.08, (N, 3)), g["a3"] + rng.normal(0, 0.08, (N, 3)))
+    top, conf = str(tmp_path / "t.top"), str(tmp_path / "t.dat")
+    oio.write_topology(top, g["btype"], g["n3"], g["n5"], g["strand"])
+    oio.write_conf(conf, g["box"], pos, ax[:, 0:3], ax[:, 6:9], g["vel"], g["L"])
+    r = RH.Reference(top, conf, interaction_type="DNA3_nomesh", salt_concentration=0.5, T="300K", use_average_seq=0,
+                     seq_dep_file="/root/reference/oxDNA3_sequence_dependent_parameters.txt", max_backbone_force=5.0)
+    try:
+        tab, sc = np.zeros((215, 900)), np.zeros(40)
+        k = RH.lib().oxref_dna3_tables(RH._p(tab), RH._p(sc))
+        st, pairs, box = r.state(), r.pairs(), r.box()
+    finally:
+        r.close()
+    assert sc[1] == 1.0 and tab[3].max() > 0  # use_mbf, _mbf_xmax_SD
+    P = O.dna3_params(tab, sc[:k])
+    ax = np.ascontiguousarray(O.axes_from_a1a3(st["a1"], st["a3"]))
+    ref = O.forces(P, st["pos"], ax, g["btype"], g["n3"], g["n5"], box, pairs)
+    # some bonds are in the far branch
+    back = st["pos"] + ax[:, 0:3] * P.back_a1 + ax[:, 3:6] * P.back_a2
+    i = np.flatnonzero(g["n3"] >= 0)
+    d = np.linalg.norm(back[g["n3"][i]] - back[i], axis=1)
+    assert (np.abs(d - 0.7564) > tab[3].max()).sum() >= 3
+    S = capi.dna3_scalars(sc[:k])
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    posc, boxc = np.ascontiguousarray(st["pos"]), np.ascontiguousarray(box, dtype=np.float64)
+    bt, n3, n5 = (np.ascontiguousarray(g[x], dtype=np.int32) for x in ("btype", "n3", "n5"))
+    pr = np.ascontiguousarray(pairs, dtype=np.int32)
+    F, Tl, ep, es = np.zeros((N, 3)), np.zeros((N, 3)), np.zeros(N), np.zeros(8)
+    tabc = np.ascontiguousarray(tab)
+    hostlib.host_dna3_forces(p(tabc), C.byref(S), N, p(posc), p(ax), p(bt), p(n3), p(n5), p(boxc), p(pr), C.c_longlong(len(pr)), p(F), p(Tl), p(ep), p(es))
+    fmax = np.linalg.norm(ref["force"], axis=1).max()
+    assert np.linalg.norm(F - ref["force"], axis=1).max() <= 1e-4 * fmax
+    assert abs(es[0] - ref["eterms"][0]) <= 1e-5 * abs(ref["eterms"][0])
+    assert abs(ep.sum() - ref["U"]) <= 1e-5 * abs(ref["U"])
