@@ -48,6 +48,9 @@ def workload(name):
     elif name == "c2_dna3":
         sysm = lattice.duplex_lattice(2048, bp=20, spacing=10.0, seed=12345)
         desc = "C2 geometry under oxDNA3 (interaction_type = DNA3, average-sequence tetramer tables): 2,048 x 20-bp duplexes (81,920 nt), L=130, salt 0.5, T=300K"
+    elif name == "c4_dna3":
+        sysm = lattice.duplex_lattice(25000, bp=20, spacing=10.0, seed=12345, sites_per_side=30)
+        desc = "C4 geometry under oxDNA3 (interaction_type = DNA3, average-sequence tetramer tables): 1M nt (25,000 x 20-bp), L=300, salt 0.5, T=300K, no external forces"
     elif name == "small":
         sysm = lattice.duplex_lattice(64, bp=20, spacing=10.0, seed=12345)
         desc = "small: 64 x 20-bp duplexes (2,560 nt)"
@@ -58,7 +61,7 @@ def workload(name):
 
 def model_keys(name, tmpdir=None):
     """interaction keys of the workload; with tmpdir the sequence-dependent table is written to a file (reference binaries)"""
-    if name == "c2_dna3":
+    if name in ("c2_dna3", "c4_dna3"):
         # oxDNA3 with use_average_seq = 1 (the reference binaries fill their tables without a parameter file); our side takes the tables the
         # reference CPU class derives for T = 300 K, salt 0.5 from the committed fixture (oracle/make_golden.py dna3)
         if tmpdir is not None:
@@ -242,7 +245,7 @@ def run_ref_cuda(sysm, workload_name, steps_a, steps_b, state, quick=False):
         variants = [(1, 0)] if quick else [(1, 0), (0, 0)]
         kw["ext_forces"] = lattice.mutual_traps(sysm)
     else:
-        variants = [(1, 0)] if quick else [(1, 1), (0, 1), (1, 0), (0, 0)]
+        variants = [(1, 0)] if quick else ([(1, 1), (1, 0)] if workload_name == "c4_dna3" else [(1, 1), (0, 1), (1, 0), (0, 0)])
         kw["model_keys"] = model_keys(workload_name, d)
     res = R.time_reference_cuda(top, conf, N, steps_a, steps_b, variants, **kw)
     best = res["best"]
@@ -383,7 +386,7 @@ def measure_single(args, wl, steps, warmup, equil, md, full, local_rank=0):
         sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
         fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
         flops = N * (FLOP_FAR * ps["listed"] + FLOP_DH * ps["dh"] + FLOP_CONTACT * ps["contact"] + FLOP_BONDED * 1.0)
-        particle_centric = (not args.use_edge) or wl == "c2_dna3"  # oxDNA3: one particle-centric kernel serves both use_edge settings
+        particle_centric = not args.use_edge
         if particle_centric:
             flops = N * (2 * (FLOP_FAR * ps["listed"] + FLOP_DH * ps["dh"] + FLOP_CONTACT * ps["contact"]) + 2 * FLOP_BONDED)
         tf = flops / (t_force * 1e-3) / 1e12
@@ -462,7 +465,7 @@ def measure_single(args, wl, steps, warmup, equil, md, full, local_rank=0):
     ref_cuda = None
     if not args.no_ref_cuda:
         try:
-            a, b = args.ref_cuda_steps or ([3000, 9000] if wl == "c4" else [10000, 20000])
+            a, b = args.ref_cuda_steps or ([3000, 9000] if wl == "c4" else ([2000, 5000] if wl == "c4_dna3" else [10000, 20000]))
             ref_cuda = run_ref_cuda(sysm, wl, a, b, state)
         except Exception as e:  # pragma: no cover
             ref_cuda = {"value": None, "unavailable": repr(e)[-300:]}
@@ -652,7 +655,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cuda"])
-    ap.add_argument("--workload", default=None, choices=["c2", "c3", "c4", "c5", "small", "c2_dna3"], help="default: c4 on one GPU, c5 (replica ensemble) on several")
+    ap.add_argument("--workload", default=None, choices=["c2", "c3", "c4", "c5", "small", "c2_dna3", "c4_dna3"], help="default: c4 on one GPU, c5 (replica ensemble) on several")
     ap.add_argument("--md-steps", type=int, default=1000, help="MD steps per bench step")
     ap.add_argument("--equil", type=int, default=10000, help="untimed equilibration MD steps")
     ap.add_argument("--use-edge", type=int, default=1)
