@@ -800,7 +800,8 @@ __device__ __forceinline__ ExclRefine refine3e(const oxb_dna3_dev &M, const BoxF
 	return R;
 }
 
-__global__ void __launch_bounds__(128, 4) k3_edge_near(const __grid_constant__ oxb_dna3_dev M, BoxF box, const int *__restrict__ n_edges,
+template<int MB>
+__global__ void __launch_bounds__(128, MB) k3_edge_near(const __grid_constant__ oxb_dna3_dev M, BoxF box, const int *__restrict__ n_edges,
 		const int2 *__restrict__ edges, const int4 *__restrict__ ipos, const float4 *__restrict__ axf, float4 *__restrict__ F, float4 *__restrict__ T,
 		int2 *__restrict__ hb_list, int2 *__restrict__ cx_list, int *__restrict__ seg_counts, int hb_seg, int cx_seg, const double4 *__restrict__ posd,
 		const double4 *__restrict__ quatd, int *__restrict__ flags, int hw) {
@@ -863,8 +864,8 @@ __global__ void __launch_bounds__(128, 4) k3_edge_near(const __grid_constant__ o
 }
 
 // MODE 0: hydrogen bonding + cross stacking | 1: coaxial stacking, on this producer block's segment of the list (gridDim.y blocks share it)
-template<int MODE>
-__global__ void __launch_bounds__(64, 6) k3_edge_heavy(const __grid_constant__ oxb_dna3_dev M, BoxF box, const int *__restrict__ seg_counts, const int2 *__restrict__ list,
+template<int MODE, int MB>
+__global__ void __launch_bounds__(64, MB) k3_edge_heavy(const __grid_constant__ oxb_dna3_dev M, BoxF box, const int *__restrict__ seg_counts, const int2 *__restrict__ list,
 		int seg, const int4 *__restrict__ ipos, const float4 *__restrict__ axf, float4 *__restrict__ F, float4 *__restrict__ T, int *__restrict__ flags, int hw) {
 	if(flags[hw]) return;
 	const int n = seg_counts[MODE * gridDim.x + blockIdx.x];
@@ -894,7 +895,8 @@ __global__ void __launch_bounds__(64, 6) k3_edge_heavy(const __grid_constant__ o
 	}
 }
 
-__global__ void __launch_bounds__(128, 4) k3_bonded(const __grid_constant__ oxb_dna3_dev M, BoxF box, int N, const int4 *__restrict__ ipos,
+template<int MB>
+__global__ void __launch_bounds__(128, MB) k3_bonded(const __grid_constant__ oxb_dna3_dev M, BoxF box, int N, const int4 *__restrict__ ipos,
 		const int4 *__restrict__ iback, const float4 *__restrict__ axf, const int2 *__restrict__ bonds, float4 *__restrict__ F, float4 *__restrict__ T,
 		const double4 *__restrict__ posd, const double4 *__restrict__ quatd, int *__restrict__ flags, int hw) {
 	if(blockIdx.x == 0 && threadIdx.x == 0) prof_mark(flags, flags[hw] ? OXB_PROF_WAIT : OXB_PROF_FORCE);
@@ -1491,17 +1493,23 @@ static void launch_edge_stage_t(cudaStream_t s, int which, const typename MD::Pa
 static void launch_edge_stage_dna3(cudaStream_t s, int which, const oxb_dna3_dev &M, BoxF box, const EdgeArgs &a, int *flags, int hw) {
 	const int nb = (a.N + 127) / 128;
 	const double4 *posd = a.refine ? a.posd : nullptr;
-	switch(which) {
+	static const int cfg = std::min(2, std::max(0, env_int("OXB_DNA3_EDGE_MB", 0)));
+	switch(which == 0 ? 0 : 10 * cfg + which) {
 	case 0:
 		if(a.dh_half) k_dh_particle<Dna3Dh, 1, false, true><<<nb, 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, nullptr, 1, flags, hw);
 		else k_dh_particle<Dna3Dh, 1, false, false><<<nb, 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, nullptr, 1, flags, hw);
 		break;
-	case 1:
-		k3_edge_near<<<a.n_seg, 128, 0, s>>>(M, box, a.n_edges, a.edges, a.ipos, a.axf, a.F, a.T, a.hb_list, a.cx_list, a.seg_counts, a.hb_seg, a.cx_seg, posd, a.quatd, flags, hw);
-		break;
-	case 2: k3_edge_heavy<0><<<dim3(a.n_seg, a.hb_split), 64, 0, s>>>(M, box, a.seg_counts, a.hb_list, a.hb_seg, a.ipos, a.axf, a.F, a.T, flags, hw); break;
-	case 3: k3_edge_heavy<1><<<a.n_seg, 64, 0, s>>>(M, box, a.seg_counts, a.cx_list, a.cx_seg, a.ipos, a.axf, a.F, a.T, flags, hw); break;
-	case 4: k3_bonded<<<nb, 128, 0, s>>>(M, box, a.N, a.ipos, a.iback, a.axf, a.bonds, a.F, a.T, posd, a.quatd, flags, hw); break;
+	// register caps (resident blocks per SM asked of the compiler), OXB_DNA3_EDGE_MB = 0: 128 / 120 / 128 registers for near / heavy / bonded,
+	// 1: 80 / 80 / 96, 2: 64 / 64 / 80 (measured: profiles/sweeps_r02.txt, aw)
+#define OXB_K3(CFG, NEAR, HEAVY, BONDED)                                                                                                                           \
+	case 10 * CFG + 1: k3_edge_near<NEAR><<<a.n_seg, 128, 0, s>>>(M, box, a.n_edges, a.edges, a.ipos, a.axf, a.F, a.T, a.hb_list, a.cx_list, a.seg_counts, a.hb_seg, a.cx_seg, posd, a.quatd, flags, hw); break; \
+	case 10 * CFG + 2: k3_edge_heavy<0, HEAVY><<<dim3(a.n_seg, a.hb_split), 64, 0, s>>>(M, box, a.seg_counts, a.hb_list, a.hb_seg, a.ipos, a.axf, a.F, a.T, flags, hw); break;  \
+	case 10 * CFG + 3: k3_edge_heavy<1, HEAVY><<<a.n_seg, 64, 0, s>>>(M, box, a.seg_counts, a.cx_list, a.cx_seg, a.ipos, a.axf, a.F, a.T, flags, hw); break;                    \
+	case 10 * CFG + 4: k3_bonded<BONDED><<<nb, 128, 0, s>>>(M, box, a.N, a.ipos, a.iback, a.axf, a.bonds, a.F, a.T, posd, a.quatd, flags, hw); break;
+	OXB_K3(0, 4, 6, 4)
+	OXB_K3(1, 6, 12, 5)
+	OXB_K3(2, 8, 16, 6)
+#undef OXB_K3
 	default: break;
 	}
 }
