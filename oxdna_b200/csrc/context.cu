@@ -688,9 +688,11 @@ int dna3_upload_codes(oxb_ctx *c) {
 	const int N = c->N;
 	std::vector<int> code(N);
 	for(int i = 0; i < N; i++) {
-		const int t = btype_to_type(c->h_btype[i]);
-		const int t3 = c->h_n3[i] >= 0 ? btype_to_type(c->h_btype[c->h_n3[i]]) : 5;
-		const int t5 = c->h_n5[i] >= 0 ? btype_to_type(c->h_btype[c->h_n5[i]]) : 5;
+		// the dummy base 'D' has btype = type = 4 (TopologyParser.cpp:96-99, Utils.cpp:33-34)
+		auto ty = [](int b) { return b == 4 ? 4 : btype_to_type(b); };
+		const int t = ty(c->h_btype[i]);
+		const int t3 = c->h_n3[i] >= 0 ? ty(c->h_btype[c->h_n3[i]]) : 5;
+		const int t5 = c->h_n5[i] >= 0 ? ty(c->h_btype[c->h_n5[i]]) : 5;
 		code[i] = t | (t3 << 3) | (t5 << 6) | ((c->h_btype[i] == 4) ? (1 << 9) : 0);
 	}
 	if(c->d3_tcode == nullptr) CU(dalloc(&c->d3_tcode, (size_t) N));

@@ -7,7 +7,7 @@ Host-side helpers used by the tests, the benchmark and the Python REMD driver.  
 import numpy as np
 
 BASE_TO_BTYPE = {"A": 0, "G": 1, "C": 2, "T": 3, "U": 3, "D": 4}
-BTYPE_TO_BASE = {0: "A", 1: "G", 2: "C", 3: "T"}
+BTYPE_TO_BASE = {0: "A", 1: "G", 2: "C", 3: "T", 4: "D"}  # D: the dummy base (Utils::decode_base, src/Utilities/Utils.cpp:25-38)
 
 
 def read_topology(path):

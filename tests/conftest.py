@@ -34,3 +34,20 @@ def pair_set(pairs):
 
 
 from oracle.fixtures import ext2_forces, ext3_forces  # noqa: E402,F401  (the force lists of the lattice8_ext2 / _ext3 fixtures)
+
+
+def dna3_special_types(g, hb_multiplier=1.7):
+    """The oxDNA3 fixture with base types outside 0..3: A-T pairs of the first duplex become the custom pair -300 / 303 (hydrogen bonding
+    times hb_multiplier), two nucleotides become dummy bases (btype = type = 4).  Returns (btype, scalars)."""
+    import numpy as np
+    bt = np.array(g["btype"]).copy()
+    for i in range(20):
+        j = 39 - i
+        if (bt[i], bt[j]) == (3, 0):
+            bt[i], bt[j] = 303, -300
+        elif (bt[i], bt[j]) == (0, 3):
+            bt[i], bt[j] = -300, 303
+    bt[45], bt[130] = 4, 4
+    sc = np.array(g["dna3_scalars"]).copy()
+    sc[4] = hb_multiplier
+    return bt, sc

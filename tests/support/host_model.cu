@@ -90,8 +90,9 @@ extern "C" void host_dna3_forces(const double *tables, const oxb_dna3_scalars *S
 		quatd q = quat_from_axes(axes + 9 * i, axes + 9 * i + 3, axes + 9 * i + 6);
 		ax[i] = axes_from_quat(make_float4((float) q.x, (float) q.y, (float) q.z, (float) q.w));
 		back[i] = ax[i].a1 * M.back_a1 + ax[i].a2 * M.back_a2;
-		const int t3 = n3[i] >= 0 ? btype_to_type(btype[n3[i]]) : 5, t5 = n5[i] >= 0 ? btype_to_type(btype[n5[i]]) : 5;
-		nuc[i] = nuc3_from_code(btype_to_type(btype[i]) | (t3 << 3) | (t5 << 6) | ((btype[i] == 4) ? (1 << 9) : 0));
+		auto ty = [](int b) { return b == 4 ? 4 : btype_to_type(b); };
+		const int t3 = n3[i] >= 0 ? ty(btype[n3[i]]) : 5, t5 = n5[i] >= 0 ? ty(btype[n5[i]]) : 5;
+		nuc[i] = nuc3_from_code(ty(btype[i]) | (t3 << 3) | (t5 << 6) | ((btype[i] == 4) ? (1 << 9) : 0));
 	}
 	for(int i = 0; i < 3 * N; i++) F[i] = Tlab[i] = 0.;
 	for(int i = 0; i < N; i++) epart[i] = 0.;

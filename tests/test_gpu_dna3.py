@@ -177,3 +177,20 @@ def test_dna3_refuses_what_it_does_not_serve():
             c.set_model_dna3(g["dna3_tables"], g["dna3_scalars"])
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("use_edge", [0, 1])
+def test_dna3_special_base_types_vs_oracle(use_edge):
+    """dummy bases (btype = type = 4) and a custom pair -300 / 303 with hb_multiplier, both force variants, against the oracle"""
+    from conftest import dna3_special_types
+    g = load_golden("dna3_lattice8")
+    bt, sc = dna3_special_types(g)
+    sim = make_sim(g, topo=dict(btype=bt, n3=g["n3"], n5=g["n5"], strand=g["strand"]), dna3_scalars=sc, use_edge=use_edge, CUDA_sort_every=1)
+    try:
+        P = O.dna3_params(g["dna3_tables"], sc)
+        ref = O.forces(P, g["pos"], O.axes_from_a1a3(g["a1"], g["a3"]), bt, g["n3"], g["n5"], g["box"], g["pairs"])
+        assert abs(ref["eterms"][4] - float(g["energy_split"][4])) > 0.5
+        check_forces(sim.ctx.get_forces(), ref)
+        assert np.abs(np.asarray(sim.ctx.energy_split())[:8] - ref["eterms"]).max() <= 2e-6 * abs(ref["U"])
+    finally:
+        sim.close()

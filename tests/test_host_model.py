@@ -347,3 +347,30 @@ def test_dna3_fp32_max_backbone_force_branch(hostlib, tmp_path):
     assert np.linalg.norm(F - ref["force"], axis=1).max() <= 1e-4 * fmax
     assert abs(es[0] - ref["eterms"][0]) <= 1e-5 * abs(ref["eterms"][0])
     assert abs(ep.sum() - ref["U"]) <= 1e-5 * abs(ref["U"])
+
+
+def test_dna3_fp32_special_base_types(hostlib):
+    """dummy bases (btype = type = 4, sites at the oxDNA2 offsets) and a custom pair with hb_multiplier: FP32 device formulation against the
+    oracle (which test_oracle_dna3.py pins to the live reference on the same construction)"""
+    from conftest import dna3_special_types
+    g = load_golden("dna3_lattice8")
+    bt, sc = dna3_special_types(g)
+    N = len(bt)
+    P = O.dna3_params(g["dna3_tables"], sc)
+    ax = np.ascontiguousarray(O.axes_from_a1a3(g["a1"], g["a3"]))
+    ref = O.forces(P, g["pos"], ax, bt, g["n3"], g["n5"], g["box"], g["pairs"])
+    assert abs(ref["eterms"][4] - float(g["energy_split"][4])) > 0.5
+    S = capi.dna3_scalars(sc)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    tab = np.ascontiguousarray(g["dna3_tables"], dtype=np.float64)
+    pos, box = np.ascontiguousarray(g["pos"]), np.ascontiguousarray(g["box"], dtype=np.float64)
+    btc, n3, n5 = (np.ascontiguousarray(x, dtype=np.int32) for x in (bt, g["n3"], g["n5"]))
+    pairs = np.ascontiguousarray(g["pairs"], dtype=np.int32)
+    F, Tl, ep, es = np.zeros((N, 3)), np.zeros((N, 3)), np.zeros(N), np.zeros(8)
+    hostlib.host_dna3_forces(p(tab), C.byref(S), N, p(pos), p(ax), p(btc), p(n3), p(n5), p(box), p(pairs), C.c_longlong(len(pairs)), p(F), p(Tl), p(ep), p(es))
+    fmax, tmax = np.linalg.norm(ref["force"], axis=1).max(), np.linalg.norm(ref["torque_lab"], axis=1).max()
+    # (pure FP32 here: the dummy bases put excluded-volume site pairs in range, which the device re-evaluates in double -- DESIGN 4;
+    # the GPU test of the same construction holds 1e-5)
+    assert np.linalg.norm(F - ref["force"], axis=1).max() <= 3e-5 * fmax
+    assert np.linalg.norm(Tl - ref["torque_lab"], axis=1).max() <= 3e-5 * tmax
+    assert np.abs(es - ref["eterms"]).max() <= 2e-6 * abs(ref["U"])

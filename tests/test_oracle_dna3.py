@@ -146,3 +146,46 @@ def _coaxial_particles(P, st, ax, topo, box, pairs):
         if e[6] != 0.0:
             hit.update((int(a), int(b)))
     return np.array(sorted(hit), dtype=int)
+
+
+@pytest.mark.skipif(not (RH.available() and os.path.exists(SEQ)), reason="oracle/_ref not built (needs /root/reference)")
+def test_dna3_special_base_types_against_the_live_reference(tmp_path):
+    """Base types outside 0..3: a dummy base (btype 4: stacking / base sites at the oxDNA2 offsets 0.34 / 0.40, DNANucleotide.cpp:71-79) and a
+    custom pair 303 / -300 (hydrogen-bonds as T-A, |btype| >= 300: strength times hb_multiplier, DNA3Interaction.cpp:1483-1484): the oracle
+    against the live DNA3Interaction_nomesh (the device formulation is held to the oracle on the same construction: test_host_model.py, test_gpu_dna3.py)"""
+    g = load_golden("dna3_lattice8")
+    bt = g["btype"].copy()
+    N = len(bt)
+    # duplex 0: strand 0 = particles 0..19, strand 1 = 20..39, base i pairs with 39 - i
+    n_special = 0
+    for i in range(20):
+        j = 39 - i
+        if (bt[i], bt[j]) == (3, 0):
+            bt[i], bt[j] = 303, -300  # type_of(303) = 3 (T), type_of(-300) = 0 (A)
+            n_special += 1
+        elif (bt[i], bt[j]) == (0, 3):
+            bt[i], bt[j] = -300, 303
+            n_special += 1
+    assert n_special >= 3
+    bt[45], bt[130] = 4, 4
+    top, conf = str(tmp_path / "t.top"), str(tmp_path / "t.dat")
+    oio.write_topology(top, bt, g["n3"], g["n5"], g["strand"])
+    oio.write_conf(conf, g["box"], g["pos"], g["a1"], g["a3"], g["vel"], g["L"])
+    r = RH.Reference(top, conf, interaction_type="DNA3_nomesh", salt_concentration=0.5, T="300K", use_average_seq=0, seq_dep_file=SEQ, hb_multiplier=1.7)
+    try:
+        tab, sc = np.zeros((215, 900)), np.zeros(40)
+        k = RH.lib().oxref_dna3_tables(RH._p(tab), RH._p(sc))
+        st, ref, split, pairs, topo, box = r.state(), r.compute_forces(), r.energy_split(), r.pairs(), r.topology(), r.box()
+    finally:
+        r.close()
+    assert sc[4] == 1.7 and (topo["btype"] == bt).all()
+    P = O.dna3_params(tab, sc[:k])
+    ax = O.axes_from_a1a3(st["a1"], st["a3"])
+    out = O.forces(P, st["pos"], ax, bt, g["n3"], g["n5"], box, pairs)
+    assert np.abs(out["eterms"] - split).max() < 1e-9
+    assert np.abs(out["force"] - ref["force"]).max() < 1e-9
+    assert np.abs(out["torque_body"] - ref["torque_body"]).max() < 1e-9
+    # the multiplier and the dummy sites matter: with plain types the hydrogen-bonding energy is smaller
+    plain = O.forces(P, st["pos"], ax, g["btype"], g["n3"], g["n5"], box, pairs)
+    assert out["eterms"][4] < plain["eterms"][4] - 0.5
+    assert np.abs(out["force"] - plain["force"])[[45, 130]].max() > 1e-3  # the dummy bases sit elsewhere and carry other parameters
