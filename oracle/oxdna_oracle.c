@@ -142,6 +142,9 @@ void oxo_dna2_params_seqdep(oxo_dna2_params *P, const double *stck_raw16, double
 		P->stck.eps[i][j] = stck_raw16[4 * i + j] * (1.0 - stck_fact_eps + (P->T * 9.0 * stck_fact_eps));
 		P->stck.shift[i][j] = P->stck.eps[i][j] * sh_st;
 	}
+	/* dummy base (type 4): the optional keys STCK_D_X / STCK_X_D are read into a variable that still holds the last mandatory key, STCK_T_T
+	 * (DNAInteraction.cpp:349-359): with the stock parameter file every dummy entry gets the T-T strength */
+	for(int i = 0; i < 5; i++) for(int j = 0; j < 5; j++) if(i == 4 || j == 4) { P->stck.eps[i][j] = P->stck.eps[3][3]; P->stck.shift[i][j] = P->stck.shift[3][3]; }
 	P->hb.eps[0][3] = P->hb.eps[3][0] = hb_AT;
 	P->hb.eps[1][2] = P->hb.eps[2][1] = hb_GC;
 	P->hb.shift[0][3] = P->hb.shift[3][0] = hb_AT * sh_hb;
@@ -536,7 +539,8 @@ static void nonbonded_pair(const oxo_dna2_params *P, const double *r, const site
 	}
 }
 
-static inline int type_of(int btype) { return (btype < 0) ? 3 - ((3 - btype) % 4) : btype % 4; }
+/* base 'D' of the topology: btype = type = N_DUMMY = 4 (src/Utilities/TopologyParser.cpp:96-99, Utils.cpp:33-34); numeric bases: TopologyParser.cpp:101-109 */
+static inline int type_of(int btype) { return (btype == 4) ? 4 : ((btype < 0) ? 3 - ((3 - btype) % 4) : btype % 4); }
 
 static void min_image(const double *box, const double *p, const double *q, double *r) {
 	/* src/Boxes/CubicBox.cpp:51-57 (and OrthogonalBox) */

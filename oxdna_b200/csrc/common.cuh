@@ -97,7 +97,8 @@ __host__ __device__ __forceinline__ int pack_word(int btype, int index) { return
 __host__ __device__ __forceinline__ int word_btype(int w) { return w >> 22; }
 __host__ __device__ __forceinline__ int word_index(int w) { return w & 0x003FFFFF; }
 // base type 0..3 (A, G, C, T) from a possibly "special" btype (src/Interactions/DNAInteraction.cpp:1543)
-__host__ __device__ __forceinline__ int btype_to_type(int b) { return (b < 0) ? 3 - ((3 - b) % 4) : b % 4; }
+// (the dummy base 'D' of a topology has btype = type = 4: src/Utilities/TopologyParser.cpp:96-99, Utils.cpp:33-34; numeric bases have two digits or a sign)
+__host__ __device__ __forceinline__ int btype_to_type(int b) { return (b == 4) ? 4 : ((b < 0) ? 3 - ((3 - b) % 4) : b % 4); }
 
 // ---- periodic box in fixed point: a coordinate x is stored as u = frac(x / L) * 2^32, so that the
 // minimum-image separation is the wrapped 32-bit difference (exact, branch-free) times L / 2^32.

@@ -198,6 +198,14 @@ extern "C" int oxb_dna2_params_seqdep(oxb_dna2_params *P, double T, const double
 			P->stck_shift[5 * i + j] = (float) (eps * morse_shift(kSTCK));
 		}
 	}
+	// stacking with the dummy base 'D' (type 4): the reference reads the OPTIONAL keys STCK_D_X / STCK_X_D with a value variable that still
+	// holds the last mandatory key, STCK_T_T (DNAInteraction.cpp:349-359: getInputFloat(..., 0) leaves it untouched when the key is absent),
+	// so with the stock parameter file every dummy entry gets the T-T strength.  Restated as is.
+	for(int i = 0; i < 5; i++) {
+		for(int j = 0; j < 5; j++) {
+			if(i == 4 || j == 4) { P->stck_eps[5 * i + j] = P->stck_eps[5 * 3 + 3]; P->stck_shift[5 * i + j] = P->stck_shift[5 * 3 + 3]; }
+		}
+	}
 	const int A = 0, G = 1, C = 2, Tt = 3;
 	P->hb_eps[5 * A + Tt] = P->hb_eps[5 * Tt + A] = (float) hb_AT;
 	P->hb_eps[5 * G + C] = P->hb_eps[5 * C + G] = (float) hb_GC;

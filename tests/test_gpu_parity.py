@@ -1102,3 +1102,29 @@ def test_work_list_segment_overflow_is_recovered(case, monkeypatch):
         assert np.abs(got["pos"] - want["pos"]).max() < 1e-4
     finally:
         sim.close()
+
+
+@pytest.mark.parametrize("use_edge", [0, 1])
+def test_dna2_sequence_dependent_with_dummy_bases_vs_oracle(use_edge):
+    """oxDNA2 with sequence-dependent strengths and two dummy bases ('D': btype = type = 4; they take the stacking strength the reference
+    leaves in its optional-key variable, T-T, and pair with nothing): the oracle is pinned to the live reference on this construction
+    (test_oracle.py: test_oracle_dna2_sequence_dependent_with_dummy_bases_matches_live_reference)"""
+    from oxdna_b200 import seqdep
+    g = load_golden("lattice8")
+    bt = g["btype"].copy()
+    bt[45], bt[130] = 4, 4
+    sd = seqdep.DNA2_SEQ_DEP
+    inp = dict(backend="CUDA", interaction_type="DNA2", T="300K", salt_concentration=0.5, dt=0.003, verlet_skin=0.05, thermostat="no",
+               CUDA_sort_every=1, use_edge=use_edge, seed=11, use_average_seq=0, seq_dep_file=sd)
+    sim = Simulation(inp, dict(btype=bt, n3=g["n3"], n5=g["n5"], strand=g["strand"]),
+                     dict(box=g["box"], pos=g["pos"], a1=g["a1"], a3=g["a3"], vel=g["vel"], L=g["L"]))
+    try:
+        B = "AGCT"
+        P = O.dna2_params(parse_temperature("300K"), 0.5)
+        O.dna2_params_seqdep(P, [sd[f"STCK_{a}_{b}"] for a in B for b in B], sd["STCK_FACT_EPS"], sd["HYDR_A_T"], sd["HYDR_C_G"])
+        ref = O.forces(P, g["pos"], O.axes_from_a1a3(g["a1"], g["a3"]), bt, g["n3"], g["n5"], g["box"], g["pairs"])
+        plain = O.forces(P, g["pos"], O.axes_from_a1a3(g["a1"], g["a3"]), g["btype"], g["n3"], g["n5"], g["box"], g["pairs"])
+        assert abs(ref["U"] - plain["U"]) > 1e-2
+        check_forces(sim.ctx.get_forces(), ref)
+    finally:
+        sim.close()

@@ -448,3 +448,33 @@ def test_meta_coordination_restatement_matches_live_reference(tmp_path, mode, ex
     assert not np.abs(dF[40:]).max() > 1e-12                            # and only on the particles of the pairs
     assert np.abs(out["force"] - dF).max() < 1e-9
     assert np.abs(out["torque_lab"] - dT).max() < 1e-9
+
+
+SEQ2 = "/root/reference/oxDNA2_sequence_dependent_parameters.txt"
+
+
+@pytest.mark.skipif(not (RH.available() and os.path.exists(SEQ2)), reason="oracle/_ref not built (needs /root/reference)")
+def test_oracle_dna2_sequence_dependent_with_dummy_bases_matches_live_reference(tmp_path):
+    """oxDNA2 with the sequence-dependent stacking / hydrogen-bonding strengths and two dummy bases ('D': btype = type = 4,
+    TopologyParser.cpp:96-99 -- they keep the average strengths, DNAInteraction.cpp:329-375, and pair with nothing)"""
+    from oxdna_b200.sim import read_seq_dep
+    g = load_golden("lattice8")
+    bt = g["btype"].copy()
+    bt[45], bt[130] = 4, 4
+    top, conf = str(tmp_path / "t.top"), str(tmp_path / "t.dat")
+    oio.write_topology(top, bt, g["n3"], g["n5"], g["strand"])
+    oio.write_conf(conf, g["box"], g["pos"], g["a1"], g["a3"], g["vel"], g["L"])
+    r = RH.Reference(top, conf, interaction_type="DNA2_nomesh", salt_concentration=0.5, T="300K", use_average_seq=0, seq_dep_file=SEQ2)
+    try:
+        ref, split, pairs, topo = r.compute_forces(), r.energy_split(), r.pairs(), r.topology()
+    finally:
+        r.close()
+    assert (topo["btype"] == bt).all() and (topo["type"][[45, 130]] == 4).all()
+    sd = read_seq_dep(SEQ2)
+    B = "AGCT"
+    P = O.dna2_params(parse_temperature("300K"), 0.5)
+    O.dna2_params_seqdep(P, [sd[f"STCK_{a}_{b}"] for a in B for b in B], sd["STCK_FACT_EPS"], sd["HYDR_A_T"], sd["HYDR_C_G"])
+    out = O.forces(P, g["pos"], O.axes_from_a1a3(g["a1"], g["a3"]), bt, g["n3"], g["n5"], g["box"], pairs)
+    assert np.abs(out["eterms"] - split).max() < 1e-9
+    assert np.abs(out["force"] - ref["force"]).max() < 1e-9
+    assert np.abs(out["torque_body"] - ref["torque_body"]).max() < 1e-9
