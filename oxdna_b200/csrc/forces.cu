@@ -395,7 +395,7 @@ __device__ __forceinline__ bool segmented_reduce(int key, unsigned lane, float (
 // HALF: the matrix lists every pair in ONE of its two rows; the thread evaluates it once, keeps its own share in registers and sends
 // the partner's with one 128-bit red.global.add (half the evaluations and half the index traffic of the full matrix; Fb is then an
 // accumulator that the integrator zeroes, and the sum is no longer order-deterministic -- like the rest of the edge pipeline).
-template<class MD, int LPP, bool REP, bool HALF>
+template<class MD, int LPP, bool REP, bool HALF, bool SORTED = false>
 __global__ void __launch_bounds__(128) k_dh_particle(const __grid_constant__ typename MD::Params M, BoxF box, int N, const int4 *__restrict__ iback,
 		const int *__restrict__ dh_nbr, const int *__restrict__ dh_nnbr, float4 *__restrict__ Fb, const oxb_replica_consts *__restrict__ rep, int n_per,
 		int *__restrict__ flags, int hw) {
@@ -419,7 +419,21 @@ __global__ void __launch_bounds__(128) k_dh_particle(const __grid_constant__ typ
 		// therefore share their two rows evenly: the one with the shorter row takes the tail of the other's and hands the partial force
 		// back with one shuffle at the end.  The schedule is fixed by the row lengths, so the full-matrix variant stays deterministic.
 		const unsigned lane = threadIdx.x & 31;
-		const int pl = 31 - (int) lane;
+		int pl = 31 - (int) lane;
+		if(SORTED) {
+			// ... and which two lanes share is decided by the row lengths: the lane of rank r (ties by lane) pairs with the lane of rank 31 - r,
+			// the longest row with the shortest.  With the fixed pairing l <-> 31 - l two long rows meet as often as not (ncu r02c: 17.9 lanes).
+			int rank = 0;
+#pragma unroll
+			for(int j = 0; j < 32; j++) {
+				const int o = __shfl_sync(0xffffffffu, nn, j);
+				rank += (o < nn || (o == nn && j < (int) lane)) ? 1 : 0;
+			}
+			__shared__ unsigned char s_lane_of_rank[4][32]; // (the kernel is launched with 128 threads)
+			s_lane_of_rank[threadIdx.x >> 5][rank] = (unsigned char) lane;
+			__syncwarp();
+			pl = s_lane_of_rank[threadIdx.x >> 5][31 - rank];
+		}
 		const int nn_o = __shfl_sync(0xffffffffu, nn, pl), i_o = __shfl_sync(0xffffffffu, i, pl);
 		int4 bo;
 		bo.x = __shfl_sync(0xffffffffu, bp.x, pl); bo.y = __shfl_sync(0xffffffffu, bp.y, pl); bo.z = __shfl_sync(0xffffffffu, bp.z, pl); bo.w = __shfl_sync(0xffffffffu, bp.w, pl);
@@ -1455,7 +1469,13 @@ static void launch_edge_stage_t(cudaStream_t s, int which, const typename MD::Pa
 		// (profiles/smalln_sweep_r01.txt): the kernel is bound by L2 gather bandwidth, not by loads in flight.  OXB_DH_LPP overrides.
 		static const int lpp_env = env_int("OXB_DH_LPP", 0);
 		const int lpp = lpp_env > 0 ? lpp_env : 1;
-		if(a.rep != nullptr) {
+		// OXB_DH_SORTED=0: fixed lane pairs l <-> 31 - l in the half-matrix kernel instead of pairs chosen by row length
+		static const int dh_sorted = env_int("OXB_DH_SORTED", 1);
+		if(a.dh_half && dh_sorted) {
+			if(a.rep != nullptr) k_dh_particle<MD, 1, true, true, true><<<blocks_for(a.N), 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, a.rep, a.n_per, flags, hw);
+			else k_dh_particle<MD, 1, false, true, true><<<blocks_for(a.N), 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, nullptr, 1, flags, hw);
+		}
+		else if(a.rep != nullptr) {
 			if(a.dh_half) k_dh_particle<MD, 1, true, true><<<blocks_for(a.N), 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, a.rep, a.n_per, flags, hw);
 			else k_dh_particle<MD, 1, true, false><<<blocks_for(a.N), 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, a.rep, a.n_per, flags, hw);
 		}
@@ -1496,7 +1516,8 @@ static void launch_edge_stage_dna3(cudaStream_t s, int which, const oxb_dna3_dev
 	static const int cfg = std::min(2, std::max(0, env_int("OXB_DNA3_EDGE_MB", 0)));
 	switch(which == 0 ? 0 : 10 * cfg + which) {
 	case 0:
-		if(a.dh_half) k_dh_particle<Dna3Dh, 1, false, true><<<nb, 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, nullptr, 1, flags, hw);
+		if(a.dh_half && env_int("OXB_DH_SORTED", 1)) k_dh_particle<Dna3Dh, 1, false, true, true><<<nb, 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, nullptr, 1, flags, hw);
+		else if(a.dh_half) k_dh_particle<Dna3Dh, 1, false, true><<<nb, 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, nullptr, 1, flags, hw);
 		else k_dh_particle<Dna3Dh, 1, false, false><<<nb, 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, nullptr, 1, flags, hw);
 		break;
 	// register caps (resident blocks per SM asked of the compiler), OXB_DNA3_EDGE_MB = 0: 128 / 120 / 128 registers for near / heavy / bonded,
