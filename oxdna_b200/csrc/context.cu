@@ -70,7 +70,6 @@ struct oxb_ctx {
 	float4 *d3_buf = nullptr;
 	int *d3_tcode = nullptr;
 	bool d3_tcode_valid = false;
-	int use_edge_asked = 0; // what oxb_set_lists was given
 	oxb::ModelRef mref() const {
 		if(is_dna3) return oxb::ModelRef{ nullptr, nullptr, &d3 };
 		return is_rna ? oxb::ModelRef{ nullptr, &rmodel, nullptr } : oxb::ModelRef{ &model, nullptr, nullptr };
@@ -1034,14 +1033,10 @@ int oxb_set_topology(oxb_ctx *c, const int *btype, const int *n3, const int *n5,
 	return 0;
 }
 
-static void leave_dna3(oxb_ctx *c) {
-	c->is_dna3 = false;
-}
-
 int oxb_set_model_dna2(oxb_ctx *c, const oxb_dna2_params *P, double rcut) {
 	if(c == nullptr || P == nullptr) return 1;
 	if(c->is_rna || c->is_dna3) { drop_graphs(c); c->lists_valid = false; }
-	if(c->is_dna3) leave_dna3(c);
+	c->is_dna3 = false;
 	c->model = *P;
 	c->is_rna = false;
 	c->back_a3 = 0.f;
@@ -1059,7 +1054,7 @@ int oxb_set_model_dna2(oxb_ctx *c, const oxb_dna2_params *P, double rcut) {
 int oxb_set_model_rna2(oxb_ctx *c, const oxb_rna2_params *P, double rcut) {
 	if(c == nullptr || P == nullptr) return 1;
 	if(!c->is_rna && c->have_model) { drop_graphs(c); c->lists_valid = false; }
-	if(c->is_dna3) leave_dna3(c);
+	c->is_dna3 = false;
 	c->rmodel = *P;
 	c->is_rna = true;
 	// the subset the context reads (list radii, site offsets)
@@ -1201,7 +1196,7 @@ int oxb_replica_energies(oxb_ctx *c, double *U) {
 int oxb_set_lists(oxb_ctx *c, double verlet_skin, int use_edge, int sort_every, double max_density_multiplier) {
 	if(c == nullptr) return 1;
 	if(!(verlet_skin > 0)) return fail(c, 1, "verlet_skin must be > 0");
-	c->skin = verlet_skin; c->use_edge_asked = use_edge ? 1 : 0; c->use_edge = use_edge ? 1 : 0; c->sort_every = sort_every < 0 ? 0 : sort_every;
+	c->skin = verlet_skin; c->use_edge = use_edge ? 1 : 0; c->sort_every = sort_every < 0 ? 0 : sort_every;
 	c->max_density_multiplier = max_density_multiplier;
 	c->lists_valid = false; c->forces_valid = false;
 	if(c->lists_allocated) free_lists(c);

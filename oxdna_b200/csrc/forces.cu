@@ -1514,9 +1514,10 @@ static void launch_edge_stage_dna3(cudaStream_t s, int which, const oxb_dna3_dev
 	const int nb = (a.N + 127) / 128;
 	const double4 *posd = a.refine ? a.posd : nullptr;
 	static const int cfg = std::min(2, std::max(0, env_int("OXB_DNA3_EDGE_MB", 0)));
+	static const int dh_sorted = env_int("OXB_DH_SORTED", 1);
 	switch(which == 0 ? 0 : 10 * cfg + which) {
 	case 0:
-		if(a.dh_half && env_int("OXB_DH_SORTED", 1)) k_dh_particle<Dna3Dh, 1, false, true, true><<<nb, 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, nullptr, 1, flags, hw);
+		if(a.dh_half && dh_sorted) k_dh_particle<Dna3Dh, 1, false, true, true><<<nb, 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, nullptr, 1, flags, hw);
 		else if(a.dh_half) k_dh_particle<Dna3Dh, 1, false, true><<<nb, 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, nullptr, 1, flags, hw);
 		else k_dh_particle<Dna3Dh, 1, false, false><<<nb, 128, 0, s>>>(M, box, a.N, a.iback, a.dh_nbr, a.dh_nnbr, a.Fb, nullptr, 1, flags, hw);
 		break;
