@@ -194,3 +194,20 @@ def test_dna3_special_base_types_vs_oracle(use_edge):
         assert np.abs(np.asarray(sim.ctx.energy_split())[:8] - ref["eterms"]).max() <= 2e-6 * abs(ref["U"])
     finally:
         sim.close()
+
+
+@pytest.mark.parametrize("use_edge", [0, 1])
+def test_dna3_average_sequence_tables_vs_oracle(use_edge):
+    """the average-sequence tables bench.py --workload c2_dna3 / c4_dna3 runs on (pinned to the live reference in test_oracle_dna3.py)"""
+    import os
+    g = load_golden("dna3_lattice8")
+    avg = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dna3_tables_avg_300K_salt05.npz"))
+    sim = make_sim(g, dna3_tables=avg["dna3_tables"], dna3_scalars=avg["dna3_scalars"], use_edge=use_edge, CUDA_sort_every=1)
+    try:
+        P = O.dna3_params(avg["dna3_tables"], avg["dna3_scalars"])
+        pairs = O.verlet_pairs(g["pos"], g["n3"], g["n5"], g["box"], P.rcut + 0.1)
+        assert pair_set(sim.ctx.get_pairs()) == pair_set(pairs)
+        ref = O.forces(P, g["pos"], O.axes_from_a1a3(g["a1"], g["a3"]), g["btype"], g["n3"], g["n5"], g["box"], pairs)
+        check_forces(sim.ctx.get_forces(), ref)
+    finally:
+        sim.close()

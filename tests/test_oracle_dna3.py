@@ -189,3 +189,27 @@ def test_dna3_special_base_types_against_the_live_reference(tmp_path):
     plain = O.forces(P, st["pos"], ax, g["btype"], g["n3"], g["n5"], box, pairs)
     assert out["eterms"][4] < plain["eterms"][4] - 0.5
     assert np.abs(out["force"] - plain["force"])[[45, 130]].max() > 1e-3  # the dummy bases sit elsewhere and carry other parameters
+
+
+@pytest.mark.skipif(not RH.available(), reason="oracle/_ref not built (needs /root/reference)")
+def test_dna3_average_sequence_tables_match_the_live_reference(tmp_path):
+    """use_average_seq = 1 (no parameter file): the committed average-sequence tables (tests/golden/dna3_tables_avg_300K_salt05.npz, what
+    bench.py --workload c2_dna3 / c4_dna3 feeds the device) are what the live class holds, and the oracle reproduces its forces with them"""
+    g = load_golden("dna3_lattice8")
+    avg = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dna3_tables_avg_300K_salt05.npz"))
+    top, conf = str(tmp_path / "t.top"), str(tmp_path / "t.dat")
+    oio.write_topology(top, g["btype"], g["n3"], g["n5"], g["strand"])
+    oio.write_conf(conf, g["box"], g["pos"], g["a1"], g["a3"], g["vel"], g["L"])
+    r = RH.Reference(top, conf, interaction_type="DNA3_nomesh", salt_concentration=0.5, T="300K")
+    try:
+        tab, sc = np.zeros((215, 900)), np.zeros(40)
+        k = RH.lib().oxref_dna3_tables(RH._p(tab), RH._p(sc))
+        ref, split, pairs = r.compute_forces(), r.energy_split(), r.pairs()
+    finally:
+        r.close()
+    assert np.array_equal(tab, avg["dna3_tables"]) and np.array_equal(sc[:k], avg["dna3_scalars"])
+    P = O.dna3_params(avg["dna3_tables"], avg["dna3_scalars"])
+    out = O.forces(P, g["pos"], O.axes_from_a1a3(g["a1"], g["a3"]), g["btype"], g["n3"], g["n5"], g["box"], pairs)
+    assert np.abs(out["eterms"] - split).max() < 1e-9
+    assert np.abs(out["force"] - ref["force"]).max() < 1e-9
+    assert np.abs(out["torque_body"] - ref["torque_body"]).max() < 1e-9
