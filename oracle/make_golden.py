@@ -280,9 +280,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "dna3":
         # oxDNA3 (DNA3Interaction_nomesh: the class the CUDA backend instantiates, InteractionFactory.cpp:63-65), sequence-dependent tables
-        sd = dict(use_average_seq=0, seq_dep_file="/root/reference/oxDNA3_sequence_dependent_parameters.txt")
-        lattice_case("dna3_lattice8", 8, 10.0, 3000, itype="DNA3_nomesh", more_keys=sd, dna3=True, nve_steps=100)
-        lattice_case("dna3_lattice27_dense", 27, 8.5, 4000, T="330K", salt=0.2, itype="DNA3_nomesh", more_keys=sd, dna3=True, nve_steps=100)
+        # FIRST, while the process is fresh: with use_average_seq = 1 the reference fills the stacking F1_SD_EPS from a temperature that is
+        # not set yet and never assigns F1_SD_SHIFT (DNA3Interaction.cpp:82-83): the tables are what the heap holds -- zeros in a new
+        # process (what the reference's CLI and its CUDA backend see), leftovers of an earlier interaction object otherwise
         # the average-sequence tables (use_average_seq = 1: no parameter file) at the bench's temperature and salt: bench.py --workload c2_dna3
         sysm = lattice.duplex_lattice(8, bp=20, spacing=10.0, seed=3)
         d = tempfile.mkdtemp()
@@ -295,6 +295,9 @@ if __name__ == "__main__":
         k = RH.lib().oxref_dna3_tables(RH._p(tab), RH._p(sc))
         r.close()
         np.savez_compressed(os.path.join(GOLD, "dna3_tables_avg_300K_salt05.npz"), dna3_tables=tab, dna3_scalars=sc[:k], T="300K", salt=0.5)
+        sd = dict(use_average_seq=0, seq_dep_file="/root/reference/oxDNA3_sequence_dependent_parameters.txt")
+        lattice_case("dna3_lattice8", 8, 10.0, 3000, itype="DNA3_nomesh", more_keys=sd, dna3=True, nve_steps=100)
+        lattice_case("dna3_lattice27_dense", 27, 8.5, 4000, T="330K", salt=0.2, itype="DNA3_nomesh", more_keys=sd, dna3=True, nve_steps=100)
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "ext2":
         ext2_case()

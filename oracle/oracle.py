@@ -84,7 +84,7 @@ class DNA3Params(C.Structure):
                 + [(n, C.c_double) for n in "mbf_fmax mbf_finf hb_multiplier dh_rc dh_rhigh dh_prefactor dh_b dh_minus_kappa".split()]
                 + [("dh_half_charged_ends", C.c_int), ("rcut", C.c_double), ("cxst_t1", _F4), ("cxst_t4", _F4), ("cxst_t5", _F4)]
                 + [(n, C.c_double) for n in "cxst_t1_sa cxst_t1_sb excl_eps back_a1 back_a2 backref_a1".split()]
-                + [("pos_stack", C.c_double * 5), ("pos_base", C.c_double * 5), ("ref_form", C.c_int)])
+                + [("pos_stack", C.c_double * 5), ("pos_base", C.c_double * 5), ("ref_form", C.c_int), ("cxst_mesh", C.c_int)])
 
 
 DNA3_NTAB, DNA3_TSIZE, DNA3_NSCALARS = 215, 900, 29

@@ -170,6 +170,9 @@ typedef struct {
 	/* 1 (default): the stacking phi1 / phi2 force exactly as the reference writes it (CPU class and CUDA kernel), with the oxDNA2 lever
 	 * gamma = 0.74 -- NOT the gradient of the energy for the oxDNA3 stacking site at 0.37; 0: the gradient (finite-difference checks) */
 	int ref_form;
+	/* 1: coaxial theta4 / theta5 / theta6 through the 6-interval cubic meshes of the CPU class (DNA3Interaction_nomesh inherits the meshed scalar f4 of
+	 * DNA2Interaction); 0 (default): analytic f4, as the reference's CUDA kernel */
+	int cxst_mesh;
 } oxo_dna3_params;
 /* scalars: the block written by oxref_dna3_tables (oracle/ref_harness.cpp), also stored in the fixtures */
 void oxo_dna3_params_fill(oxo_dna3_params *P, const double *tab, const double *scalars);

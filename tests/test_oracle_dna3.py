@@ -125,17 +125,21 @@ def test_dna3_oracle_matches_live_reference_after_perturbation(tmp_path, T, salt
     d = np.abs(out["eterms"] - split)
     assert abs(split[6]) > 1e-3, "coaxial stacking must be active"
     assert np.delete(d, 6).max() < 1e-9, d
-    assert d[6] < 2e-4 * abs(split[6]), d          # meshed theta4/5/6 in the CPU class
+    assert d[6] < 2e-4 * abs(split[6]), d          # meshed theta4/5/6 in the CPU class, analytic in the restatement (and on the device)
     fm = np.abs(ref["force"]).max()
     assert np.abs(out["force"] - ref["force"]).max() < 2e-4 * fm
     # particles of pairs without coaxial stacking agree to rounding: find them through the restatement itself
-    P0 = O.dna3_params(tab, sc[:k])
-    per = O.forces(P0, st["pos"], ax, topo["btype"], topo["n3"], topo["n5"], box, pairs)
-    cx = _coaxial_particles(P0, st, ax, topo, box, pairs)
+    cx = _coaxial_particles(P, st, ax, topo, box, pairs)
     quiet = np.setdiff1d(np.arange(N), cx)
     assert len(quiet) > N // 2
-    assert np.abs(per["force"][quiet] - ref["force"][quiet]).max() < 1e-9
-    assert np.abs(per["torque_body"][quiet] - ref["torque_body"][quiet]).max() < 1e-9
+    assert np.abs(out["force"][quiet] - ref["force"][quiet]).max() < 1e-9
+    assert np.abs(out["torque_body"][quiet] - ref["torque_body"][quiet]).max() < 1e-9
+    # with the reference's 6-interval cubic meshes for those three factors (cxst_mesh = 1) the restatement IS the CPU class, coaxial term included
+    P.cxst_mesh = 1
+    m = O.forces(P, st["pos"], ax, topo["btype"], topo["n3"], topo["n5"], box, pairs)
+    assert np.abs(m["eterms"] - split).max() < 1e-9
+    assert np.abs(m["force"] - ref["force"]).max() < 1e-9
+    assert np.abs(m["torque_body"] - ref["torque_body"]).max() < 1e-9
 
 
 def _coaxial_particles(P, st, ax, topo, box, pairs):
@@ -191,25 +195,43 @@ def test_dna3_special_base_types_against_the_live_reference(tmp_path):
     assert np.abs(out["force"] - plain["force"])[[45, 130]].max() > 1e-3  # the dummy bases sit elsewhere and carry other parameters
 
 
+_AVG_SCRIPT = r"""
+import os, sys
+import numpy as np
+root, tmp = sys.argv[1], sys.argv[2]
+sys.path.insert(0, root); sys.path.insert(0, os.path.join(root, "tests"))
+from conftest import load_golden
+from oracle import oracle as O, refharness as RH
+from oxdna_b200 import io as oio
+g = load_golden("dna3_lattice8")
+avg = np.load(os.path.join(root, "tests", "golden", "dna3_tables_avg_300K_salt05.npz"))
+top, conf = os.path.join(tmp, "t.top"), os.path.join(tmp, "t.dat")
+oio.write_topology(top, g["btype"], g["n3"], g["n5"], g["strand"])
+oio.write_conf(conf, g["box"], g["pos"], g["a1"], g["a3"], g["vel"], g["L"])
+r = RH.Reference(top, conf, interaction_type="DNA3_nomesh", salt_concentration=0.5, T="300K")
+tab, sc = np.zeros((215, 900)), np.zeros(40)
+k = RH.lib().oxref_dna3_tables(RH._p(tab), RH._p(sc))
+ref, split, pairs = r.compute_forces(), r.energy_split(), r.pairs()
+r.close()
+assert np.array_equal(tab, avg["dna3_tables"]) and np.array_equal(sc[:k], avg["dna3_scalars"]), "tables differ"
+P = O.dna3_params(avg["dna3_tables"], avg["dna3_scalars"])
+out = O.forces(P, g["pos"], O.axes_from_a1a3(g["a1"], g["a3"]), g["btype"], g["n3"], g["n5"], g["box"], pairs)
+assert np.abs(out["eterms"] - split).max() < 1e-9
+assert np.abs(out["force"] - ref["force"]).max() < 1e-9
+assert np.abs(out["torque_body"] - ref["torque_body"]).max() < 1e-9
+"""
+
+
 @pytest.mark.skipif(not RH.available(), reason="oracle/_ref not built (needs /root/reference)")
 def test_dna3_average_sequence_tables_match_the_live_reference(tmp_path):
     """use_average_seq = 1 (no parameter file): the committed average-sequence tables (tests/golden/dna3_tables_avg_300K_salt05.npz, what
-    bench.py --workload c2_dna3 / c4_dna3 feeds the device) are what the live class holds, and the oracle reproduces its forces with them"""
-    g = load_golden("dna3_lattice8")
-    avg = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dna3_tables_avg_300K_salt05.npz"))
-    top, conf = str(tmp_path / "t.top"), str(tmp_path / "t.dat")
-    oio.write_topology(top, g["btype"], g["n3"], g["n5"], g["strand"])
-    oio.write_conf(conf, g["box"], g["pos"], g["a1"], g["a3"], g["vel"], g["L"])
-    r = RH.Reference(top, conf, interaction_type="DNA3_nomesh", salt_concentration=0.5, T="300K")
-    try:
-        tab, sc = np.zeros((215, 900)), np.zeros(40)
-        k = RH.lib().oxref_dna3_tables(RH._p(tab), RH._p(sc))
-        ref, split, pairs = r.compute_forces(), r.energy_split(), r.pairs()
-    finally:
-        r.close()
-    assert np.array_equal(tab, avg["dna3_tables"]) and np.array_equal(sc[:k], avg["dna3_scalars"])
-    P = O.dna3_params(avg["dna3_tables"], avg["dna3_scalars"])
-    out = O.forces(P, g["pos"], O.axes_from_a1a3(g["a1"], g["a3"]), g["btype"], g["n3"], g["n5"], g["box"], pairs)
-    assert np.abs(out["eterms"] - split).max() < 1e-9
-    assert np.abs(out["force"] - ref["force"]).max() < 1e-9
-    assert np.abs(out["torque_body"] - ref["torque_body"]).max() < 1e-9
+    bench.py --workload c2_dna3 / c4_dna3 feeds the device) are what the live class holds, and the oracle reproduces its forces with them.
+    In a FRESH process, as the reference's CLI runs: with use_average_seq = 1 the class never assigns F1_SD_SHIFT and fills the stacking
+    F1_SD_EPS in its constructor from a temperature that is not set yet (DNA3Interaction.cpp:82-83), i.e. from whatever the heap holds --
+    zeros in a new process (the tables of the fixture, and of the reference CUDA run the bench compares with), leftovers of the previous
+    interaction object otherwise."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, "-c", _AVG_SCRIPT, root, str(tmp_path)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout[-2000:]
