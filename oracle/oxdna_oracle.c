@@ -281,6 +281,41 @@ static double f4_dsin(const oxo_f4 *f, double t) {
 }
 
 
+/* ------------------------------------------------------------------ the cubic mesh of the reference (src/Interactions/Mesh.{h,cpp})
+ * The CPU classes interpolate some f4 factors in cos(theta) on meshes built from the analytic function and its derivative
+ * (DNAInteraction.cpp:199-213, RNAInteraction.cpp:311-325); the CUDA kernels -- the reference's and ours -- evaluate the analytic form.
+ * Restated so that the oracle can reproduce the CPU class to rounding where a test wants that (oxDNA3: cxst_mesh, oxRNA: cpu_quirks bit 2). */
+typedef struct { int n; double xlow, xupp, delta, inv_sqr_delta, A[256], B[256], C[256], D[256]; } oxo_mesh;
+
+static void mesh_build(oxo_mesh *m, const oxo_f4 *f, int npoints) {
+	const double xupp = cos(fmax(0., f->t0 - f->tc)), xlow = cos(fmin((double) OXO_PI, f->t0 + f->tc));
+	const double dx = (xupp - xlow) / (double) npoints;
+	m->n = npoints; m->xlow = xlow; m->xupp = xupp; m->delta = dx; m->inv_sqr_delta = 1 / SQ(dx);
+	for(int i = 0; i < npoints + 1; i++) {
+		const double x = xlow + i * dx;
+		/* _fakef4 / _fakef4D: f4(acos x) and -f4Dsin(acos x); beyond x = 1 (the unused far side of the last entry) the argument is clamped */
+		const double t0 = clamp_acos(x), t1 = clamp_acos(x + dx);
+		const double fx0 = f4_val(f, t0), fx1 = f4_val(f, t1), d0 = -f4_dsin(f, t0), d1 = -f4_dsin(f, t1);
+		m->A[i] = fx0; m->B[i] = d0;
+		m->D[i] = (2 * (fx0 - fx1) + (d0 + d1) * dx) / dx;
+		m->C[i] = (fx1 - fx0 + (-d0 - m->D[i]) * dx);
+	}
+}
+static double mesh_query(const oxo_mesh *m, double x) {
+	if(x <= m->xlow) return m->A[0];
+	if(x >= m->xupp) x = m->xupp - FLT_EPSILON;
+	const int i = (int) ((x - m->xlow) / m->delta);
+	const double dx = x - m->xlow - m->delta * i;
+	return m->A[i] + dx * (m->B[i] + dx * (m->C[i] + dx * m->D[i]) * m->inv_sqr_delta);
+}
+static double mesh_query_derivative(const oxo_mesh *m, double x) {
+	if(x < m->xlow) return m->B[0];
+	if(x >= m->xupp) x = m->xupp - FLT_EPSILON;
+	const int i = (int) ((x - m->xlow) / m->delta);
+	const double dx = x - m->xlow - m->delta * i;
+	return m->B[i] + (2 * dx * m->C[i] + 3 * dx * dx * m->D[i]) * m->inv_sqr_delta;
+}
+
 /* c = shat . (bhat x u), u a body vector of p (onq = 0) or q (onq = 1); shat between the stacking sites, bhat between the
  * backbone sites; g = dE/dc.  RNAInteraction.cpp:1093-1142 */
 static void chain_triple(pacc *A, double g, const double *u, int onq, const double *sh, double sm, const double *ssp, const double *ssq,

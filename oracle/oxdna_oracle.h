@@ -135,7 +135,9 @@ typedef struct {
 	double mis_eps, mis_shift;
 	/* bit mask: reproduce two places where the CPU class's force is NOT the gradient of its energy (the reference's CUDA kernels
 	 * use the gradient): bit 0 -- the phi2 stacking term lacks the thetaB1/B2 factors (RNAInteraction.cpp:620); bit 1 -- the mirrored
-	 * coaxial theta1 term has the opposite sign (RNAInteraction.cpp:1046 vs :1302 and CUDA_RNA.cuh:896).  3: the CPU class; 0: gradient. */
+	 * coaxial theta1 term has the opposite sign (RNAInteraction.cpp:1046 vs :1302 and CUDA_RNA.cuh:896).  3: the CPU class; 0: gradient.
+	 * bit 2 (4): the six f4 factors of the hydrogen bonding interpolated on the CPU class's cubic meshes (RNAInteraction.cpp:769-794) instead of
+	 * the analytic form of the CUDA kernels: 7 reproduces the CPU class in every term */
 	int cpu_quirks;
 	double rcut;
 } oxo_rna2_params;

@@ -239,6 +239,13 @@ def test_rna_oracle_matches_reference_fixture(case):
     assert abs(d[hb]) <= 1e-4 * abs(g["energy_split"][hb])
     for k in ("force", "torque_lab", "torque_body"):
         assert np.abs(out[k] - g[k]).max() < tol * max(1.0, np.abs(g[k]).max()), k
+    # with the CPU class's cubic meshes restated for the six hydrogen-bonding factors (cpu_quirks bit 2) the restatement reproduces the
+    # fixture in EVERY term to rounding -- the analytic form above is what the CUDA kernels (the reference's and ours) evaluate
+    P.cpu_quirks = int(P.cpu_quirks) | 4
+    m = O.forces(P, g["pos"], ax, g["btype"], g["n3"], g["n5"], g["box"], pairs)
+    assert np.abs(m["eterms"] - g["energy_split"]).max() < 1e-10
+    for k in ("force", "torque_lab", "torque_body"):
+        assert np.abs(m[k] - g[k]).max() < 1e-9 * max(1.0, np.abs(g[k]).max()), k
 
 
 def test_rna_oracle_nve_matches_reference_fixture():
