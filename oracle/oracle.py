@@ -56,7 +56,7 @@ class DNA2Params(C.Structure):
         + [(n, _F4) for n in "stck_t4 stck_t5 hb_t1 hb_t2 hb_t4 hb_t7 crst_t1 crst_t2 crst_t4 crst_t7 cxst_t1 cxst_t4 cxst_t5".split()]
         + [("cxst_t1_sa", C.c_double), ("cxst_t1_sb", C.c_double), ("stck_phi1", _F5), ("stck_phi2", _F5)]
         + [(n, C.c_double) for n in "dh_minus_kappa dh_prefactor dh_rhigh dh_rc dh_b".split()]
-        + [("dh_half_charged_ends", C.c_int), ("hb_multiplier", C.c_double), ("rcut", C.c_double), ("v1", C.c_int), ("cxst_phi3", _F5)]
+        + [("dh_half_charged_ends", C.c_int), ("hb_multiplier", C.c_double), ("rcut", C.c_double), ("v1", C.c_int), ("cxst_phi3", _F5), ("mesh", C.c_int)]
     )
 
 

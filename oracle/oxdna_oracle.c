@@ -287,7 +287,8 @@ static double f4_dsin(const oxo_f4 *f, double t) {
  * Restated so that the oracle can reproduce the CPU class to rounding where a test wants that (oxDNA3: cxst_mesh, oxRNA: cpu_quirks bit 2). */
 typedef struct { int n; double xlow, xupp, delta, inv_sqr_delta, A[256], B[256], C[256], D[256]; } oxo_mesh;
 
-static void mesh_build(oxo_mesh *m, const oxo_f4 *f, int npoints) {
+/* mirror2pi: the first-generation coaxial theta1, f4(t) + f4(2 PI - t) (DNAInteraction.cpp:1335-1351) */
+static void mesh_build_mode(oxo_mesh *m, const oxo_f4 *f, int npoints, int mirror2pi) {
 	const double xupp = cos(fmax(0., f->t0 - f->tc)), xlow = cos(fmin((double) OXO_PI, f->t0 + f->tc));
 	const double dx = (xupp - xlow) / (double) npoints;
 	m->n = npoints; m->xlow = xlow; m->xupp = xupp; m->delta = dx; m->inv_sqr_delta = 1 / SQ(dx);
@@ -295,12 +296,17 @@ static void mesh_build(oxo_mesh *m, const oxo_f4 *f, int npoints) {
 		const double x = xlow + i * dx;
 		/* _fakef4 / _fakef4D: f4(acos x) and -f4Dsin(acos x); beyond x = 1 (the unused far side of the last entry) the argument is clamped */
 		const double t0 = clamp_acos(x), t1 = clamp_acos(x + dx);
-		const double fx0 = f4_val(f, t0), fx1 = f4_val(f, t1), d0 = -f4_dsin(f, t0), d1 = -f4_dsin(f, t1);
+		double fx0 = f4_val(f, t0), fx1 = f4_val(f, t1), d0 = -f4_dsin(f, t0), d1 = -f4_dsin(f, t1);
+		if(mirror2pi) {
+			fx0 += f4_val(f, 2 * OXO_PI - t0); fx1 += f4_val(f, 2 * OXO_PI - t1);
+			d0 -= f4_dsin(f, 2 * OXO_PI - t0); d1 -= f4_dsin(f, 2 * OXO_PI - t1);
+		}
 		m->A[i] = fx0; m->B[i] = d0;
 		m->D[i] = (2 * (fx0 - fx1) + (d0 + d1) * dx) / dx;
 		m->C[i] = (fx1 - fx0 + (-d0 - m->D[i]) * dx);
 	}
 }
+static void mesh_build(oxo_mesh *m, const oxo_f4 *f, int npoints) { mesh_build_mode(m, f, npoints, 0); }
 static double mesh_query(const oxo_mesh *m, double x) {
 	if(x <= m->xlow) return m->A[0];
 	if(x >= m->xupp) x = m->xupp - FLT_EPSILON;
@@ -314,6 +320,29 @@ static double mesh_query_derivative(const oxo_mesh *m, double x) {
 	const int i = (int) ((x - m->xlow) / m->delta);
 	const double dx = x - m->xlow - m->delta * i;
 	return m->B[i] + (2 * dx * m->C[i] + 3 * dx * dx * m->D[i]) * m->inv_sqr_delta;
+}
+
+/* f4 through the CPU class's mesh when P->mesh is set (DNAInteraction::_custom_f4, DNAInteraction.cpp:1173-1180; mesh sizes: model.h:410-433),
+ * analytic otherwise.  Meshes are cached by their parameters. */
+static const oxo_mesh *mesh_for(const oxo_f4 *f, int npoints) {
+	static struct { oxo_f4 key; int n; oxo_mesh m; } cache[24];
+	static int used = 0;
+	for(int i = 0; i < used; i++) if(cache[i].n == npoints && memcmp(&cache[i].key, f, sizeof(oxo_f4)) == 0) return &cache[i].m;
+	const int slot = used < 24 ? used++ : 0;
+	cache[slot].key = *f; cache[slot].n = npoints;
+	mesh_build(&cache[slot].m, f, npoints);
+	return &cache[slot].m;
+}
+static void f4m_eval(int mesh, const oxo_f4 *f, int npoints, double c, double *v, double *dc) {
+	if(!mesh) { f4_eval(f, c, v, dc); return; }
+	const oxo_mesh *m = mesh_for(f, npoints);
+	*v = mesh_query(m, c); *dc = mesh_query_derivative(m, c);
+}
+static void f4m_sym(int mesh, const oxo_f4 *f, int npoints, double c, double *v, double *dc) {
+	double v1, d1, v2, d2;
+	f4m_eval(mesh, f, npoints, c, &v1, &d1);
+	f4m_eval(mesh, f, npoints, -c, &v2, &d2);
+	*v = v1 + v2; *dc = d1 - d2;
 }
 
 /* c = shat . (bhat x u), u a body vector of p (onq = 0) or q (onq = 1); shat between the stacking sites, bhat between the
@@ -419,9 +448,9 @@ static void bonded_pair(const oxo_dna2_params *P, const double *r, const sites_t
 	double cp1 = dot3(sp->a2, wh), cp2 = dot3(sq->a2, wh);
 	double f1, f1d, g4, g4d, g5, g5d, g6, g6d, h1, h1d, h2, h2d;
 	f1_eval(&P->stck, rstm, tq, tp, &f1, &f1d);
-	f4_eval(&P->stck_t4, c4, &g4, &g4d);
-	f4_eval(&P->stck_t5, c5, &g5, &g5d);
-	f4_eval(&P->stck_t5, c6, &g6, &g6d);
+	f4m_eval(P->mesh, &P->stck_t4, 250, c4, &g4, &g4d);
+	f4m_eval(P->mesh, &P->stck_t5, 250, c5, &g5, &g5d);
+	f4m_eval(P->mesh, &P->stck_t5, 250, c6, &g6, &g6d);
 	f5_eval(&P->stck_phi1, cp1, &h1, &h1d);
 	f5_eval(&P->stck_phi2, cp2, &h2, &h2d);
 	double E = f1 * g4 * g5 * g6 * h1 * h2;
@@ -464,12 +493,12 @@ static void nonbonded_pair(const oxo_dna2_params *P, const double *r, const site
 		double f1, f1d, g[6], d[6];
 		f1_eval(&P->hb, m, tq, tp, &f1, &f1d);
 		f1 *= mult; f1d *= mult;
-		f4_eval(&P->hb_t1, c1, &g[0], &d[0]);
-		f4_eval(&P->hb_t2, c2, &g[1], &d[1]);
-		f4_eval(&P->hb_t2, c3, &g[2], &d[2]);
-		f4_eval(&P->hb_t4, c4, &g[3], &d[3]);
-		f4_eval(&P->hb_t7, c7, &g[4], &d[4]);
-		f4_eval(&P->hb_t7, c8, &g[5], &d[5]);
+		f4m_eval(P->mesh, &P->hb_t1, 6, c1, &g[0], &d[0]);
+		f4m_eval(P->mesh, &P->hb_t2, 6, c2, &g[1], &d[1]);
+		f4m_eval(P->mesh, &P->hb_t2, 6, c3, &g[2], &d[2]);
+		f4m_eval(P->mesh, &P->hb_t4, 250, c4, &g[3], &d[3]);
+		f4m_eval(P->mesh, &P->hb_t7, 12, c7, &g[4], &d[4]);
+		f4m_eval(P->mesh, &P->hb_t7, 12, c8, &g[5], &d[5]);
 		double E = f1 * g[0] * g[1] * g[2] * g[3] * g[4] * g[5];
 		e[OXO_HB] += E;
 		if(E != 0.) {
@@ -490,12 +519,12 @@ static void nonbonded_pair(const oxo_dna2_params *P, const double *r, const site
 	if(P->crst.rclow < m && m < P->crst.rchigh) {
 		double f2, f2d, g[6], d[6];
 		f2_eval(&P->crst, m, &f2, &f2d);
-		f4_eval(&P->crst_t1, c1, &g[0], &d[0]);
-		f4_eval(&P->crst_t2, c2, &g[1], &d[1]);
-		f4_eval(&P->crst_t2, c3, &g[2], &d[2]);
-		f4_sym(&P->crst_t4, c4, &g[3], &d[3]);
-		f4_sym(&P->crst_t7, c7, &g[4], &d[4]);
-		f4_sym(&P->crst_t7, c8, &g[5], &d[5]);
+		f4m_eval(P->mesh, &P->crst_t1, 250, c1, &g[0], &d[0]);
+		f4m_eval(P->mesh, &P->crst_t2, 250, c2, &g[1], &d[1]);
+		f4m_eval(P->mesh, &P->crst_t2, 250, c3, &g[2], &d[2]);
+		f4m_sym(P->mesh, &P->crst_t4, 6, c4, &g[3], &d[3]);
+		f4m_sym(P->mesh, &P->crst_t7, 250, c7, &g[4], &d[4]);
+		f4m_sym(P->mesh, &P->crst_t7, 250, c8, &g[5], &d[5]);
 		double E = f2 * g[0] * g[1] * g[2] * g[3] * g[4] * g[5];
 		e[OXO_CRST] += E;
 		if(E != 0.) {
@@ -518,16 +547,22 @@ static void nonbonded_pair(const oxo_dna2_params *P, const double *r, const site
 		double c5 = dot3(sp->a3, h), c6 = dot3(mb3, h);
 		double f2, f2d, g[4], d[4];
 		f2_eval(&P->cxst, m, &f2, &f2d);
-		if(P->v1) {
+		if(P->v1 && P->mesh) {
+			/* the meshed class interpolates this combination too (250 intervals, DNAInteraction.cpp:210-212) */
+			static oxo_mesh M; static oxo_f4 built; static int have = 0;
+			if(!have || memcmp(&built, &P->cxst_t1, sizeof(oxo_f4))) { mesh_build_mode(&M, &P->cxst_t1, 250, 1); built = P->cxst_t1; have = 1; }
+			g[0] = mesh_query(&M, c1); d[0] = mesh_query_derivative(&M, c1);
+		}
+		else if(P->v1) {
 			/* oxDNA1: f4(t1) + f4(2 PI - t1) (DNAInteraction.cpp:1331-1352) */
 			double t = rna_acos(c1);
 			g[0] = f4_val(&P->cxst_t1, t) + f4_val(&P->cxst_t1, 2 * OXO_PI - t);
 			d[0] = -f4_dsin(&P->cxst_t1, t) - f4_dsin(&P->cxst_t1, 2 * OXO_PI - t);
 		}
 		else f4_cxst_t1(P, c1, &g[0], &d[0]);
-		f4_eval(&P->cxst_t4, c4, &g[1], &d[1]);
-		f4_sym(&P->cxst_t5, c5, &g[2], &d[2]);
-		f4_sym(&P->cxst_t5, c6, &g[3], &d[3]);
+		f4m_eval(P->mesh, &P->cxst_t4, 6, c4, &g[1], &d[1]);
+		f4m_sym(P->mesh, &P->cxst_t5, 6, c5, &g[2], &d[2]);
+		f4m_sym(P->mesh, &P->cxst_t5, 6, c6, &g[3], &d[3]);
 		/* oxDNA1: times f5(cos phi3)^2, cos phi3 = shat . (bhat_ref x a1) with bhat_ref between the UNGROOVED backbone
 		 * reference sites (DNAInteraction.cpp:1049-1062) */
 		double wv[3], wm = 1, wh[3] = { 0, 0, 0 }, f5v = 1, f5d = 0;

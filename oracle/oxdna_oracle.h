@@ -49,6 +49,9 @@ typedef struct {
 	/* first-generation oxDNA (interaction_type = DNA): mirrored coaxial theta1 and the phi3 factor, no Debye-Hueckel */
 	int v1;
 	oxo_f5 cxst_phi3;
+	/* 1: the f4 factors through the cubic meshes of the CPU classes DNAInteraction / DNA2Interaction (interaction_type = DNA / DNA2; model.h:410-433;
+	 * the oxDNA2 coaxial theta1 stays analytic, DNA2Interaction.h:61-64); 0 (default): analytic, as DNA2_nomesh and the CUDA kernels */
+	int mesh;
 } oxo_dna2_params;
 
 /* average-sequence oxDNA2 parameters at temperature T (simulation units) and molar salt.

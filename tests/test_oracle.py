@@ -485,3 +485,56 @@ def test_oracle_dna2_sequence_dependent_with_dummy_bases_matches_live_reference(
     assert np.abs(out["eterms"] - split).max() < 1e-9
     assert np.abs(out["force"] - ref["force"]).max() < 1e-9
     assert np.abs(out["torque_body"] - ref["torque_body"]).max() < 1e-9
+
+
+def test_reference_golden_vector_file_with_the_meshed_class():
+    """test/DNA/FORCE_FIELD/AVG_SEQ/reference.dat was written by the MESHED class (interaction_type = DNA2).  With the reference's cubic meshes
+    restated (P.mesh = 1: src/Interactions/Mesh.{h,cpp}, DNAInteraction.cpp:199-213) the per-term energies agree to the print precision of the
+    file (6 decimals) -- the analytic form, which the CUDA kernels evaluate, is off in the 6th digit of the hydrogen bonding"""
+    ref = np.loadtxt(os.path.join(GOLD, "force_field_dna", "reference_avg_seq.dat"))
+    t = oio.read_topology(os.path.join(GOLD, "force_field_dna", "init.top"))
+    c = oio.read_conf(os.path.join(GOLD, "force_field_dna", "init.dat"))
+    P = O.dna2_params(O.celsius(20.0), 1.0)
+    ax = O.axes_from_a1a3(c["a1"], c["a3"])
+    pairs = O.verlet_pairs(c["pos"], t["n3"], t["n5"], c["box"], P.rcut + 0.1)
+    analytic = O.forces(P, c["pos"], ax, t["btype"], t["n3"], t["n5"], c["box"], pairs)["eterms"] / t["N"]
+    P.mesh = 1
+    meshed = O.forces(P, c["pos"], ax, t["btype"], t["n3"], t["n5"], c["box"], pairs)["eterms"] / t["N"]
+    assert np.abs(meshed - ref).max() <= 5.5e-7, (meshed, ref)
+    assert np.abs(analytic - ref).max() > np.abs(meshed - ref).max()
+
+
+@pytest.mark.skipif(not RH.available(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("itype", ["DNA2", "DNA"])
+def test_oracle_with_meshes_matches_the_live_meshed_classes(tmp_path, itype):
+    """interaction_type = DNA2 / DNA (the meshed CPU classes, the reference's defaults) on a perturbed dense configuration: with P.mesh = 1 the
+    restatement reproduces forces, torques and per-term energies to rounding"""
+    g = load_golden("lattice27_dense")
+    rng = np.random.default_rng(21)
+    N = len(g["pos"])
+    pos = g["pos"] + rng.normal(0, 0.02, (N, 3))
+    ax = O.axes_from_a1a3(g["a1"] + rng.normal(0, 0.05, (N, 3)), g["a3"] + rng.normal(0, 0.05, (N, 3)))
+    top, conf = str(tmp_path / "t.top"), str(tmp_path / "t.dat")
+    oio.write_topology(top, g["btype"], g["n3"], g["n5"], g["strand"])
+    oio.write_conf(conf, g["box"], pos, ax[:, 0:3], ax[:, 6:9], g["vel"], g["L"])
+    r = RH.Reference(top, conf, interaction_type=itype, salt_concentration=0.5, T="300K", max_backbone_force=10.0)
+    try:
+        st, ref, split, pairs = r.state(), r.compute_forces(), r.energy_split(), r.pairs()
+    finally:
+        r.close()
+    T = parse_temperature("300K")
+    P = O.dna2_params(T, 0.5, max_backbone_force=10.0) if itype == "DNA2" else O.dna1_params(T, max_backbone_force=10.0)
+    ax = O.axes_from_a1a3(st["a1"], st["a3"])
+    plain = O.forces(P, st["pos"], ax, g["btype"], g["n3"], g["n5"], g["box"], pairs)
+    P.mesh = 1
+    out = O.forces(P, st["pos"], ax, g["btype"], g["n3"], g["n5"], g["box"], pairs)
+    n = len(split)
+    assert np.abs(out["eterms"][:n] - split).max() < 1e-9
+    # (first-generation oxDNA: 2e-8 on the two nucleotides of an end-to-end coaxial stack, 5 % of 4e-7 that the meshes change there -- the
+    # cubic coefficients are difference quotients of node values and amplify their last bits; everything else to 1e-12)
+    tol = 1e-9 if itype == "DNA2" else 1e-7
+    assert np.abs(out["force"] - ref["force"]).max() < tol
+    assert np.abs(out["torque_body"] - ref["torque_body"]).max() < tol
+    # the analytic form (DNA2_nomesh, the CUDA kernels) differs from the meshed class by the interpolation error of its 6- to 250-interval
+    # meshes: up to a few 1e-2 in force on a perturbed configuration
+    assert 1e-9 < np.abs(plain["force"] - ref["force"]).max() < 0.2
